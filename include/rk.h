@@ -1,0 +1,112 @@
+/*
+ * rk.h -- C ABI of the B200 rollout kernels ("rk") behind JaxBackpropPlanner.
+ *
+ * The reference (pyRDDLGym-jax v3.2) has no FFI: its hot path is reached through Python
+ * closures that JAX traces and XLA compiles.  Each entry point below names the reference
+ * function whose device work it replaces (paths relative to pyRDDLGym_jax/core/).
+ *
+ * Conventions: every function returns 0 on success, a negative RK_E_* code for an invalid
+ * argument / program, or a positive cudaError_t.  The caller owns every device buffer; the
+ * library owns only the opaque program handle.  All launches go to the caller's stream and
+ * never synchronise.  Nothing here falls back to the CPU.
+ *
+ * Batched buffers are "fluent-major": a quantity with W words per rollout is stored as the
+ * concatenation over fluents f of a [B][n_f] array (the dict of [B, *objs] tensors of
+ * JaxRDDLSimState.fls, compiler.py:54-62, flattened), and [T] such blocks when it has a
+ * step axis.  Numerical error bits follow compiler.py:861-888.
+ */
+#ifndef RK_H
+#define RK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RK_E_BADARG   (-1)
+#define RK_E_BADPROG  (-2)
+#define RK_E_SMEM     (-3)
+#define RK_E_NOMEM    (-4)
+
+typedef struct rk_program rk_program;
+
+typedef struct rk_sizes {
+  int32_t kind;          /* 0 forward, 1 backward                                         */
+  int32_t relaxed;       /* 1 = JaxRDDLCompilerWithGrad model, 0 = exact JaxRDDLCompiler  */
+  int32_t S, A, N;       /* state / action-parameter / noise words per rollout(-step)     */
+  int32_t n_mparams;     /* model parameter slots (logic.py:266 aux['params'])            */
+  int32_t rpw, lanes;    /* rollouts per warp, lanes per rollout                          */
+  int32_t warp_words, const_words;
+  int32_t n_prologue, n_step, n_epilogue;
+  int32_t warps_per_cta; /* launch geometry chosen for this program                       */
+  int32_t smem_bytes;
+  int32_t static_err;
+} rk_sizes;
+
+/* Upload a program produced by core/program.py to the current device.
+ * Replaces: jax.jit tracing/compilation of compile_rollouts (compiler.py:621-666,
+ * planner.py:2687, 2930). */
+int rk_program_create(const void* blob, size_t nbytes, rk_program** out);
+void rk_program_destroy(rk_program* prog);
+int rk_program_query(const rk_program* prog, rk_sizes* out);
+/* number of warps (= gradient partial rows) a launch with batch B uses */
+int rk_program_num_warps(const rk_program* prog, int B);
+
+/* Forward rollout of B trajectories for T steps.
+ * Replaces: the jitted train_rollouts / test_rollouts executable, i.e. lax.scan over
+ * _jax_wrapped_batched_policy_step (compiler.py:561-619).
+ *   s0       [S*B]      initial state, fluent-major (init_sim_state, compiler.py:729-771)
+ *   policy   [T*A]      straight-line plan parameters (planner.py:786-868), or NULL
+ *   actions  [T*A*B]    per-rollout actions for externally computed policies, or NULL
+ *   noise    [T*N*B]    supplied draws, or NULL when N == 0
+ *   mparams  [n_mparams] relaxation weights, or NULL for the compiled defaults
+ *   disc     [T]        gamma^t, or NULL when gamma == 1 (planner.py:2754-2757)
+ *   reward   [T*B]      log['reward'] transposed (compiler.py:538)
+ *   returns  [B]        sum_t gamma^t r_t (planner.py:2761)
+ *   err      [T*B]      log['error'] bitmask (compiler.py:539), or NULL
+ *   tape     [T*S*B]    state at the start of every step (for the adjoint), or NULL
+ *   final    [S*B]      state after the last step, or NULL
+ *   traj     [T*TRAJ*B] logged fluents (cache_path_info, compiler.py:515-518), or NULL */
+int rk_rollout_forward(const rk_program* prog, void* stream, int B, int T,
+                       const void* s0, const float* policy, const void* actions,
+                       const float* noise, const float* mparams, const float* disc,
+                       float* reward, float* returns, uint32_t* err,
+                       void* tape, void* final_state, void* traj);
+
+/* Backprop-through-time of  sum_b gret[b] * return_b  w.r.t. the policy parameters.
+ * Replaces: the reverse pass of jax.value_and_grad over the scan (planner.py:2873-2882).
+ *   tape, noise, policy/actions, mparams, disc : as given to / written by the forward pass
+ *   gret     [B]        d loss / d return_b  (-1/B for utility='mean', planner.py:2817-2818)
+ *   gradp    [num_warps*T*A] per-warp partial gradients of the plan parameters (SLP), or NULL
+ *   gact     [T*A*B]    per-rollout action gradients (external policies), or NULL
+ *   gs0      [S*B]      gradient w.r.t. the initial state, or NULL */
+int rk_rollout_backward(const rk_program* prog, void* stream, int B, int T,
+                        const void* tape, const float* policy, const void* actions,
+                        const float* noise, const float* mparams, const float* disc,
+                        const float* gret, float* gradp, float* gact, float* gs0);
+
+/* Fixed-order reduction of the per-warp gradient partials: grad[i] = sum_w gradp[w][i].
+ * Replaces: the batch reduction XLA fuses into the transposed scan. */
+int rk_reduce_partials(void* stream, const float* gradp, int num_rows, int n, float* grad);
+
+/* Optimiser step + box projection on a flat parameter vector.
+ * Replaces: optax chain update + apply_updates + plan.projection (planner.py:2885-2899,
+ * 2349-2387; box projection planner.py:878-910).
+ *   kind: 0 sgd, 1 rmsprop, 2 adam.  hyper = {lr, decay|b1, eps, b2, clip_norm(<=0 off),
+ *   momentum, step(1-based)}.  state: rmsprop nu [n]; adam mu [n] then nu [n].
+ *   lo/hi [n] box (may be +-inf) or NULL.  zero_flag: set to 1 when all |g| <= 1e-8
+ *   (planner.py:2861-2864). */
+int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
+                      float* params, float* state, const float* grad,
+                      const float* lo, const float* hi, int32_t* zero_flag);
+
+/* -mean(returns) and its cotangent, for utility='mean' (planner.py:2817-2818):
+ * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */
+int rk_mean_loss(void* stream, const float* returns, int B, float* loss, float* gret);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RK_H */

@@ -1,0 +1,191 @@
+"""CPU ORACLE (test infrastructure) -- PARITY UNPINNED -- planner side.
+
+Restates, in torch-CPU fp32 with autograd:
+  * straight-line plan policies      pyRDDLGym_jax/core/planner.py:741-868
+  * box / concurrency projections    planner.py:489-617, 878-959
+  * batched scan over the horizon    compiler.py:551-619
+  * return, loss                     planner.py:2747-2822
+  * optimiser updates                planner.py:2349-2387, 2885-2899 (optax semantics assumed:
+    rmsprop  nu <- d nu + (1-d) g^2, update = g * rsqrt(nu + eps);  adam with bias
+    correction, step counted from 1;  clip_by_global_norm;  apply_updates p + u)
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .model_eval import OracleModel, REAL, INT, safe_log
+
+
+# ---- straight-line plan ----------------------------------------------------------------
+def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
+                      sigmoid_weight: Dict[str, float] | float = 1.0):
+    """planner.py:786-838 (deterministic plan: stochastic=False)."""
+    actions = {}
+    for name in model.action_fluents:
+        p = params[name][t]
+        if model.variable_ranges[name] == "bool":
+            w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
+            a = torch.sigmoid(w * p) if wrap_sigmoid else p            # planner.py:741-745
+        else:
+            a = p
+        actions[name] = a.unsqueeze(0)          # same action for every rollout
+    return actions
+
+
+def slp_test_actions(model, params: Dict[str, torch.Tensor], t: int, bounds, wrap_sigmoid=True):
+    """planner.py:842-868."""
+    actions = {}
+    thr = 0.0 if wrap_sigmoid else 0.5
+    for name in model.action_fluents:
+        p = params[name][t]
+        prange = model.variable_ranges[name]
+        if prange == "bool":
+            a = p > thr
+        else:
+            lo, hi = bounds[name]
+            lo = torch.as_tensor(np.asarray(lo, np.float32))
+            hi = torch.as_tensor(np.asarray(hi, np.float32))
+            a = torch.minimum(torch.maximum(p, lo), hi)
+            if prange != "real":
+                a = torch.round(a).to(INT)
+        actions[name] = a.unsqueeze(0)
+    return actions
+
+
+def expand_actions(actions, B):
+    return {k: v.expand((B,) + tuple(v.shape[1:])) for k, v in actions.items()}
+
+
+# ---- rollouts ------------------------------------------------------------------------------
+def rollout(om: OracleModel, policy: Callable[[int, Dict[str, torch.Tensor]], Dict[str, torch.Tensor]],
+            B: int, T: int, noise_steps: List[List[torch.Tensor]], subs=None, log_fluents=()):
+    """compiler.py:596-619: scan of the batched policy step.  Returns dict with reward [B,T],
+    error [B,T], final fluents and optional per-step fluent logs [B,T,...]."""
+    fls, nfls = om.init_fls_nfls(B, subs)
+    rewards, errs = [], []
+    logs = {f: [] for f in log_fluents}
+    states = []
+    spec = None
+    for t in range(T):
+        states.append({s: fls[s] for s in om.model.state_fluents})
+        actions = expand_actions(policy(t, fls), B)
+        if om.relaxed:
+            actions = {k: v.to(REAL) for k, v in actions.items()}
+        fls, r, e, spec = om.step(fls, nfls, actions, noise_steps[t] if noise_steps else None, B)
+        rewards.append(r)
+        errs.append(e)
+        for f in log_fluents:
+            logs[f].append(fls[f])
+    out = {"reward": torch.stack(rewards, 1) if T else torch.zeros(B, 0),
+           "error": torch.stack(errs, 1) if T else torch.zeros(B, 0, dtype=torch.int64),
+           "final": {s: fls[s] for s in om.model.state_fluents},
+           "states": states, "noise_spec": spec,
+           "fluents": {f: torch.stack(v, 1) for f, v in logs.items()}}
+    return out
+
+
+def returns_from_rewards(rewards: torch.Tensor, gamma: float = 1.0):
+    """planner.py:2751-2764."""
+    if gamma != 1:
+        T = rewards.shape[-1]
+        disc = torch.pow(torch.tensor(gamma, dtype=REAL), torch.arange(T, dtype=REAL))
+        rewards = rewards * disc.unsqueeze(0)
+    return rewards.sum(1)
+
+
+def mean_loss(rewards: torch.Tensor, gamma: float = 1.0):
+    """planner.py:2817-2818 with utility='mean'."""
+    return -returns_from_rewards(rewards, gamma).mean()
+
+
+# ---- optimisers (optax semantics) ---------------------------------------------------------------
+def clip_by_global_norm(grads: List[torch.Tensor], max_norm: float):
+    gn = torch.sqrt(sum((g * g).sum() for g in grads))
+    if gn > max_norm:
+        return [g * (max_norm / gn) for g in grads]
+    return grads
+
+
+def rmsprop_step(p, g, nu, lr, decay=0.9, eps=1e-8):
+    nu = decay * nu + (1. - decay) * g * g
+    return p - lr * g / torch.sqrt(nu + eps), nu
+
+
+def adam_step(p, g, mu, nu, step, lr, b1=0.9, b2=0.999, eps=1e-8):
+    mu = b1 * mu + (1. - b1) * g
+    nu = b2 * nu + (1. - b2) * g * g
+    mh = mu / (1. - b1 ** step)
+    nh = nu / (1. - b2 ** step)
+    return p - lr * mh / (torch.sqrt(nh) + eps), mu, nu
+
+
+def sgd_step(p, g, lr):
+    return p - lr * g
+
+
+# ---- projections ------------------------------------------------------------------------------
+def bool_box(wrap_sigmoid: bool, min_action_prob: float, weight: float):
+    """planner.py:878-882: clip bounds of a boolean action parameter."""
+    if wrap_sigmoid:
+        logit = lambda a: math.log(a / (1. - a))      # noqa: E731
+        return logit(min_action_prob) / weight, logit(1. - min_action_prob) / weight
+    return min_action_prob, 1. - min_action_prob
+
+
+def project_box(model, params, bounds, wrap_sigmoid=True, min_action_prob=1e-6, weight=1.0):
+    """planner.py:884-904."""
+    out = {}
+    for name, p in params.items():
+        if model.variable_ranges[name] == "bool":
+            lo, hi = bool_box(wrap_sigmoid, min_action_prob, weight)
+            out[name] = torch.clamp(p, lo, hi)
+        else:
+            lo, hi = bounds[name]
+            lo = torch.as_tensor(np.asarray(lo, np.float32))
+            hi = torch.as_tensor(np.asarray(hi, np.float32))
+            out[name] = torch.minimum(torch.maximum(p, lo), hi)
+    return out
+
+
+def sogbofa_project_row(actions: Dict[str, torch.Tensor], noop: Dict[str, bool], allowed: int,
+                        max_iter: int, min_action: float, max_action: float):
+    """planner.py:540-616 on one time step: actions -> adjusted actions (before the
+    action->parameter inverse map).  Returns (new_actions, converged)."""
+    def surplus_k(acts):
+        total, k = torch.tensor(0., dtype=REAL), 0
+        for var, a in acts.items():
+            if noop[var]:
+                a = 1 - a
+            total = total + a.sum()
+            k = k + int(torch.count_nonzero(a))
+        return torch.clamp(total - allowed, min=0.), k
+
+    acts = dict(actions)
+    surplus, k = surplus_k(acts)
+    it = 0
+    while it < max_iter and surplus > 0 and k > 0:
+        amount = surplus / k
+        acts = {var: (torch.clamp(a + amount, max=1.) if noop[var] else torch.clamp(a - amount, min=0.))
+                for var, a in acts.items()}
+        surplus, k = surplus_k(acts)
+        it += 1
+    converged = not bool(surplus > 0)
+    total_bool = 0
+    for var, a in acts.items():
+        total_bool += int(torch.count_nonzero(a < 0.5 if noop[var] else a > 0.5))
+    excess = max(total_bool - allowed, 0)
+    new = {}
+    for var, a in acts.items():
+        a = torch.clamp(a, min_action, max_action)
+        flat = a.reshape(-1).clone()
+        active = (flat < 0.5) if noop[var] else (flat > 0.5)
+        ranks = torch.cumsum(active.to(torch.int64), 0)
+        replace = active & (ranks <= excess)
+        flat[replace] = 0.5
+        new[var] = flat.reshape(a.shape)
+        excess = max(excess - int(torch.count_nonzero(replace)), 0)
+    return new, converged

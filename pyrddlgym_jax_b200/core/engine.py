@@ -1,0 +1,152 @@
+"""ctypes binding of the C ABI in include/rk.h (csrc/librk.so) + torch buffer plumbing.
+
+PyTorch is used only for device memory, streams and (in parallel.py) torch.distributed; all
+compute on the hot path happens in the CUDA kernels behind this binding.  There is no CPU
+fallback: using an engine without the native library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .program import Program
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "librk.so")
+
+EXPORTS = [
+    "rk_program_create", "rk_program_destroy", "rk_program_query", "rk_program_num_warps",
+    "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
+    "rk_mean_loss",
+]
+
+
+class RkError(RuntimeError):
+    pass
+
+
+class RkSizes(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "kind", "relaxed", "S", "A", "N", "n_mparams", "rpw", "lanes", "warp_words",
+        "const_words", "n_prologue", "n_step", "n_epilogue", "warps_per_cta", "smem_bytes",
+        "static_err")]
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load librk.so and declare every prototype of include/rk.h."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = os.path.abspath(path or LIB_PATH)
+    if not os.path.exists(p):
+        raise RkError(f"native library {p} is missing: run __graft_entry__.build() "
+                      f"(python -m pyrddlgym_jax_b200.build); there is no CPU fallback")
+    lib = ctypes.CDLL(p)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+    lib.rk_program_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.rk_program_create.restype = ci
+    lib.rk_program_destroy.argtypes = [vp]
+    lib.rk_program_destroy.restype = None
+    lib.rk_program_query.argtypes = [vp, ctypes.POINTER(RkSizes)]
+    lib.rk_program_query.restype = ci
+    lib.rk_program_num_warps.argtypes = [vp, ci]
+    lib.rk_program_num_warps.restype = ci
+    lib.rk_rollout_forward.argtypes = [vp, vp, ci, ci] + [cf] * 12
+    lib.rk_rollout_forward.restype = ci
+    lib.rk_rollout_backward.argtypes = [vp, vp, ci, ci] + [cf] * 10
+    lib.rk_rollout_backward.restype = ci
+    lib.rk_reduce_partials.argtypes = [vp, cf, ci, ci, cf]
+    lib.rk_reduce_partials.restype = ci
+    lib.rk_optimizer_step.argtypes = [vp, ci, cf, ci, cf, cf, cf, cf, cf, cf]
+    lib.rk_optimizer_step.restype = ci
+    lib.rk_mean_loss.argtypes = [vp, cf, ci, cf, cf]
+    lib.rk_mean_loss.restype = ci
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        kind = "invalid argument/program" if rc < 0 else "CUDA error"
+        raise RkError(f"{what} failed: {kind} {rc}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RkError("rk kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RkError("rk kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceProgram:
+    """A Program uploaded to the current CUDA device."""
+
+    def __init__(self, program: Program):
+        if not torch.cuda.is_available():
+            raise RkError("no CUDA device: the rollout kernels have no CPU fallback")
+        self.lib = load_library()
+        self.program = program
+        self.handle = ctypes.c_void_p()
+        blob = program.blob
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _check(self.lib.rk_program_create(buf, len(blob), ctypes.byref(self.handle)),
+               "rk_program_create")
+        self.sizes = RkSizes()
+        _check(self.lib.rk_program_query(self.handle, ctypes.byref(self.sizes)), "rk_program_query")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.rk_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def num_warps(self, B: int) -> int:
+        return self.lib.rk_program_num_warps(self.handle, B)
+
+    def forward(self, B, T, s0, policy=None, actions=None, noise=None, mparams=None, disc=None,
+                reward=None, returns=None, err=None, tape=None, final=None, traj=None):
+        _check(self.lib.rk_rollout_forward(
+            self.handle, _stream(), B, T, _ptr(s0), _ptr(policy), _ptr(actions), _ptr(noise),
+            _ptr(mparams), _ptr(disc), _ptr(reward), _ptr(returns), _ptr(err), _ptr(tape),
+            _ptr(final), _ptr(traj)), "rk_rollout_forward")
+
+    def backward(self, B, T, tape, gret, policy=None, actions=None, noise=None, mparams=None,
+                 disc=None, gradp=None, gact=None, gs0=None):
+        _check(self.lib.rk_rollout_backward(
+            self.handle, _stream(), B, T, _ptr(tape), _ptr(policy), _ptr(actions), _ptr(noise),
+            _ptr(mparams), _ptr(disc), _ptr(gret), _ptr(gradp), _ptr(gact), _ptr(gs0)),
+            "rk_rollout_backward")
+
+
+def reduce_partials(gradp: torch.Tensor, rows: int, n: int, grad: torch.Tensor):
+    _check(load_library().rk_reduce_partials(_stream(), _ptr(gradp), rows, n, _ptr(grad)),
+           "rk_reduce_partials")
+
+
+OPT_KIND = {"sgd": 0, "rmsprop": 1, "adam": 2}
+
+
+def optimizer_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, lo=None, hi=None,
+                   zero_flag=None):
+    _check(load_library().rk_optimizer_step(
+        _stream(), OPT_KIND[kind], _ptr(hyper), n, _ptr(params), _ptr(state), _ptr(grad),
+        _ptr(lo), _ptr(hi), _ptr(zero_flag)), "rk_optimizer_step")
+
+
+def mean_loss(returns: torch.Tensor, B: int, loss=None, gret=None):
+    _check(load_library().rk_mean_loss(_stream(), _ptr(returns), B, _ptr(loss), _ptr(gret)),
+           "rk_mean_loss")

@@ -1,0 +1,403 @@
+"""SSA value graph of one rollout step, and reverse-mode differentiation over it.
+
+This is the host-side middle layer between the expression trees (rddl/) and the flat
+instruction stream executed on the GPU (core/program.py -> csrc/rk_interp.cu).  What the
+reference gets from tracing closures through ``jax.vmap`` / ``lax.scan`` / ``value_and_grad``
+(compiler.py:551-619, planner.py:2873) is done here explicitly:
+
+* every value knows its element count per rollout (``n``) and whether it is rollout-invariant
+  (``uniform``): the "lanes over object tuples" layout of the kernel;
+* operands carry gather maps, so slices / transposes / broadcasts of pvariables
+  (compiler.py:1071-1079) cost no instruction;
+* ``differentiate`` emits the adjoint of every instruction as more instructions of the same
+  ISA, honouring stop_gradient (the STE pattern ``soft + sg(hard - soft)``, logic.py:272).
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+Map = Union[None, str, np.ndarray]      # None = identity, 'b' = broadcast element 0, table
+
+
+class V:
+    """One SSA value: ``n`` 32-bit words per rollout (or in total when ``uniform``)."""
+    _ids = itertools.count()
+    __slots__ = ("id", "op", "args", "n", "dtype", "uniform", "const", "attrs")
+
+    def __init__(self, op: str, args: Sequence[Tuple["V", Map]] = (), n: int = 1,
+                 dtype: str = "f", uniform: bool = False, const: Optional[np.ndarray] = None,
+                 attrs: Optional[Dict[str, Any]] = None):
+        self.id = next(V._ids)
+        self.op = op
+        self.args = list(args)
+        self.n = int(n)
+        self.dtype = dtype
+        self.uniform = uniform
+        self.const = const
+        self.attrs = attrs or {}
+
+    def __repr__(self):
+        return f"%{self.id}:{self.op}[{self.n}{'u' if self.uniform else ''}{self.dtype}]"
+
+
+NP_DT = {"f": np.float32, "i": np.int32, "b": np.int32}
+
+_FOLD1 = {
+    "NEG": np.negative, "ABS": np.abs, "SGN": np.sign, "FLOOR": np.floor, "CEIL": np.ceil,
+    "ROUND": np.round, "EXP": np.exp, "LOG": np.log, "SIN": np.sin, "COS": np.cos,
+    "TAN": np.tan, "TANH": np.tanh, "SQUARE": np.square, "MOV": lambda x: x,
+    "RCP": lambda x: np.float32(1.) / x, "INEG": np.negative, "IABS": np.abs,
+    "I2F": lambda x: x.astype(np.float32), "NOT": lambda x: 1 - x,
+    "F2B": lambda x: (x != 0).astype(np.int32), "I2B": lambda x: (x != 0).astype(np.int32),
+}
+_FOLD2 = {
+    "ADD": np.add, "SUB": np.subtract, "MUL": np.multiply, "DIV": np.divide,
+    "MIN": np.minimum, "MAX": np.maximum, "POW": np.power,
+    "IADD": np.add, "ISUB": np.subtract, "IMUL": np.multiply, "IMIN": np.minimum,
+    "IMAX": np.maximum, "AND": np.bitwise_and, "OR": np.bitwise_or, "XOR": np.bitwise_xor,
+    "LT": lambda a, b: (a < b).astype(np.int32), "LE": lambda a, b: (a <= b).astype(np.int32),
+    "GT": lambda a, b: (a > b).astype(np.int32), "GE": lambda a, b: (a >= b).astype(np.int32),
+    "EQ": lambda a, b: (a == b).astype(np.int32), "NE": lambda a, b: (a != b).astype(np.int32),
+    "ILT": lambda a, b: (a < b).astype(np.int32), "ILE": lambda a, b: (a <= b).astype(np.int32),
+    "IGT": lambda a, b: (a > b).astype(np.int32), "IGE": lambda a, b: (a >= b).astype(np.int32),
+    "IEQ": lambda a, b: (a == b).astype(np.int32), "INE": lambda a, b: (a != b).astype(np.int32),
+}
+
+OUT_DTYPE = {}
+for _op in ("LT", "LE", "GT", "GE", "EQ", "NE", "ILT", "ILE", "IGT", "IGE", "IEQ", "INE",
+            "AND", "OR", "XOR", "NOT", "F2B", "I2B"):
+    OUT_DTYPE[_op] = "b"
+for _op in ("INEG", "IABS", "ISGN", "IADD", "ISUB", "IMUL", "IMIN", "IMAX", "IFDIV", "IMOD",
+            "IFMOD", "IPOW", "F2I", "RISUM", "RIPROD", "RIMIN", "RIMAX", "RARGMAX", "RARGMIN"):
+    OUT_DTYPE[_op] = "i"
+
+
+def apply_map(m: Map, n_out: int) -> np.ndarray:
+    if m is None:
+        return np.arange(n_out)
+    if isinstance(m, str):
+        return np.zeros(n_out, dtype=np.int64)
+    return np.asarray(m, dtype=np.int64)
+
+
+def norm_map(table: np.ndarray, n_src: int) -> Map:
+    """Canonicalise a gather table."""
+    table = np.asarray(table, dtype=np.int64).ravel()
+    if table.size == n_src and np.array_equal(table, np.arange(n_src)):
+        return None
+    if np.all(table == 0):
+        return "b"
+    return table
+
+
+class Graph:
+    """Append-only list of SSA values (creation order is a topological order)."""
+
+    def __init__(self):
+        self.nodes: List[V] = []
+        self._consts: Dict[Tuple, V] = {}
+
+    def add(self, v: V) -> V:
+        self.nodes.append(v)
+        return v
+
+    # ---- leaves ------------------------------------------------------------------
+    def const(self, value, dtype: Optional[str] = None) -> V:
+        arr = np.asarray(value)
+        if dtype is None:
+            dtype = "f" if arr.dtype.kind == "f" else ("b" if arr.dtype == np.bool_ else "i")
+        arr = np.ascontiguousarray(arr.astype(NP_DT[dtype])).ravel()
+        key = (dtype, arr.tobytes())
+        v = self._consts.get(key)
+        if v is None:
+            v = self.add(V("const", n=arr.size, dtype=dtype, uniform=True, const=arr))
+            self._consts[key] = v
+        return v
+
+    def leaf(self, op: str, n: int, dtype: str = "f", uniform: bool = False, **attrs) -> V:
+        return self.add(V(op, n=n, dtype=dtype, uniform=uniform, attrs=attrs))
+
+    # ---- operations ----------------------------------------------------------------
+    def op(self, name: str, args: Sequence[Tuple[V, Map]], n: int, dtype: Optional[str] = None,
+           **attrs) -> V:
+        dtype = dtype or OUT_DTYPE.get(name, "f")
+        # constant folding of the simple elementwise ops
+        if all(a.const is not None for a, _ in args) and not attrs:
+            vals = [a.const[apply_map(m, n)] for a, m in args]
+            fn = _FOLD1.get(name) if len(vals) == 1 else _FOLD2.get(name)
+            if fn is not None:
+                with np.errstate(all="ignore"):
+                    return self.const(np.asarray(fn(*vals)).astype(NP_DT[dtype]), dtype)
+        uniform = all(a.uniform for a, _ in args)
+        return self.add(V(name, args, n=n, dtype=dtype, uniform=uniform, attrs=attrs))
+
+    def sg(self, a: V) -> V:
+        """stop_gradient: aliases the operand's storage, blocks differentiation."""
+        if a.const is not None:
+            return a
+        return self.add(V("sg", [(a, None)], n=a.n, dtype=a.dtype, uniform=a.uniform))
+
+    def reduce(self, name: str, a: V, ptr: np.ndarray, idx: np.ndarray,
+               dtype: Optional[str] = None) -> V:
+        n = len(ptr) - 1
+        return self.add(V(name, [(a, None)], n=n, dtype=dtype or OUT_DTYPE.get(name, "f"),
+                          uniform=a.uniform,
+                          attrs={"ptr": np.asarray(ptr, np.int64), "idx": np.asarray(idx, np.int64)}))
+
+
+# =====================================================================================
+# reverse-mode differentiation
+# =====================================================================================
+
+class NotDifferentiable(Exception):
+    pass
+
+
+def _active_set(nodes: List[V], wrt: Sequence[V]) -> set:
+    active = {v.id for v in wrt}
+    for v in nodes:
+        if v.id in active:
+            continue
+        if v.op in ("sg", "const") or v.dtype != "f":
+            continue
+        if any(a.id in active for a, _ in v.args):
+            active.add(v.id)
+    return active
+
+
+def differentiate(g: Graph, nodes: List[V], seeds: Sequence[Tuple[V, V]],
+                  wrt: Sequence[V]) -> Dict[int, V]:
+    """Emit adjoint instructions into ``g``.
+
+    nodes : forward values in topological order
+    seeds : [(value, cotangent V of the same n / uniform-ness), ...]
+    wrt   : values whose cotangents are wanted
+    Returns {value id: cotangent V} for every ``wrt`` value that receives any gradient.
+    """
+    active = _active_set(nodes, wrt)
+    contrib: Dict[int, List[V]] = {}
+    for tgt, s in seeds:
+        contrib.setdefault(tgt.id, []).append(s)
+    F = lambda x: g.const(np.float32(x))     # noqa: E731
+
+    def total(v: V) -> Optional[V]:
+        lst = contrib.get(v.id)
+        if not lst:
+            return None
+        acc = lst[0]
+        for c in lst[1:]:
+            acc = g.op("ADD", [(acc, None), (c, None)], v.n)
+        contrib[v.id] = [acc]
+        return acc
+
+    def push(v: V, arg_index: int, ct: V):
+        """Send cotangent ``ct`` (in v's element space) back through operand map."""
+        a, m = v.args[arg_index]
+        if a.id not in active:
+            return
+        n_r = v.n
+        if not (m is None and a.n == n_r):
+            table = apply_map(m, n_r)
+            order = np.argsort(table, kind="stable")
+            counts = np.bincount(table, minlength=a.n)
+            if a.n == n_r and np.all(counts == 1):
+                ct = g.op("MOV", [(ct, order.astype(np.int64))], a.n)   # inverse permutation
+            else:
+                ptr = np.concatenate([[0], np.cumsum(counts)])
+                ct = g.reduce("RSUM", ct, ptr, order)
+        if a.uniform and not ct.uniform:
+            ct = g.add(V("QSUM", [(ct, None)], n=a.n, dtype="f", uniform=True))
+        contrib.setdefault(a.id, []).append(ct)
+
+    wrt_ids = {v.id for v in wrt}
+    for v in reversed(nodes):
+        if v.id not in active or v.id in wrt_ids and not v.args:
+            continue
+        if not v.args:
+            continue
+        ct = total(v)
+        if ct is None:
+            continue
+        n = v.n
+        op = v.op
+        A = v.args
+        sam = lambda i: (A[i][0], A[i][1])     # operand i as seen in v's space  # noqa: E731
+        me = (v, None)
+        c = (ct, None)
+
+        def mul(x, y):
+            return g.op("MUL", [x, y], n)
+
+        if op in ("MOV", "sg_passthrough"):
+            push(v, 0, ct)
+        elif op == "NEG":
+            push(v, 0, g.op("NEG", [c], n))
+        elif op == "ABS":
+            push(v, 0, mul(c, (g.op("SGN", [sam(0)], n), None)))
+        elif op in ("SGN", "FLOOR", "CEIL", "ROUND", "FDIV"):
+            pass
+        elif op == "SQRT":     # softjax sj.sqrt: zero derivative at x <= 0
+            half_over = g.op("DIV", [(F(0.5), "b"), me], n)
+            d = mul(c, (half_over, None))
+            pos = g.op("GT", [sam(0), (F(0.), "b")], n)
+            push(v, 0, g.op("SELECT", [(pos, None), (d, None), (F(0.), "b")], n))
+        elif op == "EXP":
+            push(v, 0, mul(c, me))
+        elif op == "EXPM1":
+            push(v, 0, mul(c, (g.op("ADD", [me, (F(1.), "b")], n), None)))
+        elif op == "LOG":
+            push(v, 0, g.op("DIV", [c, sam(0)], n))
+        elif op == "LOG1P":
+            push(v, 0, g.op("DIV", [c, (g.op("ADD", [sam(0), (F(1.), "b")], n), None)], n))
+        elif op == "SIN":
+            push(v, 0, mul(c, (g.op("COS", [sam(0)], n), None)))
+        elif op == "COS":
+            push(v, 0, g.op("NEG", [(mul(c, (g.op("SIN", [sam(0)], n), None)), None)], n))
+        elif op == "TAN":
+            sq = g.op("SQUARE", [me], n)
+            push(v, 0, mul(c, (g.op("ADD", [(sq, None), (F(1.), "b")], n), None)))
+        elif op in ("ASIN", "ACOS"):
+            sq = g.op("SQUARE", [sam(0)], n)
+            den = g.op("SQRT", [(g.op("SUB", [(F(1.), "b"), (sq, None)], n), None)], n)
+            d = g.op("DIV", [c, (den, None)], n)
+            push(v, 0, d if op == "ASIN" else g.op("NEG", [(d, None)], n))
+        elif op == "ATAN":
+            sq = g.op("SQUARE", [sam(0)], n)
+            push(v, 0, g.op("DIV", [c, (g.op("ADD", [(sq, None), (F(1.), "b")], n), None)], n))
+        elif op == "SINH":
+            push(v, 0, mul(c, (g.op("COSH", [sam(0)], n), None)))
+        elif op == "COSH":
+            push(v, 0, mul(c, (g.op("SINH", [sam(0)], n), None)))
+        elif op in ("TANH", "STANH"):
+            sq = g.op("SQUARE", [me], n)
+            push(v, 0, mul(c, (g.op("SUB", [(F(1.), "b"), (sq, None)], n), None)))
+        elif op == "SIGMOID":
+            om = g.op("SUB", [(F(1.), "b"), me], n)
+            push(v, 0, mul(c, (mul(me, (om, None)), None)))
+        elif op == "RELU":
+            pos = g.op("GT", [sam(0), (F(0.), "b")], n)
+            push(v, 0, g.op("SELECT", [(pos, None), c, (F(0.), "b")], n))
+        elif op == "RCP":
+            push(v, 0, g.op("NEG", [(mul(c, (g.op("SQUARE", [me], n), None)), None)], n))
+        elif op == "SQUARE":
+            push(v, 0, mul(c, (mul((F(2.), "b"), sam(0)), None)))
+        elif op == "ADD":
+            push(v, 0, ct)
+            push(v, 1, ct)
+        elif op == "SUB":
+            push(v, 0, ct)
+            if A[1][0].id in active:
+                push(v, 1, g.op("NEG", [c], n))
+        elif op == "MUL":
+            if A[0][0].id in active:
+                push(v, 0, mul(c, sam(1)))
+            if A[1][0].id in active:
+                push(v, 1, mul(c, sam(0)))
+        elif op == "DIV":
+            if A[0][0].id in active:
+                push(v, 0, g.op("DIV", [c, sam(1)], n))
+            if A[1][0].id in active:
+                q = g.op("DIV", [(mul(c, me), None), sam(1)], n)
+                push(v, 1, g.op("NEG", [(q, None)], n))
+        elif op in ("MIN", "MAX"):
+            w = g.op("MINW" if op == "MIN" else "MAXW", [sam(0), sam(1)], n)
+            gx = mul(c, (w, None))
+            push(v, 0, gx)
+            if A[1][0].id in active:
+                push(v, 1, g.op("SUB", [c, (gx, None)], n))
+        elif op == "POW":
+            if A[0][0].id in active:
+                ym1 = g.op("SUB", [sam(1), (F(1.), "b")], n)
+                p = g.op("POW", [sam(0), (ym1, None)], n)
+                push(v, 0, mul(c, (mul(sam(1), (p, None)), None)))
+            if A[1][0].id in active:
+                lg = g.op("LOG", [sam(0)], n)
+                push(v, 1, mul(c, (mul(me, (lg, None)), None)))
+        elif op == "HYPOT":
+            for i in (0, 1):
+                if A[i][0].id in active:
+                    push(v, i, mul(c, (g.op("DIV", [sam(i), me], n), None)))
+        elif op == "MOD":
+            push(v, 0, ct)
+            if A[1][0].id in active:
+                fd = g.op("FDIV", [sam(0), sam(1)], n)
+                push(v, 1, g.op("NEG", [(mul(c, (fd, None)), None)], n))
+        elif op == "FMOD":
+            push(v, 0, ct)
+            if A[1][0].id in active:
+                raise NotDifferentiable("fmod with a differentiable divisor")
+        elif op == "SAFELOG":   # compiler.py:70-75: tangent xdot / (x + eps)
+            den = g.op("ADD", [sam(0), sam(1)], n)
+            push(v, 0, g.op("DIV", [c, (den, None)], n))
+        elif op == "SELECT":
+            z = (F(0.), "b")
+            if A[1][0].id in active:
+                push(v, 1, g.op("SELECT", [sam(0), c, z], n))
+            if A[2][0].id in active:
+                push(v, 2, g.op("SELECT", [sam(0), z, c], n))
+        elif op == "LERP":      # a*b + (1-a)*c
+            if A[0][0].id in active:
+                push(v, 0, mul(c, (g.op("SUB", [sam(1), sam(2)], n), None)))
+            if A[1][0].id in active:
+                push(v, 1, mul(c, sam(0)))
+            if A[2][0].id in active:
+                push(v, 2, mul(c, (g.op("SUB", [(F(1.), "b"), sam(0)], n), None)))
+        elif op == "FMA":
+            if A[0][0].id in active:
+                push(v, 0, mul(c, sam(1)))
+            if A[1][0].id in active:
+                push(v, 1, mul(c, sam(0)))
+            push(v, 2, ct)
+        elif op == "RSUM":
+            src = A[0][0]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            seg = np.repeat(np.arange(n), np.diff(ptr))          # segment of each CSR entry
+            counts = np.bincount(idx, minlength=src.n)
+            if np.all(counts == 1):
+                table = np.empty(src.n, dtype=np.int64)
+                table[idx] = seg
+                back = g.op("MOV", [(ct, table)], src.n)
+            else:
+                order = np.argsort(idx, kind="stable")
+                ptr2 = np.concatenate([[0], np.cumsum(counts)])
+                back = g.reduce("RSUM", ct, ptr2, seg[order])
+            contrib.setdefault(src.id, []).append(back) if src.id in active else None
+        elif op == "RPROD":
+            src = A[0][0]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            seg = np.repeat(np.arange(n), np.diff(ptr))
+            if not np.all(np.bincount(idx, minlength=src.n) == 1):
+                raise NotDifferentiable("product over a broadcast operand")
+            table = np.empty(src.n, dtype=np.int64)
+            table[idx] = seg
+            others = g.add(V("RPRODX", [(src, None)], n=src.n, dtype="f", uniform=src.uniform,
+                             attrs={"ptr": ptr, "idx": idx, "seg": table}))
+            back = g.op("MUL", [(ct, table), (others, None)], src.n)
+            contrib.setdefault(src.id, []).append(back) if src.id in active else None
+        elif op in ("RMIN", "RMAX"):   # ties share the cotangent evenly (JAX reduce_max rule)
+            src = A[0][0]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            seg = np.repeat(np.arange(n), np.diff(ptr))
+            if not np.all(np.bincount(idx, minlength=src.n) == 1):
+                raise NotDifferentiable("min/max over a broadcast operand")
+            table = np.empty(src.n, dtype=np.int64)
+            table[idx] = seg
+            eq = g.op("EQ", [(src, None), (v, table)], src.n)
+            cnt = g.reduce("RSUM", g.op("I2F", [(eq, None)], src.n), ptr, idx)
+            share = g.op("DIV", [c, (cnt, None)], n)
+            back = g.op("SELECT", [(eq, None), (share, table), (F(0.), "b")], src.n)
+            contrib.setdefault(src.id, []).append(back) if src.id in active else None
+        elif op in ("LGAMMA",):
+            raise NotDifferentiable(f"{op} has no adjoint rule yet")
+        else:
+            raise NotDifferentiable(f"no adjoint rule for op {op}")
+
+    out = {}
+    for w in wrt:
+        t = total(w)
+        if t is not None:
+            out[w.id] = t
+    return out

@@ -1,0 +1,845 @@
+"""Lowering of CPF / reward expression trees to the SSA step graph.
+
+One ``StepGraph`` restates what ``JaxRDDLCompiler._jax_cpfs`` + ``_jax_reward`` +
+``compile_transition`` build as nested closures (compiler.py:360-376, 490-547), for either
+the exact model (compiler.py:936-2241) or a relaxed model (logic.py:83-1789, selected by
+the ``relax`` config of core/logic.py).  Differences from the reference are layout only:
+
+* values are narrowed to the object tuples they depend on ("tuple-space narrowing") and
+  broadcast lazily through operand gather maps;
+* everything that is non-fluent and deterministic is folded on the host
+  (rddl/trace.py:eval_static) into constant tables;
+* every relaxation weight becomes a run-time *model parameter* slot, the counterpart of
+  ``aux['params'][expr.id]`` (logic.py:266), so weights can be changed per ``optimize`` call
+  (planner.py:3165-3168) without rebuilding the program.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..rddl.expr import Expr
+from ..rddl.trace import Tracer, eval_static, RDDLTraceError
+from .graph import Graph, V, Map, norm_map
+
+ERR_BITS = {  # compiler.py:861-888
+    "CAST": 0, "UNIFORM": 1, "NORMAL": 2, "EXPONENTIAL": 3, "WEIBULL": 4, "BERNOULLI": 5,
+    "POISSON": 6, "GAMMA": 7, "BETA": 8, "GEOMETRIC": 9, "PARETO": 10, "STUDENT": 11,
+    "GUMBEL": 12, "LAPLACE": 13, "CAUCHY": 14, "GOMPERTZ": 15, "CHISQUARE": 16,
+    "KUMARASWAMY": 17, "DISCRETE": 18, "KRON": 19,
+}
+
+
+class RDDLNotImplementedError(NotImplementedError):
+    pass
+
+
+@dataclass
+class TV:
+    """A lowered tensor value: SSA value + the scope positions labelling its axes.
+
+    ``idx`` (shape = sizes of ``vars``) maps each tuple to an element of ``v``; None means
+    the identity (v.n == number of tuples).
+    """
+    v: V
+    vars: Tuple[int, ...]
+    idx: Optional[np.ndarray] = None
+    full: bool = True        # reference value carries the full scope shape (vs 0-d constant)
+
+    @property
+    def dtype(self):
+        return self.v.dtype
+
+
+@dataclass
+class NoiseSlot:
+    kind: str
+    shape: Tuple[int, ...]
+    n: int
+    value: V
+    extra: Any = None
+    offset: int = 0
+
+
+@dataclass
+class StepGraph:
+    g: Graph
+    state_in: Dict[str, V] = field(default_factory=dict)
+    action_in: Dict[str, V] = field(default_factory=dict)
+    next_state: Dict[str, V] = field(default_factory=dict)
+    fluents: Dict[str, V] = field(default_factory=dict)       # every fluent value of the step
+    reward: Optional[V] = None
+    noise: List[NoiseSlot] = field(default_factory=list)
+    mparams: List[Tuple[Tuple[int, str], float, V]] = field(default_factory=list)
+    errs: List[Tuple[int, V]] = field(default_factory=list)
+    static_err: int = 0
+    relaxed: bool = False
+
+
+class Lowerer:
+    def __init__(self, model, relax: Optional[Dict[str, Any]] = None):
+        self.m = model
+        self.relax = relax
+        self.relaxed = relax is not None
+        self.variants = (relax or {}).get("variants", {})
+        self.tr = Tracer(model)
+        self.g = Graph()
+        self.sg = StepGraph(self.g, relaxed=self.relaxed)
+        self._mparam_index: Dict[Tuple[int, str], V] = {}
+
+    # ---------------------------------------------------------------------------------
+    def dtype_of_range(self, prange: str) -> str:
+        if self.relaxed:
+            return "f"
+        return {"real": "f", "int": "i", "bool": "b"}.get(prange, "i")
+
+    def mparam(self, expr: Expr, name: str, default: float) -> V:
+        key = (expr.id, name)
+        v = self._mparam_index.get(key)
+        if v is None:
+            v = self.g.leaf("mparam", 1, "f", uniform=True, key=key, default=float(default),
+                            slot=len(self.sg.mparams))
+            self.sg.mparams.append((key, float(default), v))
+            self._mparam_index[key] = v
+        return v
+
+    def sizes(self, scope) -> Tuple[int, ...]:
+        return self.tr.scope_sizes(scope)
+
+    # ---- tuple-space helpers -----------------------------------------------------------
+    def n_of(self, vars_, sizes) -> int:
+        return int(np.prod([sizes[p] for p in vars_], dtype=np.int64)) if vars_ else 1
+
+    def operand(self, tv: TV, rvars: Tuple[int, ...], sizes) -> Tuple[V, Map]:
+        """Gather map that presents ``tv`` over the tuple space ``rvars``."""
+        rshape = tuple(sizes[p] for p in rvars)
+        n_r = int(np.prod(rshape, dtype=np.int64)) if rshape else 1
+        idx = tv.idx
+        if idx is None:
+            idx = np.arange(tv.v.n, dtype=np.int64).reshape(tuple(sizes[p] for p in tv.vars))
+        # insert size-1 axes for variables of rvars that tv does not depend on
+        shape = tuple(sizes[p] if p in tv.vars else 1 for p in rvars)
+        table = np.broadcast_to(idx.reshape(shape), rshape).reshape(-1) if rshape \
+            else idx.reshape(-1)
+        if table.size != n_r:
+            table = np.broadcast_to(table, (n_r,))
+        return tv.v, norm_map(table, tv.v.n)
+
+    def union(self, tvs: Sequence[TV]) -> Tuple[int, ...]:
+        s = set()
+        for t in tvs:
+            s.update(t.vars)
+        return tuple(sorted(s))
+
+    def ew(self, op: str, tvs: Sequence[TV], sizes, dtype: Optional[str] = None, **attrs) -> TV:
+        rvars = self.union(tvs)
+        n = self.n_of(rvars, sizes)
+        args = [self.operand(t, rvars, sizes) for t in tvs]
+        v = self.g.op(op, args, n, dtype, **attrs)
+        return TV(v, rvars, None, any(t.full for t in tvs))
+
+    def const_tv(self, value, dtype=None, full=False) -> TV:
+        return TV(self.g.const(value, dtype), (), None, full)
+
+    def materialise(self, tv: TV, sizes) -> V:
+        """An SSA value holding exactly tv's tuples in order (copy only when needed)."""
+        if tv.idx is None:
+            return tv.v
+        v, m = self.operand(tv, tv.vars, sizes)
+        if m is None:
+            return v
+        return self.g.op("MOV", [(v, m)], self.n_of(tv.vars, sizes), dtype=tv.dtype)
+
+    # ---- dtype discipline (compiler.py:985-994, 1092-1093) -----------------------------
+    def to_f(self, tv: TV, sizes) -> TV:
+        if tv.dtype == "f":
+            return tv
+        return self.ew("I2F", [tv], sizes, "f")
+
+    def at_least_int(self, tv: TV) -> TV:
+        if tv.dtype == "b":
+            return TV(self._retag(tv.v, "i"), tv.vars, tv.idx, tv.full)
+        return tv
+
+    def _retag(self, v: V, dtype: str) -> V:
+        """bool and int share the 0/1 int32 representation: retagging is free."""
+        if v.dtype == dtype:
+            return v
+        if v.const is not None:
+            return self.g.const(v.const, dtype)
+        r = self.g.add(V("sg", [(v, None)], n=v.n, dtype=dtype, uniform=v.uniform))
+        r.attrs["retag"] = True
+        return r
+
+    def to_b(self, tv: TV, sizes) -> TV:
+        if tv.dtype == "b":
+            return tv
+        return self.ew("F2B" if tv.dtype == "f" else "I2B", [tv], sizes, "b")
+
+    def promote(self, tvs: Sequence[TV], sizes) -> Tuple[List[TV], str]:
+        tvs = [self.at_least_int(t) for t in tvs]
+        if any(t.dtype == "f" for t in tvs):
+            return [self.to_f(t, sizes) for t in tvs], "f"
+        return list(tvs), "i"
+
+    def ste(self, soft: TV, hard: TV, sizes) -> TV:
+        """soft + stop_gradient(hard - soft)  (logic.py:272 and friends)."""
+        hard = self.to_f(self.at_least_int(hard), sizes)
+        diff = self.ew("SUB", [hard, soft], sizes)
+        blocked = TV(self.g.sg(diff.v), diff.vars, None, diff.full)
+        return self.ew("ADD", [soft, blocked], sizes)
+
+    def static_cast_err(self, ok: bool):
+        if not ok:
+            self.sg.static_err |= 1 << ERR_BITS["CAST"]
+
+    def errchk(self, name: str, violation: TV, sizes):
+        """Record ``err |= bit`` where ``violation`` (bool) holds for any element."""
+        if violation.v.const is not None:
+            if np.any(violation.v.const != 0):
+                self.sg.static_err |= 1 << ERR_BITS[name]
+            return
+        self.sg.errs.append((ERR_BITS[name], self.materialise(violation, sizes)))
+
+    # ==================================================================================
+    def lower(self, e: Expr, scope, env: Dict[str, V]) -> TV:
+        """Dispatch of compiler.py:936-964."""
+        fam, op = e.etype
+        sizes = self.sizes(scope)
+        if fam != "constant" and self.tr.is_static(e):
+            cast_errors: list = []
+            try:
+                val = eval_static(self.m, e, scope, as_float=self.relaxed, tracer=self.tr,
+                                  cast_errors=cast_errors)
+            except RDDLTraceError:
+                val = None
+            if val is not None and cast_errors:
+                self.sg.static_err |= 1 << ERR_BITS["CAST"]
+            if val is not None:
+                return self._static_tv(e, val, scope, sizes)
+        if fam == "constant":
+            dt = {"bool": "b", "int": "i", "real": "f"}[op]
+            return self.const_tv(np.asarray(e.args), dt, full=False)
+        if fam == "pvar":
+            return self._pvar(e, scope, env, sizes)
+        if fam == "arithmetic":
+            return self._arithmetic(e, scope, env, sizes)
+        if fam == "relational":
+            return self._relational(e, scope, env, sizes)
+        if fam == "boolean":
+            return self._logical(e, scope, env, sizes)
+        if fam == "aggregation":
+            return self._aggregation(e, scope, env, sizes)
+        if fam == "func":
+            return self._function(e, scope, env, sizes)
+        if fam == "control":
+            return self._control(e, scope, env, sizes)
+        if fam == "randomvar":
+            return self._random(e, scope, env, sizes)
+        raise RDDLNotImplementedError(f"Expression type {e.etype} is not supported.")
+
+    def _static_tv(self, e, val: np.ndarray, scope, sizes) -> TV:
+        val = np.asarray(val)
+        full = self._ref_full(e)
+        if val.ndim == 0:
+            return self.const_tv(val, None, full)
+        # keepdims array over the scope -> narrow to the axes it really varies over
+        val = np.broadcast_to(val, val.shape) if val.ndim == len(scope) else val
+        vars_ = tuple(i for i in range(len(scope)) if val.shape[i] > 1)
+        flat = val.reshape(tuple(val.shape[i] for i in vars_) if vars_ else ())
+        return TV(self.g.const(flat), vars_, None, full)
+
+    def _ref_full(self, e: Expr) -> bool:
+        fam, op = e.etype
+        if fam == "constant":
+            return False
+        if fam == "pvar":
+            name, params = e.args
+            return not (params is None and self.tr.is_object(name))
+        if fam == "aggregation" or (fam == "control" and op == "switch") \
+                or (fam == "randomvar" and op in ("Discrete", "UnnormDiscrete")):
+            return True
+        return any(self._ref_full(a) for a in e.args)
+
+    # ---- leaves: compiler.py:1017-1081 ------------------------------------------------
+    def _pvar(self, e, scope, env, sizes) -> TV:
+        acc = self.tr.access(e, scope)
+        if acc.kind == "freevar":
+            n = sizes[acc.axes[0]]
+            return TV(self.g.const(np.arange(n, dtype=np.int32), "i"), acc.axes, None, True)
+        if acc.kind == "object":
+            return self.const_tv(np.int32(acc.value), "i", full=False)
+        if acc.nested:
+            raise RDDLNotImplementedError(
+                f"nested fluent-valued arguments of <{acc.name}> are not supported yet")
+        if acc.name not in env:
+            raise RDDLTraceError(f"fluent <{acc.name}> is read before it is defined")
+        src = env[acc.name]
+        idx = None if acc.identity else acc.index
+        return TV(src, acc.axes, idx, True)
+
+    def _args(self, e, scope, env, args=None) -> List[TV]:
+        return [self.lower(a, scope, env) for a in (e.args if args is None else args)]
+
+    # ---- arithmetic: compiler.py:1150-1183 --------------------------------------------
+    def _arithmetic(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        tvs = self._args(e, scope, env)
+        if op == "-" and len(tvs) == 1:
+            (x,), dt = self.promote(tvs, sizes)
+            return self.ew("NEG" if dt == "f" else "INEG", [x], sizes)
+        if op == "/":
+            tvs = [self.to_f(self.at_least_int(t), sizes) for t in tvs]
+            return self.ew("DIV", tvs, sizes)
+        out = tvs[0]
+        for t in tvs[1:]:
+            (a, b), dt = self.promote([out, t], sizes)
+            name = {"+": "ADD", "-": "SUB", "*": "MUL"}[op]
+            out = self.ew(name if dt == "f" else "I" + name, [a, b], sizes)
+        return out
+
+    # ---- relational: compiler.py:1189-1227 ; logic.py:262-344 ---------------------------
+    def _relational(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        (x, y), dt = self.promote(self._args(e, scope, env), sizes)
+        name = {">=": "GE", "<=": "LE", ">": "GT", "<": "LT", "==": "EQ", "~=": "NE"}[op]
+        hard = lambda a, b: self.ew(name if a.dtype == "f" else "I" + name, [a, b], sizes)  # noqa
+        if not (self.relaxed and self.variants.get("relational") == "sigmoid"
+                and self.tr.is_fluent(e)):
+            return hard(x, y)
+        w = TV(self.mparam(e, "sigmoid_weight", self.relax["sigmoid_weight"]), ())
+        x, y = self.to_f(x, sizes), self.to_f(y, sizes)
+        if op in (">", ">="):
+            soft = self.ew("SIGMOID", [self.ew("MUL", [w, self.ew("SUB", [x, y], sizes)], sizes)],
+                           sizes)
+            use_ste = self.relax["use_sigmoid_ste"]
+        elif op in ("<", "<="):
+            soft = self.ew("SIGMOID", [self.ew("MUL", [w, self.ew("SUB", [y, x], sizes)], sizes)],
+                           sizes)
+            use_ste = self.relax["use_sigmoid_ste"]
+        else:
+            t = self.ew("STANH", [self.ew("MUL", [w, self.ew("SUB", [y, x], sizes)], sizes)], sizes)
+            sq = self.ew("SQUARE", [t], sizes)
+            soft = self.ew("SUB", [self.const_tv(np.float32(1.)), sq], sizes) if op == "==" else sq
+            use_ste = self.relax["use_tanh_ste"]
+        return self.ste(soft, hard(x, y), sizes) if use_ste else soft
+
+    # ---- logical: compiler.py:1233-1274 ; logic.py:424-778 -----------------------------
+    def _logical(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        tvs = self._args(e, scope, env)
+        variant = self.variants.get("logic") if self.relaxed else None
+        if variant is None or not self.tr.is_fluent(e):
+            self.static_cast_err(all(t.dtype == "b" for t in tvs))
+            b = [self.to_b(t, sizes) for t in tvs]
+            if op == "~" and len(b) == 1:
+                return self.ew("NOT", b, sizes)
+            if op == "~":
+                return self.ew("XOR", b, sizes)
+            if op in ("^", "&", "|"):
+                out = b[0]
+                for t in b[1:]:
+                    out = self.ew("AND" if op != "|" else "OR", [out, t], sizes)
+                return out
+            if op == "=>":
+                return self.ew("OR", [self.ew("NOT", [b[0]], sizes), b[1]], sizes)
+            if op == "<=>":
+                (p, q), dt = self.promote(tvs, sizes)
+                return self.ew("EQ" if dt == "f" else "IEQ", [p, q], sizes)
+            raise RDDLNotImplementedError(op)
+        use_ste = self.relax["use_logic_ste"]
+        one = self.const_tv(np.float32(1.))
+        half = self.const_tv(np.float32(0.5))
+        E = lambda name, *a: self.ew(name, list(a), sizes)     # noqa: E731
+
+        def hard2(kind, x, y):
+            gx, gy = E("GT", x, half), E("GT", y, half)
+            if kind == "and":
+                return E("AND", gx, gy)
+            if kind == "or":
+                return E("OR", gx, gy)
+            if kind == "xor":
+                return E("XOR", gx, gy)
+            lx, ly = E("LE", x, half), E("LE", y, half)
+            if kind == "implies":
+                return E("OR", lx, gy)
+            return E("AND", E("OR", lx, gy), E("OR", ly, gx))
+
+        def soft2(kind, x, y):
+            if variant == "product":
+                if kind == "and":
+                    return E("MUL", x, y)
+                if kind == "or":
+                    return E("SUB", one, E("MUL", E("SUB", one, x), E("SUB", one, y)))
+                if kind == "xor":
+                    o = E("SUB", one, E("MUL", E("SUB", one, x), E("SUB", one, y)))
+                    return E("MUL", o, E("SUB", one, E("MUL", x, y)))
+                if kind == "implies":
+                    return E("SUB", one, E("MUL", x, E("SUB", one, y)))
+                a = E("SUB", one, E("MUL", x, E("SUB", one, y)))
+                b = E("SUB", one, E("MUL", y, E("SUB", one, x)))
+                return E("MUL", a, b)
+            if variant == "godel":
+                if kind == "and":
+                    return E("MIN", x, y)
+                if kind == "or":
+                    return E("MAX", x, y)
+                if kind == "xor":
+                    return E("MIN", E("MAX", x, y), E("SUB", one, E("MIN", x, y)))
+                if kind == "implies":
+                    return E("MAX", E("SUB", one, x), y)
+                return E("MIN", E("MAX", E("SUB", one, x), y), E("MAX", E("SUB", one, y), x))
+            if kind == "and":
+                return E("RELU", E("SUB", E("ADD", x, y), one))
+            if kind == "or":
+                return E("SUB", one, E("RELU", E("SUB", E("SUB", one, x), y)))
+            if kind == "xor":
+                return E("RELU", E("SUB", one, E("ABS", E("SUB", E("SUB", one, x), y))))
+            if kind == "implies":
+                return E("SUB", one, E("RELU", E("SUB", x, y)))
+            return E("RELU", E("SUB", one, E("ABS", E("SUB", x, y))))
+
+        def binop(kind, x, y):
+            x = self.to_f(self.at_least_int(x), sizes)
+            y = self.to_f(self.at_least_int(y), sizes)
+            s = soft2(kind, x, y)
+            return self.ste(s, hard2(kind, x, y), sizes) if use_ste else s
+
+        if op == "~" and len(tvs) == 1:
+            x = self.to_f(self.at_least_int(tvs[0]), sizes)
+            s = E("SUB", one, x)
+            return self.ste(s, E("LE", x, half), sizes) if use_ste else s
+        if op == "~":
+            return binop("xor", tvs[0], tvs[1])
+        if op in ("^", "&", "|"):
+            out = tvs[0]
+            for t in tvs[1:]:
+                out = binop("and" if op != "|" else "or", out, t)
+            return out
+        if op == "=>":
+            return binop("implies", tvs[0], tvs[1])
+        if op == "<=>":
+            return binop("equiv", tvs[0], tvs[1])
+        raise RDDLNotImplementedError(op)
+
+    # ---- aggregation: compiler.py:1280-1348 ; logic.py:377-417, 516-540, ... ------------
+    def _csr(self, body: TV, n_outer: int, inner_sizes) -> Tuple[Tuple[int, ...], np.ndarray, np.ndarray, int]:
+        """CSR description of reducing ``body`` over scope positions >= n_outer."""
+        dvars = tuple(p for p in body.vars if p < n_outer)
+        rvars = tuple(range(n_outer, len(inner_sizes)))
+        allv = dvars + rvars
+        v, m = self.operand(body, allv, inner_sizes)
+        n_d = self.n_of(dvars, inner_sizes)
+        K = self.n_of(rvars, inner_sizes)
+        from .graph import apply_map
+        table = apply_map(m, n_d * K)
+        ptr = np.arange(n_d + 1, dtype=np.int64) * K
+        return dvars, ptr, table, K
+
+    def _aggregation(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        *tv, body_e = e.args
+        inner = list(scope) + list(tv)
+        isz = self.sizes(inner)
+        body = self.lower(body_e, inner, env)
+        n_outer = len(scope)
+        fluent = self.tr.is_fluent(e)
+        dvars, ptr, idx, K = self._csr(body, n_outer, isz)
+        red = lambda name, src, dt=None: TV(self.g.reduce(name, src, ptr, idx, dt), dvars, None)  # noqa
+        src = body.v
+        is_bool = op in ("forall", "exists")
+        if is_bool:
+            variant = self.variants.get("logic") if self.relaxed else None
+            if variant is None or not fluent:
+                self.static_cast_err(body.dtype == "b")
+                b = self.to_b(body, isz)
+                dvars, ptr, idx, K = self._csr(b, n_outer, isz)
+                out = TV(self.g.reduce("RIMIN" if op == "forall" else "RIMAX", b.v, ptr, idx, "b"),
+                         dvars, None)
+                return out
+            x = self.to_f(self.at_least_int(body), isz)
+            dvars, ptr, idx, K = self._csr(x, n_outer, isz)
+            one = self.const_tv(np.float32(1.))
+            R = lambda name, t: TV(self.g.reduce(name, t.v, *self._csr(t, n_outer, isz)[1:3]),  # noqa
+                                   dvars, None)
+            if variant == "product":
+                if op == "forall":
+                    soft = R("RPROD", x)
+                else:
+                    soft = self.ew("SUB", [one, R("RPROD", self._mat(self.ew("SUB", [one, x], isz), isz))], sizes)
+            elif variant == "godel":
+                soft = R("RMIN" if op == "forall" else "RMAX", x)
+            else:
+                if op == "forall":
+                    s = R("RSUM", self._mat(self.ew("SUB", [x, one], isz), isz))
+                    soft = self.ew("RELU", [self.ew("ADD", [s, one], sizes)], sizes)
+                else:
+                    s = R("RSUM", self._mat(self.ew("NEG", [x], isz), isz))
+                    soft = self.ew("SUB", [one, self.ew("RELU", [self.ew("ADD", [s, one], sizes)],
+                                                        sizes)], sizes)
+            if self.relax["use_logic_ste"]:
+                hb = self._mat(self.ew("GT", [x, self.const_tv(np.float32(0.5))], isz), isz)
+                hard = R("RIMIN" if op == "forall" else "RIMAX", hb)
+                hard = TV(hard.v, hard.vars)
+                soft = self.ste(soft, TV(self._retag(hard.v, "b"), hard.vars), sizes)
+            return soft
+        body = self.at_least_int(body)
+        dvars, ptr, idx, K = self._csr(body, n_outer, isz)
+        isf = body.dtype == "f"
+        if op in ("argmin", "argmax"):
+            if len(tv) != 1:
+                raise RDDLNotImplementedError("argmin/argmax over more than one variable")
+            if self.relaxed and self.variants.get("argmax") == "softmax" and fluent:
+                w = TV(self.mparam(e, "argmax_weight", self.relax["argmax_weight"]), ())
+                x = self.to_f(body, isz)
+                if op == "argmin":
+                    x = self.ew("NEG", [x], isz)
+                x = TV(self._mat(x, isz).v, x.vars)
+                soft = self._soft_argmax(x, w, n_outer, isz, sizes)
+                if self.relax["use_argmax_ste"]:
+                    dv, p2, i2, _ = self._csr(x, n_outer, isz)
+                    hard = TV(self.g.reduce("RARGMAX", x.v, p2, i2, "i"), dv, None)
+                    soft = self.ste(soft, hard, sizes)
+                return soft
+            if not isf:
+                body = self.to_f(body, isz)
+                dvars, ptr, idx, K = self._csr(body, n_outer, isz)
+            return TV(self.g.reduce("RARGMAX" if op == "argmax" else "RARGMIN", body.v, ptr, idx,
+                                    "i"), dvars, None)
+        if op == "sum":
+            return red("RSUM" if isf else "RISUM", body.v)
+        if op == "avg":
+            body = self.to_f(body, isz)
+            dvars, ptr, idx, K = self._csr(body, n_outer, isz)
+            s = TV(self.g.reduce("RSUM", body.v, ptr, idx), dvars, None)
+            return self.ew("DIV", [s, self.const_tv(np.float32(K))], sizes)
+        if op == "prod":
+            return red("RPROD" if isf else "RIPROD", body.v)
+        if op == "minimum":
+            return red("RMIN" if isf else "RIMIN", body.v)
+        if op == "maximum":
+            return red("RMAX" if isf else "RIMAX", body.v)
+        raise RDDLNotImplementedError(op)
+
+    def _mat(self, tv: TV, sizes) -> TV:
+        return TV(self.materialise(tv, sizes), tv.vars, None, tv.full)
+
+    def _soft_argmax(self, x: TV, w: TV, n_outer: int, isz, sizes) -> TV:
+        """sum_i i * softmax(w x)_i over the reduced axis  (logic.py:377-379)."""
+        wx = self._mat(self.ew("MUL", [w, x], isz), isz)
+        dv, ptr, idx, K = self._csr(wx, n_outer, isz)
+        mx = TV(self.g.sg(self.g.reduce("RMAX", wx.v, ptr, idx)), dv, None)
+        ex = self._mat(self.ew("EXP", [self.ew("SUB", [wx, mx], isz)], isz), isz)
+        dv, ptr, idx, K = self._csr(ex, n_outer, isz)
+        Z = TV(self.g.reduce("RSUM", ex.v, ptr, idx), dv, None)
+        p = self.ew("DIV", [ex, Z], isz)
+        lit = TV(self.g.const(np.arange(isz[-1], dtype=np.float32)), (len(isz) - 1,), None)
+        term = self._mat(self.ew("MUL", [lit, p], isz), isz)
+        dv, ptr, idx, K = self._csr(term, n_outer, isz)
+        return TV(self.g.reduce("RSUM", term.v, ptr, idx), dv, None)
+
+    # ---- functions: compiler.py:1354-1529 ; logic.py:346-358, 785-896 -------------------
+    _UNARY_F = {"cos": "COS", "sin": "SIN", "tan": "TAN", "acos": "ACOS", "asin": "ASIN",
+                "atan": "ATAN", "cosh": "COSH", "sinh": "SINH", "tanh": "TANH", "exp": "EXP",
+                "ln": "LOG", "sqrt": "SQRT", "lngamma": "LGAMMA"}
+
+    def soft_floor(self, x: TV, w: TV, sizes) -> TV:
+        """logic.py:800-804."""
+        E = lambda name, *a: self.ew(name, list(a), sizes)     # noqa: E731
+        half, one = self.const_tv(np.float32(0.5)), self.const_tv(np.float32(1.))
+        r = TV(self.g.sg(E("FLOOR", E("ADD", x, half)).v), x.vars)
+        d = E("SUB", x, r)
+        ratio = E("DIV", E("STANH", E("MUL", w, d)), E("STANH", E("DIV", w, self.const_tv(np.float32(2.)))))
+        return E("ADD", E("SUB", r, one), E("MUL", half, E("ADD", one, ratio)))
+
+    def soft_round(self, x: TV, w: TV, sizes) -> TV:
+        """logic.py:879-882."""
+        E = lambda name, *a: self.ew(name, list(a), sizes)     # noqa: E731
+        half = self.const_tv(np.float32(0.5))
+        m = E("ADD", TV(self.g.sg(E("FLOOR", x).v), x.vars), half)
+        ratio = E("DIV", E("STANH", E("MUL", w, E("SUB", x, m))),
+                  E("STANH", E("DIV", w, self.const_tv(np.float32(2.)))))
+        return E("ADD", m, E("MUL", half, ratio))
+
+    def _function(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        tvs = [self.at_least_int(t) for t in self._args(e, scope, env)]
+        fluent = self.tr.is_fluent(e)
+        R = self.relax if self.relaxed else {}
+        Vv = self.variants if self.relaxed else {}
+        E = lambda name, *a: self.ew(name, list(a), sizes)     # noqa: E731
+        if len(tvs) == 1:
+            x = tvs[0]
+            if op == "sgn" and Vv.get("sgn") == "tanh" and fluent:
+                w = TV(self.mparam(e, "sigmoid_weight", R["sigmoid_weight"]), ())
+                xf = self.to_f(x, sizes)
+                soft = E("STANH", E("MUL", w, xf))
+                return self.ste(soft, E("SGN", xf), sizes) if R["use_tanh_ste"] else soft
+            if op in ("floor", "ceil") and Vv.get("floor") == "soft" and fluent:
+                w = TV(self.mparam(e, "floor_weight", R["floor_weight"]), ())
+                xf = self.to_f(x, sizes)
+                if op == "floor":
+                    soft, hard = self.soft_floor(xf, w, sizes), E("FLOOR", xf)
+                else:
+                    soft = E("NEG", self.soft_floor(E("NEG", xf), w, sizes))
+                    hard = E("CEIL", xf)
+                return self.ste(soft, hard, sizes) if R["use_floor_ste"] else soft
+            if op == "round" and Vv.get("round") == "soft" and fluent:
+                w = TV(self.mparam(e, "round_weight", R["round_weight"]), ())
+                xf = self.to_f(x, sizes)
+                soft = self.soft_round(xf, w, sizes)
+                return self.ste(soft, E("ROUND", xf), sizes) if R["use_round_ste"] else soft
+            if op in ("abs", "sgn"):
+                name = {"abs": "ABS", "sgn": "SGN"}[op]
+                return E(name if x.dtype == "f" else "I" + name, x)
+            if op in ("round", "floor", "ceil"):
+                if x.dtype != "f":
+                    return x
+                return E(op.upper(), x)
+            xf = self.to_f(x, sizes)
+            if op == "gamma":
+                return E("EXP", E("LGAMMA", xf))
+            return E(self._UNARY_F[op], xf)
+        x, y = tvs
+        if op in ("div", "mod") and Vv.get("floor") == "soft" and fluent:
+            w = TV(self.mparam(e, "floor_weight", R["floor_weight"]), ())
+            xf, yf = self.to_f(x, sizes), self.to_f(y, sizes)
+            d = self.soft_floor(E("DIV", xf, yf), w, sizes)
+            if R["use_floor_ste"]:
+                d = self.ste(d, E("FDIV", xf, yf), sizes)
+            return d if op == "div" else E("SUB", xf, E("MUL", yf, d))
+        (x, y), dt = self.promote([x, y], sizes)
+        I = "" if dt == "f" else "I"
+        if op == "div":
+            return E(I + "FDIV", x, y)
+        if op == "mod":
+            return E(I + "MOD", x, y)
+        if op == "fmod":
+            return E(I + "FMOD", x, y)
+        if op == "min":
+            return E(I + "MIN", x, y)
+        if op == "max":
+            return E(I + "MAX", x, y)
+        if op == "pow":
+            return E(I + "POW", x, y)
+        xf, yf = self.to_f(x, sizes), self.to_f(y, sizes)
+        if op == "log":
+            return E("DIV", E("LOG", xf), E("LOG", yf))
+        if op == "hypot":
+            return E("HYPOT", xf, yf)
+        raise RDDLNotImplementedError(op)
+
+    # ---- control: compiler.py:1617-1685 ; logic.py:903-941 ------------------------------
+    def _control(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        if op != "if":
+            raise RDDLNotImplementedError("switch is not lowered yet")
+        c, a, b = self._args(e, scope, env)
+        E = lambda name, *x: self.ew(name, list(x), sizes)     # noqa: E731
+        if self.relaxed and self.variants.get("if") == "linear" and self.tr.is_fluent(e.args[0]):
+            cf = self.to_f(self.at_least_int(c), sizes)
+            if self.relax["use_if_else_ste"]:
+                cf = self.ste(cf, E("GT", cf, self.const_tv(np.float32(0.5))), sizes)
+            af = self.to_f(self.at_least_int(a), sizes)
+            bf = self.to_f(self.at_least_int(b), sizes)
+            return E("LERP", cf, af, bf)
+        self.static_cast_err(c.dtype == "b")
+        if c.dtype == "f":
+            c = E("GT", c, self.const_tv(np.float32(0.5)))
+        else:
+            c = self.to_b(c, sizes)
+        if a.dtype != b.dtype:
+            (a, b), _ = self.promote([a, b], sizes)
+        out = self.ew("SELECT", [c, a, b], sizes, dtype=a.dtype)
+        return out
+
+    # ---- random variables: compiler.py:1701-2241 ; logic.py:1010-1768 --------------------
+    def _draw(self, kind: str, first_arg: Expr, scope, sizes, extra=None) -> TV:
+        full = self._ref_full(first_arg)
+        shape = tuple(sizes) if full else ()
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        v = self.g.leaf("noise", n, "f", slot=len(self.sg.noise))
+        self.sg.noise.append(NoiseSlot(kind, shape, n, v, extra))
+        return TV(v, tuple(range(len(sizes))) if full else (), None, full)
+
+    def _random(self, e, scope, env, sizes) -> TV:
+        _, name = e.etype
+        R = self.relax if self.relaxed else {}
+        Vv = self.variants if self.relaxed else {}
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        F = lambda t: self.to_f(self.at_least_int(t), sizes)   # noqa: E731
+        if name == "KronDelta":
+            v = self.lower(e.args[0], scope, env)
+            if not self.relaxed and v.dtype == "f":
+                self.sg.static_err |= 1 << ERR_BITS["KRON"]
+            return v
+        if name == "DiracDelta":
+            return F(self.lower(e.args[0], scope, env))
+        if name in ("Discrete", "UnnormDiscrete"):
+            raise RDDLNotImplementedError("Discrete distributions are not lowered yet")
+        tvs = self._args(e, scope, env)
+        a0 = e.args[0]
+        if name == "Uniform":
+            lb, ub = F(tvs[0]), F(tvs[1])
+            U = self._draw("uniform", a0, scope, sizes)
+            self.errchk("UNIFORM", E("GT", lb, ub), sizes)
+            return E("ADD", lb, E("MUL", E("SUB", ub, lb), U))
+        if name == "Normal":
+            mean, var = F(tvs[0]), F(tvs[1])
+            Z = self._draw("normal", a0, scope, sizes)
+            self.errchk("NORMAL", E("LT", var, C(0.)), sizes)
+            return E("ADD", mean, E("MUL", E("SQRT", var), Z))
+        if name == "Exponential":
+            scale = F(tvs[0])
+            Ex = self._draw("exponential", a0, scope, sizes)
+            self.errchk("EXPONENTIAL", E("LE", scale, C(0.)), sizes)
+            return E("MUL", scale, Ex)
+        if name == "Weibull":
+            shape, scale = F(tvs[0]), F(tvs[1])
+            Ex = self._draw("exponential", a0, scope, sizes)
+            self.errchk("WEIBULL", E("OR", E("LE", shape, C(0.)), E("LE", scale, C(0.))), sizes)
+            return E("MUL", scale, E("POW", Ex, E("DIV", C(1.), shape)))
+        if name == "Gamma":
+            shape, scale = F(tvs[0]), F(tvs[1])
+            if shape.v.const is None:
+                raise RDDLNotImplementedError("Gamma with a fluent shape needs an in-loop sampler")
+            full = self._ref_full(a0)
+            allv = tuple(range(len(sizes)))
+            if full:
+                from .graph import apply_map
+                _, mp = self.operand(shape, allv, sizes)
+                conc = shape.v.const[apply_map(mp, self.n_of(allv, sizes))]
+            else:
+                conc = shape.v.const[:1]
+            G = self._draw("gamma", a0, scope, sizes, extra=np.asarray(conc, dtype=np.float32).reshape(
+                tuple(sizes) if full else ()))
+            self.errchk("GAMMA", E("OR", E("LE", shape, C(0.)), E("LE", scale, C(0.))), sizes)
+            return E("MUL", scale, G)
+        if name in ("Gumbel", "Laplace", "Cauchy"):
+            mean, scale = F(tvs[0]), F(tvs[1])
+            Gn = self._draw(name.lower(), a0, scope, sizes)
+            self.errchk(name.upper(), E("LE", scale, C(0.)), sizes)
+            return E("ADD", mean, E("MUL", scale, Gn))
+        if name == "Gompertz":
+            shape, scale = F(tvs[0]), F(tvs[1])
+            Ex = self._draw("exponential", e.args[1], scope, sizes)
+            self.errchk("GOMPERTZ", E("OR", E("LE", shape, C(0.)), E("LE", scale, C(0.))), sizes)
+            return E("DIV", E("DIV", E("LOG1P", Ex), shape), scale)
+        if name == "Kumaraswamy":
+            a, b = F(tvs[0]), F(tvs[1])
+            U = self._draw("uniform", a0, scope, sizes)
+            self.errchk("KUMARASWAMY", E("OR", E("LE", a, C(0.)), E("LE", b, C(0.))), sizes)
+            inner = E("SUB", C(1.), E("POW", U, E("DIV", C(1.), b)))
+            return E("POW", inner, E("DIV", C(1.), a))
+        if name == "Bernoulli":
+            p = tvs[0]
+            variant = Vv.get("bernoulli") if self.tr.is_fluent(a0) else None
+            pf = F(p)
+            self.errchk("BERNOULLI", E("OR", E("LT", pf, C(0.)), E("GT", pf, C(1.))), sizes)
+            if variant is None:
+                U = self._draw("uniform", a0, scope, sizes)
+                return E("LT", U, pf)
+            if variant == "sigmoid":
+                w = TV(self.mparam(e, "bernoulli_sigmoid_weight", R["bernoulli_sigmoid_weight"]), ())
+                U = self._draw("uniform", a0, scope, sizes)
+                s = E("SIGMOID", E("MUL", w, E("SUB", pf, U)))
+                return self.ste(s, E("GT", pf, U), sizes) if R["use_ste_bernoulli"] else s
+            if variant == "gumbel":
+                w = TV(self.mparam(e, "bernoulli_sigmoid_weight", R["bernoulli_sigmoid_weight"]), ())
+                eps = TV(self.mparam(e, "bernoulli_prob_eps", R["bernoulli_prob_eps"]), ())
+                L = self._draw("logistic", a0, scope, sizes)
+                pc = E("MIN", E("MAX", pf, eps), E("SUB", C(1.), eps))
+                logit = E("ADD", E("LOG", E("DIV", pc, E("SUB", C(1.), pc))), L)
+                s = E("SIGMOID", E("MUL", w, logit))
+                return self.ste(s, E("GT", logit, C(0.)), sizes) if R["use_ste_bernoulli"] else s
+            return pf
+        if name == "Geometric":
+            p = F(tvs[0])
+            variant = Vv.get("geometric") if self.tr.is_fluent(a0) else None
+            self.errchk("GEOMETRIC", E("OR", E("LT", p, C(0.)), E("GT", p, C(1.))), sizes)
+            if variant is None:
+                U = self._draw("uniform", a0, scope, sizes)
+                q = E("DIV", E("LOG", U), E("LOG1P", E("NEG", p)))
+                return self.ew("F2I", [E("ADD", E("FLOOR", q), C(1.))], sizes, "i")
+            if variant == "reparam":
+                w = TV(self.mparam(e, "geometric_floor_weight", R["geometric_floor_weight"]), ())
+                eps = TV(self.mparam(e, "geometric_eps", R["geometric_eps"]), ())
+                Ex = self._draw("exponential", a0, scope, sizes)
+                ratio = E("DIV", E("NEG", Ex), E("SAFELOG", E("SUB", C(1.), p), eps))
+                return E("ADD", C(1.), self.soft_floor(ratio, w, sizes))
+            return E("DIV", C(1.), p)
+        raise RDDLNotImplementedError(f"Distribution {name} is not supported.")
+
+    # ==================================================================================
+    def build(self, action_values: Dict[str, V], state_values: Optional[Dict[str, V]] = None
+              ) -> StepGraph:
+        """Lower one transition (compiler.py:490-547) given the action values."""
+        m, sg = self.m, self.sg
+        env: Dict[str, V] = {}
+        for name in m.state_fluents:
+            if state_values is not None and name in state_values:
+                v = state_values[name]
+            else:
+                v = self.g.leaf("state_in", m.variable_size(name),
+                                self.dtype_of_range(m.variable_ranges[name]), fluent=name)
+            sg.state_in[name] = v
+            env[name] = v
+            env[m.next_state[name]] = v          # compiler.py:721-722: s' starts equal to s
+        for name, v in action_values.items():
+            sg.action_in[name] = v
+            env[name] = v
+        for name in list(m.interm_fluents) + list(m.derived_fluents) + list(m.observ_fluents):
+            pass
+        for lv in m.levels.values():
+            for name in lv:                       # compiler.py:360-368
+                params, expr = m.cpfs[name]
+                scope = list(params)
+                sizes = self.sizes(scope)
+                tv = self.lower(expr, scope, env)
+                all_vars = tuple(range(len(scope)))
+                full = TV(tv.v, tv.vars, tv.idx)
+                want = self.dtype_of_range(m.variable_ranges[name])
+                if full.dtype != want:               # _jax_cast, compiler.py:971-983
+                    full = self._cast(full, want, sizes)
+                v, mp = self.operand(full, all_vars, sizes)
+                if mp is not None or v.op in ("state_in", "action_in", "const", "mparam", "noise") \
+                        or v.const is not None:
+                    v = self.g.add(V("MOV", [(v, mp)], n=self.n_of(all_vars, sizes),
+                                     dtype=want, uniform=False))
+                if self.relaxed and name in (self.relax.get("cpfs_without_grad") or ()):
+                    v = self.g.sg(v)
+                env[name] = v
+                sg.fluents[name] = v
+        sizes = ()
+        r = self.lower(m.reward, [], env)
+        r = self.to_f(self.at_least_int(r), sizes)
+        rv = self.materialise(r, sizes)
+        if rv.uniform or rv.const is not None:
+            rv = self.g.add(V("MOV", [(rv, None)], n=1, dtype="f", uniform=False))
+        sg.reward = rv
+        for s, sp in m.next_state.items():
+            sg.next_state[s] = env[sp]
+        return sg
+
+    def _cast(self, tv: TV, want: str, sizes) -> TV:
+        src = tv.dtype
+        if want == "f":
+            return self.to_f(self.at_least_int(tv), sizes)
+        if want == "i":
+            if src == "b":
+                return self.at_least_int(tv)
+            out = self.ew("F2I", [tv], sizes, "i")          # float -> int truncates
+            back = self.ew("I2F", [out], sizes)
+            self.errchk("CAST", self.ew("NE", [back, tv], sizes), sizes)
+            return out
+        # want bool
+        out = self.to_b(tv, sizes)
+        if src == "f":
+            back = self.ew("I2F", [TV(self._retag(out.v, "i"), out.vars)], sizes)
+            self.errchk("CAST", self.ew("NE", [back, tv], sizes), sizes)
+        else:
+            self.errchk("CAST", self.ew("INE", [TV(self._retag(out.v, "i"), out.vars), tv], sizes), sizes)
+        return out

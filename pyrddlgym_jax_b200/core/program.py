@@ -1,0 +1,578 @@
+"""Assembler: SSA step graph -> binary rollout program for csrc/rk_interp.cu.
+
+A program has three instruction lists -- prologue (once), step (once per decision epoch,
+t ascending for forward programs, descending for adjoint programs), epilogue (once) -- the
+flat counterpart of ``compile_rollouts`` (compiler.py:621-666): the scan body of
+compiler.py:561-593 is the step list, and the backward pass XLA derives from
+``jax.value_and_grad`` (planner.py:2873) is a second program whose step list reloads s_t
+from the state tape, recomputes the step and runs the adjoint instructions emitted by
+core/graph.py:differentiate.
+
+Register file layout (per warp, 32-bit words in shared memory): a value with ``n`` elements
+per rollout occupies RPW*n consecutive words as [q][e] (RPW = rollouts per warp, lane = q*L+e
+for e < L); rollout-invariant values occupy n words.  Constants, gather tables and model
+parameters live in one CTA-wide constant region.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import isa
+from .graph import Graph, V, Map, apply_map, differentiate
+from .lowering import Lowerer, StepGraph, TV
+
+HEADER_WORDS = 32
+
+
+class ProgramError(Exception):
+    pass
+
+
+@dataclass
+class Ins:
+    op: str
+    dst: Optional[V] = None
+    srcs: List[Tuple[V, Map]] = field(default_factory=list)
+    n: int = 0
+    flags: int = 0
+    aux0: int = 0
+    aux1: int = 0
+    tables: Dict[str, np.ndarray] = field(default_factory=dict)
+    off: int = 0                # memory offset (words per rollout / per step)
+    buf: int = 0
+
+
+def root(v: V) -> V:
+    while v.op == "sg":
+        v = v.args[0][0]
+    return v
+
+
+@dataclass
+class Program:
+    blob: bytes
+    kind: str                   # 'forward' | 'backward'
+    relaxed: bool
+    rpw: int
+    lanes: int
+    warp_words: int
+    const_words: int
+    n_ins: Tuple[int, int, int]
+    S: int
+    A: int
+    N: int
+    state_layout: Dict[str, Tuple[int, int, str]]      # fluent -> (offset, n, dtype)
+    param_layout: Dict[str, Tuple[int, int, str]]      # action fluent -> (offset, n, range)
+    noise_layout: List[Tuple[str, Tuple[int, ...], int, int, Any]]  # kind, shape, n, offset, extra
+    mparam_keys: List[Tuple[Any, str]]
+    mparam_defaults: np.ndarray
+    traj_layout: Dict[str, Tuple[int, int, str]] = field(default_factory=dict)
+    TRAJ: int = 0
+    static_err: int = 0
+    stats: Dict[str, Any] = field(default_factory=dict)
+
+
+class Assembler:
+    def __init__(self):
+        self.const_image: List[np.ndarray] = [np.array([0.0, 1.0], dtype=np.float32).view(np.uint32)]
+        self.const_words = 2
+        self._const_cache: Dict[bytes, int] = {}
+        self.addr: Dict[int, Tuple[int, int]] = {}      # root V id -> (base, sq)
+
+    def add_const(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.kind == "f":
+            words = arr.astype(np.float32).view(np.uint32)
+        else:
+            words = arr.astype(np.int32).view(np.uint32)
+        key = words.tobytes()
+        off = self._const_cache.get(key)
+        if off is None:
+            off = self.const_words
+            self.const_image.append(words.ravel())
+            self.const_words += words.size
+            self._const_cache[key] = off
+        return off
+
+    def table(self, arr: np.ndarray) -> int:
+        return self.add_const(np.asarray(arr, dtype=np.int32))
+
+
+class _Alloc:
+    """First-fit interval allocator over a 1-D word space."""
+
+    def __init__(self, start: int):
+        self.free: List[List[int]] = [[start, 1 << 30]]
+        self.high = start
+
+    def alloc(self, size: int) -> int:
+        for iv in self.free:
+            if iv[1] - iv[0] >= size:
+                base = iv[0]
+                iv[0] += size
+                if iv[0] == iv[1]:
+                    self.free.remove(iv)
+                self.high = max(self.high, base + size)
+                return base
+        raise ProgramError("register space exhausted")
+
+    def release(self, base: int, size: int):
+        self.free.append([base, base + size])
+        self.free.sort()
+        merged = [self.free[0]]
+        for iv in self.free[1:]:
+            if iv[0] <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], iv[1])
+            else:
+                merged.append(iv)
+        self.free = merged
+
+
+# =====================================================================================
+
+@dataclass
+class PlanSpec:
+    """How actions are produced inside the step (the policy part of compiler.py:552-557)."""
+    kind: str = "slp"                      # 'slp' | 'external'
+    wrap_sigmoid: bool = True
+    wrap_non_bool: bool = False
+    sigmoid_weight: float = 1.0
+    bounds: Optional[Dict[str, Tuple[np.ndarray, np.ndarray]]] = None
+
+
+def action_layout(model) -> Tuple[Dict[str, Tuple[int, int, str]], int]:
+    layout, off = {}, 0
+    for name in model.action_fluents:
+        n = model.variable_size(name)
+        layout[name] = (off, n, model.variable_ranges[name])
+        off += n
+    return layout, off
+
+
+def state_layout(model, relaxed: bool) -> Tuple[Dict[str, Tuple[int, int, str]], int]:
+    layout, off = {}, 0
+    for name in model.state_fluents:
+        n = model.variable_size(name)
+        dt = "f" if relaxed else {"real": "f", "int": "i", "bool": "b"}.get(
+            model.variable_ranges[name], "i")
+        layout[name] = (off, n, dt)
+        off += n
+    return layout, off
+
+
+def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dict[str, V], Dict[str, V]]:
+    """Action values fed to the transition + the parameter leaves they come from.
+
+    train=True : JaxStraightLinePlan train policy, planner.py:786-838
+    train=False: test policy, planner.py:842-868
+    """
+    m, g = low.m, low.g
+    layout, _ = action_layout(m)
+    actions, leaves = {}, {}
+    for name, (off, n, prange) in layout.items():
+        if spec.kind == "external":
+            dt = low.dtype_of_range(prange)
+            leaf = g.leaf("act_in", n, dt, uniform=False, off=off, fluent=name)
+            leaves[name] = leaf
+            actions[name] = leaf
+            continue
+        p = g.leaf("param_in", n, "f", uniform=True, off=off, fluent=name)
+        leaves[name] = p
+        is_bool = prange == "bool"
+        if train:
+            if is_bool and spec.wrap_sigmoid:         # planner.py:741-745, 818
+                w = g.leaf("mparam", 1, "f", uniform=True, key=("policy", name),
+                           default=float(spec.sigmoid_weight), slot=len(low.sg.mparams))
+                low.sg.mparams.append((("policy", name), float(spec.sigmoid_weight), w))
+                a = g.op("SIGMOID", [(g.op("MUL", [(w, "b"), (p, None)], n), None)], n)
+            else:
+                a = p
+            if not low.relaxed and a.dtype != low.dtype_of_range(prange):
+                raise ProgramError("train policy requires a relaxed (all-REAL) model")
+            actions[name] = a
+        else:
+            if is_bool:                               # planner.py:856
+                thr = 0.0 if spec.wrap_sigmoid else 0.5
+                a = g.op("GT", [(p, None), (g.const(np.float32(thr)), "b")], n)
+            else:                                     # planner.py:860-865
+                lo, hi = spec.bounds[name]
+                lo = g.const(np.asarray(lo, dtype=np.float32).ravel())
+                hi = g.const(np.asarray(hi, dtype=np.float32).ravel())
+                a = g.op("MIN", [(g.op("MAX", [(p, None), (lo, None)], n), None), (hi, None)], n)
+                if prange != "real":
+                    a = g.op("F2I", [(g.op("ROUND", [(a, None)], n), None)], n, "i")
+            want = low.dtype_of_range(prange)
+            if a.dtype != want:
+                if want == "f":
+                    a = g.op("I2F", [(a, None)], n)
+                else:
+                    raise ProgramError(f"cannot feed {a.dtype} action into {want} fluent <{name}>")
+            actions[name] = a
+    return actions, leaves
+
+
+class ProgramBuilder:
+    """Builds forward / backward programs for one (model, relaxation, plan) triple."""
+
+    def __init__(self, model, relax: Optional[Dict[str, Any]], spec: PlanSpec, train_policy: bool,
+                 log_fluents: Sequence[str] = (), batch_hint: int = 0):
+        self.batch_hint = batch_hint
+        self.model = model
+        self.relax = relax
+        self.spec = spec
+        self.low = Lowerer(model, relax)
+        self.g = self.low.g
+        self.actions, self.param_leaves = build_policy_actions(self.low, spec, train_policy)
+        self.sg: StepGraph = self.low.build(self.actions)
+        self.slayout, self.S = state_layout(model, relax is not None)
+        self.alayout, self.A = action_layout(model)
+        off = 0
+        for slot in self.sg.noise:
+            slot.offset = off
+            off += slot.n
+        self.N = off
+        self.log_fluents = list(log_fluents)
+
+    # ---------------------------------------------------------------------------------
+    def _needed(self, roots: Sequence[V]) -> List[V]:
+        seen, stack = set(), [r for r in roots]
+        while stack:
+            v = stack.pop()
+            if v.id in seen:
+                continue
+            seen.add(v.id)
+            for a, _ in v.args:
+                stack.append(a)
+        return [v for v in self.g.nodes if v.id in seen]
+
+    def _compute_ins(self, nodes: Sequence[V], tstep_params: bool = True) -> List[Ins]:
+        """One instruction per value that needs computing, in topological order."""
+        out = []
+        for v in nodes:
+            if v.op in ("const", "mparam", "sg", "state_in", "persist"):
+                continue
+            if v.op == "param_in":
+                out.append(Ins("LDU", dst=v, n=v.n, flags=isa.F_UNIFORM | isa.F_TSTEP,
+                               buf=isa.BUF["PARAMS"], off=v.attrs["off"]))
+            elif v.op == "act_in":
+                out.append(Ins("LDB", dst=v, n=v.n, flags=isa.F_TSTEP, buf=isa.BUF["ACT"],
+                               off=v.attrs["off"]))
+            elif v.op == "noise":
+                slot = self.sg.noise[v.attrs["slot"]]
+                out.append(Ins("LDB", dst=v, n=v.n, flags=isa.F_TSTEP, buf=isa.BUF["NOISE"],
+                               off=slot.offset))
+            elif v.op == "disc_in":
+                out.append(Ins("LDU", dst=v, n=1, flags=isa.F_UNIFORM | isa.F_TSTEP,
+                               buf=isa.BUF["DISC"], off=0))
+            elif v.op in ("RSUM", "RPROD", "RMIN", "RMAX", "RISUM", "RIPROD", "RIMIN", "RIMAX",
+                          "RARGMAX", "RARGMIN", "RPRODX"):
+                tables = {"ptr": v.attrs["ptr"], "idx": v.attrs["idx"]}
+                if v.op == "RPRODX":
+                    tables["seg"] = v.attrs["seg"]
+                out.append(Ins(v.op, dst=v, srcs=list(v.args), n=v.n, tables=tables,
+                               flags=isa.F_UNIFORM if v.uniform else 0))
+            else:
+                out.append(Ins(v.op, dst=v, srcs=list(v.args), n=v.n,
+                               flags=isa.F_UNIFORM if v.uniform else 0))
+        return out
+
+    # ---------------------------------------------------------------------------------
+    def forward(self, write_tape: bool, gamma: float = 1.0, final_state: bool = True) -> Program:
+        g, sg = self.g, self.sg
+        ret = g.leaf("persist", 1, "f")
+        pro: List[Ins] = []
+        for name, (off, n, _) in self.slayout.items():
+            pro.append(Ins("LDB", dst=sg.state_in[name], n=n, buf=isa.BUF["S0"], off=off))
+        pro.append(Ins("MOV", dst=ret, srcs=[(g.const(np.float32(0.)), "b")], n=1))
+
+        roots = [sg.reward] + list(sg.next_state.values()) + [c for _, c in sg.errs] \
+            + [sg.fluents[f] if f in sg.fluents else sg.action_in[f] for f in self.log_fluents]
+        step: List[Ins] = []
+        if write_tape:
+            for name, (off, n, _) in self.slayout.items():
+                step.append(Ins("STB", srcs=[(sg.state_in[name], None)], n=n, flags=isa.F_TSTEP,
+                                buf=isa.BUF["TAPE"], off=off))
+        disc = None
+        if gamma != 1.0:
+            disc = g.leaf("disc_in", 1, "f", uniform=True)
+            roots.append(disc)
+        step += self._compute_ins(self._needed(roots))
+        step.append(Ins("STB", srcs=[(sg.reward, None)], n=1, flags=isa.F_TSTEP,
+                        buf=isa.BUF["REWARD"], off=0))
+        if disc is not None:       # planner.py:2754-2757
+            step.append(Ins("FMA", dst=ret, srcs=[(sg.reward, None), (disc, "b"), (ret, None)], n=1))
+        else:
+            step.append(Ins("ADD", dst=ret, srcs=[(ret, None), (sg.reward, None)], n=1))
+        for bit, cond in sg.errs:
+            step.append(Ins("ERRCHK", srcs=[(cond, None)], n=cond.n, aux0=bit))
+        step.append(Ins("STERR", n=1, flags=isa.F_TSTEP, buf=isa.BUF["ERR"]))
+        traj_layout, toff = {}, 0
+        for f in self.log_fluents:
+            v = sg.fluents[f] if f in sg.fluents else sg.action_in[f]
+            step.append(Ins("STB", srcs=[(v, None)], n=v.n, flags=isa.F_TSTEP,
+                            buf=isa.BUF["TRAJ"], off=toff))
+            traj_layout[f] = (toff, v.n, v.dtype)
+            toff += v.n
+        self._traj_words = toff
+        state_roots = {v.id for v in sg.state_in.values()}
+        moves = []
+        for name in self.slayout:
+            nxt = sg.next_state[name]
+            if root(nxt) is sg.state_in[name]:
+                continue
+            if root(nxt).id in state_roots:      # x' = y: stage through a temporary
+                tmp = g.add(V("MOV", [(nxt, None)], n=nxt.n, dtype=nxt.dtype))
+                step.append(Ins("MOV", dst=tmp, srcs=[(nxt, None)], n=nxt.n))
+                nxt = tmp
+            moves.append(Ins("MOV", dst=sg.state_in[name], srcs=[(nxt, None)],
+                             n=sg.state_in[name].n))
+        step += moves
+        epi: List[Ins] = [Ins("STB", srcs=[(ret, None)], n=1, buf=isa.BUF["RETURNS"], off=0)]
+        if final_state:
+            for name, (off, n, _) in self.slayout.items():
+                epi.append(Ins("STB", srcs=[(sg.state_in[name], None)], n=n,
+                               buf=isa.BUF["FINAL"], off=off))
+        persistent = list(sg.state_in.values()) + [ret]
+        prog = self._assemble("forward", pro, step, epi, persistent)
+        prog.traj_layout, prog.TRAJ = traj_layout, toff
+        return prog
+
+    # ---------------------------------------------------------------------------------
+    def backward(self, gamma: float = 1.0, grad_s0: bool = False) -> Program:
+        """Adjoint program: d(sum_b gret[b] * return_b) / d(policy parameters)."""
+        if self.relax is None:
+            raise ProgramError("the adjoint program needs a relaxed (all-REAL) model")
+        g, sg = self.g, self.sg
+        gret = g.leaf("persist", 1, "f")
+        carried = {name: g.leaf("persist", n, "f") for name, (_, n, _) in self.slayout.items()}
+        pro: List[Ins] = [Ins("LDB", dst=gret, n=1, buf=isa.BUF["GRET"], off=0)]
+        zero = g.const(np.float32(0.))
+        for name, c in carried.items():
+            pro.append(Ins("MOV", dst=c, srcs=[(zero, "b")], n=c.n))
+
+        if gamma != 1.0:
+            disc = g.leaf("disc_in", 1, "f", uniform=True)
+            gr = g.op("MUL", [(gret, None), (disc, "b")], 1)
+        else:
+            gr = gret
+        seeds = [(sg.reward, gr)] + [(sg.next_state[name], carried[name]) for name in self.slayout]
+        fwd_nodes = self._needed([sg.reward] + list(sg.next_state.values()))
+        wrt = list(sg.state_in.values()) + list(self.param_leaves.values())
+        n_before = len(g.nodes)
+        cts = differentiate(g, fwd_nodes, seeds, wrt)
+
+        step: List[Ins] = []
+        for name, (off, n, _) in self.slayout.items():
+            step.append(Ins("LDB", dst=sg.state_in[name], n=n, flags=isa.F_TSTEP,
+                            buf=isa.BUF["TAPE"], off=off))
+        outs = [cts[v.id] for v in wrt if v.id in cts]
+        step += self._compute_ins(self._needed(outs))
+        gbuf = isa.BUF["GRADP"] if self.spec.kind == "slp" else isa.BUF["GACT"]
+        for name, leaf in self.param_leaves.items():
+            off, n, _ = self.alayout[name]
+            ct = cts.get(leaf.id)
+            src = (ct, None) if ct is not None else (zero, "b")
+            if self.spec.kind == "slp":
+                step.append(Ins("STG", srcs=[src], n=n, flags=isa.F_TSTEP | isa.F_UNIFORM,
+                                buf=gbuf, off=off))
+            else:
+                step.append(Ins("STB", srcs=[src], n=n, flags=isa.F_TSTEP, buf=gbuf, off=off))
+        for name, c in carried.items():
+            ct = cts.get(sg.state_in[name].id)
+            src = (ct, None) if ct is not None else (zero, "b")
+            step.append(Ins("MOV", dst=c, srcs=[src], n=c.n))
+        epi: List[Ins] = []
+        if grad_s0:
+            for name, (off, n, _) in self.slayout.items():
+                epi.append(Ins("STB", srcs=[(carried[name], None)], n=n, buf=isa.BUF["GS0"], off=off))
+        persistent = list(sg.state_in.values()) + [gret] + list(carried.values())
+        self._traj_words = 0
+        prog = self._assemble("backward", pro, step, epi, persistent)
+        prog.stats["adjoint_nodes"] = len(g.nodes) - n_before
+        return prog
+
+    # ---------------------------------------------------------------------------------
+    # per-instruction fixed cost (fetch, decode, dispatch) in units of one element pass
+    INS_OVERHEAD = 4.0
+    SMEM_WORDS = 56 * 1024            # ~224 KB of shared memory per SM, in words
+    FREE_WARPS_PER_SM = 8             # warps/SM that overlap almost perfectly (latency-bound)
+
+    def _assemble(self, kind: str, pro: List[Ins], step: List[Ins], epi: List[Ins],
+                  persistent: Sequence[V]) -> Program:
+        """Try every lanes-per-rollout choice and keep the one with the lowest estimated
+        time for the batch size this builder was given."""
+        B = max(int(getattr(self, "batch_hint", 0) or 4096), 1)
+        best, best_t, last_err = None, None, None
+        for L in sorted({32 // r for r in range(1, 33)}):
+            try:
+                prog = self._assemble_for(kind, pro, step, epi, persistent, L)
+            except ProgramError as e:
+                last_err = e
+                continue
+            cost = sum(-(-max(i.n, 1) // L) + self.INS_OVERHEAD for i in step)
+            nwarps = -(-B // prog.rpw)
+            resident = max(1, min(64, self.SMEM_WORDS // max(prog.warp_words, 1)))
+            conc = 148 * min(resident, self.FREE_WARPS_PER_SM)
+            t = cost * max(1.0, nwarps / conc)
+            if best is None or t < best_t * 0.999:
+                best, best_t = prog, t
+        if best is None:
+            raise last_err
+        return best
+
+    def _assemble_for(self, kind: str, pro: List[Ins], step: List[Ins], epi: List[Ins],
+                      persistent: Sequence[V], L: int) -> Program:
+        asm = Assembler()
+        sg = self.sg
+        rpw = 32 // L
+
+        # ---- constant region: model parameters first, then constants / tables on demand
+        n_mp = len(sg.mparams)
+        mp_defaults = np.array([d for _, d, _ in sg.mparams], dtype=np.float32)
+        mparam_off = asm.const_words
+        if n_mp:
+            asm.const_image.append(mp_defaults.view(np.uint32).copy())
+            asm.const_words += n_mp
+        for i, (_, _, v) in enumerate(sg.mparams):
+            asm.addr[v.id] = ((mparam_off + i) | isa.CONST_BIT, 0)
+
+        def place_const(v: V):
+            if v.id not in asm.addr:
+                asm.addr[v.id] = (asm.add_const(v.const) | isa.CONST_BIT, 0)
+
+        # ---- persistent registers
+        alloc = _Alloc(0)
+
+        def size_of(v: V) -> int:
+            return v.n if v.uniform else v.n * rpw
+
+        err_base = alloc.alloc(rpw)                # per-rollout error accumulators
+        for v in persistent:
+            asm.addr[v.id] = (alloc.alloc(size_of(v)), 0 if v.uniform else v.n)
+        persist_high = alloc.high
+        warp_words = persist_high
+
+        encoded: List[np.ndarray] = []
+        counts = []
+        for lst in (pro, step, epi):
+            al = _Alloc(persist_high)
+            # liveness
+            last_use: Dict[int, int] = {}
+            for i, ins in enumerate(lst):
+                for a, _ in ins.srcs:
+                    last_use[root(a).id] = i
+            live: Dict[int, Tuple[int, int]] = {}
+            for i, ins in enumerate(lst):
+                for a, _ in ins.srcs:
+                    r = root(a)
+                    if r.const is not None:
+                        place_const(r)
+                    elif r.id not in asm.addr:
+                        raise ProgramError(f"value {r} used before definition in {kind} program")
+                d = ins.dst
+                if d is not None:
+                    r = root(d)
+                    if r.id not in asm.addr:
+                        base = al.alloc(size_of(r))
+                        asm.addr[r.id] = (base, 0 if r.uniform else r.n)
+                        live[r.id] = (base, size_of(r))
+                        if r.id not in last_use:
+                            last_use[r.id] = i
+                encoded.append(self._encode(asm, ins))
+                for rid in [rid for rid, lu in last_use.items() if lu == i and rid in live]:
+                    base, sz = live.pop(rid)
+                    al.release(base, sz)
+            warp_words = max(warp_words, al.high)
+            counts.append(len(lst))
+            # forget temp addresses so a stale one can never be read by the next list
+            pers_ids = {p.id for p in persistent}
+            for ins in lst:
+                if ins.dst is not None and root(ins.dst).id not in pers_ids:
+                    asm.addr.pop(root(ins.dst).id, None)
+
+        if warp_words >= 0x8000 or warp_words + asm.const_words > self.SMEM_WORDS:
+            raise ProgramError(f"warp register file too large ({warp_words} words)")
+        if asm.const_words >= 0x8000:
+            raise ProgramError(f"constant region too large ({asm.const_words} words)")
+
+        pad = (-asm.const_words) % 4
+        if pad:
+            asm.const_image.append(np.zeros(pad, dtype=np.uint32))
+            asm.const_words += pad
+        const_img = np.concatenate(asm.const_image).astype(np.uint32)
+        hdr = np.zeros(HEADER_WORDS, dtype=np.uint32)
+        hdr[0] = isa.MAGIC
+        hdr[1] = 1
+        hdr[2:5] = counts
+        hdr[5] = asm.const_words
+        hdr[6] = mparam_off
+        hdr[7] = n_mp
+        hdr[8] = warp_words
+        hdr[9] = rpw
+        hdr[10] = L
+        hdr[11] = self.S
+        hdr[12] = self.A
+        hdr[13] = self.N
+        hdr[14] = (1 if self.relax is not None else 0) | (2 if kind == "backward" else 0)
+        hdr[15] = sg.static_err
+        hdr[16] = err_base
+        hdr[17] = getattr(self, "_traj_words", 0)
+        ins_img = np.concatenate(encoded).astype(np.uint16) if encoded else np.zeros(0, np.uint16)
+        blob = hdr.tobytes() + const_img.tobytes() + ins_img.tobytes()
+        hist: Dict[str, int] = {}
+        for ins in step:
+            hist[ins.op] = hist.get(ins.op, 0) + 1
+        return Program(
+            blob=blob, kind=kind, relaxed=self.relax is not None, rpw=rpw, lanes=L,
+            warp_words=warp_words, const_words=asm.const_words, n_ins=tuple(counts),
+            S=self.S, A=self.A, N=self.N, state_layout=self.slayout, param_layout=self.alayout,
+            noise_layout=[(s.kind, s.shape, s.n, s.offset, s.extra) for s in sg.noise],
+            mparam_keys=[k for k, _, _ in sg.mparams], mparam_defaults=mp_defaults,
+            static_err=sg.static_err, stats={"step_ops": hist})
+
+    def _encode(self, asm: Assembler, ins: Ins) -> np.ndarray:
+        w = np.zeros(isa.INS_WORDS, dtype=np.uint16)
+        w[0] = isa.OPCODE[ins.op]
+        w[1] = ins.flags
+        w[2] = ins.n
+        if ins.n > 0xFFFF:
+            raise ProgramError("value too large")
+        if ins.dst is not None:
+            base, sq = asm.addr[root(ins.dst).id]
+            if base >= 0x8000 and not (base & isa.CONST_BIT and base < 0x10000):
+                raise ProgramError("warp register file too large")
+            if base >= 0x10000 or sq >= 0x10000:
+                raise ProgramError("warp register file too large")
+            w[3], w[4] = base, sq
+        for k, (a, m) in enumerate(ins.srcs[:3]):
+            base, sq = asm.addr[root(a).id]
+            if base >= 0x10000 or sq >= 0x10000:
+                raise ProgramError("register or constant space too large")
+            if m is None:
+                mp = isa.MAP_IDENT
+            elif isinstance(m, str):
+                mp = isa.MAP_BCAST
+            else:
+                mp = asm.table(m)
+                if mp >= 0x8000:
+                    raise ProgramError("constant region too large")
+            w[5 + 3 * k: 8 + 3 * k] = (base, sq, mp)
+        if ins.tables:
+            tp, ti = asm.table(ins.tables["ptr"]), asm.table(ins.tables["idx"])
+            ts = asm.table(ins.tables["seg"]) if "seg" in ins.tables else 0
+            if max(tp, ti, ts) >= 0x8000:
+                raise ProgramError("constant region too large")
+            w[14], w[15] = tp, ti
+            if "seg" in ins.tables:
+                w[8] = ts
+        elif ins.op in ("LDB", "STB", "LDU", "STG", "STERR"):
+            w[14] = ins.buf
+            w[15] = ins.off & 0xFFFF
+            w[11] = (ins.off >> 16) & 0xFFFF
+        elif ins.op == "ERRCHK":
+            w[14] = ins.aux0
+        return w

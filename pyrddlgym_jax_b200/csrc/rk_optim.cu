@@ -1,0 +1,185 @@
+// rk_optim.cu -- gradient reduction, loss and optimiser kernels (sm_100a).
+//
+// Replaces the device work of planner.py:2811-2819 (loss = -utility(returns)) and
+// planner.py:2885-2899 (optax update, apply_updates, box projection).  Every reduction
+// here runs in a fixed order (no float atomics) so results are reproducible run to run and
+// identical on every rank after the gradient all-reduce.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/rk.h"
+
+// ---- fixed-order column sums over the per-warp partial rows ------------------------------
+// pass 1: rows are split into `chunks` contiguous groups; each group is summed into its own
+// first row (in place).  pass 2: the group heads are summed into grad.
+__global__ void rk_reduce_rows_kernel(float* __restrict__ gradp, int rows, int n, int chunks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= n) return;
+  const int per = (rows + chunks - 1) / chunks;
+  const int r0 = c * per, r1 = min(rows, r0 + per);
+  if (r0 >= r1) return;
+  float acc = 0.f;
+  const float* p = gradp + (size_t)r0 * n + i;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {          // 4 independent loads in flight, fixed add order
+    float v0 = p[0], v1 = p[(size_t)n], v2 = p[2 * (size_t)n], v3 = p[3 * (size_t)n];
+    acc = (((acc + v0) + v1) + v2) + v3;
+    p += 4 * (size_t)n;
+  }
+  for (; r < r1; ++r) { acc += *p; p += n; }
+  gradp[(size_t)r0 * n + i] = acc;
+}
+
+__global__ void rk_reduce_heads_kernel(const float* __restrict__ gradp, int rows, int n,
+                                       int chunks, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int per = (rows + chunks - 1) / chunks;
+  float acc = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const int r0 = c * per;
+    if (r0 >= rows) break;
+    acc += gradp[(size_t)r0 * n + i];
+  }
+  grad[i] = acc;
+}
+
+extern "C" int rk_reduce_partials(void* stream, const float* gradp, int num_rows, int n,
+                                  float* grad) {
+  if (gradp == nullptr || grad == nullptr || num_rows <= 0 || n <= 0) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunks = 1;
+  // enough CTAs to cover the machine when the parameter vector is short
+  const int col_blocks = (n + 127) / 128;
+  while (chunks < 64 && chunks * 2 * 32 <= num_rows && col_blocks * chunks < 148 * 8) chunks *= 2;
+  dim3 grid(col_blocks, chunks);
+  rk_reduce_rows_kernel<<<grid, 128, 0, st>>>((float*)gradp, num_rows, n, chunks);
+  rk_reduce_heads_kernel<<<col_blocks, 128, 0, st>>>(gradp, num_rows, n, chunks, grad);
+  return (int)cudaGetLastError();
+}
+
+// ---- deterministic single-CTA statistics: sum of squares + all-zero test -----------------
+__device__ __forceinline__ float block_sum_1024(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (l == 0) sh[0] = r;
+  }
+  __syncthreads();
+  r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024)
+rk_grad_stats_kernel(const float* __restrict__ g, int n, float* __restrict__ stats,
+                     int32_t* __restrict__ zero_flag) {
+  __shared__ float sh[32];
+  float ss = 0.f, nz = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = g[i];
+    ss += v * v;
+    nz += (fabsf(v) > 1e-8f || v != v) ? 1.f : 0.f;     // jnp.allclose(g, 0): |g| <= 1e-8
+  }
+  ss = block_sum_1024(ss, sh);
+  nz = block_sum_1024(nz, sh);
+  if (threadIdx.x == 0) {
+    stats[0] = ss;
+    if (zero_flag != nullptr) *zero_flag = (nz == 0.f) ? 1 : 0;
+  }
+}
+
+// hyper = {lr, decay|b1, eps, b2, clip_norm, momentum, step}
+__global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, int n,
+                                    float* __restrict__ params, float* __restrict__ state,
+                                    const float* __restrict__ grad, const float* __restrict__ lo,
+                                    const float* __restrict__ hi, const float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
+  const float clip = hyper[4], mom = hyper[5], step = hyper[6];
+  float g = grad[i];
+  if (clip > 0.f) {                      // optax.clip_by_global_norm (planner.py:2368-2369)
+    const float gn = sqrtf(stats[0]);
+    if (gn > clip) g = g * (clip / gn);
+  }
+  float upd;
+  if (kind == 1) {                       // optax.rmsprop: nu <- d nu + (1-d) g^2 ; g * rsqrt(nu + eps)
+    float nu = d1 * state[i] + (1.f - d1) * g * g;
+    state[i] = nu;
+    upd = g / sqrtf(nu + eps);
+  } else if (kind == 2) {                // optax.adam with bias correction, step is 1-based
+    float mu = d1 * state[i] + (1.f - d1) * g;
+    float nu = b2 * state[n + i] + (1.f - b2) * g * g;
+    state[i] = mu;
+    state[n + i] = nu;
+    float mh = mu / (1.f - powf(d1, step));
+    float nh = nu / (1.f - powf(b2, step));
+    upd = mh / (sqrtf(nh) + eps);
+  } else {                               // optax.sgd (optional heavy-ball momentum)
+    if (mom > 0.f) {
+      float m = g + mom * state[i];
+      state[i] = m;
+      upd = m;
+    } else {
+      upd = g;
+    }
+  }
+  float p = params[i] - lr * upd;        // optax.apply_updates (planner.py:2898)
+  if (lo != nullptr) p = fmaxf(p, lo[i]);   // box projection (planner.py:896-904)
+  if (hi != nullptr) p = fminf(p, hi[i]);
+  params[i] = p;
+}
+
+static float* g_stats[64] = {nullptr};
+
+extern "C" int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
+                                 float* params, float* state, const float* grad,
+                                 const float* lo, const float* hi, int32_t* zero_flag) {
+  if (hyper == nullptr || params == nullptr || grad == nullptr || n <= 0) return RK_E_BADARG;
+  if (kind < 0 || kind > 2) return RK_E_BADARG;
+  if (kind != 0 && state == nullptr) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return RK_E_BADARG;
+  if (g_stats[dev] == nullptr) {
+    cudaError_t ce = cudaMalloc((void**)&g_stats[dev], 16);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  rk_grad_stats_kernel<<<1, 1024, 0, st>>>(grad, n, g_stats[dev], zero_flag);
+  rk_optimizer_kernel<<<(n + 255) / 256, 256, 0, st>>>(kind, hyper, n, params, state, grad, lo, hi,
+                                                        g_stats[dev]);
+  return (int)cudaGetLastError();
+}
+
+// ---- loss = -mean(returns), gret[b] = -1/B ------------------------------------------------
+__global__ void __launch_bounds__(1024)
+rk_mean_loss_kernel(const float* __restrict__ returns, int B, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s += returns[i];
+  s = block_sum_1024(s, sh);
+  if (threadIdx.x == 0) loss[0] = -s / (float)B;
+}
+
+__global__ void rk_fill_kernel(float* __restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int rk_mean_loss(void* stream, const float* returns, int B, float* loss, float* gret) {
+  if (returns == nullptr || B <= 0) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (loss != nullptr) rk_mean_loss_kernel<<<1, 1024, 0, st>>>(returns, B, loss);
+  if (gret != nullptr) rk_fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(gret, B, -1.f / (float)B);
+  return (int)cudaGetLastError();
+}

@@ -207,7 +207,7 @@ _AGG = {"sum": np.sum, "avg": np.mean, "prod": np.prod, "minimum": np.min, "maxi
 
 
 def eval_static(model, expr: Expr, scope: Scope, as_float: bool = False,
-                tracer: Optional[Tracer] = None) -> np.ndarray:
+                tracer: Optional[Tracer] = None, cast_errors: Optional[list] = None) -> np.ndarray:
     """Evaluate a non-fluent, deterministic expression with the exact semantics of
     compiler.py:1000-1685.  Result is keepdims-shaped over ``scope``.
 
@@ -253,6 +253,8 @@ def eval_static(model, expr: Expr, scope: Scope, as_float: bool = False,
             return _REL[op](a, b)
         if fam == "boolean":
             args = [ev(a, sc) for a in e.args]
+            if cast_errors is not None and any(a.dtype != np.bool_ for a in args):
+                cast_errors.append(e.id)     # check_dtype=bool, compiler.py:1112-1117
             if op == "~" and len(args) == 1:
                 return np.logical_not(args[0])
             if op == "~":
@@ -277,6 +279,8 @@ def eval_static(model, expr: Expr, scope: Scope, as_float: bool = False,
             val = ev(body, inner)
             sizes = tr.scope_sizes(inner)
             is_bool = op in ("forall", "exists")
+            if is_bool and cast_errors is not None and val.dtype != np.bool_:
+                cast_errors.append(e.id)
             if not is_bool:
                 val = _at_least_int(val)
             val = np.broadcast_to(val, sizes)
@@ -305,6 +309,8 @@ def eval_static(model, expr: Expr, scope: Scope, as_float: bool = False,
                     return _fix(f(args[0].astype(np.float32)))
         if fam == "control" and op == "if":
             c, a, b = (ev(x, sc) for x in e.args)
+            if cast_errors is not None and c.dtype != np.bool_:
+                cast_errors.append(e.id)     # compiler.py:1642-1643
             return _fix(np.where(c > 0.5, a, b))
         if fam == "randomvar" and op in ("KronDelta", "DiracDelta"):
             v = ev(e.args[0], sc)

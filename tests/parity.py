@@ -1,0 +1,156 @@
+"""Parity harness shared by the CPU (emulator) and GPU (CUDA kernel) tests.
+
+A `backend` runs assembled programs: 'emu' = oracle/isa_emulator.py on numpy (checks the
+lowering / differentiation / assembler on CPU), 'cuda' = the real kernels through the C ABI.
+Both are compared with the torch-CPU oracle on the same seeded inputs and supplied noise.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import planner as OP
+from oracle.isa_emulator import Emulator
+from oracle.model_eval import OracleModel
+from pyrddlgym_jax_b200.core import logic
+from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler
+from pyrddlgym_jax_b200.core.layout import draw_noise, noise_as_list, unpack_fluent_major
+from pyrddlgym_jax_b200.core.program import PlanSpec
+
+from .helpers import fixture_model, init_params, initial_state, pack_params
+
+
+def make_params(model, key, T, seed=42):
+    params = init_params(model, T, seed=seed, scale=0.5)
+    if key == "quadcopter":
+        params["thrust"] = params["thrust"] + 9.81
+    if key == "reservoir":
+        params["release"] = params["release"].abs() * 10 + 5.
+    return params
+
+
+def run_forward(backend, prog, B, T, s0, params_flat, noise, disc=None, mparams=None):
+    """-> dict(reward [T,B], returns [B], err [T,B], tape, final) as numpy arrays."""
+    S = prog.S
+    if backend == "emu":
+        bufs = {"S0": s0.numpy().copy(), "PARAMS": params_flat.numpy().copy(),
+                "NOISE": noise.numpy().copy(), "REWARD": np.zeros(T * B, np.float32),
+                "RETURNS": np.zeros(B, np.float32), "ERR": np.zeros(T * B, np.uint32),
+                "TAPE": np.zeros(T * S * B, np.float32), "FINAL": np.zeros(S * B, np.float32),
+                "DISC": None if disc is None else disc.numpy().copy()}
+        Emulator(prog.blob).run(B, T, bufs, None if mparams is None else mparams.numpy())
+        return {"reward": bufs["REWARD"].reshape(T, B), "returns": bufs["RETURNS"],
+                "err": bufs["ERR"].reshape(T, B), "tape": bufs["TAPE"], "final": bufs["FINAL"]}
+    from pyrddlgym_jax_b200.core.engine import DeviceProgram
+    dev = torch.device("cuda:0")
+    dp = DeviceProgram(prog)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+    out = {"reward": z(T * B), "returns": z(B), "err": z(T * B, dt=torch.int32),
+           "tape": z(T * S * B), "final": z(S * B)}
+    dp.forward(B, T, s0.to(dev), policy=params_flat.to(dev), noise=noise.to(dev).reshape(-1),
+               mparams=None if mparams is None else mparams.to(dev),
+               disc=None if disc is None else disc.to(dev),
+               reward=out["reward"], returns=out["returns"], err=out["err"],
+               tape=out["tape"], final=out["final"])
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["reward"] = res["reward"].reshape(T, B)
+    res["err"] = res["err"].view(np.uint32).reshape(T, B)
+    return res
+
+
+def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None, mparams=None):
+    """-> gradient [T, A] (sum of the per-warp partials)."""
+    A = prog.A
+    if backend == "emu":
+        em = Emulator(prog.blob)
+        nW = em.num_warps(B)
+        bufs = {"TAPE": np.asarray(tape), "PARAMS": params_flat.numpy().copy(),
+                "NOISE": noise.numpy().copy(), "GRET": gret.numpy().copy(),
+                "GRADP": np.zeros(nW * T * A, np.float32),
+                "DISC": None if disc is None else disc.numpy().copy()}
+        em.run(B, T, bufs, None if mparams is None else mparams.numpy())
+        return bufs["GRADP"].reshape(nW, T * A).sum(0).reshape(T, A)
+    from pyrddlgym_jax_b200.core.engine import DeviceProgram, reduce_partials
+    dev = torch.device("cuda:0")
+    dp = DeviceProgram(prog)
+    nW = dp.num_warps(B)
+    gradp = torch.zeros(nW * T * A, device=dev)
+    grad = torch.zeros(T * A, device=dev)
+    dp.backward(B, T, torch.as_tensor(tape).to(dev), gret.to(dev), policy=params_flat.to(dev),
+                noise=noise.to(dev).reshape(-1),
+                mparams=None if mparams is None else mparams.to(dev),
+                disc=None if disc is None else disc.to(dev), gradp=gradp)
+    reduce_partials(gradp, nW, T * A, grad)
+    torch.cuda.synchronize()
+    return grad.cpu().numpy().reshape(T, A)
+
+
+def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None, **ckw):
+    """Run program + oracle on the same inputs; returns everything a test wants to compare."""
+    m = fixture_model(key)
+    if relaxed:
+        comp = (compiler_cls or logic.DefaultJaxRDDLCompilerWithGrad)(m, **ckw)
+    else:
+        comp = JaxRDDLCompiler(m)
+    spec = PlanSpec(bounds=m.bounds)
+    builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
+    fwd = builder.forward(write_tape=relaxed, gamma=gamma)
+    params = make_params(m, key, T)
+    noise = draw_noise(fwd.noise_layout, T, B, torch.Generator().manual_seed(seed))
+    s0 = initial_state(m, fwd.state_layout, B)
+    disc = None if gamma == 1.0 else torch.pow(torch.tensor(gamma), torch.arange(T)).float()
+    got = run_forward(backend, fwd, B, T, s0, pack_params(m, params), noise, disc)
+    om = OracleModel(m, comp.relax_config())
+    if relaxed:
+        P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        pol = lambda t, fls: OP.slp_train_actions(m, P, t)      # noqa: E731
+    else:
+        P = params
+        pol = lambda t, fls: OP.slp_test_actions(m, P, t, m.bounds)   # noqa: E731
+    noise_steps = [noise_as_list(fwd.noise_layout, noise, t, B) for t in range(T)]
+    ref = OP.rollout(om, pol, B, T, noise_steps)
+    spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
+    spec_pr = [(k, tuple(s)) for k, s, _, _, _ in fwd.noise_layout]
+    assert spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
+    final = unpack_fluent_major(fwd.state_layout, torch.from_numpy(got["final"].copy()), B)
+    return dict(model=m, comp=comp, builder=builder, fwd=fwd, params=params, P=P, noise=noise,
+                s0=s0, disc=disc, got=got, ref=ref, final=final, gamma=gamma)
+
+
+def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, **ckw):
+    c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls, **ckw)
+    m = c["model"]
+    bwd = c["builder"].backward(gamma=gamma)
+    gret = torch.full((B,), -1.0 / B)
+    grad = run_backward(backend, bwd, B, T, c["got"]["tape"], pack_params(m, c["params"]),
+                        c["noise"], gret, c["disc"])
+    loss = OP.mean_loss(c["ref"]["reward"], gamma)
+    loss.backward()
+    grad_ref = pack_params(m, {k: (v.grad if v.grad is not None else torch.zeros_like(v))
+                               for k, v in c["P"].items()}).numpy()
+    c.update(bwd=bwd, grad=grad, grad_ref=grad_ref, loss_ref=float(loss))
+    return c
+
+
+def check_forward(c, rtol=1e-5):
+    """states / returns within rtol 1e-5 (fp32), bool / int fluents bit-exact."""
+    ref, got = c["ref"], c["got"]
+    r_ref = ref["reward"].detach().numpy().T
+    np.testing.assert_allclose(got["reward"], r_ref, rtol=rtol, atol=rtol * max(1.0, np.abs(r_ref).max()))
+    ret_ref = OP.returns_from_rewards(ref["reward"].detach(), c["gamma"]).numpy()
+    np.testing.assert_allclose(got["returns"], ret_ref, rtol=rtol, atol=rtol * np.abs(ret_ref).max())
+    for s in c["model"].state_fluents:
+        a = ref["final"][s].detach().reshape(c["final"][s].shape[0], -1)
+        b = c["final"][s].reshape(a.shape)
+        if a.dtype in (torch.bool, torch.int32):
+            assert torch.equal(a.to(torch.int32), b.to(torch.int32)), f"fluent {s} not bit-exact"
+        else:
+            np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=rtol,
+                                       atol=rtol * max(1.0, float(a.abs().max())))
+    np.testing.assert_array_equal(got["err"], ref["error"].numpy().T.astype(np.uint32))
+
+
+def check_gradient(c, rtol=1e-4):
+    g, gr = c["grad"], c["grad_ref"]
+    np.testing.assert_allclose(g, gr, rtol=rtol, atol=rtol * np.abs(gr).max())

@@ -1,0 +1,45 @@
+"""CPU tests: lowering + differentiation + assembler, executed by the numpy ISA emulator,
+against the torch oracle (same tolerances the GPU tests use)."""
+import pytest
+
+from pyrddlgym_jax_b200.core import logic
+
+from .parity import check_forward, check_gradient, forward_case, gradient_case
+
+KEYS = ["quadcopter", "reservoir", "wildfire"]
+
+
+@pytest.mark.parametrize("key", KEYS)
+@pytest.mark.parametrize("relaxed", [False, True])
+def test_forward_emulated(key, relaxed):
+    check_forward(forward_case("emu", key, B=13, T=6, relaxed=relaxed))
+
+
+@pytest.mark.parametrize("key", KEYS)
+@pytest.mark.parametrize("gamma", [1.0, 0.9])
+def test_gradient_emulated(key, gamma):
+    check_gradient(gradient_case("emu", key, B=11, T=5, gamma=gamma))
+
+
+class _Godel(logic.SigmoidRelational, logic.GodelNormLogical, logic.LinearIfElse,
+             logic.GumbelSigmoidBernoulli, logic.SoftFloor, logic.SoftRound):
+    pass
+
+
+class _Luka(logic.SigmoidRelational, logic.LukasiewiczNormLogical, logic.LinearIfElse,
+            logic.DeterminizedBernoulli):
+    pass
+
+
+@pytest.mark.parametrize("cls,kw", [
+    (_Godel, dict(sigmoid_weight=3.0, use_logic_ste=True, use_ste_bernoulli=True)),
+    (_Godel, dict(sigmoid_weight=3.0, use_sigmoid_ste=False, use_if_else_ste=False)),
+    (_Luka, dict(sigmoid_weight=2.0)),
+    (logic.DefaultJaxRDDLCompilerWithGrad, dict(sigmoid_weight=100.0, bernoulli_sigmoid_weight=100.0)),
+])
+def test_relaxation_variants_emulated(cls, kw):
+    """Other t-norms / Bernoulli relaxations / STE switches on the Wildfire and Reservoir CPFs."""
+    for key in ("wildfire", "reservoir"):
+        c = gradient_case("emu", key, B=7, T=4, compiler_cls=cls, **kw)
+        check_forward(c)
+        check_gradient(c)
