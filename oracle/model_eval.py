@@ -278,6 +278,10 @@ class OracleModel:
                     return out.reshape((B,) + tuple(sizes)), err
                 out = src.reshape(-1)[flat.reshape(-1)]
                 return out.reshape(full), err
+            if acc.identity:          # whole tensor in declaration order: a view
+                if batched:
+                    return src.reshape((B,) + acc.keep_shape), err
+                return src.reshape((1,) + acc.keep_shape), err
             idx = torch.from_numpy(acc.index.reshape(-1))
             if batched:
                 out = src.reshape(B, -1)[:, idx].reshape((B,) + acc.keep_shape)

@@ -1,0 +1,941 @@
+"""``JaxBackpropPlanner`` and friends: the drop-in Python surface of
+pyRDDLGym_jax/core/planner.py, driving the B200 rollout kernels instead of XLA.
+
+Kept seams: ``JaxStraightLinePlan`` kwargs (planner.py:636-648),
+``JaxBackpropPlanner`` kwargs (planner.py:2399-2429), ``optimize`` /
+``optimize_generator`` and the callback dict they yield (planner.py:3073-3087, 3368-3392),
+``get_action`` (planner.py:3527-3533), ``JaxPlannerStatus`` (planner.py:2277-2304),
+``load_config`` (planner.py:229-244) and the controllers (planner.py:3632-3831).
+
+One planner iteration = exactly what the reference does per epoch with ``pgpe=None``
+(planner.py:3236-3262): ``update`` (relaxed forward rollouts with a state tape, loss,
+backprop-through-time, gradient reduction, optimiser step, projection) followed by
+``test_loss`` (exact-model forward rollouts with the updated plan).  On the device that is
+6 kernel launches, replayed from one CUDA graph.
+"""
+from __future__ import annotations
+
+import configparser
+import pickle
+import time
+from abc import ABCMeta, abstractmethod
+from ast import literal_eval
+from collections import deque
+from enum import Enum
+from typing import Any, Callable, Dict, Iterable, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import engine, logic
+from .compiler import JaxRDDLCompiler
+from .layout import draw_noise, pack_fluent_major, unpack_fluent_major
+from .program import PlanSpec, action_layout
+
+Kwargs = Dict[str, Any]
+
+
+# =====================================================================================
+# initialisers / optimisers named in .cfg files (planner.py:140-186 resolve them with getattr
+# on jax / optax; those modules do not exist here, so the names map to local objects)
+# =====================================================================================
+
+class _Initializer:
+    def __init__(self, name: str, **kwargs):
+        self.name, self.kwargs = name, kwargs
+
+    def __call__(self, shape, generator: torch.Generator) -> torch.Tensor:
+        if self.name == "normal":
+            return torch.randn(shape, generator=generator) * self.kwargs.get("stddev", 1e-2)
+        if self.name == "uniform":
+            return torch.rand(shape, generator=generator) * self.kwargs.get("scale", 1e-2)
+        if self.name == "zeros":
+            return torch.zeros(shape)
+        if self.name == "ones":
+            return torch.ones(shape)
+        if self.name == "constant":
+            return torch.full(shape, float(self.kwargs.get("value", 0.0)))
+        raise NotImplementedError(f"initializer {self.name}")
+
+    def __repr__(self):
+        return f"{self.name}({self.kwargs})"
+
+
+class initializers:     # noqa: N801  (mirrors jax.nn.initializers)
+    @staticmethod
+    def normal(stddev: float = 1e-2):
+        return _Initializer("normal", stddev=stddev)
+
+    @staticmethod
+    def uniform(scale: float = 1e-2):
+        return _Initializer("uniform", scale=scale)
+
+    @staticmethod
+    def constant(value: float = 0.0):
+        return _Initializer("constant", value=value)
+
+    zeros = _Initializer("zeros")
+    ones = _Initializer("ones")
+
+
+OPTIMIZERS = {"sgd": "sgd", "rmsprop": "rmsprop", "adam": "adam"}
+
+
+# =====================================================================================
+# plans
+# =====================================================================================
+
+class JaxPlan(metaclass=ABCMeta):
+    """Base class of policy representations (planner.py:359-420)."""
+    history_dependent = False
+
+    def __init__(self) -> None:
+        self.bounds = None
+
+    @abstractmethod
+    def compile(self, compiled, test_compiled, _bounds, horizon, preprocessor=None) -> None:
+        pass
+
+    @abstractmethod
+    def guess_next_epoch(self, params):
+        pass
+
+
+class JaxStraightLinePlan(JaxPlan):
+    """Open-loop plan: one parameter per action element per step (planner.py:631-1018)."""
+
+    def __init__(self, initializer=None, wrap_sigmoid: bool = True, min_action_prob: float = 1e-6,
+                 sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
+                 wrap_softmax: bool = False, softmax_weight: float = 1.0,
+                 use_new_projection: bool = False, max_constraint_iter: int = 100,
+                 stochastic: bool = False, sigma_range: Tuple[float, float] = (1e-5, 1e3),
+                 sigma_entropy_grad: bool = False, action_noise_dist: Any = "normal") -> None:
+        super().__init__()
+        self._initializer_base = initializer if initializer is not None else initializers.normal()
+        self._wrap_sigmoid = wrap_sigmoid
+        self._min_action_prob = min_action_prob
+        self._sigmoid_weight = sigmoid_weight
+        self._wrap_non_bool = wrap_non_bool
+        self._wrap_softmax = wrap_softmax
+        self._softmax_weight = softmax_weight
+        self._use_new_projection = use_new_projection
+        self._max_constraint_iter = max_constraint_iter
+        self._stochastic = stochastic
+        self._sigma_range = sigma_range
+        self._sigma_entropy_grad = sigma_entropy_grad
+        self._action_noise_dist = action_noise_dist
+        if wrap_non_bool or wrap_softmax or stochastic:
+            raise NotImplementedError(
+                "wrap_non_bool / wrap_softmax / stochastic straight-line plans are not built yet")
+
+    def __str__(self) -> str:
+        return (f"[INFO] policy hyper-parameters:\n"
+                f"    initializer ={self._initializer_base}\n"
+                f"    wrap_sigmoid={self._wrap_sigmoid}\n"
+                f"    wrap_sigmoid_min_prob={self._min_action_prob}\n"
+                f"    sigmoid_weight={self._sigmoid_weight}\n"
+                f"    use_new_projection={self._use_new_projection}\n"
+                f"    max_projection_iters={self._max_constraint_iter}\n")
+
+    def compile(self, compiled, test_compiled, _bounds, horizon, preprocessor=None) -> None:
+        rddl = compiled.rddl
+        self.rddl = rddl
+        self.horizon = horizon
+        self.layout, self.A = action_layout(rddl)
+        bounds = {}
+        for name, (off, n, prange) in self.layout.items():      # get_action_info, planner.py:423-472
+            if prange == "bool":
+                bounds[name] = (None, None)
+            elif prange in rddl.enum_types:
+                shape = rddl.variable_shape(name)
+                bounds[name] = (np.zeros(shape, np.float32),
+                                np.full(shape, len(rddl.type_to_objects[prange]) - 1, np.float32))
+            else:
+                lo, hi = rddl.bounds[name]
+                lo, hi = _bounds.get(name, (lo, hi))
+                shape = rddl.variable_shape(name)
+                bounds[name] = (np.broadcast_to(np.asarray(lo, np.float32), shape).copy(),
+                                np.broadcast_to(np.asarray(hi, np.float32), shape).copy())
+        self.bounds = bounds
+        self.spec = PlanSpec(kind="slp", wrap_sigmoid=self._wrap_sigmoid,
+                             sigmoid_weight=self._sigmoid_weight,
+                             bounds={k: v for k, v in bounds.items() if v[0] is not None})
+        self.noop = {var: bool(np.ravel(v)[0]) if rddl.variable_ranges[var] == "bool" else v
+                     for var, v in rddl.action_fluents.items()}
+        self.bool_threshold = 0.0 if self._wrap_sigmoid else 0.5
+        # flat box for the projection (planner.py:878-904)
+        lo = np.full((horizon, self.A), -np.inf, np.float32)
+        hi = np.full((horizon, self.A), np.inf, np.float32)
+        for name, (off, n, prange) in self.layout.items():
+            if prange == "bool":
+                p = self._min_action_prob
+                if self._wrap_sigmoid:
+                    l, h = np.log(p / (1 - p)) / self._sigmoid_weight, \
+                        np.log((1 - p) / p) / self._sigmoid_weight
+                else:
+                    l, h = p, 1 - p
+                lo[:, off:off + n], hi[:, off:off + n] = l, h
+            else:
+                lo[:, off:off + n] = bounds[name][0].reshape(-1)
+                hi[:, off:off + n] = bounds[name][1].reshape(-1)
+        self.box = (lo, hi)
+        n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
+        self.needs_concurrency_projection = rddl.max_allowed_actions < n_bool
+
+    def initial_params(self, generator: torch.Generator) -> torch.Tensor:
+        """planner.py:974-1008: initialiser + threshold shift + box projection -> [T, A]."""
+        out = torch.zeros(self.horizon, self.A)
+        for name, (off, n, prange) in self.layout.items():
+            p = self._initializer_base((self.horizon, n), generator)
+            if prange == "bool":
+                p = p + self.bool_threshold
+            out[:, off:off + n] = p
+        lo, hi = self.box
+        return torch.minimum(torch.maximum(out, torch.from_numpy(lo)), torch.from_numpy(hi))
+
+    def params_to_pytree(self, flat: torch.Tensor) -> Dict[str, Any]:
+        """[..., T, A] -> {'bool': {var: {'logit'}}, 'real': {var: {'mu', 'log_sigma'}}}."""
+        tree: Dict[str, Any] = {"bool": {}, "real": {}}
+        for name, (off, n, prange) in self.layout.items():
+            v = flat[..., off:off + n].reshape(*flat.shape[:-1], *self.rddl.variable_shape(name))
+            if prange == "bool":
+                tree["bool"][name] = {"logit": v}
+            else:
+                tree["real"][name] = {"mu": v, "log_sigma": None}
+        return tree
+
+    def pytree_to_params(self, tree: Dict[str, Any]) -> torch.Tensor:
+        out = torch.zeros(self.horizon, self.A)
+        for name, (off, n, prange) in self.layout.items():
+            leaf = tree["bool"][name]["logit"] if prange == "bool" else tree["real"][name]["mu"]
+            out[:, off:off + n] = torch.as_tensor(np.asarray(leaf), dtype=torch.float32
+                                                  ).reshape(-1, n)[-self.horizon:]
+        return out
+
+    def test_actions(self, flat_row: np.ndarray) -> Dict[str, np.ndarray]:
+        """Test policy at one step (planner.py:842-868) -- host side, for get_action."""
+        acts = {}
+        for name, (off, n, prange) in self.layout.items():
+            p = np.asarray(flat_row[off:off + n], np.float32).reshape(self.rddl.variable_shape(name))
+            if prange == "bool":
+                acts[name] = p > self.bool_threshold
+            else:
+                a = np.minimum(np.maximum(p, self.bounds[name][0]), self.bounds[name][1])
+                if prange != "real":
+                    a = np.round(a).astype(np.int32)
+                acts[name] = a
+        return acts
+
+    def guess_next_epoch(self, params):
+        """Shift the plan one step (planner.py:1011-1018)."""
+        def shift(x):
+            if x is None:
+                return None
+            x = torch.as_tensor(np.asarray(x))
+            return torch.cat([x[1:], x[-1:]], dim=0)
+        return {k: {var: {leaf: shift(v) for leaf, v in d.items()} for var, d in sub.items()}
+                for k, sub in params.items()}
+
+
+# =====================================================================================
+# supporting classes (planner.py:2260-2338)
+# =====================================================================================
+
+class RollingMean:
+    def __init__(self, window_size: int) -> None:
+        self._window_size = window_size
+        self._memory = deque(maxlen=window_size)
+        self._total = 0
+
+    def update(self, x):
+        memory = self._memory
+        self._total = self._total + x
+        if len(memory) == self._window_size:
+            self._total = self._total - memory.popleft()
+        memory.append(x)
+        return self._total / len(memory)
+
+
+class JaxPlannerStatus(Enum):
+    NORMAL = 0
+    STOPPING_RULE_REACHED = 1
+    NO_PROGRESS = 2
+    PRECONDITION_POSSIBLY_UNSATISFIED = 3
+    INVALID_GRADIENT = 4
+    TIME_BUDGET_REACHED = 5
+    ITER_BUDGET_REACHED = 6
+
+    def is_terminal(self) -> bool:
+        return self.value == 1 or self.value >= 4
+
+    def get_type(self) -> str:
+        if self.value in {5, 6}:
+            return "info"
+        if self.value in {0, 1}:
+            return "success"
+        if self.value in {2, 3}:
+            return "warning"
+        return "error"
+
+
+class JaxPlannerStoppingRule(metaclass=ABCMeta):
+    @abstractmethod
+    def reset(self) -> None:
+        pass
+
+    @abstractmethod
+    def monitor(self, callback: Dict[str, Any]) -> bool:
+        pass
+
+
+class NoImprovementStoppingRule(JaxPlannerStoppingRule):
+    def __init__(self, patience: int) -> None:
+        self.patience = patience
+
+    def reset(self) -> None:
+        self.callback = None
+        self.iters_since_last_update = 0
+
+    def monitor(self, callback: Dict[str, Any]) -> bool:
+        if self.callback is None or callback["best_return"] > self.callback["best_return"]:
+            self.callback = callback
+            self.iters_since_last_update = 0
+        else:
+            self.iters_since_last_update += 1
+        return self.iters_since_last_update >= self.patience
+
+    def __str__(self) -> str:
+        return f"No improvement for {self.patience} iterations"
+
+
+# =====================================================================================
+# utilities other than the mean (planner.py:2161-2247) -- evaluated with torch on the [B]
+# return vector only (never on the rollout path)
+# =====================================================================================
+
+def _utility_fn(name: str, kwargs: Kwargs) -> Callable[[torch.Tensor], torch.Tensor]:
+    if name == "mean_var":
+        return lambda r: r.mean() - 0.5 * kwargs["beta"] * r.var(unbiased=False)
+    if name == "mean_std":
+        return lambda r: r.mean() - 0.5 * kwargs["beta"] * r.std(unbiased=False)
+    if name == "mean_semivar":
+        return lambda r: r.mean() - 0.5 * kwargs["beta"] * torch.clamp(
+            r - r.mean(), max=0.).square().mean()
+    if name == "mean_semidev":
+        return lambda r: r.mean() - 0.5 * kwargs["beta"] * torch.sqrt(
+            torch.clamp(r - r.mean(), max=0.).square().mean())
+    if name in ("entropic", "exponential"):
+        return lambda r: -(torch.logsumexp(-kwargs["beta"] * r, 0)
+                           - np.log(r.numel())) / kwargs["beta"]
+    if name == "sharpe":
+        return lambda r: (r.mean() - kwargs.get("risk_free", 0.0)) / (
+            r.std(unbiased=False) + kwargs.get("eps", 1e-12))
+    if name == "cvar_ste":
+        def f(r):
+            mask = (r <= torch.quantile(r.detach(), kwargs["alpha"])).to(r.dtype)
+            return (mask * r).sum() / torch.clamp(mask.sum(), min=1.)
+        return f
+    raise NotImplementedError(f"Utility function <{name}> is not supported.")
+
+
+UTILITY_LOOKUP = {k: k for k in ("mean", "mean_var", "mean_std", "mean_semivar", "mean_semidev",
+                                 "sharpe", "entropic", "exponential", "cvar_ste")}
+
+
+# =====================================================================================
+# the planner
+# =====================================================================================
+
+class JaxBackpropPlanner:
+    """Gradient-based planner over batched differentiable rollouts (planner.py:2395)."""
+
+    def __init__(self, rddl, plan: JaxPlan, batch_size_train: int = 32,
+                 batch_size_test: Optional[int] = None, rollout_horizon: Optional[int] = None,
+                 parallel_updates: int = 1, steps_per_update: int = 1,
+                 action_bounds: Optional[Dict[str, Tuple[Any, Any]]] = None,
+                 optimizer: Union[str, Callable] = "rmsprop",
+                 optimizer_kwargs: Optional[Kwargs] = None, clip_grad: Optional[float] = None,
+                 line_search_kwargs: Optional[Kwargs] = None, noise_kwargs: Optional[Kwargs] = None,
+                 ema_decay: Optional[float] = None, reduce_on_plateau_kwargs: Optional[Kwargs] = None,
+                 pgpe: Optional[Any] = None,
+                 compiler=logic.DefaultJaxRDDLCompilerWithGrad,
+                 compiler_kwargs: Optional[Kwargs] = None, use_symlog_reward: bool = False,
+                 utility: Union[Callable, str] = "mean", utility_kwargs: Optional[Kwargs] = None,
+                 start_entropy_coeff: float = 1e-1, end_entropy_coeff: float = 1e-5,
+                 critic: Optional[Callable] = None, logger: Optional[Any] = None,
+                 dashboard: Optional[Any] = None, dashboard_viz: Optional[Any] = None,
+                 preprocessor: Optional[Any] = None, python_functions: Optional[Dict] = None,
+                 cache_full_train_rollouts: bool = False, cache_full_test_rollouts: bool = False,
+                 device: Optional[Union[str, torch.device]] = None, use_cuda_graph: bool = True
+                 ) -> None:
+        for name, val in (("line_search_kwargs", line_search_kwargs), ("noise_kwargs", noise_kwargs),
+                          ("ema_decay", ema_decay), ("reduce_on_plateau_kwargs", reduce_on_plateau_kwargs),
+                          ("critic", critic), ("preprocessor", preprocessor),
+                          ("dashboard", dashboard)):
+            if val is not None:
+                raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
+        if pgpe is not None:
+            raise NotImplementedError("PGPE is not built yet: pass pgpe=None as the shipped "
+                                      "configs do (SURVEY F6)")
+        if use_symlog_reward:
+            raise NotImplementedError("use_symlog_reward is not supported yet")
+        self.rddl = rddl
+        self.plan = plan
+        self.batch_size_train = batch_size_train
+        self.batch_size_test = batch_size_train if batch_size_test is None else batch_size_test
+        self.steps_per_update = steps_per_update
+        self.parallel_updates = parallel_updates
+        self.horizon = rddl.horizon if rollout_horizon is None else rollout_horizon
+        self._action_bounds = action_bounds or {}
+        opt_name = optimizer if isinstance(optimizer, str) else getattr(optimizer, "__name__", "")
+        if opt_name not in OPTIMIZERS:
+            raise NotImplementedError(f"optimizer <{opt_name}> (supported: {list(OPTIMIZERS)})")
+        self.optimizer_name = opt_name
+        self.optimizer_kwargs = {"learning_rate": 0.1} if optimizer_kwargs is None else dict(optimizer_kwargs)
+        self.clip_grad = clip_grad
+        self.pgpe = None
+        self.use_pgpe = False
+        if isinstance(utility, str):
+            utility = utility.lower()
+            if utility not in UTILITY_LOOKUP:
+                raise NotImplementedError(
+                    f"Utility function <{utility}> is not supported, must be one of "
+                    f"{list(UTILITY_LOOKUP.keys())}.")
+        self.utility = utility
+        self.utility_kwargs = utility_kwargs or {}
+        self.compiler_type = compiler
+        self.compiler_kwargs = compiler_kwargs or {}
+        self.start_entropy_coeff = start_entropy_coeff
+        self.end_entropy_coeff = end_entropy_coeff
+        self.logger = logger
+        self.cache_full_train_rollouts = cache_full_train_rollouts
+        self.cache_full_test_rollouts = cache_full_test_rollouts
+        self.use_cuda_graph = use_cuda_graph
+        if not torch.cuda.is_available():
+            raise engine.RkError("JaxBackpropPlanner needs a CUDA device: the rollout kernels "
+                                 "have no CPU fallback")
+        self.device = torch.device(device if device is not None else
+                                   f"cuda:{torch.cuda.current_device()}")
+        # multi-GPU: every rank owns batch_size_train rollouts; the plan is replicated and
+        # the gradient is sum-all-reduced once per iteration
+        import torch.distributed as dist
+        self._dist = dist
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world_size > 1 else 0
+        self._compile()
+
+    # ---------------------------------------------------------------------------------
+    def _compile(self):
+        rddl = self.rddl
+        self.compiled = self.compiler_type(rddl, **self.compiler_kwargs)
+        self.print_warnings = getattr(self.compiled, "print_warnings", True)
+        self.compiled.compile()
+        self.test_compiled = JaxRDDLCompiler(rddl)
+        self.test_compiled.compile()
+        self.plan.compile(self.compiled, self.test_compiled, self._action_bounds, self.horizon)
+        if getattr(self.plan, "needs_concurrency_projection", False):
+            raise NotImplementedError(
+                "max-nondef-actions below the number of boolean actions needs the concurrency "
+                "projection (planner.py:914-959), which is not built yet")
+        spec = self.plan.spec
+        gamma = float(rddl.discount)
+        self.gamma = gamma
+        train_log = tuple(rddl.state_fluents) if self.cache_full_train_rollouts else ()
+        test_log = (tuple(rddl.next_state.values()) + tuple(rddl.action_fluents)) \
+            if self.cache_full_test_rollouts else ()
+        with torch.cuda.device(self.device):
+            tb = self.compiled.builder(spec, True, (), self.batch_size_train)
+            self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=True, gamma=gamma))
+            self.train_bwd = engine.DeviceProgram(tb.backward(gamma=gamma))
+            eb = self.test_compiled.builder(spec, False, test_log, self.batch_size_test)
+            self.test_fwd = engine.DeviceProgram(eb.forward(write_tape=False, gamma=gamma))
+        self.A = self.plan.A
+        self.T = self.horizon
+        self._alloc()
+
+    def _alloc(self):
+        dev, T, A = self.device, self.T, self.A
+        Bt, Be = self.batch_size_train, self.batch_size_test
+        P = self.parallel_updates
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)   # noqa: E731
+        fw, bw, te = self.train_fwd.program, self.train_bwd.program, self.test_fwd.program
+        self.params = z(P, T * A)
+        n_state = {"sgd": 1, "rmsprop": 1, "adam": 2}[self.optimizer_name]
+        self.opt_state = z(P, n_state * T * A)
+        self.grad = z(P, T * A)
+        self.nwarps = self.train_bwd.num_warps(Bt)
+        self.gradp = z(self.nwarps * T * A)
+        self.tape = z(T * fw.S * Bt)
+        self.train_reward = z(P, T * Bt)
+        self.train_returns = z(P, Bt)
+        self.train_err = z(P, T * Bt, dt=torch.int32)
+        self.train_loss = z(P)
+        self.gret = z(Bt)
+        self.test_reward = z(P, T * Be)
+        self.test_returns = z(P, Be)
+        self.test_err = z(P, T * Be, dt=torch.int32)
+        self.test_loss_buf = z(P)
+        self.test_final = z(P, te.S * Be)
+        self.test_traj = z(P, T * te.TRAJ * Be) if te.TRAJ else None
+        self.zero_flag = z(P, dt=torch.int32)
+        self.train_noise = z(T * fw.N * Bt) if fw.N else None
+        self.test_noise = z(T * te.N * Be) if te.N else None
+        self.disc = None if self.gamma == 1.0 else torch.pow(
+            torch.tensor(self.gamma, device=dev), torch.arange(T, device=dev)).float().contiguous()
+        lo, hi = self.plan.box
+        self.box_lo = torch.from_numpy(lo.reshape(-1)).to(dev).contiguous()
+        self.box_hi = torch.from_numpy(hi.reshape(-1)).to(dev).contiguous()
+        kw = self.optimizer_kwargs
+        lr = float(kw.get("learning_rate", 0.1))
+        if self.optimizer_name == "rmsprop":
+            h = [lr, kw.get("decay", 0.9), kw.get("eps", 1e-8), 0., 0., 0., 1.]
+        elif self.optimizer_name == "adam":
+            h = [lr, kw.get("b1", 0.9), kw.get("eps", 1e-8), kw.get("b2", 0.999), 0., 0., 1.]
+        else:
+            h = [lr, 0., 0., 0., 0., kw.get("momentum", 0.) or 0., 1.]
+        h[4] = float(self.clip_grad) if self.clip_grad is not None else 0.
+        self.hyper = torch.tensor(h, dtype=torch.float32, device=dev)
+        self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
+            if len(fw.mparam_defaults) else None
+        self._graph = None
+        self._gen = torch.Generator(device=dev)
+        self.loss_pair = z(2, P)
+
+    # ---- model parameters (relaxation weights), planner.py:3165-3168 ---------------------
+    def model_parameter_info(self) -> Dict[Any, float]:
+        fw = self.train_fwd.program
+        return {k: float(v) for k, v in zip(fw.mparam_keys, fw.mparam_defaults)}
+
+    def set_model_params(self, values: Dict[Any, float]):
+        fw = self.train_fwd.program
+        cur = self.train_mparams.cpu().numpy().copy()
+        for i, k in enumerate(fw.mparam_keys):
+            if k in values:
+                cur[i] = values[k]
+        self.train_mparams.copy_(torch.from_numpy(cur))
+
+    # ---- state initialisation (init_sim_state, compiler.py:729-771) ------------------------
+    def _pack_s0(self, layout, B, subs) -> torch.Tensor:
+        vals = {}
+        for name in layout:
+            v = np.asarray(self.rddl.init_values[name])
+            if subs is not None and name in subs:
+                v = np.reshape(np.asarray(subs[name]), v.shape).astype(v.dtype)
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            vals[name] = t.unsqueeze(0).expand(B, *t.shape)
+        return pack_fluent_major(layout, vals, B).to(self.device)
+
+    def _draw(self, prog, T, B, out):
+        if out is not None:
+            out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
+
+    # ---- the two device calls of an iteration -----------------------------------------------
+    def _update_kernels(self, p: int):
+        """planner.py:2868-2917 on the device for parallel instance p."""
+        T, A, B = self.T, self.A, self.batch_size_train
+        params = self.params[p]
+        self.train_fwd.forward(B, T, self.s0_train, policy=params, noise=self.train_noise,
+                               mparams=self.train_mparams, disc=self.disc,
+                               reward=self.train_reward[p], returns=self.train_returns[p],
+                               err=self.train_err[p], tape=self.tape)
+        if self.utility == "mean":
+            engine.mean_loss(self.train_returns[p], B, self.train_loss[p:p + 1], None)
+        else:
+            r = self.train_returns[p].detach().clone().requires_grad_(True)
+            fn = self.utility if callable(self.utility) else _utility_fn(self.utility, self.utility_kwargs)
+            with torch.enable_grad():
+                loss = -fn(r, **(self.utility_kwargs if callable(self.utility) else {}))
+                (g,) = torch.autograd.grad(loss, r)
+            self.train_loss[p] = loss.detach()
+            self.gret.copy_(g)
+        self.train_bwd.backward(B, T, self.tape, self.gret, policy=params, noise=self.train_noise,
+                                mparams=self.train_mparams, disc=self.disc, gradp=self.gradp)
+        engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
+        if self.world_size > 1:      # the one exchange step of the path
+            self._dist.all_reduce(self.grad[p])
+        engine.optimizer_step(self.optimizer_name, self.hyper, T * A, params, self.opt_state[p],
+                              self.grad[p], self.box_lo, self.box_hi, self.zero_flag[p:p + 1])
+
+    def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
+        """planner.py:2695-2698: exact-model rollouts, forward only."""
+        T, B = self.T, self.batch_size_test
+        self.test_fwd.forward(B, T, self.s0_test, policy=self.params[p] if params is None else params,
+                              noise=self.test_noise, disc=self.disc,
+                              reward=self.test_reward[p], returns=self.test_returns[p],
+                              err=self.test_err[p], final=self.test_final[p],
+                              traj=None if self.test_traj is None else self.test_traj[p])
+        engine.mean_loss(self.test_returns[p], B, self.test_loss_buf[p:p + 1], None)
+
+    def _iteration_kernels(self):
+        for p in range(self.parallel_updates):
+            self._update_kernels(p)
+            self._test_kernels(p)
+        if self.optimizer_name == "adam":
+            self.hyper[6:7].add_(1.0)
+        if self.world_size > 1:
+            self.loss_pair[0].copy_(self.train_loss)
+            self.loss_pair[1].copy_(self.test_loss_buf)
+            self._dist.all_reduce(self.loss_pair)
+
+    def _capture(self):
+        """Capture one full iteration into a CUDA graph (after a warm-up on a side stream)."""
+        backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._iteration_kernels()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration_kernels()
+        self.params.copy_(backup[0])
+        self.opt_state.copy_(backup[1])
+        self.hyper.copy_(backup[2])
+        self._graph = g
+
+    def iterate(self):
+        """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""
+        if self.utility != "mean" or not self.use_cuda_graph:
+            self._iteration_kernels()
+            return
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+
+    # ---- the reference-facing jitted callables ----------------------------------------------
+    def initialize(self, key: int, subs=None, guess=None):
+        """Initial simulator and planner state (planner.py:3159-3182, 2824-2851)."""
+        with torch.cuda.device(self.device):
+            gen = torch.Generator().manual_seed(int(key))
+            self._gen.manual_seed(int(key))
+            self.s0_train = self._pack_s0(self.train_fwd.program.state_layout,
+                                          self.batch_size_train, subs)
+            self.s0_test = self._pack_s0(self.test_fwd.program.state_layout,
+                                         self.batch_size_test, subs)
+            for p in range(self.parallel_updates):
+                if guess is not None:
+                    flat = self.plan.pytree_to_params(guess)
+                else:
+                    flat = self.plan.initial_params(gen)
+                self.params[p].copy_(flat.reshape(-1))
+            self.opt_state.zero_()
+            self.hyper[6] = 1.0
+            engine.mean_loss(self.train_returns[0], self.batch_size_train, None, self.gret)
+            if self.world_size > 1:          # d(-mean over the GLOBAL batch)/d return_b
+                self.gret.mul_(1.0 / self.world_size)
+                self._gen.manual_seed(int(key) + 7919 * (self.rank + 1))
+            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
+            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+
+    def update(self):
+        for p in range(self.parallel_updates):
+            self._update_kernels(p)
+
+    def test_loss(self):
+        for p in range(self.parallel_updates):
+            self._test_kernels(p)
+
+    # ---------------------------------------------------------------------------------
+    def _train_log(self) -> Dict[str, Any]:
+        P, T, B = self.parallel_updates, self.T, self.batch_size_train
+        return {"reward": self.train_reward.view(P, T, B).transpose(1, 2),
+                "error": self.train_err.view(P, T, B).transpose(1, 2),
+                "grad": self.plan.params_to_pytree(self.grad.view(P, T, self.A)),
+                "fluents": {}}
+
+    def _test_log(self) -> Dict[str, Any]:
+        P, T, B = self.parallel_updates, self.T, self.batch_size_test
+        te = self.test_fwd.program
+        log = {"reward": self.test_reward.view(P, T, B).transpose(1, 2),
+               "error": self.test_err.view(P, T, B).transpose(1, 2)}
+        if self.test_traj is not None:
+            shapes = {f: self.rddl.variable_shape(f) for f in te.traj_layout}
+            fl = unpack_fluent_major(te.traj_layout, self.test_traj.view(P, T, te.TRAJ * B), B,
+                                     shapes, lead=(P, T))
+            log["fluents"] = {k: v.transpose(1, 2) for k, v in fl.items()}
+        else:
+            shapes = {f: self.rddl.variable_shape(f) for f in te.state_layout}
+            fl = unpack_fluent_major(te.state_layout, self.test_final, B, shapes, lead=(P,))
+            log["fluents"] = {k: v.unsqueeze(2) for k, v in fl.items()}
+        return log
+
+    def optimize(self, *args, **kwargs) -> Optional[Dict[str, Any]]:
+        """Run the generator to completion and return the last callback (planner.py:3033)."""
+        it = self.optimize_generator(*args, **kwargs)
+        callback = None
+        for callback in it:
+            pass
+        return callback
+
+    def optimize_generator(self, key: Optional[int] = None, epochs: int = 999999,
+                           train_seconds: float = 120., model_params: Optional[Dict] = None,
+                           policy_hyperparams: Optional[Dict] = None, subs: Optional[Dict] = None,
+                           guess: Optional[Dict] = None, critic_params=None,
+                           print_summary: bool = True, print_progress: bool = True,
+                           print_hyperparams: bool = False, dashboard_id=None,
+                           stopping_rule: Optional[JaxPlannerStoppingRule] = None,
+                           test_rolling_window: int = 10, tqdm_position: Optional[int] = None
+                           ) -> Iterable[Dict[str, Any]]:
+        """The optimisation loop of planner.py:3073-3469 (pgpe=None branch)."""
+        start_time = time.time()
+        elapsed_outside_loop = 0.
+        if key is None:
+            key = round(time.time() * 1000) % (2 ** 31)
+        if hasattr(key, "__len__"):
+            key = int(np.asarray(key).ravel()[-1])
+        if model_params is not None:
+            self.set_model_params(model_params)
+        self.initialize(key, subs, guess)
+        P = self.parallel_updates
+        hyper = policy_hyperparams if policy_hyperparams is not None else \
+            {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents}
+        best_params = self.plan.params_to_pytree(self.params[0].view(self.T, self.A).clone().cpu())
+        best_loss, best_grad, best_index = np.inf, None, 0
+        last_iter_improve = 0
+        rolling = RollingMean(test_rolling_window)
+        status = JaxPlannerStatus.NORMAL
+        if stopping_rule is not None:
+            stopping_rule.reset()
+        shown_train, shown_test = set(), set()
+        it = -1
+        for it in range(epochs):
+            status = JaxPlannerStatus.NORMAL
+            with torch.cuda.device(self.device):
+                if self.train_noise is not None or self.test_noise is not None:
+                    self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
+                    self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+                self.iterate()
+                if self.world_size > 1:
+                    stats = torch.stack([self.loss_pair[0] / self.world_size,
+                                         self.loss_pair[1] / self.world_size,
+                                         self.zero_flag.float()]).cpu().numpy()
+                else:
+                    stats = torch.stack([self.train_loss, self.test_loss_buf,
+                                         self.zero_flag.float()]).cpu().numpy()   # the host sync
+            train_loss, test_loss, zero_grads = stats[0], stats[1], stats[2] > 0
+            test_loss_smooth = rolling.update(test_loss)
+            best_index = int(np.argmin(test_loss_smooth))
+            if test_loss_smooth[best_index] < best_loss:
+                best_params = self.plan.params_to_pytree(
+                    self.params[best_index].view(self.T, self.A).clone().cpu())
+                best_grad = self.plan.params_to_pytree(
+                    self.grad[best_index].view(self.T, self.A).clone().cpu())
+                best_loss = float(test_loss_smooth[best_index])
+                last_iter_improve = it
+            if np.all(zero_grads):
+                status = JaxPlannerStatus.NO_PROGRESS
+            if np.all(~np.isfinite(train_loss)):
+                status = JaxPlannerStatus.INVALID_GRADIENT
+            if print_progress and it % 50 == 0:
+                for name, buf, shown in (("Training", self.train_err, shown_train),
+                                         ("Testing", self.test_err, shown_test)):
+                    for code in torch.unique(buf).cpu().numpy():
+                        if int(code) not in shown:
+                            shown.add(int(code))
+                            for msg in JaxRDDLCompiler.get_error_messages(int(code)):
+                                print(f"[FAIL] {name} model error: {msg}")
+            elapsed = time.time() - start_time - elapsed_outside_loop
+            if elapsed >= train_seconds:
+                status = JaxPlannerStatus.TIME_BUDGET_REACHED
+            if it >= epochs - 1:
+                status = JaxPlannerStatus.ITER_BUDGET_REACHED
+            progress_time = elapsed / train_seconds
+            progress_it = it / (epochs - 1) if epochs > 1 else 0
+            progress_percent = 100 * min(1, max(0, progress_time, progress_it))
+            callback = {
+                "iteration": it, "elapsed_time": elapsed, "progress": progress_percent,
+                "status": status, "key": key, "test_key": key,
+                "train_return": -train_loss, "test_return": -test_loss_smooth,
+                "best_return": -best_loss, "pgpe_return": None,
+                "last_iteration_improved": last_iter_improve, "pgpe_improved": False,
+                "params": self.plan.params_to_pytree(self.params.view(P, self.T, self.A)),
+                "best_params": best_params, "best_index": best_index, "pgpe_params": None,
+                "model_params": self.model_parameter_info(), "policy_hyperparams": hyper,
+                "grad": self.plan.params_to_pytree(self.grad.view(P, self.T, self.A)),
+                "best_grad": best_grad, "train_log": self._train_log(),
+                "test_log": self._test_log(), "planner_state": self,
+            }
+            if stopping_rule is not None and stopping_rule.monitor(callback):
+                callback["status"] = status = JaxPlannerStatus.STOPPING_RULE_REACHED
+            if print_progress and (it % 100 == 0 or status.is_terminal()):
+                print(f"{it:6d} it | {-np.min(train_loss):13.5f} train | "
+                      f"{-np.min(test_loss_smooth):13.5f} test | {-best_loss:13.5f} best | "
+                      f"{status.value} status | {(it + 1) / (elapsed + 1e-6):.2f}it/s")
+            t_out = time.time()
+            yield callback
+            elapsed_outside_loop += time.time() - t_out
+            if status.is_terminal():
+                break
+        if print_summary:
+            print(f"[INFO] Summary of optimization:\n    status:         {status}\n"
+                  f"    time:           {time.time() - start_time - elapsed_outside_loop:.2f} seconds\n"
+                  f"    iterations:     {it}\n    best objective: {-best_loss:.5f}\n")
+
+    def get_action(self, key, params: Dict[str, Any], step: int, state: Dict[str, Any],
+                   policy_hyperparams: Optional[Dict] = None, history=None,
+                   copy_state: bool = True) -> Dict[str, Any]:
+        """Action of the test policy at one decision epoch (planner.py:3527-3586)."""
+        flat = self.plan.pytree_to_params(params)
+        step = min(int(step), flat.shape[0] - 1)
+        return self.plan.test_actions(flat[step].numpy())
+
+
+# =====================================================================================
+# config files (planner.py:101-244)
+# =====================================================================================
+
+def _parse_config_file(path: str):
+    config = configparser.RawConfigParser()
+    config.optionxform = str
+    if not config.read(path):
+        raise FileNotFoundError(f"No config file found at {path}.")
+    return config, {s: {k: literal_eval(v) for k, v in config.items(s)} for s in config.sections()}
+
+
+def _parse_config_string(value: str):
+    config = configparser.RawConfigParser()
+    config.optionxform = str
+    config.read_string(value)
+    return config, {s: {k: literal_eval(v) for k, v in config.items(s)} for s in config.sections()}
+
+
+def _getattr_any(packages, item):
+    for pkg in packages:
+        val = getattr(pkg, item, None)
+        if val is not None:
+            return val
+    return None
+
+
+def _load_config(config, args):
+    compiler_kwargs = {k: args["Compiler"][k] for k in args.get("Compiler", {})}
+    planner_args = {k: args["Planner"][k] for k in args.get("Planner", {})}
+    train_args = {k: args["Optimize"][k] for k in args.get("Optimize", {})}
+    if "method" in compiler_kwargs:                             # planner.py:130-137
+        name = compiler_kwargs.pop("method")
+        cls = getattr(logic, name, None)
+        if cls is None:
+            raise ValueError(f"Invalid compiler class <{name}>.")
+        planner_args["compiler"] = cls
+    planner_args["compiler_kwargs"] = compiler_kwargs
+    plan_method = planner_args.pop("method")
+    plan_kwargs = planner_args.pop("method_kwargs", {})
+    if "initializer" in plan_kwargs:                            # planner.py:140-155
+        init = getattr(initializers, plan_kwargs["initializer"], None)
+        kw = plan_kwargs.pop("initializer_kwargs", {})
+        plan_kwargs["initializer"] = init(**kw) if callable(init) and kw else (
+            init() if callable(init) and not isinstance(init, _Initializer) else init)
+    import sys
+    this = sys.modules[__name__]
+    plan_cls = getattr(this, plan_method, None)
+    if plan_cls is None:
+        from . import drp
+        plan_cls = getattr(drp, plan_method, None)
+    if plan_cls is None:
+        raise ValueError(f"Invalid plan class <{plan_method}>.")
+    planner_args["plan"] = plan_cls(**plan_kwargs)
+    opt = planner_args.get("optimizer")
+    if isinstance(opt, str) and opt not in OPTIMIZERS:          # planner.py:180-186
+        raise ValueError(f"Invalid optimizer <{opt}>.")
+    if planner_args.get("pgpe", None) is not None:
+        raise NotImplementedError("PGPE is not built yet; set pgpe=None in the [Planner] section")
+    planner_args.pop("pgpe_kwargs", None)
+    if "stopping_rule" in train_args:                           # planner.py:219-226
+        rule = getattr(this, train_args["stopping_rule"])
+        train_args["stopping_rule"] = rule(**train_args.pop("stopping_rule_kwargs", {}))
+    return planner_args, plan_kwargs, train_args
+
+
+def load_config(path: str):
+    """(planner_args, plan_kwargs, train_args) from a .cfg file (planner.py:229-235)."""
+    return _load_config(*_parse_config_file(path))
+
+
+def load_config_from_string(value: str):
+    return _load_config(*_parse_config_string(value))
+
+
+# =====================================================================================
+# controllers (planner.py:3632-3831)
+# =====================================================================================
+
+class JaxOfflineController:
+    """Optimise once, then replay the plan (planner.py:3632-3726)."""
+    use_tensor_obs = True
+
+    def __init__(self, planner: JaxBackpropPlanner, key: Optional[int] = None,
+                 eval_hyperparams: Optional[Dict] = None, params: Optional[Any] = None,
+                 train_on_reset: bool = False, save_path: Optional[str] = None,
+                 **train_kwargs) -> None:
+        self.planner = planner
+        self.key = key if key is not None else round(time.time() * 1000) % (2 ** 31)
+        self.eval_hyperparams = eval_hyperparams
+        self.train_on_reset = train_on_reset
+        self.train_kwargs = train_kwargs
+        self.params_given = params is not None
+        self.hyperparams_given = eval_hyperparams is not None
+        if isinstance(params, str):
+            with open(params, "rb") as f:
+                data = pickle.load(f)
+            params, self.eval_hyperparams = data["params"], data["hyperparams"]
+            self.hyperparams_given = True
+        self.step = 0
+        self.callback = None
+        if not self.train_on_reset and not self.params_given:
+            self.callback = self.planner.optimize(key=self.key, **self.train_kwargs)
+            params = self.callback["best_params"]
+            if not self.hyperparams_given:
+                self.eval_hyperparams = self.callback["policy_hyperparams"]
+            if save_path is not None:
+                with open(save_path, "wb") as f:
+                    pickle.dump({"params": params, "hyperparams": self.eval_hyperparams}, f)
+        self.params = params
+
+    def sample_action(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        actions = self.planner.get_action(self.key, self.params, self.step, state,
+                                          self.eval_hyperparams)
+        self.step += 1
+        return actions
+
+    def reset(self) -> None:
+        self.step = 0
+        if self.train_on_reset and not self.params_given:
+            self.callback = self.planner.optimize(key=self.key, **self.train_kwargs)
+            self.params = self.callback["best_params"]
+            if not self.hyperparams_given:
+                self.eval_hyperparams = self.callback["policy_hyperparams"]
+
+
+class JaxOnlineController:
+    """Re-optimise at every decision epoch with a warm start (planner.py:3729-3831)."""
+    use_tensor_obs = True
+
+    def __init__(self, planner: JaxBackpropPlanner, key: Optional[int] = None,
+                 eval_hyperparams: Optional[Dict] = None, warm_start: bool = True,
+                 max_attempts: int = 3, **train_kwargs) -> None:
+        self.planner = planner
+        self.key = key if key is not None else round(time.time() * 1000) % (2 ** 31)
+        self.eval_hyperparams = eval_hyperparams
+        self.warm_start = warm_start
+        self.max_attempts = max_attempts
+        self.train_kwargs = train_kwargs
+        self.reset()
+
+    def sample_action(self, state: Dict[str, Any]) -> Dict[str, Any]:
+        planner = self.planner
+        callback = planner.optimize(key=self.key, guess=self.guess, subs=state,
+                                    **self.train_kwargs)
+        self.key += 1
+        params = callback["best_params"]
+        hyper = self.eval_hyperparams if self.eval_hyperparams is not None \
+            else callback["policy_hyperparams"]
+        actions = planner.get_action(self.key, params, 0, state, hyper)
+        if self.warm_start:
+            self.guess = planner.plan.guess_next_epoch(params)
+        self.callback = callback
+        return actions
+
+    def reset(self) -> None:
+        self.guess = None
+        self.callback = None

@@ -112,7 +112,7 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     ref = OP.rollout(om, pol, B, T, noise_steps)
     spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
     spec_pr = [(k, tuple(s)) for k, s, _, _, _ in fwd.noise_layout]
-    assert spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
+    assert T == 0 or spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
     final = unpack_fluent_major(fwd.state_layout, torch.from_numpy(got["final"].copy()), B)
     return dict(model=m, comp=comp, builder=builder, fwd=fwd, params=params, P=P, noise=noise,
                 s0=s0, disc=disc, got=got, ref=ref, final=final, gamma=gamma)
