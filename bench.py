@@ -329,17 +329,21 @@ def main():
         "gpu_launches": 9 * planner.parallel_updates * args.steps,
         "kernels_ms": {"train_forward": t_fwd, "adjoint": t_bwd, "exact_test_forward": t_test,
                        "reduce_partials": t_red},
-        "roofline": {"bound": "hbm", "kernel": "rk_interp_kernel (adjoint program)",
+        "roofline": {"bound": "hbm",
+                     "kernel": ("rk_spec_kernel" if planner.train_bwd.specialized
+                                else "rk_interp_kernel") + " (adjoint program)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes": bytes_bwd,
-                     "note": "latency/issue-bound interpreter: 48 state words per rollout-step "
-                             "cost ~290 interpreted instructions in the adjoint"},
+                     "note": "not HBM-bound by construction: 48 state words per rollout-step "
+                             "carry ~290 adjoint instructions (19 sin + 19 cos + 2 tan); with "
+                             "B=4096 there are only 512 warps, so the kernel is latency-bound"},
         "roofline_other": {
             "train_forward_GBs": bytes_fwd / (t_fwd * 1e-3) / 1e9,
             "exact_test_forward_GBs": bytes_test / (t_test * 1e-3) / 1e9},
         "clocks": clocks,
-        "program": {"fwd_step_ins": fw.n_ins[1], "bwd_step_ins": bw.n_ins[1],
+        "program": {"specialized": bool(planner.train_bwd.specialized),
+                    "fwd_step_ins": fw.n_ins[1], "bwd_step_ins": bw.n_ins[1],
                     "test_step_ins": te.n_ins[1], "rpw": bw.rpw, "lanes": bw.lanes,
                     "warp_words": bw.warp_words},
     }

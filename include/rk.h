@@ -51,6 +51,12 @@ typedef struct rk_sizes {
 int rk_program_create(const void* blob, size_t nbytes, rk_program** out);
 void rk_program_destroy(rk_program* prog);
 int rk_program_query(const rk_program* prog, rk_sizes* out);
+/* Attach a per-program specialised kernel (a cubin compiled from the CUDA C that
+ * core/codegen.py generates out of the same instruction stream).  Subsequent launches of the
+ * program use it instead of the generic interpreter kernel; semantics are identical.
+ * Plays the role of the XLA executable cache behind jax.jit (planner.py:2687, 2930). */
+int rk_program_attach_cubin(rk_program* prog, const void* image, size_t nbytes,
+                            const char* entry);
 /* number of warps (= gradient partial rows) a launch with batch B uses */
 int rk_program_num_warps(const rk_program* prog, int B);
 

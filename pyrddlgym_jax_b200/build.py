@@ -12,7 +12,7 @@ SOURCES = ["rk_interp.cu", "rk_optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # no FMA contraction: keep per-op roundings like the reference
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -1,0 +1,517 @@
+"""Per-program kernel specialisation: instruction stream -> straight-line CUDA C.
+
+The interpreter (csrc/rk_interp.cu) spends ~128 SASS instructions per interpreted instruction
+on fetch / decode / dispatch / address arithmetic (profiles/r01_ncu_interp_first.md).  For a
+given program all of that is known ahead of time, so this module unrolls the instruction
+stream into one kernel per program:
+
+* no fetch, decode or dispatch: every instruction becomes one C statement with its
+  element count, addresses and gather tables baked in;
+* values that only ever take part in single-pass instructions (n <= lanes per rollout) live
+  in *registers* -- lane (q, e) holds element e of rollout q -- and are exchanged with
+  ``__shfl_sync`` for gathers, aggregations and cross-rollout sums; only multi-pass values
+  stay in the shared-memory register file of the interpreter layout;
+* nvcc then schedules independent CPFs against each other (ILP), which the interpreter,
+  executing one instruction at a time per warp, cannot.
+
+The generated kernel has the interpreter's exact semantics (same program, same layouts, same
+``RkLaunch`` argument block) and sits behind the same C ABI (rk_program_attach_cubin), so every
+parity test runs against both back-ends.  This is the role XLA's jit plays for the reference
+(planner.py:2687, 2930), done per RDDL domain/instance instead of per Python trace.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+
+from . import isa
+from .program import Program
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
+JIT_DIR = os.path.join(CSRC, "jit")
+KERNEL_NAME = "rk_spec_kernel"
+CODEGEN_VERSION = 3
+
+_F1 = {
+    "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
+    "ROUND": "rintf(x)", "SQRT": "sqrtf(x)", "EXP": "expf(x)", "LOG": "logf(x)", "SIN": "sinf(x)",
+    "COS": "cosf(x)", "TAN": "tanf(x)", "ASIN": "asinf(x)", "ACOS": "acosf(x)",
+    "ATAN": "atanf(x)", "SINH": "sinhf(x)", "COSH": "coshf(x)", "TANH": "tanhf(x)",
+    "LGAMMA": "lgammaf(x)", "SIGMOID": "(1.f / (1.f + expf(-x)))", "STANH": "stable_tanh(x)",
+    "RELU": "fmaxf(x, 0.f)", "RCP": "(1.f / x)", "SQUARE": "(x * x)", "LOG1P": "log1pf(x)",
+    "EXPM1": "expm1f(x)",
+}
+_F2 = {
+    "ADD": "(x + y)", "SUB": "(x - y)", "MUL": "(x * y)", "DIV": "(x / y)", "MIN": "fminf(x, y)",
+    "MAX": "fmaxf(x, y)", "POW": "powf(x, y)", "HYPOT": "hypotf(x, y)", "FMOD": "fmodf(x, y)",
+    "MOD": "py_modf(x, y)", "FDIV": "floorf(x / y)",
+    "SAFELOG": "((x > 0.f) ? logf(x) : -CUDART_INF_F + 0.f * y)",
+    "MINW": "((x < y) ? 1.f : ((x == y) ? 0.5f : 0.f))",
+    "MAXW": "((x > y) ? 1.f : ((x == y) ? 0.5f : 0.f))",
+}
+_F2B = {"LT": "<", "LE": "<=", "GT": ">", "GE": ">=", "EQ": "==", "NE": "!="}
+_I1 = {"INEG": "(-x)", "IABS": "abs(x)", "ISGN": "((x > 0) - (x < 0))", "NOT": "(x == 0)",
+       "I2B": "(x != 0)"}
+_I2 = {"IADD": "(x + y)", "ISUB": "(x - y)", "IMUL": "(x * y)", "IMIN": "min(x, y)",
+       "IMAX": "max(x, y)", "IFDIV": "ifloordiv(x, y)", "IMOD": "ipymod(x, y)",
+       "IFMOD": "((y == 0) ? 0 : (x % y))", "IPOW": "ipow(x, y)", "ILT": "(x < y)",
+       "ILE": "(x <= y)", "IGT": "(x > y)", "IGE": "(x >= y)", "IEQ": "(x == y)",
+       "INE": "(x != y)", "AND": "(x & y)", "OR": "(x | y)", "XOR": "(x ^ y)"}
+_RED = {  # op -> (ctype, init, update)
+    "RSUM": ("float", "0.f", "acc = acc + t"), "RPROD": ("float", "1.f", "acc = acc * t"),
+    "RMIN": ("float", "CUDART_INF_F", "acc = fminf(acc, t)"),
+    "RMAX": ("float", "-CUDART_INF_F", "acc = fmaxf(acc, t)"),
+    "RISUM": ("int", "0", "acc = acc + t"), "RIPROD": ("int", "1", "acc = acc * t"),
+    "RIMIN": ("int", "2147483647", "acc = min(acc, t)"),
+    "RIMAX": ("int", "(-2147483647 - 1)", "acc = max(acc, t)"),
+}
+
+
+def _flit(x: float) -> str:
+    x = np.float32(x)
+    if np.isnan(x):
+        return "CUDART_NAN_F"
+    if np.isinf(x):
+        return "CUDART_INF_F" if x > 0 else "(-CUDART_INF_F)"
+    return f"__uint_as_float(0x{np.float32(x).view(np.uint32):08x}u)"
+
+
+class _Gen:
+    def __init__(self, prog: Program):
+        self.p = prog
+        self.ins = prog.meta["ins"]
+        self.L, self.rpw = prog.lanes, prog.rpw
+        self.n_pro, self.n_step, self.n_epi = prog.n_ins
+        self.persistent = set(prog.meta["persistent"])
+        self.err_base = prog.meta["err_base"]
+        self._classify()
+        self.lines: List[str] = []
+        self.tmp = 0
+
+    # ---- register vs shared-memory residency ------------------------------------------
+    def _classify(self):
+        L = self.L
+        smem = set()
+        dtype: Dict[int, str] = {}
+        for rec in self.ins:
+            vals = ([rec["dst"]] if rec["dst"] else []) + rec["srcs"]
+            multi = rec["n"] > L
+            for v in vals:
+                if v["kind"] != "val":
+                    continue
+                dtype.setdefault(v["id"], v["dtype"])
+                if multi or v["n"] > L:
+                    smem.add(v["id"])
+            # a flat shared-memory copy is the cheapest way to move multi-word rows
+        self.smem = smem
+        self.dtype = dtype
+
+    def is_reg(self, v) -> bool:
+        return v["kind"] == "val" and v["id"] not in self.smem
+
+    @staticmethod
+    def ctype(dt: str) -> str:
+        return "float" if dt == "f" else "int"
+
+    def var(self, v) -> str:
+        return f"v{v['id']}"
+
+    # ---- operand expressions --------------------------------------------------------------
+    def from_bits(self, expr: str, dt: str) -> str:
+        return f"__uint_as_float({expr})" if dt == "f" else f"(int)({expr})"
+
+    def to_bits(self, expr: str, dt: str) -> str:
+        return f"__float_as_uint({expr})" if dt == "f" else f"(uint32_t)({expr})"
+
+    def map_index(self, v, e: str, n_r: int) -> str:
+        """``e`` is always an in-range element index (callers clamp idle lanes to 0)."""
+        mp = v["map"]
+        if mp == isa.MAP_IDENT:
+            return e
+        if mp == isa.MAP_BCAST:
+            return "0u"
+        return f"C[{mp}u + {e}]"
+
+    def opnd(self, v, e: str, n_r: int, want: str) -> str:
+        """C expression of operand ``v`` for element ``e`` of an n_r-element instruction,
+        typed ``want`` ('f' float, 'i' int -- bool shares int)."""
+        want_c = "f" if want == "f" else "i"
+        if v["kind"] == "const":
+            c = v["const"]
+            mp = v["map"]
+            if mp == isa.MAP_BCAST or c.size == 1:
+                if want_c == "f":
+                    return _flit(float(c[0]))
+                return f"({int(c[0])})"
+            return self.from_bits(f"C[{v['base']}u + {self.map_index(v, e, n_r)}]", want_c)
+        if v["kind"] == "mparam":
+            return self.from_bits(f"C[{v['base']}u]", want_c)
+        if self.is_reg(v):
+            name = self.var(v)
+            src_c = "f" if self.dtype[v["id"]] == "f" else "i"
+            if v["map"] == isa.MAP_IDENT:
+                ex = name
+            elif v["map"] == isa.MAP_BCAST:
+                ex = f"__shfl_sync(0xffffffffu, {name}, {'0u' if v['uniform'] else 'qL'})"
+            else:
+                base = "0u" if v["uniform"] else "qL"
+                ex = f"__shfl_sync(0xffffffffu, {name}, {base} + {self.map_index(v, e, n_r)})"
+            if src_c != want_c:
+                ex = f"__uint_as_float((uint32_t)({ex}))" if want_c == "f" else f"(int)__float_as_uint({ex})"
+            return ex
+        # shared-memory resident value (q clamped: spare lanes must stay inside the warp region)
+        qs = f" + qc * {v['sq']}u" if v["sq"] else ""
+        return self.from_bits(f"R[{v['base']}u{qs} + {self.map_index(v, e, n_r)}]", want_c)
+
+    def emit(self, s: str):
+        self.lines.append(s)
+
+    # ---- one instruction ----------------------------------------------------------------------
+    def gen_ins(self, rec):
+        op, n, L = rec["op"], rec["n"], self.L
+        dst, srcs = rec["dst"], rec["srcs"]
+        self.emit(f"  // {op} n={n}")
+        if op == "NOP":
+            return
+        if op in ("LDB", "STB", "LDU", "STG", "STERR", "ERRCHK", "QSUM"):
+            return self.gen_special(rec)
+        if op in _RED or op in ("RARGMAX", "RARGMIN", "RPRODX"):
+            return self.gen_reduce(rec)
+        # ---- elementwise
+        dt_out = dst["dtype"]
+        single = n <= L and (self.is_reg(dst) or True)
+        if op in _F1:
+            body, tin = _F1[op], "f"
+        elif op in _F2:
+            body, tin = _F2[op], "ff"
+        elif op in _F2B:
+            body, tin = f"((x {_F2B[op]} y) ? 1 : 0)", "ff"
+        elif op in _I1:
+            body, tin = _I1[op], "i"
+        elif op in _I2:
+            body, tin = _I2[op], "ii"
+        elif op == "MOV":
+            body, tin = "x", dt_out if dt_out == "f" else "i"
+        elif op == "SELECT":
+            d = "f" if dt_out == "f" else "i"
+            body, tin = "((x != 0) ? y : z)", "i" + d + d
+        elif op == "FMA":
+            body, tin = "__fadd_rn(__fmul_rn(x, y), z)", "fff"
+        elif op == "LERP":
+            body, tin = "__fadd_rn(__fmul_rn(x, y), __fmul_rn(__fsub_rn(1.f, x), z))", "fff"
+        elif op == "I2F":
+            body, tin = "(float)x", "i"
+        elif op == "F2I":
+            body, tin = "(int)x", "f"
+        elif op == "F2B":
+            body, tin = "((x != 0.f) ? 1 : 0)", "f"
+        else:
+            raise NotImplementedError(f"codegen: op {op}")
+        names = "xyz"
+        out_c = "f" if dt_out == "f" else "i"
+
+        def stmt(e: str) -> List[str]:
+            ls = []
+            for k, tk in enumerate(tin):
+                ls.append(f"const {self.ctype(tk)} {names[k]} = {self.opnd(srcs[k], e, n, tk)};")
+            ls.append(f"const {self.ctype(out_c)} r = {body};")
+            return ls
+
+        uni = dst["uniform"]
+        ec = f"const uint32_t ec = le < {n}u ? le : 0u;"
+        if n <= L and self.is_reg(dst):
+            self.emit("  { " + ec + " " + " ".join(stmt("ec")) + f" {self.var(dst)} = r; }}")
+            return
+        guard_q = "q == 0u" if uni else f"q < {self.rpw}u"
+        qs = f" + q * {dst['sq']}u" if dst["sq"] else ""
+        if n <= L:
+            # single pass into shared memory: every lane evaluates (shuffles need all lanes)
+            self.emit("  { " + ec + " " + " ".join(stmt("ec")) +
+                      f" if ({guard_q} && le < {n}u) R[{dst['base']}u{qs} + le] = {self.to_bits('r', out_c)}; }}")
+        else:
+            self.emit(f"  if ({guard_q}) for (uint32_t e = le; e < {n}u; e += {L}u) {{ " +
+                      " ".join(stmt("e")) +
+                      f" R[{dst['base']}u{qs} + e] = {self.to_bits('r', out_c)}; }}")
+        self.emit("  __syncwarp();")
+
+    # ---- reductions ---------------------------------------------------------------------------
+    def gen_reduce(self, rec):
+        op, n, L = rec["op"], rec["n"], self.L
+        dst, src = rec["dst"], rec["srcs"][0]
+        ptr, idx, kmax = rec["aux0"], rec["aux1"], rec.get("kmax", 0)
+        uni = dst["uniform"]
+        guard_q = "q == 0u" if uni else f"q < {self.rpw}u"
+        qs_d = f" + q * {dst['sq']}u" if dst["sq"] else ""
+        src_reg = self.is_reg(src)
+        if op in _RED:
+            ct, init, upd = _RED[op]
+            tin = "f" if ct == "float" else "i"
+        elif op in ("RARGMAX", "RARGMIN"):
+            ct, tin = "int", "f"
+        else:
+            ct, tin = "float", "f"
+
+        def fetch(sidx: str, ok: str) -> str:
+            """value of source element sidx (per-lane), evaluated by all lanes."""
+            if src["kind"] == "const":
+                return self.from_bits(f"C[{src['base']}u + {sidx}]", tin)
+            if src_reg:
+                base = "0u" if src["uniform"] else "qL"
+                ex = f"__shfl_sync(0xffffffffu, {self.var(src)}, {base} + {sidx})"
+                if (self.dtype[src["id"]] == "f") != (tin == "f"):
+                    ex = (f"__uint_as_float((uint32_t)({ex}))" if tin == "f"
+                          else f"(int)__float_as_uint({ex})")
+                return ex
+            qs = f" + qc * {src['sq']}u" if src["sq"] else ""
+            rd = self.from_bits(f"R[{src['base']}u{qs} + {sidx}]", tin)
+            return f"(({ok}) ? {rd} : ({ct})0)"
+
+        def body(e: str, shuffle_safe: bool) -> List[str]:
+            ls = [f"const bool act = ({e}) < {n}u && q < {self.rpw}u;",
+                  f"const uint32_t j0 = act ? C[{ptr}u + ({e})] : 0u;",
+                  f"const uint32_t j1 = act ? C[{ptr}u + ({e}) + 1u] : 0u;"]
+            if op == "RPRODX":
+                seg = rec["seg"]
+                ls = [f"const bool act = ({e}) < {n}u && q < {self.rpw}u;",
+                      f"const uint32_t sg_ = act ? C[{seg}u + ({e})] : 0u;",
+                      f"const uint32_t j0 = act ? C[{ptr}u + sg_] : 0u;",
+                      f"const uint32_t j1 = act ? C[{ptr}u + sg_ + 1u] : 0u;"]
+                ls.append("float acc = 1.f;")
+                loop_hdr = f"for (uint32_t k = 0; k < {kmax}u; ++k)" if shuffle_safe else \
+                    "for (uint32_t k = 0; k < j1 - j0; ++k)"
+                ls.append(loop_hdr + " { const bool ok = j0 + k < j1; "
+                          f"const uint32_t s = ok ? C[{idx}u + j0 + k] : 0u; "
+                          f"const float t = {fetch('s', 'ok')}; if (ok && s != ({e})) acc = acc * t; }}")
+                return ls
+            if op in ("RARGMAX", "RARGMIN"):
+                sgn = "1.f" if op == "RARGMAX" else "-1.f"
+                ls += ["float best = -CUDART_INF_F; int acc = 0;"]
+                loop_hdr = f"for (uint32_t k = 0; k < {kmax}u; ++k)" if shuffle_safe else \
+                    "for (uint32_t k = 0; k < j1 - j0; ++k)"
+                ls.append(loop_hdr + " { const bool ok = j0 + k < j1; "
+                          f"const uint32_t s = ok ? C[{idx}u + j0 + k] : 0u; "
+                          f"const float t = {sgn} * {fetch('s', 'ok')}; "
+                          "if (ok && t > best) { best = t; acc = (int)k; } }")
+                return ls
+            ls.append(f"{ct} acc = {init};")
+            loop_hdr = f"for (uint32_t k = 0; k < {kmax}u; ++k)" if shuffle_safe else \
+                "for (uint32_t k = 0; k < j1 - j0; ++k)"
+            ls.append(loop_hdr + " { const bool ok = j0 + k < j1; "
+                      f"const uint32_t s = ok ? C[{idx}u + j0 + k] : 0u; "
+                      f"const {ct} t = {fetch('s', 'ok')}; if (ok) {{ {upd}; }} }}")
+            return ls
+
+        out_c = "f" if ct == "float" else "i"
+        if n <= L:
+            pre = "#pragma unroll\n" if False else ""
+            code = " ".join(body("le", True))
+            if self.is_reg(dst):
+                self.emit(f"  {{ {code} {self.var(dst)} = acc; }}")
+            else:
+                self.emit(f"  {{ {code} if ({guard_q} && le < {n}u) "
+                          f"R[{dst['base']}u{qs_d} + le] = {self.to_bits('acc', out_c)}; }}")
+                self.emit("  __syncwarp();")
+        else:
+            assert not src_reg
+            code = " ".join(body("e", False))
+            self.emit(f"  if ({guard_q}) for (uint32_t e = le; e < {n}u; e += {L}u) {{ {code} "
+                      f"R[{dst['base']}u{qs_d} + e] = {self.to_bits('acc', out_c)}; }}")
+            self.emit("  __syncwarp();")
+
+    # ---- memory / cross-rollout / error instructions ------------------------------------------------
+    def gen_special(self, rec):
+        op, n, L, rpw = rec["op"], rec["n"], self.L, self.rpw
+        dst, srcs = rec["dst"], rec["srcs"]
+        buf, off = rec["buf"], rec["off"]
+        tt = "t" if rec["flags"] & isa.F_TSTEP else "0ll"
+        if op == "QSUM":
+            src = srcs[0]
+            if self.is_reg(src):
+                code = (f"float acc = 0.f; for (uint32_t qq = 0; qq < {rpw}u; ++qq) {{ "
+                        f"const float tq = __shfl_sync(0xffffffffu, {self.var(src)}, qq * {L}u + le); "
+                        f"if (qq < nvalid) acc += tq; }}")
+            else:
+                code = (f"float acc = 0.f; if (le < {n}u) for (uint32_t qq = 0; qq < nvalid; ++qq) "
+                        f"acc += __uint_as_float(R[{src['base']}u + qq * {src['sq']}u + le]);")
+            if self.is_reg(dst):
+                self.emit(f"  {{ {code} {self.var(dst)} = acc; }}")
+            else:
+                self.emit(f"  {{ {code} if (q == 0u && le < {n}u) R[{dst['base']}u + le] = __float_as_uint(acc); }}")
+                self.emit("  __syncwarp();")
+            return
+        if op == "LDB":
+            g = f"((const uint32_t*)K.buf[{buf}])"
+            addr = f"({tt} * K.W[{buf}] + {off}ll) * (long long)K.B + b0 * {n}ll"
+            if self.is_reg(dst):
+                dt = self.dtype[dst["id"]]
+                self.emit(f"  {self.var(dst)} = (K.buf[{buf}] != nullptr && q < nvalid && le < {n}u) ? "
+                          f"{self.from_bits(f'{g}[{addr} + q * {n}u + le]', dt)} : ({self.ctype(dt)})0;")
+            else:
+                self.emit(f"  if (K.buf[{buf}] != nullptr) {{ const uint32_t* src_ = {g} + {addr}; "
+                          f"for (uint32_t i = lane; i < nvalid * {n}u; i += 32u) R[{dst['base']}u + i] = src_[i]; }}")
+                self.emit("  __syncwarp();")
+            return
+        if op == "STB":
+            src = srcs[0]
+            g = f"((uint32_t*)K.buf[{buf}])"
+            addr = f"({tt} * K.W[{buf}] + {off}ll) * (long long)K.B + b0 * {n}ll"
+            if n <= L:
+                dt = src["dtype"] if src["kind"] != "val" else self.dtype[src["id"]]
+                dtc = "f" if dt == "f" else "i"
+                val = self.opnd(src, "ec", n, dtc)
+                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const {self.ctype(dtc)} sv = {val}; if (K.buf[{buf}] != nullptr && q < nvalid && le < {n}u) "
+                          f"{g}[{addr} + q * {n}u + le] = {self.to_bits('sv', dtc)}; }}")
+            elif src["kind"] == "val" and src["map"] == isa.MAP_IDENT and src["sq"] == n:
+                self.emit(f"  if (K.buf[{buf}] != nullptr) {{ uint32_t* dst_ = {g} + {addr}; "
+                          f"for (uint32_t i = lane; i < nvalid * {n}u; i += 32u) dst_[i] = R[{src['base']}u + i]; }}")
+            else:
+                val = self.opnd(src, "e", n, "i")
+                self.emit(f"  if (K.buf[{buf}] != nullptr && q < nvalid) for (uint32_t e = le; e < {n}u; e += {L}u) "
+                          f"{g}[{addr} + q * {n}u + e] = (uint32_t)({val});")
+            return
+        if op == "LDU":
+            g = f"((const uint32_t*)K.buf[{buf}])"
+            addr = f"{tt} * K.W[{buf}] + {off}ll"
+            if self.is_reg(dst):
+                dt = self.dtype[dst["id"]]
+                self.emit(f"  {self.var(dst)} = (K.buf[{buf}] != nullptr && le < {n}u) ? "
+                          f"{self.from_bits(f'__ldg({g} + {addr} + le)', dt)} : ({self.ctype(dt)})0;")
+            else:
+                self.emit(f"  if (K.buf[{buf}] != nullptr) for (uint32_t i = lane; i < {n}u; i += 32u) "
+                          f"R[{dst['base']}u + i] = __ldg({g} + {addr} + i);")
+                self.emit("  __syncwarp();")
+            return
+        if op == "STG":
+            src = srcs[0]
+            g = f"((uint32_t*)K.buf[{buf}])"
+            addr = f"(gwarp * (long long)K.T + t) * K.W[{buf}] + {off}ll"
+            if n <= L:
+                val = self.opnd(src, "ec", n, "f")
+                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const float sv = {val}; if (K.buf[{buf}] != nullptr && q == 0u && le < {n}u) "
+                          f"{g}[{addr} + le] = __float_as_uint(sv); }}")
+            else:
+                val = self.opnd(src, "e", n, "f")
+                self.emit(f"  if (K.buf[{buf}] != nullptr && q == 0u) for (uint32_t e = le; e < {n}u; e += {L}u) "
+                          f"{g}[{addr} + e] = __float_as_uint({val});")
+            return
+        if op == "ERRCHK":
+            src = srcs[0]
+            bit = rec["aux0"]
+            if n <= L:
+                val = self.opnd(src, "ec", n, "i")
+                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const int cv = {val}; if (q < nvalid && le < {n}u && cv != 0) "
+                          f"atomicOr(R + {self.err_base}u + q, {1 << bit}u); }}")
+            else:
+                val = self.opnd(src, "e", n, "i")
+                self.emit(f"  if (q < nvalid) {{ bool bad = false; for (uint32_t e = le; e < {n}u; e += {L}u) "
+                          f"bad |= ({val}) != 0; if (bad) atomicOr(R + {self.err_base}u + q, {1 << bit}u); }}")
+            self.emit("  __syncwarp();")
+            return
+        if op == "STERR":
+            self.emit(f"  if (lane < nvalid) {{ if (K.buf[{buf}] != nullptr) ((uint32_t*)K.buf[{buf}])"
+                      f"[t * (long long)K.B + b0 + lane] = R[{self.err_base}u + lane] | {self.p.static_err}u; "
+                      f"R[{self.err_base}u + lane] = 0u; }}")
+            self.emit("  __syncwarp();")
+            return
+        raise NotImplementedError(op)
+
+    # ---- whole kernel ---------------------------------------------------------------------------
+    def source(self) -> str:
+        p = self.p
+        decl = []
+        seen = set()
+        for rec in self.ins:
+            for v in ([rec["dst"]] if rec["dst"] else []) + rec["srcs"]:
+                if v["kind"] == "val" and v["id"] not in self.smem and v["id"] not in seen:
+                    seen.add(v["id"])
+                    dt = self.dtype[v["id"]]
+                    decl.append(f"  {self.ctype(dt)} v{v['id']} = ({self.ctype(dt)})0;")
+        lists = [self.ins[:self.n_pro], self.ins[self.n_pro:self.n_pro + self.n_step],
+                 self.ins[self.n_pro + self.n_step:]]
+        bodies = []
+        for lst in lists:
+            self.lines = []
+            for rec in lst:
+                self.gen_ins(rec)
+            bodies.append("\n".join(self.lines))
+        backward = p.kind == "backward"
+        loop = "for (long long t = (long long)K.T - 1; t >= 0; --t)" if backward else \
+            "for (long long t = 0; t < (long long)K.T; ++t)"
+        src = f"""// GENERATED by pyrddlgym_jax_b200/core/codegen.py (version {CODEGEN_VERSION}) -- do not edit.
+// program: kind={p.kind} relaxed={p.relaxed} lanes={p.lanes} rpw={p.rpw} S={p.S} A={p.A} N={p.N}
+//          instructions={p.n_ins} register-resident values={len(seen)} shared-memory values={len(self.smem)}
+#include "rk_launch.h"
+#include "rk_device.cuh"
+
+extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
+  extern __shared__ __align__(16) uint32_t smem[];
+  const uint32_t* prog = K.prog;
+  for (int i = threadIdx.x; i < K.const_words; i += blockDim.x) smem[i] = prog[RK_HEADER_WORDS + i];
+  __syncthreads();
+  if (K.mparams != nullptr)
+    for (int i = threadIdx.x; i < K.n_mparams; i += blockDim.x)
+      smem[K.mparam_off + i] = __float_as_uint(K.mparams[i]);
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long b0 = gwarp * {p.rpw}ll;
+  if (b0 >= K.B) return;
+  const uint32_t nvalid = (uint32_t)min({p.rpw}ll, (long long)K.B - b0);
+  const uint32_t q = lane / {p.lanes}u, le = lane - q * {p.lanes}u;
+  const uint32_t qc = q < {p.rpw}u ? q : 0u;
+  const uint32_t qL = qc * {p.lanes}u;
+  const uint32_t* C = smem;
+  uint32_t* R = smem + {p.const_words}u + warp * {p.warp_words}u;
+  for (uint32_t i = lane; i < {p.rpw}u; i += 32u) R[{self.err_base}u + i] = 0u;
+  __syncwarp();
+  (void)qL; (void)qc; (void)le; (void)nvalid; (void)gwarp;
+{chr(10).join(decl)}
+  {{ const long long t = 0; (void)t;
+{bodies[0]}
+  }}
+  {loop} {{
+{bodies[1]}
+  }}
+  {{ const long long t = 0; (void)t;
+{bodies[2]}
+  }}
+}}
+"""
+        return src
+
+
+def generate_source(prog: Program) -> str:
+    return _Gen(prog).source()
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-cubin"]
+
+
+def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:
+    """Generate + compile the specialised kernel (cached by content hash under csrc/jit/)."""
+    src = generate_source(prog)
+    deps = b""
+    for h in ("rk_launch.h", "rk_device.cuh", "rk_isa.h"):
+        with open(os.path.join(CSRC, h), "rb") as f:
+            deps += f.read()
+    key = hashlib.sha1(src.encode() + deps + " ".join(NVCC_FLAGS).encode()).hexdigest()[:16]
+    os.makedirs(JIT_DIR, exist_ok=True)
+    cu = os.path.join(JIT_DIR, f"rk_{key}.cu")
+    cubin = os.path.join(JIT_DIR, f"rk_{key}.cubin")
+    if not os.path.exists(cubin):
+        with open(cu, "w") as f:
+            f.write(src)
+        cmd = [os.environ.get("NVCC", "nvcc"), *NVCC_FLAGS, "-I", CSRC,
+               *(["-Xptxas", "-v"] if verbose else []), cu, "-o", cubin + ".tmp"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on generated kernel:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+        os.replace(cubin + ".tmp", cubin)
+    return cubin, cu

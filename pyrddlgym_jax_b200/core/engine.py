@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"
 
 EXPORTS = [
     "rk_program_create", "rk_program_destroy", "rk_program_query", "rk_program_num_warps",
+    "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss",
 ]
@@ -53,6 +54,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_program_destroy.restype = None
     lib.rk_program_query.argtypes = [vp, ctypes.POINTER(RkSizes)]
     lib.rk_program_query.restype = ci
+    lib.rk_program_attach_cubin.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_char_p]
+    lib.rk_program_attach_cubin.restype = ci
     lib.rk_program_num_warps.argtypes = [vp, ci]
     lib.rk_program_num_warps.restype = ci
     lib.rk_rollout_forward.argtypes = [vp, vp, ci, ci] + [cf] * 12
@@ -93,7 +96,11 @@ def _stream() -> int:
 class DeviceProgram:
     """A Program uploaded to the current CUDA device."""
 
-    def __init__(self, program: Program):
+    def __init__(self, program: Program, specialize: Optional[bool] = None):
+        """``specialize``: attach the per-program generated kernel (default: on, unless the
+        environment sets RK_SPECIALIZE=0); otherwise the generic interpreter kernel runs."""
+        if specialize is None:
+            specialize = os.environ.get("RK_SPECIALIZE", "1") != "0"
         if not torch.cuda.is_available():
             raise RkError("no CUDA device: the rollout kernels have no CPU fallback")
         self.lib = load_library()
@@ -105,6 +112,17 @@ class DeviceProgram:
                "rk_program_create")
         self.sizes = RkSizes()
         _check(self.lib.rk_program_query(self.handle, ctypes.byref(self.sizes)), "rk_program_query")
+        self.specialized = False
+        if specialize:
+            from .codegen import compile_cubin, KERNEL_NAME
+            cubin, _ = compile_cubin(program)
+            with open(cubin, "rb") as f:
+                image = f.read()
+            self._image = ctypes.create_string_buffer(image, len(image))
+            _check(self.lib.rk_program_attach_cubin(self.handle, self._image, len(image),
+                                                    KERNEL_NAME.encode()),
+                   "rk_program_attach_cubin")
+            self.specialized = True
 
     def __del__(self):
         try:

@@ -74,6 +74,7 @@ class Program:
     TRAJ: int = 0
     static_err: int = 0
     stats: Dict[str, Any] = field(default_factory=dict)
+    meta: Dict[str, Any] = field(default_factory=dict)    # decoded instructions for codegen
 
 
 class Assembler:
@@ -221,6 +222,10 @@ class ProgramBuilder:
     def __init__(self, model, relax: Optional[Dict[str, Any]], spec: PlanSpec, train_policy: bool,
                  log_fluents: Sequence[str] = (), batch_hint: int = 0):
         self.batch_hint = batch_hint
+        # the specialised kernels (core/codegen.py) have almost no per-instruction overhead
+        import os as _os
+        if _os.environ.get("RK_SPECIALIZE", "1") != "0":
+            self.INS_OVERHEAD = 0.5
         self.model = model
         self.relax = relax
         self.spec = spec
@@ -457,6 +462,7 @@ class ProgramBuilder:
         warp_words = persist_high
 
         encoded: List[np.ndarray] = []
+        records: List[Dict[str, Any]] = []
         counts = []
         for lst in (pro, step, epi):
             al = _Alloc(persist_high)
@@ -483,6 +489,7 @@ class ProgramBuilder:
                         if r.id not in last_use:
                             last_use[r.id] = i
                 encoded.append(self._encode(asm, ins))
+                records.append(self._record(asm, ins, encoded[-1]))
                 for rid in [rid for rid, lu in last_use.items() if lu == i and rid in live]:
                     base, sz = live.pop(rid)
                     al.release(base, sz)
@@ -532,7 +539,29 @@ class ProgramBuilder:
             S=self.S, A=self.A, N=self.N, state_layout=self.slayout, param_layout=self.alayout,
             noise_layout=[(s.kind, s.shape, s.n, s.offset, s.extra) for s in sg.noise],
             mparam_keys=[k for k, _, _ in sg.mparams], mparam_defaults=mp_defaults,
-            static_err=sg.static_err, stats={"step_ops": hist})
+            static_err=sg.static_err, stats={"step_ops": hist},
+            meta={"ins": records, "persistent": [root(p).id for p in persistent],
+                  "err_base": err_base, "mparam_off": mparam_off,
+                  "const_image": const_img.copy()})
+
+    def _record(self, asm: Assembler, ins: Ins, w: np.ndarray) -> Dict[str, Any]:
+        """Decoded form of one instruction (value ids, dtypes, constants) for core/codegen.py."""
+        def val(v: V, m: Map = None, k: int = -1):
+            r = root(v)
+            base, sq = asm.addr[r.id]
+            kind = "const" if r.const is not None else ("mparam" if r.op == "mparam" else "val")
+            mp = int(w[7 + 3 * k]) if k >= 0 else 0
+            return {"id": r.id, "kind": kind, "base": int(base) & 0x7FFF if kind != "val" else int(base),
+                    "sq": int(sq), "n": r.n, "dtype": v.dtype, "uniform": r.uniform,
+                    "map": mp, "const": None if r.const is None else r.const.copy()}
+        rec = {"op": ins.op, "n": int(ins.n), "flags": int(ins.flags),
+               "dst": None if ins.dst is None else val(ins.dst),
+               "srcs": [val(a, m, k) for k, (a, m) in enumerate(ins.srcs[:3])],
+               "aux0": int(w[14]), "aux1": int(w[15]), "buf": int(ins.buf), "off": int(ins.off),
+               "seg": int(w[8]) if "seg" in ins.tables else 0}
+        if ins.tables:
+            rec["kmax"] = int(np.max(np.diff(ins.tables["ptr"]))) if len(ins.tables["ptr"]) > 1 else 0
+        return rec
 
     def _encode(self, asm: Assembler, ins: Ins) -> np.ndarray:
         w = np.zeros(isa.INS_WORDS, dtype=np.uint16)

@@ -21,19 +21,7 @@
 #include "../../include/rk.h"
 #include "rk_isa.h"
 
-#define RK_HEADER_WORDS 32
-
-struct RkLaunch {
-  const uint32_t* prog;
-  int B, T, t_dir;
-  int const_words, warp_words, rpw, lanes;
-  int n_pro, n_step, n_epi;
-  int mparam_off, n_mparams;
-  int err_base, static_err;
-  const float* mparams;
-  void* buf[RK_NUM_BUFFERS];
-  long long W[RK_NUM_BUFFERS];
-};
+#include "rk_launch.h"
 
 struct Opnd {
   const uint32_t* p;
@@ -57,45 +45,7 @@ __device__ __forceinline__ float ldf(const Opnd& o, uint32_t e, const uint32_t* 
   return __uint_as_float(ldw(o, e, C));
 }
 
-__device__ __forceinline__ float stable_tanh(float x) {       // logic.py:57-65
-  float ax = fabsf(x);
-  float s;
-  if (ax < 20.f) {
-    float em = expm1f(2.f * ax);
-    s = em / (em + 2.f);
-  } else {
-    s = 1.f - 2.f * expf(-2.f * ax);
-  }
-  return copysignf(1.f, x) * ((x == 0.f) ? 0.f : s);
-}
-
-__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
-
-__device__ __forceinline__ float py_modf(float x, float y) {  // jnp.mod: sign of divisor
-  float r = fmodf(x, y);
-  if (r != 0.f && ((r < 0.f) != (y < 0.f))) r += y;
-  return r;
-}
-
-__device__ __forceinline__ int ifloordiv(int a, int b) {
-  if (b == 0) return 0;
-  int qd = a / b;
-  if ((a % b != 0) && ((a < 0) != (b < 0))) --qd;
-  return qd;
-}
-
-__device__ __forceinline__ int ipymod(int a, int b) {
-  if (b == 0) return 0;
-  int r = a % b;
-  if (r != 0 && ((r < 0) != (b < 0))) r += b;
-  return r;
-}
-
-__device__ __forceinline__ int ipow(int a, int b) {
-  int r = 1;
-  for (int i = 0; i < b; ++i) r *= a;
-  return r;
-}
+#include "rk_device.cuh"
 
 #define F2U(x) __float_as_uint(x)
 
@@ -439,7 +389,64 @@ struct rk_program {
   int warps_per_cta;
   int smem_bytes;
   int device;
+  void* module;     // CUmodule of the specialised kernel (core/codegen.py), or NULL
+  void* func;       // CUfunction
 };
+
+// ---- CUDA driver API, resolved lazily so that the library also loads on hosts without a
+// driver (CPU-only CI boxes only check the exported symbols) -----------------------------
+#include <dlfcn.h>
+typedef int (*cuModuleLoadData_t)(void**, const void*);
+typedef int (*cuModuleGetFunction_t)(void**, void*, const char*);
+typedef int (*cuModuleUnload_t)(void*);
+typedef int (*cuFuncSetAttribute_t)(void*, int, int);
+typedef int (*cuLaunchKernel_t)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                unsigned, void*, void**, void**);
+static struct {
+  void* lib;
+  cuModuleLoadData_t moduleLoadData;
+  cuModuleGetFunction_t moduleGetFunction;
+  cuModuleUnload_t moduleUnload;
+  cuFuncSetAttribute_t funcSetAttribute;
+  cuLaunchKernel_t launchKernel;
+} g_drv = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static int load_driver() {
+  if (g_drv.lib != nullptr) return 0;
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) return RK_E_BADARG;
+  g_drv.moduleLoadData = (cuModuleLoadData_t)dlsym(lib, "cuModuleLoadData");
+  g_drv.moduleGetFunction = (cuModuleGetFunction_t)dlsym(lib, "cuModuleGetFunction");
+  g_drv.moduleUnload = (cuModuleUnload_t)dlsym(lib, "cuModuleUnload");
+  g_drv.funcSetAttribute = (cuFuncSetAttribute_t)dlsym(lib, "cuFuncSetAttribute");
+  g_drv.launchKernel = (cuLaunchKernel_t)dlsym(lib, "cuLaunchKernel");
+  if (!g_drv.moduleLoadData || !g_drv.moduleGetFunction || !g_drv.moduleUnload ||
+      !g_drv.funcSetAttribute || !g_drv.launchKernel) return RK_E_BADARG;
+  g_drv.lib = lib;
+  return 0;
+}
+
+extern "C" int rk_program_attach_cubin(rk_program* p, const void* image, size_t nbytes,
+                                       const char* entry) {
+  if (p == nullptr || image == nullptr || nbytes == 0 || entry == nullptr) return RK_E_BADARG;
+  int rc = load_driver();
+  if (rc != 0) return rc;
+  cudaFree(0);                                   // make sure the primary context is current
+  void* mod = nullptr;
+  void* fn = nullptr;
+  rc = g_drv.moduleLoadData(&mod, image);
+  if (rc != 0) return rc;
+  rc = g_drv.moduleGetFunction(&fn, mod, entry);
+  if (rc != 0) { g_drv.moduleUnload(mod); return rc; }
+  // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
+  rc = g_drv.funcSetAttribute(fn, 8, p->smem_bytes);
+  if (rc != 0) { g_drv.moduleUnload(mod); return rc; }
+  if (p->module != nullptr) g_drv.moduleUnload(p->module);
+  p->module = mod;
+  p->func = fn;
+  return 0;
+}
 
 static int pick_geometry(rk_program* p) {
   const int const_words = (int)p->hdr[5], warp_words = (int)p->hdr[8];
@@ -486,6 +493,7 @@ extern "C" int rk_program_create(const void* blob, size_t nbytes, rk_program** o
 
 extern "C" void rk_program_destroy(rk_program* p) {
   if (p == nullptr) return;
+  if (p->module != nullptr && g_drv.moduleUnload != nullptr) g_drv.moduleUnload(p->module);
   if (p->d_blob) cudaFree(p->d_blob);
   free(p);
 }
@@ -533,6 +541,11 @@ static int launch(const rk_program* p, cudaStream_t st, RkLaunch& K) {
   if (K.B == 0) return 0;
   const int nwarps = (K.B + K.rpw - 1) / K.rpw;
   const int grid = (nwarps + p->warps_per_cta - 1) / p->warps_per_cta;
+  if (p->func != nullptr) {                      // per-program specialised kernel
+    void* args[] = {(void*)&K};
+    return g_drv.launchKernel(p->func, (unsigned)grid, 1, 1, (unsigned)(p->warps_per_cta * 32), 1,
+                              1, (unsigned)p->smem_bytes, (void*)st, args, nullptr);
+  }
   rk_interp_kernel<<<grid, p->warps_per_cta * 32, p->smem_bytes, st>>>(K);
   return (int)cudaGetLastError();
 }

@@ -20,8 +20,8 @@ from pyrddlgym_jax_b200.core.program import PlanSpec
 from .helpers import fixture_model, init_params, initial_state, pack_params
 
 
-def make_params(model, key, T, seed=42):
-    params = init_params(model, T, seed=seed, scale=0.5)
+def make_params(model, key, T, seed=42, scale=0.5):
+    params = init_params(model, T, seed=seed, scale=scale)
     if key == "quadcopter":
         params["thrust"] = params["thrust"] + 9.81
     if key == "reservoir":
@@ -43,7 +43,7 @@ def run_forward(backend, prog, B, T, s0, params_flat, noise, disc=None, mparams=
                 "err": bufs["ERR"].reshape(T, B), "tape": bufs["TAPE"], "final": bufs["FINAL"]}
     from pyrddlgym_jax_b200.core.engine import DeviceProgram
     dev = torch.device("cuda:0")
-    dp = DeviceProgram(prog)
+    dp = DeviceProgram(prog, specialize=(backend == "jit"))
     z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
     out = {"reward": z(T * B), "returns": z(B), "err": z(T * B, dt=torch.int32),
            "tape": z(T * S * B), "final": z(S * B)}
@@ -73,7 +73,7 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
         return bufs["GRADP"].reshape(nW, T * A).sum(0).reshape(T, A)
     from pyrddlgym_jax_b200.core.engine import DeviceProgram, reduce_partials
     dev = torch.device("cuda:0")
-    dp = DeviceProgram(prog)
+    dp = DeviceProgram(prog, specialize=(backend == "jit"))
     nW = dp.num_warps(B)
     gradp = torch.zeros(nW * T * A, device=dev)
     grad = torch.zeros(T * A, device=dev)
@@ -86,7 +86,8 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
     return grad.cpu().numpy().reshape(T, A)
 
 
-def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None, **ckw):
+def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None,
+                 param_scale=0.5, **ckw):
     """Run program + oracle on the same inputs; returns everything a test wants to compare."""
     m = fixture_model(key)
     if relaxed:
@@ -96,7 +97,7 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     spec = PlanSpec(bounds=m.bounds)
     builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
     fwd = builder.forward(write_tape=relaxed, gamma=gamma)
-    params = make_params(m, key, T)
+    params = make_params(m, key, T, scale=param_scale)
     noise = draw_noise(fwd.noise_layout, T, B, torch.Generator().manual_seed(seed))
     s0 = initial_state(m, fwd.state_layout, B)
     disc = None if gamma == 1.0 else torch.pow(torch.tensor(gamma), torch.arange(T)).float()
@@ -118,8 +119,9 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
                 s0=s0, disc=disc, got=got, ref=ref, final=final, gamma=gamma)
 
 
-def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, **ckw):
-    c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls, **ckw)
+def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, **ckw):
+    c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
+                     param_scale=param_scale, **ckw)
     m = c["model"]
     bwd = c["builder"].backward(gamma=gamma)
     gret = torch.full((B,), -1.0 / B)
