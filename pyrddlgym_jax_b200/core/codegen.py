@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 3
+CODEGEN_VERSION = 4
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -170,6 +170,68 @@ class _Gen:
     def emit(self, s: str):
         self.lines.append(s)
 
+    # ---- sin / cos / tan of one argument share a single range reduction -------------------
+    def plan_trig(self, lst):
+        """Group the SIN / COS / TAN instructions of one list by operand: a group of two or
+        more becomes one sincosf() (tan = sin / cos), emitted where the first member stood."""
+        self.trig_skip, self.trig_lead = set(), {}
+        groups: Dict[Tuple, List[Any]] = {}
+        gen: Dict[int, int] = {}          # value id -> how often it has been (re)assigned so far
+        for rec in lst:
+            if rec["op"] in ("SIN", "COS", "TAN") and rec["n"] <= self.L and self.is_reg(rec["dst"]):
+                a = rec["srcs"][0]
+                if a["kind"] == "val":      # same operand *and* same assignment of it
+                    key = (a["id"], a["map"], rec["n"], gen.get(a["id"], 0))
+                    groups.setdefault(key, []).append(rec)
+            if rec["dst"] is not None and rec["dst"]["kind"] == "val":
+                gen[rec["dst"]["id"]] = gen.get(rec["dst"]["id"], 0) + 1
+        for recs in groups.values():
+            if len({r["op"] for r in recs}) >= 2:
+                self.trig_lead[id(recs[0])] = recs
+                for r in recs[1:]:
+                    self.trig_skip.add(id(r))
+
+    def gen_trig_group(self, recs):
+        n = recs[0]["n"]
+        x = self.opnd(recs[0]["srcs"][0], "ec", n, "f")
+        self.emit(f"  // sincos group: {' '.join(r['op'] for r in recs)} n={n}")
+        asg = []
+        for r in recs:
+            ex = {"SIN": "sn_", "COS": "cs_", "TAN": "(sn_ / cs_)"}[r["op"]]
+            asg.append(f"{self.var(r['dst'])} = {ex};")
+        self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; float sn_, cs_; "
+                  f"sincosf({x}, &sn_, &cs_); " + " ".join(asg) + " }")
+
+    # ---- global-memory addressing: one 64-bit base per buffer per step, 32-bit offsets ----
+    def gbase(self, buf: int, kind: str, tstep: bool) -> str:
+        """Name of the (per list, per step) base pointer of a global buffer.
+        kind: 'b' per-rollout [W][B] blocks, 'u' uniform rows, 'g' gradient partial rows."""
+        name = f"gp{buf}"
+        if buf not in self.bases:
+            tt = "t" if tstep else "0ll"
+            if kind == "b":
+                ex = f"{tt} * K.W[{buf}] * (long long)K.B"
+            elif kind == "u":
+                ex = f"{tt} * K.W[{buf}]"
+            else:
+                ex = f"(gwarp * (long long)K.T + {tt}) * K.W[{buf}]"
+            self.bases[buf] = f"  uint32_t* const {name} = (uint32_t*)K.buf[{buf}] + {ex};"
+        return name
+
+    def lane_off(self, n: int) -> str:
+        """b0*n + q*n + le for an n-element per-rollout value (hoisted out of the step loop)."""
+        self.lane_offs.add(n)
+        return f"lo{n}"
+
+    def tables(self, rec):
+        img = self.p.meta["const_image"]
+        n = rec["n"]
+        if rec["op"] == "RPRODX":
+            return None, None
+        ptr = img[rec["aux0"]: rec["aux0"] + n + 1].astype(np.int64)
+        idx = img[rec["aux1"]: rec["aux1"] + int(ptr[-1])].astype(np.int64)
+        return ptr, idx
+
     # ---- one instruction ----------------------------------------------------------------------
     def gen_ins(self, rec):
         op, n, L = rec["op"], rec["n"], self.L
@@ -177,6 +239,10 @@ class _Gen:
         self.emit(f"  // {op} n={n}")
         if op == "NOP":
             return
+        if id(rec) in self.trig_skip:
+            return
+        if id(rec) in self.trig_lead:
+            return self.gen_trig_group(self.trig_lead[id(rec)])
         if op in ("LDB", "STB", "LDU", "STG", "STERR", "ERRCHK", "QSUM"):
             return self.gen_special(rec)
         if op in _RED or op in ("RARGMAX", "RARGMIN", "RPRODX"):
@@ -247,6 +313,8 @@ class _Gen:
         guard_q = "q == 0u" if uni else f"q < {self.rpw}u"
         qs_d = f" + q * {dst['sq']}u" if dst["sq"] else ""
         src_reg = self.is_reg(src)
+        if op in _RED and src_reg and n <= L and self.gen_reduce_static(rec):
+            return
         if op in _RED:
             ct, init, upd = _RED[op]
             tin = "f" if ct == "float" else "i"
@@ -322,6 +390,61 @@ class _Gen:
                       f"R[{dst['base']}u{qs_d} + e] = {self.to_bits('acc', out_c)}; }}")
             self.emit("  __syncwarp();")
 
+    def gen_reduce_static(self, rec) -> bool:
+        """Register-resident segment reduction with the CSR tables resolved at generation
+        time: one shuffle per member, in the reference's (left-to-right) member order; lane
+        indices that are the same for every element, or a fixed shift of the element index,
+        cost no table load at all."""
+        op, n, L = rec["op"], rec["n"], self.L
+        dst, src = rec["dst"], rec["srcs"][0]
+        ptr, idx = self.tables(rec)
+        deg = np.diff(ptr)
+        kmax = int(deg.max()) if len(deg) else 0
+        if kmax > 64:
+            return False
+        ct, init, upd = _RED[op]
+        tin = "f" if ct == "float" else "i"
+        base = "0u" if src["uniform"] else "qL"
+        conv = (self.dtype[src["id"]] == "f") != (tin == "f")
+        need_dyn = False
+        body = [f"{ct} acc = {init};"]
+        for k in range(kmax):
+            valid = deg > k
+            tab = np.array([idx[ptr[e] + k] if valid[e] else -1 for e in range(n)])
+            tv = tab[valid]
+            if np.all(tv == tv[0]):
+                lane = f"{base} + {int(tv[0])}u"
+            elif np.all(tv - np.arange(n)[valid] == tv[0] - np.arange(n)[valid][0]):
+                sh = int(tv[0] - np.arange(n)[valid][0])
+                lane = f"(uint32_t)((int)({base} + ec) + ({sh}))"
+            else:
+                need_dyn = True
+                lane = f"{base} + (({k}u < dg_) ? C[{rec['aux1']}u + j0_ + {k}u] : 0u)"
+            ex = f"__shfl_sync(0xffffffffu, {self.var(src)}, {lane})"
+            if conv:
+                ex = (f"__uint_as_float((uint32_t)({ex}))" if tin == "f"
+                      else f"(int)__float_as_uint({ex})")
+            if np.all(valid):
+                body.append(f"{{ const {ct} t = {ex}; {upd}; }}")
+            else:
+                need_dyn = True
+                body.append(f"{{ const {ct} t = {ex}; if ({k}u < dg_) {{ {upd}; }} }}")
+        pre = f"const uint32_t ec = le < {n}u ? le : 0u; "
+        if need_dyn:
+            pre += (f"const uint32_t j0_ = C[{rec['aux0']}u + ec]; "
+                    f"const uint32_t dg_ = C[{rec['aux0']}u + ec + 1u] - j0_; ")
+        code = pre + " ".join(body)
+        out_c = "f" if ct == "float" else "i"
+        if self.is_reg(dst):
+            self.emit(f"  {{ {code} {self.var(dst)} = acc; }}")
+        else:
+            guard_q = "q == 0u" if dst["uniform"] else f"q < {self.rpw}u"
+            qs_d = f" + q * {dst['sq']}u" if dst["sq"] else ""
+            self.emit(f"  {{ {code} if ({guard_q} && le < {n}u) "
+                      f"R[{dst['base']}u{qs_d} + le] = {self.to_bits('acc', out_c)}; }}")
+            self.emit("  __syncwarp();")
+        return True
+
     # ---- memory / cross-rollout / error instructions ------------------------------------------------
     def gen_special(self, rec):
         op, n, L, rpw = rec["op"], rec["n"], self.L, self.rpw
@@ -330,7 +453,16 @@ class _Gen:
         tt = "t" if rec["flags"] & isa.F_TSTEP else "0ll"
         if op == "QSUM":
             src = srcs[0]
-            if self.is_reg(src):
+            if self.is_reg(src) and rpw * L == 32 and (rpw & (rpw - 1)) == 0:
+                # full warps: xor-butterfly over the rollouts of the warp (log2(rpw) shuffles);
+                # the ragged last warp keeps the sequential sum over its valid rollouts
+                fly = " ".join(f"acc += __shfl_xor_sync(0xffffffffu, acc, {o}u);"
+                               for o in [L << i for i in range(rpw.bit_length() - 1)])
+                code = (f"float acc = {self.var(src)}; if (nvalid == {rpw}u) {{ {fly} }} else {{ "
+                        f"const float mine = acc; acc = 0.f; for (uint32_t qq = 0; qq < {rpw}u; ++qq) {{ "
+                        f"const float tq = __shfl_sync(0xffffffffu, mine, qq * {L}u + le); "
+                        f"if (qq < nvalid) acc += tq; }} }}")
+            elif self.is_reg(src):
                 code = (f"float acc = 0.f; for (uint32_t qq = 0; qq < {rpw}u; ++qq) {{ "
                         f"const float tq = __shfl_sync(0xffffffffu, {self.var(src)}, qq * {L}u + le); "
                         f"if (qq < nvalid) acc += tq; }}")
@@ -343,60 +475,59 @@ class _Gen:
                 self.emit(f"  {{ {code} if (q == 0u && le < {n}u) R[{dst['base']}u + le] = __float_as_uint(acc); }}")
                 self.emit("  __syncwarp();")
             return
+        tstep = bool(rec["flags"] & isa.F_TSTEP)
         if op == "LDB":
-            g = f"((const uint32_t*)K.buf[{buf}])"
-            addr = f"({tt} * K.W[{buf}] + {off}ll) * (long long)K.B + b0 * {n}ll"
+            gp = self.gbase(buf, "b", tstep)
+            idx = f"{off}u * Bu + {self.lane_off(n)}"
             if self.is_reg(dst):
                 dt = self.dtype[dst["id"]]
-                self.emit(f"  {self.var(dst)} = (K.buf[{buf}] != nullptr && q < nvalid && le < {n}u) ? "
-                          f"{self.from_bits(f'{g}[{addr} + q * {n}u + le]', dt)} : ({self.ctype(dt)})0;")
+                self.emit(f"  {self.var(dst)} = (has{buf} && q < nvalid && le < {n}u) ? "
+                          f"{self.from_bits(f'{gp}[{idx}]', dt)} : ({self.ctype(dt)})0;")
             else:
-                self.emit(f"  if (K.buf[{buf}] != nullptr) {{ const uint32_t* src_ = {g} + {addr}; "
+                self.emit(f"  if (has{buf}) {{ const uint32_t* src_ = {gp} + {off}u * Bu + b0u * {n}u; "
                           f"for (uint32_t i = lane; i < nvalid * {n}u; i += 32u) R[{dst['base']}u + i] = src_[i]; }}")
                 self.emit("  __syncwarp();")
             return
         if op == "STB":
             src = srcs[0]
-            g = f"((uint32_t*)K.buf[{buf}])"
-            addr = f"({tt} * K.W[{buf}] + {off}ll) * (long long)K.B + b0 * {n}ll"
+            gp = self.gbase(buf, "b", tstep)
             if n <= L:
                 dt = src["dtype"] if src["kind"] != "val" else self.dtype[src["id"]]
                 dtc = "f" if dt == "f" else "i"
                 val = self.opnd(src, "ec", n, dtc)
-                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const {self.ctype(dtc)} sv = {val}; if (K.buf[{buf}] != nullptr && q < nvalid && le < {n}u) "
-                          f"{g}[{addr} + q * {n}u + le] = {self.to_bits('sv', dtc)}; }}")
+                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const {self.ctype(dtc)} sv = {val}; "
+                          f"if (has{buf} && q < nvalid && le < {n}u) "
+                          f"{gp}[{off}u * Bu + {self.lane_off(n)}] = {self.to_bits('sv', dtc)}; }}")
             elif src["kind"] == "val" and src["map"] == isa.MAP_IDENT and src["sq"] == n:
-                self.emit(f"  if (K.buf[{buf}] != nullptr) {{ uint32_t* dst_ = {g} + {addr}; "
+                self.emit(f"  if (has{buf}) {{ uint32_t* dst_ = {gp} + {off}u * Bu + b0u * {n}u; "
                           f"for (uint32_t i = lane; i < nvalid * {n}u; i += 32u) dst_[i] = R[{src['base']}u + i]; }}")
             else:
                 val = self.opnd(src, "e", n, "i")
-                self.emit(f"  if (K.buf[{buf}] != nullptr && q < nvalid) for (uint32_t e = le; e < {n}u; e += {L}u) "
-                          f"{g}[{addr} + q * {n}u + e] = (uint32_t)({val});")
+                self.emit(f"  if (has{buf} && q < nvalid) for (uint32_t e = le; e < {n}u; e += {L}u) "
+                          f"{gp}[{off}u * Bu + b0u * {n}u + q * {n}u + e] = (uint32_t)({val});")
             return
         if op == "LDU":
-            g = f"((const uint32_t*)K.buf[{buf}])"
-            addr = f"{tt} * K.W[{buf}] + {off}ll"
+            gp = self.gbase(buf, "u", tstep)
             if self.is_reg(dst):
                 dt = self.dtype[dst["id"]]
-                self.emit(f"  {self.var(dst)} = (K.buf[{buf}] != nullptr && le < {n}u) ? "
-                          f"{self.from_bits(f'__ldg({g} + {addr} + le)', dt)} : ({self.ctype(dt)})0;")
+                self.emit(f"  {self.var(dst)} = (has{buf} && le < {n}u) ? "
+                          f"{self.from_bits(f'__ldg({gp} + {off}u + le)', dt)} : ({self.ctype(dt)})0;")
             else:
-                self.emit(f"  if (K.buf[{buf}] != nullptr) for (uint32_t i = lane; i < {n}u; i += 32u) "
-                          f"R[{dst['base']}u + i] = __ldg({g} + {addr} + i);")
+                self.emit(f"  if (has{buf}) for (uint32_t i = lane; i < {n}u; i += 32u) "
+                          f"R[{dst['base']}u + i] = __ldg({gp} + {off}u + i);")
                 self.emit("  __syncwarp();")
             return
         if op == "STG":
             src = srcs[0]
-            g = f"((uint32_t*)K.buf[{buf}])"
-            addr = f"(gwarp * (long long)K.T + t) * K.W[{buf}] + {off}ll"
+            gp = self.gbase(buf, "g", tstep)
             if n <= L:
                 val = self.opnd(src, "ec", n, "f")
-                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const float sv = {val}; if (K.buf[{buf}] != nullptr && q == 0u && le < {n}u) "
-                          f"{g}[{addr} + le] = __float_as_uint(sv); }}")
+                self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const float sv = {val}; "
+                          f"if (has{buf} && q == 0u && le < {n}u) {gp}[{off}u + le] = __float_as_uint(sv); }}")
             else:
                 val = self.opnd(src, "e", n, "f")
-                self.emit(f"  if (K.buf[{buf}] != nullptr && q == 0u) for (uint32_t e = le; e < {n}u; e += {L}u) "
-                          f"{g}[{addr} + e] = __float_as_uint({val});")
+                self.emit(f"  if (has{buf} && q == 0u) for (uint32_t e = le; e < {n}u; e += {L}u) "
+                          f"{gp}[{off}u + e] = __float_as_uint({val});")
             return
         if op == "ERRCHK":
             src = srcs[0]
@@ -412,8 +543,9 @@ class _Gen:
             self.emit("  __syncwarp();")
             return
         if op == "STERR":
-            self.emit(f"  if (lane < nvalid) {{ if (K.buf[{buf}] != nullptr) ((uint32_t*)K.buf[{buf}])"
-                      f"[t * (long long)K.B + b0 + lane] = R[{self.err_base}u + lane] | {self.p.static_err}u; "
+            gp = self.gbase(buf, "b", bool(rec["flags"] & isa.F_TSTEP))
+            self.emit(f"  if (lane < nvalid) {{ if (has{buf}) {gp}[b0u + lane] = "
+                      f"R[{self.err_base}u + lane] | {self.p.static_err}u; "
                       f"R[{self.err_base}u + lane] = 0u; }}")
             self.emit("  __syncwarp();")
             return
@@ -433,11 +565,18 @@ class _Gen:
         lists = [self.ins[:self.n_pro], self.ins[self.n_pro:self.n_pro + self.n_step],
                  self.ins[self.n_pro + self.n_step:]]
         bodies = []
+        self.lane_offs = set()
         for lst in lists:
             self.lines = []
+            self.bases: Dict[int, str] = {}
+            self.plan_trig(lst)
             for rec in lst:
                 self.gen_ins(rec)
-            bodies.append("\n".join(self.lines))
+            bodies.append("\n".join(list(self.bases.values()) + self.lines))
+        hoist = [f"  const bool has{b} = K.buf[{b}] != nullptr; (void)has{b};"
+                 for b in range(len(isa.BUFFERS))]
+        hoist += [f"  const uint32_t lo{n} = b0u * {n}u + q * {n}u + le; (void)lo{n};"
+                  for n in sorted(self.lane_offs)]
         backward = p.kind == "backward"
         loop = "for (long long t = (long long)K.T - 1; t >= 0; --t)" if backward else \
             "for (long long t = 0; t < (long long)K.T; ++t)"
@@ -468,7 +607,9 @@ extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
   uint32_t* R = smem + {p.const_words}u + warp * {p.warp_words}u;
   for (uint32_t i = lane; i < {p.rpw}u; i += 32u) R[{self.err_base}u + i] = 0u;
   __syncwarp();
-  (void)qL; (void)qc; (void)le; (void)nvalid; (void)gwarp;
+  const uint32_t Bu = (uint32_t)K.B, b0u = (uint32_t)b0;   // host checks W*B < 2^31
+  (void)qL; (void)qc; (void)le; (void)nvalid; (void)gwarp; (void)Bu; (void)b0u;
+{chr(10).join(hoist)}
 {chr(10).join(decl)}
   {{ const long long t = 0; (void)t;
 {bodies[0]}

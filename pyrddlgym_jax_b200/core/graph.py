@@ -99,6 +99,20 @@ class Graph:
     def __init__(self):
         self.nodes: List[V] = []
         self._consts: Dict[Tuple, V] = {}
+        self._cse: Dict[Tuple, V] = {}      # value numbering: identical pure ops share a value
+
+    @staticmethod
+    def _map_key(m: Map):
+        if m is None or isinstance(m, str):
+            return m
+        return np.asarray(m, dtype=np.int64).tobytes()
+
+    def _numbered(self, key: Tuple, make) -> V:
+        v = self._cse.get(key)
+        if v is None:
+            v = self.add(make())
+            self._cse[key] = v
+        return v
 
     def add(self, v: V) -> V:
         self.nodes.append(v)
@@ -132,20 +146,62 @@ class Graph:
                 with np.errstate(all="ignore"):
                     return self.const(np.asarray(fn(*vals)).astype(NP_DT[dtype]), dtype)
         uniform = all(a.uniform for a, _ in args)
-        return self.add(V(name, args, n=n, dtype=dtype, uniform=uniform, attrs=attrs))
+        simp = self._simplify(name, args, n, dtype)
+        if simp is not None:
+            return simp
+        if attrs:
+            return self.add(V(name, args, n=n, dtype=dtype, uniform=uniform, attrs=attrs))
+        key = (name, dtype, n, tuple((a.id, self._map_key(m)) for a, m in args))
+        return self._numbered(key, lambda: V(name, args, n=n, dtype=dtype, uniform=uniform))
+
+    def _simplify(self, name: str, args, n: int, dtype: str) -> Optional[V]:
+        """Value-preserving rewrites (bit-identical results, so parity is unaffected):
+        pow(x, 2) -> x*x, pow(x, 1) -> x (what XLA's algebraic simplifier and torch.pow do
+        as well), x*1 -> x, x/1 -> x, x-0 -> x, -(-x) -> x."""
+        def scalar_const(a: V):
+            if a.const is None or a.const.size == 0:
+                return None
+            c = a.const
+            return float(c[0]) if np.all(c == c[0]) else None
+
+        def same_space(a: V, m: Map) -> bool:
+            return m is None and a.n == n and a.dtype == dtype
+
+        if name == "POW" and dtype == "f" and args[0][0].dtype == "f":
+            y = scalar_const(args[1][0])
+            if y == 2.0:
+                return self.op("SQUARE", [args[0]], n)
+            if y == 1.0 and same_space(*args[0]):
+                return args[0][0]
+        if name in ("MUL", "DIV") and dtype == "f":
+            if scalar_const(args[1][0]) == 1.0 and same_space(*args[0]):
+                return args[0][0]
+            if name == "MUL" and scalar_const(args[0][0]) == 1.0 and same_space(*args[1]):
+                return args[1][0]
+        if name == "SUB" and dtype == "f":
+            y = scalar_const(args[1][0])
+            if y == 0.0 and not np.signbit(args[1][0].const[0]) and same_space(*args[0]):
+                return args[0][0]
+        if name == "NEG" and args[0][0].op == "NEG" and same_space(*args[0]) \
+                and same_space(*args[0][0].args[0]):
+            return args[0][0].args[0][0]
+        return None
 
     def sg(self, a: V) -> V:
         """stop_gradient: aliases the operand's storage, blocks differentiation."""
         if a.const is not None:
             return a
-        return self.add(V("sg", [(a, None)], n=a.n, dtype=a.dtype, uniform=a.uniform))
+        return self._numbered(("sg", a.id), lambda: V("sg", [(a, None)], n=a.n, dtype=a.dtype,
+                                                      uniform=a.uniform))
 
     def reduce(self, name: str, a: V, ptr: np.ndarray, idx: np.ndarray,
                dtype: Optional[str] = None) -> V:
         n = len(ptr) - 1
-        return self.add(V(name, [(a, None)], n=n, dtype=dtype or OUT_DTYPE.get(name, "f"),
-                          uniform=a.uniform,
-                          attrs={"ptr": np.asarray(ptr, np.int64), "idx": np.asarray(idx, np.int64)}))
+        ptr, idx = np.asarray(ptr, np.int64), np.asarray(idx, np.int64)
+        dtype = dtype or OUT_DTYPE.get(name, "f")
+        key = (name, dtype, a.id, ptr.tobytes(), idx.tobytes())
+        return self._numbered(key, lambda: V(name, [(a, None)], n=n, dtype=dtype,
+                                             uniform=a.uniform, attrs={"ptr": ptr, "idx": idx}))
 
 
 # =====================================================================================

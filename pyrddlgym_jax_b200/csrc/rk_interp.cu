@@ -542,6 +542,9 @@ static int launch(const rk_program* p, cudaStream_t st, RkLaunch& K) {
   const int nwarps = (K.B + K.rpw - 1) / K.rpw;
   const int grid = (nwarps + p->warps_per_cta - 1) / p->warps_per_cta;
   if (p->func != nullptr) {                      // per-program specialised kernel
+    // generated kernels index one step's [W][B] block with 32-bit word offsets
+    for (int i = 0; i < RK_NUM_BUFFERS; ++i)
+      if (K.W[i] * (long long)K.B >= (1ll << 31)) return RK_E_BADARG;
     void* args[] = {(void*)&K};
     return g_drv.launchKernel(p->func, (unsigned)grid, 1, 1, (unsigned)(p->warps_per_cta * 32), 1,
                               1, (unsigned)p->smem_bytes, (void*)st, args, nullptr);
