@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 4
+CODEGEN_VERSION = 6
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -147,9 +147,18 @@ class _Gen:
                 if want_c == "f":
                     return _flit(float(c[0]))
                 return f"({int(c[0])})"
+            if e == "ec" and n_r <= self.L:
+                # loop-invariant per-lane word of the constant region: read it once, before
+                # the step loop (the compiler cannot hoist it past the shared-memory stores)
+                name = f"hc{v['base']}_{mp}_{n_r}"
+                self.hoisted[name] = (f"  const uint32_t {name} = C[{v['base']}u + "
+                                      f"{self.map_index(v, f'(le < {n_r}u ? le : 0u)', n_r)}];")
+                return self.from_bits(name, want_c)
             return self.from_bits(f"C[{v['base']}u + {self.map_index(v, e, n_r)}]", want_c)
         if v["kind"] == "mparam":
-            return self.from_bits(f"C[{v['base']}u]", want_c)
+            name = f"hm{v['base']}"
+            self.hoisted[name] = f"  const uint32_t {name} = C[{v['base']}u];"
+            return self.from_bits(name, want_c)
         if self.is_reg(v):
             name = self.var(v)
             src_c = "f" if self.dtype[v["id"]] == "f" else "i"
@@ -203,10 +212,17 @@ class _Gen:
                   f"sincosf({x}, &sn_, &cs_); " + " ".join(asg) + " }")
 
     # ---- global-memory addressing: one 64-bit base per buffer per step, 32-bit offsets ----
-    def gbase(self, buf: int, kind: str, tstep: bool) -> str:
+    def gbase(self, buf: int, kind: str, tstep: bool, nxt: bool = False) -> str:
         """Name of the (per list, per step) base pointer of a global buffer.
-        kind: 'b' per-rollout [W][B] blocks, 'u' uniform rows, 'g' gradient partial rows."""
-        name = f"gp{buf}"
+        kind: 'b' per-rollout [W][B] blocks, 'u' uniform rows, 'g' gradient partial rows.
+        nxt: the base for the step after this one (software prefetch of per-step loads)."""
+        name = f"gn{buf}" if nxt else f"gp{buf}"
+        if nxt:
+            if buf not in self.next_bases:
+                ex = "tn * K.W[%d] * (long long)K.B" % buf if kind == "b" else "tn * K.W[%d]" % buf
+                self.next_bases[buf] = (f"  const uint32_t* const {name} = "
+                                        f"(const uint32_t*)K.buf[{buf}] + {ex};")
+            return name
         if buf not in self.bases:
             tt = "t" if tstep else "0ll"
             if kind == "b":
@@ -476,6 +492,24 @@ class _Gen:
                 self.emit("  __syncwarp();")
             return
         tstep = bool(rec["flags"] & isa.F_TSTEP)
+        if op in ("LDB", "LDU") and tstep and self.in_step and self.is_reg(dst) and n <= L:
+            # software prefetch: this step consumes what the previous step loaded and issues
+            # the load for the next step, so the L2 / HBM latency overlaps a whole step
+            dt = self.dtype[dst["id"]]
+            if op == "LDB":
+                gn = self.gbase(buf, "b", True, nxt=True)
+                ld = self.from_bits(f"{gn}[{off}u * Bu + {self.lane_off(n)}]", dt)
+                cond = f"has{buf} && q < nvalid && le < {n}u"
+            else:
+                gn = self.gbase(buf, "u", True, nxt=True)
+                ld = self.from_bits(f"__ldg({gn} + {off}u + le)", dt)
+                cond = f"has{buf} && le < {n}u"
+            pf = f"pf{dst['id']}"
+            self.pf_decl.append(f"  {self.ctype(dt)} {pf} = ({self.ctype(dt)})0;")
+            stmt = f"{pf} = (more && {cond}) ? {ld} : ({self.ctype(dt)})0;"
+            self.pf_stmts.append("    " + stmt)
+            self.emit(f"  {self.var(dst)} = {pf}; {stmt}")
+            return
         if op == "LDB":
             gp = self.gbase(buf, "b", tstep)
             idx = f"{off}u * Bu + {self.lane_off(n)}"
@@ -566,18 +600,32 @@ class _Gen:
                  self.ins[self.n_pro + self.n_step:]]
         bodies = []
         self.lane_offs = set()
-        for lst in lists:
+        self.pf_decl, self.pf_stmts = [], []
+        self.hoisted: Dict[str, str] = {}
+        self.next_bases: Dict[int, str] = {}
+        backward = p.kind == "backward"
+        for li, lst in enumerate(lists):
             self.lines = []
             self.bases: Dict[int, str] = {}
+            self.in_step = li == 1
             self.plan_trig(lst)
             for rec in lst:
                 self.gen_ins(rec)
-            bodies.append("\n".join(list(self.bases.values()) + self.lines))
+            head = list(self.bases.values())
+            if li == 1 and self.pf_stmts:
+                head = [f"  const long long tn = t {'-' if backward else '+'} 1; "
+                        f"const bool more = tn >= 0 && tn < (long long)K.T;"] \
+                    + list(self.next_bases.values()) + head
+            bodies.append("\n".join(head + self.lines))
+        prefetch0 = ""
+        if self.pf_stmts:
+            t0 = "(long long)K.T - 1" if backward else "0ll"
+            prefetch0 = ("  { const long long tn = " + t0 + "; const bool more = K.T > 0;\n"
+                         + "\n".join(list(self.next_bases.values()) + self.pf_stmts) + "\n  }")
         hoist = [f"  const bool has{b} = K.buf[{b}] != nullptr; (void)has{b};"
                  for b in range(len(isa.BUFFERS))]
         hoist += [f"  const uint32_t lo{n} = b0u * {n}u + q * {n}u + le; (void)lo{n};"
                   for n in sorted(self.lane_offs)]
-        backward = p.kind == "backward"
         loop = "for (long long t = (long long)K.T - 1; t >= 0; --t)" if backward else \
             "for (long long t = 0; t < (long long)K.T; ++t)"
         src = f"""// GENERATED by pyrddlgym_jax_b200/core/codegen.py (version {CODEGEN_VERSION}) -- do not edit.
@@ -610,10 +658,13 @@ extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
   const uint32_t Bu = (uint32_t)K.B, b0u = (uint32_t)b0;   // host checks W*B < 2^31
   (void)qL; (void)qc; (void)le; (void)nvalid; (void)gwarp; (void)Bu; (void)b0u;
 {chr(10).join(hoist)}
+{chr(10).join(self.hoisted.values())}
 {chr(10).join(decl)}
+{chr(10).join(self.pf_decl)}
   {{ const long long t = 0; (void)t;
 {bodies[0]}
   }}
+{prefetch0}
   {loop} {{
 {bodies[1]}
   }}
@@ -629,8 +680,13 @@ def generate_source(prog: Program) -> str:
     return _Gen(prog).source()
 
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-fmad=false", "-cubin"]
+def nvcc_flags() -> List[str]:
+    """-fmad=false by default: every RDDL multiply and add rounds separately, like the oracle
+    and like un-fused XLA code.  RK_FMAD=1 lets ptxas contract a*b+c into FMAs (fewer
+    instructions, results differ in the last bits but stay inside the parity tolerances)."""
+    fmad = "true" if os.environ.get("RK_FMAD", "0") == "1" else "false"
+    return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            f"-fmad={fmad}", "-cubin"]
 
 
 def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:
@@ -640,14 +696,15 @@ def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:
     for h in ("rk_launch.h", "rk_device.cuh", "rk_isa.h"):
         with open(os.path.join(CSRC, h), "rb") as f:
             deps += f.read()
-    key = hashlib.sha1(src.encode() + deps + " ".join(NVCC_FLAGS).encode()).hexdigest()[:16]
+    flags = nvcc_flags()
+    key = hashlib.sha1(src.encode() + deps + " ".join(flags).encode()).hexdigest()[:16]
     os.makedirs(JIT_DIR, exist_ok=True)
     cu = os.path.join(JIT_DIR, f"rk_{key}.cu")
     cubin = os.path.join(JIT_DIR, f"rk_{key}.cubin")
     if not os.path.exists(cubin):
         with open(cu, "w") as f:
             f.write(src)
-        cmd = [os.environ.get("NVCC", "nvcc"), *NVCC_FLAGS, "-I", CSRC,
+        cmd = [os.environ.get("NVCC", "nvcc"), *flags, "-I", CSRC,
                *(["-Xptxas", "-v"] if verbose else []), cu, "-o", cubin + ".tmp"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

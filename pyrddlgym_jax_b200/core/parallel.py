@@ -1,0 +1,82 @@
+"""Multi-GPU sharding of the rollout batch: one process per GPU, every rank owns a
+contiguous slice of the rollouts, the plan / optimiser state / non-fluents are replicated, and
+the only exchange of the path is one sum all-reduce of the policy gradient (+ the scalar
+losses) per iteration.  The reference has no counterpart: it runs ``jax.vmap`` over the batch
+on one device (compiler.py:575-577) and takes the batch mean inside ``value_and_grad``
+(planner.py:2817-2818, 2873).
+
+Everything here is backend-agnostic torch.distributed (NCCL on the GPUs, gloo in the CPU
+tests); it never touches rollout data -- there is no data-path collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the default process group, (0, 1) when there is none."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_global: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Rollouts [b0, b1) owned by ``rank``: contiguous, sizes differ by at most one."""
+    base, rem = divmod(n_global, world_size)
+    b0 = rank * base + min(rank, rem)
+    return b0, b0 + base + (1 if rank < rem else 0)
+
+
+def slice_rollouts(flat: torch.Tensor, widths: Sequence[int], B: int, b0: int, b1: int,
+                   lead: int = 1) -> torch.Tensor:
+    """Rows [b0, b1) of every [B, n] block of a fluent-major buffer [lead, sum(n)*B]
+    (state, tape, noise or trajectory layout of include/rk.h)."""
+    flat = flat.reshape(lead, -1)
+    out, off = [], 0
+    for n in widths:
+        blk = flat[:, off * B:(off + n) * B].reshape(lead, B, n)
+        out.append(blk[:, b0:b1].reshape(lead, -1))
+        off += n
+    return torch.cat(out, dim=1).contiguous() if out else flat[:, :0]
+
+
+def mean_cotangent(n_local: int, n_global: int, device=None) -> torch.Tensor:
+    """d(-mean over the GLOBAL batch)/d return_b for the local rollouts (planner.py:2817)."""
+    return torch.full((n_local,), -1.0 / n_global, dtype=torch.float32, device=device)
+
+
+def allreduce_gradient(grad: torch.Tensor) -> torch.Tensor:
+    """The exchange step: grad <- sum over ranks (in place).  Every rank then applies the
+    same optimiser step to its replica, so replicas stay bit-identical without a broadcast."""
+    if world()[1] > 1:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+    return grad
+
+
+def allreduce_losses(local_sums: torch.Tensor) -> torch.Tensor:
+    """Sum of per-rank partial sums of returns (callers divide by the global batch)."""
+    if world()[1] > 1:
+        dist.all_reduce(local_sums, op=dist.ReduceOp.SUM)
+    return local_sums
+
+
+def allreduce_error_bits(err: torch.Tensor) -> torch.Tensor:
+    """Bitwise OR over ranks of the per-step error masks (log['error'], compiler.py:539)."""
+    if world()[1] > 1:
+        dist.all_reduce(err, op=dist.ReduceOp.BOR)
+    return err
+
+
+def replicas_identical(t: torch.Tensor) -> bool:
+    """True when every rank holds bit-identical ``t`` (debug check of the replication)."""
+    rank, ws = world()
+    if ws == 1:
+        return True
+    ref = t.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([int(torch.equal(ref, t))], device=t.device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return bool(same.item())

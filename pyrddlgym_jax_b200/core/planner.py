@@ -27,7 +27,7 @@ from typing import Any, Callable, Dict, Iterable, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import engine, logic
+from . import engine, logic, parallel
 from .compiler import JaxRDDLCompiler
 from .layout import draw_noise, pack_fluent_major, unpack_fluent_major
 from .program import PlanSpec, action_layout
@@ -418,10 +418,7 @@ class JaxBackpropPlanner:
                                    f"cuda:{torch.cuda.current_device()}")
         # multi-GPU: every rank owns batch_size_train rollouts; the plan is replicated and
         # the gradient is sum-all-reduced once per iteration
-        import torch.distributed as dist
-        self._dist = dist
-        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank() if self.world_size > 1 else 0
+        self.rank, self.world_size = parallel.world()
         self._compile()
 
     # ---------------------------------------------------------------------------------
@@ -552,7 +549,7 @@ class JaxBackpropPlanner:
                                 mparams=self.train_mparams, disc=self.disc, gradp=self.gradp)
         engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
         if self.world_size > 1:      # the one exchange step of the path
-            self._dist.all_reduce(self.grad[p])
+            parallel.allreduce_gradient(self.grad[p])
         engine.optimizer_step(self.optimizer_name, self.hyper, T * A, params, self.opt_state[p],
                               self.grad[p], self.box_lo, self.box_hi, self.zero_flag[p:p + 1])
 
@@ -575,7 +572,7 @@ class JaxBackpropPlanner:
         if self.world_size > 1:
             self.loss_pair[0].copy_(self.train_loss)
             self.loss_pair[1].copy_(self.test_loss_buf)
-            self._dist.all_reduce(self.loss_pair)
+            parallel.allreduce_losses(self.loss_pair)
 
     def _capture(self):
         """Capture one full iteration into a CUDA graph (after a warm-up on a side stream)."""
