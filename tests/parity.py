@@ -87,7 +87,7 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
 
 
 def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None,
-                 param_scale=0.5, **ckw):
+                 param_scale=0.5, given=None, **ckw):
     """Run program + oracle on the same inputs; returns everything a test wants to compare."""
     m = fixture_model(key)
     if relaxed:
@@ -99,6 +99,9 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     fwd = builder.forward(write_tape=relaxed, gamma=gamma)
     params = make_params(m, key, T, scale=param_scale)
     noise = draw_noise(fwd.noise_layout, T, B, torch.Generator().manual_seed(seed))
+    if given is not None:        # committed golden inputs (tests/golden/*.npz)
+        params = {k: torch.from_numpy(np.array(given["param_" + k])) for k in params}
+        noise = torch.from_numpy(np.array(given["noise"])).reshape(noise.shape)
     s0 = initial_state(m, fwd.state_layout, B)
     disc = None if gamma == 1.0 else torch.pow(torch.tensor(gamma), torch.arange(T)).float()
     got = run_forward(backend, fwd, B, T, s0, pack_params(m, params), noise, disc)
@@ -119,9 +122,10 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
                 s0=s0, disc=disc, got=got, ref=ref, final=final, gamma=gamma)
 
 
-def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, **ckw):
+def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, given=None,
+                  **ckw):
     c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
-                     param_scale=param_scale, **ckw)
+                     param_scale=param_scale, given=given, **ckw)
     m = c["model"]
     bwd = c["builder"].backward(gamma=gamma)
     gret = torch.full((B,), -1.0 / B)

@@ -1,0 +1,274 @@
+"""Known-answer tests that pin the CPU oracle to the reference's closed forms.
+
+Each case evaluates one RDDL expression through oracle/model_eval.py and compares value and
+gradient with the formula written in the reference source (file:line in each case; SURVEY
+Appendix A), computed independently here in float64 numpy.  These are what stands between the
+oracle and the real reference, which cannot be executed offline."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.model_eval import OracleModel
+from pyrddlgym_jax_b200.core import logic
+from pyrddlgym_jax_b200.rddl.model import load_model
+
+TEMPLATE = """
+domain kat {{
+    types {{ obj : object; }};
+    pvariables {{
+        C(obj) : {{ non-fluent, real, default = 0.5 }};
+        x(obj) : {{ state-fluent, real, default = 0.0 }};
+        y(obj) : {{ state-fluent, real, default = 0.0 }};
+        a(obj) : {{ action-fluent, real, default = 0.0 }};
+    }};
+    cpfs {{
+        x'(?o) = {expr};
+        y'(?o) = y(?o);
+    }};
+    reward = sum_{{?o : obj}} [ x'(?o) ];
+}}
+non-fluents nf {{ domain = kat; objects {{ obj : {{o1, o2, o3, o4}}; }}; non-fluents {{ C(o2) = 1.5; }}; }}
+instance inst {{ domain = kat; non-fluents = nf; init-state {{ x(o1) = 0.0; }}; max-nondef-actions = pos-inf; horizon = 3; discount = 1.0; }}
+"""
+
+X = np.array([[0.3, -1.2, 2.5, 0.51], [1.7, 0.49, -0.2, 3.9]])
+Y = np.array([[0.1, 0.4, 2.6, -0.3], [1.7, -2.0, 0.8, 4.4]])
+U = np.array([[0.2, 0.9, 0.55, 0.4], [0.7, 0.1, 0.3, 0.95]])
+
+
+def sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def evaluate(expr, relax_kw=None, cls=logic.DefaultJaxRDDLCompilerWithGrad, noise=None,
+             exact=False):
+    """-> (value [B,4], dvalue/dx [B,4], dvalue/dy [B,4]) of x' for one step."""
+    m = load_model(TEMPLATE.format(expr=expr))
+    relax = None if exact else cls(m, **(relax_kw or {})).relax_config()
+    om = OracleModel(m, relax)
+    B = X.shape[0]
+    fls, nfls = om.init_fls_nfls(B)
+    x = torch.tensor(X, dtype=torch.float32, requires_grad=True)
+    y = torch.tensor(Y, dtype=torch.float32, requires_grad=True)
+    fls = dict(fls)
+    fls["x"], fls["y"] = x, y
+    act = {"a": torch.zeros(B, 4)}
+    out, _, err, _ = om.step(fls, nfls, act, noise, B)
+    v = out["x"]
+    if exact or not v.requires_grad:
+        return v.detach().numpy(), None, None
+    gx, gy = torch.autograd.grad(v.sum(), [x, y], allow_unused=True)
+    z = lambda g: np.zeros_like(X) if g is None else g.numpy()   # noqa: E731
+    return v.detach().numpy(), z(gx), z(gy)
+
+
+W = 3.0
+CASES = [
+    # expr, soft value f(x,y), d/dx, d/dy, hard value, kwargs (weight), STE flag name
+    ("x(?o) > y(?o)", lambda x, y: sigmoid(W * (x - y)),                      # logic.py:269-272
+     lambda x, y: W * sigmoid(W * (x - y)) * (1 - sigmoid(W * (x - y))),
+     lambda x, y: -W * sigmoid(W * (x - y)) * (1 - sigmoid(W * (x - y))),
+     lambda x, y: (x > y) * 1.0, {"sigmoid_weight": W}, "use_sigmoid_ste"),
+    ("x(?o) <= y(?o)", lambda x, y: sigmoid(W * (y - x)),                     # logic.py:311-314
+     lambda x, y: -W * sigmoid(W * (y - x)) * (1 - sigmoid(W * (y - x))),
+     lambda x, y: W * sigmoid(W * (y - x)) * (1 - sigmoid(W * (y - x))),
+     lambda x, y: (x <= y) * 1.0, {"sigmoid_weight": W}, "use_sigmoid_ste"),
+    ("x(?o) == y(?o)", lambda x, y: 1 - np.tanh(W * (y - x)) ** 2,            # logic.py:325-328
+     lambda x, y: 2 * np.tanh(W * (y - x)) * (1 - np.tanh(W * (y - x)) ** 2) * W,
+     lambda x, y: -2 * np.tanh(W * (y - x)) * (1 - np.tanh(W * (y - x)) ** 2) * W,
+     lambda x, y: (x == y) * 1.0, {"sigmoid_weight": W}, "use_tanh_ste"),
+    ("sgn[x(?o)]", lambda x, y: np.tanh(W * x),                               # logic.py:353-356
+     lambda x, y: W * (1 - np.tanh(W * x) ** 2), lambda x, y: 0 * x,
+     lambda x, y: np.sign(x), {"sigmoid_weight": W}, "use_tanh_ste"),
+    ("floor[x(?o)]",                                                         # logic.py:801-804, 816
+     lambda x, y: np.floor(x + .5) - 1 + .5 * (1 + np.tanh(W * (x - np.floor(x + .5))) / np.tanh(W / 2)),
+     lambda x, y: .5 * W * (1 - np.tanh(W * (x - np.floor(x + .5))) ** 2) / np.tanh(W / 2),
+     lambda x, y: 0 * x, lambda x, y: np.floor(x), {"floor_weight": W}, "use_floor_ste"),
+    ("ceil[x(?o)]",                                                          # logic.py:827-830
+     lambda x, y: -(np.floor(-x + .5) - 1 + .5 * (1 + np.tanh(W * (-x - np.floor(-x + .5))) / np.tanh(W / 2))),
+     lambda x, y: .5 * W * (1 - np.tanh(W * (-x - np.floor(-x + .5))) ** 2) / np.tanh(W / 2),
+     lambda x, y: 0 * x, lambda x, y: np.ceil(x), {"floor_weight": W}, "use_floor_ste"),
+    ("round[x(?o)]",                                                         # logic.py:880-882, 894
+     lambda x, y: np.floor(x) + .5 + .5 * np.tanh(W * (x - np.floor(x) - .5)) / np.tanh(W / 2),
+     lambda x, y: .5 * W * (1 - np.tanh(W * (x - np.floor(x) - .5)) ** 2) / np.tanh(W / 2),
+     lambda x, y: 0 * x, lambda x, y: np.round(x), {"round_weight": W}, "use_round_ste"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("ste", [False, True])
+def test_relaxed_op_closed_form(case, ste):
+    expr, soft, dx, dy, hard, kw, flag = case
+    v, gx, gy = evaluate(expr, {**kw, flag: ste})
+    want = hard(X, Y) if ste else soft(X, Y)
+    np.testing.assert_allclose(v, want, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(gx, dx(X, Y), rtol=2e-5, atol=2e-6)     # gradient is the soft one
+    np.testing.assert_allclose(gy, dy(X, Y), rtol=2e-5, atol=2e-6)
+
+
+def test_product_tnorm_closed_forms():
+    """logic.py:441, 454, 467, 480, 493, 506 on soft truth values p = (x > 0), q = (y > 0)."""
+    kw = {"sigmoid_weight": 1.0, "use_sigmoid_ste": False}
+    p, q = sigmoid(X), sigmoid(Y)
+    forms = {
+        "~(x(?o) > 0.0)": 1 - p,
+        "(x(?o) > 0.0) ^ (y(?o) > 0.0)": p * q,
+        "(x(?o) > 0.0) | (y(?o) > 0.0)": 1 - (1 - p) * (1 - q),
+        "(x(?o) > 0.0) => (y(?o) > 0.0)": 1 - p * (1 - q),
+        "(x(?o) > 0.0) <=> (y(?o) > 0.0)": (1 - p * (1 - q)) * (1 - q * (1 - p)),
+    }
+    for expr, want in forms.items():
+        v, _, _ = evaluate(expr, kw)
+        np.testing.assert_allclose(v, want, rtol=3e-6, atol=1e-6, err_msg=expr)
+
+
+def test_forall_exists_are_products():
+    """logic.py:521, 534: forall = prod x, exists = 1 - prod (1 - x)."""
+    kw = {"sigmoid_weight": 1.0, "use_sigmoid_ste": False}
+    p = sigmoid(X)
+    v, _, _ = evaluate("forall_{?u : obj} [ x(?u) > 0.0 ]", kw)
+    np.testing.assert_allclose(v, np.repeat(p.prod(1, keepdims=True), 4, 1), rtol=3e-6)
+    v, gx, _ = evaluate("exists_{?u : obj} [ x(?u) > 0.0 ]", kw)
+    np.testing.assert_allclose(v, np.repeat(1 - (1 - p).prod(1, keepdims=True), 4, 1), rtol=3e-6)
+    # d/dx_j of 4 copies of 1 - prod(1 - p_i) = 4 * prod_{i != j}(1 - p_i) * p_j (1 - p_j)
+    others = np.stack([np.delete(1 - p, j, 1).prod(1) for j in range(4)], 1)
+    np.testing.assert_allclose(gx, 4 * others * p * (1 - p), rtol=2e-5)
+
+
+def test_godel_and_lukasiewicz_closed_forms():
+    """logic.py:573-653 (min / max) and logic.py:692-744 (relu forms)."""
+    class Godel(logic.SigmoidRelational, logic.GodelNormLogical):
+        pass
+
+    class Luka(logic.SigmoidRelational, logic.LukasiewiczNormLogical):
+        pass
+    kw = {"sigmoid_weight": 1.0, "use_sigmoid_ste": False}
+    p, q = sigmoid(X), sigmoid(Y)
+    relu = lambda z: np.maximum(z, 0)      # noqa: E731
+    for cls, forms in ((Godel, {"^": np.minimum(p, q), "|": np.maximum(p, q)}),
+                       (Luka, {"^": relu(p + q - 1), "|": 1 - relu(1 - p - q)})):
+        for op, want in forms.items():
+            v, _, _ = evaluate(f"(x(?o) > 0.0) {op} (y(?o) > 0.0)", kw, cls=cls)
+            np.testing.assert_allclose(v, want, rtol=3e-6, atol=1e-6, err_msg=f"{cls.__name__} {op}")
+
+
+@pytest.mark.parametrize("ste", [False, True])
+def test_linear_if_else(ste):
+    """logic.py:933-936: c' = c + sg(1[c > 0.5] - c); value c' a + (1 - c') b."""
+    kw = {"sigmoid_weight": W, "use_sigmoid_ste": False, "use_if_else_ste": ste}
+    v, gx, gy = evaluate("if (x(?o) > 0.0) then y(?o) * 2.0 else -y(?o)", kw)
+    c = sigmoid(W * X)
+    cv = (c > 0.5) * 1.0 if ste else c
+    np.testing.assert_allclose(v, cv * (2 * Y) + (1 - cv) * (-Y), rtol=3e-6, atol=2e-6)
+    np.testing.assert_allclose(gx, W * c * (1 - c) * (2 * Y + Y), rtol=2e-5, atol=1e-5)  # fp32 s(1-s)
+    np.testing.assert_allclose(gy, cv * 2 - (1 - cv), rtol=2e-5, atol=2e-6)
+
+
+def test_exact_if_thresholds_at_half_and_fold_order():
+    """compiler.py:1640 (if = where(pred > 0.5)), compiler.py:1140-1143 (left fold)."""
+    v, _, _ = evaluate("if (x(?o) > y(?o)) then 1.0 else -1.0", exact=True)
+    np.testing.assert_array_equal(v, np.where(X > Y, 1.0, -1.0).astype(np.float32))
+    v, _, _ = evaluate("x(?o) + y(?o) + C(?o) + 1e8 - 1e8", exact=True)
+    f = np.float32
+    want = ((((f(X) + f(Y)) + f(np.array([0.5, 1.5, 0.5, 0.5]))) + f(1e8)) - f(1e8))
+    np.testing.assert_array_equal(v, want)
+
+
+@pytest.mark.parametrize("ste", [False, True])
+def test_sigmoid_bernoulli(ste):
+    """logic.py:1125-1129: sigma(w (p - U)); STE value 1[p > U]."""
+    kw = {"bernoulli_sigmoid_weight": W, "use_ste_bernoulli": ste}
+    noise = [torch.tensor(U, dtype=torch.float32)]
+    v, gx, _ = evaluate("Bernoulli(1.0 / (1.0 + exp[-x(?o)]))", kw, noise=noise)
+    p = sigmoid(X)
+    s = sigmoid(W * (p - U))
+    np.testing.assert_allclose(v, (p > U) * 1.0 if ste else s, rtol=3e-6, atol=1e-6)
+    np.testing.assert_allclose(gx, W * s * (1 - s) * p * (1 - p), rtol=3e-5, atol=1e-6)
+
+
+def test_gumbel_sigmoid_bernoulli():
+    """logic.py:1177-1179: z = logit(clip(p)) + Logistic; sigma(w z)."""
+    class G(logic.SigmoidRelational, logic.ProductNormLogical, logic.LinearIfElse,
+            logic.GumbelSigmoidBernoulli):
+        pass
+    lg = np.log(U) - np.log1p(-U)
+    noise = [torch.tensor(lg, dtype=torch.float32)]
+    v, gx, _ = evaluate("Bernoulli(1.0 / (1.0 + exp[-x(?o)]))", {"bernoulli_sigmoid_weight": W},
+                        cls=G, noise=noise)
+    p = sigmoid(X)
+    z = np.log(p) - np.log1p(-p) + lg
+    s = sigmoid(W * z)
+    np.testing.assert_allclose(v, s, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(gx, W * s * (1 - s), rtol=1e-4, atol=1e-6)   # dz/dx = 1
+
+
+def test_exact_bernoulli_and_uniform_normal():
+    """compiler.py:1874 (U < p), 1793-1794 (a + (b-a) U), 1813-1816 (m + sqrt(v) Z)."""
+    noise = [torch.tensor(U, dtype=torch.float32)]
+    v, _, _ = evaluate("Bernoulli(C(?o) * 0.5)", exact=True, noise=noise)
+    np.testing.assert_array_equal(v, (U < np.array([0.25, 0.75, 0.25, 0.25])).astype(np.float32))
+    v, _, _ = evaluate("Uniform(x(?o), x(?o) + 2.0)", exact=True, noise=noise)
+    np.testing.assert_allclose(v, X + 2 * U, rtol=1e-6, atol=1e-6)
+    v, _, _ = evaluate("Normal(x(?o), 4.0)", exact=True, noise=noise)
+    np.testing.assert_allclose(v, X + 2 * U, rtol=1e-6, atol=1e-6)
+
+
+def test_aggregations_and_functions_exact():
+    """compiler.py:1303-1348, 1421-1529."""
+    v, _, _ = evaluate("(sum_{?u : obj} [ x(?u) ]) + (max_{?u : obj} [ y(?u) ]) * 0.0 "
+                       "+ (prod_{?u : obj} [ C(?u) ])", exact=True)
+    want = X.sum(1, keepdims=True) + 0.5 * 1.5 * 0.5 * 0.5
+    np.testing.assert_allclose(v, np.repeat(want, 4, 1), rtol=1e-6)
+    v, _, _ = evaluate("pow[x(?o), 2] + abs[y(?o)] + min[x(?o), y(?o)] + hypot[x(?o), y(?o)]",
+                       exact=True)
+    np.testing.assert_allclose(v, X ** 2 + np.abs(Y) + np.minimum(X, Y) + np.hypot(X, Y), rtol=2e-6)
+    v, _, _ = evaluate("log[exp[x(?o)] + 1.0, 2.0] + sqrt[abs[y(?o)]] + mod[x(?o), 0.7]",
+                       exact=True)
+    np.testing.assert_allclose(v, np.log(np.exp(X) + 1) / np.log(2.0) + np.sqrt(np.abs(Y))
+                               + np.mod(X, 0.7), rtol=3e-6, atol=1e-6)
+
+
+def test_gradient_finite_differences_through_a_rollout():
+    """Central differences (fp64 inputs, fp32 model) of the oracle's reservoir return."""
+    from oracle import planner as OP
+    from .helpers import fixture_model
+    from .parity import make_params
+    m = fixture_model("reservoir")
+    comp = logic.DefaultJaxRDDLCompilerWithGrad(m, use_sigmoid_ste=False, use_if_else_ste=False,
+                                                sigmoid_weight=0.2)
+    om = OracleModel(m, comp.relax_config())
+    T, B = 3, 2
+    params = make_params(m, "reservoir", T)
+    torch.manual_seed(0)
+    noise = [[torch.rand(B, 3) * 4 + 1] for _ in range(T)]
+
+    def loss_of(p):
+        out = OP.rollout(om, lambda t, fls: OP.slp_train_actions(m, p, t), B, T, noise)
+        return OP.mean_loss(out["reward"], 1.0)
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    loss_of(P).backward()
+    g = P["release"].grad.numpy()
+    eps = 2e-2
+    for (t, i) in [(0, 0), (1, 2), (2, 1)]:
+        hi = {k: v.clone() for k, v in params.items()}
+        lo = {k: v.clone() for k, v in params.items()}
+        hi["release"][t, i] += eps
+        lo["release"][t, i] -= eps
+        fd = (float(loss_of(hi)) - float(loss_of(lo))) / (2 * eps)
+        assert abs(fd - g[t, i]) <= 2e-2 * max(1.0, abs(g[t, i])), (t, i, fd, g[t, i])
+
+
+def test_optimizers_known_answers():
+    """optax rmsprop / adam closed forms + clip_by_global_norm."""
+    from oracle import planner as OP
+    p, g = torch.tensor([1.0, -2.0]), torch.tensor([0.5, -4.0])
+    p1, nu = OP.rmsprop_step(p, g, torch.zeros(2), lr=0.1)
+    nu_w = 0.1 * np.array([0.25, 16.0])
+    np.testing.assert_allclose(nu.numpy(), nu_w, rtol=1e-6)
+    np.testing.assert_allclose(p1.numpy(), np.array([1.0, -2.0]) - 0.1 * np.array([0.5, -4.0])
+                               / np.sqrt(nu_w + 1e-8), rtol=1e-6)
+    p1, mu, nu = OP.adam_step(p, g, torch.zeros(2), torch.zeros(2), 1, lr=0.1)
+    # first adam step moves every coordinate by ~lr against the gradient sign
+    np.testing.assert_allclose(p1.numpy(), np.array([1.0 - 0.1, -2.0 + 0.1]), rtol=1e-5)
+    (c,) = OP.clip_by_global_norm([g], 1.0)
+    np.testing.assert_allclose(c.numpy(), g.numpy() / np.sqrt(0.25 + 16.0), rtol=1e-6)
