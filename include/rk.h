@@ -108,6 +108,24 @@ int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
                       float* params, float* state, const float* grad,
                       const float* lo, const float* hi, int32_t* zero_flag);
 
+/* Concurrency projection of the boolean plan parameters onto max-nondef-actions, run after
+ * rk_optimizer_step's box projection.
+ * Replaces: _jax_wrapped_slp_project_to_max_constraint (planner.py:947-954), i.e. the
+ * per-time-step JaxSogbofaActionProjection (method 0, planner.py:530-617) or
+ * JaxSortingActionProjection (method 1, planner.py:489-527) vmapped over the horizon.
+ *   params [T*A] plan parameters (in place); the boolean action fluents occupy the column
+ *   ranges seg_off[i] .. seg_off[i]+seg_len[i] (HOST arrays, n_seg <= RK_MAX_BOOL_FLUENTS,
+ *   in action-fluent order); seg_noop[i] = 1 when the fluent's default is true;
+ *   seg_weight[i] = the sigmoid weight hyper-parameter of that fluent (planner.py:743).
+ *   allowed = rddl.max_allowed_actions; wrap_sigmoid / min_prob as in JaxStraightLinePlan.
+ *   converged [1]: cleared to 0 when some step still has surplus after max_iter (SOGBOFA);
+ *   the caller sets it to 1 beforehand. */
+#define RK_MAX_BOOL_FLUENTS 16
+int rk_project_slp(void* stream, int method, int T, int A, float* params, int n_seg,
+                   const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_noop,
+                   const float* seg_weight, int allowed, int max_iter, int wrap_sigmoid,
+                   float min_prob, int32_t* converged);
+
 /* -mean(returns) and its cotangent, for utility='mean' (planner.py:2817-2818):
  * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */
 int rk_mean_loss(void* stream, const float* returns, int B, float* loss, float* gret);

@@ -189,3 +189,50 @@ def sogbofa_project_row(actions: Dict[str, torch.Tensor], noop: Dict[str, bool],
         new[var] = flat.reshape(a.shape)
         excess = max(excess - int(torch.count_nonzero(replace)), 0)
     return new, converged
+
+
+def sorting_project_row(logits: Dict[str, torch.Tensor], noop: Dict[str, bool], allowed: int,
+                        wrap_sigmoid: bool, bool_threshold: float, box: Dict[str, Tuple[float, float]]):
+    """planner.py:499-527 on one time step: shift every boolean parameter by the surplus of
+    the (allowed+1)-th largest score over the threshold, then clip to the boolean box."""
+    scores = []
+    for var, p in logits.items():
+        flat = p.reshape(-1)
+        if noop[var]:
+            flat = -flat if wrap_sigmoid else 1. - flat
+        scores.append(flat)
+    scores = torch.cat(scores)
+    descending = torch.sort(scores, descending=True).values
+    surplus = torch.clamp(descending[allowed] - bool_threshold, min=0.)
+    out = {}
+    for var, p in logits.items():
+        shifted = p + surplus if noop[var] else p - surplus
+        out[var] = torch.clamp(shifted, box[var][0], box[var][1])
+    return out, True
+
+
+def project_max_constraint(model, params: Dict[str, torch.Tensor], method: str, allowed: int,
+                           wrap_sigmoid=True, min_action_prob=1e-6, weight=1.0, max_iter=100):
+    """planner.py:947-954: the per-step projection vmapped over the horizon axis; ``params``
+    are the box-projected plan parameters {var: [T, n]} (non-boolean entries pass through)."""
+    bools = [v for v in params if model.variable_ranges[v] == "bool"]
+    noop = {v: bool(np.ravel(model.action_fluents[v])[0]) for v in bools}
+    T = next(iter(params.values())).shape[0]
+    out = {v: p.clone() for v, p in params.items()}
+    converged = True
+    thr = 0.0 if wrap_sigmoid else 0.5
+    box = {v: bool_box(wrap_sigmoid, min_action_prob, weight) for v in bools}
+    for t in range(T):
+        row = {v: params[v][t] for v in bools}
+        if method == "sorting":
+            new, ok = sorting_project_row(row, noop, allowed, wrap_sigmoid, thr, box)
+        else:
+            acts = {v: (torch.sigmoid(weight * p) if wrap_sigmoid else p) for v, p in row.items()}
+            acts, ok = sogbofa_project_row(acts, noop, allowed, max_iter, min_action_prob,
+                                           1. - min_action_prob)
+            new = {v: (torch.log(a / (1. - a)) / weight if wrap_sigmoid else a)
+                   for v, a in acts.items()}
+        converged = converged and ok
+        for v in bools:
+            out[v][t] = new[v]
+    return out, converged

@@ -22,7 +22,7 @@ EXPORTS = [
     "rk_program_create", "rk_program_destroy", "rk_program_query", "rk_program_num_warps",
     "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
-    "rk_mean_loss",
+    "rk_mean_loss", "rk_project_slp",
 ]
 
 
@@ -68,6 +68,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_optimizer_step.restype = ci
     lib.rk_mean_loss.argtypes = [vp, cf, ci, cf, cf]
     lib.rk_mean_loss.restype = ci
+    lib.rk_project_slp.argtypes = [vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, ci, ci, ci,
+                                   ctypes.c_float, cf]
+    lib.rk_project_slp.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -168,3 +171,18 @@ def optimizer_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, 
 def mean_loss(returns: torch.Tensor, B: int, loss=None, gret=None):
     _check(load_library().rk_mean_loss(_stream(), _ptr(returns), B, _ptr(loss), _ptr(gret)),
            "rk_mean_loss")
+
+
+def project_slp(method: str, T: int, A: int, params: torch.Tensor, segs, allowed: int,
+                max_iter: int, wrap_sigmoid: bool, min_prob: float, converged=None):
+    """segs: [(offset, length, noop, sigmoid_weight), ...] of the boolean action fluents."""
+    n = len(segs)
+    I32, F32 = ctypes.c_int32 * max(n, 1), ctypes.c_float * max(n, 1)
+    off, ln = I32(*[int(s[0]) for s in segs]), I32(*[int(s[1]) for s in segs])
+    noop, w = I32(*[int(bool(s[2])) for s in segs]), F32(*[float(s[3]) for s in segs])
+    _check(load_library().rk_project_slp(
+        _stream(), {"sogbofa": 0, "sorting": 1}[method], T, A, _ptr(params), n,
+        ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+        ctypes.cast(noop, ctypes.c_void_p), ctypes.cast(w, ctypes.c_void_p), int(allowed),
+        int(max_iter), int(bool(wrap_sigmoid)), float(min_prob), _ptr(converged)),
+        "rk_project_slp")

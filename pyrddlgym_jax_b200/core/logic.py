@@ -346,3 +346,19 @@ class DefaultJaxRDDLCompilerWithGrad(SigmoidRelational, SoftmaxArgmax,
             if base.__name__ != "object":
                 kwargs = {**kwargs, **base.get_kwargs(self)}
         return kwargs
+
+
+class GumbelBernoulliJaxRDDLCompilerWithGrad(SigmoidRelational, SoftmaxArgmax,
+                                            ProductNormLogical,
+                                            SoftFloor, SoftRound,
+                                            LinearIfElse, SoftmaxSwitch,
+                                            ReparameterizedGeometric,
+                                            GumbelSigmoidBernoulli,
+                                            GumbelSoftmaxDiscrete, GumbelSoftmaxBinomial,
+                                            ExponentialPoisson):
+    """The default composition with the Gumbel-sigmoid Bernoulli relaxation (logic.py:1137-1186)
+    in place of the sigmoid one: the composite class BASELINE.json's Wildfire configuration
+    needs ("FuzzyLogic + Gumbel-softmax Bernoulli"); the reference's cfg loader can only name
+    existing classes (planner.py:135-136), so a user would define exactly this."""
+
+    get_kwargs = DefaultJaxRDDLCompilerWithGrad.get_kwargs

@@ -180,7 +180,12 @@ class JaxStraightLinePlan(JaxPlan):
                 hi[:, off:off + n] = bounds[name][1].reshape(-1)
         self.box = (lo, hi)
         n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
+        # concurrency projection (planner.py:914-959): sort-based or SOGBOFA, per time step
+        self.max_allowed_actions = int(min(rddl.max_allowed_actions, n_bool))
         self.needs_concurrency_projection = rddl.max_allowed_actions < n_bool
+        self.projection_method = "sorting" if self._use_new_projection else "sogbofa"
+        self.bool_segs = [(off, n, bool(self.noop[name]), float(self._sigmoid_weight))
+                          for name, (off, n, prange) in self.layout.items() if prange == "bool"]
 
     def initial_params(self, generator: torch.Generator) -> torch.Tensor:
         """planner.py:974-1008: initialiser + threshold shift + box projection -> [T, A]."""
@@ -430,10 +435,6 @@ class JaxBackpropPlanner:
         self.test_compiled = JaxRDDLCompiler(rddl)
         self.test_compiled.compile()
         self.plan.compile(self.compiled, self.test_compiled, self._action_bounds, self.horizon)
-        if getattr(self.plan, "needs_concurrency_projection", False):
-            raise NotImplementedError(
-                "max-nondef-actions below the number of boolean actions needs the concurrency "
-                "projection (planner.py:914-959), which is not built yet")
         spec = self.plan.spec
         gamma = float(rddl.discount)
         self.gamma = gamma
@@ -466,15 +467,20 @@ class JaxBackpropPlanner:
         self.train_reward = z(P, T * Bt)
         self.train_returns = z(P, Bt)
         self.train_err = z(P, T * Bt, dt=torch.int32)
-        self.train_loss = z(P)
+        # the three per-iteration scalars the host reads (planner.py:3261-3262, 2916) share one
+        # buffer so that a planner iteration costs a single device->host copy
+        self._stats = z(3 * P, dt=torch.int32)
+        self._stats_host = torch.zeros(3 * P, dtype=torch.int32).pin_memory()
+        self.train_loss = self._stats[0:P].view(torch.float32)
         self.gret = z(Bt)
         self.test_reward = z(P, T * Be)
         self.test_returns = z(P, Be)
         self.test_err = z(P, T * Be, dt=torch.int32)
-        self.test_loss_buf = z(P)
+        self.test_loss_buf = self._stats[P:2 * P].view(torch.float32)
         self.test_final = z(P, te.S * Be)
         self.test_traj = z(P, T * te.TRAJ * Be) if te.TRAJ else None
-        self.zero_flag = z(P, dt=torch.int32)
+        self.zero_flag = self._stats[2 * P:3 * P]
+        self.converged = torch.ones(P, dtype=torch.int32, device=dev)
         self.train_noise = z(T * fw.N * Bt) if fw.N else None
         self.test_noise = z(T * te.N * Be) if te.N else None
         self.disc = None if self.gamma == 1.0 else torch.pow(
@@ -552,6 +558,13 @@ class JaxBackpropPlanner:
             parallel.allreduce_gradient(self.grad[p])
         engine.optimizer_step(self.optimizer_name, self.hyper, T * A, params, self.opt_state[p],
                               self.grad[p], self.box_lo, self.box_hi, self.zero_flag[p:p + 1])
+        plan = self.plan
+        if getattr(plan, "needs_concurrency_projection", False):     # planner.py:947-954
+            self.converged[p:p + 1].fill_(1)
+            engine.project_slp(plan.projection_method, T, A, params, plan.bool_segs,
+                               plan.max_allowed_actions, plan._max_constraint_iter,
+                               plan._wrap_sigmoid, plan._min_action_prob,
+                               self.converged[p:p + 1])
 
     def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
         """planner.py:2695-2698: exact-model rollouts, forward only."""
@@ -622,6 +635,28 @@ class JaxBackpropPlanner:
             if self.world_size > 1:          # d(-mean over the GLOBAL batch)/d return_b
                 self.gret.mul_(1.0 / self.world_size)
                 self._gen.manual_seed(int(key) + 7919 * (self.rank + 1))
+            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
+            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+
+    def read_stats(self):
+        """(train_loss [P], test_loss [P], zero_grads [P]) of the last iteration: one pinned
+        device->host copy + the iteration's only host synchronisation."""
+        P = self.parallel_updates
+        self._stats_host.copy_(self._stats, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        raw = self._stats_host.numpy()
+        train = raw[0:P].view(np.float32).copy()
+        test = raw[P:2 * P].view(np.float32).copy()
+        zero = raw[2 * P:3 * P] > 0
+        if self.world_size > 1:
+            pair = self.loss_pair.cpu().numpy() / self.world_size
+            train, test = pair[0], pair[1]
+        return train, test, zero
+
+    def redraw_noise(self):
+        """Fresh supplied-noise tensors for the next iteration (the reference splits its PRNG
+        key once per update and once per test evaluation, planner.py:2880, 3257)."""
+        with torch.cuda.device(self.device):
             self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
             self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
 
@@ -700,17 +735,9 @@ class JaxBackpropPlanner:
             status = JaxPlannerStatus.NORMAL
             with torch.cuda.device(self.device):
                 if self.train_noise is not None or self.test_noise is not None:
-                    self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
-                    self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+                    self.redraw_noise()
                 self.iterate()
-                if self.world_size > 1:
-                    stats = torch.stack([self.loss_pair[0] / self.world_size,
-                                         self.loss_pair[1] / self.world_size,
-                                         self.zero_flag.float()]).cpu().numpy()
-                else:
-                    stats = torch.stack([self.train_loss, self.test_loss_buf,
-                                         self.zero_flag.float()]).cpu().numpy()   # the host sync
-            train_loss, test_loss, zero_grads = stats[0], stats[1], stats[2] > 0
+                train_loss, test_loss, zero_grads = self.read_stats()       # the host sync
             test_loss_smooth = rolling.update(test_loss)
             best_index = int(np.argmin(test_loss_smooth))
             if test_loss_smooth[best_index] < best_loss:

@@ -403,6 +403,7 @@ class ProgramBuilder:
     # ---------------------------------------------------------------------------------
     # per-instruction fixed cost (fetch, decode, dispatch) in units of one element pass
     INS_OVERHEAD = 4.0
+    MULTIPASS_PENALTY = 3.0
     SMEM_WORDS = 56 * 1024            # ~224 KB of shared memory per SM, in words
     FREE_WARPS_PER_SM = 8             # warps/SM that overlap almost perfectly (latency-bound)
 
@@ -418,7 +419,11 @@ class ProgramBuilder:
             except ProgramError as e:
                 last_err = e
                 continue
-            cost = sum(-(-max(i.n, 1) // L) + self.INS_OVERHEAD for i in step)
+            # specialised kernels keep single-pass values (n <= L) in registers; multi-pass
+            # values live in shared memory and cost about three times as much per pass
+            mp = self.MULTIPASS_PENALTY if self.INS_OVERHEAD < 1.0 else 1.0
+            cost = sum((-(-max(i.n, 1) // L)) * (mp if i.n > L else 1.0) + self.INS_OVERHEAD
+                       for i in step)
             nwarps = -(-B // prog.rpw)
             resident = max(1, min(64, self.SMEM_WORDS // max(prog.warp_words, 1)))
             conc = 148 * min(resident, self.FREE_WARPS_PER_SM)

@@ -183,3 +183,204 @@ extern "C" int rk_mean_loss(void* stream, const float* returns, int B, float* lo
   if (gret != nullptr) rk_fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(gret, B, -1.f / (float)B);
   return (int)cudaGetLastError();
 }
+
+// ---- concurrency projection of the boolean plan parameters --------------------------------
+// planner.py:914-959: after the box projection, every time step's boolean action parameters
+// are projected so that at most `allowed` actions differ from their no-op value; the reference
+// vmaps the per-step projection over the horizon axis, here one warp owns one time step.
+// method 0 = SOGBOFA loop (planner.py:540-616), 1 = sort-based shift (planner.py:499-527).
+struct RkProjSegs {
+  int n;
+  int off[RK_MAX_BOOL_FLUENTS], len[RK_MAX_BOOL_FLUENTS], noop[RK_MAX_BOOL_FLUENTS];
+  float weight[RK_MAX_BOOL_FLUENTS];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+rk_project_slp_kernel(int method, int T, int A, float* __restrict__ params, RkProjSegs S,
+                      int K, int allowed, int max_iter, int wrap_sigmoid, float min_prob,
+                      int32_t* __restrict__ converged) {
+  extern __shared__ float sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= T) return;
+  float* a = sh + (size_t)warp * 2 * K;          // action values of this step
+  float* prm = a + K;                            // raw parameters of this step
+  float* row = params + (size_t)t * A;
+  // gather the boolean parameters of the step (fluent order, flattened)
+  int base = 0;
+  for (int s = 0; s < S.n; ++s) {
+    for (int i = lane; i < S.len[s]; i += 32) {
+      const float p = row[S.off[s] + i];
+      prm[base + i] = p;
+      a[base + i] = wrap_sigmoid ? 1.f / (1.f + expf(-(S.weight[s] * p))) : p;
+    }
+    base += S.len[s];
+  }
+  __syncwarp();
+
+  if (method == 1) {
+    // ---- sort-based: shift so that only the top `allowed` scores stay above the threshold
+    const float thr = wrap_sigmoid ? 0.f : 0.5f;
+    float kth = 0.f;
+    int found = 0;
+    int b0 = 0;
+    for (int s = 0; s < S.n && allowed < K; ++s) {
+      for (int i0 = 0; i0 < S.len[s]; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < S.len[s];
+        float si = 0.f;
+        int rank = -1;
+        if (ok) {
+          const float p = prm[b0 + i];
+          si = S.noop[s] ? (wrap_sigmoid ? -p : 1.f - p) : p;
+          rank = 0;
+          int c0 = 0;
+          for (int s2 = 0; s2 < S.n; ++s2) {
+            for (int j = 0; j < S.len[s2]; ++j) {
+              const float q = prm[c0 + j];
+              const float sj = S.noop[s2] ? (wrap_sigmoid ? -q : 1.f - q) : q;
+              rank += (sj > si || (sj == si && (c0 + j) < (b0 + i))) ? 1 : 0;
+            }
+            c0 += S.len[s2];
+          }
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, ok && rank == allowed);
+        if (hit) {
+          kth = __shfl_sync(0xffffffffu, si, __ffs(hit) - 1);
+          found = 1;
+        }
+      }
+      b0 += S.len[s];
+    }
+    const float surplus = found ? fmaxf(kth - thr, 0.f) : 0.f;
+    b0 = 0;
+    for (int s = 0; s < S.n; ++s) {
+      float lo, hi;
+      if (wrap_sigmoid) {
+        lo = logf(min_prob / (1.f - min_prob)) / S.weight[s];
+        hi = logf((1.f - min_prob) / min_prob) / S.weight[s];
+      } else {
+        lo = min_prob;
+        hi = 1.f - min_prob;
+      }
+      for (int i = lane; i < S.len[s]; i += 32) {
+        const float p = prm[b0 + i];
+        const float sh_ = S.noop[s] ? p + surplus : p - surplus;
+        row[S.off[s] + i] = fminf(fmaxf(sh_, lo), hi);
+      }
+      b0 += S.len[s];
+    }
+    return;
+  }
+
+  // ---- SOGBOFA: subtract surplus / k from every active action until the sum fits
+  float surplus = 0.f;
+  int k = 0;
+  for (int it = 0; it <= max_iter; ++it) {
+    float sum = 0.f;
+    int cnt = 0;
+    int b0 = 0;
+    const float amount = (it == 0 || k == 0) ? 0.f : surplus / (float)k;
+    for (int s = 0; s < S.n; ++s) {
+      for (int i = lane; i < S.len[s]; i += 32) {
+        float v = a[b0 + i];
+        if (it > 0) {
+          v = S.noop[s] ? fminf(v + amount, 1.f) : fmaxf(v - amount, 0.f);
+          a[b0 + i] = v;
+        }
+        const float act = S.noop[s] ? 1.f - v : v;
+        sum += act;
+        cnt += (act != 0.f) ? 1 : 0;
+      }
+      b0 += S.len[s];
+    }
+    surplus = fmaxf(warp_sum(sum) - (float)allowed, 0.f);
+    k = warp_sum_i(cnt);
+    if (!(it < max_iter && surplus > 0.f && k > 0)) break;
+  }
+  __syncwarp();
+  if (lane == 0 && surplus > 0.f && converged != nullptr) atomicAnd(converged, 0);
+
+  // remaining violations: set the first `excess` still-active actions to 0.5
+  int total = 0;
+  {
+    int b0 = 0, cnt = 0;
+    for (int s = 0; s < S.n; ++s) {
+      for (int i = lane; i < S.len[s]; i += 32) {
+        const float v = a[b0 + i];
+        cnt += (S.noop[s] ? (v < 0.5f) : (v > 0.5f)) ? 1 : 0;
+      }
+      b0 += S.len[s];
+    }
+    total = warp_sum_i(cnt);
+  }
+  int excess = max(total - allowed, 0);
+  const float amin = min_prob, amax = 1.f - min_prob;
+  int b0 = 0;
+  for (int s = 0; s < S.n; ++s) {
+    int seen = 0;                                  // active flags before this chunk
+    int replaced = 0;
+    for (int i0 = 0; i0 < S.len[s]; i0 += 32) {
+      const int i = i0 + lane;
+      const bool ok = i < S.len[s];
+      float v = ok ? fminf(fmaxf(a[b0 + i], amin), amax) : 0.f;
+      const bool active = ok && (S.noop[s] ? (v < 0.5f) : (v > 0.5f));
+      const unsigned m = __ballot_sync(0xffffffffu, active);
+      const int rank = seen + __popc(m & ((2u << lane) - 1u));      // inclusive cumsum
+      const bool rep = active && rank <= excess;
+      if (rep) v = 0.5f;
+      replaced += __popc(__ballot_sync(0xffffffffu, rep));
+      seen += __popc(m);
+      if (ok) {
+        const float w = S.weight[s];
+        row[S.off[s] + i] = wrap_sigmoid ? logf(v / (1.f - v)) / w : v;
+      }
+    }
+    excess = max(excess - replaced, 0);
+    b0 += S.len[s];
+  }
+}
+
+extern "C" int rk_project_slp(void* stream, int method, int T, int A, float* params, int n_seg,
+                              const int32_t* seg_off, const int32_t* seg_len,
+                              const int32_t* seg_noop, const float* seg_weight, int allowed,
+                              int max_iter, int wrap_sigmoid, float min_prob,
+                              int32_t* converged) {
+  if (params == nullptr || T < 0 || A <= 0 || n_seg < 0 || n_seg > RK_MAX_BOOL_FLUENTS)
+    return RK_E_BADARG;
+  if (method < 0 || method > 1 || allowed < 0) return RK_E_BADARG;
+  if (n_seg > 0 && (seg_off == nullptr || seg_len == nullptr || seg_noop == nullptr ||
+                    seg_weight == nullptr)) return RK_E_BADARG;
+  if (T == 0 || n_seg == 0) return 0;
+  RkProjSegs S;
+  S.n = n_seg;
+  int K = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    if (seg_off[s] < 0 || seg_len[s] < 0 || seg_off[s] + seg_len[s] > A) return RK_E_BADARG;
+    S.off[s] = seg_off[s]; S.len[s] = seg_len[s]; S.noop[s] = seg_noop[s];
+    S.weight[s] = seg_weight[s];
+    K += seg_len[s];
+  }
+  if (K == 0) return 0;
+  const int wpc = 4;
+  const size_t smem = (size_t)wpc * 2 * K * sizeof(float);
+  if (smem > 200 * 1024) return RK_E_SMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_project_slp_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  rk_project_slp_kernel<<<(T + wpc - 1) / wpc, wpc * 32, smem, st>>>(
+      method, T, A, params, S, K, allowed, max_iter, wrap_sigmoid, min_prob, converged);
+  return (int)cudaGetLastError();
+}

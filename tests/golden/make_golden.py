@@ -27,6 +27,8 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("reservoir_relaxed", "reservoir", 6, 5, True, 0.9, {}),
     ("wildfire_exact", "wildfire", 7, 5, False, 1.0, {}),
     ("wildfire_relaxed", "wildfire", 7, 5, True, 1.0, {}),
+    ("marsrover_exact", "marsrover", 6, 6, False, 1.0, {}),
+    ("marsrover_relaxed", "marsrover", 6, 6, True, 1.0, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]

@@ -20,6 +20,7 @@ FIXTURES = {
     "quadcopter": ("Quadcopter", "instance1"),
     "reservoir": ("Reservoir_Continuous", "instance1"),
     "wildfire": ("Wildfire_MDP_ippc2014", "instance5"),
+    "marsrover": ("MarsRover_ippc2023", "instance5"),
 }
 
 

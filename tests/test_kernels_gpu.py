@@ -12,7 +12,7 @@ from pyrddlgym_jax_b200.core import logic
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 pytestmark = pytest.mark.gpu
-KEYS = ["quadcopter", "reservoir", "wildfire"]
+KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover"]
 # 'cuda' = generic interpreter kernel, 'jit' = per-program specialised kernel (core/codegen.py)
 BACKENDS = ["cuda", "jit"]
 
@@ -90,3 +90,41 @@ def test_deterministic_cuda(cuda_device):
     a = gradient_case("jit", "wildfire", B=300, T=5)["grad"]
     b = gradient_case("jit", "wildfire", B=300, T=5)["grad"]
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("method", ["sogbofa", "sorting"])
+@pytest.mark.parametrize("wrap_sigmoid", [True, False])
+def test_concurrency_projection_cuda(cuda_device, method, wrap_sigmoid):
+    """rk_project_slp against the oracle's restatement of planner.py:489-617, 947-954 on the
+    Wildfire plan (50 boolean actions, max-nondef-actions = 1 and 3)."""
+    from oracle import planner as OP
+    from pyrddlgym_jax_b200.core import engine
+    from .helpers import fixture_model, pack_params
+    m = fixture_model("wildfire")
+    T, w, pmin = 7, 2.5, 1e-3
+    g = torch.Generator().manual_seed(5)
+    for allowed in (1, 3):
+        if wrap_sigmoid:
+            params = {a: torch.randn(T, m.variable_size(a), generator=g) * 1.5
+                      for a in m.action_fluents}
+        else:
+            params = {a: torch.rand(T, m.variable_size(a), generator=g) * 0.8 + 0.1
+                      for a in m.action_fluents}
+        params["put-out"][0] = -3.0 if wrap_sigmoid else 0.05        # a step with nothing active
+        boxed = OP.project_box(m, params, m.bounds, wrap_sigmoid, pmin, w)
+        want, _ = OP.project_max_constraint(m, boxed, method, allowed, wrap_sigmoid, pmin, w, 100)
+        flat = pack_params(m, boxed).to(cuda_device).contiguous()
+        segs, off = [], 0
+        for a in m.action_fluents:
+            n = m.variable_size(a)
+            segs.append((off, n, False, w))
+            off += n
+        conv = torch.ones(1, dtype=torch.int32, device=cuda_device)
+        engine.project_slp(method, T, off, flat.view(-1), segs, allowed, 100, wrap_sigmoid, pmin, conv)
+        torch.cuda.synchronize()
+        got = flat.cpu().numpy()
+        ref = pack_params(m, want).numpy()
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+        # the projected plan satisfies the constraint under the test policy
+        thr = 0.0 if wrap_sigmoid else 0.5
+        assert int((got > thr).sum(1).max()) <= allowed

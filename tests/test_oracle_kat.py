@@ -272,3 +272,22 @@ def test_optimizers_known_answers():
     np.testing.assert_allclose(p1.numpy(), np.array([1.0 - 0.1, -2.0 + 0.1]), rtol=1e-5)
     (c,) = OP.clip_by_global_norm([g], 1.0)
     np.testing.assert_allclose(c.numpy(), g.numpy() / np.sqrt(0.25 + 16.0), rtol=1e-6)
+
+
+def test_projection_known_answers():
+    """planner.py:499-527 (sorting) and 540-616 (SOGBOFA) on hand-checkable rows."""
+    from oracle import planner as OP
+    noop = {"a": False}
+    box = {"a": (-10.0, 10.0)}
+    row = {"a": torch.tensor([3.0, -1.0, 2.0, 0.5])}
+    new, _ = OP.sorting_project_row(row, noop, 1, True, 0.0, box)      # 2nd largest = 2.0
+    np.testing.assert_allclose(new["a"].numpy(), [1.0, -3.0, 0.0, -1.5])
+    new, _ = OP.sorting_project_row(row, noop, 3, True, 0.0, box)      # 4th largest = -1 < 0
+    np.testing.assert_allclose(new["a"].numpy(), [3.0, -1.0, 2.0, 0.5])
+    acts = {"a": torch.tensor([0.9, 0.8, 0.1, 0.0])}                   # sum 1.8, allowed 1
+    new, ok = OP.sogbofa_project_row(acts, noop, 1, 100, 1e-6, 1 - 1e-6)
+    assert ok
+    # surplus .8 over k=3 -> [.6333, .5333, 0, 0]: sum 1.1667, k=2 -> -.0833 each -> [.55, .45]
+    np.testing.assert_allclose(float(new["a"].sum()), 1.0, atol=2e-6)
+    # only one action may stay above 0.5: the first active one is reset to 0.5
+    assert int((new["a"] > 0.5).sum()) <= 1
