@@ -209,13 +209,17 @@ def run_reference(args):
     model = workload_model(name)
     B, T = cpu_sample_batch(name), WORKLOADS[name]["T"]
     it = oracle_iteration_fn(name, model, B, T)
-    for _ in range(args.warmup):
+    # bounded: at most 3 warm-up and 40 timed CPU steps (about a second each), whatever K is,
+    # so the arm ends within a few minutes; the executed counts are what the line reports
+    n_warm, n_steps = min(args.warmup, 3), max(1, min(args.steps, 40))
+    for _ in range(n_warm):
         it()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         it()
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    dt = (time.perf_counter() - t0) / n_steps
     val = B * T / dt
+    args.steps, args.warmup = n_steps, n_warm
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -237,8 +241,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="quadcopter", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="rollouts per GPU (default: the workload's)")
@@ -255,6 +259,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -288,6 +294,10 @@ def main():
         planner.iterate()
 
     # ---- warm-up (also captures the CUDA graph) ------------------------------------------
+    # the clock sampler runs from here to the end of the e2e loop: a timed region of a few
+    # hundred sub-millisecond iterations is shorter than nvidia-smi's sampling period
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     W = max(args.warmup, 3)
     for _ in range(W):
         step()
@@ -299,8 +309,6 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
     # ---- device-resident timed loop: EXACTLY K iterations ---------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -309,7 +317,6 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     t_local = torch.tensor([ms], device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -340,6 +347,7 @@ def main():
         import torch.distributed as dist
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * B * T / (float(t_e2e.item()) / args.steps * 1e-3)
+    clocks = sampler.stop()
 
     # ---- per-kernel timing (CUDA events on the launch stream, L2 flushed between launches) --
     def time_kernel(fn, reps=20):
@@ -451,10 +459,14 @@ def main():
                                           f"steps (of the workload's {wl['B']}) on the torch-CPU "
                                           f"oracle restatement, {cores} threads"}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroying the process group while the captured
+        # iteration graph (which holds the all-reduce) is alive can block forever
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # figures read from the committed ncu captures of the same workload (profiles/), per launch

@@ -702,14 +702,17 @@ def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:
     cu = os.path.join(JIT_DIR, f"rk_{key}.cu")
     cubin = os.path.join(JIT_DIR, f"rk_{key}.cubin")
     if not os.path.exists(cubin):
-        with open(cu, "w") as f:
+        # several ranks may generate the same kernel at once: private temporaries, atomic rename
+        tag = f".{os.getpid()}.tmp"
+        with open(cu + tag, "w") as f:
             f.write(src)
+        os.replace(cu + tag, cu)
         cmd = [os.environ.get("NVCC", "nvcc"), *flags, "-I", CSRC,
-               *(["-Xptxas", "-v"] if verbose else []), cu, "-o", cubin + ".tmp"]
+               *(["-Xptxas", "-v"] if verbose else []), cu, "-o", cubin + tag]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed on generated kernel:\n" + res.stdout + res.stderr)
         if verbose:
             print(res.stderr)
-        os.replace(cubin + ".tmp", cubin)
+        os.replace(cubin + tag, cubin)
     return cubin, cu

@@ -403,7 +403,7 @@ class ProgramBuilder:
     # ---------------------------------------------------------------------------------
     # per-instruction fixed cost (fetch, decode, dispatch) in units of one element pass
     INS_OVERHEAD = 4.0
-    MULTIPASS_PENALTY = 3.0
+    MULTIPASS_PENALTY = 16.0       # measured: MarsRover L=4 (smem, 8 passes) 8.0 ms vs L=32 (registers) 1.7 ms
     SMEM_WORDS = 56 * 1024            # ~224 KB of shared memory per SM, in words
     FREE_WARPS_PER_SM = 8             # warps/SM that overlap almost perfectly (latency-bound)
 
@@ -413,14 +413,18 @@ class ProgramBuilder:
         time for the batch size this builder was given."""
         B = max(int(getattr(self, "batch_hint", 0) or 4096), 1)
         best, best_t, last_err = None, None, None
+        import os as _os
+        forced = int(_os.environ.get("RK_LANES", "0") or 0)     # tuning / experiments only
         for L in sorted({32 // r for r in range(1, 33)}):
+            if forced and L != forced:
+                continue
             try:
                 prog = self._assemble_for(kind, pro, step, epi, persistent, L)
             except ProgramError as e:
                 last_err = e
                 continue
             # specialised kernels keep single-pass values (n <= L) in registers; multi-pass
-            # values live in shared memory and cost about three times as much per pass
+            # values live in shared memory and cost an order of magnitude more per pass
             mp = self.MULTIPASS_PENALTY if self.INS_OVERHEAD < 1.0 else 1.0
             cost = sum((-(-max(i.n, 1) // L)) * (mp if i.n > L else 1.0) + self.INS_OVERHEAD
                        for i in step)
