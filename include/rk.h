@@ -87,11 +87,16 @@ int rk_rollout_forward(const rk_program* prog, void* stream, int B, int T,
  *   gret     [B]        d loss / d return_b  (-1/B for utility='mean', planner.py:2817-2818)
  *   gradp    [num_warps*T*A] per-warp partial gradients of the plan parameters (SLP), or NULL
  *   gact     [T*A*B]    per-rollout action gradients (external policies), or NULL
- *   gs0      [S*B]      gradient w.r.t. the initial state, or NULL */
+ *   gs0      [S*B]      gradient w.r.t. the initial state, or NULL
+ *   gs_in    [S*B]      cotangent of the state after the last step (programs built with
+ *                       state_ct_in; NULL = zero).  With T = 1 launches this chains the adjoint
+ *                       across decision epochs when a closed-loop policy (DRP) sits between
+ *                       them. */
 int rk_rollout_backward(const rk_program* prog, void* stream, int B, int T,
                         const void* tape, const float* policy, const void* actions,
                         const float* noise, const float* mparams, const float* disc,
-                        const float* gret, float* gradp, float* gact, float* gs0);
+                        const float* gret, float* gradp, float* gact, float* gs0,
+                        const float* gs_in);
 
 /* Fixed-order reduction of the per-warp gradient partials: grad[i] = sum_w gradp[w][i].
  * Replaces: the batch reduction XLA fuses into the transposed scan. */
@@ -125,6 +130,43 @@ int rk_project_slp(void* stream, int method, int T, int A, float* params, int n_
                    const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_noop,
                    const float* seg_weight, int allowed, int max_iter, int wrap_sigmoid,
                    float min_prob, int32_t* converged);
+
+/* ---- deep reactive policy (JaxDeepReactivePolicy, planner.py:1122-1534) ------------------
+ * The flax MLP (planner.py:1342-1449) runs between two T = 1 launches of the rollout kernel.
+ *
+ * rk_sgemm: C[M][N] = epi(op(A)[M][K] * B[K][N]), fp32, row-major.
+ *   flags: RK_GEMM_A_TRANS (A stored [K][M]), RK_GEMM_ACCUMULATE (C += ...), and the epilogue
+ *   in bits 4..7: RK_EPI_NONE, RK_EPI_BIAS (+ bias[n]), RK_EPI_BIAS_TANH (nn.Dense + tanh,
+ *   planner.py:1359-1361), RK_EPI_DTANH (* (1 - aux[m][n]^2): the tanh adjoint).
+ *   split_k > 1 runs a deterministic split-K through `workspace` ([split_k][M][N] floats).
+ * Replaces: nn.Dense forward (planner.py:1360, 1376, 1398, 1407) and its transposes in the
+ * reverse pass. */
+#define RK_GEMM_A_TRANS    1
+#define RK_GEMM_ACCUMULATE 2
+#define RK_EPI_NONE        (0 << 4)
+#define RK_EPI_BIAS        (1 << 4)
+#define RK_EPI_BIAS_TANH   (2 << 4)
+#define RK_EPI_DTANH       (3 << 4)
+int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int lda,
+             const float* B, int ldb, float* C, int ldc, const float* bias, const float* aux,
+             int ldaux, float* workspace, int split_k);
+
+/* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).
+ *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise; noise [A][B] or NULL;
+ *   train = 1 (train policy) or 0 (test policy, planner.py:1486); lo/hi [A] or NULL;
+ *   actions [A][B] fluent-major (the rollout kernel's `actions` layout);
+ *   entropy [B] = sum_a clip(log_sigma) (planner.py:1416-1419), or NULL. */
+int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, const float* heads,
+                           const float* noise, float train, const float* lo, const float* hi,
+                           float ls_lo, float ls_hi, float* actions, float* entropy);
+/* gheads [B][2A or A] = d actions / d heads applied to gact [A][B] (clip: gradient 1 inside). */
+int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, const float* heads,
+                            const float* noise, float train, const float* lo, const float* hi,
+                            float ls_lo, float ls_hi, const float* gact, float* gheads);
+/* dst[D][B] (+)= src[B][D]^T: adds the first layer's input cotangent to the fluent-major state
+ * cotangent. */
+int rk_transpose_add(void* stream, int B, int D, const float* src, int lds, float* dst,
+                     int accumulate);
 
 /* -mean(returns) and its cotangent, for utility='mean' (planner.py:2817-2818):
  * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */

@@ -59,7 +59,8 @@ class Emulator:
         R = np.zeros((nW, self.ww), dtype=np.uint32)
         Wd = {"S0": self.S, "TAPE": self.S, "NOISE": self.N, "PARAMS": self.A, "ACT": self.A,
               "REWARD": 1, "RETURNS": 1, "ERR": 1, "DISC": 1, "FINAL": self.S,
-              "TRAJ": self.traj_w, "GRET": 1, "GRADP": self.A, "GACT": self.A, "GS0": self.S}
+              "TRAJ": self.traj_w, "GRET": 1, "GRADP": self.A, "GACT": self.A, "GS0": self.S,
+              "GSIN": self.S}
         G = {}
         for name in isa.BUFFERS:
             a = bufs.get(name)

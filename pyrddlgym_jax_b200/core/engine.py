@@ -22,7 +22,8 @@ EXPORTS = [
     "rk_program_create", "rk_program_destroy", "rk_program_query", "rk_program_num_warps",
     "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
-    "rk_mean_loss", "rk_project_slp",
+    "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
+    "rk_drp_actions_backward", "rk_transpose_add",
 ]
 
 
@@ -60,7 +61,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_program_num_warps.restype = ci
     lib.rk_rollout_forward.argtypes = [vp, vp, ci, ci] + [cf] * 12
     lib.rk_rollout_forward.restype = ci
-    lib.rk_rollout_backward.argtypes = [vp, vp, ci, ci] + [cf] * 10
+    lib.rk_rollout_backward.argtypes = [vp, vp, ci, ci] + [cf] * 11
     lib.rk_rollout_backward.restype = ci
     lib.rk_reduce_partials.argtypes = [vp, cf, ci, ci, cf]
     lib.rk_reduce_partials.restype = ci
@@ -71,6 +72,15 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_project_slp.argtypes = [vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, ci, ci, ci,
                                    ctypes.c_float, cf]
     lib.rk_project_slp.restype = ci
+    fl = ctypes.c_float
+    lib.rk_sgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf, cf, ci, cf, ci]
+    lib.rk_sgemm.restype = ci
+    lib.rk_drp_actions_forward.argtypes = [vp, ci, ci, ci, cf, cf, fl, cf, cf, fl, fl, cf, cf]
+    lib.rk_drp_actions_forward.restype = ci
+    lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, cf, cf, fl, cf, cf, fl, fl, cf, cf]
+    lib.rk_drp_actions_backward.restype = ci
+    lib.rk_transpose_add.argtypes = [vp, ci, ci, cf, ci, cf, ci]
+    lib.rk_transpose_add.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -146,11 +156,11 @@ class DeviceProgram:
             _ptr(final), _ptr(traj)), "rk_rollout_forward")
 
     def backward(self, B, T, tape, gret, policy=None, actions=None, noise=None, mparams=None,
-                 disc=None, gradp=None, gact=None, gs0=None):
+                 disc=None, gradp=None, gact=None, gs0=None, gs_in=None):
         _check(self.lib.rk_rollout_backward(
             self.handle, _stream(), B, T, _ptr(tape), _ptr(policy), _ptr(actions), _ptr(noise),
-            _ptr(mparams), _ptr(disc), _ptr(gret), _ptr(gradp), _ptr(gact), _ptr(gs0)),
-            "rk_rollout_backward")
+            _ptr(mparams), _ptr(disc), _ptr(gret), _ptr(gradp), _ptr(gact), _ptr(gs0),
+            _ptr(gs_in)), "rk_rollout_backward")
 
 
 def reduce_partials(gradp: torch.Tensor, rows: int, n: int, grad: torch.Tensor):
@@ -186,3 +196,35 @@ def project_slp(method: str, T: int, A: int, params: torch.Tensor, segs, allowed
         ctypes.cast(noop, ctypes.c_void_p), ctypes.cast(w, ctypes.c_void_p), int(allowed),
         int(max_iter), int(bool(wrap_sigmoid)), float(min_prob), _ptr(converged)),
         "rk_project_slp")
+
+
+GEMM_A_TRANS, GEMM_ACCUMULATE = 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_DTANH = 0 << 4, 1 << 4, 2 << 4, 3 << 4
+
+
+def sgemm(flags: int, M: int, N: int, K: int, A, lda: int, Bm, ldb: int, C, ldc: int, bias=None,
+          aux=None, ldaux: int = 0, workspace=None, split_k: int = 1):
+    _check(load_library().rk_sgemm(_stream(), flags, M, N, K, _ptr(A), lda, _ptr(Bm), ldb,
+                                   _ptr(C), ldc, _ptr(bias), _ptr(aux), ldaux, _ptr(workspace),
+                                   split_k), "rk_sgemm")
+
+
+def drp_actions_forward(B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, actions,
+                        entropy=None):
+    _check(load_library().rk_drp_actions_forward(
+        _stream(), B, A, int(stochastic), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
+        _ptr(hi), float(ls_lo), float(ls_hi), _ptr(actions), _ptr(entropy)),
+        "rk_drp_actions_forward")
+
+
+def drp_actions_backward(B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, gact,
+                         gheads):
+    _check(load_library().rk_drp_actions_backward(
+        _stream(), B, A, int(stochastic), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
+        _ptr(hi), float(ls_lo), float(ls_hi), _ptr(gact), _ptr(gheads)),
+        "rk_drp_actions_backward")
+
+
+def transpose_add(B, D, src, lds, dst, accumulate=True):
+    _check(load_library().rk_transpose_add(_stream(), B, D, _ptr(src), lds, _ptr(dst),
+                                           int(bool(accumulate))), "rk_transpose_add")

@@ -236,6 +236,11 @@ def differentiate(g: Graph, nodes: List[V], seeds: Sequence[Tuple[V, V]],
     active = _active_set(nodes, wrt)
     contrib: Dict[int, List[V]] = {}
     for tgt, s in seeds:
+        if tgt.uniform and not s.uniform:
+            # a rollout-invariant value (e.g. a next-state fluent that depends on the plan
+            # only) seeded with a per-rollout cotangent: sum over the rollouts first, exactly
+            # as push() does for operands, or later QSUMs would count uniform parts twice
+            s = g.add(V("QSUM", [(s, None)], n=tgt.n, dtype="f", uniform=True))
         contrib.setdefault(tgt.id, []).append(s)
     F = lambda x: g.const(np.float32(x))     # noqa: E731
 

@@ -347,8 +347,13 @@ class ProgramBuilder:
         return prog
 
     # ---------------------------------------------------------------------------------
-    def backward(self, gamma: float = 1.0, grad_s0: bool = False) -> Program:
-        """Adjoint program: d(sum_b gret[b] * return_b) / d(policy parameters)."""
+    def backward(self, gamma: float = 1.0, grad_s0: bool = False,
+                 state_ct_in: bool = False) -> Program:
+        """Adjoint program: d(sum_b gret[b] * return_b) / d(policy parameters).
+
+        state_ct_in: start from a supplied cotangent of the final state (buffer GSIN) instead
+        of zero -- used when the horizon is walked one step per launch with a closed-loop
+        policy between the launches (deep reactive policy, planner.py:1468-1500)."""
         if self.relax is None:
             raise ProgramError("the adjoint program needs a relaxed (all-REAL) model")
         g, sg = self.g, self.sg
@@ -357,7 +362,11 @@ class ProgramBuilder:
         pro: List[Ins] = [Ins("LDB", dst=gret, n=1, buf=isa.BUF["GRET"], off=0)]
         zero = g.const(np.float32(0.))
         for name, c in carried.items():
-            pro.append(Ins("MOV", dst=c, srcs=[(zero, "b")], n=c.n))
+            if state_ct_in:
+                off, n, _ = self.slayout[name]
+                pro.append(Ins("LDB", dst=c, n=n, buf=isa.BUF["GSIN"], off=off))
+            else:
+                pro.append(Ins("MOV", dst=c, srcs=[(zero, "b")], n=c.n))
 
         if gamma != 1.0:
             disc = g.leaf("disc_in", 1, "f", uniform=True)

@@ -1,0 +1,304 @@
+// rk_drp.cu -- deep reactive policy (DRP) kernels: dense layers and the action heads (sm_100a).
+//
+// Replaces the flax MLP behind JaxDeepReactivePolicy (planner.py:1342-1449: nn.Dense +
+// activation stack, per-action mu / log_sigma heads) and the reverse pass jax.value_and_grad
+// derives for it (planner.py:2873).  The MLP runs once per decision epoch between two
+// launches of the rollout kernel (closed loop: actions depend on the current state).
+//
+// rk_sgemm is an fp32 SIMT GEMM (128x128x8 tiles, 8x8 register micro-tiles, float4 global
+// loads, register-staged double buffering) with the layer epilogues fused in; results are
+// bit-reproducible (fixed summation order, deterministic split-K through a workspace).
+// It is the parity build of the dense layers; the tcgen05 (3xTF32) path replaces the
+// hidden-layer GEMM where the batch is large enough to fill 128-row MMA tiles.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/rk.h"
+
+#define BM 128
+#define BN 128
+#define BK 8
+#define TM 8
+#define TN 8
+
+// C[M][N] (row-major, ldc) = epi( op(A)[M][K] * B[K][N] )
+//   A_TRANS = 0: A stored [M][K] (lda >= K);  1: A stored [K][M] (lda >= M)
+//   split-K: blockIdx.z handles K range [z*kchunk, (z+1)*kchunk); partial tiles go to
+//   `out` = workspace + z*M*N (ldc = N) and the epilogue is applied by the reduce kernel.
+template <bool A_TRANS>
+__global__ void __launch_bounds__(256)
+rk_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                const float* __restrict__ bias, const float* __restrict__ aux, int ldaux,
+                int epi, int accumulate, int kchunk, float* __restrict__ workspace) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, each 8 x 8 outputs
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // global -> register staging: each thread moves 4 A values and 4 B values per k-tile
+  float ra[4], rb[4];
+  auto load_tiles = [&](int k0) {
+    if (A_TRANS) {                                 // A[k][m]: 8 rows of 128 floats
+      const int kk = tid >> 5, mm = (tid & 31) * 4;
+      const int k = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + mm + i;
+        ra[i] = (k < kend && m < M) ? A[(size_t)k * lda + m] : 0.f;
+      }
+    } else {                                       // A[m][k]: 128 rows of 8 floats
+      const int mm = tid >> 1, kk = (tid & 1) * 4;
+      const int m = m0 + mm;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + kk + i;
+        ra[i] = (m < M && k < kend) ? A[(size_t)m * lda + k] : 0.f;
+      }
+    }
+    {
+      const int kk = tid >> 5, nn = (tid & 31) * 4;
+      const int k = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + nn + i;
+        rb[i] = (k < kend && n < N) ? B[(size_t)k * ldb + n] : 0.f;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    if (A_TRANS) {
+      const int kk = tid >> 5, mm = (tid & 31) * 4;
+      *reinterpret_cast<float4*>(&As[buf][kk][mm]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    } else {
+      const int mm = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[buf][kk + i][mm] = ra[i];
+    }
+    const int kk = tid >> 5, nn = (tid & 31) * 4;
+    *reinterpret_cast<float4*>(&Bs[buf][kk][nn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    load_tiles(kbeg);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) load_tiles(k0 + BK);                 // next tile's loads overlap the math
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  const bool split = gridDim.z > 1;
+  float* out = split ? workspace + (size_t)blockIdx.z * M * N : C;
+  const int ldo = split ? N : ldc;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (!split) {
+        if (epi == 1 || epi == 2) v += bias[n];
+        if (epi == 2) v = tanhf(v);
+        if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+        if (accumulate) v += out[(size_t)m * ldo + n];
+      }
+      out[(size_t)m * ldo + n] = v;
+    }
+  }
+}
+
+__global__ void rk_sgemm_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws,
+                                       float* __restrict__ C, int ldc,
+                                       const float* __restrict__ bias,
+                                       const float* __restrict__ aux, int ldaux, int epi,
+                                       int accumulate) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += ws[(size_t)z * M * N + i];      // fixed order
+  if (epi == 1 || epi == 2) v += bias[n];
+  if (epi == 2) v = tanhf(v);
+  if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+  if (accumulate) v += C[(size_t)m * ldc + n];
+  C[(size_t)m * ldc + n] = v;
+}
+
+extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int lda,
+                        const float* B, int ldb, float* C, int ldc, const float* bias,
+                        const float* aux, int ldaux, float* workspace, int split_k) {
+  if (M <= 0 || N <= 0 || K <= 0 || A == nullptr || B == nullptr || C == nullptr)
+    return RK_E_BADARG;
+  const int a_trans = flags & RK_GEMM_A_TRANS, accumulate = (flags & RK_GEMM_ACCUMULATE) ? 1 : 0;
+  const int epi = (flags >> 4) & 0xf;
+  if (epi > 3 || ((epi == 1 || epi == 2) && bias == nullptr) || (epi == 3 && aux == nullptr))
+    return RK_E_BADARG;
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && workspace == nullptr) return RK_E_BADARG;
+  int kchunk = (K + split_k - 1) / split_k;
+  kchunk = ((kchunk + BK - 1) / BK) * BK;
+  const int splits = (K + kchunk - 1) / kchunk;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+  if (a_trans)
+    rk_sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux,
+                                                 epi, accumulate, kchunk, workspace);
+  else
+    rk_sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux,
+                                                  ldaux, epi, accumulate, kchunk, workspace);
+  if (splits > 1) {
+    const size_t total = (size_t)M * N;
+    rk_sgemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        M, N, splits, workspace, C, ldc, bias, aux, ldaux, epi, accumulate);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- action heads (planner.py:1394-1429, 1472-1475) ---------------------------------------
+// heads [B][2A]: columns [0, A) = mu, [A, 2A) = log_sigma (pre-clip); noise [A][B];
+// action = clip(mu + train * exp(clip(log_sigma)) * noise, lo, hi), stored fluent-major [A][B].
+// entropy[b] = sum_a clip(log_sigma)   (value only: stop_gradient unless sigma_entropy_grad)
+__global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic,
+                                          const float* __restrict__ heads,
+                                          const float* __restrict__ noise, float train,
+                                          const float* __restrict__ lo,
+                                          const float* __restrict__ hi, float ls_lo, float ls_hi,
+                                          float* __restrict__ actions,
+                                          float* __restrict__ entropy) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int ld = stochastic ? 2 * A : A;
+  float ent = 0.f;
+  for (int a = 0; a < A; ++a) {
+    float act = heads[(size_t)b * ld + a];
+    if (stochastic) {
+      const float ls = fminf(fmaxf(heads[(size_t)b * ld + A + a], ls_lo), ls_hi);
+      ent += ls;
+      const float z = (noise != nullptr) ? noise[(size_t)a * B + b] : 0.f;
+      act = act + train * expf(ls) * z;
+    }
+    if (lo != nullptr) act = fminf(fmaxf(act, lo[a]), hi[a]);
+    actions[(size_t)a * B + b] = act;
+  }
+  if (entropy != nullptr) entropy[b] = ent;
+}
+
+__global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic,
+                                          const float* __restrict__ heads,
+                                          const float* __restrict__ noise, float train,
+                                          const float* __restrict__ lo,
+                                          const float* __restrict__ hi, float ls_lo, float ls_hi,
+                                          const float* __restrict__ gact,
+                                          float* __restrict__ gheads) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int ld = stochastic ? 2 * A : A;
+  for (int a = 0; a < A; ++a) {
+    const float mu = heads[(size_t)b * ld + a];
+    float pre = mu, e = 0.f, z = 0.f, raw = 0.f;
+    if (stochastic) {
+      raw = heads[(size_t)b * ld + A + a];
+      const float ls = fminf(fmaxf(raw, ls_lo), ls_hi);
+      z = (noise != nullptr) ? noise[(size_t)a * B + b] : 0.f;
+      e = expf(ls);
+      pre = mu + train * e * z;
+    }
+    float g = gact[(size_t)a * B + b];
+    // jnp.clip: gradient 1 inside [lo, hi] (bounds included), 0 outside
+    if (lo != nullptr && (pre < lo[a] || pre > hi[a])) g = 0.f;
+    gheads[(size_t)b * ld + a] = g;
+    if (stochastic) {
+      const bool inside = raw >= ls_lo && raw <= ls_hi;
+      gheads[(size_t)b * ld + A + a] = inside ? g * train * e * z : 0.f;
+    }
+  }
+}
+
+extern "C" int rk_drp_actions_forward(void* stream, int B, int A, int stochastic,
+                                      const float* heads, const float* noise, float train,
+                                      const float* lo, const float* hi, float ls_lo, float ls_hi,
+                                      float* actions, float* entropy) {
+  if (B <= 0 || A <= 0 || heads == nullptr || actions == nullptr) return RK_E_BADARG;
+  if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
+  rk_drp_actions_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, actions, entropy);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochastic,
+                                       const float* heads, const float* noise, float train,
+                                       const float* lo, const float* hi, float ls_lo, float ls_hi,
+                                       const float* gact, float* gheads) {
+  if (B <= 0 || A <= 0 || heads == nullptr || gact == nullptr || gheads == nullptr)
+    return RK_E_BADARG;
+  if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
+  rk_drp_actions_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, gact, gheads);
+  return (int)cudaGetLastError();
+}
+
+// dst[d][b] (+)= src[b][d]: the input cotangent of the first dense layer, added to the
+// fluent-major state cotangent the rollout adjoint carries.
+__global__ void rk_transpose_add_kernel(int B, int D, const float* __restrict__ src, int lds,
+                                        float* __restrict__ dst, int accumulate) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int b = b0 + r, d = d0 + threadIdx.x;
+    tile[r][threadIdx.x] = (b < B && d < D) ? src[(size_t)b * lds + d] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, b = b0 + threadIdx.x;
+    if (d < D && b < B) {
+      float v = tile[threadIdx.x][r];
+      if (accumulate) v += dst[(size_t)d * B + b];
+      dst[(size_t)d * B + b] = v;
+    }
+  }
+}
+
+extern "C" int rk_transpose_add(void* stream, int B, int D, const float* src, int lds,
+                                float* dst, int accumulate) {
+  if (B <= 0 || D <= 0 || src == nullptr || dst == nullptr) return RK_E_BADARG;
+  dim3 grid((B + 31) / 32, (D + 31) / 32), block(32, 8);
+  rk_transpose_add_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(B, D, src, lds, dst, accumulate);
+  return (int)cudaGetLastError();
+}

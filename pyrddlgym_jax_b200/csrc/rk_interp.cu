@@ -583,7 +583,8 @@ extern "C" int rk_rollout_forward(const rk_program* p, void* stream, int B, int 
 extern "C" int rk_rollout_backward(const rk_program* p, void* stream, int B, int T,
                                    const void* tape, const float* policy, const void* actions,
                                    const float* noise, const float* mparams, const float* disc,
-                                   const float* gret, float* gradp, float* gact, float* gs0) {
+                                   const float* gret, float* gradp, float* gact, float* gs0,
+                                   const float* gs_in) {
   if (p == nullptr || B < 0 || T < 0) return RK_E_BADARG;
   if (!(p->hdr[14] & 2u)) return RK_E_BADPROG;
   if ((tape == nullptr || gret == nullptr) && B > 0) return RK_E_BADARG;
@@ -601,5 +602,6 @@ extern "C" int rk_rollout_backward(const rk_program* p, void* stream, int B, int
   K.buf[RK_BUF_GRADP] = gradp;            K.W[RK_BUF_GRADP] = A;
   K.buf[RK_BUF_GACT] = gact;              K.W[RK_BUF_GACT] = A;
   K.buf[RK_BUF_GS0] = gs0;                K.W[RK_BUF_GS0] = S;
+  K.buf[RK_BUF_GSIN] = (void*)gs_in;      K.W[RK_BUF_GSIN] = S;
   return launch(p, (cudaStream_t)stream, K);
 }

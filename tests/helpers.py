@@ -21,6 +21,7 @@ FIXTURES = {
     "reservoir": ("Reservoir_Continuous", "instance1"),
     "wildfire": ("Wildfire_MDP_ippc2014", "instance5"),
     "marsrover": ("MarsRover_ippc2023", "instance5"),
+    "powergen": ("PowerGen_Continuous", "instance1"),
 }
 
 

@@ -26,6 +26,8 @@ def make_params(model, key, T, seed=42, scale=0.5):
         params["thrust"] = params["thrust"] + 9.81
     if key == "reservoir":
         params["release"] = params["release"].abs() * 10 + 5.
+    if key == "powergen":
+        params["curProd"] = params["curProd"] * 2 + 3.
     if key == "marsrover":          # power within the box, rovers near minerals harvest
         params["power-x"] = params["power-x"] * 0.2
         params["power-y"] = params["power-y"] * 0.2

@@ -52,7 +52,7 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     assert lib.rk_program_create(junk, 256, ctypes.byref(out)) == -2      # RK_E_BADPROG (magic)
     assert lib.rk_program_query(None, None) == -1
     assert lib.rk_rollout_forward(None, None, 1, 1, *([None] * 12)) == -1
-    assert lib.rk_rollout_backward(None, None, 1, 1, *([None] * 10)) == -1
+    assert lib.rk_rollout_backward(None, None, 1, 1, *([None] * 11)) == -1
     lib.rk_program_destroy(None)                                          # no-op
 
 

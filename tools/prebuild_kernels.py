@@ -1,28 +1,36 @@
-"""Pre-compiles the specialised kernels of the bench / smoke workloads (csrc/jit/*.cubin) so
-that a fresh GPU box does not pay nvcc time (the cubins are git-ignored but travel with the
-repo snapshot)."""
+"""Pre-compiles the specialised kernels of the bench workloads (csrc/jit/*.cubin) so that a
+fresh GPU box does not pay nvcc time (the cubins are git-ignored but travel with the repo
+snapshot)."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from pyrddlgym_jax_b200.core import logic  # noqa: E402
 from pyrddlgym_jax_b200.core.codegen import compile_cubin  # noqa: E402
 from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler  # noqa: E402
 from pyrddlgym_jax_b200.core.planner import JaxStraightLinePlan  # noqa: E402
 
 
-def prebuild(model, B, T, **ckw):
-    comp = logic.DefaultJaxRDDLCompilerWithGrad(model, **ckw)
+def prebuild_workload(name: str, verbose: bool = True):
+    w = bench.WORKLOADS[name]
+    model = bench.workload_model(name)
+    comp = bench.make_compiler(name, model)
     exact = JaxRDDLCompiler(model)
-    plan = JaxStraightLinePlan()
-    plan.compile(comp, exact, {}, T)
-    tb = comp.builder(plan.spec, True, (), B)
+    plan = JaxStraightLinePlan(**w["plan_kwargs"])
+    plan.compile(comp, exact, {}, w["T"])
+    tb = comp.builder(plan.spec, True, (), w["B"])
     gamma = float(model.discount)
     for prog in (tb.forward(write_tape=True, gamma=gamma), tb.backward(gamma=gamma),
-                 exact.builder(plan.spec, False, (), B).forward(write_tape=False, gamma=gamma)):
-        print(compile_cubin(prog)[0])
+                 exact.builder(plan.spec, False, (), w["B"]).forward(write_tape=False, gamma=gamma)):
+        path = compile_cubin(prog)[0]
+        if verbose:
+            print(name, os.path.basename(path))
+
+
+def prebuild_all(verbose: bool = True):
+    for name in bench.WORKLOADS:
+        prebuild_workload(name, verbose)
 
 
 if __name__ == "__main__":
-    prebuild(bench.quadcopter_model(), bench.B_PER_GPU, bench.HORIZON, sigmoid_weight=10.)
+    prebuild_all()
