@@ -135,7 +135,8 @@ int rk_project_slp(void* stream, int method, int T, int A, float* params, int n_
  * The flax MLP (planner.py:1342-1449) runs between two T = 1 launches of the rollout kernel.
  *
  * rk_sgemm: C[M][N] = epi(op(A)[M][K] * B[K][N]), fp32, row-major.
- *   flags: RK_GEMM_A_TRANS (A stored [K][M]), RK_GEMM_ACCUMULATE (C += ...), and the epilogue
+ *   flags: RK_GEMM_A_TRANS (A stored [K][M]), RK_GEMM_ACCUMULATE (C_in + A*B, before the
+ *   epilogue: lets a layer whose input is several fluent blocks be summed block by block), and the epilogue
  *   in bits 4..7: RK_EPI_NONE, RK_EPI_BIAS (+ bias[n]), RK_EPI_BIAS_TANH (nn.Dense + tanh,
  *   planner.py:1359-1361), RK_EPI_DTANH (* (1 - aux[m][n]^2): the tanh adjoint).
  *   split_k > 1 runs a deterministic split-K through `workspace` ([split_k][M][N] floats).
@@ -152,21 +153,22 @@ int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int l
              int ldaux, float* workspace, int split_k);
 
 /* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).
- *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise; noise [A][B] or NULL;
+ *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise;
+ *   seg_off / seg_len (HOST arrays, n_seg <= RK_MAX_ACTION_FLUENTS): the action fluents' word
+ *   ranges, contiguous and in action-fluent order; actions, noise and gact use the rollout
+ *   kernels' fluent-major layout (fluent f = block [B][len_f] at word offset off_f * B);
  *   train = 1 (train policy) or 0 (test policy, planner.py:1486); lo/hi [A] or NULL;
- *   actions [A][B] fluent-major (the rollout kernel's `actions` layout);
  *   entropy [B] = sum_a clip(log_sigma) (planner.py:1416-1419), or NULL. */
-int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, const float* heads,
+#define RK_MAX_ACTION_FLUENTS 16
+int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg,
+                           const int32_t* seg_off, const int32_t* seg_len, const float* heads,
                            const float* noise, float train, const float* lo, const float* hi,
                            float ls_lo, float ls_hi, float* actions, float* entropy);
-/* gheads [B][2A or A] = d actions / d heads applied to gact [A][B] (clip: gradient 1 inside). */
-int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, const float* heads,
+/* gheads [B][2A or A] = d actions / d heads applied to gact (clip: gradient 1 inside). */
+int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
+                            const int32_t* seg_off, const int32_t* seg_len, const float* heads,
                             const float* noise, float train, const float* lo, const float* hi,
                             float ls_lo, float ls_hi, const float* gact, float* gheads);
-/* dst[D][B] (+)= src[B][D]^T: adds the first layer's input cotangent to the fluent-major state
- * cotangent. */
-int rk_transpose_add(void* stream, int B, int D, const float* src, int lds, float* dst,
-                     int accumulate);
 
 /* -mean(returns) and its cotangent, for utility='mean' (planner.py:2817-2818):
  * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */

@@ -236,3 +236,97 @@ def project_max_constraint(model, params: Dict[str, torch.Tensor], method: str, 
         for v in bools:
             out[v][t] = new[v]
     return out, converged
+
+
+# ---- deep reactive policy (planner.py:1122-1534) ---------------------------------------------
+def drp_input_order(model) -> List[str]:
+    """Order in which observed fluents enter the state vector (planner.py:1302-1313): the
+    fluent dict crosses a jit boundary, so it iterates in sorted-key order; non-bool fluents
+    first, then bool ones."""
+    names = sorted(model.state_fluents)
+    return [v for v in names if model.variable_ranges[v] != "bool"] + \
+           [v for v in names if model.variable_ranges[v] == "bool"]
+
+
+def drp_init(model, topology, generator: torch.Generator, stochastic: bool = True):
+    """variance_scaling(2.0, 'fan_in', 'truncated_normal') kernels, zero biases
+    (planner.py:1129-1130; flax nn.Dense), as a dict layer -> {'kernel' [in, out], 'bias'}."""
+    def kernel(fan_in, fan_out):
+        std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+        w = torch.empty(fan_in, fan_out)
+        torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
+        return w * std
+    D = sum(model.variable_size(v) for v in drp_input_order(model))
+    params, fan = {}, D
+    for i, h in enumerate(topology):
+        params[f"dense_{i}"] = {"kernel": kernel(fan, h), "bias": torch.zeros(h)}
+        fan = h
+    for var in model.action_fluents:
+        n = model.variable_size(var)
+        name = var.replace("-", "_")
+        if model.variable_ranges[var] == "bool":
+            params[f"dense_{name}_logit"] = {"kernel": kernel(fan, n), "bias": torch.zeros(n)}
+        else:
+            params[f"dense_{name}_mu"] = {"kernel": kernel(fan, n), "bias": torch.zeros(n)}
+            if stochastic:
+                params[f"dense_{name}_log_sigma"] = {"kernel": kernel(fan, n),
+                                                     "bias": torch.zeros(n)}
+    return params
+
+
+def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], train: float,
+                bounds, topology_len: int, stochastic: bool = True,
+                sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0):
+    """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
+    noise: action name -> [B, n] standard draws.  Returns (actions name -> [B, *objs],
+    entropy [B])."""
+    B = next(iter(fls.values())).shape[0]
+    x = torch.cat([fls[v].reshape(B, -1).to(REAL) for v in drp_input_order(model)], dim=1)
+    h = x
+    for i in range(topology_len):
+        layer = params[f"dense_{i}"]
+        h = torch.tanh(h @ layer["kernel"] + layer["bias"])
+    ls_lo, ls_hi = math.log(sigma_range[0]), math.log(sigma_range[1])
+    actions, entropy = {}, torch.zeros(B, dtype=REAL)
+    for var in model.action_fluents:
+        name = var.replace("-", "_")
+        shape = (B,) + tuple(model.variable_shape(var))
+        if model.variable_ranges[var] == "bool":
+            layer = params[f"dense_{name}_logit"]
+            logits = h @ layer["kernel"] + layer["bias"]
+            if stochastic:
+                prob = torch.sigmoid(sigmoid_weight * logits)
+                entropy = entropy - (prob * safe_log(prob) + (1. - prob) * safe_log(1. - prob)).sum(1)
+                logits = logits + train * noise[var]
+            actions[var] = torch.sigmoid(sigmoid_weight * logits).reshape(shape)
+            continue
+        layer = params[f"dense_{name}_mu"]
+        a = h @ layer["kernel"] + layer["bias"]
+        if stochastic:
+            layer = params[f"dense_{name}_log_sigma"]
+            ls = torch.clamp(h @ layer["kernel"] + layer["bias"], ls_lo, ls_hi)
+            entropy = entropy + ls.detach().sum(1)            # sigma_entropy_grad = False
+            a = a + train * torch.exp(ls) * noise[var]
+        lo, hi = bounds[var]
+        lo = torch.as_tensor(np.asarray(lo, np.float32)).reshape(1, -1)
+        hi = torch.as_tensor(np.asarray(hi, np.float32)).reshape(1, -1)
+        a = torch.minimum(torch.maximum(a, lo), hi)           # planner.py:1472-1475
+        actions[var] = a.reshape(shape)
+    return actions, entropy
+
+
+def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True):
+    """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
+    zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
+             for v in model.action_fluents}
+    acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic)
+    out = {}
+    for var, a in acts.items():
+        prange = model.variable_ranges[var]
+        if prange == "bool":
+            out[var] = a > 0.5
+        elif prange == "int" or prange in model.enum_types:
+            out[var] = torch.round(a).to(INT)
+        else:
+            out[var] = a
+    return out

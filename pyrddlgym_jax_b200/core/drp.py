@@ -1,0 +1,416 @@
+"""Deep reactive policy (closed-loop MLP plan) on the B200 kernels.
+
+``JaxDeepReactivePolicy`` mirrors planner.py:1122-1534 of the reference (constructor keywords,
+parameter pytree with flax layer names ``dense_{i}`` / ``dense_{var}_mu`` /
+``dense_{var}_log_sigma``); ``DrpPipeline`` is the device side of one planner iteration for
+such a plan.  Because the policy reads the current state, the horizon is walked one decision
+epoch per launch:
+
+    forward  t = 0..T-1 :  dense layers (rk_sgemm, bias+tanh fused) -> heads -> actions
+                           (rk_drp_actions_forward) -> one T=1 launch of the rollout kernel
+    backward t = T-1..0 :  T=1 adjoint launch (state cotangent chained through GSIN/GS0, action
+                           cotangent out) -> heads/dense adjoints (rk_sgemm with the tanh
+                           adjoint fused; weight gradients accumulated with a deterministic
+                           split-K) -> input cotangent added to the state cotangent
+
+Hidden activations of every step are kept in HBM (T*B*H floats per layer) rather than
+recomputed: at B=32768, T=100, H=256 that is 3.4 GB per layer, far below the 180 GB available.
+All of it is captured into the iteration's CUDA graph by the planner.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import engine
+from .planner_base import JaxPlan, initializers
+from .program import PlanSpec, action_layout
+
+
+class JaxDeepReactivePolicy(JaxPlan):
+    """A deep reactive policy network (planner.py:1122)."""
+
+    kind = "drp"
+    history_dependent = False
+
+    def __init__(self, topology: Optional[Sequence[int]] = None, activation: Any = "tanh",
+                 initializer: Any = None, normalize: bool = False,
+                 normalize_per_layer: bool = False, normalizer_kwargs: Optional[Dict] = None,
+                 sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
+                 softmax_weight: float = 1.0, stochastic: bool = True,
+                 sigma_range: Tuple[float, float] = (1e-5, 1e3), sigma_entropy_grad: bool = False,
+                 action_noise_dist: Any = "normal", time_dependent: bool = False,
+                 time_embedding: Any = None, time_embedding_kwargs: Optional[Dict] = None) -> None:
+        super().__init__()
+        self._topology = list(topology) if topology is not None else [64, 64]
+        act = getattr(activation, "__name__", activation)
+        if act != "tanh":
+            raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
+        for flag, name in ((normalize, "normalize"), (wrap_non_bool, "wrap_non_bool"),
+                           (time_dependent, "time_dependent"),
+                           (sigma_entropy_grad, "sigma_entropy_grad")):
+            if flag:
+                raise NotImplementedError(f"JaxDeepReactivePolicy({name}=True) is not built yet")
+        dist = getattr(action_noise_dist, "__name__", action_noise_dist)
+        if dist != "normal":
+            raise NotImplementedError("action_noise_dist other than normal is not built yet")
+        self._initializer_base = initializer
+        self._sigmoid_weight = sigmoid_weight
+        self._softmax_output_weight = softmax_weight
+        self._stochastic = stochastic
+        self._sigma_range = sigma_range
+        self._normalize = normalize
+        self._time_dependent = time_dependent
+
+    def __str__(self) -> str:
+        return (f"[INFO] policy hyper-parameters:\n"
+                f"    topology          ={self._topology}\n"
+                f"    activation_fn     =tanh\n"
+                f"    stochastic        ={self._stochastic}\n"
+                f"    sigma_range       ={self._sigma_range}\n")
+
+    # ---------------------------------------------------------------------------------
+    def compile(self, compiled, test_compiled, _bounds, horizon, preprocessor=None) -> None:
+        rddl = compiled.rddl
+        self.rddl = rddl
+        self.horizon = horizon
+        self.layout, self.A = action_layout(rddl)
+        for name, (_, _, prange) in self.layout.items():
+            if prange != "real":
+                raise NotImplementedError(
+                    f"DRP heads for <{prange}> action-fluent <{name}> are not built yet "
+                    f"(real-valued actions only)")
+        if rddl.observ_fluents:
+            raise NotImplementedError("DRP over observ-fluents (POMDP) is not built yet")
+        bounds = {}
+        for name in self.layout:
+            lo, hi = rddl.bounds[name]
+            lo, hi = _bounds.get(name, (lo, hi))
+            shape = rddl.variable_shape(name)
+            bounds[name] = (np.broadcast_to(np.asarray(lo, np.float32), shape).copy(),
+                            np.broadcast_to(np.asarray(hi, np.float32), shape).copy())
+        self.bounds = bounds
+        self.spec = PlanSpec(kind="external", bounds=bounds)
+        # input vector: the state words in the kernels' fluent-major order; `input_perm` maps
+        # the reference's row order (sorted names, non-bool first, planner.py:1302-1313) to it
+        off, pos = 0, {}
+        for name in rddl.state_fluents:
+            n = rddl.variable_size(name)
+            pos[name] = (off, n)
+            off += n
+        self.D = off
+        self.state_segs = [(pos[v][0], pos[v][1]) for v in rddl.state_fluents]
+        self.action_segs = [(o, n) for (o, n, _) in self.layout.values()]
+        names = sorted(rddl.state_fluents)
+        ref = [v for v in names if rddl.variable_ranges[v] != "bool"] + \
+              [v for v in names if rddl.variable_ranges[v] == "bool"]
+        self.input_perm = np.concatenate([np.arange(pos[v][0], pos[v][0] + pos[v][1]) for v in ref])
+        # flat parameter vector: [W_i | b_i]* then [W_heads | b_heads]
+        self.NH = self.A * (2 if self._stochastic else 1)
+        dims = [self.D] + self._topology
+        self.segments: List[Tuple[str, int, int, int]] = []     # (name, offset, rows, cols)
+        o = 0
+        for i in range(len(self._topology)):
+            self.segments.append((f"W{i}", o, dims[i], dims[i + 1]))
+            o += dims[i] * dims[i + 1]
+            self.segments.append((f"b{i}", o, 1, dims[i + 1]))
+            o += dims[i + 1]
+        self.segments.append(("Wh", o, dims[-1], self.NH))
+        o += dims[-1] * self.NH
+        self.segments.append(("bh", o, 1, self.NH))
+        o += self.NH
+        self.n_params = o
+        self.seg = {name: (off, r, c) for name, off, r, c in self.segments}
+        self.box = (None, None)
+        self.needs_concurrency_projection = False
+
+    def num_params(self, horizon: int) -> int:
+        return self.n_params
+
+    def initial_params(self, generator: torch.Generator) -> torch.Tensor:
+        """variance_scaling(2.0, fan_in, truncated_normal) kernels, zero biases
+        (planner.py:1129-1130, 1520-1529)."""
+        flat = torch.zeros(self.n_params)
+        for name, off, r, c in self.segments:
+            if name.startswith("W"):
+                if self._initializer_base is not None:
+                    w = self._initializer_base((r, c), generator)
+                else:
+                    std = math.sqrt(2.0 / r) / 0.87962566103423978
+                    w = torch.empty(r, c)
+                    torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
+                    w = w * std
+                flat[off:off + r * c] = w.reshape(-1)
+        return flat
+
+    # ---- flat vector <-> flax-style pytree ------------------------------------------------
+    def params_to_pytree(self, flat: torch.Tensor) -> Dict[str, Any]:
+        lead = flat.shape[:-1]
+        tree: Dict[str, Any] = {}
+        for i in range(len(self._topology)):
+            off, r, c = self.seg[f"W{i}"]
+            W = flat[..., off:off + r * c].reshape(*lead, r, c)
+            if i == 0:
+                W = W[..., torch.as_tensor(self.input_perm), :]
+            ob, _, cb = self.seg[f"b{i}"]
+            tree[f"dense_{i}"] = {"kernel": W, "bias": flat[..., ob:ob + cb]}
+        off, r, c = self.seg["Wh"]
+        Wh = flat[..., off:off + r * c].reshape(*lead, r, c)
+        ob = self.seg["bh"][0]
+        bh = flat[..., ob:ob + c]
+        for var, (aoff, n, _) in self.layout.items():
+            nm = var.replace("-", "_")
+            tree[f"dense_{nm}_mu"] = {"kernel": Wh[..., aoff:aoff + n], "bias": bh[..., aoff:aoff + n]}
+            if self._stochastic:
+                tree[f"dense_{nm}_log_sigma"] = {
+                    "kernel": Wh[..., self.A + aoff:self.A + aoff + n],
+                    "bias": bh[..., self.A + aoff:self.A + aoff + n]}
+        return {"params": tree}
+
+    def pytree_to_params(self, tree: Dict[str, Any]) -> torch.Tensor:
+        tree = tree.get("params", tree)
+        flat = torch.zeros(self.n_params)
+        as_t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32)   # noqa: E731
+        for i in range(len(self._topology)):
+            off, r, c = self.seg[f"W{i}"]
+            W = as_t(tree[f"dense_{i}"]["kernel"]).reshape(r, c)
+            if i == 0:
+                Wi = torch.empty_like(W)
+                Wi[torch.as_tensor(self.input_perm)] = W
+                W = Wi
+            flat[off:off + r * c] = W.reshape(-1)
+            ob, _, cb = self.seg[f"b{i}"]
+            flat[ob:ob + cb] = as_t(tree[f"dense_{i}"]["bias"]).reshape(-1)
+        off, r, c = self.seg["Wh"]
+        Wh = torch.zeros(r, c)
+        bh = torch.zeros(c)
+        for var, (aoff, n, _) in self.layout.items():
+            nm = var.replace("-", "_")
+            Wh[:, aoff:aoff + n] = as_t(tree[f"dense_{nm}_mu"]["kernel"]).reshape(r, n)
+            bh[aoff:aoff + n] = as_t(tree[f"dense_{nm}_mu"]["bias"]).reshape(-1)
+            if self._stochastic:
+                Wh[:, self.A + aoff:self.A + aoff + n] = \
+                    as_t(tree[f"dense_{nm}_log_sigma"]["kernel"]).reshape(r, n)
+                bh[self.A + aoff:self.A + aoff + n] = \
+                    as_t(tree[f"dense_{nm}_log_sigma"]["bias"]).reshape(-1)
+        flat[off:off + r * c] = Wh.reshape(-1)
+        ob = self.seg["bh"][0]
+        flat[ob:ob + c] = bh
+        return flat
+
+    def guess_next_epoch(self, params):
+        return params                      # planner.py:1531-1534: warm start from the same policy
+
+    def test_actions_host(self, flat: torch.Tensor, state_vec: np.ndarray) -> Dict[str, np.ndarray]:
+        """Test policy on one state (controllers' get_action, planner.py:3527): a handful of
+        tiny mat-vecs on the host."""
+        h = torch.as_tensor(state_vec, dtype=torch.float32).reshape(1, -1)
+        for i in range(len(self._topology)):
+            off, r, c = self.seg[f"W{i}"]
+            ob = self.seg[f"b{i}"][0]
+            h = torch.tanh(h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c])
+        off, r, c = self.seg["Wh"]
+        ob = self.seg["bh"][0]
+        out = (h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c]).reshape(-1)
+        acts = {}
+        for var, (aoff, n, _) in self.layout.items():
+            lo, hi = self.bounds[var]
+            a = out[aoff:aoff + n].numpy().reshape(self.rddl.variable_shape(var))
+            acts[var] = np.minimum(np.maximum(a, lo), hi)
+        return acts
+
+
+class DrpPipeline:
+    """Device buffers + launch sequence of one planner iteration with a DRP (see module doc)."""
+
+    def __init__(self, planner):
+        self.pl = planner
+        plan: JaxDeepReactivePolicy = planner.plan
+        self.plan = plan
+        dev = planner.device
+        self.dev = dev
+        T, Bt, Be = planner.T, planner.batch_size_train, planner.batch_size_test
+        fw, te = planner.train_fwd.program, planner.test_fwd.program
+        self.S, self.A, self.NH, self.D = fw.S, plan.A, plan.NH, plan.D
+        assert self.D == self.S
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)   # noqa: E731
+        self.hid = plan._topology
+        self.tape = z((T + 1) * self.S * Bt)
+        self.H = [z(T, Bt, h) for h in self.hid]
+        self.heads = z(T, Bt, self.NH)
+        self.act = z(T, self.A * Bt)
+        self.entropy = z(T, Bt)
+        self.pol_noise = z(T, self.A * Bt) if plan._stochastic else None
+        self.gact = z(self.A * Bt)
+        self.gs = [z(self.S * Bt), z(self.S * Bt)]
+        self.gheads = z(Bt, self.NH)
+        self.gz = [z(Bt, h) for h in self.hid]
+        self.ones = torch.ones(max(Bt, Be), dtype=torch.float32, device=dev)
+        self.split_k = int(max(1, min(64, Bt // 2048)))
+        big = max([self.D * self.hid[0]] + [a * b for a, b in zip(self.hid[:-1], self.hid[1:])]
+                  + [self.hid[-1] * self.NH])
+        self.ws = z(self.split_k * big) if self.split_k > 1 else None
+        self.wT = z(plan.n_params)                    # transposed kernels, same offsets
+        lo = np.concatenate([plan.bounds[v][0].reshape(-1) for v in plan.layout])
+        hi = np.concatenate([plan.bounds[v][1].reshape(-1) for v in plan.layout])
+        self.lo = torch.from_numpy(lo.astype(np.float32)).to(dev)
+        self.hi = torch.from_numpy(hi.astype(np.float32)).to(dev)
+        self.ls_lo, self.ls_hi = math.log(plan._sigma_range[0]), math.log(plan._sigma_range[1])
+        # exact test model: a single slot of activations is enough (forward only)
+        self.t_state = [z(te.S * Be), z(te.S * Be)]
+        self.t_H = [z(Be, h) for h in self.hid]
+        self.t_heads = z(Be, self.NH)
+        self.t_act = z(self.A * Be)
+        self.ent_coeff = z(1)
+
+    # ---- views into a flat parameter / gradient vector ---------------------------------------
+    def _W(self, flat, name):
+        off, r, c = self.plan.seg[name]
+        return flat[off:off + r * c]
+
+    def refresh_transposes(self, params: torch.Tensor):
+        for name, off, r, c in self.plan.segments:
+            if name.startswith("W"):
+                self.wT[off:off + r * c].view(c, r).copy_(params[off:off + r * c].view(r, c).t())
+
+    # ---- the MLP ------------------------------------------------------------------------------
+    def mlp_forward(self, params, B, x_fm, H, heads):
+        """x_fm: the state in the kernels' fluent-major layout (fluent f = block [B][n_f] at word
+        offset off_f * B); H: per-layer outputs [B][h]; heads [B][NH].  The first layer is the
+        sum over fluent blocks of X_f [B][n_f] * W0[rows of f] (accumulated in place; bias and
+        tanh are applied with the last block)."""
+        h0 = self.hid[0]
+        W0 = self._W(params, "W0")
+        segs = self.plan.state_segs
+        for j, (off, n) in enumerate(segs):
+            last = j == len(segs) - 1
+            flags = (engine.GEMM_ACCUMULATE if j > 0 else 0) | \
+                (engine.EPI_BIAS_TANH if last else engine.EPI_NONE)
+            engine.sgemm(flags, B, h0, n, x_fm[off * B:], n, W0[off * h0:], h0, H[0], h0,
+                         bias=self._W(params, "b0"))
+        fan, src = h0, H[0]
+        for i in range(1, len(self.hid)):
+            h = self.hid[i]
+            engine.sgemm(engine.EPI_BIAS_TANH, B, h, fan, src, fan, self._W(params, f"W{i}"), h,
+                         H[i], h, bias=self._W(params, f"b{i}"))
+            fan, src = h, H[i]
+        engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"), self.NH,
+                     heads, self.NH, bias=self._W(params, "bh"))
+
+    def mlp_backward(self, grad, B, x_fm, H, gs_cur):
+        """Consumes self.gheads [B][NH]; accumulates weight gradients into ``grad`` and adds the
+        input cotangent to the fluent-major state cotangent ``gs_cur``."""
+        AT, ACC = engine.GEMM_A_TRANS, engine.GEMM_ACCUMULATE
+        sk, ws = self.split_k, self.ws
+        last = len(self.hid) - 1
+        hl = self.hid[last]
+        engine.sgemm(AT | ACC, hl, self.NH, B, H[last], hl, self.gheads, self.NH,
+                     self._W(grad, "Wh"), self.NH, workspace=ws, split_k=sk)
+        engine.sgemm(AT | ACC, 1, self.NH, B, self.ones, 1, self.gheads, self.NH,
+                     self._W(grad, "bh"), self.NH, workspace=ws, split_k=sk)
+        engine.sgemm(engine.EPI_DTANH, B, hl, self.NH, self.gheads, self.NH,
+                     self._W(self.wT, "Wh"), hl, self.gz[last], hl, aux=H[last], ldaux=hl)
+        for i in range(last, -1, -1):
+            h = self.hid[i]
+            fan = self.D if i == 0 else self.hid[i - 1]
+            if i == 0:      # one block of rows of W0 per state fluent
+                gW0 = self._W(grad, "W0")
+                for off, n in self.plan.state_segs:
+                    engine.sgemm(AT | ACC, n, h, B, x_fm[off * B:], n, self.gz[0], h,
+                                 gW0[off * h:], h, workspace=ws, split_k=sk)
+            else:
+                engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
+                             self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
+            engine.sgemm(AT | ACC, 1, h, B, self.ones, 1, self.gz[i], h, self._W(grad, f"b{i}"), h,
+                         workspace=ws, split_k=sk)
+            if i > 0:
+                engine.sgemm(engine.EPI_DTANH, B, fan, h, self.gz[i], h, self._W(self.wT, f"W{i}"),
+                             fan, self.gz[i - 1], fan, aux=H[i - 1], ldaux=fan)
+            else:           # input cotangent, added block by block to the state cotangent
+                W0T = self._W(self.wT, "W0")
+                for off, n in self.plan.state_segs:
+                    engine.sgemm(ACC, B, n, h, self.gz[0], h, W0T[off:], fan, gs_cur[off * B:], n)
+
+    # ---- one update (planner.py:2868-2917) -----------------------------------------------------
+    def update_kernels(self, p: int):
+        pl, plan = self.pl, self.plan
+        T, B, S, A = pl.T, pl.batch_size_train, self.S, self.A
+        params, grad = pl.params[p], pl.grad[p]
+        fwd, bwd = pl.train_fwd, pl.train_bwd
+        N = fwd.program.N
+        self.tape[:S * B].copy_(pl.s0_train)
+        for t in range(T):
+            x = self.tape[t * S * B:(t + 1) * S * B]
+            Ht = [Hl[t] for Hl in self.H]
+            self.mlp_forward(params, B, x, Ht, self.heads[t])
+            engine.drp_actions_forward(
+                B, A, plan._stochastic, plan.action_segs, self.heads[t],
+                None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
+                self.ls_lo, self.ls_hi, self.act[t], self.entropy[t])
+            fwd.forward(B, 1, x, actions=self.act[t],
+                        noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
+                        mparams=pl.train_mparams,
+                        disc=None if pl.disc is None else pl.disc[t:],
+                        reward=pl.train_reward[p][t * B:], returns=pl.train_returns[p],
+                        err=pl.train_err[p][t * B:], final=self.tape[(t + 1) * S * B:])
+        # returns and loss (planner.py:2747-2765, 2811-2819); entropy regulariser is value-only
+        rew = pl.train_reward[p].view(T, B)
+        if pl.disc is not None:
+            rew = rew * pl.disc.view(T, 1)
+        torch.sum(rew, dim=0, out=pl.train_returns[p])
+        engine.mean_loss(pl.train_returns[p], B, pl.train_loss[p:p + 1], None)
+        if plan._stochastic:
+            pl.train_loss[p:p + 1].sub_(self.ent_coeff * (self.entropy.sum() / B))
+        # ---- backward sweep
+        grad.zero_()
+        self.refresh_transposes(params)
+        self.gs[0].zero_()
+        cur = 0
+        for t in range(T - 1, -1, -1):
+            x = self.tape[t * S * B:(t + 1) * S * B]
+            nxt, out = self.gs[cur], self.gs[cur ^ 1]
+            bwd.backward(B, 1, x, pl.gret, actions=self.act[t],
+                         noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
+                         mparams=pl.train_mparams, disc=None if pl.disc is None else pl.disc[t:],
+                         gact=self.gact, gs0=out, gs_in=nxt)
+            engine.drp_actions_backward(
+                B, A, plan._stochastic, plan.action_segs, self.heads[t],
+                None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
+                self.ls_lo, self.ls_hi, self.gact, self.gheads)
+            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out)
+            cur ^= 1
+
+    def test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
+        """Exact-model rollouts with the test policy (train = 0, planner.py:1482-1499)."""
+        pl, plan = self.pl, self.plan
+        T, B, A = pl.T, pl.batch_size_test, self.A
+        params = pl.params[p] if params is None else params
+        te = pl.test_fwd
+        N = te.program.N
+        self.t_state[0].copy_(pl.s0_test)
+        cur = 0
+        for t in range(T):
+            x, nxt = self.t_state[cur], self.t_state[cur ^ 1]
+            self.mlp_forward(params, B, x, self.t_H, self.t_heads)
+            engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,
+                                       None, 0.0, self.lo,
+                                       self.hi, self.ls_lo, self.ls_hi, self.t_act, None)
+            te.forward(B, 1, x, actions=self.t_act,
+                       noise=None if pl.test_noise is None else pl.test_noise[t * N * B:],
+                       disc=None if pl.disc is None else pl.disc[t:],
+                       reward=pl.test_reward[p][t * B:], returns=pl.test_returns[p],
+                       err=pl.test_err[p][t * B:], final=nxt)
+            cur ^= 1
+        pl.test_final[p].copy_(self.t_state[cur])
+        rew = pl.test_reward[p].view(T, B)
+        if pl.disc is not None:
+            rew = rew * pl.disc.view(T, 1)
+        torch.sum(rew, dim=0, out=pl.test_returns[p])
+        engine.mean_loss(pl.test_returns[p], B, pl.test_loss_buf[p:p + 1], None)
+
+    def redraw_noise(self, gen: torch.Generator):
+        if self.pol_noise is not None:
+            self.pol_noise.normal_(generator=gen)

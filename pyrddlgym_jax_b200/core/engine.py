@@ -23,7 +23,7 @@ EXPORTS = [
     "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
-    "rk_drp_actions_backward", "rk_transpose_add",
+    "rk_drp_actions_backward",
 ]
 
 
@@ -75,12 +75,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     fl = ctypes.c_float
     lib.rk_sgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf, cf, ci, cf, ci]
     lib.rk_sgemm.restype = ci
-    lib.rk_drp_actions_forward.argtypes = [vp, ci, ci, ci, cf, cf, fl, cf, cf, fl, fl, cf, cf]
+    lib.rk_drp_actions_forward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, fl, cf, cf, fl, fl,
+                                           cf, cf]
     lib.rk_drp_actions_forward.restype = ci
-    lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, cf, cf, fl, cf, cf, fl, fl, cf, cf]
+    lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, fl, cf, cf, fl, fl,
+                                            cf, cf]
     lib.rk_drp_actions_backward.restype = ci
-    lib.rk_transpose_add.argtypes = [vp, ci, ci, cf, ci, cf, ci]
-    lib.rk_transpose_add.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -209,22 +209,29 @@ def sgemm(flags: int, M: int, N: int, K: int, A, lda: int, Bm, ldb: int, C, ldc:
                                    split_k), "rk_sgemm")
 
 
-def drp_actions_forward(B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, actions,
+def _segs(segs):
+    n = len(segs)
+    I32 = ctypes.c_int32 * max(n, 1)
+    off, ln = I32(*[int(s[0]) for s in segs]), I32(*[int(s[1]) for s in segs])
+    return n, off, ln
+
+
+def drp_actions_forward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_lo, ls_hi, actions,
                         entropy=None):
+    """segs: [(word offset, length), ...] of the action fluents (fluent-major layout)."""
+    n, off, ln = _segs(segs)
     _check(load_library().rk_drp_actions_forward(
-        _stream(), B, A, int(stochastic), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
+        _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
         _ptr(hi), float(ls_lo), float(ls_hi), _ptr(actions), _ptr(entropy)),
         "rk_drp_actions_forward")
 
 
-def drp_actions_backward(B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, gact,
+def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_lo, ls_hi, gact,
                          gheads):
+    n, off, ln = _segs(segs)
     _check(load_library().rk_drp_actions_backward(
-        _stream(), B, A, int(stochastic), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
+        _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
         _ptr(hi), float(ls_lo), float(ls_hi), _ptr(gact), _ptr(gheads)),
         "rk_drp_actions_backward")
-
-
-def transpose_add(B, D, src, lds, dst, accumulate=True):
-    _check(load_library().rk_transpose_add(_stream(), B, D, _ptr(src), lds, _ptr(dst),
-                                           int(bool(accumulate))), "rk_transpose_add")

@@ -40,42 +40,7 @@ Kwargs = Dict[str, Any]
 # on jax / optax; those modules do not exist here, so the names map to local objects)
 # =====================================================================================
 
-class _Initializer:
-    def __init__(self, name: str, **kwargs):
-        self.name, self.kwargs = name, kwargs
-
-    def __call__(self, shape, generator: torch.Generator) -> torch.Tensor:
-        if self.name == "normal":
-            return torch.randn(shape, generator=generator) * self.kwargs.get("stddev", 1e-2)
-        if self.name == "uniform":
-            return torch.rand(shape, generator=generator) * self.kwargs.get("scale", 1e-2)
-        if self.name == "zeros":
-            return torch.zeros(shape)
-        if self.name == "ones":
-            return torch.ones(shape)
-        if self.name == "constant":
-            return torch.full(shape, float(self.kwargs.get("value", 0.0)))
-        raise NotImplementedError(f"initializer {self.name}")
-
-    def __repr__(self):
-        return f"{self.name}({self.kwargs})"
-
-
-class initializers:     # noqa: N801  (mirrors jax.nn.initializers)
-    @staticmethod
-    def normal(stddev: float = 1e-2):
-        return _Initializer("normal", stddev=stddev)
-
-    @staticmethod
-    def uniform(scale: float = 1e-2):
-        return _Initializer("uniform", scale=scale)
-
-    @staticmethod
-    def constant(value: float = 0.0):
-        return _Initializer("constant", value=value)
-
-    zeros = _Initializer("zeros")
-    ones = _Initializer("ones")
+from .planner_base import JaxPlan, _Initializer, initializers  # noqa: E402,F401
 
 
 OPTIMIZERS = {"sgd": "sgd", "rmsprop": "rmsprop", "adam": "adam"}
@@ -84,22 +49,6 @@ OPTIMIZERS = {"sgd": "sgd", "rmsprop": "rmsprop", "adam": "adam"}
 # =====================================================================================
 # plans
 # =====================================================================================
-
-class JaxPlan(metaclass=ABCMeta):
-    """Base class of policy representations (planner.py:359-420)."""
-    history_dependent = False
-
-    def __init__(self) -> None:
-        self.bounds = None
-
-    @abstractmethod
-    def compile(self, compiled, test_compiled, _bounds, horizon, preprocessor=None) -> None:
-        pass
-
-    @abstractmethod
-    def guess_next_epoch(self, params):
-        pass
-
 
 class JaxStraightLinePlan(JaxPlan):
     """Open-loop plan: one parameter per action element per step (planner.py:631-1018)."""
@@ -441,15 +390,25 @@ class JaxBackpropPlanner:
         train_log = tuple(rddl.state_fluents) if self.cache_full_train_rollouts else ()
         test_log = (tuple(rddl.next_state.values()) + tuple(rddl.action_fluents)) \
             if self.cache_full_test_rollouts else ()
+        self.is_drp = getattr(self.plan, "kind", "slp") == "drp"
         with torch.cuda.device(self.device):
             tb = self.compiled.builder(spec, True, (), self.batch_size_train)
-            self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=True, gamma=gamma))
-            self.train_bwd = engine.DeviceProgram(tb.backward(gamma=gamma))
+            if self.is_drp:
+                # closed loop: one decision epoch per launch, the MLP between the launches; the
+                # state slot passed as s0 is the tape entry, the adjoint chains through GSIN/GS0
+                self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=False, gamma=gamma))
+                self.train_bwd = engine.DeviceProgram(
+                    tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
+            else:
+                self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=True, gamma=gamma))
+                self.train_bwd = engine.DeviceProgram(tb.backward(gamma=gamma))
             eb = self.test_compiled.builder(spec, False, test_log, self.batch_size_test)
             self.test_fwd = engine.DeviceProgram(eb.forward(write_tape=False, gamma=gamma))
         self.A = self.plan.A
         self.T = self.horizon
+        self.n_params = self.plan.n_params if self.is_drp else self.T * self.A
         self._alloc()
+        self.drp = DrpPipeline(self) if self.is_drp else None
 
     def _alloc(self):
         dev, T, A = self.device, self.T, self.A
@@ -457,13 +416,14 @@ class JaxBackpropPlanner:
         P = self.parallel_updates
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)   # noqa: E731
         fw, bw, te = self.train_fwd.program, self.train_bwd.program, self.test_fwd.program
-        self.params = z(P, T * A)
+        NP = self.n_params
+        self.params = z(P, NP)
         n_state = {"sgd": 1, "rmsprop": 1, "adam": 2}[self.optimizer_name]
-        self.opt_state = z(P, n_state * T * A)
-        self.grad = z(P, T * A)
+        self.opt_state = z(P, n_state * NP)
+        self.grad = z(P, NP)
         self.nwarps = self.train_bwd.num_warps(Bt)
-        self.gradp = z(self.nwarps * T * A)
-        self.tape = z(T * fw.S * Bt)
+        self.gradp = None if self.is_drp else z(self.nwarps * T * A)
+        self.tape = None if self.is_drp else z(T * fw.S * Bt)
         self.train_reward = z(P, T * Bt)
         self.train_returns = z(P, Bt)
         self.train_err = z(P, T * Bt, dt=torch.int32)
@@ -486,8 +446,8 @@ class JaxBackpropPlanner:
         self.disc = None if self.gamma == 1.0 else torch.pow(
             torch.tensor(self.gamma, device=dev), torch.arange(T, device=dev)).float().contiguous()
         lo, hi = self.plan.box
-        self.box_lo = torch.from_numpy(lo.reshape(-1)).to(dev).contiguous()
-        self.box_hi = torch.from_numpy(hi.reshape(-1)).to(dev).contiguous()
+        self.box_lo = None if lo is None else torch.from_numpy(lo.reshape(-1)).to(dev).contiguous()
+        self.box_hi = None if hi is None else torch.from_numpy(hi.reshape(-1)).to(dev).contiguous()
         kw = self.optimizer_kwargs
         lr = float(kw.get("learning_rate", 0.1))
         if self.optimizer_name == "rmsprop":
@@ -537,6 +497,14 @@ class JaxBackpropPlanner:
         """planner.py:2868-2917 on the device for parallel instance p."""
         T, A, B = self.T, self.A, self.batch_size_train
         params = self.params[p]
+        if self.is_drp:
+            self.drp.update_kernels(p)
+            if self.world_size > 1:
+                parallel.allreduce_gradient(self.grad[p])
+            engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
+                                  self.opt_state[p], self.grad[p], None, None,
+                                  self.zero_flag[p:p + 1])
+            return
         self.train_fwd.forward(B, T, self.s0_train, policy=params, noise=self.train_noise,
                                mparams=self.train_mparams, disc=self.disc,
                                reward=self.train_reward[p], returns=self.train_returns[p],
@@ -569,6 +537,9 @@ class JaxBackpropPlanner:
     def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
         """planner.py:2695-2698: exact-model rollouts, forward only."""
         T, B = self.T, self.batch_size_test
+        if self.is_drp:
+            self.drp.test_kernels(p, params)
+            return
         self.test_fwd.forward(B, T, self.s0_test, policy=self.params[p] if params is None else params,
                               noise=self.test_noise, disc=self.disc,
                               reward=self.test_reward[p], returns=self.test_returns[p],
@@ -638,6 +609,12 @@ class JaxBackpropPlanner:
             self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
             self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
 
+    def _plan_view(self, flat: torch.Tensor) -> torch.Tensor:
+        """[..., n_params] in the shape the plan's pytree conversion expects."""
+        if self.is_drp:
+            return flat
+        return flat.view(*flat.shape[:-1], self.T, self.A)
+
     def read_stats(self):
         """(train_loss [P], test_loss [P], zero_grads [P]) of the last iteration: one pinned
         device->host copy + the iteration's only host synchronisation."""
@@ -659,6 +636,8 @@ class JaxBackpropPlanner:
         with torch.cuda.device(self.device):
             self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
             self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+            if self.drp is not None:
+                self.drp.redraw_noise(self._gen)
 
     def update(self):
         for p in range(self.parallel_updates):
@@ -673,7 +652,7 @@ class JaxBackpropPlanner:
         P, T, B = self.parallel_updates, self.T, self.batch_size_train
         return {"reward": self.train_reward.view(P, T, B).transpose(1, 2),
                 "error": self.train_err.view(P, T, B).transpose(1, 2),
-                "grad": self.plan.params_to_pytree(self.grad.view(P, T, self.A)),
+                "grad": self.plan.params_to_pytree(self._plan_view(self.grad)),
                 "fluents": {}}
 
     def _test_log(self) -> Dict[str, Any]:
@@ -722,7 +701,7 @@ class JaxBackpropPlanner:
         P = self.parallel_updates
         hyper = policy_hyperparams if policy_hyperparams is not None else \
             {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents}
-        best_params = self.plan.params_to_pytree(self.params[0].view(self.T, self.A).clone().cpu())
+        best_params = self.plan.params_to_pytree(self._plan_view(self.params[0]).clone().cpu())
         best_loss, best_grad, best_index = np.inf, None, 0
         last_iter_improve = 0
         rolling = RollingMean(test_rolling_window)
@@ -731,20 +710,25 @@ class JaxBackpropPlanner:
             stopping_rule.reset()
         shown_train, shown_test = set(), set()
         it = -1
+        progress_percent = 0.
         for it in range(epochs):
             status = JaxPlannerStatus.NORMAL
             with torch.cuda.device(self.device):
-                if self.train_noise is not None or self.test_noise is not None:
+                if self.train_noise is not None or self.test_noise is not None \
+                        or (self.drp is not None and self.drp.pol_noise is not None):
                     self.redraw_noise()
+                if self.drp is not None:      # planner.py:2775-2778, 2812-2813
+                    self.drp.ent_coeff.fill_(self.start_entropy_coeff * (
+                        self.end_entropy_coeff / self.start_entropy_coeff) ** (progress_percent / 100.))
                 self.iterate()
                 train_loss, test_loss, zero_grads = self.read_stats()       # the host sync
             test_loss_smooth = rolling.update(test_loss)
             best_index = int(np.argmin(test_loss_smooth))
             if test_loss_smooth[best_index] < best_loss:
                 best_params = self.plan.params_to_pytree(
-                    self.params[best_index].view(self.T, self.A).clone().cpu())
+                    self._plan_view(self.params[best_index]).clone().cpu())
                 best_grad = self.plan.params_to_pytree(
-                    self.grad[best_index].view(self.T, self.A).clone().cpu())
+                    self._plan_view(self.grad[best_index]).clone().cpu())
                 best_loss = float(test_loss_smooth[best_index])
                 last_iter_improve = it
             if np.all(zero_grads):
@@ -773,10 +757,10 @@ class JaxBackpropPlanner:
                 "train_return": -train_loss, "test_return": -test_loss_smooth,
                 "best_return": -best_loss, "pgpe_return": None,
                 "last_iteration_improved": last_iter_improve, "pgpe_improved": False,
-                "params": self.plan.params_to_pytree(self.params.view(P, self.T, self.A)),
+                "params": self.plan.params_to_pytree(self._plan_view(self.params)),
                 "best_params": best_params, "best_index": best_index, "pgpe_params": None,
                 "model_params": self.model_parameter_info(), "policy_hyperparams": hyper,
-                "grad": self.plan.params_to_pytree(self.grad.view(P, self.T, self.A)),
+                "grad": self.plan.params_to_pytree(self._plan_view(self.grad)),
                 "best_grad": best_grad, "train_log": self._train_log(),
                 "test_log": self._test_log(), "planner_state": self,
             }
@@ -801,6 +785,10 @@ class JaxBackpropPlanner:
                    copy_state: bool = True) -> Dict[str, Any]:
         """Action of the test policy at one decision epoch (planner.py:3527-3586)."""
         flat = self.plan.pytree_to_params(params)
+        if self.is_drp:
+            vec = np.concatenate([np.asarray(state[name], np.float32).reshape(-1)
+                                  for name in self.rddl.state_fluents])
+            return self.plan.test_actions_host(flat, vec)
         step = min(int(step), flat.shape[0] - 1)
         return self.plan.test_actions(flat[step].numpy())
 
@@ -963,3 +951,6 @@ class JaxOnlineController:
     def reset(self) -> None:
         self.guess = None
         self.callback = None
+
+
+from .drp import DrpPipeline, JaxDeepReactivePolicy  # noqa: E402,F401

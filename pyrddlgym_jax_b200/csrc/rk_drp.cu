@@ -133,11 +133,11 @@ rk_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
       const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n >= N) continue;
       float v = acc[i][j];
-      if (!split) {
+      if (!split) {                      // C_in + A*B first, then the layer epilogue
+        if (accumulate) v += out[(size_t)m * ldo + n];
         if (epi == 1 || epi == 2) v += bias[n];
         if (epi == 2) v = tanhf(v);
         if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
-        if (accumulate) v += out[(size_t)m * ldo + n];
       }
       out[(size_t)m * ldo + n] = v;
     }
@@ -154,10 +154,10 @@ __global__ void rk_sgemm_reduce_kernel(int M, int N, int splits, const float* __
   const int m = (int)(i / N), n = (int)(i % N);
   float v = 0.f;
   for (int z = 0; z < splits; ++z) v += ws[(size_t)z * M * N + i];      // fixed order
+  if (accumulate) v += C[(size_t)m * ldc + n];
   if (epi == 1 || epi == 2) v += bias[n];
   if (epi == 2) v = tanhf(v);
   if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
-  if (accumulate) v += C[(size_t)m * ldc + n];
   C[(size_t)m * ldc + n] = v;
 }
 
@@ -192,10 +192,18 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
 }
 
 // ---- action heads (planner.py:1394-1429, 1472-1475) ---------------------------------------
-// heads [B][2A]: columns [0, A) = mu, [A, 2A) = log_sigma (pre-clip); noise [A][B];
-// action = clip(mu + train * exp(clip(log_sigma)) * noise, lo, hi), stored fluent-major [A][B].
+// heads [B][2A]: columns [0, A) = mu, [A, 2A) = log_sigma (pre-clip).  Actions, their noise and
+// their cotangents use the rollout kernels' fluent-major layout: action fluent f with n_f
+// elements is the block [B][n_f] at word offset off_f * B (include/rk.h), so head column
+// a = off_f + e of rollout b lives at off_f * B + b * n_f + e.
+// action = clip(mu + train * exp(clip(log_sigma)) * noise, lo, hi);
 // entropy[b] = sum_a clip(log_sigma)   (value only: stop_gradient unless sigma_entropy_grad)
-__global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic,
+struct RkActSegs {
+  int n;
+  int off[RK_MAX_ACTION_FLUENTS], len[RK_MAX_ACTION_FLUENTS];
+};
+
+__global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSegs S,
                                           const float* __restrict__ heads,
                                           const float* __restrict__ noise, float train,
                                           const float* __restrict__ lo,
@@ -206,21 +214,25 @@ __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic,
   if (b >= B) return;
   const int ld = stochastic ? 2 * A : A;
   float ent = 0.f;
-  for (int a = 0; a < A; ++a) {
-    float act = heads[(size_t)b * ld + a];
-    if (stochastic) {
-      const float ls = fminf(fmaxf(heads[(size_t)b * ld + A + a], ls_lo), ls_hi);
-      ent += ls;
-      const float z = (noise != nullptr) ? noise[(size_t)a * B + b] : 0.f;
-      act = act + train * expf(ls) * z;
+  for (int f = 0; f < S.n; ++f) {
+    for (int e = 0; e < S.len[f]; ++e) {
+      const int a = S.off[f] + e;
+      const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
+      float act = heads[(size_t)b * ld + a];
+      if (stochastic) {
+        const float ls = fminf(fmaxf(heads[(size_t)b * ld + A + a], ls_lo), ls_hi);
+        ent += ls;
+        const float z = (noise != nullptr) ? noise[w] : 0.f;
+        act = act + train * expf(ls) * z;
+      }
+      if (lo != nullptr) act = fminf(fmaxf(act, lo[a]), hi[a]);
+      actions[w] = act;
     }
-    if (lo != nullptr) act = fminf(fmaxf(act, lo[a]), hi[a]);
-    actions[(size_t)a * B + b] = act;
   }
   if (entropy != nullptr) entropy[b] = ent;
 }
 
-__global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic,
+__global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSegs S,
                                           const float* __restrict__ heads,
                                           const float* __restrict__ noise, float train,
                                           const float* __restrict__ lo,
@@ -230,75 +242,73 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic,
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int ld = stochastic ? 2 * A : A;
-  for (int a = 0; a < A; ++a) {
-    const float mu = heads[(size_t)b * ld + a];
-    float pre = mu, e = 0.f, z = 0.f, raw = 0.f;
-    if (stochastic) {
-      raw = heads[(size_t)b * ld + A + a];
-      const float ls = fminf(fmaxf(raw, ls_lo), ls_hi);
-      z = (noise != nullptr) ? noise[(size_t)a * B + b] : 0.f;
-      e = expf(ls);
-      pre = mu + train * e * z;
-    }
-    float g = gact[(size_t)a * B + b];
-    // jnp.clip: gradient 1 inside [lo, hi] (bounds included), 0 outside
-    if (lo != nullptr && (pre < lo[a] || pre > hi[a])) g = 0.f;
-    gheads[(size_t)b * ld + a] = g;
-    if (stochastic) {
-      const bool inside = raw >= ls_lo && raw <= ls_hi;
-      gheads[(size_t)b * ld + A + a] = inside ? g * train * e * z : 0.f;
+  for (int f = 0; f < S.n; ++f) {
+    for (int e = 0; e < S.len[f]; ++e) {
+      const int a = S.off[f] + e;
+      const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
+      const float mu = heads[(size_t)b * ld + a];
+      float pre = mu, ex = 0.f, z = 0.f, raw = 0.f;
+      if (stochastic) {
+        raw = heads[(size_t)b * ld + A + a];
+        const float ls = fminf(fmaxf(raw, ls_lo), ls_hi);
+        z = (noise != nullptr) ? noise[w] : 0.f;
+        ex = expf(ls);
+        pre = mu + train * ex * z;
+      }
+      float g = gact[w];
+      // jnp.clip: gradient 1 inside [lo, hi] (bounds included), 0 outside
+      if (lo != nullptr && (pre < lo[a] || pre > hi[a])) g = 0.f;
+      gheads[(size_t)b * ld + a] = g;
+      if (stochastic) {
+        const bool inside = raw >= ls_lo && raw <= ls_hi;
+        gheads[(size_t)b * ld + A + a] = inside ? g * train * ex * z : 0.f;
+      }
     }
   }
 }
 
-extern "C" int rk_drp_actions_forward(void* stream, int B, int A, int stochastic,
+static int make_segs(int A, int n_seg, const int32_t* seg_off, const int32_t* seg_len,
+                     RkActSegs* S) {
+  if (n_seg <= 0 || n_seg > RK_MAX_ACTION_FLUENTS || seg_off == nullptr || seg_len == nullptr)
+    return RK_E_BADARG;
+  S->n = n_seg;
+  int total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_off[i] != total || seg_len[i] <= 0) return RK_E_BADARG;   // contiguous, in order
+    S->off[i] = seg_off[i];
+    S->len[i] = seg_len[i];
+    total += seg_len[i];
+  }
+  return total == A ? 0 : RK_E_BADARG;
+}
+
+extern "C" int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg,
+                                      const int32_t* seg_off, const int32_t* seg_len,
                                       const float* heads, const float* noise, float train,
                                       const float* lo, const float* hi, float ls_lo, float ls_hi,
                                       float* actions, float* entropy) {
   if (B <= 0 || A <= 0 || heads == nullptr || actions == nullptr) return RK_E_BADARG;
   if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S);
+  if (rc != 0) return rc;
   rk_drp_actions_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, actions, entropy);
+      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, actions, entropy);
   return (int)cudaGetLastError();
 }
 
-extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochastic,
+extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
+                                       const int32_t* seg_off, const int32_t* seg_len,
                                        const float* heads, const float* noise, float train,
                                        const float* lo, const float* hi, float ls_lo, float ls_hi,
                                        const float* gact, float* gheads) {
   if (B <= 0 || A <= 0 || heads == nullptr || gact == nullptr || gheads == nullptr)
     return RK_E_BADARG;
   if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S);
+  if (rc != 0) return rc;
   rk_drp_actions_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      B, A, stochastic, heads, noise, train, lo, hi, ls_lo, ls_hi, gact, gheads);
-  return (int)cudaGetLastError();
-}
-
-// dst[d][b] (+)= src[b][d]: the input cotangent of the first dense layer, added to the
-// fluent-major state cotangent the rollout adjoint carries.
-__global__ void rk_transpose_add_kernel(int B, int D, const float* __restrict__ src, int lds,
-                                        float* __restrict__ dst, int accumulate) {
-  __shared__ float tile[32][33];
-  const int b0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int b = b0 + r, d = d0 + threadIdx.x;
-    tile[r][threadIdx.x] = (b < B && d < D) ? src[(size_t)b * lds + d] : 0.f;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int d = d0 + r, b = b0 + threadIdx.x;
-    if (d < D && b < B) {
-      float v = tile[threadIdx.x][r];
-      if (accumulate) v += dst[(size_t)d * B + b];
-      dst[(size_t)d * B + b] = v;
-    }
-  }
-}
-
-extern "C" int rk_transpose_add(void* stream, int B, int D, const float* src, int lds,
-                                float* dst, int accumulate) {
-  if (B <= 0 || D <= 0 || src == nullptr || dst == nullptr) return RK_E_BADARG;
-  dim3 grid((B + 31) / 32, (D + 31) / 32), block(32, 8);
-  rk_transpose_add_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(B, D, src, lds, dst, accumulate);
+      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, gact, gheads);
   return (int)cudaGetLastError();
 }

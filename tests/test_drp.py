@@ -1,0 +1,218 @@
+"""Deep reactive policy: host-side pytree / oracle checks on CPU, and GPU parity of the whole
+closed-loop update (dense layers, heads, T=1 rollout launches chained through GSIN/GS0, weight
+gradients) against the torch-CPU oracle restatement of planner.py:1122-1534."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import planner as OP
+from oracle.model_eval import OracleModel
+from pyrddlgym_jax_b200.core import logic
+from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler
+from pyrddlgym_jax_b200.core.drp import JaxDeepReactivePolicy
+from pyrddlgym_jax_b200.core.layout import noise_as_list
+
+from .helpers import fixture_model
+
+
+def compiled_plan(topology=(8, 8), stochastic=True):
+    m = fixture_model("powergen")
+    plan = JaxDeepReactivePolicy(topology=list(topology), stochastic=stochastic)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, 5)
+    return m, plan
+
+
+def test_pytree_roundtrip_and_layer_names():
+    m, plan = compiled_plan()
+    flat = plan.initial_params(torch.Generator().manual_seed(3))
+    tree = plan.params_to_pytree(flat)
+    names = set(tree["params"])
+    assert names == {"dense_0", "dense_1", "dense_curProd_mu", "dense_curProd_log_sigma"}
+    assert tuple(tree["params"]["dense_0"]["kernel"].shape) == (6, 8)
+    assert torch.equal(plan.pytree_to_params(tree), flat)
+    # biases start at zero, kernels follow variance_scaling(2, fan_in, truncated normal)
+    assert float(tree["params"]["dense_1"]["bias"].abs().max()) == 0.0
+    k = tree["params"]["dense_1"]["kernel"]
+    assert float(k.abs().max()) <= 2.0 * np.sqrt(2.0 / 8) / 0.87962566103423978 + 1e-6
+
+
+def test_input_order_matches_reference_sorting():
+    """planner.py:1302-1313: sorted fluent names, non-bool first."""
+    m, plan = compiled_plan()
+    assert OP.drp_input_order(m) == ["prevProd", "temperature"]
+    assert list(plan.input_perm) == list(range(6))
+
+
+def test_host_test_policy_matches_oracle():
+    m, plan = compiled_plan()
+    flat = plan.initial_params(torch.Generator().manual_seed(5)) * 3
+    tree = plan.params_to_pytree(flat)["params"]
+    fls = {"prevProd": torch.tensor([[1., 2., 0., .5, 3.]]), "temperature": torch.tensor([15.])}
+    want = OP.drp_test_actions(m, tree, fls, m.bounds, 2)["curProd"].numpy().reshape(-1)
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def oracle_update(m, plan, flat, B, T, model_noise, pol_noise, gamma, ent_coeff, relax):
+    tree = plan.params_to_pytree(flat)["params"]
+    P = {k: {kk: vv.clone().requires_grad_(True) for kk, vv in v.items()} for k, v in tree.items()}
+    om = OracleModel(m, relax)
+    ents = []
+
+    def pol(t, fls):
+        noise = {"curProd": pol_noise[t].reshape(B, 5)}       # fluent-major block [B][n]
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents}, noise, 1.0, m.bounds,
+                              len(plan._topology), plan._stochastic)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, model_noise)
+    loss = OP.mean_loss(out["reward"], gamma) - ent_coeff * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    grads = {k: {kk: (vv.grad if vv.grad is not None else torch.zeros_like(vv))
+                 for kk, vv in v.items()} for k, v in P.items()}
+    return out, float(loss.detach()), plan.pytree_to_params(grads)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("topology,B", [((8, 8), 37), ((32, 16), 5), ((64, 64), 200)])
+def test_drp_update_matches_oracle(cuda_device, topology, B):
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    T = 4
+    plan = JaxDeepReactivePolicy(topology=list(topology))
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    flat[plan.seg["bh"][0]:plan.seg["bh"][0] + 5] = torch.tensor([2., 3., 4., 1., 5.])   # mu bias
+    flat[plan.seg["bh"][0] + 5:plan.seg["bh"][0] + 10] = -1.0                              # log_sigma
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    model_noise = [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)]
+    out, loss, grad = oracle_update(m, plan, flat, B, T, model_noise, pol_noise, 1.0, 0.05,
+                                    pl.compiled.relax_config())
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - loss) <= 1e-5 * abs(loss)
+    got = pl.grad[0].cpu().numpy()
+    np.testing.assert_allclose(got, grad.numpy(), rtol=1e-4, atol=1e-4 * np.abs(grad.numpy()).max())
+
+
+@pytest.mark.gpu
+def test_drp_test_policy_matches_oracle(cuda_device):
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    T, B = 5, 33
+    plan = JaxDeepReactivePolicy(topology=[16, 16])
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(3)
+    te = pl.test_fwd.program
+    g = torch.Generator().manual_seed(2)
+    noise = torch.randn(T, te.N * B, generator=g)
+    pl.test_noise.copy_(noise.reshape(-1))
+    flat = pl.params[0].cpu().clone()
+    pl.test_loss()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    om = OracleModel(m, None)
+    out = OP.rollout(om, lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, m.bounds, 2), B, T,
+        [noise_as_list(te.noise_layout, noise, t, B) for t in range(T)])
+    r_ref = out["reward"].numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.test_loss_buf[0]) + float(out["reward"].sum(1).mean())) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_drp_optimises_with_cuda_graph(cuda_device):
+    """A few captured iterations run, losses are finite and the policy moves."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    plan = JaxDeepReactivePolicy(topology=[32, 32])
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=64, rollout_horizon=10, optimizer="rmsprop",
+                            optimizer_kwargs={"learning_rate": 1e-3}, pgpe=None)
+    cb = None
+    for cb in pl.optimize_generator(key=1, epochs=6, print_summary=False, print_progress=False):
+        pass
+    assert np.isfinite(cb["train_return"]).all() and np.isfinite(cb["test_return"]).all()
+    assert "dense_0" in cb["best_params"]["params"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(37, 10, 6), (128, 128, 8), (200, 64, 64), (1, 16, 300),
+                                   (300, 257, 129), (5, 5, 5)])
+@pytest.mark.parametrize("a_trans", [False, True])
+def test_sgemm_against_torch(cuda_device, M, N, K, a_trans):
+    """rk_sgemm (all epilogues, accumulate, split-K) against torch fp32 matmul."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M * 1000 + N * 10 + K)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    aux = torch.rand(M, N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    Ad = (A.t().contiguous() if a_trans else A).to(cuda_device)
+    lda = M if a_trans else K
+    fl = engine.GEMM_A_TRANS if a_trans else 0
+    ref = A.double() @ Bm.double()
+    # the epilogue is applied to C_in + A*B when ACCUMULATE is set
+    cases = [(engine.EPI_NONE, lambda x: x), (engine.EPI_BIAS, lambda x: x + bias),
+             (engine.EPI_BIAS_TANH, lambda x: torch.tanh(x + bias)),
+             (engine.EPI_DTANH, lambda x: x * (1 - aux.double() ** 2))]
+    for split in (1, 3):
+        ws = torch.zeros(split * M * N, device=cuda_device)
+        for epi, want in cases:
+            for acc in (0, engine.GEMM_ACCUMULATE):
+                C = C0.clone().to(cuda_device)
+                engine.sgemm(fl | epi | acc, M, N, K, Ad, lda, Bm.to(cuda_device), N, C, N,
+                             bias=bias.to(cuda_device), aux=aux.to(cuda_device), ldaux=N,
+                             workspace=ws, split_k=split)
+                torch.cuda.synchronize()
+                w = want(ref + (C0.double() if acc else 0))
+                np.testing.assert_allclose(C.cpu().numpy(), w.float().numpy(), rtol=2e-5,
+                                           atol=2e-5 * float(w.abs().max()))
+
+
+@pytest.mark.gpu
+def test_action_heads_against_torch(cuda_device):
+    from pyrddlgym_jax_b200.core import engine
+    B, A = 45, 3
+    g = torch.Generator().manual_seed(4)
+    heads = torch.randn(B, 2 * A, generator=g) * 3
+    heads[:, A:] *= 4                                   # exercise the log_sigma clip
+    segs = [(0, 2), (2, 1)]                              # two action fluents: [B][2] and [B][1]
+    noise_f = [torch.randn(B, n, generator=g) for _, n in segs]
+    gact_f = [torch.randn(B, n, generator=g) for _, n in segs]
+    noise = torch.cat(noise_f, 1).t().contiguous()      # [A][B] view used by the torch model
+    gact = torch.cat(gact_f, 1).t().contiguous()
+    lo, hi = torch.tensor([-1., 0., -5.]), torch.tensor([1., 2., 5.])
+    fm = lambda blocks: torch.cat([b.reshape(-1) for b in blocks])     # noqa: E731
+    ls_lo, ls_hi = float(np.log(1e-2)), float(np.log(1e2))
+    h = heads.clone().requires_grad_(True)
+    ls = torch.clamp(h[:, A:], ls_lo, ls_hi)
+    act = torch.minimum(torch.maximum(h[:, :A] + torch.exp(ls) * noise.t(), lo), hi)
+    (act * gact.t()).sum().backward()
+    dev = cuda_device
+    out, ent, gh = torch.zeros(A * B, device=dev), torch.zeros(B, device=dev), torch.zeros(B, 2 * A, device=dev)
+    engine.drp_actions_forward(B, A, True, segs, heads.to(dev), fm(noise_f).to(dev), 1.0,
+                               lo.to(dev), hi.to(dev), ls_lo, ls_hi, out, ent)
+    engine.drp_actions_backward(B, A, True, segs, heads.to(dev), fm(noise_f).to(dev), 1.0,
+                                lo.to(dev), hi.to(dev), ls_lo, ls_hi, fm(gact_f).to(dev), gh)
+    torch.cuda.synchronize()
+    want = fm([act.detach()[:, o:o + n] for o, n in segs])
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ent.cpu().numpy(), ls.detach().sum(1).numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(gh.cpu().numpy(), h.grad.numpy(), rtol=1e-5, atol=1e-5)
