@@ -58,6 +58,13 @@ WORKLOADS = {
         domain="MarsRover_ippc2023", instance="instance5", B=32768, T=60, lr=0.01,
         compiler="DefaultJaxRDDLCompilerWithGrad", compiler_kwargs={"sigmoid_weight": 10.},
         plan_kwargs={}),
+    # configs[3] -- deep reactive policy, 2x256 tanh MLP (the only dense contraction of the path)
+    "powergen_drp": dict(
+        label="PowerGen_Continuous instance 1 (5 plants), drp 2x256 tanh MLP (stochastic heads), "
+              "batch 32768/GPU, horizon 100, fp32, rmsprop lr 1e-4, pgpe=None",
+        domain="PowerGen_Continuous", instance="instance1", B=32768, T=100, lr=1e-4,
+        compiler="DefaultJaxRDDLCompilerWithGrad", compiler_kwargs={},
+        plan="drp", plan_kwargs={"topology": [256, 256]}),
     # configs[0] -- the reference's own CPU-sized case (launch-latency bound on a GPU)
     "reservoir": dict(
         label="Reservoir_Continuous instance 1, slp, batch 32, horizon 40, fp32, rmsprop lr 0.2, pgpe=None",
@@ -156,7 +163,8 @@ def oracle_iteration_fn(name, model, B, T):
     from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler
     from pyrddlgym_jax_b200.core.layout import draw_noise, noise_as_list
     from pyrddlgym_jax_b200.core.program import PlanSpec
-    spec = PlanSpec(bounds=bounds, sigmoid_weight=pw)
+    spec = PlanSpec(bounds=bounds, sigmoid_weight=pw,
+                    kind="external" if w.get("plan") == "drp" else "slp")
     lay_train = make_compiler(name, model).builder(spec, True, (), B).forward(True).noise_layout
     lay_test = JaxRDDLCompiler(model).builder(spec, False, (), B).forward(False).noise_layout
 
@@ -165,6 +173,40 @@ def oracle_iteration_fn(name, model, B, T):
             return None
         z = draw_noise(layout, T, B, g)
         return [noise_as_list(layout, z, t, B) for t in range(T)]
+
+    if w.get("plan") == "drp":
+        topo = w["plan_kwargs"]["topology"]
+        tree = OP.drp_init(model, topo, g)
+        nu_d = {k: {kk: torch.zeros_like(vv) for kk, vv in v.items()} for k, v in tree.items()}
+        acts = list(model.action_fluents)
+
+        def drp_iteration():
+            P = {k: {kk: vv.clone().requires_grad_(True) for kk, vv in v.items()}
+                 for k, v in tree.items()}
+            pn = [{a: torch.randn(B, model.variable_size(a), generator=g) for a in acts}
+                  for _ in range(T)]
+            ents = []
+
+            def pol(t, fls):
+                a, e = OP.drp_actions(model, P, {k: fls[k] for k in model.state_fluents}, pn[t],
+                                      1.0, bounds, len(topo))
+                ents.append(e)
+                return a
+            out = OP.rollout(om_train, pol, B, T, noise_for(lay_train))
+            loss = OP.mean_loss(out["reward"], model.discount) \
+                - 0.1 * torch.stack(ents, 1).sum(1).mean()
+            loss.backward()
+            with torch.no_grad():
+                for k in tree:
+                    for kk in tree[k]:
+                        tree[k][kk], nu_d[k][kk] = OP.rmsprop_step(tree[k][kk], P[k][kk].grad,
+                                                                   nu_d[k][kk], lr)
+                test = OP.rollout(om_test, lambda t, fls: OP.drp_test_actions(
+                    model, tree, {k: fls[k] for k in model.state_fluents}, bounds, len(topo)),
+                    B, T, noise_for(lay_test))
+                tl = OP.mean_loss(test["reward"], model.discount)
+            return float(loss.detach()), float(tl)
+        return drp_iteration
 
     def iteration():
         P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
@@ -264,22 +306,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner, JaxStraightLinePlan
+    from pyrddlgym_jax_b200.core.planner import (JaxBackpropPlanner, JaxStraightLinePlan,
+                                                 JaxDeepReactivePolicy)
     from pyrddlgym_jax_b200.core import engine, logic
 
     name = args.workload
     wl = WORKLOADS[name]
     model = workload_model(name)
     B, T = (args.batch or wl["B"]), wl["T"]
+    plan_cls = JaxDeepReactivePolicy if wl.get("plan") == "drp" else JaxStraightLinePlan
     planner = JaxBackpropPlanner(
-        model, JaxStraightLinePlan(**wl["plan_kwargs"]), batch_size_train=B, batch_size_test=B,
+        model, plan_cls(**wl["plan_kwargs"]), batch_size_train=B, batch_size_test=B,
         rollout_horizon=T, optimizer="rmsprop", optimizer_kwargs={"learning_rate": wl["lr"]},
         pgpe=None, compiler=getattr(logic, wl["compiler"]), compiler_kwargs=wl["compiler_kwargs"],
         device=dev)
     planner.initialize(42)
     fw, bw, te = planner.train_fwd.program, planner.train_bwd.program, planner.test_fwd.program
     S, A, N = fw.S, fw.A, fw.N
-    has_noise = planner.train_noise is not None or planner.test_noise is not None
+    has_noise = planner.train_noise is not None or planner.test_noise is not None \
+        or (planner.drp is not None and planner.drp.pol_noise is not None)
 
     def barrier():
         if world > 1:
@@ -362,33 +407,6 @@ def main():
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts)), float(np.min(ts))
 
-    p0 = planner.params[0]
-
-    def k_fwd():
-        planner.train_fwd.forward(B, T, planner.s0_train, policy=p0, noise=planner.train_noise,
-                                  mparams=planner.train_mparams, disc=planner.disc,
-                                  reward=planner.train_reward[0], returns=planner.train_returns[0],
-                                  err=planner.train_err[0], tape=planner.tape)
-
-    def k_bwd():
-        planner.train_bwd.backward(B, T, planner.tape, planner.gret, policy=p0,
-                                   noise=planner.train_noise, mparams=planner.train_mparams,
-                                   disc=planner.disc, gradp=planner.gradp)
-
-    def k_test():
-        planner.test_fwd.forward(B, T, planner.s0_test, policy=p0, noise=planner.test_noise,
-                                 disc=planner.disc, reward=planner.test_reward[0],
-                                 returns=planner.test_returns[0], err=planner.test_err[0],
-                                 final=planner.test_final[0])
-
-    def k_red():
-        engine.reduce_partials(planner.gradp, planner.nwarps, T * A, planner.grad[0])
-
-    t_fwd, _ = time_kernel(k_fwd)
-    t_bwd, _ = time_kernel(k_bwd)
-    t_test, _ = time_kernel(k_test)
-    t_red, _ = time_kernel(k_red)
-
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -397,16 +415,97 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    # algorithmic bytes per launch: adjoint = tape + noise read once per
-    # rollout-step + dL/dreturn + per-warp gradient partial rows written
-    bytes_bwd = B * T * 4 * (S + N) + 4 * B + planner.nwarps * T * A * 4
-    bytes_fwd = B * T * (4 * S + 4 * N + 4 + 4) + 4 * S * B + 4 * B
-    bytes_test = B * T * (4 * te.N + 4 + 4) + 4 * te.S * B * 2 + 4 * B
-    achieved = bytes_bwd / (t_bwd * 1e-3) / 1e9
-    test_steps_per_s = B * T / (t_test * 1e-3)
     prof = PROFILED.get(name, {})
 
-    n_launch = 9 + (1 if planner.plan.needs_concurrency_projection else 0)
+    if planner.is_drp:
+        # closed-loop plan: the iteration is 2T sweeps of small launches; time the three sweeps
+        # and the dominant kernel (the hidden-layer GEMM, the only dense contraction)
+        drp = planner.drp
+        t_upd, _ = time_kernel(lambda: drp.update_kernels(0), reps=5)
+        t_test, _ = time_kernel(lambda: drp.test_kernels(0), reps=5)
+        hid = drp.hid
+        h_in, h_out = hid[-2] if len(hid) > 1 else drp.D, hid[-1]
+        src = drp.H[-2][0] if len(hid) > 1 else None
+
+        def k_gemm():
+            engine.sgemm(engine.EPI_BIAS_TANH, B, h_out, h_in, src, h_in,
+                         drp._W(planner.params[0], f"W{len(hid) - 1}"), h_out, drp.H[-1][0], h_out,
+                         bias=drp._W(planner.params[0], f"b{len(hid) - 1}"))
+        t_gemm, _ = time_kernel(k_gemm) if src is not None else (float("nan"), 0)
+        dims = [drp.D] + hid + [drp.NH]
+        mlp_flops = 2.0 * B * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        flops_iter = T * mlp_flops * (3 + 1)          # train fwd + dX + dW, + the test forward
+        tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved_tf = 2.0 * B * h_in * h_out / (t_gemm * 1e-3) / 1e12
+        kernels_ms = {"train_update_sweeps": t_upd, "exact_test_sweep": t_test,
+                      "hidden_layer_gemm": t_gemm}
+        roofline = {"bound": "tensor", "kernel": "rk_sgemm_kernel (hidden dense layer, fp32 SIMT)",
+                    "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_flops": 2.0 * B * h_in * h_out,
+                    "mlp_tflop_per_iteration": flops_iter / 1e12,
+                    "note": "parity build of the dense layers: fp32 SIMT GEMM with fused "
+                            "bias+tanh / tanh-adjoint epilogues, measured against the sustained "
+                            "bf16 tensor peak; the tcgen05 3xTF32 kernel for this GEMM is the next "
+                            "step (DESIGN.md 4.4)"}
+        roofline_other = {}
+        test_steps_per_s = B * T / (t_test * 1e-3)
+        n_state = len(planner.plan.state_segs)
+        L = len(hid)
+        n_launch = T * ((n_state + L) + 2) \
+            + T * (2 + 2 * 2 + 1 + L * 2 + (n_state * 2 - 1) * 2 + (L - 1) + n_state) \
+            + T * ((n_state + L) + 2) + 12
+        bytes_note = f"activation tape {sum(H.numel() for H in drp.H) * 4 / 1e9:.1f} GB"
+    else:
+        p0 = planner.params[0]
+
+        def k_fwd():
+            planner.train_fwd.forward(B, T, planner.s0_train, policy=p0, noise=planner.train_noise,
+                                      mparams=planner.train_mparams, disc=planner.disc,
+                                      reward=planner.train_reward[0], returns=planner.train_returns[0],
+                                      err=planner.train_err[0], tape=planner.tape)
+
+        def k_bwd():
+            planner.train_bwd.backward(B, T, planner.tape, planner.gret, policy=p0,
+                                       noise=planner.train_noise, mparams=planner.train_mparams,
+                                       disc=planner.disc, gradp=planner.gradp)
+
+        def k_test():
+            planner.test_fwd.forward(B, T, planner.s0_test, policy=p0, noise=planner.test_noise,
+                                     disc=planner.disc, reward=planner.test_reward[0],
+                                     returns=planner.test_returns[0], err=planner.test_err[0],
+                                     final=planner.test_final[0])
+
+        def k_red():
+            engine.reduce_partials(planner.gradp, planner.nwarps, T * A, planner.grad[0])
+
+        t_fwd, _ = time_kernel(k_fwd)
+        t_bwd, _ = time_kernel(k_bwd)
+        t_test, _ = time_kernel(k_test)
+        t_red, _ = time_kernel(k_red)
+
+        # algorithmic bytes per launch: adjoint = tape + noise read once per
+        # rollout-step + dL/dreturn + per-warp gradient partial rows written
+        bytes_bwd = B * T * 4 * (S + N) + 4 * B + planner.nwarps * T * A * 4
+        bytes_fwd = B * T * (4 * S + 4 * N + 4 + 4) + 4 * S * B + 4 * B
+        bytes_test = B * T * (4 * te.N + 4 + 4) + 4 * te.S * B * 2 + 4 * B
+        achieved = bytes_bwd / (t_bwd * 1e-3) / 1e9
+        test_steps_per_s = B * T / (t_test * 1e-3)
+
+        kernels_ms = {"train_forward": t_fwd, "adjoint": t_bwd, "exact_test_forward": t_test,
+                      "reduce_partials": t_red}
+        roofline = {"bound": "hbm",
+                    "kernel": ("rk_spec_kernel" if planner.train_bwd.specialized
+                               else "rk_interp_kernel") + " (adjoint program)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": prof.get("adjoint_traffic_bytes"),
+                    "peak_source": peak_src, "algorithmic_bytes": bytes_bwd,
+                    "issue_slot_utilisation": prof.get("adjoint_issue_active"),
+                    "note": prof.get("note", "")}
+        roofline_other = {"train_forward_GBs": bytes_fwd / (t_fwd * 1e-3) / 1e9,
+                          "exact_test_forward_GBs": bytes_test / (t_test * 1e-3) / 1e9}
+        n_launch = 9 + (1 if planner.plan.needs_concurrency_projection else 0)
+        bytes_note = f"tape+noise+logs ({(bytes_fwd + bytes_bwd) / 1e6:.0f} MB/iter)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -414,7 +513,7 @@ def main():
         "config": {"workload": wl["label"], "global_batch": n_gpus * B, "horizon": T,
                    "state_words": S, "action_words": A, "noise_words": N,
                    "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
-                   "timing": f"tape+noise+logs ({(bytes_fwd + bytes_bwd) / 1e6:.0f} MB/iter) streamed "
+                   "timing": f"{bytes_note} streamed "
                              "through HBM/L2 every iteration; per-kernel numbers taken with a "
                              "256 MB L2 flush between launches",
                    "cuda_graph": bool(planner._graph is not None)},
@@ -423,21 +522,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "iters_per_sec": e2e_value / (n_gpus * B * T)},
         "gpu_launches": n_launch * planner.parallel_updates * args.steps,
-        "kernels_ms": {"train_forward": t_fwd, "adjoint": t_bwd, "exact_test_forward": t_test,
-                       "reduce_partials": t_red},
-        "roofline": {"bound": "hbm",
-                     "kernel": ("rk_spec_kernel" if planner.train_bwd.specialized
-                                else "rk_interp_kernel") + " (adjoint program)",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": prof.get("adjoint_traffic_bytes"),
-                     "peak_source": peak_src, "algorithmic_bytes": bytes_bwd,
-                     "issue_slot_utilisation": prof.get("adjoint_issue_active"),
-                     "note": prof.get("note", "")},
-        "roofline_other": {
-            "train_forward_GBs": bytes_fwd / (t_fwd * 1e-3) / 1e9,
-            "exact_test_forward_GBs": bytes_test / (t_test * 1e-3) / 1e9},
+        "kernels_ms": kernels_ms,
+        "roofline": roofline,
+        "roofline_other": roofline_other,
         "clocks": clocks,
         "program": {"specialized": bool(planner.train_bwd.specialized),
+                    "plan": "drp" if planner.is_drp else "slp", "trainable_words": planner.n_params,
                     "fwd_step_ins": fw.n_ins[1], "bwd_step_ins": bw.n_ins[1],
                     "test_step_ins": te.n_ins[1], "rpw": bw.rpw, "lanes": bw.lanes,
                     "warp_words": bw.warp_words},

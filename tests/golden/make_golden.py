@@ -29,6 +29,8 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("wildfire_relaxed", "wildfire", 7, 5, True, 1.0, {}),
     ("marsrover_exact", "marsrover", 6, 6, False, 1.0, {}),
     ("marsrover_relaxed", "marsrover", 6, 6, True, 1.0, {}),
+    ("powergen_exact", "powergen", 6, 6, False, 1.0, {}),
+    ("powergen_relaxed", "powergen", 6, 6, True, 0.95, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from pyrddlgym_jax_b200.core.codegen import compile_cubin  # noqa: E402
 from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler  # noqa: E402
-from pyrddlgym_jax_b200.core.planner import JaxStraightLinePlan  # noqa: E402
+from pyrddlgym_jax_b200.core.planner import JaxDeepReactivePolicy, JaxStraightLinePlan  # noqa: E402
 
 
 def prebuild_workload(name: str, verbose: bool = True):
@@ -16,11 +16,17 @@ def prebuild_workload(name: str, verbose: bool = True):
     model = bench.workload_model(name)
     comp = bench.make_compiler(name, model)
     exact = JaxRDDLCompiler(model)
-    plan = JaxStraightLinePlan(**w["plan_kwargs"])
+    drp = w.get("plan") == "drp"
+    plan = (JaxDeepReactivePolicy if drp else JaxStraightLinePlan)(**w["plan_kwargs"])
     plan.compile(comp, exact, {}, w["T"])
     tb = comp.builder(plan.spec, True, (), w["B"])
     gamma = float(model.discount)
-    for prog in (tb.forward(write_tape=True, gamma=gamma), tb.backward(gamma=gamma),
+    if drp:     # the programs JaxBackpropPlanner._compile builds for a closed-loop plan
+        train = (tb.forward(write_tape=False, gamma=gamma),
+                 tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
+    else:
+        train = (tb.forward(write_tape=True, gamma=gamma), tb.backward(gamma=gamma))
+    for prog in (*train,
                  exact.builder(plan.spec, False, (), w["B"]).forward(write_tape=False, gamma=gamma)):
         path = compile_cubin(prog)[0]
         if verbose:
