@@ -171,7 +171,10 @@ class Emulator:
                 continue
             if op.startswith("R") and op not in ("RELU", "RCP", "ROUND"):
                 base, sq = int(w[5]), int(w[6])
-                ptr = C[aux0:aux0 + n + 1].astype(np.int64)
+                nseg = n
+                if op == "RPRODX":      # n counts source elements; the CSR has one row per segment
+                    nseg = int(C[int(w[8]):int(w[8]) + n].astype(np.int64).max()) + 1 if n else 0
+                ptr = C[aux0:aux0 + nseg + 1].astype(np.int64)
                 idx = C[aux1:aux1 + int(ptr[-1])].astype(np.int64)
                 qs = np.arange(rpw)[:, None] if sq else np.zeros((1, 1), dtype=np.int64)
                 const = bool(base & isa.CONST_BIT)

@@ -462,3 +462,201 @@ def differentiate(g: Graph, nodes: List[V], seeds: Sequence[Tuple[V, V]],
         if t is not None:
             out[w.id] = t
     return out
+
+
+# =====================================================================================
+# sparsification: compile-time known elements, identity pruning, element compaction
+# =====================================================================================
+# The reference evaluates aggregations over full object-tuple spaces, e.g. Wildfire's
+# exists / sum over (x2, y2) of NEIGHBOR(x, y, x2, y2) ^ burning(x2, y2): 625 terms per step of
+# which ~90% are multiplied by a non-fluent 0 (logic.py:454, compiler.py:1316).  Because the
+# mask is known when the program is built, those terms are exactly 0 (sum) or 1 (product) and
+# can be dropped without changing any result bit (for finite fluents), and the wide
+# intermediate vectors shrink to the non-zero pattern.
+
+_LEAF_OPS = {"const", "mparam", "state_in", "persist", "param_in", "act_in", "noise", "disc_in"}
+_RED_OPS = {"RSUM", "RPROD", "RMIN", "RMAX", "RISUM", "RIPROD", "RIMIN", "RIMAX", "RARGMAX",
+            "RARGMIN"}
+_RED_FOLD = {"RSUM": np.sum, "RISUM": np.sum, "RPROD": np.prod, "RIPROD": np.prod,
+             "RMIN": np.min, "RIMIN": np.min, "RMAX": np.max, "RIMAX": np.max}
+_RED_IDENTITY = {"RSUM": 0.0, "RISUM": 0.0, "RPROD": 1.0, "RIPROD": 1.0}
+
+
+def _reachable(g: Graph, roots: Sequence[V]) -> List[V]:
+    seen, stack = set(), list(roots)
+    while stack:
+        v = stack.pop()
+        if v.id in seen:
+            continue
+        seen.add(v.id)
+        for a, _ in v.args:
+            stack.append(a)
+    return [v for v in g.nodes if v.id in seen]
+
+
+def sparsify(g: Graph, roots: Sequence[V]) -> Dict[str, int]:
+    """Rewrite, IN PLACE, the sub-graph under ``roots`` (see the section comment).  Roots and
+    leaves keep their element spaces; interior values may shrink.  Returns statistics."""
+    nodes = _reachable(g, roots)
+    root_ids = {r.id for r in roots}
+    stats = {"dropped_members": 0, "elements_before": 0, "elements_after": 0, "to_const": 0}
+
+    def cast(vals, dtype):
+        return np.asarray(vals).astype(NP_DT[dtype]).astype(np.float64)
+
+    # ---- phase 1: known elements (forward), pruning identity members of sums / products -----
+    KM: Dict[int, np.ndarray] = {}
+    KV: Dict[int, np.ndarray] = {}
+    for v in nodes:
+        n = v.n
+        if v.const is not None:
+            KM[v.id], KV[v.id] = np.ones(n, bool), v.const.astype(np.float64)
+            continue
+        mask, vals = np.zeros(n, bool), np.zeros(n)
+        if v.op in _LEAF_OPS or not v.args or v.op in ("RPRODX", "QSUM"):
+            KM[v.id], KV[v.id] = mask, vals
+            continue
+        if v.op == "sg":
+            a = v.args[0][0]
+            KM[v.id], KV[v.id] = KM[a.id], KV[a.id]
+            continue
+        if v.op in _RED_OPS:
+            src = v.args[0][0]
+            km, kv = KM[src.id], KV[src.id]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            ident = _RED_IDENTITY.get(v.op)
+            if v.op == "RIMAX" and src.dtype == "b":
+                ident = 0.0
+            if v.op == "RIMIN" and src.dtype == "b":
+                ident = 1.0
+            new_ptr, new_idx = [0], []
+            for e in range(n):
+                mem = idx[ptr[e]:ptr[e + 1]]
+                if ident is not None and len(mem):
+                    keep = ~(km[mem] & (kv[mem] == ident))
+                    stats["dropped_members"] += int((~keep).sum())
+                    mem = mem[keep]
+                new_idx.append(mem)
+                new_ptr.append(new_ptr[-1] + len(mem))
+                if v.op in _RED_FOLD and (len(mem) == 0 or km[mem].all()):
+                    if len(mem) == 0 and ident is None:
+                        continue
+                    mask[e] = True
+                    vals[e] = ident if len(mem) == 0 else float(
+                        cast(_RED_FOLD[v.op](cast(kv[mem], v.dtype)), v.dtype))
+            v.attrs["ptr"] = np.asarray(new_ptr, np.int64)
+            v.attrs["idx"] = (np.concatenate(new_idx) if new_idx else np.zeros(0)).astype(np.int64)
+            KM[v.id], KV[v.id] = mask, vals
+            continue
+        # elementwise
+        tabs = [apply_map(m, n) for _, m in v.args]
+        ms = [KM[a.id][t] for (a, _), t in zip(v.args, tabs)]
+        vs = [KV[a.id][t] for (a, _), t in zip(v.args, tabs)]
+        allk = np.logical_and.reduce(ms)
+        fn = (_FOLD1.get(v.op) if len(v.args) == 1 else _FOLD2.get(v.op)) if len(v.args) <= 2 else None
+        if fn is not None and allk.any():
+            with np.errstate(all="ignore"):
+                ins = [cast(x, a.dtype).astype(NP_DT[a.dtype]) for x, (a, _) in zip(vs, v.args)]
+                out = np.asarray(fn(*ins)).astype(NP_DT[v.dtype]).astype(np.float64)
+            mask |= allk
+            vals = np.where(allk, out, vals)
+        if v.op in ("MUL", "IMUL", "AND"):          # annihilator (finite operands assumed)
+            for m_, x_ in zip(ms, vs):
+                z = m_ & (x_ == 0)
+                mask |= z
+                vals = np.where(z, 0.0, vals)
+        if v.op == "OR":
+            for m_, x_ in zip(ms, vs):
+                z = m_ & (x_ != 0)
+                mask |= z
+                vals = np.where(z, 1.0, vals)
+        KM[v.id], KV[v.id] = mask, vals
+
+    # ---- phase 2: demand (backward) ------------------------------------------------------------
+    need: Dict[int, np.ndarray] = {v.id: np.zeros(v.n, bool) for v in nodes}
+    for r in roots:
+        need[r.id][:] = True
+        x = r
+        while x.op == "sg":                            # a root alias pins its operand too
+            x = x.args[0][0]
+            need[x.id][:] = True
+            root_ids.add(x.id)
+    for v in reversed(nodes):
+        nd = need[v.id]
+        if not nd.any() or v.op in _LEAF_OPS or not v.args:
+            continue
+        if v.id not in root_ids and KM[v.id][nd].all():
+            continue                                  # becomes a constant: needs no operand
+        if v.op in _RED_OPS:
+            src = v.args[0][0]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            for e in np.nonzero(nd)[0]:
+                need[src.id][idx[ptr[e]:ptr[e + 1]]] = True
+        elif v.op == "RPRODX":
+            need[v.args[0][0].id][:] = True            # opaque: keeps its operand whole
+            need[v.id][:] = True
+        else:
+            for a, m in v.args:
+                need[a.id][apply_map(m, v.n)[nd]] = True
+
+    # ---- phase 3: rebuild in place (forward) ----------------------------------------------------
+    pos: Dict[int, np.ndarray] = {}
+    for v in nodes:
+        n = v.n
+        nd = need[v.id]
+        stats["elements_before"] += n if v.op not in _LEAF_OPS else 0
+        if v.op in _LEAF_OPS or not v.args or v.id in root_ids or v.op == "RPRODX":
+            pos[v.id] = np.arange(n)
+            keep_all = True
+        else:
+            keep_all = bool(nd.all())
+            pos[v.id] = np.arange(n) if keep_all else \
+                np.where(nd, np.cumsum(nd) - 1, -1)
+        if v.op in _LEAF_OPS or not v.args:
+            continue
+        if v.op == "sg":
+            # stop_gradient aliases its operand's storage (program.py:root): it keeps exactly the
+            # elements its operand keeps, whatever its own consumers asked for
+            a = v.args[0][0]
+            pos[v.id] = pos[a.id]
+            v.n = a.n
+            v.args = [(a, None)]
+            if a.const is not None:
+                v.op, v.args, v.const, v.uniform = "const", [], a.const.astype(NP_DT[v.dtype]), True
+            continue
+        if not nd.any():
+            continue                                   # dead: no instruction will be emitted
+        sel = np.arange(n) if keep_all else np.nonzero(nd)[0]
+        if v.id not in root_ids and v.op != "RPRODX" and KM[v.id][sel].all():
+            v.op, v.args, v.attrs = "const", [], {}
+            v.const = KV[v.id][sel].astype(NP_DT[v.dtype])
+            v.n, v.uniform = len(sel), True
+            stats["to_const"] += 1
+            stats["elements_after"] += v.n
+            continue
+        if v.op in _RED_OPS:
+            src = v.args[0][0]
+            ptr, idx = v.attrs["ptr"], v.attrs["idx"]
+            new_ptr, new_idx = [0], []
+            for e in sel:
+                mem = pos[src.id][idx[ptr[e]:ptr[e + 1]]]
+                assert (mem >= 0).all()
+                new_idx.append(mem)
+                new_ptr.append(new_ptr[-1] + len(mem))
+            v.attrs["ptr"] = np.asarray(new_ptr, np.int64)
+            v.attrs["idx"] = (np.concatenate(new_idx) if new_idx else np.zeros(0)).astype(np.int64)
+        elif v.op == "RPRODX":
+            src = v.args[0][0]
+            assert (pos[src.id] == np.arange(src.n)).all()
+        else:
+            new_args = []
+            for a, m in v.args:
+                tab = pos[a.id][apply_map(m, n)[sel]]
+                assert (tab >= 0).all(), (v, a)
+                new_args.append((a, norm_map(tab, a.n if a.op in _LEAF_OPS or a.const is not None
+                                             else int((pos[a.id] >= 0).sum()))))
+            v.args = new_args
+        v.n = len(sel)
+        stats["elements_after"] += v.n
+    g._cse.clear()            # keys describe the old element spaces
+    return stats

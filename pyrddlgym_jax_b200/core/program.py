@@ -22,7 +22,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import isa
-from .graph import Graph, V, Map, apply_map, differentiate
+from .graph import Graph, V, Map, apply_map, differentiate, sparsify
 from .lowering import Lowerer, StepGraph, TV
 
 HEADER_WORDS = 32
@@ -305,6 +305,7 @@ class ProgramBuilder:
         if gamma != 1.0:
             disc = g.leaf("disc_in", 1, "f", uniform=True)
             roots.append(disc)
+        self.sparsity = sparsify(g, roots) if self.SPARSIFY else {}
         step += self._compute_ins(self._needed(roots))
         step.append(Ins("STB", srcs=[(sg.reward, None)], n=1, flags=isa.F_TSTEP,
                         buf=isa.BUF["REWARD"], off=0))
@@ -374,6 +375,8 @@ class ProgramBuilder:
         else:
             gr = gret
         seeds = [(sg.reward, gr)] + [(sg.next_state[name], carried[name]) for name in self.slayout]
+        if self.SPARSIFY:       # differentiate the pruned forward graph (RPRODX tables follow it)
+            sparsify(g, [sg.reward] + list(sg.next_state.values()))
         fwd_nodes = self._needed([sg.reward] + list(sg.next_state.values()))
         wrt = list(sg.state_in.values()) + list(self.param_leaves.values())
         n_before = len(g.nodes)
@@ -384,6 +387,7 @@ class ProgramBuilder:
             step.append(Ins("LDB", dst=sg.state_in[name], n=n, flags=isa.F_TSTEP,
                             buf=isa.BUF["TAPE"], off=off))
         outs = [cts[v.id] for v in wrt if v.id in cts]
+        self.sparsity = sparsify(g, outs) if self.SPARSIFY else {}
         step += self._compute_ins(self._needed(outs))
         gbuf = isa.BUF["GRADP"] if self.spec.kind == "slp" else isa.BUF["GACT"]
         for name, leaf in self.param_leaves.items():
@@ -411,6 +415,8 @@ class ProgramBuilder:
 
     # ---------------------------------------------------------------------------------
     # per-instruction fixed cost (fetch, decode, dispatch) in units of one element pass
+    import os as _os
+    SPARSIFY = _os.environ.get("RK_SPARSIFY", "1") != "0"
     INS_OVERHEAD = 4.0
     MULTIPASS_PENALTY = 16.0       # measured: MarsRover L=4 (smem, 8 passes) 8.0 ms vs L=32 (registers) 1.7 ms
     SMEM_WORDS = 56 * 1024            # ~224 KB of shared memory per SM, in words
