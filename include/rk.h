@@ -139,7 +139,8 @@ int rk_project_slp(void* stream, int method, int T, int A, float* params, int n_
  *   epilogue: lets a layer whose input is several fluent blocks be summed block by block), and the epilogue
  *   in bits 4..7: RK_EPI_NONE, RK_EPI_BIAS (+ bias[n]), RK_EPI_BIAS_TANH (nn.Dense + tanh,
  *   planner.py:1359-1361), RK_EPI_DTANH (* (1 - aux[m][n]^2): the tanh adjoint).
- *   split_k > 1 runs a deterministic split-K through `workspace` ([split_k][M][N] floats).
+ *   split_k > 1 runs a deterministic split-K through `workspace` ([split_k][M][N] floats);
+ *   split_k < 0 lets the library pick up to -split_k slices (enough CTAs for two waves).
  * Replaces: nn.Dense forward (planner.py:1360, 1376, 1398, 1407) and its transposes in the
  * reverse pass. */
 #define RK_GEMM_A_TRANS    1

@@ -249,10 +249,13 @@ class DrpPipeline:
         self.gheads = z(Bt, self.NH)
         self.gz = [z(Bt, h) for h in self.hid]
         self.ones = torch.ones(max(Bt, Be), dtype=torch.float32, device=dev)
-        self.split_k = int(max(1, min(64, Bt // 2048)))
+        # weight-gradient GEMMs reduce over the batch: deterministic split-K, slice count chosen
+        # by the library (negative = "up to"), workspace sized for the largest product
+        max_split = int(max(1, min(128, Bt // 256)))
+        self.split_k = -max_split if max_split > 1 else 1
         big = max([self.D * self.hid[0]] + [a * b for a, b in zip(self.hid[:-1], self.hid[1:])]
                   + [self.hid[-1] * self.NH])
-        self.ws = z(self.split_k * big) if self.split_k > 1 else None
+        self.ws = z(max_split * big) if max_split > 1 else None
         self.wT = z(plan.n_params)                    # transposed kernels, same offsets
         lo = np.concatenate([plan.bounds[v][0].reshape(-1) for v in plan.layout])
         hi = np.concatenate([plan.bounds[v][1].reshape(-1) for v in plan.layout])

@@ -161,6 +161,80 @@ __global__ void rk_sgemm_reduce_kernel(int M, int N, int splits, const float* __
   C[(size_t)m * ldc + n] = v;
 }
 
+// Skinny shapes (N <= 16: action heads, state cotangent blocks; M <= 16: bias and first-layer
+// weight gradients): the 128x128 tile would spend > 90% of its FMAs on padding, and these
+// products are bound by streaming the [B][h] operand once.  16 x 16 threads, thread (tx, ty)
+// owns rows ty + 16 i and columns tx + 16 j of a BM_ x BN_ tile.
+#define SBK 16
+template <int BM_, int BN_, bool A_TRANS>
+__global__ void __launch_bounds__(256)
+rk_sgemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                       const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                       const float* __restrict__ bias, const float* __restrict__ aux, int ldaux,
+                       int epi, int accumulate, int kchunk, float* __restrict__ workspace) {
+  constexpr int TM_ = BM_ / 16, TN_ = BN_ / 16;
+  __shared__ float As[SBK][BM_ + 1];
+  __shared__ float Bs[SBK][BN_ + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM_, n0 = blockIdx.x * BN_;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  float acc[TM_][TN_];
+#pragma unroll
+  for (int i = 0; i < TM_; ++i)
+#pragma unroll
+    for (int j = 0; j < TN_; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += SBK) {
+    for (int idx = tid; idx < SBK * BM_; idx += 256) {
+      int kk, mm;
+      if (A_TRANS) { kk = idx / BM_; mm = idx % BM_; } else { mm = idx / SBK; kk = idx % SBK; }
+      const int k = k0 + kk, m = m0 + mm;
+      float v = 0.f;
+      if (k < kend && m < M) v = A_TRANS ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+      As[kk][mm] = v;
+    }
+    for (int idx = tid; idx < SBK * BN_; idx += 256) {
+      const int kk = idx / BN_, nn = idx % BN_;
+      const int k = k0 + kk, n = n0 + nn;
+      Bs[kk][nn] = (k < kend && n < N) ? B[(size_t)k * ldb + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      float a[TM_], b[TN_];
+#pragma unroll
+      for (int i = 0; i < TM_; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < TN_; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < TM_; ++i)
+#pragma unroll
+        for (int j = 0; j < TN_; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool split = gridDim.z > 1;
+  float* out = split ? workspace + (size_t)blockIdx.z * M * N : C;
+  const int ldo = split ? N : ldc;
+#pragma unroll
+  for (int i = 0; i < TM_; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN_; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (!split) {
+        if (accumulate) v += out[(size_t)m * ldo + n];
+        if (epi == 1 || epi == 2) v += bias[n];
+        if (epi == 2) v = tanhf(v);
+        if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+      }
+      out[(size_t)m * ldo + n] = v;
+    }
+  }
+}
+
 extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int lda,
                         const float* B, int ldb, float* C, int ldc, const float* bias,
                         const float* aux, int ldaux, float* workspace, int split_k) {
@@ -170,19 +244,38 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   const int epi = (flags >> 4) & 0xf;
   if (epi > 3 || ((epi == 1 || epi == 2) && bias == nullptr) || (epi == 3 && aux == nullptr))
     return RK_E_BADARG;
-  if (split_k < 1) split_k = 1;
+  // tile shape: skinny variants when one output dimension is <= 16
+  int bm = BM, bn = BN, bk = BK;
+  if (N <= 16 && M > 16) { bm = 128; bn = 16; bk = SBK; }
+  else if (M <= 16) { bm = 16; bn = 128; bk = SBK; }
+  const int tiles = ((N + bn - 1) / bn) * ((M + bm - 1) / bm);
+  if (split_k == 0) split_k = 1;
+  if (split_k < 0) {                 // auto: enough CTAs for two waves, at most -split_k slices
+    int want = (2 * 148 + tiles - 1) / tiles;
+    if (want > -split_k) want = -split_k;
+    if (want > K / 256) want = K / 256;
+    split_k = want < 1 ? 1 : want;
+  }
   if (split_k > 1 && workspace == nullptr) return RK_E_BADARG;
   int kchunk = (K + split_k - 1) / split_k;
-  kchunk = ((kchunk + BK - 1) / BK) * BK;
+  kchunk = ((kchunk + bk - 1) / bk) * bk;
   const int splits = (K + kchunk - 1) / kchunk;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-  if (a_trans)
-    rk_sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux,
-                                                 epi, accumulate, kchunk, workspace);
-  else
-    rk_sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux,
-                                                  ldaux, epi, accumulate, kchunk, workspace);
+  dim3 grid((N + bn - 1) / bn, (M + bm - 1) / bm, splits);
+#define RK_LAUNCH(KERNEL)                                                                     \
+  KERNEL<<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi,        \
+                               accumulate, kchunk, workspace)
+  if (bn == 16) {
+    if (a_trans) RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, true>));
+    else RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, false>));
+  } else if (bm == 16) {
+    if (a_trans) RK_LAUNCH((rk_sgemm_skinny_kernel<16, 128, true>));
+    else RK_LAUNCH((rk_sgemm_skinny_kernel<16, 128, false>));
+  } else {
+    if (a_trans) RK_LAUNCH(rk_sgemm_kernel<true>);
+    else RK_LAUNCH(rk_sgemm_kernel<false>);
+  }
+#undef RK_LAUNCH
   if (splits > 1) {
     const size_t total = (size_t)M * N;
     rk_sgemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(

@@ -153,13 +153,14 @@ def test_drp_optimises_with_cuda_graph(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,N,K", [(37, 10, 6), (128, 128, 8), (200, 64, 64), (1, 16, 300),
-                                   (300, 257, 129), (5, 5, 5)])
+                                   (300, 257, 129), (5, 5, 5), (1, 200, 3000), (5, 256, 2100),
+                                   (700, 10, 256), (256, 10, 4000), (17, 17, 600)])
 @pytest.mark.parametrize("a_trans", [False, True])
 def test_sgemm_against_torch(cuda_device, M, N, K, a_trans):
     """rk_sgemm (all epilogues, accumulate, split-K) against torch fp32 matmul."""
     from pyrddlgym_jax_b200.core import engine
     g = torch.Generator().manual_seed(M * 1000 + N * 10 + K)
-    A = torch.randn(M, K, generator=g)
+    A = torch.randn(M, K, generator=g) / np.sqrt(K)      # O(1) pre-activations
     Bm = torch.randn(K, N, generator=g)
     bias = torch.randn(N, generator=g)
     aux = torch.rand(M, N, generator=g)
@@ -172,8 +173,8 @@ def test_sgemm_against_torch(cuda_device, M, N, K, a_trans):
     cases = [(engine.EPI_NONE, lambda x: x), (engine.EPI_BIAS, lambda x: x + bias),
              (engine.EPI_BIAS_TANH, lambda x: torch.tanh(x + bias)),
              (engine.EPI_DTANH, lambda x: x * (1 - aux.double() ** 2))]
-    for split in (1, 3):
-        ws = torch.zeros(split * M * N, device=cuda_device)
+    for split in (1, 3, -8):
+        ws = torch.zeros(abs(split) * M * N, device=cuda_device)
         for epi, want in cases:
             for acc in (0, engine.GEMM_ACCUMULATE):
                 C = C0.clone().to(cuda_device)
