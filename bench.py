@@ -562,8 +562,8 @@ def main():
 # figures read from the committed ncu captures of the same workload (profiles/), per launch
 PROFILED = {
     "quadcopter": {
-        "adjoint_traffic_bytes": 78703104 + 2099200,       # dram read + write, r01_ncu_spec_v6.md
-        "adjoint_issue_active": 0.261,
+        "adjoint_traffic_bytes": 78702848 + 2117632,       # dram read + write, r01_ncu_spec_v6.md
+        "adjoint_issue_active": 0.258,
         "note": "not HBM-bound by construction: 192 B per rollout-step carry ~670 adjoint SASS "
                 "instructions (3 sincos, 8 IEEE divides, ~150 mul/add); B=4096 gives 512 warps "
                 "for 592 SM sub-partitions, so every warp runs alone on its scheduler and the "
