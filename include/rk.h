@@ -153,6 +153,17 @@ int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int l
              const float* B, int ldb, float* C, int ldc, const float* bias, const float* aux,
              int ldaux, float* workspace, int split_k);
 
+/* The hidden dense layers on the tensor cores (tcgen05 + TMEM + TMA), 3xTF32 split for fp32-grade
+ * accuracy:  C[M][N] = epi(A[M][K] * Bt[N][K]^T) with A = A_hi + A_lo, Bt = Bt_hi + Bt_lo as
+ * produced by rk_tf32_split (hi exactly representable in TF32, lo the fp32 remainder).
+ * Constraints: 32 <= N <= 256, N % 32 == 0, K % 32 == 0, leading dimensions % 4 == 0,
+ * 16-byte aligned pointers.  epi: 0 none, 1 + bias, 2 tanh(+ bias), 3 * (1 - aux^2).
+ * Replaces: nn.Dense + tanh of the hidden stack (planner.py:1358-1361) and its transpose. */
+int rk_tf32_split(void* stream, const float* x, float* hi, float* lo, size_t n);
+int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A_hi, const float* A_lo,
+              int lda, const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
+              const float* bias, const float* aux, int ldaux);
+
 /* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).
  *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise;
  *   seg_off / seg_len (HOST arrays, n_seg <= RK_MAX_ACTION_FLUENTS): the action fluents' word

@@ -23,7 +23,7 @@ EXPORTS = [
     "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
-    "rk_drp_actions_backward",
+    "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm",
 ]
 
 
@@ -81,6 +81,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, fl, cf, cf, fl, fl,
                                             cf, cf]
     lib.rk_drp_actions_backward.restype = ci
+    lib.rk_tf32_split.argtypes = [vp, cf, cf, cf, ctypes.c_size_t]
+    lib.rk_tf32_split.restype = ci
+    lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
+    lib.rk_tcgemm.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -235,3 +239,16 @@ def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls
         ctypes.cast(ln, ctypes.c_void_p), _ptr(heads), _ptr(noise), float(train), _ptr(lo),
         _ptr(hi), float(ls_lo), float(ls_hi), _ptr(gact), _ptr(gheads)),
         "rk_drp_actions_backward")
+
+
+def tf32_split(x: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, n: Optional[int] = None):
+    _check(load_library().rk_tf32_split(_stream(), _ptr(x), _ptr(hi), _ptr(lo),
+                                        int(x.numel() if n is None else n)), "rk_tf32_split")
+
+
+def tcgemm(epi: int, M: int, N: int, K: int, A_hi, A_lo, lda: int, Bt_hi, Bt_lo, ldb: int, C,
+           ldc: int, bias=None, aux=None, ldaux: int = 0):
+    """Tensor-core (tcgen05, 3xTF32) C = epi(A * Bt^T); epi as EPI_* >> 4."""
+    _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A_hi), _ptr(A_lo), lda,
+                                    _ptr(Bt_hi), _ptr(Bt_lo), ldb, _ptr(C), ldc, _ptr(bias),
+                                    _ptr(aux), ldaux), "rk_tcgemm")

@@ -1,0 +1,319 @@
+// rk_tcgemm.cu -- the hidden dense layers of the deep reactive policy on the 5th-generation
+// tensor cores (tcgen05 + TMEM + TMA), fp32-grade accuracy through a 3xTF32 split.
+//
+// Replaces: flax nn.Dense + tanh of the DRP hidden stack (planner.py:1358-1361) and its
+// input-side transpose in the reverse pass -- the only dense contraction on the path.
+//
+//   C[M][N] = epi( A[M][K] * Bt[N][K]^T ),   A = A_hi + A_lo,  Bt = Bt_hi + Bt_lo
+//   A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo      (the lo*lo term is below fp32 rounding)
+//
+// hi parts are exactly representable in TF32 (cvt.rna), lo parts are the fp32 remainders
+// (rk_tf32_split), so the tensor core's fp32->tf32 operand conversion is exact for hi and costs
+// < 2^-22 relative for lo: the sum matches an fp32 GEMM to ~1e-6.
+//
+// One CTA per 128-row tile, full N (<= 256) in one TMEM accumulator (N fp32 columns):
+//   warp 0   : TMA producer  (4 tiles per k-block: A_hi, A_lo, B_hi, B_lo; 128B-swizzled, K-major)
+//   warp 1   : MMA issuer    (one elected lane; 3 tcgen05.mma.kind::tf32 per 8-wide k-slice)
+//   warps 2-5: epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/tanh or tanh-adjoint -> C)
+// 2-stage smem ring (96 KB per stage at N=256), mbarrier full/empty + tcgen05.commit.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+
+#include "../../include/rk.h"
+
+#define TC_BM 128
+#define TC_BK 32          // fp32 elements per k-block = one 128-byte swizzle row
+#define TC_STAGES 2
+#define TC_UMMA_K 8       // kind::tf32: 32 bytes of K per instruction
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart):
+// start address, SBO = 1024 B, version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// epi: 2 = bias + tanh, 3 = * (1 - aux^2), 1 = bias, 0 = none
+__global__ void __launch_bounds__(192, 1)
+rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
+                 const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi,
+                 const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int epi,
+                 float* __restrict__ C, int ldc, const float* __restrict__ bias,
+                 const float* __restrict__ aux, int ldaux, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;            // 16 KB
+  const uint32_t b_bytes = (uint32_t)N * TC_BK * 4;      // 32 KB at N = 256
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * stage_bytes);
+  uint64_t* full = bars;                  // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;     // [TC_STAGES]
+  uint64_t* acc_ready = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int num_kb = K / TC_BK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {      // one warp allocates the TMEM accumulator (N fp32 columns, power of 2)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_expect_tx(&full[s], stage_bytes);
+        tma_load_2d(st, &tmA_hi, &full[s], kb * TC_BK, m0);
+        tma_load_2d(st + a_bytes, &tmA_lo, &full[s], kb * TC_BK, m0);
+        tma_load_2d(st + 2 * a_bytes, &tmB_hi, &full[s], kb * TC_BK, 0);
+        tma_load_2d(st + 2 * a_bytes + b_bytes, &tmB_lo, &full[s], kb * TC_BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        const uint64_t dAh = make_desc(st), dAl = make_desc(st + a_bytes);
+        const uint64_t dBh = make_desc(st + 2 * a_bytes);
+        const uint64_t dBl = make_desc(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);   // +32 B along K
+          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1);
+          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1);
+        }
+        umma_commit(&empty[s]);                 // frees the smem stage when the MMAs retire
+      }
+      umma_commit(acc_ready);                   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes 32 * (w % 4) .. + 31 =====
+    const int q = warp & 3;
+    mbar_wait(acc_ready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (row < M) {
+        float* out = C + (size_t)row * ldc + c0;
+        const float* ax = (epi == 3) ? aux + (size_t)row * ldaux + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x = __uint_as_float(r[j + i]);
+            if (epi == 1 || epi == 2) x += __ldg(bias + c0 + j + i);
+            if (epi == 2) x = tanhf(x);
+            v[i] = x;
+          }
+          if (epi == 3) {
+            const float4 h = *reinterpret_cast<const float4*>(ax + j);
+            v[0] *= (1.f - h.x * h.x);
+            v[1] *= (1.f - h.y * h.y);
+            v[2] *= (1.f - h.z * h.z);
+            v[3] *= (1.f - h.w * h.w);
+          }
+          *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols));
+  }
+}
+
+// ---- fp32 -> (tf32-exact hi, fp32 remainder lo) ------------------------------------------------
+__global__ void rk_tf32_split_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                     float4* __restrict__ lo, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  float4 h, l;
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+  hi[i] = h;
+  lo[i] = l;
+}
+
+extern "C" int rk_tf32_split(void* stream, const float* x, float* hi, float* lo, size_t n) {
+  if (x == nullptr || hi == nullptr || lo == nullptr || (n & 3) != 0) return RK_E_BADARG;
+  if (n == 0) return 0;
+  const size_t n4 = n / 4;
+  rk_tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (float4*)hi, (float4*)lo, n4);
+  return (int)cudaGetLastError();
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_t g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode != nullptr) return 0;
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) return RK_E_BADARG;
+  g_encode = (encode_tiled_t)dlsym(lib, "cuTensorMapEncodeTiled");
+  return g_encode != nullptr ? 0 : RK_E_BADARG;
+}
+
+// row-major [rows][K] fp32 matrix, box = 32 (k) x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A_hi,
+                         const float* A_lo, int lda, const float* Bt_hi, const float* Bt_lo,
+                         int ldb, float* C, int ldc, const float* bias, const float* aux,
+                         int ldaux) {
+  if (M <= 0 || A_hi == nullptr || A_lo == nullptr || Bt_hi == nullptr || Bt_lo == nullptr ||
+      C == nullptr)
+    return RK_E_BADARG;
+  if (N < 32 || N > 256 || (N % 32) != 0 || K < TC_BK || (K % TC_BK) != 0) return RK_E_BADARG;
+  if ((lda % 4) != 0 || (ldb % 4) != 0 || (ldc % 4) != 0) return RK_E_BADARG;
+  if (epi < 0 || epi > 3 || ((epi == 1 || epi == 2) && bias == nullptr) ||
+      (epi == 3 && (aux == nullptr || (ldaux % 4) != 0)))
+    return RK_E_BADARG;
+  int rc = load_encode();
+  if (rc != 0) return rc;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if ((rc = make_map(&mAh, A_hi, M, K, lda, TC_BM)) != 0) return rc;
+  if ((rc = make_map(&mAl, A_lo, M, K, lda, TC_BM)) != 0) return rc;
+  if ((rc = make_map(&mBh, Bt_hi, N, K, ldb, N)) != 0) return rc;
+  if ((rc = make_map(&mBl, Bt_lo, N, K, ldb, N)) != 0) return rc;
+  const size_t stage = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)N * TC_BK * 4;
+  const size_t smem = TC_STAGES * stage + 128 + 1024;       // barriers + alignment slack
+  static int configured = 0;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_tcgemm_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    configured = 1;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < N) cols <<= 1;
+  rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, 192, smem, (cudaStream_t)stream>>>(
+      mAh, mAl, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols);
+  return (int)cudaGetLastError();
+}

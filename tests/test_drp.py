@@ -217,3 +217,33 @@ def test_action_heads_against_torch(cuda_device):
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(ent.cpu().numpy(), ls.detach().sum(1).numpy(), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(gh.cpu().numpy(), h.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 256, 256), (333, 64, 128), (4096, 256, 32),
+                                   (32768, 256, 256)])
+def test_tcgemm_3xtf32_against_fp64(cuda_device, M, N, K):
+    """rk_tcgemm (tcgen05 + TMEM + TMA, 3xTF32 split) against an fp64 reference: fp32-grade
+    accuracy (a single-pass TF32 product would be ~1e-3 off)."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) / np.sqrt(K)).to(cuda_device)
+    Bt = torch.randn(N, K, generator=g).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    aux = torch.rand(M, N, generator=g).to(cuda_device)
+    Ah, Al, Bh, Bl = (torch.empty_like(A), torch.empty_like(A), torch.empty_like(Bt),
+                      torch.empty_like(Bt))
+    engine.tf32_split(A, Ah, Al)
+    engine.tf32_split(Bt, Bh, Bl)
+    torch.cuda.synchronize()
+    assert torch.equal(Ah + Al, A) and torch.equal(Bh + Bl, Bt)          # the split is exact
+    assert int((Ah.view(torch.int32) & 0x1FFF).abs().max()) == 0         # hi is TF32-exact
+    ref = A.double() @ Bt.double().t()
+    wants = {0: ref, 1: ref + bias, 2: torch.tanh(ref + bias), 3: ref * (1 - aux.double() ** 2)}
+    for epi, want in wants.items():
+        C = torch.full((M, N), float("nan"), device=cuda_device)
+        engine.tcgemm(epi, M, N, K, Ah, Al, K, Bh, Bl, K, C, N, bias=bias, aux=aux, ldaux=N)
+        torch.cuda.synchronize()
+        err = float((C.double() - want).abs().max())
+        # ~1e-6 of the pre-activation scale (dropped lo*lo term + fp32 accumulation over K)
+        assert err <= 4e-6 * max(1.0, float(ref.abs().max())), (epi, err)
