@@ -257,6 +257,17 @@ class DrpPipeline:
                   + [self.hid[-1] * self.NH])
         self.ws = z(max_split * big) if max_split > 1 else None
         self.wT = z(plan.n_params)                    # transposed kernels, same offsets
+        # tensor-core path (tcgen05, 3xTF32) for hidden layers whose shapes fit the MMA tiles
+        import os as _os
+        ok = lambda a, b: a % 32 == 0 and b % 32 == 0 and 32 <= a <= 256 and 32 <= b <= 256  # noqa
+        self.tc_layers = [i for i in range(1, len(self.hid))
+                          if _os.environ.get("RK_TCGEMM", "1") != "0" and Bt >= 128
+                          and ok(self.hid[i - 1], self.hid[i])]
+        if self.tc_layers:
+            hmax = max(self.hid)
+            self.a_hi, self.a_lo = z(max(Bt, Be) * hmax), z(max(Bt, Be) * hmax)
+            self.w_hi, self.w_lo = z(plan.n_params), z(plan.n_params)       # split of W  [in][out]
+            self.wT_hi, self.wT_lo = z(plan.n_params), z(plan.n_params)     # split of W^T [out][in]
         lo = np.concatenate([plan.bounds[v][0].reshape(-1) for v in plan.layout])
         hi = np.concatenate([plan.bounds[v][1].reshape(-1) for v in plan.layout])
         self.lo = torch.from_numpy(lo.astype(np.float32)).to(dev)
@@ -278,6 +289,16 @@ class DrpPipeline:
         for name, off, r, c in self.plan.segments:
             if name.startswith("W"):
                 self.wT[off:off + r * c].view(c, r).copy_(params[off:off + r * c].view(r, c).t())
+        self.refresh_splits(params)
+
+    def refresh_splits(self, params: torch.Tensor):
+        """hi / lo parts of the hidden kernels for the tensor-core layers (once per update)."""
+        for i in self.tc_layers:
+            off, r, c = self.plan.seg[f"W{i}"]
+            n = r * c
+            engine.tf32_split(params[off:off + n], self.w_hi[off:off + n], self.w_lo[off:off + n], n)
+            engine.tf32_split(self.wT[off:off + n], self.wT_hi[off:off + n],
+                              self.wT_lo[off:off + n], n)
 
     # ---- the MLP ------------------------------------------------------------------------------
     def mlp_forward(self, params, B, x_fm, H, heads):
@@ -297,8 +318,15 @@ class DrpPipeline:
         fan, src = h0, H[0]
         for i in range(1, len(self.hid)):
             h = self.hid[i]
-            engine.sgemm(engine.EPI_BIAS_TANH, B, h, fan, src, fan, self._W(params, f"W{i}"), h,
-                         H[i], h, bias=self._W(params, f"b{i}"))
+            if i in self.tc_layers:     # Y = tanh(X W + b) as X * (W^T)^T on the tensor cores
+                n = B * fan
+                engine.tf32_split(src, self.a_hi, self.a_lo, n)
+                engine.tcgemm(2, B, h, fan, self.a_hi, self.a_lo, fan, self._W(self.wT_hi, f"W{i}"),
+                              self._W(self.wT_lo, f"W{i}"), fan, H[i], h,
+                              bias=self._W(params, f"b{i}"))
+            else:
+                engine.sgemm(engine.EPI_BIAS_TANH, B, h, fan, src, fan, self._W(params, f"W{i}"),
+                             h, H[i], h, bias=self._W(params, f"b{i}"))
             fan, src = h, H[i]
         engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"), self.NH,
                      heads, self.NH, bias=self._W(params, "bh"))
@@ -329,7 +357,12 @@ class DrpPipeline:
                              self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
             engine.sgemm(AT | ACC, 1, h, B, self.ones, 1, self.gz[i], h, self._W(grad, f"b{i}"), h,
                          workspace=ws, split_k=sk)
-            if i > 0:
+            if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
+                engine.tf32_split(self.gz[i], self.a_hi, self.a_lo, B * h)
+                engine.tcgemm(3, B, fan, h, self.a_hi, self.a_lo, h, self._W(self.w_hi, f"W{i}"),
+                              self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan,
+                              aux=H[i - 1], ldaux=fan)
+            elif i > 0:
                 engine.sgemm(engine.EPI_DTANH, B, fan, h, self.gz[i], h, self._W(self.wT, f"W{i}"),
                              fan, self.gz[i - 1], fan, aux=H[i - 1], ldaux=fan)
             else:           # input cotangent, added block by block to the state cotangent
@@ -344,6 +377,7 @@ class DrpPipeline:
         params, grad = pl.params[p], pl.grad[p]
         fwd, bwd = pl.train_fwd, pl.train_bwd
         N = fwd.program.N
+        self.refresh_transposes(params)          # W^T and the hi / lo splits of this update's W
         self.tape[:S * B].copy_(pl.s0_train)
         for t in range(T):
             x = self.tape[t * S * B:(t + 1) * S * B]
@@ -369,7 +403,6 @@ class DrpPipeline:
             pl.train_loss[p:p + 1].sub_(self.ent_coeff * (self.entropy.sum() / B))
         # ---- backward sweep
         grad.zero_()
-        self.refresh_transposes(params)
         self.gs[0].zero_()
         cur = 0
         for t in range(T - 1, -1, -1):
@@ -393,6 +426,7 @@ class DrpPipeline:
         params = pl.params[p] if params is None else params
         te = pl.test_fwd
         N = te.program.N
+        self.refresh_transposes(params)
         self.t_state[0].copy_(pl.s0_test)
         cur = 0
         for t in range(T):

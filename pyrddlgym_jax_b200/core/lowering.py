@@ -679,7 +679,7 @@ class Lowerer:
         if name == "DiracDelta":
             return F(self.lower(e.args[0], scope, env))
         if name in ("Discrete", "UnnormDiscrete"):
-            raise RDDLNotImplementedError("Discrete distributions are not lowered yet")
+            return self._discrete(e, scope, env, sizes, name == "UnnormDiscrete")
         tvs = self._args(e, scope, env)
         a0 = e.args[0]
         if name == "Uniform":
@@ -772,6 +772,60 @@ class Lowerer:
                 return E("ADD", C(1.), self.soft_floor(ratio, w, sizes))
             return E("DIV", C(1.), p)
         raise RDDLNotImplementedError(f"Distribution {name} is not supported.")
+
+    def _discrete(self, e, scope, env, sizes, unnorm: bool) -> TV:
+        """Discrete / UnnormDiscrete over an enumerated type: exact = categorical sample
+        argmax_k(Gumbel_k + safe_log p_k) (compiler.py:2203-2215); relaxed = Gumbel-softmax
+        soft arg-max, no straight-through (logic.py:1243-1267); determinised = sum_k k p_k
+        (logic.py:1321-1327).  The K case probabilities are stacked along an extra trailing
+        axis of the tuple space (element = scope index * K + k)."""
+        etype_name, cases = e.args
+        objs = self.m.type_to_objects[etype_name]
+        K = len(objs)
+        table = dict(cases)
+        R = self.relax if self.relaxed else {}
+        inner = list(scope) + [("?__case__", etype_name)]
+        isz = self.sizes(inner)
+        n_outer, kpos = len(scope), len(scope)
+        allv = tuple(range(len(isz)))
+        EI = lambda nm, *x: self.ew(nm, list(x), isz)      # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        prob = None
+        for k, o in enumerate(objs):
+            pk = self.to_f(self.at_least_int(self.lower(table[o], scope, env)), sizes)
+            onehot = TV(self.g.const(np.eye(K, dtype=np.float32)[k]), (kpos,), None)
+            term = EI("MUL", onehot, pk)
+            prob = term if prob is None else EI("ADD", prob, term)
+        prob = self._mat(prob, isz)
+
+        def total(x: TV) -> TV:
+            dv, ptr, idx, _ = self._csr(x, n_outer, isz)
+            return TV(self.g.reduce("RSUM", x.v, ptr, idx), dv, None)
+        tot = total(prob)
+        if unnorm:                                   # compiler.py:2197-2199 (sj.div == divide)
+            prob = self._mat(EI("DIV", prob, tot), isz)
+            tot = total(prob)
+        # _jax_update_discrete_oob_error: any p < 0 or not allclose(sum p, 1)
+        self.errchk("DISCRETE", EI("LT", prob, C(0.)), isz)
+        dev = self.ew("ABS", [self.ew("SUB", [tot, C(1.)], sizes)], sizes)
+        self.errchk("DISCRETE", self.ew("GT", [dev, C(1e-5 + 1e-8)], sizes), sizes)
+        fluent = any(self.tr.is_fluent(table[o]) for o in objs)
+        variant = self.variants.get("discrete") if (self.relaxed and fluent) else None
+        lit = TV(self.g.const(np.arange(K, dtype=np.float32)), (kpos,), None)
+        if variant == "determinized":
+            return total(self._mat(EI("MUL", lit, prob), isz))
+        n = int(np.prod(isz, dtype=np.int64))
+        gv = self.g.leaf("noise", n, "f", slot=len(self.sg.noise))
+        self.sg.noise.append(NoiseSlot("gumbel", tuple(isz), n, gv, None))
+        G = TV(gv, allv, None, True)
+        if variant == "gumbel":
+            w = TV(self.mparam(e, "discrete_softmax_weight", R["discrete_softmax_weight"]), ())
+            eps = TV(self.mparam(e, "discrete_eps", R["discrete_eps"]), ())
+            logits = self._mat(EI("ADD", G, EI("SAFELOG", prob, eps)), isz)
+            return self._soft_argmax(TV(logits.v, allv, None, True), w, n_outer, isz, sizes)
+        logits = self._mat(EI("ADD", G, EI("SAFELOG", prob, C(1e-12))), isz)
+        dv, ptr, idx, _ = self._csr(logits, n_outer, isz)
+        return TV(self.g.reduce("RARGMAX", logits.v, ptr, idx, "i"), dv, None)
 
     # ==================================================================================
     def build(self, action_values: Dict[str, V], state_values: Optional[Dict[str, V]] = None

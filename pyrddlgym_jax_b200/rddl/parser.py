@@ -402,7 +402,7 @@ class _Parser:
                     label = None
                 else:
                     self.expect("case")
-                    label = self.next()[1].lstrip("$")
+                    label = self.next()[1].lstrip("$@")
                 self.expect(":")
                 cases.append((label, self.parse_expr()))
                 self.accept(",")
@@ -428,7 +428,7 @@ class _Parser:
                 etype_name = self.ident()
                 cases = []
                 while self.accept(","):
-                    label = self.next()[1].lstrip("$")
+                    label = self.next()[1].lstrip("$@")
                     self.expect(":")
                     cases.append((label, self.parse_expr()))
                 self.expect(")")

@@ -31,6 +31,8 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("marsrover_relaxed", "marsrover", 6, 6, True, 1.0, {}),
     ("powergen_exact", "powergen", 6, 6, False, 1.0, {}),
     ("powergen_relaxed", "powergen", 6, 6, True, 0.95, {}),
+    ("discrete_exact", "discrete", 6, 5, False, 1.0, {}),
+    ("discrete_relaxed", "discrete", 6, 5, True, 1.0, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]

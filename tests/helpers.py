@@ -22,6 +22,7 @@ FIXTURES = {
     "wildfire": ("Wildfire_MDP_ippc2014", "instance5"),
     "marsrover": ("MarsRover_ippc2023", "instance5"),
     "powergen": ("PowerGen_Continuous", "instance1"),
+    "discrete": ("Discrete_Toy", "instance1"),
 }
 
 

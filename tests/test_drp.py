@@ -75,7 +75,8 @@ def oracle_update(m, plan, flat, B, T, model_noise, pol_noise, gamma, ent_coeff,
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("topology,B", [((8, 8), 37), ((32, 16), 5), ((64, 64), 200)])
+@pytest.mark.parametrize("topology,B", [((8, 8), 37), ((32, 16), 5), ((64, 64), 200),
+                                        ((256, 256), 300), ((64, 128, 32), 129)])
 def test_drp_update_matches_oracle(cuda_device, topology, B):
     from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
     m = fixture_model("powergen")
