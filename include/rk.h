@@ -153,6 +153,22 @@ int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int l
              const float* B, int ldb, float* C, int ldc, const float* bias, const float* aux,
              int ldaux, float* workspace, int split_k);
 
+/* First dense layer read straight from the fluent-major state (seg_off / seg_len: the state
+ * fluents' word ranges, HOST arrays as for the action heads): out[B][H] = tanh(x W0 + b0); when
+ * xp != NULL also packs xp[B][D+1] = [x | 1], the operand of the fused dW0 / db0 product.
+ * Replaces: DRPStateLayer + the first nn.Dense (planner.py:1287-1319, 1358-1361). */
+int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg, const int32_t* seg_off,
+                  const int32_t* seg_len, const float* x, const float* W0, const float* b0,
+                  float* out, float* xp);
+/* Bias gradients: y[N] (+)= sum_b G[b][n], deterministic two-stage sum through
+ * workspace[chunks][N]. */
+int rk_colsum(void* stream, int B, int N, const float* G, int ldg, float* y, int accumulate,
+              float* workspace, int chunks);
+/* Skinny products with N <= 16 (action heads, state-cotangent blocks), A read exactly once:
+ * out[b][n] = (accumulate ? out : 0) + sum_k A[b][k] W[k][n] (+ bias[n]). */
+int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A, int lda,
+              const float* W, int ldw, float* out, int ldo, const float* bias);
+
 /* The hidden dense layers on the tensor cores (tcgen05 + TMEM + TMA), 3xTF32 split for fp32-grade
  * accuracy:  C[M][N] = epi(A[M][K] * Bt[N][K]^T) with A = A_hi + A_lo, Bt = Bt_hi + Bt_lo as
  * produced by rk_tf32_split (hi exactly representable in TF32, lo the fp32 remainder).

@@ -253,10 +253,13 @@ class DrpPipeline:
         # by the library (negative = "up to"), workspace sized for the largest product
         max_split = int(max(1, min(128, Bt // 256)))
         self.split_k = -max_split if max_split > 1 else 1
-        big = max([self.D * self.hid[0]] + [a * b for a, b in zip(self.hid[:-1], self.hid[1:])]
+        big = max([(self.D + 1) * self.hid[0]] + [a * b for a, b in zip(self.hid[:-1], self.hid[1:])]
                   + [self.hid[-1] * self.NH])
         self.ws = z(max_split * big) if max_split > 1 else None
         self.wT = z(plan.n_params)                    # transposed kernels, same offsets
+        self.xp = z(T, Bt * (self.D + 1))             # [x | 1] per step: fused dW0 / db0 operand
+        self.cs_chunks = int(max(1, min(64, Bt // 64)))
+        self.cs_ws = z(self.cs_chunks * max(max(self.hid), self.NH))
         # tensor-core path (tcgen05, 3xTF32) for hidden layers whose shapes fit the MMA tiles
         import os as _os
         ok = lambda a, b: a % 32 == 0 and b % 32 == 0 and 32 <= a <= 256 and 32 <= b <= 256  # noqa
@@ -301,20 +304,13 @@ class DrpPipeline:
                               self.wT_lo[off:off + n], n)
 
     # ---- the MLP ------------------------------------------------------------------------------
-    def mlp_forward(self, params, B, x_fm, H, heads):
+    def mlp_forward(self, params, B, x_fm, H, heads, xp=None):
         """x_fm: the state in the kernels' fluent-major layout (fluent f = block [B][n_f] at word
-        offset off_f * B); H: per-layer outputs [B][h]; heads [B][NH].  The first layer is the
-        sum over fluent blocks of X_f [B][n_f] * W0[rows of f] (accumulated in place; bias and
-        tanh are applied with the last block)."""
+        offset off_f * B); H: per-layer outputs [B][h]; heads [B][NH]; xp: optional [B][D+1]
+        packed copy [x | 1] for the backward pass."""
         h0 = self.hid[0]
-        W0 = self._W(params, "W0")
-        segs = self.plan.state_segs
-        for j, (off, n) in enumerate(segs):
-            last = j == len(segs) - 1
-            flags = (engine.GEMM_ACCUMULATE if j > 0 else 0) | \
-                (engine.EPI_BIAS_TANH if last else engine.EPI_NONE)
-            engine.sgemm(flags, B, h0, n, x_fm[off * B:], n, W0[off * h0:], h0, H[0], h0,
-                         bias=self._W(params, "b0"))
+        engine.drp_layer0(B, self.D, h0, self.plan.state_segs, x_fm, self._W(params, "W0"),
+                          self._W(params, "b0"), H[0], xp)
         fan, src = h0, H[0]
         for i in range(1, len(self.hid)):
             h = self.hid[i]
@@ -328,10 +324,14 @@ class DrpPipeline:
                 engine.sgemm(engine.EPI_BIAS_TANH, B, h, fan, src, fan, self._W(params, f"W{i}"),
                              h, H[i], h, bias=self._W(params, f"b{i}"))
             fan, src = h, H[i]
-        engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"), self.NH,
-                     heads, self.NH, bias=self._W(params, "bh"))
+        if self.NH <= 16:
+            engine.rowdot(False, B, self.NH, fan, src, fan, self._W(params, "Wh"), self.NH, heads,
+                          self.NH, bias=self._W(params, "bh"))
+        else:
+            engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"),
+                         self.NH, heads, self.NH, bias=self._W(params, "bh"))
 
-    def mlp_backward(self, grad, B, x_fm, H, gs_cur):
+    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp):
         """Consumes self.gheads [B][NH]; accumulates weight gradients into ``grad`` and adds the
         input cotangent to the fluent-major state cotangent ``gs_cur``."""
         AT, ACC = engine.GEMM_A_TRANS, engine.GEMM_ACCUMULATE
@@ -340,23 +340,21 @@ class DrpPipeline:
         hl = self.hid[last]
         engine.sgemm(AT | ACC, hl, self.NH, B, H[last], hl, self.gheads, self.NH,
                      self._W(grad, "Wh"), self.NH, workspace=ws, split_k=sk)
-        engine.sgemm(AT | ACC, 1, self.NH, B, self.ones, 1, self.gheads, self.NH,
-                     self._W(grad, "bh"), self.NH, workspace=ws, split_k=sk)
+        engine.colsum(B, self.NH, self.gheads, self.NH, self._W(grad, "bh"), True, self.cs_ws,
+                      self.cs_chunks)
         engine.sgemm(engine.EPI_DTANH, B, hl, self.NH, self.gheads, self.NH,
                      self._W(self.wT, "Wh"), hl, self.gz[last], hl, aux=H[last], ldaux=hl)
         for i in range(last, -1, -1):
             h = self.hid[i]
             fan = self.D if i == 0 else self.hid[i - 1]
-            if i == 0:      # one block of rows of W0 per state fluent
-                gW0 = self._W(grad, "W0")
-                for off, n in self.plan.state_segs:
-                    engine.sgemm(AT | ACC, n, h, B, x_fm[off * B:], n, self.gz[0], h,
-                                 gW0[off * h:], h, workspace=ws, split_k=sk)
+            if i == 0:      # [x | 1]^T dZ: the rows of dW0 and, in row D, db0 (contiguous in grad)
+                engine.sgemm(AT | ACC, fan + 1, h, B, xp, fan + 1, self.gz[0], h,
+                             self._W(grad, "W0"), h, workspace=ws, split_k=sk)
             else:
                 engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
                              self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
-            engine.sgemm(AT | ACC, 1, h, B, self.ones, 1, self.gz[i], h, self._W(grad, f"b{i}"), h,
-                         workspace=ws, split_k=sk)
+                engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
+                              self.cs_chunks)
             if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
                 engine.tf32_split(self.gz[i], self.a_hi, self.a_lo, B * h)
                 engine.tcgemm(3, B, fan, h, self.a_hi, self.a_lo, h, self._W(self.w_hi, f"W{i}"),
@@ -368,7 +366,12 @@ class DrpPipeline:
             else:           # input cotangent, added block by block to the state cotangent
                 W0T = self._W(self.wT, "W0")
                 for off, n in self.plan.state_segs:
-                    engine.sgemm(ACC, B, n, h, self.gz[0], h, W0T[off:], fan, gs_cur[off * B:], n)
+                    if n <= 16:
+                        engine.rowdot(True, B, n, h, self.gz[0], h, W0T[off:], fan,
+                                      gs_cur[off * B:], n)
+                    else:
+                        engine.sgemm(ACC, B, n, h, self.gz[0], h, W0T[off:], fan,
+                                     gs_cur[off * B:], n)
 
     # ---- one update (planner.py:2868-2917) -----------------------------------------------------
     def update_kernels(self, p: int):
@@ -382,7 +385,7 @@ class DrpPipeline:
         for t in range(T):
             x = self.tape[t * S * B:(t + 1) * S * B]
             Ht = [Hl[t] for Hl in self.H]
-            self.mlp_forward(params, B, x, Ht, self.heads[t])
+            self.mlp_forward(params, B, x, Ht, self.heads[t], self.xp[t])
             engine.drp_actions_forward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
@@ -416,7 +419,7 @@ class DrpPipeline:
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.gact, self.gheads)
-            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out)
+            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t])
             cur ^= 1
 
     def test_kernels(self, p: int, params: Optional[torch.Tensor] = None):

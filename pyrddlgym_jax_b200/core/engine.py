@@ -23,7 +23,8 @@ EXPORTS = [
     "rk_program_attach_cubin",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
-    "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm",
+    "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
+    "rk_rowdot",
 ]
 
 
@@ -81,6 +82,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, fl, cf, cf, fl, fl,
                                             cf, cf]
     lib.rk_drp_actions_backward.restype = ci
+    lib.rk_drp_layer0.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
+    lib.rk_drp_layer0.restype = ci
+    lib.rk_colsum.argtypes = [vp, ci, ci, cf, ci, cf, ci, cf, ci]
+    lib.rk_colsum.restype = ci
+    lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
+    lib.rk_rowdot.restype = ci
     lib.rk_tf32_split.argtypes = [vp, cf, cf, cf, ctypes.c_size_t]
     lib.rk_tf32_split.restype = ci
     lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
@@ -252,3 +259,20 @@ def tcgemm(epi: int, M: int, N: int, K: int, A_hi, A_lo, lda: int, Bt_hi, Bt_lo,
     _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A_hi), _ptr(A_lo), lda,
                                     _ptr(Bt_hi), _ptr(Bt_lo), ldb, _ptr(C), ldc, _ptr(bias),
                                     _ptr(aux), ldaux), "rk_tcgemm")
+
+
+def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None):
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_drp_layer0(
+        _stream(), B, D, H, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+        _ptr(x), _ptr(W0), _ptr(b0), _ptr(out), _ptr(xp)), "rk_drp_layer0")
+
+
+def colsum(B, N, G, ldg, y, accumulate, workspace, chunks):
+    _check(load_library().rk_colsum(_stream(), B, N, _ptr(G), ldg, _ptr(y), int(bool(accumulate)),
+                                    _ptr(workspace), int(chunks)), "rk_colsum")
+
+
+def rowdot(accumulate, B, N, K, A, lda, W, ldw, out, ldo, bias=None):
+    _check(load_library().rk_rowdot(_stream(), int(bool(accumulate)), B, N, K, _ptr(A), lda,
+                                    _ptr(W), ldw, _ptr(out), ldo, _ptr(bias)), "rk_rowdot")

@@ -405,3 +405,165 @@ extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochasti
       B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, gact, gheads);
   return (int)cudaGetLastError();
 }
+
+// ---- first dense layer straight from the fluent-major state (planner.py:1300-1313, 1358-1361)
+// out[b][j] = tanh(sum_d x[b][d] * W0[d][j] + b0[j]), where the state vector x[b][:] is the
+// concatenation of the fluent blocks ([B][n_f] at word offset off_f * B).  D is small (the state
+// dimension), so the kernel is bound by writing out (B x H floats once).  Optionally also packs
+// xp[b][0..D) = x[b][:], xp[b][D] = 1: the operand of the fused weight+bias gradient GEMM.
+__global__ void __launch_bounds__(256)
+rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
+                     const float* __restrict__ W0, const float* __restrict__ b0,
+                     float* __restrict__ out, float* __restrict__ xp) {
+  extern __shared__ float sh0[];
+  float* Ws = sh0;                       // [D][H]
+  float* xs = sh0 + (size_t)D * H;       // [64][D]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < D * H; i += 256) Ws[i] = W0[i];
+  const int r0 = blockIdx.x * 64;
+  for (int i = tid; i < 64 * D; i += 256) {
+    const int r = i / D, d = i % D, b = r0 + r;
+    float v = 0.f;
+    if (b < B) {
+      int f = 0;
+      while (f + 1 < S.n && d >= S.off[f + 1]) ++f;
+      v = x[(size_t)S.off[f] * B + (size_t)b * S.len[f] + (d - S.off[f])];
+      if (xp != nullptr) xp[(size_t)b * (D + 1) + d] = v;
+    }
+    xs[i] = v;
+  }
+  if (xp != nullptr)
+    for (int r = tid; r < 64; r += 256)
+      if (r0 + r < B) xp[(size_t)(r0 + r) * (D + 1) + D] = 1.f;
+  __syncthreads();
+  for (int r = warp; r < 64; r += 8) {
+    const int b = r0 + r;
+    if (b >= B) break;
+    for (int j = lane; j < H; j += 32) {
+      float acc = 0.f;
+      for (int d = 0; d < D; ++d) acc = fmaf(xs[r * D + d], Ws[d * H + j], acc);
+      out[(size_t)b * H + j] = tanhf(acc + b0[j]);
+    }
+  }
+}
+
+extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
+                             const int32_t* seg_off, const int32_t* seg_len, const float* x,
+                             const float* W0, const float* b0, float* out, float* xp) {
+  if (B <= 0 || D <= 0 || H <= 0 || x == nullptr || W0 == nullptr || b0 == nullptr ||
+      out == nullptr)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(D, n_seg, seg_off, seg_len, &S);
+  if (rc != 0) return rc;
+  const size_t smem = ((size_t)D * H + 64 * (size_t)D) * sizeof(float);
+  if (smem > 200 * 1024) return RK_E_SMEM;
+  if (smem > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_drp_layer0_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  rk_drp_layer0_kernel<<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0,
+                                                                           out, xp);
+  return (int)cudaGetLastError();
+}
+
+// ---- column sums over the batch (bias gradients): y[n] (+)= sum_b G[b][n] --------------------
+// stage 1: chunk c sums its rows for 32 columns per block into ws[c][n]; stage 2 (the split-K
+// reduce kernel) adds the chunks in a fixed order.  G is read exactly once.
+__global__ void __launch_bounds__(256)
+rk_colsum_kernel(int B, int N, const float* __restrict__ G, int ldg, int rows_per_chunk,
+                 float* __restrict__ ws) {
+  __shared__ float part[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 32 + lane;
+  const int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
+  float acc = 0.f;
+  if (n < N)
+    for (int b = b0 + warp; b < b1; b += 8) acc += G[(size_t)b * ldg + n];
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][lane];
+    ws[(size_t)blockIdx.y * N + n] = s;
+  }
+}
+
+extern "C" int rk_colsum(void* stream, int B, int N, const float* G, int ldg, float* y,
+                         int accumulate, float* workspace, int chunks) {
+  if (B <= 0 || N <= 0 || G == nullptr || y == nullptr || workspace == nullptr || chunks < 1)
+    return RK_E_BADARG;
+  if (chunks > B) chunks = B;
+  const int rpc = (B + chunks - 1) / chunks;
+  chunks = (B + rpc - 1) / rpc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((N + 31) / 32, chunks);
+  rk_colsum_kernel<<<grid, 256, 0, st>>>(B, N, G, ldg, rpc, workspace);
+  rk_sgemm_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(1, N, chunks, workspace, y, N, nullptr,
+                                                           nullptr, 0, 0, accumulate ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+// ---- skinny products with N <= 16 (action heads, state-cotangent blocks) ----------------------
+// out[b][n] = (accumulate ? out[b][n] : 0) + sum_k A[b][k] * W[k][n] (+ bias[n]).
+// One warp per row: lanes stride over k (coalesced 128-byte reads of A, read exactly once),
+// W staged in shared memory with an odd row stride, N warp reductions per row.
+__global__ void __launch_bounds__(256)
+rk_rowdot_kernel(int B, int N, int K, const float* __restrict__ A, int lda,
+                 const float* __restrict__ W, int ldw, float* __restrict__ out, int ldo,
+                 const float* __restrict__ bias, int accumulate) {
+  extern __shared__ float Wsh[];
+  const int Np = N | 1;
+  for (int i = threadIdx.x; i < K * N; i += 256) Wsh[(i / N) * Np + (i % N)] = W[(size_t)(i / N) * ldw + (i % N)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    float acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    const float* a = A + (size_t)b * lda;
+    for (int k = lane; k < K; k += 32) {
+      const float av = a[k];
+      const float* w = Wsh + k * Np;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < N) acc[n] = fmaf(av, w[n], acc[n]);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      if (n < N) {
+        float v = acc[n];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == n) mine = v;
+      }
+    }
+    if (lane < N) {
+      float v = mine;
+      if (bias != nullptr) v += bias[lane];
+      if (accumulate) v += out[(size_t)b * ldo + lane];
+      out[(size_t)b * ldo + lane] = v;
+    }
+  }
+}
+
+extern "C" int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A,
+                         int lda, const float* W, int ldw, float* out, int ldo,
+                         const float* bias) {
+  if (B <= 0 || N <= 0 || N > 16 || K <= 0 || A == nullptr || W == nullptr || out == nullptr)
+    return RK_E_BADARG;
+  const size_t smem = (size_t)K * (N | 1) * sizeof(float);
+  if (smem > 200 * 1024) return RK_E_SMEM;
+  if (smem > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_rowdot_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
+  }
+  int grid = (B + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  rk_rowdot_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(B, N, K, A, lda, W, ldw, out, ldo,
+                                                               bias, accumulate ? 1 : 0);
+  return (int)cudaGetLastError();
+}

@@ -248,3 +248,47 @@ def test_tcgemm_3xtf32_against_fp64(cuda_device, M, N, K):
         err = float((C.double() - want).abs().max())
         # ~1e-6 of the pre-activation scale (dropped lo*lo term + fp32 accumulation over K)
         assert err <= 4e-6 * max(1.0, float(ref.abs().max())), (epi, err)
+
+
+@pytest.mark.gpu
+def test_layer0_colsum_rowdot_against_torch(cuda_device):
+    """The three DRP helper kernels: first layer from fluent-major state blocks (+ packed [x|1]),
+    deterministic column sums, one-pass skinny products."""
+    from pyrddlgym_jax_b200.core import engine
+    dev = cuda_device
+    g = torch.Generator().manual_seed(9)
+    B, H = 777, 96
+    segs = [(0, 5), (5, 1), (6, 3)]
+    D = 9
+    blocks = [torch.randn(B, n, generator=g) for _, n in segs]
+    x_fm = torch.cat([b.reshape(-1) for b in blocks]).to(dev)
+    X = torch.cat(blocks, 1)
+    W0, b0 = torch.randn(D, H, generator=g) / 3, torch.randn(H, generator=g)
+    out, xp = torch.empty(B, H, device=dev), torch.empty(B, D + 1, device=dev)
+    engine.drp_layer0(B, D, H, segs, x_fm, W0.to(dev), b0.to(dev), out, xp)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), torch.tanh(X @ W0 + b0).numpy(), rtol=2e-6, atol=2e-6)
+    assert torch.equal(xp.cpu(), torch.cat([X, torch.ones(B, 1)], 1))
+    # column sums
+    G = torch.randn(B, H, generator=g)
+    y0 = torch.randn(H, generator=g)
+    for acc in (False, True):
+        y = y0.clone().to(dev)
+        ws = torch.zeros(64 * H, device=dev)
+        engine.colsum(B, H, G.to(dev), H, y, acc, ws, 64)
+        torch.cuda.synchronize()
+        want = G.double().sum(0) + (y0.double() if acc else 0)
+        np.testing.assert_allclose(y.cpu().numpy(), want.float().numpy(), rtol=1e-5, atol=1e-4)
+    # skinny products
+    for N, K in ((10, 256), (5, 64), (1, 96), (16, 33)):
+        A = torch.randn(B, K, generator=g) / np.sqrt(K)
+        W = torch.randn(K, N + 3, generator=g)            # a column window of a wider matrix
+        bias = torch.randn(N, generator=g)
+        o0 = torch.randn(B, N, generator=g)
+        for acc in (False, True):
+            o = o0.clone().to(dev)
+            engine.rowdot(acc, B, N, K, A.to(dev), K, W.to(dev)[:, 2:].contiguous() if False else
+                          W.to(dev).view(-1)[2:], N + 3, o, N, bias=bias.to(dev))
+            torch.cuda.synchronize()
+            want = A.double() @ W[:, 2:2 + N].double() + bias + (o0.double() if acc else 0)
+            np.testing.assert_allclose(o.cpu().numpy(), want.float().numpy(), rtol=1e-5, atol=1e-5)
