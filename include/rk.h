@@ -170,14 +170,15 @@ int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A,
               const float* W, int ldw, float* out, int ldo, const float* bias);
 
 /* The hidden dense layers on the tensor cores (tcgen05 + TMEM + TMA), 3xTF32 split for fp32-grade
- * accuracy:  C[M][N] = epi(A[M][K] * Bt[N][K]^T) with A = A_hi + A_lo, Bt = Bt_hi + Bt_lo as
- * produced by rk_tf32_split (hi exactly representable in TF32, lo the fp32 remainder).
+ * accuracy:  C[M][N] = epi(A[M][K] * Bt[N][K]^T).  A is plain fp32 (split into TF32-exact hi +
+ * fp32 remainder lo inside the kernel); the weight operand is passed pre-split, Bt = Bt_hi +
+ * Bt_lo as produced by rk_tf32_split (once per optimiser step).
  * Constraints: 32 <= N <= 256, N % 32 == 0, K % 32 == 0, leading dimensions % 4 == 0,
  * 16-byte aligned pointers.  epi: 0 none, 1 + bias, 2 tanh(+ bias), 3 * (1 - aux^2).
  * Replaces: nn.Dense + tanh of the hidden stack (planner.py:1358-1361) and its transpose. */
 int rk_tf32_split(void* stream, const float* x, float* hi, float* lo, size_t n);
-int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A_hi, const float* A_lo,
-              int lda, const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
+int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int lda,
+              const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
               const float* bias, const float* aux, int ldaux);
 
 /* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).

@@ -267,8 +267,6 @@ class DrpPipeline:
                           if _os.environ.get("RK_TCGEMM", "1") != "0" and Bt >= 128
                           and ok(self.hid[i - 1], self.hid[i])]
         if self.tc_layers:
-            hmax = max(self.hid)
-            self.a_hi, self.a_lo = z(max(Bt, Be) * hmax), z(max(Bt, Be) * hmax)
             self.w_hi, self.w_lo = z(plan.n_params), z(plan.n_params)       # split of W  [in][out]
             self.wT_hi, self.wT_lo = z(plan.n_params), z(plan.n_params)     # split of W^T [out][in]
         lo = np.concatenate([plan.bounds[v][0].reshape(-1) for v in plan.layout])
@@ -315,9 +313,7 @@ class DrpPipeline:
         for i in range(1, len(self.hid)):
             h = self.hid[i]
             if i in self.tc_layers:     # Y = tanh(X W + b) as X * (W^T)^T on the tensor cores
-                n = B * fan
-                engine.tf32_split(src, self.a_hi, self.a_lo, n)
-                engine.tcgemm(2, B, h, fan, self.a_hi, self.a_lo, fan, self._W(self.wT_hi, f"W{i}"),
+                engine.tcgemm(2, B, h, fan, src, fan, self._W(self.wT_hi, f"W{i}"),
                               self._W(self.wT_lo, f"W{i}"), fan, H[i], h,
                               bias=self._W(params, f"b{i}"))
             else:
@@ -356,8 +352,7 @@ class DrpPipeline:
                 engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
                               self.cs_chunks)
             if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
-                engine.tf32_split(self.gz[i], self.a_hi, self.a_lo, B * h)
-                engine.tcgemm(3, B, fan, h, self.a_hi, self.a_lo, h, self._W(self.w_hi, f"W{i}"),
+                engine.tcgemm(3, B, fan, h, self.gz[i], h, self._W(self.w_hi, f"W{i}"),
                               self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan,
                               aux=H[i - 1], ldaux=fan)
             elif i > 0:

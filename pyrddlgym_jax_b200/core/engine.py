@@ -90,7 +90,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_rowdot.restype = ci
     lib.rk_tf32_split.argtypes = [vp, cf, cf, cf, ctypes.c_size_t]
     lib.rk_tf32_split.restype = ci
-    lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
+    lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
     lib.rk_tcgemm.restype = ci
     if path is None:
         _LIB = lib
@@ -253,10 +253,10 @@ def tf32_split(x: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, n: Optional[
                                         int(x.numel() if n is None else n)), "rk_tf32_split")
 
 
-def tcgemm(epi: int, M: int, N: int, K: int, A_hi, A_lo, lda: int, Bt_hi, Bt_lo, ldb: int, C,
+def tcgemm(epi: int, M: int, N: int, K: int, A, lda: int, Bt_hi, Bt_lo, ldb: int, C,
            ldc: int, bias=None, aux=None, ldaux: int = 0):
     """Tensor-core (tcgen05, 3xTF32) C = epi(A * Bt^T); epi as EPI_* >> 4."""
-    _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A_hi), _ptr(A_lo), lda,
+    _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A), lda,
                                     _ptr(Bt_hi), _ptr(Bt_lo), ldb, _ptr(C), ldc, _ptr(bias),
                                     _ptr(aux), ldaux), "rk_tcgemm")
 

@@ -7,15 +7,18 @@
 //   C[M][N] = epi( A[M][K] * Bt[N][K]^T ),   A = A_hi + A_lo,  Bt = Bt_hi + Bt_lo
 //   A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo      (the lo*lo term is below fp32 rounding)
 //
-// hi parts are exactly representable in TF32 (cvt.rna), lo parts are the fp32 remainders
-// (rk_tf32_split), so the tensor core's fp32->tf32 operand conversion is exact for hi and costs
+// hi parts are exactly representable in TF32 (cvt.rna), lo parts are the fp32 remainders, so the tensor core's fp32->tf32 operand conversion is exact for hi and costs
 // < 2^-22 relative for lo: the sum matches an fp32 GEMM to ~1e-6.
 //
 // One CTA per 128-row tile, full N (<= 256) in one TMEM accumulator (N fp32 columns):
-//   warp 0   : TMA producer  (4 tiles per k-block: A_hi, A_lo, B_hi, B_lo; 128B-swizzled, K-major)
+//   warp 0   : TMA producer  (3 tiles per k-block: raw A, B_hi, B_lo; 64B-swizzled, K-major)
 //   warp 1   : MMA issuer    (one elected lane; 3 tcgen05.mma.kind::tf32 per 8-wide k-slice)
-//   warps 2-5: epilogue      (tcgen05.ld 32 lanes x 32 columns -> bias/tanh or tanh-adjoint -> C)
-// 2-stage smem ring (96 KB per stage at N=256), mbarrier full/empty + tcgen05.commit.
+//   warps 2-9: during the main loop split the raw A tile into hi (in place) / lo (second buffer)
+//              -- an elementwise map, so the swizzled layout does not matter -- then run the
+//              epilogue (tcgen05.ld 32 lanes x 32 columns -> bias/tanh or tanh-adjoint -> C)
+// The activation matrix is therefore read from HBM exactly once, as plain fp32; only the small
+// weight matrix is pre-split (rk_tf32_split, once per update).
+// 4-stage smem ring (48 KB per stage at N=256), mbarriers full -> split -> (tcgen05.commit) empty.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -25,8 +28,8 @@
 #include "../../include/rk.h"
 
 #define TC_BM 128
-#define TC_BK 32          // fp32 elements per k-block = one 128-byte swizzle row
-#define TC_STAGES 2
+#define TC_BK 16          // fp32 elements per k-block = one 64-byte swizzle row
+#define TC_STAGES 4       // 48 KB per stage at N = 256: three loads in flight behind the MMA
 #define TC_UMMA_K 8       // kind::tf32: 32 bytes of K per instruction
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -92,21 +95,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128B-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row groups 1024 B apart):
-// start address, SBO = 1024 B, version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+// K-major, 64B-swizzled operand tile (rows of 16 fp32 = 64 B, 8-row groups 512 B apart):
+// start address, SBO = 512 B, version 1 (sm_100), layout type 4 (SWIZZLE_64B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)((8 * TC_BK * 4) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 
 // epi: 2 = bias + tanh, 3 = * (1 - aux^2), 1 = bias, 0 = none
-__global__ void __launch_bounds__(192, 1)
-rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
-                 const __grid_constant__ CUtensorMap tmA_lo,
+#define TC_THREADS 320     // producer warp, MMA warp, 8 converter / epilogue warps
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int epi,
                  float* __restrict__ C, int ldc, const float* __restrict__ bias,
@@ -114,14 +117,16 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = TC_BM * TC_BK * 4;            // 16 KB
-  const uint32_t b_bytes = (uint32_t)N * TC_BK * 4;      // 32 KB at N = 256
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;            // 8 KB
+  const uint32_t b_bytes = (uint32_t)N * TC_BK * 4;      // 16 KB at N = 256
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = (uint64_t*)(smem + TC_STAGES * stage_bytes);
   uint64_t* full = bars;                  // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;     // [TC_STAGES]
-  uint64_t* acc_ready = bars + 2 * TC_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+  uint64_t* split_done = bars + 2 * TC_STAGES;     // [TC_STAGES], one arrival per converter warp
+  uint64_t* acc_ready = bars + 3 * TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 1);
+  float* bias_s = (float*)(bars + 3 * TC_STAGES + 2);   // [N] when the epilogue adds a bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
@@ -131,6 +136,7 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&split_done[s], 8);
     }
     mbar_init(acc_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,6 +147,8 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                  "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  if (warp >= 2 && (epi == 1 || epi == 2))
+    for (int i = threadIdx.x - 64; i < N; i += 256) bias_s[i] = bias[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -154,9 +162,8 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
-        mbar_expect_tx(&full[s], stage_bytes);
-        tma_load_2d(st, &tmA_hi, &full[s], kb * TC_BK, m0);
-        tma_load_2d(st + a_bytes, &tmA_lo, &full[s], kb * TC_BK, m0);
+        mbar_expect_tx(&full[s], a_bytes + 2 * b_bytes);
+        tma_load_2d(st, &tmA, &full[s], kb * TC_BK, m0);
         tma_load_2d(st + 2 * a_bytes, &tmB_hi, &full[s], kb * TC_BK, 0);
         tma_load_2d(st + 2 * a_bytes + b_bytes, &tmB_lo, &full[s], kb * TC_BK, 0);
       }
@@ -170,7 +177,8 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait(&full[s], ph);                // B_hi / B_lo landed
+        mbar_wait(&split_done[s], ph);          // A split into hi / lo by the converter warps
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + s * stage_bytes);
         const uint64_t dAh = make_desc(st), dAl = make_desc(st + a_bytes);
@@ -188,12 +196,45 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       umma_commit(acc_ready);                   // accumulator complete
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes 32 * (w % 4) .. + 31 =====
+    // ===== main loop: split the raw fp32 A tile into TF32-exact hi (in place) + remainder lo =====
+    const int ct = threadIdx.x - 64;            // 0..255
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      float4* raw = reinterpret_cast<float4*>(smem + s * stage_bytes);
+      float4* lo = reinterpret_cast<float4*>(smem + s * stage_bytes + a_bytes);
+#pragma unroll
+      for (int i = 0; i < (TC_BM * TC_BK / 4) / 256; ++i) {
+        const int idx = ct + 256 * i;
+        const float4 v = raw[idx];
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+        raw[idx] = h;
+        lo[idx] = l;
+      }
+      // generic-proxy writes must be visible to the tensor core's async-proxy reads
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s]))
+                     : "memory");
+      }
+    }
+    // ===== epilogue: warp w reads TMEM lanes 32 * (w % 4) .. + 31; the two warps that share a
+    // lane quarter take one half of the columns each =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int nh = ((N / 32 + 1) / 2) * 32;      // columns of the first half (multiple of 32)
+    const int c_beg = half ? nh : 0, c_end = half ? N : nh;
     mbar_wait(acc_ready, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = m0 + q * 32 + lane;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = c_beg; c0 < c_end; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       if (row < M) {
@@ -205,7 +246,7 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float x = __uint_as_float(r[j + i]);
-            if (epi == 1 || epi == 2) x += __ldg(bias + c0 + j + i);
+            if (epi == 1 || epi == 2) x += bias_s[c0 + j + i];
             if (epi == 2) x = tanhf(x);
             v[i] = x;
           }
@@ -271,24 +312,22 @@ static int load_encode() {
   return g_encode != nullptr ? 0 : RK_E_BADARG;
 }
 
-// row-major [rows][K] fp32 matrix, box = 32 (k) x box_rows, 128B swizzle
+// row-major [rows][K] fp32 matrix, box = TC_BK (k) x box_rows, 64B swizzle
 static int make_map(CUtensorMap* map, const float* base, int rows, int K, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }
 
-extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A_hi,
-                         const float* A_lo, int lda, const float* Bt_hi, const float* Bt_lo,
-                         int ldb, float* C, int ldc, const float* bias, const float* aux,
-                         int ldaux) {
-  if (M <= 0 || A_hi == nullptr || A_lo == nullptr || Bt_hi == nullptr || Bt_lo == nullptr ||
-      C == nullptr)
+extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int lda,
+                         const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
+                         const float* bias, const float* aux, int ldaux) {
+  if (M <= 0 || A == nullptr || Bt_hi == nullptr || Bt_lo == nullptr || C == nullptr)
     return RK_E_BADARG;
   if (N < 32 || N > 256 || (N % 32) != 0 || K < TC_BK || (K % TC_BK) != 0) return RK_E_BADARG;
   if ((lda % 4) != 0 || (ldb % 4) != 0 || (ldc % 4) != 0) return RK_E_BADARG;
@@ -297,13 +336,12 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
     return RK_E_BADARG;
   int rc = load_encode();
   if (rc != 0) return rc;
-  CUtensorMap mAh, mAl, mBh, mBl;
-  if ((rc = make_map(&mAh, A_hi, M, K, lda, TC_BM)) != 0) return rc;
-  if ((rc = make_map(&mAl, A_lo, M, K, lda, TC_BM)) != 0) return rc;
+  CUtensorMap mA, mBh, mBl;
+  if ((rc = make_map(&mA, A, M, K, lda, TC_BM)) != 0) return rc;
   if ((rc = make_map(&mBh, Bt_hi, N, K, ldb, N)) != 0) return rc;
   if ((rc = make_map(&mBl, Bt_lo, N, K, ldb, N)) != 0) return rc;
   const size_t stage = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)N * TC_BK * 4;
-  const size_t smem = TC_STAGES * stage + 128 + 1024;       // barriers + alignment slack
+  const size_t smem = TC_STAGES * stage + 128 + (size_t)N * 4 + 1024;   // barriers, bias, slack
   static int configured = 0;
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(rk_tcgemm_kernel,
@@ -313,7 +351,7 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
   }
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
-  rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, 192, smem, (cudaStream_t)stream>>>(
-      mAh, mAl, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols);
+  rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
+      mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols);
   return (int)cudaGetLastError();
 }

@@ -30,5 +30,5 @@ def t(fn, reps=20):
 
 print("sgemm      us", t(lambda: engine.sgemm(engine.EPI_BIAS_TANH, M, N, K, A, K, W, N, C, N, bias=b)))
 print("tf32_split us", t(lambda: engine.tf32_split(A, Ah, Al)))
-print("tcgemm     us", t(lambda: engine.tcgemm(2, M, N, K, Ah, Al, K, Bh, Bl, K, C, N, bias=b)))
+print("tcgemm     us", t(lambda: engine.tcgemm(2, M, N, K, A, K, Bh, Bl, K, C, N, bias=b)))
 print("copy 33MB  us", t(lambda: C.copy_(A)))
