@@ -181,6 +181,14 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
               const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
               const float* bias, const float* aux, int ldaux);
 
+/* Weight gradient of a hidden layer on the tensor cores: C[M][N] (+)= A[K][M]^T * B[K][N] with
+ * both operands plain fp32 activations stored batch-major (K = rollouts), MN-major UMMA tiles,
+ * 3xTF32 split done in the kernel, deterministic split-K (at most max_splits slices) through
+ * workspace[max_splits][M][N].  Constraints: M % 32 == 0, 32 <= N <= 256, N % 32 == 0.
+ * Replaces: the dW = X^T dZ transpose of nn.Dense in the reverse pass (planner.py:2873). */
+int rk_tcgemm_tn(void* stream, int accumulate, int M, int N, int K, const float* A, int lda,
+                 const float* B, int ldb, float* C, float* workspace, int max_splits);
+
 /* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).
  *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise;
  *   seg_off / seg_len (HOST arrays, n_seg <= RK_MAX_ACTION_FLUENTS): the action fluents' word

@@ -252,6 +252,7 @@ class DrpPipeline:
         # weight-gradient GEMMs reduce over the batch: deterministic split-K, slice count chosen
         # by the library (negative = "up to"), workspace sized for the largest product
         max_split = int(max(1, min(128, Bt // 256)))
+        self.max_split = max_split
         self.split_k = -max_split if max_split > 1 else 1
         big = max([(self.D + 1) * self.hid[0]] + [a * b for a, b in zip(self.hid[:-1], self.hid[1:])]
                   + [self.hid[-1] * self.NH])
@@ -347,8 +348,12 @@ class DrpPipeline:
                 engine.sgemm(AT | ACC, fan + 1, h, B, xp, fan + 1, self.gz[0], h,
                              self._W(grad, "W0"), h, workspace=ws, split_k=sk)
             else:
-                engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
-                             self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
+                if i in self.tc_layers and self.ws is not None:     # dW = H^T dZ on the tensor cores
+                    engine.tcgemm_tn(True, fan, h, B, H[i - 1], fan, self.gz[i], h,
+                                     self._W(grad, f"W{i}"), self.ws, self.max_split)
+                else:
+                    engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
+                                 self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
                 engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
                               self.cs_chunks)
             if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself

@@ -24,7 +24,7 @@ EXPORTS = [
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
-    "rk_rowdot",
+    "rk_rowdot", "rk_tcgemm_tn",
 ]
 
 
@@ -88,6 +88,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_colsum.restype = ci
     lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
     lib.rk_rowdot.restype = ci
+    lib.rk_tcgemm_tn.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, cf, ci]
+    lib.rk_tcgemm_tn.restype = ci
     lib.rk_tf32_split.argtypes = [vp, cf, cf, cf, ctypes.c_size_t]
     lib.rk_tf32_split.restype = ci
     lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
@@ -276,3 +278,10 @@ def colsum(B, N, G, ldg, y, accumulate, workspace, chunks):
 def rowdot(accumulate, B, N, K, A, lda, W, ldw, out, ldo, bias=None):
     _check(load_library().rk_rowdot(_stream(), int(bool(accumulate)), B, N, K, _ptr(A), lda,
                                     _ptr(W), ldw, _ptr(out), ldo, _ptr(bias)), "rk_rowdot")
+
+
+def tcgemm_tn(accumulate, M, N, K, A, lda, Bm, ldb, C, workspace, max_splits):
+    """Tensor-core (tcgen05, 3xTF32) C (+)= A^T * B, both operands [K][.] row-major."""
+    _check(load_library().rk_tcgemm_tn(_stream(), int(bool(accumulate)), M, N, K, _ptr(A), lda,
+                                       _ptr(Bm), ldb, _ptr(C), _ptr(workspace), int(max_splits)),
+           "rk_tcgemm_tn")

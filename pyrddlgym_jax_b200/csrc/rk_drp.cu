@@ -250,8 +250,8 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   else if (M <= 16) { bm = 16; bn = 128; bk = SBK; }
   const int tiles = ((N + bn - 1) / bn) * ((M + bm - 1) / bm);
   if (split_k == 0) split_k = 1;
-  if (split_k < 0) {                 // auto: enough CTAs for two waves, at most -split_k slices
-    int want = (2 * 148 + tiles - 1) / tiles;
+  if (split_k < 0) {                 // auto: enough CTAs for one wave, at most -split_k slices
+    int want = (148 + tiles - 1) / tiles;        // one full wave of CTAs
     if (want > -split_k) want = -split_k;
     if (want > K / 256) want = K / 256;
     split_k = want < 1 ? 1 : want;
@@ -524,12 +524,19 @@ rk_rowdot_kernel(int B, int N, int K, const float* __restrict__ A, int lda,
 #pragma unroll
     for (int n = 0; n < 16; ++n) acc[n] = 0.f;
     const float* a = A + (size_t)b * lda;
-    for (int k = lane; k < K; k += 32) {
-      const float av = a[k];
-      const float* w = Wsh + k * Np;
+    for (int k0 = lane; k0 < K; k0 += 256) {     // 8 independent loads in flight per lane
+      float av[8];
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
-        if (n < N) acc[n] = fmaf(av, w[n], acc[n]);
+      for (int u = 0; u < 8; ++u) av[u] = (k0 + 32 * u < K) ? a[k0 + 32 * u] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k0 + 32 * u < K) {
+          const float* w = Wsh + (k0 + 32 * u) * Np;
+#pragma unroll
+          for (int n = 0; n < 16; ++n)
+            if (n < N) acc[n] = fmaf(av[u], w[n], acc[n]);
+        }
+      }
     }
     float mine = 0.f;
 #pragma unroll

@@ -271,6 +271,187 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 }
 
+// ---- weight gradients: C[M][N] (+)= A[K][M]^T * B[K][N], reduction over the batch ---------------
+// Both operands are activations stored batch-major, so the contraction index K (= rollout) is
+// the slow one: the tiles are MN-major.  For 32-bit MN-major operands the only UMMA layout is
+// SWIZZLE_128B_BASE32B (32-byte swizzle chunks; TMA mode 128B_ATOM_32B): TMA boxes of 32 (mn) x
+// TC_BK (k) land as k-rows of 128 bytes, 4 k-rows per 512-byte atom, next mn-atom at
+// LBO = TC_BK * 128 B, next 4-k group at SBO = 512 B; one K=8 MMA spans two atoms (1024 B).
+// Both raw fp32 tiles are split into hi (in place) / lo by the converter warps.  Split-K over
+// gridDim.y; every CTA writes its partial tile to workspace[split][M][N].
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)(((TC_BK * 128) >> 4) & 0x3fff) << 16;   // LBO: next 32-wide mn atom
+  d |= (uint64_t)((512 >> 4) & 0x3fff) << 32;             // SBO: next group of 4 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rk_tcgemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                    int kb_per_split, float* __restrict__ ws, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;            // 8 KB: 4 mn-atoms x 16 k-rows x 128 B
+  const uint32_t b_bytes = (uint32_t)N * TC_BK * 4;      // 16 KB at N = 256
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* split_done = bars + 2 * TC_STAGES;
+  uint64_t* acc_ready = bars + 3 * TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.y * kb_per_split;
+  const int kb1 = min(kb_total, kb0 + kb_per_split);
+  const int num_kb = max(0, kb1 - kb0);
+  const int a_boxes = min(TC_BM, M - m0) / 32, b_boxes = N / 32;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&split_done[s], 8);
+    }
+    mbar_init(acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // mn-atoms of A beyond M (when M - m0 < 128) are never loaded: keep them zero
+  if (a_boxes < TC_BM / 32)
+    for (uint32_t i = threadIdx.x; i < TC_STAGES * stage_bytes / 16; i += TC_THREADS)
+      reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * stage_bytes;
+        const int k0 = (kb0 + i) * TC_BK;
+        mbar_expect_tx(&full[s], (uint32_t)(a_boxes + b_boxes) * TC_BK * 128);
+        for (int j = 0; j < a_boxes; ++j)
+          tma_load_2d(st + j * TC_BK * 128, &tmA, &full[s], m0 + 32 * j, k0);
+        for (int j = 0; j < b_boxes; ++j)
+          tma_load_2d(st + 2 * a_bytes + j * TC_BK * 128, &tmB, &full[s], 32 * j, k0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&split_done[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + s * stage_bytes);
+        const uint64_t dAh = make_desc_mn(st), dAl = make_desc_mn(st + a_bytes);
+        const uint64_t dBh = make_desc_mn(st + 2 * a_bytes);
+        const uint64_t dBl = make_desc_mn(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * 1024) >> 4);       // next group of 8 k-rows
+          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (i | k) != 0);
+          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1);
+          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_ready);
+    }
+  } else {
+    const int ct = threadIdx.x - 64;
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % TC_STAGES;
+      const uint32_t ph = (i / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      // raw A | A_lo | raw B | B_lo : split both raw tiles (layout-agnostic elementwise map)
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t off = part ? 2 * a_bytes : 0, bytes = part ? b_bytes : a_bytes;
+        float4* raw = reinterpret_cast<float4*>(smem + s * stage_bytes + off);
+        float4* lo = reinterpret_cast<float4*>(smem + s * stage_bytes + off + bytes);
+        for (uint32_t idx = ct; idx < bytes / 16; idx += 256) {
+          const float4 v = raw[idx];
+          float4 h, l;
+          uint32_t t;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+          raw[idx] = h;
+          lo[idx] = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s]))
+                     : "memory");
+      }
+    }
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int nh = ((N / 32 + 1) / 2) * 32;
+    const int c_beg = half ? nh : 0, c_end = half ? N : nh;
+    mbar_wait(acc_ready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    float* out = ws + (size_t)blockIdx.y * M * N + (size_t)row * N;
+    for (int c0 = c_beg; c0 < c_end; c0 += 32) {
+      uint32_t r[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + c0 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols));
+  }
+}
+
+__global__ void rk_tc_reduce_kernel(int MN, int splits, const float* __restrict__ ws,
+                                    float* __restrict__ C, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += ws[(size_t)z * MN + i];       // fixed order
+  if (accumulate) v += C[i];
+  C[i] = v;
+}
+
 // ---- fp32 -> (tf32-exact hi, fp32 remainder lo) ------------------------------------------------
 __global__ void rk_tf32_split_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
                                      float4* __restrict__ lo, size_t n4) {
@@ -353,5 +534,56 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
   while ((int)cols < N) cols <<= 1;
   rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
       mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols);
+  return (int)cudaGetLastError();
+}
+
+// row-major [K][cols] fp32 matrix read as an MN-major operand: box = 32 (cols) x TC_BK (k)
+static int make_map_mn(CUtensorMap* map, const float* base, int K, int cols, int ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, TC_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+extern "C" int rk_tcgemm_tn(void* stream, int accumulate, int M, int N, int K, const float* A,
+                            int lda, const float* B, int ldb, float* C, float* workspace,
+                            int max_splits) {
+  if (A == nullptr || B == nullptr || C == nullptr || workspace == nullptr || K <= 0)
+    return RK_E_BADARG;
+  if (M < 32 || (M % 32) != 0 || N < 32 || N > 256 || (N % 32) != 0 || max_splits < 1)
+    return RK_E_BADARG;
+  if ((lda % 4) != 0 || (ldb % 4) != 0) return RK_E_BADARG;
+  int rc = load_encode();
+  if (rc != 0) return rc;
+  CUtensorMap mA, mB;
+  if ((rc = make_map_mn(&mA, A, K, M, lda)) != 0) return rc;
+  if ((rc = make_map_mn(&mB, B, K, N, ldb)) != 0) return rc;
+  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  int splits = (148 + m_tiles - 1) / m_tiles;                  // one wave of CTAs
+  if (splits > max_splits) splits = max_splits;
+  if (splits > kb_total) splits = kb_total;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per - 1) / kb_per;
+  const size_t stage = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)N * TC_BK * 4;
+  const size_t smem = TC_STAGES * stage + 128 + 1024;
+  static int configured = 0;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_tcgemm_tn_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    configured = 1;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < N) cols <<= 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(m_tiles, splits);
+  rk_tcgemm_tn_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, M, N, K, kb_per, workspace, cols);
+  rk_tc_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(M * N, splits, workspace, C,
+                                                           accumulate ? 1 : 0);
   return (int)cudaGetLastError();
 }

@@ -290,3 +290,30 @@ def test_layer0_colsum_rowdot_against_torch(cuda_device):
             torch.cuda.synchronize()
             want = A.double() @ W[:, 2:2 + N].double() + bias + (o0.double() if acc else 0)
             np.testing.assert_allclose(o.cpu().numpy(), want.float().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 4000), (64, 64, 1000), (256, 128, 32768),
+                                   (96, 32, 37)])
+def test_tcgemm_tn_against_fp64(cuda_device, M, N, K):
+    """rk_tcgemm_tn: C (+)= A^T B over the batch axis on tcgen05 (MN-major tiles, in-kernel
+    3xTF32 split, deterministic split-K) against fp64."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    A = torch.randn(K, M, generator=g).to(cuda_device)
+    Bm = (torch.randn(K, N, generator=g) / np.sqrt(K)).to(cuda_device)
+    C0 = torch.randn(M, N, generator=g).to(cuda_device)
+    ws = torch.zeros(148 * M * N, device=cuda_device)
+    ref = A.double().t() @ Bm.double()
+    for acc in (False, True):
+        C = C0.clone()
+        engine.tcgemm_tn(acc, M, N, K, A, M, Bm, N, C, ws, 148)
+        torch.cuda.synchronize()
+        want = ref + (C0.double() if acc else 0)
+        err = float((C.double() - want).abs().max())
+        assert err <= 4e-6 * max(1.0, float(ref.abs().max())), (acc, err)
+    C1, C2 = C0.clone(), C0.clone()
+    engine.tcgemm_tn(False, M, N, K, A, M, Bm, N, C1, ws, 148)
+    engine.tcgemm_tn(False, M, N, K, A, M, Bm, N, C2, ws, 148)
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)                        # deterministic
