@@ -1,0 +1,190 @@
+"""Drop-in surface: the .cfg format (planner.py:101-244), the planner / controller API and the
+callback contract (planner.py:3368-3392) -- CPU tests for the host logic, GPU tests end to end."""
+import numpy as np
+import pytest
+import torch
+
+from pyrddlgym_jax_b200.core import logic
+from pyrddlgym_jax_b200.core.planner import (JaxBackpropPlanner, JaxDeepReactivePolicy,
+                                             JaxOfflineController, JaxOnlineController,
+                                             JaxPlannerStatus, JaxStraightLinePlan,
+                                             NoImprovementStoppingRule, load_config_from_string)
+
+from .helpers import fixture_model
+
+# the text of three configs shipped by the reference (examples/configs/*.cfg)
+QUADCOPTER_SLP = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+sigmoid_weight=10
+
+[Planner]
+method='JaxStraightLinePlan'
+method_kwargs={}
+optimizer='rmsprop'
+optimizer_kwargs={'learning_rate': 0.03}
+batch_size_train=1
+batch_size_test=1
+pgpe=None
+
+[Optimize]
+key=42
+epochs=100000
+train_seconds=360
+"""
+HVAC_DRP = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+bernoulli_sigmoid_weight=5
+sigmoid_weight=5
+
+[Planner]
+method='JaxDeepReactivePolicy'
+method_kwargs={'topology': [64, 64]}
+optimizer='rmsprop'
+optimizer_kwargs={'learning_rate': 0.001}
+batch_size_train=1
+batch_size_test=1
+pgpe=None
+
+[Optimize]
+key=42
+epochs=6000
+train_seconds=90
+"""
+WILDFIRE_SLP = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+sigmoid_weight=100
+bernoulli_sigmoid_weight=100
+
+[Planner]
+method='JaxStraightLinePlan'
+method_kwargs={'sigmoid_weight': 10.0}
+optimizer='rmsprop'
+optimizer_kwargs={'learning_rate': 0.01}
+batch_size_train=32
+batch_size_test=32
+pgpe=None
+
+[Optimize]
+key=42
+epochs=1000
+train_seconds=30
+stopping_rule='NoImprovementStoppingRule'
+stopping_rule_kwargs={'patience': 7}
+"""
+
+
+def test_load_config_resolves_names_like_the_reference():
+    planner_args, plan_kwargs, train_args = load_config_from_string(QUADCOPTER_SLP)
+    assert planner_args["compiler"] is logic.DefaultJaxRDDLCompilerWithGrad
+    assert planner_args["compiler_kwargs"] == {"sigmoid_weight": 10}
+    assert isinstance(planner_args["plan"], JaxStraightLinePlan)
+    assert planner_args["optimizer"] == "rmsprop"
+    assert planner_args["optimizer_kwargs"] == {"learning_rate": 0.03}
+    assert planner_args["batch_size_train"] == 1 and planner_args["pgpe"] is None
+    assert train_args == {"key": 42, "epochs": 100000, "train_seconds": 360}
+    planner_args, plan_kwargs, _ = load_config_from_string(HVAC_DRP)
+    assert isinstance(planner_args["plan"], JaxDeepReactivePolicy)
+    assert plan_kwargs == {"topology": [64, 64]} and planner_args["plan"]._topology == [64, 64]
+    planner_args, plan_kwargs, train_args = load_config_from_string(WILDFIRE_SLP)
+    assert planner_args["plan"]._sigmoid_weight == 10.0
+    assert isinstance(train_args["stopping_rule"], NoImprovementStoppingRule)
+    assert train_args["stopping_rule"].patience == 7
+
+
+def test_load_config_rejects_unknown_names():
+    with pytest.raises(ValueError):
+        load_config_from_string(QUADCOPTER_SLP.replace("DefaultJaxRDDLCompilerWithGrad", "Nope"))
+    with pytest.raises(ValueError):
+        load_config_from_string(QUADCOPTER_SLP.replace("JaxStraightLinePlan", "NoSuchPlan"))
+    with pytest.raises(ValueError):
+        load_config_from_string(QUADCOPTER_SLP.replace("'rmsprop'", "'lion'"))
+
+
+def test_compiler_classes_expose_reference_kwargs():
+    m = fixture_model("reservoir")
+    c = logic.DefaultJaxRDDLCompilerWithGrad(m, sigmoid_weight=7., use_if_else_ste=False)
+    kw = c.get_kwargs()
+    for key in ("sigmoid_weight", "use_sigmoid_ste", "use_tanh_ste", "argmax_weight", "use_logic_ste",
+                "floor_weight", "round_weight", "use_if_else_ste", "switch_weight",
+                "bernoulli_sigmoid_weight", "use_ste_bernoulli", "discrete_softmax_weight",
+                "binomial_nbins", "poisson_nbins"):
+        assert key in kw, key
+    assert kw["sigmoid_weight"] == 7. and kw["use_if_else_ste"] is False
+
+
+def test_status_machine_matches_reference():
+    """planner.py:2277-2304."""
+    assert [s.value for s in JaxPlannerStatus] == [0, 1, 2, 3, 4, 5, 6]
+    terminal = {s.name for s in JaxPlannerStatus if s.is_terminal()}
+    assert terminal == {"STOPPING_RULE_REACHED", "INVALID_GRADIENT", "TIME_BUDGET_REACHED",
+                        "ITER_BUDGET_REACHED"}
+
+
+CALLBACK_KEYS = {"iteration", "elapsed_time", "progress", "status", "key", "test_key", "train_return",
+                 "test_return", "best_return", "pgpe_return", "last_iteration_improved",
+                 "pgpe_improved", "params", "best_params", "best_index", "pgpe_params",
+                 "model_params", "policy_hyperparams", "grad", "best_grad", "train_log", "test_log",
+                 "planner_state"}
+
+
+@pytest.mark.gpu
+def test_optimize_generator_callback_contract(cuda_device):
+    planner_args, _, train_args = load_config_from_string(QUADCOPTER_SLP)
+    planner_args.update(batch_size_train=64, batch_size_test=64, rollout_horizon=20)
+    m = fixture_model("quadcopter")
+    pl = JaxBackpropPlanner(m, **planner_args)
+    train_args.update(epochs=25, print_summary=False, print_progress=False)
+    returns, last = [], None
+    for cb in pl.optimize_generator(**train_args):
+        assert CALLBACK_KEYS <= set(cb), CALLBACK_KEYS - set(cb)
+        returns.append(float(cb["train_return"][0]))
+        last = cb
+    assert last["iteration"] == 24 and last["status"] == JaxPlannerStatus.ITER_BUDGET_REACHED
+    assert returns[-1] > returns[0]                       # the plan improves
+    assert last["best_return"] >= -1e30 and np.isfinite(last["best_return"])
+    mu = last["best_params"]["real"]["thrust"]["mu"]
+    assert tuple(mu.shape) == (20, 4)
+    assert tuple(last["train_log"]["reward"].shape) == (1, 64, 20)
+    assert tuple(last["test_log"]["reward"].shape) == (1, 64, 20)
+    # actions from the returned plan respect the action box (test policy, planner.py:842-868)
+    act = pl.get_action(None, last["best_params"], 3, None)
+    assert set(act) == set(m.action_fluents) and np.all(act["thrust"] >= 0) and np.all(act["thrust"] <= 20)
+
+
+@pytest.mark.gpu
+def test_offline_and_online_controllers(cuda_device):
+    m = fixture_model("reservoir")
+    pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=32, rollout_horizon=8,
+                            optimizer_kwargs={"learning_rate": 0.2}, pgpe=None)
+    off = JaxOfflineController(pl, key=42, epochs=10, print_summary=False, print_progress=False)
+    state = {"rlevel": np.array([50., 60., 40.], np.float32)}
+    a0 = off.sample_action(state)
+    a1 = off.sample_action(state)
+    assert set(a0) == {"release"} and a0["release"].shape == (3,) and off.step == 2
+    off.reset()
+    assert off.step == 0
+    on = JaxOnlineController(pl, key=3, epochs=5, print_summary=False, print_progress=False)
+    b0 = on.sample_action(state)
+    assert on.guess is not None and b0["release"].shape == (3,)       # warm start for the next epoch
+    b1 = on.sample_action({"rlevel": np.array([55., 58., 42.], np.float32)})
+    assert np.all(b1["release"] >= 0)
+
+
+@pytest.mark.gpu
+def test_wildfire_plan_respects_max_nondef_actions(cuda_device):
+    """After every update the SOGBOFA projection leaves at most max-nondef-actions (= 1) boolean
+    actions on under the test policy (planner.py:914-959, 856)."""
+    planner_args, _, train_args = load_config_from_string(WILDFIRE_SLP)
+    planner_args.update(batch_size_train=64, batch_size_test=64, rollout_horizon=10)
+    m = fixture_model("wildfire")
+    pl = JaxBackpropPlanner(m, **planner_args)
+    train_args.pop("stopping_rule")
+    train_args.update(epochs=8, print_summary=False, print_progress=False)
+    for cb in pl.optimize_generator(**train_args):
+        # callback['params'] are device tensors (views of the live plan), [P, T, *objs]
+        flat = torch.cat([v["logit"][0].cpu().reshape(10, -1)
+                          for v in cb["params"]["bool"].values()], 1)
+        assert int((flat > 0).sum(1).max()) <= 1
