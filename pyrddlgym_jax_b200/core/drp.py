@@ -374,7 +374,7 @@ class DrpPipeline:
                                      gs_cur[off * B:], n)
 
     # ---- one update (planner.py:2868-2917) -----------------------------------------------------
-    def update_kernels(self, p: int):
+    def update_kernels(self, p: int, loss_out: Optional[torch.Tensor] = None):
         pl, plan = self.pl, self.plan
         T, B, S, A = pl.T, pl.batch_size_train, self.S, self.A
         params, grad = pl.params[p], pl.grad[p]
@@ -401,9 +401,10 @@ class DrpPipeline:
         if pl.disc is not None:
             rew = rew * pl.disc.view(T, 1)
         torch.sum(rew, dim=0, out=pl.train_returns[p])
-        engine.mean_loss(pl.train_returns[p], B, pl.train_loss[p:p + 1], None)
+        loss_out = pl.train_loss[p:p + 1] if loss_out is None else loss_out
+        engine.mean_loss(pl.train_returns[p], B, loss_out, None)
         if plan._stochastic:
-            pl.train_loss[p:p + 1].sub_(self.ent_coeff * (self.entropy.sum() / B))
+            loss_out.sub_(self.ent_coeff * (self.entropy.sum() / B))
         # ---- backward sweep
         grad.zero_()
         self.gs[0].zero_()

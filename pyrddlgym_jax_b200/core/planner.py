@@ -461,6 +461,15 @@ class JaxBackpropPlanner:
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
             if len(fw.mparam_defaults) else None
         self._graph = None
+        self._primed = False
+        # software pipelining of the captured iteration (opt -> test || next gradient); the two
+        # branches share NCCL / DRP scratch buffers in the multi-GPU and DRP cases, so only the
+        # single-GPU straight-line plan runs them concurrently
+        import os as _os
+        self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
+        self._overlap = self._pipeline and self.world_size == 1 and not self.is_drp
+        self._train_loss_tmp = z(P)
+        self.grad_used = z(P, NP)
         self._gen = torch.Generator(device=dev)
         self.loss_pair = z(2, P)
 
@@ -493,39 +502,46 @@ class JaxBackpropPlanner:
             out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
 
     # ---- the two device calls of an iteration -----------------------------------------------
-    def _update_kernels(self, p: int):
-        """planner.py:2868-2917 on the device for parallel instance p."""
+    def _train_grad_kernels(self, p: int):
+        """Relaxed rollouts, loss and its gradient w.r.t. the plan for parallel instance p
+        (the value_and_grad of planner.py:2873-2882); the loss goes to a staging word."""
         T, A, B = self.T, self.A, self.batch_size_train
         params = self.params[p]
+        loss_out = self._train_loss_tmp[p:p + 1]
         if self.is_drp:
-            self.drp.update_kernels(p)
-            if self.world_size > 1:
-                parallel.allreduce_gradient(self.grad[p])
-            engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
-                                  self.opt_state[p], self.grad[p], None, None,
-                                  self.zero_flag[p:p + 1])
-            return
-        self.train_fwd.forward(B, T, self.s0_train, policy=params, noise=self.train_noise,
-                               mparams=self.train_mparams, disc=self.disc,
-                               reward=self.train_reward[p], returns=self.train_returns[p],
-                               err=self.train_err[p], tape=self.tape)
-        if self.utility == "mean":
-            engine.mean_loss(self.train_returns[p], B, self.train_loss[p:p + 1], None)
+            self.drp.update_kernels(p, loss_out)
         else:
-            r = self.train_returns[p].detach().clone().requires_grad_(True)
-            fn = self.utility if callable(self.utility) else _utility_fn(self.utility, self.utility_kwargs)
-            with torch.enable_grad():
-                loss = -fn(r, **(self.utility_kwargs if callable(self.utility) else {}))
-                (g,) = torch.autograd.grad(loss, r)
-            self.train_loss[p] = loss.detach()
-            self.gret.copy_(g)
-        self.train_bwd.backward(B, T, self.tape, self.gret, policy=params, noise=self.train_noise,
-                                mparams=self.train_mparams, disc=self.disc, gradp=self.gradp)
-        engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
+            self.train_fwd.forward(B, T, self.s0_train, policy=params, noise=self.train_noise,
+                                   mparams=self.train_mparams, disc=self.disc,
+                                   reward=self.train_reward[p], returns=self.train_returns[p],
+                                   err=self.train_err[p], tape=self.tape)
+            if self.utility == "mean":
+                engine.mean_loss(self.train_returns[p], B, loss_out, None)
+            else:
+                r = self.train_returns[p].detach().clone().requires_grad_(True)
+                fn = self.utility if callable(self.utility) else _utility_fn(self.utility, self.utility_kwargs)
+                with torch.enable_grad():
+                    loss = -fn(r, **(self.utility_kwargs if callable(self.utility) else {}))
+                    (g,) = torch.autograd.grad(loss, r)
+                loss_out.copy_(loss.detach().reshape(1))
+                self.gret.copy_(g)
+            self.train_bwd.backward(B, T, self.tape, self.gret, policy=params,
+                                    noise=self.train_noise, mparams=self.train_mparams,
+                                    disc=self.disc, gradp=self.gradp)
+            engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
         if self.world_size > 1:      # the one exchange step of the path (SURVEY 8e)
             parallel.allreduce_gradient(self.grad[p])
-        engine.optimizer_step(self.optimizer_name, self.hyper, T * A, params, self.opt_state[p],
-                              self.grad[p], self.box_lo, self.box_hi, self.zero_flag[p:p + 1])
+
+    def _opt_kernels(self, p: int):
+        """optax update + apply_updates + projection (planner.py:2885-2899) from the gradient the
+        train stage left in self.grad; publishes that stage's loss."""
+        T, A = self.T, self.A
+        params = self.params[p]
+        self.train_loss[p:p + 1].copy_(self._train_loss_tmp[p:p + 1])
+        self.grad_used[p].copy_(self.grad[p])       # callback['grad']: the gradient of THIS update
+        engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
+                              self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
+                              self.zero_flag[p:p + 1])
         plan = self.plan
         if getattr(plan, "needs_concurrency_projection", False):     # planner.py:947-954
             self.converged[p:p + 1].fill_(1)
@@ -533,6 +549,11 @@ class JaxBackpropPlanner:
                                plan.max_allowed_actions, plan._max_constraint_iter,
                                plan._wrap_sigmoid, plan._min_action_prob,
                                self.converged[p:p + 1])
+
+    def _update_kernels(self, p: int):
+        """planner.py:2868-2917 on the device for parallel instance p."""
+        self._train_grad_kernels(p)
+        self._opt_kernels(p)
 
     def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
         """planner.py:2695-2698: exact-model rollouts, forward only."""
@@ -551,6 +572,9 @@ class JaxBackpropPlanner:
         for p in range(self.parallel_updates):
             self._update_kernels(p)
             self._test_kernels(p)
+        self._finish_iteration()
+
+    def _finish_iteration(self):
         if self.optimizer_name == "adam":
             self.hyper[6:7].add_(1.0)
         if self.world_size > 1:
@@ -558,22 +582,50 @@ class JaxBackpropPlanner:
             self.loss_pair[1].copy_(self.test_loss_buf)
             parallel.allreduce_losses(self.loss_pair)
 
+    def _pipelined_kernels(self, side: Optional[torch.cuda.Stream]):
+        """One iteration in software-pipelined order: the optimiser step for the gradient the
+        previous replay left behind, then -- concurrently when ``side`` is given -- the exact
+        test rollouts of the new plan and the relaxed rollouts + gradient for the NEXT step.
+        Both read the plan only, and at B = 4096 each fills a fraction of the machine
+        (one warp per SM sub-partition), so they overlap almost perfectly.  Results per
+        iteration are identical to update-then-test (planner.py:3245-3260)."""
+        P = self.parallel_updates
+        for p in range(P):
+            self._opt_kernels(p)
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for p in range(P):
+                    self._test_kernels(p)
+        else:
+            for p in range(P):
+                self._test_kernels(p)
+        for p in range(P):
+            self._train_grad_kernels(p)
+        if side is not None:
+            main.wait_stream(side)
+        self._finish_iteration()
+
     def _capture(self):
         """Capture one full iteration into a CUDA graph (after a warm-up on a side stream)."""
         backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
         s = torch.cuda.Stream(device=self.device)
+        side = torch.cuda.Stream(device=self.device) if self._overlap else None
+        body = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            self._iteration_kernels()
+            body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._iteration_kernels()
+            body()
         self.params.copy_(backup[0])
         self.opt_state.copy_(backup[1])
         self.hyper.copy_(backup[2])
         self._graph = g
+        self._primed = False
 
     def iterate(self):
         """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""
@@ -582,6 +634,10 @@ class JaxBackpropPlanner:
             return
         if self._graph is None:
             self._capture()
+        if self._pipeline and not self._primed:
+            for p in range(self.parallel_updates):     # gradient for the first optimiser step
+                self._train_grad_kernels(p)
+            self._primed = True
         self._graph.replay()
 
     # ---- the reference-facing jitted callables ----------------------------------------------
@@ -601,6 +657,7 @@ class JaxBackpropPlanner:
                     flat = self.plan.initial_params(gen)
                 self.params[p].copy_(flat.reshape(-1))
             self.opt_state.zero_()
+            self._primed = False
             self.hyper[6] = 1.0
             engine.mean_loss(self.train_returns[0], self.batch_size_train, None, self.gret)
             if self.world_size > 1:          # d(-mean over the GLOBAL batch)/d return_b
@@ -652,7 +709,7 @@ class JaxBackpropPlanner:
         P, T, B = self.parallel_updates, self.T, self.batch_size_train
         return {"reward": self.train_reward.view(P, T, B).transpose(1, 2),
                 "error": self.train_err.view(P, T, B).transpose(1, 2),
-                "grad": self.plan.params_to_pytree(self._plan_view(self.grad)),
+                "grad": self.plan.params_to_pytree(self._plan_view(self.grad_used)),
                 "fluents": {}}
 
     def _test_log(self) -> Dict[str, Any]:
@@ -728,7 +785,7 @@ class JaxBackpropPlanner:
                 best_params = self.plan.params_to_pytree(
                     self._plan_view(self.params[best_index]).clone().cpu())
                 best_grad = self.plan.params_to_pytree(
-                    self._plan_view(self.grad[best_index]).clone().cpu())
+                    self._plan_view(self.grad_used[best_index]).clone().cpu())
                 best_loss = float(test_loss_smooth[best_index])
                 last_iter_improve = it
             if np.all(zero_grads):
@@ -760,7 +817,7 @@ class JaxBackpropPlanner:
                 "params": self.plan.params_to_pytree(self._plan_view(self.params)),
                 "best_params": best_params, "best_index": best_index, "pgpe_params": None,
                 "model_params": self.model_parameter_info(), "policy_hyperparams": hyper,
-                "grad": self.plan.params_to_pytree(self._plan_view(self.grad)),
+                "grad": self.plan.params_to_pytree(self._plan_view(self.grad_used)),
                 "best_grad": best_grad, "train_log": self._train_log(),
                 "test_log": self._test_log(), "planner_state": self,
             }

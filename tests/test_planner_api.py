@@ -188,3 +188,28 @@ def test_wildfire_plan_respects_max_nondef_actions(cuda_device):
         flat = torch.cat([v["logit"][0].cpu().reshape(10, -1)
                           for v in cb["params"]["bool"].values()], 1)
         assert int((flat > 0).sum(1).max()) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["quadcopter", "wildfire"])
+def test_pipelined_graph_equals_sequential_iterations(cuda_device, key, monkeypatch):
+    """The captured, software-pipelined iteration (opt -> test || next gradient) produces the
+    same losses and plan, iteration by iteration, as plain update-then-test launches."""
+    m = fixture_model(key)
+
+    def run(graph):
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=96, rollout_horizon=12,
+                                optimizer_kwargs={"learning_rate": 0.05}, pgpe=None,
+                                use_cuda_graph=graph)
+        pl.initialize(5)
+        out = []
+        for _ in range(6):
+            pl.iterate()                                 # fixed noise: initialise() drew it once
+            tr, te, _ = pl.read_stats()
+            out.append((float(tr[0]), float(te[0]), pl.params[0].cpu().clone(),
+                        pl.grad_used[0].cpu().clone()))
+        return out
+    a, b = run(True), run(False)
+    for (tr1, te1, p1, g1), (tr2, te2, p2, g2) in zip(a, b):
+        assert tr1 == tr2 and te1 == te2
+        assert torch.equal(p1, p2) and torch.equal(g1, g2)
