@@ -371,17 +371,18 @@ def main():
     value = n_gpus * B * T / (ms_per_step * 1e-3)
 
     # ---- e2e: public API with host buffers, H2D + D2H inside the timed region --------------
-    s0_train_h = planner.s0_train.cpu().pin_memory()
-    s0_test_h = planner.s0_test.cpu().pin_memory()
+    # inputs of one optimize() call as the public API takes them: the initial state (`subs`,
+    # un-batched: S words per model, tiled to the B rollouts on the device) and the plan to start
+    # from (`guess`); outputs: the three status scalars and the plan (callback['params'])
+    init_train_h, init_test_h = planner.init_train_host, planner.init_test_host
     params_h = planner.params.cpu().pin_memory()
     pback_h = torch.empty_like(params_h).pin_memory()
-    h2d = (s0_train_h.numel() + s0_test_h.numel() + params_h.numel()) * 4
+    h2d = (init_train_h.numel() + init_test_h.numel() + params_h.numel()) * 4
     d2h = planner._stats_host.numel() * 4 + params_h.numel() * 4
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        planner.s0_train.copy_(s0_train_h, non_blocking=True)      # init_sim_state from host
-        planner.s0_test.copy_(s0_test_h, non_blocking=True)
+        planner.load_initial_state(init_train_h, init_test_h)      # init_sim_state from host
         planner.params.copy_(params_h, non_blocking=True)          # warm-start guess
         step()
         pback_h.copy_(planner.params, non_blocking=True)           # callback['params']

@@ -207,6 +207,15 @@ int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_se
                             const float* noise, float train, const float* lo, const float* hi,
                             float ls_lo, float ls_hi, const float* gact, float* gheads);
 
+/* Tile the un-batched initial state (S words: float bits, or int32 0/1 / int words for the exact
+ * model) into the fluent-major s0 buffer of B rollouts.  seg_off / seg_len: HOST arrays with the
+ * state fluents' word ranges (n_seg <= RK_MAX_STATE_FLUENTS).
+ * Replaces: the host-side np.tile of init_fls_and_nfls (compiler.py:668-727) and the transfer of
+ * the tiled arrays: only S words cross PCIe per optimize() call / online-replanning step. */
+#define RK_MAX_STATE_FLUENTS 64
+int rk_tile_state(void* stream, int B, int n_seg, const int32_t* seg_off, const int32_t* seg_len,
+                  const void* init, void* s0);
+
 /* -mean(returns) and its cotangent, for utility='mean' (planner.py:2817-2818):
  * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */
 int rk_mean_loss(void* stream, const float* returns, int B, float* loss, float* gret);

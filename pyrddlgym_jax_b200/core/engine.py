@@ -24,7 +24,7 @@ EXPORTS = [
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
-    "rk_rowdot", "rk_tcgemm_tn",
+    "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state",
 ]
 
 
@@ -90,6 +90,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_rowdot.restype = ci
     lib.rk_tcgemm_tn.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, cf, ci]
     lib.rk_tcgemm_tn.restype = ci
+    lib.rk_tile_state.argtypes = [vp, ci, ci, vp, vp, cf, cf]
+    lib.rk_tile_state.restype = ci
     lib.rk_tf32_split.argtypes = [vp, cf, cf, cf, ctypes.c_size_t]
     lib.rk_tf32_split.restype = ci
     lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
@@ -285,3 +287,11 @@ def tcgemm_tn(accumulate, M, N, K, A, lda, Bm, ldb, C, workspace, max_splits):
     _check(load_library().rk_tcgemm_tn(_stream(), int(bool(accumulate)), M, N, K, _ptr(A), lda,
                                        _ptr(Bm), ldb, _ptr(C), _ptr(workspace), int(max_splits)),
            "rk_tcgemm_tn")
+
+
+def tile_state(B, segs, init, s0):
+    """segs: [(word offset, length), ...] of the state fluents; init: [S] device words."""
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_tile_state(_stream(), B, n, ctypes.cast(off, ctypes.c_void_p),
+                                        ctypes.cast(ln, ctypes.c_void_p), _ptr(init), _ptr(s0)),
+           "rk_tile_state")

@@ -469,6 +469,8 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and self.world_size == 1 and not self.is_drp
         self._train_loss_tmp = z(P)
+        self.s0_train, self.s0_test = z(fw.S * Bt), z(te.S * Be)
+        self._init_train, self._init_test = z(fw.S), z(te.S)
         self.grad_used = z(P, NP)
         self._gen = torch.Generator(device=dev)
         self.loss_pair = z(2, P)
@@ -487,15 +489,29 @@ class JaxBackpropPlanner:
         self.train_mparams.copy_(torch.from_numpy(cur))
 
     # ---- state initialisation (init_sim_state, compiler.py:729-771) ------------------------
-    def _pack_s0(self, layout, B, subs) -> torch.Tensor:
+    def _init_words(self, layout, subs) -> torch.Tensor:
+        """The un-batched initial state as [S] words in the kernels' layout (pinned host)."""
         vals = {}
         for name in layout:
             v = np.asarray(self.rddl.init_values[name])
             if subs is not None and name in subs:
                 v = np.reshape(np.asarray(subs[name]), v.shape).astype(v.dtype)
             t = torch.from_numpy(np.ascontiguousarray(v))
-            vals[name] = t.unsqueeze(0).expand(B, *t.shape)
-        return pack_fluent_major(layout, vals, B).to(self.device)
+            vals[name] = t.unsqueeze(0)
+        return pack_fluent_major(layout, vals, 1).pin_memory()
+
+    def load_initial_state(self, train_words: torch.Tensor, test_words: torch.Tensor):
+        """Host -> device transfer of the S initial-state words of each model and on-device
+        tiling into the [B] rollouts (init_sim_state, compiler.py:729-771): the per-call input
+        path of optimize() and of every online-replanning step."""
+        for words, dev_words, prog, B, s0 in (
+                (train_words, self._init_train, self.train_fwd.program, self.batch_size_train,
+                 self.s0_train),
+                (test_words, self._init_test, self.test_fwd.program, self.batch_size_test,
+                 self.s0_test)):
+            dev_words.copy_(words, non_blocking=True)
+            segs = [(off, n) for (off, n, _) in prog.state_layout.values()]
+            engine.tile_state(B, segs, dev_words, s0)
 
     def _draw(self, prog, T, B, out):
         if out is not None:
@@ -646,10 +662,9 @@ class JaxBackpropPlanner:
         with torch.cuda.device(self.device):
             gen = torch.Generator().manual_seed(int(key))
             self._gen.manual_seed(int(key))
-            self.s0_train = self._pack_s0(self.train_fwd.program.state_layout,
-                                          self.batch_size_train, subs)
-            self.s0_test = self._pack_s0(self.test_fwd.program.state_layout,
-                                         self.batch_size_test, subs)
+            self.init_train_host = self._init_words(self.train_fwd.program.state_layout, subs)
+            self.init_test_host = self._init_words(self.test_fwd.program.state_layout, subs)
+            self.load_initial_state(self.init_train_host, self.init_test_host)
             for p in range(self.parallel_updates):
                 if guess is not None:
                     flat = self.plan.pytree_to_params(guess)

@@ -384,3 +384,46 @@ extern "C" int rk_project_slp(void* stream, int method, int T, int A, float* par
       method, T, A, params, S, K, allowed, max_iter, wrap_sigmoid, min_prob, converged);
   return (int)cudaGetLastError();
 }
+
+// ---- initial-state tiling on the device (init_sim_state, compiler.py:700) ---------------------
+// The reference tiles the un-batched initial fluent values to [B, ...] on the host and ships the
+// tiled arrays; here only the S state words cross PCIe and every rollout's copy is written
+// straight into the fluent-major s0 buffer (fluent f = block [B][n_f] at word offset off_f * B).
+struct RkStateSegs {
+  int n;
+  int off[RK_MAX_STATE_FLUENTS], len[RK_MAX_STATE_FLUENTS];
+};
+
+__global__ void rk_tile_state_kernel(int B, RkStateSegs S, const uint32_t* __restrict__ init,
+                                     uint32_t* __restrict__ s0) {
+  const int f = blockIdx.y;
+  const long long total = (long long)B * S.len[f];
+  uint32_t* dst = s0 + (size_t)S.off[f] * B;
+  const uint32_t* src = init + S.off[f];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i % S.len[f]];
+}
+
+extern "C" int rk_tile_state(void* stream, int B, int n_seg, const int32_t* seg_off,
+                             const int32_t* seg_len, const void* init, void* s0) {
+  if (B <= 0 || n_seg <= 0 || n_seg > RK_MAX_STATE_FLUENTS || seg_off == nullptr ||
+      seg_len == nullptr || init == nullptr || s0 == nullptr)
+    return RK_E_BADARG;
+  RkStateSegs S;
+  S.n = n_seg;
+  int maxlen = 1;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_off[i] < 0 || seg_len[i] <= 0) return RK_E_BADARG;
+    S.off[i] = seg_off[i];
+    S.len[i] = seg_len[i];
+    if (seg_len[i] > maxlen) maxlen = seg_len[i];
+  }
+  long long work = (long long)B * maxlen;
+  int gx = (int)((work + 255) / 256);
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(gx, n_seg);
+  rk_tile_state_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, S, (const uint32_t*)init,
+                                                               (uint32_t*)s0);
+  return (int)cudaGetLastError();
+}
