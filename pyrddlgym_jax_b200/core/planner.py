@@ -462,12 +462,13 @@ class JaxBackpropPlanner:
             if len(fw.mparam_defaults) else None
         self._graph = None
         self._primed = False
-        # software pipelining of the captured iteration (opt -> test || next gradient); the two
-        # branches share NCCL / DRP scratch buffers in the multi-GPU and DRP cases, so only the
-        # single-GPU straight-line plan runs them concurrently
+        # software pipelining of the captured iteration (opt -> test || next gradient).  All NCCL
+        # calls stay on the main branch (gradient all-reduce in the train stage, loss all-reduce
+        # after the join); the DRP branches share scratch buffers, so only straight-line plans
+        # run the two branches concurrently
         import os as _os
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
-        self._overlap = self._pipeline and self.world_size == 1 and not self.is_drp
+        self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
         self.s0_train, self.s0_test = z(fw.S * Bt), z(te.S * Be)
         self._init_train, self._init_test = z(fw.S), z(te.S)
