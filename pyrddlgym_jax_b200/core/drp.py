@@ -423,9 +423,14 @@ class DrpPipeline:
             self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t])
             cur ^= 1
 
-    def test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
-        """Exact-model rollouts with the test policy (train = 0, planner.py:1482-1499)."""
+    def test_kernels(self, p: int, params: Optional[torch.Tensor] = None, out=None):
+        """Exact-model rollouts with the test policy (train = 0, planner.py:1482-1499).
+        ``out`` = (reward, returns, err, final, loss) overrides the logged test buffers."""
         pl, plan = self.pl, self.plan
+        if out is None:
+            out = (pl.test_reward[p], pl.test_returns[p], pl.test_err[p], pl.test_final[p],
+                   pl.test_loss_buf[p:p + 1])
+        o_reward, o_returns, o_err, o_final, o_loss = out
         T, B, A = pl.T, pl.batch_size_test, self.A
         params = pl.params[p] if params is None else params
         te = pl.test_fwd
@@ -442,15 +447,15 @@ class DrpPipeline:
             te.forward(B, 1, x, actions=self.t_act,
                        noise=None if pl.test_noise is None else pl.test_noise[t * N * B:],
                        disc=None if pl.disc is None else pl.disc[t:],
-                       reward=pl.test_reward[p][t * B:], returns=pl.test_returns[p],
-                       err=pl.test_err[p][t * B:], final=nxt)
+                       reward=o_reward[t * B:], returns=o_returns,
+                       err=o_err[t * B:], final=nxt)
             cur ^= 1
-        pl.test_final[p].copy_(self.t_state[cur])
-        rew = pl.test_reward[p].view(T, B)
+        o_final.copy_(self.t_state[cur])
+        rew = o_reward.view(T, B)
         if pl.disc is not None:
             rew = rew * pl.disc.view(T, 1)
-        torch.sum(rew, dim=0, out=pl.test_returns[p])
-        engine.mean_loss(pl.test_returns[p], B, pl.test_loss_buf[p:p + 1], None)
+        torch.sum(rew, dim=0, out=o_returns)
+        engine.mean_loss(o_returns, B, o_loss, None)
 
     def redraw_noise(self, gen: torch.Generator):
         if self.pol_noise is not None:

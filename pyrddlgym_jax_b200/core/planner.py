@@ -328,9 +328,6 @@ class JaxBackpropPlanner:
                           ("dashboard", dashboard)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
-        if pgpe is not None:
-            raise NotImplementedError("PGPE is not built yet: pass pgpe=None as the shipped "
-                                      "configs do (SURVEY F6)")
         if use_symlog_reward:
             raise NotImplementedError("use_symlog_reward is not supported yet")
         self.rddl = rddl
@@ -347,8 +344,10 @@ class JaxBackpropPlanner:
         self.optimizer_name = opt_name
         self.optimizer_kwargs = {"learning_rate": 0.1} if optimizer_kwargs is None else dict(optimizer_kwargs)
         self.clip_grad = clip_grad
-        self.pgpe = None
-        self.use_pgpe = False
+        # NOTE: the reference's constructor default is pgpe=GaussianPGPE(); every shipped
+        # straight-line config passes pgpe=None, and so does this default
+        self.pgpe = pgpe
+        self.use_pgpe = pgpe is not None
         if isinstance(utility, str):
             utility = utility.lower()
             if utility not in UTILITY_LOOKUP:
@@ -409,6 +408,8 @@ class JaxBackpropPlanner:
         self.n_params = self.plan.n_params if self.is_drp else self.T * self.A
         self._alloc()
         self.drp = DrpPipeline(self) if self.is_drp else None
+        if self.use_pgpe:
+            self.pgpe.compile(self)
 
     def _alloc(self):
         dev, T, A = self.device, self.T, self.A
@@ -470,6 +471,10 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
+        if self.use_pgpe:
+            self._pg_reward, self._pg_returns = z(T * Be), z(Be)
+            self._pg_err, self._pg_final = z(T * Be, dt=torch.int32), z(te.S * Be)
+            self._pg_loss = z(P)
         self.s0_train, self.s0_test = z(fw.S * Bt), z(te.S * Be)
         self._init_train, self._init_test = z(fw.S), z(te.S)
         self.grad_used = z(P, NP)
@@ -572,18 +577,38 @@ class JaxBackpropPlanner:
         self._train_grad_kernels(p)
         self._opt_kernels(p)
 
-    def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None):
-        """planner.py:2695-2698: exact-model rollouts, forward only."""
+    def _test_kernels(self, p: int, params: Optional[torch.Tensor] = None, scratch: bool = False,
+                      loss_out: Optional[torch.Tensor] = None):
+        """planner.py:2695-2698: exact-model rollouts, forward only.  ``scratch`` evaluates a
+        candidate plan (PGPE samples) without touching the logged test buffers."""
         T, B = self.T, self.batch_size_test
+        loss_out = self.test_loss_buf[p:p + 1] if loss_out is None else loss_out
+        if scratch:
+            reward, returns, err, final = self._pg_reward, self._pg_returns, self._pg_err, self._pg_final
+        else:
+            reward, returns, err, final = (self.test_reward[p], self.test_returns[p],
+                                           self.test_err[p], self.test_final[p])
         if self.is_drp:
-            self.drp.test_kernels(p, params)
+            self.drp.test_kernels(p, params, (reward, returns, err, final, loss_out))
             return
         self.test_fwd.forward(B, T, self.s0_test, policy=self.params[p] if params is None else params,
                               noise=self.test_noise, disc=self.disc,
-                              reward=self.test_reward[p], returns=self.test_returns[p],
-                              err=self.test_err[p], final=self.test_final[p],
-                              traj=None if self.test_traj is None else self.test_traj[p])
-        engine.mean_loss(self.test_returns[p], B, self.test_loss_buf[p:p + 1], None)
+                              reward=reward, returns=returns, err=err, final=final,
+                              traj=None if (self.test_traj is None or scratch) else self.test_traj[p])
+        engine.mean_loss(returns, B, loss_out, None)
+
+    def project_params(self, params: torch.Tensor, p: int = 0):
+        """plan.projection on a flat parameter vector: box clip (planner.py:878-910) and, when
+        the instance limits concurrent actions, the max-nondef-actions projection (914-959)."""
+        if self.box_lo is not None:
+            torch.maximum(params, self.box_lo, out=params)
+            torch.minimum(params, self.box_hi, out=params)
+        plan = self.plan
+        if getattr(plan, "needs_concurrency_projection", False):
+            self.converged[p:p + 1].fill_(1)
+            engine.project_slp(plan.projection_method, self.T, self.A, params, plan.bool_segs,
+                               plan.max_allowed_actions, plan._max_constraint_iter,
+                               plan._wrap_sigmoid, plan._min_action_prob, self.converged[p:p + 1])
 
     def _iteration_kernels(self):
         for p in range(self.parallel_updates):
@@ -778,6 +803,11 @@ class JaxBackpropPlanner:
         best_loss, best_grad, best_index = np.inf, None, 0
         last_iter_improve = 0
         rolling = RollingMean(test_rolling_window)
+        rolling_pgpe = RollingMean(test_rolling_window)
+        pbest_loss = np.full(P, np.inf)
+        pgpe_return = None
+        if self.use_pgpe:
+            self.pgpe.initialize(self.params, self._gen)
         status = JaxPlannerStatus.NORMAL
         if stopping_rule is not None:
             stopping_rule.reset()
@@ -796,6 +826,25 @@ class JaxBackpropPlanner:
                 self.iterate()
                 train_loss, test_loss, zero_grads = self.read_stats()       # the host sync
             test_loss_smooth = rolling.update(test_loss)
+            pgpe_improve = False
+            if self.use_pgpe:                           # planner.py:3270-3296
+                with torch.cuda.device(self.device):
+                    self.pgpe.update(progress_percent)
+                    for p in range(P):
+                        self._test_kernels(p, params=self.pgpe.mu[p], scratch=True,
+                                           loss_out=self._pg_loss[p:p + 1])
+                    pgpe_loss = self._pg_loss.cpu().numpy()
+                pgpe_loss_smooth = rolling_pgpe.update(pgpe_loss)
+                pgpe_return = -pgpe_loss_smooth
+                mask = np.less(pgpe_loss_smooth, pbest_loss) | ~np.isfinite(train_loss)
+                if np.any(mask):                        # hard replacement (planner.py:2932-2949)
+                    for p in np.nonzero(mask)[0]:
+                        self.params[p].copy_(self.pgpe.mu[p])
+                    test_loss = np.where(mask, pgpe_loss, test_loss)
+                    test_loss_smooth = np.where(mask, pgpe_loss_smooth, test_loss_smooth)
+                    self._primed = False                # the pending gradient is for the old plan
+                    pgpe_improve = True
+            pbest_loss = np.minimum(pbest_loss, test_loss_smooth)
             best_index = int(np.argmin(test_loss_smooth))
             if test_loss_smooth[best_index] < best_loss:
                 best_params = self.plan.params_to_pytree(
@@ -804,7 +853,7 @@ class JaxBackpropPlanner:
                     self._plan_view(self.grad_used[best_index]).clone().cpu())
                 best_loss = float(test_loss_smooth[best_index])
                 last_iter_improve = it
-            if np.all(zero_grads):
+            if (not pgpe_improve) and np.all(zero_grads):
                 status = JaxPlannerStatus.NO_PROGRESS
             if np.all(~np.isfinite(train_loss)):
                 status = JaxPlannerStatus.INVALID_GRADIENT
@@ -828,10 +877,12 @@ class JaxBackpropPlanner:
                 "iteration": it, "elapsed_time": elapsed, "progress": progress_percent,
                 "status": status, "key": key, "test_key": key,
                 "train_return": -train_loss, "test_return": -test_loss_smooth,
-                "best_return": -best_loss, "pgpe_return": None,
-                "last_iteration_improved": last_iter_improve, "pgpe_improved": False,
+                "best_return": -best_loss, "pgpe_return": pgpe_return,
+                "last_iteration_improved": last_iter_improve, "pgpe_improved": pgpe_improve,
                 "params": self.plan.params_to_pytree(self._plan_view(self.params)),
-                "best_params": best_params, "best_index": best_index, "pgpe_params": None,
+                "best_params": best_params, "best_index": best_index,
+                "pgpe_params": (self.plan.params_to_pytree(self._plan_view(self.pgpe.mu))
+                                if self.use_pgpe else None),
                 "model_params": self.model_parameter_info(), "policy_hyperparams": hyper,
                 "grad": self.plan.params_to_pytree(self._plan_view(self.grad_used)),
                 "best_grad": best_grad, "train_log": self._train_log(),
@@ -923,9 +974,14 @@ def _load_config(config, args):
     opt = planner_args.get("optimizer")
     if isinstance(opt, str) and opt not in OPTIMIZERS:          # planner.py:180-186
         raise ValueError(f"Invalid optimizer <{opt}>.")
-    if planner_args.get("pgpe", None) is not None:
-        raise NotImplementedError("PGPE is not built yet; set pgpe=None in the [Planner] section")
-    planner_args.pop("pgpe_kwargs", None)
+    pgpe_method = planner_args.get("pgpe", None)                # planner.py:188-198
+    pgpe_kwargs = planner_args.pop("pgpe_kwargs", {})
+    if pgpe_method is not None:
+        from . import pgpe as pgpe_mod
+        cls = getattr(pgpe_mod, pgpe_method, None)
+        if cls is None:
+            raise ValueError(f"Invalid PGPE class <{pgpe_method}>.")
+        planner_args["pgpe"] = cls(**pgpe_kwargs)
     if "stopping_rule" in train_args:                           # planner.py:219-226
         rule = getattr(this, train_args["stopping_rule"])
         train_args["stopping_rule"] = rule(**train_args.pop("stopping_rule_kwargs", {}))
@@ -1027,3 +1083,4 @@ class JaxOnlineController:
 
 
 from .drp import DrpPipeline, JaxDeepReactivePolicy  # noqa: E402,F401
+from .pgpe import GaussianPGPE, PGPE  # noqa: E402,F401

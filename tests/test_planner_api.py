@@ -213,3 +213,64 @@ def test_pipelined_graph_equals_sequential_iterations(cuda_device, key, monkeypa
     for (tr1, te1, p1, g1), (tr2, te2, p2, g2) in zip(a, b):
         assert tr1 == tr2 and te1 == te2
         assert torch.equal(p1, p2) and torch.equal(g1, g2)
+
+
+def test_pgpe_formulas_known_answers():
+    """Super-symmetric sample, mean / sigma gradient estimates of GaussianPGPE against an
+    independent numpy restatement of planner.py:1888-1916, 1954-2003."""
+    from pyrddlgym_jax_b200.core.pgpe import GaussianPGPE
+    pg = GaussianPGPE()
+    sigma = torch.tensor([1.0, 0.5, 2.0, 1.0, 0.3])
+    eps = torch.tensor([0.3, -0.5, 3.5, 0.0, 0.3])             # |eps| <, =, > sigma, zero
+    got = pg.eps_star(sigma, eps).numpy()
+    s, e = sigma.numpy().astype(np.float64), eps.numpy().astype(np.float64)
+    a = (s - np.abs(e)) / s
+    aa = np.abs(a)
+    c1, c2, c3 = -0.06655, -0.9706, 0.124
+    with np.errstate(all="ignore"):
+        neg = np.exp(np.where(aa == 1., 2 * c1 + c2, c1 * aa * (aa * aa - 1) / np.log(aa) + c2 * aa))
+        pos = np.exp(aa) / np.power(np.maximum(1 - aa ** 3, np.finfo(np.float32).tiny), c3 * aa)
+    want = np.where(e == 0, 0., np.sign(e) * 0.67449 * s * np.where(a < 0, neg, pos))
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-7)
+    r = torch.tensor([-10., -14., -11., -12.])
+    m = torch.tensor(-9.)
+    es = torch.tensor(want, dtype=torch.float32)
+    g_mu, g_sigma = pg.grads(eps, es, sigma, r, m, 0.01)
+    s1 = max(1e-5, -9 - (-10 - 14) / 2)
+    s2 = max(1e-5, -9 - (-11 - 12) / 2)
+    want_mu = -(((-10 + 14) / (2 * s1)) * e + ((-11 + 12) / (2 * s2)) * want)
+    tau = e if (-10 - 14) >= (-11 - 12) else want
+    sc = max(1e-5, -9 - (-10 - 14 - 11 - 12) / 4)
+    want_sigma = -((((-10 - 14) - (-11 - 12)) / (4 * sc)) * (tau ** 2 / s ** 3 - 1 / s) + 0.01 / s)
+    np.testing.assert_allclose(g_mu.numpy(), want_mu, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(g_sigma.numpy(), want_sigma, rtol=2e-5, atol=1e-7)
+
+
+def test_load_config_builds_pgpe():
+    from pyrddlgym_jax_b200.core.pgpe import GaussianPGPE
+    text = QUADCOPTER_SLP.replace("pgpe=None", "pgpe='GaussianPGPE'\npgpe_kwargs={'init_sigma': 0.5, 'batch_size': 2}")
+    planner_args, _, _ = load_config_from_string(text)
+    assert isinstance(planner_args["pgpe"], GaussianPGPE)
+    assert planner_args["pgpe"].init_sigma == 0.5 and planner_args["pgpe"].batch_size == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plan_kind", ["slp", "drp"])
+def test_pgpe_runs_next_to_backprop_and_can_take_over(cuda_device, plan_kind):
+    """With a zero learning rate the backprop plan never moves, so any improvement of the best
+    return must come from the PGPE instance replacing it (planner.py:3283-3295)."""
+    from pyrddlgym_jax_b200.core.pgpe import GaussianPGPE
+    m = fixture_model("powergen" if plan_kind == "drp" else "reservoir")
+    plan = JaxDeepReactivePolicy(topology=[16, 16]) if plan_kind == "drp" else JaxStraightLinePlan()
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=64, rollout_horizon=8, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0},
+                            pgpe=GaussianPGPE(init_sigma=0.3, optimizer_kwargs_mu={"learning_rate": 0.2}))
+    first, last, took_over = None, None, False
+    for cb in pl.optimize_generator(key=4, epochs=30, print_summary=False, print_progress=False):
+        first = cb if first is None else first
+        last = cb
+        took_over |= bool(cb["pgpe_improved"])
+        assert cb["pgpe_return"] is not None and np.isfinite(cb["pgpe_return"]).all()
+        assert cb["pgpe_params"] is not None
+    assert took_over
+    assert last["best_return"] > first["best_return"]
