@@ -13,6 +13,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+_SEEDED = set()
 _TORCH_DT = {"f": torch.float32, "i": torch.int32, "b": torch.int32}
 
 
@@ -78,16 +79,26 @@ def draw_noise(noise_layout: Sequence[Tuple[str, Tuple[int, ...], int, int, Any]
             elif kind == "gamma":
                 conc = torch.as_tensor(np.asarray(extra, dtype=np.float32).reshape(-1),
                                        device="cpu").clamp_min(1e-6)
-                g = torch.distributions.Gamma(conc, torch.ones_like(conc))
-                # torch's sampler ignores `generator`: seed from it for reproducibility
-                seed = int(torch.randint(0, 2**31 - 1, (1,), generator=generator,
-                                         device=device).item()) if generator is not None else None
-                if seed is not None:
-                    state = torch.random.get_rng_state()
-                    torch.manual_seed(seed)
-                z = g.sample((T, B)).to(device)
-                if seed is not None:
-                    torch.random.set_rng_state(state)
+                if device is not None and torch.device(device).type == "cuda":
+                    # standard Gamma(shape) draws on the device (torch's CUDA sampler uses the
+                    # default CUDA generator: seed it from the caller's stream of seeds)
+                    key = ("gamma_seeded", str(device))
+                    if generator is not None and key not in _SEEDED:
+                        torch.cuda.manual_seed(int(generator.initial_seed()) + 12345)
+                        _SEEDED.add(key)
+                    a = conc.to(device).expand(T, B, conc.numel()).contiguous()
+                    z = torch._standard_gamma(a)
+                else:
+                    g = torch.distributions.Gamma(conc, torch.ones_like(conc))
+                    # torch's sampler ignores `generator`: seed from it for reproducibility
+                    seed = int(torch.randint(0, 2**31 - 1, (1,), generator=generator,
+                                             device=device).item()) if generator is not None else None
+                    if seed is not None:
+                        state = torch.random.get_rng_state()
+                        torch.manual_seed(seed)
+                    z = g.sample((T, B)).to(device)
+                    if seed is not None:
+                        torch.random.set_rng_state(state)
             else:
                 raise NotImplementedError(f"noise kind {kind}")
         out[:, off * B:(off + n) * B] = z.reshape(T, B * n)
