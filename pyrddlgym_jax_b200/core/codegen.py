@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 6
+CODEGEN_VERSION = 7
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -89,6 +89,9 @@ class _Gen:
         self.persistent = set(prog.meta["persistent"])
         self.err_base = prog.meta["err_base"]
         self._classify()
+        # relaxed programs may trade last-bit identity for speed (reciprocal of constants, FMA
+        # contraction); exact programs never do.  RK_FAST_RELAXED=0 switches it off.
+        self.fast = bool(prog.relaxed) and os.environ.get("RK_FAST_RELAXED", "1") != "0"
         self.lines: List[str] = []
         self.tmp = 0
 
@@ -179,6 +182,17 @@ class _Gen:
     def emit(self, s: str):
         self.lines.append(s)
 
+    def recip_opnd(self, v, n_r: int) -> str:
+        """1 / (constant operand) as a literal or a hoisted per-lane register."""
+        c = v["const"]
+        if v["map"] == isa.MAP_BCAST or c.size == 1:
+            with np.errstate(all="ignore"):
+                return _flit(float(np.float32(1.0) / np.float32(c[0])))
+        name = f"hr{v['base']}_{v['map']}_{n_r}"
+        idx = self.map_index(v, f"(le < {n_r}u ? le : 0u)", n_r)
+        self.hoisted[name] = (f"  const float {name} = 1.f / __uint_as_float(C[{v['base']}u + {idx}]);")
+        return name
+
     # ---- sin / cos / tan of one argument share a single range reduction -------------------
     def plan_trig(self, lst):
         """Group the SIN / COS / TAN instructions of one list by operand: a group of two or
@@ -266,6 +280,24 @@ class _Gen:
         # ---- elementwise
         dt_out = dst["dtype"]
         single = n <= L and (self.is_reg(dst) or True)
+        recip = None
+        if op == "DIV" and self.fast and srcs[1]["kind"] == "const" and n <= L:
+            # relaxed (train / adjoint) programs: x / c with a build-time constant c becomes
+            # x * (1/c) -- one rounding of difference, inside the 1e-5 / 1e-4 parity tolerances;
+            # exact programs keep the IEEE division (bit-exact bool / int contract)
+            recip = self.recip_opnd(srcs[1], n)
+        if recip is not None:
+            self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const float x = "
+                      f"{self.opnd(srcs[0], 'ec', n, 'f')}; {self.var(dst)} = x * {recip}; }}"
+                      if self.is_reg(dst) else
+                      f"  {{ const uint32_t ec = le < {n}u ? le : 0u; const float x = "
+                      f"{self.opnd(srcs[0], 'ec', n, 'f')}; const float r = x * {recip}; "
+                      f"if ({'q == 0u' if dst['uniform'] else f'q < {self.rpw}u'} && le < {n}u) "
+                      f"R[{dst['base']}u{(' + q * %du' % dst['sq']) if dst['sq'] else ''} + le] = "
+                      f"__float_as_uint(r); }}")
+            if not self.is_reg(dst):
+                self.emit("  __syncwarp();")
+            return
         if op in _F1:
             body, tin = _F1[op], "f"
         elif op in _F2:
@@ -680,11 +712,14 @@ def generate_source(prog: Program) -> str:
     return _Gen(prog).source()
 
 
-def nvcc_flags() -> List[str]:
-    """-fmad=false by default: every RDDL multiply and add rounds separately, like the oracle
-    and like un-fused XLA code.  RK_FMAD=1 lets ptxas contract a*b+c into FMAs (fewer
-    instructions, results differ in the last bits but stay inside the parity tolerances)."""
-    fmad = "true" if os.environ.get("RK_FMAD", "0") == "1" else "false"
+def nvcc_flags(relaxed: bool = False) -> List[str]:
+    """Exact programs: -fmad=false, every RDDL multiply and add rounds separately like the
+    oracle (bit-exact bool / int contract).  Relaxed (train / adjoint) programs let ptxas
+    contract a*b+c into FMAs, as XLA does for the reference: fewer instructions, results differ
+    in the last bits and stay inside the 1e-5 / 1e-4 tolerances.  RK_FAST_RELAXED=0 disables
+    it, RK_FMAD=1 forces contraction everywhere."""
+    fast = relaxed and os.environ.get("RK_FAST_RELAXED", "1") != "0"
+    fmad = "true" if (fast or os.environ.get("RK_FMAD", "0") == "1") else "false"
     return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             f"-fmad={fmad}", "-cubin"]
 
@@ -696,7 +731,7 @@ def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:
     for h in ("rk_launch.h", "rk_device.cuh", "rk_isa.h"):
         with open(os.path.join(CSRC, h), "rb") as f:
             deps += f.read()
-    flags = nvcc_flags()
+    flags = nvcc_flags(bool(prog.relaxed))
     key = hashlib.sha1(src.encode() + deps + " ".join(flags).encode()).hexdigest()[:16]
     os.makedirs(JIT_DIR, exist_ok=True)
     cu = os.path.join(JIT_DIR, f"rk_{key}.cu")
