@@ -43,6 +43,7 @@ typedef struct rk_sizes {
   int32_t warps_per_cta; /* launch geometry chosen for this program                       */
   int32_t smem_bytes;
   int32_t static_err;
+  int32_t tape_words;    /* words per rollout-step of the tape: S, or S + taped forward values */
 } rk_sizes;
 
 /* Upload a program produced by core/program.py to the current device.
@@ -72,7 +73,8 @@ int rk_program_num_warps(const rk_program* prog, int B);
  *   reward   [T*B]      log['reward'] transposed (compiler.py:538)
  *   returns  [B]        sum_t gamma^t r_t (planner.py:2761)
  *   err      [T*B]      log['error'] bitmask (compiler.py:539), or NULL
- *   tape     [T*S*B]    state at the start of every step (for the adjoint), or NULL
+ *   tape     [T*tape_words*B] state at the start of every step (+ the forward values the adjoint
+ *                       program reads back when it was built with a full tape), or NULL
  *   final    [S*B]      state after the last step, or NULL
  *   traj     [T*TRAJ*B] logged fluents (cache_path_info, compiler.py:515-518), or NULL */
 int rk_rollout_forward(const rk_program* prog, void* stream, int B, int T,

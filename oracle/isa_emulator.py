@@ -41,6 +41,7 @@ class Emulator:
         self.backward = bool(self.hdr[14] & 2)
         self.static_err, self.err_base = int(self.hdr[15]), int(self.hdr[16])
         self.traj_w = int(self.hdr[17])
+        self.tape_w = int(self.hdr[18]) or int(self.hdr[11])
         self.C0 = words[H:H + self.cw].copy()
         ins = np.frombuffer(blob, dtype=np.uint16, offset=(H + self.cw) * 4)
         self.ins = ins.reshape(-1, isa.INS_WORDS).astype(np.int64)
@@ -57,7 +58,7 @@ class Emulator:
             C[self.mparam_off:self.mparam_off + self.n_mp] = \
                 np.asarray(mparams, np.float32).view(np.uint32)
         R = np.zeros((nW, self.ww), dtype=np.uint32)
-        Wd = {"S0": self.S, "TAPE": self.S, "NOISE": self.N, "PARAMS": self.A, "ACT": self.A,
+        Wd = {"S0": self.S, "TAPE": self.tape_w, "NOISE": self.N, "PARAMS": self.A, "ACT": self.A,
               "REWARD": 1, "RETURNS": 1, "ERR": 1, "DISC": 1, "FINAL": self.S,
               "TRAJ": self.traj_w, "GRET": 1, "GRADP": self.A, "GACT": self.A, "GS0": self.S,
               "GSIN": self.S}

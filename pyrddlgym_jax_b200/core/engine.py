@@ -36,7 +36,7 @@ class RkSizes(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "kind", "relaxed", "S", "A", "N", "n_mparams", "rpw", "lanes", "warp_words",
         "const_words", "n_prologue", "n_step", "n_epilogue", "warps_per_cta", "smem_bytes",
-        "static_err")]
+        "static_err", "tape_words")]
 
 
 def load_library(path: Optional[str] = None) -> ctypes.CDLL:

@@ -658,5 +658,21 @@ def sparsify(g: Graph, roots: Sequence[V]) -> Dict[str, int]:
             v.args = new_args
         v.n = len(sel)
         stats["elements_after"] += v.n
-    g._cse.clear()            # keys describe the old element spaces
+    # value numbering: re-key the surviving values with their new element spaces, so that the
+    # adjoint rules emitted afterwards (cos x for d sin x, ...) still find the forward values
+    g._cse.clear()
+    for v in g.nodes:
+        if v.const is not None or v.op in _LEAF_OPS or not v.args or v.op in ("QSUM", "RPRODX"):
+            continue
+        if v.op == "sg":
+            if not v.attrs:
+                g._cse.setdefault(("sg", v.args[0][0].id), v)
+            continue
+        if v.op in _RED_OPS:
+            key = (v.op, v.dtype, v.args[0][0].id, v.attrs["ptr"].tobytes(), v.attrs["idx"].tobytes())
+        elif v.attrs:
+            continue
+        else:
+            key = (v.op, v.dtype, v.n, tuple((a.id, g._map_key(m)) for a, m in v.args))
+        g._cse.setdefault(key, v)
     return stats

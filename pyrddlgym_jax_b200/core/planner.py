@@ -398,9 +398,10 @@ class JaxBackpropPlanner:
                 self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=False, gamma=gamma))
                 self.train_bwd = engine.DeviceProgram(
                     tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
-            else:
+            else:   # adjoint first: it decides what the forward program tapes for it
+                bwd_prog = tb.backward(gamma=gamma)
                 self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=True, gamma=gamma))
-                self.train_bwd = engine.DeviceProgram(tb.backward(gamma=gamma))
+                self.train_bwd = engine.DeviceProgram(bwd_prog)
             eb = self.test_compiled.builder(spec, False, test_log, self.batch_size_test)
             self.test_fwd = engine.DeviceProgram(eb.forward(write_tape=False, gamma=gamma))
         self.A = self.plan.A
@@ -424,7 +425,7 @@ class JaxBackpropPlanner:
         self.grad = z(P, NP)
         self.nwarps = self.train_bwd.num_warps(Bt)
         self.gradp = None if self.is_drp else z(self.nwarps * T * A)
-        self.tape = None if self.is_drp else z(T * fw.S * Bt)
+        self.tape = None if self.is_drp else z(T * fw.tape_words * Bt)
         self.train_reward = z(P, T * Bt)
         self.train_returns = z(P, Bt)
         self.train_err = z(P, T * Bt, dt=torch.int32)

@@ -15,6 +15,7 @@ parameters live in one CTA-wide constant region.
 """
 from __future__ import annotations
 
+import os as _os
 import struct
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -72,6 +73,7 @@ class Program:
     mparam_defaults: np.ndarray
     traj_layout: Dict[str, Tuple[int, int, str]] = field(default_factory=dict)
     TRAJ: int = 0
+    tape_words: int = 0         # words per rollout-step of the tape (S, or S + taped values)
     static_err: int = 0
     stats: Dict[str, Any] = field(default_factory=dict)
     meta: Dict[str, Any] = field(default_factory=dict)    # decoded instructions for codegen
@@ -243,13 +245,17 @@ class ProgramBuilder:
         self.log_fluents = list(log_fluents)
 
     # ---------------------------------------------------------------------------------
-    def _needed(self, roots: Sequence[V]) -> List[V]:
+    def _needed(self, roots: Sequence[V], stop: Optional[set] = None) -> List[V]:
+        """Values reachable from ``roots``; the operands of values in ``stop`` (taped values,
+        which are loaded instead of computed) are not followed."""
         seen, stack = set(), [r for r in roots]
         while stack:
             v = stack.pop()
             if v.id in seen:
                 continue
             seen.add(v.id)
+            if stop is not None and root(v).id in stop and v.op != "sg":
+                continue
             for a, _ in v.args:
                 stack.append(a)
         return [v for v in self.g.nodes if v.id in seen]
@@ -257,8 +263,13 @@ class ProgramBuilder:
     def _compute_ins(self, nodes: Sequence[V], tstep_params: bool = True) -> List[Ins]:
         """One instruction per value that needs computing, in topological order."""
         out = []
+        taped = getattr(self, "_load_taped", None) or {}
         for v in nodes:
             if v.op in ("const", "mparam", "sg", "state_in", "persist"):
+                continue
+            if v.id in taped:          # adjoint program: forward value read back from the tape
+                out.append(Ins("LDB", dst=v, n=v.n, flags=isa.F_TSTEP, buf=isa.BUF["TAPE"],
+                               off=self.S + taped[v.id]))
                 continue
             if v.op == "param_in":
                 out.append(Ins("LDU", dst=v, n=v.n, flags=isa.F_UNIFORM | isa.F_TSTEP,
@@ -297,16 +308,24 @@ class ProgramBuilder:
         roots = [sg.reward] + list(sg.next_state.values()) + [c for _, c in sg.errs] \
             + [sg.fluents[f] if f in sg.fluents else sg.action_in[f] for f in self.log_fluents]
         step: List[Ins] = []
+        extras = dict(getattr(self, "tape_extra", {})) if write_tape else {}
+        self._fwd_built = True
         if write_tape:
             for name, (off, n, _) in self.slayout.items():
                 step.append(Ins("STB", srcs=[(sg.state_in[name], None)], n=n, flags=isa.F_TSTEP,
                                 buf=isa.BUF["TAPE"], off=off))
+            roots += [v for v, _ in extras.values()]
         disc = None
         if gamma != 1.0:
             disc = g.leaf("disc_in", 1, "f", uniform=True)
             roots.append(disc)
-        self.sparsity = sparsify(g, roots) if self.SPARSIFY else {}
+        if not extras:      # (with a planned tape the adjoint builder already pruned the graph)
+            self.sparsity = sparsify(g, roots) if self.SPARSIFY else {}
+        self._tape_words = self.S + sum(v.n for v, _ in extras.values())
         step += self._compute_ins(self._needed(roots))
+        for v, off in extras.values():      # forward values the adjoint reads back (full tape)
+            step.append(Ins("STB", srcs=[(v, None)], n=v.n, flags=isa.F_TSTEP,
+                            buf=isa.BUF["TAPE"], off=self.S + off))
         step.append(Ins("STB", srcs=[(sg.reward, None)], n=1, flags=isa.F_TSTEP,
                         buf=isa.BUF["REWARD"], off=0))
         if disc is not None:       # planner.py:2754-2757
@@ -387,8 +406,17 @@ class ProgramBuilder:
             step.append(Ins("LDB", dst=sg.state_in[name], n=n, flags=isa.F_TSTEP,
                             buf=isa.BUF["TAPE"], off=off))
         outs = [cts[v.id] for v in wrt if v.id in cts]
-        self.sparsity = sparsify(g, outs) if self.SPARSIFY else {}
-        step += self._compute_ins(self._needed(outs))
+        # prune with the forward roots kept alive too: the forward program may be assembled
+        # from this graph afterwards (it must store exactly what this program loads)
+        fwd_roots = [sg.reward] + list(sg.next_state.values()) + [c for _, c in sg.errs]
+        self.sparsity = sparsify(g, outs + fwd_roots) if self.SPARSIFY else {}
+        self._load_taped = self._plan_tape(outs, fwd_roots, state_ct_in)
+        step_nodes = self._needed(outs, stop=set(self._load_taped))
+        used_state = {root(a).id for v in step_nodes for a, _ in v.args} | \
+            {root(o).id for o in outs}
+        step = [i for i in step if not (i.op == "LDB" and i.buf == isa.BUF["TAPE"]
+                                        and root(i.dst).id not in used_state)]
+        step += self._compute_ins(step_nodes)
         gbuf = isa.BUF["GRADP"] if self.spec.kind == "slp" else isa.BUF["GACT"]
         for name, leaf in self.param_leaves.items():
             off, n, _ = self.alayout[name]
@@ -409,13 +437,58 @@ class ProgramBuilder:
                 epi.append(Ins("STB", srcs=[(carried[name], None)], n=n, buf=isa.BUF["GS0"], off=off))
         persistent = list(sg.state_in.values()) + [gret] + list(carried.values())
         self._traj_words = 0
+        self._tape_words = self.S + sum(v.n for v, _ in self.tape_extra.values())
         prog = self._assemble("backward", pro, step, epi, persistent)
+        self._load_taped = None
         prog.stats["adjoint_nodes"] = len(g.nodes) - n_before
+        prog.stats["taped_values"] = len(self.tape_extra)
         return prog
 
     # ---------------------------------------------------------------------------------
+    # measured (Quadcopter, B=4096, T=100): "full" makes the adjoint 10% faster (no recompute) but
+    # the forward 40% slower (19 extra stores per lane-step), a net loss -> minimal tape by default
+    TAPE_MODE = _os.environ.get("RK_TAPE", "state")     # state | full | auto
+
+    def _plan_tape(self, outs: Sequence[V], fwd_roots: Sequence[V], external: bool) -> Dict[int, int]:
+        """Decide what the adjoint reads back instead of recomputing.
+
+        'state' : only s_t (S words per rollout-step), the step is recomputed -- the minimum of
+                  HBM traffic, right when the batch fills the machine;
+        'full'  : additionally every per-rollout forward value the reverse instructions read (the
+                  "frontier"), no recompute -- right when the launch is latency-bound (few warps)
+                  and the extra words are cheap next to the saved instructions.
+        Returns {value id: word offset after the state words}; also sets self.tape_extra for the
+        forward program, which must then be assembled AFTER this adjoint program."""
+        self.tape_extra: Dict[int, Tuple[V, int]] = {}
+        if self.TAPE_MODE == "state" or external or getattr(self, "_fwd_built", False):
+            return {}
+        fwd_ids = {v.id for v in self._needed(fwd_roots)}
+        adj = [v for v in self._needed(outs) if v.id not in fwd_ids]
+        leaf = ("const", "mparam", "state_in", "persist", "param_in", "act_in", "noise", "disc_in")
+        frontier: Dict[int, V] = {}
+        for v in adj:
+            for a, _ in v.args:
+                r = root(a)
+                if r.id in fwd_ids and r.op not in leaf and r.const is None and not r.uniform:
+                    frontier[r.id] = r
+        words = sum(r.n for r in frontier.values())
+        if self.TAPE_MODE != "full":
+            B = max(int(self.batch_hint or 4096), 1)
+            widest = max([1] + [v.n for v in self._needed(outs)])
+            lanes = min(32, 1 << max(0, (widest - 1).bit_length()))
+            nwarps = -(-B // max(1, 32 // lanes))
+            latency_bound = nwarps <= 4 * 148 * 4            # under ~4 warps per sub-partition
+            if not (latency_bound and words <= 4 * self.S):
+                return {}
+        off, plan = 0, {}
+        for r in sorted(frontier.values(), key=lambda v: v.id):
+            self.tape_extra[r.id] = (r, off)
+            plan[r.id] = off
+            off += r.n
+        return plan
+
+    # ---------------------------------------------------------------------------------
     # per-instruction fixed cost (fetch, decode, dispatch) in units of one element pass
-    import os as _os
     SPARSIFY = _os.environ.get("RK_SPARSIFY", "1") != "0"
     INS_OVERHEAD = 4.0
     MULTIPASS_PENALTY = 16.0       # measured: MarsRover L=4 (smem, 8 passes) 8.0 ms vs L=32 (registers) 1.7 ms
@@ -552,6 +625,7 @@ class ProgramBuilder:
         hdr[15] = sg.static_err
         hdr[16] = err_base
         hdr[17] = getattr(self, "_traj_words", 0)
+        hdr[18] = getattr(self, "_tape_words", 0) or self.S
         ins_img = np.concatenate(encoded).astype(np.uint16) if encoded else np.zeros(0, np.uint16)
         blob = hdr.tobytes() + const_img.tobytes() + ins_img.tobytes()
         hist: Dict[str, int] = {}
@@ -564,6 +638,7 @@ class ProgramBuilder:
             noise_layout=[(s.kind, s.shape, s.n, s.offset, s.extra) for s in sg.noise],
             mparam_keys=[k for k, _, _ in sg.mparams], mparam_defaults=mp_defaults,
             static_err=sg.static_err, stats={"step_ops": hist},
+            tape_words=int(hdr[18]),
             meta={"ins": records, "persistent": [root(p).id for p in persistent],
                   "err_base": err_base, "mparam_off": mparam_off,
                   "const_image": const_img.copy()})

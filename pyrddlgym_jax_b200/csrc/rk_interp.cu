@@ -516,6 +516,7 @@ extern "C" int rk_program_query(const rk_program* p, rk_sizes* o) {
   o->warps_per_cta = p->warps_per_cta;
   o->smem_bytes = p->smem_bytes;
   o->static_err = (int)p->hdr[15];
+  o->tape_words = p->hdr[18] ? (int)p->hdr[18] : (int)p->hdr[11];
   return 0;
 }
 
@@ -567,7 +568,7 @@ extern "C" int rk_rollout_forward(const rk_program* p, void* stream, int B, int 
   K.B = B; K.T = T; K.t_dir = 1; K.mparams = mparams;
   const long long S = p->hdr[11], A = p->hdr[12], N = p->hdr[13];
   K.buf[RK_BUF_S0] = (void*)s0;           K.W[RK_BUF_S0] = S;
-  K.buf[RK_BUF_TAPE] = tape;              K.W[RK_BUF_TAPE] = S;
+  K.buf[RK_BUF_TAPE] = tape;              K.W[RK_BUF_TAPE] = p->hdr[18] ? p->hdr[18] : S;
   K.buf[RK_BUF_NOISE] = (void*)noise;     K.W[RK_BUF_NOISE] = N;
   K.buf[RK_BUF_PARAMS] = (void*)policy;   K.W[RK_BUF_PARAMS] = A;
   K.buf[RK_BUF_ACT] = (void*)actions;     K.W[RK_BUF_ACT] = A;
@@ -593,7 +594,7 @@ extern "C" int rk_rollout_backward(const rk_program* p, void* stream, int B, int
   memset(&K, 0, sizeof(K));
   K.B = B; K.T = T; K.t_dir = -1; K.mparams = mparams;
   const long long S = p->hdr[11], A = p->hdr[12], N = p->hdr[13];
-  K.buf[RK_BUF_TAPE] = (void*)tape;       K.W[RK_BUF_TAPE] = S;
+  K.buf[RK_BUF_TAPE] = (void*)tape;       K.W[RK_BUF_TAPE] = p->hdr[18] ? p->hdr[18] : S;
   K.buf[RK_BUF_NOISE] = (void*)noise;     K.W[RK_BUF_NOISE] = N;
   K.buf[RK_BUF_PARAMS] = (void*)policy;   K.W[RK_BUF_PARAMS] = A;
   K.buf[RK_BUF_ACT] = (void*)actions;     K.W[RK_BUF_ACT] = A;

@@ -42,7 +42,8 @@ def run_forward(backend, prog, B, T, s0, params_flat, noise, disc=None, mparams=
         bufs = {"S0": s0.numpy().copy(), "PARAMS": params_flat.numpy().copy(),
                 "NOISE": noise.numpy().copy(), "REWARD": np.zeros(T * B, np.float32),
                 "RETURNS": np.zeros(B, np.float32), "ERR": np.zeros(T * B, np.uint32),
-                "TAPE": np.zeros(T * S * B, np.float32), "FINAL": np.zeros(S * B, np.float32),
+                "TAPE": np.zeros(T * prog.tape_words * B, np.float32),
+                "FINAL": np.zeros(S * B, np.float32),
                 "DISC": None if disc is None else disc.numpy().copy()}
         Emulator(prog.blob).run(B, T, bufs, None if mparams is None else mparams.numpy())
         return {"reward": bufs["REWARD"].reshape(T, B), "returns": bufs["RETURNS"],
@@ -52,7 +53,7 @@ def run_forward(backend, prog, B, T, s0, params_flat, noise, disc=None, mparams=
     dp = DeviceProgram(prog, specialize=(backend == "jit"))
     z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
     out = {"reward": z(T * B), "returns": z(B), "err": z(T * B, dt=torch.int32),
-           "tape": z(T * S * B), "final": z(S * B)}
+           "tape": z(T * prog.tape_words * B), "final": z(S * B)}
     dp.forward(B, T, s0.to(dev), policy=params_flat.to(dev), noise=noise.to(dev).reshape(-1),
                mparams=None if mparams is None else mparams.to(dev),
                disc=None if disc is None else disc.to(dev),
@@ -102,6 +103,8 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
         comp = JaxRDDLCompiler(m)
     spec = PlanSpec(bounds=m.bounds)
     builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
+    # the adjoint program is assembled first: it decides what the forward program tapes for it
+    bwd = builder.backward(gamma=gamma) if relaxed else None
     fwd = builder.forward(write_tape=relaxed, gamma=gamma)
     params = make_params(m, key, T, scale=param_scale)
     noise = draw_noise(fwd.noise_layout, T, B, torch.Generator().manual_seed(seed))
@@ -124,7 +127,7 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     spec_pr = [(k, tuple(s)) for k, s, _, _, _ in fwd.noise_layout]
     assert T == 0 or spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
     final = unpack_fluent_major(fwd.state_layout, torch.from_numpy(got["final"].copy()), B)
-    return dict(model=m, comp=comp, builder=builder, fwd=fwd, params=params, P=P, noise=noise,
+    return dict(model=m, comp=comp, builder=builder, fwd=fwd, bwd=bwd, params=params, P=P, noise=noise,
                 s0=s0, disc=disc, got=got, ref=ref, final=final, gamma=gamma)
 
 
@@ -133,7 +136,7 @@ def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=
     c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
                      param_scale=param_scale, given=given, **ckw)
     m = c["model"]
-    bwd = c["builder"].backward(gamma=gamma)
+    bwd = c["bwd"]
     gret = torch.full((B,), -1.0 / B)
     grad = run_backward(backend, bwd, B, T, c["got"]["tape"], pack_params(m, c["params"]),
                         c["noise"], gret, c["disc"])
