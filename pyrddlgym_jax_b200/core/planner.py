@@ -613,12 +613,15 @@ class JaxBackpropPlanner:
 
     def _iteration_kernels(self):
         for p in range(self.parallel_updates):
-            self._update_kernels(p)
+            for _ in range(max(1, self.steps_per_update)):      # planner.py:2905-2914
+                self._update_kernels(p)
+                if self.optimizer_name == "adam" and self.steps_per_update > 1:
+                    self.hyper[6:7].add_(1.0)
             self._test_kernels(p)
         self._finish_iteration()
 
     def _finish_iteration(self):
-        if self.optimizer_name == "adam":
+        if self.optimizer_name == "adam" and self.steps_per_update <= 1:
             self.hyper[6:7].add_(1.0)
         if self.world_size > 1:
             self.loss_pair[0].copy_(self.train_loss)
@@ -635,6 +638,13 @@ class JaxBackpropPlanner:
         P = self.parallel_updates
         for p in range(P):
             self._opt_kernels(p)
+            for _ in range(max(1, self.steps_per_update) - 1):   # K updates per iteration
+                if self.optimizer_name == "adam":
+                    self.hyper[6:7].add_(1.0)
+                self._train_grad_kernels(p)
+                self._opt_kernels(p)
+            if self.optimizer_name == "adam" and self.steps_per_update > 1:
+                self.hyper[6:7].add_(1.0)
         main = torch.cuda.current_stream(self.device)
         if side is not None:
             side.wait_stream(main)

@@ -274,3 +274,25 @@ def test_pgpe_runs_next_to_backprop_and_can_take_over(cuda_device, plan_kind):
         assert cb["pgpe_params"] is not None
     assert took_over
     assert last["best_return"] > first["best_return"]
+
+
+@pytest.mark.gpu
+def test_steps_per_update_equals_repeated_updates(cuda_device):
+    """steps_per_update = K performs K optimiser steps per iteration (planner.py:2905-2914): two
+    iterations with K = 3 land on the same plan as six iterations with K = 1 (fixed noise)."""
+    m = fixture_model("quadcopter")
+
+    def run(K, iters, graph):
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=64, rollout_horizon=10,
+                                steps_per_update=K, optimizer="adam",
+                                optimizer_kwargs={"learning_rate": 0.02}, pgpe=None,
+                                use_cuda_graph=graph)
+        pl.initialize(9)
+        for _ in range(iters):
+            pl.iterate()
+        torch.cuda.synchronize()
+        return pl.params[0].cpu().clone()
+    ref = run(1, 6, False)
+    for graph in (False, True):
+        assert torch.equal(run(3, 2, graph), ref)
+        assert torch.equal(run(1, 6, graph), ref)
