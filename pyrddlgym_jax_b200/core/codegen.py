@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 7
+CODEGEN_VERSION = 8
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -52,6 +52,13 @@ _F2 = {
     "SAFELOG": "((x > 0.f) ? logf(x) : -CUDART_INF_F + 0.f * y)",
     "MINW": "((x < y) ? 1.f : ((x == y) ? 0.5f : 0.f))",
     "MAXW": "((x > y) ? 1.f : ((x == y) ? 0.5f : 0.f))",
+}
+# relaxed programs: branch-free division / sqrt / trigonometry (rk_device.cuh), so that a whole
+# step is one basic block the scheduler can interleave freely
+_FAST = {
+    "DIV": "rk_fdiv(x, y)", "RCP": "rk_fdiv(1.f, x)", "SQRT": "rk_fsqrt(x)",
+    "SIGMOID": "rk_fdiv(1.f, 1.f + expf(-x))", "STANH": "rk_fstable_tanh(x)",
+    "SIN": "rk_fsin(x)", "COS": "rk_fcos(x)", "TAN": "rk_ftan(x)",
 }
 _F2B = {"LT": "<", "LE": "<=", "GT": ">", "GE": ">=", "EQ": "==", "NE": "!="}
 _I1 = {"INEG": "(-x)", "IABS": "abs(x)", "ISGN": "((x > 0) - (x < 0))", "NOT": "(x == 0)",
@@ -220,10 +227,12 @@ class _Gen:
         self.emit(f"  // sincos group: {' '.join(r['op'] for r in recs)} n={n}")
         asg = []
         for r in recs:
-            ex = {"SIN": "sn_", "COS": "cs_", "TAN": "(sn_ / cs_)"}[r["op"]]
+            ex = {"SIN": "sn_", "COS": "cs_",
+                  "TAN": "rk_fdiv(sn_, cs_)" if self.fast else "(sn_ / cs_)"}[r["op"]]
             asg.append(f"{self.var(r['dst'])} = {ex};")
         self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; float sn_, cs_; "
-                  f"sincosf({x}, &sn_, &cs_); " + " ".join(asg) + " }")
+                  f"{'rk_fsincos' if self.fast else 'sincosf'}({x}, &sn_, &cs_); " +
+                  " ".join(asg) + " }")
 
     # ---- global-memory addressing: one 64-bit base per buffer per step, 32-bit offsets ----
     def gbase(self, buf: int, kind: str, tstep: bool, nxt: bool = False) -> str:
@@ -298,7 +307,9 @@ class _Gen:
             if not self.is_reg(dst):
                 self.emit("  __syncwarp();")
             return
-        if op in _F1:
+        if self.fast and op in _FAST:
+            body, tin = _FAST[op], ("ff" if op in _F2 else "f")
+        elif op in _F1:
             body, tin = _F1[op], "f"
         elif op in _F2:
             body, tin = _F2[op], "ff"
@@ -503,13 +514,10 @@ class _Gen:
             src = srcs[0]
             if self.is_reg(src) and rpw * L == 32 and (rpw & (rpw - 1)) == 0:
                 # full warps: xor-butterfly over the rollouts of the warp (log2(rpw) shuffles);
-                # the ragged last warp keeps the sequential sum over its valid rollouts
+                # rollouts past the end of the batch (ragged last warp) contribute zero: no branch
                 fly = " ".join(f"acc += __shfl_xor_sync(0xffffffffu, acc, {o}u);"
                                for o in [L << i for i in range(rpw.bit_length() - 1)])
-                code = (f"float acc = {self.var(src)}; if (nvalid == {rpw}u) {{ {fly} }} else {{ "
-                        f"const float mine = acc; acc = 0.f; for (uint32_t qq = 0; qq < {rpw}u; ++qq) {{ "
-                        f"const float tq = __shfl_sync(0xffffffffu, mine, qq * {L}u + le); "
-                        f"if (qq < nvalid) acc += tq; }} }}")
+                code = f"float acc = (q < nvalid) ? {self.var(src)} : 0.f; {fly}"
             elif self.is_reg(src):
                 code = (f"float acc = 0.f; for (uint32_t qq = 0; qq < {rpw}u; ++qq) {{ "
                         f"const float tq = __shfl_sync(0xffffffffu, {self.var(src)}, qq * {L}u + le); "

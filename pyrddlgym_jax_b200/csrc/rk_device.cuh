@@ -17,6 +17,58 @@ __device__ __forceinline__ float stable_tanh(float x) {       // logic.py:57-65
   return copysignf(1.f, x) * ((x == 0.f) ? 0.f : s);
 }
 
+// ---- branch-free variants used by relaxed (train / adjoint) programs -----------------------
+// libdevice's sincosf / sqrtf and the IEEE division guard a slow path with a branch; every such
+// branch ends a basic block, so a step with a dozen of them cannot be scheduled as one block
+// and a warp that runs alone on its scheduler stalls on every dependent pair.  These versions
+// have no branch (<= 1-2 ulp for normal operands; infinities, zeros and NaNs handled by a
+// select on the seed result).  Exact programs never use them.
+__device__ __forceinline__ float rk_fdiv(float x, float y) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(y));
+  const float r = fmaf(fmaf(-y, r0, 1.f), r0, r0);          // Newton step on the reciprocal
+  const float q0 = x * r;
+  const float q1 = fmaf(fmaf(-y, q0, x), r, q0);            // residual correction of the quotient
+  return (fabsf(q1) < CUDART_INF_F) ? q1 : x * r0;          // inf / 0 / NaN: the seed's answer
+}
+
+__device__ __forceinline__ float rk_fsqrt(float x) {
+  float s0, y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(x));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  const float s1 = fmaf(fmaf(-s0, s0, x), 0.5f * y, s0);
+  return (fabsf(s1) < CUDART_INF_F) ? s1 : s0;
+}
+
+__device__ __forceinline__ void rk_fsincos(float x, float* sn, float* cs) {
+  // Cody-Waite reduction by pi/2 in three fp32 pieces (accurate for |x| up to ~1e5, the range
+  // of libdevice's own fast path), then the cephes minimax polynomials on [-pi/4, pi/4]
+  const float j = rintf(x * __uint_as_float(0x3f22f983u));
+  const int i = (int)j;
+  float r = fmaf(j, -__uint_as_float(0x3fc90fdbu), x);
+  r = fmaf(j, -__uint_as_float(0xb33bbd2eu), r);
+  r = fmaf(j, -__uint_as_float(0xa7000000u), r);
+  const float z = r * r;
+  const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f),
+                        z * r, r);
+  const float cp = fmaf(fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z,
+                                  4.166664568298827e-2f), z, -0.5f), z, 1.f);
+  const bool sw = (i & 1) != 0;
+  const float ss = sw ? cp : sp, cc = sw ? sp : cp;
+  *sn = (i & 2) ? -ss : ss;
+  *cs = ((i + 1) & 2) ? -cc : cc;
+}
+
+__device__ __forceinline__ float rk_fsin(float x) { float s, c; rk_fsincos(x, &s, &c); return s; }
+__device__ __forceinline__ float rk_fcos(float x) { float s, c; rk_fsincos(x, &s, &c); return c; }
+__device__ __forceinline__ float rk_ftan(float x) { float s, c; rk_fsincos(x, &s, &c); return rk_fdiv(s, c); }
+
+__device__ __forceinline__ float rk_fstable_tanh(float x) {   // stable_tanh without the branch
+  const float ax = fminf(fabsf(x), 20.f);                     // tanh(20) == 1.f in fp32
+  const float em = expm1f(2.f * ax);
+  return copysignf(1.f, x) * ((x == 0.f) ? 0.f : rk_fdiv(em, em + 2.f));
+}
+
 __device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 
 __device__ __forceinline__ float py_modf(float x, float y) {  // jnp.mod: sign of divisor
