@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 8
+CODEGEN_VERSION = 11
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -99,6 +99,10 @@ class _Gen:
         # relaxed programs may trade last-bit identity for speed (reciprocal of constants, FMA
         # contraction); exact programs never do.  RK_FAST_RELAXED=0 switches it off.
         self.fast = bool(prog.relaxed) and os.environ.get("RK_FAST_RELAXED", "1") != "0"
+        # per-step loads run this many steps ahead of their use (a cp.async ring in shared memory): one step of
+        # a lone warp is shorter than an HBM round trip, so a distance of 1 leaves the step time
+        # pinned at the memory latency
+        self.pf_depth = max(1, int(os.environ.get("RK_PREFETCH", "3")))
         self.lines: List[str] = []
         self.tmp = 0
 
@@ -532,23 +536,25 @@ class _Gen:
                 self.emit("  __syncwarp();")
             return
         tstep = bool(rec["flags"] & isa.F_TSTEP)
-        if op in ("LDB", "LDU") and tstep and self.in_step and self.is_reg(dst) and n <= L:
-            # software prefetch: this step consumes what the previous step loaded and issues
-            # the load for the next step, so the L2 / HBM latency overlaps a whole step
+        if op in ("LDB", "LDU") and tstep and self.in_step and self.is_reg(dst) and n <= L \
+                and self.pf_depth > 1:
+            # asynchronous prefetch ring: the words a step reads from global memory are copied
+            # into a per-warp shared-memory ring D steps ahead (cp.async, one 4-byte word per
+            # lane), so the L2 / HBM latency overlaps D - 1 whole steps instead of stalling the
+            # lone warp of a scheduler; this step reads its slot and refills it for step t +- D
             dt = self.dtype[dst["id"]]
             if op == "LDB":
                 gn = self.gbase(buf, "b", True, nxt=True)
-                ld = self.from_bits(f"{gn}[{off}u * Bu + {self.lane_off(n)}]", dt)
+                src = f"{gn} + ({off}u * Bu + {self.lane_off(n)})"
                 cond = f"has{buf} && q < nvalid && le < {n}u"
             else:
                 gn = self.gbase(buf, "u", True, nxt=True)
-                ld = self.from_bits(f"__ldg({gn} + {off}u + le)", dt)
+                src = f"{gn} + ({off}u + le)"
                 cond = f"has{buf} && le < {n}u"
-            pf = f"pf{dst['id']}"
-            self.pf_decl.append(f"  {self.ctype(dt)} {pf} = ({self.ctype(dt)})0;")
-            stmt = f"{pf} = (more && {cond}) ? {ld} : ({self.ctype(dt)})0;"
-            self.pf_stmts.append("    " + stmt)
-            self.emit(f"  {self.var(dst)} = {pf}; {stmt}")
+            i = len(self.pf_stmts)
+            self.pf_stmts.append(f"    rk_cp_async4(ring_w + {i * 32}u, {src}, more && {cond}, K.prog);")
+            self.emit(f"  {self.var(dst)} = {self.from_bits(f'ring_r[{i * 32}u]', dt)};")
+            self.pf_last = len(self.lines)
             return
         if op == "LDB":
             gp = self.gbase(buf, "b", tstep)
@@ -640,7 +646,14 @@ class _Gen:
                  self.ins[self.n_pro + self.n_step:]]
         bodies = []
         self.lane_offs = set()
-        self.pf_decl, self.pf_stmts = [], []
+        # ring budget: 4 warps x D stages x (loads x 32 lanes) words of static shared memory
+        nld = sum(1 for rec in lists[1] if rec["op"] in ("LDB", "LDU")
+                  and rec["flags"] & isa.F_TSTEP and rec["n"] <= self.L and self.is_reg(rec["dst"]))
+        dyn = (p.const_words + 4 * p.warp_words) * 4
+        while self.pf_depth > 1 and (4 * self.pf_depth * nld * 128 > 40 * 1024
+                                     or dyn + 4 * self.pf_depth * nld * 128 > 200 * 1024):
+            self.pf_depth -= 1
+        self.pf_stmts, self.pf_last = [], 0
         self.hoisted: Dict[str, str] = {}
         self.next_bases: Dict[int, str] = {}
         backward = p.kind == "backward"
@@ -653,15 +666,32 @@ class _Gen:
                 self.gen_ins(rec)
             head = list(self.bases.values())
             if li == 1 and self.pf_stmts:
-                head = [f"  const long long tn = t {'-' if backward else '+'} 1; "
-                        f"const bool more = tn >= 0 && tn < (long long)K.T;"] \
-                    + list(self.next_bases.values()) + head
+                D = self.pf_depth
+                refill = [f"  {{ const long long tn = t {'-' if backward else '+'} {D}; "
+                          f"const bool more = tn >= 0 && tn < (long long)K.T;"] \
+                    + list(self.next_bases.values()) \
+                    + [f"    uint32_t* const ring_w = ring + slot * {len(self.pf_stmts) * 32}u;"] \
+                    + self.pf_stmts + ["    rk_cp_async_commit(); }",
+                                       f"  slot = (slot + 1u == {D}u) ? 0u : slot + 1u;"]
+                self.lines[self.pf_last:self.pf_last] = refill
+                head = [f"  rk_cp_async_wait<{D - 1}>();",
+                        f"  const uint32_t* const ring_r = ring + slot * {len(self.pf_stmts) * 32}u;"] + head
             bodies.append("\n".join(head + self.lines))
-        prefetch0 = ""
+        prefetch0, ring_decl = "", ""
         if self.pf_stmts:
             t0 = "(long long)K.T - 1" if backward else "0ll"
-            prefetch0 = ("  { const long long tn = " + t0 + "; const bool more = K.T > 0;\n"
-                         + "\n".join(list(self.next_bases.values()) + self.pf_stmts) + "\n  }")
+            sgn = "-" if backward else "+"
+            nld = len(self.pf_stmts)
+            prefetch0 = "\n".join(
+                "  { const long long tn = " + t0 + f" {sgn} {k}; "
+                "const bool more = tn >= 0 && tn < (long long)K.T;\n"
+                + "\n".join(list(self.next_bases.values())
+                            + [f"    uint32_t* const ring_w = ring + {k * nld * 32}u;"]
+                            + self.pf_stmts) + "\n    rk_cp_async_commit();\n  }"
+                for k in range(self.pf_depth))
+            ring_decl = (f"  __shared__ uint32_t ring_all[{4 * self.pf_depth * nld * 32}];\n"
+                         f"  uint32_t* const ring = ring_all + warp * {self.pf_depth * nld * 32}u + lane;\n"
+                         f"  uint32_t slot = 0u;")
         hoist = [f"  const bool has{b} = K.buf[{b}] != nullptr; (void)has{b};"
                  for b in range(len(isa.BUFFERS))]
         hoist += [f"  const uint32_t lo{n} = b0u * {n}u + q * {n}u + le; (void)lo{n};"
@@ -700,7 +730,7 @@ extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
 {chr(10).join(hoist)}
 {chr(10).join(self.hoisted.values())}
 {chr(10).join(decl)}
-{chr(10).join(self.pf_decl)}
+{ring_decl}
   {{ const long long t = 0; (void)t;
 {bodies[0]}
   }}

@@ -17,6 +17,24 @@ __device__ __forceinline__ float stable_tanh(float x) {       // logic.py:57-65
   return copysignf(1.f, x) * ((x == 0.f) ? 0.f : s);
 }
 
+// ---- asynchronous global -> shared copies of one word per lane (prefetch ring of the generated
+// kernels); a false predicate zero-fills the destination without touching global memory
+__device__ __forceinline__ void rk_cp_async4(uint32_t* dst, const uint32_t* src, bool pred,
+                                             const void* safe) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const void* s = pred ? (const void*)src : safe;
+  const int nbytes = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(s), "r"(nbytes)
+               : "memory");
+}
+__device__ __forceinline__ void rk_cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void rk_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- branch-free variants used by relaxed (train / adjoint) programs -----------------------
 // libdevice's sincosf / sqrtf and the IEEE division guard a slow path with a branch; every such
 // branch ends a basic block, so a step with a dozen of them cannot be scheduled as one block

@@ -442,6 +442,11 @@ extern "C" int rk_program_attach_cubin(rk_program* p, const void* image, size_t 
   // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
   rc = g_drv.funcSetAttribute(fn, 8, p->smem_bytes);
   if (rc != 0) { g_drv.moduleUnload(mod); return rc; }
+  // CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT = 9: every rollout kernel asks for the
+  // same L1 / shared split, so the exact test kernel and the train kernels of the pipelined
+  // iteration can share an SM (kernels with different splits cannot co-reside)
+  if (getenv("RK_CARVEOUT") == nullptr || atoi(getenv("RK_CARVEOUT")) >= 0)
+    g_drv.funcSetAttribute(fn, 9, getenv("RK_CARVEOUT") ? atoi(getenv("RK_CARVEOUT")) : 100);
   if (p->module != nullptr) g_drv.moduleUnload(p->module);
   p->module = mod;
   p->func = fn;
