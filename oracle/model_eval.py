@@ -43,7 +43,9 @@ ERR = {  # compiler.py:861-888
     "BETA": 1 << 8, "GEOMETRIC": 1 << 9, "PARETO": 1 << 10, "STUDENT": 1 << 11,
     "GUMBEL": 1 << 12, "LAPLACE": 1 << 13, "CAUCHY": 1 << 14, "GOMPERTZ": 1 << 15,
     "CHISQUARE": 1 << 16, "KUMARASWAMY": 1 << 17, "DISCRETE": 1 << 18, "KRON": 1 << 19,
+    "BINOMIAL": 1 << 23, "NEGATIVE_BINOMIAL": 1 << 24,
 }
+COUNT_NBINS = 100      # truncation of the exact Poisson / Binomial samplers (see _random)
 
 
 # ---- custom-derivative helpers ------------------------------------------------------
@@ -672,14 +674,92 @@ class OracleModel:
             E = self._draw(cur, "exponential", a0, scope, B)
             return scale * torch.pow(E, 1. / _f(shape)), \
                 err | oob((shape > 0) & (scale > 0)) * ERR["WEIBULL"]
+        def gamma_draw(shape, shape_e, scale=1.0):
+            if not self.tracer.is_static(shape_e):
+                raise NotImplementedError(
+                    "Gamma-family distributions with a fluent shape need an in-loop sampler")
+            c0 = shape[0].numpy() * np.float32(scale)
+            conc = np.broadcast_to(c0, self._shape(scope)).copy() if self._ref_full(a0) \
+                else np.asarray(c0, dtype=np.float32).reshape(-1)[0].reshape(())
+            return self._draw(cur, "gamma", a0, scope, B, extra=conc)
+
         if name == "Gamma":                                        # compiler.py:1899-1919
             shape, scale = vals
-            if not self.tracer.is_static(e.args[0]):
-                raise NotImplementedError("Gamma with a fluent shape needs an in-loop sampler")
-            G = self._draw(cur, "gamma", a0, scope, B,
-                           extra=np.broadcast_to(shape[0].numpy(), self._shape(scope)
-                                                 if self._ref_full(a0) else ()).copy())
+            G = gamma_draw(shape, e.args[0])
             return scale * G, err | oob((shape > 0) & (scale > 0)) * ERR["GAMMA"]
+        if name == "ChiSquare":                                    # compiler.py:2130-2147
+            (df,) = vals
+            G = gamma_draw(_f(df), e.args[0], 0.5)
+            return 2.0 * G, err | oob(df > 0) * ERR["CHISQUARE"]
+        if name == "Student":              # compiler.py:2028-2044; jax.random.t = Z sqrt(h / Gamma(h))
+            (df,) = vals
+            Z = self._draw(cur, "normal", a0, scope, B)
+            G = gamma_draw(_f(df), e.args[0], 0.5)
+            return Z * torch.sqrt(0.5 * _f(df) / G), err | oob(df > 0) * ERR["STUDENT"]
+        if name == "Beta":                 # compiler.py:1969-1986; Ga / (Ga + Gb)
+            a, b = vals
+            Ga = gamma_draw(_f(a), e.args[0])
+            Gb = gamma_draw(_f(b), e.args[1])
+            return Ga / (Ga + Gb), err | oob((a > 0) & (b > 0)) * ERR["BETA"]
+        if name == "Pareto":               # compiler.py:2007-2026; jax.random.pareto = exp(Exp(1)/b)
+            shape, scale = vals
+            E = self._draw(cur, "exponential", a0, scope, B)
+            return scale * torch.exp(E / _f(shape)), \
+                err | oob((shape > 0) & (scale > 0)) * ERR["PARETO"]
+        if name == "Poisson":
+            (rate,) = vals
+            rate = _f(rate)
+            perr = err | oob(rate >= 0) * ERR["POISSON"]
+            variant = V.get("poisson") if self.tracer.is_fluent(a0) else None
+            if variant == "determinized":                          # logic.py:1733-1741
+                return rate, perr
+            if variant == "exponential":                           # logic.py:1508-1531
+                from scipy import optimize, stats
+                K = int(R["poisson_nbins"])
+                w = self.param(e, "poisson_comparison_weight", R["poisson_comparison_weight"])
+                cut = float(optimize.brentq(
+                    lambda r: stats.poisson.cdf(K, r) - float(R["poisson_min_cdf"]),
+                    1e-6, 10.0 * K + 10))
+                cum, cnt = 0.0, 0.0
+                for _ in range(K):
+                    cum = cum + self._draw(cur, "exponential", a0, scope, B) / rate
+                    cnt = cnt + torch.sigmoid(w * (1.0 - cum))
+                Z = self._draw(cur, "normal", a0, scope, B)
+                return torch.where(rate.detach() <= cut, cnt, rate + safe_sqrt(rate) * Z), perr
+            if variant is not None:
+                raise NotImplementedError(f"Poisson relaxation <{variant}> is not built")
+            # exact: inverse CDF of one uniform, truncated at COUNT_NBINS terms (jax.random.poisson's
+            # own bits cannot be reproduced from supplied noise; same law below the truncation)
+            U = self._draw(cur, "uniform", a0, scope, B)
+            pk = torch.exp(-rate)
+            cdf, cnt = pk, torch.zeros(())
+            for k in range(1, COUNT_NBINS + 1):
+                cnt = cnt + (U > cdf).to(REAL)
+                pk = pk * (rate * np.float32(1.0 / k))
+                cdf = cdf + pk
+            return (cnt if self.relaxed else cnt.to(INT)), perr
+        if name == "Binomial":
+            trials, prob = _f(vals[0]), _f(vals[1])
+            perr = err | oob((prob >= 0) & (prob <= 1) & (trials >= 0)) * ERR["BINOMIAL"]
+            fluent = self.tracer.is_fluent(e.args[0]) or self.tracer.is_fluent(e.args[1])
+            variant = V.get("binomial") if fluent else None
+            if variant == "determinized":                          # logic.py:1476
+                return trials * prob, perr
+            if variant is not None:
+                raise NotImplementedError(f"Binomial relaxation <{variant}> is not built")
+            cnt = torch.zeros(())
+            for j in range(COUNT_NBINS):     # successes among the first `trials` uniform draws
+                U = self._draw(cur, "uniform", a0, scope, B)
+                cnt = cnt + ((float(j) < trials) & (U < prob)).to(REAL)
+            return (cnt if self.relaxed else cnt.to(INT)), perr
+        if name == "NegativeBinomial":
+            trials, prob = _f(vals[0]), _f(vals[1])
+            perr = err | oob((prob >= 0) & (prob <= 1) & (trials > 0)) * ERR["NEGATIVE_BINOMIAL"]
+            fluent = self.tracer.is_fluent(e.args[0]) or self.tracer.is_fluent(e.args[1])
+            if self.relaxed and fluent and V.get("poisson") == "determinized":
+                return (1.0 / prob - 1.0) * trials, perr           # logic.py:1762
+            raise NotImplementedError(
+                "NegativeBinomial is only available determinised (DeterminizedPoisson)")
         if name == "Gumbel":                                       # compiler.py:2046-2065
             mean, scale = vals
             g = self._draw(cur, "gumbel", a0, scope, B)

@@ -28,8 +28,12 @@ ERR_BITS = {  # compiler.py:861-888
     "CAST": 0, "UNIFORM": 1, "NORMAL": 2, "EXPONENTIAL": 3, "WEIBULL": 4, "BERNOULLI": 5,
     "POISSON": 6, "GAMMA": 7, "BETA": 8, "GEOMETRIC": 9, "PARETO": 10, "STUDENT": 11,
     "GUMBEL": 12, "LAPLACE": 13, "CAUCHY": 14, "GOMPERTZ": 15, "CHISQUARE": 16,
-    "KUMARASWAMY": 17, "DISCRETE": 18, "KRON": 19,
+    "KUMARASWAMY": 17, "DISCRETE": 18, "KRON": 19, "BINOMIAL": 23, "NEGATIVE_BINOMIAL": 24,
 }
+
+# exact Poisson / Binomial samplers are truncated at this many terms (the reference's relaxations
+# default to the same number of bins, logic.py:1362, 1492)
+COUNT_NBINS = 100
 
 
 class RDDLNotImplementedError(NotImplementedError):
@@ -634,10 +638,10 @@ class Lowerer:
     # ---- control: compiler.py:1617-1685 ; logic.py:903-941 ------------------------------
     def _control(self, e, scope, env, sizes) -> TV:
         _, op = e.etype
-        if op != "if":
-            raise RDDLNotImplementedError("switch is not lowered yet")
-        c, a, b = self._args(e, scope, env)
         E = lambda name, *x: self.ew(name, list(x), sizes)     # noqa: E731
+        if op == "switch":
+            return self._switch(e, scope, env, sizes)
+        c, a, b = self._args(e, scope, env)
         if self.relaxed and self.variants.get("if") == "linear" and self.tr.is_fluent(e.args[0]):
             cf = self.to_f(self.at_least_int(c), sizes)
             if self.relax["use_if_else_ste"]:
@@ -655,7 +659,76 @@ class Lowerer:
         out = self.ew("SELECT", [c, a, b], sizes, dtype=a.dtype)
         return out
 
+    def _switch(self, e, scope, env, sizes) -> TV:
+        """switch over an enum-valued predicate.  Exact: the case selected by the integer
+        predicate (take_along_axis over the stacked cases, compiler.py:1661-1684), here a chain
+        of selects -- every case is evaluated, as in the reference.  Relaxed (SoftmaxSwitch,
+        logic.py:959-1002): cases weighted by softmax_k(-w |pred - k|), straight-through to the
+        hard selection when use_switch_ste."""
+        pred_e, cases = e.args
+        E = lambda name, *x: self.ew(name, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))             # noqa: E731
+        if pred_e.etype[0] != "pvar" or pred_e.args[0] not in self.m.variable_ranges:
+            raise RDDLNotImplementedError("switch predicate must be an enum-valued pvariable")
+        objs = self.m.type_to_objects[self.m.variable_ranges[pred_e.args[0]]]
+        table = dict(cases)
+        default = table.get(None)
+        p = self.lower(pred_e, scope, env)
+        vals = []
+        for o in objs:
+            ce = table.get(o, default)
+            if ce is None:
+                raise RDDLNotImplementedError(f"switch is missing case <{o}> and has no default")
+            vals.append(self.lower(ce, scope, env))
+        vals, dt = self.promote(vals, sizes)
+        K = len(objs)
+
+        def hard_select() -> TV:
+            acc = vals[K - 1]
+            for k in range(K - 2, -1, -1):
+                hit = E("EQ", p, C(k)) if p.dtype == "f" else \
+                    E("IEQ", self.at_least_int(p), self.const_tv(np.int32(k), "i"))
+                acc = self.ew("SELECT", [hit, vals[k], acc], sizes, dtype=dt)
+            return acc
+        if not (self.relaxed and self.variants.get("switch") == "softmax"
+                and self.tr.is_fluent(pred_e)):
+            return hard_select()
+        w = TV(self.mparam(e, "switch_weight", self.relax["switch_weight"]), ())
+        pf = self.to_f(self.at_least_int(p), sizes)
+        logits = [E("NEG", E("MUL", w, E("ABS", E("SUB", pf, C(k))))) for k in range(K)]
+        top = logits[0]
+        for lk in logits[1:]:
+            top = E("MAX", top, lk)
+        num = den = None
+        for lk, vk in zip(logits, vals):
+            ek = E("EXP", E("SUB", lk, top))
+            term = E("MUL", ek, self.to_f(vk, sizes))
+            num = term if num is None else E("ADD", num, term)
+            den = ek if den is None else E("ADD", den, ek)
+        soft = E("DIV", num, den)
+        if self.relax["use_switch_ste"]:
+            soft = self.ste(soft, hard_select(), sizes)
+        return soft
+
     # ---- random variables: compiler.py:1701-2241 ; logic.py:1010-1768 --------------------
+    def _gamma_draw(self, shape: TV, a0: Expr, scope, sizes, scale: float = 1.0) -> TV:
+        """standard Gamma(scale * shape) noise; the shape must be known at build time because the
+        draw is supplied from outside the kernel."""
+        if shape.v.const is None:
+            raise RDDLNotImplementedError(
+                "Gamma-family distributions with a fluent shape need an in-loop sampler")
+        full = self._ref_full(a0)
+        allv = tuple(range(len(sizes)))
+        if full:
+            from .graph import apply_map
+            _, mp = self.operand(shape, allv, sizes)
+            conc = shape.v.const[apply_map(mp, self.n_of(allv, sizes))]
+        else:
+            conc = shape.v.const[:1]
+        conc = np.asarray(conc, dtype=np.float32) * np.float32(scale)
+        return self._draw("gamma", a0, scope, sizes,
+                          extra=conc.reshape(tuple(sizes) if full else ()))
+
     def _draw(self, kind: str, first_arg: Expr, scope, sizes, extra=None) -> TV:
         full = self._ref_full(first_arg)
         shape = tuple(sizes) if full else ()
@@ -704,20 +777,44 @@ class Lowerer:
             return E("MUL", scale, E("POW", Ex, E("DIV", C(1.), shape)))
         if name == "Gamma":
             shape, scale = F(tvs[0]), F(tvs[1])
-            if shape.v.const is None:
-                raise RDDLNotImplementedError("Gamma with a fluent shape needs an in-loop sampler")
-            full = self._ref_full(a0)
-            allv = tuple(range(len(sizes)))
-            if full:
-                from .graph import apply_map
-                _, mp = self.operand(shape, allv, sizes)
-                conc = shape.v.const[apply_map(mp, self.n_of(allv, sizes))]
-            else:
-                conc = shape.v.const[:1]
-            G = self._draw("gamma", a0, scope, sizes, extra=np.asarray(conc, dtype=np.float32).reshape(
-                tuple(sizes) if full else ()))
+            G = self._gamma_draw(shape, a0, scope, sizes)
             self.errchk("GAMMA", E("OR", E("LE", shape, C(0.)), E("LE", scale, C(0.))), sizes)
             return E("MUL", scale, G)
+        if name == "ChiSquare":                 # compiler.py:2130-2147: 2 Gamma(df / 2)
+            df = F(tvs[0])
+            G = self._gamma_draw(df, a0, scope, sizes, scale=0.5)
+            self.errchk("CHISQUARE", E("LE", df, C(0.)), sizes)
+            return E("MUL", C(2.), G)
+        if name == "Student":                   # compiler.py:2028-2044: Z sqrt((df/2) / Gamma(df/2))
+            df = F(tvs[0])
+            Z = self._draw("normal", a0, scope, sizes)
+            G = self._gamma_draw(df, a0, scope, sizes, scale=0.5)
+            self.errchk("STUDENT", E("LE", df, C(0.)), sizes)
+            return E("MUL", Z, E("SQRT", E("DIV", E("MUL", C(0.5), df), G)))
+        if name == "Beta":                      # compiler.py:1969-1986: Ga / (Ga + Gb)
+            a, b = F(tvs[0]), F(tvs[1])
+            Ga = self._gamma_draw(a, a0, scope, sizes)
+            Gb = self._gamma_draw(b, a0, scope, sizes)
+            self.errchk("BETA", E("OR", E("LE", a, C(0.)), E("LE", b, C(0.))), sizes)
+            return E("DIV", Ga, E("ADD", Ga, Gb))
+        if name == "Pareto":                    # compiler.py:2007-2026: scale exp(Exp(1) / shape)
+            shape, scale = F(tvs[0]), F(tvs[1])
+            Ex = self._draw("exponential", a0, scope, sizes)
+            self.errchk("PARETO", E("OR", E("LE", shape, C(0.)), E("LE", scale, C(0.))), sizes)
+            return E("MUL", scale, E("EXP", E("DIV", Ex, shape)))
+        if name == "Poisson":
+            return self._poisson(e, F(tvs[0]), a0, scope, sizes)
+        if name == "Binomial":
+            return self._binomial(e, tvs, scope, sizes)
+        if name == "NegativeBinomial":
+            trials, prob = F(tvs[0]), F(tvs[1])
+            fluent = self.tr.is_fluent(e.args[0]) or self.tr.is_fluent(e.args[1])
+            bad = E("OR", E("OR", E("LT", prob, C(0.)), E("GT", prob, C(1.))), E("LE", trials, C(0.)))
+            self.errchk("NEGATIVE_BINOMIAL", bad, sizes)
+            if self.relaxed and fluent and Vv.get("poisson") == "determinized":
+                return E("MUL", E("SUB", E("DIV", C(1.), prob), C(1.)), trials)   # logic.py:1762
+            raise RDDLNotImplementedError(
+                "NegativeBinomial is only available determinised (DeterminizedPoisson)")
         if name in ("Gumbel", "Laplace", "Cauchy"):
             mean, scale = F(tvs[0]), F(tvs[1])
             Gn = self._draw(name.lower(), a0, scope, sizes)
@@ -772,6 +869,76 @@ class Lowerer:
                 return E("ADD", C(1.), self.soft_floor(ratio, w, sizes))
             return E("DIV", C(1.), p)
         raise RDDLNotImplementedError(f"Distribution {name} is not supported.")
+
+    def _poisson(self, e, rate: TV, a0, scope, sizes) -> TV:
+        """Poisson(rate).  Exact programs invert the CDF of one uniform draw, truncated at
+        COUNT_NBINS terms (the reference calls jax.random.poisson, compiler.py:1880-1897, whose
+        bits cannot be reproduced from supplied noise; the law is the same for rates whose mass
+        above COUNT_NBINS is negligible).  Relaxed (ExponentialPoisson, logic.py:1508-1531): the
+        count of exponential inter-arrival times before time 1, each indicator a sigmoid; rates
+        whose CDF at nbins falls below poisson_min_cdf use the normal approximation instead.
+        DeterminizedPoisson returns the rate (logic.py:1733-1741)."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        self.errchk("POISSON", E("LT", rate, C(0.)), sizes)
+        variant = self.variants.get("poisson") if (self.relaxed and self.tr.is_fluent(a0)) else None
+        if variant == "determinized":
+            return rate
+        if variant == "exponential":
+            R = self.relax
+            K = int(R["poisson_nbins"])
+            w = TV(self.mparam(e, "poisson_comparison_weight", R["poisson_comparison_weight"]), ())
+            # largest rate whose CDF at K still reaches min_cdf (the branch is under stop_gradient)
+            from scipy import optimize, stats
+            cut = float(optimize.brentq(
+                lambda r: stats.poisson.cdf(K, r) - float(R["poisson_min_cdf"]), 1e-6, 10.0 * K + 10))
+            cum = cnt = None
+            for _ in range(K):
+                Ex = self._draw("exponential", a0, scope, sizes)
+                dt = E("DIV", Ex, rate)
+                cum = dt if cum is None else E("ADD", cum, dt)
+                ind = E("SIGMOID", E("MUL", w, E("SUB", C(1.), cum)))
+                cnt = ind if cnt is None else E("ADD", cnt, ind)
+            Z = self._draw("normal", a0, scope, sizes)
+            normal = E("ADD", rate, E("MUL", E("SQRT", rate), Z))
+            return self.ew("SELECT", [E("LE", rate, C(cut)), cnt, normal], sizes, dtype="f")
+        if variant is not None:
+            raise RDDLNotImplementedError(f"Poisson relaxation <{variant}> is not built")
+        U = self._draw("uniform", a0, scope, sizes)
+        pk = E("EXP", E("NEG", rate))
+        cdf, cnt = pk, None
+        for k in range(1, COUNT_NBINS + 1):
+            over = self.to_f(self.at_least_int(E("GT", U, cdf)), sizes)
+            cnt = over if cnt is None else E("ADD", cnt, over)
+            pk = E("MUL", pk, E("MUL", rate, C(1.0 / k)))
+            cdf = E("ADD", cdf, pk)
+        return cnt if self.relaxed else self.ew("F2I", [cnt], sizes, "i")
+
+    def _binomial(self, e, tvs, scope, sizes) -> TV:
+        """Binomial(trials, prob).  Exact: the number of successes among the first ``trials`` of
+        COUNT_NBINS supplied uniform draws (compiler.py:1921-1943 calls jax.random.binomial; same
+        law for trials <= COUNT_NBINS).  DeterminizedBinomial: trials * prob (logic.py:1476)."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        F = lambda t: self.to_f(self.at_least_int(t), sizes)   # noqa: E731
+        trials, prob = F(tvs[0]), F(tvs[1])
+        a0 = e.args[0]
+        bad = E("OR", E("OR", E("LT", prob, C(0.)), E("GT", prob, C(1.))), E("LT", trials, C(0.)))
+        self.errchk("BINOMIAL", bad, sizes)
+        fluent = self.tr.is_fluent(e.args[0]) or self.tr.is_fluent(e.args[1])
+        variant = self.variants.get("binomial") if (self.relaxed and fluent) else None
+        if variant == "determinized":
+            return E("MUL", trials, prob)
+        if variant is not None:
+            raise RDDLNotImplementedError(
+                f"Binomial relaxation <{variant}> is not built (use DeterminizedBinomial)")
+        cnt = None
+        for j in range(COUNT_NBINS):
+            U = self._draw("uniform", a0, scope, sizes)
+            hit = E("AND", E("LT", C(float(j)), trials), E("LT", U, prob))
+            hf = self.to_f(self.at_least_int(hit), sizes)
+            cnt = hf if cnt is None else E("ADD", cnt, hf)
+        return cnt if self.relaxed else self.ew("F2I", [cnt], sizes, "i")
 
     def _discrete(self, e, scope, env, sizes, unnorm: bool) -> TV:
         """Discrete / UnnormDiscrete over an enumerated type: exact = categorical sample

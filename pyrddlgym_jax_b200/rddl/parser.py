@@ -373,7 +373,7 @@ class _Parser:
             return Expr(("pvar", val), (val, None))
         if kind in ("enum", "obj"):
             self.next()
-            return Expr(("pvar", val.lstrip("$")), (val.lstrip("$"), None))
+            return Expr(("pvar", val.lstrip("$@")), (val.lstrip("$@"), None))
         if kind != "id":
             self.error("unexpected token in expression")
         # identifiers
@@ -450,7 +450,7 @@ class _Parser:
                     params.append(v2)
                 elif k2 in ("enum", "obj"):
                     self.next()
-                    params.append(v2.lstrip("$"))
+                    params.append(v2.lstrip("$@"))
                 elif k2 == "id" and self.peek(1)[1] in (",", ")"):
                     self.next()
                     params.append(v2)  # object literal or zero-arity pvar; resolved later

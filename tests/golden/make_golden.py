@@ -33,6 +33,8 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("powergen_relaxed", "powergen", 6, 6, True, 0.95, {}),
     ("discrete_exact", "discrete", 6, 5, False, 1.0, {}),
     ("discrete_relaxed", "discrete", 6, 5, True, 1.0, {}),
+    ("distributions_exact", "distributions", 6, 4, False, 1.0, {}),
+    ("distributions_relaxed", "distributions", 6, 4, True, 1.0, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]
@@ -47,8 +49,10 @@ def pack_final(c):
     return out
 
 
-def main():
+def main(only=()):
     for name, key, B, T, relaxed, gamma, ckw in CASES:
+        if only and name not in only:
+            continue
         if relaxed:
             c = gradient_case("emu", key, B, T, gamma=gamma, **ckw)
         else:
@@ -72,4 +76,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))      # optional: names of the cases to (re)generate

@@ -23,6 +23,7 @@ FIXTURES = {
     "marsrover": ("MarsRover_ippc2023", "instance5"),
     "powergen": ("PowerGen_Continuous", "instance1"),
     "discrete": ("Discrete_Toy", "instance1"),
+    "distributions": ("Distributions_Toy", "instance1"),
 }
 
 

@@ -12,7 +12,8 @@ from pyrddlgym_jax_b200.core import logic
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 pytestmark = pytest.mark.gpu
-KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete"]
+KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
+        "distributions"]
 # 'cuda' = generic interpreter kernel, 'jit' = per-program specialised kernel (core/codegen.py)
 BACKENDS = ["cuda", "jit"]
 

@@ -6,7 +6,8 @@ from pyrddlgym_jax_b200.core import logic
 
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
-KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete"]
+KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
+        "distributions"]
 
 
 @pytest.mark.parametrize("key", KEYS)

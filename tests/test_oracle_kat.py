@@ -291,3 +291,87 @@ def test_projection_known_answers():
     np.testing.assert_allclose(float(new["a"].sum()), 1.0, atol=2e-6)
     # only one action may stay above 0.5: the first active one is reset to 0.5
     assert int((new["a"] > 0.5).sum()) <= 1
+
+
+SWITCH_DOMAIN = """
+domain sw {
+    types { obj : object; gear : {@a, @b, @c}; };
+    pvariables {
+        x(obj) : { state-fluent, real, default = 0.0 };
+        g(obj) : { state-fluent, gear, default = @a };
+        u(obj) : { action-fluent, real, default = 0.0 };
+    };
+    cpfs {
+        x'(?o) = switch (g(?o)) { case @a : 1.0 + x(?o), case @c : 5.0 * x(?o), default : -2.0 };
+        g'(?o) = g(?o);
+    };
+    reward = sum_{?o : obj} [ x'(?o) ];
+}
+non-fluents nf { domain = sw; objects { obj : {o1, o2, o3}; }; non-fluents { }; }
+instance inst { domain = sw; non-fluents = nf; init-state { x(o1) = 0.5; x(o2) = 0.25; x(o3) = 2.0; g(o2) = @b; g(o3) = @c; }; max-nondef-actions = pos-inf; horizon = 2; discount = 1.0; }
+"""
+
+
+@pytest.mark.parametrize("ste", [True, False])
+def test_switch_exact_and_softmax(ste):
+    """compiler.py:1661-1684 (take_along_axis over the stacked cases) and logic.py:983-1002
+    (cases weighted by softmax_k(-w |pred - k|), straight-through to the hard case)."""
+    m = load_model(SWITCH_DOMAIN)
+    x0 = np.array([0.5, 0.25, 2.0])
+    cases = np.stack([1.0 + x0, np.full(3, -2.0), 5.0 * x0])          # [K, obj]
+    pred = np.array([0, 1, 2])
+    hard = cases[pred, np.arange(3)]
+    om = OracleModel(m, None)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 3)}, None, 2)
+    np.testing.assert_allclose(out["x"].numpy(), np.stack([hard, hard]), rtol=1e-6)
+    w = 2.0
+    relax = logic.DefaultJaxRDDLCompilerWithGrad(m, switch_weight=w, use_switch_ste=ste).relax_config()
+    om = OracleModel(m, relax)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 3)}, None, 2)
+    logits = -w * np.abs(pred[None, :] - np.arange(3)[:, None])
+    sm = np.exp(logits) / np.exp(logits).sum(0, keepdims=True)
+    soft = (sm * cases).sum(0)
+    np.testing.assert_allclose(out["x"].detach().numpy()[0], hard if ste else soft, rtol=1e-5)
+
+
+def test_count_and_gamma_family_sampler_moments():
+    """The exact samplers fed with supplied noise reproduce the laws the reference draws from
+    (compiler.py:1880-2147): Poisson / Binomial means and variances, and the means of Pareto,
+    Student, ChiSquare and Beta through the fixture's shock term."""
+    from .parity import forward_case
+    B = 6000
+    c = forward_case("emu", "distributions", B, 1, False, seed=7)
+    fin = c["final"]
+    level0 = np.array([0.2, 1.0, 1.8])
+    lam = 0.5 + level0 ** 2
+    q = fin["queue"].numpy().astype(np.float64)
+    np.testing.assert_allclose(q.mean(0), lam, rtol=0.06)
+    np.testing.assert_allclose(q.var(0), lam, rtol=0.10)
+    p = 0.25 + 0.5 * np.array([0.3, 0.6, 0.3])
+    s = fin["served"].numpy().astype(np.float64)
+    assert s.min() >= 0 and s.max() <= 5
+    np.testing.assert_allclose(s.mean(0), 5 * p, rtol=0.04)
+    np.testing.assert_allclose(s.var(0), 5 * p * (1 - p), rtol=0.10)
+    # the emulated program and the oracle agree draw for draw
+    np.testing.assert_array_equal(q, c["ref"]["final"]["queue"].numpy())
+    np.testing.assert_array_equal(s, c["ref"]["final"]["served"].numpy())
+
+
+def test_gamma_family_closed_forms():
+    """ChiSquare = 2 Gamma(df/2), Student = Z sqrt((df/2)/Gamma(df/2)), Beta = Ga/(Ga+Gb),
+    Pareto = scale exp(Exp(1)/shape): each evaluated on hand-written noise."""
+    Z = torch.tensor(U * 2 - 1, dtype=torch.float32)
+    G = torch.tensor(U * 3 + 0.2, dtype=torch.float32)
+    G2 = torch.tensor(Y ** 2 + 0.1, dtype=torch.float32)
+    v, _, _ = evaluate("ChiSquare(3.0)", exact=True, noise=[G[:, 0]])     # scalar draw per rollout
+    np.testing.assert_allclose(v, np.repeat(2 * G[:, :1].numpy(), 4, 1), rtol=1e-6)
+    v, _, _ = evaluate("Student(C(?o) * 8.0)", exact=True, noise=[Z, G])
+    df = np.array([4.0, 12.0, 4.0, 4.0])
+    np.testing.assert_allclose(v, Z.numpy() * np.sqrt(0.5 * df / G.numpy()), rtol=1e-5)
+    v, _, _ = evaluate("Beta(C(?o), 2.0)", exact=True, noise=[G, G2])
+    np.testing.assert_allclose(v, G.numpy() / (G.numpy() + G2.numpy()), rtol=1e-6)
+    v, _, _ = evaluate("Pareto(C(?o) * 4.0, x(?o) + 3.0)", exact=True, noise=[G])
+    np.testing.assert_allclose(v, (X + 3.0) * np.exp(G.numpy() / np.array([2.0, 6.0, 2.0, 2.0])),
+                               rtol=2e-6)
