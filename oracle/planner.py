@@ -21,8 +21,22 @@ from .model_eval import OracleModel, REAL, INT, safe_log
 
 
 # ---- straight-line plan ----------------------------------------------------------------
+def bound_action(lo, hi, param: torch.Tensor) -> torch.Tensor:
+    """_jax_bound_action, planner.py:620-628."""
+    lo = torch.as_tensor(np.asarray(lo, np.float32))
+    hi = torch.as_tensor(np.asarray(hi, np.float32))
+    fl, fh = torch.isfinite(lo), torch.isfinite(hi)
+    lo0, hi0 = torch.where(fl, lo, torch.zeros(())), torch.where(fh, hi, torch.zeros(()))
+    sp = torch.nn.functional.softplus
+    both = lo0 + (hi0 - lo0) * torch.sigmoid(param)
+    out = torch.where(fl & fh, both, torch.where(fl, lo0 + sp(param),
+                                                 torch.where(fh, hi0 - sp(-param), param)))
+    return out
+
+
 def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
-                      sigmoid_weight: Dict[str, float] | float = 1.0):
+                      sigmoid_weight: Dict[str, float] | float = 1.0, wrap_non_bool=False,
+                      bounds=None):
     """planner.py:786-838 (deterministic plan: stochastic=False)."""
     actions = {}
     for name in model.action_fluents:
@@ -30,13 +44,16 @@ def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmo
         if model.variable_ranges[name] == "bool":
             w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
             a = torch.sigmoid(w * p) if wrap_sigmoid else p            # planner.py:741-745
+        elif wrap_non_bool:
+            a = bound_action(*bounds[name], p)                         # planner.py:755-762
         else:
             a = p
         actions[name] = a.unsqueeze(0)          # same action for every rollout
     return actions
 
 
-def slp_test_actions(model, params: Dict[str, torch.Tensor], t: int, bounds, wrap_sigmoid=True):
+def slp_test_actions(model, params: Dict[str, torch.Tensor], t: int, bounds, wrap_sigmoid=True,
+                     wrap_non_bool=False):
     """planner.py:842-868."""
     actions = {}
     thr = 0.0 if wrap_sigmoid else 0.5
@@ -49,6 +66,8 @@ def slp_test_actions(model, params: Dict[str, torch.Tensor], t: int, bounds, wra
             lo, hi = bounds[name]
             lo = torch.as_tensor(np.asarray(lo, np.float32))
             hi = torch.as_tensor(np.asarray(hi, np.float32))
+            if wrap_non_bool:
+                p = bound_action(lo, hi, p)
             a = torch.minimum(torch.maximum(p, lo), hi)
             if prange != "real":
                 a = torch.round(a).to(INT)

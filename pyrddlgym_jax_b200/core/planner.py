@@ -73,9 +73,9 @@ class JaxStraightLinePlan(JaxPlan):
         self._sigma_range = sigma_range
         self._sigma_entropy_grad = sigma_entropy_grad
         self._action_noise_dist = action_noise_dist
-        if wrap_non_bool or wrap_softmax or stochastic:
+        if wrap_softmax or stochastic:
             raise NotImplementedError(
-                "wrap_non_bool / wrap_softmax / stochastic straight-line plans are not built yet")
+                "wrap_softmax / stochastic straight-line plans are not built yet")
 
     def __str__(self) -> str:
         return (f"[INFO] policy hyper-parameters:\n"
@@ -107,6 +107,7 @@ class JaxStraightLinePlan(JaxPlan):
                                 np.broadcast_to(np.asarray(hi, np.float32), shape).copy())
         self.bounds = bounds
         self.spec = PlanSpec(kind="slp", wrap_sigmoid=self._wrap_sigmoid,
+                             wrap_non_bool=self._wrap_non_bool,
                              sigmoid_weight=self._sigmoid_weight,
                              bounds={k: v for k, v in bounds.items() if v[0] is not None})
         self.noop = {var: bool(np.ravel(v)[0]) if rddl.variable_ranges[var] == "bool" else v
@@ -124,7 +125,7 @@ class JaxStraightLinePlan(JaxPlan):
                 else:
                     l, h = p, 1 - p
                 lo[:, off:off + n], hi[:, off:off + n] = l, h
-            else:
+            elif not self._wrap_non_bool:           # planner.py:898-899: wrapped means stay free
                 lo[:, off:off + n] = bounds[name][0].reshape(-1)
                 hi[:, off:off + n] = bounds[name][1].reshape(-1)
         self.box = (lo, hi)
@@ -174,6 +175,14 @@ class JaxStraightLinePlan(JaxPlan):
             if prange == "bool":
                 acts[name] = p > self.bool_threshold
             else:
+                if self._wrap_non_bool:                 # _jax_bound_action, planner.py:620-628
+                    lo, hi = self.bounds[name]
+                    fl, fh = np.isfinite(lo), np.isfinite(hi)
+                    lo0, hi0 = np.where(fl, lo, 0.0), np.where(fh, hi, 0.0)
+                    sp = lambda x: np.logaddexp(0.0, x)      # noqa: E731
+                    p = np.where(fl & fh, lo0 + (hi0 - lo0) / (1.0 + np.exp(-p)),
+                                 np.where(fl, lo0 + sp(p), np.where(fh, hi0 - sp(-p), p))
+                                 ).astype(np.float32)
                 a = np.minimum(np.maximum(p, self.bounds[name][0]), self.bounds[name][1])
                 if prange != "real":
                     a = np.round(a).astype(np.int32)

@@ -167,6 +167,34 @@ def state_layout(model, relaxed: bool) -> Tuple[Dict[str, Tuple[int, int, str]],
     return layout, off
 
 
+def _bound_action(g, p: V, lo: np.ndarray, hi: np.ndarray, n: int) -> V:
+    """_jax_bound_action (planner.py:620-628): sigmoid wrap for two-sided boxes, softplus wraps for
+    one-sided ones, identity when unbounded; the branch of every element is known at build time."""
+    lo = np.asarray(lo, np.float32).ravel()
+    hi = np.asarray(hi, np.float32).ravel()
+    fl, fh = np.isfinite(lo), np.isfinite(hi)
+    lo0, hi0 = np.where(fl, lo, 0).astype(np.float32), np.where(fh, hi, 0).astype(np.float32)
+    C = lambda a: g.const(np.asarray(a, np.float32))       # noqa: E731
+    O = lambda op, *a: g.op(op, [(x, None) for x in a], n)  # noqa: E731
+
+    def softplus(x):            # log1p(exp(-|x|)) + relu(x)
+        return O("ADD", O("LOG1P", O("EXP", O("NEG", O("ABS", x)))), O("RELU", x))
+    out = p
+    if np.any(~fl & fh):
+        f_hi = O("SUB", C(hi0), softplus(O("NEG", p)))
+        out = g.op("SELECT", [(g.const((~fl & fh).astype(np.int32), "b"), None), (f_hi, None),
+                              (out, None)], n, "f")
+    if np.any(fl & ~fh):
+        f_lo = O("ADD", C(lo0), softplus(p))
+        out = g.op("SELECT", [(g.const((fl & ~fh).astype(np.int32), "b"), None), (f_lo, None),
+                              (out, None)], n, "f")
+    if np.any(fl & fh):
+        f_both = O("ADD", C(lo0), O("MUL", C(hi0 - lo0), O("SIGMOID", p)))
+        out = g.op("SELECT", [(g.const((fl & fh).astype(np.int32), "b"), None), (f_both, None),
+                              (out, None)], n, "f")
+    return out
+
+
 def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dict[str, V], Dict[str, V]]:
     """Action values fed to the transition + the parameter leaves they come from.
 
@@ -192,6 +220,8 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
                            default=float(spec.sigmoid_weight), slot=len(low.sg.mparams))
                 low.sg.mparams.append((("policy", name), float(spec.sigmoid_weight), w))
                 a = g.op("SIGMOID", [(g.op("MUL", [(w, "b"), (p, None)], n), None)], n)
+            elif not is_bool and spec.wrap_non_bool:  # planner.py:755-762
+                a = _bound_action(g, p, *spec.bounds[name], n)
             else:
                 a = p
             if not low.relaxed and a.dtype != low.dtype_of_range(prange):
@@ -203,6 +233,8 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
                 a = g.op("GT", [(p, None), (g.const(np.float32(thr)), "b")], n)
             else:                                     # planner.py:860-865
                 lo, hi = spec.bounds[name]
+                if spec.wrap_non_bool:                # planner.py:862
+                    p = _bound_action(g, p, lo, hi, n)
                 lo = g.const(np.asarray(lo, dtype=np.float32).ravel())
                 hi = g.const(np.asarray(hi, dtype=np.float32).ravel())
                 a = g.op("MIN", [(g.op("MAX", [(p, None), (lo, None)], n), None), (hi, None)], n)

@@ -94,14 +94,14 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
 
 
 def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None,
-                 param_scale=0.5, given=None, **ckw):
+                 param_scale=0.5, given=None, wrap_non_bool=False, **ckw):
     """Run program + oracle on the same inputs; returns everything a test wants to compare."""
     m = fixture_model(key)
     if relaxed:
         comp = (compiler_cls or logic.DefaultJaxRDDLCompilerWithGrad)(m, **ckw)
     else:
         comp = JaxRDDLCompiler(m)
-    spec = PlanSpec(bounds=m.bounds)
+    spec = PlanSpec(bounds=m.bounds, wrap_non_bool=wrap_non_bool)
     builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
     # the adjoint program is assembled first: it decides what the forward program tapes for it
     bwd = builder.backward(gamma=gamma) if relaxed else None
@@ -117,10 +117,12 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     om = OracleModel(m, comp.relax_config())
     if relaxed:
         P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-        pol = lambda t, fls: OP.slp_train_actions(m, P, t)      # noqa: E731
+        pol = lambda t, fls: OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool,   # noqa: E731
+                                                  bounds=m.bounds)
     else:
         P = params
-        pol = lambda t, fls: OP.slp_test_actions(m, P, t, m.bounds)   # noqa: E731
+        pol = lambda t, fls: OP.slp_test_actions(m, P, t, m.bounds,    # noqa: E731
+                                                 wrap_non_bool=wrap_non_bool)
     noise_steps = [noise_as_list(fwd.noise_layout, noise, t, B) for t in range(T)]
     ref = OP.rollout(om, pol, B, T, noise_steps)
     spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
@@ -132,9 +134,9 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
 
 
 def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, given=None,
-                  **ckw):
+                  wrap_non_bool=False, **ckw):
     c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
-                     param_scale=param_scale, given=given, **ckw)
+                     param_scale=param_scale, given=given, wrap_non_bool=wrap_non_bool, **ckw)
     m = c["model"]
     bwd = c["bwd"]
     gret = torch.full((B,), -1.0 / B)

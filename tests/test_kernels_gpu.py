@@ -86,6 +86,16 @@ def test_variants_cuda(cuda_device, backend):
     check_gradient(c)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("key", ["reservoir", "quadcopter"])
+def test_wrap_non_bool_cuda(cuda_device, backend, key):
+    """Box-wrapped real actions (planner.py:620-628) in the train and the test policy."""
+    check_forward(forward_case(backend, key, B=21, T=5, relaxed=False, wrap_non_bool=True))
+    c = gradient_case(backend, key, B=21, T=5, wrap_non_bool=True)
+    check_forward(c)
+    check_gradient(c)
+
+
 def test_deterministic_cuda(cuda_device):
     """Two runs give bit-identical gradients (fixed reduction order, no float atomics)."""
     a = gradient_case("jit", "wildfire", B=300, T=5)["grad"]

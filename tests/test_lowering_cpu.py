@@ -44,3 +44,13 @@ def test_relaxation_variants_emulated(cls, kw):
         c = gradient_case("emu", key, B=7, T=4, compiler_cls=cls, **kw)
         check_forward(c)
         check_gradient(c)
+
+
+@pytest.mark.parametrize("key", ["reservoir", "quadcopter", "powergen"])
+def test_wrap_non_bool_emulated(key):
+    """Box-wrapped real actions (_jax_bound_action, planner.py:620-628, 755-762, 862): sigmoid
+    for two-sided boxes, softplus for one-sided ones, in the train and the test policy."""
+    check_forward(forward_case("emu", key, B=9, T=5, relaxed=False, wrap_non_bool=True))
+    c = gradient_case("emu", key, B=9, T=5, wrap_non_bool=True)
+    check_forward(c)
+    check_gradient(c)
