@@ -34,21 +34,66 @@ def bound_action(lo, hi, param: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def slp_policy_noise_spec(model, wrap_sigmoid=True, action_noise="normal"):
+    """Draw sites of a stochastic straight-line plan, in the order planner.py:811-833 splits
+    its key: (kind, shape) per action fluent that receives noise."""
+    spec = []
+    for name in model.action_fluents:
+        shape = tuple(model.variable_shape(name))
+        if model.variable_ranges[name] == "bool":
+            if wrap_sigmoid:
+                spec.append(("logistic", shape))
+        else:
+            spec.append((action_noise, shape))
+    return spec
+
+
+def slp_entropy(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
+                sigmoid_weight=1.0, sigma_range=(1e-5, 1e3), sigma_entropy_grad=False):
+    """Entropy term of one step of a stochastic plan (planner.py:812-830)."""
+    from oracle.model_eval import safe_log
+    ent = torch.zeros(())
+    for name in model.action_fluents:
+        p = params[name][t]
+        if model.variable_ranges[name] == "bool":
+            if wrap_sigmoid:
+                w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
+                prob = torch.sigmoid(w * p)
+                ent = ent - torch.sum(prob * safe_log(prob) + (1. - prob) * safe_log(1. - prob))
+        else:
+            ls = torch.clamp(params[name + "/log_sigma"][t], float(np.log(sigma_range[0])),
+                             float(np.log(sigma_range[1])))
+            ent = ent + torch.sum(ls if sigma_entropy_grad else ls.detach())
+    return ent
+
+
 def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
                       sigmoid_weight: Dict[str, float] | float = 1.0, wrap_non_bool=False,
-                      bounds=None):
-    """planner.py:786-838 (deterministic plan: stochastic=False)."""
+                      bounds=None, stochastic=False, sigma_range=(1e-5, 1e3), pnoise=None):
+    """planner.py:786-838.  ``pnoise``: this step's policy draws [B, *shape] in the order of
+    slp_policy_noise_spec (stochastic plans only)."""
     actions = {}
+    k = 0
     for name in model.action_fluents:
         p = params[name][t]
         if model.variable_ranges[name] == "bool":
             w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
+            if stochastic and wrap_sigmoid:                            # planner.py:811-817
+                p = p.reshape(-1).unsqueeze(0) + pnoise[k].reshape(pnoise[k].shape[0], -1)
+                k += 1
             a = torch.sigmoid(w * p) if wrap_sigmoid else p            # planner.py:741-745
-        elif wrap_non_bool:
-            a = bound_action(*bounds[name], p)                         # planner.py:755-762
         else:
             a = p
-        actions[name] = a.unsqueeze(0)          # same action for every rollout
+            if stochastic:                                             # planner.py:825-833
+                ls = torch.clamp(params[name + "/log_sigma"][t], float(np.log(sigma_range[0])),
+                                 float(np.log(sigma_range[1])))
+                z = pnoise[k].reshape(pnoise[k].shape[0], -1)
+                k += 1
+                a = a.reshape(-1).unsqueeze(0) + torch.exp(ls).reshape(-1).unsqueeze(0) * z
+            if wrap_non_bool:
+                a = bound_action(np.asarray(bounds[name][0]).reshape(-1),
+                                 np.asarray(bounds[name][1]).reshape(-1), a)   # planner.py:755-762
+        actions[name] = a if a.dim() > 1 and stochastic else a.unsqueeze(0)
     return actions
 
 
@@ -91,10 +136,16 @@ def rollout(om: OracleModel, policy: Callable[[int, Dict[str, torch.Tensor]], Di
     spec = None
     for t in range(T):
         states.append({s: fls[s] for s in om.model.state_fluents})
-        actions = expand_actions(policy(t, fls), B)
+        n_pol = getattr(policy, "n_noise", 0)      # stochastic plans draw before the model does
+        step_noise = noise_steps[t] if noise_steps else None
+        if n_pol:
+            actions = expand_actions(policy(t, fls, step_noise[:n_pol]), B)
+            step_noise = step_noise[n_pol:]
+        else:
+            actions = expand_actions(policy(t, fls), B)
         if om.relaxed:
             actions = {k: v.to(REAL) for k, v in actions.items()}
-        fls, r, e, spec = om.step(fls, nfls, actions, noise_steps[t] if noise_steps else None, B)
+        fls, r, e, spec = om.step(fls, nfls, actions, step_noise, B)
         rewards.append(r)
         errs.append(e)
         for f in log_fluents:

@@ -73,9 +73,11 @@ class JaxStraightLinePlan(JaxPlan):
         self._sigma_range = sigma_range
         self._sigma_entropy_grad = sigma_entropy_grad
         self._action_noise_dist = action_noise_dist
-        if wrap_softmax or stochastic:
-            raise NotImplementedError(
-                "wrap_softmax / stochastic straight-line plans are not built yet")
+        if wrap_softmax:
+            raise NotImplementedError("softmax-pooled boolean plans (wrap_softmax) are not built yet")
+        if action_noise_dist not in ("normal", "logistic", "laplace", "gumbel", "cauchy", "uniform"):
+            raise NotImplementedError(f"action_noise_dist <{action_noise_dist}>: name one of the "
+                                      "noise kinds the engine draws (e.g. 'normal')")
 
     def __str__(self) -> str:
         return (f"[INFO] policy hyper-parameters:\n"
@@ -90,7 +92,15 @@ class JaxStraightLinePlan(JaxPlan):
         rddl = compiled.rddl
         self.rddl = rddl
         self.horizon = horizon
-        self.layout, self.A = action_layout(rddl)
+        self.layout, self.A_act = action_layout(rddl)
+        self.A = self.A_act
+        # stochastic plans: one log_sigma block per non-boolean fluent after the action rows
+        self.sigma_layout: Dict[str, Tuple[int, int]] = {}
+        if self._stochastic:
+            for name, (off, n, prange) in self.layout.items():
+                if prange != "bool":
+                    self.sigma_layout[name] = (self.A, n)
+                    self.A += n
         bounds = {}
         for name, (off, n, prange) in self.layout.items():      # get_action_info, planner.py:423-472
             if prange == "bool":
@@ -108,6 +118,8 @@ class JaxStraightLinePlan(JaxPlan):
         self.bounds = bounds
         self.spec = PlanSpec(kind="slp", wrap_sigmoid=self._wrap_sigmoid,
                              wrap_non_bool=self._wrap_non_bool,
+                             stochastic=self._stochastic, sigma_range=tuple(self._sigma_range),
+                             action_noise=self._action_noise_dist,
                              sigmoid_weight=self._sigmoid_weight,
                              bounds={k: v for k, v in bounds.items() if v[0] is not None})
         self.noop = {var: bool(np.ravel(v)[0]) if rddl.variable_ranges[var] == "bool" else v
@@ -128,6 +140,9 @@ class JaxStraightLinePlan(JaxPlan):
             elif not self._wrap_non_bool:           # planner.py:898-899: wrapped means stay free
                 lo[:, off:off + n] = bounds[name][0].reshape(-1)
                 hi[:, off:off + n] = bounds[name][1].reshape(-1)
+        for name, (off, n) in self.sigma_layout.items():     # planner.py:900-902
+            lo[:, off:off + n] = np.log(self._sigma_range[0])
+            hi[:, off:off + n] = np.log(self._sigma_range[1])
         self.box = (lo, hi)
         n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
         # concurrency projection (planner.py:914-959): sort-based or SOGBOFA, per time step
@@ -145,6 +160,9 @@ class JaxStraightLinePlan(JaxPlan):
             if prange == "bool":
                 p = p + self.bool_threshold
             out[:, off:off + n] = p
+            if name in self.sigma_layout:                    # planner.py:990-993
+                so, sn = self.sigma_layout[name]
+                out[:, so:so + sn] = self._initializer_base((self.horizon, n), generator)
         lo, hi = self.box
         return torch.minimum(torch.maximum(out, torch.from_numpy(lo)), torch.from_numpy(hi))
 
@@ -156,8 +174,43 @@ class JaxStraightLinePlan(JaxPlan):
             if prange == "bool":
                 tree["bool"][name] = {"logit": v}
             else:
-                tree["real"][name] = {"mu": v, "log_sigma": None}
+                ls = None
+                if name in self.sigma_layout:
+                    so, sn = self.sigma_layout[name]
+                    ls = flat[..., so:so + sn].reshape(*flat.shape[:-1],
+                                                       *self.rddl.variable_shape(name))
+                tree["real"][name] = {"mu": v, "log_sigma": ls}
         return tree
+
+    def entropy_terms(self, params: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Entropy of a stochastic plan summed over the horizon, and its gradient w.r.t. the
+        parameters [T, A] (planner.py:812-830): Bernoulli entropy of sigmoid(w logit) for wrapped
+        booleans (safe_log, whose tangent is 1 / (x + 1e-12), compiler.py:65-75), sum of the
+        clipped log_sigma for the others -- differentiated only when sigma_entropy_grad."""
+        H = params.new_zeros(())
+        dH = torch.zeros_like(params)
+        eps = 1e-12
+        for name, (off, n, prange) in self.layout.items():
+            if prange == "bool":
+                if not self._wrap_sigmoid:
+                    continue
+                w = float(self._sigmoid_weight)
+                pr = torch.sigmoid(w * params[:, off:off + n])
+                q = 1.0 - pr
+                lp = torch.where(pr > 0, torch.log(pr.clamp_min(1e-45)), torch.full_like(pr, -np.inf))
+                lq = torch.where(q > 0, torch.log(q.clamp_min(1e-45)), torch.full_like(q, -np.inf))
+                H = H - torch.sum(torch.nan_to_num(pr * lp) + torch.nan_to_num(q * lq))
+                df = torch.nan_to_num(lp, neginf=0.0) + pr / (pr + eps) \
+                    - torch.nan_to_num(lq, neginf=0.0) - q / (q + eps)
+                dH[:, off:off + n] = -df * w * pr * q
+            elif name in self.sigma_layout:
+                so, sn = self.sigma_layout[name]
+                lo, hi = float(np.log(self._sigma_range[0])), float(np.log(self._sigma_range[1]))
+                ls = params[:, so:so + sn]
+                H = H + torch.sum(ls.clamp(lo, hi))
+                if self._sigma_entropy_grad:
+                    dH[:, so:so + sn] = ((ls >= lo) & (ls <= hi)).to(params.dtype)
+        return H, dH
 
     def pytree_to_params(self, tree: Dict[str, Any]) -> torch.Tensor:
         out = torch.zeros(self.horizon, self.A)
@@ -165,6 +218,11 @@ class JaxStraightLinePlan(JaxPlan):
             leaf = tree["bool"][name]["logit"] if prange == "bool" else tree["real"][name]["mu"]
             out[:, off:off + n] = torch.as_tensor(np.asarray(leaf), dtype=torch.float32
                                                   ).reshape(-1, n)[-self.horizon:]
+            if name in self.sigma_layout and tree["real"][name].get("log_sigma") is not None:
+                so, sn = self.sigma_layout[name]
+                out[:, so:so + sn] = torch.as_tensor(
+                    np.asarray(tree["real"][name]["log_sigma"]), dtype=torch.float32
+                ).reshape(-1, sn)[-self.horizon:]
         return out
 
     def test_actions(self, flat_row: np.ndarray) -> Dict[str, np.ndarray]:
@@ -481,6 +539,7 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
+        self.ent_coeff = torch.full((1,), float(self.start_entropy_coeff), device=self.device)
         if self.use_pgpe:
             self._pg_reward, self._pg_returns = z(T * Be), z(Be)
             self._pg_err, self._pg_final = z(T * Be, dt=torch.int32), z(te.S * Be)
@@ -563,6 +622,12 @@ class JaxBackpropPlanner:
             engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
         if self.world_size > 1:      # the one exchange step of the path
             parallel.allreduce_gradient(self.grad[p])
+        if not self.is_drp and getattr(self.plan, "_stochastic", False):
+            # entropy regulariser of a stochastic plan (planner.py:2812-2813): the same for every
+            # rollout, so value and gradient come from the parameters alone
+            H, dH = self.plan.entropy_terms(params.view(T, A))
+            loss_out.sub_(self.ent_coeff * H)
+            self.grad[p].view(T, A).sub_(self.ent_coeff * dH)
 
     def _opt_kernels(self, p: int):
         """optax update + apply_updates + projection (planner.py:2885-2899) from the gradient the
@@ -842,6 +907,9 @@ class JaxBackpropPlanner:
                     self.redraw_noise()
                 if self.drp is not None:      # planner.py:2775-2778, 2812-2813
                     self.drp.ent_coeff.fill_(self.start_entropy_coeff * (
+                        self.end_entropy_coeff / self.start_entropy_coeff) ** (progress_percent / 100.))
+                elif getattr(self.plan, "_stochastic", False):      # planner.py:2775-2778
+                    self.ent_coeff.fill_(self.start_entropy_coeff * (
                         self.end_entropy_coeff / self.start_entropy_coeff) ** (progress_percent / 100.))
                 self.iterate()
                 train_loss, test_loss, zero_grads = self.read_stats()       # the host sync

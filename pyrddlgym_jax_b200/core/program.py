@@ -145,6 +145,24 @@ class PlanSpec:
     wrap_non_bool: bool = False
     sigmoid_weight: float = 1.0
     bounds: Optional[Dict[str, Tuple[np.ndarray, np.ndarray]]] = None
+    # stochastic straight-line plan (planner.py:811-834): logistic noise on the boolean logits,
+    # mu + exp(clip(log_sigma)) * noise for the others; the log_sigma rows follow the action rows
+    stochastic: bool = False
+    sigma_range: Tuple[float, float] = (1e-5, 1e3)
+    action_noise: str = "normal"
+
+
+def param_layout(model, spec: "PlanSpec") -> Tuple[Dict[str, Tuple[int, int, str]], int]:
+    """Row layout of the plan parameters: the action layout, followed (stochastic plans) by one
+    log_sigma block per non-boolean action fluent, keyed '<fluent>/log_sigma'."""
+    layout, off = action_layout(model)
+    layout = dict(layout)
+    if spec.kind == "slp" and spec.stochastic:
+        for name, (_, n, prange) in list(layout.items()):
+            if prange != "bool":
+                layout[name + "/log_sigma"] = (off, n, "real")
+                off += n
+    return layout, off
 
 
 def action_layout(model) -> Tuple[Dict[str, Tuple[int, int, str]], int]:
@@ -203,7 +221,15 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
     """
     m, g = low.m, low.g
     layout, _ = action_layout(m)
+    playout, _ = param_layout(m, spec)
+    stoch = spec.kind == "slp" and spec.stochastic and train
     actions, leaves = {}, {}
+
+    def policy_noise(kind: str, name: str, n: int) -> V:     # drawn before the model's own noise
+        from .lowering import NoiseSlot
+        v = g.leaf("noise", n, "f", slot=len(low.sg.noise))
+        low.sg.noise.append(NoiseSlot(kind, tuple(m.variable_shape(name)), n, v, None))
+        return v
     for name, (off, n, prange) in layout.items():
         if spec.kind == "external":
             dt = low.dtype_of_range(prange)
@@ -219,9 +245,25 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
                 w = g.leaf("mparam", 1, "f", uniform=True, key=("policy", name),
                            default=float(spec.sigmoid_weight), slot=len(low.sg.mparams))
                 low.sg.mparams.append((("policy", name), float(spec.sigmoid_weight), w))
-                a = g.op("SIGMOID", [(g.op("MUL", [(w, "b"), (p, None)], n), None)], n)
-            elif not is_bool and spec.wrap_non_bool:  # planner.py:755-762
-                a = _bound_action(g, p, *spec.bounds[name], n)
+                logit = p
+                if stoch:                             # planner.py:811-819
+                    logit = g.op("ADD", [(p, None), (policy_noise("logistic", name, n), None)], n)
+                a = g.op("SIGMOID", [(g.op("MUL", [(w, "b"), (logit, None)], n), None)], n)
+            elif not is_bool:
+                a = p
+                if stoch:                             # planner.py:825-834
+                    loff = playout[name + "/log_sigma"][0]
+                    ls = g.leaf("param_in", n, "f", uniform=True, off=loff,
+                                fluent=name + "/log_sigma")
+                    leaves[name + "/log_sigma"] = ls
+                    lo_s, hi_s = (np.float32(np.log(x)) for x in spec.sigma_range)
+                    ls = g.op("MIN", [(g.op("MAX", [(ls, None), (g.const(lo_s), "b")], n), None),
+                                      (g.const(hi_s), "b")], n)
+                    z = policy_noise(spec.action_noise, name, n)
+                    a = g.op("ADD", [(p, None), (g.op("MUL", [(g.op("EXP", [(ls, None)], n), None),
+                                                              (z, None)], n), None)], n)
+                if spec.wrap_non_bool:                # planner.py:755-762
+                    a = _bound_action(g, a, *spec.bounds[name], n)
             else:
                 a = p
             if not low.relaxed and a.dtype != low.dtype_of_range(prange):
@@ -268,7 +310,9 @@ class ProgramBuilder:
         self.actions, self.param_leaves = build_policy_actions(self.low, spec, train_policy)
         self.sg: StepGraph = self.low.build(self.actions)
         self.slayout, self.S = state_layout(model, relax is not None)
-        self.alayout, self.A = action_layout(model)
+        # straight-line plans: A is the width of one parameter row (actions + log_sigma blocks)
+        self.alayout, self.A = param_layout(model, spec) if spec.kind == "slp" \
+            else action_layout(model)
         off = 0
         for slot in self.sg.noise:
             slot.offset = off

@@ -43,7 +43,10 @@ def init_params(model, T: int, seed: int = 42, scale: float = 0.01) -> Dict[str,
 
 
 def pack_params(model, params: Dict[str, torch.Tensor]) -> torch.Tensor:
-    layout, A = action_layout(model)
+    """-> [T, A] rows; stochastic plans carry '<fluent>/log_sigma' entries after the actions."""
+    from pyrddlgym_jax_b200.core.program import param_layout
+    stochastic = any(k.endswith("/log_sigma") for k in params)
+    layout, A = param_layout(model, PlanSpec(stochastic=stochastic))
     T = next(iter(params.values())).shape[0]
     flat = torch.zeros(T, A)
     for name, (off, n, _) in layout.items():

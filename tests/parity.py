@@ -94,19 +94,25 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
 
 
 def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None,
-                 param_scale=0.5, given=None, wrap_non_bool=False, **ckw):
+                 param_scale=0.5, given=None, wrap_non_bool=False, stochastic=False, **ckw):
     """Run program + oracle on the same inputs; returns everything a test wants to compare."""
     m = fixture_model(key)
     if relaxed:
         comp = (compiler_cls or logic.DefaultJaxRDDLCompilerWithGrad)(m, **ckw)
     else:
         comp = JaxRDDLCompiler(m)
-    spec = PlanSpec(bounds=m.bounds, wrap_non_bool=wrap_non_bool)
+    spec = PlanSpec(bounds=m.bounds, wrap_non_bool=wrap_non_bool, stochastic=stochastic)
     builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
     # the adjoint program is assembled first: it decides what the forward program tapes for it
     bwd = builder.backward(gamma=gamma) if relaxed else None
     fwd = builder.forward(write_tape=relaxed, gamma=gamma)
     params = make_params(m, key, T, scale=param_scale)
+    if stochastic:      # log_sigma rows follow the action rows (core/program.py: param_layout)
+        gls = torch.Generator().manual_seed(seed + 1000)
+        for name in m.action_fluents:
+            if m.variable_ranges[name] != "bool":
+                params[name + "/log_sigma"] = torch.randn(
+                    T, m.variable_size(name), generator=gls) * 0.3 - 1.5
     noise = draw_noise(fwd.noise_layout, T, B, torch.Generator().manual_seed(seed))
     if given is not None:        # committed golden inputs (tests/golden/*.npz)
         params = {k: torch.from_numpy(np.array(given["param_" + k])) for k in params}
@@ -117,8 +123,14 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     om = OracleModel(m, comp.relax_config())
     if relaxed:
         P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-        pol = lambda t, fls: OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool,   # noqa: E731
-                                                  bounds=m.bounds)
+        if stochastic:
+            def pol(t, fls, pnoise):
+                return OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool, bounds=m.bounds,
+                                            stochastic=True, pnoise=pnoise)
+            pol.n_noise = len(OP.slp_policy_noise_spec(m))
+        else:
+            pol = lambda t, fls: OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool,   # noqa: E731
+                                                      bounds=m.bounds)
     else:
         P = params
         pol = lambda t, fls: OP.slp_test_actions(m, P, t, m.bounds,    # noqa: E731
@@ -126,6 +138,8 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     noise_steps = [noise_as_list(fwd.noise_layout, noise, t, B) for t in range(T)]
     ref = OP.rollout(om, pol, B, T, noise_steps)
     spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
+    if relaxed and stochastic:
+        spec_or = OP.slp_policy_noise_spec(m) + spec_or
     spec_pr = [(k, tuple(s)) for k, s, _, _, _ in fwd.noise_layout]
     assert T == 0 or spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
     final = unpack_fluent_major(fwd.state_layout, torch.from_numpy(got["final"].copy()), B)
@@ -134,9 +148,10 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
 
 
 def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, given=None,
-                  wrap_non_bool=False, **ckw):
+                  wrap_non_bool=False, stochastic=False, **ckw):
     c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
-                     param_scale=param_scale, given=given, wrap_non_bool=wrap_non_bool, **ckw)
+                     param_scale=param_scale, given=given, wrap_non_bool=wrap_non_bool,
+                     stochastic=stochastic, **ckw)
     m = c["model"]
     bwd = c["bwd"]
     gret = torch.full((B,), -1.0 / B)

@@ -54,3 +54,17 @@ def test_wrap_non_bool_emulated(key):
     c = gradient_case("emu", key, B=9, T=5, wrap_non_bool=True)
     check_forward(c)
     check_gradient(c)
+
+
+@pytest.mark.parametrize("key,wrap", [("reservoir", False), ("wildfire", False), ("quadcopter", True)])
+def test_stochastic_plan_emulated(key, wrap):
+    """Stochastic straight-line plans (planner.py:811-834): logistic noise on boolean logits,
+    mu + exp(clip(log_sigma)) * noise on the others; gradients reach mu, log_sigma and logits."""
+    check_forward(forward_case("emu", key, B=9, T=5, relaxed=False, stochastic=True,
+                               wrap_non_bool=wrap))
+    c = gradient_case("emu", key, B=9, T=5, stochastic=True, wrap_non_bool=wrap)
+    check_forward(c)
+    check_gradient(c)
+    ls = [k for k in c["P"] if k.endswith("/log_sigma")]
+    if ls:
+        assert any(c["P"][k].grad is not None and float(c["P"][k].grad.abs().sum()) > 0 for k in ls)

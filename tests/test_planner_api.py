@@ -296,3 +296,52 @@ def test_steps_per_update_equals_repeated_updates(cuda_device):
     for graph in (False, True):
         assert torch.equal(run(3, 2, graph), ref)
         assert torch.equal(run(1, 6, graph), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["reservoir", "wildfire"])
+def test_stochastic_plan_update_matches_oracle(cuda_device, key):
+    """One planner update of a stochastic straight-line plan (planner.py:811-834, 2811-2819):
+    loss (returns + entropy regulariser) and gradient w.r.t. mu / log_sigma / logits against the
+    oracle's autograd on the same parameters and supplied noise."""
+    from oracle import planner as OP
+    from oracle.model_eval import OracleModel
+    from pyrddlgym_jax_b200.core.layout import noise_as_list
+    m = fixture_model(key)
+    B, T = 16, 5
+    plan = JaxStraightLinePlan(stochastic=True, sigma_entropy_grad=(key == "reservoir"))
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False, start_entropy_coeff=0.3, end_entropy_coeff=0.3)
+    pl.initialize(5)
+    flat = pl.params[0].cpu().view(T, plan.A).clone()   # the update's concurrency projection moves them
+    pl.iterate()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)
+    P = {}
+    for name in m.action_fluents:
+        if m.variable_ranges[name] == "bool":
+            P[name] = tree["bool"][name]["logit"].reshape(T, -1).clone().requires_grad_(True)
+        else:
+            P[name] = tree["real"][name]["mu"].reshape(T, -1).clone().requires_grad_(True)
+            P[name + "/log_sigma"] = tree["real"][name]["log_sigma"].reshape(T, -1).clone(
+                ).requires_grad_(True)
+    om = OracleModel(m, pl.compiled.relax_config())
+    layout = pl.train_fwd.program.noise_layout
+    noise = pl.train_noise.cpu().view(T, -1)
+    steps = [noise_as_list(layout, noise, t, B) for t in range(T)]
+
+    def pol(t, fls, pnoise):
+        return OP.slp_train_actions(m, P, t, stochastic=True, pnoise=pnoise)
+    pol.n_noise = len(OP.slp_policy_noise_spec(m))
+    ref = OP.rollout(om, pol, B, T, steps)
+    ent = sum(OP.slp_entropy(m, P, t, sigma_entropy_grad=(key == "reservoir")) for t in range(T))
+    loss = OP.mean_loss(ref["reward"], float(m.discount)) - 0.3 * ent
+    loss.backward()
+    from tests.helpers import pack_params
+    want = pack_params(m, {k: (v.grad if v.grad is not None else torch.zeros_like(v))
+                           for k, v in P.items()})
+    got = pl.grad_used[0].cpu().view(T, plan.A)
+    np.testing.assert_allclose(float(pl.train_loss[0]), float(loss), rtol=2e-5)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
+                               atol=1e-4 * float(want.abs().max()))
