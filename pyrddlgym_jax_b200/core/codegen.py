@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 11
+CODEGEN_VERSION = 12
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -378,6 +378,8 @@ class _Gen:
         src_reg = self.is_reg(src)
         if op in _RED and src_reg and n <= L and self.gen_reduce_static(rec):
             return
+        if op == "RPRODX" and self.gen_prodx_scan(rec):
+            return
         if op in _RED:
             ct, init, upd = _RED[op]
             tin = "f" if ct == "float" else "i"
@@ -452,6 +454,39 @@ class _Gen:
             self.emit(f"  if ({guard_q}) for (uint32_t e = le; e < {n}u; e += {L}u) {{ {code} "
                       f"R[{dst['base']}u{qs_d} + e] = {self.to_bits('acc', out_c)}; }}")
             self.emit("  __syncwarp();")
+
+    def gen_prodx_scan(self, rec) -> bool:
+        """Product of the OTHER members of each element's segment (the derivative of RPROD) as a
+        prefix scan and a suffix scan: one lane owns one segment, so a value of n elements costs
+        2 * max-degree steps in a single pass instead of n * max-degree.  Needs shared-memory
+        operands and segments that partition the elements (checked here, else the generic loop)."""
+        n, L = rec["n"], self.L
+        dst, src = rec["dst"], rec["srcs"][0]
+        tab = rec.get("tab")
+        if tab is None or src["kind"] != "val" or self.is_reg(src) or self.is_reg(dst):
+            return False
+        ptr, idx, seg = (np.asarray(tab[k]).astype(np.int64) for k in ("ptr", "idx", "seg"))
+        nseg = len(ptr) - 1
+        if len(idx) != n or len(seg) != n or not np.array_equal(np.sort(idx), np.arange(n)):
+            return False
+        for g_ in range(nseg):
+            if np.any(seg[idx[ptr[g_]:ptr[g_ + 1]]] != g_):
+                return False
+        guard_q = "q == 0u" if dst["uniform"] else f"q < {self.rpw}u"
+        qs_d = f" + q * {dst['sq']}u" if dst["sq"] else ""
+        qs_s = f" + qc * {src['sq']}u" if src["sq"] else ""
+        P, I = rec["aux0"], rec["aux1"]
+        self.emit(
+            f"  if ({guard_q}) for (uint32_t sgi = le; sgi < {nseg}u; sgi += {L}u) {{ "
+            f"const uint32_t j0 = C[{P}u + sgi], j1 = C[{P}u + sgi + 1u]; float run = 1.f; "
+            f"for (uint32_t j = j0; j < j1; ++j) {{ const uint32_t s = C[{I}u + j]; "
+            f"R[{dst['base']}u{qs_d} + s] = __float_as_uint(run); "
+            f"run *= __uint_as_float(R[{src['base']}u{qs_s} + s]); }} run = 1.f; "
+            f"for (uint32_t j = j1; j > j0; --j) {{ const uint32_t s = C[{I}u + j - 1u]; "
+            f"R[{dst['base']}u{qs_d} + s] = __float_as_uint(__uint_as_float(R[{dst['base']}u{qs_d} + s]) * run); "
+            f"run *= __uint_as_float(R[{src['base']}u{qs_s} + s]); }} }}")
+        self.emit("  __syncwarp();")
+        return True
 
     def gen_reduce_static(self, rec) -> bool:
         """Register-resident segment reduction with the CSR tables resolved at generation

@@ -736,6 +736,7 @@ class ProgramBuilder:
                "seg": int(w[8]) if "seg" in ins.tables else 0}
         if ins.tables:
             rec["kmax"] = int(np.max(np.diff(ins.tables["ptr"]))) if len(ins.tables["ptr"]) > 1 else 0
+            rec["tab"] = {k: np.asarray(t) for k, t in ins.tables.items()}    # for the code generator
         return rec
 
     def _encode(self, asm: Assembler, ins: Ins) -> np.ndarray:
