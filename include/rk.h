@@ -166,6 +166,22 @@ int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg, const int32_t* s
  * workspace[chunks][N]. */
 int rk_colsum(void* stream, int B, int N, const float* G, int ldg, float* y, int accumulate,
               float* workspace, int chunks);
+/* Fused backward of the action heads (NH <= 16, hl <= 1024), Hl and G read once:
+ *   gz[b][c] = (sum_j G[b][j] Wh[c][j]) (1 - Hl[b][c]^2);
+ *   grad_tail = [db_last (hl) | dWh (hl x NH) | dbh (NH)] += batch sums (the three blocks are
+ *   contiguous in the flat parameter vector).  workspace: rk_drp_head_backward_ctas(B) rows of
+ *   hl + hl NH + NH floats; partials are added in CTA order (deterministic).
+ * Replaces: the VJP of the head nn.Dense + the last tanh (planner.py:1397-1421). */
+int rk_drp_head_backward_ctas(int B);
+int rk_drp_head_backward(void* stream, int B, int hl, int NH, const float* Hl, const float* G,
+                         const float* Wh, float* gz, float* grad_tail, float* workspace);
+/* Backward of the first layer (D <= 16) in two passes over gz0 [B][H]:
+ *   grad_W0b0 = [dW0 (D x H) | db0 (H)] += batch sums of x^T gz0 and gz0;
+ *   gs (fluent-major state cotangent) += gz0 W0T, W0T = the transposed kernel [H][D].
+ * workspace: rk_drp_head_backward_ctas(B) rows of (D + 1) H floats. */
+int rk_drp_layer0_backward(void* stream, int B, int D, int H, int n_seg, const int32_t* seg_off,
+                           const int32_t* seg_len, const float* x, const float* gz0,
+                           const float* W0T, float* gs, float* grad_W0b0, float* workspace);
 /* Skinny products with N <= 16 (action heads, state-cotangent blocks), A read exactly once:
  * out[b][n] = (accumulate ? out : 0) + sum_k A[b][k] W[k][n] (+ bias[n]). */
 int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A, int lda,

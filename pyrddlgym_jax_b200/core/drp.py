@@ -261,6 +261,14 @@ class DrpPipeline:
         self.xp = z(T, Bt * (self.D + 1))             # [x | 1] per step: fused dW0 / db0 operand
         self.cs_chunks = int(max(1, min(64, Bt // 64)))
         self.cs_ws = z(self.cs_chunks * max(max(self.hid), self.NH))
+        # fused streaming backward kernels (one pass over [B][h] instead of four / three)
+        import os as _os0
+        fuse = _os0.environ.get("RK_DRP_FUSED", "1") != "0"
+        hl = self.hid[-1]
+        self.fused_head = fuse and len(self.hid) >= 2 and self.NH <= 16 and hl <= 1024
+        self.fused_l0 = fuse and self.D <= 16
+        ctas = engine.drp_head_backward_ctas(Bt)
+        self.fb_ws = z(ctas * max(hl + hl * self.NH + self.NH, (self.D + 1) * self.hid[0]))
         # tensor-core path (tcgen05, 3xTF32) for hidden layers whose shapes fit the MMA tiles
         import os as _os
         ok = lambda a, b: a % 32 == 0 and b % 32 == 0 and 32 <= a <= 256 and 32 <= b <= 256  # noqa
@@ -328,22 +336,31 @@ class DrpPipeline:
             engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"),
                          self.NH, heads, self.NH, bias=self._W(params, "bh"))
 
-    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp):
+    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp, params_w=None):
         """Consumes self.gheads [B][NH]; accumulates weight gradients into ``grad`` and adds the
         input cotangent to the fluent-major state cotangent ``gs_cur``."""
         AT, ACC = engine.GEMM_A_TRANS, engine.GEMM_ACCUMULATE
         sk, ws = self.split_k, self.ws
         last = len(self.hid) - 1
         hl = self.hid[last]
-        engine.sgemm(AT | ACC, hl, self.NH, B, H[last], hl, self.gheads, self.NH,
-                     self._W(grad, "Wh"), self.NH, workspace=ws, split_k=sk)
-        engine.colsum(B, self.NH, self.gheads, self.NH, self._W(grad, "bh"), True, self.cs_ws,
-                      self.cs_chunks)
-        engine.sgemm(engine.EPI_DTANH, B, hl, self.NH, self.gheads, self.NH,
-                     self._W(self.wT, "Wh"), hl, self.gz[last], hl, aux=H[last], ldaux=hl)
+        if self.fused_head:     # gz, dWh, dbh and db_last in one pass over H[last] / gheads
+            engine.drp_head_backward(B, hl, self.NH, H[last], self.gheads, self._W(params_w, "Wh"),
+                                     self.gz[last], grad[self.plan.seg[f"b{last}"][0]:], self.fb_ws)
+        else:
+            engine.sgemm(AT | ACC, hl, self.NH, B, H[last], hl, self.gheads, self.NH,
+                         self._W(grad, "Wh"), self.NH, workspace=ws, split_k=sk)
+            engine.colsum(B, self.NH, self.gheads, self.NH, self._W(grad, "bh"), True, self.cs_ws,
+                          self.cs_chunks)
+            engine.sgemm(engine.EPI_DTANH, B, hl, self.NH, self.gheads, self.NH,
+                         self._W(self.wT, "Wh"), hl, self.gz[last], hl, aux=H[last], ldaux=hl)
         for i in range(last, -1, -1):
             h = self.hid[i]
             fan = self.D if i == 0 else self.hid[i - 1]
+            if i == 0 and self.fused_l0:   # dW0, db0 and the state cotangent in one pass over gz[0]
+                engine.drp_layer0_backward(B, self.D, h, self.plan.state_segs, x_fm, self.gz[0],
+                                           self._W(self.wT, "W0"), gs_cur, self._W(grad, "W0"),
+                                           self.fb_ws)
+                continue
             if i == 0:      # [x | 1]^T dZ: the rows of dW0 and, in row D, db0 (contiguous in grad)
                 engine.sgemm(AT | ACC, fan + 1, h, B, xp, fan + 1, self.gz[0], h,
                              self._W(grad, "W0"), h, workspace=ws, split_k=sk)
@@ -354,8 +371,9 @@ class DrpPipeline:
                 else:
                     engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
                                  self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
-                engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
-                              self.cs_chunks)
+                if not (i == last and self.fused_head):     # db_last came with the head backward
+                    engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
+                                  self.cs_chunks)
             if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
                 engine.tcgemm(3, B, fan, h, self.gz[i], h, self._W(self.w_hi, f"W{i}"),
                               self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan,
@@ -420,7 +438,7 @@ class DrpPipeline:
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.gact, self.gheads)
-            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t])
+            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
             cur ^= 1
 
     def test_kernels(self, p: int, params: Optional[torch.Tensor] = None, out=None):

@@ -24,7 +24,8 @@ EXPORTS = [
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
-    "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state",
+    "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state", "rk_drp_head_backward",
+    "rk_drp_head_backward_ctas", "rk_drp_layer0_backward",
 ]
 
 
@@ -84,6 +85,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_actions_backward.restype = ci
     lib.rk_drp_layer0.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
     lib.rk_drp_layer0.restype = ci
+    lib.rk_drp_head_backward_ctas.argtypes = [ci]
+    lib.rk_drp_head_backward_ctas.restype = ci
+    lib.rk_drp_head_backward.argtypes = [vp, ci, ci, ci, cf, cf, cf, cf, cf, cf]
+    lib.rk_drp_head_backward.restype = ci
+    lib.rk_drp_layer0_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf, cf]
+    lib.rk_drp_layer0_backward.restype = ci
     lib.rk_colsum.argtypes = [vp, ci, ci, cf, ci, cf, ci, cf, ci]
     lib.rk_colsum.restype = ci
     lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
@@ -270,6 +277,24 @@ def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None):
     _check(load_library().rk_drp_layer0(
         _stream(), B, D, H, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
         _ptr(x), _ptr(W0), _ptr(b0), _ptr(out), _ptr(xp)), "rk_drp_layer0")
+
+
+def drp_head_backward_ctas(B: int) -> int:
+    return int(load_library().rk_drp_head_backward_ctas(int(B)))
+
+
+def drp_head_backward(B, hl, NH, Hl, G, Wh, gz, grad_tail, workspace):
+    _check(load_library().rk_drp_head_backward(
+        _stream(), B, hl, NH, _ptr(Hl), _ptr(G), _ptr(Wh), _ptr(gz), _ptr(grad_tail),
+        _ptr(workspace)), "rk_drp_head_backward")
+
+
+def drp_layer0_backward(B, D, H, segs, x, gz0, W0, gs, grad_W0b0, workspace):
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_drp_layer0_backward(
+        _stream(), B, D, H, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+        _ptr(x), _ptr(gz0), _ptr(W0), _ptr(gs), _ptr(grad_W0b0), _ptr(workspace)),
+        "rk_drp_layer0_backward")
 
 
 def colsum(B, N, G, ldg, y, accumulate, workspace, chunks):

@@ -447,6 +447,64 @@ rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__
   }
 }
 
+// D <= 16, H <= 256: a thread owns one output column (its column of W0 in registers), the CTA walks
+// over 64-row tiles of the state staged in shared memory as [64][16] (float4 broadcast reads).
+__global__ void __launch_bounds__(256)
+rk_drp_layer0_cols_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
+                          const float* __restrict__ W0, const float* __restrict__ b0,
+                          float* __restrict__ out, float* __restrict__ xp) {
+  __shared__ __align__(16) float xs[64 * 16];
+  __shared__ int foff[16], flen[16], fd[16];
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    int f = 0;
+    while (f + 1 < S.n && tid >= S.off[f + 1]) ++f;
+    foff[tid] = S.off[f];
+    flen[tid] = S.len[f];
+    fd[tid] = tid - S.off[f];
+  }
+  const bool live = tid < H;
+  float w[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) w[d] = (live && d < D) ? W0[(size_t)d * H + tid] : 0.f;
+  const float bias = live ? b0[tid] : 0.f;
+  const int nq = (D + 3) >> 2;
+  __syncthreads();
+  for (int r0 = blockIdx.x * 64; r0 < B; r0 += gridDim.x * 64) {
+    for (int i = tid; i < 64 * 16; i += 256) {
+      const int r = i >> 4, d = i & 15, b = r0 + r;
+      float v = 0.f;
+      if (b < B && d < D) {
+        v = x[(size_t)foff[d] * B + (size_t)b * flen[d] + fd[d]];
+        if (xp != nullptr) xp[(size_t)b * (D + 1) + d] = v;
+      }
+      if (b < B && d == D && xp != nullptr) xp[(size_t)b * (D + 1) + D] = 1.f;
+      xs[i] = v;
+    }
+    __syncthreads();
+    const int rows = min(64, B - r0);
+    if (live) {
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float4* xr = reinterpret_cast<const float4*>(xs + r * 16);
+        float acc = bias;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (v < nq) {
+            const float4 q = xr[v];
+            acc = fmaf(q.x, w[4 * v], acc);
+            acc = fmaf(q.y, w[4 * v + 1], acc);
+            acc = fmaf(q.z, w[4 * v + 2], acc);
+            acc = fmaf(q.w, w[4 * v + 3], acc);
+          }
+        }
+        out[(size_t)(r0 + r) * H + tid] = tanhf(acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
                              const int32_t* seg_off, const int32_t* seg_len, const float* x,
                              const float* W0, const float* b0, float* out, float* xp) {
@@ -456,6 +514,13 @@ extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
   RkActSegs S;
   int rc = make_segs(D, n_seg, seg_off, seg_len, &S);
   if (rc != 0) return rc;
+  if (D < 16 && H <= 256) {       // (D < 16: slot D of a tile row carries the packed 1)
+    int grid = (B + 63) / 64;
+    if (grid > 148 * 4) grid = 148 * 4;
+    rk_drp_layer0_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0, out,
+                                                                      xp);
+    return (int)cudaGetLastError();
+  }
   const size_t smem = ((size_t)D * H + 64 * (size_t)D) * sizeof(float);
   if (smem > 200 * 1024) return RK_E_SMEM;
   if (smem > 48 * 1024) {
@@ -506,54 +571,350 @@ extern "C" int rk_colsum(void* stream, int B, int N, const float* G, int ldg, fl
   return (int)cudaGetLastError();
 }
 
-// ---- skinny products with N <= 16 (action heads, state-cotangent blocks) ----------------------
-// out[b][n] = (accumulate ? out[b][n] : 0) + sum_k A[b][k] * W[k][n] (+ bias[n]).
-// One warp per row: lanes stride over k (coalesced 128-byte reads of A, read exactly once),
-// W staged in shared memory with an odd row stride, N warp reductions per row.
-__global__ void __launch_bounds__(256)
-rk_rowdot_kernel(int B, int N, int K, const float* __restrict__ A, int lda,
-                 const float* __restrict__ W, int ldw, float* __restrict__ out, int ldo,
-                 const float* __restrict__ bias, int accumulate) {
-  extern __shared__ float Wsh[];
-  const int Np = N | 1;
-  for (int i = threadIdx.x; i < K * N; i += 256) Wsh[(i / N) * Np + (i % N)] = W[(size_t)(i / N) * ldw + (i % N)];
+// ---- fused backward of the action heads -----------------------------------------------------
+// Given the head cotangent G[B][NH] and the last hidden activation Hl[B][hl] (both read ONCE):
+//   gz[b][c]  = (sum_j G[b][j] Wh[c][j]) * (1 - Hl[b][c]^2)     cotangent of the last pre-activation
+//   dWh[c][j] += sum_b Hl[b][c] G[b][j]      dbh[j] += sum_b G[b][j]      dbl[c] += sum_b gz[b][c]
+// Grid = (32-column blocks, row chunks).  A lane owns one column (its row of Wh and its
+// accumulators stay in registers), the 8 warps of a CTA stride over the chunk's rows two at a
+// time, and the CTA leaves its partial [dbl | dWh | dbh] in ws[chunk][...]; the caller adds the
+// chunk partials in order (deterministic).  Replaces four streaming passes over [B][hl] (two
+// skinny GEMMs and two column sums) by one read and one write.
+#define RK_FB_WARPS 8
+__device__ __forceinline__ float cta_sum_in_warp_order(float v, float (*part)[33], int warp,
+                                                       int lane) {
   __syncthreads();
+  part[warp][lane] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < RK_FB_WARPS; ++q) s += part[q][lane];
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+rk_drp_head_bwd_kernel(int B, int hl, int NH, const float* __restrict__ Hl,
+                       const float* __restrict__ G, const float* __restrict__ Wh,
+                       float* __restrict__ gz, float* __restrict__ ws, int rows_per_chunk) {
+  __shared__ float part[RK_FB_WARPS][33];
+  extern __shared__ __align__(16) float Gs[];          // [rows_per_chunk][16], zero padded
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
-    float acc[16];
+  const int c = blockIdx.x * 32 + lane;
+  const bool live = c < hl;
+  const int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
+  for (int i = threadIdx.x; i < (b1 - b0) * 16; i += 256) {
+    const int r = i >> 4, j = i & 15;
+    Gs[i] = (j < NH) ? G[(size_t)(b0 + r) * NH + j] : 0.f;
+  }
+  float w[16], dw[16];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
-    const float* a = A + (size_t)b * lda;
-    for (int k0 = lane; k0 < K; k0 += 256) {     // 8 independent loads in flight per lane
-      float av[8];
+  for (int j = 0; j < 16; ++j) {
+    w[j] = (live && j < NH) ? Wh[(size_t)c * NH + j] : 0.f;
+    dw[j] = 0.f;
+  }
+  __syncthreads();
+  float dbl = 0.f, dbh = 0.f;
+  const int nq = (NH + 3) >> 2;
+  for (int b = b0 + warp; b < b1; b += 2 * RK_FB_WARPS) {
+    const int bb = b + RK_FB_WARPS;
+    const bool two = bb < b1;
+    const float h0 = live ? Hl[(size_t)b * hl + c] : 0.f;
+    const float h1 = (live && two) ? Hl[(size_t)bb * hl + c] : 0.f;
+    const float4* ga = reinterpret_cast<const float4*>(Gs + (size_t)(b - b0) * 16);
+    const float4* gb = reinterpret_cast<const float4*>(Gs + (size_t)((two ? bb : b) - b0) * 16);
+    if (blockIdx.x == 0 && lane < NH) {
+      dbh += Gs[(size_t)(b - b0) * 16 + lane];
+      if (two) dbh += Gs[(size_t)(bb - b0) * 16 + lane];
+    }
+    float z0 = 0.f, z1 = 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) av[u] = (k0 + 32 * u < K) ? a[k0 + 32 * u] : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (k0 + 32 * u < K) {
-          const float* w = Wsh + (k0 + 32 * u) * Np;
-#pragma unroll
-          for (int n = 0; n < 16; ++n)
-            if (n < N) acc[n] = fmaf(av[u], w[n], acc[n]);
-        }
+    for (int v = 0; v < 4; ++v) {
+      if (v < nq) {
+        const float4 p = ga[v];
+        float4 q = gb[v];
+        if (!two) q = make_float4(0.f, 0.f, 0.f, 0.f);
+        z0 = fmaf(p.x, w[4 * v], z0);     z1 = fmaf(q.x, w[4 * v], z1);
+        z0 = fmaf(p.y, w[4 * v + 1], z0); z1 = fmaf(q.y, w[4 * v + 1], z1);
+        z0 = fmaf(p.z, w[4 * v + 2], z0); z1 = fmaf(q.z, w[4 * v + 2], z1);
+        z0 = fmaf(p.w, w[4 * v + 3], z0); z1 = fmaf(q.w, w[4 * v + 3], z1);
+        dw[4 * v] = fmaf(h1, q.x, fmaf(h0, p.x, dw[4 * v]));
+        dw[4 * v + 1] = fmaf(h1, q.y, fmaf(h0, p.y, dw[4 * v + 1]));
+        dw[4 * v + 2] = fmaf(h1, q.z, fmaf(h0, p.z, dw[4 * v + 2]));
+        dw[4 * v + 3] = fmaf(h1, q.w, fmaf(h0, p.w, dw[4 * v + 3]));
       }
     }
-    float mine = 0.f;
-#pragma unroll
-    for (int n = 0; n < 16; ++n) {
-      if (n < N) {
-        float v = acc[n];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == n) mine = v;
-      }
+    const float v0 = z0 * (1.f - h0 * h0), v1 = z1 * (1.f - h1 * h1);
+    if (live) {
+      gz[(size_t)b * hl + c] = v0;
+      if (two) gz[(size_t)bb * hl + c] = v1;
     }
-    if (lane < N) {
-      float v = mine;
-      if (bias != nullptr) v += bias[lane];
-      if (accumulate) v += out[(size_t)b * ldo + lane];
-      out[(size_t)b * ldo + lane] = v;
+    dbl += v0 + v1;
+  }
+  float* out = ws + (size_t)blockIdx.y * ((size_t)hl + (size_t)hl * NH + NH);
+  float s = cta_sum_in_warp_order(dbl, part, warp, lane);
+  if (warp == 0 && live) out[c] = s;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < NH) {                                // NH is uniform: every thread reaches the barriers
+      s = cta_sum_in_warp_order(dw[j], part, warp, lane);
+      if (warp == 0 && live) out[hl + (size_t)c * NH + j] = s;
     }
   }
+  if (blockIdx.x == 0) {
+    s = cta_sum_in_warp_order(dbh, part, warp, lane);
+    if (warp == 0 && lane < NH) out[(size_t)hl + (size_t)hl * NH + lane] = s;
+  }
+}
+
+// adds rows [0, R) of ws[R][n] to y[n] in row order
+__global__ void rk_add_rows_kernel(int R, int n, const float* __restrict__ ws,
+                                   float* __restrict__ y, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = accumulate ? y[i] : 0.f;
+  const float* p = ws + i;
+  int r = 0;
+  for (; r + 4 <= R; r += 4) {
+    const float v0 = p[0], v1 = p[(size_t)n], v2 = p[2 * (size_t)n], v3 = p[3 * (size_t)n];
+    acc = (((acc + v0) + v1) + v2) + v3;
+    p += 4 * (size_t)n;
+  }
+  for (; r < R; ++r) { acc += *p; p += n; }
+  y[i] = acc;
+}
+
+extern "C" int rk_drp_head_backward_ctas(int B) {     // row chunks of the fused backward kernels
+  int chunks = (B + 255) / 256;                       // at most 256 rows per chunk (smem tile)
+  return chunks < 1 ? 1 : chunks;
+}
+
+extern "C" int rk_drp_head_backward(void* stream, int B, int hl, int NH, const float* Hl,
+                                    const float* G, const float* Wh, float* gz, float* grad_tail,
+                                    float* workspace) {
+  if (B <= 0 || hl <= 0 || hl > 1024 || NH <= 0 || NH > 16 || Hl == nullptr || G == nullptr ||
+      Wh == nullptr || gz == nullptr || grad_tail == nullptr || workspace == nullptr)
+    return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks0 = rk_drp_head_backward_ctas(B);
+  const int rpc = (B + chunks0 - 1) / chunks0;
+  const int chunks = (B + rpc - 1) / rpc;
+  dim3 grid((hl + 31) / 32, chunks);
+  const size_t smem = (size_t)rpc * 16 * sizeof(float);     // <= 256 rows x 64 B
+  rk_drp_head_bwd_kernel<<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc);
+  const int n = hl + hl * NH + NH;
+  rk_add_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(chunks, n, workspace, grad_tail, 1);
+  return (int)cudaGetLastError();
+}
+
+// ---- fused weight / bias gradient of the first layer -------------------------------------------
+// Given gz0[B][H] (read once) and the fluent-major state x (D <= 16 input words per rollout):
+//   dW0[d][c] += sum_b x[b][d] gz0[b][c]     db0[c] += sum_b gz0[b][c]
+// Same decomposition as the head kernel: a lane owns a column, warps stride over the chunk's
+// rows, per-chunk partials [dW0 | db0] go to ws[chunk][(D + 1) * H] and are added in order.
+// (The input cotangent gs += gz0 W0^T is a row reduction: rk_rowdot_segs below.)
+__global__ void __launch_bounds__(256)
+rk_drp_layer0_bwd_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
+                         const float* __restrict__ gz0, float* __restrict__ ws,
+                         int rows_per_chunk) {
+  __shared__ float part[RK_FB_WARPS][33];
+  __shared__ int foff[16], flen[16], fd[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 16) {
+    const int d = threadIdx.x;
+    int f = 0;
+    while (f + 1 < S.n && d >= S.off[f + 1]) ++f;
+    foff[d] = S.off[f];
+    flen[d] = S.len[f];
+    fd[d] = d - S.off[f];
+  }
+  __syncthreads();
+  extern __shared__ __align__(16) float Xs[];          // [rows_per_chunk][16], zero padded
+  const int c = blockIdx.x * 32 + lane;
+  const bool live = c < H;
+  const int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
+  for (int i = threadIdx.x; i < (b1 - b0) * 16; i += 256) {
+    const int r = i >> 4, d = i & 15;
+    Xs[i] = (d < D) ? x[(size_t)foff[d] * B + (size_t)(b0 + r) * flen[d] + fd[d]] : 0.f;
+  }
+  __syncthreads();
+  float dw[16], db = 0.f;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) dw[d] = 0.f;
+  const int nq = (D + 3) >> 2;
+  for (int b = b0 + warp; b < b1; b += 2 * RK_FB_WARPS) {
+    const int bb = b + RK_FB_WARPS;
+    const bool two = bb < b1;
+    const float g0 = live ? gz0[(size_t)b * H + c] : 0.f;
+    const float g1 = (live && two) ? gz0[(size_t)bb * H + c] : 0.f;
+    db += g0 + g1;
+    const float4* xa = reinterpret_cast<const float4*>(Xs + (size_t)(b - b0) * 16);
+    const float4* xb = reinterpret_cast<const float4*>(Xs + (size_t)((two ? bb : b) - b0) * 16);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (v < nq) {
+        const float4 p = xa[v], q = xb[v];       // g1 == 0 when there is no second row
+        dw[4 * v] = fmaf(q.x, g1, fmaf(p.x, g0, dw[4 * v]));
+        dw[4 * v + 1] = fmaf(q.y, g1, fmaf(p.y, g0, dw[4 * v + 1]));
+        dw[4 * v + 2] = fmaf(q.z, g1, fmaf(p.z, g0, dw[4 * v + 2]));
+        dw[4 * v + 3] = fmaf(q.w, g1, fmaf(p.w, g0, dw[4 * v + 3]));
+      }
+    }
+  }
+  float* out = ws + (size_t)blockIdx.y * ((size_t)(D + 1) * H);
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    if (d < D) {
+      const float s = cta_sum_in_warp_order(dw[d], part, warp, lane);
+      if (warp == 0 && live) out[(size_t)d * H + c] = s;
+    }
+  }
+  const float s = cta_sum_in_warp_order(db, part, warp, lane);
+  if (warp == 0 && live) out[(size_t)D * H + c] = s;
+}
+
+// ---- skinny products with N <= 16 (action heads, state-cotangent blocks) ----------------------
+// out[b][n] = (accumulate ? out[b][n] : 0) + sum_k A[b][k] * W[k][n] (+ bias[n]).
+// One warp owns FOUR rows at a time: lanes stride over k (coalesced 128-byte reads of A, read
+// exactly once), W sits in shared memory as [K][20] (float4 reads, conflict-free stride) and is
+// shared by the four rows; the 16 partial sums of a row are reduced across the warp by a
+// transposing butterfly (16 shuffles instead of 80).  With segments (S.n > 0) output n of row b
+// goes to the fluent-major block of its fluent: out[off_f * B + b * len_f + (n - off_f)].
+#define RK_RD_NP 20
+__device__ __forceinline__ float warp_transpose_sum16(const float (&acc)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? acc[i] : acc[i + 8], keep = b4 ? acc[i + 8] : acc[i];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? a8[i] : a8[i + 4], keep = b3 ? a8[i + 4] : a8[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? a4[i] : a4[i + 2], keep = b2 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? a2[0] : a2[1], keep = b1 ? a2[1] : a2[0];
+  float a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;        // total of output n = 8 b4 + 4 b3 + 2 b2 + b1
+}
+
+template <int RK_RD_ROWS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+rk_rowdot_kernel(int B, int N, int K, const float* __restrict__ A, int lda,
+                 const float* __restrict__ W, int ldw, float* __restrict__ out, int ldo,
+                 const float* __restrict__ bias, int accumulate, RkActSegs S) {
+  extern __shared__ __align__(16) float Wsh[];
+  __shared__ int ooff[16], olen[16];
+  for (int i = threadIdx.x; i < K * RK_RD_NP; i += 256) {
+    const int k = i / RK_RD_NP, n = i % RK_RD_NP;
+    Wsh[i] = (n < N) ? W[(size_t)k * ldw + n] : 0.f;
+  }
+  if (threadIdx.x < 16) {
+    const int n = threadIdx.x;
+    int f = 0;
+    while (f + 1 < S.n && n >= S.off[f + 1]) ++f;
+    ooff[n] = S.n > 0 ? S.off[f] : 0;
+    olen[n] = S.n > 0 ? S.len[f] : 0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (N + 3) >> 2;
+  for (int b = (blockIdx.x * 8 + warp) * RK_RD_ROWS; b < B; b += gridDim.x * 8 * RK_RD_ROWS) {
+    float acc[RK_RD_ROWS][16];
+#pragma unroll
+    for (int r = 0; r < RK_RD_ROWS; ++r)
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc[r][n] = 0.f;
+    for (int k0 = lane; k0 < K; k0 += 64) {       // two k per trip: 2 x ROWS loads in flight
+     float av2[2][RK_RD_ROWS];
+#pragma unroll
+     for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int r = 0; r < RK_RD_ROWS; ++r)
+        av2[u][r] = (b + r < B && k0 + 32 * u < K) ? A[(size_t)(b + r) * lda + k0 + 32 * u] : 0.f;
+#pragma unroll
+     for (int u = 0; u < 2; ++u) {
+      const int k = min(k0 + 32 * u, K - 1);       // out-of-range k: av == 0
+      const float* av = av2[u];
+      const float4* w4 = reinterpret_cast<const float4*>(Wsh + k * RK_RD_NP);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (v < nq) {
+          const float4 w = w4[v];
+#pragma unroll
+          for (int r = 0; r < RK_RD_ROWS; ++r) {
+            acc[r][4 * v + 0] = fmaf(av[r], w.x, acc[r][4 * v + 0]);
+            acc[r][4 * v + 1] = fmaf(av[r], w.y, acc[r][4 * v + 1]);
+            acc[r][4 * v + 2] = fmaf(av[r], w.z, acc[r][4 * v + 2]);
+            acc[r][4 * v + 3] = fmaf(av[r], w.w, acc[r][4 * v + 3]);
+          }
+        }
+      }
+     }
+    }
+    const int n = lane >> 1;
+#pragma unroll
+    for (int r = 0; r < RK_RD_ROWS; ++r) {
+      float v = warp_transpose_sum16(acc[r], lane);
+      const int bb = b + r;
+      if ((lane & 1) == 0 && n < N && bb < B) {
+        if (bias != nullptr) v += bias[n];
+        float* dst = (S.n > 0) ? out + (size_t)ooff[n] * B + (size_t)bb * olen[n] + (n - ooff[n])
+                               : out + (size_t)bb * ldo + n;
+        if (accumulate) v += *dst;
+        *dst = v;
+      }
+    }
+  }
+}
+
+static int launch_rowdot(cudaStream_t st, int accumulate, int B, int N, int K, const float* A,
+                         int lda, const float* W, int ldw, float* out, int ldo, const float* bias,
+                         const RkActSegs& S) {
+  const size_t smem = (size_t)K * RK_RD_NP * sizeof(float);
+  if (smem > 200 * 1024) return RK_E_SMEM;
+  auto launch = [&](auto kern, int rows, int ctas_per_sm) -> int {
+    if (smem > 48 * 1024) {
+      cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem);
+      if (ce != cudaSuccess) return (int)ce;
+    }
+    int grid = (B + 8 * rows - 1) / (8 * rows);
+    // persistent: W (K x 20 floats) is staged once per CTA
+    if (grid > 148 * ctas_per_sm) grid = 148 * ctas_per_sm;
+    kern<<<grid, 256, smem, st>>>(B, N, K, A, lda, W, ldw, out, ldo, bias, accumulate ? 1 : 0, S);
+    return (int)cudaGetLastError();
+  };
+  return launch(rk_rowdot_kernel<4, 2>, 4, 2);
+}
+
+extern "C" int rk_drp_layer0_backward(void* stream, int B, int D, int H, int n_seg,
+                                      const int32_t* seg_off, const int32_t* seg_len,
+                                      const float* x, const float* gz0, const float* W0T,
+                                      float* gs, float* grad_W0b0, float* workspace) {
+  if (B <= 0 || D <= 0 || D > 16 || H <= 0 || x == nullptr || gz0 == nullptr ||
+      W0T == nullptr || gs == nullptr || grad_W0b0 == nullptr || workspace == nullptr)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(D, n_seg, seg_off, seg_len, &S);
+  if (rc != 0) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks0 = rk_drp_head_backward_ctas(B);
+  const int rpc = (B + chunks0 - 1) / chunks0;
+  const int chunks = (B + rpc - 1) / rpc;
+  dim3 grid((H + 31) / 32, chunks);
+  rk_drp_layer0_bwd_kernel<<<grid, 256, (size_t)rpc * 16 * sizeof(float), st>>>(
+      B, D, H, S, x, gz0, workspace, rpc);
+  const int n = (D + 1) * H;
+  rk_add_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(chunks, n, workspace, grad_W0b0, 1);
+  // input cotangent: gs[b][d] += sum_c gz0[b][c] W0T[c][d], scattered to the fluents' blocks
+  return launch_rowdot(st, 1, B, D, H, gz0, H, W0T, D, gs, 0, nullptr, S);
 }
 
 extern "C" int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A,
@@ -561,16 +922,7 @@ extern "C" int rk_rowdot(void* stream, int accumulate, int B, int N, int K, cons
                          const float* bias) {
   if (B <= 0 || N <= 0 || N > 16 || K <= 0 || A == nullptr || W == nullptr || out == nullptr)
     return RK_E_BADARG;
-  const size_t smem = (size_t)K * (N | 1) * sizeof(float);
-  if (smem > 200 * 1024) return RK_E_SMEM;
-  if (smem > 48 * 1024) {
-    cudaError_t ce = cudaFuncSetAttribute(rk_rowdot_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return (int)ce;
-  }
-  int grid = (B + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
-  rk_rowdot_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(B, N, K, A, lda, W, ldw, out, ldo,
-                                                               bias, accumulate ? 1 : 0);
-  return (int)cudaGetLastError();
+  RkActSegs S;
+  S.n = 0;
+  return launch_rowdot((cudaStream_t)stream, accumulate, B, N, K, A, lda, W, ldw, out, ldo, bias, S);
 }

@@ -317,3 +317,56 @@ def test_tcgemm_tn_against_fp64(cuda_device, M, N, K):
     engine.tcgemm_tn(False, M, N, K, A, M, Bm, N, C2, ws, 148)
     torch.cuda.synchronize()
     assert torch.equal(C1, C2)                        # deterministic
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,hl,NH", [(1000, 256, 10), (77, 64, 3), (4096, 512, 16), (300, 96, 1)])
+def test_fused_head_backward_against_fp64(cuda_device, B, hl, NH):
+    """rk_drp_head_backward == the four separate products it replaces (fp64 reference)."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(B + hl)
+    Hl = torch.tanh(torch.randn(B, hl, generator=g)).cuda()
+    G = torch.randn(B, NH, generator=g).cuda()
+    Wh = (torch.randn(hl, NH, generator=g) * 0.2).cuda()
+    gz = torch.zeros(B, hl, device="cuda")
+    n = hl + hl * NH + NH
+    tail0 = torch.randn(n, generator=g).cuda()
+    tail = tail0.clone()
+    ws = torch.zeros(engine.drp_head_backward_ctas(B) * n, device="cuda")
+    engine.drp_head_backward(B, hl, NH, Hl, G, Wh, gz, tail, ws)
+    torch.cuda.synchronize()
+    H64, G64, W64 = Hl.double(), G.double(), Wh.double()
+    gz_ref = (G64 @ W64.t()) * (1 - H64 * H64)
+    want = torch.cat([gz_ref.sum(0), (H64.t() @ G64).reshape(-1), G64.sum(0)]) + tail0.double()
+    torch.testing.assert_close(gz.double(), gz_ref, rtol=1e-5, atol=1e-5)
+    scale = float(want.abs().max())
+    torch.testing.assert_close(tail.double(), want, rtol=1e-5, atol=2e-6 * max(scale, 1.0) * B ** 0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,segs,H", [(1000, [(0, 5), (5, 1)], 256), (77, [(0, 1), (1, 3), (4, 4)], 64),
+                                      (513, [(0, 2)], 96)])
+def test_fused_layer0_backward_against_fp64(cuda_device, B, segs, H):
+    """rk_drp_layer0_backward == [x | 1]^T gz0 and gs += gz0 W0^T on the fluent-major state."""
+    from pyrddlgym_jax_b200.core import engine
+    D = sum(n for _, n in segs)
+    g = torch.Generator().manual_seed(B + H)
+    X = torch.randn(B, D, generator=g)                       # row-major copy for the reference
+    x_fm = torch.cat([X[:, o:o + n].reshape(-1) for o, n in segs]).cuda()
+    gz0 = torch.randn(B, H, generator=g).cuda()
+    W0 = (torch.randn(D, H, generator=g) * 0.3).cuda()
+    gs0 = torch.randn(D * B, generator=g).cuda()
+    gs = gs0.clone()
+    n = (D + 1) * H
+    gw0 = torch.randn(n, generator=g).cuda()
+    gw = gw0.clone()
+    ws = torch.zeros(engine.drp_head_backward_ctas(B) * n, device="cuda")
+    engine.drp_layer0_backward(B, D, H, segs, x_fm, gz0, W0.t().contiguous(), gs, gw, ws)
+    torch.cuda.synchronize()
+    X64, g64, W64 = X.double().cuda(), gz0.double(), W0.double()
+    want_w = torch.cat([(X64.t() @ g64).reshape(-1), g64.sum(0)]) + gw0.double()
+    dx = g64 @ W64.t()                                       # [B, D]
+    want_s = torch.cat([dx[:, o:o + k].reshape(-1) for o, k in segs]) + gs0.double()
+    torch.testing.assert_close(gw.double(), want_w, rtol=1e-5,
+                               atol=2e-6 * max(float(want_w.abs().max()), 1.0) * B ** 0.5)
+    torch.testing.assert_close(gs.double(), want_s, rtol=1e-5, atol=1e-4)
