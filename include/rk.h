@@ -238,6 +238,19 @@ int rk_tile_state(void* stream, int B, int n_seg, const int32_t* seg_off, const 
  * loss[0] = -(1/B) sum_b returns[b];  gret[b] = -1/B. */
 int rk_mean_loss(void* stream, const float* returns, int B, float* loss, float* gret);
 
+/* One-shot sum all-reduce of a short vector (n <= n_max floats) over NVLink peer memory, in
+ * place, the same bits on every rank (sum in rank order).  peer_bufs[r] / peer_flags[r]: HOST
+ * arrays of the device addresses, valid on THIS rank, of rank r's symmetric buffer (2 * world *
+ * n_max floats) and flag words (2 * RK_MAX_PEERS uint32, zero at start-up); epoch_ctr: one device word
+ * per rank, zero at start-up, advanced by the kernel (graph replay safe).  status (nullable) is
+ * set to 1 if a peer does not answer within ~10 s.  Every rank must issue the same sequence of
+ * calls.  Replaces: the batch mean inside value_and_grad (planner.py:2817-2818, 2873) once the
+ * batch is sharded over GPUs. */
+#define RK_MAX_PEERS 16
+int rk_peer_allreduce(void* stream, int world, int rank, const uint64_t* peer_bufs,
+                      const uint64_t* peer_flags, int n, int n_max, float* vec,
+                      uint32_t* epoch_ctr, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ EXPORTS = [
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
     "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state", "rk_drp_head_backward",
-    "rk_drp_head_backward_ctas", "rk_drp_layer0_backward",
+    "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_head_backward.restype = ci
     lib.rk_drp_layer0_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf, cf]
     lib.rk_drp_layer0_backward.restype = ci
+    lib.rk_peer_allreduce.argtypes = [vp, ci, ci, vp, vp, ci, ci, cf, cf, cf]
+    lib.rk_peer_allreduce.restype = ci
     lib.rk_colsum.argtypes = [vp, ci, ci, cf, ci, cf, ci, cf, ci]
     lib.rk_colsum.restype = ci
     lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
@@ -295,6 +297,15 @@ def drp_layer0_backward(B, D, H, segs, x, gz0, W0, gs, grad_W0b0, workspace):
         _stream(), B, D, H, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
         _ptr(x), _ptr(gz0), _ptr(W0), _ptr(gs), _ptr(grad_W0b0), _ptr(workspace)),
         "rk_drp_layer0_backward")
+
+
+def peer_allreduce(world: int, rank: int, peer_bufs, peer_flags, n: int, n_max: int, vec, epoch,
+                   status=None):
+    """peer_bufs / peer_flags: ctypes arrays of uint64 device addresses (one per rank)."""
+    _check(load_library().rk_peer_allreduce(
+        _stream(), world, rank, ctypes.cast(peer_bufs, ctypes.c_void_p),
+        ctypes.cast(peer_flags, ctypes.c_void_p), n, n_max, _ptr(vec), _ptr(epoch), _ptr(status)),
+        "rk_peer_allreduce")
 
 
 def colsum(B, N, G, ldg, y, accumulate, workspace, chunks):

@@ -56,6 +56,60 @@ def allreduce_gradient(grad: torch.Tensor) -> torch.Tensor:
     return grad
 
 
+class PeerAllReduce:
+    """One-shot sum all-reduce of a short fp32 vector over NVLink peer memory
+    (csrc/rk_comm.cu): symmetric buffers and flag words are allocated with torch's symmetric
+    memory allocator and their peer addresses exchanged ONCE here; every call is then a single
+    kernel launch on the caller's stream (CUDA-graph capturable).  ``create`` returns None --
+    and the caller keeps using NCCL -- when symmetric memory is unavailable, the vector is long
+    (bandwidth-bound: NCCL's job), or RK_PEER_ALLREDUCE=0."""
+
+    MAX_WORDS = 65536
+
+    def __init__(self, n_max: int, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from .engine import RkError  # noqa: F401  (library must be loadable)
+        self.rank, self.world = world()
+        self.n_max = int(n_max)
+        group = dist.group.WORLD
+        self.buf = symm.empty(2 * self.world * self.n_max, dtype=torch.float32, device=device)
+        self.flags = symm.empty(2 * 16, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.flags.zero_()
+        hb = symm.rendezvous(self.buf, group=group)
+        hf = symm.rendezvous(self.flags, group=group)
+        U64 = ctypes.c_uint64 * self.world
+        self.peer_bufs = U64(*[int(p) for p in hb.buffer_ptrs])
+        self.peer_flags = U64(*[int(p) for p in hf.buffer_ptrs])
+        self._handles = (hb, hf)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)     # (create()'s all-reduce is the barrier before first use)
+
+    @classmethod
+    def create(cls, n_max: int, device):
+        import os
+        if world()[1] <= 1 or n_max > cls.MAX_WORDS or world()[1] > 16 \
+                or os.environ.get("RK_PEER_ALLREDUCE", "1") == "0" \
+                or torch.device(device).type != "cuda":
+            return None
+        ok = torch.ones(1, dtype=torch.int32, device=device)
+        obj = None
+        try:
+            obj = cls(n_max, device)
+        except Exception:              # no symmetric memory / no peer access on this box
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        return obj if int(ok.item()) == 1 else None
+
+    def __call__(self, vec: torch.Tensor) -> torch.Tensor:
+        from . import engine
+        engine.peer_allreduce(self.world, self.rank, self.peer_bufs, self.peer_flags, vec.numel(),
+                              self.n_max, vec, self.epoch, self.status)
+        return vec
+
+
 def allreduce_losses(local_sums: torch.Tensor) -> torch.Tensor:
     """Sum of per-rank partial sums of returns (callers divide by the global batch)."""
     if world()[1] > 1:

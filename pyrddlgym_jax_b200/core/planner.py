@@ -539,6 +539,19 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
+        # multi-GPU exchange: one message per iteration.  In the pipelined order the
+        # gradient is not needed before the NEXT replay's optimiser step, so it travels together
+        # with the two loss sums after the branches join: [grad | train loss | test loss], summed
+        # by the one-shot NVLink peer kernel (csrc/rk_comm.cu) or, failing that, NCCL.
+        self._peer_ar = None
+        self._fold_msg = False
+        self._defer_ar = False
+        if self.world_size > 1:
+            self._fold_msg = (self._pipeline and P == 1 and self.steps_per_update <= 1)
+            self._msg = z(NP + 2)
+            if self._fold_msg:
+                self.grad = self._msg[:NP].view(1, NP)
+            self._peer_ar = parallel.PeerAllReduce.create(NP + 2, self.device)
         self.ent_coeff = torch.full((1,), float(self.start_entropy_coeff), device=self.device)
         if self.use_pgpe:
             self._pg_reward, self._pg_returns = z(T * Be), z(Be)
@@ -620,8 +633,8 @@ class JaxBackpropPlanner:
                                     noise=self.train_noise, mparams=self.train_mparams,
                                     disc=self.disc, gradp=self.gradp)
             engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
-        if self.world_size > 1:      # the one exchange step of the path
-            parallel.allreduce_gradient(self.grad[p])
+        if self.world_size > 1 and not self._defer_ar:   # the exchange step of the path
+            self._allreduce(self.grad[p])
         if not self.is_drp and getattr(self.plan, "_stochastic", False):
             # entropy regulariser of a stochastic plan (planner.py:2812-2813): the same for every
             # rollout, so value and gradient come from the parameters alone
@@ -694,13 +707,26 @@ class JaxBackpropPlanner:
             self._test_kernels(p)
         self._finish_iteration()
 
+    def _allreduce(self, vec: torch.Tensor):
+        if self._peer_ar is not None and vec.numel() <= self._peer_ar.n_max:
+            self._peer_ar(vec)
+        else:
+            parallel.allreduce_gradient(vec)
+
     def _finish_iteration(self):
         if self.optimizer_name == "adam" and self.steps_per_update <= 1:
             self.hyper[6:7].add_(1.0)
         if self.world_size > 1:
-            self.loss_pair[0].copy_(self.train_loss)
-            self.loss_pair[1].copy_(self.test_loss_buf)
-            parallel.allreduce_losses(self.loss_pair)
+            if self._defer_ar:          # [grad | train loss | test loss] in one message
+                NP = self.n_params
+                self._msg[NP:NP + 1].copy_(self.train_loss)
+                self._msg[NP + 1:NP + 2].copy_(self.test_loss_buf)
+                self._allreduce(self._msg)
+                self.loss_pair.view(-1).copy_(self._msg[NP:])
+            else:
+                self.loss_pair[0].copy_(self.train_loss)
+                self.loss_pair[1].copy_(self.test_loss_buf)
+                self._allreduce(self.loss_pair.view(-1))
 
     def _pipelined_kernels(self, side: Optional[torch.cuda.Stream]):
         """One iteration in software-pipelined order: the optimiser step for the gradient the
@@ -728,11 +754,13 @@ class JaxBackpropPlanner:
         else:
             for p in range(P):
                 self._test_kernels(p)
+        self._defer_ar = self._fold_msg
         for p in range(P):
             self._train_grad_kernels(p)
         if side is not None:
             main.wait_stream(side)
         self._finish_iteration()
+        self._defer_ar = False
 
     def _capture(self):
         """Capture one full iteration into a CUDA graph (after a warm-up on a side stream)."""
