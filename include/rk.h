@@ -207,23 +207,33 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
 int rk_tcgemm_tn(void* stream, int accumulate, int M, int N, int K, const float* A, int lda,
                  const float* B, int ldb, float* C, float* workspace, int max_splits);
 
-/* Action heads of the DRP (planner.py:1394-1429) + clip to the action box (planner.py:1472-1475).
+/* Action heads of the DRP (planner.py:1366-1429) + clip to the action box (planner.py:1472-1475).
  *   heads [B][2A] (mu | log_sigma) when stochastic, [B][A] otherwise;
- *   seg_off / seg_len (HOST arrays, n_seg <= RK_MAX_ACTION_FLUENTS): the action fluents' word
- *   ranges, contiguous and in action-fluent order; actions, noise and gact use the rollout
- *   kernels' fluent-major layout (fluent f = block [B][len_f] at word offset off_f * B);
+ *   seg_off / seg_len / seg_kind (HOST arrays, n_seg <= RK_MAX_ACTION_FLUENTS): the action
+ *   fluents' word ranges, contiguous and in action-fluent order, and their kind: 0 real, 1 bool,
+ *   2 int / enum (seg_kind NULL = all real); actions, noise and gact use the rollout kernels'
+ *   fluent-major layout (fluent f = block [B][len_f] at word offset off_f * B);
+ *   real / int: clip(mu + train * exp(clip(log_sigma)) * noise, lo, hi);
+ *   bool: sigmoid(bool_weight * (logit + train * noise)), noise ~ Logistic (planner.py:1381-1391);
  *   train = 1 (train policy) or 0 (test policy, planner.py:1486); lo/hi [A] or NULL;
- *   entropy [B] = sum_a clip(log_sigma) (planner.py:1416-1419), or NULL. */
+ *   typed != 0: bool actions are written as int32 (p > 0.5) and int actions as int32 round(.), the
+ *   input words of the exact test program (planner.py:1488-1497);
+ *   entropy [B] = sum clip(log_sigma) - sum_bool [p log p + (1-p) log(1-p)], or NULL. */
 #define RK_MAX_ACTION_FLUENTS 16
 int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg,
-                           const int32_t* seg_off, const int32_t* seg_len, const float* heads,
-                           const float* noise, float train, const float* lo, const float* hi,
-                           float ls_lo, float ls_hi, float* actions, float* entropy);
-/* gheads [B][2A or A] = d actions / d heads applied to gact (clip: gradient 1 inside). */
+                           const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
+                           const float* heads, const float* noise, float train, const float* lo,
+                           const float* hi, float ls_lo, float ls_hi, float bool_weight, int typed,
+                           float* actions, float* entropy);
+/* gheads [B][2A or A] = d actions / d heads applied to gact (clip: gradient 1 inside); boolean
+ * logits also receive the gradient of the entropy regulariser, ent_coeff[0] * inv_batch * dH/dlogit
+ * (ent_coeff: device scalar, NULL = none; the log_sigma entropy is stop_gradient). */
 int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
-                            const int32_t* seg_off, const int32_t* seg_len, const float* heads,
-                            const float* noise, float train, const float* lo, const float* hi,
-                            float ls_lo, float ls_hi, const float* gact, float* gheads);
+                            const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
+                            const float* heads, const float* noise, float train, const float* lo,
+                            const float* hi, float ls_lo, float ls_hi, float bool_weight,
+                            const float* ent_coeff, float inv_batch, const float* gact,
+                            float* gheads);
 
 /* Tile the un-batched initial state (S words: float bits, or int32 0/1 / int words for the exact
  * model) into the fluent-major s0 buffer of B rollouts.  seg_off / seg_len: HOST arrays with the

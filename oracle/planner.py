@@ -385,11 +385,13 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
     return actions, entropy
 
 
-def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True):
+def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True,
+                     sigmoid_weight: float = 1.0):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
-    acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic)
+    acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic,
+                          sigmoid_weight=sigmoid_weight)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]

@@ -78,18 +78,28 @@ class JaxDeepReactivePolicy(JaxPlan):
         self.rddl = rddl
         self.horizon = horizon
         self.layout, self.A = action_layout(rddl)
-        for name, (_, _, prange) in self.layout.items():
-            if prange != "real":
-                raise NotImplementedError(
-                    f"DRP heads for <{prange}> action-fluent <{name}> are not built yet "
-                    f"(real-valued actions only)")
+        # head kind per action fluent (planner.py:1368-1409): 0 real, 1 bool (sigmoid of a logit
+        # head), 2 int / enum (real head, rounded by the test policy)
+        self.action_kinds = [1 if prange == "bool" else (0 if prange == "real" else 2)
+                             for (_, _, prange) in self.layout.values()]
+        n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
+        if n_bool and rddl.max_allowed_actions < n_bool:
+            raise NotImplementedError(
+                "DRP with max-nondef-actions below the number of boolean actions needs the "
+                "dense_topk / GumbelSoftmaxTopK head (planner.py:1435-1447), which is not built yet")
         if rddl.observ_fluents:
             raise NotImplementedError("DRP over observ-fluents (POMDP) is not built yet")
         bounds = {}
-        for name in self.layout:
-            lo, hi = rddl.bounds[name]
-            lo, hi = _bounds.get(name, (lo, hi))
+        for name, (_, _, prange) in self.layout.items():
             shape = rddl.variable_shape(name)
+            if prange == "bool":
+                bounds[name] = (np.full(shape, -np.inf, np.float32), np.full(shape, np.inf, np.float32))
+                continue
+            if prange in rddl.enum_types:
+                lo, hi = 0.0, float(len(rddl.type_to_objects[prange]) - 1)
+            else:
+                lo, hi = rddl.bounds[name]
+            lo, hi = _bounds.get(name, (lo, hi))
             bounds[name] = (np.broadcast_to(np.asarray(lo, np.float32), shape).copy(),
                             np.broadcast_to(np.asarray(hi, np.float32), shape).copy())
         self.bounds = bounds
@@ -103,6 +113,8 @@ class JaxDeepReactivePolicy(JaxPlan):
             off += n
         self.D = off
         self.state_segs = [(pos[v][0], pos[v][1]) for v in rddl.state_fluents]
+        # exact-model state words of bool / int fluents are int32: converted before the first layer
+        self.state_is_int = [rddl.variable_ranges[v] != "real" for v in rddl.state_fluents]
         self.action_segs = [(o, n) for (o, n, _) in self.layout.values()]
         names = sorted(rddl.state_fluents)
         ref = [v for v in names if rddl.variable_ranges[v] != "bool"] + \
@@ -161,8 +173,12 @@ class JaxDeepReactivePolicy(JaxPlan):
         Wh = flat[..., off:off + r * c].reshape(*lead, r, c)
         ob = self.seg["bh"][0]
         bh = flat[..., ob:ob + c]
-        for var, (aoff, n, _) in self.layout.items():
+        for var, (aoff, n, prange) in self.layout.items():
             nm = var.replace("-", "_")
+            if prange == "bool":        # planner.py:1375-1377: a single logit head
+                tree[f"dense_{nm}_logit"] = {"kernel": Wh[..., aoff:aoff + n],
+                                             "bias": bh[..., aoff:aoff + n]}
+                continue
             tree[f"dense_{nm}_mu"] = {"kernel": Wh[..., aoff:aoff + n], "bias": bh[..., aoff:aoff + n]}
             if self._stochastic:
                 tree[f"dense_{nm}_log_sigma"] = {
@@ -187,8 +203,12 @@ class JaxDeepReactivePolicy(JaxPlan):
         off, r, c = self.seg["Wh"]
         Wh = torch.zeros(r, c)
         bh = torch.zeros(c)
-        for var, (aoff, n, _) in self.layout.items():
+        for var, (aoff, n, prange) in self.layout.items():
             nm = var.replace("-", "_")
+            if prange == "bool":
+                Wh[:, aoff:aoff + n] = as_t(tree[f"dense_{nm}_logit"]["kernel"]).reshape(r, n)
+                bh[aoff:aoff + n] = as_t(tree[f"dense_{nm}_logit"]["bias"]).reshape(-1)
+                continue
             Wh[:, aoff:aoff + n] = as_t(tree[f"dense_{nm}_mu"]["kernel"]).reshape(r, n)
             bh[aoff:aoff + n] = as_t(tree[f"dense_{nm}_mu"]["bias"]).reshape(-1)
             if self._stochastic:
@@ -216,10 +236,14 @@ class JaxDeepReactivePolicy(JaxPlan):
         ob = self.seg["bh"][0]
         out = (h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c]).reshape(-1)
         acts = {}
-        for var, (aoff, n, _) in self.layout.items():
+        for var, (aoff, n, prange) in self.layout.items():
             lo, hi = self.bounds[var]
             a = out[aoff:aoff + n].numpy().reshape(self.rddl.variable_shape(var))
-            acts[var] = np.minimum(np.maximum(a, lo), hi)
+            if prange == "bool":        # sigmoid(w * logit) > 0.5  (planner.py:1489)
+                acts[var] = (self._sigmoid_weight * a) > 0.0
+                continue
+            a = np.minimum(np.maximum(a, lo), hi)
+            acts[var] = a if prange == "real" else np.round(a).astype(np.int32)
         return acts
 
 
@@ -288,6 +312,7 @@ class DrpPipeline:
         self.t_H = [z(Be, h) for h in self.hid]
         self.t_heads = z(Be, self.NH)
         self.t_act = z(self.A * Be)
+        self.t_xf = z(te.S * Be) if any(plan.state_is_int) else None
         self.ent_coeff = z(1)
 
     # ---- views into a flat parameter / gradient vector ---------------------------------------
@@ -407,7 +432,8 @@ class DrpPipeline:
             engine.drp_actions_forward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
-                self.ls_lo, self.ls_hi, self.act[t], self.entropy[t])
+                self.ls_lo, self.ls_hi, self.act[t], self.entropy[t], kinds=plan.action_kinds,
+                bool_weight=plan._sigmoid_weight)
             fwd.forward(B, 1, x, actions=self.act[t],
                         noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
                         mparams=pl.train_mparams,
@@ -437,7 +463,9 @@ class DrpPipeline:
             engine.drp_actions_backward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
-                self.ls_lo, self.ls_hi, self.gact, self.gheads)
+                self.ls_lo, self.ls_hi, self.gact, self.gheads, kinds=plan.action_kinds,
+                bool_weight=plan._sigmoid_weight, ent_coeff=self.ent_coeff,
+                inv_batch=1.0 / (B * pl.world_size))
             self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
             cur ^= 1
 
@@ -458,10 +486,18 @@ class DrpPipeline:
         cur = 0
         for t in range(T):
             x, nxt = self.t_state[cur], self.t_state[cur ^ 1]
-            self.mlp_forward(params, B, x, self.t_H, self.t_heads)
+            xin = x
+            if any(plan.state_is_int):      # bool / int state words of the exact model -> fp32
+                xin = self.t_xf
+                for (off, n), is_int in zip(plan.state_segs, plan.state_is_int):
+                    blk = x[off * B:(off + n) * B]
+                    xin[off * B:(off + n) * B].copy_(blk.view(torch.int32) if is_int else blk)
+            self.mlp_forward(params, B, xin, self.t_H, self.t_heads)
             engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,
                                        None, 0.0, self.lo,
-                                       self.hi, self.ls_lo, self.ls_hi, self.t_act, None)
+                                       self.hi, self.ls_lo, self.ls_hi, self.t_act, None,
+                                       kinds=plan.action_kinds, bool_weight=plan._sigmoid_weight,
+                                       typed=True)
             te.forward(B, 1, x, actions=self.t_act,
                        noise=None if pl.test_noise is None else pl.test_noise[t * N * B:],
                        disc=None if pl.disc is None else pl.disc[t:],
@@ -478,3 +514,9 @@ class DrpPipeline:
     def redraw_noise(self, gen: torch.Generator):
         if self.pol_noise is not None:
             self.pol_noise.normal_(generator=gen)
+            B = self.pl.batch_size_train
+            for (off, n), kind in zip(self.plan.action_segs, self.plan.action_kinds):
+                if kind == 1:           # boolean logits take Logistic(0, 1) noise (planner.py:1386)
+                    blk = self.pol_noise[:, off * B:(off + n) * B]
+                    u = torch.rand(blk.shape, generator=gen, device=blk.device).clamp_(1e-7, 1 - 1e-7)
+                    blk.copy_(torch.log(u) - torch.log1p(-u))

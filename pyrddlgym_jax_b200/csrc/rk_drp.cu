@@ -294,13 +294,23 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
 struct RkActSegs {
   int n;
   int off[RK_MAX_ACTION_FLUENTS], len[RK_MAX_ACTION_FLUENTS];
+  int kind[RK_MAX_ACTION_FLUENTS];       // 0 real, 1 bool (sigmoid head), 2 int / enum (real head)
 };
 
+__device__ __forceinline__ float rk_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// x * safe_log(x) of compiler.py:65-75, with 0 * log 0 taken as 0 (the reference yields NaN there)
+__device__ __forceinline__ float rk_xlogx(float x) { return x > 0.f ? x * logf(x) : 0.f; }
+
+// Boolean fluents (kind 1, planner.py:1371-1391): p = sigmoid(w * (logit + train * logistic noise)),
+// entropy -= p0 log p0 + (1 - p0) log(1 - p0) with p0 = sigmoid(w * logit); the exact test program
+// receives (p > 0.5) as an int32 word.  Int / enum fluents (kind 2) are real heads whose exact-
+// program input is round(clip(.)) as int32 (planner.py:1491-1493).
 __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSegs S,
                                           const float* __restrict__ heads,
                                           const float* __restrict__ noise, float train,
                                           const float* __restrict__ lo,
                                           const float* __restrict__ hi, float ls_lo, float ls_hi,
+                                          float bool_weight, int typed,
                                           float* __restrict__ actions,
                                           float* __restrict__ entropy) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,14 +322,26 @@ __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSeg
       const int a = S.off[f] + e;
       const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
       float act = heads[(size_t)b * ld + a];
+      const float z = (stochastic && noise != nullptr) ? noise[w] : 0.f;
+      if (S.kind[f] == 1) {
+        if (stochastic) {
+          const float p0 = rk_sigmoid(bool_weight * act);
+          ent -= rk_xlogx(p0) + rk_xlogx(1.f - p0);
+          act = act + train * z;
+        }
+        act = rk_sigmoid(bool_weight * act);
+        if (typed) ((int32_t*)actions)[w] = act > 0.5f ? 1 : 0;
+        else actions[w] = act;
+        continue;
+      }
       if (stochastic) {
         const float ls = fminf(fmaxf(heads[(size_t)b * ld + A + a], ls_lo), ls_hi);
         ent += ls;
-        const float z = (noise != nullptr) ? noise[w] : 0.f;
         act = act + train * expf(ls) * z;
       }
       if (lo != nullptr) act = fminf(fmaxf(act, lo[a]), hi[a]);
-      actions[w] = act;
+      if (typed && S.kind[f] == 2) ((int32_t*)actions)[w] = (int32_t)rintf(act);
+      else actions[w] = act;
     }
   }
   if (entropy != nullptr) entropy[b] = ent;
@@ -330,7 +352,8 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
                                           const float* __restrict__ noise, float train,
                                           const float* __restrict__ lo,
                                           const float* __restrict__ hi, float ls_lo, float ls_hi,
-                                          const float* __restrict__ gact,
+                                          float bool_weight, const float* __restrict__ ent_coeff,
+                                          float inv_batch, const float* __restrict__ gact,
                                           float* __restrict__ gheads) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -340,11 +363,25 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
       const int a = S.off[f] + e;
       const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
       const float mu = heads[(size_t)b * ld + a];
-      float pre = mu, ex = 0.f, z = 0.f, raw = 0.f;
+      const float z = (stochastic && noise != nullptr) ? noise[w] : 0.f;
+      if (S.kind[f] == 1) {
+        const float s = rk_sigmoid(bool_weight * (mu + (stochastic ? train * z : 0.f)));
+        float g = gact[w] * bool_weight * s * (1.f - s);
+        if (stochastic && ent_coeff != nullptr) {
+          // loss term -coeff * mean_b sum_t H: dH/dlogit through safe_log's tangent 1 / (x + eps)
+          const float p0 = rk_sigmoid(bool_weight * mu), q0 = 1.f - p0, eps = 1e-12f;
+          const float df = (p0 > 0.f ? logf(p0) : 0.f) + p0 / (p0 + eps)
+                         - (q0 > 0.f ? logf(q0) : 0.f) - q0 / (q0 + eps);
+          g += ent_coeff[0] * inv_batch * df * bool_weight * p0 * q0;
+        }
+        gheads[(size_t)b * ld + a] = g;
+        if (stochastic) gheads[(size_t)b * ld + A + a] = 0.f;
+        continue;
+      }
+      float pre = mu, ex = 0.f, raw = 0.f;
       if (stochastic) {
         raw = heads[(size_t)b * ld + A + a];
         const float ls = fminf(fmaxf(raw, ls_lo), ls_hi);
-        z = (noise != nullptr) ? noise[w] : 0.f;
         ex = expf(ls);
         pre = mu + train * ex * z;
       }
@@ -361,48 +398,55 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
 }
 
 static int make_segs(int A, int n_seg, const int32_t* seg_off, const int32_t* seg_len,
-                     RkActSegs* S) {
+                     RkActSegs* S, const int32_t* seg_kind = nullptr) {
   if (n_seg <= 0 || n_seg > RK_MAX_ACTION_FLUENTS || seg_off == nullptr || seg_len == nullptr)
     return RK_E_BADARG;
   S->n = n_seg;
   int total = 0;
-  for (int i = 0; i < n_seg; ++i) {
-    if (seg_off[i] != total || seg_len[i] <= 0) return RK_E_BADARG;   // contiguous, in order
-    S->off[i] = seg_off[i];
-    S->len[i] = seg_len[i];
-    total += seg_len[i];
+  for (int f = 0; f < n_seg; ++f) {
+    if (seg_len[f] <= 0 || seg_off[f] != total) return RK_E_BADARG;
+    S->off[f] = seg_off[f];
+    S->len[f] = seg_len[f];
+    S->kind[f] = seg_kind != nullptr ? seg_kind[f] : 0;
+    total += seg_len[f];
   }
   return total == A ? 0 : RK_E_BADARG;
 }
 
 extern "C" int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg,
                                       const int32_t* seg_off, const int32_t* seg_len,
-                                      const float* heads, const float* noise, float train,
-                                      const float* lo, const float* hi, float ls_lo, float ls_hi,
-                                      float* actions, float* entropy) {
+                                      const int32_t* seg_kind, const float* heads,
+                                      const float* noise, float train, const float* lo,
+                                      const float* hi, float ls_lo, float ls_hi,
+                                      float bool_weight, int typed, float* actions,
+                                      float* entropy) {
   if (B <= 0 || A <= 0 || heads == nullptr || actions == nullptr) return RK_E_BADARG;
   if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
   RkActSegs S;
-  int rc = make_segs(A, n_seg, seg_off, seg_len, &S);
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S, seg_kind);
   if (rc != 0) return rc;
   rk_drp_actions_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, actions, entropy);
+      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, bool_weight, typed, actions,
+      entropy);
   return (int)cudaGetLastError();
 }
 
 extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
                                        const int32_t* seg_off, const int32_t* seg_len,
-                                       const float* heads, const float* noise, float train,
-                                       const float* lo, const float* hi, float ls_lo, float ls_hi,
+                                       const int32_t* seg_kind, const float* heads,
+                                       const float* noise, float train, const float* lo,
+                                       const float* hi, float ls_lo, float ls_hi,
+                                       float bool_weight, const float* ent_coeff, float inv_batch,
                                        const float* gact, float* gheads) {
   if (B <= 0 || A <= 0 || heads == nullptr || gact == nullptr || gheads == nullptr)
     return RK_E_BADARG;
   if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
   RkActSegs S;
-  int rc = make_segs(A, n_seg, seg_off, seg_len, &S);
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S, seg_kind);
   if (rc != 0) return rc;
   rk_drp_actions_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, gact, gheads);
+      B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, bool_weight, ent_coeff,
+      inv_batch, gact, gheads);
   return (int)cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@ FIXTURES = {
     "powergen": ("PowerGen_Continuous", "instance1"),
     "discrete": ("Discrete_Toy", "instance1"),
     "distributions": ("Distributions_Toy", "instance1"),
+    "wildfire_free": ("Wildfire_MDP_ippc2014", "instance5free"),    # no concurrency constraint
 }
 
 

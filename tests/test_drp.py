@@ -370,3 +370,80 @@ def test_fused_layer0_backward_against_fp64(cuda_device, B, segs, H):
     torch.testing.assert_close(gw.double(), want_w, rtol=1e-5,
                                atol=2e-6 * max(float(want_w.abs().max()), 1.0) * B ** 0.5)
     torch.testing.assert_close(gs.double(), want_s, rtol=1e-5, atol=1e-4)
+
+
+def _segment_noise(plan, m, pol_noise_t, B):
+    """{action fluent: [B, n]} views of one step's fluent-major policy-noise row."""
+    out = {}
+    for var, (off, n, _) in plan.layout.items():
+        out[var] = pol_noise_t[off * B:(off + n) * B].reshape(B, n)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stochastic", [True, False])
+def test_drp_bool_heads_match_oracle(cuda_device, stochastic):
+    """Boolean action heads (planner.py:1371-1391): sigmoid(w (logit + logistic noise)) in the
+    train policy with the Bernoulli entropy (value AND gradient), (p > 0.5) in the test policy;
+    boolean state fluents feed the first layer as 0 / 1."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("wildfire_free")
+    T, B = 3, 21
+    plan = JaxDeepReactivePolicy(topology=[16, 16], stochastic=stochastic, sigmoid_weight=2.0)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.rand(T, fw.N * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pol_noise = torch.randn(T, plan.A * B, generator=g)
+    if stochastic:
+        pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    assert "dense_cut_out_logit" in tree and "dense_cut_out_mu" not in tree
+    P = {k: {kk: vv.clone().requires_grad_(True) for kk, vv in v.items()} for k, v in tree.items()}
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              _segment_noise(plan, m, pol_noise[t], B), 1.0, m.bounds, 2,
+                              stochastic, sigmoid_weight=2.0)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount))
+    if stochastic:
+        loss = loss - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    grads = {k: {kk: (vv.grad if vv.grad is not None else torch.zeros_like(vv))
+                 for kk, vv in v.items()} for k, v in P.items()}
+    want = plan.pytree_to_params(grads).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss)) <= 2e-5 * abs(float(loss))
+    got = pl.grad[0].cpu().numpy()
+    live = np.abs(want) > 0          # the unused log_sigma columns of boolean heads get no gradient
+    np.testing.assert_allclose(got[live], want[live], rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    assert np.all(got[~live] == 0)
+    # test policy on the exact model
+    te = pl.test_fwd.program
+    tnoise = torch.rand(T, te.N * B, generator=g)
+    pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    om = OracleModel(m, None)
+    out = OP.rollout(om, lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, m.bounds, 2, stochastic,
+        sigmoid_weight=2.0), B, T,
+        [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(),
+                               out["reward"].numpy().T, rtol=1e-5, atol=1e-4)
