@@ -619,7 +619,20 @@ class JaxBackpropPlanner:
                                    mparams=self.train_mparams, disc=self.disc,
                                    reward=self.train_reward[p], returns=self.train_returns[p],
                                    err=self.train_err[p], tape=self.tape)
-            if self.utility == "mean":
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_published", None) is not None:
+                main.wait_event(self._published)
+            side = getattr(self, "_loss_stream", None)
+            if self.utility == "mean" and side is not None \
+                    and not getattr(self.plan, "_stochastic", False):
+                # the loss value is not an input of the adjoint (its cotangent is the constant
+                # -1/B): reduce it on the side stream, off the critical chain
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    engine.mean_loss(self.train_returns[p], B, loss_out, None)
+            elif self.utility == "mean":
                 engine.mean_loss(self.train_returns[p], B, loss_out, None)
             else:
                 r = self.train_returns[p].detach().clone().requires_grad_(True)
@@ -642,13 +655,18 @@ class JaxBackpropPlanner:
             loss_out.sub_(self.ent_coeff * H)
             self.grad[p].view(T, A).sub_(self.ent_coeff * dH)
 
-    def _opt_kernels(self, p: int):
+    def _publish_kernels(self, p: int):
+        """Publish the loss and the gradient of the update being applied (callback['grad'])."""
+        self.train_loss[p:p + 1].copy_(self._train_loss_tmp[p:p + 1])
+        self.grad_used[p].copy_(self.grad[p])
+
+    def _opt_kernels(self, p: int, publish: bool = True):
         """optax update + apply_updates + projection (planner.py:2885-2899) from the gradient the
         train stage left in self.grad; publishes that stage's loss."""
         T, A = self.T, self.A
         params = self.params[p]
-        self.train_loss[p:p + 1].copy_(self._train_loss_tmp[p:p + 1])
-        self.grad_used[p].copy_(self.grad[p])       # callback['grad']: the gradient of THIS update
+        if publish:
+            self._publish_kernels(p)
         engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
                               self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
                               self.zero_flag[p:p + 1])
@@ -736,8 +754,12 @@ class JaxBackpropPlanner:
         (one warp per SM sub-partition), so they overlap almost perfectly.  Results per
         iteration are identical to update-then-test (planner.py:3245-3260)."""
         P = self.parallel_updates
+        # the two small copies that publish the previous stage's loss / gradient only READ what the
+        # optimiser reads, so with a side stream they leave the critical chain (K = 1 only: with
+        # more updates per iteration the intermediate stages overwrite what they read)
+        off_chain = side is not None and self.steps_per_update <= 1
         for p in range(P):
-            self._opt_kernels(p)
+            self._opt_kernels(p, publish=not off_chain)
             for _ in range(max(1, self.steps_per_update) - 1):   # K updates per iteration
                 if self.optimizer_name == "adam":
                     self.hyper[6:7].add_(1.0)
@@ -746,17 +768,27 @@ class JaxBackpropPlanner:
             if self.optimizer_name == "adam" and self.steps_per_update > 1:
                 self.hyper[6:7].add_(1.0)
         main = torch.cuda.current_stream(self.device)
+        published = None
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                if off_chain:
+                    for p in range(P):
+                        self._publish_kernels(p)
+                    published = torch.cuda.Event()
+                    published.record(side)
                 for p in range(P):
                     self._test_kernels(p)
         else:
             for p in range(P):
                 self._test_kernels(p)
         self._defer_ar = self._fold_msg
+        self._published = published      # the train stage overwrites what the copies read
+        self._loss_stream = side if off_chain else None
         for p in range(P):
             self._train_grad_kernels(p)
+        self._published = None
+        self._loss_stream = None
         if side is not None:
             main.wait_stream(side)
         self._finish_iteration()

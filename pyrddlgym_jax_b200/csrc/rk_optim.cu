@@ -47,10 +47,46 @@ __global__ void rk_reduce_heads_kernel(const float* __restrict__ gradp, int rows
   grad[i] = acc;
 }
 
+// few rows (a straight-line plan at B = 4096 has 512 warp rows): one launch, one memory round trip.
+// A CTA owns 32 columns; each of its 32 warps sums a contiguous slice of at most 32 rows with all
+// loads of a batch of 8 in flight, and the slices are added in slice order.
+__global__ void __launch_bounds__(1024)
+rk_reduce_small_kernel(const float* __restrict__ gradp, int rows, int n, float* __restrict__ grad) {
+  __shared__ float part[32][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;
+  const int per = (rows + 31) / 32;
+  const int r0 = g * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  if (i < n) {
+    const float* p = gradp + (size_t)r0 * n + i;
+    for (int r = r0; r < r1; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (r + u < r1) ? p[(size_t)u * n] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+      p += 8 * (size_t)n;
+    }
+  }
+  part[g][c] = acc;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s += part[q][c];
+    grad[i] = s;
+  }
+}
+
 extern "C" int rk_reduce_partials(void* stream, const float* gradp, int num_rows, int n,
                                   float* grad) {
   if (gradp == nullptr || grad == nullptr || num_rows <= 0 || n <= 0) return RK_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (num_rows <= 1024) {
+    rk_reduce_small_kernel<<<(n + 31) / 32, 1024, 0, st>>>(gradp, num_rows, n, grad);
+    return (int)cudaGetLastError();
+  }
   int chunks = 1;
   // enough CTAs to cover the machine when the parameter vector is short
   const int col_blocks = (n + 127) / 128;
@@ -139,6 +175,62 @@ __global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, i
   params[i] = p;
 }
 
+// short parameter vectors: statistics and update in one single-CTA launch
+__global__ void __launch_bounds__(1024)
+rk_optimizer_small_kernel(int kind, const float* __restrict__ hyper, int n, float* params,
+                          float* state, const float* __restrict__ grad,
+                          const float* __restrict__ lo, const float* __restrict__ hi,
+                          int32_t* __restrict__ zero_flag) {
+  __shared__ float sh[32];
+  float ss = 0.f, nz = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = grad[i];
+    ss += v * v;
+    nz += (fabsf(v) > 1e-8f || v != v) ? 1.f : 0.f;
+  }
+  ss = block_sum_1024(ss, sh);
+  nz = block_sum_1024(nz, sh);
+  if (threadIdx.x == 0 && zero_flag != nullptr) *zero_flag = (nz == 0.f) ? 1 : 0;
+  const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
+  const float clip = hyper[4], mom = hyper[5], step = hyper[6];
+  float scale = 1.f;
+  bool clipped = false;
+  if (clip > 0.f) {
+    const float gn = sqrtf(ss);
+    if (gn > clip) { scale = clip / gn; clipped = true; }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float g = grad[i];
+    if (clipped) g = g * scale;
+    float upd;
+    if (kind == 1) {
+      float nu = d1 * state[i] + (1.f - d1) * g * g;
+      state[i] = nu;
+      upd = g / sqrtf(nu + eps);
+    } else if (kind == 2) {
+      float mu = d1 * state[i] + (1.f - d1) * g;
+      float nu = b2 * state[n + i] + (1.f - b2) * g * g;
+      state[i] = mu;
+      state[n + i] = nu;
+      float mh = mu / (1.f - powf(d1, step));
+      float nh = nu / (1.f - powf(b2, step));
+      upd = mh / (sqrtf(nh) + eps);
+    } else {
+      if (mom > 0.f) {
+        float m = g + mom * state[i];
+        state[i] = m;
+        upd = m;
+      } else {
+        upd = g;
+      }
+    }
+    float p = params[i] - lr * upd;
+    if (lo != nullptr) p = fmaxf(p, lo[i]);
+    if (hi != nullptr) p = fminf(p, hi[i]);
+    params[i] = p;
+  }
+}
+
 static float* g_stats[64] = {nullptr};
 
 extern "C" int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
@@ -148,6 +240,11 @@ extern "C" int rk_optimizer_step(void* stream, int kind, const float* hyper, int
   if (kind < 0 || kind > 2) return RK_E_BADARG;
   if (kind != 0 && state == nullptr) return RK_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 16384) {
+    rk_optimizer_small_kernel<<<1, 1024, 0, st>>>(kind, hyper, n, params, state, grad, lo, hi,
+                                                  zero_flag);
+    return (int)cudaGetLastError();
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return RK_E_BADARG;
