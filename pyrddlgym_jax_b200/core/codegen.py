@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 12
+CODEGEN_VERSION = 13
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -587,7 +587,7 @@ class _Gen:
                 src = f"{gn} + ({off}u + le)"
                 cond = f"has{buf} && le < {n}u"
             i = len(self.pf_stmts)
-            self.pf_stmts.append(f"    rk_cp_async4(ring_w + {i * 32}u, {src}, more && {cond}, K.prog);")
+            self.pf_stmts.append(f"    rk_cp_async4(ring_w + {i * 32}u, {src}, more && {cond});")
             self.emit(f"  {self.var(dst)} = {self.from_bits(f'ring_r[{i * 32}u]', dt)};")
             self.pf_last = len(self.lines)
             return

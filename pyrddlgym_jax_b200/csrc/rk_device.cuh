@@ -18,13 +18,12 @@ __device__ __forceinline__ float stable_tanh(float x) {       // logic.py:57-65
 }
 
 // ---- asynchronous global -> shared copies of one word per lane (prefetch ring of the generated
-// kernels); a false predicate zero-fills the destination without touching global memory
-__device__ __forceinline__ void rk_cp_async4(uint32_t* dst, const uint32_t* src, bool pred,
-                                             const void* safe) {
+// kernels); a false predicate zero-fills the destination: with a source size of 0 nothing is read
+// from global memory, so the (possibly out-of-range) address is never dereferenced
+__device__ __forceinline__ void rk_cp_async4(uint32_t* dst, const uint32_t* src, bool pred) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const void* s = pred ? (const void*)src : safe;
   const int nbytes = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(s), "r"(nbytes)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nbytes)
                : "memory");
 }
 __device__ __forceinline__ void rk_cp_async_commit() {
