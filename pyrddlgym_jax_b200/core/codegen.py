@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 13
+CODEGEN_VERSION = 14
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -99,6 +99,11 @@ class _Gen:
         # relaxed programs may trade last-bit identity for speed (reciprocal of constants, FMA
         # contraction); exact programs never do.  RK_FAST_RELAXED=0 switches it off.
         self.fast = bool(prog.relaxed) and os.environ.get("RK_FAST_RELAXED", "1") != "0"
+        # sin / cos / tan: the branch-free Cody-Waite + minimax evaluation (rk_fsincos, ~1 ulp, the
+        # accuracy class of libdevice's own fast path) in exact programs too -- libdevice's slow-
+        # path branch per call splits the step into small basic blocks; the IEEE division and
+        # sqrt of exact programs stay.  RK_FAST_TRIG=0 restores sincosf.
+        self.fast_trig = self.fast or os.environ.get("RK_FAST_TRIG", "1") != "0"
         # per-step loads run this many steps ahead of their use (a cp.async ring in shared memory): one step of
         # a lone warp is shorter than an HBM round trip, so a distance of 1 leaves the step time
         # pinned at the memory latency
@@ -235,7 +240,7 @@ class _Gen:
                   "TAN": "rk_fdiv(sn_, cs_)" if self.fast else "(sn_ / cs_)"}[r["op"]]
             asg.append(f"{self.var(r['dst'])} = {ex};")
         self.emit(f"  {{ const uint32_t ec = le < {n}u ? le : 0u; float sn_, cs_; "
-                  f"{'rk_fsincos' if self.fast else 'sincosf'}({x}, &sn_, &cs_); " +
+                  f"{'rk_fsincos' if self.fast_trig else 'sincosf'}({x}, &sn_, &cs_); " +
                   " ".join(asg) + " }")
 
     # ---- global-memory addressing: one 64-bit base per buffer per step, 32-bit offsets ----
@@ -313,6 +318,10 @@ class _Gen:
             return
         if self.fast and op in _FAST:
             body, tin = _FAST[op], ("ff" if op in _F2 else "f")
+        elif self.fast_trig and op in ("SIN", "COS"):
+            body, tin = _FAST[op], "f"
+        elif self.fast_trig and op == "TAN":
+            body, tin = "rk_ftan_ieee(x)", "f"
         elif op in _F1:
             body, tin = _F1[op], "f"
         elif op in _F2:

@@ -79,6 +79,7 @@ __device__ __forceinline__ void rk_fsincos(float x, float* sn, float* cs) {
 __device__ __forceinline__ float rk_fsin(float x) { float s, c; rk_fsincos(x, &s, &c); return s; }
 __device__ __forceinline__ float rk_fcos(float x) { float s, c; rk_fsincos(x, &s, &c); return c; }
 __device__ __forceinline__ float rk_ftan(float x) { float s, c; rk_fsincos(x, &s, &c); return rk_fdiv(s, c); }
+__device__ __forceinline__ float rk_ftan_ieee(float x) { float s, c; rk_fsincos(x, &s, &c); return s / c; }
 
 __device__ __forceinline__ float rk_fstable_tanh(float x) {   // stable_tanh without the branch
   const float ax = fminf(fabsf(x), 20.f);                     // tanh(20) == 1.f in fp32
