@@ -383,17 +383,19 @@ def main():
     # from (`guess`); outputs: the three status scalars and the plan (callback['params'])
     init_train_h, init_test_h = planner.init_train_host, planner.init_test_host
     params_h = planner.params.cpu().pin_memory()
-    pback_h = torch.empty_like(params_h).pin_memory()
     h2d = (init_train_h.numel() + init_test_h.numel() + params_h.numel()) * 4
     d2h = planner._stats_host.numel() * 4 + params_h.numel() * 4
+    # (the host copies are nodes of the same CUDA graph as the iteration: one launch and one
+    # synchronisation per step, JaxBackpropPlanner.iterate_from_host)
+    for _ in range(3):
+        planner.iterate_from_host(init_train_h, init_test_h, params_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        planner.load_initial_state(init_train_h, init_test_h)      # init_sim_state from host
-        planner.params.copy_(params_h, non_blocking=True)          # warm-start guess
-        step()
-        pback_h.copy_(planner.params, non_blocking=True)           # callback['params']
-        planner.read_stats()                                       # losses; synchronises
+        if has_noise:
+            planner.redraw_noise()
+        # in: init_sim_state words + warm-start guess; out: losses + callback['params']
+        _, _, _, pback_h = planner.iterate_from_host(init_train_h, init_test_h, params_h)
         params_h.copy_(pback_h)
     t_e2e = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
     if world > 1:

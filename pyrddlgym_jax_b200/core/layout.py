@@ -13,7 +13,6 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-_SEEDED = set()
 _TORCH_DT = {"f": torch.float32, "i": torch.int32, "b": torch.int32}
 
 
@@ -80,14 +79,9 @@ def draw_noise(noise_layout: Sequence[Tuple[str, Tuple[int, ...], int, int, Any]
                 conc = torch.as_tensor(np.asarray(extra, dtype=np.float32).reshape(-1),
                                        device="cpu").clamp_min(1e-6)
                 if device is not None and torch.device(device).type == "cuda":
-                    # standard Gamma(shape) draws on the device (torch's CUDA sampler uses the
-                    # default CUDA generator: seed it from the caller's stream of seeds)
-                    key = ("gamma_seeded", str(device))
-                    if generator is not None and key not in _SEEDED:
-                        torch.cuda.manual_seed(int(generator.initial_seed()) + 12345)
-                        _SEEDED.add(key)
+                    # standard Gamma(shape) draws on the device from the caller's generator
                     a = conc.to(device).expand(T, B, conc.numel()).contiguous()
-                    z = torch._standard_gamma(a)
+                    z = torch._standard_gamma(a, generator=generator)
                 else:
                     g = torch.distributions.Gamma(conc, torch.ones_like(conc))
                     # torch's sampler ignores `generator`: seed from it for reproducibility

@@ -530,6 +530,7 @@ class JaxBackpropPlanner:
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
             if len(fw.mparam_defaults) else None
         self._graph = None
+        self._graph_host = None
         self._primed = False
         # software pipelining of the captured iteration (opt -> test || next gradient).  All NCCL
         # calls stay on the main branch (gradient all-reduce in the train stage, loss all-reduce
@@ -794,12 +795,34 @@ class JaxBackpropPlanner:
         self._finish_iteration()
         self._defer_ar = False
 
-    def _capture(self):
-        """Capture one full iteration into a CUDA graph (after a warm-up on a side stream)."""
+    def _capture(self, from_host: bool = False):
+        """Capture one full iteration into a CUDA graph (after a warm-up on a side stream).
+        ``from_host``: the graph also carries the host<->device copies of one optimize() call
+        (initial-state words and plan in, status words and plan out, through pinned staging
+        buffers), so a whole replanning step is ONE graph launch and ONE synchronisation."""
         backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
         s = torch.cuda.Stream(device=self.device)
         side = torch.cuda.Stream(device=self.device) if self._overlap else None
-        body = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
+        inner = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
+        if from_host:
+            pin = lambda t: torch.empty_like(t, device="cpu").pin_memory()   # noqa: E731
+            self._h_init_train, self._h_init_test = pin(self._init_train), pin(self._init_test)
+            self._h_params_in, self._h_params_out = pin(self.params), pin(self.params)
+            self._h_pair = pin(self.loss_pair)
+            self._h_init_train.copy_(self.init_train_host)
+            self._h_init_test.copy_(self.init_test_host)
+            self._h_params_in.copy_(self.params)
+
+            def body():
+                self.load_initial_state(self._h_init_train, self._h_init_test)
+                self.params.copy_(self._h_params_in, non_blocking=True)
+                inner()
+                self._h_params_out.copy_(self.params, non_blocking=True)
+                self._stats_host.copy_(self._stats, non_blocking=True)
+                if self.world_size > 1:
+                    self._h_pair.copy_(self.loss_pair, non_blocking=True)
+        else:
+            body = inner
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             body()
@@ -811,8 +834,46 @@ class JaxBackpropPlanner:
         self.params.copy_(backup[0])
         self.opt_state.copy_(backup[1])
         self.hyper.copy_(backup[2])
-        self._graph = g
+        if from_host:
+            self._graph_host = g
+        else:
+            self._graph = g
         self._primed = False
+
+    def iterate_from_host(self, init_train: torch.Tensor, init_test: torch.Tensor,
+                          params: torch.Tensor):
+        """One replanning step driven from host buffers (the per-call path of optimize() and of
+        JaxOnlineController): initial-state words of both models and the plan to start from go
+        in, (train loss, test loss, zero-gradient flags, plan) come back -- one graph launch and
+        one synchronisation.  Returns (train [P], test [P], zero [P], plan [P, NP] pinned view)."""
+        if self.utility != "mean" or not self.use_cuda_graph:
+            self.load_initial_state(init_train, init_test)
+            self.params.copy_(params, non_blocking=True)
+            self.iterate()
+            train, test, zero = self.read_stats()
+            return train, test, zero, self.params.cpu()
+        if getattr(self, "_graph_host", None) is None:
+            self._capture(from_host=True)
+        self._h_init_train.copy_(init_train)
+        self._h_init_test.copy_(init_test)
+        self._h_params_in.copy_(params)
+        if self._pipeline and not self._primed:
+            self.load_initial_state(self._h_init_train, self._h_init_test)
+            self.params.copy_(self._h_params_in, non_blocking=True)
+            for p in range(self.parallel_updates):     # gradient for the first optimiser step
+                self._train_grad_kernels(p)
+            self._primed = True
+        self._graph_host.replay()
+        torch.cuda.current_stream(self.device).synchronize()
+        P = self.parallel_updates
+        raw = self._stats_host.numpy()
+        train = raw[0:P].view(np.float32).copy()
+        test = raw[P:2 * P].view(np.float32).copy()
+        zero = raw[2 * P:3 * P] > 0
+        if self.world_size > 1:
+            pair = self._h_pair.numpy() / self.world_size
+            train, test = pair[0].copy(), pair[1].copy()
+        return train, test, zero, self._h_params_out
 
     def iterate(self):
         """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""

@@ -345,3 +345,31 @@ def test_stochastic_plan_update_matches_oracle(cuda_device, key):
     np.testing.assert_allclose(float(pl.train_loss[0]), float(loss), rtol=2e-5)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
                                atol=1e-4 * float(want.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["quadcopter", "reservoir"])
+def test_host_driven_step_equals_separate_calls(cuda_device, key):
+    """iterate_from_host (host copies captured in the iteration's CUDA graph: one launch, one
+    synchronisation per replanning step) == load_initial_state + params upload + iterate +
+    read_stats, bit for bit."""
+    m = fixture_model(key)
+
+    def make():
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=32, rollout_horizon=8,
+                                optimizer_kwargs={"learning_rate": 0.05}, pgpe=None)
+        pl.initialize(3)
+        return pl
+    a, b = make(), make()
+    pa = a.params.cpu().pin_memory()
+    pb = b.params.cpu().pin_memory()
+    for it in range(4):
+        a.load_initial_state(a.init_train_host, a.init_test_host)
+        a.params.copy_(pa, non_blocking=True)
+        a.iterate()
+        ta, sa, za = a.read_stats()
+        pa.copy_(a.params.cpu())
+        tb, sb, zb, out = b.iterate_from_host(b.init_train_host, b.init_test_host, pb)
+        pb.copy_(out)
+        assert np.array_equal(ta, tb) and np.array_equal(sa, sb) and np.array_equal(za, zb), it
+        assert torch.equal(pa, pb), it
