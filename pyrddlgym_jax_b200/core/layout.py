@@ -13,6 +13,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+_GAMMA_CONC: Dict[Any, torch.Tensor] = {}
 _TORCH_DT = {"f": torch.float32, "i": torch.int32, "b": torch.int32}
 
 
@@ -79,8 +80,13 @@ def draw_noise(noise_layout: Sequence[Tuple[str, Tuple[int, ...], int, int, Any]
                 conc = torch.as_tensor(np.asarray(extra, dtype=np.float32).reshape(-1),
                                        device="cpu").clamp_min(1e-6)
                 if device is not None and torch.device(device).type == "cuda":
-                    # standard Gamma(shape) draws on the device from the caller's generator
-                    a = conc.to(device).expand(T, B, conc.numel()).contiguous()
+                    # standard Gamma(shape) draws on the device from the caller's generator; the
+                    # concentrations are uploaded once (no host copy inside a captured graph)
+                    key = (conc.numpy().tobytes(), T, B, str(device))
+                    a = _GAMMA_CONC.get(key)
+                    if a is None:
+                        a = conc.to(device).expand(T, B, conc.numel()).contiguous()
+                        _GAMMA_CONC[key] = a
                     z = torch._standard_gamma(a, generator=generator)
                 else:
                     g = torch.distributions.Gamma(conc, torch.ones_like(conc))

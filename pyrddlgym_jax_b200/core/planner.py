@@ -529,14 +529,18 @@ class JaxBackpropPlanner:
         self.hyper = torch.tensor(h, dtype=torch.float32, device=dev)
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
             if len(fw.mparam_defaults) else None
+        import os as _os
         self._graph = None
         self._graph_host = None
+        # the noise draws (torch's Philox generator, registered with the graph) replay with the
+        # iteration instead of costing a dozen eager launches per step; RK_NOISE_IN_GRAPH=0 disables
+        self._noise_in_graph = (_os.environ.get("RK_NOISE_IN_GRAPH", "1") != "0" and not self.is_drp
+                                and (self.train_noise is not None or self.test_noise is not None))
         self._primed = False
         # software pipelining of the captured iteration (opt -> test || next gradient).  All NCCL
         # calls stay on the main branch (gradient all-reduce in the train stage, loss all-reduce
         # after the join); the DRP branches share scratch buffers, so only straight-line plans
         # run the two branches concurrently
-        import os as _os
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
@@ -803,7 +807,13 @@ class JaxBackpropPlanner:
         backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
         s = torch.cuda.Stream(device=self.device)
         side = torch.cuda.Stream(device=self.device) if self._overlap else None
-        inner = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
+        inner0 = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
+        if self._noise_in_graph:
+            def inner():
+                self.redraw_noise(force=True)
+                inner0()
+        else:
+            inner = inner0
         if from_host:
             pin = lambda t: torch.empty_like(t, device="cpu").pin_memory()   # noqa: E731
             self._h_init_train, self._h_init_test = pin(self._init_train), pin(self._init_test)
@@ -829,6 +839,8 @@ class JaxBackpropPlanner:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
+        if self._noise_in_graph:
+            g.register_generator_state(self._gen)
         with torch.cuda.graph(g):
             body()
         self.params.copy_(backup[0])
@@ -934,9 +946,14 @@ class JaxBackpropPlanner:
             train, test = pair[0], pair[1]
         return train, test, zero
 
-    def redraw_noise(self):
+    def redraw_noise(self, force: bool = False):
         """Fresh supplied-noise tensors for the next iteration (the reference splits its PRNG
-        key once per update and once per test evaluation, planner.py:2880, 3257)."""
+        key once per update and once per test evaluation, planner.py:2880, 3257).  Once the
+        iteration graph has been captured with the draws inside it (``_noise_in_graph``), every
+        replay redraws by itself and this call is a no-op."""
+        if not force and self._noise_in_graph and \
+                (self._graph is not None or self._graph_host is not None):
+            return
         with torch.cuda.device(self.device):
             self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
             self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)

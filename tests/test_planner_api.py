@@ -196,6 +196,7 @@ def test_pipelined_graph_equals_sequential_iterations(cuda_device, key, monkeypa
     """The captured, software-pipelined iteration (opt -> test || next gradient) produces the
     same losses and plan, iteration by iteration, as plain update-then-test launches."""
     m = fixture_model(key)
+    monkeypatch.setenv("RK_NOISE_IN_GRAPH", "0")        # fixed noise in both runs
 
     def run(graph):
         pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=96, rollout_horizon=12,
