@@ -588,14 +588,14 @@ def main():
 # figures read from the committed ncu captures of the same workload (profiles/), per launch
 PROFILED = {
     "quadcopter": {
-        "adjoint_traffic_bytes": 78687232 + 2000640,       # dram read + write, r01_ncu_spec_v12.md
-        "adjoint_issue_active": 0.571,
+        "adjoint_traffic_bytes": 78689024 + 2202624,       # dram read + write, r01_ncu_spec_v14.md
+        "adjoint_issue_active": 0.537,
         "note": "not HBM-bound by construction: 192 B per rollout-step carry ~420 adjoint SASS "
                 "instructions (3 sincos, 8 divisions, ~150 mul/add, all branch-free); B=4096 gives "
                 "512 warps for 592 SM sub-partitions, so every warp runs alone on its scheduler: "
                 "the tape is prefetched 3 steps ahead through a cp.async ring (long-scoreboard "
-                "stall 0.13 per issue) and the kernel is bound by single-warp issue (ncu: issue "
-                "slots 57% busy, DRAM 23%)"},
+                "stall 0.1 per issue) and the kernel is bound by single-warp issue (ncu: issue "
+                "slots 54% busy, DRAM 23%)"},
 }
 
 
