@@ -275,14 +275,52 @@ class Lowerer:
             return TV(self.g.const(np.arange(n, dtype=np.int32), "i"), acc.axes, None, True)
         if acc.kind == "object":
             return self.const_tv(np.int32(acc.value), "i", full=False)
-        if acc.nested:
-            raise RDDLNotImplementedError(
-                f"nested fluent-valued arguments of <{acc.name}> are not supported yet")
+        if acc.name not in env and acc.nested and acc.name in self.m.non_fluents:
+            # a non-fluent indexed by a fluent: its table becomes a constant of the program
+            vals = np.asarray(self.m.non_fluents[acc.name]).reshape(-1)
+            prange = self.m.variable_ranges[acc.name]
+            dt = "f" if (self.relaxed or prange == "real") else ("b" if prange == "bool" else "i")
+            env = dict(env)
+            env[acc.name] = self.g.const(vals.astype(np.float32 if dt == "f" else np.int32), dt)
         if acc.name not in env:
             raise RDDLTraceError(f"fluent <{acc.name}> is read before it is defined")
+        if acc.nested:
+            return self._nested_pvar(acc, scope, env, sizes)
         src = env[acc.name]
         idx = None if acc.identity else acc.index
         return TV(src, acc.axes, idx, True)
+
+    def _nested_pvar(self, acc, scope, env, sizes) -> TV:
+        """A pvariable whose arguments are themselves computed (compiler.py:1046-1064: gather by
+        integer indices, no gradient w.r.t. the indices).  The index expressions range over the
+        objects of their parameter type, so the gather is a select chain over the statically
+        sliced candidates -- every candidate is a plain static gather of the source."""
+        import itertools
+        src = env[acc.name]
+        vshape = self.m.variable_shape(acc.name)
+        subs = []
+        for d, sub in acc.nested:
+            tv = self.lower(sub, scope, env)
+            if tv.dtype == "f":                    # jnp.asarray(index, dtype=int): truncation
+                tv = self.ew("F2I", [tv], sizes, "i")
+            subs.append((d, self.at_least_int(tv)))
+        ranges = [range(int(vshape[d])) for d, _ in subs]
+        if int(np.prod([len(r) for r in ranges], dtype=np.int64)) > 64:
+            raise RDDLNotImplementedError(
+                f"nested arguments of <{acc.name}> range over more than 64 combinations")
+        out = None
+        for combo in reversed(list(itertools.product(*ranges))):
+            off = sum(int(k) * int(acc.strides[d]) for k, (d, _) in zip(combo, subs))
+            cand = TV(src, acc.axes, np.asarray(acc.index) + off, True)
+            if out is None:             # out-of-range indices fall on the last candidate
+                out = cand
+                continue
+            hit = None
+            for k, (_, ti) in zip(combo, subs):
+                h = self.ew("IEQ", [ti, self.const_tv(np.int32(k), "i")], sizes)
+                hit = h if hit is None else self.ew("AND", [hit, h], sizes)
+            out = self.ew("SELECT", [hit, cand, out], sizes, dtype=src.dtype)
+        return out
 
     def _args(self, e, scope, env, args=None) -> List[TV]:
         return [self.lower(a, scope, env) for a in (e.args if args is None else args)]
