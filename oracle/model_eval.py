@@ -108,6 +108,12 @@ class _SafeSqrt(torch.autograd.Function):
                            torch.zeros_like(g))
 
 
+def soft_argmax(logits, w):
+    """sum_k k softmax(w logits)_k over the last axis (SoftmaxArgmax.soft_argmax, logic.py:377-379)."""
+    lit = torch.arange(logits.shape[-1], dtype=REAL)
+    return torch.sum(lit * torch.softmax(w * logits, dim=-1), dim=-1)
+
+
 def safe_sqrt(x):
     return _SafeSqrt.apply(x)
 
@@ -726,6 +732,25 @@ class OracleModel:
                     cnt = cnt + torch.sigmoid(w * (1.0 - cum))
                 Z = self._draw(cur, "normal", a0, scope, B)
                 return torch.where(rate.detach() <= cut, cnt, rate + safe_sqrt(rate) * Z), perr
+            if variant == "gumbel":                                # logic.py:1618-1641
+                from scipy import optimize, stats
+                K = int(R["poisson_nbins"])
+                w = self.param(e, "poisson_softmax_weight", R["poisson_softmax_weight"])
+                eps = self.param(e, "poisson_eps", R["poisson_eps"])
+                cut = float(optimize.brentq(
+                    lambda r: stats.poisson.cdf(K, r) - float(R["poisson_min_cdf"]),
+                    1e-6, 10.0 * K + 10))
+                ks = torch.arange(K, dtype=REAL)
+                r_ = rate.unsqueeze(-1)
+                term = torch.where(ks == 0, torch.zeros(()), ks * safe_log(r_, eps))
+                log_prob = term - r_ - torch.lgamma(ks + 1)
+                shp = tuple(self._shape(scope)) if self._ref_full(a0) else ()
+                g = cur.draw("gumbel", shp + (K,), B)
+                if not shp:
+                    g = g.reshape((B,) + (1,) * len(scope) + (K,))
+                cnt = soft_argmax(g + log_prob, w)
+                Z = self._draw(cur, "normal", a0, scope, B)
+                return torch.where(rate.detach() <= cut, cnt, rate + safe_sqrt(rate) * Z), perr
             if variant is not None:
                 raise NotImplementedError(f"Poisson relaxation <{variant}> is not built")
             # exact: inverse CDF of one uniform, truncated at COUNT_NBINS terms (jax.random.poisson's
@@ -745,6 +770,29 @@ class OracleModel:
             variant = V.get("binomial") if fluent else None
             if variant == "determinized":                          # logic.py:1476
                 return trials * prob, perr
+            if variant == "gumbel":                                # logic.py:1381-1434
+                K = int(R["binomial_nbins"])
+                w = self.param(e, "binomial_softmax_weight", R["binomial_softmax_weight"])
+                eps = self.param(e, "binomial_eps", R["binomial_eps"])
+                ks0 = torch.arange(K, dtype=REAL)
+                n_, p_ = trials.unsqueeze(-1), prob.unsqueeze(-1)
+                in_support = ks0 <= n_
+                ks = torch.minimum(ks0, n_)
+                term_k = torch.where(ks == 0, torch.zeros(()), ks * safe_log(p_, eps))
+                term_nk = torch.where(ks == n_, torch.zeros(()), (n_ - ks) * safe_log(1. - p_, eps))
+                log_prob = (torch.lgamma(n_ + 1) - torch.lgamma(ks + 1) - torch.lgamma(n_ - ks + 1)
+                            + term_k + term_nk)
+                log_prob = torch.where(in_support, log_prob, torch.full((), -float("inf")))
+                shp = tuple(self._shape(scope)) \
+                    if (self._ref_full(e.args[0]) or self._ref_full(e.args[1])) else ()
+                g = cur.draw("gumbel", shp + (K,), B)
+                if not shp:
+                    g = g.reshape((B,) + (1,) * len(scope) + (K,))
+                cnt = soft_argmax(g + log_prob, w)
+                Z = self._draw(cur, "normal", a0, scope, B)
+                var = trials * torch.clamp(prob * (1. - prob), 0., 1.)
+                normal = trials * prob + safe_sqrt(var) * Z
+                return torch.where(trials.detach() < K, cnt, normal), perr
             if variant is not None:
                 raise NotImplementedError(f"Binomial relaxation <{variant}> is not built")
             cnt = torch.zeros(())

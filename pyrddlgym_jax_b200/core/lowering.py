@@ -908,6 +908,27 @@ class Lowerer:
             return E("DIV", C(1.), p)
         raise RDDLNotImplementedError(f"Distribution {name} is not supported.")
 
+    def _bins_scope(self, scope, K: int):
+        """scope + one trailing axis of K count bins (a synthetic object type)."""
+        tname = f"__bins{K}__"
+        if tname not in self.m.type_to_objects:
+            self.m.type_to_objects[tname] = [f"__bin{i}" for i in range(K)]
+        inner = list(scope) + [("?__bin__", tname)]
+        return inner, self.sizes(inner)
+
+    def _gumbel_softmax_count(self, log_prob: TV, w: TV, scope, isz, sizes, full: bool = True) -> TV:
+        """soft arg-max over the bins of Gumbel noise + log pmf (logic.py:1381-1384, 1626-1629).
+        The noise has the shape of the log pmf: the scope's (when an argument carries it) + bins."""
+        allv = tuple(range(len(isz)))
+        gvars = allv if full else (len(isz) - 1,)
+        gshape = tuple(isz[p] for p in gvars)
+        n = int(np.prod(gshape, dtype=np.int64))
+        gv = self.g.leaf("noise", n, "f", slot=len(self.sg.noise))
+        self.sg.noise.append(NoiseSlot("gumbel", gshape, n, gv, None))
+        G = TV(gv, gvars, None, True)
+        logits = self._mat(self.ew("ADD", [G, log_prob], isz), isz)
+        return self._soft_argmax(TV(logits.v, allv, None, True), w, len(scope), isz, sizes)
+
     def _poisson(self, e, rate: TV, a0, scope, sizes) -> TV:
         """Poisson(rate).  Exact programs invert the CDF of one uniform draw, truncated at
         COUNT_NBINS terms (the reference calls jax.random.poisson, compiler.py:1880-1897, whose
@@ -940,6 +961,26 @@ class Lowerer:
             Z = self._draw("normal", a0, scope, sizes)
             normal = E("ADD", rate, E("MUL", E("SQRT", rate), Z))
             return self.ew("SELECT", [E("LE", rate, C(cut)), cnt, normal], sizes, dtype="f")
+        if variant == "gumbel":           # GumbelSoftmaxPoisson, logic.py:1618-1641
+            R = self.relax
+            K = int(R["poisson_nbins"])
+            w = TV(self.mparam(e, "poisson_softmax_weight", R["poisson_softmax_weight"]), ())
+            eps = TV(self.mparam(e, "poisson_eps", R["poisson_eps"]), ())
+            from scipy import optimize, special, stats
+            cut = float(optimize.brentq(
+                lambda r: stats.poisson.cdf(K, r) - float(R["poisson_min_cdf"]), 1e-6, 10.0 * K + 10))
+            inner, isz = self._bins_scope(scope, K)
+            EI = lambda nm, *x: self.ew(nm, list(x), isz)      # noqa: E731
+            kpos = len(scope)
+            ks = TV(self.g.const(np.arange(K, dtype=np.float32)), (kpos,), None)
+            lgk = TV(self.g.const(special.gammaln(np.arange(K) + 1.0).astype(np.float32)), (kpos,), None)
+            term = self.ew("SELECT", [EI("EQ", ks, C(0.)), C(0.),
+                                      EI("MUL", ks, EI("SAFELOG", rate, eps))], isz, dtype="f")
+            log_prob = EI("SUB", EI("SUB", term, rate), lgk)
+            cnt = self._gumbel_softmax_count(log_prob, w, scope, isz, sizes, self._ref_full(a0))
+            Z = self._draw("normal", a0, scope, sizes)
+            normal = E("ADD", rate, E("MUL", E("SQRT", rate), Z))
+            return self.ew("SELECT", [E("LE", rate, C(cut)), cnt, normal], sizes, dtype="f")
         if variant is not None:
             raise RDDLNotImplementedError(f"Poisson relaxation <{variant}> is not built")
         U = self._draw("uniform", a0, scope, sizes)
@@ -967,9 +1008,37 @@ class Lowerer:
         variant = self.variants.get("binomial") if (self.relaxed and fluent) else None
         if variant == "determinized":
             return E("MUL", trials, prob)
+        if variant == "gumbel":           # GumbelSoftmaxBinomial, logic.py:1381-1434
+            R = self.relax
+            K = int(R["binomial_nbins"])
+            w = TV(self.mparam(e, "binomial_softmax_weight", R["binomial_softmax_weight"]), ())
+            eps = TV(self.mparam(e, "binomial_eps", R["binomial_eps"]), ())
+            inner, isz = self._bins_scope(scope, K)
+            EI = lambda nm, *x: self.ew(nm, list(x), isz)      # noqa: E731
+            SEL = lambda c, a, b: self.ew("SELECT", [c, a, b], isz, dtype="f")   # noqa: E731
+            kpos = len(scope)
+            ks0 = TV(self.g.const(np.arange(K, dtype=np.float32)), (kpos,), None)
+            in_support = EI("LE", ks0, trials)
+            ks = EI("MIN", ks0, trials)
+            q = E("SUB", C(1.), prob)
+            term_k = SEL(EI("EQ", ks, C(0.)), C(0.), EI("MUL", ks, EI("SAFELOG", prob, eps)))
+            nk = EI("SUB", trials, ks)
+            term_nk = SEL(EI("EQ", ks, trials), C(0.), EI("MUL", nk, EI("SAFELOG", q, eps)))
+            lg = lambda x: EI("LGAMMA", x)                      # noqa: E731
+            comb = EI("SUB", EI("SUB", lg(EI("ADD", trials, C(1.))), lg(EI("ADD", ks, C(1.)))),
+                      lg(EI("ADD", nk, C(1.))))
+            log_prob = EI("ADD", EI("ADD", comb, term_k), term_nk)
+            log_prob = SEL(in_support, log_prob, C(-np.inf))
+            cnt = self._gumbel_softmax_count(
+                log_prob, w, scope, isz, sizes,
+                self._ref_full(e.args[0]) or self._ref_full(e.args[1]))
+            Z = self._draw("normal", a0, scope, sizes)          # logic.py:1372-1378
+            var = E("MUL", trials, E("MIN", E("MAX", E("MUL", prob, q), C(0.)), C(1.)))
+            normal = E("ADD", E("MUL", trials, prob), E("MUL", E("SQRT", var), Z))
+            small = E("LT", trials, C(float(K)))
+            return self.ew("SELECT", [small, cnt, normal], sizes, dtype="f")
         if variant is not None:
-            raise RDDLNotImplementedError(
-                f"Binomial relaxation <{variant}> is not built (use DeterminizedBinomial)")
+            raise RDDLNotImplementedError(f"Binomial relaxation <{variant}> is not built")
         cnt = None
         for j in range(COUNT_NBINS):
             U = self._draw("uniform", a0, scope, sizes)

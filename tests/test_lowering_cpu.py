@@ -68,3 +68,18 @@ def test_stochastic_plan_emulated(key, wrap):
     ls = [k for k in c["P"] if k.endswith("/log_sigma")]
     if ls:
         assert any(c["P"][k].grad is not None and float(c["P"][k].grad.abs().sum()) > 0 for k in ls)
+
+
+class _GumbelCounts(logic.SigmoidRelational, logic.ProductNormLogical, logic.LinearIfElse,
+                    logic.SoftmaxSwitch, logic.GumbelSoftmaxPoisson, logic.GumbelSoftmaxBinomial):
+    pass
+
+
+def test_gumbel_softmax_count_relaxations_emulated():
+    """GumbelSoftmaxPoisson / GumbelSoftmaxBinomial (logic.py:1381-1434, 1618-1641): soft arg-max
+    over the bins of Gumbel noise + log pmf, with the normal-approximation branch; 12 bins keep
+    the emulated program small."""
+    c = gradient_case("emu", "distributions", B=5, T=3, compiler_cls=_GumbelCounts,
+                      poisson_nbins=12, binomial_nbins=12, poisson_softmax_weight=3.0)
+    check_forward(c)
+    check_gradient(c)

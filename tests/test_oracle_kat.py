@@ -349,7 +349,7 @@ def test_count_and_gamma_family_sampler_moments():
     q = fin["queue"].numpy().astype(np.float64)
     np.testing.assert_allclose(q.mean(0), lam, rtol=0.06)
     np.testing.assert_allclose(q.var(0), lam, rtol=0.10)
-    p = 0.25 + 0.5 * np.array([0.3, 0.6, 0.3])
+    p = 0.2 + 0.2 * np.minimum(level0, 3.0)
     s = fin["served"].numpy().astype(np.float64)
     assert s.min() >= 0 and s.max() <= 5
     np.testing.assert_allclose(s.mean(0), 5 * p, rtol=0.04)
