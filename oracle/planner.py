@@ -34,6 +34,22 @@ def bound_action(lo, hi, param: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def slp_pooled_softmax(model, params: Dict[str, torch.Tensor], t: int, weight: float):
+    """planner.py:764-808: softmax over the pooled boolean logits of step t, unstacked per fluent
+    (1 - p for fluents whose no-op value is true)."""
+    names = [v for v in model.action_fluents if model.variable_ranges[v] == "bool"]
+    z = torch.cat([params[v][t].reshape(-1) for v in names])
+    out = torch.softmax(weight * z, dim=0)
+    acts, pos = {}, 0
+    for v in names:
+        n = params[v][t].numel()
+        a = out[pos:pos + n]
+        pos += n
+        noop = bool(np.ravel(np.asarray(model.action_fluents[v]))[0])
+        acts[v] = (1.0 - a) if noop else a
+    return acts
+
+
 def slp_policy_noise_spec(model, wrap_sigmoid=True, action_noise="normal"):
     """Draw sites of a stochastic straight-line plan, in the order planner.py:811-833 splits
     its key: (kind, shape) per action fluent that receives noise."""
@@ -69,13 +85,18 @@ def slp_entropy(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=Tru
 
 def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
                       sigmoid_weight: Dict[str, float] | float = 1.0, wrap_non_bool=False,
-                      bounds=None, stochastic=False, sigma_range=(1e-5, 1e3), pnoise=None):
+                      bounds=None, stochastic=False, sigma_range=(1e-5, 1e3), pnoise=None,
+                      pooled_softmax=False, softmax_weight=1.0):
     """planner.py:786-838.  ``pnoise``: this step's policy draws [B, *shape] in the order of
     slp_policy_noise_spec (stochastic plans only)."""
     actions = {}
     k = 0
+    pooled = slp_pooled_softmax(model, params, t, softmax_weight) if pooled_softmax else {}
     for name in model.action_fluents:
         p = params[name][t]
+        if name in pooled:
+            actions[name] = pooled[name].unsqueeze(0)
+            continue
         if model.variable_ranges[name] == "bool":
             w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
             if stochastic and wrap_sigmoid:                            # planner.py:811-817
@@ -98,14 +119,17 @@ def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmo
 
 
 def slp_test_actions(model, params: Dict[str, torch.Tensor], t: int, bounds, wrap_sigmoid=True,
-                     wrap_non_bool=False):
+                     wrap_non_bool=False, pooled_softmax=False, softmax_weight=1.0):
     """planner.py:842-868."""
     actions = {}
     thr = 0.0 if wrap_sigmoid else 0.5
+    pooled = slp_pooled_softmax(model, params, t, softmax_weight) if pooled_softmax else {}
     for name in model.action_fluents:
         p = params[name][t]
         prange = model.variable_ranges[name]
-        if prange == "bool":
+        if name in pooled:
+            a = pooled[name] > 0.5
+        elif prange == "bool":
             a = p > thr
         else:
             lo, hi = bounds[name]

@@ -73,8 +73,8 @@ class JaxStraightLinePlan(JaxPlan):
         self._sigma_range = sigma_range
         self._sigma_entropy_grad = sigma_entropy_grad
         self._action_noise_dist = action_noise_dist
-        if wrap_softmax:
-            raise NotImplementedError("softmax-pooled boolean plans (wrap_softmax) are not built yet")
+        if wrap_softmax and stochastic:
+            raise NotImplementedError("stochastic plans with wrap_softmax are not built yet")
         if action_noise_dist not in ("normal", "logistic", "laplace", "gumbel", "cauchy", "uniform"):
             raise NotImplementedError(f"action_noise_dist <{action_noise_dist}>: name one of the "
                                       "noise kinds the engine draws (e.g. 'normal')")
@@ -116,19 +116,32 @@ class JaxStraightLinePlan(JaxPlan):
                 bounds[name] = (np.broadcast_to(np.asarray(lo, np.float32), shape).copy(),
                                 np.broadcast_to(np.asarray(hi, np.float32), shape).copy())
         self.bounds = bounds
+        self.noop = {var: bool(np.ravel(v)[0]) if rddl.variable_ranges[var] == "bool" else v
+                     for var, v in rddl.action_fluents.items()}
+        n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
+        # wrap_softmax: one softmax over the pooled boolean parameters of a step when the
+        # concurrency constraint binds (planner.py:764-808, 924-933); ignored otherwise
+        self.stack_bool = bool(self._wrap_softmax) and rddl.max_allowed_actions < n_bool
+        if self.stack_bool and rddl.max_allowed_actions > 1:
+            raise ValueError("SLPs with wrap_softmax currently do not support action cardinality "
+                             f"constraint {rddl.max_allowed_actions} > 1.")
         self.spec = PlanSpec(kind="slp", wrap_sigmoid=self._wrap_sigmoid,
+                             pooled_softmax=self.stack_bool,
+                             softmax_weight=float(self._softmax_weight),
+                             noop_true=tuple(v for v, (_, _, r) in self.layout.items()
+                                             if r == "bool" and self.noop[v]),
                              wrap_non_bool=self._wrap_non_bool,
                              stochastic=self._stochastic, sigma_range=tuple(self._sigma_range),
                              action_noise=self._action_noise_dist,
                              sigmoid_weight=self._sigmoid_weight,
                              bounds={k: v for k, v in bounds.items() if v[0] is not None})
-        self.noop = {var: bool(np.ravel(v)[0]) if rddl.variable_ranges[var] == "bool" else v
-                     for var, v in rddl.action_fluents.items()}
-        self.bool_threshold = 0.0 if self._wrap_sigmoid else 0.5
+        self.bool_threshold = 0.0 if (self._wrap_sigmoid or self.stack_bool) else 0.5
         # flat box for the projection (planner.py:878-904)
         lo = np.full((horizon, self.A), -np.inf, np.float32)
         hi = np.full((horizon, self.A), np.inf, np.float32)
         for name, (off, n, prange) in self.layout.items():
+            if prange == "bool" and self.stack_bool:
+                continue                                # pooled logits are not projected
             if prange == "bool":
                 p = self._min_action_prob
                 if self._wrap_sigmoid:
@@ -144,10 +157,9 @@ class JaxStraightLinePlan(JaxPlan):
             lo[:, off:off + n] = np.log(self._sigma_range[0])
             hi[:, off:off + n] = np.log(self._sigma_range[1])
         self.box = (lo, hi)
-        n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
         # concurrency projection (planner.py:914-959): sort-based or SOGBOFA, per time step
         self.max_allowed_actions = int(min(rddl.max_allowed_actions, n_bool))
-        self.needs_concurrency_projection = rddl.max_allowed_actions < n_bool
+        self.needs_concurrency_projection = rddl.max_allowed_actions < n_bool and not self.stack_bool
         self.projection_method = "sorting" if self._use_new_projection else "sogbofa"
         self.bool_segs = [(off, n, bool(self.noop[name]), float(self._sigmoid_weight))
                           for name, (off, n, prange) in self.layout.items() if prange == "bool"]
@@ -169,10 +181,15 @@ class JaxStraightLinePlan(JaxPlan):
     def params_to_pytree(self, flat: torch.Tensor) -> Dict[str, Any]:
         """[..., T, A] -> {'bool': {var: {'logit'}}, 'real': {var: {'mu', 'log_sigma'}}}."""
         tree: Dict[str, Any] = {"bool": {}, "real": {}}
+        if self.stack_bool:         # planner.py:1000-1005: one [T, n_bool] tensor under '__bool__'
+            tree["bool"]["__bool__"] = {"logit": torch.cat(
+                [flat[..., off:off + n] for _, (off, n, r) in self.layout.items() if r == "bool"],
+                dim=-1)}
         for name, (off, n, prange) in self.layout.items():
             v = flat[..., off:off + n].reshape(*flat.shape[:-1], *self.rddl.variable_shape(name))
             if prange == "bool":
-                tree["bool"][name] = {"logit": v}
+                if not self.stack_bool:
+                    tree["bool"][name] = {"logit": v}
             else:
                 ls = None
                 if name in self.sigma_layout:
@@ -214,7 +231,16 @@ class JaxStraightLinePlan(JaxPlan):
 
     def pytree_to_params(self, tree: Dict[str, Any]) -> torch.Tensor:
         out = torch.zeros(self.horizon, self.A)
+        pooled, pos = None, 0
+        if self.stack_bool:
+            pooled = torch.as_tensor(np.asarray(tree["bool"]["__bool__"]["logit"]),
+                                     dtype=torch.float32).reshape(-1, sum(
+                                         n for _, n, r in self.layout.values() if r == "bool"))
         for name, (off, n, prange) in self.layout.items():
+            if prange == "bool" and pooled is not None:
+                out[:, off:off + n] = pooled[-self.horizon:, pos:pos + n]
+                pos += n
+                continue
             leaf = tree["bool"][name]["logit"] if prange == "bool" else tree["real"][name]["mu"]
             out[:, off:off + n] = torch.as_tensor(np.asarray(leaf), dtype=torch.float32
                                                   ).reshape(-1, n)[-self.horizon:]
@@ -228,9 +254,19 @@ class JaxStraightLinePlan(JaxPlan):
     def test_actions(self, flat_row: np.ndarray) -> Dict[str, np.ndarray]:
         """Test policy at one step (planner.py:842-868) -- host side, for get_action."""
         acts = {}
+        soft = None
+        if self.stack_bool:         # planner.py:848-853: softmax over the pooled logits, > 0.5
+            z = np.concatenate([np.asarray(flat_row[off:off + n], np.float64)
+                                for _, (off, n, r) in self.layout.items() if r == "bool"])
+            z = np.exp(self._softmax_weight * (z - z.max()))
+            soft, pos = z / z.sum(), 0
         for name, (off, n, prange) in self.layout.items():
             p = np.asarray(flat_row[off:off + n], np.float32).reshape(self.rddl.variable_shape(name))
-            if prange == "bool":
+            if prange == "bool" and soft is not None:
+                a = soft[pos:pos + n].reshape(self.rddl.variable_shape(name))
+                pos += n
+                acts[name] = ((1.0 - a) if self.noop[name] else a) > 0.5
+            elif prange == "bool":
                 acts[name] = p > self.bool_threshold
             else:
                 if self._wrap_non_bool:                 # _jax_bound_action, planner.py:620-628

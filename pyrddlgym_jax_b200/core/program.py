@@ -150,6 +150,12 @@ class PlanSpec:
     stochastic: bool = False
     sigma_range: Tuple[float, float] = (1e-5, 1e3)
     action_noise: str = "normal"
+    # softmax over ALL boolean action parameters of a step instead of per-element sigmoids
+    # (planner.py:764-808, 848-853), used when max-nondef-actions = 1 < number of boolean actions;
+    # fluents whose no-op value is true receive 1 - softmax
+    pooled_softmax: bool = False
+    softmax_weight: float = 1.0
+    noop_true: Tuple[str, ...] = ()
 
 
 def param_layout(model, spec: "PlanSpec") -> Tuple[Dict[str, Tuple[int, int, str]], int]:
@@ -230,12 +236,52 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
         v = g.leaf("noise", n, "f", slot=len(low.sg.noise))
         low.sg.noise.append(NoiseSlot(kind, tuple(m.variable_shape(name)), n, v, None))
         return v
+    pooled: Dict[str, V] = {}
+    if spec.kind == "slp" and spec.pooled_softmax:
+        # softmax_i(w p_i) over the pooled boolean parameters: per-fluent maxima / sums are
+        # 1-element reductions, combined across fluents and broadcast back
+        plist = []
+        for name, (off, n, prange) in layout.items():
+            if prange == "bool":
+                p = g.leaf("param_in", n, "f", uniform=True, off=off, fluent=name)
+                leaves[name] = p
+                plist.append((name, n, p))
+        if spec.stochastic:
+            raise ProgramError("stochastic plans with pooled softmax booleans are not built")
+        w = g.const(np.float32(spec.softmax_weight))
+        z = {name: g.op("MUL", [(w, "b"), (p, None)], n) for name, n, p in plist}
+        whole = lambda n: (np.array([0, n], np.int64), np.arange(n, dtype=np.int64))   # noqa: E731
+        top = None
+        for name, n, _ in plist:
+            m1 = g.reduce("RMAX", z[name], *whole(n))
+            top = m1 if top is None else g.op("MAX", [(top, None), (m1, None)], 1)
+        top = g.sg(top)
+        ex = {name: g.op("EXP", [(g.op("SUB", [(z[name], None), (top, "b")], n), None)], n)
+              for name, n, _ in plist}
+        tot = None
+        for name, n, _ in plist:
+            s1 = g.reduce("RSUM", ex[name], *whole(n))
+            tot = s1 if tot is None else g.op("ADD", [(tot, None), (s1, None)], 1)
+        for name, n, _ in plist:
+            a = g.op("DIV", [(ex[name], None), (tot, "b")], n)
+            if name in spec.noop_true:
+                a = g.op("SUB", [(g.const(np.float32(1.0)), "b"), (a, None)], n)
+            pooled[name] = a
     for name, (off, n, prange) in layout.items():
         if spec.kind == "external":
             dt = low.dtype_of_range(prange)
             leaf = g.leaf("act_in", n, dt, uniform=False, off=off, fluent=name)
             leaves[name] = leaf
             actions[name] = leaf
+            continue
+        if name in pooled:
+            a = pooled[name]
+            if not train:                             # planner.py:852: softmax output > 0.5
+                a = g.op("GT", [(a, None), (g.const(np.float32(0.5)), "b")], n)
+                want = low.dtype_of_range(prange)
+                if a.dtype != want and want == "f":
+                    a = g.op("I2F", [(a, None)], n)
+            actions[name] = a
             continue
         p = g.leaf("param_in", n, "f", uniform=True, off=off, fluent=name)
         leaves[name] = p

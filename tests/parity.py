@@ -94,14 +94,18 @@ def run_backward(backend, prog, B, T, tape, params_flat, noise, gret, disc=None,
 
 
 def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=None,
-                 param_scale=0.5, given=None, wrap_non_bool=False, stochastic=False, **ckw):
+                 param_scale=0.5, given=None, wrap_non_bool=False, stochastic=False,
+                 pooled_softmax=False, **ckw):
     """Run program + oracle on the same inputs; returns everything a test wants to compare."""
     m = fixture_model(key)
     if relaxed:
         comp = (compiler_cls or logic.DefaultJaxRDDLCompilerWithGrad)(m, **ckw)
     else:
         comp = JaxRDDLCompiler(m)
-    spec = PlanSpec(bounds=m.bounds, wrap_non_bool=wrap_non_bool, stochastic=stochastic)
+    noop_true = tuple(v for v in m.action_fluents if m.variable_ranges[v] == "bool"
+                      and bool(np.ravel(np.asarray(m.action_fluents[v]))[0]))
+    spec = PlanSpec(bounds=m.bounds, wrap_non_bool=wrap_non_bool, stochastic=stochastic,
+                    pooled_softmax=pooled_softmax, softmax_weight=2.0, noop_true=noop_true)
     builder = comp.builder(spec, train_policy=relaxed, batch_hint=B)
     # the adjoint program is assembled first: it decides what the forward program tapes for it
     bwd = builder.backward(gamma=gamma) if relaxed else None
@@ -130,11 +134,13 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
             pol.n_noise = len(OP.slp_policy_noise_spec(m))
         else:
             pol = lambda t, fls: OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool,   # noqa: E731
-                                                      bounds=m.bounds)
+                                                      bounds=m.bounds, pooled_softmax=pooled_softmax,
+                                                      softmax_weight=2.0)
     else:
         P = params
         pol = lambda t, fls: OP.slp_test_actions(m, P, t, m.bounds,    # noqa: E731
-                                                 wrap_non_bool=wrap_non_bool)
+                                                 wrap_non_bool=wrap_non_bool,
+                                                 pooled_softmax=pooled_softmax, softmax_weight=2.0)
     noise_steps = [noise_as_list(fwd.noise_layout, noise, t, B) for t in range(T)]
     ref = OP.rollout(om, pol, B, T, noise_steps)
     spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
@@ -148,10 +154,10 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
 
 
 def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=0.5, given=None,
-                  wrap_non_bool=False, stochastic=False, **ckw):
+                  wrap_non_bool=False, stochastic=False, pooled_softmax=False, **ckw):
     c = forward_case(backend, key, B, T, True, gamma, compiler_cls=compiler_cls,
                      param_scale=param_scale, given=given, wrap_non_bool=wrap_non_bool,
-                     stochastic=stochastic, **ckw)
+                     stochastic=stochastic, pooled_softmax=pooled_softmax, **ckw)
     m = c["model"]
     bwd = c["bwd"]
     gret = torch.full((B,), -1.0 / B)

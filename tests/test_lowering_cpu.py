@@ -83,3 +83,13 @@ def test_gumbel_softmax_count_relaxations_emulated():
                       poisson_nbins=12, binomial_nbins=12, poisson_softmax_weight=3.0)
     check_forward(c)
     check_gradient(c)
+
+
+def test_pooled_softmax_plan_emulated():
+    """wrap_softmax (planner.py:764-808, 848-853): one softmax over the pooled boolean parameters
+    of a step, 1 - p for fluents whose no-op is true, (p > 0.5) in the test policy."""
+    check_forward(forward_case("emu", "wildfire", B=7, T=4, relaxed=False, pooled_softmax=True,
+                               param_scale=3.0))
+    c = gradient_case("emu", "wildfire", B=7, T=4, pooled_softmax=True, param_scale=3.0)
+    check_forward(c)
+    check_gradient(c)

@@ -374,3 +374,30 @@ def test_host_driven_step_equals_separate_calls(cuda_device, key):
         pb.copy_(out)
         assert np.array_equal(ta, tb) and np.array_equal(sa, sb) and np.array_equal(za, zb), it
         assert torch.equal(pa, pb), it
+
+
+@pytest.mark.gpu
+def test_wrap_softmax_plan_runs_and_respects_the_constraint(cuda_device):
+    """wrap_softmax with max-nondef-actions = 1 (planner.py:764-808): pooled '__bool__' logits, no
+    projection, and a test policy that can switch on at most one boolean action per step."""
+    m = fixture_model("wildfire")
+    plan = JaxStraightLinePlan(wrap_softmax=True, softmax_weight=5.0)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=64, rollout_horizon=6,
+                            optimizer_kwargs={"learning_rate": 0.5}, pgpe=None)
+    pl.initialize(1)
+    assert plan.stack_bool and not plan.needs_concurrency_projection
+    p0 = pl.params[0].cpu().clone()
+    for _ in range(5):
+        pl.iterate()
+    tr, te, _ = pl.read_stats()
+    assert np.isfinite(tr).all() and np.isfinite(te).all()
+    flat = pl.params[0].cpu()
+    assert not torch.equal(flat, p0)
+    tree = plan.params_to_pytree(flat.view(6, plan.A))
+    assert set(tree["bool"]) == {"__bool__"} and tree["bool"]["__bool__"]["logit"].shape == (6, plan.A)
+    back = plan.pytree_to_params(tree)
+    assert torch.equal(back.reshape(-1), flat.reshape(-1))
+    for t in range(6):
+        acts = plan.test_actions(flat.view(6, plan.A)[t].numpy())
+        on = sum(int(np.sum(a != plan.noop[name])) for name, a in acts.items())
+        assert on <= 1
