@@ -425,8 +425,10 @@ class JaxBackpropPlanner:
                  cache_full_train_rollouts: bool = False, cache_full_test_rollouts: bool = False,
                  device: Optional[Union[str, torch.device]] = None, use_cuda_graph: bool = True
                  ) -> None:
-        for name, val in (("line_search_kwargs", line_search_kwargs), ("noise_kwargs", noise_kwargs),
-                          ("ema_decay", ema_decay), ("reduce_on_plateau_kwargs", reduce_on_plateau_kwargs),
+        self.noise_kwargs = dict(noise_kwargs) if noise_kwargs is not None else None
+        self.ema_decay = None if ema_decay is None else float(ema_decay)
+        for name, val in (("line_search_kwargs", line_search_kwargs),
+                          ("reduce_on_plateau_kwargs", reduce_on_plateau_kwargs),
                           ("critic", critic), ("preprocessor", preprocessor),
                           ("dashboard", dashboard)):
             if val is not None:
@@ -563,6 +565,7 @@ class JaxBackpropPlanner:
             h = [lr, 0., 0., 0., 0., kw.get("momentum", 0.) or 0., 1.]
         h[4] = float(self.clip_grad) if self.clip_grad is not None else 0.
         self.hyper = torch.tensor(h, dtype=torch.float32, device=dev)
+        self._hyper_noclip = self.hyper.clone()     # the chain path clips before the noise link
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
             if len(fw.mparam_defaults) else None
         import os as _os
@@ -580,6 +583,11 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
+        if self.noise_kwargs is not None or self.ema_decay is not None:
+            self._chain_count = z(P)
+            self._chain_grad, self._chain_old, self._chain_ema = z(P, NP), z(P, NP), z(P, NP)
+            self._chain_gen = torch.Generator(device=dev)
+            self._chain_gen.manual_seed(int((self.noise_kwargs or {}).get("seed", 0)))
         # multi-GPU exchange: one message per iteration.  In the pipelined order the
         # gradient is not needed before the NEXT replay's optimiser step, so it travels together
         # with the two loss sums after the branches join: [grad | train loss | test loss], summed
@@ -708,9 +716,12 @@ class JaxBackpropPlanner:
         params = self.params[p]
         if publish:
             self._publish_kernels(p)
-        engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
-                              self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
-                              self.zero_flag[p:p + 1])
+        if self.noise_kwargs is None and self.ema_decay is None:
+            engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
+                                  self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
+                                  self.zero_flag[p:p + 1])
+        else:
+            self._opt_chain_kernels(p)
         plan = self.plan
         if getattr(plan, "needs_concurrency_projection", False):     # planner.py:947-954
             self.converged[p:p + 1].fill_(1)
@@ -718,6 +729,42 @@ class JaxBackpropPlanner:
                                plan.max_allowed_actions, plan._max_constraint_iter,
                                plan._wrap_sigmoid, plan._min_action_prob,
                                self.converged[p:p + 1])
+
+    def _opt_chain_kernels(self, p: int):
+        """The optional links of the optax chain (planner.py:2366-2386) around the optimiser kernel:
+        clip_by_global_norm -> add_noise(eta, gamma) -> optimiser -> ema(decay), then apply_updates
+        and the box projection.  add_noise: g + N(0, eta / t^gamma) with the 1-based step count t;
+        ema: the debiased exponential moving average of the optimiser's updates is what is applied."""
+        params, grad = self.params[p], self.grad[p]
+        g = grad
+        self._chain_count[p:p + 1].add_(1.0)
+        t = self._chain_count[p:p + 1]
+        clip = float(self.clip_grad) if self.clip_grad is not None else 0.0
+        if clip > 0.0:
+            gn = torch.linalg.vector_norm(g)
+            g = g * torch.clamp(clip / gn.clamp_min(1e-30), max=1.0)
+        self.zero_flag[p:p + 1].copy_((g.abs().max() <= 1e-8).to(torch.int32).reshape(1))
+        if self.noise_kwargs is not None:
+            eta = float(self.noise_kwargs.get("eta", 0.01))
+            gamma = float(self.noise_kwargs.get("gamma", 0.55))
+            std = torch.sqrt(eta / torch.pow(t, gamma))
+            g = g + std * torch.randn(g.shape, generator=self._chain_gen, device=g.device)
+        self._chain_grad[p].copy_(g)
+        self._hyper_noclip.copy_(self.hyper)
+        self._hyper_noclip[4:5].zero_()
+        old = self._chain_old[p]
+        old.copy_(params)
+        engine.optimizer_step(self.optimizer_name, self._hyper_noclip, self.n_params, params,
+                              self.opt_state[p], self._chain_grad[p], None, None, None)
+        if self.ema_decay is not None:
+            d = self.ema_decay
+            ema = self._chain_ema[p]
+            ema.mul_(d).add_(params - old, alpha=1.0 - d)
+            params.copy_(old + ema / (1.0 - torch.pow(torch.full_like(t, d), t)))
+        if self.box_lo is not None:
+            torch.maximum(params, self.box_lo, out=params)
+        if self.box_hi is not None:
+            torch.minimum(params, self.box_hi, out=params)
 
     def _update_kernels(self, p: int):
         """planner.py:2868-2917 on the device for parallel instance p."""
@@ -841,6 +888,8 @@ class JaxBackpropPlanner:
         (initial-state words and plan in, status words and plan out, through pinned staging
         buffers), so a whole replanning step is ONE graph launch and ONE synchronisation."""
         backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
+        chain = [t.clone() for t in (self._chain_count, self._chain_ema)] \
+            if hasattr(self, "_chain_count") else None
         s = torch.cuda.Stream(device=self.device)
         side = torch.cuda.Stream(device=self.device) if self._overlap else None
         inner0 = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
@@ -877,11 +926,16 @@ class JaxBackpropPlanner:
         g = torch.cuda.CUDAGraph()
         if self._noise_in_graph:
             g.register_generator_state(self._gen)
+        if self.noise_kwargs is not None:
+            g.register_generator_state(self._chain_gen)
         with torch.cuda.graph(g):
             body()
         self.params.copy_(backup[0])
         self.opt_state.copy_(backup[1])
         self.hyper.copy_(backup[2])
+        if chain is not None:
+            self._chain_count.copy_(chain[0])
+            self._chain_ema.copy_(chain[1])
         if from_host:
             self._graph_host = g
         else:

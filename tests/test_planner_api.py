@@ -401,3 +401,42 @@ def test_wrap_softmax_plan_runs_and_respects_the_constraint(cuda_device):
         acts = plan.test_actions(flat.view(6, plan.A)[t].numpy())
         on = sum(int(np.sum(a != plan.noop[name])) for name, a in acts.items())
         assert on <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_optimizer_chain_noise_and_ema(cuda_device, graph):
+    """add_noise and ema links of the optax chain (planner.py:2366-2386).  With eta = 0 the noise
+    link is the identity, and the EMA link is checked against its recurrence: the applied step is
+    the debiased moving average of the plain optimiser steps (sgd: -lr * clipped gradient)."""
+    m = fixture_model("quadcopter")
+
+    def make(**kw):
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=32, rollout_horizon=6,
+                                optimizer="sgd", optimizer_kwargs={"learning_rate": 0.01},
+                                clip_grad=0.5, pgpe=None, use_cuda_graph=graph, **kw)
+        pl.initialize(2)
+        return pl
+    decay = 0.8
+    pl = make(ema_decay=decay, noise_kwargs={"eta": 0.0, "gamma": 0.55, "seed": 1})
+    ema = torch.zeros_like(pl.params[0]).cpu()
+    for it in range(1, 5):
+        before = pl.params[0].cpu().clone()
+        pl.iterate()
+        torch.cuda.synchronize()
+        g = pl.grad_used[0].cpu()
+        gn = float(torch.linalg.vector_norm(g))
+        step = -0.01 * g * min(1.0, 0.5 / gn)
+        ema = decay * ema + (1 - decay) * step
+        want = before + ema / (1 - decay ** it)
+        lo, hi = pl.box_lo.cpu(), pl.box_hi.cpu()
+        want = torch.minimum(torch.maximum(want, lo), hi)
+        torch.testing.assert_close(pl.params[0].cpu(), want, rtol=1e-5, atol=1e-6)
+    noisy = make(noise_kwargs={"eta": 1.0, "gamma": 0.55, "seed": 3})
+    plain = make()
+    for _ in range(2):
+        noisy.iterate()
+        plain.iterate()
+    torch.cuda.synchronize()
+    assert not torch.equal(noisy.params, plain.params)
+    assert torch.isfinite(noisy.params).all()
