@@ -433,8 +433,7 @@ class JaxBackpropPlanner:
                           ("dashboard", dashboard)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
-        if use_symlog_reward:
-            raise NotImplementedError("use_symlog_reward is not supported yet")
+        self.use_symlog_reward = bool(use_symlog_reward)
         self.rddl = rddl
         self.plan = plan
         self.batch_size_train = batch_size_train
@@ -672,7 +671,13 @@ class JaxBackpropPlanner:
             if getattr(self, "_published", None) is not None:
                 main.wait_event(self._published)
             side = getattr(self, "_loss_stream", None)
-            if self.utility == "mean" and side is not None \
+            if self.utility == "mean" and self.use_symlog_reward:
+                # planner.py:2761-2763: returns -> sign(R) log1p(|R|) in the TRAIN loss only;
+                # the cotangent of the batch mean becomes -(1 / B) / (1 + |R_b|)
+                r = self.train_returns[p]
+                loss_out.copy_(-(torch.sign(r) * torch.log1p(r.abs())).mean().reshape(1))
+                torch.div(-1.0 / (B * self.world_size), 1.0 + r.abs(), out=self.gret)
+            elif self.utility == "mean" and side is not None \
                     and not getattr(self.plan, "_stochastic", False):
                 # the loss value is not an input of the adjoint (its cotangent is the constant
                 # -1/B): reduce it on the side stream, off the critical chain

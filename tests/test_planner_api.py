@@ -440,3 +440,34 @@ def test_optimizer_chain_noise_and_ema(cuda_device, graph):
     torch.cuda.synchronize()
     assert not torch.equal(noisy.params, plain.params)
     assert torch.isfinite(noisy.params).all()
+
+
+@pytest.mark.gpu
+def test_symlog_reward_matches_oracle(cuda_device):
+    """use_symlog_reward (planner.py:2761-2763): the train loss is -mean(sign(R) log1p|R|)."""
+    from oracle import planner as OP
+    from oracle.model_eval import OracleModel
+    m = fixture_model("quadcopter")
+    B, T = 24, 6
+    plan = JaxStraightLinePlan()
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False, use_symlog_reward=True)
+    pl.initialize(4)
+    flat = pl.params[0].cpu().view(T, plan.A).clone()
+    pl.iterate()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)
+    P = {name: tree["real"][name]["mu"].reshape(T, -1).clone().requires_grad_(True)
+         for name in m.action_fluents}
+    om = OracleModel(m, pl.compiled.relax_config())
+    ref = OP.rollout(om, lambda t, fls: OP.slp_train_actions(m, P, t), B, T, None)
+    R = OP.returns_from_rewards(ref["reward"], float(m.discount))
+    loss = -(torch.sign(R) * torch.log1p(R.abs())).mean()
+    loss.backward()
+    from tests.helpers import pack_params
+    want = pack_params(m, {k: v.grad for k, v in P.items()})
+    np.testing.assert_allclose(float(pl.train_loss[0]), float(loss.detach()), rtol=2e-5)
+    got = pl.grad_used[0].cpu().view(T, plan.A)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
+                               atol=1e-4 * float(want.abs().max()))
