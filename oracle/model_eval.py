@@ -712,11 +712,7 @@ class OracleModel:
             E = self._draw(cur, "exponential", a0, scope, B)
             return scale * torch.exp(E / _f(shape)), \
                 err | oob((shape > 0) & (scale > 0)) * ERR["PARETO"]
-        if name == "Poisson":
-            (rate,) = vals
-            rate = _f(rate)
-            perr = err | oob(rate >= 0) * ERR["POISSON"]
-            variant = V.get("poisson") if self.tracer.is_fluent(a0) else None
+        def poisson_sample(rate, variant, perr):
             if variant == "determinized":                          # logic.py:1733-1741
                 return rate, perr
             if variant == "exponential":                           # logic.py:1508-1531
@@ -763,6 +759,12 @@ class OracleModel:
                 pk = pk * (rate * np.float32(1.0 / k))
                 cdf = cdf + pk
             return (cnt if self.relaxed else cnt.to(INT)), perr
+        if name == "Poisson":
+            (rate,) = vals
+            rate = _f(rate)
+            perr = err | oob(rate >= 0) * ERR["POISSON"]
+            variant = V.get("poisson") if self.tracer.is_fluent(a0) else None
+            return poisson_sample(rate, variant, perr)
         if name == "Binomial":
             trials, prob = _f(vals[0]), _f(vals[1])
             perr = err | oob((prob >= 0) & (prob <= 1) & (trials >= 0)) * ERR["BINOMIAL"]
@@ -804,10 +806,15 @@ class OracleModel:
             trials, prob = _f(vals[0]), _f(vals[1])
             perr = err | oob((prob >= 0) & (prob <= 1) & (trials > 0)) * ERR["NEGATIVE_BINOMIAL"]
             fluent = self.tracer.is_fluent(e.args[0]) or self.tracer.is_fluent(e.args[1])
-            if self.relaxed and fluent and V.get("poisson") == "determinized":
+            variant = V.get("poisson") if (self.relaxed and fluent) else None
+            if variant == "determinized":
                 return (1.0 / prob - 1.0) * trials, perr           # logic.py:1762
-            raise NotImplementedError(
-                "NegativeBinomial is only available determinised (DeterminizedPoisson)")
+            G = gamma_draw(trials, e.args[0])
+            if variant is None:        # exact: tfp NegativeBinomial(total_count, probs) as a mixture
+                rate = G * prob / (1.0 - prob)
+            else:                      # logic.py:1583-1585, 1698-1700
+                rate = (1.0 / prob - 1.0) * G
+            return poisson_sample(rate, variant, perr)
         if name == "Gumbel":                                       # compiler.py:2046-2065
             mean, scale = vals
             g = self._draw(cur, "gumbel", a0, scope, B)

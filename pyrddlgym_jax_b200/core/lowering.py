@@ -849,10 +849,18 @@ class Lowerer:
             fluent = self.tr.is_fluent(e.args[0]) or self.tr.is_fluent(e.args[1])
             bad = E("OR", E("OR", E("LT", prob, C(0.)), E("GT", prob, C(1.))), E("LE", trials, C(0.)))
             self.errchk("NEGATIVE_BINOMIAL", bad, sizes)
-            if self.relaxed and fluent and Vv.get("poisson") == "determinized":
+            variant = Vv.get("poisson") if (self.relaxed and fluent) else None
+            if variant == "determinized":
                 return E("MUL", E("SUB", E("DIV", C(1.), prob), C(1.)), trials)   # logic.py:1762
-            raise RDDLNotImplementedError(
-                "NegativeBinomial is only available determinised (DeterminizedPoisson)")
+            G = self._gamma_draw(trials, a0, scope, sizes)
+            if variant is None:
+                # exact: tfp NegativeBinomial(total_count, probs) (compiler.py:1945-1967) as its
+                # Gamma-Poisson mixture, rate = Gamma(trials) p / (1 - p)
+                rate = E("DIV", E("MUL", G, prob), E("SUB", C(1.), prob))
+            else:
+                # relaxed (logic.py:1583-1585, 1698-1700): rate = (1 / p - 1) Gamma(trials)
+                rate = E("MUL", E("SUB", E("DIV", C(1.), prob), C(1.)), G)
+            return self._poisson_sample(e, rate, a0, scope, sizes, variant)
         if name in ("Gumbel", "Laplace", "Cauchy"):
             mean, scale = F(tvs[0]), F(tvs[1])
             Gn = self._draw(name.lower(), a0, scope, sizes)
@@ -941,6 +949,13 @@ class Lowerer:
         C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
         self.errchk("POISSON", E("LT", rate, C(0.)), sizes)
         variant = self.variants.get("poisson") if (self.relaxed and self.tr.is_fluent(a0)) else None
+        return self._poisson_sample(e, rate, a0, scope, sizes, variant)
+
+    def _poisson_sample(self, e, rate: TV, a0, scope, sizes, variant) -> TV:
+        """A Poisson draw of the given rate under the given relaxation (shared with
+        NegativeBinomial, a Gamma mixture of Poissons)."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
         if variant == "determinized":
             return rate
         if variant == "exponential":

@@ -354,6 +354,12 @@ def test_count_and_gamma_family_sampler_moments():
     assert s.min() >= 0 and s.max() <= 5
     np.testing.assert_allclose(s.mean(0), 5 * p, rtol=0.04)
     np.testing.assert_allclose(s.var(0), 5 * p * (1 - p), rtol=0.10)
+    # NegativeBinomial(r, p) of the exact model: tfp's convention, mean r p / (1 - p)
+    pn = 0.3 + 0.1 * np.minimum(level0, 3.0)
+    nb = fin["backlog"].numpy().astype(np.float64)
+    np.testing.assert_allclose(nb.mean(0), 3 * pn / (1 - pn), rtol=0.08)
+    np.testing.assert_allclose(nb.var(0), 3 * pn / (1 - pn) ** 2, rtol=0.15)
+    np.testing.assert_array_equal(nb, c["ref"]["final"]["backlog"].numpy())
     # the emulated program and the oracle agree draw for draw
     np.testing.assert_array_equal(q, c["ref"]["final"]["queue"].numpy())
     np.testing.assert_array_equal(s, c["ref"]["final"]["served"].numpy())
