@@ -216,8 +216,10 @@ int rk_tcgemm_tn(void* stream, int accumulate, int M, int N, int K, const float*
  *   real / int: clip(mu + train * exp(clip(log_sigma)) * noise, lo, hi);
  *   bool: sigmoid(bool_weight * (logit + train * noise)), noise ~ Logistic (planner.py:1381-1391);
  *   train = 1 (train policy) or 0 (test policy, planner.py:1486); lo/hi [A] or NULL;
- *   typed != 0: bool actions are written as int32 (p > 0.5) and int actions as int32 round(.), the
- *   input words of the exact test program (planner.py:1488-1497);
+ *   typed bit 0: bool actions are written as int32 (p > 0.5) and int actions as int32 round(.),
+ *   the input words of the exact test program (planner.py:1488-1497); typed bit 1: wrap_non_bool,
+ *   real / int heads go through the sigmoid / softplus box wrap of planner.py:620-628 instead of
+ *   the clip (the test policy applies both);
  *   entropy [B] = sum clip(log_sigma) - sum_bool [p log p + (1-p) log(1-p)], or NULL. */
 #define RK_MAX_ACTION_FLUENTS 16
 int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg,
@@ -227,12 +229,13 @@ int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg
                            float* actions, float* entropy);
 /* gheads [B][2A or A] = d actions / d heads applied to gact (clip: gradient 1 inside); boolean
  * logits also receive the gradient of the entropy regulariser, ent_coeff[0] * inv_batch * dH/dlogit
- * (ent_coeff: device scalar, NULL = none; the log_sigma entropy is stop_gradient). */
+ * (ent_coeff: device scalar, NULL = none; the log_sigma entropy is stop_gradient); wrap != 0
+ * differentiates the box wrap instead of the clip. */
 int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
                             const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
                             const float* heads, const float* noise, float train, const float* lo,
                             const float* hi, float ls_lo, float ls_hi, float bool_weight,
-                            const float* ent_coeff, float inv_batch, const float* gact,
+                            const float* ent_coeff, float inv_batch, int wrap, const float* gact,
                             float* gheads);
 
 /* Tile the un-batched initial state (S words: float bits, or int32 0/1 / int words for the exact

@@ -370,7 +370,8 @@ def drp_init(model, topology, generator: torch.Generator, stochastic: bool = Tru
 
 def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], train: float,
                 bounds, topology_len: int, stochastic: bool = True,
-                sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0):
+                sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0,
+                wrap_non_bool: bool = False):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
     noise: action name -> [B, n] standard draws.  Returns (actions name -> [B, *objs],
     entropy [B])."""
@@ -404,25 +405,33 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
         lo, hi = bounds[var]
         lo = torch.as_tensor(np.asarray(lo, np.float32)).reshape(1, -1)
         hi = torch.as_tensor(np.asarray(hi, np.float32)).reshape(1, -1)
-        a = torch.minimum(torch.maximum(a, lo), hi)           # planner.py:1472-1475
+        if wrap_non_bool:                                     # planner.py:1411-1415
+            a = bound_action(lo, hi, a)
+        else:
+            a = torch.minimum(torch.maximum(a, lo), hi)       # planner.py:1472-1475
         actions[var] = a.reshape(shape)
     return actions, entropy
 
 
 def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True,
-                     sigmoid_weight: float = 1.0):
+                     sigmoid_weight: float = 1.0, wrap_non_bool: bool = False):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
     acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic,
-                          sigmoid_weight=sigmoid_weight)
+                          sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]
         if prange == "bool":
             out[var] = a > 0.5
         elif prange == "int" or prange in model.enum_types:
+            lo, hi = bounds[var]
+            a = torch.minimum(torch.maximum(a, torch.as_tensor(np.asarray(lo, np.float32))),
+                              torch.as_tensor(np.asarray(hi, np.float32)))
             out[var] = torch.round(a).to(INT)
         else:
-            out[var] = a
+            lo, hi = bounds[var]
+            out[var] = torch.minimum(torch.maximum(a, torch.as_tensor(np.asarray(lo, np.float32))),
+                                     torch.as_tensor(np.asarray(hi, np.float32)))
     return out

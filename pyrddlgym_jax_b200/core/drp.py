@@ -49,8 +49,8 @@ class JaxDeepReactivePolicy(JaxPlan):
         act = getattr(activation, "__name__", activation)
         if act != "tanh":
             raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
-        for flag, name in ((normalize, "normalize"), (wrap_non_bool, "wrap_non_bool"),
-                           (time_dependent, "time_dependent"),
+        self._wrap_non_bool = bool(wrap_non_bool)
+        for flag, name in ((normalize, "normalize"), (time_dependent, "time_dependent"),
                            (sigma_entropy_grad, "sigma_entropy_grad")):
             if flag:
                 raise NotImplementedError(f"JaxDeepReactivePolicy({name}=True) is not built yet")
@@ -242,6 +242,12 @@ class JaxDeepReactivePolicy(JaxPlan):
             if prange == "bool":        # sigmoid(w * logit) > 0.5  (planner.py:1489)
                 acts[var] = (self._sigmoid_weight * a) > 0.0
                 continue
+            if self._wrap_non_bool:     # planner.py:1411-1415
+                fl, fh = np.isfinite(lo), np.isfinite(hi)
+                lo0, hi0 = np.where(fl, lo, 0.0), np.where(fh, hi, 0.0)
+                sp = lambda x: np.logaddexp(0.0, x)      # noqa: E731
+                a = np.where(fl & fh, lo0 + (hi0 - lo0) / (1.0 + np.exp(-a)),
+                             np.where(fl, lo0 + sp(a), np.where(fh, hi0 - sp(-a), a))).astype(np.float32)
             a = np.minimum(np.maximum(a, lo), hi)
             acts[var] = a if prange == "real" else np.round(a).astype(np.int32)
         return acts
@@ -433,7 +439,7 @@ class DrpPipeline:
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.act[t], self.entropy[t], kinds=plan.action_kinds,
-                bool_weight=plan._sigmoid_weight)
+                bool_weight=plan._sigmoid_weight, wrap=plan._wrap_non_bool)
             fwd.forward(B, 1, x, actions=self.act[t],
                         noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
                         mparams=pl.train_mparams,
@@ -465,7 +471,7 @@ class DrpPipeline:
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.gact, self.gheads, kinds=plan.action_kinds,
                 bool_weight=plan._sigmoid_weight, ent_coeff=self.ent_coeff,
-                inv_batch=1.0 / (B * pl.world_size))
+                inv_batch=1.0 / (B * pl.world_size), wrap=plan._wrap_non_bool)
             self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
             cur ^= 1
 
@@ -497,7 +503,7 @@ class DrpPipeline:
                                        None, 0.0, self.lo,
                                        self.hi, self.ls_lo, self.ls_hi, self.t_act, None,
                                        kinds=plan.action_kinds, bool_weight=plan._sigmoid_weight,
-                                       typed=True)
+                                       typed=True, wrap=plan._wrap_non_bool)
             te.forward(B, 1, x, actions=self.t_act,
                        noise=None if pl.test_noise is None else pl.test_noise[t * N * B:],
                        disc=None if pl.disc is None else pl.disc[t:],

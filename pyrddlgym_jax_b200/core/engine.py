@@ -81,7 +81,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                            fl, fl, ci, cf, cf]
     lib.rk_drp_actions_forward.restype = ci
     lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, cf, cf, fl, cf, cf, fl,
-                                            fl, fl, cf, fl, cf, cf]
+                                            fl, fl, cf, fl, ci, cf, cf]
     lib.rk_drp_actions_backward.restype = ci
     lib.rk_drp_layer0.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
     lib.rk_drp_layer0.restype = ci
@@ -246,7 +246,8 @@ def _kinds(segs, kinds):
 
 
 def drp_actions_forward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_lo, ls_hi, actions,
-                        entropy=None, kinds=None, bool_weight: float = 1.0, typed: bool = False):
+                        entropy=None, kinds=None, bool_weight: float = 1.0, typed: bool = False,
+                        wrap: bool = False):
     """segs: [(word offset, length), ...] of the action fluents (fluent-major layout); kinds:
     0 real / 1 bool / 2 int per fluent; typed: write bool / int actions as int32 words (the exact
     test program's input) instead of floats."""
@@ -256,20 +257,21 @@ def drp_actions_forward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_
         _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
         ctypes.cast(ln, ctypes.c_void_p), ctypes.cast(kd, ctypes.c_void_p), _ptr(heads),
         _ptr(noise), float(train), _ptr(lo), _ptr(hi), float(ls_lo), float(ls_hi),
-        float(bool_weight), int(bool(typed)), _ptr(actions), _ptr(entropy)),
+        float(bool_weight), int(bool(typed)) | (2 if wrap else 0), _ptr(actions), _ptr(entropy)),
         "rk_drp_actions_forward")
 
 
 def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_lo, ls_hi, gact,
                          gheads, kinds=None, bool_weight: float = 1.0, ent_coeff=None,
-                         inv_batch: float = 0.0):
+                         inv_batch: float = 0.0, wrap: bool = False):
     n, off, ln = _segs(segs)
     kd = _kinds(segs, kinds)
     _check(load_library().rk_drp_actions_backward(
         _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
         ctypes.cast(ln, ctypes.c_void_p), ctypes.cast(kd, ctypes.c_void_p), _ptr(heads),
         _ptr(noise), float(train), _ptr(lo), _ptr(hi), float(ls_lo), float(ls_hi),
-        float(bool_weight), _ptr(ent_coeff), float(inv_batch), _ptr(gact), _ptr(gheads)),
+        float(bool_weight), _ptr(ent_coeff), float(inv_batch), int(bool(wrap)), _ptr(gact),
+        _ptr(gheads)),
         "rk_drp_actions_backward")
 
 

@@ -298,6 +298,17 @@ struct RkActSegs {
 };
 
 __device__ __forceinline__ float rk_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float rk_softplus(float x) { return log1pf(expf(-fabsf(x))) + fmaxf(x, 0.f); }
+// _jax_bound_action (planner.py:620-628): sigmoid wrap for two-sided boxes, softplus wraps for
+// one-sided ones, identity when unbounded; *d receives the derivative
+__device__ __forceinline__ float rk_bound_action(float x, float lo, float hi, float* d) {
+  const bool fl = isfinite(lo), fh = isfinite(hi);
+  if (fl && fh) { const float s = rk_sigmoid(x); *d = (hi - lo) * s * (1.f - s); return lo + (hi - lo) * s; }
+  if (fl) { *d = rk_sigmoid(x); return lo + rk_softplus(x); }
+  if (fh) { *d = rk_sigmoid(-x); return hi - rk_softplus(-x); }
+  *d = 1.f;
+  return x;
+}
 // x * safe_log(x) of compiler.py:65-75, with 0 * log 0 taken as 0 (the reference yields NaN there)
 __device__ __forceinline__ float rk_xlogx(float x) { return x > 0.f ? x * logf(x) : 0.f; }
 
@@ -330,7 +341,7 @@ __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSeg
           act = act + train * z;
         }
         act = rk_sigmoid(bool_weight * act);
-        if (typed) ((int32_t*)actions)[w] = act > 0.5f ? 1 : 0;
+        if (typed & 1) ((int32_t*)actions)[w] = act > 0.5f ? 1 : 0;
         else actions[w] = act;
         continue;
       }
@@ -339,8 +350,13 @@ __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSeg
         ent += ls;
         act = act + train * expf(ls) * z;
       }
-      if (lo != nullptr) act = fminf(fmaxf(act, lo[a]), hi[a]);
-      if (typed && S.kind[f] == 2) ((int32_t*)actions)[w] = (int32_t)rintf(act);
+      if (lo != nullptr && (typed & 2)) {           // wrap_non_bool (planner.py:1411-1415)
+        float d;
+        act = rk_bound_action(act, lo[a], hi[a], &d);
+      }
+      if (lo != nullptr && (!(typed & 2) || (typed & 1)))
+        act = fminf(fmaxf(act, lo[a]), hi[a]);      // planner.py:1472-1475, 1493-1496
+      if ((typed & 1) && S.kind[f] == 2) ((int32_t*)actions)[w] = (int32_t)rintf(act);
       else actions[w] = act;
     }
   }
@@ -353,7 +369,8 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
                                           const float* __restrict__ lo,
                                           const float* __restrict__ hi, float ls_lo, float ls_hi,
                                           float bool_weight, const float* __restrict__ ent_coeff,
-                                          float inv_batch, const float* __restrict__ gact,
+                                          float inv_batch, int wrap,
+                                          const float* __restrict__ gact,
                                           float* __restrict__ gheads) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -386,8 +403,13 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
         pre = mu + train * ex * z;
       }
       float g = gact[w];
-      // jnp.clip: gradient 1 inside [lo, hi] (bounds included), 0 outside
-      if (lo != nullptr && (pre < lo[a] || pre > hi[a])) g = 0.f;
+      if (lo != nullptr && wrap) {                  // through the box wrap instead of the clip
+        float d;
+        rk_bound_action(pre, lo[a], hi[a], &d);
+        g *= d;
+      } else if (lo != nullptr && (pre < lo[a] || pre > hi[a])) {
+        g = 0.f;    // jnp.clip: gradient 1 inside [lo, hi] (bounds included), 0 outside
+      }
       gheads[(size_t)b * ld + a] = g;
       if (stochastic) {
         const bool inside = raw >= ls_lo && raw <= ls_hi;
@@ -437,7 +459,7 @@ extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochasti
                                        const float* noise, float train, const float* lo,
                                        const float* hi, float ls_lo, float ls_hi,
                                        float bool_weight, const float* ent_coeff, float inv_batch,
-                                       const float* gact, float* gheads) {
+                                       int wrap, const float* gact, float* gheads) {
   if (B <= 0 || A <= 0 || heads == nullptr || gact == nullptr || gheads == nullptr)
     return RK_E_BADARG;
   if ((lo == nullptr) != (hi == nullptr)) return RK_E_BADARG;
@@ -446,7 +468,7 @@ extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochasti
   if (rc != 0) return rc;
   rk_drp_actions_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, bool_weight, ent_coeff,
-      inv_batch, gact, gheads);
+      inv_batch, wrap, gact, gheads);
   return (int)cudaGetLastError();
 }
 

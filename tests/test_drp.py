@@ -447,3 +447,54 @@ def test_drp_bool_heads_match_oracle(cuda_device, stochastic):
         [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
     np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(),
                                out["reward"].numpy().T, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_drp_wrap_non_bool_heads_match_oracle(cuda_device):
+    """wrap_non_bool heads (planner.py:1411-1415): the sigmoid / softplus box wrap replaces the clip
+    in the train policy (value and gradient); the test policy applies wrap then clip."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    T, B = 3, 19
+    plan = JaxDeepReactivePolicy(topology=[16, 16], wrap_non_bool=True)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = {k: {kk: vv.clone().requires_grad_(True) for kk, vv in v.items()} for k, v in tree.items()}
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              {"curProd": pol_noise[t].reshape(B, 5)}, 1.0, m.bounds, 2, True,
+                              wrap_non_bool=True)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    grads = {k: {kk: (vv.grad if vv.grad is not None else torch.zeros_like(vv))
+                 for kk, vv in v.items()} for k, v in P.items()}
+    want = plan.pytree_to_params(grads).numpy()
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    np.testing.assert_allclose(pl.grad[0].cpu().numpy(), want, rtol=1e-4,
+                               atol=1e-4 * np.abs(want).max())
+    # host-side test policy against the oracle's
+    fls = {"prevProd": torch.tensor([[1., 2., 0., .5, 3.]]), "temperature": torch.tensor([15.])}
+    ref = OP.drp_test_actions(m, tree, fls, m.bounds, 2, wrap_non_bool=True)["curProd"].numpy()
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
+    np.testing.assert_allclose(got, ref.reshape(-1), rtol=1e-5, atol=1e-5)
