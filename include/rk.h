@@ -182,6 +182,22 @@ int rk_drp_head_backward(void* stream, int B, int hl, int NH, const float* Hl, c
 int rk_drp_layer0_backward(void* stream, int B, int D, int H, int n_seg, const int32_t* seg_off,
                            const int32_t* seg_len, const float* x, const float* gz0,
                            const float* W0T, float* gs, float* grad_W0b0, float* workspace);
+/* Input LayerNorm of the DRP over the non-boolean state words (planner.py:1300-1319; flax
+ * nn.LayerNorm: y = (x - mean) rsqrt(var + eps) scale + bias, var = E[x^2] - E[x]^2).  x, y, gy, gx
+ * are fluent-major state buffers; seg_norm[f] = 0 passes fluent f through, g >= 1 normalises it
+ * together with the other fluents of group g (groups numbered 1..G: `normalize` = one group of all
+ * non-bool fluents, `normalize_per_layer` = one group per fluent); scale / bias [Dn] follow the
+ * normalised words in fluent order.  backward: gx += LayerNorm^T gy and grad_scale_bias =
+ * [dscale (Dn) | dbias (Dn)] += batch sums through workspace[rk_state_layernorm_ctas(B)][2 Dn]
+ * (added in CTA order). */
+int rk_state_layernorm_ctas(int B);
+int rk_state_layernorm_forward(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
+                               const int32_t* seg_len, const int32_t* seg_norm, float eps,
+                               const float* x, const float* scale, const float* bias, float* y);
+int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
+                                const int32_t* seg_len, const int32_t* seg_norm, float eps,
+                                const float* x, const float* scale, const float* gy, float* gx,
+                                float* grad_scale_bias, float* workspace);
 /* Skinny products with N <= 16 (action heads, state-cotangent blocks), A read exactly once:
  * out[b][n] = (accumulate ? out : 0) + sum_k A[b][k] W[k][n] (+ bias[n]). */
 int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A, int lda,

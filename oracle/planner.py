@@ -342,9 +342,48 @@ def drp_input_order(model) -> List[str]:
            [v for v in names if model.variable_ranges[v] == "bool"]
 
 
-def drp_init(model, topology, generator: torch.Generator, stochastic: bool = True):
+def drp_norm_layers(model, normalize: bool, normalize_per_layer: bool):
+    """The LayerNorm modules of the input layer (planner.py:1259-1282, 1300-1319) as a list of
+    (flax name, [fluents]); falls back like the reference when a normalised tensor has size 1."""
+    if not normalize:
+        return []
+    non_bool = [v for v in drp_input_order(model) if model.variable_ranges[v] != "bool"]
+    sizes = [model.variable_size(v) for v in non_bool]
+    if normalize_per_layer and any(n == 1 for n in sizes):
+        normalize_per_layer = False
+    if normalize_per_layer:
+        return [("norm_" + v.replace("-", "_"), [v]) for v in non_bool]
+    if sum(sizes) <= 1:
+        return []
+    return [("norm", non_bool)]
+
+
+def drp_state_vector(model, params, fls, normalize: bool = False,
+                     normalize_per_layer: bool = False, eps: float = 1e-6):
+    """DRPStateLayer (planner.py:1287-1320): ravel + concatenate the observed fluents (non-bool
+    first), LayerNorm on the non-bool part (flax nn.LayerNorm: biased variance E[x^2] - E[x]^2,
+    epsilon 1e-6, learned scale and bias under params['inputs'][name])."""
+    B = next(iter(fls.values())).shape[0]
+    cols = {v: fls[v].reshape(B, -1).to(REAL) for v in drp_input_order(model)}
+    for name, members in drp_norm_layers(model, normalize, normalize_per_layer):
+        x = torch.cat([cols[v] for v in members], dim=1)
+        mean = x.mean(1, keepdim=True)
+        var = torch.clamp((x * x).mean(1, keepdim=True) - mean * mean, min=0.0)
+        layer = params["inputs"][name]
+        y = (x - mean) * torch.rsqrt(var + eps) * layer["scale"] + layer["bias"]
+        o = 0
+        for v in members:
+            n = cols[v].shape[1]
+            cols[v] = y[:, o:o + n]
+            o += n
+    return torch.cat([cols[v] for v in drp_input_order(model)], dim=1)
+
+
+def drp_init(model, topology, generator: torch.Generator, stochastic: bool = True,
+             normalize: bool = False, normalize_per_layer: bool = False):
     """variance_scaling(2.0, 'fan_in', 'truncated_normal') kernels, zero biases
-    (planner.py:1129-1130; flax nn.Dense), as a dict layer -> {'kernel' [in, out], 'bias'}."""
+    (planner.py:1129-1130; flax nn.Dense), as a dict layer -> {'kernel' [in, out], 'bias'};
+    LayerNorm scales start at one and biases at zero (flax defaults)."""
     def kernel(fan_in, fan_out):
         std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
         w = torch.empty(fan_in, fan_out)
@@ -352,6 +391,9 @@ def drp_init(model, topology, generator: torch.Generator, stochastic: bool = Tru
         return w * std
     D = sum(model.variable_size(v) for v in drp_input_order(model))
     params, fan = {}, D
+    for name, members in drp_norm_layers(model, normalize, normalize_per_layer):
+        n = sum(model.variable_size(v) for v in members)
+        params.setdefault("inputs", {})[name] = {"scale": torch.ones(n), "bias": torch.zeros(n)}
     for i, h in enumerate(topology):
         params[f"dense_{i}"] = {"kernel": kernel(fan, h), "bias": torch.zeros(h)}
         fan = h
@@ -371,12 +413,13 @@ def drp_init(model, topology, generator: torch.Generator, stochastic: bool = Tru
 def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], train: float,
                 bounds, topology_len: int, stochastic: bool = True,
                 sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0,
-                wrap_non_bool: bool = False):
+                wrap_non_bool: bool = False, normalize: bool = False,
+                normalize_per_layer: bool = False):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
     noise: action name -> [B, n] standard draws.  Returns (actions name -> [B, *objs],
     entropy [B])."""
     B = next(iter(fls.values())).shape[0]
-    x = torch.cat([fls[v].reshape(B, -1).to(REAL) for v in drp_input_order(model)], dim=1)
+    x = drp_state_vector(model, params, fls, normalize, normalize_per_layer)
     h = x
     for i in range(topology_len):
         layer = params[f"dense_{i}"]
@@ -414,12 +457,14 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
 
 
 def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True,
-                     sigmoid_weight: float = 1.0, wrap_non_bool: bool = False):
+                     sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
+                     normalize: bool = False, normalize_per_layer: bool = False):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
     acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic,
-                          sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool)
+                          sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool,
+                          normalize=normalize, normalize_per_layer=normalize_per_layer)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]

@@ -50,7 +50,7 @@ class JaxDeepReactivePolicy(JaxPlan):
         if act != "tanh":
             raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
         self._wrap_non_bool = bool(wrap_non_bool)
-        for flag, name in ((normalize, "normalize"), (time_dependent, "time_dependent"),
+        for flag, name in ((time_dependent, "time_dependent"),
                            (sigma_entropy_grad, "sigma_entropy_grad")):
             if flag:
                 raise NotImplementedError(f"JaxDeepReactivePolicy({name}=True) is not built yet")
@@ -62,13 +62,26 @@ class JaxDeepReactivePolicy(JaxPlan):
         self._softmax_output_weight = softmax_weight
         self._stochastic = stochastic
         self._sigma_range = sigma_range
-        self._normalize = normalize
+        self._normalize = bool(normalize)
+        self._normalize_per_layer = bool(normalize_per_layer)
+        if normalizer_kwargs is None:       # planner.py:1179-1181
+            normalizer_kwargs = {"use_bias": True, "use_scale": True}
+        extra = set(normalizer_kwargs) - {"use_bias", "use_scale", "epsilon"}
+        if extra or not normalizer_kwargs.get("use_bias", True) \
+                or not normalizer_kwargs.get("use_scale", True):
+            raise NotImplementedError(
+                f"normalizer_kwargs {normalizer_kwargs}: only epsilon (with scale and bias) is built")
+        self._normalizer_kwargs = dict(normalizer_kwargs)
+        self._norm_eps = float(normalizer_kwargs.get("epsilon", 1e-6))     # flax nn.LayerNorm
         self._time_dependent = time_dependent
 
     def __str__(self) -> str:
         return (f"[INFO] policy hyper-parameters:\n"
                 f"    topology          ={self._topology}\n"
                 f"    activation_fn     =tanh\n"
+                f"    apply_input_norm  ={self._normalize}\n"
+                f"    input_norm_layerwise={self._normalize_per_layer}\n"
+                f"    input_norm_args   ={self._normalizer_kwargs}\n"
                 f"    stochastic        ={self._stochastic}\n"
                 f"    sigma_range       ={self._sigma_range}\n")
 
@@ -120,7 +133,36 @@ class JaxDeepReactivePolicy(JaxPlan):
         ref = [v for v in names if rddl.variable_ranges[v] != "bool"] + \
               [v for v in names if rddl.variable_ranges[v] == "bool"]
         self.input_perm = np.concatenate([np.arange(pos[v][0], pos[v][0] + pos[v][1]) for v in ref])
-        # flat parameter vector: [W_i | b_i]* then [W_heads | b_heads]
+        # input LayerNorm (planner.py:1259-1282, 1300-1319): `norm_layers` = [(flax name, fluents)]
+        # in the reference's order, `norm_groups[f]` = group of state fluent f for the kernels
+        # (0 = not normalised), `norm_perm[name]` = kernel positions of that module's scale / bias
+        non_bool = [v for v in names if rddl.variable_ranges[v] != "bool"]
+        per_layer = self._normalize_per_layer
+        self.norm_layers: List[Tuple[str, List[str]]] = []
+        if self._normalize:
+            if per_layer and any(pos[v][1] == 1 for v in non_bool):
+                if getattr(compiled, "print_warnings", False):
+                    print("[WARN] Cannot apply layer norm to a state-fluent of size 1: "
+                          "setting normalize_per_layer = False.")
+                per_layer = False
+            if per_layer:
+                self.norm_layers = [("norm_" + v.replace("-", "_"), [v]) for v in non_bool]
+            elif sum(pos[v][1] for v in non_bool) > 1:
+                self.norm_layers = [("norm", non_bool)]
+            elif non_bool and getattr(compiled, "print_warnings", False):
+                print("[WARN] Cannot apply layer norm to state-fluents of total size 1: "
+                      "setting normalize = False.")
+        group_of = {v: g + 1 for g, (_, members) in enumerate(self.norm_layers) for v in members}
+        self.norm_groups = [group_of.get(v, 0) for v in rddl.state_fluents]
+        kpos, j = {}, 0
+        for v in rddl.state_fluents:
+            if v in group_of:
+                kpos[v] = np.arange(j, j + pos[v][1])
+                j += pos[v][1]
+        self.Dn = j
+        self.norm_perm = {name: np.concatenate([kpos[v] for v in members])
+                          for name, members in self.norm_layers}
+        # flat parameter vector: [W_i | b_i]* then [W_heads | b_heads] (then [ln_scale | ln_bias])
         self.NH = self.A * (2 if self._stochastic else 1)
         dims = [self.D] + self._topology
         self.segments: List[Tuple[str, int, int, int]] = []     # (name, offset, rows, cols)
@@ -134,6 +176,10 @@ class JaxDeepReactivePolicy(JaxPlan):
         o += dims[-1] * self.NH
         self.segments.append(("bh", o, 1, self.NH))
         o += self.NH
+        if self.Dn:
+            self.segments.append(("ln_scale", o, 1, self.Dn))
+            self.segments.append(("ln_bias", o + self.Dn, 1, self.Dn))
+            o += 2 * self.Dn
         self.n_params = o
         self.seg = {name: (off, r, c) for name, off, r, c in self.segments}
         self.box = (None, None)
@@ -156,12 +202,19 @@ class JaxDeepReactivePolicy(JaxPlan):
                     torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
                     w = w * std
                 flat[off:off + r * c] = w.reshape(-1)
+            elif name == "ln_scale":
+                flat[off:off + c] = 1.0
         return flat
 
     # ---- flat vector <-> flax-style pytree ------------------------------------------------
     def params_to_pytree(self, flat: torch.Tensor) -> Dict[str, Any]:
         lead = flat.shape[:-1]
         tree: Dict[str, Any] = {}
+        for name, idx in self.norm_perm.items():       # DRPStateLayer 'inputs' / LayerNorm modules
+            so, sb = self.seg["ln_scale"][0], self.seg["ln_bias"][0]
+            idx = torch.as_tensor(idx)
+            tree.setdefault("inputs", {})[name] = {"scale": flat[..., so + idx],
+                                                   "bias": flat[..., sb + idx]}
         for i in range(len(self._topology)):
             off, r, c = self.seg[f"W{i}"]
             W = flat[..., off:off + r * c].reshape(*lead, r, c)
@@ -190,6 +243,11 @@ class JaxDeepReactivePolicy(JaxPlan):
         tree = tree.get("params", tree)
         flat = torch.zeros(self.n_params)
         as_t = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32)   # noqa: E731
+        for name, idx in self.norm_perm.items():
+            so, sb = self.seg["ln_scale"][0], self.seg["ln_bias"][0]
+            idx = torch.as_tensor(idx)
+            flat[so + idx] = as_t(tree["inputs"][name]["scale"]).reshape(-1)
+            flat[sb + idx] = as_t(tree["inputs"][name]["bias"]).reshape(-1)
         for i in range(len(self._topology)):
             off, r, c = self.seg[f"W{i}"]
             W = as_t(tree[f"dense_{i}"]["kernel"]).reshape(r, c)
@@ -227,7 +285,23 @@ class JaxDeepReactivePolicy(JaxPlan):
     def test_actions_host(self, flat: torch.Tensor, state_vec: np.ndarray) -> Dict[str, np.ndarray]:
         """Test policy on one state (controllers' get_action, planner.py:3527): a handful of
         tiny mat-vecs on the host."""
-        h = torch.as_tensor(state_vec, dtype=torch.float32).reshape(1, -1)
+        h = torch.as_tensor(state_vec, dtype=torch.float32).reshape(1, -1).clone()
+        if self.Dn:
+            so, sb = self.seg["ln_scale"][0], self.seg["ln_bias"][0]
+            words = {g: [] for g in range(1, len(self.norm_layers) + 1)}
+            j = 0
+            for (off, n), g in zip(self.state_segs, self.norm_groups):
+                if g:
+                    words[g].append((off, n, j))
+                    j += n
+            for g, blocks in words.items():
+                cols = torch.cat([torch.arange(o, o + n) for o, n, _ in blocks])
+                par = torch.cat([torch.arange(jj, jj + n) for _, n, jj in blocks])
+                x = h[0, cols]
+                mean = x.mean()
+                var = torch.clamp((x * x).mean() - mean * mean, min=0.0)
+                h[0, cols] = (x - mean) * torch.rsqrt(var + self._norm_eps) * flat[so + par] \
+                    + flat[sb + par]
         for i in range(len(self._topology)):
             off, r, c = self.seg[f"W{i}"]
             ob = self.seg[f"b{i}"][0]
@@ -320,6 +394,19 @@ class DrpPipeline:
         self.t_act = z(self.A * Be)
         self.t_xf = z(te.S * Be) if any(plan.state_is_int) else None
         self.ent_coeff = z(1)
+        # input LayerNorm: normalised inputs of every step (operands of the first layer's weight
+        # gradient), cotangent of the normalised input, per-CTA partials of [dscale | dbias]
+        self.Dn = plan.Dn
+        if self.Dn:
+            self.xn = z(T, self.S * Bt)
+            self.gy = z(self.S * Bt)
+            self.ln_ws = z(engine.state_layernorm_ctas(Bt) * 2 * self.Dn)
+            self.t_xn = z(te.S * Be)
+
+    def layernorm_forward(self, params, B, x, y):
+        plan = self.plan
+        engine.state_layernorm_forward(B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps,
+                                       x, self._W(params, "ln_scale"), self._W(params, "ln_bias"), y)
 
     # ---- views into a flat parameter / gradient vector ---------------------------------------
     def _W(self, flat, name):
@@ -434,7 +521,11 @@ class DrpPipeline:
         for t in range(T):
             x = self.tape[t * S * B:(t + 1) * S * B]
             Ht = [Hl[t] for Hl in self.H]
-            self.mlp_forward(params, B, x, Ht, self.heads[t], self.xp[t])
+            xin = x
+            if self.Dn:
+                xin = self.xn[t]
+                self.layernorm_forward(params, B, x, xin)
+            self.mlp_forward(params, B, xin, Ht, self.heads[t], self.xp[t])
             engine.drp_actions_forward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
@@ -472,7 +563,16 @@ class DrpPipeline:
                 self.ls_lo, self.ls_hi, self.gact, self.gheads, kinds=plan.action_kinds,
                 bool_weight=plan._sigmoid_weight, ent_coeff=self.ent_coeff,
                 inv_batch=1.0 / (B * pl.world_size), wrap=plan._wrap_non_bool)
-            self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
+            if self.Dn:     # MLP input cotangent -> gy, then gs += LayerNorm^T gy (+ dscale, dbias)
+                self.gy.zero_()
+                self.mlp_backward(grad, B, self.xn[t], [Hl[t] for Hl in self.H], self.gy,
+                                  self.xp[t], params)
+                engine.state_layernorm_backward(
+                    B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps, x,
+                    self._W(params, "ln_scale"), self.gy, out, self._W(grad, "ln_scale"),
+                    self.ln_ws)
+            else:
+                self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
             cur ^= 1
 
     def test_kernels(self, p: int, params: Optional[torch.Tensor] = None, out=None):
@@ -498,6 +598,9 @@ class DrpPipeline:
                 for (off, n), is_int in zip(plan.state_segs, plan.state_is_int):
                     blk = x[off * B:(off + n) * B]
                     xin[off * B:(off + n) * B].copy_(blk.view(torch.int32) if is_int else blk)
+            if self.Dn:
+                self.layernorm_forward(params, B, xin, self.t_xn)
+                xin = self.t_xn
             self.mlp_forward(params, B, xin, self.t_H, self.t_heads)
             engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,
                                        None, 0.0, self.lo,

@@ -26,6 +26,7 @@ EXPORTS = [
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
     "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state", "rk_drp_head_backward",
     "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
+    "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
 ]
 
 
@@ -93,6 +94,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_layer0_backward.restype = ci
     lib.rk_peer_allreduce.argtypes = [vp, ci, ci, vp, vp, ci, ci, cf, cf, cf]
     lib.rk_peer_allreduce.restype = ci
+    lib.rk_state_layernorm_ctas.argtypes = [ci]
+    lib.rk_state_layernorm_ctas.restype = ci
+    lib.rk_state_layernorm_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf]
+    lib.rk_state_layernorm_forward.restype = ci
+    lib.rk_state_layernorm_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf, cf, cf]
+    lib.rk_state_layernorm_backward.restype = ci
     lib.rk_colsum.argtypes = [vp, ci, ci, cf, ci, cf, ci, cf, ci]
     lib.rk_colsum.restype = ci
     lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
@@ -320,6 +327,28 @@ def peer_allreduce(world: int, rank: int, peer_bufs, peer_flags, n: int, n_max: 
         _stream(), world, rank, ctypes.cast(peer_bufs, ctypes.c_void_p),
         ctypes.cast(peer_flags, ctypes.c_void_p), n, n_max, _ptr(vec), _ptr(epoch), _ptr(status)),
         "rk_peer_allreduce")
+
+
+def state_layernorm_ctas(B: int) -> int:
+    return int(load_library().rk_state_layernorm_ctas(int(B)))
+
+
+def state_layernorm_forward(B, D, segs, norm, eps, x, scale, bias, y):
+    n, off, ln = _segs(segs)
+    kd = _kinds(segs, [int(k) for k in norm])
+    _check(load_library().rk_state_layernorm_forward(
+        _stream(), B, D, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+        ctypes.cast(kd, ctypes.c_void_p), float(eps), _ptr(x), _ptr(scale), _ptr(bias), _ptr(y)),
+        "rk_state_layernorm_forward")
+
+
+def state_layernorm_backward(B, D, segs, norm, eps, x, scale, gy, gx, grad_scale_bias, workspace):
+    n, off, ln = _segs(segs)
+    kd = _kinds(segs, [int(k) for k in norm])
+    _check(load_library().rk_state_layernorm_backward(
+        _stream(), B, D, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+        ctypes.cast(kd, ctypes.c_void_p), float(eps), _ptr(x), _ptr(scale), _ptr(gy), _ptr(gx),
+        _ptr(grad_scale_bias), _ptr(workspace)), "rk_state_layernorm_backward")
 
 
 def colsum(B, N, G, ldg, y, accumulate, workspace, chunks):

@@ -838,6 +838,189 @@ rk_drp_layer0_bwd_kernel(int B, int D, int H, RkActSegs S, const float* __restri
   if (warp == 0 && live) out[(size_t)D * H + c] = s;
 }
 
+// ---- input LayerNorm over the non-boolean state words (planner.py:1300-1319) -------------------
+// y = (x - mean) * rsqrt(var + eps) * scale + bias, var = E[x^2] - E[x]^2 (flax nn.LayerNorm,
+// use_fast_variance), taken over the words of one GROUP of fluents: seg_norm[f] = 0 passes fluent f
+// through, g >= 1 puts it in group g (normalize: every non-bool fluent in group 1;
+// normalize_per_layer: one group per fluent).  All buffers are fluent-major; scale / bias are
+// indexed by the word's position among the normalised words in fluent order.  One thread per
+// rollout (the state dimension is tens of words).
+__device__ __forceinline__ int rk_ln_stats(int B, int b, const RkActSegs& S, int g,
+                                           const float* __restrict__ x, float eps, float* mean,
+                                           float* rstd) {
+  float s = 0.f, ss = 0.f;
+  int n = 0;
+  for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] != g) continue;
+    const float* p = x + (size_t)S.off[f] * B + (size_t)b * S.len[f];
+    for (int e = 0; e < S.len[f]; ++e) { const float v = p[e]; s += v; ss += v * v; }
+    n += S.len[f];
+  }
+  const float m = s / (float)n;
+  const float var = fmaxf(ss / (float)n - m * m, 0.f);
+  *mean = m;
+  *rstd = rsqrtf(var + eps);
+  return n;
+}
+
+__global__ void rk_state_layernorm_fwd_kernel(int B, RkActSegs S, int G, float eps,
+                                              const float* __restrict__ x,
+                                              const float* __restrict__ scale,
+                                              const float* __restrict__ bias,
+                                              float* __restrict__ y) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] != 0) continue;
+    const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f];
+    for (int e = 0; e < S.len[f]; ++e) y[w + e] = x[w + e];
+  }
+  for (int g = 1; g <= G; ++g) {
+    float mean, rstd;
+    rk_ln_stats(B, b, S, g, x, eps, &mean, &rstd);
+    int j = 0;
+    for (int f = 0; f < S.n; ++f) {
+      if (S.kind[f] == g) {
+        const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f];
+        for (int e = 0; e < S.len[f]; ++e)
+          y[w + e] = (x[w + e] - mean) * rstd * scale[j + e] + bias[j + e];
+      }
+      if (S.kind[f] != 0) j += S.len[f];
+    }
+  }
+}
+
+// gx += LayerNorm^T gy; per-CTA partials of [dscale | dbias] go to ws[cta][2 * Dn]
+__global__ void __launch_bounds__(128)
+rk_state_layernorm_bwd_kernel(int B, RkActSegs S, int G, int Dn, float eps,
+                              const float* __restrict__ x, const float* __restrict__ scale,
+                              const float* __restrict__ gy, float* __restrict__ gx,
+                              float* __restrict__ ws) {
+  __shared__ float red[2][4];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = b < B;
+  float* out = ws + (size_t)blockIdx.x * (2 * (size_t)Dn);
+  if (live) {
+    for (int f = 0; f < S.n; ++f) {
+      if (S.kind[f] != 0) continue;
+      const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f];
+      for (int e = 0; e < S.len[f]; ++e) gx[w + e] += gy[w + e];
+    }
+  }
+  for (int g = 1; g <= G; ++g) {
+    float mean = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
+    if (live) {
+      const int n = rk_ln_stats(B, b, S, g, x, eps, &mean, &rstd);
+      int j = 0;
+      for (int f = 0; f < S.n; ++f) {
+        if (S.kind[f] == g) {
+          const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f];
+          for (int e = 0; e < S.len[f]; ++e) {
+            const float gt = gy[w + e] * scale[j + e], xh = (x[w + e] - mean) * rstd;
+            m1 += gt;
+            m2 += gt * xh;
+          }
+        }
+        if (S.kind[f] != 0) j += S.len[f];
+      }
+      m1 /= (float)n;
+      m2 /= (float)n;
+    }
+    int j = 0;
+    for (int f = 0; f < S.n; ++f) {
+      if (S.kind[f] == g) {
+        for (int e = 0; e < S.len[f]; ++e) {
+          float ds = 0.f, db = 0.f;
+          if (live) {
+            const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
+            const float gg = gy[w], xh = (x[w] - mean) * rstd;
+            gx[w] += rstd * (gg * scale[j + e] - m1 - xh * m2);
+            ds = gg * xh;
+            db = gg;
+          }
+          // block sums in lane / warp order (deterministic)
+          for (int o = 16; o > 0; o >>= 1) {
+            ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            db += __shfl_xor_sync(0xffffffffu, db, o);
+          }
+          __syncthreads();
+          if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = ds;
+            red[1][threadIdx.x >> 5] = db;
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            out[j + e] = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
+            out[Dn + j + e] = ((red[1][0] + red[1][1]) + red[1][2]) + red[1][3];
+          }
+        }
+      }
+      if (S.kind[f] != 0) j += S.len[f];
+    }
+  }
+}
+
+extern "C" int rk_state_layernorm_ctas(int B) { return (B + 127) / 128; }
+
+// groups must be numbered 1..G without holes; returns G (or a negative error) and the number of
+// normalised words
+static int rk_ln_groups(const RkActSegs& S, int* Dn) {
+  int G = 0;
+  *Dn = 0;
+  for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] < 0 || S.kind[f] > S.n) return RK_E_BADARG;
+    if (S.kind[f] > G) G = S.kind[f];
+    if (S.kind[f] != 0) *Dn += S.len[f];
+  }
+  for (int g = 1; g <= G; ++g) {
+    bool any = false;
+    for (int f = 0; f < S.n; ++f) any = any || S.kind[f] == g;
+    if (!any) return RK_E_BADARG;
+  }
+  return G > 0 ? G : RK_E_BADARG;
+}
+
+extern "C" int rk_state_layernorm_forward(void* stream, int B, int D, int n_seg,
+                                          const int32_t* seg_off, const int32_t* seg_len,
+                                          const int32_t* seg_norm, float eps, const float* x,
+                                          const float* scale, const float* bias, float* y) {
+  if (B <= 0 || x == nullptr || y == nullptr || scale == nullptr || bias == nullptr ||
+      seg_norm == nullptr)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(D, n_seg, seg_off, seg_len, &S, seg_norm);
+  if (rc != 0) return rc;
+  int Dn = 0;
+  const int G = rk_ln_groups(S, &Dn);
+  if (G < 0) return G;
+  rk_state_layernorm_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, S, G, eps, x, scale, bias, y);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg,
+                                           const int32_t* seg_off, const int32_t* seg_len,
+                                           const int32_t* seg_norm, float eps, const float* x,
+                                           const float* scale, const float* gy, float* gx,
+                                           float* grad_scale_bias, float* workspace) {
+  if (B <= 0 || x == nullptr || gy == nullptr || gx == nullptr || scale == nullptr ||
+      grad_scale_bias == nullptr || workspace == nullptr || seg_norm == nullptr)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(D, n_seg, seg_off, seg_len, &S, seg_norm);
+  if (rc != 0) return rc;
+  int Dn = 0;
+  const int G = rk_ln_groups(S, &Dn);
+  if (G < 0) return G;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ctas = rk_state_layernorm_ctas(B);
+  rk_state_layernorm_bwd_kernel<<<ctas, 128, 0, st>>>(B, S, G, Dn, eps, x, scale, gy, gx,
+                                                      workspace);
+  rk_add_rows_kernel<<<(2 * Dn + 127) / 128, 128, 0, st>>>(ctas, 2 * Dn, workspace,
+                                                           grad_scale_bias, 1);
+  return (int)cudaGetLastError();
+}
+
 // ---- skinny products with N <= 16 (action heads, state-cotangent blocks) ----------------------
 // out[b][n] = (accumulate ? out[b][n] : 0) + sum_k A[b][k] * W[k][n] (+ bias[n]).
 // One warp owns FOUR rows at a time: lanes stride over k (coalesced 128-byte reads of A, read

@@ -498,3 +498,185 @@ def test_drp_wrap_non_bool_heads_match_oracle(cuda_device):
     vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
     got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
     np.testing.assert_allclose(got, ref.reshape(-1), rtol=1e-5, atol=1e-5)
+
+
+# ---- input LayerNorm (planner.py:1300-1319) -----------------------------------------------------
+def _with_grad(tree):
+    if isinstance(tree, dict):
+        return {k: _with_grad(v) for k, v in tree.items()}
+    return tree.clone().requires_grad_(True)
+
+
+def _grads(tree):
+    if isinstance(tree, dict):
+        return {k: _grads(v) for k, v in tree.items()}
+    return tree.grad if tree.grad is not None else torch.zeros_like(tree)
+
+
+def _normalised_plan(fixture, per_layer, topology=(16, 16)):
+    m = fixture_model(fixture)
+    plan = JaxDeepReactivePolicy(topology=list(topology), normalize=True,
+                                 normalize_per_layer=per_layer)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, 5)
+    return m, plan
+
+
+def test_oracle_layernorm_against_torch():
+    """drp_state_vector restates flax nn.LayerNorm (biased variance, epsilon 1e-6)."""
+    m = fixture_model("powergen")
+    g = torch.Generator().manual_seed(1)
+    fls = {"prevProd": torch.randn(7, 5, generator=g) * 3 + 1, "temperature": torch.randn(7, generator=g)}
+    scale, bias = torch.randn(6, generator=g), torch.randn(6, generator=g)
+    got = OP.drp_state_vector(m, {"inputs": {"norm": {"scale": scale, "bias": bias}}}, fls, True)
+    x = torch.cat([fls["prevProd"], fls["temperature"].reshape(7, 1)], 1)
+    want = torch.nn.functional.layer_norm(x.double(), (6,), scale.double(), bias.double(), 1e-6)
+    np.testing.assert_allclose(got.numpy(), want.float().numpy(), rtol=1e-5, atol=1e-6)
+    # a size-1 fluent turns per-layer normalisation off (planner.py:1268-1274)
+    assert OP.drp_norm_layers(m, True, True) == [("norm", ["prevProd", "temperature"])]
+
+
+@pytest.mark.parametrize("fixture,per_layer", [("powergen", False), ("quadcopter", True),
+                                               ("quadcopter", False)])
+def test_layernorm_pytree_and_host_policy(fixture, per_layer):
+    m, plan = _normalised_plan(fixture, per_layer)
+    g = torch.Generator().manual_seed(4)
+    flat = plan.initial_params(g)
+    so, sb = plan.seg["ln_scale"][0], plan.seg["ln_bias"][0]
+    assert torch.all(flat[so:so + plan.Dn] == 1) and torch.all(flat[sb:sb + plan.Dn] == 0)
+    flat[so:so + 2 * plan.Dn] += torch.randn(2 * plan.Dn, generator=g) * 0.3
+    tree = plan.params_to_pytree(flat)
+    mods = set(tree["params"]["inputs"])
+    non_bool = [v for v in OP.drp_input_order(m) if m.variable_ranges[v] != "bool"]
+    if per_layer:
+        assert mods == {"norm_" + v.replace("-", "_") for v in non_bool}
+    else:
+        assert mods == {"norm"}
+        assert tree["params"]["inputs"]["norm"]["scale"].numel() == plan.Dn
+    assert torch.equal(plan.pytree_to_params(tree), flat)
+    assert OP.drp_norm_layers(m, True, per_layer) == plan.norm_layers
+    fls = {v: torch.randn(1, m.variable_size(v), generator=g) * 2 for v in m.state_fluents}
+    ref = OP.drp_test_actions(m, tree["params"], fls, plan.bounds, 2, normalize=True,
+                              normalize_per_layer=per_layer)
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    got = plan.test_actions_host(flat, vec)
+    for var in m.action_fluents:
+        np.testing.assert_allclose(got[var].reshape(-1), ref[var].numpy().reshape(-1), rtol=1e-5,
+                                   atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,segs,groups", [(1000, [(0, 5), (5, 1)], [1, 1]),
+                                           (77, [(0, 4), (4, 3), (7, 2), (9, 4)], [1, 0, 2, 1]),
+                                           (129, [(0, 1), (1, 6)], [0, 1])])
+def test_state_layernorm_kernels_against_fp64(cuda_device, B, segs, groups):
+    from pyrddlgym_jax_b200.core import engine
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    D = sum(n for _, n in segs)
+    Dn = sum(n for (_, n), k in zip(segs, groups) if k)
+    eps = 1e-6
+    blocks = [(torch.randn(B, n, generator=g) * 2 + 0.5).double().requires_grad_(True) for _, n in segs]
+    scale = (torch.randn(Dn, generator=g)).double().requires_grad_(True)
+    bias = (torch.randn(Dn, generator=g)).double().requires_grad_(True)
+    gyb = [torch.randn(B, n, generator=g).double() for _, n in segs]
+    gx0 = [torch.randn(B, n, generator=g) for _, n in segs]
+    # fp64 reference: parameters follow the normalised words in fluent order
+    jpos, j = [], 0
+    for (_, n), k in zip(segs, groups):
+        jpos.append(j)
+        j += n if k else 0
+    ys = list(blocks)
+    for grp in sorted(set(groups) - {0}):
+        mem = [f for f, k in enumerate(groups) if k == grp]
+        x = torch.cat([blocks[f] for f in mem], 1)
+        idx = torch.cat([torch.arange(jpos[f], jpos[f] + segs[f][1]) for f in mem])
+        mean = x.mean(1, keepdim=True)
+        var = (x * x).mean(1, keepdim=True) - mean * mean
+        y = (x - mean) * torch.rsqrt(var + eps) * scale[idx] + bias[idx]
+        o = 0
+        for f in mem:
+            ys[f] = y[:, o:o + segs[f][1]]
+            o += segs[f][1]
+    sum((y * gg).sum() for y, gg in zip(ys, gyb)).backward()
+    fm = lambda bl: torch.cat([b.detach().float().reshape(-1) for b in bl]).to(dev)   # noqa: E731
+    x_fm, gy_fm, gx = fm(blocks), fm(gyb), fm(gx0)
+    y_fm = torch.empty_like(x_fm)
+    sc, bi = scale.detach().float().to(dev), bias.detach().float().to(dev)
+    engine.state_layernorm_forward(B, D, segs, groups, eps, x_fm, sc, bi, y_fm)
+    gsb0 = torch.randn(2 * Dn, generator=g)
+    gsb = gsb0.clone().to(dev)
+    ws = torch.zeros(engine.state_layernorm_ctas(B) * 2 * Dn, device=dev)
+    engine.state_layernorm_backward(B, D, segs, groups, eps, x_fm, sc, gy_fm, gx, gsb, ws)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y_fm.cpu().numpy(), fm(ys).cpu().numpy(), rtol=1e-5, atol=1e-5)
+    want_gx = torch.cat([(b.grad + g0.double()).float().reshape(-1) for b, g0 in zip(blocks, gx0)])
+    np.testing.assert_allclose(gx.cpu().numpy(), want_gx.numpy(), rtol=1e-4,
+                               atol=1e-4 * float(want_gx.abs().max()))
+    want_sb = torch.cat([scale.grad, bias.grad]).float() + gsb0
+    np.testing.assert_allclose(gsb.cpu().numpy(), want_sb.numpy(), rtol=1e-4,
+                               atol=1e-4 * float(want_sb.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,per_layer", [("powergen", False), ("quadcopter", True)])
+def test_drp_layernorm_update_matches_oracle(cuda_device, fixture, per_layer):
+    """normalize / normalize_per_layer: rewards, loss and the whole gradient (dense layers, heads,
+    LayerNorm scale and bias) of one update, and the exact test rollouts, against the oracle."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model(fixture)
+    T, B = 3, 23
+    plan = JaxDeepReactivePolicy(topology=[16, 16], normalize=True, normalize_per_layer=per_layer)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    so = plan.seg["ln_scale"][0]
+    flat[so:so + 2 * plan.Dn] += torch.randn(2 * plan.Dn, generator=g) * 0.2
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, plan.A * B, generator=g)
+    if pl.train_noise is not None:
+        pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              _segment_noise(plan, m, pol_noise[t], B), 1.0, plan.bounds, 2, True,
+                              normalize=True, normalize_per_layer=per_layer)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    got = pl.grad[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    assert np.abs(want[so:so + 2 * plan.Dn]).max() > 0
+    # exact test rollouts with the normalised test policy
+    te = pl.test_fwd.program
+    tnoise = torch.randn(T, te.N * B, generator=g)
+    if pl.test_noise is not None:
+        pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    out = OP.rollout(OracleModel(m, None), lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, plan.bounds, 2, normalize=True,
+        normalize_per_layer=per_layer), B, T,
+        [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    r_ref = out["reward"].numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
