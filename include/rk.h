@@ -245,14 +245,38 @@ int rk_drp_actions_forward(void* stream, int B, int A, int stochastic, int n_seg
                            float* actions, float* entropy);
 /* gheads [B][2A or A] = d actions / d heads applied to gact (clip: gradient 1 inside); boolean
  * logits also receive the gradient of the entropy regulariser, ent_coeff[0] * inv_batch * dH/dlogit
- * (ent_coeff: device scalar, NULL = none; the log_sigma entropy is stop_gradient); wrap != 0
- * differentiates the box wrap instead of the clip. */
+ * (ent_coeff: device scalar, NULL = none); wrap bit 0 differentiates the box wrap instead of the
+ * clip, bit 1 = sigma_entropy_grad (planner.py:1414-1417: the log_sigma entropy keeps its gradient,
+ * otherwise it is stop_gradient).  Fluents of kind 3 / 4 are left to rk_drp_topk_*. */
 int rk_drp_actions_backward(void* stream, int B, int A, int stochastic, int n_seg,
                             const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
                             const float* heads, const float* noise, float train, const float* lo,
                             const float* hi, float ls_lo, float ls_hi, float bool_weight,
                             const float* ent_coeff, float inv_batch, int wrap, const float* gact,
                             float* gheads);
+
+/* Pooled boolean heads under a concurrency constraint: the 'dense_topk' head + GumbelSoftmaxTopK of
+ * planner.py:1027-1080, 1435-1447, 1456-1463.  Action fluents of seg_kind 3 (kind 4: default value
+ * true, output flipped to 1 - a) share one head whose columns, in fluent order, are the pooled logits
+ * (at most *max_pooled of them, allowed = max-nondef-actions <= *max_allowed: rk_drp_topk_limits).
+ *   allowed == 1       : a = softmax(logits + train * gumbel)
+ *   allowed > 1, train : allowed rounds of  l += safe_log(1 - khot);  khot += softmax(weight * l)
+ *                        starting from l = logits + gumbel
+ *   allowed > 1, test  : exact k-hot of the allowed largest logits
+ * noise: Gumbel(0, 1) draws in the fluent-major action layout (NULL or stochastic == 0: none);
+ * entropy[b] += -sum p log p with p = softmax(weight * logits) when stochastic; typed & 1 writes
+ * (a > 0.5) as int32 words.  backward (train form): gheads columns of the pooled fluents =
+ * d loss / d logits from gact and from the entropy term ent_coeff[0] * inv_batch (NULL = none); their
+ * log_sigma columns are zeroed.  Launch after rk_drp_actions_forward / backward on the same buffers. */
+int rk_drp_topk_limits(int* max_pooled, int* max_allowed);
+int rk_drp_topk_forward(void* stream, int B, int A, int stochastic, int n_seg,
+                        const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
+                        const float* heads, const float* noise, int train, int allowed, float weight,
+                        int typed, float* actions, float* entropy);
+int rk_drp_topk_backward(void* stream, int B, int A, int stochastic, int n_seg,
+                         const int32_t* seg_off, const int32_t* seg_len, const int32_t* seg_kind,
+                         const float* heads, const float* noise, int allowed, float weight,
+                         const float* ent_coeff, float inv_batch, const float* gact, float* gheads);
 
 /* Tile the un-batched initial state (S words: float bits, or int32 0/1 / int words for the exact
  * model) into the fluent-major s0 buffer of B rollouts.  seg_off / seg_len: HOST arrays with the

@@ -397,9 +397,14 @@ def drp_init(model, topology, generator: torch.Generator, stochastic: bool = Tru
     for i, h in enumerate(topology):
         params[f"dense_{i}"] = {"kernel": kernel(fan, h), "bias": torch.zeros(h)}
         fan = h
+    n_bool = sum(model.variable_size(v) for v in model.action_fluents
+                 if model.variable_ranges[v] == "bool")
+    pooled = model.max_allowed_actions < n_bool
     for var in model.action_fluents:
         n = model.variable_size(var)
         name = var.replace("-", "_")
+        if model.variable_ranges[var] == "bool" and pooled:
+            continue
         if model.variable_ranges[var] == "bool":
             params[f"dense_{name}_logit"] = {"kernel": kernel(fan, n), "bias": torch.zeros(n)}
         else:
@@ -407,6 +412,8 @@ def drp_init(model, topology, generator: torch.Generator, stochastic: bool = Tru
             if stochastic:
                 params[f"dense_{name}_log_sigma"] = {"kernel": kernel(fan, n),
                                                      "bias": torch.zeros(n)}
+    if pooled:
+        params["dense_topk"] = {"kernel": kernel(fan, n_bool), "bias": torch.zeros(n_bool)}
     return params
 
 
@@ -414,22 +421,29 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
                 bounds, topology_len: int, stochastic: bool = True,
                 sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0,
                 wrap_non_bool: bool = False, normalize: bool = False,
-                normalize_per_layer: bool = False):
+                normalize_per_layer: bool = False, norm_eps: float = 1e-6,
+                softmax_weight: float = 1.0, sigma_entropy_grad: bool = False):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
-    noise: action name -> [B, n] standard draws.  Returns (actions name -> [B, *objs],
-    entropy [B])."""
+    noise: action name -> [B, n] standard draws (Gumbel for boolean fluents under a binding
+    max-nondef-actions, Logistic for other boolean fluents).  Returns (actions name ->
+    [B, *objs], entropy [B])."""
     B = next(iter(fls.values())).shape[0]
-    x = drp_state_vector(model, params, fls, normalize, normalize_per_layer)
+    x = drp_state_vector(model, params, fls, normalize, normalize_per_layer, norm_eps)
     h = x
     for i in range(topology_len):
         layer = params[f"dense_{i}"]
         h = torch.tanh(h @ layer["kernel"] + layer["bias"])
     ls_lo, ls_hi = math.log(sigma_range[0]), math.log(sigma_range[1])
     actions, entropy = {}, torch.zeros(B, dtype=REAL)
+    bools = [v for v in model.action_fluents if model.variable_ranges[v] == "bool"]
+    n_bool = sum(model.variable_size(v) for v in bools)
+    pooled = model.max_allowed_actions < n_bool             # planner.py:1322-1326
     for var in model.action_fluents:
         name = var.replace("-", "_")
         shape = (B,) + tuple(model.variable_shape(var))
         if model.variable_ranges[var] == "bool":
+            if pooled:
+                continue
             layer = params[f"dense_{name}_logit"]
             logits = h @ layer["kernel"] + layer["bias"]
             if stochastic:
@@ -443,7 +457,7 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
         if stochastic:
             layer = params[f"dense_{name}_log_sigma"]
             ls = torch.clamp(h @ layer["kernel"] + layer["bias"], ls_lo, ls_hi)
-            entropy = entropy + ls.detach().sum(1)            # sigma_entropy_grad = False
+            entropy = entropy + (ls if sigma_entropy_grad else ls.detach()).sum(1)
             a = a + train * torch.exp(ls) * noise[var]
         lo, hi = bounds[var]
         lo = torch.as_tensor(np.asarray(lo, np.float32)).reshape(1, -1)
@@ -453,18 +467,58 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
         else:
             a = torch.minimum(torch.maximum(a, lo), hi)       # planner.py:1472-1475
         actions[var] = a.reshape(shape)
+    if pooled:      # one 'dense_topk' head + GumbelSoftmaxTopK (planner.py:1435-1447, 1027-1080)
+        layer = params["dense_topk"]
+        logits = h @ layer["kernel"] + layer["bias"]
+        if stochastic:
+            log_prob = torch.log_softmax(softmax_weight * logits, dim=1)
+            entropy = entropy - (torch.exp(log_prob) * log_prob).sum(1)
+        g = torch.cat([noise[v].reshape(B, -1) for v in bools], dim=1) if stochastic else 0.0
+        out = gumbel_softmax_topk(logits, g, int(model.max_allowed_actions), softmax_weight, train)
+        o = 0
+        for v in bools:                                        # planner.py:1453-1465
+            n = model.variable_size(v)
+            a = out[:, o:o + n]
+            if bool(np.ravel(np.asarray(model.action_fluents[v]))[0]):
+                a = 1.0 - a
+            actions[v] = a.reshape((B,) + tuple(model.variable_shape(v)))
+            o += n
     return actions, entropy
+
+
+def gumbel_softmax_topk(logits, gumbel, allowed: int, weight: float, train: float):
+    """GumbelSoftmaxTopK.__call__ (planner.py:1034-1080).  logits [B, n]; gumbel: Gumbel(0, 1)
+    draws of the same shape (0 = not stochastic)."""
+    if allowed == 1:                                           # planner.py:1039-1045
+        return torch.softmax(logits + train * gumbel, dim=1)
+    if train:                                                  # soft_top_k, planner.py:1048-1063
+        l = logits + gumbel
+        khot = torch.zeros_like(logits)
+        for _ in range(allowed):
+            l = l + safe_log(1.0 - khot)
+            khot = khot + torch.softmax(weight * l, dim=1)
+        return khot
+    l = logits.clone()                                         # hard_top_k, planner.py:1066-1078
+    khot = torch.zeros_like(logits)
+    rows = torch.arange(logits.shape[0])
+    for _ in range(allowed):
+        idx = torch.argmax(l, dim=1)
+        l[rows, idx] = -float("inf")
+        khot[rows, idx] = 1.0
+    return khot
 
 
 def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True,
                      sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
-                     normalize: bool = False, normalize_per_layer: bool = False):
+                     normalize: bool = False, normalize_per_layer: bool = False,
+                     norm_eps: float = 1e-6, softmax_weight: float = 1.0):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
     acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic,
                           sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool,
-                          normalize=normalize, normalize_per_layer=normalize_per_layer)
+                          normalize=normalize, normalize_per_layer=normalize_per_layer,
+                          norm_eps=norm_eps, softmax_weight=softmax_weight)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]

@@ -50,13 +50,14 @@ class JaxDeepReactivePolicy(JaxPlan):
         if act != "tanh":
             raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
         self._wrap_non_bool = bool(wrap_non_bool)
-        for flag, name in ((time_dependent, "time_dependent"),
-                           (sigma_entropy_grad, "sigma_entropy_grad")):
-            if flag:
-                raise NotImplementedError(f"JaxDeepReactivePolicy({name}=True) is not built yet")
+        if time_dependent:
+            raise NotImplementedError("JaxDeepReactivePolicy(time_dependent=True) is not built yet")
+        self._sigma_entropy_grad = bool(sigma_entropy_grad)
+        # the reference takes a jax.random sampler (planner.py:1139, 1418-1420); here its name
         dist = getattr(action_noise_dist, "__name__", action_noise_dist)
-        if dist != "normal":
-            raise NotImplementedError("action_noise_dist other than normal is not built yet")
+        if dist not in ("normal", "laplace", "logistic", "cauchy", "gumbel"):
+            raise NotImplementedError(f"action_noise_dist <{dist}> is not built")
+        self._action_noise_dist = dist
         self._initializer_base = initializer
         self._sigmoid_weight = sigmoid_weight
         self._softmax_output_weight = softmax_weight
@@ -93,13 +94,23 @@ class JaxDeepReactivePolicy(JaxPlan):
         self.layout, self.A = action_layout(rddl)
         # head kind per action fluent (planner.py:1368-1409): 0 real, 1 bool (sigmoid of a logit
         # head), 2 int / enum (real head, rounded by the test policy)
+        # with a binding max-nondef-actions the boolean fluents share the 'dense_topk' head
+        # (planner.py:1322-1326, 1435-1447): kind 3, or 4 when the fluent's default is true
         self.action_kinds = [1 if prange == "bool" else (0 if prange == "real" else 2)
                              for (_, _, prange) in self.layout.values()]
         n_bool = sum(n for _, n, r in self.layout.values() if r == "bool")
-        if n_bool and rddl.max_allowed_actions < n_bool:
-            raise NotImplementedError(
-                "DRP with max-nondef-actions below the number of boolean actions needs the "
-                "dense_topk / GumbelSoftmaxTopK head (planner.py:1435-1447), which is not built yet")
+        self.use_topk = bool(n_bool and rddl.max_allowed_actions < n_bool)
+        self.allowed = int(rddl.max_allowed_actions)
+        if self.use_topk:
+            if n_bool > engine.TOPK_MAX_POOLED or self.allowed > engine.TOPK_MAX_ALLOWED:
+                raise NotImplementedError(
+                    f"dense_topk head: {n_bool} pooled boolean actions / max-nondef-actions "
+                    f"{self.allowed} exceed the kernel limits ({engine.TOPK_MAX_POOLED} / "
+                    f"{engine.TOPK_MAX_ALLOWED})")
+            self.action_kinds = [
+                (4 if bool(np.ravel(np.asarray(rddl.action_fluents[v]))[0]) else 3)
+                if prange == "bool" else k
+                for k, (v, (_, _, prange)) in zip(self.action_kinds, self.layout.items())]
         if rddl.observ_fluents:
             raise NotImplementedError("DRP over observ-fluents (POMDP) is not built yet")
         bounds = {}
@@ -226,8 +237,13 @@ class JaxDeepReactivePolicy(JaxPlan):
         Wh = flat[..., off:off + r * c].reshape(*lead, r, c)
         ob = self.seg["bh"][0]
         bh = flat[..., ob:ob + c]
+        if self.use_topk:               # planner.py:1436-1438: the pooled boolean logits
+            cols = torch.as_tensor(self._pooled_columns())
+            tree["dense_topk"] = {"kernel": Wh[..., cols], "bias": bh[..., cols]}
         for var, (aoff, n, prange) in self.layout.items():
             nm = var.replace("-", "_")
+            if prange == "bool" and self.use_topk:
+                continue
             if prange == "bool":        # planner.py:1375-1377: a single logit head
                 tree[f"dense_{nm}_logit"] = {"kernel": Wh[..., aoff:aoff + n],
                                              "bias": bh[..., aoff:aoff + n]}
@@ -261,8 +277,14 @@ class JaxDeepReactivePolicy(JaxPlan):
         off, r, c = self.seg["Wh"]
         Wh = torch.zeros(r, c)
         bh = torch.zeros(c)
+        if self.use_topk:
+            cols = torch.as_tensor(self._pooled_columns())
+            Wh[:, cols] = as_t(tree["dense_topk"]["kernel"]).reshape(r, len(cols))
+            bh[cols] = as_t(tree["dense_topk"]["bias"]).reshape(-1)
         for var, (aoff, n, prange) in self.layout.items():
             nm = var.replace("-", "_")
+            if prange == "bool" and self.use_topk:
+                continue
             if prange == "bool":
                 Wh[:, aoff:aoff + n] = as_t(tree[f"dense_{nm}_logit"]["kernel"]).reshape(r, n)
                 bh[aoff:aoff + n] = as_t(tree[f"dense_{nm}_logit"]["bias"]).reshape(-1)
@@ -278,6 +300,12 @@ class JaxDeepReactivePolicy(JaxPlan):
         ob = self.seg["bh"][0]
         flat[ob:ob + c] = bh
         return flat
+
+    def _pooled_columns(self) -> np.ndarray:
+        """Head columns of the pooled boolean actions in the order of the reference's softmax
+        output (layer_sizes order, planner.py:1453-1465)."""
+        return np.concatenate([np.arange(aoff, aoff + n)
+                               for (aoff, n, prange) in self.layout.values() if prange == "bool"])
 
     def guess_next_epoch(self, params):
         return params                      # planner.py:1531-1534: warm start from the same policy
@@ -310,9 +338,28 @@ class JaxDeepReactivePolicy(JaxPlan):
         ob = self.seg["bh"][0]
         out = (h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c]).reshape(-1)
         acts = {}
+        if self.use_topk:               # train = 0 (planner.py:1039-1045, 1066-1078), then > 0.5
+            cols = torch.as_tensor(self._pooled_columns())
+            lg = out[cols]
+            if self.allowed == 1:
+                pooled = torch.softmax(lg, 0)
+            else:
+                pooled = torch.zeros_like(lg)
+                lg = lg.clone()
+                for _ in range(self.allowed):
+                    i = int(torch.argmax(lg))
+                    lg[i] = -math.inf
+                    pooled[i] = 1.0
+            out = out.clone()
+            out[cols] = pooled
         for var, (aoff, n, prange) in self.layout.items():
             lo, hi = self.bounds[var]
             a = out[aoff:aoff + n].numpy().reshape(self.rddl.variable_shape(var))
+            if prange == "bool" and self.use_topk:
+                if bool(np.ravel(np.asarray(self.rddl.action_fluents[var]))[0]):
+                    a = 1.0 - a
+                acts[var] = a > 0.5
+                continue
             if prange == "bool":        # sigmoid(w * logit) > 0.5  (planner.py:1489)
                 acts[var] = (self._sigmoid_weight * a) > 0.0
                 continue
@@ -531,6 +578,11 @@ class DrpPipeline:
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.act[t], self.entropy[t], kinds=plan.action_kinds,
                 bool_weight=plan._sigmoid_weight, wrap=plan._wrap_non_bool)
+            if plan.use_topk:
+                engine.drp_topk_forward(
+                    B, A, plan._stochastic, plan.action_segs, plan.action_kinds, self.heads[t],
+                    None if self.pol_noise is None else self.pol_noise[t], True, plan.allowed,
+                    plan._softmax_output_weight, self.act[t], self.entropy[t])
             fwd.forward(B, 1, x, actions=self.act[t],
                         noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
                         mparams=pl.train_mparams,
@@ -562,7 +614,14 @@ class DrpPipeline:
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
                 self.ls_lo, self.ls_hi, self.gact, self.gheads, kinds=plan.action_kinds,
                 bool_weight=plan._sigmoid_weight, ent_coeff=self.ent_coeff,
-                inv_batch=1.0 / (B * pl.world_size), wrap=plan._wrap_non_bool)
+                inv_batch=1.0 / (B * pl.world_size), wrap=plan._wrap_non_bool,
+                sigma_entropy_grad=plan._sigma_entropy_grad)
+            if plan.use_topk:
+                engine.drp_topk_backward(
+                    B, A, plan._stochastic, plan.action_segs, plan.action_kinds, self.heads[t],
+                    None if self.pol_noise is None else self.pol_noise[t], plan.allowed,
+                    plan._softmax_output_weight, self.gact, self.gheads,
+                    ent_coeff=self.ent_coeff, inv_batch=1.0 / (B * pl.world_size))
             if self.Dn:     # MLP input cotangent -> gy, then gs += LayerNorm^T gy (+ dscale, dbias)
                 self.gy.zero_()
                 self.mlp_backward(grad, B, self.xn[t], [Hl[t] for Hl in self.H], self.gy,
@@ -607,6 +666,10 @@ class DrpPipeline:
                                        self.hi, self.ls_lo, self.ls_hi, self.t_act, None,
                                        kinds=plan.action_kinds, bool_weight=plan._sigmoid_weight,
                                        typed=True, wrap=plan._wrap_non_bool)
+            if plan.use_topk:
+                engine.drp_topk_forward(B, A, plan._stochastic, plan.action_segs, plan.action_kinds,
+                                        self.t_heads, None, False, plan.allowed,
+                                        plan._softmax_output_weight, self.t_act, None, typed=True)
             te.forward(B, 1, x, actions=self.t_act,
                        noise=None if pl.test_noise is None else pl.test_noise[t * N * B:],
                        disc=None if pl.disc is None else pl.disc[t:],
@@ -622,10 +685,26 @@ class DrpPipeline:
 
     def redraw_noise(self, gen: torch.Generator):
         if self.pol_noise is not None:
-            self.pol_noise.normal_(generator=gen)
+            dist = self.plan._action_noise_dist
+            if dist == "normal":
+                self.pol_noise.normal_(generator=gen)
+            else:                       # standard laws as jax.random draws them
+                u = torch.rand(self.pol_noise.shape, generator=gen,
+                               device=self.pol_noise.device).clamp_(1e-7, 1 - 1e-7)
+                if dist == "logistic":
+                    self.pol_noise.copy_(torch.log(u) - torch.log1p(-u))
+                elif dist == "gumbel":
+                    self.pol_noise.copy_(-torch.log(-torch.log(u)))
+                elif dist == "cauchy":
+                    self.pol_noise.copy_(torch.tan(math.pi * (u - 0.5)))
+                else:                   # laplace
+                    self.pol_noise.copy_(torch.sign(u - 0.5) * -torch.log1p(-2 * (u - 0.5).abs()))
             B = self.pl.batch_size_train
             for (off, n), kind in zip(self.plan.action_segs, self.plan.action_kinds):
-                if kind == 1:           # boolean logits take Logistic(0, 1) noise (planner.py:1386)
+                if kind in (1, 3, 4):
                     blk = self.pol_noise[:, off * B:(off + n) * B]
                     u = torch.rand(blk.shape, generator=gen, device=blk.device).clamp_(1e-7, 1 - 1e-7)
-                    blk.copy_(torch.log(u) - torch.log1p(-u))
+                    if kind == 1:       # boolean logits take Logistic(0, 1) noise (planner.py:1386)
+                        blk.copy_(torch.log(u) - torch.log1p(-u))
+                    else:               # pooled logits take Gumbel(0, 1) noise (planner.py:1041, 1051)
+                        blk.copy_(-torch.log(-torch.log(u)))

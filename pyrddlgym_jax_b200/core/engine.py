@@ -27,6 +27,7 @@ EXPORTS = [
     "rk_rowdot", "rk_tcgemm_tn", "rk_tile_state", "rk_drp_head_backward",
     "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
+    "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
 ]
 
 
@@ -100,6 +101,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_state_layernorm_forward.restype = ci
     lib.rk_state_layernorm_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf, cf, cf]
     lib.rk_state_layernorm_backward.restype = ci
+    lib.rk_drp_topk_limits.argtypes = [vp, vp]
+    lib.rk_drp_topk_limits.restype = ci
+    lib.rk_drp_topk_forward.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, cf, cf, ci, ci, fl, ci, cf, cf]
+    lib.rk_drp_topk_forward.restype = ci
+    lib.rk_drp_topk_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, cf, cf, ci, fl, cf, fl, cf, cf]
+    lib.rk_drp_topk_backward.restype = ci
     lib.rk_colsum.argtypes = [vp, ci, ci, cf, ci, cf, ci, cf, ci]
     lib.rk_colsum.restype = ci
     lib.rk_rowdot.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, ci, cf, ci, cf]
@@ -270,16 +277,50 @@ def drp_actions_forward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_
 
 def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls_lo, ls_hi, gact,
                          gheads, kinds=None, bool_weight: float = 1.0, ent_coeff=None,
-                         inv_batch: float = 0.0, wrap: bool = False):
+                         inv_batch: float = 0.0, wrap: bool = False,
+                         sigma_entropy_grad: bool = False):
     n, off, ln = _segs(segs)
     kd = _kinds(segs, kinds)
     _check(load_library().rk_drp_actions_backward(
         _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
         ctypes.cast(ln, ctypes.c_void_p), ctypes.cast(kd, ctypes.c_void_p), _ptr(heads),
         _ptr(noise), float(train), _ptr(lo), _ptr(hi), float(ls_lo), float(ls_hi),
-        float(bool_weight), _ptr(ent_coeff), float(inv_batch), int(bool(wrap)), _ptr(gact),
+        float(bool_weight), _ptr(ent_coeff), float(inv_batch),
+        int(bool(wrap)) | (2 if sigma_entropy_grad else 0), _ptr(gact),
         _ptr(gheads)),
         "rk_drp_actions_backward")
+
+
+TOPK_MAX_POOLED, TOPK_MAX_ALLOWED = 64, 8      # RK_TOPK_MAX_N / RK_TOPK_MAX_K of csrc/rk_drp.cu
+
+
+def drp_topk_limits():
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    _check(load_library().rk_drp_topk_limits(ctypes.byref(a), ctypes.byref(b)), "rk_drp_topk_limits")
+    return a.value, b.value
+
+
+def drp_topk_forward(B, A, stochastic, segs, kinds, heads, noise, train, allowed, weight, actions,
+                     entropy=None, typed: bool = False):
+    """Pooled boolean heads (kinds 3 / 4) under max-nondef-actions = allowed; see include/rk.h."""
+    n, off, ln = _segs(segs)
+    kd = _kinds(segs, kinds)
+    _check(load_library().rk_drp_topk_forward(
+        _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), ctypes.cast(kd, ctypes.c_void_p), _ptr(heads),
+        _ptr(noise), int(bool(train)), int(allowed), float(weight), int(bool(typed)),
+        _ptr(actions), _ptr(entropy)), "rk_drp_topk_forward")
+
+
+def drp_topk_backward(B, A, stochastic, segs, kinds, heads, noise, allowed, weight, gact, gheads,
+                      ent_coeff=None, inv_batch: float = 0.0):
+    n, off, ln = _segs(segs)
+    kd = _kinds(segs, kinds)
+    _check(load_library().rk_drp_topk_backward(
+        _stream(), B, A, int(stochastic), n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), ctypes.cast(kd, ctypes.c_void_p), _ptr(heads),
+        _ptr(noise), int(allowed), float(weight), _ptr(ent_coeff), float(inv_batch), _ptr(gact),
+        _ptr(gheads)), "rk_drp_topk_backward")
 
 
 def tf32_split(x: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, n: Optional[int] = None):

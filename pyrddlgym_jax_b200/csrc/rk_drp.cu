@@ -329,6 +329,7 @@ __global__ void rk_drp_actions_fwd_kernel(int B, int A, int stochastic, RkActSeg
   const int ld = stochastic ? 2 * A : A;
   float ent = 0.f;
   for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] >= 3) continue;       // pooled boolean fluents: rk_drp_topk_forward
     for (int e = 0; e < S.len[f]; ++e) {
       const int a = S.off[f] + e;
       const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
@@ -375,7 +376,10 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int ld = stochastic ? 2 * A : A;
+  const bool sigma_entropy_grad = (wrap & 2) != 0;      // planner.py:1414-1417
+  wrap &= 1;
   for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] >= 3) continue;       // pooled boolean fluents: rk_drp_topk_backward
     for (int e = 0; e < S.len[f]; ++e) {
       const int a = S.off[f] + e;
       const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + e;
@@ -413,11 +417,162 @@ __global__ void rk_drp_actions_bwd_kernel(int B, int A, int stochastic, RkActSeg
       gheads[(size_t)b * ld + a] = g;
       if (stochastic) {
         const bool inside = raw >= ls_lo && raw <= ls_hi;
-        gheads[(size_t)b * ld + A + a] = inside ? g * train * ex * z : 0.f;
+        float gl = inside ? g * train * ex * z : 0.f;
+        // entropy term -coeff * mean_b sum_t sum_a clip(log_sigma) with its gradient kept
+        if (sigma_entropy_grad && inside && ent_coeff != nullptr) gl -= ent_coeff[0] * inv_batch;
+        gheads[(size_t)b * ld + A + a] = gl;
       }
     }
   }
 }
+
+// ---- pooled boolean heads under a concurrency constraint (planner.py:1027-1080, 1435-1447) ------
+// The boolean action fluents (kind 3; kind 4 = default value true, output flipped to 1 - a,
+// planner.py:1456-1463) share ONE 'dense_topk' head: their head columns, in fluent order, are the
+// n <= RK_TOPK_MAX_N pooled logits.  With allowed = max-nondef-actions:
+//   allowed == 1        : a = softmax(logits + train * gumbel)                 (no weight, P:1040-1045)
+//   allowed > 1, train  : khot_0 = 0, l_0 = logits + gumbel;  l_i = l_{i-1} + safe_log(1 - khot_{i-1}),
+//                         khot_i = khot_{i-1} + softmax(w l_i), i = 1..allowed (P:1048-1063)
+//   allowed > 1, test   : allowed times arg-max (first index on ties) -> exact k-hot (P:1066-1078)
+// entropy (stochastic): -sum p log p with p = softmax(w logits) (P:1441-1444), ADDED to entropy[b].
+// One thread per rollout; the per-iteration softmax outputs stay in local memory for the adjoint.
+#define RK_TOPK_MAX_N 64
+#define RK_TOPK_MAX_K 8
+
+struct RkTopkPool {
+  int n;                       // pooled logits
+  int col[RK_TOPK_MAX_N];      // head column of pooled element j
+  int seg[RK_TOPK_MAX_N];      // its fluent
+  int elt[RK_TOPK_MAX_N];      // its element inside the fluent
+};
+
+__device__ __forceinline__ void rk_softmax_n(int n, float w, const float* l, float* p) {
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, w * l[j]);
+  float z = 0.f;
+  for (int j = 0; j < n; ++j) { p[j] = expf(w * l[j] - m); z += p[j]; }
+  const float r = 1.f / z;
+  for (int j = 0; j < n; ++j) p[j] *= r;
+}
+
+// Fills P[i][0..n) = softmax(w l_i), i = 0..K-1, and returns the final khot in kh.
+__device__ __forceinline__ void rk_soft_topk(int n, int K, float w, float* l, float* kh, float* P) {
+  for (int j = 0; j < n; ++j) kh[j] = 0.f;
+  for (int i = 0; i < K; ++i) {
+    for (int j = 0; j < n; ++j) {
+      const float r = 1.f - kh[j];
+      l[j] += r > 0.f ? logf(r) : -INFINITY;        // safe_log (compiler.py:65-67)
+    }
+    float* p = P + i * RK_TOPK_MAX_N;
+    rk_softmax_n(n, w, l, p);
+    for (int j = 0; j < n; ++j) kh[j] += p[j];
+  }
+}
+
+__global__ void rk_drp_topk_fwd_kernel(int B, int ld, int stochastic, RkActSegs S, RkTopkPool Q,
+                                       const float* __restrict__ heads,
+                                       const float* __restrict__ noise, int train, int allowed,
+                                       float weight, int typed, float* __restrict__ actions,
+                                       float* __restrict__ entropy) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float l[RK_TOPK_MAX_N], a[RK_TOPK_MAX_N], P[RK_TOPK_MAX_K * RK_TOPK_MAX_N];
+  const int n = Q.n;
+  for (int j = 0; j < n; ++j) l[j] = heads[(size_t)b * ld + Q.col[j]];
+  if (stochastic && entropy != nullptr) {
+    rk_softmax_n(n, weight, l, a);
+    float m = -INFINITY, z = 0.f, h = 0.f;
+    for (int j = 0; j < n; ++j) m = fmaxf(m, weight * l[j]);
+    for (int j = 0; j < n; ++j) z += expf(weight * l[j] - m);
+    const float lz = logf(z);
+    for (int j = 0; j < n; ++j) h -= a[j] * (weight * l[j] - m - lz);     // p * log_softmax
+    entropy[b] += h;
+  }
+  if (allowed > 1 && !train) {            // exact k-hot
+    for (int j = 0; j < n; ++j) a[j] = 0.f;
+    for (int i = 0; i < allowed; ++i) {
+      int best = 0;
+      for (int j = 1; j < n; ++j) if (l[j] > l[best]) best = j;
+      l[best] = -INFINITY;
+      a[best] = 1.f;
+    }
+  } else {
+    if (stochastic && noise != nullptr && (train || allowed > 1)) {
+      for (int j = 0; j < n; ++j) {
+        const int f = Q.seg[j];
+        l[j] += noise[(size_t)S.off[f] * B + (size_t)b * S.len[f] + Q.elt[j]];
+      }
+    }
+    if (allowed == 1) rk_softmax_n(n, 1.f, l, a);
+    else rk_soft_topk(n, allowed, weight, l, a, P);
+  }
+  for (int j = 0; j < n; ++j) {
+    const int f = Q.seg[j];
+    const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + Q.elt[j];
+    const float v = S.kind[f] == 4 ? 1.f - a[j] : a[j];
+    if (typed & 1) ((int32_t*)actions)[w] = v > 0.5f ? 1 : 0;
+    else actions[w] = v;
+  }
+}
+
+__global__ void rk_drp_topk_bwd_kernel(int B, int A, int ld, int stochastic, RkActSegs S,
+                                       RkTopkPool Q, const float* __restrict__ heads,
+                                       const float* __restrict__ noise, int allowed, float weight,
+                                       const float* __restrict__ ent_coeff, float inv_batch,
+                                       const float* __restrict__ gact, float* __restrict__ gheads) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float l[RK_TOPK_MAX_N], kh[RK_TOPK_MAX_N], gk[RK_TOPK_MAX_N], gl[RK_TOPK_MAX_N];
+  float P[RK_TOPK_MAX_K * RK_TOPK_MAX_N];
+  const int n = Q.n;
+  for (int j = 0; j < n; ++j) {
+    const int f = Q.seg[j];
+    const size_t w = (size_t)S.off[f] * B + (size_t)b * S.len[f] + Q.elt[j];
+    l[j] = heads[(size_t)b * ld + Q.col[j]];
+    if (stochastic && noise != nullptr) l[j] += noise[w];
+    gk[j] = S.kind[f] == 4 ? -gact[w] : gact[w];
+    gl[j] = 0.f;
+  }
+  if (allowed == 1) {
+    rk_softmax_n(n, 1.f, l, kh);
+    float d = 0.f;
+    for (int j = 0; j < n; ++j) d += kh[j] * gk[j];
+    for (int j = 0; j < n; ++j) gl[j] = kh[j] * (gk[j] - d);
+  } else {
+    rk_soft_topk(n, allowed, weight, l, kh, P);
+    for (int i = allowed - 1; i >= 0; --i) {
+      const float* p = P + i * RK_TOPK_MAX_N;
+      float d = 0.f;
+      for (int j = 0; j < n; ++j) d += p[j] * gk[j];
+      for (int j = 0; j < n; ++j) gl[j] += weight * p[j] * (gk[j] - d);
+      // khot_{i-1} in the forward order of additions; l_i = l_{i-1} + safe_log(1 - khot_{i-1})
+      for (int j = 0; j < n; ++j) {
+        float k0 = 0.f;
+        for (int q = 0; q < i; ++q) k0 += P[q * RK_TOPK_MAX_N + j];
+        gk[j] -= gl[j] / ((1.f - k0) + 1e-12f);       // safe_log tangent (compiler.py:70-75)
+      }
+    }
+  }
+  if (stochastic && ent_coeff != nullptr) {     // loss term -coeff * mean_b sum_t H(softmax(w logits))
+    float lg[RK_TOPK_MAX_N];
+    for (int j = 0; j < n; ++j) lg[j] = heads[(size_t)b * ld + Q.col[j]];
+    rk_softmax_n(n, weight, lg, kh);
+    float m = -INFINITY, z = 0.f, h = 0.f;
+    for (int j = 0; j < n; ++j) m = fmaxf(m, weight * lg[j]);
+    for (int j = 0; j < n; ++j) z += expf(weight * lg[j] - m);
+    const float lz = logf(z);
+    for (int j = 0; j < n; ++j) h -= kh[j] * (weight * lg[j] - m - lz);
+    // dH/dlogit_j = -w p_j (log p_j + H)
+    const float c = ent_coeff[0] * inv_batch;
+    for (int j = 0; j < n; ++j)
+      gl[j] += c * weight * kh[j] * ((weight * lg[j] - m - lz) + h);
+  }
+  for (int j = 0; j < n; ++j) {
+    gheads[(size_t)b * ld + Q.col[j]] = gl[j];
+    if (stochastic) gheads[(size_t)b * ld + A + Q.col[j]] = 0.f;
+  }
+}
+
 
 static int make_segs(int A, int n_seg, const int32_t* seg_off, const int32_t* seg_len,
                      RkActSegs* S, const int32_t* seg_kind = nullptr) {
@@ -469,6 +624,69 @@ extern "C" int rk_drp_actions_backward(void* stream, int B, int A, int stochasti
   rk_drp_actions_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       B, A, stochastic, S, heads, noise, train, lo, hi, ls_lo, ls_hi, bool_weight, ent_coeff,
       inv_batch, wrap, gact, gheads);
+  return (int)cudaGetLastError();
+}
+
+static int make_pool(const RkActSegs& S, RkTopkPool* Q) {
+  Q->n = 0;
+  for (int f = 0; f < S.n; ++f) {
+    if (S.kind[f] < 3) continue;
+    if (S.kind[f] > 4) return RK_E_BADARG;
+    for (int e = 0; e < S.len[f]; ++e) {
+      if (Q->n >= RK_TOPK_MAX_N) return RK_E_BADARG;
+      Q->col[Q->n] = S.off[f] + e;
+      Q->seg[Q->n] = f;
+      Q->elt[Q->n] = e;
+      ++Q->n;
+    }
+  }
+  return Q->n > 0 ? 0 : RK_E_BADARG;
+}
+
+extern "C" int rk_drp_topk_limits(int* max_pooled, int* max_allowed) {
+  if (max_pooled != nullptr) *max_pooled = RK_TOPK_MAX_N;
+  if (max_allowed != nullptr) *max_allowed = RK_TOPK_MAX_K;
+  return 0;
+}
+
+extern "C" int rk_drp_topk_forward(void* stream, int B, int A, int stochastic, int n_seg,
+                                   const int32_t* seg_off, const int32_t* seg_len,
+                                   const int32_t* seg_kind, const float* heads, const float* noise,
+                                   int train, int allowed, float weight, int typed, float* actions,
+                                   float* entropy) {
+  if (B <= 0 || A <= 0 || heads == nullptr || actions == nullptr || seg_kind == nullptr ||
+      allowed < 1 || allowed > RK_TOPK_MAX_K)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S, seg_kind);
+  if (rc != 0) return rc;
+  RkTopkPool Q;
+  rc = make_pool(S, &Q);
+  if (rc != 0) return rc;
+  rk_drp_topk_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, stochastic ? 2 * A : A, stochastic, S, Q, heads, noise, train, allowed, weight, typed,
+      actions, entropy);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_drp_topk_backward(void* stream, int B, int A, int stochastic, int n_seg,
+                                    const int32_t* seg_off, const int32_t* seg_len,
+                                    const int32_t* seg_kind, const float* heads,
+                                    const float* noise, int allowed, float weight,
+                                    const float* ent_coeff, float inv_batch, const float* gact,
+                                    float* gheads) {
+  if (B <= 0 || A <= 0 || heads == nullptr || gact == nullptr || gheads == nullptr ||
+      seg_kind == nullptr || allowed < 1 || allowed > RK_TOPK_MAX_K)
+    return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(A, n_seg, seg_off, seg_len, &S, seg_kind);
+  if (rc != 0) return rc;
+  RkTopkPool Q;
+  rc = make_pool(S, &Q);
+  if (rc != 0) return rc;
+  rk_drp_topk_bwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, A, stochastic ? 2 * A : A, stochastic, S, Q, heads, noise, allowed, weight, ent_coeff,
+      inv_batch, gact, gheads);
   return (int)cudaGetLastError();
 }
 

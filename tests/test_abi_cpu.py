@@ -56,6 +56,13 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     lib.rk_program_destroy(None)                                          # no-op
 
 
+def test_topk_limits_match_the_binding(lib):
+    from pyrddlgym_jax_b200.core import engine
+    assert engine.drp_topk_limits() == (engine.TOPK_MAX_POOLED, engine.TOPK_MAX_ALLOWED)
+    assert lib.rk_drp_topk_forward(None, 1, 1, 1, 1, *([None] * 5), 1, 99, 1.0, 0, None, None) == -1
+    assert lib.rk_state_layernorm_forward(None, 0, 1, 1, None, None, None, 1e-6, *([None] * 4)) == -1
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     """The product path must fail loudly when there is no CUDA device (never run on the CPU)."""
