@@ -198,6 +198,16 @@ int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg, const int
                                 const int32_t* seg_len, const int32_t* seg_norm, float eps,
                                 const float* x, const float* scale, const float* gy, float* gx,
                                 float* grad_scale_bias, float* workspace);
+/* FiLM time conditioning of a hidden layer (planner.py:1083-1092, 1362-1363):
+ * out[b][c] = gamma[c] z[b][c] + beta[c], gamma / beta [H] = the two Dense(time embedding) vectors of
+ * the decision epoch.  backward: g = cotangent of out, z = the tanh output it was applied to;
+ * gz = g gamma (1 - z^2) (may alias g), grad_gamma_beta = [dgamma (H) | dbeta (H)] += batch sums
+ * through workspace[rk_film_chunks(B)][2 H] (added in chunk order). */
+int rk_film_chunks(int B);
+int rk_film_forward(void* stream, int B, int H, const float* z, const float* gamma,
+                    const float* beta, float* out);
+int rk_film_backward(void* stream, int B, int H, const float* g, const float* z,
+                     const float* gamma, float* gz, float* grad_gamma_beta, float* workspace);
 /* Skinny products with N <= 16 (action heads, state-cotangent blocks), A read exactly once:
  * out[b][n] = (accumulate ? out : 0) + sum_k A[b][k] W[k][n] (+ bias[n]). */
 int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A, int lda,

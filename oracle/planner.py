@@ -422,7 +422,8 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
                 sigma_range: Tuple[float, float] = (1e-5, 1e3), sigmoid_weight: float = 1.0,
                 wrap_non_bool: bool = False, normalize: bool = False,
                 normalize_per_layer: bool = False, norm_eps: float = 1e-6,
-                softmax_weight: float = 1.0, sigma_entropy_grad: bool = False):
+                softmax_weight: float = 1.0, sigma_entropy_grad: bool = False,
+                step: int = 0, time_embedding: Optional[str] = None, time_dim: int = 8):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
     noise: action name -> [B, n] standard draws (Gumbel for boolean fluents under a binding
     max-nondef-actions, Logistic for other boolean fluents).  Returns (actions name ->
@@ -430,9 +431,16 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
     B = next(iter(fls.values())).shape[0]
     x = drp_state_vector(model, params, fls, normalize, normalize_per_layer, norm_eps)
     h = x
+    t_emb = None if time_embedding is None else drp_time_embedding(params, step, time_embedding,
+                                                                   time_dim)
     for i in range(topology_len):
         layer = params[f"dense_{i}"]
         h = torch.tanh(h @ layer["kernel"] + layer["bias"])
+        if t_emb is not None:           # FiLM (planner.py:1083-1092, 1362-1363)
+            film = params[f"film_{i}"]
+            gamma = t_emb @ film["gamma"]["kernel"] + film["gamma"]["bias"]
+            beta = t_emb @ film["beta"]["kernel"] + film["beta"]["bias"]
+            h = gamma * h + beta
     ls_lo, ls_hi = math.log(sigma_range[0]), math.log(sigma_range[1])
     actions, entropy = {}, torch.zeros(B, dtype=REAL)
     bools = [v for v in model.action_fluents if model.variable_ranges[v] == "bool"]
@@ -486,6 +494,34 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
     return actions, entropy
 
 
+def drp_time_embedding(params, step: int, kind: str, dim: int = 8):
+    """SinusoidalTimeEmbedding (planner.py:1108-1119): angles t * 10000^(-2 i / dim), (sin, cos)
+    pairs interleaved and cut to the first `dim` entries; FixedTimeEmbedding (planner.py:1095-1105):
+    row `step` of a learned [max_t + 1, dim] table."""
+    if kind == "fixed":
+        return params["fixed_time_embed"]["kernel"][step]
+    freqs = 10000.0 ** (-2.0 * torch.arange(dim, dtype=REAL) / dim)
+    angles = float(step) * freqs
+    return torch.stack([torch.sin(angles), torch.cos(angles)], dim=-1).reshape(-1)[:dim]
+
+
+def drp_film_init(params, topology, generator: torch.Generator, kind: str, dim: int = 8,
+                  max_t: int = 500):
+    """flax defaults: Dense kernels lecun_normal (variance_scaling(1, fan_in, truncated normal)),
+    zero biases; the fixed table normal(stddev 0.01)."""
+    def kernel(fan_in, fan_out):
+        std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
+        w = torch.empty(fan_in, fan_out)
+        torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
+        return w * std
+    for i, h in enumerate(topology):
+        params[f"film_{i}"] = {"gamma": {"kernel": kernel(dim, h), "bias": torch.zeros(h)},
+                               "beta": {"kernel": kernel(dim, h), "bias": torch.zeros(h)}}
+    if kind == "fixed":
+        params["fixed_time_embed"] = {"kernel": torch.randn(max_t + 1, dim, generator=generator) * 0.01}
+    return params
+
+
 def gumbel_softmax_topk(logits, gumbel, allowed: int, weight: float, train: float):
     """GumbelSoftmaxTopK.__call__ (planner.py:1034-1080).  logits [B, n]; gumbel: Gumbel(0, 1)
     draws of the same shape (0 = not stochastic)."""
@@ -511,14 +547,16 @@ def gumbel_softmax_topk(logits, gumbel, allowed: int, weight: float, train: floa
 def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: bool = True,
                      sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
                      normalize: bool = False, normalize_per_layer: bool = False,
-                     norm_eps: float = 1e-6, softmax_weight: float = 1.0):
+                     norm_eps: float = 1e-6, softmax_weight: float = 1.0, step: int = 0,
+                     time_embedding: Optional[str] = None, time_dim: int = 8):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
     acts, _ = drp_actions(model, params, fls, zeros, 0.0, bounds, topology_len, stochastic,
                           sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool,
                           normalize=normalize, normalize_per_layer=normalize_per_layer,
-                          norm_eps=norm_eps, softmax_weight=softmax_weight)
+                          norm_eps=norm_eps, softmax_weight=softmax_weight, step=step,
+                          time_embedding=time_embedding, time_dim=time_dim)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]
@@ -534,3 +572,31 @@ def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: 
             out[var] = torch.minimum(torch.maximum(a, torch.as_tensor(np.asarray(lo, np.float32))),
                                      torch.as_tensor(np.asarray(hi, np.float32)))
     return out
+
+
+# ---- optax.contrib.reduce_on_plateau (planner.py:2375-2384, 2889-2891) --------------------------
+def reduce_on_plateau_init():
+    """optax (>= 0.2.7, un-vendored third-party code: parity unpinned) ReduceLROnPlateauState."""
+    return {"scale": 1.0, "best_value": math.inf, "plateau_count": 0, "cooldown_count": 0,
+            "count": 0, "avg_value": 0.0}
+
+
+def reduce_on_plateau_step(state, value: float, factor=0.1, patience=10, rtol=1e-4, atol=0.0,
+                           cooldown=0, accumulation_size=1, min_scale=0.0):
+    """One `update` of optax.contrib.reduce_on_plateau as a plain Python state machine; returns the
+    new state, whose 'scale' multiplies the optimiser's updates of this step."""
+    count = state["count"] + 1
+    avg = (state["count"] * state["avg_value"] + value) / count
+    if count != accumulation_size:
+        return dict(state, count=count, avg_value=avg)
+    improved = avg < (1.0 - rtol) * state["best_value"] - atol
+    best = avg if improved else state["best_value"]
+    cur = 0 if improved else state["plateau_count"] + 1
+    if state["cooldown_count"] > 0:         # bad steps are ignored while cooling down
+        plat, scale, cool = 0, state["scale"], state["cooldown_count"] - 1
+    elif cur == patience:
+        plat, scale, cool = 0, max(state["scale"] * factor, min_scale), cooldown
+    else:
+        plat, scale, cool = cur, state["scale"], 0
+    return {"scale": scale, "best_value": best, "plateau_count": plat, "cooldown_count": cool,
+            "count": 0, "avg_value": 0.0}

@@ -30,6 +30,36 @@ from .planner_base import JaxPlan, initializers
 from .program import PlanSpec, action_layout
 
 
+class SinusoidalTimeEmbedding:
+    """Sinusoidal positional encoding of the decision epoch (planner.py:1108-1119)."""
+    kind = "sin"
+
+    def __init__(self, dim: int = 8, name: str = "sin_time_embed") -> None:
+        self.dim, self.name = int(dim), name
+
+    def table(self, T: int) -> torch.Tensor:
+        """Rows 0..T-1: (sin, cos) pairs of t * 10000^(-2 i / dim), interleaved, first dim entries."""
+        freqs = 10000.0 ** (-2.0 * torch.arange(self.dim, dtype=torch.float32) / self.dim)
+        angles = torch.arange(T, dtype=torch.float32).reshape(T, 1) * freqs
+        return torch.stack([torch.sin(angles), torch.cos(angles)], dim=-1).reshape(T, -1)[:, :self.dim] \
+            .contiguous()
+
+
+class FixedTimeEmbedding:
+    """Learnable table of time embeddings (planner.py:1095-1105)."""
+    kind = "fixed"
+
+    def __init__(self, max_t: int = 500, dim: int = 8, init: Any = None,
+                 name: str = "fixed_time_embed") -> None:
+        if init is not None:
+            raise NotImplementedError("FixedTimeEmbedding(init=...): only the default normal(0.01)")
+        self.max_t, self.dim, self.name = int(max_t), int(dim), name
+
+
+TIME_EMBEDDINGS = {"SinusoidalTimeEmbedding": SinusoidalTimeEmbedding,
+                   "FixedTimeEmbedding": FixedTimeEmbedding}
+
+
 class JaxDeepReactivePolicy(JaxPlan):
     """A deep reactive policy network (planner.py:1122)."""
 
@@ -50,8 +80,15 @@ class JaxDeepReactivePolicy(JaxPlan):
         if act != "tanh":
             raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
         self._wrap_non_bool = bool(wrap_non_bool)
-        if time_dependent:
-            raise NotImplementedError("JaxDeepReactivePolicy(time_dependent=True) is not built yet")
+        self._time_dependent = bool(time_dependent)
+        if time_embedding is None:
+            time_embedding = SinusoidalTimeEmbedding
+        if isinstance(time_embedding, str):
+            time_embedding = TIME_EMBEDDINGS[time_embedding]
+        self._time_embedding = time_embedding
+        self._time_embedding_kwargs = dict(time_embedding_kwargs or {})
+        self.time_embed = time_embedding(**self._time_embedding_kwargs) if self._time_dependent \
+            else None
         self._sigma_entropy_grad = bool(sigma_entropy_grad)
         # the reference takes a jax.random sampler (planner.py:1139, 1418-1420); here its name
         dist = getattr(action_noise_dist, "__name__", action_noise_dist)
@@ -74,7 +111,6 @@ class JaxDeepReactivePolicy(JaxPlan):
                 f"normalizer_kwargs {normalizer_kwargs}: only epsilon (with scale and bias) is built")
         self._normalizer_kwargs = dict(normalizer_kwargs)
         self._norm_eps = float(normalizer_kwargs.get("epsilon", 1e-6))     # flax nn.LayerNorm
-        self._time_dependent = time_dependent
 
     def __str__(self) -> str:
         return (f"[INFO] policy hyper-parameters:\n"
@@ -191,6 +227,21 @@ class JaxDeepReactivePolicy(JaxPlan):
             self.segments.append(("ln_scale", o, 1, self.Dn))
             self.segments.append(("ln_bias", o + self.Dn, 1, self.Dn))
             o += 2 * self.Dn
+        # FiLM time conditioning (planner.py:1083-1092, 1353-1363): per hidden layer the kernels and
+        # biases of the gamma / beta Dense layers over the time embedding; then the learned table
+        self.film = self.time_embed is not None
+        if self.film:
+            dim = self.time_embed.dim
+            if self.time_embed.kind == "fixed" and horizon > self.time_embed.max_t + 1:
+                raise ValueError(f"FixedTimeEmbedding(max_t={self.time_embed.max_t}) is shorter "
+                                 f"than the horizon {horizon}")
+            for i, h in enumerate(self._topology):
+                for nm, r in ((f"fgW{i}", dim), (f"fgb{i}", 1), (f"fbW{i}", dim), (f"fbb{i}", 1)):
+                    self.segments.append((nm, o, r, h))
+                    o += r * h
+            if self.time_embed.kind == "fixed":
+                self.segments.append(("temb", o, self.time_embed.max_t + 1, dim))
+                o += (self.time_embed.max_t + 1) * dim
         self.n_params = o
         self.seg = {name: (off, r, c) for name, off, r, c in self.segments}
         self.box = (None, None)
@@ -215,6 +266,12 @@ class JaxDeepReactivePolicy(JaxPlan):
                 flat[off:off + r * c] = w.reshape(-1)
             elif name == "ln_scale":
                 flat[off:off + c] = 1.0
+            elif name.startswith("fgW") or name.startswith("fbW"):     # flax Dense: lecun_normal
+                w = torch.empty(r, c)
+                torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
+                flat[off:off + r * c] = (w * (math.sqrt(1.0 / r) / 0.87962566103423978)).reshape(-1)
+            elif name == "temb":                                        # nn.initializers.normal()
+                flat[off:off + r * c] = torch.randn(r * c, generator=generator) * 0.01
         return flat
 
     # ---- flat vector <-> flax-style pytree ------------------------------------------------
@@ -237,6 +294,14 @@ class JaxDeepReactivePolicy(JaxPlan):
         Wh = flat[..., off:off + r * c].reshape(*lead, r, c)
         ob = self.seg["bh"][0]
         bh = flat[..., ob:ob + c]
+        if self.film:
+            blk = lambda nm: (lambda o, r, c: flat[..., o:o + r * c].reshape(*lead, r, c) if r > 1  # noqa
+                              else flat[..., o:o + c])(*self.seg[nm])
+            for i in range(len(self._topology)):
+                tree[f"film_{i}"] = {"gamma": {"kernel": blk(f"fgW{i}"), "bias": blk(f"fgb{i}")},
+                                     "beta": {"kernel": blk(f"fbW{i}"), "bias": blk(f"fbb{i}")}}
+            if self.time_embed.kind == "fixed":
+                tree[self.time_embed.name] = {"kernel": blk("temb")}
         if self.use_topk:               # planner.py:1436-1438: the pooled boolean logits
             cols = torch.as_tensor(self._pooled_columns())
             tree["dense_topk"] = {"kernel": Wh[..., cols], "bias": bh[..., cols]}
@@ -274,6 +339,17 @@ class JaxDeepReactivePolicy(JaxPlan):
             flat[off:off + r * c] = W.reshape(-1)
             ob, _, cb = self.seg[f"b{i}"]
             flat[ob:ob + cb] = as_t(tree[f"dense_{i}"]["bias"]).reshape(-1)
+        if self.film:
+            def put(nm, x):
+                o, r, c = self.seg[nm]
+                flat[o:o + r * c] = as_t(x).reshape(-1)
+            for i in range(len(self._topology)):
+                put(f"fgW{i}", tree[f"film_{i}"]["gamma"]["kernel"])
+                put(f"fgb{i}", tree[f"film_{i}"]["gamma"]["bias"])
+                put(f"fbW{i}", tree[f"film_{i}"]["beta"]["kernel"])
+                put(f"fbb{i}", tree[f"film_{i}"]["beta"]["bias"])
+            if self.time_embed.kind == "fixed":
+                put("temb", tree[self.time_embed.name]["kernel"])
         off, r, c = self.seg["Wh"]
         Wh = torch.zeros(r, c)
         bh = torch.zeros(c)
@@ -310,7 +386,15 @@ class JaxDeepReactivePolicy(JaxPlan):
     def guess_next_epoch(self, params):
         return params                      # planner.py:1531-1534: warm start from the same policy
 
-    def test_actions_host(self, flat: torch.Tensor, state_vec: np.ndarray) -> Dict[str, np.ndarray]:
+    def time_embedding_rows(self, flat: torch.Tensor, T: int) -> torch.Tensor:
+        """[T, dim] embeddings of the decision epochs 0..T-1 (a view of the parameters when learned)."""
+        if self.time_embed.kind == "fixed":
+            o, r, c = self.seg["temb"]
+            return flat[o:o + r * c].view(r, c)[:T]
+        return self.time_embed.table(T).to(flat.device)
+
+    def test_actions_host(self, flat: torch.Tensor, state_vec: np.ndarray,
+                          step: int = 0) -> Dict[str, np.ndarray]:
         """Test policy on one state (controllers' get_action, planner.py:3527): a handful of
         tiny mat-vecs on the host."""
         h = torch.as_tensor(state_vec, dtype=torch.float32).reshape(1, -1).clone()
@@ -334,6 +418,12 @@ class JaxDeepReactivePolicy(JaxPlan):
             off, r, c = self.seg[f"W{i}"]
             ob = self.seg[f"b{i}"][0]
             h = torch.tanh(h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c])
+            if self.film:
+                emb = self.time_embedding_rows(flat, int(step) + 1)[int(step)].reshape(1, -1)
+                vec = lambda nm: (lambda o, rr, cc: flat[o:o + rr * cc].reshape(rr, cc))(*self.seg[nm])  # noqa
+                gamma = emb @ vec(f"fgW{i}") + vec(f"fgb{i}")
+                beta = emb @ vec(f"fbW{i}") + vec(f"fbb{i}")
+                h = gamma * h + beta
         off, r, c = self.seg["Wh"]
         ob = self.seg["bh"][0]
         out = (h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c]).reshape(-1)
@@ -450,6 +540,50 @@ class DrpPipeline:
             self.ln_ws = z(engine.state_layernorm_ctas(Bt) * 2 * self.Dn)
             self.t_xn = z(te.S * Be)
 
+        # FiLM: conditioned activations of every step (inputs of the next layer), the per-step gamma /
+        # beta vectors of this update and their cotangents [dgamma | dbeta]
+        self.film = plan.film
+        if self.film:
+            self.fused_head = False       # the head adjoint's (1 - H^2) factor moves behind FiLM
+            self.Hf = [z(T, Bt, h) for h in self.hid]
+            self.t_Hf = [z(Be, h) for h in self.hid]
+            self.gam = [z(T, h) for h in self.hid]
+            self.bet = [z(T, h) for h in self.hid]
+            self.dgb = [z(T, 2 * h) for h in self.hid]
+            self.film_ws = z(engine.film_chunks(max(Bt, Be)) * 2 * max(self.hid))
+            self.sin_table = None if plan.time_embed.kind == "fixed" \
+                else plan.time_embed.table(T).to(dev)
+
+    def film_tables(self, params):
+        """gamma_t = Dense(t_emb), beta_t = Dense(t_emb) for every decision epoch of the horizon
+        (planner.py:1088-1091): [T, dim] x [dim, h] products, once per update."""
+        plan = self.plan
+        emb = self.sin_table if self.sin_table is not None \
+            else plan.time_embedding_rows(params, self.pl.T)
+        for i, h in enumerate(self.hid):
+            dim = emb.shape[1]
+            torch.addmm(self._W(params, f"fgb{i}"), emb, self._W(params, f"fgW{i}").view(dim, h),
+                        out=self.gam[i])
+            torch.addmm(self._W(params, f"fbb{i}"), emb, self._W(params, f"fbW{i}").view(dim, h),
+                        out=self.bet[i])
+        return emb
+
+    def film_param_grads(self, params, grad, emb):
+        """Chain the per-step [dgamma | dbeta] sums into the FiLM Dense layers and, when it is
+        learned, the rows of the time-embedding table."""
+        plan = self.plan
+        T, dim = emb.shape
+        for i, h in enumerate(self.hid):
+            dg, db = self.dgb[i][:, :h], self.dgb[i][:, h:]
+            self._W(grad, f"fgW{i}").view(dim, h).addmm_(emb.t(), dg)
+            self._W(grad, f"fgb{i}").add_(dg.sum(0))
+            self._W(grad, f"fbW{i}").view(dim, h).addmm_(emb.t(), db)
+            self._W(grad, f"fbb{i}").add_(db.sum(0))
+            if plan.time_embed.kind == "fixed":
+                rows = self._W(grad, "temb").view(-1, dim)[:T]
+                rows.addmm_(dg, self._W(params, f"fgW{i}").view(dim, h).t())
+                rows.addmm_(db, self._W(params, f"fbW{i}").view(dim, h).t())
+
     def layernorm_forward(self, params, B, x, y):
         plan = self.plan
         engine.state_layernorm_forward(B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps,
@@ -476,7 +610,7 @@ class DrpPipeline:
                               self.wT_lo[off:off + n], n)
 
     # ---- the MLP ------------------------------------------------------------------------------
-    def mlp_forward(self, params, B, x_fm, H, heads, xp=None):
+    def mlp_forward(self, params, B, x_fm, H, heads, xp=None, film=None):
         """x_fm: the state in the kernels' fluent-major layout (fluent f = block [B][n_f] at word
         offset off_f * B); H: per-layer outputs [B][h]; heads [B][NH]; xp: optional [B][D+1]
         packed copy [x | 1] for the backward pass."""
@@ -484,6 +618,10 @@ class DrpPipeline:
         engine.drp_layer0(B, self.D, h0, self.plan.state_segs, x_fm, self._W(params, "W0"),
                           self._W(params, "b0"), H[0], xp)
         fan, src = h0, H[0]
+        if film is not None:            # film = (decision epoch, conditioned-activation buffers)
+            t, Hf = film
+            engine.film_forward(B, h0, H[0], self.gam[0][t], self.bet[0][t], Hf[0])
+            src = Hf[0]
         for i in range(1, len(self.hid)):
             h = self.hid[i]
             if i in self.tc_layers:     # Y = tanh(X W + b) as X * (W^T)^T on the tensor cores
@@ -494,6 +632,9 @@ class DrpPipeline:
                 engine.sgemm(engine.EPI_BIAS_TANH, B, h, fan, src, fan, self._W(params, f"W{i}"),
                              h, H[i], h, bias=self._W(params, f"b{i}"))
             fan, src = h, H[i]
+            if film is not None:
+                engine.film_forward(B, h, H[i], self.gam[i][t], self.bet[i][t], Hf[i])
+                src = Hf[i]
         if self.NH <= 16:
             engine.rowdot(False, B, self.NH, fan, src, fan, self._W(params, "Wh"), self.NH, heads,
                           self.NH, bias=self._W(params, "bh"))
@@ -501,14 +642,24 @@ class DrpPipeline:
             engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"),
                          self.NH, heads, self.NH, bias=self._W(params, "bh"))
 
-    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp, params_w=None):
+    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp, params_w=None, film=None):
         """Consumes self.gheads [B][NH]; accumulates weight gradients into ``grad`` and adds the
         input cotangent to the fluent-major state cotangent ``gs_cur``."""
         AT, ACC = engine.GEMM_A_TRANS, engine.GEMM_ACCUMULATE
         sk, ws = self.split_k, self.ws
         last = len(self.hid) - 1
         hl = self.hid[last]
-        if self.fused_head:     # gz, dWh, dbh and db_last in one pass over H[last] / gheads
+        if film is not None:    # layer inputs are the conditioned activations; z = H stays the tanh
+            t, Hf = film
+            engine.sgemm(AT | ACC, hl, self.NH, B, Hf[last], hl, self.gheads, self.NH,
+                         self._W(grad, "Wh"), self.NH, workspace=ws, split_k=sk)
+            engine.colsum(B, self.NH, self.gheads, self.NH, self._W(grad, "bh"), True, self.cs_ws,
+                          self.cs_chunks)
+            engine.sgemm(engine.EPI_NONE, B, hl, self.NH, self.gheads, self.NH,
+                         self._W(self.wT, "Wh"), hl, self.gz[last], hl)
+            engine.film_backward(B, hl, self.gz[last], H[last], self.gam[last][t], self.gz[last],
+                                 self.dgb[last][t], self.film_ws)
+        elif self.fused_head:     # gz, dWh, dbh and db_last in one pass over H[last] / gheads
             engine.drp_head_backward(B, hl, self.NH, H[last], self.gheads, self._W(params_w, "Wh"),
                                      self.gz[last], grad[self.plan.seg[f"b{last}"][0]:], self.fb_ws)
         else:
@@ -530,16 +681,26 @@ class DrpPipeline:
                 engine.sgemm(AT | ACC, fan + 1, h, B, xp, fan + 1, self.gz[0], h,
                              self._W(grad, "W0"), h, workspace=ws, split_k=sk)
             else:
+                src = H[i - 1] if film is None else Hf[i - 1]
                 if i in self.tc_layers and self.ws is not None:     # dW = H^T dZ on the tensor cores
-                    engine.tcgemm_tn(True, fan, h, B, H[i - 1], fan, self.gz[i], h,
+                    engine.tcgemm_tn(True, fan, h, B, src, fan, self.gz[i], h,
                                      self._W(grad, f"W{i}"), self.ws, self.max_split)
                 else:
-                    engine.sgemm(AT | ACC, fan, h, B, H[i - 1], fan, self.gz[i], h,
+                    engine.sgemm(AT | ACC, fan, h, B, src, fan, self.gz[i], h,
                                  self._W(grad, f"W{i}"), h, workspace=ws, split_k=sk)
                 if not (i == last and self.fused_head):     # db_last came with the head backward
                     engine.colsum(B, h, self.gz[i], h, self._W(grad, f"b{i}"), True, self.cs_ws,
                                   self.cs_chunks)
-            if i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
+            if i > 0 and film is not None:       # dX = dZ W^T, then back through FiLM and tanh
+                if i in self.tc_layers:
+                    engine.tcgemm(0, B, fan, h, self.gz[i], h, self._W(self.w_hi, f"W{i}"),
+                                  self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan)
+                else:
+                    engine.sgemm(engine.EPI_NONE, B, fan, h, self.gz[i], h,
+                                 self._W(self.wT, f"W{i}"), fan, self.gz[i - 1], fan)
+                engine.film_backward(B, fan, self.gz[i - 1], H[i - 1], self.gam[i - 1][t],
+                                     self.gz[i - 1], self.dgb[i - 1][t], self.film_ws)
+            elif i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
                 engine.tcgemm(3, B, fan, h, self.gz[i], h, self._W(self.w_hi, f"W{i}"),
                               self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan,
                               aux=H[i - 1], ldaux=fan)
@@ -564,6 +725,7 @@ class DrpPipeline:
         fwd, bwd = pl.train_fwd, pl.train_bwd
         N = fwd.program.N
         self.refresh_transposes(params)          # W^T and the hi / lo splits of this update's W
+        emb = self.film_tables(params) if self.film else None
         self.tape[:S * B].copy_(pl.s0_train)
         for t in range(T):
             x = self.tape[t * S * B:(t + 1) * S * B]
@@ -572,7 +734,8 @@ class DrpPipeline:
             if self.Dn:
                 xin = self.xn[t]
                 self.layernorm_forward(params, B, x, xin)
-            self.mlp_forward(params, B, xin, Ht, self.heads[t], self.xp[t])
+            self.mlp_forward(params, B, xin, Ht, self.heads[t], self.xp[t],
+                             film=(t, [Hl[t] for Hl in self.Hf]) if self.film else None)
             engine.drp_actions_forward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
@@ -601,6 +764,9 @@ class DrpPipeline:
         # ---- backward sweep
         grad.zero_()
         self.gs[0].zero_()
+        if self.film:
+            for d in self.dgb:
+                d.zero_()
         cur = 0
         for t in range(T - 1, -1, -1):
             x = self.tape[t * S * B:(t + 1) * S * B]
@@ -622,17 +788,21 @@ class DrpPipeline:
                     None if self.pol_noise is None else self.pol_noise[t], plan.allowed,
                     plan._softmax_output_weight, self.gact, self.gheads,
                     ent_coeff=self.ent_coeff, inv_batch=1.0 / (B * pl.world_size))
+            film = (t, [Hl[t] for Hl in self.Hf]) if self.film else None
             if self.Dn:     # MLP input cotangent -> gy, then gs += LayerNorm^T gy (+ dscale, dbias)
                 self.gy.zero_()
                 self.mlp_backward(grad, B, self.xn[t], [Hl[t] for Hl in self.H], self.gy,
-                                  self.xp[t], params)
+                                  self.xp[t], params, film=film)
                 engine.state_layernorm_backward(
                     B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps, x,
                     self._W(params, "ln_scale"), self.gy, out, self._W(grad, "ln_scale"),
                     self.ln_ws)
             else:
-                self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params)
+                self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params,
+                                  film=film)
             cur ^= 1
+        if self.film:
+            self.film_param_grads(params, grad, emb)
 
     def test_kernels(self, p: int, params: Optional[torch.Tensor] = None, out=None):
         """Exact-model rollouts with the test policy (train = 0, planner.py:1482-1499).
@@ -647,6 +817,8 @@ class DrpPipeline:
         te = pl.test_fwd
         N = te.program.N
         self.refresh_transposes(params)
+        if self.film:
+            self.film_tables(params)
         self.t_state[0].copy_(pl.s0_test)
         cur = 0
         for t in range(T):
@@ -660,7 +832,8 @@ class DrpPipeline:
             if self.Dn:
                 self.layernorm_forward(params, B, xin, self.t_xn)
                 xin = self.t_xn
-            self.mlp_forward(params, B, xin, self.t_H, self.t_heads)
+            self.mlp_forward(params, B, xin, self.t_H, self.t_heads,
+                             film=(t, self.t_Hf) if self.film else None)
             engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,
                                        None, 0.0, self.lo,
                                        self.hi, self.ls_lo, self.ls_hi, self.t_act, None,

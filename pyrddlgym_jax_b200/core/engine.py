@@ -28,6 +28,7 @@ EXPORTS = [
     "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
+    "rk_film_chunks", "rk_film_forward", "rk_film_backward",
 ]
 
 
@@ -101,6 +102,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_state_layernorm_forward.restype = ci
     lib.rk_state_layernorm_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf, cf, cf]
     lib.rk_state_layernorm_backward.restype = ci
+    lib.rk_film_chunks.argtypes = [ci]
+    lib.rk_film_chunks.restype = ci
+    lib.rk_film_forward.argtypes = [vp, ci, ci, cf, cf, cf, cf]
+    lib.rk_film_forward.restype = ci
+    lib.rk_film_backward.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf]
+    lib.rk_film_backward.restype = ci
     lib.rk_drp_topk_limits.argtypes = [vp, vp]
     lib.rk_drp_topk_limits.restype = ci
     lib.rk_drp_topk_forward.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, cf, cf, ci, ci, fl, ci, cf, cf]
@@ -289,6 +296,21 @@ def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls
         int(bool(wrap)) | (2 if sigma_entropy_grad else 0), _ptr(gact),
         _ptr(gheads)),
         "rk_drp_actions_backward")
+
+
+def film_chunks(B: int) -> int:
+    return int(load_library().rk_film_chunks(int(B)))
+
+
+def film_forward(B, H, z, gamma, beta, out):
+    _check(load_library().rk_film_forward(_stream(), B, H, _ptr(z), _ptr(gamma), _ptr(beta),
+                                          _ptr(out)), "rk_film_forward")
+
+
+def film_backward(B, H, g, z, gamma, gz, grad_gamma_beta, workspace):
+    _check(load_library().rk_film_backward(_stream(), B, H, _ptr(g), _ptr(z), _ptr(gamma), _ptr(gz),
+                                           _ptr(grad_gamma_beta), _ptr(workspace)),
+           "rk_film_backward")
 
 
 TOPK_MAX_POOLED, TOPK_MAX_ALLOWED = 64, 8      # RK_TOPK_MAX_N / RK_TOPK_MAX_K of csrc/rk_drp.cu

@@ -16,6 +16,7 @@ backprop-through-time, gradient reduction, optimiser step, projection) followed 
 from __future__ import annotations
 
 import configparser
+import math
 import pickle
 import time
 from abc import ABCMeta, abstractmethod
@@ -403,6 +404,52 @@ UTILITY_LOOKUP = {k: k for k in ("mean", "mean_var", "mean_std", "mean_semivar",
 # the planner
 # =====================================================================================
 
+# ---- optax.contrib.reduce_on_plateau (third-party, optax >= 0.2.7; planner.py:2375-2384) ----------
+def plateau_kwargs(kw: Dict[str, Any]) -> Dict[str, float]:
+    out = {"factor": 0.1, "patience": 10, "rtol": 1e-4, "atol": 0.0, "cooldown": 0,
+           "accumulation_size": 1, "min_scale": 0.0}
+    extra = set(kw) - set(out)
+    if extra:
+        raise TypeError(f"reduce_on_plateau_kwargs: unknown arguments {sorted(extra)}")
+    out.update(kw)
+    return out
+
+
+def plateau_init(P: int, device) -> torch.Tensor:
+    """[P][6] = scale, best_value, plateau_count, cooldown_count, count, avg_value."""
+    st = torch.zeros(P, 6, dtype=torch.float32, device=device)
+    st[:, 0] = 1.0
+    st[:, 1] = math.inf
+    return st
+
+
+def plateau_step(st: torch.Tensor, value: torch.Tensor, factor: float, patience: int, rtol: float,
+                 atol: float, cooldown: int, accumulation_size: int, min_scale: float) -> None:
+    """One update of the plateau state st[6] from the loss ``value`` (a 1-element tensor), in place
+    and without a host round trip (graph-capturable): the loss is averaged over accumulation_size
+    steps; an average below (1 - rtol) best - atol is an improvement; after ``patience`` steps
+    without one the scale is multiplied by ``factor`` (not below min_scale) and ``cooldown`` steps
+    are ignored."""
+    scale, best, plat, cool, count, avg = (st[i:i + 1] for i in range(6))
+    new_count = count + 1.0
+    new_avg = (count * avg + value) / new_count
+    fire = new_count == float(accumulation_size)
+    improved = new_avg < (1.0 - rtol) * best - atol
+    nb = torch.where(improved, new_avg, best)
+    cur = torch.where(improved, torch.zeros_like(plat), plat + 1.0)
+    in_cd = cool > 0
+    hit = cur == float(patience)
+    plat_n = torch.where(in_cd | hit, torch.zeros_like(cur), cur)
+    scale_n = torch.where(~in_cd & hit, torch.clamp(scale * factor, min=min_scale), scale)
+    cool_n = torch.where(in_cd, cool - 1.0,
+                         torch.where(hit, torch.full_like(cool, float(cooldown)), torch.zeros_like(cool)))
+    new = torch.cat([torch.where(fire, scale_n, scale), torch.where(fire, nb, best),
+                     torch.where(fire, plat_n, plat), torch.where(fire, cool_n, cool),
+                     torch.where(fire, torch.zeros_like(count), new_count),
+                     torch.where(fire, torch.zeros_like(avg), new_avg)])
+    st.copy_(new)
+
+
 class JaxBackpropPlanner:
     """Gradient-based planner over batched differentiable rollouts (planner.py:2395)."""
 
@@ -427,8 +474,9 @@ class JaxBackpropPlanner:
                  ) -> None:
         self.noise_kwargs = dict(noise_kwargs) if noise_kwargs is not None else None
         self.ema_decay = None if ema_decay is None else float(ema_decay)
+        self.reduce_on_plateau_kwargs = None if reduce_on_plateau_kwargs is None \
+            else plateau_kwargs(reduce_on_plateau_kwargs)
         for name, val in (("line_search_kwargs", line_search_kwargs),
-                          ("reduce_on_plateau_kwargs", reduce_on_plateau_kwargs),
                           ("critic", critic), ("preprocessor", preprocessor),
                           ("dashboard", dashboard)):
             if val is not None:
@@ -582,8 +630,14 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
-        if self.noise_kwargs is not None or self.ema_decay is not None:
+        self._use_chain = (self.noise_kwargs is not None or self.ema_decay is not None
+                           or self.reduce_on_plateau_kwargs is not None)
+        if self.reduce_on_plateau_kwargs is not None and self.world_size > 1:
+            raise NotImplementedError("reduce_on_plateau_kwargs with more than one GPU: the plateau "
+                                      "test needs the all-reduced loss before the optimiser step")
+        if self._use_chain:
             self._chain_count = z(P)
+            self._chain_plateau = plateau_init(P, dev)
             self._chain_grad, self._chain_old, self._chain_ema = z(P, NP), z(P, NP), z(P, NP)
             self._chain_gen = torch.Generator(device=dev)
             self._chain_gen.manual_seed(int((self.noise_kwargs or {}).get("seed", 0)))
@@ -721,7 +775,7 @@ class JaxBackpropPlanner:
         params = self.params[p]
         if publish:
             self._publish_kernels(p)
-        if self.noise_kwargs is None and self.ema_decay is None:
+        if not self._use_chain:
             engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
                                   self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
                                   self.zero_flag[p:p + 1])
@@ -737,9 +791,11 @@ class JaxBackpropPlanner:
 
     def _opt_chain_kernels(self, p: int):
         """The optional links of the optax chain (planner.py:2366-2386) around the optimiser kernel:
-        clip_by_global_norm -> add_noise(eta, gamma) -> optimiser -> ema(decay), then apply_updates
-        and the box projection.  add_noise: g + N(0, eta / t^gamma) with the 1-based step count t;
-        ema: the debiased exponential moving average of the optimiser's updates is what is applied."""
+        clip_by_global_norm -> add_noise(eta, gamma) -> optimiser -> reduce_on_plateau -> ema(decay),
+        then apply_updates and the box projection.  add_noise: g + N(0, eta / t^gamma) with the
+        1-based step count t; reduce_on_plateau: the updates are scaled by a factor that shrinks when
+        the train loss stops improving (plateau_step); ema: the debiased exponential moving average
+        of the updates is what is applied."""
         params, grad = self.params[p], self.grad[p]
         g = grad
         self._chain_count[p:p + 1].add_(1.0)
@@ -761,6 +817,10 @@ class JaxBackpropPlanner:
         old.copy_(params)
         engine.optimizer_step(self.optimizer_name, self._hyper_noclip, self.n_params, params,
                               self.opt_state[p], self._chain_grad[p], None, None, None)
+        if self.reduce_on_plateau_kwargs is not None:     # value = the loss of this gradient
+            st = self._chain_plateau[p]
+            plateau_step(st, self._train_loss_tmp[p:p + 1], **self.reduce_on_plateau_kwargs)
+            params.copy_(old + st[0:1] * (params - old))
         if self.ema_decay is not None:
             d = self.ema_decay
             ema = self._chain_ema[p]
@@ -893,7 +953,7 @@ class JaxBackpropPlanner:
         (initial-state words and plan in, status words and plan out, through pinned staging
         buffers), so a whole replanning step is ONE graph launch and ONE synchronisation."""
         backup = (self.params.clone(), self.opt_state.clone(), self.hyper.clone())
-        chain = [t.clone() for t in (self._chain_count, self._chain_ema)] \
+        chain = [t.clone() for t in (self._chain_count, self._chain_ema, self._chain_plateau)] \
             if hasattr(self, "_chain_count") else None
         s = torch.cuda.Stream(device=self.device)
         side = torch.cuda.Stream(device=self.device) if self._overlap else None
@@ -941,6 +1001,7 @@ class JaxBackpropPlanner:
         if chain is not None:
             self._chain_count.copy_(chain[0])
             self._chain_ema.copy_(chain[1])
+            self._chain_plateau.copy_(chain[2])
         if from_host:
             self._graph_host = g
         else:
@@ -1011,6 +1072,10 @@ class JaxBackpropPlanner:
                     flat = self.plan.initial_params(gen)
                 self.params[p].copy_(flat.reshape(-1))
             self.opt_state.zero_()
+            if self._use_chain:         # the optax chain state is re-initialised too (P:2824-2851)
+                self._chain_count.zero_()
+                self._chain_ema.zero_()
+                self._chain_plateau.copy_(plateau_init(self.parallel_updates, self.device))
             self._primed = False
             self.hyper[6] = 1.0
             engine.mean_loss(self.train_returns[0], self.batch_size_train, None, self.gret)
@@ -1233,7 +1298,7 @@ class JaxBackpropPlanner:
         if self.is_drp:
             vec = np.concatenate([np.asarray(state[name], np.float32).reshape(-1)
                                   for name in self.rddl.state_fluents])
-            return self.plan.test_actions_host(flat, vec)
+            return self.plan.test_actions_host(flat, vec, step=int(step))
         step = min(int(step), flat.shape[0] - 1)
         return self.plan.test_actions(flat[step].numpy())
 

@@ -855,6 +855,91 @@ extern "C" int rk_colsum(void* stream, int B, int N, const float* G, int ldg, fl
   return (int)cudaGetLastError();
 }
 
+// ---- FiLM time conditioning of a hidden layer (planner.py:1083-1092, 1362-1363) ------------------
+// out[b][c] = gamma[c] * z[b][c] + beta[c]: gamma / beta are the two Dense(time embedding) vectors
+// of this decision epoch, the same for every rollout.  The adjoint takes the cotangent g of `out`
+// and produces, in one pass over [B][H] (g and z read once): the pre-activation cotangent
+// gz = g * gamma * (1 - z^2) (z = tanh output; gz may alias g) and the column sums
+// dgamma[c] += sum_b g z, dbeta[c] += sum_b g through per-chunk partials ws[chunk][2 H] added in
+// chunk order (deterministic).
+__global__ void rk_add_rows_kernel(int R, int n, const float* __restrict__ ws,
+                                   float* __restrict__ y, int accumulate);
+
+__global__ void rk_film_fwd_kernel(size_t n, int H, const float* __restrict__ z,
+                                   const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (size_t)H);
+    out[i] = fmaf(gamma[c], z[i], beta[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rk_film_bwd_kernel(int B, int H, int rows_per_chunk, const float* g,
+                   const float* __restrict__ z, const float* __restrict__ gamma, float* gz,
+                   float* __restrict__ ws) {
+  __shared__ float part[2][8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const int b0 = blockIdx.y * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
+  float ag = 0.f, ab = 0.f;
+  if (c < H) {
+    const float gm = gamma[c];
+    for (int b = b0 + warp; b < b1; b += 8) {
+      const size_t i = (size_t)b * H + c;
+      const float gv = g[i], zv = z[i];
+      ag += gv * zv;
+      ab += gv;
+      gz[i] = gv * gm * (1.f - zv * zv);
+    }
+  }
+  part[0][warp][lane] = ag;
+  part[1][warp][lane] = ab;
+  __syncthreads();
+  if (warp < 2 && c < H) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[warp][w][lane];
+    ws[(size_t)blockIdx.y * (2 * (size_t)H) + (size_t)warp * H + c] = s;
+  }
+}
+
+extern "C" int rk_film_chunks(int B) {
+  int chunks = B / 64;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 74) chunks = 74;       // 8 column blocks x 74 chunks = 4 x 148 CTAs at H = 256
+  const int rpc = (B + chunks - 1) / chunks;
+  return (B + rpc - 1) / rpc;
+}
+
+extern "C" int rk_film_forward(void* stream, int B, int H, const float* z, const float* gamma,
+                               const float* beta, float* out) {
+  if (B <= 0 || H <= 0 || z == nullptr || gamma == nullptr || beta == nullptr || out == nullptr)
+    return RK_E_BADARG;
+  const size_t n = (size_t)B * H;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rk_film_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, H, z, gamma, beta, out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_film_backward(void* stream, int B, int H, const float* g, const float* z,
+                                const float* gamma, float* gz, float* grad_gamma_beta,
+                                float* workspace) {
+  if (B <= 0 || H <= 0 || g == nullptr || z == nullptr || gamma == nullptr || gz == nullptr ||
+      grad_gamma_beta == nullptr || workspace == nullptr)
+    return RK_E_BADARG;
+  const int chunks = rk_film_chunks(B);
+  const int rpc = (B + chunks - 1) / chunks;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((H + 31) / 32, chunks);
+  rk_film_bwd_kernel<<<grid, 256, 0, st>>>(B, H, rpc, g, z, gamma, gz, workspace);
+  rk_add_rows_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(chunks, 2 * H, workspace,
+                                                          grad_gamma_beta, 1);
+  return (int)cudaGetLastError();
+}
+
 // ---- fused backward of the action heads -----------------------------------------------------
 // Given the head cotangent G[B][NH] and the last hidden activation Hl[B][hl] (both read ONCE):
 //   gz[b][c]  = (sum_j G[b][j] Wh[c][j]) * (1 - Hl[b][c]^2)     cotangent of the last pre-activation

@@ -909,3 +909,141 @@ def test_drp_sigma_entropy_grad_matches_oracle(cuda_device):
     ob = plan.seg["bh"][0]
     np.testing.assert_allclose(want[ob + 5:ob + 10].sum(), pl.grad[0][ob + 5:ob + 10].sum().item(),
                                rtol=1e-4)
+
+
+# ---- FiLM time conditioning (planner.py:1083-1119, 1353-1363) --------------------------------------
+def _film_plan(kind, topology=(16, 16), **kw):
+    from pyrddlgym_jax_b200.core.drp import FixedTimeEmbedding, SinusoidalTimeEmbedding
+    m = fixture_model("powergen")
+    emb = {"sin": (SinusoidalTimeEmbedding, {"dim": 6}), "fixed": (FixedTimeEmbedding, {"max_t": 9, "dim": 4})}
+    plan = JaxDeepReactivePolicy(topology=list(topology), time_dependent=True,
+                                 time_embedding=emb[kind][0], time_embedding_kwargs=emb[kind][1], **kw)
+    return m, plan, emb[kind][1]["dim"]
+
+
+def test_sinusoidal_embedding_known_answer():
+    """dim = 4: freqs 1, 1e-2, 1e-4, 1e-6; interleaved (sin, cos) pairs cut to 4 entries use the
+    first two frequencies only (planner.py:1114-1119)."""
+    from pyrddlgym_jax_b200.core.drp import SinusoidalTimeEmbedding
+    tab = SinusoidalTimeEmbedding(dim=4).table(3)
+    want = [[np.sin(t), np.cos(t), np.sin(t * 1e-2), np.cos(t * 1e-2)] for t in range(3)]
+    np.testing.assert_allclose(tab.numpy(), np.asarray(want, np.float32), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(OP.drp_time_embedding({}, 2, "sin", 4).numpy(), tab[2].numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["sin", "fixed"])
+def test_film_pytree_and_host_policy(kind):
+    m, plan, dim = _film_plan(kind)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, 5)
+    g = torch.Generator().manual_seed(6)
+    flat = plan.initial_params(g)
+    tree = plan.params_to_pytree(flat)["params"]
+    assert {"film_0", "film_1"} <= set(tree)
+    assert ("fixed_time_embed" in tree) == (kind == "fixed")
+    assert tuple(tree["film_1"]["gamma"]["kernel"].shape) == (dim, 16)
+    assert float(tree["film_0"]["beta"]["bias"].abs().max()) == 0.0
+    assert torch.equal(plan.pytree_to_params({"params": tree}), flat)
+    fls = {"prevProd": torch.tensor([[1., 2., 0., .5, 3.]]), "temperature": torch.tensor([15.])}
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    for step in (0, 3):
+        ref = OP.drp_test_actions(m, tree, fls, m.bounds, 2, step=step, time_embedding=kind,
+                                  time_dim=dim)["curProd"].numpy().reshape(-1)
+        got = plan.test_actions_host(flat, vec, step=step)["curProd"].reshape(-1)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    a0 = plan.test_actions_host(flat, vec, step=0)["curProd"]
+    a3 = plan.test_actions_host(flat, vec, step=3)["curProd"]
+    assert not np.allclose(a0, a3)          # the policy depends on the decision epoch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H", [(1000, 256), (77, 48), (4100, 33)])
+def test_film_kernels_against_fp64(cuda_device, B, H):
+    from pyrddlgym_jax_b200.core import engine
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B)
+    z = torch.tanh(torch.randn(B, H, generator=g))
+    gamma, beta = torch.randn(H, generator=g), torch.randn(H, generator=g)
+    gout = torch.randn(B, H, generator=g)
+    out = torch.empty(B, H, device=dev)
+    engine.film_forward(B, H, z.to(dev), gamma.to(dev), beta.to(dev), out)
+    dgb0 = torch.randn(2 * H, generator=g)
+    dgb = dgb0.clone().to(dev)
+    gz = gout.clone().to(dev)                  # in place
+    ws = torch.zeros(engine.film_chunks(B) * 2 * H, device=dev)
+    engine.film_backward(B, H, gz, z.to(dev), gamma.to(dev), gz, dgb, ws)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), (gamma * z + beta).numpy(), rtol=1e-6, atol=1e-6)
+    want = (gout.double() * gamma.double() * (1 - z.double() ** 2)).float()
+    np.testing.assert_allclose(gz.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    want_gb = torch.cat([(gout.double() * z.double()).sum(0), gout.double().sum(0)]).float() + dgb0
+    np.testing.assert_allclose(dgb.cpu().numpy(), want_gb.numpy(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,topology,B,normalize", [("sin", (16, 16), 23, False),
+                                                       ("fixed", (32,), 19, False),
+                                                       ("fixed", (64, 64, 32), 130, True)])
+def test_drp_film_update_matches_oracle(cuda_device, kind, topology, B, normalize):
+    """time_dependent policies: rewards, loss and the whole gradient (dense layers, heads, FiLM
+    gamma / beta layers, the learned embedding table) of one update and the exact test rollouts
+    against the oracle; B = 130 with 64-wide layers runs the tensor-core layers."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m, plan, dim = _film_plan(kind, topology, normalize=normalize)
+    T, L = 4, len(topology)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    if kind == "fixed":
+        o, r, c = plan.seg["temb"]
+        flat[o:o + r * c] = torch.randn(r * c, generator=g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              {"curProd": pol_noise[t].reshape(B, 5)}, 1.0, m.bounds, L, True,
+                              normalize=normalize, step=t, time_embedding=kind, time_dim=dim)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    got = pl.grad[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    o, r, c = plan.seg["fgW0"]
+    assert np.abs(want[o:o + r * c]).max() > 0
+    if kind == "fixed":
+        o, r, c = plan.seg["temb"]
+        rows = want[o:o + r * c].reshape(r, c)
+        assert np.abs(rows[:T]).max() > 0 and np.all(rows[T:] == 0)
+    te = pl.test_fwd.program
+    tnoise = torch.randn(T, te.N * B, generator=g)
+    pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    out = OP.rollout(OracleModel(m, None), lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, m.bounds, L, normalize=normalize, step=t,
+        time_embedding=kind, time_dim=dim), B, T,
+        [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    r_ref = out["reward"].numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())

@@ -471,3 +471,71 @@ def test_symlog_reward_matches_oracle(cuda_device):
     got = pl.grad_used[0].cpu().view(T, plan.A)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
                                atol=1e-4 * float(want.abs().max()))
+
+
+# ---- reduce_on_plateau link of the optimiser chain (planner.py:2375-2384) -------------------------
+@pytest.mark.parametrize("kw", [{}, {"factor": 0.5, "patience": 3, "cooldown": 2, "min_scale": 0.2},
+                                {"patience": 2, "accumulation_size": 3, "factor": 0.7, "rtol": 0.05},
+                                {"patience": 1, "atol": 0.5, "factor": 0.25}])
+def test_plateau_state_machine_matches_oracle(kw):
+    from oracle import planner as OP
+    from pyrddlgym_jax_b200.core.planner import plateau_init, plateau_kwargs, plateau_step
+    full = plateau_kwargs(kw)
+    g = torch.Generator().manual_seed(5)
+    # a loss that improves, stalls, jumps and improves again
+    losses = torch.cat([torch.linspace(10, 5, 8), 5 + 0.3 * torch.rand(25, generator=g),
+                        torch.linspace(5, 1, 6), 1 + 0.2 * torch.rand(20, generator=g)])
+    st = plateau_init(1, "cpu")[0]
+    ref = OP.reduce_on_plateau_init()
+    scales = []
+    for v in losses:
+        plateau_step(st, v.reshape(1), **full)
+        ref = OP.reduce_on_plateau_step(ref, float(v), **full)
+        got = st.tolist()
+        want = [ref[k] for k in ("scale", "best_value", "plateau_count", "cooldown_count", "count",
+                                 "avg_value")]
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+        scales.append(got[0])
+    assert scales[-1] < 1.0 and min(scales) >= full["min_scale"]
+    with pytest.raises(TypeError):
+        plateau_kwargs({"patients": 3})
+
+
+@pytest.mark.gpu
+def test_reduce_on_plateau_scales_the_updates(cuda_device):
+    """sgd on Reservoir with a plateau test that can never see an improvement after the first step
+    (atol 1e9, patience 2): the scale halves every second update, in the eager form and inside the
+    captured graph alike, and follows the oracle's state machine on the losses the planner saw."""
+    from oracle import planner as OP
+    m = fixture_model("reservoir")
+    kw = {"factor": 0.5, "patience": 2, "atol": 1e9}
+    for graph in (False, True):
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=5,
+                                optimizer="sgd", optimizer_kwargs={"learning_rate": 1e-3}, pgpe=None,
+                                reduce_on_plateau_kwargs=kw, use_cuda_graph=graph)
+        scales = []
+        for cb in pl.optimize_generator(key=3, epochs=8, print_summary=False, print_progress=False):
+            assert np.isfinite(cb["train_loss"])
+            scales.append(float(pl._chain_plateau[0, 0]))
+        assert all(b <= a for a, b in zip(scales, scales[1:])), scales
+        assert scales[-1] <= 0.25 and set(scales) <= {1.0, 0.5, 0.25, 0.125, 0.0625}, scales
+    pl2 = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=5,
+                             optimizer="sgd", optimizer_kwargs={"learning_rate": 0.05}, pgpe=None,
+                             reduce_on_plateau_kwargs={"factor": 0.5, "patience": 1, "rtol": 1e-3},
+                             use_cuda_graph=False)
+    pl2.initialize(3)
+    ref = OP.reduce_on_plateau_init()
+    for _ in range(6):
+        before = pl2.params[0].clone()
+        pl2.update()
+        torch.cuda.synchronize()
+        ref = OP.reduce_on_plateau_step(ref, float(pl2.train_loss[0]), factor=0.5, patience=1,
+                                        rtol=1e-3)
+        assert abs(float(pl2._chain_plateau[0, 0]) - ref["scale"]) < 1e-7
+        # sgd: update = -lr * scale * grad (inside the box)
+        want = before - 0.05 * ref["scale"] * pl2.grad_used[0]
+        if pl2.box_lo is not None:
+            want = torch.maximum(want, pl2.box_lo)
+        if pl2.box_hi is not None:
+            want = torch.minimum(want, pl2.box_hi)
+        np.testing.assert_allclose(pl2.params[0].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
