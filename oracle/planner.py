@@ -34,29 +34,40 @@ def bound_action(lo, hi, param: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def slp_pooled_softmax(model, params: Dict[str, torch.Tensor], t: int, weight: float):
+def slp_pooled_softmax(model, params: Dict[str, torch.Tensor], t: int, weight: float,
+                       gumbel=None):
     """planner.py:764-808: softmax over the pooled boolean logits of step t, unstacked per fluent
-    (1 - p for fluents whose no-op value is true)."""
+    (1 - p for fluents whose no-op value is true).  gumbel: per fluent [B, n] draws added to the
+    logits of a stochastic plan (planner.py:801-805); the result then has a leading batch axis."""
     names = [v for v in model.action_fluents if model.variable_ranges[v] == "bool"]
     z = torch.cat([params[v][t].reshape(-1) for v in names])
-    out = torch.softmax(weight * z, dim=0)
+    if gumbel is not None:
+        z = z.unsqueeze(0) + torch.cat([x.reshape(x.shape[0], -1) for x in gumbel], dim=1)
+    out = torch.softmax(weight * z, dim=-1)
     acts, pos = {}, 0
     for v in names:
         n = params[v][t].numel()
-        a = out[pos:pos + n]
+        a = out[..., pos:pos + n]
         pos += n
         noop = bool(np.ravel(np.asarray(model.action_fluents[v]))[0])
         acts[v] = (1.0 - a) if noop else a
     return acts
 
 
-def slp_policy_noise_spec(model, wrap_sigmoid=True, action_noise="normal"):
+def slp_policy_noise_spec(model, wrap_sigmoid=True, action_noise="normal", pooled_softmax=False):
     """Draw sites of a stochastic straight-line plan, in the order planner.py:811-833 splits
-    its key: (kind, shape) per action fluent that receives noise."""
+    its key: (kind, shape) per action fluent that receives noise.  The pooled '__bool__' entry
+    (one Gumbel draw over all boolean parameters, planner.py:801-803) comes first and is listed
+    fluent by fluent."""
     spec = []
+    if pooled_softmax:
+        spec += [("gumbel", tuple(model.variable_shape(v))) for v in model.action_fluents
+                 if model.variable_ranges[v] == "bool"]
     for name in model.action_fluents:
         shape = tuple(model.variable_shape(name))
         if model.variable_ranges[name] == "bool":
+            if pooled_softmax:
+                continue
             if wrap_sigmoid:
                 spec.append(("logistic", shape))
         else:
@@ -65,14 +76,20 @@ def slp_policy_noise_spec(model, wrap_sigmoid=True, action_noise="normal"):
 
 
 def slp_entropy(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmoid=True,
-                sigmoid_weight=1.0, sigma_range=(1e-5, 1e3), sigma_entropy_grad=False):
-    """Entropy term of one step of a stochastic plan (planner.py:812-830)."""
+                sigmoid_weight=1.0, sigma_range=(1e-5, 1e3), sigma_entropy_grad=False,
+                pooled_softmax=False, softmax_weight=1.0):
+    """Entropy term of one step of a stochastic plan (planner.py:797-800, 812-830)."""
     from oracle.model_eval import safe_log
     ent = torch.zeros(())
+    if pooled_softmax:
+        z = torch.cat([params[v][t].reshape(-1) for v in model.action_fluents
+                       if model.variable_ranges[v] == "bool"])
+        log_prob = torch.log_softmax(softmax_weight * z, dim=0)
+        ent = ent - torch.sum(torch.exp(log_prob) * log_prob)
     for name in model.action_fluents:
         p = params[name][t]
         if model.variable_ranges[name] == "bool":
-            if wrap_sigmoid:
+            if wrap_sigmoid and not pooled_softmax:
                 w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight
                 prob = torch.sigmoid(w * p)
                 ent = ent - torch.sum(prob * safe_log(prob) + (1. - prob) * safe_log(1. - prob))
@@ -91,11 +108,17 @@ def slp_train_actions(model, params: Dict[str, torch.Tensor], t: int, wrap_sigmo
     slp_policy_noise_spec (stochastic plans only)."""
     actions = {}
     k = 0
-    pooled = slp_pooled_softmax(model, params, t, softmax_weight) if pooled_softmax else {}
+    pooled = {}
+    if pooled_softmax:
+        gumbel = None
+        if stochastic:
+            k = sum(1 for v in model.action_fluents if model.variable_ranges[v] == "bool")
+            gumbel = pnoise[:k]
+        pooled = slp_pooled_softmax(model, params, t, softmax_weight, gumbel)
     for name in model.action_fluents:
         p = params[name][t]
         if name in pooled:
-            actions[name] = pooled[name].unsqueeze(0)
+            actions[name] = pooled[name] if pooled[name].dim() > 1 else pooled[name].unsqueeze(0)
             continue
         if model.variable_ranges[name] == "bool":
             w = sigmoid_weight[name] if isinstance(sigmoid_weight, dict) else sigmoid_weight

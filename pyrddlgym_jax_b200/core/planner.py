@@ -74,8 +74,6 @@ class JaxStraightLinePlan(JaxPlan):
         self._sigma_range = sigma_range
         self._sigma_entropy_grad = sigma_entropy_grad
         self._action_noise_dist = action_noise_dist
-        if wrap_softmax and stochastic:
-            raise NotImplementedError("stochastic plans with wrap_softmax are not built yet")
         if action_noise_dist not in ("normal", "logistic", "laplace", "gumbel", "cauchy", "uniform"):
             raise NotImplementedError(f"action_noise_dist <{action_noise_dist}>: name one of the "
                                       "noise kinds the engine draws (e.g. 'normal')")
@@ -208,9 +206,19 @@ class JaxStraightLinePlan(JaxPlan):
         H = params.new_zeros(())
         dH = torch.zeros_like(params)
         eps = 1e-12
+        if self.stack_bool:     # planner.py:797-800: entropy of softmax(w pooled logits) per step
+            cols = torch.as_tensor(np.concatenate(
+                [np.arange(off, off + n) for (off, n, r) in self.layout.values() if r == "bool"]),
+                device=params.device)
+            w = float(self._softmax_weight)
+            lp = torch.log_softmax(w * params[:, cols], dim=1)
+            pr = torch.exp(lp)
+            Ht = -(pr * lp).sum(1, keepdim=True)
+            H = H + Ht.sum()
+            dH[:, cols] = -w * pr * (lp + Ht)
         for name, (off, n, prange) in self.layout.items():
             if prange == "bool":
-                if not self._wrap_sigmoid:
+                if not self._wrap_sigmoid or self.stack_bool:
                     continue
                 w = float(self._sigmoid_weight)
                 pr = torch.sigmoid(w * params[:, off:off + n])

@@ -246,8 +246,9 @@ def build_policy_actions(low: Lowerer, spec: PlanSpec, train: bool) -> Tuple[Dic
                 p = g.leaf("param_in", n, "f", uniform=True, off=off, fluent=name)
                 leaves[name] = p
                 plist.append((name, n, p))
-        if spec.stochastic:
-            raise ProgramError("stochastic plans with pooled softmax booleans are not built")
+        if stoch:                                     # planner.py:797-805: logits + Gumbel noise
+            plist = [(name, n, g.op("ADD", [(p, None), (policy_noise("gumbel", name, n), None)], n))
+                     for name, n, p in plist]
         w = g.const(np.float32(spec.softmax_weight))
         z = {name: g.op("MUL", [(w, "b"), (p, None)], n) for name, n, p in plist}
         whole = lambda n: (np.array([0, n], np.int64), np.arange(n, dtype=np.int64))   # noqa: E731

@@ -130,8 +130,9 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
         if stochastic:
             def pol(t, fls, pnoise):
                 return OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool, bounds=m.bounds,
-                                            stochastic=True, pnoise=pnoise)
-            pol.n_noise = len(OP.slp_policy_noise_spec(m))
+                                            stochastic=True, pnoise=pnoise,
+                                            pooled_softmax=pooled_softmax, softmax_weight=2.0)
+            pol.n_noise = len(OP.slp_policy_noise_spec(m, pooled_softmax=pooled_softmax))
         else:
             pol = lambda t, fls: OP.slp_train_actions(m, P, t, wrap_non_bool=wrap_non_bool,   # noqa: E731
                                                       bounds=m.bounds, pooled_softmax=pooled_softmax,
@@ -145,7 +146,7 @@ def forward_case(backend, key, B, T, relaxed, gamma=1.0, seed=1, compiler_cls=No
     ref = OP.rollout(om, pol, B, T, noise_steps)
     spec_or = [(x[0], tuple(x[1])) for x in (ref["noise_spec"] or [])]
     if relaxed and stochastic:
-        spec_or = OP.slp_policy_noise_spec(m) + spec_or
+        spec_or = OP.slp_policy_noise_spec(m, pooled_softmax=pooled_softmax) + spec_or
     spec_pr = [(k, tuple(s)) for k, s, _, _, _ in fwd.noise_layout]
     assert T == 0 or spec_or == spec_pr, "oracle and lowering disagree on the draw sites"
     final = unpack_fluent_major(fwd.state_layout, torch.from_numpy(got["final"].copy()), B)

@@ -93,3 +93,14 @@ def test_pooled_softmax_plan_emulated():
     c = gradient_case("emu", "wildfire", B=7, T=4, pooled_softmax=True, param_scale=3.0)
     check_forward(c)
     check_gradient(c)
+
+
+def test_stochastic_pooled_softmax_plan_emulated():
+    """stochastic + wrap_softmax (planner.py:797-806): Gumbel noise on the pooled boolean logits
+    before the softmax, per rollout."""
+    c = gradient_case("emu", "wildfire", B=7, T=4, pooled_softmax=True, stochastic=True,
+                      param_scale=2.0)
+    check_forward(c)
+    check_gradient(c)
+    acts = [c["P"][k].grad for k in c["P"]]
+    assert all(g is not None and float(g.abs().sum()) > 0 for g in acts)

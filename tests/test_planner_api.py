@@ -539,3 +539,84 @@ def test_reduce_on_plateau_scales_the_updates(cuda_device):
         if pl2.box_hi is not None:
             want = torch.minimum(want, pl2.box_hi)
         np.testing.assert_allclose(pl2.params[0].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ---- stochastic plans with wrap_softmax (planner.py:797-806) ---------------------------------------
+def _plan_params_by_fluent(m, plan, flat):
+    P = {}
+    for name, (off, n, prange) in plan.layout.items():
+        P[name] = flat[:, off:off + n].clone().requires_grad_(True)
+        if name in plan.sigma_layout:
+            so, sn = plan.sigma_layout[name]
+            P[name + "/log_sigma"] = flat[:, so:so + sn].clone().requires_grad_(True)
+    return P
+
+
+@pytest.mark.parametrize("key,kw", [("wildfire", {"wrap_softmax": True, "softmax_weight": 3.0}),
+                                    ("wildfire_free", {"sigmoid_weight": 2.0}),
+                                    ("reservoir", {"sigma_entropy_grad": True})])
+def test_entropy_terms_match_oracle_autograd(key, kw):
+    """JaxStraightLinePlan.entropy_terms (value and gradient of the horizon's entropy, computed from
+    the parameters alone) against autograd of the oracle's per-step entropy."""
+    from oracle import planner as OP
+    from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler
+    m = fixture_model(key)
+    T = 4
+    plan = JaxStraightLinePlan(stochastic=True, **kw)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, T)
+    flat = torch.randn(T, plan.A, generator=torch.Generator().manual_seed(1))
+    H, dH = plan.entropy_terms(flat)
+    P = _plan_params_by_fluent(m, plan, flat)
+    ent = sum(OP.slp_entropy(m, P, t, sigmoid_weight=kw.get("sigmoid_weight", 1.0),
+                             sigma_entropy_grad=kw.get("sigma_entropy_grad", False),
+                             pooled_softmax=plan.stack_bool,
+                             softmax_weight=kw.get("softmax_weight", 1.0)) for t in range(T))
+    ent.backward()
+    from tests.helpers import pack_params
+    want = pack_params(m, {k: (v.grad if v.grad is not None else torch.zeros_like(v))
+                           for k, v in P.items()})
+    np.testing.assert_allclose(float(H), float(ent.detach()), rtol=1e-5)
+    np.testing.assert_allclose(dH.numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
+    assert float(dH.abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_stochastic_wrap_softmax_update_matches_oracle(cuda_device):
+    """One update of a stochastic plan whose boolean parameters are pooled under one softmax:
+    Gumbel-perturbed logits per rollout, softmax entropy regulariser; loss and gradient against the
+    oracle's autograd on the same parameters and supplied noise."""
+    from oracle import planner as OP
+    from oracle.model_eval import OracleModel
+    from pyrddlgym_jax_b200.core.layout import noise_as_list
+    m = fixture_model("wildfire")
+    B, T = 16, 5
+    plan = JaxStraightLinePlan(stochastic=True, wrap_softmax=True, softmax_weight=3.0)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False, start_entropy_coeff=0.3, end_entropy_coeff=0.3)
+    pl.initialize(5)
+    pl.params[0].copy_(torch.randn(T * plan.A, generator=torch.Generator().manual_seed(2)))
+    flat = pl.params[0].cpu().view(T, plan.A).clone()
+    pl.iterate()
+    torch.cuda.synchronize()
+    P = _plan_params_by_fluent(m, plan, flat)
+    om = OracleModel(m, pl.compiled.relax_config())
+    layout = pl.train_fwd.program.noise_layout
+    noise = pl.train_noise.cpu().view(T, -1)
+    steps = [noise_as_list(layout, noise, t, B) for t in range(T)]
+
+    def pol(t, fls, pnoise):
+        return OP.slp_train_actions(m, P, t, stochastic=True, pnoise=pnoise, pooled_softmax=True,
+                                    softmax_weight=3.0)
+    pol.n_noise = len(OP.slp_policy_noise_spec(m, pooled_softmax=True))
+    ref = OP.rollout(om, pol, B, T, steps)
+    ent = sum(OP.slp_entropy(m, P, t, pooled_softmax=True, softmax_weight=3.0) for t in range(T))
+    loss = OP.mean_loss(ref["reward"], float(m.discount)) - 0.3 * ent
+    loss.backward()
+    from tests.helpers import pack_params
+    want = pack_params(m, {k: (v.grad if v.grad is not None else torch.zeros_like(v))
+                           for k, v in P.items()})
+    got = pl.grad_used[0].cpu().view(T, plan.A)
+    np.testing.assert_allclose(float(pl.train_loss[0]), float(loss.detach()), rtol=2e-5)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
+                               atol=1e-4 * float(want.abs().max()))
