@@ -198,6 +198,13 @@ int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg, const int
                                 const int32_t* seg_len, const int32_t* seg_norm, float eps,
                                 const float* x, const float* scale, const float* gy, float* gx,
                                 float* grad_scale_bias, float* workspace);
+/* Hidden-layer activation of the DRP kernels (planner.py:1128, 1358-1361): 0 tanh (default), 1 relu,
+ * 2 sigmoid, 3 softplus, 4 elu, 5 leaky_relu(0.01) -- the jax.nn functions whose derivative is a function
+ * of the output, so the adjoints need only the stored activation.  Process-wide; every launcher of a
+ * kernel with a fused activation (rk_sgemm / rk_tcgemm bias+activation and activation-adjoint epilogues,
+ * rk_drp_layer0, rk_drp_head_backward, rk_film_backward) reads it at launch and passes it to the kernel,
+ * so a captured CUDA graph keeps the value it was captured with. */
+int rk_drp_set_activation(int act);
 /* FiLM time conditioning of a hidden layer (planner.py:1083-1092, 1362-1363):
  * out[b][c] = gamma[c] z[b][c] + beta[c], gamma / beta [H] = the two Dense(time embedding) vectors of
  * the decision epoch.  backward: g = cotangent of out, z = the tanh output it was applied to;

@@ -446,7 +446,8 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
                 wrap_non_bool: bool = False, normalize: bool = False,
                 normalize_per_layer: bool = False, norm_eps: float = 1e-6,
                 softmax_weight: float = 1.0, sigma_entropy_grad: bool = False,
-                step: int = 0, time_embedding: Optional[str] = None, time_dim: int = 8):
+                step: int = 0, time_embedding: Optional[str] = None, time_dim: int = 8,
+                activation: str = "tanh"):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
     noise: action name -> [B, n] standard draws (Gumbel for boolean fluents under a binding
     max-nondef-actions, Logistic for other boolean fluents).  Returns (actions name ->
@@ -458,7 +459,7 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
                                                                    time_dim)
     for i in range(topology_len):
         layer = params[f"dense_{i}"]
-        h = torch.tanh(h @ layer["kernel"] + layer["bias"])
+        h = DRP_ACTIVATIONS[activation](h @ layer["kernel"] + layer["bias"])
         if t_emb is not None:           # FiLM (planner.py:1083-1092, 1362-1363)
             film = params[f"film_{i}"]
             gamma = t_emb @ film["gamma"]["kernel"] + film["gamma"]["bias"]
@@ -517,6 +518,13 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
     return actions, entropy
 
 
+# jax.nn functions a .cfg can name for the hidden layers (planner.py:144-150, 1358-1361)
+DRP_ACTIVATIONS = {
+    "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid,
+    "softplus": torch.nn.functional.softplus, "elu": torch.nn.functional.elu,
+    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01)}
+
+
 def drp_time_embedding(params, step: int, kind: str, dim: int = 8):
     """SinusoidalTimeEmbedding (planner.py:1108-1119): angles t * 10000^(-2 i / dim), (sin, cos)
     pairs interleaved and cut to the first `dim` entries; FixedTimeEmbedding (planner.py:1095-1105):
@@ -571,7 +579,8 @@ def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: 
                      sigmoid_weight: float = 1.0, wrap_non_bool: bool = False,
                      normalize: bool = False, normalize_per_layer: bool = False,
                      norm_eps: float = 1e-6, softmax_weight: float = 1.0, step: int = 0,
-                     time_embedding: Optional[str] = None, time_dim: int = 8):
+                     time_embedding: Optional[str] = None, time_dim: int = 8,
+                     activation: str = "tanh"):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
@@ -579,7 +588,7 @@ def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: 
                           sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool,
                           normalize=normalize, normalize_per_layer=normalize_per_layer,
                           norm_eps=norm_eps, softmax_weight=softmax_weight, step=step,
-                          time_embedding=time_embedding, time_dim=time_dim)
+                          time_embedding=time_embedding, time_dim=time_dim, activation=activation)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]

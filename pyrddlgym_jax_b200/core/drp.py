@@ -30,6 +30,12 @@ from .planner_base import JaxPlan, initializers
 from .program import PlanSpec, action_layout
 
 
+HOST_ACTIVATIONS = {
+    "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid,
+    "softplus": torch.nn.functional.softplus, "elu": torch.nn.functional.elu,
+    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01)}
+
+
 class SinusoidalTimeEmbedding:
     """Sinusoidal positional encoding of the decision epoch (planner.py:1108-1119)."""
     kind = "sin"
@@ -76,9 +82,13 @@ class JaxDeepReactivePolicy(JaxPlan):
                  time_embedding: Any = None, time_embedding_kwargs: Optional[Dict] = None) -> None:
         super().__init__()
         self._topology = list(topology) if topology is not None else [64, 64]
+        # the reference takes a jax.nn function (planner.py:1128, 144-150 resolve the .cfg name);
+        # here the name selects the epilogue of the layer kernels
         act = getattr(activation, "__name__", activation)
-        if act != "tanh":
-            raise NotImplementedError(f"activation <{act}>: only tanh is built (planner.py:1128)")
+        if act not in engine.ACTIVATIONS:
+            raise NotImplementedError(f"activation <{act}>: one of {sorted(engine.ACTIVATIONS)} "
+                                      "(planner.py:1128)")
+        self._activation = act
         self._wrap_non_bool = bool(wrap_non_bool)
         self._time_dependent = bool(time_dependent)
         if time_embedding is None:
@@ -115,7 +125,7 @@ class JaxDeepReactivePolicy(JaxPlan):
     def __str__(self) -> str:
         return (f"[INFO] policy hyper-parameters:\n"
                 f"    topology          ={self._topology}\n"
-                f"    activation_fn     =tanh\n"
+                f"    activation_fn     ={self._activation}\n"
                 f"    apply_input_norm  ={self._normalize}\n"
                 f"    input_norm_layerwise={self._normalize_per_layer}\n"
                 f"    input_norm_args   ={self._normalizer_kwargs}\n"
@@ -417,7 +427,8 @@ class JaxDeepReactivePolicy(JaxPlan):
         for i in range(len(self._topology)):
             off, r, c = self.seg[f"W{i}"]
             ob = self.seg[f"b{i}"][0]
-            h = torch.tanh(h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c])
+            h = HOST_ACTIVATIONS[self._activation](
+                h @ flat[off:off + r * c].reshape(r, c) + flat[ob:ob + c])
             if self.film:
                 emb = self.time_embedding_rows(flat, int(step) + 1)[int(step)].reshape(1, -1)
                 vec = lambda nm: (lambda o, rr, cc: flat[o:o + rr * cc].reshape(rr, cc))(*self.seg[nm])  # noqa
@@ -724,6 +735,7 @@ class DrpPipeline:
         params, grad = pl.params[p], pl.grad[p]
         fwd, bwd = pl.train_fwd, pl.train_bwd
         N = fwd.program.N
+        engine.drp_set_activation(plan._activation)
         self.refresh_transposes(params)          # W^T and the hi / lo splits of this update's W
         emb = self.film_tables(params) if self.film else None
         self.tape[:S * B].copy_(pl.s0_train)
@@ -816,6 +828,7 @@ class DrpPipeline:
         params = pl.params[p] if params is None else params
         te = pl.test_fwd
         N = te.program.N
+        engine.drp_set_activation(plan._activation)
         self.refresh_transposes(params)
         if self.film:
             self.film_tables(params)

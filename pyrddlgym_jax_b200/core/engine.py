@@ -28,7 +28,7 @@ EXPORTS = [
     "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
-    "rk_film_chunks", "rk_film_forward", "rk_film_backward",
+    "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_state_layernorm_forward.restype = ci
     lib.rk_state_layernorm_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf, cf, cf]
     lib.rk_state_layernorm_backward.restype = ci
+    lib.rk_drp_set_activation.argtypes = [ci]
+    lib.rk_drp_set_activation.restype = ci
     lib.rk_film_chunks.argtypes = [ci]
     lib.rk_film_chunks.restype = ci
     lib.rk_film_forward.argtypes = [vp, ci, ci, cf, cf, cf, cf]
@@ -296,6 +298,14 @@ def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls
         int(bool(wrap)) | (2 if sigma_entropy_grad else 0), _ptr(gact),
         _ptr(gheads)),
         "rk_drp_actions_backward")
+
+
+ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "elu": 4, "leaky_relu": 5}
+
+
+def drp_set_activation(name: str) -> None:
+    """Hidden-layer activation read by the DRP kernels' launchers (see include/rk.h)."""
+    _check(load_library().rk_drp_set_activation(ACTIVATIONS[name]), "rk_drp_set_activation")
 
 
 def film_chunks(B: int) -> int:

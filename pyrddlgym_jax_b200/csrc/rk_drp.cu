@@ -16,6 +16,17 @@
 #include <stdint.h>
 
 #include "../../include/rk.h"
+#include "rk_act.cuh"
+
+// hidden-layer activation of the DRP kernels (rk_drp_set_activation); read by every launcher and
+// passed to its kernel as an argument, so a captured graph keeps the value it was captured with
+int g_rk_act = RK_ACT_TANH;
+
+extern "C" int rk_drp_set_activation(int act) {
+  if (act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
+  g_rk_act = act;
+  return 0;
+}
 
 #define BM 128
 #define BN 128
@@ -135,9 +146,9 @@ rk_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
       float v = acc[i][j];
       if (!split) {                      // C_in + A*B first, then the layer epilogue
         if (accumulate) v += out[(size_t)m * ldo + n];
-        if (epi == 1 || epi == 2) v += bias[n];
-        if (epi == 2) v = tanhf(v);
-        if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+        if ((epi & 0xff) == 1 || (epi & 0xff) == 2) v += bias[n];
+        if ((epi & 0xff) == 2) v = rk_act_fn(epi >> 8, v);
+        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(epi >> 8, h); }
       }
       out[(size_t)m * ldo + n] = v;
     }
@@ -155,9 +166,9 @@ __global__ void rk_sgemm_reduce_kernel(int M, int N, int splits, const float* __
   float v = 0.f;
   for (int z = 0; z < splits; ++z) v += ws[(size_t)z * M * N + i];      // fixed order
   if (accumulate) v += C[(size_t)m * ldc + n];
-  if (epi == 1 || epi == 2) v += bias[n];
-  if (epi == 2) v = tanhf(v);
-  if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+  if ((epi & 0xff) == 1 || (epi & 0xff) == 2) v += bias[n];
+  if ((epi & 0xff) == 2) v = rk_act_fn(epi >> 8, v);
+  if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(epi >> 8, h); }
   C[(size_t)m * ldc + n] = v;
 }
 
@@ -226,9 +237,9 @@ rk_sgemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int lda
       float v = acc[i][j];
       if (!split) {
         if (accumulate) v += out[(size_t)m * ldo + n];
-        if (epi == 1 || epi == 2) v += bias[n];
-        if (epi == 2) v = tanhf(v);
-        if (epi == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= (1.f - h * h); }
+        if ((epi & 0xff) == 1 || (epi & 0xff) == 2) v += bias[n];
+        if ((epi & 0xff) == 2) v = rk_act_fn(epi >> 8, v);
+        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(epi >> 8, h); }
       }
       out[(size_t)m * ldo + n] = v;
     }
@@ -263,8 +274,8 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + bn - 1) / bn, (M + bm - 1) / bm, splits);
 #define RK_LAUNCH(KERNEL)                                                                     \
-  KERNEL<<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi,        \
-                               accumulate, kchunk, workspace)
+  KERNEL<<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux,             \
+                               epi | (g_rk_act << 8), accumulate, kchunk, workspace)
   if (bn == 16) {
     if (a_trans) RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, true>));
     else RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, false>));
@@ -279,7 +290,7 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   if (splits > 1) {
     const size_t total = (size_t)M * N;
     rk_sgemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        M, N, splits, workspace, C, ldc, bias, aux, ldaux, epi, accumulate);
+        M, N, splits, workspace, C, ldc, bias, aux, ldaux, epi | (g_rk_act << 8), accumulate);
   }
   return (int)cudaGetLastError();
 }
@@ -698,7 +709,7 @@ extern "C" int rk_drp_topk_backward(void* stream, int B, int A, int stochastic, 
 __global__ void __launch_bounds__(256)
 rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
                      const float* __restrict__ W0, const float* __restrict__ b0,
-                     float* __restrict__ out, float* __restrict__ xp) {
+                     float* __restrict__ out, float* __restrict__ xp, int act) {
   extern __shared__ float sh0[];
   float* Ws = sh0;                       // [D][H]
   float* xs = sh0 + (size_t)D * H;       // [64][D]
@@ -726,7 +737,7 @@ rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__
     for (int j = lane; j < H; j += 32) {
       float acc = 0.f;
       for (int d = 0; d < D; ++d) acc = fmaf(xs[r * D + d], Ws[d * H + j], acc);
-      out[(size_t)b * H + j] = tanhf(acc + b0[j]);
+      out[(size_t)b * H + j] = rk_act_fn(act, acc + b0[j]);
     }
   }
 }
@@ -736,7 +747,7 @@ rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__
 __global__ void __launch_bounds__(256)
 rk_drp_layer0_cols_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
                           const float* __restrict__ W0, const float* __restrict__ b0,
-                          float* __restrict__ out, float* __restrict__ xp) {
+                          float* __restrict__ out, float* __restrict__ xp, int act) {
   __shared__ __align__(16) float xs[64 * 16];
   __shared__ int foff[16], flen[16], fd[16];
   const int tid = threadIdx.x;
@@ -782,7 +793,7 @@ rk_drp_layer0_cols_kernel(int B, int D, int H, RkActSegs S, const float* __restr
             acc = fmaf(q.w, w[4 * v + 3], acc);
           }
         }
-        out[(size_t)(r0 + r) * H + tid] = tanhf(acc);
+        out[(size_t)(r0 + r) * H + tid] = rk_act_fn(act, acc);
       }
     }
     __syncthreads();
@@ -802,7 +813,7 @@ extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
     int grid = (B + 63) / 64;
     if (grid > 148 * 4) grid = 148 * 4;
     rk_drp_layer0_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0, out,
-                                                                      xp);
+                                                                      xp, g_rk_act);
     return (int)cudaGetLastError();
   }
   const size_t smem = ((size_t)D * H + 64 * (size_t)D) * sizeof(float);
@@ -813,7 +824,7 @@ extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
     if (ce != cudaSuccess) return (int)ce;
   }
   rk_drp_layer0_kernel<<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0,
-                                                                           out, xp);
+                                                                           out, xp, g_rk_act);
   return (int)cudaGetLastError();
 }
 
@@ -878,7 +889,7 @@ __global__ void rk_film_fwd_kernel(size_t n, int H, const float* __restrict__ z,
 __global__ void __launch_bounds__(256)
 rk_film_bwd_kernel(int B, int H, int rows_per_chunk, const float* g,
                    const float* __restrict__ z, const float* __restrict__ gamma, float* gz,
-                   float* __restrict__ ws) {
+                   float* __restrict__ ws, int act) {
   __shared__ float part[2][8][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane;
@@ -891,7 +902,7 @@ rk_film_bwd_kernel(int B, int H, int rows_per_chunk, const float* g,
       const float gv = g[i], zv = z[i];
       ag += gv * zv;
       ab += gv;
-      gz[i] = gv * gm * (1.f - zv * zv);
+      gz[i] = gv * gm * rk_act_grad(act, zv);
     }
   }
   part[0][warp][lane] = ag;
@@ -934,7 +945,7 @@ extern "C" int rk_film_backward(void* stream, int B, int H, const float* g, cons
   const int rpc = (B + chunks - 1) / chunks;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((H + 31) / 32, chunks);
-  rk_film_bwd_kernel<<<grid, 256, 0, st>>>(B, H, rpc, g, z, gamma, gz, workspace);
+  rk_film_bwd_kernel<<<grid, 256, 0, st>>>(B, H, rpc, g, z, gamma, gz, workspace, g_rk_act);
   rk_add_rows_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(chunks, 2 * H, workspace,
                                                           grad_gamma_beta, 1);
   return (int)cudaGetLastError();
@@ -964,7 +975,8 @@ __device__ __forceinline__ float cta_sum_in_warp_order(float v, float (*part)[33
 __global__ void __launch_bounds__(256)
 rk_drp_head_bwd_kernel(int B, int hl, int NH, const float* __restrict__ Hl,
                        const float* __restrict__ G, const float* __restrict__ Wh,
-                       float* __restrict__ gz, float* __restrict__ ws, int rows_per_chunk) {
+                       float* __restrict__ gz, float* __restrict__ ws, int rows_per_chunk,
+                       int act) {
   __shared__ float part[RK_FB_WARPS][33];
   extern __shared__ __align__(16) float Gs[];          // [rows_per_chunk][16], zero padded
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1012,7 +1024,7 @@ rk_drp_head_bwd_kernel(int B, int hl, int NH, const float* __restrict__ Hl,
         dw[4 * v + 3] = fmaf(h1, q.w, fmaf(h0, p.w, dw[4 * v + 3]));
       }
     }
-    const float v0 = z0 * (1.f - h0 * h0), v1 = z1 * (1.f - h1 * h1);
+    const float v0 = z0 * rk_act_grad(act, h0), v1 = z1 * rk_act_grad(act, h1);
     if (live) {
       gz[(size_t)b * hl + c] = v0;
       if (two) gz[(size_t)bb * hl + c] = v1;
@@ -1069,7 +1081,8 @@ extern "C" int rk_drp_head_backward(void* stream, int B, int hl, int NH, const f
   const int chunks = (B + rpc - 1) / rpc;
   dim3 grid((hl + 31) / 32, chunks);
   const size_t smem = (size_t)rpc * 16 * sizeof(float);     // <= 256 rows x 64 B
-  rk_drp_head_bwd_kernel<<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc);
+  rk_drp_head_bwd_kernel<<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc,
+                                                  g_rk_act);
   const int n = hl + hl * NH + NH;
   rk_add_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(chunks, n, workspace, grad_tail, 1);
   return (int)cudaGetLastError();

@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include "../../include/rk.h"
+#include "rk_act.cuh"
 
 #define TC_BM 128
 #define TC_BK 16          // fp32 elements per k-block = one 64-byte swizzle row
@@ -113,7 +114,7 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int epi,
                  float* __restrict__ C, int ldc, const float* __restrict__ bias,
-                 const float* __restrict__ aux, int ldaux, uint32_t tmem_cols) {
+                 const float* __restrict__ aux, int ldaux, uint32_t tmem_cols, int act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -247,15 +248,15 @@ rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int i = 0; i < 4; ++i) {
             float x = __uint_as_float(r[j + i]);
             if (epi == 1 || epi == 2) x += bias_s[c0 + j + i];
-            if (epi == 2) x = tanhf(x);
+            if (epi == 2) x = rk_act_fn(act, x);
             v[i] = x;
           }
           if (epi == 3) {
             const float4 h = *reinterpret_cast<const float4*>(ax + j);
-            v[0] *= (1.f - h.x * h.x);
-            v[1] *= (1.f - h.y * h.y);
-            v[2] *= (1.f - h.z * h.z);
-            v[3] *= (1.f - h.w * h.w);
+            v[0] *= rk_act_grad(act, h.x);
+            v[1] *= rk_act_grad(act, h.y);
+            v[2] *= rk_act_grad(act, h.z);
+            v[3] *= rk_act_grad(act, h.w);
           }
           *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -533,7 +534,7 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
   rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
-      mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols);
+      mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
   return (int)cudaGetLastError();
 }
 

@@ -18,3 +18,13 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _tanh_after_each_test():
+    """The DRP kernels' activation is process-wide (rk_drp_set_activation): tests that select
+    another one must not leak it into kernel-level tests that expect tanh epilogues."""
+    yield
+    mod = sys.modules.get("pyrddlgym_jax_b200.core.engine")
+    if mod is not None and getattr(mod, "_LIB", None) is not None:
+        mod.drp_set_activation("tanh")

@@ -1047,3 +1047,176 @@ def test_drp_film_update_matches_oracle(cuda_device, kind, topology, B, normaliz
     r_ref = out["reward"].numpy().T
     np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
                                atol=1e-5 * np.abs(r_ref).max())
+
+
+# ---- hidden-layer activations other than tanh (planner.py:1128, 1358-1361) -------------------------
+ACTS = ["relu", "sigmoid", "softplus", "elu", "leaky_relu"]
+
+
+@pytest.mark.parametrize("act", ACTS)
+def test_activation_host_policy_matches_oracle(act):
+    m = fixture_model("powergen")
+    plan = JaxDeepReactivePolicy(topology=[8, 8], activation=act)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, 5)
+    flat = plan.initial_params(torch.Generator().manual_seed(5)) * 3
+    tree = plan.params_to_pytree(flat)["params"]
+    fls = {"prevProd": torch.tensor([[1., 2., 0., .5, 3.]]), "temperature": torch.tensor([15.])}
+    want = OP.drp_test_actions(m, tree, fls, m.bounds, 2, activation=act)["curProd"].numpy().reshape(-1)
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        JaxDeepReactivePolicy(activation="gelu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", ACTS)
+def test_activation_epilogues_against_torch(cuda_device, act):
+    """Every kernel with a fused activation, under each activation: SIMT and tensor-core layer
+    (bias + activation, activation adjoint from the stored output), the first layer, the fused head
+    adjoint and the FiLM adjoint."""
+    from pyrddlgym_jax_b200.core import engine
+    dev = cuda_device
+    f = OP.DRP_ACTIVATIONS[act]
+    g = torch.Generator().manual_seed(3)
+    engine.drp_set_activation(act)
+
+    def dact(pre):      # derivative at the pre-activation, fp64
+        p = pre.double().clone().requires_grad_(True)
+        OP.DRP_ACTIVATIONS[act](p).sum().backward()
+        return p.grad
+    M, N, K = 200, 64, 48
+    A = torch.randn(M, K, generator=g) / np.sqrt(K) * 2
+    W = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    pre = A.double() @ W.double() + bias.double()
+    Y = torch.empty(M, N, device=dev)
+    engine.sgemm(engine.EPI_BIAS_TANH, M, N, K, A.to(dev), K, W.to(dev), N, Y, N, bias=bias.to(dev))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(Y.cpu().numpy(), f(pre).float().numpy(), rtol=2e-5, atol=2e-5)
+    # adjoint epilogue: dX = (dZ W2^T) * act'(stored output)
+    dZ = torch.randn(M, K, generator=g)
+    W2T = torch.randn(K, N, generator=g)
+    dX = torch.empty(M, N, device=dev)
+    engine.sgemm(engine.EPI_DTANH, M, N, K, dZ.to(dev), K, W2T.to(dev), N, dX, N, aux=Y, ldaux=N)
+    torch.cuda.synchronize()
+    want = (dZ.double() @ W2T.double()) * dact(pre)
+    keep = (pre.abs() > 1e-3).numpy()            # away from the kinks of relu / leaky_relu / elu
+    np.testing.assert_allclose(dX.cpu().numpy()[keep], want.float().numpy()[keep], rtol=2e-4, atol=2e-4)
+    # tensor-core layer
+    M2, N2, K2 = 384, 64, 64
+    A2 = torch.randn(M2, K2, generator=g) / 4
+    Wt = torch.randn(N2, K2, generator=g)                  # [out][in]
+    b2 = torch.randn(N2, generator=g)
+    hi, lo = torch.empty(N2 * K2, device=dev), torch.empty(N2 * K2, device=dev)
+    engine.tf32_split(Wt.to(dev).view(-1), hi, lo, N2 * K2)
+    Y2 = torch.empty(M2, N2, device=dev)
+    engine.tcgemm(2, M2, N2, K2, A2.to(dev), K2, hi, lo, K2, Y2, N2, bias=b2.to(dev))
+    torch.cuda.synchronize()
+    pre2 = A2.double() @ Wt.double().t() + b2.double()
+    np.testing.assert_allclose(Y2.cpu().numpy(), f(pre2).float().numpy(), rtol=2e-5, atol=2e-5)
+    dZ2 = torch.randn(M2, K2, generator=g)
+    dX2 = torch.empty(M2, N2, device=dev)
+    engine.tcgemm(3, M2, N2, K2, dZ2.to(dev), K2, hi, lo, K2, dX2, N2, aux=Y2, ldaux=N2)
+    torch.cuda.synchronize()
+    want2 = (dZ2.double() @ Wt.double().t()) * dact(pre2)
+    keep2 = (pre2.abs() > 1e-3).numpy()
+    np.testing.assert_allclose(dX2.cpu().numpy()[keep2], want2.float().numpy()[keep2], rtol=2e-4,
+                               atol=2e-4)
+    # first layer from fluent-major blocks (both kernels: D < 16 and D >= 16)
+    for segs in ([(0, 5), (5, 1)], [(0, 12), (12, 9)]):
+        B, H = 333, 96
+        D = sum(n for _, n in segs)
+        blocks = [torch.randn(B, n, generator=g) for _, n in segs]
+        X = torch.cat(blocks, 1)
+        W0, b0 = torch.randn(D, H, generator=g) / 3, torch.randn(H, generator=g)
+        out = torch.empty(B, H, device=dev)
+        engine.drp_layer0(B, D, H, segs, torch.cat([b.reshape(-1) for b in blocks]).to(dev),
+                          W0.to(dev), b0.to(dev), out, None)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(out.cpu().numpy(), f(X.double() @ W0.double() + b0.double()).float().numpy(),
+                                   rtol=2e-5, atol=2e-5)
+    # fused head adjoint: gz = (G Wh^T) * act'(Hl)
+    B, hl, NH = 500, 64, 6
+    preH = torch.randn(B, hl, generator=g)
+    Hl = f(preH)
+    G = torch.randn(B, NH, generator=g)
+    Wh = torch.randn(hl, NH, generator=g)
+    gz = torch.empty(B, hl, device=dev)
+    tail = torch.zeros(hl + hl * NH + NH, device=dev)
+    ws = torch.zeros(engine.drp_head_backward_ctas(B) * (hl + hl * NH + NH), device=dev)
+    engine.drp_head_backward(B, hl, NH, Hl.to(dev), G.to(dev), Wh.to(dev), gz, tail, ws)
+    torch.cuda.synchronize()
+    want = (G.double() @ Wh.double().t()) * dact(preH)
+    keepH = (preH.abs() > 1e-3).numpy()
+    np.testing.assert_allclose(gz.cpu().numpy()[keepH], want.float().numpy()[keepH], rtol=2e-4, atol=2e-4)
+    # FiLM adjoint
+    gamma = torch.randn(hl, generator=g)
+    gout = torch.randn(B, hl, generator=g)
+    gzf = gout.clone().to(dev)
+    dgb = torch.zeros(2 * hl, device=dev)
+    engine.film_backward(B, hl, gzf, Hl.to(dev), gamma.to(dev), gzf, dgb,
+                         torch.zeros(engine.film_chunks(B) * 2 * hl, device=dev))
+    torch.cuda.synchronize()
+    want = gout.double() * gamma.double() * dact(preH)
+    np.testing.assert_allclose(gzf.cpu().numpy()[keepH], want.float().numpy()[keepH], rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act,topology,B,film", [("relu", (16, 16), 23, False),
+                                                 ("softplus", (64, 64), 130, False),
+                                                 ("elu", (32, 16), 19, True),
+                                                 ("sigmoid", (64, 64, 32), 129, False)])
+def test_drp_activation_update_matches_oracle(cuda_device, act, topology, B, film):
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    T, L = 4, len(topology)
+    plan = JaxDeepReactivePolicy(topology=list(topology), activation=act, time_dependent=film)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+    tkw = dict(time_embedding="sin", time_dim=8) if film else {}
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              {"curProd": pol_noise[t].reshape(B, 5)}, 1.0, m.bounds, L, True,
+                              activation=act, step=t, **tkw)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    got = pl.grad[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    te = pl.test_fwd.program
+    tnoise = torch.randn(T, te.N * B, generator=g)
+    pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    out = OP.rollout(OracleModel(m, None), lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, m.bounds, L, activation=act, step=t, **tkw),
+        B, T, [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    r_ref = out["reward"].numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
