@@ -198,6 +198,15 @@ int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg, const int
                                 const int32_t* seg_len, const int32_t* seg_norm, float eps,
                                 const float* x, const float* scale, const float* gy, float* gx,
                                 float* grad_scale_bias, float* workspace);
+/* Static min-max scaling of the policy input (StaticNormalizer, planner.py:284-338):
+ * y = (x - lo[d]) / (hi[d] - lo[d]) per state word d (lo = 0, hi = 1 passes a word through);
+ * backward: gx += gy / (hi[d] - lo[d]).  Fluent-major state buffers, lo / hi [D] on the device. */
+int rk_state_scale_forward(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
+                           const int32_t* seg_len, const float* lo, const float* hi, const float* x,
+                           float* y);
+int rk_state_scale_backward(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
+                            const int32_t* seg_len, const float* lo, const float* hi,
+                            const float* gy, float* gx);
 /* Hidden-layer activation of the DRP kernels (planner.py:1128, 1358-1361): 0 tanh (default), 1 relu,
  * 2 sigmoid, 3 softplus, 4 elu, 5 leaky_relu(0.01) -- the jax.nn functions whose derivative is a function
  * of the output, so the adjoints need only the stored activation.  Process-wide; every launcher of a

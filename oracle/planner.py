@@ -381,12 +381,28 @@ def drp_norm_layers(model, normalize: bool, normalize_per_layer: bool):
     return [("norm", non_bool)]
 
 
+def static_normalizer_transform(fls, stats):
+    """StaticNormalizer.transform (planner.py:326-338): (values - lower) / (upper - lower) on the
+    fluents that have stats, the others unchanged."""
+    out = {}
+    for var, values in fls.items():
+        if stats is not None and var in stats:
+            lower = torch.as_tensor(np.asarray(stats[var][0], np.float32))
+            upper = torch.as_tensor(np.asarray(stats[var][1], np.float32))
+            out[var] = (values.to(REAL) - lower) / (upper - lower)
+        else:
+            out[var] = values
+    return out
+
+
 def drp_state_vector(model, params, fls, normalize: bool = False,
-                     normalize_per_layer: bool = False, eps: float = 1e-6):
+                     normalize_per_layer: bool = False, eps: float = 1e-6, preprocess=None):
     """DRPStateLayer (planner.py:1287-1320): ravel + concatenate the observed fluents (non-bool
     first), LayerNorm on the non-bool part (flax nn.LayerNorm: biased variance E[x^2] - E[x]^2,
     epsilon 1e-6, learned scale and bias under params['inputs'][name])."""
     B = next(iter(fls.values())).shape[0]
+    if preprocess is not None:          # planner.py:1293-1296: before everything else
+        fls = static_normalizer_transform(fls, preprocess)
     cols = {v: fls[v].reshape(B, -1).to(REAL) for v in drp_input_order(model)}
     for name, members in drp_norm_layers(model, normalize, normalize_per_layer):
         x = torch.cat([cols[v] for v in members], dim=1)
@@ -447,13 +463,13 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
                 normalize_per_layer: bool = False, norm_eps: float = 1e-6,
                 softmax_weight: float = 1.0, sigma_entropy_grad: bool = False,
                 step: int = 0, time_embedding: Optional[str] = None, time_dim: int = 8,
-                activation: str = "tanh"):
+                activation: str = "tanh", preprocess=None):
     """planner.py:1342-1449 + 1468-1476 for one decision epoch.  fls: name -> [B, *objs];
     noise: action name -> [B, n] standard draws (Gumbel for boolean fluents under a binding
     max-nondef-actions, Logistic for other boolean fluents).  Returns (actions name ->
     [B, *objs], entropy [B])."""
     B = next(iter(fls.values())).shape[0]
-    x = drp_state_vector(model, params, fls, normalize, normalize_per_layer, norm_eps)
+    x = drp_state_vector(model, params, fls, normalize, normalize_per_layer, norm_eps, preprocess)
     h = x
     t_emb = None if time_embedding is None else drp_time_embedding(params, step, time_embedding,
                                                                    time_dim)
@@ -580,7 +596,7 @@ def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: 
                      normalize: bool = False, normalize_per_layer: bool = False,
                      norm_eps: float = 1e-6, softmax_weight: float = 1.0, step: int = 0,
                      time_embedding: Optional[str] = None, time_dim: int = 8,
-                     activation: str = "tanh"):
+                     activation: str = "tanh", preprocess=None):
     """planner.py:1482-1499: train = 0, then threshold / round / clip to the fluent's range."""
     zeros = {v: torch.zeros(next(iter(fls.values())).shape[0], model.variable_size(v))
              for v in model.action_fluents}
@@ -588,7 +604,8 @@ def drp_test_actions(model, params, fls, bounds, topology_len: int, stochastic: 
                           sigmoid_weight=sigmoid_weight, wrap_non_bool=wrap_non_bool,
                           normalize=normalize, normalize_per_layer=normalize_per_layer,
                           norm_eps=norm_eps, softmax_weight=softmax_weight, step=step,
-                          time_embedding=time_embedding, time_dim=time_dim, activation=activation)
+                          time_embedding=time_embedding, time_dim=time_dim, activation=activation,
+                          preprocess=preprocess)
     out = {}
     for var, a in acts.items():
         prange = model.variable_ranges[var]

@@ -190,6 +190,21 @@ class JaxDeepReactivePolicy(JaxPlan):
         ref = [v for v in names if rddl.variable_ranges[v] != "bool"] + \
               [v for v in names if rddl.variable_ranges[v] == "bool"]
         self.input_perm = np.concatenate([np.arange(pos[v][0], pos[v][0] + pos[v][1]) for v in ref])
+        # optional state preprocessing before everything else (planner.py:1293-1296): per state word
+        # (x - lo) / (hi - lo); words without stats keep lo = 0, hi = 1
+        self.pre_lo = self.pre_hi = None
+        if preprocessor is not None:
+            preprocessor.compile(compiled)
+            stats = preprocessor.initialize()
+            lo_w, hi_w = np.zeros(self.D, np.float32), np.ones(self.D, np.float32)
+            for v, (lower, upper) in stats.items():
+                o, n = pos[v]
+                shape = rddl.variable_shape(v)
+                lo_w[o:o + n] = np.broadcast_to(lower, shape).reshape(-1)
+                hi_w[o:o + n] = np.broadcast_to(upper, shape).reshape(-1)
+            if stats:
+                self.pre_lo, self.pre_hi = lo_w, hi_w
+            self.hyperparams_extra = {preprocessor.HYPERPARAMS_KEY: stats}
         # input LayerNorm (planner.py:1259-1282, 1300-1319): `norm_layers` = [(flax name, fluents)]
         # in the reference's order, `norm_groups[f]` = group of state fluent f for the kernels
         # (0 = not normalised), `norm_perm[name]` = kernel positions of that module's scale / bias
@@ -408,6 +423,9 @@ class JaxDeepReactivePolicy(JaxPlan):
         """Test policy on one state (controllers' get_action, planner.py:3527): a handful of
         tiny mat-vecs on the host."""
         h = torch.as_tensor(state_vec, dtype=torch.float32).reshape(1, -1).clone()
+        if self.pre_lo is not None:
+            lo_w, hi_w = torch.from_numpy(self.pre_lo), torch.from_numpy(self.pre_hi)
+            h = (h - lo_w) / (hi_w - lo_w)
         if self.Dn:
             so, sb = self.seg["ln_scale"][0], self.seg["ln_bias"][0]
             words = {g: [] for g in range(1, len(self.norm_layers) + 1)}
@@ -545,11 +563,19 @@ class DrpPipeline:
         # input LayerNorm: normalised inputs of every step (operands of the first layer's weight
         # gradient), cotangent of the normalised input, per-CTA partials of [dscale | dbias]
         self.Dn = plan.Dn
+        self.pre = plan.pre_lo is not None
+        if self.Dn or self.pre:
+            self.gy = z(self.S * Bt)
         if self.Dn:
             self.xn = z(T, self.S * Bt)
-            self.gy = z(self.S * Bt)
             self.ln_ws = z(engine.state_layernorm_ctas(Bt) * 2 * self.Dn)
             self.t_xn = z(te.S * Be)
+        if self.pre:        # scaled inputs of every step (LayerNorm / first-layer operands)
+            self.pre_lo = torch.from_numpy(plan.pre_lo).to(dev)
+            self.pre_hi = torch.from_numpy(plan.pre_hi).to(dev)
+            self.xa = z(T, self.S * Bt)
+            self.gya = z(self.S * Bt)
+            self.t_xa = z(te.S * Be)
 
         # FiLM: conditioned activations of every step (inputs of the next layer), the per-step gamma /
         # beta vectors of this update and their cotangents [dgamma | dbeta]
@@ -743,9 +769,12 @@ class DrpPipeline:
             x = self.tape[t * S * B:(t + 1) * S * B]
             Ht = [Hl[t] for Hl in self.H]
             xin = x
+            if self.pre:
+                engine.state_scale(B, self.D, plan.state_segs, self.pre_lo, self.pre_hi, x, self.xa[t])
+                xin = self.xa[t]
             if self.Dn:
+                self.layernorm_forward(params, B, xin, self.xn[t])
                 xin = self.xn[t]
-                self.layernorm_forward(params, B, x, xin)
             self.mlp_forward(params, B, xin, Ht, self.heads[t], self.xp[t],
                              film=(t, [Hl[t] for Hl in self.Hf]) if self.film else None)
             engine.drp_actions_forward(
@@ -801,14 +830,27 @@ class DrpPipeline:
                     plan._softmax_output_weight, self.gact, self.gheads,
                     ent_coeff=self.ent_coeff, inv_batch=1.0 / (B * pl.world_size))
             film = (t, [Hl[t] for Hl in self.Hf]) if self.film else None
-            if self.Dn:     # MLP input cotangent -> gy, then gs += LayerNorm^T gy (+ dscale, dbias)
+            if self.Dn or self.pre:
+                # MLP input cotangent -> gy, then back through LayerNorm (+ dscale, dbias) and the
+                # static scaling into the state cotangent
                 self.gy.zero_()
-                self.mlp_backward(grad, B, self.xn[t], [Hl[t] for Hl in self.H], self.gy,
-                                  self.xp[t], params, film=film)
-                engine.state_layernorm_backward(
-                    B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps, x,
-                    self._W(params, "ln_scale"), self.gy, out, self._W(grad, "ln_scale"),
-                    self.ln_ws)
+                xin = self.xn[t] if self.Dn else self.xa[t]
+                self.mlp_backward(grad, B, xin, [Hl[t] for Hl in self.H], self.gy, self.xp[t], params,
+                                  film=film)
+                g_in = self.gy
+                if self.Dn:
+                    dst = out
+                    if self.pre:
+                        self.gya.zero_()
+                        dst = self.gya
+                    engine.state_layernorm_backward(
+                        B, self.D, plan.state_segs, plan.norm_groups, plan._norm_eps,
+                        self.xa[t] if self.pre else x, self._W(params, "ln_scale"), self.gy, dst,
+                        self._W(grad, "ln_scale"), self.ln_ws)
+                    g_in = dst
+                if self.pre:
+                    engine.state_scale(B, self.D, plan.state_segs, self.pre_lo, self.pre_hi, g_in, out,
+                                       backward=True)
             else:
                 self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params,
                                   film=film)
@@ -842,6 +884,10 @@ class DrpPipeline:
                 for (off, n), is_int in zip(plan.state_segs, plan.state_is_int):
                     blk = x[off * B:(off + n) * B]
                     xin[off * B:(off + n) * B].copy_(blk.view(torch.int32) if is_int else blk)
+            if self.pre:
+                engine.state_scale(B, self.D, plan.state_segs, self.pre_lo, self.pre_hi, xin,
+                                   self.t_xa)
+                xin = self.t_xa
             if self.Dn:
                 self.layernorm_forward(params, B, xin, self.t_xn)
                 xin = self.t_xn

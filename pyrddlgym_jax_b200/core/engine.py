@@ -29,6 +29,7 @@ EXPORTS = [
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
     "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
+    "rk_state_scale_forward", "rk_state_scale_backward",
 ]
 
 
@@ -102,6 +103,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_state_layernorm_forward.restype = ci
     lib.rk_state_layernorm_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf, cf, cf]
     lib.rk_state_layernorm_backward.restype = ci
+    lib.rk_state_scale_forward.argtypes = [vp, ci, ci, ci, vp, vp, cf, cf, cf, cf]
+    lib.rk_state_scale_forward.restype = ci
+    lib.rk_state_scale_backward.argtypes = [vp, ci, ci, ci, vp, vp, cf, cf, cf, cf]
+    lib.rk_state_scale_backward.restype = ci
     lib.rk_drp_set_activation.argtypes = [ci]
     lib.rk_drp_set_activation.restype = ci
     lib.rk_film_chunks.argtypes = [ci]
@@ -298,6 +303,15 @@ def drp_actions_backward(B, A, stochastic, segs, heads, noise, train, lo, hi, ls
         int(bool(wrap)) | (2 if sigma_entropy_grad else 0), _ptr(gact),
         _ptr(gheads)),
         "rk_drp_actions_backward")
+
+
+def state_scale(B, D, segs, lo, hi, x, y, backward: bool = False):
+    """forward: y = (x - lo) / (hi - lo) per state word; backward: y += x / (hi - lo)."""
+    n, off, ln = _segs(segs)
+    lib = load_library()
+    fn = lib.rk_state_scale_backward if backward else lib.rk_state_scale_forward
+    _check(fn(_stream(), B, D, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
+              _ptr(lo), _ptr(hi), _ptr(x), _ptr(y)), "rk_state_scale")
 
 
 ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "elu": 4, "leaky_relu": 5}

@@ -41,7 +41,8 @@ Kwargs = Dict[str, Any]
 # on jax / optax; those modules do not exist here, so the names map to local objects)
 # =====================================================================================
 
-from .planner_base import JaxPlan, _Initializer, initializers  # noqa: E402,F401
+from .planner_base import (JaxPlan, Preprocessor, StaticNormalizer,  # noqa: E402,F401
+                           _Initializer, initializers)
 
 
 OPTIMIZERS = {"sgd": "sgd", "rmsprop": "rmsprop", "adam": "adam"}
@@ -485,11 +486,12 @@ class JaxBackpropPlanner:
         self.reduce_on_plateau_kwargs = None if reduce_on_plateau_kwargs is None \
             else plateau_kwargs(reduce_on_plateau_kwargs)
         for name, val in (("line_search_kwargs", line_search_kwargs),
-                          ("critic", critic), ("preprocessor", preprocessor),
+                          ("critic", critic),
                           ("dashboard", dashboard)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
         self.use_symlog_reward = bool(use_symlog_reward)
+        self.preprocessor = preprocessor
         self.rddl = rddl
         self.plan = plan
         self.batch_size_train = batch_size_train
@@ -542,7 +544,10 @@ class JaxBackpropPlanner:
         self.compiled.compile()
         self.test_compiled = JaxRDDLCompiler(rddl)
         self.test_compiled.compile()
-        self.plan.compile(self.compiled, self.test_compiled, self._action_bounds, self.horizon)
+        # only the DRP input layer reads the preprocessor (planner.py:1293-1296)
+        preprocessor = self.preprocessor if getattr(self.plan, "kind", "slp") == "drp" else None
+        self.plan.compile(self.compiled, self.test_compiled, self._action_bounds, self.horizon,
+                          preprocessor=preprocessor)
         spec = self.plan.spec
         gamma = float(rddl.discount)
         self.gamma = gamma

@@ -1337,6 +1337,52 @@ extern "C" int rk_state_layernorm_backward(void* stream, int B, int D, int n_seg
   return (int)cudaGetLastError();
 }
 
+// ---- static min-max scaling of the policy input (StaticNormalizer, planner.py:284-338) ----------
+// y = (x - lo[d]) / (hi[d] - lo[d]) per state word d (the caller passes lo = 0, hi = 1 for the words
+// that are not scaled: exact pass-through); backward: gx += gy / (hi[d] - lo[d]).  Fluent-major
+// buffers, one thread per (rollout, word) of a fluent block: fully coalesced.
+__global__ void rk_state_scale_kernel(int B, RkActSegs S, const float* __restrict__ lo,
+                                      const float* __restrict__ hi, const float* __restrict__ x,
+                                      float* __restrict__ y, int backward) {
+  const size_t total = (size_t)(S.off[S.n - 1] + S.len[S.n - 1]) * B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int f = 0;
+    while (f + 1 < S.n && i >= (size_t)S.off[f + 1] * B) ++f;
+    const int d = S.off[f] + (int)((i - (size_t)S.off[f] * B) % (size_t)S.len[f]);
+    const float w = hi[d] - lo[d];
+    if (backward) y[i] += x[i] / w;
+    else y[i] = (x[i] - lo[d]) / w;
+  }
+}
+
+static int rk_state_scale(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
+                          const int32_t* seg_len, const float* lo, const float* hi, const float* x,
+                          float* y, int backward) {
+  if (B <= 0 || lo == nullptr || hi == nullptr || x == nullptr || y == nullptr) return RK_E_BADARG;
+  RkActSegs S;
+  int rc = make_segs(D, n_seg, seg_off, seg_len, &S);
+  if (rc != 0) return rc;
+  size_t blocks = ((size_t)D * B + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rk_state_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, S, lo, hi, x, y,
+                                                                            backward);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_state_scale_forward(void* stream, int B, int D, int n_seg,
+                                      const int32_t* seg_off, const int32_t* seg_len,
+                                      const float* lo, const float* hi, const float* x, float* y) {
+  return rk_state_scale(stream, B, D, n_seg, seg_off, seg_len, lo, hi, x, y, 0);
+}
+
+extern "C" int rk_state_scale_backward(void* stream, int B, int D, int n_seg,
+                                       const int32_t* seg_off, const int32_t* seg_len,
+                                       const float* lo, const float* hi, const float* gy,
+                                       float* gx) {
+  return rk_state_scale(stream, B, D, n_seg, seg_off, seg_len, lo, hi, gy, gx, 1);
+}
+
 // ---- skinny products with N <= 16 (action heads, state-cotangent blocks) ----------------------
 // out[b][n] = (accumulate ? out[b][n] : 0) + sum_k A[b][k] * W[k][n] (+ bias[n]).
 // One warp owns FOUR rows at a time: lanes stride over k (coalesced 128-byte reads of A, read

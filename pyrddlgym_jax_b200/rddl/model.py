@@ -145,6 +145,7 @@ class RDDLLiftedModel:
 
         self.levels = self._compute_levels()
         self.bounds = self._extract_action_bounds()
+        self.state_bounds = self._extract_state_bounds()
 
     # ---------------------------------------------------------------------------------
     def variable_shape(self, name: str) -> Tuple[int, ...]:
@@ -216,22 +217,36 @@ class RDDLLiftedModel:
             self._bounds_from(pre, [], bounds, eval_static)
         return bounds
 
-    def _bounds_from(self, expr, scope, bounds, eval_static):
+    def _extract_state_bounds(self) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
+        """Box bounds of the state fluents from state-invariants and action-preconditions (the
+        RDDLConstraints bounds that StaticNormalizer reads, planner.py:300-312)."""
+        bounds = {}
+        for s in self.state_fluents:
+            shape = self.variable_shape(s)
+            bounds[s] = (np.full(shape, -np.inf, dtype=np.float32),
+                         np.full(shape, np.inf, dtype=np.float32))
+        from .trace import eval_static
+        for expr in list(self.invariants) + list(self.preconditions):
+            self._bounds_from(expr, [], bounds, eval_static, self.state_fluents)
+        return bounds
+
+    def _bounds_from(self, expr, scope, bounds, eval_static, names=None):
+        names = self.action_fluents if names is None else names
         fam, op = expr.etype
         if fam == "aggregation" and op == "forall":
             *tv, body = expr.args
-            self._bounds_from(body, scope + list(tv), bounds, eval_static)
+            self._bounds_from(body, scope + list(tv), bounds, eval_static, names)
             return
         if fam == "boolean" and op in ("^", "&"):
             for a in expr.args:
-                self._bounds_from(a, scope, bounds, eval_static)
+                self._bounds_from(a, scope, bounds, eval_static, names)
             return
         if fam != "relational" or op not in ("<=", ">=", "<", ">"):
             return
         lhs, rhs = expr.args
         for act_side, other, sense in ((lhs, rhs, op), (rhs, lhs, {"<=": ">=", ">=": "<=",
                                                                     "<": ">", ">": "<"}[op])):
-            if act_side.etype[0] != "pvar" or act_side.args[0] not in self.action_fluents:
+            if act_side.etype[0] != "pvar" or act_side.args[0] not in names:
                 continue
             name, params = act_side.args
             params = params or []

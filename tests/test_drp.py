@@ -1220,3 +1220,140 @@ def test_drp_activation_update_matches_oracle(cuda_device, act, topology, B, fil
     r_ref = out["reward"].numpy().T
     np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
                                atol=1e-5 * np.abs(r_ref).max())
+
+
+# ---- StaticNormalizer preprocessor (planner.py:284-338, 1293-1296) ---------------------------------
+INVARIANT_RDDL = """
+domain bounds_toy {
+    types { tank : object; };
+    pvariables {
+        CAP(tank) : { non-fluent, real, default = 10.0 };
+        level(tank) : { state-fluent, real, default = 1.0 };
+        heat : { state-fluent, real, default = 0.0 };
+        free : { state-fluent, real, default = 0.0 };
+        pump(tank) : { action-fluent, real, default = 0.0 };
+    };
+    cpfs {
+        level'(?t) = level(?t) + pump(?t);
+        heat' = heat;
+        free' = free;
+    };
+    reward = sum_{?t : tank} [ level(?t) ];
+    state-invariants {
+        forall_{?t : tank} [ level(?t) >= 0.5 ];
+        forall_{?t : tank} [ level(?t) <= CAP(?t) ];
+        heat >= -2.0;
+        3.0 >= heat;
+        free >= 0.0;
+    };
+    action-preconditions {
+        forall_{?t : tank} [ pump(?t) >= 0.0 ];
+        forall_{?t : tank} [ pump(?t) <= 1.0 ];
+    };
+}
+non-fluents nf { domain = bounds_toy; objects { tank : {t1, t2}; };
+    non-fluents { CAP(t2) = 20.0; }; }
+instance inst { domain = bounds_toy; non-fluents = nf; max-nondef-actions = pos-inf;
+    horizon = 3; discount = 1.0; }
+"""
+
+
+def test_static_normalizer_reads_state_invariants():
+    from pyrddlgym_jax_b200.core.planner import StaticNormalizer
+    from pyrddlgym_jax_b200.rddl.model import load_model
+    m = load_model(INVARIANT_RDDL)
+    np.testing.assert_array_equal(m.state_bounds["level"][0], [0.5, 0.5])
+    np.testing.assert_array_equal(m.state_bounds["level"][1], [10.0, 20.0])
+    assert m.state_bounds["heat"] == (np.float32(-2.0), np.float32(3.0)) or \
+        (float(m.state_bounds["heat"][0]) == -2.0 and float(m.state_bounds["heat"][1]) == 3.0)
+    pre = StaticNormalizer(fluent_bounds={"free": (1.0, 5.0)})
+    pre.compile(logic.DefaultJaxRDDLCompilerWithGrad(m))
+    stats = pre.initialize()
+    assert set(stats) == {"level", "heat", "free"}      # 'free' only through the user's bounds
+    out = pre.transform({"level": torch.tensor([[5.25, 10.25]]), "heat": torch.tensor([0.5])}, stats)
+    np.testing.assert_allclose(out["level"].numpy(), [[0.5, 0.5]], rtol=1e-6)
+    np.testing.assert_allclose(out["heat"].numpy(), [0.5], rtol=1e-6)
+    # a half-open box is not used
+    pre2 = StaticNormalizer()
+    pre2.compile(logic.DefaultJaxRDDLCompilerWithGrad(m))
+    assert set(pre2.initialize()) == {"level", "heat"}
+
+
+POWERGEN_BOUNDS = {"prevProd": (np.zeros(5, np.float32), np.array([5., 6., 7., 8., 10.], np.float32)),
+                   "temperature": (-30.0, 40.0)}
+
+
+def test_preprocessor_host_policy_matches_oracle():
+    from pyrddlgym_jax_b200.core.planner import StaticNormalizer
+    m = fixture_model("powergen")
+    plan = JaxDeepReactivePolicy(topology=[8, 8], normalize=True)
+    pre = StaticNormalizer(fluent_bounds=POWERGEN_BOUNDS)
+    plan.compile(logic.DefaultJaxRDDLCompilerWithGrad(m), JaxRDDLCompiler(m), {}, 5, preprocessor=pre)
+    flat = plan.initial_params(torch.Generator().manual_seed(5)) * 3
+    tree = plan.params_to_pytree(flat)["params"]
+    fls = {"prevProd": torch.tensor([[1., 2., 0., .5, 3.]]), "temperature": torch.tensor([15.])}
+    want = OP.drp_test_actions(m, tree, fls, m.bounds, 2, normalize=True,
+                               preprocess=pre.initialize())["curProd"].numpy().reshape(-1)
+    vec = np.concatenate([fls[s].numpy().reshape(-1) for s in m.state_fluents])
+    got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalize", [False, True])
+def test_drp_preprocessor_update_matches_oracle(cuda_device, normalize):
+    """preprocessor=StaticNormalizer: min-max scaled inputs (before the optional LayerNorm) in the
+    train and test policies; rewards, loss, gradient and test rollouts against the oracle."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner, StaticNormalizer
+    m = fixture_model("powergen")
+    T, B = 4, 27
+    plan = JaxDeepReactivePolicy(topology=[16, 16], normalize=normalize)
+    pre = StaticNormalizer(fluent_bounds=POWERGEN_BOUNDS)
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None, preprocessor=pre,
+                            use_cuda_graph=False)
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(11)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    stats = pre.initialize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              {"curProd": pol_noise[t].reshape(B, 5)}, 1.0, m.bounds, 2, True,
+                              normalize=normalize, preprocess=stats)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    np.testing.assert_allclose(pl.grad[0].cpu().numpy(), want, rtol=1e-4,
+                               atol=1e-4 * np.abs(want).max())
+    te = pl.test_fwd.program
+    tnoise = torch.randn(T, te.N * B, generator=g)
+    pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    out = OP.rollout(OracleModel(m, None), lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in m.state_fluents}, m.bounds, 2, normalize=normalize,
+        preprocess=stats), B, T, [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    r_ref = out["reward"].numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
