@@ -402,11 +402,30 @@ def _utility_fn(name: str, kwargs: Kwargs) -> Callable[[torch.Tensor], torch.Ten
             mask = (r <= torch.quantile(r.detach(), kwargs["alpha"])).to(r.dtype)
             return (mask * r).sum() / torch.clamp(mask.sum(), min=1.)
         return f
+    if name == "var":           # sj.percentile in its default (hard, linear interpolation) mode
+        return lambda r: torch.quantile(r, kwargs["alpha"])
+    if name == "cvar":
+        def f(r):
+            var = torch.quantile(r, kwargs["alpha"])
+            return var - torch.relu(var - r).mean() / kwargs["alpha"]
+        return f
+    if name == "expectile":     # planner.py:2213-2220: fixed-point iterations, differentiated through
+        def f(r):
+            alpha, val = kwargs["alpha"], r.mean()
+            for _ in range(int(kwargs.get("max_iter", 30))):
+                w = torch.where(r > val, torch.full_like(r, alpha), torch.full_like(r, 1.0 - alpha))
+                val = (w * r).sum() / w.sum()
+            return val
+        return f
+    if name == "gini":          # planner.py:2223-2229: mean - gamma * 2 * mean(relu(r_j - r_i))
+        return lambda r: r.mean() - kwargs["gamma"] * 2.0 * torch.relu(
+            r.unsqueeze(0) - r.unsqueeze(1)).mean()
     raise NotImplementedError(f"Utility function <{name}> is not supported.")
 
 
 UTILITY_LOOKUP = {k: k for k in ("mean", "mean_var", "mean_std", "mean_semivar", "mean_semidev",
-                                 "sharpe", "entropic", "exponential", "cvar_ste")}
+                                 "sharpe", "entropic", "exponential", "var", "cvar", "cvar_ste",
+                                 "expectile", "gini")}
 
 
 # =====================================================================================

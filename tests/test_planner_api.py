@@ -620,3 +620,46 @@ def test_stochastic_wrap_softmax_update_matches_oracle(cuda_device):
     np.testing.assert_allclose(float(pl.train_loss[0]), float(loss.detach()), rtol=2e-5)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4,
                                atol=1e-4 * float(want.abs().max()))
+
+
+# ---- utilities (planner.py:2161-2247) ----------------------------------------------------------------
+def test_utilities_known_answers():
+    """Closed forms on a small return vector, written from the reference's formulas with numpy."""
+    from pyrddlgym_jax_b200.core.planner import UTILITY_LOOKUP, _utility_fn
+    assert set(UTILITY_LOOKUP) == {"mean", "mean_var", "mean_std", "mean_semivar", "mean_semidev",
+                                   "sharpe", "entropic", "exponential", "var", "cvar", "cvar_ste",
+                                   "expectile", "gini"}
+    r = np.array([3.0, -1.0, 4.0, 1.0, -5.0, 9.0, 2.0, 6.0], np.float64)
+    t = torch.tensor(r, dtype=torch.float32)
+    mu, beta, alpha = r.mean(), 0.7, 0.25
+    down = np.minimum(0.0, r - mu)
+    var = np.percentile(r, 100 * alpha)
+    mask = r <= var
+    ex = mu
+    for _ in range(30):
+        w = np.where(r > ex, alpha, 1 - alpha)
+        ex = (w * r).sum() / w.sum()
+    want = {
+        ("mean_var", "beta"): mu - 0.5 * beta * r.var(),
+        ("mean_std", "beta"): mu - 0.5 * beta * r.std(),
+        ("mean_semivar", "beta"): mu - 0.5 * beta * (down ** 2).mean(),
+        ("mean_semidev", "beta"): mu - 0.5 * beta * np.sqrt((down ** 2).mean()),
+        ("entropic", "beta"): -np.log(np.mean(np.exp(-beta * r))) / beta,
+        ("var", "alpha"): var,
+        ("cvar", "alpha"): var - np.maximum(var - r, 0).mean() / alpha,
+        ("cvar_ste", "alpha"): (mask * r).sum() / max(1, mask.sum()),
+        ("expectile", "alpha"): ex,
+        ("gini", "gamma"): mu - 0.3 * 2.0 * np.maximum(-(r[:, None] - r[None, :]), 0).mean(),
+    }
+    for (name, key), w in want.items():
+        val = {"beta": beta, "alpha": alpha, "gamma": 0.3}[key]
+        got = float(_utility_fn(name, {key: val})(t))
+        assert abs(got - w) <= 1e-5 * max(1.0, abs(w)), (name, got, w)
+    got = float(_utility_fn("sharpe", {"risk_free": 0.5})(t))
+    assert abs(got - (mu - 0.5) / (r.std() + 1e-12)) < 1e-5
+    # every utility is differentiable w.r.t. the returns (what the adjoint kernel is fed)
+    for name, kw in (("cvar", {"alpha": 0.25}), ("expectile", {"alpha": 0.3}), ("gini", {"gamma": 0.5}),
+                     ("var", {"alpha": 0.4})):
+        x = t.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(_utility_fn(name, kw)(x), x)
+        assert torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
