@@ -38,7 +38,7 @@ extern "C" int rk_drp_set_activation(int act) {
 //   A_TRANS = 0: A stored [M][K] (lda >= K);  1: A stored [K][M] (lda >= M)
 //   split-K: blockIdx.z handles K range [z*kchunk, (z+1)*kchunk); partial tiles go to
 //   `out` = workspace + z*M*N (ldc = N) and the epilogue is applied by the reduce kernel.
-template <bool A_TRANS>
+template <bool A_TRANS, int ACT_CT>
 __global__ void __launch_bounds__(256)
 rk_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                 const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
@@ -147,8 +147,8 @@ rk_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
       if (!split) {                      // C_in + A*B first, then the layer epilogue
         if (accumulate) v += out[(size_t)m * ldo + n];
         if ((epi & 0xff) == 1 || (epi & 0xff) == 2) v += bias[n];
-        if ((epi & 0xff) == 2) v = rk_act_fn(epi >> 8, v);
-        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(epi >> 8, h); }
+        if ((epi & 0xff) == 2) v = rk_act_fn(ACT_CT >= 0 ? ACT_CT : (epi >> 8), v);
+        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(ACT_CT >= 0 ? ACT_CT : (epi >> 8), h); }
       }
       out[(size_t)m * ldo + n] = v;
     }
@@ -177,7 +177,7 @@ __global__ void rk_sgemm_reduce_kernel(int M, int N, int splits, const float* __
 // products are bound by streaming the [B][h] operand once.  16 x 16 threads, thread (tx, ty)
 // owns rows ty + 16 i and columns tx + 16 j of a BM_ x BN_ tile.
 #define SBK 16
-template <int BM_, int BN_, bool A_TRANS>
+template <int BM_, int BN_, bool A_TRANS, int ACT_CT>
 __global__ void __launch_bounds__(256)
 rk_sgemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                        const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
@@ -238,8 +238,8 @@ rk_sgemm_skinny_kernel(int M, int N, int K, const float* __restrict__ A, int lda
       if (!split) {
         if (accumulate) v += out[(size_t)m * ldo + n];
         if ((epi & 0xff) == 1 || (epi & 0xff) == 2) v += bias[n];
-        if ((epi & 0xff) == 2) v = rk_act_fn(epi >> 8, v);
-        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(epi >> 8, h); }
+        if ((epi & 0xff) == 2) v = rk_act_fn(ACT_CT >= 0 ? ACT_CT : (epi >> 8), v);
+        if ((epi & 0xff) == 3) { const float h = aux[(size_t)m * ldaux + n]; v *= rk_act_grad(ACT_CT >= 0 ? ACT_CT : (epi >> 8), h); }
       }
       out[(size_t)m * ldo + n] = v;
     }
@@ -273,18 +273,27 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   const int splits = (K + kchunk - 1) / kchunk;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + bn - 1) / bn, (M + bm - 1) / bm, splits);
-#define RK_LAUNCH(KERNEL)                                                                     \
-  KERNEL<<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux,             \
-                               epi | (g_rk_act << 8), accumulate, kchunk, workspace)
+  // the tanh build of each kernel has the activation as a compile-time constant
+#define RK_LAUNCH(KERNEL, ...)                                                                \
+  do {                                                                                        \
+    if (g_rk_act == RK_ACT_TANH)                                                              \
+      KERNEL<__VA_ARGS__, RK_ACT_TANH><<<grid, 256, 0, st>>>(                                 \
+          M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi, accumulate, kchunk,         \
+          workspace);                                                                         \
+    else                                                                                      \
+      KERNEL<__VA_ARGS__, -1><<<grid, 256, 0, st>>>(                                          \
+          M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi | (g_rk_act << 8),           \
+          accumulate, kchunk, workspace);                                                     \
+  } while (0)
   if (bn == 16) {
-    if (a_trans) RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, true>));
-    else RK_LAUNCH((rk_sgemm_skinny_kernel<128, 16, false>));
+    if (a_trans) RK_LAUNCH(rk_sgemm_skinny_kernel, 128, 16, true);
+    else RK_LAUNCH(rk_sgemm_skinny_kernel, 128, 16, false);
   } else if (bm == 16) {
-    if (a_trans) RK_LAUNCH((rk_sgemm_skinny_kernel<16, 128, true>));
-    else RK_LAUNCH((rk_sgemm_skinny_kernel<16, 128, false>));
+    if (a_trans) RK_LAUNCH(rk_sgemm_skinny_kernel, 16, 128, true);
+    else RK_LAUNCH(rk_sgemm_skinny_kernel, 16, 128, false);
   } else {
-    if (a_trans) RK_LAUNCH(rk_sgemm_kernel<true>);
-    else RK_LAUNCH(rk_sgemm_kernel<false>);
+    if (a_trans) RK_LAUNCH(rk_sgemm_kernel, true);
+    else RK_LAUNCH(rk_sgemm_kernel, false);
   }
 #undef RK_LAUNCH
   if (splits > 1) {
@@ -706,10 +715,12 @@ extern "C" int rk_drp_topk_backward(void* stream, int B, int A, int stochastic, 
 // concatenation of the fluent blocks ([B][n_f] at word offset off_f * B).  D is small (the state
 // dimension), so the kernel is bound by writing out (B x H floats once).  Optionally also packs
 // xp[b][0..D) = x[b][:], xp[b][D] = 1: the operand of the fused weight+bias gradient GEMM.
+template <int ACT_CT>
 __global__ void __launch_bounds__(256)
 rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
                      const float* __restrict__ W0, const float* __restrict__ b0,
-                     float* __restrict__ out, float* __restrict__ xp, int act) {
+                     float* __restrict__ out, float* __restrict__ xp, int act_rt) {
+  const int act = ACT_CT >= 0 ? ACT_CT : act_rt;
   extern __shared__ float sh0[];
   float* Ws = sh0;                       // [D][H]
   float* xs = sh0 + (size_t)D * H;       // [64][D]
@@ -744,10 +755,12 @@ rk_drp_layer0_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__
 
 // D <= 16, H <= 256: a thread owns one output column (its column of W0 in registers), the CTA walks
 // over 64-row tiles of the state staged in shared memory as [64][16] (float4 broadcast reads).
+template <int ACT_CT>
 __global__ void __launch_bounds__(256)
 rk_drp_layer0_cols_kernel(int B, int D, int H, RkActSegs S, const float* __restrict__ x,
                           const float* __restrict__ W0, const float* __restrict__ b0,
-                          float* __restrict__ out, float* __restrict__ xp, int act) {
+                          float* __restrict__ out, float* __restrict__ xp, int act_rt) {
+  const int act = ACT_CT >= 0 ? ACT_CT : act_rt;
   __shared__ __align__(16) float xs[64 * 16];
   __shared__ int foff[16], flen[16], fd[16];
   const int tid = threadIdx.x;
@@ -812,19 +825,30 @@ extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
   if (D < 16 && H <= 256) {       // (D < 16: slot D of a tile row carries the packed 1)
     int grid = (B + 63) / 64;
     if (grid > 148 * 4) grid = 148 * 4;
-    rk_drp_layer0_cols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0, out,
-                                                                      xp, g_rk_act);
+    if (g_rk_act == RK_ACT_TANH)
+      rk_drp_layer0_cols_kernel<RK_ACT_TANH><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+    else
+      rk_drp_layer0_cols_kernel<-1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          B, D, H, S, x, W0, b0, out, xp, g_rk_act);
     return (int)cudaGetLastError();
   }
   const size_t smem = ((size_t)D * H + 64 * (size_t)D) * sizeof(float);
   if (smem > 200 * 1024) return RK_E_SMEM;
   if (smem > 48 * 1024) {
-    cudaError_t ce = cudaFuncSetAttribute(rk_drp_layer0_kernel,
+    cudaError_t ce = cudaFuncSetAttribute(rk_drp_layer0_kernel<RK_ACT_TANH>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(rk_drp_layer0_kernel<-1>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
   }
-  rk_drp_layer0_kernel<<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(B, D, H, S, x, W0, b0,
-                                                                           out, xp, g_rk_act);
+  if (g_rk_act == RK_ACT_TANH)
+    rk_drp_layer0_kernel<RK_ACT_TANH><<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(
+        B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+  else
+    rk_drp_layer0_kernel<-1><<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(
+        B, D, H, S, x, W0, b0, out, xp, g_rk_act);
   return (int)cudaGetLastError();
 }
 
@@ -972,11 +996,13 @@ __device__ __forceinline__ float cta_sum_in_warp_order(float v, float (*part)[33
   return s;
 }
 
+template <int ACT_CT>
 __global__ void __launch_bounds__(256)
 rk_drp_head_bwd_kernel(int B, int hl, int NH, const float* __restrict__ Hl,
                        const float* __restrict__ G, const float* __restrict__ Wh,
                        float* __restrict__ gz, float* __restrict__ ws, int rows_per_chunk,
-                       int act) {
+                       int act_rt) {
+  const int act = ACT_CT >= 0 ? ACT_CT : act_rt;
   __shared__ float part[RK_FB_WARPS][33];
   extern __shared__ __align__(16) float Gs[];          // [rows_per_chunk][16], zero padded
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1081,8 +1107,12 @@ extern "C" int rk_drp_head_backward(void* stream, int B, int hl, int NH, const f
   const int chunks = (B + rpc - 1) / rpc;
   dim3 grid((hl + 31) / 32, chunks);
   const size_t smem = (size_t)rpc * 16 * sizeof(float);     // <= 256 rows x 64 B
-  rk_drp_head_bwd_kernel<<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc,
-                                                  g_rk_act);
+  if (g_rk_act == RK_ACT_TANH)
+    rk_drp_head_bwd_kernel<RK_ACT_TANH><<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace,
+                                                                 rpc, g_rk_act);
+  else
+    rk_drp_head_bwd_kernel<-1><<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc,
+                                                        g_rk_act);
   const int n = hl + hl * NH + NH;
   rk_add_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(chunks, n, workspace, grad_tail, 1);
   return (int)cudaGetLastError();

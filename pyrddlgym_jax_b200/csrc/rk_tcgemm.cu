@@ -109,12 +109,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 
 // epi: 2 = bias + tanh, 3 = * (1 - aux^2), 1 = bias, 0 = none
 #define TC_THREADS 320     // producer warp, MMA warp, 8 converter / epilogue warps
+// ACT_CT: the activation as a compile-time constant (the tanh build keeps a straight-line
+// epilogue), or -1 = the run-time value `act_rt`
+template <int ACT_CT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rk_tcgemm_kernel(const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmB_hi,
                  const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int epi,
                  float* __restrict__ C, int ldc, const float* __restrict__ bias,
-                 const float* __restrict__ aux, int ldaux, uint32_t tmem_cols, int act) {
+                 const float* __restrict__ aux, int ldaux, uint32_t tmem_cols, int act_rt) {
+  const int act = ACT_CT >= 0 ? ACT_CT : act_rt;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -526,15 +530,22 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
   const size_t smem = TC_STAGES * stage + 128 + (size_t)N * 4 + 1024;   // barriers, bias, slack
   static int configured = 0;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(rk_tcgemm_kernel,
+    cudaError_t ce = cudaFuncSetAttribute(rk_tcgemm_kernel<RK_ACT_TANH>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(rk_tcgemm_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              227 * 1024);
     if (ce != cudaSuccess) return (int)ce;
     configured = 1;
   }
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
-  rk_tcgemm_kernel<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
-      mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
+  if (g_rk_act == RK_ACT_TANH)
+    rk_tcgemm_kernel<RK_ACT_TANH><<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
+        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
+  else
+    rk_tcgemm_kernel<-1><<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
+        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
   return (int)cudaGetLastError();
 }
 
