@@ -380,52 +380,116 @@ class NoImprovementStoppingRule(JaxPlannerStoppingRule):
 # return vector only (never on the rollout path)
 # =====================================================================================
 
+def entropic_utility(returns: torch.Tensor, beta: float) -> torch.Tensor:
+    return -(torch.logsumexp(-beta * returns, 0) - np.log(returns.numel())) / beta
+
+
+def mean_variance_utility(returns: torch.Tensor, beta: float) -> torch.Tensor:
+    return returns.mean() - 0.5 * beta * returns.var(unbiased=False)
+
+
+def mean_deviation_utility(returns: torch.Tensor, beta: float) -> torch.Tensor:
+    return returns.mean() - 0.5 * beta * returns.std(unbiased=False)
+
+
+def mean_semideviation_utility(returns: torch.Tensor, beta: float) -> torch.Tensor:
+    mu = returns.mean()
+    return mu - 0.5 * beta * torch.sqrt(torch.clamp(returns - mu, max=0.).square().mean())
+
+
+def mean_semivariance_utility(returns: torch.Tensor, beta: float) -> torch.Tensor:
+    mu = returns.mean()
+    return mu - 0.5 * beta * torch.clamp(returns - mu, max=0.).square().mean()
+
+
+def sharpe_utility(returns: torch.Tensor, risk_free: float = 0.0, eps: float = 1e-12) -> torch.Tensor:
+    return (returns.mean() - risk_free) / (returns.std(unbiased=False) + eps)
+
+
+def var_utility(returns: torch.Tensor, alpha: float) -> torch.Tensor:
+    """sj.percentile in its default (hard, linear interpolation) mode."""
+    return torch.quantile(returns, alpha)
+
+
+def cvar_utility(returns: torch.Tensor, alpha: float) -> torch.Tensor:
+    var = torch.quantile(returns, alpha)
+    return var - torch.relu(var - returns).mean() / alpha
+
+
+def cvar_ste_utility(returns: torch.Tensor, alpha: float) -> torch.Tensor:
+    mask = (returns <= torch.quantile(returns.detach(), alpha)).to(returns.dtype)
+    return (mask * returns).sum() / torch.clamp(mask.sum(), min=1.)
+
+
+def expectile_utility(returns: torch.Tensor, alpha: float, max_iter: int = 30) -> torch.Tensor:
+    """planner.py:2213-2220: fixed-point iterations from the mean, differentiated through."""
+    val = returns.mean()
+    for _ in range(int(max_iter)):
+        w = torch.where(returns > val, torch.full_like(returns, alpha),
+                        torch.full_like(returns, 1.0 - alpha))
+        val = (w * returns).sum() / w.sum()
+    return val
+
+
+def gini_utility(returns: torch.Tensor, gamma: float) -> torch.Tensor:
+    """planner.py:2223-2229: mean - gamma * 2 * mean_ij relu(r_j - r_i)."""
+    return returns.mean() - gamma * 2.0 * torch.relu(
+        returns.unsqueeze(0) - returns.unsqueeze(1)).mean()
+
+
+# the reference's table (planner.py:2233-2247); 'mean' is handled by the loss kernel
+UTILITY_LOOKUP = {
+    "mean": torch.mean,
+    "mean_var": mean_variance_utility,
+    "mean_std": mean_deviation_utility,
+    "mean_semivar": mean_semivariance_utility,
+    "mean_semidev": mean_semideviation_utility,
+    "sharpe": sharpe_utility,
+    "entropic": entropic_utility,
+    "exponential": entropic_utility,
+    "var": var_utility,
+    "cvar": cvar_utility,
+    "cvar_ste": cvar_ste_utility,
+    "expectile": expectile_utility,
+    "gini": gini_utility,
+}
+
+
 def _utility_fn(name: str, kwargs: Kwargs) -> Callable[[torch.Tensor], torch.Tensor]:
-    if name == "mean_var":
-        return lambda r: r.mean() - 0.5 * kwargs["beta"] * r.var(unbiased=False)
-    if name == "mean_std":
-        return lambda r: r.mean() - 0.5 * kwargs["beta"] * r.std(unbiased=False)
-    if name == "mean_semivar":
-        return lambda r: r.mean() - 0.5 * kwargs["beta"] * torch.clamp(
-            r - r.mean(), max=0.).square().mean()
-    if name == "mean_semidev":
-        return lambda r: r.mean() - 0.5 * kwargs["beta"] * torch.sqrt(
-            torch.clamp(r - r.mean(), max=0.).square().mean())
-    if name in ("entropic", "exponential"):
-        return lambda r: -(torch.logsumexp(-kwargs["beta"] * r, 0)
-                           - np.log(r.numel())) / kwargs["beta"]
-    if name == "sharpe":
-        return lambda r: (r.mean() - kwargs.get("risk_free", 0.0)) / (
-            r.std(unbiased=False) + kwargs.get("eps", 1e-12))
-    if name == "cvar_ste":
-        def f(r):
-            mask = (r <= torch.quantile(r.detach(), kwargs["alpha"])).to(r.dtype)
-            return (mask * r).sum() / torch.clamp(mask.sum(), min=1.)
-        return f
-    if name == "var":           # sj.percentile in its default (hard, linear interpolation) mode
-        return lambda r: torch.quantile(r, kwargs["alpha"])
-    if name == "cvar":
-        def f(r):
-            var = torch.quantile(r, kwargs["alpha"])
-            return var - torch.relu(var - r).mean() / kwargs["alpha"]
-        return f
-    if name == "expectile":     # planner.py:2213-2220: fixed-point iterations, differentiated through
-        def f(r):
-            alpha, val = kwargs["alpha"], r.mean()
-            for _ in range(int(kwargs.get("max_iter", 30))):
-                w = torch.where(r > val, torch.full_like(r, alpha), torch.full_like(r, 1.0 - alpha))
-                val = (w * r).sum() / w.sum()
-            return val
-        return f
-    if name == "gini":          # planner.py:2223-2229: mean - gamma * 2 * mean(relu(r_j - r_i))
-        return lambda r: r.mean() - kwargs["gamma"] * 2.0 * torch.relu(
-            r.unsqueeze(0) - r.unsqueeze(1)).mean()
-    raise NotImplementedError(f"Utility function <{name}> is not supported.")
+    if name not in UTILITY_LOOKUP:
+        raise NotImplementedError(f"Utility function <{name}> is not supported.")
+    fn = UTILITY_LOOKUP[name]
+    return lambda r: fn(r, **kwargs)
 
 
-UTILITY_LOOKUP = {k: k for k in ("mean", "mean_var", "mean_std", "mean_semivar", "mean_semidev",
-                                 "sharpe", "entropic", "exponential", "var", "cvar", "cvar_ste",
-                                 "expectile", "gini")}
+def get_action_info(compiled, user_bounds, horizon: int):
+    """Shapes, box bounds and finite-ness masks of the action fluents (planner.py:423-472):
+    shapes[name] = (horizon, *objects); bounds[name] = (None, None) for booleans, (0, n - 1) for
+    enums, the RDDL / user box otherwise; cond_lists[name] = [both finite, lower only, upper only,
+    neither] as boolean masks (the branches of the box wrap, planner.py:620-628)."""
+    rddl = compiled.rddl
+    shapes, bounds, cond_lists = {}, {}, {}
+    for name in rddl.action_fluents:
+        prange = rddl.variable_ranges[name]
+        if prange not in ("bool", "int", "real") and prange not in rddl.enum_types:
+            raise TypeError(f"Invalid range <{prange}> of action-fluent <{name}>.")
+        shape = tuple(rddl.variable_shape(name))
+        shapes[name] = (horizon,) + shape
+        if prange == "bool":
+            bounds[name] = (None, None)
+            continue
+        if prange in rddl.enum_types:
+            lower = np.zeros(shape)
+            upper = np.ones(shape) * (len(rddl.type_to_objects[prange]) - 1)
+        else:
+            lower, upper = rddl.bounds[name]
+        lower, upper = (user_bounds or {}).get(name, (lower, upper))
+        lower = np.broadcast_to(np.asarray(lower, np.float32), shape).copy()
+        upper = np.broadcast_to(np.asarray(upper, np.float32), shape).copy()
+        lf, uf = np.isfinite(lower), np.isfinite(upper)
+        cond_lists[name] = [lf & uf, lf & ~uf, ~lf & uf, ~lf & ~uf]
+        bounds[name] = (lower, upper)
+    return shapes, bounds, cond_lists
 
 
 # =====================================================================================

@@ -663,3 +663,22 @@ def test_utilities_known_answers():
         x = t.clone().requires_grad_(True)
         (g,) = torch.autograd.grad(_utility_fn(name, kw)(x), x)
         assert torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
+
+
+def test_get_action_info_matches_reference_contract():
+    """planner.py:423-472: shapes carry the horizon, booleans have no box, user bounds override the
+    RDDL ones, cond_lists are the four finite-ness masks."""
+    from pyrddlgym_jax_b200.core.planner import get_action_info
+    m = fixture_model("powergen")
+    comp = logic.DefaultJaxRDDLCompilerWithGrad(m)
+    shapes, bounds, conds = get_action_info(comp, {}, 7)
+    assert shapes == {"curProd": (7, 5)}
+    lo, hi = bounds["curProd"]
+    np.testing.assert_array_equal(lo, np.asarray(m.bounds["curProd"][0], np.float32) * np.ones(5, np.float32))
+    assert [c.shape for c in conds["curProd"]] == [(5,)] * 4
+    assert np.all(np.sum(np.stack(conds["curProd"]), 0) == 1)        # exactly one branch per element
+    _, b2, c2 = get_action_info(comp, {"curProd": (-np.inf, 3.0)}, 7)
+    assert np.all(b2["curProd"][1] == 3.0) and np.all(c2["curProd"][2])
+    w = fixture_model("wildfire")
+    _, bw, cw = get_action_info(logic.DefaultJaxRDDLCompilerWithGrad(w), {}, 3)
+    assert all(v == (None, None) for v in bw.values()) and cw == {}
