@@ -92,6 +92,7 @@ class Lowerer:
         self.g = Graph()
         self.sg = StepGraph(self.g, relaxed=self.relaxed)
         self._mparam_index: Dict[Tuple[int, str], V] = {}
+        self.mparam_ops: Dict[Tuple[int, str], str] = {}       # key -> 'family op' of its expression
 
     # ---------------------------------------------------------------------------------
     def dtype_of_range(self, prange: str) -> str:
@@ -107,6 +108,7 @@ class Lowerer:
                             slot=len(self.sg.mparams))
             self.sg.mparams.append((key, float(default), v))
             self._mparam_index[key] = v
+            self.mparam_ops[key] = " ".join(str(x) for x in expr.etype)
         return v
 
     def sizes(self, scope) -> Tuple[int, ...]:

@@ -682,3 +682,19 @@ def test_get_action_info_matches_reference_contract():
     w = fixture_model("wildfire")
     _, bw, cw = get_action_info(logic.DefaultJaxRDDLCompilerWithGrad(w), {}, 3)
     assert all(v == (None, None) for v in bw.values()) and cw == {}
+
+
+def test_compiler_relaxation_info():
+    """model_parameter_info / overriden_ops_info (compiler.py:804-823): one entry per relaxed
+    expression with its weight, grouped by the mixin class that relaxes it."""
+    c = logic.DefaultJaxRDDLCompilerWithGrad(fixture_model("reservoir"), sigmoid_weight=7.0)
+    info = c.model_parameter_info()
+    assert info and all(set(v) == {"id", "rddl_op", "init_value"} for v in info.values())
+    assert all(v["init_value"] == {"sigmoid_weight": 7.0} for v in info.values()
+               if v["rddl_op"].startswith("relational"))
+    over = c.overriden_ops_info()
+    assert "SigmoidRelational" in over
+    assert sorted(i for ids in over["SigmoidRelational"].values() for i in ids) == \
+        sorted(k for k, v in info.items() if v["rddl_op"].startswith("relational"))
+    w = logic.DefaultJaxRDDLCompilerWithGrad(fixture_model("wildfire"))
+    assert list(w.overriden_ops_info()) == ["ReparameterizedSigmoidBernoulli"]
