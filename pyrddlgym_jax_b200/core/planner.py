@@ -1220,6 +1220,48 @@ class JaxBackpropPlanner:
         for p in range(self.parallel_updates):
             self._update_kernels(p)
 
+    def as_optimization_problem(self, key: Optional[int] = None, critic_params=None,
+                                print_values: bool = False):
+        """(loss_fn, grad_fn, guess_1d, unravel_fn) for off-the-shelf optimisers such as scipy
+        (planner.py:2962-3031): loss and gradient of the relaxed train objective as functions of a
+        1-D parameter vector, each call on fresh noise like the reference splits its key per call;
+        unravel_fn maps the vector to the plan's parameter pytree.  Action constraints are the
+        caller's, as in the reference."""
+        if self.parallel_updates > 1:
+            raise ValueError("Cannot compile static optimization problem when parallel_updates "
+                             "is not None.")
+        if self.world_size > 1:
+            raise NotImplementedError("as_optimization_problem runs on one GPU")
+        if critic_params is not None:
+            raise NotImplementedError("critic is not supported by the B200 planner yet")
+        if key is None:
+            key = round(time.time() * 1000) % (2 ** 31)
+        self.initialize(int(key))
+        guess = self.params[0].detach().cpu().numpy().astype(np.float64)
+
+        def _evaluate(params_1d):
+            flat = torch.as_tensor(np.asarray(params_1d, dtype=np.float32).reshape(-1))
+            self.params[0].copy_(flat.to(self.device))
+            self.redraw_noise(force=True)
+            self._train_grad_kernels(0)
+            torch.cuda.synchronize(self.device)
+            return float(self._train_loss_tmp[0]), \
+                self.grad[0].detach().cpu().numpy().astype(np.float64)
+
+        def _loss_function(params_1d):
+            loss, _ = _evaluate(params_1d)
+            if print_values:
+                print(f"Loss: {loss:.6f}")
+            return loss
+
+        def _grad_function(params_1d):
+            return _evaluate(params_1d)[1]
+
+        def _unravel(params_1d):
+            flat = torch.as_tensor(np.asarray(params_1d, dtype=np.float32).reshape(-1))
+            return self.plan.params_to_pytree(self._plan_view(flat))
+        return _loss_function, _grad_function, guess, _unravel
+
     def test_loss(self):
         for p in range(self.parallel_updates):
             self._test_kernels(p)

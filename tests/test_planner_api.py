@@ -698,3 +698,31 @@ def test_compiler_relaxation_info():
         sorted(k for k, v in info.items() if v["rddl_op"].startswith("relational"))
     w = logic.DefaultJaxRDDLCompilerWithGrad(fixture_model("wildfire"))
     assert list(w.overriden_ops_info()) == ["ReparameterizedSigmoidBernoulli"]
+
+
+@pytest.mark.gpu
+def test_as_optimization_problem(cuda_device):
+    """planner.py:2962-3031: loss / gradient of the train objective as functions of a 1-D vector.
+    Quadcopter is deterministic, so a small step against the gradient must lower the loss and the
+    directional derivative must agree with a central difference."""
+    m = fixture_model("quadcopter")
+    pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=12,
+                            pgpe=None, use_cuda_graph=False)
+    loss_fn, grad_fn, guess, unravel = pl.as_optimization_problem(key=4)
+    assert guess.shape == (12 * pl.A,) and guess.dtype == np.float64
+    f0, g0 = loss_fn(guess), grad_fn(guess)
+    assert np.isfinite(f0) and g0.shape == guess.shape and np.abs(g0).max() > 0
+    d = g0 / np.linalg.norm(g0)
+    eps = 1e-2
+    slope = float(g0 @ d)
+    noise = 1e-6 * max(1.0, abs(f0))            # fp32 rounding of the loss value
+    if eps * slope > 50 * noise:                # the step is visible above the rounding
+        fd = (loss_fn(guess + eps * d) - loss_fn(guess - eps * d)) / (2 * eps)
+        assert abs(fd - slope) <= 5e-2 * abs(slope) + 50 * noise / eps, (fd, slope)
+        assert loss_fn(guess - eps * d) < f0
+    tree = unravel(guess)
+    assert tuple(tree["real"]["thrust"]["mu"].shape) == (12, 4)
+    with pytest.raises(ValueError):
+        JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=12,
+                           pgpe=None, parallel_updates=2,
+                           use_cuda_graph=False).as_optimization_problem(key=1)
