@@ -1220,6 +1220,64 @@ class JaxBackpropPlanner:
         for p in range(self.parallel_updates):
             self._update_kernels(p)
 
+    # ---- summaries printed by optimize() (planner.py:2563-2628) ----------------------------------
+    def summarize_system(self) -> str:
+        name = torch.cuda.get_device_name(self.device) if torch.cuda.is_available() else "n/a"
+        return (f"\nStarting the B200 planner behind the JaxPlan API on device {self.device} ({name}), "
+                f"rank {self.rank} of {self.world_size}\n")
+
+    def summarize_relaxations(self) -> str:
+        """Table of the non-differentiable operations and the classes that relax them."""
+        try:
+            info = getattr(self.compiled, "overriden_ops_info", lambda: {})()
+        except Exception:           # a summary must never stop an optimisation
+            info = {}
+        if not info:
+            return ""
+        out = ("[INFO] Some RDDL operations are non-differentiable and will be approximated "
+               "as follows:\n")
+        for klass, ops in info.items():
+            out += f"    {klass}:\n"
+            for op, ids in ops.items():
+                out += f"        {op} [{len(ids)} relaxed]\n"
+        return out
+
+    def summarize_hyperparameters(self) -> str:
+        utility = self.utility if isinstance(self.utility, str) else getattr(
+            self.utility, "__name__", str(self.utility))
+        out = (f"[INFO] objective hyper-parameters:\n"
+               f"    utility_fn         ={utility}\n"
+               f"    utility args       ={self.utility_kwargs}\n"
+               f"    use_symlog         ={self.use_symlog_reward}\n"
+               f"    use_critic         =False\n"
+               f"    lookahead          ={self.horizon}\n"
+               f"    user_action_bounds ={self._action_bounds}\n"
+               f"    start_entropy_coeff={self.start_entropy_coeff}\n"
+               f"    end_entropy_coeff  ={self.end_entropy_coeff}\n"
+               f"[INFO] optimizer hyper-parameters:\n"
+               f"    optimizer         ={self.optimizer_name}\n"
+               f"    optimizer args    ={self.optimizer_kwargs}\n"
+               f"    clip_gradient     ={self.clip_grad}\n"
+               f"    line_search_kwargs=None\n"
+               f"    noise_kwargs      ={self.noise_kwargs}\n"
+               f"    ema_decay         ={self.ema_decay}\n"
+               f"    reduce_on_plateau ={self.reduce_on_plateau_kwargs}\n"
+               f"    batch_size_train  ={self.batch_size_train}\n"
+               f"    batch_size_test   ={self.batch_size_test}\n"
+               f"    steps_per_update  ={self.steps_per_update}\n"
+               f"    parallel_updates  ={self.parallel_updates}\n"
+               f"    preprocessor      ={self.preprocessor}\n")
+        out += str(self.plan)
+        if self.use_pgpe:
+            out += str(self.pgpe)
+        out += "test compiler:\n"
+        for k, v in self.test_compiled.get_kwargs().items():
+            out += f"    {k}={v}\n"
+        out += "train compiler:\n"
+        for k, v in self.compiled.get_kwargs().items():
+            out += f"    {k}={v}\n"
+        return out
+
     def as_optimization_problem(self, key: Optional[int] = None, critic_params=None,
                                 print_values: bool = False):
         """(loss_fn, grad_fn, guess_1d, unravel_fn) for off-the-shelf optimisers such as scipy
@@ -1316,6 +1374,20 @@ class JaxBackpropPlanner:
             key = int(np.asarray(key).ravel()[-1])
         if model_params is not None:
             self.set_model_params(model_params)
+        if print_summary:           # planner.py:3132-3134
+            print(self.summarize_system())
+            print(self.summarize_relaxations())
+        if print_hyperparams:       # planner.py:3135-3147
+            print(self.summarize_hyperparameters())
+            print(f"[INFO] optimize call hyper-parameters:\n"
+                  f"    PRNG key           ={key}\n"
+                  f"    max_iterations     ={epochs}\n"
+                  f"    max_seconds        ={train_seconds}\n"
+                  f"    model_params       ={model_params}\n"
+                  f"    policy_hyper_params={policy_hyperparams}\n"
+                  f"    override_subs_dict ={subs is not None}\n"
+                  f"    provide_param_guess={guess is not None}\n"
+                  f"    test_rolling_window={test_rolling_window}\n")
         self.initialize(key, subs, guess)
         P = self.parallel_updates
         hyper = policy_hyperparams if policy_hyperparams is not None else \
