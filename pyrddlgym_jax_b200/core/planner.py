@@ -1392,6 +1392,8 @@ class JaxBackpropPlanner:
         P = self.parallel_updates
         hyper = policy_hyperparams if policy_hyperparams is not None else \
             {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents}
+        if policy_hyperparams is None:      # preprocessor statistics travel with them (P:1519-1521)
+            hyper.update(getattr(self.plan, "hyperparams_extra", {}))
         best_params = self.plan.params_to_pytree(self._plan_view(self.params[0]).clone().cpu())
         best_loss, best_grad, best_index = np.inf, None, 0
         last_iter_improve = 0
