@@ -726,3 +726,16 @@ def test_as_optimization_problem(cuda_device):
         JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=12,
                            pgpe=None, parallel_updates=2,
                            use_cuda_graph=False).as_optimization_problem(key=1)
+
+
+@pytest.mark.gpu
+def test_optimize_prints_summaries(cuda_device, capsys):
+    """optimize() with the reference's default print_summary=True / print_hyperparams=True
+    (planner.py:3132-3147): system line, relaxation table, hyper-parameter listing."""
+    m = fixture_model("reservoir")
+    pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=8, rollout_horizon=5, pgpe=None)
+    cb = pl.optimize(key=1, epochs=3, print_progress=False, print_hyperparams=True)
+    out = capsys.readouterr().out
+    assert "SigmoidRelational" in out and "relational" in out
+    assert "optimizer hyper-parameters" in out and "batch_size_train  =8" in out
+    assert "Summary of optimization" in out and cb["iteration"] == 2
