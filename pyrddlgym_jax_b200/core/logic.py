@@ -42,40 +42,43 @@ class JaxRDDLCompilerWithGrad(JaxRDDLCompiler):
         kwargs["sample_callback"] = self.sample_callback
         return kwargs
 
-    # ---- information about the relaxed operations (compiler.py:804-823) ---------------------
-    def _relaxed_ops(self):
-        """(expression id, parameter name) -> ('family op', default) of every model parameter the
-        relaxed step graph reads, from a lowering of the model with externally supplied actions."""
-        if getattr(self, "_relaxed_ops_cache", None) is None:
+    # ---- information about the relaxed operations (compiler.py:804-832) ---------------------
+    def _lowered(self):
+        """A lowering of the relaxed model with externally supplied actions (cached): the source
+        of the model parameters and of the relaxed / exact bookkeeping."""
+        if getattr(self, "_lowered_cache", None) is None:
             from .program import PlanSpec
-            low = self.builder(PlanSpec(kind="external", bounds=self.rddl.bounds), True).low
-            self._relaxed_ops_cache = {key: (low.mparam_ops.get(key, "policy"), default)
-                                       for key, default, _ in low.sg.mparams}
-        return self._relaxed_ops_cache
+            self._lowered_cache = self.builder(
+                PlanSpec(kind="external", bounds=self.rddl.bounds), True).low
+        return self._lowered_cache
 
     def model_parameter_info(self) -> Dict[int, Dict[str, Any]]:
         """id -> {'id', 'rddl_op', 'init_value': {parameter name: value}} (compiler.py:804-814)."""
+        low = self._lowered()
         out: Dict[int, Dict[str, Any]] = {}
-        for (eid, name), (op, default) in self._relaxed_ops().items():
+        for (eid, name), default, _ in low.sg.mparams:
+            op = low.mparam_ops.get((eid, name), "policy")
             out.setdefault(eid, {"id": eid, "rddl_op": op, "init_value": {}})["init_value"][name] = default
         return out
 
     def overriden_ops_info(self) -> Dict[str, Dict[str, List[int]]]:
         """relaxation class -> {rddl op: [expression ids]} (compiler.py:816-823): the class is the
-        mixin of this compiler's MRO whose constructor owns the parameter the expression reads."""
-        import inspect
+        mixin of this compiler's MRO that declares the relaxation family of the operation."""
         owner: Dict[str, str] = {}
         for klass in type(self).__mro__:
-            init = vars(klass).get("__init__")
-            if init is None or klass in (JaxRDDLCompilerWithGrad, JaxRDDLCompiler, object):
-                continue
-            for kw in inspect.signature(init).parameters:
-                owner.setdefault(kw, klass.__name__)
+            for family in vars(klass).get("_RELAX", {}):
+                owner.setdefault(family, klass.__name__)
         out: Dict[str, Dict[str, List[int]]] = {}
-        for (eid, name), (op, _) in self._relaxed_ops().items():
-            ids = out.setdefault(owner.get(name, type(self).__name__), {}).setdefault(op, [])
-            if eid not in ids:
-                ids.append(eid)
+        for eid, (family, op) in self._lowered().relaxed_ops.items():
+            out.setdefault(owner.get(family, type(self).__name__), {}).setdefault(op, []).append(eid)
+        return out
+
+    def exact_ops_info(self) -> Dict[str, List[int]]:
+        """rddl op -> [expression ids] of the relaxable operations evaluated exactly, because their
+        arguments are not fluent or the compiler has no relaxation for them (compiler.py:825-832)."""
+        out: Dict[str, List[int]] = {}
+        for eid, (_, op) in self._lowered().exact_ops.items():
+            out.setdefault(op, []).append(eid)
         return out
 
     def relax_config(self) -> Dict[str, Any]:

@@ -93,6 +93,10 @@ class Lowerer:
         self.sg = StepGraph(self.g, relaxed=self.relaxed)
         self._mparam_index: Dict[Tuple[int, str], V] = {}
         self.mparam_ops: Dict[Tuple[int, str], str] = {}       # key -> 'family op' of its expression
+        # bookkeeping for overriden_ops_info / exact_ops_info (compiler.py:816-832): expression id ->
+        # (relaxation family, 'family op') of the relaxable operations that were relaxed / kept exact
+        self.relaxed_ops: Dict[int, Tuple[str, str]] = {}
+        self.exact_ops: Dict[int, Tuple[str, str]] = {}
 
     # ---------------------------------------------------------------------------------
     def dtype_of_range(self, prange: str) -> str:
@@ -210,10 +214,48 @@ class Lowerer:
         self.sg.errs.append((ERR_BITS[name], self.materialise(violation, sizes)))
 
     # ==================================================================================
+    _RELAX_FAMILY = {
+        "relational": lambda op: "relational",
+        "boolean": lambda op: "logic",
+        "aggregation": lambda op: {"forall": "logic", "exists": "logic", "argmin": "argmax",
+                                   "argmax": "argmax"}.get(op),
+        "func": lambda op: {"sgn": "sgn", "floor": "floor", "ceil": "floor", "div": "floor",
+                            "mod": "floor", "round": "round"}.get(op),
+        "control": lambda op: {"if": "if", "switch": "switch"}.get(op),
+        "randomvar": lambda op: {"Bernoulli": "bernoulli", "Geometric": "geometric",
+                                 "Poisson": "poisson", "NegativeBinomial": "poisson",
+                                 "Binomial": "binomial", "Discrete": "discrete",
+                                 "UnnormDiscrete": "discrete"}.get(op),
+    }
+
+    def _note_relaxable(self, e: Expr) -> None:
+        """Record whether a relaxable operation is relaxed (its deciding argument is fluent and the
+        compiler has a relaxation for its family) or evaluated exactly.  Bookkeeping only."""
+        try:
+            fam, op = e.etype
+            key = self._RELAX_FAMILY.get(fam, lambda _: None)(op)
+            if key is None or e.id in self.relaxed_ops or e.id in self.exact_ops:
+                return
+            if fam == "control" or (fam == "randomvar" and op in ("Bernoulli", "Geometric", "Poisson")):
+                fluent = self.tr.is_fluent(e.args[0])
+            elif fam == "randomvar" and op in ("NegativeBinomial", "Binomial"):
+                fluent = self.tr.is_fluent(e.args[0]) or self.tr.is_fluent(e.args[1])
+            else:
+                fluent = self.tr.is_fluent(e)
+            name = f"{fam} {op}"
+            if fluent and key in self.variants:
+                self.relaxed_ops[e.id] = (key, name)
+            else:
+                self.exact_ops[e.id] = (key, name)
+        except Exception:           # never let the bookkeeping stop a lowering
+            pass
+
     def lower(self, e: Expr, scope, env: Dict[str, V]) -> TV:
         """Dispatch of compiler.py:936-964."""
         fam, op = e.etype
         sizes = self.sizes(scope)
+        if self.relaxed:
+            self._note_relaxable(e)
         if fam != "constant" and self.tr.is_static(e):
             cast_errors: list = []
             try:

@@ -1236,10 +1236,14 @@ class JaxBackpropPlanner:
             return ""
         out = ("[INFO] Some RDDL operations are non-differentiable and will be approximated "
                "as follows:\n")
+        try:
+            exact = getattr(self.compiled, "exact_ops_info", lambda: {})()
+        except Exception:
+            exact = {}
         for klass, ops in info.items():
             out += f"    {klass}:\n"
             for op, ids in ops.items():
-                out += f"        {op} [{len(ids)} relaxed]\n"
+                out += f"        {op} [{len(ids)} relaxed, {len(exact.get(op, []))} exact]\n"
         return out
 
     def summarize_hyperparameters(self) -> str:

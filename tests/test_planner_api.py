@@ -697,7 +697,15 @@ def test_compiler_relaxation_info():
     assert sorted(i for ids in over["SigmoidRelational"].values() for i in ids) == \
         sorted(k for k, v in info.items() if v["rddl_op"].startswith("relational"))
     w = logic.DefaultJaxRDDLCompilerWithGrad(fixture_model("wildfire"))
-    assert list(w.overriden_ops_info()) == ["ReparameterizedSigmoidBernoulli"]
+    over = w.overriden_ops_info()
+    assert set(over) == {"ReparameterizedSigmoidBernoulli", "ProductNormLogical", "LinearIfElse"}
+    assert len(over["ReparameterizedSigmoidBernoulli"]["randomvar Bernoulli"]) == 1
+    # relaxable operations over non-fluents stay exact (compiler.py:825-832)
+    d = logic.DefaultJaxRDDLCompilerWithGrad(fixture_model("discrete"))
+    assert "randomvar Discrete" in d.exact_ops_info()
+    assert "randomvar UnnormDiscrete" in d.overriden_ops_info()["GumbelSoftmaxDiscrete"]
+    ids = {i for ops in over.values() for v in ops.values() for i in v}
+    assert not ids & {i for v in w.exact_ops_info().values() for i in v}
 
 
 @pytest.mark.gpu
