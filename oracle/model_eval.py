@@ -680,10 +680,32 @@ class OracleModel:
             E = self._draw(cur, "exponential", a0, scope, B)
             return scale * torch.pow(E, 1. / _f(shape)), \
                 err | oob((shape > 0) & (scale > 0)) * ERR["WEIBULL"]
+        def gamma_sampler(shape, scale):
+            """standard Gamma(scale * shape) for a fluent shape from supplied draws (the reference
+            calls jax.random.gamma, whose bits cannot be reproduced):
+            Marsaglia-Tsang on alpha + 1, first accepted of 4 proposals, times U^(1 / alpha)."""
+            alpha = _f(shape) if scale == 1.0 else np.float32(scale) * _f(shape)
+            d = alpha + np.float32(2.0 / 3.0)
+            c = 1.0 / torch.sqrt(9.0 * d)
+            props = []
+            for _ in range(4):
+                z = self._draw(cur, "normal", a0, scope, B)
+                u = self._draw(cur, "uniform", a0, scope, B)
+                t = 1.0 + c * z
+                v = t * t * t
+                logv = torch.log(torch.clamp(v, min=1e-30))
+                bound = 0.5 * (z * z) + d - d * v + d * logv
+                ok = (t > 0) & (torch.log(u) < bound)
+                props.append((ok, d * torch.clamp(v, min=1e-30)))
+            x = props[-1][1]
+            for ok, xv in reversed(props[:-1]):
+                x = torch.where(ok, xv, x)
+            ub = self._draw(cur, "uniform", a0, scope, B)
+            return x * torch.exp(torch.log(ub) / alpha)
+
         def gamma_draw(shape, shape_e, scale=1.0):
             if not self.tracer.is_static(shape_e):
-                raise NotImplementedError(
-                    "Gamma-family distributions with a fluent shape need an in-loop sampler")
+                return gamma_sampler(shape, scale)
             c0 = shape[0].numpy() * np.float32(scale)
             conc = np.broadcast_to(c0, self._shape(scope)).copy() if self._ref_full(a0) \
                 else np.asarray(c0, dtype=np.float32).reshape(-1)[0].reshape(())

@@ -793,12 +793,43 @@ class Lowerer:
         return soft
 
     # ---- random variables: compiler.py:1701-2241 ; logic.py:1010-1768 --------------------
+    GAMMA_PROPOSALS = 4     # Marsaglia-Tsang proposals per draw; each is accepted with p >= 0.95
+
+    def _gamma_sampler(self, shape: TV, a0: Expr, scope, sizes, scale: float) -> TV:
+        """standard Gamma(scale * shape) for a FLUENT shape, from supplied draws: Marsaglia-Tsang
+        on alpha + 1 (d = alpha + 2/3, c = 1 / sqrt(9 d); proposal d (1 + c z)^3, accepted when
+        1 + c z > 0 and log u < z^2 / 2 + d - d v + d log v), the first accepted of GAMMA_PROPOSALS
+        proposals (the last one if none is), times U^(1 / alpha) to come back to alpha.  Draw
+        order: (normal, uniform) per proposal, then the uniform of the power.  Differentiable in
+        alpha through d, c and the exponent (the accept tests are constants)."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        alpha = shape if scale == 1.0 else E("MUL", C(scale), shape)
+        d = E("ADD", alpha, C(2.0 / 3.0))
+        c = E("DIV", C(1.0), E("SQRT", E("MUL", C(9.0), d)))
+        props = []
+        for _ in range(self.GAMMA_PROPOSALS):
+            z = self._draw("normal", a0, scope, sizes)
+            u = self._draw("uniform", a0, scope, sizes)
+            t = E("ADD", C(1.0), E("MUL", c, z))
+            v = E("MUL", E("MUL", t, t), t)
+            logv = E("LOG", E("MAX", v, C(1e-30)))
+            bound = E("ADD", E("SUB", E("ADD", E("MUL", C(0.5), E("MUL", z, z)), d), E("MUL", d, v)),
+                      E("MUL", d, logv))
+            ok = E("AND", E("GT", t, C(0.0)), E("LT", E("LOG", u), bound))
+            props.append((ok, E("MUL", d, E("MAX", v, C(1e-30)))))
+        x = props[-1][1]
+        for ok, xv in reversed(props[:-1]):
+            x = self.ew("SELECT", [ok, xv, x], sizes, dtype="f")
+        ub = self._draw("uniform", a0, scope, sizes)
+        return E("MUL", x, E("EXP", E("DIV", E("LOG", ub), alpha)))
+
     def _gamma_draw(self, shape: TV, a0: Expr, scope, sizes, scale: float = 1.0) -> TV:
-        """standard Gamma(scale * shape) noise; the shape must be known at build time because the
-        draw is supplied from outside the kernel."""
+        """standard Gamma(scale * shape) noise: supplied from outside the kernel when the shape is
+        known at build time, sampled in the step from supplied normal / uniform
+        draws when it is a fluent."""
         if shape.v.const is None:
-            raise RDDLNotImplementedError(
-                "Gamma-family distributions with a fluent shape need an in-loop sampler")
+            return self._gamma_sampler(shape, a0, scope, sizes, scale)
         full = self._ref_full(a0)
         allv = tuple(range(len(sizes)))
         if full:

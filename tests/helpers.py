@@ -25,6 +25,7 @@ FIXTURES = {
     "discrete": ("Discrete_Toy", "instance1"),
     "distributions": ("Distributions_Toy", "instance1"),
     "wildfire_free": ("Wildfire_MDP_ippc2014", "instance5free"),    # no concurrency constraint
+    "gammafluent": ("Gamma_Fluent_Toy", "instance1"),
 }
 
 

@@ -104,3 +104,14 @@ def test_stochastic_pooled_softmax_plan_emulated():
     check_gradient(c)
     acts = [c["P"][k].grad for k in c["P"]]
     assert all(g is not None and float(g.abs().sum()) > 0 for g in acts)
+
+
+def test_gamma_family_with_fluent_shapes_emulated():
+    """Gamma / ChiSquare / Student / Beta / NegativeBinomial whose shape is a fluent: sampled in the
+    step (Marsaglia-Tsang on supplied normal / uniform draws); exact and relaxed programs against the
+    oracle, gradients through the shapes included."""
+    check_forward(forward_case("emu", "gammafluent", B=9, T=4, relaxed=False))
+    c = gradient_case("emu", "gammafluent", B=9, T=4)
+    check_forward(c)
+    check_gradient(c)
+    assert float(abs(c["grad"]).max()) > 0

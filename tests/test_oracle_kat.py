@@ -381,3 +381,34 @@ def test_gamma_family_closed_forms():
     v, _, _ = evaluate("Pareto(C(?o) * 4.0, x(?o) + 3.0)", exact=True, noise=[G])
     np.testing.assert_allclose(v, (X + 3.0) * np.exp(G.numpy() / np.array([2.0, 6.0, 2.0, 2.0])),
                                rtol=2e-6)
+
+
+def test_fluent_shape_gamma_sampler_moments():
+    """The in-step Gamma sampler (Marsaglia-Tsang on supplied normal / uniform draws, used when the
+    shape is a fluent) reproduces the Gamma law: mean and variance of Gamma(alpha, scale) for shapes
+    below and above one, the mean of Beta and of the Gamma-Poisson mixture, through the
+    Gamma_Fluent_Toy fixture's first step; the emulated program and the oracle agree draw for draw."""
+    from .parity import forward_case
+    B = 20000
+    c = forward_case("emu", "gammafluent", B, 1, False, seed=11)
+    fin = c["final"]
+    level0 = np.array([0.3, 1.0, 1.7])
+    rate = np.array([0.5, 0.8, 0.5])
+    feed = np.clip(c["params"]["feed"].numpy()[0], 0.0, 1.0)            # test policy clips to the box
+    alpha = 0.4 + level0 ** 2 + feed
+    # level' = 0.7 level + 0.1 inflow + 0.2 mix - 0.01 count, inflow = Gamma + 0.05 Chi2 + 0.02 Student
+    lv = fin["level"].numpy().astype(np.float64)
+    inflow = (lv - 0.7 * level0 - 0.2 * 0.5) / 0.1
+    want_mean = alpha * rate + 0.05 * (1.0 + level0)                    # E Student = 0 (df > 1)
+    want_var = alpha * rate ** 2 + 0.05 ** 2 * 2 * (1.0 + level0) \
+        + 0.02 ** 2 * (3 + level0 ** 2) / (1 + level0 ** 2)
+    np.testing.assert_allclose(inflow.mean(0), want_mean, rtol=0.03)
+    np.testing.assert_allclose(inflow.var(0), want_var, rtol=0.08)
+    mix = fin["mix"].numpy().astype(np.float64).reshape(-1)
+    a, b = 0.5 + 0.5, 1.0 + level0.sum()
+    assert abs(mix.mean() - a / (a + b)) < 0.01 and mix.min() > 0 and mix.max() < 1
+    cnt = fin["count"].numpy().astype(np.float64)
+    r, p = 1.5 + level0, 0.4
+    np.testing.assert_allclose(cnt.mean(0), r * p / (1 - p), rtol=0.06)
+    np.testing.assert_array_equal(cnt, c["ref"]["final"]["count"].numpy())
+    np.testing.assert_allclose(lv, c["ref"]["final"]["level"].numpy(), rtol=1e-5, atol=1e-5)
