@@ -1566,6 +1566,15 @@ def _load_config(config, args):
             init() if callable(init) and not isinstance(init, _Initializer) else init)
     import sys
     this = sys.modules[__name__]
+    from . import drp as drp_mod
+    act = plan_kwargs.get("activation")                         # planner.py:157-164
+    if isinstance(act, str) and act not in engine.ACTIVATIONS:
+        raise ValueError(f"Invalid activation <{act}>.")
+    emb = plan_kwargs.get("time_embedding")                     # planner.py:166-169
+    if isinstance(emb, str):
+        if emb not in drp_mod.TIME_EMBEDDINGS:
+            raise ValueError(f"Invalid time embedding <{emb}>.")
+        plan_kwargs["time_embedding"] = drp_mod.TIME_EMBEDDINGS[emb]
     plan_cls = getattr(this, plan_method, None)
     if plan_cls is None:
         from . import drp
@@ -1584,6 +1593,15 @@ def _load_config(config, args):
         if cls is None:
             raise ValueError(f"Invalid PGPE class <{pgpe_method}>.")
         planner_args["pgpe"] = cls(**pgpe_kwargs)
+    preproc = planner_args.get("preprocessor", None)            # planner.py:200-205
+    preproc_kwargs = planner_args.pop("preprocessor_kwargs", {})
+    if isinstance(preproc, str):
+        cls = getattr(this, preproc, None)
+        if cls is None or not (isinstance(cls, type) and issubclass(cls, Preprocessor)):
+            raise ValueError(f"Invalid preprocessor class <{preproc}>.")
+        planner_args["preprocessor"] = cls(**preproc_kwargs)
+    if "dashboard" in planner_args:                             # planner.py:212-217: no dashboard here
+        del planner_args["dashboard"]
     if "stopping_rule" in train_args:                           # planner.py:219-226
         rule = getattr(this, train_args["stopping_rule"])
         train_args["stopping_rule"] = rule(**train_args.pop("stopping_rule_kwargs", {}))

@@ -747,3 +747,45 @@ def test_optimize_prints_summaries(cuda_device, capsys):
     assert "SigmoidRelational" in out and "relational" in out
     assert "optimizer hyper-parameters" in out and "batch_size_train  =8" in out
     assert "Summary of optimization" in out and cb["iteration"] == 2
+
+
+DRP_FULL = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+
+[Planner]
+method='JaxDeepReactivePolicy'
+method_kwargs={'topology': [32, 32], 'activation': 'relu', 'normalize': True, 'time_dependent': True, 'time_embedding': 'FixedTimeEmbedding', 'time_embedding_kwargs': {'max_t': 50, 'dim': 4}, 'action_noise_dist': 'laplace'}
+optimizer='adam'
+optimizer_kwargs={'learning_rate': 0.001}
+preprocessor='StaticNormalizer'
+preprocessor_kwargs={'fluent_bounds': {'temperature': (-30.0, 40.0)}}
+reduce_on_plateau_kwargs={'factor': 0.5, 'patience': 5}
+dashboard=False
+batch_size_train=8
+pgpe=None
+
+[Optimize]
+key=1
+epochs=10
+"""
+
+
+def test_load_config_resolves_drp_options_and_preprocessor():
+    """planner.py:157-173, 200-217: activation / time embedding / noise law by name, the preprocessor
+    class with its kwargs, the dashboard key dropped."""
+    from pyrddlgym_jax_b200.core.drp import FixedTimeEmbedding
+    from pyrddlgym_jax_b200.core.planner import StaticNormalizer
+    planner_args, plan_kwargs, train_args = load_config_from_string(DRP_FULL)
+    plan = planner_args["plan"]
+    assert isinstance(plan, JaxDeepReactivePolicy) and plan._activation == "relu"
+    assert isinstance(plan.time_embed, FixedTimeEmbedding) and plan.time_embed.max_t == 50
+    assert plan._action_noise_dist == "laplace" and plan._normalize
+    assert isinstance(planner_args["preprocessor"], StaticNormalizer)
+    assert planner_args["preprocessor"].fluent_bounds == {"temperature": (-30.0, 40.0)}
+    assert "dashboard" not in planner_args and "preprocessor_kwargs" not in planner_args
+    assert planner_args["reduce_on_plateau_kwargs"] == {"factor": 0.5, "patience": 5}
+    for bad in (DRP_FULL.replace("'relu'", "'gelu'"), DRP_FULL.replace("FixedTimeEmbedding", "Nope"),
+                DRP_FULL.replace("'StaticNormalizer'", "'JaxPlan'")):
+        with pytest.raises(ValueError):
+            load_config_from_string(bad)
