@@ -789,3 +789,27 @@ def test_load_config_resolves_drp_options_and_preprocessor():
                 DRP_FULL.replace("'StaticNormalizer'", "'JaxPlan'")):
         with pytest.raises(ValueError):
             load_config_from_string(bad)
+
+
+REFERENCE_CONFIGS = "/root/reference/pyRDDLGym_jax/examples/configs"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REFERENCE_CONFIGS),
+                    reason="the reference tree is only present in the build container")
+def test_every_shipped_reference_config_loads():
+    """Drop-in check of the .cfg format: every hyper-parameter file the reference ships
+    (examples/configs/*.cfg) loads and instantiates its plan; the three tuning_*.cfg templates hold
+    placeholders that the reference's tuner substitutes first."""
+    import glob
+    from pyrddlgym_jax_b200.core.planner import load_config
+    files = sorted(glob.glob(REFERENCE_CONFIGS + "/*.cfg"))
+    assert len(files) >= 20
+    loaded = 0
+    for f in files:
+        if __import__("os").path.basename(f).startswith("tuning_"):
+            continue
+        planner_args, plan_kwargs, train_args = load_config(f)
+        assert isinstance(planner_args["plan"], (JaxStraightLinePlan, JaxDeepReactivePolicy)), f
+        assert "compiler_kwargs" in planner_args and isinstance(train_args, dict)
+        loaded += 1
+    assert loaded >= 20
