@@ -1394,8 +1394,15 @@ class JaxBackpropPlanner:
                   f"    test_rolling_window={test_rolling_window}\n")
         self.initialize(key, subs, guess)
         P = self.parallel_updates
-        hyper = policy_hyperparams if policy_hyperparams is not None else \
-            {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents}
+        if policy_hyperparams is not None:
+            hyper = policy_hyperparams
+        elif self.is_drp:           # planner.py:1519-1521
+            hyper = {"softmax_weight": self.plan._softmax_output_weight,
+                     "sigmoid_weight": self.plan._sigmoid_weight}
+        else:                       # planner.py:976 (+ the pooled softmax weight, planner.py:1003)
+            hyper = {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents}
+            if getattr(self.plan, "stack_bool", False):
+                hyper["__bool__"] = self.plan._softmax_weight
         if policy_hyperparams is None:      # preprocessor statistics travel with them (P:1519-1521)
             hyper.update(getattr(self.plan, "hyperparams_extra", {}))
         best_params = self.plan.params_to_pytree(self._plan_view(self.params[0]).clone().cpu())
