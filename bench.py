@@ -261,6 +261,16 @@ def run_reference(args):
         it()
     dt = (time.perf_counter() - t0) / n_steps
     val = B * T / dt
+    # XLA's CPU code for these element-wise graphs is essentially single-threaded, so
+    # a 1-thread figure is reported beside the all-threads one (2 steps at most)
+    torch.set_num_threads(1)
+    it()
+    t1 = time.perf_counter()
+    n_one = 1 if dt > 2.0 else 2
+    for _ in range(n_one):
+        it()
+    val_one = B * T / ((time.perf_counter() - t1) / n_one)
+    torch.set_num_threads(cores)
     args.steps, args.warmup = n_steps, n_warm
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
@@ -273,7 +283,8 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} planner iterations of {B} rollouts x {T} steps "
                                    f"(of the workload's {WORKLOADS[name]['B']}) on the torch-CPU "
-                                   f"oracle, {cores} threads"},
+                                   f"oracle, {cores} threads",
+                         "value_one_thread": val_one},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
