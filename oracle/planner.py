@@ -7,7 +7,11 @@ Restates, in torch-CPU fp32 with autograd:
   * return, loss                     planner.py:2747-2822
   * optimiser updates                planner.py:2349-2387, 2885-2899 (optax semantics assumed:
     rmsprop  nu <- d nu + (1-d) g^2, update = g * rsqrt(nu + eps);  adam with bias
-    correction, step counted from 1;  clip_by_global_norm;  apply_updates p + u)
+    correction, step counted from 1;  clip_by_global_norm;  apply_updates p + u;
+    optax.contrib.reduce_on_plateau as a plain state machine)
+  * deep reactive policy             planner.py:1027-1119 (GumbelSoftmaxTopK, FiLM, time
+    embeddings), 1223-1530 (input layer with StaticNormalizer / LayerNorm, hidden layers and
+    activations, logit / mu / log_sigma / dense_topk heads, train and test policies)
 """
 from __future__ import annotations
 
