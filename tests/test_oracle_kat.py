@@ -412,3 +412,74 @@ def test_fluent_shape_gamma_sampler_moments():
     np.testing.assert_allclose(cnt.mean(0), r * p / (1 - p), rtol=0.06)
     np.testing.assert_array_equal(cnt, c["ref"]["final"]["count"].numpy())
     np.testing.assert_allclose(lv, c["ref"]["final"]["level"].numpy(), rtol=1e-5, atol=1e-5)
+
+
+def _soft_floor(x, w):
+    """logic.py:801-804."""
+    r = np.floor(x + 0.5)
+    return r - 1 + 0.5 * (1 + np.tanh(w * (x - r)) / np.tanh(w / 2))
+
+
+def test_remaining_relational_and_soft_division_closed_forms():
+    """`~=`, `<`, `>=` (logic.py:283, 297, 339) and soft `div` / `mod` (logic.py:841, 855-858):
+    soft_floor of the quotient, x - y * soft_floor(x / y)."""
+    v, gx, gy = evaluate("x(?o) ~= y(?o)", {"sigmoid_weight": W, "use_tanh_ste": False})
+    t = np.tanh(W * (Y - X))
+    np.testing.assert_allclose(v, t ** 2, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(gy, 2 * t * (1 - t ** 2) * W, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(gx, -2 * t * (1 - t ** 2) * W, rtol=2e-5, atol=2e-6)
+    for expr, z in (("x(?o) < y(?o)", Y - X), ("x(?o) >= y(?o)", X - Y)):
+        v, gx, _ = evaluate(expr, {"sigmoid_weight": W, "use_sigmoid_ste": False})
+        np.testing.assert_allclose(v, sigmoid(W * z), rtol=2e-6, atol=2e-6)
+        sign = -1.0 if "<" in expr else 1.0
+        np.testing.assert_allclose(gx, sign * W * sigmoid(W * z) * (1 - sigmoid(W * z)), rtol=2e-5,
+                                   atol=2e-6)
+    yy = "(2.0 + y(?o) * y(?o))"                                  # a positive divisor
+    D = 2.0 + Y ** 2
+    v, gx, _ = evaluate(f"div[x(?o), {yy}]", {"floor_weight": W, "use_floor_ste": False})
+    np.testing.assert_allclose(v, _soft_floor(X / D, W), rtol=2e-6, atol=2e-6)
+    q = X / D
+    dq = 0.5 * W * (1 - np.tanh(W * (q - np.floor(q + 0.5))) ** 2) / np.tanh(W / 2)
+    np.testing.assert_allclose(gx, dq / D, rtol=2e-5, atol=2e-6)
+    v, _, _ = evaluate(f"mod[x(?o), {yy}]", {"floor_weight": W, "use_floor_ste": False})
+    np.testing.assert_allclose(v, X - D * _soft_floor(X / D, W), rtol=2e-6, atol=2e-5)
+    v, _, _ = evaluate(f"div[x(?o), {yy}]", {"floor_weight": W, "use_floor_ste": True})
+    np.testing.assert_allclose(v, np.floor(X / D), rtol=0, atol=1e-6)
+
+
+def test_geometric_reparameterised_closed_form():
+    """ReparameterizedGeometric (logic.py:1046-1047): 1 + soft_floor(-E / safe_log(1 - p), w) with an
+    Exp(1) draw E; the exact model floors log U / log(1 - p) + 1 (compiler.py:2001-2003)."""
+    Ex = torch.tensor(-np.log(U), dtype=torch.float32)           # Exp(1) draws from the uniforms
+    p = "(0.2 + 0.1 * x(?o) * x(?o) / (1.0 + x(?o) * x(?o)))"
+    P = 0.2 + 0.1 * X ** 2 / (1 + X ** 2)
+    v, gx, _ = evaluate(f"Geometric({p})", {"geometric_floor_weight": W}, noise=[Ex])
+    ratio = -Ex.numpy().astype(np.float64) / np.log(1 - P)
+    np.testing.assert_allclose(v, 1 + _soft_floor(ratio, W), rtol=1e-5, atol=1e-5)
+    assert np.abs(gx).max() > 0
+    Un = torch.tensor(U, dtype=torch.float32)
+    v, _, _ = evaluate(f"Geometric({p})", exact=True, noise=[Un])
+    np.testing.assert_array_equal(v, np.floor(np.log(U) / np.log(1 - P)) + 1)
+
+
+def test_location_scale_and_power_law_samplers_closed_forms():
+    """Gumbel / Laplace / Cauchy are location + scale * standard draw (compiler.py:2060-2103);
+    Gompertz(s, r) = ln(1 + E) / s / r with E ~ Exp(1) as coded at compiler.py:2123-2124; Kumaraswamy(a, b) =
+    (1 - U^(1/b))^(1/a) (compiler.py:2163-2164); Weibull = scale * E^(1/shape) (compiler.py:1857)."""
+    Z = torch.tensor(Y, dtype=torch.float32)                      # any standard draws
+    for name in ("Gumbel", "Laplace", "Cauchy"):
+        v, _, _ = evaluate(f"{name}(C(?o), 2.0)", exact=True, noise=[Z])
+        loc = np.array([0.5, 1.5, 0.5, 0.5])
+        np.testing.assert_allclose(v, loc + 2.0 * Y, rtol=1e-6, atol=1e-6)
+    Ex = torch.tensor(-np.log(U), dtype=torch.float32)
+    E64 = Ex.numpy().astype(np.float64)
+    shape = np.array([1.0, 3.0, 1.0, 1.0])
+    # the draw takes the shape of the SCALE argument (compiler.py:2121)
+    v, _, _ = evaluate("Gompertz(3.0, C(?o) * 2.0)", exact=True, noise=[Ex])
+    # the CODE computes log(1 + E) / shape / scale (its comment states ln(1 + E / s) / r): follow the code
+    np.testing.assert_allclose(v, np.log(1 + E64) / 3.0 / shape, rtol=1e-5, atol=1e-6)
+    Un = torch.tensor(U, dtype=torch.float32)
+    v, _, _ = evaluate("Kumaraswamy(C(?o) * 2.0, 3.0)", exact=True, noise=[Un])
+    np.testing.assert_allclose(v, (1 - U ** (1 / 3.0)) ** (1 / shape), rtol=1e-5, atol=1e-6)
+    v, _, _ = evaluate("Weibull(C(?o) * 4.0, 1.5)", exact=True, noise=[Ex])
+    np.testing.assert_allclose(v, 1.5 * E64 ** (1 / (2 * shape)), rtol=1e-5, atol=1e-6)
