@@ -483,3 +483,62 @@ def test_location_scale_and_power_law_samplers_closed_forms():
     np.testing.assert_allclose(v, (1 - U ** (1 / 3.0)) ** (1 / shape), rtol=1e-5, atol=1e-6)
     v, _, _ = evaluate("Weibull(C(?o) * 4.0, 1.5)", exact=True, noise=[Ex])
     np.testing.assert_allclose(v, 1.5 * E64 ** (1 / (2 * shape)), rtol=1e-5, atol=1e-6)
+
+
+def test_exponential_poisson_relaxation_closed_form():
+    """ExponentialPoisson (logic.py:1508-1531): sum_k sigmoid(w (1 - cumsum_k(E_k / rate))) over
+    nbins Exp(1) draws while cdf(nbins, rate) >= min_cdf, rate + sqrt(rate) z above it; value and the
+    derivative w.r.t. the rate."""
+    K, w = 6, 4.0
+    g = np.random.default_rng(3)
+    Es = [torch.tensor(g.exponential(size=X.shape), dtype=torch.float32) for _ in range(K)]
+    Zn = torch.tensor(g.normal(size=X.shape), dtype=torch.float32)
+    rate_expr = "(0.3 + 0.2 * x(?o) * x(?o))"
+    lam = 0.3 + 0.2 * X ** 2                                     # <= 3.4: cdf(6, 3.4) = 0.94 < 0.999 there
+    v, gx, _ = evaluate(f"Poisson({rate_expr})", {"poisson_nbins": K, "poisson_comparison_weight": w},
+                        noise=Es + [Zn])
+    from scipy import stats
+    small = stats.poisson.cdf(K, lam) >= 0.999
+    assert small.any() and (~small).any()                        # both branches are exercised
+    times = np.cumsum([e.numpy().astype(np.float64) / lam for e in Es], axis=0)
+    s = sigmoid(w * (1 - times))
+    soft = s.sum(0)
+    normal = lam + np.sqrt(lam) * Zn.numpy()
+    np.testing.assert_allclose(v, np.where(small, soft, normal), rtol=1e-5, atol=1e-5)
+    # d soft / d lam = sum_k s (1 - s) w times_k / lam ; d normal / d lam = 1 + z / (2 sqrt lam)
+    dsoft = (s * (1 - s) * w * times / lam).sum(0)
+    dnorm = 1 + Zn.numpy() / (2 * np.sqrt(lam))
+    dlam_dx = 0.4 * X
+    np.testing.assert_allclose(gx, np.where(small, dsoft, dnorm) * dlam_dx, rtol=2e-4, atol=1e-5)
+
+
+def test_gumbel_softmax_binomial_relaxation_closed_form():
+    """GumbelSoftmaxBinomial (logic.py:1381-1434): soft arg-max, sum_k k softmax(w (g_k + log pmf_k)),
+    over nbins bins of Gumbel noise plus the Binomial log-pmf (bins above n masked out), for n < nbins."""
+    from scipy import special
+
+    class Comp(logic.SigmoidRelational, logic.ProductNormLogical, logic.LinearIfElse,
+               logic.GumbelSoftmaxBinomial):
+        pass
+    K, w, n = 8, 3.0, 5
+    g = np.random.default_rng(5)
+    G = torch.tensor(g.gumbel(size=X.shape + (K,)), dtype=torch.float32)
+    Zn = torch.tensor(g.normal(size=X.shape[:1]), dtype=torch.float32)   # shaped like the trials argument
+    P = 0.2 + 0.6 * sigmoid(X)
+    v, gx, _ = evaluate(f"Binomial({n}, 0.2 + 0.6 / (1.0 + exp[-x(?o)]))",
+                        {"binomial_nbins": K, "binomial_softmax_weight": w}, cls=Comp, noise=[G, Zn])
+    ks = np.arange(K)
+    logpmf = (special.gammaln(n + 1) - special.gammaln(np.minimum(ks, n) + 1)
+              - special.gammaln(n - np.minimum(ks, n) + 1)
+              + np.minimum(ks, n) * np.log(P[..., None]) + (n - np.minimum(ks, n)) * np.log(1 - P[..., None]))
+    logpmf = np.where(ks <= n, logpmf, -np.inf)
+    z = w * (G.numpy().astype(np.float64) + logpmf)
+    sm = np.exp(z - z.max(-1, keepdims=True))
+    sm /= sm.sum(-1, keepdims=True)
+    np.testing.assert_allclose(v, (ks * sm).sum(-1), rtol=2e-5, atol=2e-5)
+    # d/dp: softmax chain through d logpmf_k / dp = k / p - (n - k) / (1 - p)
+    dl = np.where(ks <= n, ks / P[..., None] - (n - ks) / (1 - P[..., None]), 0.0)
+    mean_k = (ks * sm).sum(-1, keepdims=True)
+    dv_dp = (w * sm * (ks - mean_k) * dl).sum(-1)
+    dp_dx = 0.6 * sigmoid(X) * (1 - sigmoid(X))
+    np.testing.assert_allclose(gx, dv_dp * dp_dx, rtol=2e-4, atol=2e-5)
