@@ -542,3 +542,48 @@ def test_gumbel_softmax_binomial_relaxation_closed_form():
     dv_dp = (w * sm * (ks - mean_k) * dl).sum(-1)
     dp_dx = 0.6 * sigmoid(X) * (1 - sigmoid(X))
     np.testing.assert_allclose(gx, dv_dp * dp_dx, rtol=2e-4, atol=2e-5)
+
+
+DISCRETE_DOMAIN = """
+domain dk {
+    types { obj : object; lvl : {@low, @mid, @high}; };
+    pvariables {
+        x(obj) : { state-fluent, real, default = 0.0 };
+        m(obj) : { state-fluent, lvl, default = @low };
+        u(obj) : { action-fluent, real, default = 0.0 };
+    };
+    cpfs {
+        m'(?o) = Discrete(lvl, @low : 0.2 + 0.3 * x(?o), @mid : 0.5 - 0.3 * x(?o), @high : 0.3);
+        x'(?o) = x(?o);
+    };
+    reward = sum_{?o : obj} [ x'(?o) ];
+}
+non-fluents nf { domain = dk; objects { obj : {o1, o2, o3}; }; non-fluents { }; }
+instance inst { domain = dk; non-fluents = nf; init-state { x(o1) = 0.5; x(o2) = 0.25; x(o3) = 1.0; }; max-nondef-actions = pos-inf; horizon = 2; discount = 1.0; }
+"""
+
+
+def test_gumbel_softmax_discrete_closed_form():
+    """GumbelSoftmaxDiscrete (logic.py:1258-1267): soft arg-max over the cases of Gumbel noise plus
+    safe_log of the case probabilities (no straight-through); the exact model takes the arg-max of
+    the same perturbed logits (compiler.py:2212)."""
+    m = load_model(DISCRETE_DOMAIN)
+    x0 = np.array([0.5, 0.25, 1.0])
+    prob = np.stack([0.2 + 0.3 * x0, 0.5 - 0.3 * x0, np.full(3, 0.3)], -1)      # [obj, K]
+    g = np.random.default_rng(9)
+    G = torch.tensor(g.gumbel(size=(2, 3, 3)), dtype=torch.float32)
+    w = 2.5
+    relax = logic.DefaultJaxRDDLCompilerWithGrad(m, discrete_softmax_weight=w).relax_config()
+    om = OracleModel(m, relax)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 3)}, [G], 2)
+    z = w * (G.numpy().astype(np.float64) + np.log(prob)[None])
+    sm = np.exp(z - z.max(-1, keepdims=True))
+    sm /= sm.sum(-1, keepdims=True)
+    np.testing.assert_allclose(out["m"].detach().numpy(), (np.arange(3) * sm).sum(-1), rtol=1e-5,
+                               atol=1e-5)
+    om = OracleModel(m, None)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 3)}, [G], 2)
+    hard = np.argmax(G.numpy().astype(np.float64) + np.log(prob)[None], -1)
+    np.testing.assert_array_equal(out["m"].numpy(), hard)
