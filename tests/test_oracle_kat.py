@@ -587,3 +587,51 @@ def test_gumbel_softmax_discrete_closed_form():
     out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 3)}, [G], 2)
     hard = np.argmax(G.numpy().astype(np.float64) + np.log(prob)[None], -1)
     np.testing.assert_array_equal(out["m"].numpy(), hard)
+
+
+ARGMAX_DOMAIN = """
+domain ak {
+    types { obj : object; };
+    pvariables {
+        x(obj)   : { state-fluent, real, default = 0.0 };
+        hi(obj)  : { state-fluent, obj, default = $o1 };
+        lo(obj)  : { state-fluent, obj, default = $o1 };
+        u(obj)   : { action-fluent, real, default = 0.0 };
+    };
+    cpfs {
+        hi'(?o) = argmax_{?p : obj} [ x(?p) * x(?o) ];
+        lo'(?o) = argmin_{?p : obj} [ x(?p) * x(?o) ];
+        x'(?o) = x(?o);
+    };
+    reward = sum_{?o : obj} [ x'(?o) ];
+}
+non-fluents nf { domain = ak; objects { obj : {o1, o2, o3, o4}; }; non-fluents { }; }
+instance inst { domain = ak; non-fluents = nf; init-state { x(o1) = 0.5; x(o2) = -0.25; x(o3) = 1.0; x(o4) = 0.8; }; max-nondef-actions = pos-inf; horizon = 2; discount = 1.0; }
+"""
+
+
+@pytest.mark.parametrize("ste", [True, False])
+def test_softmax_argmax_closed_form(ste):
+    """SoftmaxArgmax (logic.py:377-417): sum_i i softmax(w x)_i over the aggregated axis, arg-min on
+    -x; straight-through to the exact index; the exact model returns the index itself."""
+    m = load_model(ARGMAX_DOMAIN)
+    x0 = np.array([0.5, -0.25, 1.0, 0.8])
+    body = x0[None, :] * x0[:, None]                      # [o, p]
+    om = OracleModel(m, None)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 4)}, None, 2)
+    np.testing.assert_array_equal(out["hi"].numpy()[0], body.argmax(1))
+    np.testing.assert_array_equal(out["lo"].numpy()[0], body.argmin(1))
+    w = 3.0
+    relax = logic.DefaultJaxRDDLCompilerWithGrad(m, argmax_weight=w, use_argmax_ste=ste).relax_config()
+    om = OracleModel(m, relax)
+    fls, nfls = om.init_fls_nfls(2)
+    out, _, _, _ = om.step(dict(fls), nfls, {"u": torch.zeros(2, 4)}, None, 2)
+
+    def soft(z):
+        e = np.exp(w * z - (w * z).max(1, keepdims=True))
+        return (np.arange(4) * e / e.sum(1, keepdims=True)).sum(1)
+    want_hi = body.argmax(1) if ste else soft(body)
+    want_lo = body.argmin(1) if ste else soft(-body)
+    np.testing.assert_allclose(out["hi"].detach().numpy()[0], want_hi, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["lo"].detach().numpy()[0], want_lo, rtol=1e-5, atol=1e-6)
