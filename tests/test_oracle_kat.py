@@ -635,3 +635,31 @@ def test_softmax_argmax_closed_form(ste):
     want_lo = body.argmin(1) if ste else soft(-body)
     np.testing.assert_allclose(out["hi"].detach().numpy()[0], want_hi, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out["lo"].detach().numpy()[0], want_lo, rtol=1e-5, atol=1e-6)
+
+
+def test_gumbel_softmax_poisson_relaxation_closed_form():
+    """GumbelSoftmaxPoisson (logic.py:1618-1641): soft arg-max over nbins bins of Gumbel noise plus the
+    Poisson log-pmf k log(rate) - rate - lgamma(k + 1), below the rate where cdf(nbins) >= min_cdf."""
+    from scipy import special, stats
+
+    class Comp(logic.SigmoidRelational, logic.ProductNormLogical, logic.LinearIfElse,
+               logic.GumbelSoftmaxPoisson):
+        pass
+    K, w = 9, 2.0
+    g = np.random.default_rng(8)
+    G = torch.tensor(g.gumbel(size=X.shape + (K,)), dtype=torch.float32)
+    Zn = torch.tensor(g.normal(size=X.shape), dtype=torch.float32)
+    lam = 0.4 + 0.1 * X ** 2                                     # <= 1.9: cdf(9, 1.9) > 0.999
+    assert (stats.poisson.cdf(K, lam) >= 0.999).all()
+    v, gx, _ = evaluate("Poisson(0.4 + 0.1 * x(?o) * x(?o))",
+                        {"poisson_nbins": K, "poisson_softmax_weight": w}, cls=Comp, noise=[G, Zn])
+    ks = np.arange(K)
+    logpmf = ks * np.log(lam[..., None]) - lam[..., None] - special.gammaln(ks + 1)
+    z = w * (G.numpy().astype(np.float64) + logpmf)
+    sm = np.exp(z - z.max(-1, keepdims=True))
+    sm /= sm.sum(-1, keepdims=True)
+    np.testing.assert_allclose(v, (ks * sm).sum(-1), rtol=2e-5, atol=2e-5)
+    dl = ks / lam[..., None] - 1.0                                # d logpmf_k / d rate
+    mean_k = (ks * sm).sum(-1, keepdims=True)
+    dv = (w * sm * (ks - mean_k) * dl).sum(-1)
+    np.testing.assert_allclose(gx, dv * 0.2 * X, rtol=2e-4, atol=2e-5)
