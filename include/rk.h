@@ -107,8 +107,9 @@ int rk_reduce_partials(void* stream, const float* gradp, int num_rows, int n, fl
 /* Optimiser step + box projection on a flat parameter vector.
  * Replaces: optax chain update + apply_updates + plan.projection (planner.py:2885-2899,
  * 2349-2387; box projection planner.py:878-910).
- *   kind: 0 sgd, 1 rmsprop, 2 adam.  hyper = {lr, decay|b1, eps, b2, clip_norm(<=0 off),
- *   momentum, step(1-based)}.  state: rmsprop nu [n]; adam mu [n] then nu [n].
+ *   kind: 0 sgd, 1 rmsprop, 2 adam.  hyper[9] = {lr, decay|b1, eps, b2, clip_norm(<=0 off),
+ *   momentum, step(1-based), 1 - decay|b1, 1 - b2}: the two complements are computed by the caller in
+ *   double precision and rounded once, as optax does with its Python-float decay rates.  state: rmsprop nu [n]; adam mu [n] then nu [n].
  *   lo/hi [n] box (may be +-inf) or NULL.  zero_flag: set to 1 when all |g| <= 1e-8
  *   (planner.py:2861-2864). */
 int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,

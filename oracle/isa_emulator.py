@@ -258,6 +258,9 @@ class Emulator:
                 elif op == "SQUARE": r = xf * xf
                 elif op == "LOG1P": r = np.log1p(xf)
                 elif op == "EXPM1": r = np.expm1(xf)
+                elif op == "DIGAMMA":
+                    from scipy.special import digamma
+                    r = digamma(xf.astype(np.float64)).astype(np.float32)
                 elif op == "ADD": r = xf + yf
                 elif op == "SUB": r = xf - yf
                 elif op == "MUL": r = xf * yf

@@ -248,6 +248,12 @@ def sgd_step(p, g, lr):
     return p - lr * g
 
 
+def sgd_momentum_step(p, g, trace, lr, momentum):
+    """optax.sgd(momentum=m): trace <- g + m * trace ; update = -lr * trace."""
+    trace = g + momentum * trace
+    return p - lr * trace, trace
+
+
 # ---- projections ------------------------------------------------------------------------------
 def bool_box(wrap_sigmoid: bool, min_action_prob: float, weight: float):
     """planner.py:878-882: clip bounds of a boolean action parameter."""

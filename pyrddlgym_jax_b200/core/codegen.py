@@ -43,7 +43,7 @@ _F1 = {
     "ATAN": "atanf(x)", "SINH": "sinhf(x)", "COSH": "coshf(x)", "TANH": "tanhf(x)",
     "LGAMMA": "lgammaf(x)", "SIGMOID": "(1.f / (1.f + expf(-x)))", "STANH": "stable_tanh(x)",
     "RELU": "fmaxf(x, 0.f)", "RCP": "(1.f / x)", "SQUARE": "(x * x)", "LOG1P": "log1pf(x)",
-    "EXPM1": "expm1f(x)",
+    "EXPM1": "expm1f(x)", "DIGAMMA": "rk_digamma(x)",
 }
 _F2 = {
     "ADD": "(x + y)", "SUB": "(x - y)", "MUL": "(x * y)", "DIV": "(x / y)", "MIN": "fminf(x, y)",

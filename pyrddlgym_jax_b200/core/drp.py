@@ -559,7 +559,9 @@ class DrpPipeline:
         self.t_heads = z(Be, self.NH)
         self.t_act = z(self.A * Be)
         self.t_xf = z(te.S * Be) if any(plan.state_is_int) else None
-        self.ent_coeff = z(1)
+        # entropy-regulariser coefficient: starts at start_entropy_coeff (planner.py:2775-2778, progress 0);
+        # optimize_generator anneals it every iteration
+        self.ent_coeff = torch.full((1,), float(planner.start_entropy_coeff), device=dev)
         # input LayerNorm: normalised inputs of every step (operands of the first layer's weight
         # gradient), cotangent of the normalised input, per-CTA partials of [dscale | dbias]
         self.Dn = plan.Dn
@@ -940,3 +942,57 @@ class DrpPipeline:
                         blk.copy_(torch.log(u) - torch.log1p(-u))
                     else:               # pooled logits take Gumbel(0, 1) noise (planner.py:1041, 1051)
                         blk.copy_(-torch.log(-torch.log(u)))
+
+    # ---- measurement hooks of bench.py ------------------------------------------------------------
+    def tape_bytes(self) -> int:
+        """Bytes of hidden activations + state tape one update keeps in HBM for its backward sweep."""
+        return 4 * (sum(H.numel() for H in self.H) + self.tape.numel())
+
+    def bench_roofline(self, time_kernel, peaks, peak_src):
+        """(roofline, kernels_ms, launches per iteration) of the dominant kernel of a DRP iteration: the
+        last hidden dense layer (the only dense contraction of the path), timed alone through
+        ``time_kernel`` (CUDA events, L2 flushed).  Algorithmic FLOPs are the fp32-equivalent
+        2 * B * K * N of Y = act(X W + b); the tensor cores execute 3 TF32 passes per product (the
+        error-compensated split the 1e-5 / 1e-4 parity tolerances need) at half the bf16 rate, so
+        the hardware ceiling of this kernel is peak / 6."""
+        pl = self.pl
+        B, T = pl.batch_size_train, pl.T
+        params = pl.params[0]
+        hid = self.hid
+        li = len(hid) - 1
+        h_in, h_out = (hid[-2] if len(hid) > 1 else self.D), hid[-1]
+        src = self.H[-2][0] if len(hid) > 1 else None
+        use_tc = li in self.tc_layers
+
+        def k_gemm():
+            if use_tc:
+                engine.tcgemm(2, B, h_out, h_in, src, h_in, self._W(self.wT_hi, f"W{li}"),
+                              self._W(self.wT_lo, f"W{li}"), h_in, self.H[-1][0], h_out,
+                              bias=self._W(params, f"b{li}"))
+            else:
+                engine.sgemm(engine.EPI_BIAS_TANH, B, h_out, h_in, src, h_in,
+                             self._W(params, f"W{li}"), h_out, self.H[-1][0], h_out,
+                             bias=self._W(params, f"b{li}"))
+        t_gemm = time_kernel(k_gemm) if src is not None else float("nan")
+        dims = [self.D] + list(hid) + [self.NH]
+        mlp_flops = 2.0 * B * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        flops_iter = T * mlp_flops * (3 + 1)          # train fwd + dX + dW, + the test forward
+        tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved_tf = 2.0 * B * h_in * h_out / (t_gemm * 1e-3) / 1e12
+        roofline = {"bound": "tensor",
+                    "kernel": ("rk_tcgemm_kernel (hidden dense layer, tcgen05 3xTF32, bias+tanh "
+                               "epilogue)" if use_tc else "rk_sgemm_kernel (hidden dense layer, fp32 SIMT)"),
+                    "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_flops": 2.0 * B * h_in * h_out,
+                    "executed_tf32_tflops": (3 if use_tc else 1) * achieved_tf,
+                    "mlp_tflop_per_iteration": flops_iter / 1e12,
+                    "note": "algorithmic (fp32-equivalent) FLOPs of Y = tanh(X W + b) over the kernel "
+                            "time, against the sustained bf16 tensor peak; 3 TF32 passes per product at "
+                            "half the bf16 rate put the hardware ceiling of this kernel at peak/6"}
+        n_state = len(self.plan.state_segs)
+        L = len(hid)
+        n_launch = T * ((n_state + L) + 2) \
+            + T * (2 + 2 * 2 + 1 + L * 2 + (n_state * 2 - 1) * 2 + (L - 1) + n_state) \
+            + T * ((n_state + L) + 2) + 12
+        return roofline, {"hidden_layer_gemm": t_gemm}, n_launch

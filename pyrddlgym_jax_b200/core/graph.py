@@ -451,8 +451,8 @@ def differentiate(g: Graph, nodes: List[V], seeds: Sequence[Tuple[V, V]],
             share = g.op("DIV", [c, (cnt, None)], n)
             back = g.op("SELECT", [(eq, None), (share, table), (F(0.), "b")], src.n)
             contrib.setdefault(src.id, []).append(back) if src.id in active else None
-        elif op in ("LGAMMA",):
-            raise NotDifferentiable(f"{op} has no adjoint rule yet")
+        elif op == "LGAMMA":   # d/dx ln Gamma(x) = digamma(x)  (jax.scipy.special.gammaln's JVP)
+            push(v, 0, mul(c, (g.op("DIGAMMA", [sam(0)], n), None)))
         else:
             raise NotDifferentiable(f"no adjoint rule for op {op}")
 

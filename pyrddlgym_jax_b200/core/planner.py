@@ -707,6 +707,8 @@ class JaxBackpropPlanner:
         else:
             h = [lr, 0., 0., 0., 0., kw.get("momentum", 0.) or 0., 1.]
         h[4] = float(self.clip_grad) if self.clip_grad is not None else 0.
+        # optax forms (1 - decay) from its Python-float rates in double precision: pass the complements
+        h += [1.0 - float(h[1]), 1.0 - float(h[3])]
         self.hyper = torch.tensor(h, dtype=torch.float32, device=dev)
         self._hyper_noclip = self.hyper.clone()     # the chain path clips before the noise link
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \

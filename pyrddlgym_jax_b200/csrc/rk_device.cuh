@@ -17,6 +17,27 @@ __device__ __forceinline__ float stable_tanh(float x) {       // logic.py:57-65
   return copysignf(1.f, x) * ((x == 0.f) ? 0.f : s);
 }
 
+// digamma(x) = d/dx ln Gamma(x): the derivative of LGAMMA in adjoint programs.  Reflection for
+// x < 0.5, upward recurrence to x >= 6, then the asymptotic series (error < 1e-7 relative).
+__device__ __forceinline__ float rk_digamma(float x) {
+  float refl = 0.f;
+  bool neg = false;
+  if (x < 0.5f) {                          // psi(x) = psi(1 - x) - pi / tan(pi x)
+    refl = 3.14159265358979f / tanf(3.14159265358979f * x);
+    x = 1.f - x;
+    neg = true;
+  }
+  float acc = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) {
+    if (x < 6.f) { acc -= 1.f / x; x += 1.f; }
+  }
+  const float r = 1.f / x, r2 = r * r;
+  const float ser = r2 * (1.f / 12.f - r2 * (1.f / 120.f - r2 * (1.f / 252.f - r2 * (1.f / 240.f))));
+  const float v = acc + logf(x) - 0.5f * r - ser;
+  return neg ? v - refl : v;
+}
+
 // ---- asynchronous global -> shared copies of one word per lane (prefetch ring of the generated
 // kernels); a false predicate zero-fills the destination: with a source size of 0 nothing is read
 // from global memory, so the (possibly out-of-range) address is never dereferenced

@@ -165,6 +165,7 @@ __device__ __forceinline__ void run_list(const RkLaunch& K, const uint4* __restr
       case OP_SQUARE: EW1F(x * x)
       case OP_LOG1P: EW1F(log1pf(x))
       case OP_EXPM1: EW1F(expm1f(x))
+      case OP_DIGAMMA: EW1F(rk_digamma(x))
       case OP_ADD: EW2F(x + y)
       case OP_SUB: EW2F(x - y)
       case OP_MUL: EW2F(x * y)

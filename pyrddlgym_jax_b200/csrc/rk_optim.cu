@@ -133,7 +133,7 @@ rk_grad_stats_kernel(const float* __restrict__ g, int n, float* __restrict__ sta
   }
 }
 
-// hyper = {lr, decay|b1, eps, b2, clip_norm, momentum, step}
+// hyper = {lr, decay|b1, eps, b2, clip_norm, momentum, step, 1 - decay|b1, 1 - b2}
 __global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, int n,
                                     float* __restrict__ params, float* __restrict__ state,
                                     const float* __restrict__ grad, const float* __restrict__ lo,
@@ -142,6 +142,7 @@ __global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, i
   if (i >= n) return;
   const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
   const float clip = hyper[4], mom = hyper[5], step = hyper[6];
+  const float om1 = hyper[7], om2 = hyper[8];      // 1 - decay|b1, 1 - b2 rounded from double (optax)
   float g = grad[i];
   if (clip > 0.f) {                      // optax.clip_by_global_norm (planner.py:2368-2369)
     const float gn = sqrtf(stats[0]);
@@ -149,12 +150,12 @@ __global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, i
   }
   float upd;
   if (kind == 1) {                       // optax.rmsprop: nu <- d nu + (1-d) g^2 ; g * rsqrt(nu + eps)
-    float nu = d1 * state[i] + (1.f - d1) * g * g;
+    float nu = d1 * state[i] + om1 * g * g;
     state[i] = nu;
     upd = g / sqrtf(nu + eps);
   } else if (kind == 2) {                // optax.adam with bias correction, step is 1-based
-    float mu = d1 * state[i] + (1.f - d1) * g;
-    float nu = b2 * state[n + i] + (1.f - b2) * g * g;
+    float mu = d1 * state[i] + om1 * g;
+    float nu = b2 * state[n + i] + om2 * g * g;
     state[i] = mu;
     state[n + i] = nu;
     float mh = mu / (1.f - powf(d1, step));
@@ -193,6 +194,7 @@ rk_optimizer_small_kernel(int kind, const float* __restrict__ hyper, int n, floa
   if (threadIdx.x == 0 && zero_flag != nullptr) *zero_flag = (nz == 0.f) ? 1 : 0;
   const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
   const float clip = hyper[4], mom = hyper[5], step = hyper[6];
+  const float om1 = hyper[7], om2 = hyper[8];      // 1 - decay|b1, 1 - b2 rounded from double (optax)
   float scale = 1.f;
   bool clipped = false;
   if (clip > 0.f) {
@@ -204,12 +206,12 @@ rk_optimizer_small_kernel(int kind, const float* __restrict__ hyper, int n, floa
     if (clipped) g = g * scale;
     float upd;
     if (kind == 1) {
-      float nu = d1 * state[i] + (1.f - d1) * g * g;
+      float nu = d1 * state[i] + om1 * g * g;
       state[i] = nu;
       upd = g / sqrtf(nu + eps);
     } else if (kind == 2) {
-      float mu = d1 * state[i] + (1.f - d1) * g;
-      float nu = b2 * state[n + i] + (1.f - b2) * g * g;
+      float mu = d1 * state[i] + om1 * g;
+      float nu = b2 * state[n + i] + om2 * g * g;
       state[i] = mu;
       state[n + i] = nu;
       float mh = mu / (1.f - powf(d1, step));

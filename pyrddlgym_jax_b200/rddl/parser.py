@@ -49,6 +49,7 @@ DISTRIBUTIONS = {
 _BINARY = {
     "<=>": (1, "boolean"), "=>": (2, "boolean"), "|": (3, "boolean"),
     "^": (4, "boolean"), "&": (4, "boolean"),
+    "~": (4, "boolean"),          # binary form = xor (compiler.py:1233-1274: '~' with two arguments)
     "==": (6, "relational"), "~=": (6, "relational"), "<": (6, "relational"),
     "<=": (6, "relational"), ">": (6, "relational"), ">=": (6, "relational"),
     "+": (7, "arithmetic"), "-": (7, "arithmetic"),

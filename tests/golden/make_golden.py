@@ -35,6 +35,10 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("discrete_relaxed", "discrete", 6, 5, True, 1.0, {}),
     ("distributions_exact", "distributions", 6, 4, False, 1.0, {}),
     ("distributions_relaxed", "distributions", 6, 4, True, 1.0, {}),
+    ("ops_exact", "ops", 6, 5, False, 1.0, {}),
+    ("ops_relaxed", "ops", 6, 5, True, 0.9, {}),
+    ("samplers_exact", "samplers", 6, 5, False, 1.0, {}),
+    ("samplers_relaxed", "samplers", 6, 5, True, 1.0, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]

@@ -26,6 +26,9 @@ FIXTURES = {
     "distributions": ("Distributions_Toy", "instance1"),
     "wildfire_free": ("Wildfire_MDP_ippc2014", "instance5free"),    # no concurrency constraint
     "gammafluent": ("Gamma_Fluent_Toy", "instance1"),
+    # every operator / sampler of SURVEY Appendix G that the domains above do not use
+    "ops": ("Ops_Toy", "instance1"),
+    "samplers": ("Samplers_Toy", "instance1"),
 }
 
 

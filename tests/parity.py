@@ -172,24 +172,54 @@ def gradient_case(backend, key, B, T, gamma=1.0, compiler_cls=None, param_scale=
     return c
 
 
+# Tolerances are ELEMENT-WISE: |got - ref| <= rtol * |ref| + floor, with rtol = 1e-5 for states,
+# rewards and returns and 1e-4 for gradients (BASELINE.json north_star) and an absolute floor
+# floor_frac * rtol * max|ref| for the entries that are sums with cancellation: 1e-6 of the largest
+# entry for states / rewards / returns (FLOOR_FWD: a Reservoir reward of -5.4 is the fp32 sum of
+# penalties of size 1000, whose own last-bit differences are 6e-5) and 1e-6 of the largest entry for
+# gradients (FLOOR_FRAC).
+FLOOR_FRAC = 1e-2
+FLOOR_FWD = 1e-1
+
+
+def assert_close(got, ref, rtol, what, floor_frac=FLOOR_FRAC, scale_min=0.0):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    if ref.size == 0:
+        return
+    both_nan = np.isnan(got) & np.isnan(ref)
+    same_inf = np.isinf(ref) & (got == ref)
+    floor = floor_frac * rtol * max(scale_min, float(np.nanmax(np.abs(np.where(np.isfinite(ref), ref, 0.0)))))
+    with np.errstate(invalid="ignore"):
+        bad = ~(np.abs(got - ref) <= rtol * np.abs(ref) + floor) & ~both_nan & ~same_inf
+    if bad.any():
+        idx = np.argwhere(bad)
+        err = np.where(bad, np.abs(got - ref) / (np.abs(ref) + floor), 0.0)
+        w = np.unravel_index(np.argmax(err), err.shape)
+        raise AssertionError(
+            f"{what}: {int(bad.sum())} of {ref.size} entries outside rtol {rtol:g} + floor {floor:.3g}; "
+            f"worst at {tuple(int(i) for i in w)}: got {got[w]!r} ref {ref[w]!r} "
+            f"(|diff| {abs(got[w] - ref[w]):.3g}); first {idx[:5].tolist()}")
+
+
 def check_forward(c, rtol=1e-5):
-    """states / returns within rtol 1e-5 (fp32), bool / int fluents bit-exact."""
+    """states / rewards / returns element-wise within rtol 1e-5 (fp32), bool / int fluents and the
+    error words bit-exact."""
     ref, got = c["ref"], c["got"]
     r_ref = ref["reward"].detach().numpy().T
-    np.testing.assert_allclose(got["reward"], r_ref, rtol=rtol, atol=rtol * max(1.0, np.abs(r_ref).max()))
+    assert_close(got["reward"], r_ref, rtol, "reward", FLOOR_FWD, scale_min=1.0)
     ret_ref = OP.returns_from_rewards(ref["reward"].detach(), c["gamma"]).numpy()
-    np.testing.assert_allclose(got["returns"], ret_ref, rtol=rtol, atol=rtol * np.abs(ret_ref).max())
+    assert_close(got["returns"], ret_ref, rtol, "returns", FLOOR_FWD, scale_min=float(np.abs(r_ref).max()) if r_ref.size else 0.0)
     for s in c["model"].state_fluents:
         a = ref["final"][s].detach().reshape(c["final"][s].shape[0], -1)
         b = c["final"][s].reshape(a.shape)
         if a.dtype in (torch.bool, torch.int32):
             assert torch.equal(a.to(torch.int32), b.to(torch.int32)), f"fluent {s} not bit-exact"
         else:
-            np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=rtol,
-                                       atol=rtol * max(1.0, float(a.abs().max())))
+            assert_close(b.numpy(), a.numpy(), rtol, f"final state {s}", FLOOR_FWD, scale_min=1.0)
     np.testing.assert_array_equal(got["err"], ref["error"].numpy().T.astype(np.uint32))
 
 
 def check_gradient(c, rtol=1e-4):
-    g, gr = c["grad"], c["grad_ref"]
-    np.testing.assert_allclose(g, gr, rtol=rtol, atol=rtol * np.abs(gr).max())
+    """plan gradient element-wise within rtol 1e-4 (fp32)."""
+    assert_close(c["grad"], c["grad_ref"], rtol, "gradient")

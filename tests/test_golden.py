@@ -10,7 +10,7 @@ import torch
 
 from oracle import planner as OP
 
-from .parity import forward_case, gradient_case
+from .parity import FLOOR_FWD, assert_close, forward_case, gradient_case
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
@@ -47,9 +47,8 @@ def check_against_golden(g, c, rtol, gtol, oracle_side):
         err = c["got"]["err"].T
         final = {s: c["final"][s].reshape(int(g["B"]), -1) for s in c["model"].state_fluents}
         grad = c.get("grad")
-    np.testing.assert_allclose(r, gold_r, rtol=rtol, atol=rtol * scale)
-    np.testing.assert_allclose(ret, g["returns"], rtol=rtol,
-                               atol=rtol * max(1.0, float(np.abs(g["returns"]).max())))
+    assert_close(r, gold_r, rtol, "reward", FLOOR_FWD, scale_min=1.0)
+    assert_close(ret, g["returns"], rtol, "returns", FLOOR_FWD, scale_min=scale)
     np.testing.assert_array_equal(err, g["error"])
     for s, v in final.items():
         gold = g["final_" + s]
@@ -57,10 +56,9 @@ def check_against_golden(g, c, rtol, gtol, oracle_side):
             assert np.array_equal(v.to(torch.int32).numpy(), gold.astype(np.int32)), \
                 f"{s}: bool/int fluent not bit-exact"
         else:
-            np.testing.assert_allclose(v.numpy(), gold, rtol=rtol,
-                                       atol=rtol * max(1.0, float(np.abs(gold).max())))
+            assert_close(v.numpy(), gold, rtol, f"final state {s}", FLOOR_FWD, scale_min=1.0)
     if relaxed:
-        np.testing.assert_allclose(grad, g["grad"], rtol=gtol, atol=gtol * np.abs(g["grad"]).max())
+        assert_close(grad, g["grad"], gtol, "gradient")
 
 
 def test_golden_files_exist():

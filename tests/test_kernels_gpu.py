@@ -13,7 +13,7 @@ from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 pytestmark = pytest.mark.gpu
 KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
-        "distributions"]
+        "distributions", "ops", "samplers"]
 # 'cuda' = generic interpreter kernel, 'jit' = per-program specialised kernel (core/codegen.py)
 BACKENDS = ["cuda", "jit"]
 
@@ -84,6 +84,34 @@ def test_variants_cuda(cuda_device, backend):
                       bernoulli_sigmoid_weight=100.0)
     check_forward(c)
     check_gradient(c)
+
+
+class _Luka(logic.SigmoidRelational, logic.LukasiewiczNormLogical, logic.LinearIfElse,
+            logic.DeterminizedBernoulli):
+    pass
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_lukasiewicz_cuda(cuda_device, backend):
+    """The Lukasiewicz t-norm (logic.py:674-778) on the Wildfire / Reservoir CPFs."""
+    for key in ("wildfire", "reservoir"):
+        c = gradient_case(backend, key, B=19, T=5, compiler_cls=_Luka, sigmoid_weight=2.0)
+        check_forward(c)
+        check_gradient(c)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("variant", range(6))
+def test_ops_variants_cuda(cuda_device, backend, variant):
+    """Every relaxation family with and without straight-through estimators, under the product,
+    Goedel and Lukasiewicz t-norms, on the fixtures that use every operator and sampler of the
+    instruction set (tests/test_lowering_cpu.py::OPS_VARIANTS)."""
+    from .test_lowering_cpu import OPS_VARIANTS
+    cls, kw = OPS_VARIANTS[variant]
+    for key in ("ops", "samplers"):
+        c = gradient_case(backend, key, B=23, T=5, compiler_cls=cls, **kw)
+        check_forward(c)
+        check_gradient(c)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)

@@ -7,7 +7,7 @@ from pyrddlgym_jax_b200.core import logic
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
-        "distributions"]
+        "distributions", "ops", "samplers"]
 
 
 @pytest.mark.parametrize("key", KEYS)
@@ -44,6 +44,43 @@ def test_relaxation_variants_emulated(cls, kw):
         c = gradient_case("emu", key, B=7, T=4, compiler_cls=cls, **kw)
         check_forward(c)
         check_gradient(c)
+
+
+class _GodelOps(logic.SigmoidRelational, logic.SoftmaxArgmax, logic.GodelNormLogical,
+                logic.SoftFloor, logic.SoftRound, logic.LinearIfElse, logic.SoftmaxSwitch,
+                logic.ReparameterizedGeometric):
+    pass
+
+
+class _LukaOps(logic.SigmoidRelational, logic.SoftmaxArgmax, logic.LukasiewiczNormLogical,
+               logic.SoftFloor, logic.SoftRound, logic.LinearIfElse, logic.SoftmaxSwitch,
+               logic.DeterminizedGeometric):
+    pass
+
+
+OPS_VARIANTS = [
+    (logic.DefaultJaxRDDLCompilerWithGrad, dict(use_sigmoid_ste=False, use_tanh_ste=False,
+                                                use_argmax_ste=False, use_floor_ste=False,
+                                                use_round_ste=False, use_if_else_ste=False)),
+    (logic.DefaultJaxRDDLCompilerWithGrad, dict(use_logic_ste=True, sigmoid_weight=4.0,
+                                                argmax_weight=3.0, floor_weight=6.0, round_weight=7.0)),
+    (_GodelOps, dict(sigmoid_weight=3.0)),
+    (_GodelOps, dict(sigmoid_weight=3.0, use_logic_ste=True)),
+    (_LukaOps, dict(sigmoid_weight=2.0)),
+    (_LukaOps, dict(sigmoid_weight=2.0, use_logic_ste=True, use_sigmoid_ste=False)),
+]
+
+
+@pytest.mark.parametrize("cls,kw", OPS_VARIANTS)
+def test_ops_relaxation_variants_emulated(cls, kw):
+    """Every relaxation family (SigmoidRelational incl. == ~= sgn, SoftmaxArgmax, the three t-norms
+    incl. => <=> xor, SoftFloor / SoftRound incl. div mod, ReparameterizedGeometric) with and without
+    straight-through estimators, on the fixtures that use every operator of the instruction set."""
+    for key in ("ops", "samplers"):
+        c = gradient_case("emu", key, B=7, T=4, compiler_cls=cls, **kw)
+        check_forward(c)
+        check_gradient(c)
+        assert float(abs(c["grad"]).max()) > 0
 
 
 @pytest.mark.parametrize("key", ["reservoir", "quadcopter", "powergen"])

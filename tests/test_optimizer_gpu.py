@@ -1,0 +1,103 @@
+"""GPU parity of rk_optimizer_step (through the C ABI) against the oracle's restatement of the optax
+chain (oracle/planner.py: clip_by_global_norm, rmsprop_step, adam_step, sgd_step, sgd_momentum_step;
+reference planner.py:2349-2387, 2885-2899) and of the box projection (planner.py:896-904): five
+consecutive steps from the same gradients, parameters and optimiser state compared element-wise
+after every step."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import planner as OP
+
+from .parity import assert_close
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # kind, kwargs, clip, box
+    ("rmsprop", {}, None, False),
+    ("rmsprop", {"decay": 0.95, "eps": 1e-6}, 0.5, True),
+    ("adam", {}, None, False),
+    ("adam", {"b1": 0.8, "b2": 0.99, "eps": 1e-6}, 2.0, True),
+    ("sgd", {}, None, True),
+    ("sgd", {"momentum": 0.9}, 1.0, False),
+]
+
+
+def _hyper(kind, lr, kw, clip, step):
+    if kind == "rmsprop":
+        h = [lr, kw.get("decay", 0.9), kw.get("eps", 1e-8), 0., 0., 0., step]
+    elif kind == "adam":
+        h = [lr, kw.get("b1", 0.9), kw.get("eps", 1e-8), kw.get("b2", 0.999), 0., 0., step]
+    else:
+        h = [lr, 0., 0., 0., 0., kw.get("momentum", 0.) or 0., step]
+    h[4] = float(clip) if clip is not None else 0.
+    return h + [1.0 - h[1], 1.0 - h[3]]
+
+
+@pytest.mark.parametrize("n", [37, 1600, 70154])          # single-CTA path, SLP size, DRP size
+@pytest.mark.parametrize("kind,kw,clip,box", CASES)
+def test_optimizer_step_matches_oracle(cuda_device, n, kind, kw, clip, box):
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(1234 + n)
+    lr = 0.03
+    p = torch.randn(n, generator=g)
+    lo = (p - torch.rand(n, generator=g) * 0.05) if box else None
+    hi = (p + torch.rand(n, generator=g) * 0.05) if box else None
+    if box:                                              # one-sided and open boxes too
+        lo[::7] = -float("inf")
+        hi[::5] = float("inf")
+    n_state = 2 if kind == "adam" else 1
+    state_ref = [torch.zeros(n) for _ in range(n_state)]
+    p_ref = p.clone()
+    p_dev = p.to(cuda_device)
+    st_dev = torch.zeros(n_state * n, device=cuda_device)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    lo_d = None if lo is None else lo.to(cuda_device)
+    hi_d = None if hi is None else hi.to(cuda_device)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-3, 2, (1,), generator=g)))
+        if step == 4:
+            grad = torch.zeros(n)                        # zero-gradient flag (planner.py:2861-2864)
+        gr = grad
+        if clip is not None:
+            (gr,) = OP.clip_by_global_norm([grad], clip)
+        if kind == "rmsprop":
+            p_ref, state_ref[0] = OP.rmsprop_step(p_ref, gr, state_ref[0], lr, kw.get("decay", 0.9),
+                                                  kw.get("eps", 1e-8))
+        elif kind == "adam":
+            p_ref, state_ref[0], state_ref[1] = OP.adam_step(
+                p_ref, gr, state_ref[0], state_ref[1], step, lr, kw.get("b1", 0.9),
+                kw.get("b2", 0.999), kw.get("eps", 1e-8))
+        elif kw.get("momentum"):
+            p_ref, state_ref[0] = OP.sgd_momentum_step(p_ref, gr, state_ref[0], lr, kw["momentum"])
+        else:
+            p_ref = OP.sgd_step(p_ref, gr, lr)
+        if box:
+            p_ref = torch.minimum(torch.maximum(p_ref, lo), hi)
+        hyper = torch.tensor(_hyper(kind, lr, kw, clip, float(step)), device=cuda_device)
+        engine.optimizer_step(kind, hyper, n, p_dev, st_dev, grad.to(cuda_device), lo_d, hi_d, flag)
+        torch.cuda.synchronize()
+        assert_close(p_dev.cpu().numpy(), p_ref.numpy(), 2e-6, f"{kind} params after step {step}")
+        if kind != "sgd" or kw.get("momentum"):
+            for k in range(n_state):
+                assert_close(st_dev[k * n:(k + 1) * n].cpu().numpy(), state_ref[k].numpy(), 2e-6,
+                             f"{kind} state {k} after step {step}")
+        assert int(flag.item()) == (1 if step == 4 else 0)
+
+
+def test_reduce_partials_and_mean_loss_match_numpy(cuda_device):
+    """rk_reduce_partials (fixed-order sum of the per-warp gradient rows) and rk_mean_loss."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(7)
+    rows, n = 513, 1600
+    gp = torch.randn(rows, n, generator=g)
+    out = torch.zeros(n, device=cuda_device)
+    engine.reduce_partials(gp.to(cuda_device).reshape(-1), rows, n, out)
+    ret = torch.randn(4097, generator=g) * 50
+    loss = torch.zeros(1, device=cuda_device)
+    gret = torch.zeros(4097, device=cuda_device)
+    engine.mean_loss(ret.to(cuda_device), 4097, loss, gret)
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), gp.double().sum(0).numpy(), 1e-5, "reduce_partials", floor_frac=1.0)
+    assert abs(float(loss) + float(ret.double().mean())) <= 1e-5 * float(ret.abs().mean())
+    np.testing.assert_array_equal(gret.cpu().numpy(), np.full(4097, np.float32(-1.0 / 4097)))

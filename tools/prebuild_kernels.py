@@ -19,18 +19,22 @@ def prebuild_workload(name: str, verbose: bool = True):
     drp = w.get("plan") == "drp"
     plan = (JaxDeepReactivePolicy if drp else JaxStraightLinePlan)(**w["plan_kwargs"])
     plan.compile(comp, exact, {}, w["T"])
-    tb = comp.builder(plan.spec, True, (), w["B"])
     gamma = float(model.discount)
-    if drp:     # the programs JaxBackpropPlanner._compile builds for a closed-loop plan
-        train = (tb.forward(write_tape=False, gamma=gamma),
-                 tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
-    else:
-        train = (tb.forward(write_tape=True, gamma=gamma), tb.backward(gamma=gamma))
-    for prog in (*train,
-                 exact.builder(plan.spec, False, (), w["B"]).forward(write_tape=False, gamma=gamma)):
-        path = compile_cubin(prog)[0]
-        if verbose:
-            print(name, os.path.basename(path))
+    # a strong-scaling workload runs at global batch / N rollouts per GPU: the batch hint may change
+    # the lanes-per-rollout choice, so every N of the scaling run gets its kernels
+    batches = sorted({bench.per_gpu_batch(name, n) for n in (1, 2, 4, 8)})
+    for B in batches:
+        tb = comp.builder(plan.spec, True, (), B)
+        if drp:     # the programs JaxBackpropPlanner._compile builds for a closed-loop plan
+            train = (tb.forward(write_tape=False, gamma=gamma),
+                     tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
+        else:
+            train = (tb.backward(gamma=gamma), tb.forward(write_tape=True, gamma=gamma))
+        for prog in (*train,
+                     exact.builder(plan.spec, False, (), B).forward(write_tape=False, gamma=gamma)):
+            path = compile_cubin(prog)[0]
+            if verbose:
+                print(name, B, os.path.basename(path))
 
 
 def prebuild_all(verbose: bool = True):
