@@ -58,6 +58,13 @@ int rk_program_query(const rk_program* prog, rk_sizes* out);
  * Plays the role of the XLA executable cache behind jax.jit (planner.py:2687, 2930). */
 int rk_program_attach_cubin(rk_program* prog, const void* image, size_t nbytes,
                             const char* entry);
+/* The same with the launch geometry of the kernel given by the caller: threads per CTA (a multiple
+ * of 32; 0 = the interpreter layout's warps_per_cta * 32), dynamic shared memory in bytes (-1 = the
+ * interpreter layout's) and the preferred shared-memory carve-out in percent (-1 = driver default).
+ * Thread-per-rollout kernels (core/codegen_tpr.py: lanes = 1, a warp carries 32 rollouts) keep all
+ * their values in registers and attach with (128, 0, 0). */
+int rk_program_attach_cubin_ex(rk_program* prog, const void* image, size_t nbytes,
+                               const char* entry, int threads_per_cta, int smem_bytes, int carveout);
 /* number of warps (= gradient partial rows) a launch with batch B uses */
 int rk_program_num_warps(const rk_program* prog, int B);
 

@@ -791,6 +791,9 @@ extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
 
 
 def generate_source(prog: Program) -> str:
+    if prog.lanes == 1:         # a lane owns a whole rollout: registers only, no shuffles
+        from .codegen_tpr import generate_source as generate_tpr
+        return generate_tpr(prog)
     return _Gen(prog).source()
 
 

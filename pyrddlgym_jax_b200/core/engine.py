@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"
 
 EXPORTS = [
     "rk_program_create", "rk_program_destroy", "rk_program_query", "rk_program_num_warps",
-    "rk_program_attach_cubin",
+    "rk_program_attach_cubin", "rk_program_attach_cubin_ex",
     "rk_rollout_forward", "rk_rollout_backward", "rk_reduce_partials", "rk_optimizer_step",
     "rk_mean_loss", "rk_project_slp", "rk_sgemm", "rk_drp_actions_forward",
     "rk_drp_actions_backward", "rk_tf32_split", "rk_tcgemm", "rk_drp_layer0", "rk_colsum",
@@ -63,6 +63,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_program_query.restype = ci
     lib.rk_program_attach_cubin.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_char_p]
     lib.rk_program_attach_cubin.restype = ci
+    lib.rk_program_attach_cubin_ex.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_char_p, ci, ci, ci]
+    lib.rk_program_attach_cubin_ex.restype = ci
     lib.rk_program_num_warps.argtypes = [vp, ci]
     lib.rk_program_num_warps.restype = ci
     lib.rk_rollout_forward.argtypes = [vp, vp, ci, ci] + [cf] * 12
@@ -184,9 +186,15 @@ class DeviceProgram:
             with open(cubin, "rb") as f:
                 image = f.read()
             self._image = ctypes.create_string_buffer(image, len(image))
-            _check(self.lib.rk_program_attach_cubin(self.handle, self._image, len(image),
-                                                    KERNEL_NAME.encode()),
-                   "rk_program_attach_cubin")
+            if program.lanes == 1:      # thread-per-rollout kernel: registers only (codegen_tpr.py)
+                from .codegen_tpr import THREADS
+                _check(self.lib.rk_program_attach_cubin_ex(
+                    self.handle, self._image, len(image), KERNEL_NAME.encode(), THREADS, 0,
+                    int(os.environ.get("RK_CARVEOUT_TPR", "0"))), "rk_program_attach_cubin_ex")
+            else:
+                _check(self.lib.rk_program_attach_cubin(self.handle, self._image, len(image),
+                                                        KERNEL_NAME.encode()),
+                       "rk_program_attach_cubin")
             self.specialized = True
 
     def __del__(self):

@@ -647,6 +647,30 @@ class ProgramBuilder:
                 best, best_t = prog, t
         if best is None:
             raise last_err
+        # thread-per-rollout kernels (lanes = 1, core/codegen_tpr.py): a warp carries 32 rollouts and
+        # every value lives in registers, so the step costs ~1.4 SASS instructions per ELEMENT instead
+        # of 2 - 4 per instruction-pass of an L-lane layout (measured on the MarsRover adjoint: 54
+        # against 332 per rollout-step) -- but the launch has 32 / rpw times fewer warps.  Estimated
+        # time = issue slots per scheduler, a lone warp issuing at ipc < 1.
+        if self.INS_OVERHEAD < 1.0 and best.lanes != 1 and not forced \
+                and _os.environ.get("RK_TPR", "1") != "0":
+            try:
+                tpr = self._assemble_for(kind, pro, step, epi, persistent, 1)
+            except ProgramError:
+                tpr = None
+            if tpr is not None:
+                def est(prog, sass, ipc):
+                    wps = (-(-B // prog.rpw)) / (148 * 4)
+                    return sass * max(1.0 / ipc, wps)
+                L = best.lanes
+                sass_multi = 2.2 * sum((-(-max(i.n, 1) // L)) * (self.MULTIPASS_PENALTY if i.n > L else 1.0)
+                                       for i in step)
+                sass_tpr = sum((10.0 if i.op == "QSUM" else 1.4) * max(i.n, 1) for i in step)
+                live = tpr.warp_words / 32.0                  # scalar values alive at once, per lane
+                if live > 400:
+                    sass_tpr *= 1.0 + (live - 400.0) / 200.0  # local-memory spills
+                if est(tpr, sass_tpr, 0.7) < 0.8 * est(best, sass_multi, 0.4):
+                    best = tpr
         return best
 
     def _assemble_for(self, kind: str, pro: List[Ins], step: List[Ins], epi: List[Ins],

@@ -392,6 +392,8 @@ struct rk_program {
   int device;
   void* module;     // CUmodule of the specialised kernel (core/codegen.py), or NULL
   void* func;       // CUfunction
+  int spec_threads; // launch geometry of the attached kernel: threads per CTA (0 = warps_per_cta * 32)
+  int spec_smem;    //   dynamic shared memory in bytes (-1 = smem_bytes of the interpreter layout)
 };
 
 // ---- CUDA driver API, resolved lazily so that the library also loads on hosts without a
@@ -428,9 +430,22 @@ static int load_driver() {
   return 0;
 }
 
+extern "C" int rk_program_attach_cubin_ex(rk_program* p, const void* image, size_t nbytes,
+                                          const char* entry, int threads_per_cta, int smem_bytes,
+                                          int carveout);
+
 extern "C" int rk_program_attach_cubin(rk_program* p, const void* image, size_t nbytes,
                                        const char* entry) {
+  const char* co = getenv("RK_CARVEOUT");
+  return rk_program_attach_cubin_ex(p, image, nbytes, entry, 0, -1, co ? atoi(co) : 100);
+}
+
+extern "C" int rk_program_attach_cubin_ex(rk_program* p, const void* image, size_t nbytes,
+                                          const char* entry, int threads_per_cta, int smem_bytes,
+                                          int carveout) {
   if (p == nullptr || image == nullptr || nbytes == 0 || entry == nullptr) return RK_E_BADARG;
+  if (threads_per_cta < 0 || threads_per_cta > 1024 || (threads_per_cta & 31) != 0) return RK_E_BADARG;
+  if (smem_bytes < -1 || smem_bytes > 227 * 1024) return RK_E_BADARG;
   int rc = load_driver();
   if (rc != 0) return rc;
   cudaFree(0);                                   // make sure the primary context is current
@@ -441,16 +456,17 @@ extern "C" int rk_program_attach_cubin(rk_program* p, const void* image, size_t 
   rc = g_drv.moduleGetFunction(&fn, mod, entry);
   if (rc != 0) { g_drv.moduleUnload(mod); return rc; }
   // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
-  rc = g_drv.funcSetAttribute(fn, 8, p->smem_bytes);
+  rc = g_drv.funcSetAttribute(fn, 8, smem_bytes >= 0 ? smem_bytes : p->smem_bytes);
   if (rc != 0) { g_drv.moduleUnload(mod); return rc; }
   // CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT = 9: every rollout kernel asks for the
   // same L1 / shared split, so the exact test kernel and the train kernels of the pipelined
   // iteration can share an SM (kernels with different splits cannot co-reside)
-  if (getenv("RK_CARVEOUT") == nullptr || atoi(getenv("RK_CARVEOUT")) >= 0)
-    g_drv.funcSetAttribute(fn, 9, getenv("RK_CARVEOUT") ? atoi(getenv("RK_CARVEOUT")) : 100);
+  if (carveout >= 0) g_drv.funcSetAttribute(fn, 9, carveout > 100 ? 100 : carveout);
   if (p->module != nullptr) g_drv.moduleUnload(p->module);
   p->module = mod;
   p->func = fn;
+  p->spec_threads = threads_per_cta;
+  p->spec_smem = smem_bytes;
   return 0;
 }
 
@@ -553,8 +569,11 @@ static int launch(const rk_program* p, cudaStream_t st, RkLaunch& K) {
     for (int i = 0; i < RK_NUM_BUFFERS; ++i)
       if (K.W[i] * (long long)K.B >= (1ll << 31)) return RK_E_BADARG;
     void* args[] = {(void*)&K};
-    return g_drv.launchKernel(p->func, (unsigned)grid, 1, 1, (unsigned)(p->warps_per_cta * 32), 1,
-                              1, (unsigned)p->smem_bytes, (void*)st, args, nullptr);
+    const int threads = p->spec_threads > 0 ? p->spec_threads : p->warps_per_cta * 32;
+    const int sgrid = (nwarps + threads / 32 - 1) / (threads / 32);
+    const int smem = p->spec_smem >= 0 ? p->spec_smem : p->smem_bytes;
+    return g_drv.launchKernel(p->func, (unsigned)sgrid, 1, 1, (unsigned)threads, 1, 1,
+                              (unsigned)smem, (void*)st, args, nullptr);
   }
   rk_interp_kernel<<<grid, p->warps_per_cta * 32, p->smem_bytes, st>>>(K);
   return (int)cudaGetLastError();

@@ -86,6 +86,31 @@ def test_variants_cuda(cuda_device, backend):
     check_gradient(c)
 
 
+@pytest.mark.parametrize("key", KEYS + ["gammafluent"])
+def test_thread_per_rollout_kernels_cuda(cuda_device, key, monkeypatch):
+    """lanes = 1 programs (a lane owns a whole rollout, core/codegen_tpr.py): generated kernel and
+    interpreter, exact forward + relaxed forward + gradient, ragged batch."""
+    from pyrddlgym_jax_b200.core.program import ProgramError
+    monkeypatch.setenv("RK_LANES", "1")
+    for backend in BACKENDS:
+        try:
+            c = gradient_case(backend, key, B=77, T=5, gamma=0.95)
+        except ProgramError:
+            pytest.skip("the program does not fit a lanes = 1 layout")
+        assert c["fwd"].lanes == 1 and c["bwd"].lanes == 1
+        check_forward(c)
+        check_gradient(c)
+        check_forward(forward_case(backend, key, B=77, T=5, relaxed=False))
+
+
+def test_thread_per_rollout_large_batch_cuda(cuda_device):
+    """The assembler's own choice at a batch that fills the machine: MarsRover picks lanes = 1."""
+    c = gradient_case("jit", "marsrover", B=40000, T=6)
+    assert c["bwd"].lanes == 1 and c["fwd"].lanes == 1
+    check_forward(c)
+    check_gradient(c)
+
+
 class _Luka(logic.SigmoidRelational, logic.LukasiewiczNormLogical, logic.LinearIfElse,
             logic.DeterminizedBernoulli):
     pass
