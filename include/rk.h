@@ -249,6 +249,24 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
               const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
               const float* bias, const float* aux, int ldaux);
 
+/* Fused forward of a policy network with two hidden layers for one decision epoch:
+ *   heads[B][NH] = act(act(x W0 + b0) W1 + b1) Wh + bh
+ * Replaces: DRPStateLayer + the two Dense/activation layers + the per-action Dense heads of
+ * JaxDeepReactivePolicy (planner.py:1287-1449) inside the scan body (compiler.py:552-558).
+ *   x_fm   : the state in the rollout kernels' fluent-major layout (fluent f = block [B][len_f] at word
+ *            offset off_f * B); D = sum of len_f <= 16 inputs; H0n, H1n multiples of 16 / 32, <= 256
+ *   W0 [D][H0n], b0 [H0n]; W1T_hi / W1T_lo [H1n][H0n]: W1^T split by rk_tf32_split; b1 [H1n];
+ *   Wh [H1n][NH], bh [NH], NH <= 16
+ *   H0 [B][H0n], H1 [B][H1n]: hidden activations for the adjoint, or NULL (the exact test sweep
+ *            writes nothing but the head outputs)
+ * One launch: layer 0 is computed straight into the tensor-core operand tiles, the hidden layer
+ * runs on tcgen05 (3xTF32), the head product is taken from the accumulator tile in the epilogue. */
+int rk_drp_mlp2_forward(void* stream, int B, int D, int H0n, int H1n, int NH, int n_seg,
+                        const int32_t* seg_off, const int32_t* seg_len, const float* x_fm,
+                        const float* W0, const float* b0, const float* W1T_hi, const float* W1T_lo,
+                        const float* b1, const float* Wh, const float* bh, float* H0, float* H1,
+                        float* heads);
+
 /* Weight gradient of a hidden layer on the tensor cores: C[M][N] (+)= A[K][M]^T * B[K][N] with
  * both operands plain fp32 activations stored batch-major (K = rollouts), MN-major UMMA tiles,
  * 3xTF32 split done in the kernel, deterministic split-K (at most max_splits slices) through

@@ -237,10 +237,14 @@ def rmsprop_step(p, g, nu, lr, decay=0.9, eps=1e-8):
 
 
 def adam_step(p, g, mu, nu, step, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """optax.adam.  The moment updates take (1 - decay) from the Python floats (double precision,
+    rounded once); optax.bias_correction forms ``1 - decay ** count`` with ``count`` an int32 ARRAY,
+    i.e. a float32 power of the float32-rounded decay."""
     mu = b1 * mu + (1. - b1) * g
     nu = b2 * nu + (1. - b2) * g * g
-    mh = mu / (1. - b1 ** step)
-    nh = nu / (1. - b2 ** step)
+    t = torch.tensor(float(step), dtype=REAL)
+    mh = mu / (1. - torch.pow(torch.tensor(b1, dtype=REAL), t))
+    nh = nu / (1. - torch.pow(torch.tensor(b2, dtype=REAL), t))
     return p - lr * mh / (torch.sqrt(nh) + eps), mu, nu
 
 

@@ -537,6 +537,12 @@ class DrpPipeline:
         hl = self.hid[-1]
         self.fused_head = fuse and len(self.hid) >= 2 and self.NH <= 16 and hl <= 1024
         self.fused_l0 = fuse and self.D <= 16
+        # whole forward of a 2-hidden-layer network in one launch per decision epoch (rk_drp_mlp2_forward)
+        self.fused_fwd = (fuse and self.fused_l0 and len(self.hid) == 2 and self.D <= 16 and self.NH <= 16
+                          and Bt >= 128 and self.hid[0] % 16 == 0 and self.hid[0] <= 256
+                          and self.hid[1] % 32 == 0 and 32 <= self.hid[1] <= 256
+                          and _os0.environ.get("RK_TCGEMM", "1") != "0"
+                          and _os0.environ.get("RK_DRP_FUSED_FWD", "1") != "0")
         ctas = engine.drp_head_backward_ctas(Bt)
         self.fb_ws = z(ctas * max(hl + hl * self.NH + self.NH, (self.D + 1) * self.hid[0]))
         # tensor-core path (tcgen05, 3xTF32) for hidden layers whose shapes fit the MMA tiles
@@ -649,11 +655,20 @@ class DrpPipeline:
                               self.wT_lo[off:off + n], n)
 
     # ---- the MLP ------------------------------------------------------------------------------
-    def mlp_forward(self, params, B, x_fm, H, heads, xp=None, film=None):
+    def mlp_forward(self, params, B, x_fm, H, heads, xp=None, film=None, keep_hidden=True):
         """x_fm: the state in the kernels' fluent-major layout (fluent f = block [B][n_f] at word
         offset off_f * B); H: per-layer outputs [B][h]; heads [B][NH]; xp: optional [B][D+1]
-        packed copy [x | 1] for the backward pass."""
+        packed copy [x | 1] for the backward pass; keep_hidden=False (exact test sweep): the
+        hidden activations are not needed afterwards."""
         h0 = self.hid[0]
+        if self.fused_fwd and film is None and 1 in self.tc_layers:
+            engine.drp_mlp2_forward(
+                B, self.D, h0, self.hid[1], self.NH, self.plan.state_segs, x_fm,
+                self._W(params, "W0"), self._W(params, "b0"), self._W(self.wT_hi, "W1"),
+                self._W(self.wT_lo, "W1"), self._W(params, "b1"), self._W(params, "Wh"),
+                self._W(params, "bh"), H[0] if keep_hidden else None, H[1] if keep_hidden else None,
+                heads)
+            return
         engine.drp_layer0(B, self.D, h0, self.plan.state_segs, x_fm, self._W(params, "W0"),
                           self._W(params, "b0"), H[0], xp)
         fan, src = h0, H[0]
@@ -894,7 +909,7 @@ class DrpPipeline:
                 self.layernorm_forward(params, B, xin, self.t_xn)
                 xin = self.t_xn
             self.mlp_forward(params, B, xin, self.t_H, self.t_heads,
-                             film=(t, self.t_Hf) if self.film else None)
+                             film=(t, self.t_Hf) if self.film else None, keep_hidden=False)
             engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,
                                        None, 0.0, self.lo,
                                        self.hi, self.ls_lo, self.ls_hi, self.t_act, None,

@@ -29,7 +29,7 @@ EXPORTS = [
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
     "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
-    "rk_state_scale_forward", "rk_state_scale_backward",
+    "rk_state_scale_forward", "rk_state_scale_backward", "rk_drp_mlp2_forward",
 ]
 
 
@@ -135,6 +135,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_tf32_split.restype = ci
     lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
     lib.rk_tcgemm.restype = ci
+    lib.rk_drp_mlp2_forward.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp] + [cf] * 11
+    lib.rk_drp_mlp2_forward.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -388,6 +390,15 @@ def tcgemm(epi: int, M: int, N: int, K: int, A, lda: int, Bt_hi, Bt_lo, ldb: int
     _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A), lda,
                                     _ptr(Bt_hi), _ptr(Bt_lo), ldb, _ptr(C), ldc, _ptr(bias),
                                     _ptr(aux), ldaux), "rk_tcgemm")
+
+
+def drp_mlp2_forward(B, D, h0, h1, NH, segs, x, W0, b0, W1T_hi, W1T_lo, b1, Wh, bh, H0, H1, heads):
+    """Fused forward of a 2-hidden-layer policy network (one launch per decision epoch)."""
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_drp_mlp2_forward(
+        _stream(), B, D, h0, h1, NH, n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(x), _ptr(W0), _ptr(b0), _ptr(W1T_hi), _ptr(W1T_lo),
+        _ptr(b1), _ptr(Wh), _ptr(bh), _ptr(H0), _ptr(H1), _ptr(heads)), "rk_drp_mlp2_forward")
 
 
 def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None):

@@ -667,8 +667,8 @@ class ProgramBuilder:
                                        for i in step)
                 sass_tpr = sum((10.0 if i.op == "QSUM" else 1.4) * max(i.n, 1) for i in step)
                 live = tpr.warp_words / 32.0                  # scalar values alive at once, per lane
-                if live > 400:
-                    sass_tpr *= 1.0 + (live - 400.0) / 200.0  # local-memory spills
+                if live > 320:      # measured: Wildfire forward, 441 live scalars, spills and loses
+                    sass_tpr *= 1.0 + (live - 320.0) / 40.0
                 if est(tpr, sass_tpr, 0.7) < 0.8 * est(best, sass_multi, 0.4):
                     best = tpr
         return best

@@ -372,6 +372,50 @@ def test_fused_layer0_backward_against_fp64(cuda_device, B, segs, H):
     torch.testing.assert_close(gs.double(), want_s, rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,segs,h0,h1,NH", [(300, [(0, 5), (5, 1)], 256, 256, 10),
+                                              (129, [(0, 16)], 64, 128, 16),
+                                              (1000, [(0, 1), (1, 2)], 32, 32, 1),
+                                              (4096, [(0, 3), (3, 4), (7, 2)], 128, 256, 7)])
+@pytest.mark.parametrize("keep", [True, False])
+def test_fused_mlp2_forward_against_fp64(cuda_device, B, segs, h0, h1, NH, keep):
+    """rk_drp_mlp2_forward (layer 0 computed into the tcgen05 operand tiles, hidden layer 3xTF32, head
+    product in the TMEM epilogue) against an fp64 evaluation of the same two-hidden-layer network."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(B + h0 + NH)
+    D = sum(n for _, n in segs)
+    x = torch.randn(B, D, generator=g, dtype=torch.float64) * 1.5
+    W0 = torch.randn(D, h0, generator=g, dtype=torch.float64) * (1.0 / D ** 0.5)
+    b0 = torch.randn(h0, generator=g, dtype=torch.float64) * 0.2
+    W1 = torch.randn(h0, h1, generator=g, dtype=torch.float64) * (1.5 / h0 ** 0.5)
+    b1 = torch.randn(h1, generator=g, dtype=torch.float64) * 0.2
+    Wh = torch.randn(h1, NH, generator=g, dtype=torch.float64) * (1.0 / h1 ** 0.5)
+    bh = torch.randn(NH, generator=g, dtype=torch.float64)
+    f32 = lambda t: t.float().contiguous().to(cuda_device)      # noqa: E731
+    xs, W0s, b0s, W1s, b1s, Whs, bhs = (f32(t) for t in (x, W0, b0, W1, b1, Wh, bh))
+    # reference on the fp32-rounded inputs
+    xr, W0r, b0r, W1r, b1r, Whr, bhr = (t.double().cpu() for t in (xs, W0s, b0s, W1s, b1s, Whs, bhs))
+    H0r = torch.tanh(xr @ W0r + b0r)
+    H1r = torch.tanh(H0r @ W1r + b1r)
+    want = H1r @ Whr + bhr
+    # fluent-major state blocks
+    x_fm = torch.cat([xs[:, off:off + n].contiguous().reshape(-1) for off, n in segs])
+    W1T = W1s.t().contiguous()
+    hi, lo = torch.empty_like(W1T), torch.empty_like(W1T)
+    engine.tf32_split(W1T.reshape(-1), hi.reshape(-1), lo.reshape(-1), W1T.numel())
+    H0 = torch.zeros(B, h0, device=cuda_device) if keep else None
+    H1 = torch.zeros(B, h1, device=cuda_device) if keep else None
+    heads = torch.zeros(B, NH, device=cuda_device)
+    engine.drp_set_activation("tanh")
+    engine.drp_mlp2_forward(B, D, h0, h1, NH, segs, x_fm, W0s.reshape(-1), b0s, hi.reshape(-1),
+                            lo.reshape(-1), b1s, Whs.reshape(-1), bhs, H0, H1, heads)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(heads.double().cpu(), want, rtol=2e-5, atol=2e-5)
+    if keep:
+        torch.testing.assert_close(H0.double().cpu(), H0r, rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(H1.double().cpu(), H1r, rtol=1e-5, atol=1e-5)
+
+
 def _segment_noise(plan, m, pol_noise_t, B):
     """{action fluent: [B, n]} views of one step's fluent-major policy-noise row."""
     out = {}
