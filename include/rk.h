@@ -253,19 +253,58 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
  *   heads[B][NH] = act(act(x W0 + b0) W1 + b1) Wh + bh
  * Replaces: DRPStateLayer + the two Dense/activation layers + the per-action Dense heads of
  * JaxDeepReactivePolicy (planner.py:1287-1449) inside the scan body (compiler.py:552-558).
+ *   act    : RK_ACT_* id of the hidden activation (an argument, not process state)
  *   x_fm   : the state in the rollout kernels' fluent-major layout (fluent f = block [B][len_f] at word
- *            offset off_f * B); D = sum of len_f <= 16 inputs; H0n, H1n multiples of 16 / 32, <= 256
- *   W0 [D][H0n], b0 [H0n]; W1T_hi / W1T_lo [H1n][H0n]: W1^T split by rk_tf32_split; b1 [H1n];
- *   Wh [H1n][NH], bh [NH], NH <= 16
+ *            offset off_f * B); D = sum of len_f <= 16 inputs; H0n, H1n multiples of 16, <= 256
+ *   fwd_img: operand image of W0 / Wh built by rk_drp_mlp2_prepare (once per optimiser step),
+ *            rk_drp_mlp2_image_floats(D, H0n, H1n, NH, 0) floats, 16-byte aligned
+ *   b0 [H0n]; W1T_hi / W1T_lo [H1n][H0n]: W1^T split by rk_tf32_split; b1 [H1n]; bh [NH], NH <= 16
  *   H0 [B][H0n], H1 [B][H1n]: hidden activations for the adjoint, or NULL (the exact test sweep
- *            writes nothing but the head outputs)
- * One launch: layer 0 is computed straight into the tensor-core operand tiles, the hidden layer
- * runs on tcgen05 (3xTF32), the head product is taken from the accumulator tile in the epilogue. */
-int rk_drp_mlp2_forward(void* stream, int B, int D, int H0n, int H1n, int NH, int n_seg,
+ *            writes nothing but the head outputs); 32-byte aligned
+ * One launch, one CTA per <= 256 rollouts: layer 0 is computed straight into the tensor-core operand
+ * stages, the hidden layer runs on tcgen05 (3xTF32, both 128-row tiles share each weight tile), the
+ * head product is a second tcgen05 product fed from the epilogue (csrc/rk_mlp2.cu). */
+int rk_drp_mlp2_image_floats(int D, int H0n, int H1n, int NH, int backward);
+int rk_drp_mlp2_prepare(void* stream, int D, int H0n, int H1n, int NH, const float* W0,
+                        const float* Wh, float* fwd_img, float* bwd_img);
+int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n, int H1n, int NH, int n_seg,
                         const int32_t* seg_off, const int32_t* seg_len, const float* x_fm,
-                        const float* W0, const float* b0, const float* W1T_hi, const float* W1T_lo,
-                        const float* b1, const float* Wh, const float* bh, float* H0, float* H1,
+                        const float* fwd_img, const float* b0, const float* W1T_hi,
+                        const float* W1T_lo, const float* b1, const float* bh, float* H0, float* H1,
                         float* heads);
+
+/* Fused input-side adjoint of the same network for one decision epoch (the transpose of the scan
+ * body's policy call in the reverse pass, planner.py:2873):
+ *   gz1[B][H1n] = (gheads Wh^T) * act'(H1);  gz0[B][H0n] = (gz1 W1^T) * act'(H0);  gs += gz0 W0^T
+ *   gheads [B][NH]: cotangent of the head outputs; H0 / H1: the activations rk_drp_mlp2_forward kept;
+ *   bwd_img: operand image of W0 / Wh (rk_drp_mlp2_prepare; ..._image_floats(.., 1) floats);
+ *   W1_hi / W1_lo [H0n][H1n]: W1 split by rk_tf32_split;
+ *   gz0 / gz1: pre-activation cotangents, written once (operands of the weight-gradient products
+ *   rk_drp_wgrad_*); gs: the fluent-major state cotangent, the input cotangent is ADDED to it.
+ * Same pipeline and constraints as the forward. */
+int rk_drp_mlp2_backward(void* stream, int act, int B, int D, int H0n, int H1n, int NH, int n_seg,
+                         const int32_t* seg_off, const int32_t* seg_len, const float* gheads,
+                         const float* H0, const float* H1, const float* bwd_img, const float* W1_hi,
+                         const float* W1_lo, float* gz0, float* gz1, float* gs);
+
+/* Weight gradients of the policy network as ONE reduction over all K = T * B (epoch, rollout) rows of
+ * the tapes the two sweeps left in HBM (csrc/rk_wgrad.cu; the transposes of nn.Dense in the reverse
+ * pass, planner.py:2873).  tcgen05 3xTF32, MN-major operands split in the kernel, one CTA per K-slice
+ * holding the whole result in TMEM, partials added in CTA order (deterministic).
+ *   hidden: dW [M][N] (+)= A[K][M]^T B[K][N], db [N] (+)= column sums of B (db may be NULL);
+ *           32 <= M, N <= 256, multiples of 32; workspace rk_drp_wgrad_ctas() * (M * N + N) floats
+ *   heads : dWh [M][NH] (+)= H[K][M]^T G[K][NH], NH <= 16; workspace ..._ctas() * M * 16 floats
+ *   input : dW0 [D][M] (+)= x^T gz0, db0 [M] (+)= column sums of gz0; gz0 [T * Bt][M]; x_tape: the
+ *           fluent-major state tape, epoch t at word offset t * S_words * Bt, D <= 15 of its words in the
+ *           seg_off / seg_len fluents; workspace ..._ctas() * M * 16 floats */
+int rk_drp_wgrad_ctas(void);
+int rk_drp_wgrad_hidden(void* stream, int accumulate, int M, int N, long long K, const float* A,
+                        const float* B, float* dW, float* db, float* workspace);
+int rk_drp_wgrad_heads(void* stream, int accumulate, int M, int NH, long long K, const float* H,
+                       const float* G, float* dWh, float* workspace);
+int rk_drp_wgrad_input(void* stream, int accumulate, int M, int D, int T, int Bt, int S_words,
+                       int n_seg, const int32_t* seg_off, const int32_t* seg_len, const float* gz0,
+                       const float* x_tape, float* dW0, float* db0, float* workspace);
 
 /* Weight gradient of a hidden layer on the tensor cores: C[M][N] (+)= A[K][M]^T * B[K][N] with
  * both operands plain fp32 activations stored batch-major (K = rollouts), MN-major UMMA tiles,

@@ -543,6 +543,19 @@ class DrpPipeline:
                           and self.hid[1] % 32 == 0 and 32 <= self.hid[1] <= 256
                           and _os0.environ.get("RK_TCGEMM", "1") != "0"
                           and _os0.environ.get("RK_DRP_FUSED_FWD", "1") != "0")
+        self.fused_bwd = self.fused_fwd and self.fused_head and self.hid[0] % 32 == 0 \
+            and self.D <= 15 and _os0.environ.get("RK_DRP_FUSED_BWD", "1") != "0"
+        if self.fused_fwd:
+            # operand images of the fused kernels (W0 / Wh; rebuilt by refresh_splits)
+            shp = (self.D, self.hid[0], self.hid[1], self.NH)
+            self.img_f = z(engine.drp_mlp2_image_floats(*shp, False))
+            self.img_b = z(engine.drp_mlp2_image_floats(*shp, True))
+        if self.fused_bwd:
+            # pre-activation cotangents and head cotangents of EVERY epoch stay in HBM: the weight
+            # gradients are one reduction over all T * B rows after the reverse sweep (rk_wgrad.cu)
+            self.gz_tape = [z(T, Bt, h) for h in self.hid]
+            self.gheads_tape = z(T, Bt, self.NH)
+            self.wg_ws = z(engine.drp_wgrad_ctas() * (self.hid[0] * self.hid[1] + self.hid[1]))
         ctas = engine.drp_head_backward_ctas(Bt)
         self.fb_ws = z(ctas * max(hl + hl * self.NH + self.NH, (self.D + 1) * self.hid[0]))
         # tensor-core path (tcgen05, 3xTF32) for hidden layers whose shapes fit the MMA tiles
@@ -653,6 +666,9 @@ class DrpPipeline:
             engine.tf32_split(params[off:off + n], self.w_hi[off:off + n], self.w_lo[off:off + n], n)
             engine.tf32_split(self.wT[off:off + n], self.wT_hi[off:off + n],
                               self.wT_lo[off:off + n], n)
+        if self.fused_fwd and self.tc_layers:
+            engine.drp_mlp2_prepare(self.D, self.hid[0], self.hid[1], self.NH, self._W(params, "W0"),
+                                    self._W(params, "Wh"), self.img_f, self.img_b)
 
     # ---- the MLP ------------------------------------------------------------------------------
     def mlp_forward(self, params, B, x_fm, H, heads, xp=None, film=None, keep_hidden=True):
@@ -663,11 +679,10 @@ class DrpPipeline:
         h0 = self.hid[0]
         if self.fused_fwd and film is None and 1 in self.tc_layers:
             engine.drp_mlp2_forward(
-                B, self.D, h0, self.hid[1], self.NH, self.plan.state_segs, x_fm,
-                self._W(params, "W0"), self._W(params, "b0"), self._W(self.wT_hi, "W1"),
-                self._W(self.wT_lo, "W1"), self._W(params, "b1"), self._W(params, "Wh"),
-                self._W(params, "bh"), H[0] if keep_hidden else None, H[1] if keep_hidden else None,
-                heads)
+                self.plan._activation, B, self.D, h0, self.hid[1], self.NH, self.plan.state_segs, x_fm,
+                self.img_f, self._W(params, "b0"), self._W(self.wT_hi, "W1"),
+                self._W(self.wT_lo, "W1"), self._W(params, "b1"), self._W(params, "bh"),
+                H[0] if keep_hidden else None, H[1] if keep_hidden else None, heads)
             return
         engine.drp_layer0(B, self.D, h0, self.plan.state_segs, x_fm, self._W(params, "W0"),
                           self._W(params, "b0"), H[0], xp)
@@ -696,13 +711,37 @@ class DrpPipeline:
             engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"),
                          self.NH, heads, self.NH, bias=self._W(params, "bh"))
 
-    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp, params_w=None, film=None):
+    def wgrad_all(self, grad, x_tape):
+        """Weight gradients of the fused path: one reduction over all T * B (epoch, rollout) rows of the
+        activation / cotangent tapes (``x_tape``: the first layer's inputs of every epoch, fluent-major)."""
+        pl = self.pl
+        T, B = pl.T, pl.batch_size_train
+        h0, h1 = self.hid
+        K = T * B
+        engine.drp_wgrad_hidden(True, h0, h1, K, self.H[0], self.gz_tape[1], self._W(grad, "W1"),
+                                self._W(grad, "b1"), self.wg_ws)
+        engine.drp_wgrad_heads(True, h1, self.NH, K, self.H[1], self.gheads_tape, self._W(grad, "Wh"),
+                               self.wg_ws)
+        engine.colsum(K, self.NH, self.gheads_tape, self.NH, self._W(grad, "bh"), True, self.cs_ws,
+                      self.cs_chunks)
+        engine.drp_wgrad_input(True, h0, self.D, T, B, self.S, self.plan.state_segs, self.gz_tape[0],
+                               x_tape, self._W(grad, "W0"), self._W(grad, "b0"), self.wg_ws)
+
+    def mlp_backward(self, grad, B, x_fm, H, gs_cur, xp, params_w=None, film=None, t=0):
         """Consumes self.gheads [B][NH]; accumulates weight gradients into ``grad`` and adds the
         input cotangent to the fluent-major state cotangent ``gs_cur``."""
         AT, ACC = engine.GEMM_A_TRANS, engine.GEMM_ACCUMULATE
         sk, ws = self.split_k, self.ws
         last = len(self.hid) - 1
         hl = self.hid[last]
+        if self.fused_bwd and film is None and 1 in self.tc_layers:
+            # one launch for the whole input-side adjoint of the epoch: gz1, gz0 (kept for the weight
+            # gradients, see wgrad_all) and the state cotangent
+            engine.drp_mlp2_backward(
+                self.plan._activation, B, self.D, self.hid[0], hl, self.NH, self.plan.state_segs,
+                self.gheads_tape[t], H[0], H[1], self.img_b, self._W(self.w_hi, "W1"),
+                self._W(self.w_lo, "W1"), self.gz_tape[0][t], self.gz_tape[1][t], gs_cur)
+            return
         if film is not None:    # layer inputs are the conditioned activations; z = H stays the tanh
             t, Hf = film
             engine.sgemm(AT | ACC, hl, self.NH, B, Hf[last], hl, self.gheads, self.NH,
@@ -826,9 +865,11 @@ class DrpPipeline:
             for d in self.dgb:
                 d.zero_()
         cur = 0
+        fused = self.fused_bwd and not self.film and 1 in self.tc_layers
         for t in range(T - 1, -1, -1):
             x = self.tape[t * S * B:(t + 1) * S * B]
             nxt, out = self.gs[cur], self.gs[cur ^ 1]
+            gh = self.gheads_tape[t] if fused else self.gheads
             bwd.backward(B, 1, x, pl.gret, actions=self.act[t],
                          noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
                          mparams=pl.train_mparams, disc=None if pl.disc is None else pl.disc[t:],
@@ -836,7 +877,7 @@ class DrpPipeline:
             engine.drp_actions_backward(
                 B, A, plan._stochastic, plan.action_segs, self.heads[t],
                 None if self.pol_noise is None else self.pol_noise[t], 1.0, self.lo, self.hi,
-                self.ls_lo, self.ls_hi, self.gact, self.gheads, kinds=plan.action_kinds,
+                self.ls_lo, self.ls_hi, self.gact, gh, kinds=plan.action_kinds,
                 bool_weight=plan._sigmoid_weight, ent_coeff=self.ent_coeff,
                 inv_batch=1.0 / (B * pl.world_size), wrap=plan._wrap_non_bool,
                 sigma_entropy_grad=plan._sigma_entropy_grad)
@@ -844,7 +885,7 @@ class DrpPipeline:
                 engine.drp_topk_backward(
                     B, A, plan._stochastic, plan.action_segs, plan.action_kinds, self.heads[t],
                     None if self.pol_noise is None else self.pol_noise[t], plan.allowed,
-                    plan._softmax_output_weight, self.gact, self.gheads,
+                    plan._softmax_output_weight, self.gact, gh,
                     ent_coeff=self.ent_coeff, inv_batch=1.0 / (B * pl.world_size))
             film = (t, [Hl[t] for Hl in self.Hf]) if self.film else None
             if self.Dn or self.pre:
@@ -853,7 +894,7 @@ class DrpPipeline:
                 self.gy.zero_()
                 xin = self.xn[t] if self.Dn else self.xa[t]
                 self.mlp_backward(grad, B, xin, [Hl[t] for Hl in self.H], self.gy, self.xp[t], params,
-                                  film=film)
+                                  film=film, t=t)
                 g_in = self.gy
                 if self.Dn:
                     dst = out
@@ -870,8 +911,10 @@ class DrpPipeline:
                                        backward=True)
             else:
                 self.mlp_backward(grad, B, x, [Hl[t] for Hl in self.H], out, self.xp[t], params,
-                                  film=film)
+                                  film=film, t=t)
             cur ^= 1
+        if fused:
+            self.wgrad_all(grad, self.xn if self.Dn else (self.xa if self.pre else self.tape))
         if self.film:
             self.film_param_grads(params, grad, emb)
 
@@ -961,7 +1004,10 @@ class DrpPipeline:
     # ---- measurement hooks of bench.py ------------------------------------------------------------
     def tape_bytes(self) -> int:
         """Bytes of hidden activations + state tape one update keeps in HBM for its backward sweep."""
-        return 4 * (sum(H.numel() for H in self.H) + self.tape.numel())
+        n = sum(H.numel() for H in self.H) + self.tape.numel()
+        if self.fused_bwd:
+            n += sum(g.numel() for g in self.gz_tape) + self.gheads_tape.numel()
+        return 4 * n
 
     def bench_roofline(self, time_kernel, peaks, peak_src):
         """(roofline, kernels_ms, launches per iteration) of the dominant kernel of a DRP iteration: the

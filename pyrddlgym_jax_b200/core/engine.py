@@ -30,6 +30,8 @@ EXPORTS = [
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
     "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
     "rk_state_scale_forward", "rk_state_scale_backward", "rk_drp_mlp2_forward",
+    "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare",
+    "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
 ]
 
 
@@ -135,8 +137,23 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_tf32_split.restype = ci
     lib.rk_tcgemm.argtypes = [vp, ci, ci, ci, ci, cf, ci, cf, cf, ci, cf, ci, cf, cf, ci]
     lib.rk_tcgemm.restype = ci
-    lib.rk_drp_mlp2_forward.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp] + [cf] * 11
+    lib.rk_drp_mlp2_forward.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp] + [cf] * 10
     lib.rk_drp_mlp2_forward.restype = ci
+    lib.rk_drp_mlp2_backward.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp] + [cf] * 9
+    lib.rk_drp_mlp2_backward.restype = ci
+    lib.rk_drp_mlp2_image_floats.argtypes = [ci] * 5
+    lib.rk_drp_mlp2_image_floats.restype = ci
+    lib.rk_drp_mlp2_prepare.argtypes = [vp, ci, ci, ci, ci, cf, cf, cf, cf]
+    lib.rk_drp_mlp2_prepare.restype = ci
+    lib.rk_drp_wgrad_ctas.argtypes = []
+    lib.rk_drp_wgrad_ctas.restype = ci
+    ll = ctypes.c_longlong
+    lib.rk_drp_wgrad_hidden.argtypes = [vp, ci, ci, ci, ll, cf, cf, cf, cf, cf]
+    lib.rk_drp_wgrad_hidden.restype = ci
+    lib.rk_drp_wgrad_heads.argtypes = [vp, ci, ci, ci, ll, cf, cf, cf, cf]
+    lib.rk_drp_wgrad_heads.restype = ci
+    lib.rk_drp_wgrad_input.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
+    lib.rk_drp_wgrad_input.restype = ci
     if path is None:
         _LIB = lib
     return lib
@@ -392,13 +409,61 @@ def tcgemm(epi: int, M: int, N: int, K: int, A, lda: int, Bt_hi, Bt_lo, ldb: int
                                     _ptr(aux), ldaux), "rk_tcgemm")
 
 
-def drp_mlp2_forward(B, D, h0, h1, NH, segs, x, W0, b0, W1T_hi, W1T_lo, b1, Wh, bh, H0, H1, heads):
-    """Fused forward of a 2-hidden-layer policy network (one launch per decision epoch)."""
+def drp_mlp2_image_floats(D, h0, h1, NH, backward: bool) -> int:
+    n = int(load_library().rk_drp_mlp2_image_floats(D, h0, h1, NH, 1 if backward else 0))
+    if n < 0:
+        raise RkError(f"rk_drp_mlp2_image_floats: unsupported shape {(D, h0, h1, NH)}")
+    return n
+
+
+def drp_mlp2_prepare(D, h0, h1, NH, W0, Wh, fwd_img, bwd_img):
+    """Operand images of the fused policy kernels (once per optimiser step)."""
+    _check(load_library().rk_drp_mlp2_prepare(_stream(), D, h0, h1, NH, _ptr(W0), _ptr(Wh),
+                                              _ptr(fwd_img), _ptr(bwd_img)), "rk_drp_mlp2_prepare")
+
+
+def drp_mlp2_forward(act, B, D, h0, h1, NH, segs, x, fwd_img, b0, W1T_hi, W1T_lo, b1, bh, H0, H1, heads):
+    """Fused forward of a 2-hidden-layer policy network (one launch per decision epoch);
+    ``act`` is the activation's name."""
     n, off, ln = _segs(segs)
     _check(load_library().rk_drp_mlp2_forward(
-        _stream(), B, D, h0, h1, NH, n, ctypes.cast(off, ctypes.c_void_p),
-        ctypes.cast(ln, ctypes.c_void_p), _ptr(x), _ptr(W0), _ptr(b0), _ptr(W1T_hi), _ptr(W1T_lo),
-        _ptr(b1), _ptr(Wh), _ptr(bh), _ptr(H0), _ptr(H1), _ptr(heads)), "rk_drp_mlp2_forward")
+        _stream(), ACTIVATIONS[act], B, D, h0, h1, NH, n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(x), _ptr(fwd_img), _ptr(b0), _ptr(W1T_hi), _ptr(W1T_lo),
+        _ptr(b1), _ptr(bh), _ptr(H0), _ptr(H1), _ptr(heads)), "rk_drp_mlp2_forward")
+
+
+def drp_mlp2_backward(act, B, D, h0, h1, NH, segs, gheads, H0, H1, bwd_img, W1_hi, W1_lo, gz0, gz1, gs):
+    """Fused input-side adjoint of a 2-hidden-layer policy network: pre-activation cotangents gz1, gz0
+    (written once) and the input cotangent added to the fluent-major state cotangent ``gs``."""
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_drp_mlp2_backward(
+        _stream(), ACTIVATIONS[act], B, D, h0, h1, NH, n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(gheads), _ptr(H0), _ptr(H1), _ptr(bwd_img), _ptr(W1_hi),
+        _ptr(W1_lo), _ptr(gz0), _ptr(gz1), _ptr(gs)), "rk_drp_mlp2_backward")
+
+
+def drp_wgrad_ctas() -> int:
+    return int(load_library().rk_drp_wgrad_ctas())
+
+
+def drp_wgrad_hidden(accumulate, M, N, K, A, Bm, dW, db, workspace):
+    """dW [M][N] (+)= A[K][M]^T B[K][N]; db [N] (+)= column sums of B (or None)."""
+    _check(load_library().rk_drp_wgrad_hidden(_stream(), 1 if accumulate else 0, M, N, K, _ptr(A),
+                                              _ptr(Bm), _ptr(dW), _ptr(db), _ptr(workspace)),
+           "rk_drp_wgrad_hidden")
+
+
+def drp_wgrad_heads(accumulate, M, NH, K, H, G, dWh, workspace):
+    _check(load_library().rk_drp_wgrad_heads(_stream(), 1 if accumulate else 0, M, NH, K, _ptr(H),
+                                             _ptr(G), _ptr(dWh), _ptr(workspace)), "rk_drp_wgrad_heads")
+
+
+def drp_wgrad_input(accumulate, M, D, T, Bt, S_words, segs, gz0, x_tape, dW0, db0, workspace):
+    n, off, ln = _segs(segs)
+    _check(load_library().rk_drp_wgrad_input(
+        _stream(), 1 if accumulate else 0, M, D, T, Bt, S_words, n, ctypes.cast(off, ctypes.c_void_p),
+        ctypes.cast(ln, ctypes.c_void_p), _ptr(gz0), _ptr(x_tape), _ptr(dW0), _ptr(db0),
+        _ptr(workspace)), "rk_drp_wgrad_input")
 
 
 def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None):

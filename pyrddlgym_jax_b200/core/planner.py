@@ -23,7 +23,7 @@ from abc import ABCMeta, abstractmethod
 from ast import literal_eval
 from collections import deque
 from enum import Enum
-from typing import Any, Callable, Dict, Iterable, Optional, Tuple, Union
+from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -309,21 +309,28 @@ class JaxStraightLinePlan(JaxPlan):
 # =====================================================================================
 
 class RollingMean:
+    """Mean of the last ``window_size`` observations of a stream (floats or arrays): a fixed ring of
+    slots and a running sum, so an update is O(1) whatever the window."""
+
     def __init__(self, window_size: int) -> None:
-        self._window_size = window_size
-        self._memory = deque(maxlen=window_size)
-        self._total = 0
+        self._window_size = int(window_size)
+        self._slots: List[Any] = []
+        self._next = 0
+        self._sum: Any = 0
 
     def update(self, x):
-        memory = self._memory
-        self._total = self._total + x
-        if len(memory) == self._window_size:
-            self._total = self._total - memory.popleft()
-        memory.append(x)
-        return self._total / len(memory)
+        if len(self._slots) < self._window_size:
+            self._slots.append(x)
+            self._sum = self._sum + x
+        else:
+            self._sum = self._sum + x - self._slots[self._next]
+            self._slots[self._next] = x
+        self._next = (self._next + 1) % self._window_size
+        return self._sum / len(self._slots)
 
 
 class JaxPlannerStatus(Enum):
+    """Outcome of one planner update (same members and values as planner.py:2276-2303)."""
     NORMAL = 0
     STOPPING_RULE_REACHED = 1
     NO_PROGRESS = 2
@@ -333,42 +340,49 @@ class JaxPlannerStatus(Enum):
     ITER_BUDGET_REACHED = 6
 
     def is_terminal(self) -> bool:
-        return self.value == 1 or self.value >= 4
+        return self in _TERMINAL_STATUS
 
     def get_type(self) -> str:
-        if self.value in {5, 6}:
-            return "info"
-        if self.value in {0, 1}:
-            return "success"
-        if self.value in {2, 3}:
-            return "warning"
-        return "error"
+        return _STATUS_TYPE[self]
+
+
+_TERMINAL_STATUS = frozenset({JaxPlannerStatus.STOPPING_RULE_REACHED, JaxPlannerStatus.INVALID_GRADIENT,
+                              JaxPlannerStatus.TIME_BUDGET_REACHED, JaxPlannerStatus.ITER_BUDGET_REACHED})
+_STATUS_TYPE = {JaxPlannerStatus.NORMAL: "success", JaxPlannerStatus.STOPPING_RULE_REACHED: "success",
+                JaxPlannerStatus.NO_PROGRESS: "warning",
+                JaxPlannerStatus.PRECONDITION_POSSIBLY_UNSATISFIED: "warning",
+                JaxPlannerStatus.INVALID_GRADIENT: "error",
+                JaxPlannerStatus.TIME_BUDGET_REACHED: "info", JaxPlannerStatus.ITER_BUDGET_REACHED: "info"}
 
 
 class JaxPlannerStoppingRule(metaclass=ABCMeta):
+    """Interface of the stopping rules ``optimize_generator`` consults after every update."""
+
     @abstractmethod
     def reset(self) -> None:
-        pass
+        ...
 
     @abstractmethod
     def monitor(self, callback: Dict[str, Any]) -> bool:
-        pass
+        ...
 
 
 class NoImprovementStoppingRule(JaxPlannerStoppingRule):
+    """Stops once ``best_return`` has not improved for ``patience`` consecutive updates."""
+
     def __init__(self, patience: int) -> None:
         self.patience = patience
+        self.reset()
 
     def reset(self) -> None:
-        self.callback = None
+        self.callback = None                    # the callback that held the best return so far
         self.iters_since_last_update = 0
 
     def monitor(self, callback: Dict[str, Any]) -> bool:
-        if self.callback is None or callback["best_return"] > self.callback["best_return"]:
+        improved = self.callback is None or callback["best_return"] > self.callback["best_return"]
+        if improved:
             self.callback = callback
-            self.iters_since_last_update = 0
-        else:
-            self.iters_since_last_update += 1
+        self.iters_since_last_update = 0 if improved else self.iters_since_last_update + 1
         return self.iters_since_last_update >= self.patience
 
     def __str__(self) -> str:
@@ -1532,27 +1546,35 @@ class JaxBackpropPlanner:
 # config files (planner.py:101-244)
 # =====================================================================================
 
+def _config_sections(parser: "configparser.RawConfigParser"):
+    """(parser, {section: {key: python literal}}) of a case-preserving .cfg parser."""
+    return parser, {sec: {key: literal_eval(text) for key, text in parser.items(sec)}
+                    for sec in parser.sections()}
+
+
+def _new_cfg_parser() -> "configparser.RawConfigParser":
+    parser = configparser.RawConfigParser()
+    parser.optionxform = str                  # keys are keyword-argument names: keep their case
+    return parser
+
+
 def _parse_config_file(path: str):
-    config = configparser.RawConfigParser()
-    config.optionxform = str
-    if not config.read(path):
+    parser = _new_cfg_parser()
+    if not parser.read(path):
         raise FileNotFoundError(f"No config file found at {path}.")
-    return config, {s: {k: literal_eval(v) for k, v in config.items(s)} for s in config.sections()}
+    return _config_sections(parser)
 
 
 def _parse_config_string(value: str):
-    config = configparser.RawConfigParser()
-    config.optionxform = str
-    config.read_string(value)
-    return config, {s: {k: literal_eval(v) for k, v in config.items(s)} for s in config.sections()}
+    parser = _new_cfg_parser()
+    parser.read_string(value)
+    return _config_sections(parser)
 
 
 def _getattr_any(packages, item):
-    for pkg in packages:
-        val = getattr(pkg, item, None)
-        if val is not None:
-            return val
-    return None
+    """First non-None attribute ``item`` among ``packages`` (None when nobody has it)."""
+    found = (getattr(pkg, item, None) for pkg in packages)
+    return next((val for val in found if val is not None), None)
 
 
 def _load_config(config, args):

@@ -1,0 +1,710 @@
+// rk_mlp2.cu -- one launch per decision epoch and direction for a deep reactive policy with two
+// hidden layers (planner.py:1342-1449: DRPStateLayer -> Dense + activation -> Dense + activation ->
+// per-action heads, and its transpose in the reverse pass of planner.py:2873).
+//
+//   forward :  heads = act(act(x W0 + b0) W1 + b1) Wh + bh                 (+ H0, H1 kept for the adjoint)
+//   backward:  gz1 = (gheads Wh^T) * act'(H1),  gz0 = (gz1 W1^T) * act'(H0),  gs += gz0 W0^T
+//              (gz1, gz0 are written once: operands of the weight-gradient products)
+//
+// Both directions are the same pipeline, one CTA per <= 256 rollouts (two 128-row MMA tiles that
+// SHARE every streamed weight tile, so the pre-split weights cross L2 -> shared memory once per CTA
+// instead of once per 128 rows; with B = 32768 and 148 SMs: 148 CTAs x 222 rows, one wave):
+//
+//   warps 2-17 (SIMT) : produce the A operand of the hidden-layer product one 16-column k-block at a
+//                       time STRAIGHT INTO the MMA stage (K-major, 64-byte swizzle: 16-byte chunk c of
+//                       row r lives at chunk c ^ ((r >> 1) & 3)), already split into the TF32-exact hi
+//                       part and the fp32 remainder lo.  forward: layer 0 from the fluent-major state
+//                       words (D <= 16, packed FFMA2); backward: (gheads Wh^T) * act'(H1) (NH <= 16).
+//   warp 0            : TMA producer of the weight tiles hi / lo of the k-block (3-deep ring).
+//   warp 1            : tcgen05.mma issuer: 3 TF32 products per 8-wide k-slice and tile into the two
+//                       TMEM accumulators (2 x N <= 512 columns).
+//   warps 2-17        : epilogue, 16 columns at a time: tcgen05.ld -> bias + activation (forward) /
+//                       * act'(H0) (backward) -> the [B][N] result to HBM (32-byte stores) -> split into
+//                       hi / lo INTO THE SAME A STAGES, from which warp 1 issues the small second product
+//                       on the tensor cores as well (forward: H1 Wh, N = 16 head columns; backward:
+//                       gz0 W0^T, N = 16 state words), accumulating in the TMEM columns the epilogue
+//                       has already drained.  Its operand (Wh^T / W0, hi | lo, 32 KB) is an image
+//                       built once per optimiser step (rk_drp_mlp2_prepare), copied in by the prologue.
+//
+// Per decision epoch the hidden activations cross HBM once per direction and the exact test sweep
+// writes nothing but the head outputs.  SIMT work per hidden unit: ~14 instructions to produce, ~10 in
+// the epilogue (the separate layer-0 / GEMM / head kernels needed ~57 and five passes over [B][256]).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rk.h"
+#include "rk_act.cuh"
+#include "rk_tc.cuh"
+
+#define M2_CW 16                          // compute warps
+#define M2_THREADS ((2 + M2_CW) * 32)     // 576
+#define M2_AST 2                          // A stages (both tiles, hi | lo): 32 KB each
+#define M2_BST 3                          // weight stages (hi | lo): N * 128 bytes each
+#define M2_A_TILE (TC_BM * TC_BK * 4)     // 8 KB
+#define M2_A_STAGE (4 * M2_A_TILE)        // tile 0 hi, tile 0 lo, tile 1 hi, tile 1 lo
+#define M2_MAXS 16                        // widest small side (state words / head columns)
+
+struct RkMlpSegs {
+  int n;
+  int off[16], len[16];
+};
+
+struct M2Args {
+  int B, R;                 // rollouts; rows per CTA (<= 256)
+  int NS;                   // width of the SIMT product (forward: state words D; backward: head columns NH)
+  int Kdim, Ndim;           // contraction / output width of the tensor-core layer
+  int NO;                   // stored columns of the second product (forward: NH; backward: D)
+  RkMlpSegs S;              // state fluents (forward: gather x; backward: scatter the input cotangent)
+  const float* x_fm;        // forward : state words, fluent-major
+  const float* Wsm;         // forward : W0 [D][Kdim];      backward: Wh^T [NH][Kdim]   (16-byte aligned)
+  const float* bsm;         // forward : b0 [Kdim]
+  const float* bN;          // forward : b1 [Ndim]
+  const float* W2;          // operand image of the second product (rk_mlp2_prepare_kernel)
+  const float* b2;          // forward : bh [NH]
+  const float* G;           // backward: gheads [B][NH]
+  const float* Hk;          // backward: H1 [B][Kdim]
+  const float* Hn;          // backward: H0 [B][Ndim]
+  float* Ok;                // forward : H0 out or NULL;    backward: gz1 out
+  float* On;                // forward : H1 out or NULL;    backward: gz0 out
+  float* out;               // forward : heads [B][NH];     backward: state cotangent (fluent-major, +=)
+  int act;
+};
+
+// ---- small device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long m2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void m2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// acc = a * b + acc on both halves (FFMA2)
+__device__ __forceinline__ void m2_ffma2(unsigned long long& acc, unsigned long long a,
+                                         unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+// tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU + three ALU instructions, absolute error <= 2e-7
+// (saturates correctly: e = inf -> 1, e = 0 -> -1)
+__device__ __forceinline__ float m2_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+template <int ACT_CT>
+__device__ __forceinline__ float m2_act(int act, float x) {
+  if (ACT_CT == RK_ACT_TANH) return m2_tanh(x);
+  return rk_act_fn(act, x);
+}
+template <int ACT_CT>
+__device__ __forceinline__ float m2_act_grad(int act, float y) {
+  if (ACT_CT == RK_ACT_TANH) return fmaf(-y, y, 1.f);
+  return rk_act_grad(act, y);
+}
+__device__ __forceinline__ void m2_ld8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+                 "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void m2_st8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory accesses with explicit 32-bit shared addresses (no generic-pointer LD / ST)
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds128_u64(uint32_t addr, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+// TF32-exact hi part (round to nearest, ties away: add half an ulp of the 10-bit mantissa and clear the
+// 13 low bits; finite inputs of ordinary magnitude only) and the fp32 remainder
+__device__ __forceinline__ void m2_split(float v, float& h, float& l) {
+  h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  l = v - h;
+}
+// store n4 = 2 or 4 consecutive 16-byte chunks (starting at chunk c0) of row r of a K-major 64B-swizzled
+// [128][16] tile: hi at tile, lo at tile + M2_A_TILE (chunk c of row r lives at chunk c ^ ((r >> 1) & 3))
+template <int NCH>
+__device__ __forceinline__ void m2_store_split(uint32_t tile, int r, int c0, const float* v) {
+  const uint32_t swz = (uint32_t)(r >> 1) & 3u;
+  const uint32_t rowa = tile + (uint32_t)r * 64u;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m2_split(v[4 * c + i], h[i], l[i]);
+    const uint32_t o = rowa + ((((uint32_t)(c0 + c)) ^ swz) << 4);
+    sts128(o, h[0], h[1], h[2], h[3]);
+    sts128(o + M2_A_TILE, l[0], l[1], l[2], l[3]);
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+
+// ---- operand images, built once per optimiser step -----------------------------------------------
+// fwd_img : h1 / 16 blocks of the head product's operand Wh^T: [16 head columns][16 k] K-major,
+//           64B-swizzled, TF32 hi (1 KB) | lo (1 KB); then W0 [D][h0] as plain fp32 (16-byte aligned copy)
+// bwd_img : h0 / 16 such blocks of W0 (rows = state words), then Wh^T [NH][h1] as plain fp32
+__global__ void rk_mlp2_prepare_kernel(int D, int h0, int h1, int NH, const float* __restrict__ W0,
+                                       const float* __restrict__ Wh, float* __restrict__ fwd_img,
+                                       float* __restrict__ bwd_img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_f = h1 * 16, n_b = h0 * 16, n_t = NH * h1;
+  if (i < n_f + n_b) {
+    const bool fwd = i < n_f;
+    const int e = fwd ? i : i - n_f;
+    const int j = e >> 8, n = (e >> 4) & 15, kk = e & 15;
+    float v = 0.f;
+    if (fwd) {
+      if (n < NH) v = Wh[(size_t)(16 * j + kk) * NH + n];
+    } else {
+      if (n < D) v = W0[(size_t)n * h0 + 16 * j + kk];
+    }
+    const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    const uint32_t off = (uint32_t)n * 16u + ((((uint32_t)kk >> 2) ^ (((uint32_t)n >> 1) & 3u)) << 2) +
+                         ((uint32_t)kk & 3u);                       // in floats
+    float* blk = (fwd ? fwd_img : bwd_img) + (size_t)j * 512;
+    blk[off] = h;
+    blk[256 + off] = v - h;
+  } else if (i < n_f + n_b + n_t) {
+    const int e = i - n_f - n_b;
+    const int k = e / NH, n = e - k * NH;
+    bwd_img[(size_t)n_b * 2 + (size_t)n * h1 + k] = Wh[e];
+  } else if (i < n_f + n_b + n_t + D * h0) {
+    const int e = i - n_f - n_b - n_t;
+    fwd_img[(size_t)n_f * 2 + e] = W0[e];
+  }
+}
+
+// MODE 0 = forward, 1 = backward.  ACT_CT: the activation as a compile-time constant or -1 = P.act.
+template <int MODE, int ACT_CT>
+__global__ void __launch_bounds__(M2_THREADS, 1)
+rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
+               const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ M2Args P,
+               uint32_t tmem_cols) {
+  const int act = ACT_CT >= 0 ? ACT_CT : P.act;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment (swizzle atoms) by pointer arithmetic, so the compiler keeps the shared state space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int Kd = P.Kdim, Nd = P.Ndim;
+  const int nkb = Kd / TC_BK, nj = Nd / TC_BK;
+  const uint32_t b_half = (uint32_t)Nd * TC_BK * 4;     // one weight tile (hi or lo) of a k-block
+  const uint32_t b_stage = 2 * b_half;
+  uint8_t* a_base = smem;
+  uint8_t* b_base = a_base + M2_AST * M2_A_STAGE;
+  uint8_t* s_base = b_base + M2_BST * b_stage;          // second-product operand: nj blocks (hi 1 KB | lo 1 KB)
+  uint8_t* tail = s_base + (size_t)nj * 2048;
+  uint64_t* bars = (uint64_t*)tail;
+  uint64_t* b_full = bars;                              // [M2_BST] weight tiles landed (TMA)
+  uint64_t* b_empty = bars + M2_BST;                    // [M2_BST] MMAs of the stage retired
+  uint64_t* a_done = bars + 2 * M2_BST;                 // [M2_AST] operand tile written (16 arrivals)
+  uint64_t* a_empty = bars + 2 * M2_BST + M2_AST;       // [M2_AST] MMAs that read the stage retired
+  uint64_t* acc_ready = bars + 2 * M2_BST + 2 * M2_AST;
+  uint64_t* s_ready = acc_ready + 1;
+  uint32_t* tmem_slot = (uint32_t*)(s_ready + 1);
+  float* fsm = (float*)(tail + 128);
+  // forward : W0_s [D][Kd] | b0_s [Kd] | b1_s [Nd] | bh_s [16];   backward: WhT_s [NH][Kd]
+  float* Wsm_s = fsm;
+  float* bsm_s = Wsm_s + (size_t)P.NS * Kd;
+  float* bN_s = bsm_s + Kd;
+  float* b2_s = bN_s + Nd;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * P.R;
+  const int rows_here = (int)min((long long)P.R, (long long)P.B - r0);
+  const int ntiles = rows_here > TC_BM ? 2 : 1;
+  // uses of A stage s during the main loop (the epilogue continues the same phase sequence)
+  const int n_use0 = (nkb + 1) / 2, n_use1 = nkb / 2;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < M2_BST; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < M2_AST; ++s) {
+      mbar_init(&a_done[s], M2_CW);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    mbar_init(s_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp >= 2) {
+    const int ct = threadIdx.x - 64;
+    // second-product operand image and the SIMT product's weights: coalesced 16-byte copies
+    const float4* img = reinterpret_cast<const float4*>(P.W2);
+    float4* sdst = reinterpret_cast<float4*>(s_base);
+    for (int i = ct; i < Nd * 8; i += M2_CW * 32) sdst[i] = img[i];
+    const float4* wsrc = reinterpret_cast<const float4*>(P.Wsm);
+    float4* wdst = reinterpret_cast<float4*>(Wsm_s);
+    for (int i = ct; i < P.NS * Kd / 4; i += M2_CW * 32) wdst[i] = wsrc[i];
+    if (MODE == 0) {
+      for (int i = ct; i < Kd; i += M2_CW * 32) bsm_s[i] = P.bsm[i];
+      for (int i = ct; i < Nd; i += M2_CW * 32) bN_s[i] = P.bN[i];
+      if (ct < 16) b2_s[ct] = ct < P.NO ? P.b2[ct] : 0.f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: the weight tiles hi / lo of every k-block =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % M2_BST;
+        const uint32_t ph = (kb / M2_BST) & 1;
+        mbar_wait(&b_empty[s], ph ^ 1);
+        uint8_t* st = b_base + (size_t)s * b_stage;
+        mbar_expect_tx(&b_full[s], b_stage);
+        tma_load_2d(st, &tmB_hi, &b_full[s], kb * TC_BK, 0);
+        tma_load_2d(st + b_half, &tmB_lo, &b_full[s], kb * TC_BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = idesc0 | ((uint32_t)(Nd >> 3) << 17);
+      const uint32_t idesc2 = idesc0 | ((uint32_t)(16 >> 3) << 17);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb & 1, sb = kb % M2_BST;
+        mbar_wait(&b_full[sb], (kb / M2_BST) & 1);
+        mbar_wait(&a_done[sa], (kb >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t bs = smem_u32(b_base + (size_t)sb * b_stage);
+        const uint64_t dBh = make_desc(bs), dBl = make_desc(bs + b_half);
+        for (int tl = 0; tl < ntiles; ++tl) {
+          const uint32_t as = smem_u32(a_base + (size_t)sa * M2_A_STAGE + (size_t)tl * 2 * M2_A_TILE);
+          const uint64_t dAh = make_desc(as), dAl = make_desc(as + M2_A_TILE);
+          const uint32_t d = tmem_base + (uint32_t)(tl * Nd);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
+            umma_tf32(d, dAh + adv, dBh + adv, idesc, (kb | k) != 0);
+            umma_tf32(d, dAl + adv, dBh + adv, idesc, 1);
+            umma_tf32(d, dAh + adv, dBl + adv, idesc, 1);
+          }
+        }
+        umma_commit(&a_empty[sa]);
+        umma_commit(&b_empty[sb]);
+      }
+      umma_commit(acc_ready);
+      // second product: the epilogue's 16-column result chunks x the resident [16][16] operand blocks
+      for (int j = 0; j < nj; ++j) {
+        const int sa = j & 1;
+        const int use = (sa ? n_use1 : n_use0) + (j >> 1);
+        mbar_wait(&a_done[sa], use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ss = smem_u32(s_base + (size_t)j * 2048);
+        const uint64_t dBh = make_desc(ss), dBl = make_desc(ss + 1024);
+        for (int tl = 0; tl < ntiles; ++tl) {
+          const uint32_t as = smem_u32(a_base + (size_t)sa * M2_A_STAGE + (size_t)tl * 2 * M2_A_TILE);
+          const uint64_t dAh = make_desc(as), dAl = make_desc(as + M2_A_TILE);
+          const uint32_t d = tmem_base + (uint32_t)(tl * Nd);      // columns 0..15: drained by chunk 0
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
+            umma_tf32(d, dAh + adv, dBh + adv, idesc2, (j | k) != 0);
+            umma_tf32(d, dAl + adv, dBh + adv, idesc2, 1);
+            umma_tf32(d, dAh + adv, dBl + adv, idesc2, 1);
+          }
+        }
+        umma_commit(&a_empty[sa]);
+      }
+      umma_commit(s_ready);
+    }
+  } else {
+    const int ct = threadIdx.x - 64;                 // 0..511
+    const uint32_t a_base32 = smem_u32(a_base);
+    // ===== producer: thread = (row of the CTA's 256, half of the k-block's 16 columns) =====
+    {
+      const int hc = ct >> 8, row = ct & 255, tl = row >> 7, r = row & 127;
+      const bool valid = row < rows_here;
+      const bool tile_on = tl < ntiles;
+      const long long grow = r0 + (valid ? row : 0);
+      unsigned long long sv[M2_MAXS];                // the row's small-side values, duplicated (v, v)
+#pragma unroll
+      for (int d = 0; d < M2_MAXS; ++d) sv[d] = 0ull;
+      if (valid) {
+        if (MODE == 0) {
+          int f = 0;
+#pragma unroll
+          for (int d = 0; d < M2_MAXS; ++d) {
+            if (d < P.NS) {
+              while (f + 1 < P.S.n && d >= P.S.off[f + 1]) ++f;
+              const float v = P.x_fm[(size_t)P.S.off[f] * P.B + (size_t)grow * P.S.len[f] + (d - P.S.off[f])];
+              sv[d] = m2_pack(v, v);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < M2_MAXS; ++d) {
+            if (d < P.NS) {
+              const float v = P.G[(size_t)grow * P.NS + d];
+              sv[d] = m2_pack(v, v);
+            }
+          }
+        }
+      }
+      float hk[8];                                    // backward: the H1 chunk of the next k-block
+      const float* hk_row = MODE == 1 ? P.Hk + (size_t)grow * Kd + hc * 8 : nullptr;
+      float* ok_row = P.Ok != nullptr ? P.Ok + (size_t)grow * Kd + hc * 8 : nullptr;
+      if (MODE == 1 && valid) m2_ld8(hk_row, hk);
+      const uint32_t w_row0 = smem_u32(Wsm_s) + (uint32_t)hc * 32u;
+      const uint32_t b_row0 = smem_u32(bsm_s) + (uint32_t)hc * 32u;
+      const uint32_t kd4 = (uint32_t)Kd * 4u;
+      const uint32_t tile32 = a_base32 + (uint32_t)tl * 2u * M2_A_TILE;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb & 1;
+        float v[8];
+        if (tile_on && valid) {
+          unsigned long long acc[4];
+          if (MODE == 0) {
+            lds128_u64(b_row0 + (uint32_t)kb * 64u, acc[0], acc[1]);
+            lds128_u64(b_row0 + (uint32_t)kb * 64u + 16u, acc[2], acc[3]);
+          } else {
+            acc[0] = acc[1] = acc[2] = acc[3] = 0ull;
+          }
+          uint32_t wp = w_row0 + (uint32_t)kb * 64u;
+#pragma unroll
+          for (int d = 0; d < M2_MAXS; ++d) {
+            if (d >= P.NS) break;
+            unsigned long long w0, w1, w2, w3;
+            lds128_u64(wp, w0, w1);
+            lds128_u64(wp + 16u, w2, w3);
+            wp += kd4;
+            m2_ffma2(acc[0], sv[d], w0);
+            m2_ffma2(acc[1], sv[d], w1);
+            m2_ffma2(acc[2], sv[d], w2);
+            m2_ffma2(acc[3], sv[d], w3);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m2_unpack(acc[i], v[2 * i], v[2 * i + 1]);
+          if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = m2_act<ACT_CT>(act, v[i]);
+            if (ok_row != nullptr) m2_st8(ok_row + kb * TC_BK, v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = v[i] * m2_act_grad<ACT_CT>(act, hk[i]);
+            if (kb + 1 < nkb) m2_ld8(hk_row + (kb + 1) * TC_BK, hk);
+            m2_st8(ok_row + kb * TC_BK, v);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        mbar_wait(&a_empty[sa], ((kb >> 1) & 1) ^ 1);      // the MMAs that read this stage retired
+        if (tile_on) m2_store_split<2>(tile32 + (uint32_t)sa * M2_A_STAGE, r, 2 * hc, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_done[sa]);
+      }
+    }
+    // ===== epilogue: warp = (tile, TMEM lane quarter, parity of the 16-column chunks it drains) =====
+    {
+      const int cw = warp - 2;
+      const int q = warp & 3, grp = cw >> 2, tl = grp & 1, sub = grp >> 1;
+      const int r = q * 32 + lane, row = tl * TC_BM + r;
+      const bool tile_on = tl < ntiles;
+      const bool valid = row < rows_here;
+      const long long grow = r0 + (valid ? row : 0);
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * Nd);
+      const uint32_t stage32 = a_base32 + (uint32_t)sub * M2_A_STAGE + (uint32_t)tl * 2u * M2_A_TILE;
+      const uint32_t bn32 = smem_u32(bN_s);
+      const int n_use = sub ? n_use1 : n_use0;
+      const float* hn_row = MODE == 1 ? P.Hn + (size_t)grow * Nd : nullptr;
+      float* on_row = P.On != nullptr ? P.On + (size_t)grow * Nd : nullptr;
+      float hn[16];
+      if (MODE == 1 && valid && sub < nj) {
+        m2_ld8(hn_row + sub * TC_BK, hn);
+        m2_ld8(hn_row + sub * TC_BK + 8, hn + 8);
+      }
+      mbar_wait(acc_ready, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int j = sub; j < nj; j += 2) {
+        const int c0 = j * TC_BK;
+        float v[16];
+        if (tile_on) {
+          uint32_t rr[16];
+          tmem_ld16(tbase + (uint32_t)c0, rr);
+          if (MODE == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 bb = lds128(bn32 + (uint32_t)(c0 + 4 * g) * 4u);
+              v[4 * g] = m2_act<ACT_CT>(act, __uint_as_float(rr[4 * g]) + bb.x);
+              v[4 * g + 1] = m2_act<ACT_CT>(act, __uint_as_float(rr[4 * g + 1]) + bb.y);
+              v[4 * g + 2] = m2_act<ACT_CT>(act, __uint_as_float(rr[4 * g + 2]) + bb.z);
+              v[4 * g + 3] = m2_act<ACT_CT>(act, __uint_as_float(rr[4 * g + 3]) + bb.w);
+            }
+            if (on_row != nullptr && valid) {
+              m2_st8(on_row + c0, v);
+              m2_st8(on_row + c0 + 8, v + 8);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = __uint_as_float(rr[i]) * m2_act_grad<ACT_CT>(act, valid ? hn[i] : 0.f);
+            if (valid) {
+              if (j + 2 < nj) {
+                m2_ld8(hn_row + c0 + 2 * TC_BK, hn);
+                m2_ld8(hn_row + c0 + 2 * TC_BK + 8, hn + 8);
+              }
+              m2_st8(on_row + c0, v);
+              m2_st8(on_row + c0 + 8, v + 8);
+            }
+          }
+        }
+        mbar_wait(&a_empty[sub], (((n_use + (j >> 1)) & 1) ^ 1));
+        if (tile_on) m2_store_split<4>(stage32, r, 0, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_n(&a_done[sub], 2);      // 8 warps drain a chunk: 2 arrivals each
+      }
+      // result of the second product: columns 0..15 of the tile's accumulator
+      mbar_wait(s_ready, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (sub == 0 && tile_on) {
+        uint32_t rr[16];
+        tmem_ld16(tbase, rr);
+        if (valid) {
+          if (MODE == 0) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n)
+              if (n < P.NO) P.out[(size_t)grow * P.NO + n] = __uint_as_float(rr[n]) + b2_s[n];
+          } else {
+            int f = 0;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+              if (d < P.NO) {
+                while (f + 1 < P.S.n && d >= P.S.off[f + 1]) ++f;
+                float* g = P.out + (size_t)P.S.off[f] * P.B + (size_t)grow * P.S.len[f] + (d - P.S.off[f]);
+                *g = *g + __uint_as_float(rr[d]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols));
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int m2_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// rows per CTA (<= 256: two 128-row MMA tiles): single-tile CTAs while SMs are spare, otherwise the
+// split with the fewest (waves x tiles per CTA)
+static int m2_rows_per_cta(int B) {
+  const int nsm = m2_sm_count();
+  if ((B + 255) / 256 < nsm) {
+    int n = (B + 127) / 128;
+    if (n > nsm) n = nsm;
+    return (B + n - 1) / n;
+  }
+  int best_R = 256, best_cost = 1 << 30;
+  for (int k = 1; k <= 64; ++k) {
+    const long long n = (long long)k * nsm;
+    const int R = (int)((B + n - 1) / n);
+    if (R > 256) continue;
+    const int cost = k * (R > 128 ? 2 : 1);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_R = R;
+    }
+    if (R <= 128) break;
+  }
+  return best_R;
+}
+
+template <int MODE>
+static int m2_launch(void* stream, const M2Args& P, const float* Bt_hi, const float* Bt_lo) {
+  int rc = load_encode();
+  if (rc != 0) return rc;
+  CUtensorMap mBh, mBl;
+  if ((rc = make_map(&mBh, Bt_hi, P.Ndim, P.Kdim, P.Kdim, P.Ndim)) != 0) return rc;
+  if ((rc = make_map(&mBl, Bt_lo, P.Ndim, P.Kdim, P.Kdim, P.Ndim)) != 0) return rc;
+  const size_t fl = MODE == 0 ? (size_t)P.NS * P.Kdim + P.Kdim + P.Ndim + 16 : (size_t)P.NS * P.Kdim;
+  const size_t smem = (size_t)M2_AST * M2_A_STAGE + (size_t)M2_BST * P.Ndim * TC_BK * 8 +
+                      (size_t)(P.Ndim / TC_BK) * 2048 + 128 + fl * 4 + 1024;
+  if (smem > 227 * 1024) return RK_E_SMEM;
+  static int configured = 0;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, RK_ACT_TANH>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    configured = 1;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < 2 * P.Ndim) cols <<= 1;
+  const int grid = (P.B + P.R - 1) / P.R;
+  if (P.act == RK_ACT_TANH)
+    rk_mlp2_kernel<MODE, RK_ACT_TANH><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P, cols);
+  else
+    rk_mlp2_kernel<MODE, -1><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P, cols);
+  return (int)cudaGetLastError();
+}
+
+static int m2_segs(RkMlpSegs* S, int D, int n_seg, const int32_t* seg_off, const int32_t* seg_len) {
+  if (n_seg <= 0 || n_seg > 16 || seg_off == nullptr || seg_len == nullptr) return RK_E_BADARG;
+  S->n = n_seg;
+  int total = 0;
+  for (int f = 0; f < n_seg; ++f) {
+    if (seg_len[f] <= 0 || seg_off[f] != total) return RK_E_BADARG;
+    S->off[f] = seg_off[f];
+    S->len[f] = seg_len[f];
+    total += seg_len[f];
+  }
+  return total == D ? 0 : RK_E_BADARG;
+}
+
+static bool m2_dims_ok(int D, int H0n, int H1n, int NH) {
+  return D > 0 && D <= M2_MAXS && NH > 0 && NH <= M2_MAXS && H0n >= TC_BK && H0n <= 256 &&
+         (H0n % TC_BK) == 0 && H1n >= TC_BK && H1n <= 256 && (H1n % TC_BK) == 0;
+}
+
+extern "C" int rk_drp_mlp2_image_floats(int D, int H0n, int H1n, int NH, int backward) {
+  if (!m2_dims_ok(D, H0n, H1n, NH)) return RK_E_BADARG;
+  return backward ? H0n * 32 + NH * H1n : H1n * 32 + D * H0n;
+}
+
+extern "C" int rk_drp_mlp2_prepare(void* stream, int D, int H0n, int H1n, int NH, const float* W0,
+                                   const float* Wh, float* fwd_img, float* bwd_img) {
+  if (W0 == nullptr || Wh == nullptr || fwd_img == nullptr || bwd_img == nullptr) return RK_E_BADARG;
+  if (!m2_dims_ok(D, H0n, H1n, NH)) return RK_E_BADARG;
+  if (((uintptr_t)fwd_img & 15) != 0 || ((uintptr_t)bwd_img & 15) != 0) return RK_E_BADARG;
+  const int n = H1n * 16 + H0n * 16 + NH * H1n + D * H0n;
+  rk_mlp2_prepare_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(D, H0n, H1n, NH, W0, Wh,
+                                                                            fwd_img, bwd_img);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n, int H1n, int NH,
+                                   int n_seg, const int32_t* seg_off, const int32_t* seg_len,
+                                   const float* x_fm, const float* fwd_img, const float* b0,
+                                   const float* W1T_hi, const float* W1T_lo, const float* b1,
+                                   const float* bh, float* H0, float* H1, float* heads) {
+  if (B <= 0 || x_fm == nullptr || fwd_img == nullptr || b0 == nullptr || W1T_hi == nullptr ||
+      W1T_lo == nullptr || b1 == nullptr || bh == nullptr || heads == nullptr)
+    return RK_E_BADARG;
+  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
+  if (((uintptr_t)fwd_img & 15) != 0 || ((uintptr_t)H0 & 31) != 0 || ((uintptr_t)H1 & 31) != 0)
+    return RK_E_BADARG;
+  M2Args P = {};
+  int rc = m2_segs(&P.S, D, n_seg, seg_off, seg_len);
+  if (rc != 0) return rc;
+  P.B = B;
+  P.R = m2_rows_per_cta(B);
+  P.NS = D;
+  P.Kdim = H0n;
+  P.Ndim = H1n;
+  P.NO = NH;
+  P.x_fm = x_fm;
+  P.W2 = fwd_img;
+  P.Wsm = fwd_img + (size_t)H1n * 32;
+  P.bsm = b0;
+  P.bN = b1;
+  P.b2 = bh;
+  P.Ok = H0;
+  P.On = H1;
+  P.out = heads;
+  P.act = act;
+  return m2_launch<0>(stream, P, W1T_hi, W1T_lo);
+}
+
+extern "C" int rk_drp_mlp2_backward(void* stream, int act, int B, int D, int H0n, int H1n, int NH,
+                                    int n_seg, const int32_t* seg_off, const int32_t* seg_len,
+                                    const float* gheads, const float* H0, const float* H1,
+                                    const float* bwd_img, const float* W1_hi, const float* W1_lo,
+                                    float* gz0, float* gz1, float* gs) {
+  if (B <= 0 || gheads == nullptr || H0 == nullptr || H1 == nullptr || bwd_img == nullptr ||
+      W1_hi == nullptr || W1_lo == nullptr || gz0 == nullptr || gz1 == nullptr || gs == nullptr)
+    return RK_E_BADARG;
+  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
+  if (((uintptr_t)bwd_img & 15) != 0 || ((uintptr_t)H0 & 31) != 0 || ((uintptr_t)H1 & 31) != 0 ||
+      ((uintptr_t)gz0 & 31) != 0 || ((uintptr_t)gz1 & 31) != 0)
+    return RK_E_BADARG;
+  M2Args P = {};
+  int rc = m2_segs(&P.S, D, n_seg, seg_off, seg_len);
+  if (rc != 0) return rc;
+  P.B = B;
+  P.R = m2_rows_per_cta(B);
+  P.NS = NH;
+  P.Kdim = H1n;
+  P.Ndim = H0n;
+  P.NO = D;
+  P.W2 = bwd_img;
+  P.Wsm = bwd_img + (size_t)H0n * 32;
+  P.G = gheads;
+  P.Hk = H1;
+  P.Hn = H0;
+  P.Ok = gz1;
+  P.On = gz0;
+  P.out = gs;
+  P.act = act;
+  return m2_launch<1>(stream, P, W1_hi, W1_lo);
+}

@@ -45,3 +45,21 @@ def test_cited_entry_points_are_declared():
             # "rk_foo_forward / backward" style mentions name a declared prefix
             assert name in declared or any(d.startswith(name) for d in declared), \
                 f"{doc} names {name}, which include/rk.h does not declare"
+
+
+def test_integration_stub_struct_matches_header():
+    """The ctypes stub a reference maintainer would paste declares ``RkSizes`` with the
+    same fields, in the same order, as ``struct rk_sizes`` of include/rk.h and as the package's own
+    binding -- a shorter struct makes rk_program_query write past its end."""
+    header = _read(os.path.join("include", "rk.h"))
+    body = re.search(r"typedef struct rk_sizes \{(.*?)\} rk_sizes;", header, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    want = []
+    for decl in re.findall(r"int32_t\s+([^;]+);", body):
+        want += [n.strip() for n in decl.split(",")]
+    stub = re.search(r"class RkSizes\(ctypes\.Structure\):.*?_fields_ = \[.*?for n in \((.*?)\)\]",
+                     _read("INTEGRATION.md"), flags=re.S).group(1)
+    got = re.findall(r'"([A-Za-z_0-9]+)"', stub)
+    assert got == want, (got, want)
+    from pyrddlgym_jax_b200.core.engine import RkSizes
+    assert [n for n, _ in RkSizes._fields_] == want

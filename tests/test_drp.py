@@ -376,7 +376,8 @@ def test_fused_layer0_backward_against_fp64(cuda_device, B, segs, H):
 @pytest.mark.parametrize("B,segs,h0,h1,NH", [(300, [(0, 5), (5, 1)], 256, 256, 10),
                                               (129, [(0, 16)], 64, 128, 16),
                                               (1000, [(0, 1), (1, 2)], 32, 32, 1),
-                                              (4096, [(0, 3), (3, 4), (7, 2)], 128, 256, 7)])
+                                              (4096, [(0, 3), (3, 4), (7, 2)], 128, 256, 7),
+                                              (40000, [(0, 2), (2, 4)], 256, 256, 10)])
 @pytest.mark.parametrize("keep", [True, False])
 def test_fused_mlp2_forward_against_fp64(cuda_device, B, segs, h0, h1, NH, keep):
     """rk_drp_mlp2_forward (layer 0 computed into the tcgen05 operand tiles, hidden layer 3xTF32, head
@@ -406,14 +407,140 @@ def test_fused_mlp2_forward_against_fp64(cuda_device, B, segs, h0, h1, NH, keep)
     H0 = torch.zeros(B, h0, device=cuda_device) if keep else None
     H1 = torch.zeros(B, h1, device=cuda_device) if keep else None
     heads = torch.zeros(B, NH, device=cuda_device)
-    engine.drp_set_activation("tanh")
-    engine.drp_mlp2_forward(B, D, h0, h1, NH, segs, x_fm, W0s.reshape(-1), b0s, hi.reshape(-1),
-                            lo.reshape(-1), b1s, Whs.reshape(-1), bhs, H0, H1, heads)
+    img_f = torch.zeros(engine.drp_mlp2_image_floats(D, h0, h1, NH, False), device=cuda_device)
+    img_b = torch.zeros(engine.drp_mlp2_image_floats(D, h0, h1, NH, True), device=cuda_device)
+    engine.drp_mlp2_prepare(D, h0, h1, NH, W0s.reshape(-1), Whs.reshape(-1), img_f, img_b)
+    engine.drp_mlp2_forward("tanh", B, D, h0, h1, NH, segs, x_fm, img_f, b0s, hi.reshape(-1),
+                            lo.reshape(-1), b1s, bhs, H0, H1, heads)
     torch.cuda.synchronize()
     torch.testing.assert_close(heads.double().cpu(), want, rtol=2e-5, atol=2e-5)
     if keep:
-        torch.testing.assert_close(H0.double().cpu(), H0r, rtol=1e-5, atol=2e-6)
-        torch.testing.assert_close(H1.double().cpu(), H1r, rtol=1e-5, atol=1e-5)
+        # tanh = 1 - 2 / (1 + e^2x) on the MUFU units: absolute error <= 2e-7 per activation
+        torch.testing.assert_close(H0.double().cpu(), H0r, rtol=1e-6, atol=5e-7)
+        # the tensor core truncates when it aligns products to the accumulator (not IEEE round-to-nearest):
+        # over the 96 accumulating MMAs of a 256-wide layer that is up to ~1e-5 of the pre-activation
+        torch.testing.assert_close(H1.double().cpu(), H1r, rtol=1e-5, atol=1.5e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", ["tanh", "softplus"])
+@pytest.mark.parametrize("B,segs,h0,h1,NH", [(300, [(0, 5), (5, 1)], 256, 256, 10),
+                                              (129, [(0, 16)], 64, 128, 16),
+                                              (1000, [(0, 1), (1, 2)], 32, 32, 1),
+                                              (40000, [(0, 3), (3, 4), (7, 2)], 128, 256, 7)])
+def test_fused_mlp2_backward_against_fp64(cuda_device, B, segs, h0, h1, NH, act):
+    """rk_drp_mlp2_backward: gz1 = (g Wh^T) act'(H1), gz0 = (gz1 W1^T) act'(H0), gs += gz0 W0^T against
+    fp64 on the same fp32 inputs (the second and third products run as 3xTF32 on the tensor cores)."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(B + h0 + NH + 1)
+    D = sum(n for _, n in segs)
+    f32 = lambda t: t.float().contiguous().to(cuda_device)      # noqa: E731
+    if act == "tanh":
+        H0 = torch.tanh(torch.randn(B, h0, generator=g, dtype=torch.float64))
+        H1 = torch.tanh(torch.randn(B, h1, generator=g, dtype=torch.float64))
+        dact = lambda y: 1 - y * y                                  # noqa: E731
+    else:
+        H0 = torch.nn.functional.softplus(torch.randn(B, h0, generator=g, dtype=torch.float64))
+        H1 = torch.nn.functional.softplus(torch.randn(B, h1, generator=g, dtype=torch.float64))
+        dact = lambda y: 1 - torch.exp(-y)                          # noqa: E731
+    W0 = torch.randn(D, h0, generator=g, dtype=torch.float64) * (1.0 / D ** 0.5)
+    W1 = torch.randn(h0, h1, generator=g, dtype=torch.float64) * (1.5 / h0 ** 0.5)
+    Wh = torch.randn(h1, NH, generator=g, dtype=torch.float64) * (1.0 / h1 ** 0.5)
+    G = torch.randn(B, NH, generator=g, dtype=torch.float64)
+    gs0 = torch.randn(D * B, generator=g, dtype=torch.float64)
+    H0s, H1s, W0s, W1s, Whs, Gs, gs = (f32(t) for t in (H0, H1, W0, W1, Wh, G, gs0))
+    H0r, H1r, W0r, W1r, Whr, Gr, gsr = (t.double().cpu() for t in (H0s, H1s, W0s, W1s, Whs, Gs, gs))
+    gz1r = (Gr @ Whr.t()) * dact(H1r)
+    gz0r = (gz1r @ W1r.t()) * dact(H0r)
+    dx = gz0r @ W0r.t()
+    want_gs = gsr + torch.cat([dx[:, off:off + n].contiguous().reshape(-1) for off, n in segs])
+    hi, lo = torch.empty_like(W1s), torch.empty_like(W1s)
+    engine.tf32_split(W1s.reshape(-1), hi.reshape(-1), lo.reshape(-1), W1s.numel())
+    gz0 = torch.zeros(B, h0, device=cuda_device)
+    gz1 = torch.zeros(B, h1, device=cuda_device)
+    img_f = torch.zeros(engine.drp_mlp2_image_floats(D, h0, h1, NH, False), device=cuda_device)
+    img_b = torch.zeros(engine.drp_mlp2_image_floats(D, h0, h1, NH, True), device=cuda_device)
+    engine.drp_mlp2_prepare(D, h0, h1, NH, W0s.reshape(-1), Whs.reshape(-1), img_f, img_b)
+    engine.drp_mlp2_backward(act, B, D, h0, h1, NH, segs, Gs, H0s, H1s, img_b, hi.reshape(-1),
+                             lo.reshape(-1), gz0, gz1, gs)
+    torch.cuda.synchronize()
+    s1, s0, sx = float(gz1r.abs().max()), float(gz0r.abs().max()), float(dx.abs().max())
+    torch.testing.assert_close(gz1.double().cpu(), gz1r, rtol=1e-5, atol=1e-6 * s1)
+    torch.testing.assert_close(gz0.double().cpu(), gz0r, rtol=1e-5, atol=2e-6 * s0)
+    torch.testing.assert_close(gs.double().cpu(), want_gs, rtol=1e-5, atol=2e-6 * sx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(256, 256, 40000), (64, 32, 1000), (160, 96, 3000), (256, 128, 17)])
+def test_wgrad_hidden_against_fp64(cuda_device, M, N, K):
+    """rk_drp_wgrad_hidden: dW += A^T B over all K rows in one launch (tcgen05 3xTF32, MN-major
+    operands), db += column sums of B taken by the converter warps."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(K, M, generator=g).to(cuda_device)
+    Bm = torch.randn(K, N, generator=g).to(cuda_device)
+    dW0 = torch.randn(M, N, generator=g).to(cuda_device)
+    db0 = torch.randn(N, generator=g).to(cuda_device)
+    dW, db = dW0.clone(), db0.clone()
+    ws = torch.zeros(engine.drp_wgrad_ctas() * (M * N + N), device=cuda_device)
+    engine.drp_wgrad_hidden(True, M, N, K, A, Bm, dW, db, ws)
+    torch.cuda.synchronize()
+    want = dW0.double() + A.double().t() @ Bm.double()
+    want_b = db0.double() + Bm.double().sum(0)
+    # entries are sums of K products of unit normals (|entry| ~ sqrt(K)); the tensor core's truncating
+    # accumulator leaves ~4e-6 of that
+    torch.testing.assert_close(dW.double(), want, rtol=1e-5, atol=6e-6 * K ** 0.5)
+    torch.testing.assert_close(db.double(), want_b, rtol=1e-5, atol=1e-6 * K ** 0.5)
+    dW2 = torch.empty_like(dW)
+    engine.drp_wgrad_hidden(False, M, N, K, A, Bm, dW2, None, ws)        # overwrite, no bias sum
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dW2.double(), want - dW0.double(), rtol=1e-5, atol=6e-6 * K ** 0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,NH,K", [(256, 10, 40000), (32, 16, 500), (128, 1, 3001)])
+def test_wgrad_heads_against_fp64(cuda_device, M, NH, K):
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M + NH + K)
+    H = torch.randn(K, M, generator=g).to(cuda_device)
+    G = torch.randn(K, NH, generator=g).to(cuda_device)
+    d0 = torch.randn(M, NH, generator=g).to(cuda_device)
+    d = d0.clone()
+    ws = torch.zeros(engine.drp_wgrad_ctas() * M * 16, device=cuda_device)
+    engine.drp_wgrad_heads(True, M, NH, K, H, G, d, ws)
+    torch.cuda.synchronize()
+    want = d0.double() + H.double().t() @ G.double()
+    torch.testing.assert_close(d.double(), want, rtol=1e-5, atol=6e-6 * K ** 0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,segs,T,Bt,extra", [(256, [(0, 5), (5, 1)], 7, 3000, 0),
+                                                (64, [(0, 15)], 3, 100, 2),
+                                                (128, [(0, 1), (1, 2), (3, 4)], 2, 1001, 1)])
+def test_wgrad_input_against_fp64(cuda_device, M, segs, T, Bt, extra):
+    """rk_drp_wgrad_input: dW0 += x^T gz0 and db0 += column sums of gz0 with x gathered from the
+    fluent-major state tape of every epoch (``extra`` further state words the policy does not read)."""
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(M + T + Bt)
+    D = sum(n for _, n in segs)
+    S = D + extra
+    x = torch.randn(T, Bt, S, generator=g)
+    gz0 = torch.randn(T * Bt, M, generator=g).to(cuda_device)
+    all_segs = list(segs) + ([(D, extra)] if extra else [])
+    tape = torch.cat([torch.cat([x[t][:, off:off + n].contiguous().reshape(-1) for off, n in all_segs])
+                      for t in range(T)]).to(cuda_device)
+    dW0_0 = torch.randn(D, M, generator=g).to(cuda_device)
+    db0_0 = torch.randn(M, generator=g).to(cuda_device)
+    dW0, db0 = dW0_0.clone(), db0_0.clone()
+    ws = torch.zeros(engine.drp_wgrad_ctas() * M * 16, device=cuda_device)
+    engine.drp_wgrad_input(True, M, D, T, Bt, S, segs, gz0, tape, dW0, db0, ws)
+    torch.cuda.synchronize()
+    X = x[:, :, :D].reshape(T * Bt, D).double().to(cuda_device)
+    want = dW0_0.double() + X.t() @ gz0.double()
+    want_b = db0_0.double() + gz0.double().sum(0)
+    K = T * Bt
+    torch.testing.assert_close(dW0.double(), want, rtol=1e-5, atol=6e-6 * K ** 0.5)
+    torch.testing.assert_close(db0.double(), want_b, rtol=1e-5, atol=1e-6 * K ** 0.5)
 
 
 def _segment_noise(plan, m, pol_noise_t, B):
