@@ -265,6 +265,8 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
  * stages, the hidden layer runs on tcgen05 (3xTF32, both 128-row tiles share each weight tile), the
  * head product is a second tcgen05 product fed from the epilogue (csrc/rk_mlp2.cu). */
 int rk_drp_mlp2_image_floats(int D, int H0n, int H1n, int NH, int backward);
+/* profiling aid (tools/mlp2_phases.py): per-CTA clock64 stamps of the kernel phases, buf[grid][8]; NULL = off */
+int rk_drp_mlp2_set_timing(unsigned long long* buf);
 int rk_drp_mlp2_prepare(void* stream, int D, int H0n, int H1n, int NH, const float* W0,
                         const float* Wh, float* fwd_img, float* bwd_img);
 int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n, int H1n, int NH, int n_seg,
@@ -293,7 +295,8 @@ int rk_drp_mlp2_backward(void* stream, int act, int B, int D, int H0n, int H1n, 
  * holding the whole result in TMEM, partials added in CTA order (deterministic).
  *   hidden: dW [M][N] (+)= A[K][M]^T B[K][N], db [N] (+)= column sums of B (db may be NULL);
  *           32 <= M, N <= 256, multiples of 32; workspace rk_drp_wgrad_ctas() * (M * N + N) floats
- *   heads : dWh [M][NH] (+)= H[K][M]^T G[K][NH], NH <= 16; workspace ..._ctas() * M * 16 floats
+ *   heads : dWh [M][NH] (+)= H[K][M]^T G[K][NH], dbh [NH] (+)= column sums of G (or NULL), NH <= 16;
+ *           workspace ..._ctas() * (M + 1) * 16 floats
  *   input : dW0 [D][M] (+)= x^T gz0, db0 [M] (+)= column sums of gz0; gz0 [T * Bt][M]; x_tape: the
  *           fluent-major state tape, epoch t at word offset t * S_words * Bt, D <= 15 of its words in the
  *           seg_off / seg_len fluents; workspace ..._ctas() * M * 16 floats */
@@ -301,7 +304,7 @@ int rk_drp_wgrad_ctas(void);
 int rk_drp_wgrad_hidden(void* stream, int accumulate, int M, int N, long long K, const float* A,
                         const float* B, float* dW, float* db, float* workspace);
 int rk_drp_wgrad_heads(void* stream, int accumulate, int M, int NH, long long K, const float* H,
-                       const float* G, float* dWh, float* workspace);
+                       const float* G, float* dWh, float* dbh, float* workspace);
 int rk_drp_wgrad_input(void* stream, int accumulate, int M, int D, int T, int Bt, int S_words,
                        int n_seg, const int32_t* seg_off, const int32_t* seg_len, const float* gz0,
                        const float* x_tape, float* dW0, float* db0, float* workspace);

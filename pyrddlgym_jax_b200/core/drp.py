@@ -721,9 +721,7 @@ class DrpPipeline:
         engine.drp_wgrad_hidden(True, h0, h1, K, self.H[0], self.gz_tape[1], self._W(grad, "W1"),
                                 self._W(grad, "b1"), self.wg_ws)
         engine.drp_wgrad_heads(True, h1, self.NH, K, self.H[1], self.gheads_tape, self._W(grad, "Wh"),
-                               self.wg_ws)
-        engine.colsum(K, self.NH, self.gheads_tape, self.NH, self._W(grad, "bh"), True, self.cs_ws,
-                      self.cs_chunks)
+                               self._W(grad, "bh"), self.wg_ws)
         engine.drp_wgrad_input(True, h0, self.D, T, B, self.S, self.plan.state_segs, self.gz_tape[0],
                                x_tape, self._W(grad, "W0"), self._W(grad, "b0"), self.wg_ws)
 
@@ -1009,6 +1007,61 @@ class DrpPipeline:
             n += sum(g.numel() for g in self.gz_tape) + self.gheads_tape.numel()
         return 4 * n
 
+    def _bench_roofline_fused(self, time_kernel, peaks, peak_src):
+        """Fused path: the dominant kernel is rk_mlp2_kernel (one launch per decision epoch and direction).
+        Timed alone: the train-sweep forward (keeps H0 / H1), the backward, and the three one-shot
+        weight-gradient launches.  Algorithmic FLOPs of the forward launch = 2 B (D h0 + h0 h1 + h1 NH),
+        fp32-equivalent; the hidden layer runs as 3 TF32 passes at half the bf16 rate, so the hardware
+        ceiling of the kernel is peak / 6 (stated in the note)."""
+        pl, plan = self.pl, self.plan
+        B, T = pl.batch_size_train, pl.T
+        params = pl.params[0]
+        h0, h1 = self.hid
+        act = plan._activation
+        self.refresh_transposes(params)
+        x = self.tape[:self.S * B]
+        H = [Hl[0] for Hl in self.H]
+
+        def k_fwd():
+            engine.drp_mlp2_forward(act, B, self.D, h0, h1, self.NH, plan.state_segs, x, self.img_f,
+                                    self._W(params, "b0"), self._W(self.wT_hi, "W1"),
+                                    self._W(self.wT_lo, "W1"), self._W(params, "b1"),
+                                    self._W(params, "bh"), H[0], H[1], self.heads[0])
+
+        def k_bwd():
+            engine.drp_mlp2_backward(act, B, self.D, h0, h1, self.NH, plan.state_segs,
+                                     self.gheads_tape[0], H[0], H[1], self.img_b, self._W(self.w_hi, "W1"),
+                                     self._W(self.w_lo, "W1"), self.gz_tape[0][0], self.gz_tape[1][0],
+                                     self.gs[0])
+
+        grad = torch.zeros_like(params)
+
+        def k_wgrad():
+            self.wgrad_all(grad, self.tape)
+        t_fwd, t_bwd, t_wg = time_kernel(k_fwd), time_kernel(k_bwd), time_kernel(k_wgrad)
+        self.gs[0].zero_()
+        flops_fwd = 2.0 * B * (self.D * h0 + h0 * h1 + h1 * self.NH)
+        flops_iter = T * flops_fwd * (3 + 1)          # train fwd + dX + dW, + the test forward
+        tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved_tf = flops_fwd / (t_fwd * 1e-3) / 1e12
+        roofline = {"bound": "tensor",
+                    "kernel": "rk_mlp2_kernel<forward> (layer 0 + hidden layer tcgen05 3xTF32 + heads, one launch "
+                              "per decision epoch; train sweep, H0 / H1 kept)",
+                    "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_flops": flops_fwd, "executed_tf32_tflops": 3 * achieved_tf,
+                    "mlp_tflop_per_iteration": flops_iter / 1e12,
+                    "hbm_bytes_per_launch": 4.0 * B * (h0 + h1 + self.NH + self.D),
+                    "note": "algorithmic (fp32-equivalent) FLOPs of the three layers over the launch time, "
+                            "against the sustained bf16 tensor peak; 3 TF32 passes per product at half the "
+                            "bf16 rate put the hardware ceiling of the hidden layer at peak/6, and 256 row "
+                            "tiles on 148 SMs (two per SM) at 0.86 of that"}
+        # launches per iteration: per epoch (policy, actions, rollout step) x {train fwd, train bwd, test};
+        # weight gradients: 3 products + 4 reductions + column sums; transposes / splits / images / losses
+        n_launch = T * 3 * 3 + 10 + 24
+        return roofline, {"mlp2_forward": t_fwd, "mlp2_backward": t_bwd, "weight_gradients_all_epochs": t_wg}, \
+            n_launch
+
     def bench_roofline(self, time_kernel, peaks, peak_src):
         """(roofline, kernels_ms, launches per iteration) of the dominant kernel of a DRP iteration: the
         last hidden dense layer (the only dense contraction of the path), timed alone through
@@ -1020,6 +1073,8 @@ class DrpPipeline:
         B, T = pl.batch_size_train, pl.T
         params = pl.params[0]
         hid = self.hid
+        if self.fused_bwd and not self.film and 1 in self.tc_layers:
+            return self._bench_roofline_fused(time_kernel, peaks, peak_src)
         li = len(hid) - 1
         h_in, h_out = (hid[-2] if len(hid) > 1 else self.D), hid[-1]
         src = self.H[-2][0] if len(hid) > 1 else None

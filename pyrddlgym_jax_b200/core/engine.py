@@ -30,7 +30,7 @@ EXPORTS = [
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
     "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
     "rk_state_scale_forward", "rk_state_scale_backward", "rk_drp_mlp2_forward",
-    "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare",
+    "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare", "rk_drp_mlp2_set_timing",
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
 ]
 
@@ -145,12 +145,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_mlp2_image_floats.restype = ci
     lib.rk_drp_mlp2_prepare.argtypes = [vp, ci, ci, ci, ci, cf, cf, cf, cf]
     lib.rk_drp_mlp2_prepare.restype = ci
+    lib.rk_drp_mlp2_set_timing.argtypes = [vp]
+    lib.rk_drp_mlp2_set_timing.restype = ci
     lib.rk_drp_wgrad_ctas.argtypes = []
     lib.rk_drp_wgrad_ctas.restype = ci
     ll = ctypes.c_longlong
     lib.rk_drp_wgrad_hidden.argtypes = [vp, ci, ci, ci, ll, cf, cf, cf, cf, cf]
     lib.rk_drp_wgrad_hidden.restype = ci
-    lib.rk_drp_wgrad_heads.argtypes = [vp, ci, ci, ci, ll, cf, cf, cf, cf]
+    lib.rk_drp_wgrad_heads.argtypes = [vp, ci, ci, ci, ll, cf, cf, cf, cf, cf]
     lib.rk_drp_wgrad_heads.restype = ci
     lib.rk_drp_wgrad_input.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
     lib.rk_drp_wgrad_input.restype = ci
@@ -442,6 +444,11 @@ def drp_mlp2_backward(act, B, D, h0, h1, NH, segs, gheads, H0, H1, bwd_img, W1_h
         _ptr(W1_lo), _ptr(gz0), _ptr(gz1), _ptr(gs)), "rk_drp_mlp2_backward")
 
 
+def drp_mlp2_set_timing(buf: Optional[torch.Tensor]) -> None:
+    """Profiling aid: int64 device tensor of >= grid * 8 words receiving per-CTA phase stamps, or None."""
+    _check(load_library().rk_drp_mlp2_set_timing(_ptr(buf)), "rk_drp_mlp2_set_timing")
+
+
 def drp_wgrad_ctas() -> int:
     return int(load_library().rk_drp_wgrad_ctas())
 
@@ -453,9 +460,11 @@ def drp_wgrad_hidden(accumulate, M, N, K, A, Bm, dW, db, workspace):
            "rk_drp_wgrad_hidden")
 
 
-def drp_wgrad_heads(accumulate, M, NH, K, H, G, dWh, workspace):
+def drp_wgrad_heads(accumulate, M, NH, K, H, G, dWh, dbh, workspace):
+    """dWh [M][NH] (+)= H^T G; dbh [NH] (+)= column sums of G (or None)."""
     _check(load_library().rk_drp_wgrad_heads(_stream(), 1 if accumulate else 0, M, NH, K, _ptr(H),
-                                             _ptr(G), _ptr(dWh), _ptr(workspace)), "rk_drp_wgrad_heads")
+                                             _ptr(G), _ptr(dWh), _ptr(dbh), _ptr(workspace)),
+           "rk_drp_wgrad_heads")
 
 
 def drp_wgrad_input(accumulate, M, D, T, Bt, S_words, segs, gz0, x_tape, dW0, db0, workspace):

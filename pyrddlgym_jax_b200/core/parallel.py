@@ -56,6 +56,17 @@ def allreduce_gradient(grad: torch.Tensor) -> torch.Tensor:
     return grad
 
 
+def allgather_returns(local: torch.Tensor) -> torch.Tensor:
+    """The GLOBAL return vector [world_size * B] in rank order (equal shards): what a utility other
+    than the mean is evaluated on (planner.py:2161-2247)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    out = torch.empty(ws * local.numel(), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
+
+
 class PeerAllReduce:
     """One-shot sum all-reduce of a short fp32 vector over NVLink peer memory
     (csrc/rk_comm.cu): symmetric buffers and flag words are allocated with torch's symmetric

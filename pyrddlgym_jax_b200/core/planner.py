@@ -762,10 +762,10 @@ class JaxBackpropPlanner:
         self._defer_ar = False
         if self.world_size > 1:
             self._fold_msg = (self._pipeline and P == 1 and self.steps_per_update <= 1)
-            self._msg = z(NP + 2)
+            self._msg = z(NP + 4)
             if self._fold_msg:
                 self.grad = self._msg[:NP].view(1, NP)
-            self._peer_ar = parallel.PeerAllReduce.create(NP + 2, self.device)
+            self._peer_ar = parallel.PeerAllReduce.create(NP + 4, self.device)
         self.ent_coeff = torch.full((1,), float(self.start_entropy_coeff), device=self.device)
         if self.use_pgpe:
             self._pg_reward, self._pg_returns = z(T * Be), z(Be)
@@ -775,7 +775,15 @@ class JaxBackpropPlanner:
         self._init_train, self._init_test = z(fw.S), z(te.S)
         self.grad_used = z(P, NP)
         self._gen = torch.Generator(device=dev)
-        self.loss_pair = z(2, P)
+        # [train loss | test loss] sums over the ranks, followed by the two loop-control words every
+        # rank votes on (time budget reached, progress): they travel with the gradient exchange, so all
+        # replicas leave optimize_generator at the same iteration and anneal the same entropy coefficient
+        self._pair_ctl = z(2 * P + 2)
+        self.loss_pair = self._pair_ctl[:2 * P].view(2, P)
+        self.ctl = self._pair_ctl[2 * P:]
+        self.ctl_in = z(2)
+        self._ctl_host = torch.zeros(2, dtype=torch.float32).pin_memory() \
+            if torch.cuda.is_available() else torch.zeros(2, dtype=torch.float32)
 
     # ---- model parameters (relaxation weights), planner.py:3165-3168 ---------------------
     def model_parameter_info(self) -> Dict[Any, float]:
@@ -855,13 +863,16 @@ class JaxBackpropPlanner:
             elif self.utility == "mean":
                 engine.mean_loss(self.train_returns[p], B, loss_out, None)
             else:
-                r = self.train_returns[p].detach().clone().requires_grad_(True)
+                # a utility other than the mean is a function of the GLOBAL return vector
+                # (planner.py:2161-2247, 2817-2818): gather the shards, differentiate, keep this rank's
+                # slice of the cotangent -- the summed gradients are then exact
+                r = parallel.allgather_returns(self.train_returns[p]).detach().clone().requires_grad_(True)
                 fn = self.utility if callable(self.utility) else _utility_fn(self.utility, self.utility_kwargs)
                 with torch.enable_grad():
                     loss = -fn(r, **(self.utility_kwargs if callable(self.utility) else {}))
                     (g,) = torch.autograd.grad(loss, r)
                 loss_out.copy_(loss.detach().reshape(1))
-                self.gret.copy_(g)
+                self.gret.copy_(g[self.rank * B:(self.rank + 1) * B])
             self.train_bwd.backward(B, T, self.tape, self.gret, policy=params,
                                     noise=self.train_noise, mparams=self.train_mparams,
                                     disc=self.disc, gradp=self.gradp)
@@ -873,7 +884,10 @@ class JaxBackpropPlanner:
             # rollout, so value and gradient come from the parameters alone
             H, dH = self.plan.entropy_terms(params.view(T, A))
             loss_out.sub_(self.ent_coeff * H)
-            self.grad[p].view(T, A).sub_(self.ent_coeff * dH)
+            # with the deferred exchange every rank's gradient is still to be SUMMED over the ranks: the
+            # regulariser (the same on every rank) goes in once, not world_size times
+            scale = 1.0 / self.world_size if (self.world_size > 1 and self._defer_ar) else 1.0
+            self.grad[p].view(T, A).sub_(self.ent_coeff * dH * scale)
 
     def _publish_kernels(self, p: int):
         """Publish the loss and the gradient of the update being applied (callback['grad'])."""
@@ -1004,12 +1018,14 @@ class JaxBackpropPlanner:
                 NP = self.n_params
                 self._msg[NP:NP + 1].copy_(self.train_loss)
                 self._msg[NP + 1:NP + 2].copy_(self.test_loss_buf)
+                self._msg[NP + 2:].copy_(self.ctl_in)
                 self._allreduce(self._msg)
-                self.loss_pair.view(-1).copy_(self._msg[NP:])
+                self._pair_ctl.copy_(self._msg[NP:])
             else:
                 self.loss_pair[0].copy_(self.train_loss)
                 self.loss_pair[1].copy_(self.test_loss_buf)
-                self._allreduce(self.loss_pair.view(-1))
+                self.ctl.copy_(self.ctl_in)
+                self._allreduce(self._pair_ctl)
 
     def _pipelined_kernels(self, side: Optional[torch.cuda.Stream]):
         """One iteration in software-pipelined order: the optimiser step for the gradient the
@@ -1214,9 +1230,24 @@ class JaxBackpropPlanner:
         test = raw[P:2 * P].view(np.float32).copy()
         zero = raw[2 * P:3 * P] > 0
         if self.world_size > 1:
-            pair = self.loss_pair.cpu().numpy() / self.world_size
+            both = self._pair_ctl.cpu().numpy()
+            pair = both[:2 * P].reshape(2, P) / self.world_size
             train, test = pair[0], pair[1]
+            self._agreed_ctl = (float(both[2 * P]), float(both[2 * P + 1]) / self.world_size)
         return train, test, zero
+
+    def vote_loop_control(self, budget_reached: bool, progress_time: float):
+        """Multi-GPU: this rank's view of the loop control (its own wall clock) for the exchange of the
+        next iteration; ``agreed_loop_control`` returns what all ranks agreed on."""
+        if self.world_size > 1:
+            self._ctl_host[0] = 1.0 if budget_reached else 0.0
+            self._ctl_host[1] = float(progress_time)
+            self.ctl_in.copy_(self._ctl_host, non_blocking=True)
+
+    def agreed_loop_control(self):
+        """(any rank's time budget reached, mean progress over the ranks) of the last iteration."""
+        votes, progress = getattr(self, "_agreed_ctl", (0.0, 0.0))
+        return votes > 0.5, progress
 
     def redraw_noise(self, force: bool = False):
         """Fresh supplied-noise tensors for the next iteration (the reference splits its PRNG
@@ -1439,6 +1470,9 @@ class JaxBackpropPlanner:
         for it in range(epochs):
             status = JaxPlannerStatus.NORMAL
             with torch.cuda.device(self.device):
+                if self.world_size > 1:     # this rank's clock, agreed on through the exchange
+                    local = time.time() - start_time - elapsed_outside_loop
+                    self.vote_loop_control(local >= train_seconds, local / train_seconds)
                 if self.train_noise is not None or self.test_noise is not None \
                         or (self.drp is not None and self.drp.pol_noise is not None):
                     self.redraw_noise()
@@ -1491,11 +1525,15 @@ class JaxBackpropPlanner:
                             for msg in JaxRDDLCompiler.get_error_messages(int(code)):
                                 print(f"[FAIL] {name} model error: {msg}")
             elapsed = time.time() - start_time - elapsed_outside_loop
-            if elapsed >= train_seconds:
+            progress_time = elapsed / train_seconds
+            if self.world_size > 1:     # every rank acts on the SAME budget flag and progress
+                budget_reached, progress_time = self.agreed_loop_control()
+            else:
+                budget_reached = elapsed >= train_seconds
+            if budget_reached:
                 status = JaxPlannerStatus.TIME_BUDGET_REACHED
             if it >= epochs - 1:
                 status = JaxPlannerStatus.ITER_BUDGET_REACHED
-            progress_time = elapsed / train_seconds
             progress_it = it / (epochs - 1) if epochs > 1 else 0
             progress_percent = 100 * min(1, max(0, progress_time, progress_it))
             callback = {

@@ -63,8 +63,12 @@ rk_peer_allreduce_kernel(RkPeers P, int world, int rank, int n, int n_max, float
   }
   __syncthreads();
   if (failed) {
+    // a peer never arrived: the vector is NOT reduced.  Record it and stop the context -- every
+    // later CUDA call of this process fails loudly instead of training on an un-reduced gradient.
     if (tid == 0 && status != nullptr) *status = 1;
-    return;
+    __threadfence_system();
+    __syncthreads();
+    asm volatile("trap;");
   }
   const float* local = P.buf[rank] + half;
   for (int i = tid; i < n; i += blockDim.x) {

@@ -69,6 +69,7 @@ struct M2Args {
   float* On;                // forward : H1 out or NULL;    backward: gz0 out
   float* out;               // forward : heads [B][NH];     backward: state cotangent (fluent-major, +=)
   int act;
+  unsigned long long* timing;   // optional [grid][8] clock64 stamps of the phases (rk_drp_mlp2_set_timing)
 };
 
 // ---- small device helpers -----------------------------------------------------------------------
@@ -85,13 +86,16 @@ __device__ __forceinline__ void m2_ffma2(unsigned long long& acc, unsigned long 
                                          unsigned long long b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
-// tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU + three ALU instructions, absolute error <= 2e-7
-// (saturates correctly: e = inf -> 1, e = 0 -> -1)
+// tanh(x) = sign(x) (1 - 2 / (1 + e^(2|x|))): two MUFU + four ALU instructions.  Evaluated on |x| so
+// that q = 2 / (1 + e) keeps its RELATIVE accuracy (3e-7) as the unit saturates: 1 - q is then the
+// correctly rounded fp32 tanh, which is what the adjoint's 1 - h^2 of a saturated unit hangs on (the
+// signed form loses q to the rounding of 1 + e for x < 0: tens of percent of 1 - h^2 at |x| ~ 8).
+// Absolute error <= 1.2e-7 near 0, <= 1 ulp elsewhere; e = inf -> 1.
 __device__ __forceinline__ float m2_tanh(float x) {
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.885390081777927f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-  return fmaf(-2.f, r, 1.f);
+  return copysignf(fmaf(-2.f, r, 1.f), x);
 }
 template <int ACT_CT>
 __device__ __forceinline__ float m2_act(int act, float x) {
@@ -100,7 +104,9 @@ __device__ __forceinline__ float m2_act(int act, float x) {
 }
 template <int ACT_CT>
 __device__ __forceinline__ float m2_act_grad(int act, float y) {
-  if (ACT_CT == RK_ACT_TANH) return fmaf(-y, y, 1.f);
+  // 1 - y * y with BOTH roundings (no FMA), like the reference's tanh adjoint: for a saturated unit the
+  // two forms differ by percents of the result
+  if (ACT_CT == RK_ACT_TANH) return __fsub_rn(1.f, __fmul_rn(y, y));
   return rk_act_grad(act, y);
 }
 __device__ __forceinline__ void m2_ld8(const float* p, float* v) {
@@ -173,33 +179,46 @@ __device__ __forceinline__ void m2_store_split(uint32_t tile, int r, int c0, con
   }
 }
 
+// hacc[0 .. 2 NG) += v[c] * Wh[c][0 .. 4 NG) for the 16 columns c of a chunk (Wh rows of 16 floats at wrow)
+template <int NG>
+__device__ __forceinline__ void m2_head_accum(unsigned long long* hacc, const float* v, uint32_t wrow) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const unsigned long long vv = m2_pack(v[c], v[c]);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      unsigned long long w0, w1;
+      lds128_u64(wrow + (uint32_t)c * 64u + 16u * g, w0, w1);
+      m2_ffma2(hacc[2 * g], vv, w0);
+      m2_ffma2(hacc[2 * g + 1], vv, w1);
+    }
+  }
+}
+
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 
 // ---- operand images, built once per optimiser step -----------------------------------------------
-// fwd_img : h1 / 16 blocks of the head product's operand Wh^T: [16 head columns][16 k] K-major,
-//           64B-swizzled, TF32 hi (1 KB) | lo (1 KB); then W0 [D][h0] as plain fp32 (16-byte aligned copy)
-// bwd_img : h0 / 16 such blocks of W0 (rows = state words), then Wh^T [NH][h1] as plain fp32
+// fwd_img : Wh padded to [h1][16] and W0 [D][h0], plain fp32 (16-byte aligned copies)
+// bwd_img : h0 / 16 blocks of the input product's operand W0: [16 state words][16 k] K-major,
+//           64B-swizzled, TF32 hi (1 KB) | lo (1 KB); then Wh^T [NH][h1] as plain fp32
 __global__ void rk_mlp2_prepare_kernel(int D, int h0, int h1, int NH, const float* __restrict__ W0,
                                        const float* __restrict__ Wh, float* __restrict__ fwd_img,
                                        float* __restrict__ bwd_img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_f = h1 * 16, n_b = h0 * 16, n_t = NH * h1;
-  if (i < n_f + n_b) {
-    const bool fwd = i < n_f;
-    const int e = fwd ? i : i - n_f;
+  if (i < n_f) {                              // forward: Wh padded to 16 columns, exact fp32
+    const int c = i >> 4, n = i & 15;
+    fwd_img[i] = n < NH ? Wh[(size_t)c * NH + n] : 0.f;
+  } else if (i < n_f + n_b) {                 // backward: W0 as the second product's operand blocks
+    const int e = i - n_f;
     const int j = e >> 8, n = (e >> 4) & 15, kk = e & 15;
-    float v = 0.f;
-    if (fwd) {
-      if (n < NH) v = Wh[(size_t)(16 * j + kk) * NH + n];
-    } else {
-      if (n < D) v = W0[(size_t)n * h0 + 16 * j + kk];
-    }
+    const float v = n < D ? W0[(size_t)n * h0 + 16 * j + kk] : 0.f;
     const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
     const uint32_t off = (uint32_t)n * 16u + ((((uint32_t)kk >> 2) ^ (((uint32_t)n >> 1) & 3u)) << 2) +
                          ((uint32_t)kk & 3u);                       // in floats
-    float* blk = (fwd ? fwd_img : bwd_img) + (size_t)j * 512;
+    float* blk = bwd_img + (size_t)j * 512;
     blk[off] = h;
     blk[256 + off] = v - h;
   } else if (i < n_f + n_b + n_t) {
@@ -208,7 +227,7 @@ __global__ void rk_mlp2_prepare_kernel(int D, int h0, int h1, int NH, const floa
     bwd_img[(size_t)n_b * 2 + (size_t)n * h1 + k] = Wh[e];
   } else if (i < n_f + n_b + n_t + D * h0) {
     const int e = i - n_f - n_b - n_t;
-    fwd_img[(size_t)n_f * 2 + e] = W0[e];
+    fwd_img[(size_t)n_f + e] = W0[e];
   }
 }
 
@@ -219,6 +238,7 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ M2Args P,
                uint32_t tmem_cols) {
   const int act = ACT_CT >= 0 ? ACT_CT : P.act;
+  if (P.timing != nullptr && threadIdx.x == 64) P.timing[(size_t)blockIdx.x * 8] = clock64();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment (swizzle atoms) by pointer arithmetic, so the compiler keeps the shared state space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -228,8 +248,9 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
   const uint32_t b_stage = 2 * b_half;
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + M2_AST * M2_A_STAGE;
-  uint8_t* s_base = b_base + M2_BST * b_stage;          // second-product operand: nj blocks (hi 1 KB | lo 1 KB)
-  uint8_t* tail = s_base + (size_t)nj * 2048;
+  // backward: operand image of the second product, nj blocks (hi 1 KB | lo 1 KB); forward: Wh [Nd][16] fp32
+  uint8_t* s_base = b_base + M2_BST * b_stage;
+  uint8_t* tail = s_base + (MODE == 0 ? (size_t)Nd * 64 : (size_t)nj * 2048);
   uint64_t* bars = (uint64_t*)tail;
   uint64_t* b_full = bars;                              // [M2_BST] weight tiles landed (TMA)
   uint64_t* b_empty = bars + M2_BST;                    // [M2_BST] MMAs of the stage retired
@@ -252,6 +273,37 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
   // uses of A stage s during the main loop (the epilogue continues the same phase sequence)
   const int n_use0 = (nkb + 1) / 2, n_use1 = nkb / 2;
 
+  // the producer rows' small-side values (state words / head cotangents), duplicated (v, v) for FFMA2:
+  // fetched first, so the loads overlap the prologue's copies
+  unsigned long long sv[M2_MAXS];
+#pragma unroll
+  for (int d = 0; d < M2_MAXS; ++d) sv[d] = 0ull;
+  if (warp >= 2) {
+    const int row = (threadIdx.x - 64) & 255;
+    const bool valid = row < rows_here;
+    const long long grow = r0 + (valid ? row : 0);
+      if (valid) {
+      if (MODE == 0) {
+        int f = 0;
+#pragma unroll
+        for (int d = 0; d < M2_MAXS; ++d) {
+          if (d < P.NS) {
+            while (f + 1 < P.S.n && d >= P.S.off[f + 1]) ++f;
+            const float v = P.x_fm[(size_t)P.S.off[f] * P.B + (size_t)grow * P.S.len[f] + (d - P.S.off[f])];
+            sv[d] = m2_pack(v, v);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < M2_MAXS; ++d) {
+          if (d < P.NS) {
+            const float v = P.G[(size_t)grow * P.NS + d];
+            sv[d] = m2_pack(v, v);
+          }
+        }
+      }
+    }
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < M2_BST; ++s) {
       mbar_init(&b_full[s], 1);
@@ -274,12 +326,30 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
   if (warp >= 2) {
     const int ct = threadIdx.x - 64;
     // second-product operand image and the SIMT product's weights: coalesced 16-byte copies
-    const float4* img = reinterpret_cast<const float4*>(P.W2);
+    const float4* __restrict__ img = reinterpret_cast<const float4*>(P.W2);
     float4* sdst = reinterpret_cast<float4*>(s_base);
-    for (int i = ct; i < Nd * 8; i += M2_CW * 32) sdst[i] = img[i];
-    const float4* wsrc = reinterpret_cast<const float4*>(P.Wsm);
+    const int n_img4 = MODE == 0 ? Nd * 4 : Nd * 8;
+    for (int i0 = ct; i0 < n_img4; i0 += 4 * M2_CW * 32) {      // four loads in flight per thread
+      float4 t4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * M2_CW * 32 < n_img4) t4[u] = __ldg(img + i0 + u * M2_CW * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * M2_CW * 32 < n_img4) sdst[i0 + u * M2_CW * 32] = t4[u];
+    }
+    const float4* __restrict__ wsrc = reinterpret_cast<const float4*>(P.Wsm);
     float4* wdst = reinterpret_cast<float4*>(Wsm_s);
-    for (int i = ct; i < P.NS * Kd / 4; i += M2_CW * 32) wdst[i] = wsrc[i];
+    const int nw4 = P.NS * Kd / 4;
+    for (int i0 = ct; i0 < nw4; i0 += 2 * M2_CW * 32) {
+      float4 t4[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (i0 + u * M2_CW * 32 < nw4) t4[u] = __ldg(wsrc + i0 + u * M2_CW * 32);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (i0 + u * M2_CW * 32 < nw4) wdst[i0 + u * M2_CW * 32] = t4[u];
+    }
     if (MODE == 0) {
       for (int i = ct; i < Kd; i += M2_CW * 32) bsm_s[i] = P.bsm[i];
       for (int i = ct; i < Nd; i += M2_CW * 32) bN_s[i] = P.bN[i];
@@ -291,6 +361,8 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long* const stamp = P.timing != nullptr ? P.timing + (size_t)blockIdx.x * 8 : nullptr;
+  if (stamp != nullptr && threadIdx.x == 64) stamp[1] = clock64();      // prologue done
 
   if (warp == 0) {
     // ===== TMA producer: the weight tiles hi / lo of every k-block =====
@@ -334,8 +406,13 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
         umma_commit(&b_empty[sb]);
       }
       umma_commit(acc_ready);
-      // second product: the epilogue's 16-column result chunks x the resident [16][16] operand blocks
-      for (int j = 0; j < nj; ++j) {
+      // backward: second product gz0 W0^T, the epilogue's 16-column result chunks x the resident
+      // [16][16] operand blocks.  (The forward's head product is NOT done here: the tensor core sees a
+      // weight as hi + trunc(lo), i.e. a FIXED error of ~2^-22 |w| per weight, and because saturated
+      // hidden units are the same for every rollout that error shifts a head output by the same
+      // ~3e-7 in all B * T rows -- measured: the plan gradient of the PowerGen workload moved by 5e-3.
+      // The forward epilogue takes the head product in fp32 with the exact weights instead.)
+      for (int j = 0; MODE == 1 && j < nj; ++j) {
         const int sa = j & 1;
         const int use = (sa ? n_use1 : n_use0) + (j >> 1);
         mbar_wait(&a_done[sa], use & 1);
@@ -345,18 +422,19 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
         for (int tl = 0; tl < ntiles; ++tl) {
           const uint32_t as = smem_u32(a_base + (size_t)sa * M2_A_STAGE + (size_t)tl * 2 * M2_A_TILE);
           const uint64_t dAh = make_desc(as), dAl = make_desc(as + M2_A_TILE);
-          const uint32_t d = tmem_base + (uint32_t)(tl * Nd);      // columns 0..15: drained by chunk 0
+          // a fresh 16-column partial per chunk (see the epilogue)
+          const uint32_t d = tmem_base + (uint32_t)(tl * Nd + TC_BK * j);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);
-            umma_tf32(d, dAh + adv, dBh + adv, idesc2, (j | k) != 0);
+            umma_tf32(d, dAh + adv, dBh + adv, idesc2, k != 0);
             umma_tf32(d, dAl + adv, dBh + adv, idesc2, 1);
             umma_tf32(d, dAh + adv, dBl + adv, idesc2, 1);
           }
         }
         umma_commit(&a_empty[sa]);
       }
-      umma_commit(s_ready);
+      if (MODE == 1) umma_commit(s_ready);
     }
   } else {
     const int ct = threadIdx.x - 64;                 // 0..511
@@ -367,34 +445,16 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
       const bool valid = row < rows_here;
       const bool tile_on = tl < ntiles;
       const long long grow = r0 + (valid ? row : 0);
-      unsigned long long sv[M2_MAXS];                // the row's small-side values, duplicated (v, v)
-#pragma unroll
-      for (int d = 0; d < M2_MAXS; ++d) sv[d] = 0ull;
-      if (valid) {
-        if (MODE == 0) {
-          int f = 0;
-#pragma unroll
-          for (int d = 0; d < M2_MAXS; ++d) {
-            if (d < P.NS) {
-              while (f + 1 < P.S.n && d >= P.S.off[f + 1]) ++f;
-              const float v = P.x_fm[(size_t)P.S.off[f] * P.B + (size_t)grow * P.S.len[f] + (d - P.S.off[f])];
-              sv[d] = m2_pack(v, v);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int d = 0; d < M2_MAXS; ++d) {
-            if (d < P.NS) {
-              const float v = P.G[(size_t)grow * P.NS + d];
-              sv[d] = m2_pack(v, v);
-            }
-          }
-        }
-      }
-      float hk[8];                                    // backward: the H1 chunk of the next k-block
+      // backward: the H1 chunks of this and the next two k-blocks (an HBM round trip is longer than a
+      // k-block's MMAs)
+      float hk[8], hk1[8], hk2[8];
       const float* hk_row = MODE == 1 ? P.Hk + (size_t)grow * Kd + hc * 8 : nullptr;
       float* ok_row = P.Ok != nullptr ? P.Ok + (size_t)grow * Kd + hc * 8 : nullptr;
-      if (MODE == 1 && valid) m2_ld8(hk_row, hk);
+      if (MODE == 1 && valid) {
+        m2_ld8(hk_row, hk);
+        if (nkb > 1) m2_ld8(hk_row + TC_BK, hk1);
+        if (nkb > 2) m2_ld8(hk_row + 2 * TC_BK, hk2);
+      }
       const uint32_t w_row0 = smem_u32(Wsm_s) + (uint32_t)hc * 32u;
       const uint32_t b_row0 = smem_u32(bsm_s) + (uint32_t)hc * 32u;
       const uint32_t kd4 = (uint32_t)Kd * 4u;
@@ -432,7 +492,12 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = v[i] * m2_act_grad<ACT_CT>(act, hk[i]);
-            if (kb + 1 < nkb) m2_ld8(hk_row + (kb + 1) * TC_BK, hk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              hk[i] = hk1[i];
+              hk1[i] = hk2[i];
+            }
+            if (kb + 3 < nkb) m2_ld8(hk_row + (kb + 3) * TC_BK, hk2);
             m2_st8(ok_row + kb * TC_BK, v);
           }
         } else {
@@ -460,13 +525,19 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
       const int n_use = sub ? n_use1 : n_use0;
       const float* hn_row = MODE == 1 ? P.Hn + (size_t)grow * Nd : nullptr;
       float* on_row = P.On != nullptr ? P.On + (size_t)grow * Nd : nullptr;
+      unsigned long long hacc[8];           // forward: this warp's part of the 16 head sums, packed pairs
+#pragma unroll
+      for (int g = 0; g < 8; ++g) hacc[g] = 0ull;
+      const uint32_t wh32 = smem_u32(s_base);
       float hn[16];
       if (MODE == 1 && valid && sub < nj) {
         m2_ld8(hn_row + sub * TC_BK, hn);
         m2_ld8(hn_row + sub * TC_BK + 8, hn + 8);
       }
+      if (stamp != nullptr && threadIdx.x == 64) stamp[2] = clock64();  // last operand tile produced
       mbar_wait(acc_ready, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (stamp != nullptr && threadIdx.x == 64) stamp[3] = clock64();  // hidden-layer MMAs retired
       for (int j = sub; j < nj; j += 2) {
         const int c0 = j * TC_BK;
         float v[16];
@@ -486,6 +557,16 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
               m2_st8(on_row + c0, v);
               m2_st8(on_row + c0 + 8, v + 8);
             }
+            // heads += H1[row][c] * Wh[c][:] in fp32 with the exact weights (packed FFMA2); the number of
+            // 4-column groups is a compile-time constant inside, so the chunk is one basic block and the
+            // shared-memory loads run ahead of the FMAs
+            const uint32_t wrow = wh32 + (uint32_t)c0 * 64u;
+            switch ((P.NO + 3) >> 2) {
+              case 1: m2_head_accum<1>(hacc, v, wrow); break;
+              case 2: m2_head_accum<2>(hacc, v, wrow); break;
+              case 3: m2_head_accum<3>(hacc, v, wrow); break;
+              default: m2_head_accum<4>(hacc, v, wrow); break;
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -500,19 +581,62 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
             }
           }
         }
-        mbar_wait(&a_empty[sub], (((n_use + (j >> 1)) & 1) ^ 1));
-        if (tile_on) m2_store_split<4>(stage32, r, 0, v);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_n(&a_done[sub], 2);      // 8 warps drain a chunk: 2 arrivals each
+        if (MODE == 1) {
+          mbar_wait(&a_empty[sub], (((n_use + (j >> 1)) & 1) ^ 1));
+          if (tile_on) m2_store_split<4>(stage32, r, 0, v);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_n(&a_done[sub], 2);      // 8 warps drain a chunk: 2 arrivals each
+        }
       }
-      // result of the second product: columns 0..15 of the tile's accumulator
-      mbar_wait(s_ready, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (stamp != nullptr && threadIdx.x == 64) stamp[4] = clock64();  // epilogue chunks drained
+      float hsum[16];
+      if (MODE == 0) {
+        // the two warps of a (tile, lane quarter) pair hold the even / odd chunks' part of the head sums:
+        // combined through shared memory (the A stages are free: every hidden-layer MMA has retired)
+        float* part = reinterpret_cast<float*>(a_base) + (size_t)row * 16;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) m2_unpack(hacc[g], hsum[2 * g], hsum[2 * g + 1]);
+        if (sub == 1) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(part + 4 * g) =
+                make_float4(hsum[4 * g], hsum[4 * g + 1], hsum[4 * g + 2], hsum[4 * g + 3]);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (sub == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 o = *reinterpret_cast<const float4*>(part + 4 * g);
+            hsum[4 * g] += o.x;
+            hsum[4 * g + 1] += o.y;
+            hsum[4 * g + 2] += o.z;
+            hsum[4 * g + 3] += o.w;
+          }
+        }
+      } else {
+        // result of the second product: the sum of the chunks' partial products (each chunk accumulates
+        // its own six MMAs in the 16 accumulator columns the epilogue has just drained for it: a long
+        // chain into ONE accumulator would add the tensor core's truncation bias, -1.6e-8 per MMA)
+        mbar_wait(s_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int n = 0; n < 16; ++n) hsum[n] = 0.f;
+        if (sub == 0 && tile_on) {
+          for (int j = 0; j < nj; ++j) {              // fixed order
+            uint32_t pr[16];
+            tmem_ld16(tbase + (uint32_t)(TC_BK * j), pr);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) hsum[n] += __uint_as_float(pr[n]);
+          }
+        }
+      }
+      if (stamp != nullptr && threadIdx.x == 64) stamp[5] = clock64();  // second product retired
       if (sub == 0 && tile_on) {
         uint32_t rr[16];
-        tmem_ld16(tbase, rr);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) rr[n] = __float_as_uint(hsum[n]);
         if (valid) {
           if (MODE == 0) {
 #pragma unroll
@@ -536,6 +660,7 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (stamp != nullptr && threadIdx.x == 64) stamp[6] = clock64();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(tmem_cols));
@@ -587,7 +712,8 @@ static int m2_launch(void* stream, const M2Args& P, const float* Bt_hi, const fl
   if ((rc = make_map(&mBl, Bt_lo, P.Ndim, P.Kdim, P.Kdim, P.Ndim)) != 0) return rc;
   const size_t fl = MODE == 0 ? (size_t)P.NS * P.Kdim + P.Kdim + P.Ndim + 16 : (size_t)P.NS * P.Kdim;
   const size_t smem = (size_t)M2_AST * M2_A_STAGE + (size_t)M2_BST * P.Ndim * TC_BK * 8 +
-                      (size_t)(P.Ndim / TC_BK) * 2048 + 128 + fl * 4 + 1024;
+                      (MODE == 0 ? (size_t)P.Ndim * 64 : (size_t)(P.Ndim / TC_BK) * 2048) + 128 + fl * 4 +
+                      1024;
   if (smem > 227 * 1024) return RK_E_SMEM;
   static int configured = 0;
   if (!configured) {
@@ -627,9 +753,18 @@ static bool m2_dims_ok(int D, int H0n, int H1n, int NH) {
          (H0n % TC_BK) == 0 && H1n >= TC_BK && H1n <= 256 && (H1n % TC_BK) == 0;
 }
 
+static unsigned long long* g_m2_timing = nullptr;
+// Profiling aid: when non-NULL, every CTA of the next launches writes 8 clock64 stamps (start, prologue
+// done, last tile produced, hidden MMAs retired, epilogue drained, second product retired, end, -) to
+// buf[cta][8] (buf: >= 256 * 8 words of device memory).  NULL switches it off.
+extern "C" int rk_drp_mlp2_set_timing(unsigned long long* buf) {
+  g_m2_timing = buf;
+  return 0;
+}
+
 extern "C" int rk_drp_mlp2_image_floats(int D, int H0n, int H1n, int NH, int backward) {
   if (!m2_dims_ok(D, H0n, H1n, NH)) return RK_E_BADARG;
-  return backward ? H0n * 32 + NH * H1n : H1n * 32 + D * H0n;
+  return backward ? H0n * 32 + NH * H1n : H1n * 16 + D * H0n;
 }
 
 extern "C" int rk_drp_mlp2_prepare(void* stream, int D, int H0n, int H1n, int NH, const float* W0,
@@ -665,7 +800,7 @@ extern "C" int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n,
   P.NO = NH;
   P.x_fm = x_fm;
   P.W2 = fwd_img;
-  P.Wsm = fwd_img + (size_t)H1n * 32;
+  P.Wsm = fwd_img + (size_t)H1n * 16;
   P.bsm = b0;
   P.bN = b1;
   P.b2 = bh;
@@ -673,6 +808,7 @@ extern "C" int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n,
   P.On = H1;
   P.out = heads;
   P.act = act;
+  P.timing = g_m2_timing;
   return m2_launch<0>(stream, P, W1T_hi, W1T_lo);
 }
 
@@ -706,5 +842,6 @@ extern "C" int rk_drp_mlp2_backward(void* stream, int act, int B, int D, int H0n
   P.On = gz0;
   P.out = gs;
   P.act = act;
+  P.timing = g_m2_timing;
   return m2_launch<1>(stream, P, W1_hi, W1_lo);
 }

@@ -16,6 +16,12 @@
 // results are added in CTA order afterwards (deterministic).  Per decision epoch this replaces a
 // split-K GEMM + a 19 MB partial reduction + two streaming passes over [B][256].
 //
+// Accumulator hygiene: the tensor core truncates when it aligns a product to the TMEM accumulator
+// (measured on this path: -1.6e-8 of the accumulator per MMA, a bias that does not average out; 8300
+// chained MMAs left -1.3e-4).  The wide product therefore DRAINS its accumulators into the CTA's fp32
+// workspace slice every WG_SEG k-blocks (<= 384 chained MMAs, bias <= 6e-6) and restarts them; the narrow
+// products rotate over 16 accumulator sets (512 TMEM columns) that the epilogue adds in fp32.
+//
 // The narrow products (N = 16) read their small operand with plain loads and transpose it into a
 // K-major 64B-swizzled [16][16] block while splitting it (the head cotangents are [K][NH] rows, the
 // state tape is fluent-major): A stays MN-major, B is K-major in the instruction descriptor.
@@ -27,6 +33,9 @@
 #include "rk_tc.cuh"
 
 #define WG_THREADS 320            // TMA warp, MMA warp, 8 converter / epilogue warps
+#define WG_SEG 64                 // k-blocks per accumulator segment of the wide product
+#define WG_NSET 16                // accumulator sets of the narrow products
+#define WG_AHEAD 6                // k-blocks the narrow operand's plain loads run ahead
 
 struct RkWgSegs {
   int n;
@@ -83,7 +92,8 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* empty = bars + STAGES;
   uint64_t* split_done = bars + 2 * STAGES;
   uint64_t* acc_ready = bars + 3 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 1);
+  uint64_t* acc_drained = bars + 3 * STAGES + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long kb_total = (K + TC_BK - 1) / TC_BK;
@@ -98,6 +108,7 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&split_done[s], 8);
     }
     mbar_init(acc_ready, 1);
+    mbar_init(acc_drained, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -142,25 +153,31 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full[s], ph);
         mbar_wait(&split_done[s], ph);
+        const int seg = i / WG_SEG;
+        const bool seg_start = BMODE == 0 && (i % WG_SEG) == 0;
+        if (seg_start && seg > 0) mbar_wait(acc_drained, (seg - 1) & 1);   // restart the accumulators
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb = st + 2 * a_bytes;
+        const bool fresh = BMODE == 0 ? seg_start : i < WG_NSET;
+        const uint32_t set_off = BMODE == 0 ? 0u : (uint32_t)((i % WG_NSET) * ntiles * 16);
         for (int tl = 0; tl < ntiles; ++tl) {
           const uint32_t sa = st + (uint32_t)tl * (TC_BM * TC_BK * 4);
           const uint64_t dAh = wg_desc_mn(sa), dAl = wg_desc_mn(sa + a_bytes);
           const uint64_t dBh = BMODE == 0 ? wg_desc_mn(sb) : make_desc(sb);
           const uint64_t dBl = BMODE == 0 ? wg_desc_mn(sb + b_bytes) : make_desc(sb + b_bytes);
-          const uint32_t d = tmem_base + (uint32_t)(tl * Nacc);
+          const uint32_t d = tmem_base + set_off + (uint32_t)(tl * Nacc);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             const uint64_t adv_a = (uint64_t)((k * 1024) >> 4);           // next group of 8 k-rows
             const uint64_t adv_b = BMODE == 0 ? adv_a : (uint64_t)((k * TC_UMMA_K * 4) >> 4);
-            umma_tf32(d, dAh + adv_a, dBh + adv_b, idesc, (i | k) != 0);
+            umma_tf32(d, dAh + adv_a, dBh + adv_b, idesc, (!fresh || k != 0) ? 1u : 0u);
             umma_tf32(d, dAl + adv_a, dBh + adv_b, idesc, 1);
             umma_tf32(d, dAh + adv_a, dBl + adv_b, idesc, 1);
           }
         }
         umma_commit(&empty[s]);
+        if (BMODE == 0 && ((i + 1) % WG_SEG == 0) && i + 1 < num_kb) umma_commit(acc_ready);
       }
       umma_commit(acc_ready);
     }
@@ -170,43 +187,98 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < 16; ++j) cs[j] = 0.f;
     const uint32_t a_f4 = (uint32_t)a_boxes * TC_BK * 128 / 16, b_f4 = b_bytes / 16;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* out = ws + (size_t)blockIdx.x * M * Nacc;
+    // wide product: add the accumulators of segment `seg` to the workspace slice (the first one stores)
+    auto drain = [&](int seg, bool last) {
+      mbar_wait(acc_ready, seg & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nh = ((N / 32 + 1) / 2) * 32;
+      const int c_beg = half ? nh : 0, c_end = half ? N : nh;
+      for (int tl = 0; tl < ntiles; ++tl) {
+        const int row = tl * TC_BM + q * 32 + lane;
+        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
+          uint32_t r[32];
+          if (num_kb > 0) {
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * N + c0), r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (row < M) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)row * N + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              if (seg > 0) {
+                const float4 o = dst[j];
+                v.x += o.x;
+                v.y += o.y;
+                v.z += o.z;
+                v.w += o.w;
+              }
+              dst[j] = v;
+            }
+          }
+        }
+      }
+      if (!last) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_drained))
+                       : "memory");
+        }
+      }
+    };
+    // narrow operand: thread ct owns element (k-row kk, column n) of every k-block's [16][16] tile
+    bool bw = false;
+    uint32_t boff = 0;
+    int b_kk = 0, b_n = 0, b_f = 0;
+    if (BMODE == 1) {
+      bw = ct < 16 * NB;
+      b_kk = ct / max(NB, 1);
+      b_n = ct - b_kk * NB;
+    } else if (BMODE == 2) {
+      b_kk = ct & 15;
+      b_n = ct >> 4;
+      bw = b_n <= NB;
+      if (b_n < NB)
+        while (b_f + 1 < SG.n && b_n >= SG.off[b_f + 1]) ++b_f;
+    }
+    if (BMODE != 0)
+      boff = (uint32_t)b_n * 64u + ((((uint32_t)b_kk >> 2) ^ (((uint32_t)b_n >> 1) & 3u)) << 4) +
+             ((uint32_t)b_kk & 3u) * 4u;
+    auto fetch_b = [&](int i) -> float {
+      if (!bw || i >= num_kb) return 0.f;
+      const long long k = (kb0 + i) * TC_BK + b_kk;
+      if (k >= K) return 0.f;
+      if (BMODE == 1) return __ldg(Bsm + (size_t)k * NB + b_n);
+      if (b_n == NB) return 1.f;
+      const long long t = k / Bt;
+      const int b = (int)(k - t * Bt);
+      return __ldg(Bsm + (size_t)t * S_words * Bt + (size_t)SG.off[b_f] * Bt + (size_t)b * SG.len[b_f] +
+                   (b_n - SG.off[b_f]));
+    };
+    float bq[WG_AHEAD];
+    float bsum = 0.f;                      // BMODE 1: column sum of this thread's column (bias gradient)
+#pragma unroll
+    for (int u = 0; u < WG_AHEAD; ++u) bq[u] = BMODE != 0 ? fetch_b(u) : 0.f;
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      // the narrow operand is fetched before waiting for the TMA tiles
+      // the narrow operand's element of this thread: fetched WG_AHEAD k-blocks ahead (a plain load
+      // consumed in the same k-block would expose a full HBM round trip per k-block)
       float bv = 0.f;
-      bool bw = false;
-      uint32_t boff = 0;
-      if (BMODE == 1) {
-        if (ct < 16 * NB) {
-          const int kk = ct / NB, n = ct - kk * NB;
-          const long long k = (kb0 + i) * TC_BK + kk;
-          bv = k < K ? Bsm[(size_t)k * NB + n] : 0.f;
-          bw = true;
-          boff = (uint32_t)n * 64u + ((((uint32_t)kk >> 2) ^ (((uint32_t)n >> 1) & 3u)) << 4) +
-                 ((uint32_t)kk & 3u) * 4u;
-        }
-      } else if (BMODE == 2) {
-        const int kk = ct & 15, d = ct >> 4;
-        if (d <= NB) {
-          const long long k = (kb0 + i) * TC_BK + kk;
-          if (k < K) {
-            if (d == NB) {
-              bv = 1.f;
-            } else {
-              const long long t = k / Bt;
-              const int b = (int)(k - t * Bt);
-              int f = 0;
-              while (f + 1 < SG.n && d >= SG.off[f + 1]) ++f;
-              bv = Bsm[(size_t)t * S_words * Bt + (size_t)SG.off[f] * Bt + (size_t)b * SG.len[f] +
-                       (d - SG.off[f])];
-            }
-          }
-          bw = true;
-          boff = (uint32_t)d * 64u + ((((uint32_t)kk >> 2) ^ (((uint32_t)d >> 1) & 3u)) << 4) +
-                 ((uint32_t)kk & 3u) * 4u;
-        }
+      if (BMODE != 0) {
+        bv = bq[0];
+#pragma unroll
+        for (int u = 0; u + 1 < WG_AHEAD; ++u) bq[u] = bq[u + 1];
+        bq[WG_AHEAD - 1] = fetch_b(i + WG_AHEAD);
+        if (BMODE == 1) bsum += bv;
       }
       mbar_wait(&full[s], ph);
       {   // A: raw -> hi in place, lo behind it
@@ -250,34 +322,19 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_done[s]))
                      : "memory");
       }
-    }
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    mbar_wait(acc_ready, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* out = ws + (size_t)blockIdx.x * M * Nacc;
-    if (BMODE == 0) {
-      const int nh = ((N / 32 + 1) / 2) * 32;
-      const int c_beg = half ? nh : 0, c_end = half ? N : nh;
-      for (int tl = 0; tl < ntiles; ++tl) {
-        const int row = tl * TC_BM + q * 32 + lane;
-        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
-          uint32_t r[32];
-          if (num_kb > 0) {
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * N + c0), r);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0u;
-          }
-          if (row < M) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(out + (size_t)row * N + c0 + j) =
-                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          }
-        }
+      // wide product: a finished segment is drained (after the next STAGES - 1 k-blocks have been
+      // split, so the MMAs restart at once) into the fp32 workspace slice of this CTA
+      if (BMODE == 0) {
+        const int due = i - (STAGES - 1);          // k-block whose segment end is drained now
+        if (due >= 0 && (due + 1) % WG_SEG == 0 && due + 1 < num_kb)
+          drain((due + 1) / WG_SEG - 1, false);
       }
+    }
+    if (BMODE == 0) {
+      // segment ends hidden by the loop end, then the last (partial) segment
+      for (int due = max(0, num_kb - (STAGES - 1)); due < num_kb; ++due)
+        if ((due + 1) % WG_SEG == 0 && due + 1 < num_kb) drain((due + 1) / WG_SEG - 1, false);
+      drain(num_kb > 0 ? (num_kb - 1) / WG_SEG : 0, true);
       if (ws_cs != nullptr) {
         // column sums of B: thread ct's float4 u of every k-block covers four fixed columns
         // (128B_ATOM_32B swizzle: 32-byte chunk p of k-row r holds logical chunk p ^ (r & 3))
@@ -296,22 +353,37 @@ rk_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     } else {
+      mbar_wait(acc_ready, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (BMODE == 1 && ws_cs != nullptr) {
+        // column sums of the narrow operand: 16 threads (k-rows) per column, added in fixed order
+        float* part = reinterpret_cast<float*>(smem);          // stages are free now
+        part[ct] = bw ? bsum : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ct < NB) {
+          float acc = 0.f;
+          for (int kk = 0; kk < 16; ++kk) acc += part[kk * NB + ct];
+          ws_cs[(size_t)blockIdx.x * 16 + ct] = acc;
+        }
+      }
       const int tl = half;
       if (tl < ntiles) {
         const int row = tl * TC_BM + q * 32 + lane;
-        uint32_t r[16];
-        if (num_kb > 0) {
-          wg_tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * 16), r);
-        } else {
+        float acc[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        const int nset = min(WG_NSET, num_kb);
+        for (int st = 0; st < nset; ++st) {          // the accumulator sets, fixed order
+          uint32_t r[16];
+          wg_tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ntiles * 16 + tl * 16), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
         }
         if (row < M) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(out + (size_t)row * 16 + j) =
-                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
       }
     }
@@ -342,11 +414,11 @@ __global__ void rk_wgrad_reduce_kernel(int mode, int M, int NO, int ldw, int spl
   *dst = v;
 }
 __global__ void rk_wgrad_reduce_cs_kernel(int N, int splits, const float* __restrict__ ws_cs,
-                                          float* __restrict__ out, int accumulate) {
+                                          float* __restrict__ out, int accumulate, int ld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float v = 0.f;
-  for (int z = 0; z < splits; ++z) v += ws_cs[(size_t)z * N + i];
+  for (int z = 0; z < splits; ++z) v += ws_cs[(size_t)z * ld + i];
   if (accumulate) v += out[i];
   out[i] = v;
 }
@@ -408,7 +480,7 @@ static int wg_launch(cudaStream_t st, int M, int N, long long K, const float* A,
   }
   const int Nacc = BMODE == 0 ? N : 16;
   uint32_t cols = 32;
-  while ((int)cols < ntiles * Nacc) cols <<= 1;
+  while ((int)cols < ntiles * Nacc * (BMODE == 0 ? 1 : WG_NSET)) cols <<= 1;
   rk_wgrad_kernel<BMODE, STAGES><<<splits, WG_THREADS, smem, st>>>(
       mA, mB, M, N, K, kb_per, ws, ws_cs, Bsm, NB, Bt, S_words, SG, cols);
   *splits_out = splits;
@@ -435,23 +507,28 @@ extern "C" int rk_drp_wgrad_hidden(void* stream, int accumulate, int M, int N, l
                                                               nullptr, accumulate ? 1 : 0);
   if (db != nullptr)
     rk_wgrad_reduce_cs_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, splits, ws_cs, db,
-                                                               accumulate ? 1 : 0);
+                                                               accumulate ? 1 : 0, N);
   return (int)cudaGetLastError();
 }
 
-// dWh [M][NH] (+)= H[K][M]^T G[K][NH]  (NH <= 16).  workspace: rk_drp_wgrad_ctas() * M * 16 floats.
+// dWh [M][NH] (+)= H[K][M]^T G[K][NH], dbh [NH] (+)= column sums of G (dbh may be NULL); NH <= 16.
+// workspace: rk_drp_wgrad_ctas() * (M + 1) * 16 floats.
 extern "C" int rk_drp_wgrad_heads(void* stream, int accumulate, int M, int NH, long long K,
-                                  const float* H, const float* G, float* dWh, float* workspace) {
+                                  const float* H, const float* G, float* dWh, float* dbh,
+                                  float* workspace) {
   if (H == nullptr || G == nullptr || dWh == nullptr || workspace == nullptr || K <= 0)
     return RK_E_BADARG;
   if (!wg_m_ok(M) || NH <= 0 || NH > 16) return RK_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   RkWgSegs SG = {};
   int splits = 0;
-  int rc = wg_launch<1, 6>(st, M, 16, K, H, nullptr, G, NH, 1, 0, SG, workspace, nullptr, &splits);
+  float* ws_cs = dbh != nullptr ? workspace + (size_t)wg_sm_count() * M * 16 : nullptr;
+  int rc = wg_launch<1, 6>(st, M, 16, K, H, nullptr, G, NH, 1, 0, SG, workspace, ws_cs, &splits);
   if (rc != 0) return rc;
   rk_wgrad_reduce_kernel<<<(M * NH + 255) / 256, 256, 0, st>>>(1, M, NH, 16, splits, workspace, dWh,
                                                                nullptr, accumulate ? 1 : 0);
+  if (dbh != nullptr)
+    rk_wgrad_reduce_cs_kernel<<<1, 32, 0, st>>>(NH, splits, ws_cs, dbh, accumulate ? 1 : 0, 16);
   return (int)cudaGetLastError();
 }
 
