@@ -34,7 +34,7 @@ from .program import Program
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 JIT_DIR = os.path.join(CSRC, "jit")
 KERNEL_NAME = "rk_spec_kernel"
-CODEGEN_VERSION = 14
+CODEGEN_VERSION = 18
 
 _F1 = {
     "NEG": "-x", "ABS": "fabsf(x)", "SGN": "sgnf(x)", "FLOOR": "floorf(x)", "CEIL": "ceilf(x)",
@@ -87,6 +87,80 @@ def _flit(x: float) -> str:
     return f"__uint_as_float(0x{np.float32(x).view(np.uint32):08x}u)"
 
 
+def _edge_color(fa: List[int], fb: List[int]) -> List[int]:
+    """Proper edge colouring of the bipartite multigraph with one edge (fa[e], fb[e]) per element
+    (fb[e] < 0: no second endpoint): no two edges at a node share a colour, max-degree colours
+    (Koenig), by flipping two-coloured alternating paths."""
+    E = len(fa)
+    colA: Dict[int, Dict[int, int]] = {}
+    colB: Dict[int, Dict[int, int]] = {}
+    color = [-1] * E
+    fb = [v if v >= 0 else -(e + 1) for e, v in enumerate(fb)]
+    deg: Dict[Any, int] = {}
+    for e in range(E):
+        deg[("a", fa[e])] = deg.get(("a", fa[e]), 0) + 1
+        deg[("b", fb[e])] = deg.get(("b", fb[e]), 0) + 1
+    delta = max(deg.values()) if deg else 0
+
+    def free(used: Dict[int, int]) -> int:
+        return next(c for c in range(delta) if c not in used)
+
+    for e in range(E):
+        u, v = fa[e], fb[e]
+        ua, vb = colA.setdefault(u, {}), colB.setdefault(v, {})
+        a, b = free(ua), free(vb)
+        if a != b and a in vb:
+            # colour a is taken at v: flip the a / b alternating path that starts at v (it cannot
+            # reach u, where a is free), after which a is free at v
+            path, node, side, c = [], v, "b", a
+            while True:
+                used = colB[node] if side == "b" else colA[node]
+                if c not in used:
+                    break
+                edge = used[c]
+                path.append(edge)
+                node = fa[edge] if side == "b" else fb[edge]
+                side = "a" if side == "b" else "b"
+                c = b if c == a else a
+            for edge in path:
+                del colA[fa[edge]][color[edge]]
+                del colB[fb[edge]][color[edge]]
+            for edge in path:
+                color[edge] = b if color[edge] == a else a
+                colA[fa[edge]][color[edge]] = edge
+                colB[fb[edge]][color[edge]] = edge
+        color[e] = a
+        colA[u][a] = e
+        colB[v][a] = e
+    return color
+
+
+class _EllFamily:
+    """Register layout of a group of wide values (n > lanes per rollout) that are only combined
+    element by element, filled by gathers from narrow values and consumed by segment reductions:
+    element e lives in register ``slot[e]`` of lane ``lane[e]`` -- its segment under the family's first
+    segmentation -- so those reductions are register adds; a second segmentation (the transposed
+    reduction of an adjoint) sees at most one member per slot in every segment (edge colouring), i.e.
+    one shuffle per slot.  ELL-style storage of the sparse (lane x lane) incidence the model's object
+    relations define (Wildfire: cell x neighbour, 144 of 625 pairs, 8 slots)."""
+
+    def __init__(self, fid: int, n: int, segA: List[int], segB, L: int):
+        self.fid, self.n, self.L = fid, n, L
+        self.lane = list(segA)
+        self.segB = None if segB is None else list(segB)
+        self.slot = _edge_color(self.lane, self.segB if self.segB is not None else [-1] * n)
+        self.K = max(self.slot) + 1
+        self.elem_at = -np.ones((L, self.K), dtype=np.int64)
+        for e in range(n):
+            self.elem_at[self.lane[e], self.slot[e]] = e
+        self.elem_b = -np.ones((L, self.K), dtype=np.int64)
+        if self.segB is not None:
+            for e in range(n):
+                if self.segB[e] >= 0:
+                    assert self.elem_b[self.segB[e], self.slot[e]] < 0
+                    self.elem_b[self.segB[e], self.slot[e]] = e
+
+
 class _Gen:
     def __init__(self, prog: Program):
         self.p = prog
@@ -114,20 +188,145 @@ class _Gen:
     # ---- register vs shared-memory residency ------------------------------------------
     def _classify(self):
         L = self.L
+        self._plan_ell()
         smem = set()
         dtype: Dict[int, str] = {}
         for rec in self.ins:
             vals = ([rec["dst"]] if rec["dst"] else []) + rec["srcs"]
-            multi = rec["n"] > L
+            multi = rec["n"] > L and id(rec) not in self.ell_rec
             for v in vals:
                 if v["kind"] != "val":
                     continue
                 dtype.setdefault(v["id"], v["dtype"])
+                if v["id"] in self.ell_val:
+                    continue
                 if multi or v["n"] > L:
                     smem.add(v["id"])
             # a flat shared-memory copy is the cheapest way to move multi-word rows
         self.smem = smem
         self.dtype = dtype
+
+    def _plan_ell(self):
+        """Find the wide values that can live in registers (see _EllFamily)."""
+        self.ell_val: Dict[int, _EllFamily] = {}
+        self.ell_rec: Dict[int, _EllFamily] = {}
+        self.ell_tables: List[str] = []
+        L = self.L
+        if os.environ.get("RK_ELL", "1") == "0" or L < 2:
+            return
+        img = self.p.meta["const_image"]
+        wide = lambda v: v["kind"] == "val" and v["n"] > L          # noqa: E731
+        parent: Dict[int, int] = {}
+
+        def find(x):
+            while parent.setdefault(x, x) != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+        touching = []
+        for rec in self.ins:
+            vals = ([rec["dst"]] if rec["dst"] else []) + rec["srcs"]
+            ids = [v["id"] for v in vals if wide(v)]
+            if ids:
+                touching.append((rec, ids))
+                for i in ids[1:]:
+                    parent[find(i)] = find(ids[0])
+        comps: Dict[int, List] = {}
+        for rec, ids in touching:
+            comps.setdefault(find(ids[0]), []).append(rec)
+        fid = 0
+        for recs in comps.values():
+            fam = self._ell_component(recs, img, fid)
+            if fam is None:
+                continue
+            fid += 1
+            for rec in recs:
+                self.ell_rec[id(rec)] = fam
+                for v in ([rec["dst"]] if rec["dst"] else []) + rec["srcs"]:
+                    if wide(v):
+                        self.ell_val[v["id"]] = fam
+
+    def _ell_component(self, recs, img, fid):
+        L = self.L
+        n = None
+        segs: List[Tuple[int, ...]] = []            # distinct element -> segment functions
+        persistent = self.persistent
+
+        def seg_of(ptr, idx, n_el):
+            out = [-1] * n_el
+            for sgi in range(len(ptr) - 1):
+                for e in idx[ptr[sgi]:ptr[sgi + 1]]:
+                    if out[int(e)] >= 0:
+                        return None                 # an element in two segments
+                    out[int(e)] = sgi
+            return tuple(out)
+        for rec in recs:
+            op, dst, srcs = rec["op"], rec["dst"], rec["srcs"]
+            vals = ([dst] if dst else []) + srcs
+            for v in vals:
+                if v["kind"] == "val" and v["n"] > L:
+                    if v["uniform"] or v["id"] in persistent or (n is not None and v["n"] != n):
+                        return None
+                    n = v["n"]
+            if op in _RED:
+                src = srcs[0]
+                if not (src["kind"] == "val" and src["n"] > L and src["map"] == isa.MAP_IDENT
+                        and rec["n"] <= L and dst["n"] <= L and not dst["uniform"]):
+                    return None
+                ptr, idx = self.tables(rec)
+                sg = seg_of(ptr, idx, src["n"])
+                if sg is None:
+                    return None
+                rec["_seg"] = sg
+                if sg not in segs:
+                    segs.append(sg)
+            elif op == "RPRODX":
+                src = srcs[0]
+                tab = rec.get("tab")
+                if tab is None or not (src["kind"] == "val" and src["n"] > L and dst["n"] == src["n"]
+                                       and src["map"] == isa.MAP_IDENT and src["id"] != dst["id"]):
+                    return None
+                ptr, idx = (np.asarray(tab[k]).astype(np.int64) for k in ("ptr", "idx"))
+                sg = seg_of(ptr, idx, src["n"])
+                if sg is None or min(sg) < 0 or len(ptr) - 1 > L:
+                    return None
+                rec["_seg"] = sg
+                if sg not in segs:
+                    segs.append(sg)
+            elif op in ("LDB", "STB", "LDU", "STG", "STERR", "ERRCHK", "QSUM", "RARGMAX", "RARGMIN", "NOP"):
+                return None
+            else:                                   # element-wise
+                if dst is None or dst["n"] <= L or rec["n"] != dst["n"]:
+                    return None
+                for v in srcs:
+                    if v["kind"] == "val" and v["n"] > L:
+                        if v["map"] != isa.MAP_IDENT:
+                            return None
+                    elif v["kind"] == "val":
+                        if v["map"] == isa.MAP_IDENT:
+                            return None             # a narrow value read element-for-element: n mismatch
+                        if v["map"] != isa.MAP_BCAST and \
+                                int(img[v["map"]: v["map"] + rec["n"]].max()) >= L:
+                            return None
+        if n is None or not segs or len(segs) > 2:
+            return None
+        total = [sg for sg in segs if min(sg) >= 0 and max(sg) < L]
+        if not total:
+            return None
+        # RPRODX needs its segmentation to be the lane assignment
+        px = [rec["_seg"] for rec in recs if rec["op"] == "RPRODX"]
+        if len(set(px)) > 1 or (px and px[0] not in total):
+            return None
+        segA = px[0] if px else total[0]
+        rest = [sg for sg in segs if sg != segA]
+        segB = rest[0] if rest else None
+        if segB is not None and max(segB) >= L:
+            return None
+        fam = _EllFamily(fid, n, list(segA), None if segB is None else list(segB), L)
+        if fam.K > 12:
+            return None
+        fam.segA, fam.segB_t = segA, segB
+        return fam
 
     def is_reg(self, v) -> bool:
         return v["kind"] == "val" and v["id"] not in self.smem
@@ -291,6 +490,8 @@ class _Gen:
             return
         if id(rec) in self.trig_lead:
             return self.gen_trig_group(self.trig_lead[id(rec)])
+        if id(rec) in self.ell_rec:
+            return self.gen_ell(rec, self.ell_rec[id(rec)])
         if op in ("LDB", "STB", "LDU", "STG", "STERR", "ERRCHK", "QSUM"):
             return self.gen_special(rec)
         if op in _RED or op in ("RARGMAX", "RARGMIN", "RPRODX"):
@@ -375,6 +576,200 @@ class _Gen:
                       " ".join(stmt("e")) +
                       f" R[{dst['base']}u{qs} + e] = {self.to_bits('r', out_c)}; }}")
         self.emit("  __syncwarp();")
+
+    # ---- wide values in registers (see _EllFamily) ----------------------------------------------
+    def ell_table(self, fam, tag: str, values: np.ndarray, ctype: str = "uint32_t") -> str:
+        """A per-(slot, lane) table as a __constant__ array; returns its name."""
+        name = f"ELL{fam.fid}_{tag}"
+        if not any(name + "[" in t for t in self.ell_tables):
+            flat = values.T.reshape(-1)             # [K][L]
+            if ctype == "float":
+                body = ", ".join(_flit(float(x)) .replace("__uint_as_float(", "").rstrip(")") for x in flat)
+                self.ell_tables.append(f"__device__ const uint32_t {name}[{flat.size}] = {{{body}}};")
+            else:
+                body = ", ".join(f"{int(x)}u" for x in flat)
+                self.ell_tables.append(f"__device__ const uint32_t {name}[{flat.size}] = {{{body}}};")
+        return name
+
+    def ell_lane_reg(self, fam, tag: str, values: np.ndarray, k: int) -> str:
+        """Hoisted per-lane register holding values[lane][k]."""
+        tab = self.ell_table(fam, tag, values)
+        reg = f"el{fam.fid}_{tag}_{k}"
+        self.hoisted[reg] = f"  const uint32_t {reg} = rk_ld_tab({tab} + {k * self.L}u + le);"
+        return reg
+
+    def ell_mask(self, fam, which: str) -> str:
+        """Hoisted per-lane bit mask of the occupied slots (which = 'a': own elements, 'b': members of
+        the lane's segment under the second segmentation)."""
+        at = fam.elem_at if which == "a" else fam.elem_b
+        bits = np.array([[sum(1 << k for k in range(fam.K) if at[l, k] >= 0)] for l in range(self.L)])
+        tab = self.ell_table(fam, "m" + which, bits)
+        reg = f"el{fam.fid}_m{which}"
+        self.hoisted[reg] = f"  const uint32_t {reg} = rk_ld_tab({tab} + le);"
+        return reg
+
+    def ell_var(self, v, k: int) -> str:
+        return f"v{v['id']}_{k}"
+
+    def ell_opnd(self, fam, v, k: int, n_r: int, want: str) -> str:
+        want_c = "f" if want == "f" else "i"
+        L = self.L
+        img = self.p.meta["const_image"]
+        at = fam.elem_at[:, k]                      # element held by each lane in this slot (or -1)
+        if v["kind"] == "val" and v["id"] in self.ell_val:
+            name = self.ell_var(v, k)
+            src_c = "f" if self.dtype[v["id"]] == "f" else "i"
+            if src_c != want_c:
+                return f"__uint_as_float((uint32_t)({name}))" if want_c == "f" else f"(int)__float_as_uint({name})"
+            return name
+        if v["kind"] == "mparam":
+            return self.opnd(v, "ec", n_r, want)
+        mp = v["map"]
+        if v["kind"] == "const":
+            c = v["const"].reshape(-1)
+            if mp == isa.MAP_BCAST or c.size == 1:
+                return self.opnd(v, "ec", n_r, want)
+            idx = np.arange(n_r) if mp == isa.MAP_IDENT else img[mp: mp + n_r].astype(np.int64)
+            vals = np.array([c[idx[e]] if e >= 0 else c[idx[max(at.max(), 0)]] for e in at])
+            used = vals[at >= 0]
+            if used.size and np.all(used == used[0]):
+                return _flit(float(used[0])) if want_c == "f" else f"({int(used[0])})"
+            full = np.zeros((L, fam.K), dtype=np.float64)
+            for kk in range(fam.K):
+                a2 = fam.elem_at[:, kk]
+                full[:, kk] = [c[idx[e]] if e >= 0 else 0 for e in a2]
+            tag = f"c{v['base']}_{mp}"
+            if v["dtype"] == "f":
+                tab = self.ell_table(fam, tag, full, "float")
+            else:
+                tab = self.ell_table(fam, tag, full.astype(np.int64) & 0xFFFFFFFF)
+            reg = f"el{fam.fid}_{tag}_{k}"
+            self.hoisted[reg] = f"  const uint32_t {reg} = rk_ld_tab({tab} + {k * L}u + le);"
+            return self.from_bits(reg, want_c)
+        # narrow value
+        if mp == isa.MAP_BCAST:
+            return self.opnd(v, "ec", n_r, want)
+        tblm = img[mp: mp + n_r].astype(np.int64)
+        srcs = np.array([tblm[e] if e >= 0 else 0 for e in at])
+        lanes = np.arange(L)
+        src_c = "f" if self.dtype[v["id"]] == "f" else "i"
+        if self.is_reg(v):
+            if np.all(srcs[at >= 0] == lanes[at >= 0]):
+                ex = self.var(v)                    # the lane's own element: no shuffle
+            else:
+                full = np.zeros((L, fam.K), dtype=np.int64)
+                for kk in range(fam.K):
+                    a2 = fam.elem_at[:, kk]
+                    full[:, kk] = [tblm[e] if e >= 0 else 0 for e in a2]
+                reg = self.ell_lane_reg(fam, f"g{mp}", full, k)
+                base = "0u" if v["uniform"] else "qL"
+                ex = f"__shfl_sync(0xffffffffu, {self.var(v)}, {base} + {reg})"
+            if src_c != want_c:
+                ex = f"__uint_as_float((uint32_t)({ex}))" if want_c == "f" else f"(int)__float_as_uint({ex})"
+            return ex
+        full = np.zeros((L, fam.K), dtype=np.int64)
+        for kk in range(fam.K):
+            a2 = fam.elem_at[:, kk]
+            full[:, kk] = [tblm[e] if e >= 0 else 0 for e in a2]
+        reg = self.ell_lane_reg(fam, f"g{mp}", full, k)
+        qs = f" + qc * {v['sq']}u" if v["sq"] else ""
+        return self.from_bits(f"R[{v['base']}u{qs} + {reg}]", want_c)
+
+    def gen_ell(self, rec, fam):
+        op, n, L, K = rec["op"], rec["n"], self.L, fam.K
+        dst, srcs = rec["dst"], rec["srcs"]
+        if op in _RED:
+            ct, init, upd = _RED[op]
+            tin = "f" if ct == "float" else "i"
+            src = srcs[0]
+            second = rec["_seg"] != fam.segA
+            mask = self.ell_mask(fam, "b" if second else "a")
+            body = [f"{ct} acc = {init};"]
+            for k in range(K):
+                at = fam.elem_b[:, k] if second else fam.elem_at[:, k]
+                if not np.any(at >= 0):
+                    continue
+                x = self.ell_opnd(fam, src, k, n, tin)
+                if second:
+                    # the member of this lane's segment that sits in slot k lives in lane lane[e]
+                    lanes = np.zeros((L, K), dtype=np.int64)
+                    for kk in range(K):
+                        lanes[:, kk] = [fam.lane[e] if e >= 0 else 0 for e in fam.elem_b[:, kk]]
+                    reg = self.ell_lane_reg(fam, "sb", lanes, k)
+                    x = f"__shfl_sync(0xffffffffu, {x}, qL + {reg})"
+                ok = "true" if np.all(at[:rec["n"]] >= 0) and rec["n"] == L else f"(({mask} >> {k}u) & 1u)"
+                # the shuffle is executed by every lane; only its use is conditional
+                body.append(f"{{ const {ct} s_ = {x}; const {ct} t = {ok} ? s_ : {init}; {upd}; }}")
+            code = " ".join(body)
+            out_c = "f" if ct == "float" else "i"
+            if self.is_reg(dst):
+                self.emit(f"  {{ {code} {self.var(dst)} = acc; }}")
+            else:
+                qs_d = f" + q * {dst['sq']}u" if dst["sq"] else ""
+                self.emit(f"  {{ {code} if (q < {self.rpw}u && le < {rec['n']}u) "
+                          f"R[{dst['base']}u{qs_d} + le] = {self.to_bits('acc', out_c)}; }}")
+                self.emit("  __syncwarp();")
+            return
+        if op == "RPRODX":
+            src = srcs[0]
+            mask = self.ell_mask(fam, "a")
+            ls = ["float run = 1.f;"]
+            for k in range(K):
+                ls.append(f"{self.ell_var(dst, k)} = run; "
+                          f"run = run * ((({mask} >> {k}u) & 1u) ? {self.ell_opnd(fam, src, k, n, 'f')} : 1.f);")
+            ls.append("run = 1.f;")
+            for k in range(K - 1, -1, -1):
+                ls.append(f"{self.ell_var(dst, k)} = {self.ell_var(dst, k)} * run; "
+                          f"run = run * ((({mask} >> {k}u) & 1u) ? {self.ell_opnd(fam, src, k, n, 'f')} : 1.f);")
+            self.emit("  { " + " ".join(ls) + " }")
+            return
+        body, tin, out_c = self._ew_body(rec)
+        names = "xyz"
+        for k in range(K):
+            if not np.any(fam.elem_at[:, k] >= 0):
+                continue
+            ls = [f"const {self.ctype(tk)} {names[j]} = {self.ell_opnd(fam, srcs[j], k, n, tk)};"
+                  for j, tk in enumerate(tin)]
+            self.emit("  { " + " ".join(ls) + f" {self.ell_var(dst, k)} = {body}; }}")
+
+    def _ew_body(self, rec):
+        """(C expression in x, y, z; operand types; result type) of an element-wise instruction."""
+        op, dst, srcs = rec["op"], rec["dst"], rec["srcs"]
+        dt_out = dst["dtype"]
+        if self.fast and op in _FAST:
+            body, tin = _FAST[op], ("ff" if op in _F2 else "f")
+        elif self.fast_trig and op in ("SIN", "COS"):
+            body, tin = _FAST[op], "f"
+        elif self.fast_trig and op == "TAN":
+            body, tin = "rk_ftan_ieee(x)", "f"
+        elif op in _F1:
+            body, tin = _F1[op], "f"
+        elif op in _F2:
+            body, tin = _F2[op], "ff"
+        elif op in _F2B:
+            body, tin = f"((x {_F2B[op]} y) ? 1 : 0)", "ff"
+        elif op in _I1:
+            body, tin = _I1[op], "i"
+        elif op in _I2:
+            body, tin = _I2[op], "ii"
+        elif op == "MOV":
+            body, tin = "x", dt_out if dt_out == "f" else "i"
+        elif op == "SELECT":
+            d = "f" if dt_out == "f" else "i"
+            body, tin = "((x != 0) ? y : z)", "i" + d + d
+        elif op == "FMA":
+            body, tin = "__fadd_rn(__fmul_rn(x, y), z)", "fff"
+        elif op == "LERP":
+            body, tin = "__fadd_rn(__fmul_rn(x, y), __fmul_rn(__fsub_rn(1.f, x), z))", "fff"
+        elif op == "I2F":
+            body, tin = "(float)x", "i"
+        elif op == "F2I":
+            body, tin = "(int)x", "f"
+        elif op == "F2B":
+            body, tin = "((x != 0.f) ? 1 : 0)", "f"
+        else:
+            raise NotImplementedError(f"codegen: op {op}")
+        return body, tin, ("f" if dt_out == "f" else "i")
 
     # ---- reductions ---------------------------------------------------------------------------
     def gen_reduce(self, rec):
@@ -513,6 +908,26 @@ class _Gen:
         tin = "f" if ct == "float" else "i"
         base = "0u" if src["uniform"] else "qL"
         conv = (self.dtype[src["id"]] == "f") != (tin == "f")
+        if n == 1 and kmax >= 4 and not conv and src["uniform"] == dst["uniform"] \
+                and self.is_reg(dst) and L >= 2 and (L & (L - 1)) == 0:
+            # one segment (a reward-style total): xor-butterfly over the rollout's lanes, log2(L) shuffles
+            # instead of one per member; lanes outside the segment contribute the identity.  (The order of
+            # the additions differs from the member order -- as it does in XLA's own reductions.  A value
+            # shared by all rollouts is replicated in every rollout's lanes, so each group reduces its copy.)
+            members = [int(m) for m in idx[ptr[0]:ptr[1]]]
+            if len(set(members)) == len(members) and max(members) < L:
+                comb = {"RSUM": "a_ + b_", "RISUM": "a_ + b_", "RPROD": "a_ * b_", "RIPROD": "a_ * b_",
+                        "RMIN": "fminf(a_, b_)", "RMAX": "fmaxf(a_, b_)", "RIMIN": "min(a_, b_)",
+                        "RIMAX": "max(a_, b_)"}[op]
+                if members == list(range(len(members))):
+                    cond = f"le < {len(members)}u"
+                else:
+                    cond = f"(({sum(1 << m for m in members)}u >> le) & 1u)"
+                steps = " ".join(
+                    f"{{ const {ct} a_ = t_; const {ct} b_ = __shfl_xor_sync(0xffffffffu, t_, {o}u); t_ = {comb}; }}"
+                    for o in [L >> (i + 1) for i in range(L.bit_length() - 1)])
+                self.emit(f"  {{ {ct} t_ = ({cond}) ? {self.var(src)} : {init}; {steps} {self.var(dst)} = t_; }}")
+                return True
         need_dyn = False
         body = [f"{ct} acc = {init};"]
         for k in range(kmax):
@@ -685,6 +1100,10 @@ class _Gen:
                 if v["kind"] == "val" and v["id"] not in self.smem and v["id"] not in seen:
                     seen.add(v["id"])
                     dt = self.dtype[v["id"]]
+                    if v["id"] in self.ell_val:
+                        decl.append("  " + self.ctype(dt) + " " + ", ".join(
+                            f"v{v['id']}_{k} = ({self.ctype(dt)})0" for k in range(self.ell_val[v["id"]].K)) + ";")
+                        continue
                     decl.append(f"  {self.ctype(dt)} v{v['id']} = ({self.ctype(dt)})0;")
         lists = [self.ins[:self.n_pro], self.ins[self.n_pro:self.n_pro + self.n_step],
                  self.ins[self.n_pro + self.n_step:]]
@@ -747,6 +1166,14 @@ class _Gen:
 //          instructions={p.n_ins} register-resident values={len(seen)} shared-memory values={len(self.smem)}
 #include "rk_launch.h"
 #include "rk_device.cuh"
+{chr(10).join(self.ell_tables)}
+// per-lane layout tables are read ONCE, before the step loop (volatile: ptxas would otherwise
+// re-materialise the load inside the loop -- a lane-indexed, i.e. serialised, access)
+__device__ __forceinline__ uint32_t rk_ld_tab(const uint32_t* p) {{
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}}
 
 extern "C" __global__ void {KERNEL_NAME}(const RkLaunch K) {{
   extern __shared__ __align__(16) uint32_t smem[];

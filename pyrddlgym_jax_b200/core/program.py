@@ -635,10 +635,14 @@ class ProgramBuilder:
                 last_err = e
                 continue
             # specialised kernels keep single-pass values (n <= L) in registers; multi-pass
-            # values live in shared memory and cost an order of magnitude more per pass
+            # values live in shared memory and cost an order of magnitude more per pass -- unless the
+            # code generator can give them a register layout of K slots per lane (codegen._EllFamily)
             mp = self.MULTIPASS_PENALTY if self.INS_OVERHEAD < 1.0 else 1.0
-            cost = sum((-(-max(i.n, 1) // L)) * (mp if i.n > L else 1.0) + self.INS_OVERHEAD
-                       for i in step)
+            ell = self._ell_slots(prog) if self.INS_OVERHEAD < 1.0 else {}
+            unit = [float(ell[k]) if k in ell else
+                    (-(-max(i.n, 1) // L)) * (mp if i.n > L else 1.0) for k, i in enumerate(step)]
+            cost = sum(u + self.INS_OVERHEAD for u in unit)
+            prog.meta["unit_costs"] = unit
             nwarps = -(-B // prog.rpw)
             resident = max(1, min(64, self.SMEM_WORDS // max(prog.warp_words, 1)))
             conc = 148 * min(resident, self.FREE_WARPS_PER_SM)
@@ -663,8 +667,7 @@ class ProgramBuilder:
                     wps = (-(-B // prog.rpw)) / (148 * 4)
                     return sass * max(1.0 / ipc, wps)
                 L = best.lanes
-                sass_multi = 2.2 * sum((-(-max(i.n, 1) // L)) * (self.MULTIPASS_PENALTY if i.n > L else 1.0)
-                                       for i in step)
+                sass_multi = 2.2 * sum(best.meta["unit_costs"])
                 sass_tpr = sum((10.0 if i.op == "QSUM" else 1.4) * max(i.n, 1) for i in step)
                 live = tpr.warp_words / 32.0                  # scalar values alive at once, per lane
                 if live > 320:      # measured: Wildfire forward, 441 live scalars, spills and loses
@@ -672,6 +675,23 @@ class ProgramBuilder:
                 if est(tpr, sass_tpr, 0.7) < 0.8 * est(best, sass_multi, 0.4):
                     best = tpr
         return best
+
+    @staticmethod
+    def _ell_slots(prog: Program) -> Dict[int, int]:
+        """{index in the step list: register slots per lane} of the instructions the code generator keeps
+        in registers although they are wider than the lane group."""
+        from .codegen import _Gen
+        try:
+            gen = _Gen(prog)
+        except Exception:
+            return {}
+        n_pro, n_step, _ = prog.n_ins
+        out = {}
+        for k, rec in enumerate(prog.meta["ins"][n_pro:n_pro + n_step]):
+            fam = gen.ell_rec.get(id(rec))
+            if fam is not None:
+                out[k] = fam.K
+        return out
 
     def _assemble_for(self, kind: str, pro: List[Ins], step: List[Ins], epi: List[Ins],
                       persistent: Sequence[V], L: int) -> Program:
