@@ -249,6 +249,31 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
               const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
               const float* bias, const float* aux, int ldaux);
 
+/* Returns and loss of a closed-loop (deep reactive policy) update from the per-step logs of its T
+ * one-step rollout launches (planner.py:2747-2765, 2811-2819):
+ *   returns[b] = sum_t disc[t] reward[t][b] (disc NULL = 1);  ent_scratch[b] = sum_t entropy[t][b];
+ *   loss[0] = -mean(returns) - ent_coeff[0] * mean(ent_scratch)   (entropy NULL: no second term; loss NULL:
+ *   returns only).  Deterministic (fixed-order) sums. */
+int rk_drp_returns_loss(void* stream, int T, int B, const float* reward, const float* disc,
+                        const float* entropy, const float* ent_coeff, float* returns, float* ent_scratch,
+                        float* loss);
+
+/* W [r][c] -> WT [c][r] (or NULL) and / or its TF32 hi / lo split WT_hi, WT_lo [c][r] (both or neither):
+ * the operand forms of a Dense kernel the policy kernels read, rebuilt once per optimiser step. */
+int rk_transpose_split(void* stream, int r, int c, const float* W, float* WT, float* WT_hi, float* WT_lo);
+
+/* Supplied-noise tensor of a program from a counter-based generator (csrc/rk_optim.cu): one launch
+ * fills out[T][N * B] (draw site s = block [B][n_s] at word offset offs[s] * B of every step's row;
+ * offs[n_sites] = N) with Philox4x32-10 words (key = seed, counter = (element quad, draws[0])) through the
+ * site's law -- kinds: 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy.
+ * draws: device word holding the draw number (advance it with rk_noise_advance: a captured graph then
+ * draws fresh noise at every replay), or NULL = 0.  kinds / offs are HOST arrays.
+ * Replaces: the jax.random draws of a step's key (compiler.py:1627-2240) on the throughput path; the
+ * parity tests keep supplying the noise tensor. */
+int rk_draw_noise(void* stream, int T, int B, int n_sites, const int32_t* kinds, const int32_t* offs,
+                  unsigned long long seed, const unsigned long long* draws, float* out);
+int rk_noise_advance(void* stream, unsigned long long* draws);
+
 /* Fused forward of a policy network with two hidden layers for one decision epoch:
  *   heads[B][NH] = act(act(x W0 + b0) W1 + b1) Wh + bh
  * Replaces: DRPStateLayer + the two Dense/activation layers + the per-action Dense heads of

@@ -383,7 +383,7 @@ class _GenT:
 
 extern "C" __global__ void __launch_bounds__({THREADS}) {KERNEL_NAME}(const RkLaunch K) {{
   const uint32_t lane = threadIdx.x & 31u;
-  const long long b = (long long)blockIdx.x * {THREADS} + threadIdx.x;      // this lane's rollout
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // this lane's rollout
   const long long gwarp = b >> 5;
   if ((gwarp << 5) >= (long long)K.B) return;                   // whole warp past the batch
   const bool valid = b < (long long)K.B;

@@ -513,6 +513,7 @@ class DrpPipeline:
         self.heads = z(T, Bt, self.NH)
         self.act = z(T, self.A * Bt)
         self.entropy = z(T, Bt)
+        self.ent_b = z(Bt)                             # per-rollout entropy sums (loss reduction scratch)
         self.pol_noise = z(T, self.A * Bt) if plan._stochastic else None
         self.gact = z(self.A * Bt)
         self.gs = [z(self.S * Bt), z(self.S * Bt)]
@@ -653,19 +654,22 @@ class DrpPipeline:
         return flat[off:off + r * c]
 
     def refresh_transposes(self, params: torch.Tensor):
+        """W^T of every Dense kernel and, for the tensor-core layers, the TF32 hi / lo parts of W and W^T
+        (once per update, native kernels: rk_transpose_split / rk_tf32_split)."""
+        tc = {f"W{i}" for i in self.tc_layers}
         for name, off, r, c in self.plan.segments:
             if name.startswith("W"):
-                self.wT[off:off + r * c].view(c, r).copy_(params[off:off + r * c].view(r, c).t())
+                n = r * c
+                split = name in tc
+                engine.transpose_split(r, c, params[off:off + n], self.wT[off:off + n],
+                                       self.wT_hi[off:off + n] if split else None,
+                                       self.wT_lo[off:off + n] if split else None)
+                if split:
+                    engine.tf32_split(params[off:off + n], self.w_hi[off:off + n], self.w_lo[off:off + n], n)
         self.refresh_splits(params)
 
     def refresh_splits(self, params: torch.Tensor):
-        """hi / lo parts of the hidden kernels for the tensor-core layers (once per update)."""
-        for i in self.tc_layers:
-            off, r, c = self.plan.seg[f"W{i}"]
-            n = r * c
-            engine.tf32_split(params[off:off + n], self.w_hi[off:off + n], self.w_lo[off:off + n], n)
-            engine.tf32_split(self.wT[off:off + n], self.wT_hi[off:off + n],
-                              self.wT_lo[off:off + n], n)
+        """Operand images of the fused kernels (once per update)."""
         if self.fused_fwd and self.tc_layers:
             engine.drp_mlp2_prepare(self.D, self.hid[0], self.hid[1], self.NH, self._W(params, "W0"),
                                     self._W(params, "Wh"), self.img_f, self.img_b)
@@ -848,14 +852,9 @@ class DrpPipeline:
                         reward=pl.train_reward[p][t * B:], returns=pl.train_returns[p],
                         err=pl.train_err[p][t * B:], final=self.tape[(t + 1) * S * B:])
         # returns and loss (planner.py:2747-2765, 2811-2819); entropy regulariser is value-only
-        rew = pl.train_reward[p].view(T, B)
-        if pl.disc is not None:
-            rew = rew * pl.disc.view(T, 1)
-        torch.sum(rew, dim=0, out=pl.train_returns[p])
         loss_out = pl.train_loss[p:p + 1] if loss_out is None else loss_out
-        engine.mean_loss(pl.train_returns[p], B, loss_out, None)
-        if plan._stochastic:
-            loss_out.sub_(self.ent_coeff * (self.entropy.sum() / B))
+        engine.drp_returns_loss(T, B, pl.train_reward[p], pl.disc, self.entropy if plan._stochastic else None,
+                                self.ent_coeff, pl.train_returns[p], self.ent_b, loss_out)
         # ---- backward sweep
         grad.zero_()
         self.gs[0].zero_()
@@ -967,13 +966,20 @@ class DrpPipeline:
                        err=o_err[t * B:], final=nxt)
             cur ^= 1
         o_final.copy_(self.t_state[cur])
-        rew = o_reward.view(T, B)
-        if pl.disc is not None:
-            rew = rew * pl.disc.view(T, 1)
-        torch.sum(rew, dim=0, out=o_returns)
-        engine.mean_loss(o_returns, B, o_loss, None)
+        engine.drp_returns_loss(T, B, o_reward, pl.disc, None, None, o_returns, None, o_loss)
 
     def redraw_noise(self, gen: torch.Generator):
+        pl = self.pl
+        if self.pol_noise is not None and getattr(pl, "_philox", False):
+            # one Philox launch for the whole [T][A * B] policy-noise tensor: the action-noise law, with
+            # Logistic noise on boolean logits (planner.py:1386) and Gumbel noise on pooled logits (1041, 1051)
+            dist = self.plan._action_noise_dist
+            sites = [("logistic" if kind == 1 else ("gumbel" if kind in (3, 4) else dist), off, n)
+                     for (off, n), kind in zip(self.plan.action_segs, self.plan.action_kinds)]
+            if len(sites) <= 64 and all(k in engine.NOISE_KINDS for k, _, _ in sites):
+                engine.draw_noise(pl.T, pl.batch_size_train, sites, pl._noise_seed * 4 + 2, pl._draws,
+                                  self.pol_noise)
+                return
         if self.pol_noise is not None:
             dist = self.plan._action_noise_dist
             if dist == "normal":

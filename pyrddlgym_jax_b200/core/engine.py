@@ -32,6 +32,7 @@ EXPORTS = [
     "rk_state_scale_forward", "rk_state_scale_backward", "rk_drp_mlp2_forward",
     "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare", "rk_drp_mlp2_set_timing",
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
+    "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
 ]
 
 
@@ -145,6 +146,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_mlp2_image_floats.restype = ci
     lib.rk_drp_mlp2_prepare.argtypes = [vp, ci, ci, ci, ci, cf, cf, cf, cf]
     lib.rk_drp_mlp2_prepare.restype = ci
+    lib.rk_draw_noise.argtypes = [vp, ci, ci, ci, vp, vp, ctypes.c_ulonglong, vp, cf]
+    lib.rk_draw_noise.restype = ci
+    lib.rk_drp_returns_loss.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf, cf]
+    lib.rk_drp_returns_loss.restype = ci
+    lib.rk_transpose_split.argtypes = [vp, ci, ci, cf, cf, cf, cf]
+    lib.rk_transpose_split.restype = ci
+    lib.rk_noise_advance.argtypes = [vp, vp]
+    lib.rk_noise_advance.restype = ci
     lib.rk_drp_mlp2_set_timing.argtypes = [vp]
     lib.rk_drp_mlp2_set_timing.restype = ci
     lib.rk_drp_wgrad_ctas.argtypes = []
@@ -442,6 +451,38 @@ def drp_mlp2_backward(act, B, D, h0, h1, NH, segs, gheads, H0, H1, bwd_img, W1_h
         _stream(), ACTIVATIONS[act], B, D, h0, h1, NH, n, ctypes.cast(off, ctypes.c_void_p),
         ctypes.cast(ln, ctypes.c_void_p), _ptr(gheads), _ptr(H0), _ptr(H1), _ptr(bwd_img), _ptr(W1_hi),
         _ptr(W1_lo), _ptr(gz0), _ptr(gz1), _ptr(gs)), "rk_drp_mlp2_backward")
+
+
+NOISE_KINDS = {"uniform": 0, "normal": 1, "exponential": 2, "gumbel": 3, "logistic": 4, "laplace": 5,
+               "cauchy": 6}
+
+
+def draw_noise(T: int, B: int, sites, seed: int, draws: Optional[torch.Tensor], out: torch.Tensor):
+    """out[T][N * B] <- fresh noise of the draw sites ``sites`` = [(kind name, first word, words)], one
+    launch (Philox4x32-10 + the site's law); ``draws``: int64 device word with the draw number."""
+    n = len(sites)
+    kinds = (ctypes.c_int32 * n)(*[NOISE_KINDS[k] for k, _, _ in sites])
+    offs = (ctypes.c_int32 * (n + 1))(*([o for _, o, _ in sites] + [sites[-1][1] + sites[-1][2]]))
+    _check(load_library().rk_draw_noise(
+        _stream(), T, B, n, ctypes.cast(kinds, ctypes.c_void_p), ctypes.cast(offs, ctypes.c_void_p),
+        ctypes.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), _ptr(draws), _ptr(out)), "rk_draw_noise")
+
+
+def drp_returns_loss(T, B, reward, disc, entropy, ent_coeff, returns, ent_scratch, loss):
+    """returns[b] = sum_t disc_t reward[t][b]; loss = -mean(returns) - ent_coeff * mean_b sum_t entropy[t][b]."""
+    _check(load_library().rk_drp_returns_loss(
+        _stream(), T, B, _ptr(reward), _ptr(disc), _ptr(entropy), _ptr(ent_coeff), _ptr(returns),
+        _ptr(ent_scratch), _ptr(loss)), "rk_drp_returns_loss")
+
+
+def transpose_split(r, c, W, WT, WT_hi, WT_lo):
+    """W [r][c] -> W^T (and / or its TF32 hi / lo split)."""
+    _check(load_library().rk_transpose_split(_stream(), r, c, _ptr(W), _ptr(WT), _ptr(WT_hi),
+                                             _ptr(WT_lo)), "rk_transpose_split")
+
+
+def noise_advance(draws: torch.Tensor):
+    _check(load_library().rk_noise_advance(_stream(), _ptr(draws)), "rk_noise_advance")
 
 
 def drp_mlp2_set_timing(buf: Optional[torch.Tensor]) -> None:

@@ -775,6 +775,10 @@ class JaxBackpropPlanner:
         self._init_train, self._init_test = z(fw.S), z(te.S)
         self.grad_used = z(P, NP)
         self._gen = torch.Generator(device=dev)
+        # counter-based noise (one launch per program and redraw): seed and the device-side draw number
+        self._philox = _os.environ.get("RK_PHILOX", "1") != "0" and torch.device(dev).type == "cuda"
+        self._noise_seed = 42
+        self._draws = torch.zeros(1, dtype=torch.int64, device=dev)
         # [train loss | test loss] sums over the ranks, followed by the two loop-control words every
         # rank votes on (time budget reached, progress): they travel with the gradient exchange, so all
         # replicas leave optimize_generator at the same iteration and anneal the same entropy coefficient
@@ -823,9 +827,18 @@ class JaxBackpropPlanner:
             segs = [(off, n) for (off, n, _) in prog.state_layout.values()]
             engine.tile_state(B, segs, dev_words, s0)
 
-    def _draw(self, prog, T, B, out):
-        if out is not None:
-            out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
+    def _draw(self, prog, T, B, out, tag: int = 0):
+        """Fresh noise for every draw site of ``prog``: one Philox launch (csrc/rk_optim.cu:rk_draw_noise,
+        keyed by the optimize() key, this rank and ``tag``; the draw number advances once per redraw) --
+        or, for layouts with Gamma sites and with RK_PHILOX=0, the torch-generator form the parity tests
+        use (core/layout.py:draw_noise)."""
+        if out is None:
+            return
+        sites = [(kind, off, n) for kind, _, n, off, _ in prog.noise_layout]
+        if self._philox and all(k in engine.NOISE_KINDS for k, _, _ in sites) and len(sites) <= 64:
+            engine.draw_noise(T, B, sites, self._noise_seed * 4 + tag, self._draws, out)
+            return
+        out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
 
     # ---- the two device calls of an iteration -----------------------------------------------
     def _train_grad_kernels(self, p: int):
@@ -1190,6 +1203,8 @@ class JaxBackpropPlanner:
         with torch.cuda.device(self.device):
             gen = torch.Generator().manual_seed(int(key))
             self._gen.manual_seed(int(key))
+            self._noise_seed = int(key) + 7919 * self.rank
+            self._draws.zero_()
             self.init_train_host = self._init_words(self.train_fwd.program.state_layout, subs)
             self.init_test_host = self._init_words(self.test_fwd.program.state_layout, subs)
             self.load_initial_state(self.init_train_host, self.init_test_host)
@@ -1210,8 +1225,10 @@ class JaxBackpropPlanner:
             if self.world_size > 1:          # d(-mean over the GLOBAL batch)/d return_b
                 self.gret.mul_(1.0 / self.world_size)
                 self._gen.manual_seed(int(key) + 7919 * (self.rank + 1))
-            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
-            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise, 0)
+            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise, 1)
+            if self._philox:
+                engine.noise_advance(self._draws)
 
     def _plan_view(self, flat: torch.Tensor) -> torch.Tensor:
         """[..., n_params] in the shape the plan's pytree conversion expects."""
@@ -1258,10 +1275,12 @@ class JaxBackpropPlanner:
                 (self._graph is not None or self._graph_host is not None):
             return
         with torch.cuda.device(self.device):
-            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise)
-            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise)
+            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise, 0)
+            self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise, 1)
             if self.drp is not None:
                 self.drp.redraw_noise(self._gen)
+            if self._philox:
+                engine.noise_advance(self._draws)
 
     def update(self):
         for p in range(self.parallel_updates):

@@ -569,7 +569,28 @@ static int launch(const rk_program* p, cudaStream_t st, RkLaunch& K) {
     for (int i = 0; i < RK_NUM_BUFFERS; ++i)
       if (K.W[i] * (long long)K.B >= (1ll << 31)) return RK_E_BADARG;
     void* args[] = {(void*)&K};
-    const int threads = p->spec_threads > 0 ? p->spec_threads : p->warps_per_cta * 32;
+    int threads = p->spec_threads > 0 ? p->spec_threads : p->warps_per_cta * 32;
+    if (p->spec_threads > 0 && p->spec_smem == 0) {
+      // register-only (thread-per-rollout) kernels index rollouts by blockDim: pick the CTA width that
+      // leaves the fewest warps on the busiest SM (1024 warps as 256 CTAs of 4 put 8 warps on 108 SMs and
+      // 4 on the rest; as 1024 CTAs of 1 they put 7 on every SM)
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+          n_sm = 148;
+      }
+      long long best = -1;
+      for (int w = p->spec_threads / 32; w >= 1; w >>= 1) {
+        const long long ctas = (nwarps + w - 1) / w;
+        const long long busiest = ((ctas + n_sm - 1) / n_sm) * w;
+        if (best < 0 || busiest < best) {
+          best = busiest;
+          threads = w * 32;
+        }
+      }
+    }
     const int sgrid = (nwarps + threads / 32 - 1) / (threads / 32);
     const int smem = p->spec_smem >= 0 ? p->spec_smem : p->smem_bytes;
     return g_drv.launchKernel(p->func, (unsigned)sgrid, 1, 1, (unsigned)threads, 1, 1,

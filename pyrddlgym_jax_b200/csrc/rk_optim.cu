@@ -526,3 +526,209 @@ extern "C" int rk_tile_state(void* stream, int B, int n_seg, const int32_t* seg_
                                                                (uint32_t*)s0);
   return (int)cudaGetLastError();
 }
+
+// ---- supplied-noise tensor from a counter-based generator ---------------------------------------
+// Fills the [T][N * B] noise buffer of a program (fluent-major per step: draw site s = block
+// [B][n_s] at word offset off_s * B) in ONE launch: Philox4x32-10 keyed by (seed), counter =
+// (element quad index, draw number), followed by the site's inverse-CDF / Box-Muller transform.
+// Replaces: jax.random.split + jax.random.<law> at every draw site of a step (compiler.py:1627-2240
+// draw their noise from the step's key); the laws are the standard ones of core/layout.py:draw_noise,
+// which stays the host-side (torch generator) form used by the parity tests.
+// The draw number lives in device memory (draws[0]) and is advanced by rk_noise_advance, so a captured
+// CUDA graph draws fresh noise at every replay.
+#define RK_NOISE_MAX_SITES 64
+struct RkNoiseSites {
+  int n;
+  int kind[RK_NOISE_MAX_SITES];        // 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy
+  int off[RK_NOISE_MAX_SITES + 1];     // word offsets (in units of B words); off[n] = N
+};
+
+__device__ __forceinline__ void rk_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256)
+rk_draw_noise_kernel(long long total, long long row_words, int B, RkNoiseSites S, uint32_t seed_lo,
+                     uint32_t seed_hi, const unsigned long long* __restrict__ draws,
+                     float* __restrict__ out) {
+  const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = quad * 4;
+  if (i0 >= total) return;
+  const unsigned long long d = draws != nullptr ? draws[0] : 0ull;
+  uint32_t r[4];
+  rk_philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)d, (uint32_t)(d >> 32), seed_lo,
+                   seed_hi, r);
+  // a normal site consumes its words in pairs (Box-Muller): (r0, r1) -> elements 0, 1; (r2, r3) -> 2, 3
+  float z[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = i0 + j;
+    if (i >= total) break;
+    const long long c = i % row_words;             // column inside the step's [N * B] row
+    const int w = (int)(c / B);                    // word index 0 .. N - 1
+    int s = 0;
+    while (s + 1 < S.n && w >= S.off[s + 1]) ++s;
+    const int kind = S.kind[s];
+    const float u = ((float)(r[j] >> 8) + 0.5f) * 5.9604644775390625e-8f;      // (0, 1)
+    float v;
+    switch (kind) {
+      case 1: {                                    // normal: Box-Muller on the word pair (j & ~1, j | 1)
+        const float u1 = ((float)(r[j & ~1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float u2 = ((float)(r[j | 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        const float rad = sqrtf(-2.f * logf(u1));
+        float sn, cs;
+        sincospif(2.f * u2, &sn, &cs);
+        v = (j & 1) ? rad * sn : rad * cs;
+        break;
+      }
+      case 2: v = -log1pf(-u); break;              // exponential
+      case 3: v = -logf(-logf(u)); break;          // gumbel
+      case 4: v = logf(u) - log1pf(-u); break;     // logistic
+      case 5: v = (u < 0.5f) ? logf(2.f * u) : -logf(2.f * (1.f - u)); break;     // laplace
+      case 6: { float sn, cs; sincospif(u - 0.5f, &sn, &cs); v = sn / cs; break; }    // cauchy
+      default: v = (float)(r[j] >> 8) * 5.9604644775390625e-8f; break;           // uniform [0, 1)
+    }
+    z[j] = v;
+  }
+  if (i0 + 3 < total && (((uintptr_t)(out + i0)) & 15) == 0) {
+    *reinterpret_cast<float4*>(out + i0) = make_float4(z[0], z[1], z[2], z[3]);
+  } else {
+    for (int j = 0; j < 4 && i0 + j < total; ++j) out[i0 + j] = z[j];
+  }
+}
+
+__global__ void rk_noise_advance_kernel(unsigned long long* draws) { draws[0] += 1ull; }
+
+extern "C" int rk_draw_noise(void* stream, int T, int B, int n_sites, const int32_t* kinds,
+                             const int32_t* offs, unsigned long long seed,
+                             const unsigned long long* draws, float* out) {
+  if (T <= 0 || B <= 0 || n_sites <= 0 || n_sites > RK_NOISE_MAX_SITES || kinds == nullptr ||
+      offs == nullptr || out == nullptr)
+    return RK_E_BADARG;
+  RkNoiseSites S;
+  S.n = n_sites;
+  for (int s = 0; s < n_sites; ++s) {
+    if (kinds[s] < 0 || kinds[s] > 6 || offs[s + 1] <= offs[s]) return RK_E_BADARG;
+    S.kind[s] = kinds[s];
+    S.off[s] = offs[s];
+  }
+  if (offs[0] != 0) return RK_E_BADARG;
+  S.off[n_sites] = offs[n_sites];
+  const long long row_words = (long long)offs[n_sites] * B;
+  const long long total = row_words * T;
+  const long long quads = (total + 3) / 4;
+  rk_draw_noise_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      total, row_words, B, S, (uint32_t)seed, (uint32_t)(seed >> 32), draws, out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int rk_noise_advance(void* stream, unsigned long long* draws) {
+  if (draws == nullptr) return RK_E_BADARG;
+  rk_noise_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(draws);
+  return (int)cudaGetLastError();
+}
+
+// ---- returns and loss of a closed-loop (deep reactive policy) update ----------------------------
+// The policy is evaluated between T one-step rollout launches, so the per-step rewards [T][B] (and the
+// per-step policy entropies [T][B]) are reduced afterwards (planner.py:2747-2765, 2811-2819):
+//   returns[b] = sum_t disc[t] * reward[t][b]          (disc NULL = 1)
+//   ent[b]     = sum_t entropy[t][b]                   (entropy NULL: not touched)
+// one thread per rollout, coalesced over b; then  loss = -mean(returns) - coeff * mean(ent)  in one CTA
+// (fixed order: deterministic).
+__global__ void __launch_bounds__(256)
+rk_drp_returns_kernel(int T, int B, const float* __restrict__ reward, const float* __restrict__ disc,
+                      const float* __restrict__ entropy, float* __restrict__ returns,
+                      float* __restrict__ ent) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float r = 0.f, e = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float w = disc != nullptr ? disc[t] : 1.f;
+    r += w * reward[(size_t)t * B + b];
+    if (entropy != nullptr) e += entropy[(size_t)t * B + b];
+  }
+  returns[b] = r;
+  if (entropy != nullptr) ent[b] = e;
+}
+
+__global__ void __launch_bounds__(1024)
+rk_drp_loss_kernel(const float* __restrict__ returns, const float* __restrict__ ent,
+                   const float* __restrict__ coeff, int B, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float s = 0.f, e = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    s += returns[i];
+    if (ent != nullptr) e += ent[i];
+  }
+  s = block_sum_1024(s, sh);
+  __syncthreads();
+  e = block_sum_1024(e, sh);
+  if (threadIdx.x == 0)
+    loss[0] = -s / (float)B - (ent != nullptr ? coeff[0] * (e / (float)B) : 0.f);
+}
+
+extern "C" int rk_drp_returns_loss(void* stream, int T, int B, const float* reward, const float* disc,
+                                   const float* entropy, const float* ent_coeff, float* returns,
+                                   float* ent_scratch, float* loss) {
+  if (T <= 0 || B <= 0 || reward == nullptr || returns == nullptr) return RK_E_BADARG;
+  if (entropy != nullptr && (ent_scratch == nullptr || ent_coeff == nullptr)) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  rk_drp_returns_kernel<<<(B + 255) / 256, 256, 0, st>>>(T, B, reward, disc, entropy, returns,
+                                                         ent_scratch);
+  if (loss != nullptr)
+    rk_drp_loss_kernel<<<1, 1024, 0, st>>>(returns, entropy != nullptr ? ent_scratch : nullptr,
+                                           ent_coeff, B, loss);
+  return (int)cudaGetLastError();
+}
+
+// ---- W [r][c] -> W^T [c][r], optionally with its TF32 hi / lo split (once per optimiser step) -------
+__global__ void __launch_bounds__(256)
+rk_transpose_split_kernel(int r, int c, const float* __restrict__ W, float* __restrict__ WT,
+                          float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;          // bx: column block of W, by: row block
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
+  for (int j = ty; j < 32; j += 8)
+    if (by + j < r && bx + tx < c) tile[j][tx] = W[(size_t)(by + j) * c + bx + tx];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int row = bx + j, col = by + tx;                        // element of W^T
+    if (row < c && col < r) {
+      const float v = tile[tx][j];
+      const size_t o = (size_t)row * r + col;
+      if (WT != nullptr) WT[o] = v;
+      if (hi != nullptr) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+        const float h = __uint_as_float(t);
+        hi[o] = h;
+        lo[o] = v - h;
+      }
+    }
+  }
+}
+
+extern "C" int rk_transpose_split(void* stream, int r, int c, const float* W, float* WT, float* WT_hi,
+                                  float* WT_lo) {
+  if (r <= 0 || c <= 0 || W == nullptr || (WT == nullptr && WT_hi == nullptr)) return RK_E_BADARG;
+  if ((WT_hi == nullptr) != (WT_lo == nullptr)) return RK_E_BADARG;
+  dim3 grid((c + 31) / 32, (r + 31) / 32);
+  rk_transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r, c, W, WT, WT_hi, WT_lo);
+  return (int)cudaGetLastError();
+}

@@ -101,3 +101,83 @@ def test_reduce_partials_and_mean_loss_match_numpy(cuda_device):
     assert_close(out.cpu().numpy(), gp.double().sum(0).numpy(), 1e-5, "reduce_partials", floor_frac=1.0)
     assert abs(float(loss) + float(ret.double().mean())) <= 1e-5 * float(ret.abs().mean())
     np.testing.assert_array_equal(gret.cpu().numpy(), np.full(4097, np.float32(-1.0 / 4097)))
+
+
+def test_philox_noise_laws_and_counter(cuda_device):
+    """rk_draw_noise: every law has the moments / quantiles of its distribution, sites land in their own
+    fluent-major blocks, the same (seed, draw number) reproduces the tensor and rk_noise_advance changes it."""
+    import math
+    import torch
+    from pyrddlgym_jax_b200.core import engine
+    T, B = 8, 20000
+    sites = [("uniform", 0, 1), ("normal", 1, 2), ("exponential", 3, 1), ("gumbel", 4, 1),
+             ("logistic", 5, 3), ("laplace", 8, 1), ("cauchy", 9, 1)]
+    N = 10
+    out = torch.zeros(T, N * B, device=cuda_device)
+    draws = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    engine.draw_noise(T, B, sites, 1234, draws, out)
+    again = torch.zeros_like(out)
+    engine.draw_noise(T, B, sites, 1234, draws, again)
+    assert torch.equal(out, again)
+    engine.noise_advance(draws)
+    engine.draw_noise(T, B, sites, 1234, draws, again)
+    assert int(draws.item()) == 1 and not torch.equal(out, again)
+    other = torch.zeros_like(out)
+    engine.draw_noise(T, B, sites, 1235, None, other)
+    assert not torch.equal(out, other)
+    blk = lambda off, n: out[:, off * B:(off + n) * B].double().reshape(-1).cpu()     # noqa: E731
+    n = T * B
+    se = 6.0 / math.sqrt(n)                                     # six standard errors of a unit-variance mean
+    u = blk(0, 1)
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < se and abs(float(u.var()) - 1 / 12) < se
+    z = blk(1, 2)
+    assert abs(float(z.mean())) < se and abs(float(z.var()) - 1.0) < 3 * se
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.2            # kurtosis of a normal
+    zz = out[:, B:3 * B].double().reshape(T, B, 2).cpu()     # the two words of a rollout are independent
+    assert abs(float((zz[..., 0] * zz[..., 1]).mean())) < 2 * se
+    e = blk(3, 1)
+    assert float(e.min()) >= 0.0 and abs(float(e.mean()) - 1.0) < 2 * se
+    g = blk(4, 1)
+    assert abs(float(g.mean()) - 0.5772156649) < 2 * se and abs(float(g.var()) - math.pi ** 2 / 6) < 0.1
+    lg = blk(5, 3)
+    assert abs(float(lg.mean())) < 3 * se and abs(float(lg.var()) - math.pi ** 2 / 3) < 0.15
+    lp = blk(8, 1)
+    assert abs(float(lp.mean())) < 2 * se and abs(float(lp.var()) - 2.0) < 0.15
+    c = blk(9, 1)
+    assert abs(float(c.median())) < 0.05 and abs(float(c.quantile(0.75)) - 1.0) < 0.05
+    assert bool(torch.isfinite(out).all())
+
+
+def test_drp_returns_loss_and_transpose_split(cuda_device):
+    """rk_drp_returns_loss (discounted returns, -mean - coeff * mean entropy) and rk_transpose_split
+    (W^T and its TF32 hi / lo parts) against torch."""
+    import torch
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(5)
+    T, B = 37, 1000
+    reward = torch.randn(T * B, generator=g).to(cuda_device)
+    entropy = torch.randn(T, B, generator=g).to(cuda_device)
+    disc = (0.97 ** torch.arange(T, dtype=torch.float32)).to(cuda_device)
+    coeff = torch.tensor([0.3], device=cuda_device)
+    returns, ent, loss = (torch.zeros(B, device=cuda_device), torch.zeros(B, device=cuda_device),
+                          torch.zeros(1, device=cuda_device))
+    engine.drp_returns_loss(T, B, reward, disc, entropy, coeff, returns, ent, loss)
+    want_r = (reward.view(T, B).double() * disc.double().view(T, 1)).sum(0)
+    want_l = -want_r.mean() - 0.3 * entropy.double().sum() / B
+    torch.testing.assert_close(returns.double(), want_r, rtol=1e-5, atol=1e-5)
+    assert abs(float(loss[0]) - float(want_l)) <= 1e-5 * max(1.0, abs(float(want_l)))
+    engine.drp_returns_loss(T, B, reward, None, None, None, returns, None, loss)
+    want_r = reward.view(T, B).double().sum(0)
+    torch.testing.assert_close(returns.double(), want_r, rtol=1e-5, atol=1e-5)
+    assert abs(float(loss[0]) + float(want_r.mean())) <= 1e-5
+    for r, c in ((6, 256), (256, 10), (70, 33), (256, 256)):
+        W = torch.randn(r, c, generator=g).to(cuda_device)
+        WT, hi, lo = (torch.zeros(c, r, device=cuda_device) for _ in range(3))
+        engine.transpose_split(r, c, W.reshape(-1), WT.reshape(-1), hi.reshape(-1), lo.reshape(-1))
+        assert torch.equal(WT, W.t().contiguous())
+        assert torch.equal(hi + lo, WT)
+        assert bool(((hi.view(torch.int32) & 0x1FFF) == 0).all())        # TF32-exact high parts
+        WT2 = torch.zeros(c, r, device=cuda_device)
+        engine.transpose_split(r, c, W.reshape(-1), WT2.reshape(-1), None, None)
+        assert torch.equal(WT2, WT)
