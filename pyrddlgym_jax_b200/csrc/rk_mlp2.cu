@@ -232,7 +232,8 @@ __global__ void rk_mlp2_prepare_kernel(int D, int h0, int h1, int NH, const floa
 }
 
 // MODE 0 = forward, 1 = backward.  ACT_CT: the activation as a compile-time constant or -1 = P.act.
-template <int MODE, int ACT_CT>
+// NSP: P.NS rounded up to a multiple of 4 (sizes the register array of the row's small-side values)
+template <int MODE, int ACT_CT, int NSP>
 __global__ void __launch_bounds__(M2_THREADS, 1)
 rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ M2Args P,
@@ -275,9 +276,9 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
 
   // the producer rows' small-side values (state words / head cotangents), duplicated (v, v) for FFMA2:
   // fetched first, so the loads overlap the prologue's copies
-  unsigned long long sv[M2_MAXS];
+  unsigned long long sv[NSP];
 #pragma unroll
-  for (int d = 0; d < M2_MAXS; ++d) sv[d] = 0ull;
+  for (int d = 0; d < NSP; ++d) sv[d] = 0ull;
   if (warp >= 2) {
     const int row = (threadIdx.x - 64) & 255;
     const bool valid = row < rows_here;
@@ -286,7 +287,7 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
       if (MODE == 0) {
         int f = 0;
 #pragma unroll
-        for (int d = 0; d < M2_MAXS; ++d) {
+        for (int d = 0; d < NSP; ++d) {
           if (d < P.NS) {
             while (f + 1 < P.S.n && d >= P.S.off[f + 1]) ++f;
             const float v = P.x_fm[(size_t)P.S.off[f] * P.B + (size_t)grow * P.S.len[f] + (d - P.S.off[f])];
@@ -295,7 +296,7 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
         }
       } else {
 #pragma unroll
-        for (int d = 0; d < M2_MAXS; ++d) {
+        for (int d = 0; d < NSP; ++d) {
           if (d < P.NS) {
             const float v = P.G[(size_t)grow * P.NS + d];
             sv[d] = m2_pack(v, v);
@@ -459,7 +460,8 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
       const uint32_t b_row0 = smem_u32(bsm_s) + (uint32_t)hc * 32u;
       const uint32_t kd4 = (uint32_t)Kd * 4u;
       const uint32_t tile32 = a_base32 + (uint32_t)tl * 2u * M2_A_TILE;
-      for (int kb = 0; kb < nkb; ++kb) {
+      // one k-block; hcur: the H1 chunk of this k-block (backward), reloaded for k-block kb + 3 after use
+      auto produce = [&](int kb, float* hcur) {
         const int sa = kb & 1;
         float v[8];
         if (tile_on && valid) {
@@ -472,7 +474,7 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
           }
           uint32_t wp = w_row0 + (uint32_t)kb * 64u;
 #pragma unroll
-          for (int d = 0; d < M2_MAXS; ++d) {
+          for (int d = 0; d < NSP; ++d) {
             if (d >= P.NS) break;
             unsigned long long w0, w1, w2, w3;
             lds128_u64(wp, w0, w1);
@@ -491,13 +493,8 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
             if (ok_row != nullptr) m2_st8(ok_row + kb * TC_BK, v);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = v[i] * m2_act_grad<ACT_CT>(act, hk[i]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              hk[i] = hk1[i];
-              hk1[i] = hk2[i];
-            }
-            if (kb + 3 < nkb) m2_ld8(hk_row + (kb + 3) * TC_BK, hk2);
+            for (int i = 0; i < 8; ++i) v[i] = v[i] * m2_act_grad<ACT_CT>(act, hcur[i]);
+            if (kb + 3 < nkb) m2_ld8(hk_row + (kb + 3) * TC_BK, hcur);
             m2_st8(ok_row + kb * TC_BK, v);
           }
         } else {
@@ -509,6 +506,13 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_done[sa]);
+      };
+      // three k-blocks per trip: each H1 buffer is named statically (a register MOV of a pending load
+      // would wait for it and cut the prefetch distance to one k-block)
+      for (int kb = 0; kb < nkb; kb += 3) {
+        produce(kb, hk);
+        if (kb + 1 < nkb) produce(kb + 1, hk1);
+        if (kb + 2 < nkb) produce(kb + 2, hk2);
       }
     }
     // ===== epilogue: warp = (tile, TMEM lane quarter, parity of the 16-column chunks it drains) =====
@@ -529,16 +533,22 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
 #pragma unroll
       for (int g = 0; g < 8; ++g) hacc[g] = 0ull;
       const uint32_t wh32 = smem_u32(s_base);
-      float hn[16];
-      if (MODE == 1 && valid && sub < nj) {
-        m2_ld8(hn_row + sub * TC_BK, hn);
-        m2_ld8(hn_row + sub * TC_BK + 8, hn + 8);
+      float hn[16], hn1[16];       // backward: the H0 chunks of this warp's next two chunks
+      if (MODE == 1 && valid) {
+        if (sub < nj) {
+          m2_ld8(hn_row + sub * TC_BK, hn);
+          m2_ld8(hn_row + sub * TC_BK + 8, hn + 8);
+        }
+        if (sub + 2 < nj) {
+          m2_ld8(hn_row + (sub + 2) * TC_BK, hn1);
+          m2_ld8(hn_row + (sub + 2) * TC_BK + 8, hn1 + 8);
+        }
       }
       if (stamp != nullptr && threadIdx.x == 64) stamp[2] = clock64();  // last operand tile produced
       mbar_wait(acc_ready, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (stamp != nullptr && threadIdx.x == 64) stamp[3] = clock64();  // hidden-layer MMAs retired
-      for (int j = sub; j < nj; j += 2) {
+      auto drain = [&](int j, float* hcur) {
         const int c0 = j * TC_BK;
         float v[16];
         if (tile_on) {
@@ -570,11 +580,11 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              v[i] = __uint_as_float(rr[i]) * m2_act_grad<ACT_CT>(act, valid ? hn[i] : 0.f);
+              v[i] = __uint_as_float(rr[i]) * m2_act_grad<ACT_CT>(act, valid ? hcur[i] : 0.f);
             if (valid) {
-              if (j + 2 < nj) {
-                m2_ld8(hn_row + c0 + 2 * TC_BK, hn);
-                m2_ld8(hn_row + c0 + 2 * TC_BK + 8, hn + 8);
+              if (j + 4 < nj) {
+                m2_ld8(hn_row + c0 + 4 * TC_BK, hcur);
+                m2_ld8(hn_row + c0 + 4 * TC_BK + 8, hcur + 8);
               }
               m2_st8(on_row + c0, v);
               m2_st8(on_row + c0 + 8, v + 8);
@@ -589,6 +599,10 @@ rk_mlp2_kernel(const __grid_constant__ CUtensorMap tmB_hi,
           __syncwarp();
           if (lane == 0) mbar_arrive_n(&a_done[sub], 2);      // 8 warps drain a chunk: 2 arrivals each
         }
+      };
+      for (int j = sub; j < nj; j += 4) {        // two chunks per trip: statically named H0 buffers
+        drain(j, hn);
+        if (j + 2 < nj) drain(j + 2, hn1);
       }
       if (stamp != nullptr && threadIdx.x == 64) stamp[4] = clock64();  // epilogue chunks drained
       float hsum[16];
@@ -703,6 +717,27 @@ static int m2_rows_per_cta(int B) {
   return best_R;
 }
 
+template <int MODE, int NSP>
+static int m2_launch_ns(void* stream, const M2Args& P, const CUtensorMap& mBh, const CUtensorMap& mBl,
+                        size_t smem, uint32_t cols, int grid) {
+  static int configured = 0;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, RK_ACT_TANH, NSP>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, -1, NSP>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    configured = 1;
+  }
+  if (P.act == RK_ACT_TANH)
+    rk_mlp2_kernel<MODE, RK_ACT_TANH, NSP><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P,
+                                                                                            cols);
+  else
+    rk_mlp2_kernel<MODE, -1, NSP><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P, cols);
+  return (int)cudaGetLastError();
+}
+
 template <int MODE>
 static int m2_launch(void* stream, const M2Args& P, const float* Bt_hi, const float* Bt_lo) {
   int rc = load_encode();
@@ -715,23 +750,15 @@ static int m2_launch(void* stream, const M2Args& P, const float* Bt_hi, const fl
                       (MODE == 0 ? (size_t)P.Ndim * 64 : (size_t)(P.Ndim / TC_BK) * 2048) + 128 + fl * 4 +
                       1024;
   if (smem > 227 * 1024) return RK_E_SMEM;
-  static int configured = 0;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, RK_ACT_TANH>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (ce != cudaSuccess) return (int)ce;
-    ce = cudaFuncSetAttribute(rk_mlp2_kernel<MODE, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              227 * 1024);
-    if (ce != cudaSuccess) return (int)ce;
-    configured = 1;
-  }
   uint32_t cols = 32;
   while ((int)cols < 2 * P.Ndim) cols <<= 1;
   const int grid = (P.B + P.R - 1) / P.R;
-  if (P.act == RK_ACT_TANH)
-    rk_mlp2_kernel<MODE, RK_ACT_TANH><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P, cols);
-  else
-    rk_mlp2_kernel<MODE, -1><<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(mBh, mBl, P, cols);
+  switch ((P.NS + 3) / 4) {
+    case 1: return m2_launch_ns<MODE, 4>(stream, P, mBh, mBl, smem, cols, grid);
+    case 2: return m2_launch_ns<MODE, 8>(stream, P, mBh, mBl, smem, cols, grid);
+    case 3: return m2_launch_ns<MODE, 12>(stream, P, mBh, mBl, smem, cols, grid);
+    default: return m2_launch_ns<MODE, 16>(stream, P, mBh, mBl, smem, cols, grid);
+  }
   return (int)cudaGetLastError();
 }
 
