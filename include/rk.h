@@ -249,6 +249,14 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
               const float* Bt_hi, const float* Bt_lo, int ldb, float* C, int ldc,
               const float* bias, const float* aux, int ldaux);
 
+/* loss[0] = -U(returns) and gret[b] = -scale * dU/dreturn_b for the utilities with a closed-form cotangent
+ * (planner.py:2161-2247; the mean is rk_mean_loss): kind 1 mean_var, 2 mean_std, 3 mean_semivar,
+ * 4 mean_semidev, 5 sharpe (p0 = risk_free, p1 = eps), 6 entropic / exponential, 7 the symlog-transformed
+ * mean of use_symlog_reward (planner.py:2761-2763); p0 = beta otherwise.  One CTA, deterministic sums:
+ * the planner iteration stays one CUDA graph.  loss or gret may be NULL. */
+int rk_utility_loss(void* stream, int kind, int B, const float* returns, float p0, float p1, float scale,
+                    float* loss, float* gret);
+
 /* Returns and loss of a closed-loop (deep reactive policy) update from the per-step logs of its T
  * one-step rollout launches (planner.py:2747-2765, 2811-2819):
  *   returns[b] = sum_t disc[t] reward[t][b] (disc NULL = 1);  ent_scratch[b] = sum_t entropy[t][b];

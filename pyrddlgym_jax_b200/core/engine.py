@@ -33,6 +33,7 @@ EXPORTS = [
     "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare", "rk_drp_mlp2_set_timing",
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
     "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
+    "rk_utility_loss",
 ]
 
 
@@ -150,6 +151,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_draw_noise.restype = ci
     lib.rk_drp_returns_loss.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf, cf]
     lib.rk_drp_returns_loss.restype = ci
+    fl = ctypes.c_float
+    lib.rk_utility_loss.argtypes = [vp, ci, ci, cf, fl, fl, fl, cf, cf]
+    lib.rk_utility_loss.restype = ci
     lib.rk_transpose_split.argtypes = [vp, ci, ci, cf, cf, cf, cf]
     lib.rk_transpose_split.restype = ci
     lib.rk_noise_advance.argtypes = [vp, vp]
@@ -473,6 +477,17 @@ def drp_returns_loss(T, B, reward, disc, entropy, ent_coeff, returns, ent_scratc
     _check(load_library().rk_drp_returns_loss(
         _stream(), T, B, _ptr(reward), _ptr(disc), _ptr(entropy), _ptr(ent_coeff), _ptr(returns),
         _ptr(ent_scratch), _ptr(loss)), "rk_drp_returns_loss")
+
+
+UTILITY_KINDS = {"mean_var": 1, "mean_std": 2, "mean_semivar": 3, "mean_semidev": 4, "sharpe": 5,
+                 "entropic": 6, "exponential": 6, "symlog_mean": 7}
+
+
+def utility_loss(kind: str, B: int, returns, p0: float, p1: float, scale: float, loss, gret):
+    """loss = -U(returns), gret = -scale * dU/dreturns for the closed-form utilities (include/rk.h)."""
+    _check(load_library().rk_utility_loss(_stream(), UTILITY_KINDS[kind], B, _ptr(returns), float(p0),
+                                          float(p1), float(scale), _ptr(loss), _ptr(gret)),
+           "rk_utility_loss")
 
 
 def transpose_split(r, c, W, WT, WT_hi, WT_lo):

@@ -615,6 +615,7 @@ class JaxBackpropPlanner:
                     f"{list(UTILITY_LOOKUP.keys())}.")
         self.utility = utility
         self.utility_kwargs = utility_kwargs or {}
+        self._native_utility = None          # (kind, p0, p1) of rk_utility_loss, set in _allocate
         self.compiler_type = compiler
         self.compiler_kwargs = compiler_kwargs or {}
         self.start_entropy_coeff = start_entropy_coeff
@@ -631,6 +632,15 @@ class JaxBackpropPlanner:
         # multi-GPU: every rank owns batch_size_train rollouts; the plan is replicated and
         # the gradient is sum-all-reduced once per iteration
         self.rank, self.world_size = parallel.world()
+        # utilities with a closed-form cotangent run as one native kernel (single GPU: a utility is a
+        # function of the GLOBAL return vector, the sharded case gathers it and stays on the autograd path)
+        if isinstance(self.utility, str) and self.utility in engine.UTILITY_KINDS and self.world_size == 1:
+            kw = self.utility_kwargs
+            if self.utility == "sharpe":
+                self._native_utility = (self.utility, float(kw.get("risk_free", 0.0)), float(kw.get("eps", 1e-12)))
+            elif "beta" in kw and len(kw) == 1:
+                self._native_utility = (self.utility, float(kw["beta"]), 0.0)
+        self._utility_eager = self.utility != "mean" and self._native_utility is None
         self._compile()
 
     # ---------------------------------------------------------------------------------
@@ -861,9 +871,13 @@ class JaxBackpropPlanner:
             if self.utility == "mean" and self.use_symlog_reward:
                 # planner.py:2761-2763: returns -> sign(R) log1p(|R|) in the TRAIN loss only;
                 # the cotangent of the batch mean becomes -(1 / B) / (1 + |R_b|)
-                r = self.train_returns[p]
-                loss_out.copy_(-(torch.sign(r) * torch.log1p(r.abs())).mean().reshape(1))
-                torch.div(-1.0 / (B * self.world_size), 1.0 + r.abs(), out=self.gret)
+                engine.utility_loss("symlog_mean", B, self.train_returns[p], 0.0, 0.0,
+                                    1.0 / self.world_size, loss_out, self.gret)
+            elif self._native_utility is not None:
+                # closed-form cotangent on the device (csrc/rk_optim.cu:rk_utility_loss): no autograd,
+                # the iteration stays one CUDA graph
+                kind, p0, p1 = self._native_utility
+                engine.utility_loss(kind, B, self.train_returns[p], p0, p1, 1.0, loss_out, self.gret)
             elif self.utility == "mean" and side is not None \
                     and not getattr(self.plan, "_stochastic", False):
                 # the loss value is not an input of the adjoint (its cotangent is the constant
@@ -1155,7 +1169,7 @@ class JaxBackpropPlanner:
         JaxOnlineController): initial-state words of both models and the plan to start from go
         in, (train loss, test loss, zero-gradient flags, plan) come back -- one graph launch and
         one synchronisation.  Returns (train [P], test [P], zero [P], plan [P, NP] pinned view)."""
-        if self.utility != "mean" or not self.use_cuda_graph:
+        if self._utility_eager or not self.use_cuda_graph:
             self.load_initial_state(init_train, init_test)
             self.params.copy_(params, non_blocking=True)
             self.iterate()
@@ -1186,7 +1200,7 @@ class JaxBackpropPlanner:
 
     def iterate(self):
         """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""
-        if self.utility != "mean" or not self.use_cuda_graph:
+        if self._utility_eager or not self.use_cuda_graph:
             self._iteration_kernels()
             return
         if self._graph is None:

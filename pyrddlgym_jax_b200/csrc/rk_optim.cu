@@ -732,3 +732,105 @@ extern "C" int rk_transpose_split(void* stream, int r, int c, const float* W, fl
   rk_transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r, c, W, WT, WT_hi, WT_lo);
   return (int)cudaGetLastError();
 }
+
+// ---- utilities other than the plain mean (planner.py:2161-2247, 2761-2763, 2817-2818) ------------
+// loss = -U(returns) and its cotangent gret[b] = -dU/dreturn_b in closed form, one CTA, fixed-order
+// sums (deterministic), so the iteration stays inside one CUDA graph.
+//   kind 1 mean_var     U = mu - beta/2 var            2 mean_std   U = mu - beta/2 sigma
+//        3 mean_semivar U = mu - beta/2 E[min(r-mu,0)^2]   4 mean_semidev: its square root
+//        5 sharpe       U = (mu - p0) / (sigma + p1)   6 entropic   U = -(logsumexp(-beta r) - log B) / beta
+//        7 symlog mean  U = mean(sign(r) log1p|r|)   (use_symlog_reward with the mean utility)
+// p0 = beta (risk_free for sharpe), p1 = eps (sharpe).  scale multiplies the cotangent (1 / world size).
+__global__ void __launch_bounds__(1024)
+rk_utility_loss_kernel(int kind, int B, const float* __restrict__ r, float p0, float p1, float scale,
+                       float* __restrict__ loss, float* __restrict__ gret) {
+  __shared__ float sh[32];
+  __shared__ float bc[4];
+  const float invB = 1.f / (float)B;
+  float s = 0.f, mx = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float v = r[i];
+    s += kind == 7 ? copysignf(log1pf(fabsf(v)), v) : v;
+    mx = fmaxf(mx, -p0 * v);
+  }
+  s = block_sum_1024(s, sh);
+  __syncthreads();
+  if (kind == 6) {                      // block max for the stabilised log-sum-exp
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = sh[0];
+      for (int w = 1; w < 32; ++w) m = fmaxf(m, sh[w]);
+      bc[1] = m;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bc[0] = s * invB;
+  __syncthreads();
+  const float mu = bc[0], zmax = bc[1];
+  if (kind == 7) {
+    if (threadIdx.x == 0 && loss != nullptr) loss[0] = -mu;
+    if (gret != nullptr)
+      for (int i = threadIdx.x; i < B; i += blockDim.x) gret[i] = -scale * invB / (1.f + fabsf(r[i]));
+    return;
+  }
+  // second moment / lower partial moments / sum of exponentials
+  float a = 0.f, d1 = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float c = r[i] - mu;
+    if (kind == 1 || kind == 2 || kind == 5) {
+      a += c * c;
+    } else if (kind == 3 || kind == 4) {
+      const float d = fminf(c, 0.f);
+      a += d * d;
+      d1 += d;
+    } else {
+      a += expf(-p0 * r[i] - zmax);
+    }
+  }
+  a = block_sum_1024(a, sh);
+  __syncthreads();
+  d1 = block_sum_1024(d1, sh);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bc[2] = a;
+    bc[3] = d1 * invB;
+  }
+  __syncthreads();
+  const float A = bc[2], dmean = bc[3];
+  const float var = A * invB, sigma = sqrtf(var);
+  float U;
+  switch (kind) {
+    case 1: U = mu - 0.5f * p0 * var; break;
+    case 2: U = mu - 0.5f * p0 * sigma; break;
+    case 3: U = mu - 0.5f * p0 * var; break;
+    case 4: U = mu - 0.5f * p0 * sigma; break;
+    case 5: U = (mu - p0) / (sigma + p1); break;
+    default: U = -(logf(A) + zmax - logf((float)B)) / p0; break;
+  }
+  if (threadIdx.x == 0 && loss != nullptr) loss[0] = -U;
+  if (gret == nullptr) return;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float c = r[i] - mu;
+    float g;                             // dU / dr_i
+    switch (kind) {
+      case 1: g = invB * (1.f - p0 * c); break;
+      case 2: g = invB * (1.f - 0.5f * p0 * c / sigma); break;
+      case 3: g = invB * (1.f - p0 * (fminf(c, 0.f) - dmean)); break;
+      case 4: g = invB * (1.f - 0.5f * p0 * (fminf(c, 0.f) - dmean) / sigma); break;
+      case 5: g = invB * (1.f / (sigma + p1) - (mu - p0) * c / (sigma * (sigma + p1) * (sigma + p1))); break;
+      default: g = expf(-p0 * r[i] - zmax) / A; break;
+    }
+    gret[i] = -scale * g;
+  }
+}
+
+extern "C" int rk_utility_loss(void* stream, int kind, int B, const float* returns, float p0, float p1,
+                               float scale, float* loss, float* gret) {
+  if (kind < 1 || kind > 7 || B <= 0 || returns == nullptr || (loss == nullptr && gret == nullptr))
+    return RK_E_BADARG;
+  rk_utility_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(kind, B, returns, p0, p1, scale, loss,
+                                                                gret);
+  return (int)cudaGetLastError();
+}

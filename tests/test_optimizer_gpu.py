@@ -181,3 +181,62 @@ def test_drp_returns_loss_and_transpose_split(cuda_device):
         WT2 = torch.zeros(c, r, device=cuda_device)
         engine.transpose_split(r, c, W.reshape(-1), WT2.reshape(-1), None, None)
         assert torch.equal(WT2, WT)
+
+
+def test_native_utilities_match_autograd(cuda_device):
+    """rk_utility_loss (closed-form cotangents, one CTA) against torch autograd of the planner's own
+    utility definitions (core/planner.py, restating planner.py:2161-2247)."""
+    import torch
+    from pyrddlgym_jax_b200.core import engine, planner
+    g = torch.Generator().manual_seed(3)
+    for B in (1000, 40000):
+        r = (torch.randn(B, generator=g) * 3.0 + 1.5).to(cuda_device)
+        cases = [("mean_var", planner.mean_variance_utility, dict(beta=0.7), 0.7, 0.0),
+                 ("mean_std", planner.mean_deviation_utility, dict(beta=0.7), 0.7, 0.0),
+                 ("mean_semivar", planner.mean_semivariance_utility, dict(beta=1.3), 1.3, 0.0),
+                 ("mean_semidev", planner.mean_semideviation_utility, dict(beta=1.3), 1.3, 0.0),
+                 ("sharpe", planner.sharpe_utility, dict(risk_free=0.2, eps=1e-6), 0.2, 1e-6),
+                 ("entropic", planner.entropic_utility, dict(beta=0.4), 0.4, 0.0)]
+        for kind, fn, kw, p0, p1 in cases:
+            x = r.double().clone().requires_grad_(True)
+            want = -fn(x, **kw)
+            (gw,) = torch.autograd.grad(want, x)
+            loss, gret = torch.zeros(1, device=cuda_device), torch.zeros(B, device=cuda_device)
+            engine.utility_loss(kind, B, r, p0, p1, 1.0, loss, gret)
+            assert abs(float(loss[0]) - float(want)) <= 2e-5 * max(1.0, abs(float(want))), kind
+            torch.testing.assert_close(gret.double(), gw, rtol=2e-4, atol=2e-5 * float(gw.abs().max()))
+        x = r.double().clone().requires_grad_(True)
+        want = -(torch.sign(x) * torch.log1p(x.abs())).mean()
+        (gw,) = torch.autograd.grad(want, x)
+        loss, gret = torch.zeros(1, device=cuda_device), torch.zeros(B, device=cuda_device)
+        engine.utility_loss("symlog_mean", B, r, 0.0, 0.0, 0.5, loss, gret)
+        assert abs(float(loss[0]) - float(want)) <= 1e-5
+        torch.testing.assert_close(gret.double(), 0.5 * gw, rtol=1e-5, atol=1e-9)
+
+
+def test_native_utility_keeps_the_graph_and_matches_eager(cuda_device):
+    """A planner with utility='mean_var' runs its iteration as one CUDA graph (native cotangent) and
+    produces the same plan as the autograd path (RK-independent check: same inputs, two planners)."""
+    import torch
+    import bench
+    from pyrddlgym_jax_b200.core import logic
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner, JaxStraightLinePlan
+    model = bench.workload_model("quadcopter")            # no draw sites: both planners see the same inputs
+    plans = []
+    for native in (True, False):
+        pl = JaxBackpropPlanner(model, JaxStraightLinePlan(), batch_size_train=64, batch_size_test=64,
+                                rollout_horizon=10, optimizer="rmsprop",
+                                optimizer_kwargs={"learning_rate": 0.05}, pgpe=None,
+                                compiler=logic.DefaultJaxRDDLCompilerWithGrad,
+                                compiler_kwargs={"sigmoid_weight": 10.}, utility="mean_var",
+                                utility_kwargs={"beta": 0.01})
+        assert pl._native_utility is not None
+        if not native:
+            pl._native_utility, pl._utility_eager = None, True
+        pl.initialize(7)
+        assert pl.train_noise is None
+        for _ in range(3):
+            pl.iterate()
+        assert (pl._graph is not None) == native
+        plans.append((pl.params[0].cpu().clone(), pl.read_stats()[0].copy()))
+    torch.testing.assert_close(plans[0][0], plans[1][0], rtol=1e-4, atol=1e-5)
