@@ -123,6 +123,24 @@ int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
                       float* params, float* state, const float* grad,
                       const float* lo, const float* hi, int32_t* zero_flag);
 
+/* The optimiser step with the optional links of the optax chain (planner.py:2349-2387, 2885-2899):
+ * clip_by_global_norm -> add_noise -> optimiser -> reduce_on_plateau -> ema -> apply_updates -> box.
+ * Replaces: optax.chain(...).update + optax.apply_updates for planners built with noise_kwargs,
+ * reduce_on_plateau_kwargs or ema_decay.  kind / hyper / state / lo / hi / zero_flag as rk_optimizer_step.
+ *   cfg [13] HOST floats: eta, gamma (add_noise: N(0, eta / t^gamma), t = 1-based step), ema_decay,
+ *        factor, patience, rtol, atol, cooldown, accumulation_size, min_scale (reduce_on_plateau),
+ *        use_noise, use_plateau, use_ema (0 / 1)
+ *   count   [1] device: updates applied so far (incremented here)
+ *   plateau [6] device: scale, best_value, plateau_count, cooldown_count, count, avg_value (or NULL)
+ *   ema     [n] device: moving average of the updates (or NULL)
+ *   loss    [1] device: the value reduce_on_plateau tests (the train loss of this gradient; or NULL)
+ *   seed        key of the counter-based noise (Philox4x32-10, counter = (element quad, t))
+ *   scratch [8] device floats (caller-owned; only read between the two launches of long vectors) */
+int rk_optimizer_chain_step(void* stream, int kind, const float* hyper, int n, float* params,
+                            float* state, const float* grad, const float* lo, const float* hi,
+                            int32_t* zero_flag, const float* cfg, float* count, float* plateau,
+                            float* ema, const float* loss, unsigned long long seed, float* scratch);
+
 /* Concurrency projection of the boolean plan parameters onto max-nondef-actions, run after
  * rk_optimizer_step's box projection.
  * Replaces: _jax_wrapped_slp_project_to_max_constraint (planner.py:947-954), i.e. the
@@ -256,6 +274,23 @@ int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float* A, int ld
  * the planner iteration stays one CUDA graph.  loss or gret may be NULL. */
 int rk_utility_loss(void* stream, int kind, int B, const float* returns, float p0, float p1, float scale,
                     float* loss, float* gret);
+
+/* The same for a SHARDED batch: returns [B] is the all-gathered GLOBAL return vector (a utility
+ * other than the mean is a function of all B returns, planner.py:2817-2818), gret [n_local] receives the
+ * cotangents of this rank's rollouts [b0, b0 + n_local). */
+int rk_utility_loss_shard(void* stream, int kind, int B, int b0, int n_local, const float* returns,
+                          float p0, float p1, float scale, float* loss, float* gret);
+
+/* The order-statistic utilities (planner.py:2195-2229) and their cotangents: kind 8 var (p0 = alpha),
+ * 9 cvar (alpha), 10 cvar_ste (alpha), 11 expectile (alpha, max_iter fixed-point steps), 12 gini (p0 = gamma).
+ * The return vector is sorted once on the device (radix sort of (return, rollout) pairs); percentiles
+ * interpolate linearly like jnp.percentile.  returns [B] global vector, gret [n_local] for the rollouts
+ * [b0, b0 + n_local); work: caller-owned device scratch of rk_utility_sorted_work_bytes(B) bytes.
+ * Replaces: jit(utility) + its reverse-mode derivative inside value_and_grad (planner.py:2873). */
+size_t rk_utility_sorted_work_bytes(int B);
+int rk_utility_sorted_loss(void* stream, int kind, int B, int b0, int n_local, const float* returns,
+                           float p0, int max_iter, float scale, float* loss, float* gret, void* work,
+                           size_t work_bytes);
 
 /* Returns and loss of a closed-loop (deep reactive policy) update from the per-step logs of its T
  * one-step rollout launches (planner.py:2747-2765, 2811-2819):

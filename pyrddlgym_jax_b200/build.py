@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "librk.so")
-SOURCES = ["rk_interp.cu", "rk_optim.cu", "rk_drp.cu", "rk_tcgemm.cu", "rk_mlp2.cu", "rk_wgrad.cu", "rk_comm.cu"]
+SOURCES = ["rk_interp.cu", "rk_optim.cu", "rk_drp.cu", "rk_tcgemm.cu", "rk_mlp2.cu", "rk_wgrad.cu", "rk_comm.cu", "rk_utility.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # no FMA contraction: keep per-op roundings like the reference

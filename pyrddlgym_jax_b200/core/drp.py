@@ -514,6 +514,7 @@ class DrpPipeline:
         self.act = z(T, self.A * Bt)
         self.entropy = z(T, Bt)
         self.ent_b = z(Bt)                             # per-rollout entropy sums (loss reduction scratch)
+        self._u_loss, self._m_loss = z(1), z(1)        # -utility(returns), -mean(returns) of an update
         self.pol_noise = z(T, self.A * Bt) if plan._stochastic else None
         self.gact = z(self.A * Bt)
         self.gs = [z(self.S * Bt), z(self.S * Bt)]
@@ -855,6 +856,16 @@ class DrpPipeline:
         loss_out = pl.train_loss[p:p + 1] if loss_out is None else loss_out
         engine.drp_returns_loss(T, B, pl.train_reward[p], pl.disc, self.entropy if plan._stochastic else None,
                                 self.ent_coeff, pl.train_returns[p], self.ent_b, loss_out)
+        if pl.utility != "mean" or pl.use_symlog_reward:
+            # a utility other than the mean (planner.py:2161-2247, 2817-2818): the return term of the loss
+            # and the return cotangents the adjoint sweep is fed come from the utility kernels
+            if pl.utility == "mean":
+                engine.utility_loss("symlog_mean", B, pl.train_returns[p], 0.0, 0.0, 1.0 / pl.world_size,
+                                    self._u_loss, pl.gret)
+            else:
+                pl._native_utility_kernels(pl.train_returns[p], self._u_loss)
+            engine.mean_loss(pl.train_returns[p], B, self._m_loss, None)
+            loss_out.add_(self._u_loss - self._m_loss)
         # ---- backward sweep
         grad.zero_()
         self.gs[0].zero_()
@@ -967,6 +978,8 @@ class DrpPipeline:
             cur ^= 1
         o_final.copy_(self.t_state[cur])
         engine.drp_returns_loss(T, B, o_reward, pl.disc, None, None, o_returns, None, o_loss)
+        if pl.utility != "mean":                     # the test loss applies the utility too (P:2695-2698)
+            pl._test_loss_kernels(o_returns, o_loss)
 
     def redraw_noise(self, gen: torch.Generator):
         pl = self.pl

@@ -33,7 +33,8 @@ EXPORTS = [
     "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare", "rk_drp_mlp2_set_timing",
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
     "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
-    "rk_utility_loss",
+    "rk_utility_loss", "rk_optimizer_chain_step", "rk_utility_loss_shard",
+    "rk_utility_sorted_work_bytes", "rk_utility_sorted_loss",
 ]
 
 
@@ -59,6 +60,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                       f"(python -m pyrddlgym_jax_b200.build); there is no CPU fallback")
     lib = ctypes.CDLL(p)
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+    fl = ctypes.c_float
     lib.rk_program_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.rk_program_create.restype = ci
     lib.rk_program_destroy.argtypes = [vp]
@@ -79,6 +81,15 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_reduce_partials.restype = ci
     lib.rk_optimizer_step.argtypes = [vp, ci, cf, ci, cf, cf, cf, cf, cf, cf]
     lib.rk_optimizer_step.restype = ci
+    lib.rk_optimizer_chain_step.argtypes = [vp, ci, cf, ci, cf, cf, cf, cf, cf, cf, vp, cf, cf, cf, cf,
+                                            ctypes.c_uint64, cf]
+    lib.rk_optimizer_chain_step.restype = ci
+    lib.rk_utility_loss_shard.argtypes = [vp, ci, ci, ci, ci, cf, fl, fl, fl, cf, cf]
+    lib.rk_utility_loss_shard.restype = ci
+    lib.rk_utility_sorted_work_bytes.argtypes = [ci]
+    lib.rk_utility_sorted_work_bytes.restype = ctypes.c_size_t
+    lib.rk_utility_sorted_loss.argtypes = [vp, ci, ci, ci, ci, cf, fl, ci, fl, cf, cf, vp, ctypes.c_size_t]
+    lib.rk_utility_sorted_loss.restype = ci
     lib.rk_mean_loss.argtypes = [vp, cf, ci, cf, cf]
     lib.rk_mean_loss.restype = ci
     lib.rk_project_slp.argtypes = [vp, ci, ci, ci, cf, ci, vp, vp, vp, vp, ci, ci, ci,
@@ -270,6 +281,24 @@ def optimizer_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, 
     _check(load_library().rk_optimizer_step(
         _stream(), OPT_KIND[kind], _ptr(hyper), n, _ptr(params), _ptr(state), _ptr(grad),
         _ptr(lo), _ptr(hi), _ptr(zero_flag)), "rk_optimizer_step")
+
+
+def optimizer_chain_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, lo, hi, zero_flag,
+                         cfg: dict, count, plateau, ema, loss, seed: int, scratch):
+    """rk_optimizer_chain_step: the optimiser with the add_noise / reduce_on_plateau / ema links of the
+    optax chain.  ``cfg``: noise = (eta, gamma) or None, ema_decay or None, plateau = the seven
+    reduce_on_plateau arguments or None."""
+    noise, pk, d = cfg.get("noise"), cfg.get("plateau"), cfg.get("ema_decay")
+    vals = [noise[0] if noise else 0.0, noise[1] if noise else 0.0, d if d is not None else 0.0]
+    vals += [float(pk[k]) if pk else 0.0 for k in ("factor", "patience", "rtol", "atol", "cooldown",
+                                                    "accumulation_size", "min_scale")]
+    vals += [1.0 if noise else 0.0, 1.0 if pk else 0.0, 1.0 if d is not None else 0.0]
+    arr = (ctypes.c_float * 13)(*vals)
+    _check(load_library().rk_optimizer_chain_step(
+        _stream(), OPT_KIND[kind], _ptr(hyper), n, _ptr(params), _ptr(state), _ptr(grad), _ptr(lo),
+        _ptr(hi), _ptr(zero_flag), ctypes.cast(arr, ctypes.c_void_p), _ptr(count), _ptr(plateau),
+        _ptr(ema), _ptr(loss), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(scratch)),
+        "rk_optimizer_chain_step")
 
 
 def mean_loss(returns: torch.Tensor, B: int, loss=None, gret=None):
@@ -481,13 +510,33 @@ def drp_returns_loss(T, B, reward, disc, entropy, ent_coeff, returns, ent_scratc
 
 UTILITY_KINDS = {"mean_var": 1, "mean_std": 2, "mean_semivar": 3, "mean_semidev": 4, "sharpe": 5,
                  "entropic": 6, "exponential": 6, "symlog_mean": 7}
+# the order-statistic utilities: one device sort of the return vector (csrc/rk_utility.cu)
+UTILITY_SORTED_KINDS = {"var": 8, "cvar": 9, "cvar_ste": 10, "expectile": 11, "gini": 12}
 
 
-def utility_loss(kind: str, B: int, returns, p0: float, p1: float, scale: float, loss, gret):
-    """loss = -U(returns), gret = -scale * dU/dreturns for the closed-form utilities (include/rk.h)."""
-    _check(load_library().rk_utility_loss(_stream(), UTILITY_KINDS[kind], B, _ptr(returns), float(p0),
-                                          float(p1), float(scale), _ptr(loss), _ptr(gret)),
-           "rk_utility_loss")
+def utility_loss(kind: str, B: int, returns, p0: float, p1: float, scale: float, loss, gret,
+                 b0: int = 0, n_local: Optional[int] = None):
+    """loss = -U(returns), gret = -scale * dU/dreturns for the closed-form utilities (include/rk.h);
+    ``returns`` is the global vector [B], gret covers the rollouts [b0, b0 + n_local)."""
+    n_local = B if n_local is None else n_local
+    _check(load_library().rk_utility_loss_shard(
+        _stream(), UTILITY_KINDS[kind], B, int(b0), int(n_local), _ptr(returns), float(p0), float(p1),
+        float(scale), _ptr(loss), _ptr(gret)), "rk_utility_loss_shard")
+
+
+def utility_sorted_work(B: int, device) -> torch.Tensor:
+    n = int(load_library().rk_utility_sorted_work_bytes(int(B)))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def utility_sorted_loss(kind: str, B: int, returns, p0: float, max_iter: int, scale: float, loss, gret,
+                        work: torch.Tensor, b0: int = 0, n_local: Optional[int] = None):
+    """var / cvar / cvar_ste / expectile / gini and their cotangents (include/rk.h)."""
+    n_local = B if n_local is None else n_local
+    _check(load_library().rk_utility_sorted_loss(
+        _stream(), UTILITY_SORTED_KINDS[kind], B, int(b0), int(n_local), _ptr(returns), float(p0),
+        int(max_iter), float(scale), _ptr(loss), _ptr(gret), _ptr(work), work.numel()),
+        "rk_utility_sorted_loss")
 
 
 def transpose_split(r, c, W, WT, WT_hi, WT_lo):

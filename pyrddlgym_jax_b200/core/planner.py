@@ -529,33 +529,6 @@ def plateau_init(P: int, device) -> torch.Tensor:
     return st
 
 
-def plateau_step(st: torch.Tensor, value: torch.Tensor, factor: float, patience: int, rtol: float,
-                 atol: float, cooldown: int, accumulation_size: int, min_scale: float) -> None:
-    """One update of the plateau state st[6] from the loss ``value`` (a 1-element tensor), in place
-    and without a host round trip (graph-capturable): the loss is averaged over accumulation_size
-    steps; an average below (1 - rtol) best - atol is an improvement; after ``patience`` steps
-    without one the scale is multiplied by ``factor`` (not below min_scale) and ``cooldown`` steps
-    are ignored."""
-    scale, best, plat, cool, count, avg = (st[i:i + 1] for i in range(6))
-    new_count = count + 1.0
-    new_avg = (count * avg + value) / new_count
-    fire = new_count == float(accumulation_size)
-    improved = new_avg < (1.0 - rtol) * best - atol
-    nb = torch.where(improved, new_avg, best)
-    cur = torch.where(improved, torch.zeros_like(plat), plat + 1.0)
-    in_cd = cool > 0
-    hit = cur == float(patience)
-    plat_n = torch.where(in_cd | hit, torch.zeros_like(cur), cur)
-    scale_n = torch.where(~in_cd & hit, torch.clamp(scale * factor, min=min_scale), scale)
-    cool_n = torch.where(in_cd, cool - 1.0,
-                         torch.where(hit, torch.full_like(cool, float(cooldown)), torch.zeros_like(cool)))
-    new = torch.cat([torch.where(fire, scale_n, scale), torch.where(fire, nb, best),
-                     torch.where(fire, plat_n, plat), torch.where(fire, cool_n, cool),
-                     torch.where(fire, torch.zeros_like(count), new_count),
-                     torch.where(fire, torch.zeros_like(avg), new_avg)])
-    st.copy_(new)
-
-
 class JaxBackpropPlanner:
     """Gradient-based planner over batched differentiable rollouts (planner.py:2395)."""
 
@@ -632,14 +605,22 @@ class JaxBackpropPlanner:
         # multi-GPU: every rank owns batch_size_train rollouts; the plan is replicated and
         # the gradient is sum-all-reduced once per iteration
         self.rank, self.world_size = parallel.world()
-        # utilities with a closed-form cotangent run as one native kernel (single GPU: a utility is a
-        # function of the GLOBAL return vector, the sharded case gathers it and stays on the autograd path)
-        if isinstance(self.utility, str) and self.utility in engine.UTILITY_KINDS and self.world_size == 1:
+        # every utility of the reference's table has a closed-form cotangent and runs as native kernels
+        # (csrc/rk_optim.cu:rk_utility_loss, csrc/rk_utility.cu); a utility is a function of the GLOBAL
+        # return vector, so with several GPUs the shards are all-gathered first -- inside the
+        # iteration's graph -- and every rank keeps its own slice of the cotangent
+        if isinstance(self.utility, str):
             kw = self.utility_kwargs
-            if self.utility == "sharpe":
+            if self.utility == "sharpe" and set(kw) <= {"risk_free", "eps"}:
                 self._native_utility = (self.utility, float(kw.get("risk_free", 0.0)), float(kw.get("eps", 1e-12)))
-            elif "beta" in kw and len(kw) == 1:
+            elif self.utility in engine.UTILITY_KINDS and set(kw) == {"beta"}:
                 self._native_utility = (self.utility, float(kw["beta"]), 0.0)
+            elif self.utility in ("var", "cvar", "cvar_ste") and set(kw) == {"alpha"}:
+                self._native_utility = (self.utility, float(kw["alpha"]), 0)
+            elif self.utility == "expectile" and "alpha" in kw and set(kw) <= {"alpha", "max_iter"}:
+                self._native_utility = (self.utility, float(kw["alpha"]), int(kw.get("max_iter", 30)))
+            elif self.utility == "gini" and set(kw) == {"gamma"}:
+                self._native_utility = (self.utility, float(kw["gamma"]), 0)
         self._utility_eager = self.utility != "mean" and self._native_utility is None
         self._compile()
 
@@ -662,6 +643,10 @@ class JaxBackpropPlanner:
         test_log = (tuple(rddl.next_state.values()) + tuple(rddl.action_fluents)) \
             if self.cache_full_test_rollouts else ()
         self.is_drp = getattr(self.plan, "kind", "slp") == "drp"
+        if self.is_drp and self._utility_eager:
+            raise NotImplementedError(
+                "deep reactive policies take the built-in utilities by name (native cotangent kernels); a "
+                "callable utility is differentiated by torch autograd on the straight-line path only")
         with torch.cuda.device(self.device):
             tb = self.compiled.builder(spec, True, (), self.batch_size_train)
             if self.is_drp:
@@ -707,6 +692,11 @@ class JaxBackpropPlanner:
         self._stats_host = torch.zeros(3 * P, dtype=torch.int32).pin_memory()
         self.train_loss = self._stats[0:P].view(torch.float32)
         self.gret = z(Bt)
+        if self._native_utility is not None:
+            if self.world_size > 1:
+                self._ret_all, self._ret_all_test = z(self.world_size * Bt), z(self.world_size * Be)
+            if self._native_utility[0] in engine.UTILITY_SORTED_KINDS:
+                self._utility_work = engine.utility_sorted_work(self.world_size * max(Bt, Be), dev)
         self.test_reward = z(P, T * Be)
         self.test_returns = z(P, Be)
         self.test_err = z(P, T * Be, dt=torch.int32)
@@ -734,7 +724,6 @@ class JaxBackpropPlanner:
         # optax forms (1 - decay) from its Python-float rates in double precision: pass the complements
         h += [1.0 - float(h[1]), 1.0 - float(h[3])]
         self.hyper = torch.tensor(h, dtype=torch.float32, device=dev)
-        self._hyper_noclip = self.hyper.clone()     # the chain path clips before the noise link
         self.train_mparams = torch.from_numpy(fw.mparam_defaults.copy()).to(dev) \
             if len(fw.mparam_defaults) else None
         import os as _os
@@ -752,6 +741,16 @@ class JaxBackpropPlanner:
         self._pipeline = _os.environ.get("RK_PIPELINE", "1") != "0"
         self._overlap = self._pipeline and not self.is_drp
         self._train_loss_tmp = z(P)
+        # parallel_updates (planner.py:2920-2929 vmaps the update over P optimiser instances): the
+        # instances are independent kernel chains, so the captured iteration runs them as P concurrent
+        # branches, each with its own tape / partials / cotangent scratch.  Deep policies (shared MLP
+        # scratch), several GPUs and steps_per_update > 1 (shared step counter) keep the instances in order.
+        self._branches = (P > 1 and not self.is_drp and self.world_size == 1
+                          and self.steps_per_update <= 1
+                          and _os.environ.get("RK_PARALLEL_BRANCHES", "1") != "0")
+        if self._branches:
+            self._scratch = [(self.tape, self.gradp, self.gret)] + [
+                (z(T * fw.tape_words * Bt), z(self.nwarps * T * A), z(Bt)) for _ in range(P - 1)]
         self._use_chain = (self.noise_kwargs is not None or self.ema_decay is not None
                            or self.reduce_on_plateau_kwargs is not None)
         if self.reduce_on_plateau_kwargs is not None and self.world_size > 1:
@@ -760,9 +759,8 @@ class JaxBackpropPlanner:
         if self._use_chain:
             self._chain_count = z(P)
             self._chain_plateau = plateau_init(P, dev)
-            self._chain_grad, self._chain_old, self._chain_ema = z(P, NP), z(P, NP), z(P, NP)
-            self._chain_gen = torch.Generator(device=dev)
-            self._chain_gen.manual_seed(int((self.noise_kwargs or {}).get("seed", 0)))
+            self._chain_ema = z(P, NP)
+            self._chain_scratch = z(P, 8)
         # multi-GPU exchange: one message per iteration.  In the pipelined order the
         # gradient is not needed before the NEXT replay's optimiser step, so it travels together
         # with the two loss sums after the branches join: [grad | train loss | test loss], summed
@@ -874,10 +872,8 @@ class JaxBackpropPlanner:
                 engine.utility_loss("symlog_mean", B, self.train_returns[p], 0.0, 0.0,
                                     1.0 / self.world_size, loss_out, self.gret)
             elif self._native_utility is not None:
-                # closed-form cotangent on the device (csrc/rk_optim.cu:rk_utility_loss): no autograd,
-                # the iteration stays one CUDA graph
-                kind, p0, p1 = self._native_utility
-                engine.utility_loss(kind, B, self.train_returns[p], p0, p1, 1.0, loss_out, self.gret)
+                # closed-form cotangent on the device: no autograd, the iteration stays one CUDA graph
+                self._native_utility_kernels(self.train_returns[p], loss_out)
             elif self.utility == "mean" and side is not None \
                     and not getattr(self.plan, "_stochastic", False):
                 # the loss value is not an input of the adjoint (its cotangent is the constant
@@ -916,6 +912,28 @@ class JaxBackpropPlanner:
             scale = 1.0 / self.world_size if (self.world_size > 1 and self._defer_ar) else 1.0
             self.grad[p].view(T, A).sub_(self.ent_coeff * dH * scale)
 
+    def _native_utility_kernels(self, local_returns: torch.Tensor, loss_out: torch.Tensor,
+                                test: bool = False):
+        """loss = -U(global returns) and -- for the train batch -- this rank's slice of its cotangent
+        (planner.py:2161-2247, 2817-2818; the test loss applies the same utility, planner.py:2695-2698).
+        Several GPUs: one all-gather of the B returns per rank (4 B bytes, NCCL, captured with the
+        iteration); every rank then holds the GLOBAL loss, which the [grad | loss] exchange sums and
+        read_stats divides by the world size again."""
+        kind, p0, p1 = self._native_utility
+        B, ws = (self.batch_size_test if test else self.batch_size_train), self.world_size
+        r = local_returns
+        if ws > 1:
+            import torch.distributed as dist
+            r = self._ret_all_test if test else self._ret_all
+            dist.all_gather_into_tensor(r, local_returns)
+        gret = None if test else self.gret
+        if kind in engine.UTILITY_SORTED_KINDS:
+            engine.utility_sorted_loss(kind, B * ws, r, p0, int(p1), 1.0, loss_out, gret,
+                                       self._utility_work, self.rank * B, 0 if test else B)
+        else:
+            engine.utility_loss(kind, B * ws, r, p0, p1, 1.0, loss_out, gret, self.rank * B,
+                                0 if test else B)
+
     def _publish_kernels(self, p: int):
         """Publish the loss and the gradient of the update being applied (callback['grad'])."""
         self.train_loss[p:p + 1].copy_(self._train_loss_tmp[p:p + 1])
@@ -943,46 +961,24 @@ class JaxBackpropPlanner:
                                self.converged[p:p + 1])
 
     def _opt_chain_kernels(self, p: int):
-        """The optional links of the optax chain (planner.py:2366-2386) around the optimiser kernel:
+        """The optional links of the optax chain (planner.py:2366-2386) around the optimiser, one native
+        launch (csrc/rk_optim.cu:rk_optimizer_chain_step):
         clip_by_global_norm -> add_noise(eta, gamma) -> optimiser -> reduce_on_plateau -> ema(decay),
         then apply_updates and the box projection.  add_noise: g + N(0, eta / t^gamma) with the
-        1-based step count t; reduce_on_plateau: the updates are scaled by a factor that shrinks when
-        the train loss stops improving (plateau_step); ema: the debiased exponential moving average
-        of the updates is what is applied."""
-        params, grad = self.params[p], self.grad[p]
-        g = grad
-        self._chain_count[p:p + 1].add_(1.0)
-        t = self._chain_count[p:p + 1]
-        clip = float(self.clip_grad) if self.clip_grad is not None else 0.0
-        if clip > 0.0:
-            gn = torch.linalg.vector_norm(g)
-            g = g * torch.clamp(clip / gn.clamp_min(1e-30), max=1.0)
-        self.zero_flag[p:p + 1].copy_((g.abs().max() <= 1e-8).to(torch.int32).reshape(1))
-        if self.noise_kwargs is not None:
-            eta = float(self.noise_kwargs.get("eta", 0.01))
-            gamma = float(self.noise_kwargs.get("gamma", 0.55))
-            std = torch.sqrt(eta / torch.pow(t, gamma))
-            g = g + std * torch.randn(g.shape, generator=self._chain_gen, device=g.device)
-        self._chain_grad[p].copy_(g)
-        self._hyper_noclip.copy_(self.hyper)
-        self._hyper_noclip[4:5].zero_()
-        old = self._chain_old[p]
-        old.copy_(params)
-        engine.optimizer_step(self.optimizer_name, self._hyper_noclip, self.n_params, params,
-                              self.opt_state[p], self._chain_grad[p], None, None, None)
-        if self.reduce_on_plateau_kwargs is not None:     # value = the loss of this gradient
-            st = self._chain_plateau[p]
-            plateau_step(st, self._train_loss_tmp[p:p + 1], **self.reduce_on_plateau_kwargs)
-            params.copy_(old + st[0:1] * (params - old))
-        if self.ema_decay is not None:
-            d = self.ema_decay
-            ema = self._chain_ema[p]
-            ema.mul_(d).add_(params - old, alpha=1.0 - d)
-            params.copy_(old + ema / (1.0 - torch.pow(torch.full_like(t, d), t)))
-        if self.box_lo is not None:
-            torch.maximum(params, self.box_lo, out=params)
-        if self.box_hi is not None:
-            torch.minimum(params, self.box_hi, out=params)
+        1-based step count t (counter-based draws keyed by noise_kwargs['seed']); reduce_on_plateau: the
+        updates are scaled by a factor that shrinks when the train loss stops improving; ema: the
+        debiased exponential moving average of the updates is what is applied."""
+        nk = self.noise_kwargs
+        cfg = {"noise": None if nk is None else (float(nk.get("eta", 0.01)), float(nk.get("gamma", 0.55))),
+               "ema_decay": self.ema_decay, "plateau": self.reduce_on_plateau_kwargs}
+        engine.optimizer_chain_step(
+            self.optimizer_name, self.hyper, self.n_params, self.params[p], self.opt_state[p],
+            self.grad[p], self.box_lo, self.box_hi, self.zero_flag[p:p + 1], cfg,
+            self._chain_count[p:p + 1],
+            self._chain_plateau[p] if self.reduce_on_plateau_kwargs is not None else None,
+            self._chain_ema[p] if self.ema_decay is not None else None,
+            self._train_loss_tmp[p:p + 1], int((nk or {}).get("seed", 0)) * 1000003 + p,
+            self._chain_scratch[p])
 
     def _update_kernels(self, p: int):
         """planner.py:2868-2917 on the device for parallel instance p."""
@@ -1007,7 +1003,19 @@ class JaxBackpropPlanner:
                               noise=self.test_noise, disc=self.disc,
                               reward=reward, returns=returns, err=err, final=final,
                               traj=None if (self.test_traj is None or scratch) else self.test_traj[p])
-        engine.mean_loss(returns, B, loss_out, None)
+        self._test_loss_kernels(returns, loss_out)
+
+    def _test_loss_kernels(self, returns: torch.Tensor, loss_out: torch.Tensor):
+        """-utility(test returns) (planner.py:2695-2698: the test loss is the same loss function over the
+        exact rollouts, without the symlog transform)."""
+        if self.utility == "mean":
+            engine.mean_loss(returns, self.batch_size_test, loss_out, None)
+        elif self._native_utility is not None:
+            self._native_utility_kernels(returns, loss_out, test=True)
+        else:
+            r = parallel.allgather_returns(returns)
+            fn = self.utility if callable(self.utility) else _utility_fn(self.utility, self.utility_kwargs)
+            loss_out.copy_((-fn(r, **(self.utility_kwargs if callable(self.utility) else {}))).reshape(1))
 
     def project_params(self, params: torch.Tensor, p: int = 0):
         """plan.projection on a flat parameter vector: box clip (planner.py:878-910) and, when
@@ -1102,6 +1110,30 @@ class JaxBackpropPlanner:
         self._finish_iteration()
         self._defer_ar = False
 
+    def _use_scratch(self, p: int):
+        if self._branches:
+            self.tape, self.gradp, self.gret = self._scratch[p]
+
+    def _branch_kernels(self):
+        """One iteration with parallel_updates > 1: instance p runs `optimiser step -> exact test rollouts
+        -> relaxed rollouts + gradient for the next step` on its own stream, i.e. as its own branch of the
+        captured graph; the branches join before the statistics are read.  Per-instance results are
+        those of the sequential order (the instances share nothing but read-only inputs)."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_pstreams", None) is None:
+            self._pstreams = [torch.cuda.Stream(device=self.device) for _ in range(self.parallel_updates)]
+        for p, sp in enumerate(self._pstreams):
+            sp.wait_stream(main)
+            with torch.cuda.stream(sp):
+                self._use_scratch(p)
+                self._opt_kernels(p)
+                self._test_kernels(p)
+                self._train_grad_kernels(p)
+        for sp in self._pstreams:
+            main.wait_stream(sp)
+        self._use_scratch(0)
+        self._finish_iteration()
+
     def _capture(self, from_host: bool = False):
         """Capture one full iteration into a CUDA graph (after a warm-up on a side stream).
         ``from_host``: the graph also carries the host<->device copies of one optimize() call
@@ -1113,6 +1145,8 @@ class JaxBackpropPlanner:
         s = torch.cuda.Stream(device=self.device)
         side = torch.cuda.Stream(device=self.device) if self._overlap else None
         inner0 = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
+        if self._branches and self._pipeline:
+            inner0 = self._branch_kernels
         if self._noise_in_graph:
             def inner():
                 self.redraw_noise(force=True)
@@ -1146,8 +1180,6 @@ class JaxBackpropPlanner:
         g = torch.cuda.CUDAGraph()
         if self._noise_in_graph:
             g.register_generator_state(self._gen)
-        if self.noise_kwargs is not None:
-            g.register_generator_state(self._chain_gen)
         with torch.cuda.graph(g):
             body()
         self.params.copy_(backup[0])
@@ -1184,7 +1216,9 @@ class JaxBackpropPlanner:
             self.load_initial_state(self._h_init_train, self._h_init_test)
             self.params.copy_(self._h_params_in, non_blocking=True)
             for p in range(self.parallel_updates):     # gradient for the first optimiser step
+                self._use_scratch(p)
                 self._train_grad_kernels(p)
+            self._use_scratch(0)
             self._primed = True
         self._graph_host.replay()
         torch.cuda.current_stream(self.device).synchronize()
@@ -1207,7 +1241,9 @@ class JaxBackpropPlanner:
             self._capture()
         if self._pipeline and not self._primed:
             for p in range(self.parallel_updates):     # gradient for the first optimiser step
+                self._use_scratch(p)
                 self._train_grad_kernels(p)
+            self._use_scratch(0)
             self._primed = True
         self._graph.replay()
 
@@ -1238,6 +1274,9 @@ class JaxBackpropPlanner:
             engine.mean_loss(self.train_returns[0], self.batch_size_train, None, self.gret)
             if self.world_size > 1:          # d(-mean over the GLOBAL batch)/d return_b
                 self.gret.mul_(1.0 / self.world_size)
+            if self._branches:
+                for _, _, gret in self._scratch[1:]:
+                    gret.copy_(self.gret)
                 self._gen.manual_seed(int(key) + 7919 * (self.rank + 1))
             self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise, 0)
             self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise, 1)

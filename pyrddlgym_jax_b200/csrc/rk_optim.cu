@@ -742,8 +742,8 @@ extern "C" int rk_transpose_split(void* stream, int r, int c, const float* W, fl
 //        7 symlog mean  U = mean(sign(r) log1p|r|)   (use_symlog_reward with the mean utility)
 // p0 = beta (risk_free for sharpe), p1 = eps (sharpe).  scale multiplies the cotangent (1 / world size).
 __global__ void __launch_bounds__(1024)
-rk_utility_loss_kernel(int kind, int B, const float* __restrict__ r, float p0, float p1, float scale,
-                       float* __restrict__ loss, float* __restrict__ gret) {
+rk_utility_loss_kernel(int kind, int B, int b0, int n_local, const float* __restrict__ r, float p0,
+                       float p1, float scale, float* __restrict__ loss, float* __restrict__ gret) {
   __shared__ float sh[32];
   __shared__ float bc[4];
   const float invB = 1.f / (float)B;
@@ -772,7 +772,8 @@ rk_utility_loss_kernel(int kind, int B, const float* __restrict__ r, float p0, f
   if (kind == 7) {
     if (threadIdx.x == 0 && loss != nullptr) loss[0] = -mu;
     if (gret != nullptr)
-      for (int i = threadIdx.x; i < B; i += blockDim.x) gret[i] = -scale * invB / (1.f + fabsf(r[i]));
+      for (int i = b0 + threadIdx.x; i < b0 + n_local; i += blockDim.x)
+        gret[i - b0] = -scale * invB / (1.f + fabsf(r[i]));
     return;
   }
   // second moment / lower partial moments / sum of exponentials
@@ -811,7 +812,7 @@ rk_utility_loss_kernel(int kind, int B, const float* __restrict__ r, float p0, f
   }
   if (threadIdx.x == 0 && loss != nullptr) loss[0] = -U;
   if (gret == nullptr) return;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+  for (int i = b0 + threadIdx.x; i < b0 + n_local; i += blockDim.x) {
     const float c = r[i] - mu;
     float g;                             // dU / dr_i
     switch (kind) {
@@ -822,15 +823,210 @@ rk_utility_loss_kernel(int kind, int B, const float* __restrict__ r, float p0, f
       case 5: g = invB * (1.f / (sigma + p1) - (mu - p0) * c / (sigma * (sigma + p1) * (sigma + p1))); break;
       default: g = expf(-p0 * r[i] - zmax) / A; break;
     }
-    gret[i] = -scale * g;
+    gret[i - b0] = -scale * g;
   }
+}
+
+extern "C" int rk_utility_loss_shard(void* stream, int kind, int B, int b0, int n_local,
+                                     const float* returns, float p0, float p1, float scale, float* loss,
+                                     float* gret) {
+  if (kind < 1 || kind > 7 || B <= 0 || returns == nullptr || (loss == nullptr && gret == nullptr) ||
+      b0 < 0 || n_local < 0 || b0 + n_local > B)
+    return RK_E_BADARG;
+  rk_utility_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(kind, B, b0, n_local, returns, p0, p1,
+                                                                scale, loss, gret);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int rk_utility_loss(void* stream, int kind, int B, const float* returns, float p0, float p1,
                                float scale, float* loss, float* gret) {
-  if (kind < 1 || kind > 7 || B <= 0 || returns == nullptr || (loss == nullptr && gret == nullptr))
+  return rk_utility_loss_shard(stream, kind, B, 0, B, returns, p0, p1, scale, loss, gret);
+}
+
+// ---- the optional links of the optax chain around the optimiser, on the device ------------------
+// planner.py:2349-2387 builds  clip_by_global_norm -> add_noise(eta, gamma, seed) -> optimiser ->
+// reduce_on_plateau -> ema(decay)  and planner.py:2885-2899 applies the result and projects onto the box.
+// Stage 1 (one CTA, fixed-order sums): step count t <- t + 1, all-zero test and global norm of the RAW
+// gradient, noise deviation sqrt(eta / t^gamma), the plateau state machine of optax.contrib stepped with
+// the loss of this gradient, the EMA debias 1 - decay^t; the derived scalars go to scal[4].
+// Stage 2 (element-wise): g <- clip(g) + std * N(0, 1) (Philox4x32-10, counter = (quad, t), key = seed)
+// -> optimiser update u -> step = -lr * u * plateau_scale -> ema <- d ema + (1 - d) step -> p <- p +
+// ema / debias -> box.  Short vectors run both stages in one single-CTA launch.
+struct RkChainCfg {
+  float eta, gamma, ema_decay, factor, patience, rtol, atol, cooldown, accumulation, min_scale;
+  int use_noise, use_plateau, use_ema;
+};
+
+__device__ void rk_chain_stats(const float* __restrict__ g, int n, const float* __restrict__ hyper,
+                               const RkChainCfg& C, float* count, float* plateau,
+                               const float* __restrict__ loss, int32_t* zero_flag, float* scal,
+                               float* sh) {
+  float ss = 0.f, nz = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = g[i];
+    ss += v * v;
+    nz += (fabsf(v) > 1e-8f || v != v) ? 1.f : 0.f;
+  }
+  ss = block_sum_1024(ss, sh);
+  nz = block_sum_1024(nz, sh);
+  if (threadIdx.x == 0) {
+    if (zero_flag != nullptr) *zero_flag = (nz == 0.f) ? 1 : 0;
+    const float t = count[0] + 1.f;
+    count[0] = t;
+    const float clip = hyper[4];
+    float cs = 1.f;
+    if (clip > 0.f) {
+      const float gn = sqrtf(ss);
+      if (gn > clip) cs = clip / gn;
+    }
+    float pscale = 1.f;
+    if (C.use_plateau) {
+      float scale = plateau[0], best = plateau[1], plat = plateau[2], cool = plateau[3];
+      const float cnt = plateau[4], avg = plateau[5];
+      const float ncnt = cnt + 1.f;
+      const float navg = (cnt * avg + loss[0]) / ncnt;
+      if (ncnt == C.accumulation) {
+        const bool improved = navg < (1.f - C.rtol) * best - C.atol;
+        if (improved) best = navg;
+        const float cur = improved ? 0.f : plat + 1.f;
+        const bool in_cd = cool > 0.f, hit = cur == C.patience;
+        plat = (in_cd || hit) ? 0.f : cur;
+        if (!in_cd && hit) scale = fmaxf(scale * C.factor, C.min_scale);
+        cool = in_cd ? cool - 1.f : (hit ? C.cooldown : 0.f);
+        plateau[0] = scale; plateau[1] = best; plateau[2] = plat; plateau[3] = cool;
+        plateau[4] = 0.f; plateau[5] = 0.f;
+      } else {
+        plateau[4] = ncnt; plateau[5] = navg;
+      }
+      pscale = plateau[0];
+    }
+    scal[0] = cs;
+    scal[1] = C.use_noise ? sqrtf(C.eta / powf(t, C.gamma)) : 0.f;
+    scal[2] = pscale;
+    scal[3] = C.use_ema ? 1.f - powf(C.ema_decay, t) : 1.f;
+    scal[4] = t;
+  }
+}
+
+__device__ __forceinline__ void rk_chain_quad(int q, int kind, const float* __restrict__ hyper, int n,
+                                              float* params, float* state, const float* grad,
+                                              const float* lo, const float* hi, const RkChainCfg& C,
+                                              const float* scal, float* ema, uint32_t seed_lo,
+                                              uint32_t seed_hi) {
+  const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
+  const float mom = hyper[5], step = hyper[6], om1 = hyper[7], om2 = hyper[8];
+  const float cs = scal[0], sd = scal[1], ps = scal[2], debias = scal[3];
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (C.use_noise) {
+    uint32_t r[4];
+    rk_philox4x32_10((uint32_t)q, 0u, (uint32_t)scal[4], 0x6e6f6973u, seed_lo, seed_hi, r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+      const float u2 = ((float)(r[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+      const float rad = sqrtf(-2.f * logf(u1));
+      float sn, cn;
+      sincospif(2.f * u2, &sn, &cn);
+      z[2 * h] = rad * cn;
+      z[2 * h + 1] = rad * sn;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = 4 * q + j;
+    if (i >= n) break;
+    const float g = grad[i] * cs + sd * z[j];
+    float upd;
+    if (kind == 1) {
+      const float nu = d1 * state[i] + om1 * g * g;
+      state[i] = nu;
+      upd = g / sqrtf(nu + eps);
+    } else if (kind == 2) {
+      const float mu = d1 * state[i] + om1 * g;
+      const float nu = b2 * state[n + i] + om2 * g * g;
+      state[i] = mu;
+      state[n + i] = nu;
+      upd = (mu / (1.f - powf(d1, step))) / (sqrtf(nu / (1.f - powf(b2, step))) + eps);
+    } else if (mom > 0.f) {
+      const float m = g + mom * state[i];
+      state[i] = m;
+      upd = m;
+    } else {
+      upd = g;
+    }
+    float delta = -lr * upd * ps;                   // optimiser -> reduce_on_plateau
+    if (C.use_ema) {                                // optax.ema with debias
+      const float e = C.ema_decay * ema[i] + (1.f - C.ema_decay) * delta;
+      ema[i] = e;
+      delta = e / debias;
+    }
+    float p = params[i] + delta;                    // optax.apply_updates + box projection
+    if (lo != nullptr) p = fmaxf(p, lo[i]);
+    if (hi != nullptr) p = fminf(p, hi[i]);
+    params[i] = p;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+rk_chain_small_kernel(int kind, const float* __restrict__ hyper, int n, float* params, float* state,
+                      const float* __restrict__ grad, const float* __restrict__ lo,
+                      const float* __restrict__ hi, int32_t* zero_flag, RkChainCfg C, float* count,
+                      float* plateau, float* ema, const float* __restrict__ loss, uint32_t seed_lo,
+                      uint32_t seed_hi) {
+  __shared__ float sh[32];
+  __shared__ float scal[8];
+  rk_chain_stats(grad, n, hyper, C, count, plateau, loss, zero_flag, scal, sh);
+  __syncthreads();
+  for (int q = threadIdx.x; 4 * q < n; q += blockDim.x)
+    rk_chain_quad(q, kind, hyper, n, params, state, grad, lo, hi, C, scal, ema, seed_lo, seed_hi);
+}
+
+__global__ void __launch_bounds__(1024)
+rk_chain_stats_kernel(const float* __restrict__ grad, int n, const float* __restrict__ hyper,
+                      RkChainCfg C, float* count, float* plateau, const float* __restrict__ loss,
+                      int32_t* zero_flag, float* scal) {
+  __shared__ float sh[32];
+  rk_chain_stats(grad, n, hyper, C, count, plateau, loss, zero_flag, scal, sh);
+}
+
+__global__ void __launch_bounds__(256)
+rk_chain_apply_kernel(int kind, const float* __restrict__ hyper, int n, float* params, float* state,
+                      const float* __restrict__ grad, const float* __restrict__ lo,
+                      const float* __restrict__ hi, RkChainCfg C, const float* __restrict__ scal,
+                      float* ema, uint32_t seed_lo, uint32_t seed_hi) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (4 * q < n)
+    rk_chain_quad(q, kind, hyper, n, params, state, grad, lo, hi, C, scal, ema, seed_lo, seed_hi);
+}
+
+extern "C" int rk_optimizer_chain_step(void* stream, int kind, const float* hyper, int n, float* params,
+                                       float* state, const float* grad, const float* lo,
+                                       const float* hi, int32_t* zero_flag, const float* cfg,
+                                       float* count, float* plateau, float* ema, const float* loss,
+                                       unsigned long long seed, float* scratch) {
+  if (hyper == nullptr || params == nullptr || grad == nullptr || cfg == nullptr || count == nullptr ||
+      n <= 0)
     return RK_E_BADARG;
-  rk_utility_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(kind, B, returns, p0, p1, scale, loss,
-                                                                gret);
+  if (kind < 0 || kind > 2) return RK_E_BADARG;
+  if (kind != 0 && state == nullptr) return RK_E_BADARG;
+  RkChainCfg C;
+  C.eta = cfg[0]; C.gamma = cfg[1]; C.ema_decay = cfg[2]; C.factor = cfg[3]; C.patience = cfg[4];
+  C.rtol = cfg[5]; C.atol = cfg[6]; C.cooldown = cfg[7]; C.accumulation = cfg[8]; C.min_scale = cfg[9];
+  C.use_noise = cfg[10] != 0.f; C.use_plateau = cfg[11] != 0.f; C.use_ema = cfg[12] != 0.f;
+  if (C.use_plateau && (plateau == nullptr || loss == nullptr)) return RK_E_BADARG;
+  if (C.use_ema && ema == nullptr) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+  if (n <= 16384) {
+    rk_chain_small_kernel<<<1, 1024, 0, st>>>(kind, hyper, n, params, state, grad, lo, hi, zero_flag, C,
+                                              count, plateau, ema, loss, s_lo, s_hi);
+    return (int)cudaGetLastError();
+  }
+  if (scratch == nullptr) return RK_E_BADARG;
+  rk_chain_stats_kernel<<<1, 1024, 0, st>>>(grad, n, hyper, C, count, plateau, loss, zero_flag,
+                                            scratch);
+  const int quads = (n + 3) / 4;
+  rk_chain_apply_kernel<<<(quads + 255) / 256, 256, 0, st>>>(kind, hyper, n, params, state, grad, lo, hi,
+                                                              C, scratch, ema, s_lo, s_hi);
   return (int)cudaGetLastError();
 }

@@ -1533,3 +1533,55 @@ def test_drp_preprocessor_update_matches_oracle(cuda_device, normalize):
     r_ref = out["reward"].numpy().T
     np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
                                atol=1e-5 * np.abs(r_ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("utility,kw", [("mean_var", {"beta": 0.8}), ("cvar", {"alpha": 0.3})])
+def test_drp_utility_update_matches_oracle(cuda_device, utility, kw):
+    """A utility other than the mean with a deep reactive policy (planner.py:2817-2818 applies it to the
+    returns of either plan kind): train loss, gradient and test loss against the oracle, whose loss is
+    -utility(returns) - ent_coeff * mean entropy through torch autograd."""
+    from pyrddlgym_jax_b200.core import planner as PL
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    m = fixture_model("powergen")
+    T, B = 4, 27
+    plan = JaxDeepReactivePolicy(topology=[16, 16])
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None, utility=utility,
+                            utility_kwargs=kw, use_cuda_graph=False)
+    assert pl._native_utility is not None
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(13)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 5 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in m.state_fluents},
+                              {"curProd": pol_noise[t].reshape(B, 5)}, 1.0, m.bounds, 2, True)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    R = OP.returns_from_rewards(out["reward"], float(m.discount))
+    fn = PL.UTILITY_LOOKUP[utility]
+    loss = -fn(R, **kw) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    np.testing.assert_allclose(pl.grad[0].cpu().numpy(), want, rtol=1e-4,
+                               atol=1e-4 * np.abs(want).max())
+    pl.test_loss()
+    torch.cuda.synchronize()
+    want_test = -fn(pl.test_returns[0].cpu(), **kw)
+    assert abs(float(pl.test_loss_buf[0]) - float(want_test)) <= 2e-5 * abs(float(want_test))

@@ -214,6 +214,86 @@ def test_native_utilities_match_autograd(cuda_device):
         torch.testing.assert_close(gret.double(), 0.5 * gw, rtol=1e-5, atol=1e-9)
 
 
+def test_sorted_utilities_match_autograd(cuda_device):
+    """rk_utility_sorted_loss (var, cvar, cvar_ste, expectile, gini: one device sort, closed-form
+    cotangents) against torch autograd of the planner's utility definitions in fp64 (restating
+    planner.py:2195-2229), with ties in the return vector, and the sharded form: each of two ranks'
+    slices of the cotangent of the global vector."""
+    import torch
+    from pyrddlgym_jax_b200.core import engine, planner
+    g = torch.Generator().manual_seed(11)
+    for B in (7, 1000, 40000):
+        r = torch.randn(B, generator=g) * 3.0 + 1.5
+        r[: B // 3] = torch.round(r[: B // 3])                       # tie groups
+        r = r.to(cuda_device)
+        work = engine.utility_sorted_work(B, cuda_device)
+        cases = [("var", planner.var_utility, dict(alpha=0.3), 0.3, 0),
+                 ("var", planner.var_utility, dict(alpha=1.0), 1.0, 0),
+                 ("cvar", planner.cvar_utility, dict(alpha=0.25), 0.25, 0),
+                 ("cvar_ste", planner.cvar_ste_utility, dict(alpha=0.1), 0.1, 0),
+                 ("expectile", planner.expectile_utility, dict(alpha=0.2, max_iter=30), 0.2, 30),
+                 ("expectile", planner.expectile_utility, dict(alpha=0.7, max_iter=0), 0.7, 0),
+                 ("gini", planner.gini_utility, dict(gamma=0.6), 0.6, 0)]
+        for kind, fn, kw, p0, it in cases:
+            if kind == "gini" and B > 5000:
+                continue                                             # the autograd form is O(B^2)
+            # the C ABI takes the parameter as a float: the fp64 reference sees the same rounded value
+            p0 = float(np.float32(p0))
+            kw = {k: (p0 if k in ("alpha", "gamma") else v) for k, v in kw.items()}
+            x = r.double().clone().requires_grad_(True)
+            want = -fn(x, **kw)
+            (gw,) = torch.autograd.grad(want, x)
+            loss, gret = torch.zeros(1, device=cuda_device), torch.zeros(B, device=cuda_device)
+            engine.utility_sorted_loss(kind, B, r, p0, it, 1.0, loss, gret, work)
+            assert abs(float(loss[0]) - float(want)) <= 2e-5 * max(1.0, abs(float(want))), (kind, B)
+            torch.testing.assert_close(gret.double(), gw, rtol=2e-4, atol=2e-5 * float(gw.abs().max()),
+                                       msg=lambda m: f"{kind} B={B}: {m}")
+            # two shards of the same global vector
+            if B >= 1000:
+                h = B // 2
+                for b0, n in ((0, h), (h, B - h)):
+                    part = torch.zeros(n, device=cuda_device)
+                    engine.utility_sorted_loss(kind, B, r, p0, it, 0.5, None, part, work, b0, n)
+                    torch.testing.assert_close(part, 0.5 * gret[b0:b0 + n], rtol=0, atol=0)
+    # the closed-form family, sharded
+    B = 1000
+    r = (torch.randn(B, generator=g) * 2.0).to(cuda_device)
+    loss, full = torch.zeros(1, device=cuda_device), torch.zeros(B, device=cuda_device)
+    engine.utility_loss("mean_var", B, r, 0.7, 0.0, 1.0, loss, full)
+    part = torch.zeros(300, device=cuda_device)
+    engine.utility_loss("mean_var", B, r, 0.7, 0.0, 1.0, None, part, 500, 300)
+    torch.testing.assert_close(part, full[500:800], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("utility,kw", [("cvar", {"alpha": 0.3}), ("gini", {"gamma": 0.2}),
+                                        ("expectile", {"alpha": 0.3})])
+def test_sorted_utility_planner_matches_eager(cuda_device, utility, kw):
+    """A planner with an order-statistic utility runs as one CUDA graph and follows the autograd path."""
+    import torch
+    import bench
+    from pyrddlgym_jax_b200.core import logic
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner, JaxStraightLinePlan
+    model = bench.workload_model("quadcopter")
+    plans = []
+    for native in (True, False):
+        pl = JaxBackpropPlanner(model, JaxStraightLinePlan(), batch_size_train=64, batch_size_test=64,
+                                rollout_horizon=10, optimizer="rmsprop",
+                                optimizer_kwargs={"learning_rate": 0.05}, pgpe=None,
+                                compiler=logic.DefaultJaxRDDLCompilerWithGrad,
+                                compiler_kwargs={"sigmoid_weight": 10.}, utility=utility,
+                                utility_kwargs=kw)
+        assert pl._native_utility is not None
+        if not native:
+            pl._native_utility, pl._utility_eager = None, True
+        pl.initialize(7)
+        for _ in range(3):
+            pl.iterate()
+        assert (pl._graph is not None) == native
+        plans.append((pl.params[0].cpu().clone(), pl.read_stats()[0].copy()))
+    torch.testing.assert_close(plans[0][0], plans[1][0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(plans[0][1], plans[1][1], rtol=1e-4)
+
+
 def test_native_utility_keeps_the_graph_and_matches_eager(cuda_device):
     """A planner with utility='mean_var' runs its iteration as one CUDA graph (native cotangent) and
     produces the same plan as the autograd path (RK-independent check: same inputs, two planners)."""

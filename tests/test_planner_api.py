@@ -474,28 +474,40 @@ def test_symlog_reward_matches_oracle(cuda_device):
 
 
 # ---- reduce_on_plateau link of the optimiser chain (planner.py:2375-2384) -------------------------
+@pytest.mark.gpu
 @pytest.mark.parametrize("kw", [{}, {"factor": 0.5, "patience": 3, "cooldown": 2, "min_scale": 0.2},
                                 {"patience": 2, "accumulation_size": 3, "factor": 0.7, "rtol": 0.05},
                                 {"patience": 1, "atol": 0.5, "factor": 0.25}])
-def test_plateau_state_machine_matches_oracle(kw):
+def test_plateau_state_machine_matches_oracle(cuda_device, kw):
+    """The reduce_on_plateau state of rk_optimizer_chain_step against the oracle's restatement of
+    optax.contrib.reduce_on_plateau, loss by loss (a frozen one-word sgd step carries the link)."""
     from oracle import planner as OP
-    from pyrddlgym_jax_b200.core.planner import plateau_init, plateau_kwargs, plateau_step
+    from pyrddlgym_jax_b200.core import engine
+    from pyrddlgym_jax_b200.core.planner import plateau_init, plateau_kwargs
     full = plateau_kwargs(kw)
     g = torch.Generator().manual_seed(5)
     # a loss that improves, stalls, jumps and improves again
     losses = torch.cat([torch.linspace(10, 5, 8), 5 + 0.3 * torch.rand(25, generator=g),
                         torch.linspace(5, 1, 6), 1 + 0.2 * torch.rand(20, generator=g)])
-    st = plateau_init(1, "cpu")[0]
+    dev = cuda_device
+    st = plateau_init(1, dev)[0]
+    z = lambda *s: torch.zeros(*s, device=dev)      # noqa: E731
+    hyper = torch.tensor([0.0, 0, 0, 0, 0, 0, 1, 1, 1], dtype=torch.float32, device=dev)
+    params, grad, count, scratch, loss = z(1), z(1), z(1), z(8), z(1)
+    cfg = {"noise": None, "ema_decay": None, "plateau": full}
     ref = OP.reduce_on_plateau_init()
     scales = []
-    for v in losses:
-        plateau_step(st, v.reshape(1), **full)
+    for i, v in enumerate(losses):
+        loss.fill_(float(v))
+        engine.optimizer_chain_step("sgd", hyper, 1, params, None, grad, None, None, None, cfg, count, st,
+                                    None, loss, 0, scratch)
         ref = OP.reduce_on_plateau_step(ref, float(v), **full)
-        got = st.tolist()
+        got = st.cpu().tolist()
         want = [ref[k] for k in ("scale", "best_value", "plateau_count", "cooldown_count", "count",
                                  "avg_value")]
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
         scales.append(got[0])
+        assert float(count) == i + 1
     assert scales[-1] < 1.0 and min(scales) >= full["min_scale"]
     with pytest.raises(TypeError):
         plateau_kwargs({"patients": 3})
@@ -813,3 +825,30 @@ def test_every_shipped_reference_config_loads():
         assert "compiler_kwargs" in planner_args and isinstance(train_args, dict)
         loaded += 1
     assert loaded >= 20
+
+
+@pytest.mark.gpu
+def test_parallel_updates_branches_equal_sequential(cuda_device, monkeypatch):
+    """parallel_updates = 3 (planner.py:2920-2929 vmaps the update over the instances): the captured
+    iteration runs the instances as concurrent graph branches with private scratch; plans, losses and
+    test losses are bit-identical to the instances run one after another."""
+    m = fixture_model("quadcopter")      # no draw sites: both planners see identical inputs
+    out = []
+    for branches in ("1", "0"):
+        monkeypatch.setenv("RK_PARALLEL_BRANCHES", branches)
+        pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=32, rollout_horizon=6,
+                                optimizer="rmsprop", optimizer_kwargs={"learning_rate": 0.05}, pgpe=None,
+                                parallel_updates=3)
+        assert pl._branches == (branches == "1")
+        pl.initialize(5)
+        hist = []
+        for _ in range(4):
+            pl.redraw_noise()
+            pl.iterate()
+            hist.append([x.copy() for x in pl.read_stats()])
+        out.append((pl.params.cpu().clone(), hist))
+    assert not torch.equal(out[0][0][0], out[0][0][1])          # the instances differ from each other
+    assert torch.equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
