@@ -28,6 +28,7 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
+from .linesearch import zoom_kwargs, zoom_linesearch
 from . import engine, logic, parallel
 from .compiler import JaxRDDLCompiler
 from .layout import draw_noise, pack_fluent_major, unpack_fluent_major
@@ -555,8 +556,9 @@ class JaxBackpropPlanner:
         self.ema_decay = None if ema_decay is None else float(ema_decay)
         self.reduce_on_plateau_kwargs = None if reduce_on_plateau_kwargs is None \
             else plateau_kwargs(reduce_on_plateau_kwargs)
-        for name, val in (("line_search_kwargs", line_search_kwargs),
-                          ("critic", critic),
+        # optax.scale_by_zoom_linesearch (planner.py:2373-2374): host-driven trials, core/linesearch.py
+        self.line_search_kwargs = None if line_search_kwargs is None else zoom_kwargs(line_search_kwargs)
+        for name, val in (("critic", critic),
                           ("dashboard", dashboard)):
             if val is not None:
                 raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
@@ -946,7 +948,9 @@ class JaxBackpropPlanner:
         params = self.params[p]
         if publish:
             self._publish_kernels(p)
-        if not self._use_chain:
+        if self.line_search_kwargs is not None:
+            self._line_search_update(p)
+        elif not self._use_chain:
             engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
                                   self.opt_state[p], self.grad[p], self.box_lo, self.box_hi,
                                   self.zero_flag[p:p + 1])
@@ -959,6 +963,45 @@ class JaxBackpropPlanner:
                                plan.max_allowed_actions, plan._max_constraint_iter,
                                plan._wrap_sigmoid, plan._min_action_prob,
                                self.converged[p:p + 1])
+
+    def _line_search_update(self, p: int):
+        """optimiser -> scale_by_zoom_linesearch -> apply_updates -> box projection (planner.py:2373-2374,
+        2886-2899).  The optimiser's update u is the search direction; every trial step size re-runs the
+        relaxed rollouts and the adjoint at params + eta u on the noise of this update (the reference
+        hands value_fn the same sim_state) and the host reads back (loss, <grad, u>).  Runs outside the
+        CUDA graph, in update-then-test order."""
+        if self._use_chain or self.world_size > 1:
+            raise NotImplementedError("line_search_kwargs together with noise_kwargs / ema_decay / "
+                                      "reduce_on_plateau_kwargs or several GPUs")
+        params, grad = self.params[p], self.grad[p]
+        x0, g0 = params.clone(), grad.clone()
+        f0 = float(self._train_loss_tmp[p])
+        hyper = self.hyper.clone()
+        engine.optimizer_step(self.optimizer_name, hyper, self.n_params, params, self.opt_state[p], grad,
+                              None, None, self.zero_flag[p:p + 1])
+        u = params - x0
+        slope0 = float(torch.dot(g0, u))
+
+        def phi(eta: float):
+            params.copy_(x0 + eta * u)
+            self._train_grad_kernels(p)
+            return float(self._train_loss_tmp[p]), float(torch.dot(self.grad[p], u))
+
+        kw = self.line_search_kwargs
+        state = self.__dict__.setdefault("_ls_stepsize", {})
+        prev = state.get(p, 1.0)
+        init = 1.0 if (kw["initial_guess_strategy"] == "one" or prev <= 0.0) else prev
+        eta, f_eta, evals, ok = zoom_linesearch(phi, f0, slope0, init, **kw)
+        state[p] = eta
+        self.line_search_info = {"learning_rate": eta, "value": f_eta, "num_linesearch_steps": evals,
+                                 "converged": ok}
+        params.copy_(x0 + eta * u)
+        if self.box_lo is not None:
+            torch.maximum(params, self.box_lo, out=params)
+        if self.box_hi is not None:
+            torch.minimum(params, self.box_hi, out=params)
+        grad.copy_(g0)                       # what the callback publishes: loss and gradient at x0
+        self._train_loss_tmp[p:p + 1].fill_(f0)
 
     def _opt_chain_kernels(self, p: int):
         """The optional links of the optax chain (planner.py:2366-2386) around the optimiser, one native
@@ -1201,7 +1244,7 @@ class JaxBackpropPlanner:
         JaxOnlineController): initial-state words of both models and the plan to start from go
         in, (train loss, test loss, zero-gradient flags, plan) come back -- one graph launch and
         one synchronisation.  Returns (train [P], test [P], zero [P], plan [P, NP] pinned view)."""
-        if self._utility_eager or not self.use_cuda_graph:
+        if self._utility_eager or self.line_search_kwargs is not None or not self.use_cuda_graph:
             self.load_initial_state(init_train, init_test)
             self.params.copy_(params, non_blocking=True)
             self.iterate()
@@ -1234,7 +1277,7 @@ class JaxBackpropPlanner:
 
     def iterate(self):
         """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""
-        if self._utility_eager or not self.use_cuda_graph:
+        if self._utility_eager or self.line_search_kwargs is not None or not self.use_cuda_graph:
             self._iteration_kernels()
             return
         if self._graph is None:
@@ -1381,7 +1424,7 @@ class JaxBackpropPlanner:
                f"    optimizer         ={self.optimizer_name}\n"
                f"    optimizer args    ={self.optimizer_kwargs}\n"
                f"    clip_gradient     ={self.clip_grad}\n"
-               f"    line_search_kwargs=None\n"
+               f"    line_search_kwargs={self.line_search_kwargs}\n"
                f"    noise_kwargs      ={self.noise_kwargs}\n"
                f"    ema_decay         ={self.ema_decay}\n"
                f"    reduce_on_plateau ={self.reduce_on_plateau_kwargs}\n"

@@ -852,3 +852,50 @@ def test_parallel_updates_branches_equal_sequential(cuda_device, monkeypatch):
     for a, b in zip(out[0][1], out[1][1]):
         for x, y in zip(a, b):
             np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.gpu
+def test_zoom_line_search_link(cuda_device):
+    """line_search_kwargs (planner.py:2373-2374): every update's step size satisfies the sufficient-decrease
+    and curvature conditions along the optimiser's direction, checked by re-evaluating the relaxed loss and
+    its gradient at the accepted point on the same (deterministic) rollouts; the loss goes down every
+    iteration, and a too large learning rate that plain sgd diverges with is tamed."""
+    m = fixture_model("quadcopter")
+    kw = dict(batch_size_train=16, rollout_horizon=8, optimizer="sgd", pgpe=None)
+    pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), optimizer_kwargs={"learning_rate": 5.0},
+                            line_search_kwargs={"max_linesearch_steps": 12, "curv_rtol": 0.5}, **kw)
+    pl.initialize(3)
+    losses = []
+    for _ in range(5):
+        x0 = pl.params[0].clone()
+        pl.iterate()
+        torch.cuda.synchronize()
+        info = pl.line_search_info
+        f0, g0 = float(pl.train_loss[0]), pl.grad_used[0].clone()
+        losses.append(f0)
+        if info["learning_rate"] == 0.0:
+            continue
+        x1 = pl.params[0].clone()
+        u = (x1 - x0) / info["learning_rate"]
+        inside = True
+        if pl.box_lo is not None:      # the Wolfe test is about the un-projected step
+            inside = bool(((x0 + info["learning_rate"] * u >= pl.box_lo) &
+                           (x0 + info["learning_rate"] * u <= pl.box_hi)).all())
+        slope0 = float(torch.dot(g0, u))
+        assert slope0 < 0
+        pl._train_grad_kernels(0)                    # loss and gradient at the accepted point
+        torch.cuda.synchronize()
+        f1, slope1 = float(pl._train_loss_tmp[0]), float(torch.dot(pl.grad[0], u))
+        if inside:
+            assert f1 <= f0 + 1e-4 * info["learning_rate"] * slope0 + 1e-5 * abs(f0)
+            if info["converged"]:
+                assert abs(slope1) <= 0.5 * abs(slope0) * (1 + 1e-3)
+        assert info["num_linesearch_steps"] <= 12
+    assert all(b <= a + 1e-6 * abs(a) for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < losses[0]
+    plain = JaxBackpropPlanner(m, JaxStraightLinePlan(), optimizer_kwargs={"learning_rate": 5.0}, **kw)
+    plain.initialize(3)
+    for _ in range(5):
+        plain.iterate()
+    final_plain = float(plain.read_stats()[0][0])
+    assert not np.isfinite(final_plain) or losses[-1] <= final_plain
