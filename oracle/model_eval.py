@@ -43,6 +43,7 @@ ERR = {  # compiler.py:861-888
     "BETA": 1 << 8, "GEOMETRIC": 1 << 9, "PARETO": 1 << 10, "STUDENT": 1 << 11,
     "GUMBEL": 1 << 12, "LAPLACE": 1 << 13, "CAUCHY": 1 << 14, "GOMPERTZ": 1 << 15,
     "CHISQUARE": 1 << 16, "KUMARASWAMY": 1 << 17, "DISCRETE": 1 << 18, "KRON": 1 << 19,
+    "DIRICHLET": 1 << 20, "MULTIVARIATE_STUDENT": 1 << 21, "MULTINOMIAL": 1 << 22,
     "BINOMIAL": 1 << 23, "NEGATIVE_BINOMIAL": 1 << 24,
 }
 COUNT_NBINS = 100      # truncation of the exact Poisson / Binomial samplers (see _random)
@@ -238,7 +239,7 @@ class OracleModel:
         if fam == "pvar":
             name, params = e.args
             return not (params is None and self.tracer.is_object(name))
-        if fam == "aggregation":
+        if fam in ("aggregation", "matrix", "randomvector"):
             return True
         if fam == "control" and op == "switch":
             return True
@@ -310,7 +311,94 @@ class OracleModel:
             return self._control(e, scope, fls, nfls, cur, B)
         if fam == "randomvar":
             return self._random(e, scope, fls, nfls, cur, B)
+        if fam == "matrix":
+            return self._matrix(e, scope, fls, nfls, cur, B)
+        if fam == "randomvector":
+            return self._random_vector(e, scope, fls, nfls, cur, B)
         raise NotImplementedError(f"expression type {e.etype} is not supported")
+
+    # -- matrix algebra: compiler.py:2383-2434 (jnp.linalg on the last two axes) ------------------
+    def _matrix(self, e, scope, fls, nfls, cur, B):
+        _, op = e.etype
+        if op == "det":                                   # compiler.py:2398-2407
+            *tv, body = e.args
+            inner = list(scope) + list(tv)
+            x, err = self.ev(body, inner, fls, nfls, cur, B)
+            x = _f(x).expand((x.shape[0],) + tuple(self._shape(inner)))
+            return torch.linalg.det(x), err
+        (row, col), body = e.args                         # compiler.py:2409-2434
+        names = [v for v, _ in scope]
+        r_ax, c_ax = 1 + names.index(row), 1 + names.index(col)
+        x, err = self.ev(body, scope, fls, nfls, cur, B)
+        x = _f(x).expand((x.shape[0],) + tuple(self._shape(scope)))
+        m = torch.movedim(x, (r_ax, c_ax), (-2, -1))
+        fn = {"inverse": torch.linalg.inv, "pinverse": torch.linalg.pinv,
+              "cholesky": torch.linalg.cholesky}[op]
+        return torch.movedim(fn(m), (-2, -1), (r_ax, c_ax)), err
+
+    # -- random vectors: compiler.py:2247-2377 -----------------------------------------------------
+    def _random_vector(self, e, scope, fls, nfls, cur, B):
+        _, name = e.etype
+        svars, *args = e.args
+        names = [v for v, _ in scope]
+        i_ax = 1 + names.index(svars[0])
+        sizes = tuple(self._shape(scope))
+
+        def oob(cond):
+            c = cond.reshape(cond.shape[0], -1).all(1)
+            return (~(c.expand(B) if c.shape[0] != B else c)).to(torch.int64)
+
+        if name in ("MultivariateNormal", "MultivariateStudent"):
+            inner = list(scope) + [(svars[1], scope[i_ax - 1][1])]
+            mean, err = self.ev(args[0], scope, fls, nfls, cur, B)
+            cov, er = self.ev(args[1], inner, fls, nfls, cur, B)
+            err = err | er
+            mean = _f(mean).expand((mean.shape[0],) + sizes)
+            cov = _f(cov).expand((cov.shape[0],) + tuple(self._shape(inner)))
+            Z = cur.draw("normal", sizes, B)                           # compiler.py:2276-2278
+            if name == "MultivariateStudent":                          # compiler.py:2307-2321
+                df, er = self.ev(args[2], scope, fls, nfls, cur, B)
+                df = _f(df).expand((df.shape[0],) + sizes)
+                err = err | er | oob(df > 0) * ERR["MULTIVARIATE_STUDENT"]
+                G = cur.draw("gamma", sizes, B, (0.5 * df[0]).detach().numpy()) \
+                    if not (df.requires_grad or df.shape[0] == B) else None
+                if G is None:
+                    raise NotImplementedError("MultivariateStudent with a fluent df")
+                Z = Z * torch.sqrt(0.5 * df / G)
+            L = torch.linalg.cholesky(torch.movedim(cov, (i_ax, cov.dim() - 1), (-2, -1)))
+            z = torch.movedim(Z, i_ax, -1).unsqueeze(-1)
+            out = torch.matmul(L, z)[..., 0]                            # compiler.py:2281-2283
+            return torch.movedim(out, -1, i_ax) + mean, err
+        if name == "Dirichlet":                                         # compiler.py:2331-2348
+            alpha, err = self.ev(args[0], scope, fls, nfls, cur, B)
+            alpha = _f(alpha).expand((alpha.shape[0],) + sizes)
+            err = err | oob(alpha > 0) * ERR["DIRICHLET"]
+            if alpha.shape[0] == B and B > 1:
+                raise NotImplementedError("Dirichlet with a fluent concentration")
+            G = cur.draw("gamma", sizes, B, alpha[0].detach().numpy())
+            return G / G.sum(i_ax, keepdim=True), err
+        if name == "Multinomial":                                       # compiler.py:2350-2377
+            # same law as the tfp sampler from COUNT_NBINS supplied uniforms (see core/lowering.py)
+            trials, err = self.ev(args[0], scope, fls, nfls, cur, B)
+            prob, er = self.ev(args[1], scope, fls, nfls, cur, B)
+            trials = trials.to(INT) if trials.dtype.is_floating_point else _at_least_int(trials)
+            prob = _f(prob).expand((prob.shape[0],) + sizes)
+            cum = torch.cumsum(prob, i_ax)
+            total = cum.select(i_ax, sizes[i_ax - 1] - 1).unsqueeze(i_ax)
+            ok = (prob >= 0) & ((total - 1.0).abs() <= 1e-5) & (trials >= 0)
+            err = err | er | oob(ok) * ERR["MULTINOMIAL"]
+            n = sizes[i_ax - 1]
+            counts = torch.zeros((B,) + sizes, dtype=INT)
+            for k in range(COUNT_NBINS):
+                U = cur.draw("uniform", sizes, B).select(i_ax, 0).unsqueeze(i_ax)
+                below = U < cum.detach()
+                prev = torch.cat([torch.zeros_like(below.narrow(i_ax, 0, 1)),
+                                  below.narrow(i_ax, 0, n - 1)], i_ax)
+                last = torch.arange(n).reshape([n if d == i_ax else 1 for d in range(below.dim())]) == n - 1
+                hit = torch.where(last, ~prev, below & ~prev)
+                counts = counts + (hit & (k < trials)).to(INT)
+            return (counts.to(REAL) if self.relaxed else counts), err
+        raise NotImplementedError(f"Distribution {name} is not supported.")
 
     def _args(self, e, scope, fls, nfls, cur, B, args=None):
         vals, err = [], torch.zeros(B, dtype=torch.int64)

@@ -28,7 +28,8 @@ ERR_BITS = {  # compiler.py:861-888
     "CAST": 0, "UNIFORM": 1, "NORMAL": 2, "EXPONENTIAL": 3, "WEIBULL": 4, "BERNOULLI": 5,
     "POISSON": 6, "GAMMA": 7, "BETA": 8, "GEOMETRIC": 9, "PARETO": 10, "STUDENT": 11,
     "GUMBEL": 12, "LAPLACE": 13, "CAUCHY": 14, "GOMPERTZ": 15, "CHISQUARE": 16,
-    "KUMARASWAMY": 17, "DISCRETE": 18, "KRON": 19, "BINOMIAL": 23, "NEGATIVE_BINOMIAL": 24,
+    "KUMARASWAMY": 17, "DISCRETE": 18, "KRON": 19, "DIRICHLET": 20, "MULTIVARIATE_STUDENT": 21,
+    "MULTINOMIAL": 22, "BINOMIAL": 23, "NEGATIVE_BINOMIAL": 24,
 }
 
 # exact Poisson / Binomial samplers are truncated at this many terms (the reference's relaxations
@@ -286,6 +287,10 @@ class Lowerer:
             return self._control(e, scope, env, sizes)
         if fam == "randomvar":
             return self._random(e, scope, env, sizes)
+        if fam == "matrix":
+            return self._matrix(e, scope, env, sizes)
+        if fam == "randomvector":
+            return self._random_vector(e, scope, env, sizes)
         raise RDDLNotImplementedError(f"Expression type {e.etype} is not supported.")
 
     def _static_tv(self, e, val: np.ndarray, scope, sizes) -> TV:
@@ -306,7 +311,7 @@ class Lowerer:
         if fam == "pvar":
             name, params = e.args
             return not (params is None and self.tr.is_object(name))
-        if fam == "aggregation" or (fam == "control" and op == "switch") \
+        if fam in ("aggregation", "matrix", "randomvector") or (fam == "control" and op == "switch") \
                 or (fam == "randomvar" and op in ("Discrete", "UnnormDiscrete")):
             return True
         return any(self._ref_full(a) for a in e.args)
@@ -625,6 +630,233 @@ class Lowerer:
         term = self._mat(self.ew("MUL", [lit, p], isz), isz)
         dv, ptr, idx, K = self._csr(term, n_outer, isz)
         return TV(self.g.reduce("RSUM", term.v, ptr, idx), dv, None)
+
+    # ---- matrix algebra and random vectors: compiler.py:2247-2434 --------------------------------
+    # The reference hands [.., n, n] blocks to jnp.linalg.  Here n is the object count of a type, known
+    # at build time, so every routine is unrolled over the matrix entries: entry (i, j) is a value over
+    # the remaining tuple axes, and det / inverse / cholesky / L z become straight-line element-wise
+    # arithmetic of the step graph (no new instruction, the adjoint comes for free).
+    MATRIX_MAX_N = 6
+
+    def _slice_axes(self, tv: TV, fixed: Dict[int, int], sizes) -> TV:
+        """``tv`` restricted to scope position p = fixed[p]; the result no longer varies over them."""
+        idx = tv.idx
+        if idx is None:
+            idx = np.arange(tv.v.n, dtype=np.int64).reshape(tuple(sizes[p] for p in tv.vars))
+        take = tuple(fixed[p] if p in fixed else slice(None) for p in tv.vars)
+        vars_ = tuple(p for p in tv.vars if p not in fixed)
+        sub = np.asarray(idx[take])
+        return TV(tv.v, vars_, sub.reshape(tuple(sizes[p] for p in vars_)), tv.full)
+
+    def _stack_axes(self, parts: Dict[Tuple[int, ...], TV], axes: Tuple[int, ...], sizes) -> TV:
+        """One value over ``axes`` + the parts' own axes whose slice at axes = key is parts[key]
+        (select chain over constant one-hot masks; entries without a part read zero)."""
+        shape = tuple(sizes[a] for a in axes)
+        order = sorted(range(len(axes)), key=lambda k: axes[k])
+        out = self.const_tv(np.float32(0.), full=True)
+        for key, part in parts.items():
+            mask = np.zeros(shape, dtype=np.int32)
+            mask[key] = 1
+            mtv = TV(self.g.const(np.transpose(mask, order).copy(), "b"),
+                     tuple(axes[k] for k in order), None, True)
+            out = self.ew("SELECT", [mtv, part, out], sizes, dtype="f")
+        return out
+
+    def _matrix_entries(self, body: TV, r_ax: int, c_ax: int, sizes):
+        n = sizes[r_ax]
+        if sizes[c_ax] != n:
+            raise RDDLNotImplementedError("matrix operations need a square matrix")
+        if n > self.MATRIX_MAX_N:
+            raise RDDLNotImplementedError(
+                f"matrix operations are unrolled over the entries: n = {n} > {self.MATRIX_MAX_N}")
+        return n, [[self._slice_axes(body, {r_ax: i, c_ax: j}, sizes) for j in range(n)] for i in range(n)]
+
+    def _minor_det(self, A, rows: Tuple[int, ...], cols: Tuple[int, ...], sizes, memo) -> TV:
+        """Determinant of the sub-matrix A[rows][cols] by cofactor expansion along its first row."""
+        key = (rows, cols)
+        if key in memo:
+            return memo[key]
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        if len(rows) == 1:
+            out = A[rows[0]][cols[0]]
+        else:
+            out = None
+            for k, c in enumerate(cols):
+                sub = self._minor_det(A, rows[1:], cols[:k] + cols[k + 1:], sizes, memo)
+                term = E("MUL", A[rows[0]][c], sub)
+                if out is None:
+                    out = term
+                else:
+                    out = E("SUB" if k % 2 else "ADD", out, term)
+        memo[key] = out
+        return out
+
+    def _inverse_entries(self, A, n: int, sizes):
+        """adj(A) / det(A), entry by entry (branch-free and differentiable; jnp.linalg.inv pivots, the
+        result is the same matrix)."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        memo: Dict = {}
+        full = tuple(range(n))
+        det = self._minor_det(A, full, full, sizes, memo)
+        if n == 1:
+            return [[E("DIV", self.const_tv(np.float32(1.)), det)]]
+        inv = [[None] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(n):
+                rows = full[:j] + full[j + 1:]
+                cols = full[:i] + full[i + 1:]
+                cof = self._minor_det(A, rows, cols, sizes, memo)
+                if (i + j) % 2:
+                    cof = E("NEG", cof)
+                inv[i][j] = E("DIV", cof, det)
+        return inv
+
+    def _cholesky_entries(self, A, n: int, sizes):
+        """Lower factor of A = L L^T (Cholesky-Banachiewicz); entries above the diagonal are zero."""
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        L = [[None] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(i + 1):
+                acc = A[i][j]
+                for k in range(j):
+                    acc = E("SUB", acc, E("MUL", L[i][k], L[j][k]))
+                L[i][j] = E("SQRT", acc) if i == j else E("DIV", acc, L[j][j])
+        return L
+
+    def _matrix(self, e, scope, env, sizes) -> TV:
+        _, op = e.etype
+        F = lambda t, sz: self.to_f(self.at_least_int(t), sz)   # noqa: E731
+        if op == "det":                               # compiler.py:2398-2407
+            *tv, body_e = e.args
+            inner = list(scope) + list(tv)
+            isz = self.sizes(inner)
+            body = F(self.lower(body_e, inner, env), isz)
+            n, A = self._matrix_entries(body, len(scope), len(scope) + 1, isz)
+            full = tuple(range(n))
+            det = self._minor_det(A, full, full, isz, {})
+            return TV(self._mat(det, isz).v, det.vars, None, True)
+        (row, col), body_e = e.args                   # compiler.py:2409-2434
+        svars = [v for v, _ in scope]
+        if row not in svars or col not in svars or row == col:
+            raise RDDLTraceError(f"{op}[row={row}, col={col}]: both must be distinct variables in scope")
+        r_ax, c_ax = svars.index(row), svars.index(col)
+        body = F(self.lower(body_e, scope, env), sizes)
+        n, A = self._matrix_entries(body, r_ax, c_ax, sizes)
+        if op == "cholesky":
+            R = self._cholesky_entries(A, n, sizes)
+        elif op == "inverse":
+            R = self._inverse_entries(A, n, sizes)
+        elif op == "pinverse":
+            # full-rank square matrices: pinv(A) = (A^T A)^-1 A^T (jnp.linalg.pinv truncates small
+            # singular values; a rank-deficient argument gives inf / nan here instead)
+            E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+
+            def dot(us, vs):
+                acc = None
+                for u, v in zip(us, vs):
+                    t = E("MUL", u, v)
+                    acc = t if acc is None else E("ADD", acc, t)
+                return acc
+            G = [[dot([A[k][i] for k in range(n)], [A[k][j] for k in range(n)]) for j in range(n)]
+                 for i in range(n)]
+            Gi = self._inverse_entries(G, n, sizes)
+            R = [[dot(Gi[i], [A[j][k] for k in range(n)]) for j in range(n)] for i in range(n)]
+        else:
+            raise RDDLNotImplementedError(f"Matrix operation {op} is not supported.")
+        parts = {(i, j): R[i][j] for i in range(n) for j in range(n) if R[i][j] is not None}
+        return self._stack_axes(parts, (r_ax, c_ax), sizes)
+
+    def _random_vector(self, e, scope, env, sizes) -> TV:
+        """compiler.py:2247-2377.  Name[?i, (?j)](args): the draw is joint over the objects of ?i."""
+        _, name = e.etype
+        svars_, *arg_es = e.args
+        names = [v for v, _ in scope]
+        if svars_[0] not in names:
+            raise RDDLTraceError(f"{name}[{svars_[0]}]: the sample variable must be in scope {names}")
+        i_ax = names.index(svars_[0])
+        n = sizes[i_ax]
+        if n > self.MATRIX_MAX_N:
+            raise RDDLNotImplementedError(f"{name} over {n} > {self.MATRIX_MAX_N} objects")
+        E = lambda nm, *x: self.ew(nm, list(x), sizes)     # noqa: E731
+        C = lambda x: self.const_tv(np.float32(x))         # noqa: E731
+        F = lambda t, sz=sizes: self.to_f(self.at_least_int(t), sz)   # noqa: E731
+        col = lambda tv, a: self._slice_axes(tv, {i_ax: a}, sizes)    # noqa: E731
+        if name in ("MultivariateNormal", "MultivariateStudent"):
+            if len(svars_) != 2:
+                raise RDDLTraceError(f"{name}[?i, ?j](mean(?i), cov(?i, ?j)[, df]): name the column variable")
+            inner = list(scope) + [(svars_[1], scope[i_ax][1])]
+            isz = self.sizes(inner)
+            mean = F(self.lower(arg_es[0], scope, env))
+            cov = self.to_f(self.at_least_int(self.lower(arg_es[1], inner, env)), isz)
+            _, Cm = self._matrix_entries(cov, i_ax, len(scope), isz)
+            # entries of cov no longer vary over ?j: they are values over the outer scope again
+            Cm = [[TV(t.v, t.vars, t.idx, t.full) for t in row] for row in Cm]
+            L = self._cholesky_entries(Cm, n, sizes)
+            Z = self._draw("normal", arg_es[0], scope, sizes) if self._ref_full(arg_es[0]) else None
+            if Z is None:
+                raise RDDLTraceError(f"{name}: the mean must vary over the sample variable")
+            if name == "MultivariateStudent":           # compiler.py:2307-2321: independent t draws
+                df = F(self.lower(arg_es[2], scope, env))
+                G = self._gamma_draw(df, arg_es[0], scope, sizes, scale=0.5)
+                self.errchk("MULTIVARIATE_STUDENT", E("LE", df, C(0.)), sizes)
+                Z = E("MUL", Z, E("SQRT", E("DIV", E("MUL", C(0.5), df), G)))
+            parts = {}
+            for a in range(n):
+                acc = col(mean, a)
+                for b in range(a + 1):
+                    acc = E("ADD", acc, E("MUL", L[a][b], col(Z, b)))
+                parts[(a,)] = acc
+            return self._stack_axes(parts, (i_ax,), sizes)
+        if name == "Dirichlet":                          # compiler.py:2331-2348
+            alpha = F(self.lower(arg_es[0], scope, env))
+            G = self._gamma_draw(alpha, arg_es[0], scope, sizes)
+            self.errchk("DIRICHLET", E("LE", alpha, C(0.)), sizes)
+            total = None
+            for a in range(n):
+                total = col(G, a) if total is None else E("ADD", total, col(G, a))
+            return self._stack_axes({(a,): E("DIV", col(G, a), total) for a in range(n)}, (i_ax,), sizes)
+        if name == "Multinomial":                        # compiler.py:2350-2377 (tfp sampler)
+            # the reference's tfp bits cannot be reproduced from supplied noise: same law from COUNT_NBINS
+            # uniforms, trial k < trials falls into category a when cum_{a-1} <= U_k < cum_a (the last
+            # category takes the remainder); counts are exact integers, no gradient (as in the reference)
+            trials = self.lower(arg_es[0], scope, env)
+            if trials.dtype == "f":
+                trials = E("F2I", trials)
+            trials = self.at_least_int(trials)
+            prob = F(self.lower(arg_es[1], scope, env))
+            if i_ax in trials.vars:
+                raise RDDLTraceError("Multinomial: trials must not vary over the sample variable")
+            cum, acc = [], None
+            for a in range(n):
+                acc = col(prob, a) if acc is None else E("ADD", acc, col(prob, a))
+                cum.append(acc)
+            if n < 2:
+                raise RDDLTraceError("Multinomial needs at least two categories")
+            bad = E("OR", E("LT", prob, C(0.)), E("ILT", trials, self.const_tv(np.int32(0), "i")))
+            bad_sum = E("GT", E("ABS", E("SUB", cum[-1], C(1.))), C(1e-5))
+            self.errchk("MULTINOMIAL", E("OR", bad, bad_sum), sizes)
+            counts = [None] * n
+            for k in range(COUNT_NBINS):
+                U = col(self._draw("uniform", arg_es[1], scope, sizes), 0)
+                live = E("ILT", self.const_tv(np.int32(k), "i"), trials)
+                below_prev = None
+                for a in range(n):
+                    below = E("LT", U, cum[a]) if a < n - 1 else None
+                    if a == 0:
+                        hit = below
+                    elif a < n - 1:
+                        hit = E("AND", below, E("NOT", below_prev))
+                    else:
+                        hit = E("NOT", below_prev)
+                    below_prev = below
+                    inc = self.at_least_int(E("AND", hit, live))
+                    counts[a] = inc if counts[a] is None else E("IADD", counts[a], inc)
+            parts = {(a,): self.to_f(counts[a], sizes) for a in range(n)}
+            out = self._stack_axes(parts, (i_ax,), sizes)
+            if self.relaxed:
+                return TV(self.g.sg(out.v), out.vars, out.idx, out.full)
+            return self.ew("F2I", [out], sizes, "i")
+        raise RDDLNotImplementedError(f"Distribution {name} is not supported.")
 
     # ---- functions: compiler.py:1354-1529 ; logic.py:346-358, 785-896 -------------------
     _UNARY_F = {"cos": "COS", "sin": "SIN", "tan": "TAN", "acos": "ACOS", "asin": "ASIN",

@@ -38,6 +38,8 @@ FUNCTIONS = {
     "cosh", "sinh", "tanh", "exp", "ln", "sqrt", "lngamma", "gamma",
     "div", "mod", "fmod", "min", "max", "pow", "log", "hypot",
 }
+MATRIX_OPS = {"inverse", "pinverse", "cholesky"}
+RANDOM_VECTORS = {"MultivariateNormal", "MultivariateStudent", "Dirichlet", "Multinomial"}
 DISTRIBUTIONS = {
     "KronDelta", "DiracDelta", "Uniform", "Bernoulli", "Normal", "Poisson", "Exponential",
     "Weibull", "Gamma", "Binomial", "NegativeBinomial", "Beta", "Geometric", "Pareto",
@@ -343,6 +345,12 @@ class _Parser:
             self.accept(",")
         return tv
 
+    def _var(self) -> str:
+        kind, v, _ = self.next()
+        if kind != "var":
+            self.error("expected ?variable")
+        return v
+
     def parse_prefix(self) -> Expr:
         kind, val, _ = self.peek()
         if kind == "num":
@@ -414,6 +422,45 @@ class _Parser:
             tv = self.parse_typed_vars()
             body = self.parse_expr()
             return Expr(("aggregation", AGGREGATIONS[m.group(1)]), [*tv, body])
+        # matrix algebra (compiler.py:2383-2434):  det_{?r : t, ?c : t}[ expr ]  and
+        # inverse / pinverse / cholesky[row=?r, col=?c][ expr ]  over two variables already in scope
+        if val == "det_" and self.peek(1)[1] == "{":
+            self.next()
+            tv = self.parse_typed_vars()
+            if len(tv) != 2:
+                self.error("det_ takes two typed variables (row, column)")
+            return Expr(("matrix", "det"), [*tv, self.parse_expr()])
+        if val in MATRIX_OPS and self.peek(1)[1] == "[":
+            self.next()
+            self.expect("[")
+            self.expect("row")
+            self.expect("=")
+            row = self._var()
+            self.expect(",")
+            self.expect("col")
+            self.expect("=")
+            col = self._var()
+            self.expect("]")
+            self.expect("[")
+            body = self.parse_expr()
+            self.expect("]")
+            return Expr(("matrix", val), [(row, col), body])
+        # random vectors (compiler.py:2247-2377):  Name[?i](args) samples jointly over the objects of ?i
+        # (a variable of the enclosing scope); a second bracket variable names the column index of a
+        # covariance argument, e.g.  MultivariateNormal[?i, ?j](mu(?i), Sigma(?i, ?j))
+        if val in RANDOM_VECTORS and self.peek(1)[1] == "[":
+            self.next()
+            self.expect("[")
+            svars = [self._var()]
+            while self.accept(","):
+                svars.append(self._var())
+            self.expect("]")
+            self.expect("(")
+            args = []
+            while not self.accept(")"):
+                args.append(self.parse_expr())
+                self.accept(",")
+            return Expr(("randomvector", val), [tuple(svars), *args])
         if val in FUNCTIONS and self.peek(1)[1] == "[":
             self.next()
             self.expect("[")

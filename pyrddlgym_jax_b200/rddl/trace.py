@@ -75,6 +75,10 @@ class Tracer:
         elif fam == "control" and op == "switch":
             pred, cases = expr.args
             r = self.is_fluent(pred) or any(self.is_fluent(e) for _, e in cases)
+        elif fam == "matrix":
+            r = self.is_fluent(expr.args[-1])
+        elif fam == "randomvector":
+            r = self.stochastic_is_fluent or any(self.is_fluent(a) for a in expr.args[1:])
         elif fam == "randomvar":
             if op in ("Discrete", "UnnormDiscrete"):
                 args = [e for _, e in expr.args[1]]
@@ -92,7 +96,7 @@ class Tracer:
         m = self.model
         for node in walk(expr):
             fam, op = node.etype
-            if fam == "randomvar" and op not in ("KronDelta", "DiracDelta"):
+            if (fam == "randomvar" and op not in ("KronDelta", "DiracDelta")) or fam == "randomvector":
                 return False
             if fam == "pvar":
                 name, params = node.args

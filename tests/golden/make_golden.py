@@ -39,6 +39,8 @@ CASES = [  # name, key, B, T, relaxed, gamma, compiler kwargs
     ("ops_relaxed", "ops", 6, 5, True, 0.9, {}),
     ("samplers_exact", "samplers", 6, 5, False, 1.0, {}),
     ("samplers_relaxed", "samplers", 6, 5, True, 1.0, {}),
+    ("matrix_exact", "matrix", 6, 5, False, 1.0, {}),
+    ("matrix_relaxed", "matrix", 6, 5, True, 0.9, {}),
     ("wildfire_relaxed_w100", "wildfire", 4, 4, True, 1.0,
      {"sigmoid_weight": 100.0, "bernoulli_sigmoid_weight": 100.0}),
 ]

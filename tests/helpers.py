@@ -29,6 +29,8 @@ FIXTURES = {
     # every operator / sampler of SURVEY Appendix G that the domains above do not use
     "ops": ("Ops_Toy", "instance1"),
     "samplers": ("Samplers_Toy", "instance1"),
+    # matrix algebra and random vectors
+    "matrix": ("Matrix_Toy", "instance1"),
 }
 
 

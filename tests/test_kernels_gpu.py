@@ -13,7 +13,7 @@ from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 pytestmark = pytest.mark.gpu
 KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
-        "distributions", "ops", "samplers"]
+        "distributions", "ops", "samplers", "matrix"]
 # 'cuda' = generic interpreter kernel, 'jit' = per-program specialised kernel (core/codegen.py)
 BACKENDS = ["cuda", "jit"]
 

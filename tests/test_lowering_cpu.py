@@ -7,7 +7,7 @@ from pyrddlgym_jax_b200.core import logic
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
-        "distributions", "ops", "samplers"]
+        "distributions", "ops", "samplers", "matrix"]
 
 
 @pytest.mark.parametrize("key", KEYS)
@@ -152,3 +152,38 @@ def test_gamma_family_with_fluent_shapes_emulated():
     check_forward(c)
     check_gradient(c)
     assert float(abs(c["grad"]).max()) > 0
+
+
+def test_matrix_and_random_vector_syntax():
+    """Parser / tracer surface of the a14 families (compiler.py:2247-2434): expression kinds, scoping of
+    the row / column / sample variables, and the rejections."""
+    from pyrddlgym_jax_b200.rddl.parser import _Parser, RDDLParseError
+    from pyrddlgym_jax_b200.rddl.expr import walk
+    e = _Parser("det_{?a : dim, ?b : dim}[ cov(?a, ?b) ] + 1.0").parse_expr()
+    kinds = [n.etype for n in walk(e)]
+    assert ("matrix", "det") in kinds and ("pvar", "cov") in kinds
+    e = _Parser("inverse[row=?i, col=?j][ cov(?i, ?j) * 2.0 ]").parse_expr()
+    assert e.etype == ("matrix", "inverse") and e.args[0] == ("?i", "?j")
+    e = _Parser("MultivariateNormal[?i, ?j](mu(?i), cov(?i, ?j))").parse_expr()
+    assert e.etype == ("randomvector", "MultivariateNormal") and e.args[0] == ("?i", "?j") and len(e.args) == 3
+    e = _Parser("Dirichlet[?i](ALPHA(?i))").parse_expr()
+    assert e.etype == ("randomvector", "Dirichlet") and e.args[0] == ("?i",)
+    with pytest.raises(RDDLParseError):
+        _Parser("det_{?a : dim}[ cov(?a, ?a) ]").parse_expr()
+    with pytest.raises(RDDLParseError):
+        _Parser("cholesky[col=?i, row=?j][ cov(?i, ?j) ]").parse_expr()
+    # lowering: row and column must be two distinct variables of the scope
+    from pyrddlgym_jax_b200.core.lowering import Lowerer, RDDLNotImplementedError
+    from pyrddlgym_jax_b200.rddl.trace import RDDLTraceError
+    from .helpers import fixture_model
+    m = fixture_model("matrix")
+    lw = Lowerer(m, None)
+    env = {}
+    scope = [("?i", "dim"), ("?j", "dim")]
+    bad = _Parser("inverse[row=?i, col=?i][ BASE(?i, ?j) ]").parse_expr()
+    with pytest.raises(RDDLTraceError):
+        lw.lower(bad, scope, env)
+    multi = _Parser("Multinomial[?i](?i, ALPHA(?i))").parse_expr()     # trials vary over the sample axis
+    with pytest.raises(RDDLTraceError):
+        lw.lower(multi, scope, env)
+    assert RDDLNotImplementedError is not None
