@@ -466,6 +466,15 @@ int rk_peer_allreduce(void* stream, int world, int rank, const uint64_t* peer_bu
                       const uint64_t* peer_flags, int n, int n_max, float* vec,
                       uint32_t* epoch_ctr, int32_t* status);
 
+/* The same exchange with a gathered tail: the message is vec[0..n) followed by n_extra (<= 4) short
+ * vectors read from their own buffers (extra_src[k], extra_len[k] floats); their sums are written to
+ * extra_dst (contiguous).  One launch carries [gradient | train loss | test loss | loop-control votes]
+ * of a planner iteration without staging copies (planner.py:3245-3262 reads exactly these). */
+int rk_peer_allreduce_gather(void* stream, int world, int rank, const uint64_t* peer_bufs,
+                             const uint64_t* peer_flags, int n, int n_max, float* vec,
+                             uint32_t* epoch_ctr, int32_t* status, int n_extra,
+                             const float* const* extra_src, const int32_t* extra_len, float* extra_dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ EXPORTS = [
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
     "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
     "rk_utility_loss", "rk_optimizer_chain_step", "rk_utility_loss_shard",
-    "rk_utility_sorted_work_bytes", "rk_utility_sorted_loss",
+    "rk_utility_sorted_work_bytes", "rk_utility_sorted_loss", "rk_peer_allreduce_gather",
 ]
 
 
@@ -114,6 +114,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_layer0_backward.restype = ci
     lib.rk_peer_allreduce.argtypes = [vp, ci, ci, vp, vp, ci, ci, cf, cf, cf]
     lib.rk_peer_allreduce.restype = ci
+    lib.rk_peer_allreduce_gather.argtypes = [vp, ci, ci, vp, vp, ci, ci, cf, cf, cf, ci, vp, vp, cf]
+    lib.rk_peer_allreduce_gather.restype = ci
     lib.rk_state_layernorm_ctas.argtypes = [ci]
     lib.rk_state_layernorm_ctas.restype = ci
     lib.rk_state_layernorm_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf]
@@ -612,6 +614,20 @@ def peer_allreduce(world: int, rank: int, peer_bufs, peer_flags, n: int, n_max: 
         _stream(), world, rank, ctypes.cast(peer_bufs, ctypes.c_void_p),
         ctypes.cast(peer_flags, ctypes.c_void_p), n, n_max, _ptr(vec), _ptr(epoch), _ptr(status)),
         "rk_peer_allreduce")
+
+
+def peer_allreduce_gather(world: int, rank: int, peer_bufs, peer_flags, n: int, n_max: int, vec, epoch,
+                          status, extras, dst):
+    """The exchange with a gathered tail: ``extras`` = short device vectors appended to the message,
+    their sums land in ``dst`` (contiguous)."""
+    k = len(extras)
+    ptrs = (ctypes.c_void_p * max(k, 1))(*[_ptr(t) for t in extras])
+    lens = (ctypes.c_int32 * max(k, 1))(*[int(t.numel()) for t in extras])
+    _check(load_library().rk_peer_allreduce_gather(
+        _stream(), world, rank, ctypes.cast(peer_bufs, ctypes.c_void_p),
+        ctypes.cast(peer_flags, ctypes.c_void_p), n, n_max, _ptr(vec), _ptr(epoch), _ptr(status), k,
+        ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(lens, ctypes.c_void_p), _ptr(dst)),
+        "rk_peer_allreduce_gather")
 
 
 def state_layernorm_ctas(B: int) -> int:

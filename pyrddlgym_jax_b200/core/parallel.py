@@ -121,6 +121,15 @@ class PeerAllReduce:
         return vec
 
 
+    def gather(self, vec: torch.Tensor, extras, dst: torch.Tensor) -> torch.Tensor:
+        """Sum all-reduce of ``vec`` (in place) and of the short vectors ``extras`` (sums -> ``dst``) as
+        ONE message and one launch."""
+        from . import engine
+        engine.peer_allreduce_gather(self.world, self.rank, self.peer_bufs, self.peer_flags, vec.numel(),
+                                     self.n_max, vec, self.epoch, self.status, list(extras), dst)
+        return vec
+
+
 def allreduce_losses(local_sums: torch.Tensor) -> torch.Tensor:
     """Sum of per-rank partial sums of returns (callers divide by the global batch)."""
     if world()[1] > 1:

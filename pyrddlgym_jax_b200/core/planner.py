@@ -1092,7 +1092,11 @@ class JaxBackpropPlanner:
         if self.optimizer_name == "adam" and self.steps_per_update <= 1:
             self.hyper[6:7].add_(1.0)
         if self.world_size > 1:
-            if self._defer_ar:          # [grad | train loss | test loss] in one message
+            if self._defer_ar and self._peer_ar is not None and self._msg.numel() <= self._peer_ar.n_max:
+                # [grad | train loss | test loss | votes] gathered by the exchange kernel itself
+                self._peer_ar.gather(self._msg[:self.n_params],
+                                     [self.train_loss, self.test_loss_buf, self.ctl_in], self._pair_ctl)
+            elif self._defer_ar:        # [grad | train loss | test loss] in one message
                 NP = self.n_params
                 self._msg[NP:NP + 1].copy_(self.train_loss)
                 self._msg[NP + 1:NP + 2].copy_(self.test_loss_buf)

@@ -20,11 +20,14 @@
 //                       TMEM accumulators (2 x N <= 512 columns).
 //   warps 2-17        : epilogue, 16 columns at a time: tcgen05.ld -> bias + activation (forward) /
 //                       * act'(H0) (backward) -> the [B][N] result to HBM (32-byte stores) -> split into
-//                       hi / lo INTO THE SAME A STAGES, from which warp 1 issues the small second product
-//                       on the tensor cores as well (forward: H1 Wh, N = 16 head columns; backward:
-//                       gz0 W0^T, N = 16 state words), accumulating in the TMEM columns the epilogue
-//                       has already drained.  Its operand (Wh^T / W0, hi | lo, 32 KB) is an image
-//                       built once per optimiser step (rk_drp_mlp2_prepare), copied in by the prologue.
+//                       the small second product.  backward: gz0 is split into hi / lo INTO THE SAME A
+//                       STAGES and warp 1 issues gz0 W0^T (N = 16 state words) on the tensor cores as
+//                       well, accumulating in the TMEM columns the epilogue has already drained; its
+//                       operand (W0, hi | lo) is an image built once per optimiser step
+//                       (rk_drp_mlp2_prepare), copied in by the prologue.  forward: the head product
+//                       H1 Wh (N <= 16 head columns) is taken in fp32 SIMT with the exact weights -- on
+//                       the tensor cores the truncated lo part of Wh shifted saturated head outputs
+//                       coherently in every row (profiles/r02_ncu_mlp2.md, "Numerics").
 //
 // Per decision epoch the hidden activations cross HBM once per direction and the exact test sweep
 // writes nothing but the head outputs.  SIMT work per hidden unit: ~14 instructions to produce, ~10 in
