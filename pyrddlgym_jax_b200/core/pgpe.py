@@ -159,6 +159,10 @@ class GaussianPGPE(PGPE):
             for p in range(pl.parallel_updates):
                 mu, sigma = self.mu[p], self.sigma[p]
                 g_mu, g_sigma = torch.zeros_like(mu), torch.zeros_like(sigma)
+                # planner.py:2045-2058: every batch member scales its gradient by the running maximum
+                # as it stood BEFORE the batch joined with its own four rewards; the maxima are merged
+                # after the batch (vmap over the members, then jnp.max)
+                r_before, r_after = self.r_max[p].clone(), self.r_max[p].clone()
                 for _b in range(self.batch_size):
                     epsilon = sigma * torch.randn(mu.shape, device=mu.device, generator=self.gen)
                     es = self.eps_star(sigma, epsilon) if self.super_symmetric else epsilon
@@ -171,10 +175,12 @@ class GaussianPGPE(PGPE):
                     if not self.super_symmetric:
                         self.loss4[2:4].copy_(self.loss4[0:2])
                     r = -self.loss4
-                    self.r_max[p:p + 1].copy_(torch.maximum(self.r_max[p], r.max()).reshape(1))
-                    gm, gs = self.grads(epsilon, es, sigma, r, self.r_max[p], ent)
+                    m_b = torch.maximum(r_before, r.max())
+                    r_after = torch.maximum(r_after, m_b)
+                    gm, gs = self.grads(epsilon, es, sigma, r, m_b, ent)
                     g_mu += gm / self.batch_size
                     g_sigma += gs / self.batch_size
+                self.r_max[p:p + 1].copy_(r_after.reshape(1))
                 old_mu, old_sigma = mu.clone(), sigma.clone()
                 state = {k: (m[p].clone(), v[p].clone()) for k, (m, v) in self.adam.items()}
                 new_mu = self._adam("mu", p, mu, g_mu, self.optimizer_kwargs_mu, self.clip_grad_mu)

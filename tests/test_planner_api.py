@@ -275,6 +275,17 @@ def test_pgpe_runs_next_to_backprop_and_can_take_over(cuda_device, plan_kind):
         assert cb["pgpe_params"] is not None
     assert took_over
     assert last["best_return"] > first["best_return"]
+    if plan_kind == "slp":
+        # batched meta-gradients (planner.py:2045-2058): every member scales by max(r_max before the
+        # batch, its own rewards); the running maximum afterwards is the maximum over the members
+        pg = GaussianPGPE(init_sigma=0.3, batch_size=3, optimizer_kwargs_mu={"learning_rate": 0.2})
+        pl = JaxBackpropPlanner(m, plan, batch_size_train=64, rollout_horizon=8, optimizer="sgd",
+                                optimizer_kwargs={"learning_rate": 0.0}, pgpe=pg)
+        seen = []
+        for cb in pl.optimize_generator(key=4, epochs=6, print_summary=False, print_progress=False):
+            assert np.isfinite(cb["pgpe_return"]).all()
+            seen.append(float(pg.r_max[0]))
+        assert all(b >= a for a, b in zip(seen, seen[1:])) and np.isfinite(seen[-1])
 
 
 @pytest.mark.gpu
