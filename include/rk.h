@@ -308,13 +308,15 @@ int rk_transpose_split(void* stream, int r, int c, const float* W, float* WT, fl
 /* Supplied-noise tensor of a program from a counter-based generator (csrc/rk_optim.cu): one launch
  * fills out[T][N * B] (draw site s = block [B][n_s] at word offset offs[s] * B of every step's row;
  * offs[n_sites] = N) with Philox4x32-10 words (key = seed, counter = (element quad, draws[0])) through the
- * site's law -- kinds: 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy.
+ * site's law -- kinds: 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy,
+ * 7 standard Gamma (Marsaglia-Tsang rejection on the element's own Philox stream; conc [N] DEVICE floats =
+ * the concentration of every noise word of a rollout, read at the gamma sites; NULL without such sites).
  * draws: device word holding the draw number (advance it with rk_noise_advance: a captured graph then
  * draws fresh noise at every replay), or NULL = 0.  kinds / offs are HOST arrays.
  * Replaces: the jax.random draws of a step's key (compiler.py:1627-2240) on the throughput path; the
  * parity tests keep supplying the noise tensor. */
 int rk_draw_noise(void* stream, int T, int B, int n_sites, const int32_t* kinds, const int32_t* offs,
-                  unsigned long long seed, const unsigned long long* draws, float* out);
+                  unsigned long long seed, const unsigned long long* draws, float* out, const float* conc);
 int rk_noise_advance(void* stream, unsigned long long* draws);
 
 /* Fused forward of a policy network with two hidden layers for one decision epoch:

@@ -160,7 +160,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_mlp2_image_floats.restype = ci
     lib.rk_drp_mlp2_prepare.argtypes = [vp, ci, ci, ci, ci, cf, cf, cf, cf]
     lib.rk_drp_mlp2_prepare.restype = ci
-    lib.rk_draw_noise.argtypes = [vp, ci, ci, ci, vp, vp, ctypes.c_ulonglong, vp, cf]
+    lib.rk_draw_noise.argtypes = [vp, ci, ci, ci, vp, vp, ctypes.c_ulonglong, vp, cf, cf]
     lib.rk_draw_noise.restype = ci
     lib.rk_drp_returns_loss.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf, cf]
     lib.rk_drp_returns_loss.restype = ci
@@ -489,18 +489,20 @@ def drp_mlp2_backward(act, B, D, h0, h1, NH, segs, gheads, H0, H1, bwd_img, W1_h
 
 
 NOISE_KINDS = {"uniform": 0, "normal": 1, "exponential": 2, "gumbel": 3, "logistic": 4, "laplace": 5,
-               "cauchy": 6}
+               "cauchy": 6, "gamma": 7}
 
 
-def draw_noise(T: int, B: int, sites, seed: int, draws: Optional[torch.Tensor], out: torch.Tensor):
+def draw_noise(T: int, B: int, sites, seed: int, draws: Optional[torch.Tensor], out: torch.Tensor,
+               conc: Optional[torch.Tensor] = None):
     """out[T][N * B] <- fresh noise of the draw sites ``sites`` = [(kind name, first word, words)], one
-    launch (Philox4x32-10 + the site's law); ``draws``: int64 device word with the draw number."""
+    launch (Philox4x32-10 + the site's law); ``draws``: int64 device word with the draw number; ``conc``:
+    [N] device floats, the Gamma concentration of every noise word (read at the gamma sites only)."""
     n = len(sites)
     kinds = (ctypes.c_int32 * n)(*[NOISE_KINDS[k] for k, _, _ in sites])
     offs = (ctypes.c_int32 * (n + 1))(*([o for _, o, _ in sites] + [sites[-1][1] + sites[-1][2]]))
     _check(load_library().rk_draw_noise(
         _stream(), T, B, n, ctypes.cast(kinds, ctypes.c_void_p), ctypes.cast(offs, ctypes.c_void_p),
-        ctypes.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), _ptr(draws), _ptr(out)), "rk_draw_noise")
+        ctypes.c_ulonglong(seed & 0xFFFFFFFFFFFFFFFF), _ptr(draws), _ptr(out), _ptr(conc)), "rk_draw_noise")
 
 
 def drp_returns_loss(T, B, reward, disc, entropy, ent_coeff, returns, ent_scratch, loss):

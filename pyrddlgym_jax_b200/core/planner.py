@@ -840,15 +840,31 @@ class JaxBackpropPlanner:
     def _draw(self, prog, T, B, out, tag: int = 0):
         """Fresh noise for every draw site of ``prog``: one Philox launch (csrc/rk_optim.cu:rk_draw_noise,
         keyed by the optimize() key, this rank and ``tag``; the draw number advances once per redraw) --
-        or, for layouts with Gamma sites and with RK_PHILOX=0, the torch-generator form the parity tests
-        use (core/layout.py:draw_noise)."""
+        or, with RK_PHILOX=0, the torch-generator form the parity tests use (core/layout.py:draw_noise)."""
         if out is None:
             return
         sites = [(kind, off, n) for kind, _, n, off, _ in prog.noise_layout]
         if self._philox and all(k in engine.NOISE_KINDS for k, _, _ in sites) and len(sites) <= 64:
-            engine.draw_noise(T, B, sites, self._noise_seed * 4 + tag, self._draws, out)
+            engine.draw_noise(T, B, sites, self._noise_seed * 4 + tag, self._draws, out,
+                              self._gamma_conc(prog))
             return
         out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
+
+    def _gamma_conc(self, prog) -> Optional[torch.Tensor]:
+        """[N] concentrations of the program's Gamma draw sites (build-time shapes), uploaded
+        once; None when the program draws no Gamma noise."""
+        cache = self.__dict__.setdefault("_conc_cache", {})
+        key = id(prog)
+        if key not in cache:
+            conc = None
+            for kind, _, n, off, extra in prog.noise_layout:
+                if kind == "gamma":
+                    if conc is None:
+                        conc = np.ones(prog.N, dtype=np.float32)
+                    conc[off:off + n] = np.maximum(
+                        np.broadcast_to(np.asarray(extra, np.float32).reshape(-1), (n,)), 1e-6)
+            cache[key] = None if conc is None else torch.from_numpy(conc).to(self.device)
+        return cache[key]
 
     # ---- the two device calls of an iteration -----------------------------------------------
     def _train_grad_kernels(self, p: int):

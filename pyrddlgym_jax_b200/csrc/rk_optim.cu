@@ -539,7 +539,7 @@ extern "C" int rk_tile_state(void* stream, int B, int n_seg, const int32_t* seg_
 #define RK_NOISE_MAX_SITES 64
 struct RkNoiseSites {
   int n;
-  int kind[RK_NOISE_MAX_SITES];        // 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy
+  int kind[RK_NOISE_MAX_SITES];        // 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy, 7 gamma
   int off[RK_NOISE_MAX_SITES + 1];     // word offsets (in units of B words); off[n] = N
 };
 
@@ -563,10 +563,43 @@ __device__ __forceinline__ void rk_philox4x32_10(uint32_t c0, uint32_t c1, uint3
   out[3] = c3;
 }
 
+// standard Gamma(alpha) by Marsaglia-Tsang rejection (alpha >= 1: d = alpha - 1/3, c = 1 / sqrt(9 d),
+// accept d v with v = (1 + c x)^3 when log u < x^2 / 2 + d - d v + d log v; alpha < 1: Gamma(alpha + 1)
+// times u^(1 / alpha)).  Every element owns a Philox stream: counter = (element, draw number, attempt),
+// key = seed ^ "gamm"; the acceptance rate is >= 0.95, the attempt loop is bounded.
+__device__ float rk_gamma_draw(long long elem, unsigned long long d, uint32_t k0, uint32_t k1, float alpha) {
+  const float a = alpha < 1.f ? alpha + 1.f : alpha;
+  const float dd = a - (1.f / 3.f), c = rsqrtf(9.f * dd);
+  float g = dd;
+  uint32_t r[4];
+  for (uint32_t attempt = 0; attempt < 64u; ++attempt) {
+    rk_philox4x32_10((uint32_t)elem, (uint32_t)(elem >> 32) ^ (attempt << 8), (uint32_t)d,
+                     (uint32_t)(d >> 32), k0 ^ 0x67616d6du, k1 + attempt, r);
+    const float u1 = ((float)(r[0] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float u2 = ((float)(r[1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float u = ((float)(r[2] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    float sn, cs;
+    sincospif(2.f * u2, &sn, &cs);
+    const float x = sqrtf(-2.f * logf(u1)) * cs;
+    const float t = 1.f + c * x;
+    if (t <= 0.f) continue;
+    const float v = t * t * t;
+    if (logf(u) < 0.5f * x * x + dd - dd * v + dd * logf(v)) {
+      g = dd * v;
+      break;
+    }
+  }
+  if (alpha < 1.f) {
+    const float ub = ((float)(r[3] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    g *= powf(ub, 1.f / alpha);
+  }
+  return g;
+}
+
 __global__ void __launch_bounds__(256)
 rk_draw_noise_kernel(long long total, long long row_words, int B, RkNoiseSites S, uint32_t seed_lo,
                      uint32_t seed_hi, const unsigned long long* __restrict__ draws,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, const float* __restrict__ conc) {
   const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i0 = quad * 4;
   if (i0 >= total) return;
@@ -602,6 +635,13 @@ rk_draw_noise_kernel(long long total, long long row_words, int B, RkNoiseSites S
       case 4: v = logf(u) - log1pf(-u); break;     // logistic
       case 5: v = (u < 0.5f) ? logf(2.f * u) : -logf(2.f * (1.f - u)); break;     // laplace
       case 6: { float sn, cs; sincospif(u - 0.5f, &sn, &cs); v = sn / cs; break; }    // cauchy
+      case 7: {                                    // gamma: word w of a rollout has concentration conc[w]
+        // fluent-major block [B][n_s]: the element's word inside the site is (c - off * B) % n_s
+        const int n_s = S.off[s + 1] - S.off[s];
+        const int ws = S.off[s] + (int)((c - (long long)S.off[s] * B) % n_s);
+        v = rk_gamma_draw(i, d, seed_lo, seed_hi, conc[ws]);
+        break;
+      }
       default: v = (float)(r[j] >> 8) * 5.9604644775390625e-8f; break;           // uniform [0, 1)
     }
     z[j] = v;
@@ -617,14 +657,15 @@ __global__ void rk_noise_advance_kernel(unsigned long long* draws) { draws[0] +=
 
 extern "C" int rk_draw_noise(void* stream, int T, int B, int n_sites, const int32_t* kinds,
                              const int32_t* offs, unsigned long long seed,
-                             const unsigned long long* draws, float* out) {
+                             const unsigned long long* draws, float* out, const float* conc) {
   if (T <= 0 || B <= 0 || n_sites <= 0 || n_sites > RK_NOISE_MAX_SITES || kinds == nullptr ||
       offs == nullptr || out == nullptr)
     return RK_E_BADARG;
   RkNoiseSites S;
   S.n = n_sites;
   for (int s = 0; s < n_sites; ++s) {
-    if (kinds[s] < 0 || kinds[s] > 6 || offs[s + 1] <= offs[s]) return RK_E_BADARG;
+    if (kinds[s] < 0 || kinds[s] > 7 || offs[s + 1] <= offs[s]) return RK_E_BADARG;
+    if (kinds[s] == 7 && conc == nullptr) return RK_E_BADARG;
     S.kind[s] = kinds[s];
     S.off[s] = offs[s];
   }
@@ -634,7 +675,7 @@ extern "C" int rk_draw_noise(void* stream, int T, int B, int n_sites, const int3
   const long long total = row_words * T;
   const long long quads = (total + 3) / 4;
   rk_draw_noise_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      total, row_words, B, S, (uint32_t)seed, (uint32_t)(seed >> 32), draws, out);
+      total, row_words, B, S, (uint32_t)seed, (uint32_t)(seed >> 32), draws, out, conc);
   return (int)cudaGetLastError();
 }
 

@@ -147,6 +147,25 @@ def test_philox_noise_laws_and_counter(cuda_device):
     c = blk(9, 1)
     assert abs(float(c.median())) < 0.05 and abs(float(c.quantile(0.75)) - 1.0) < 0.05
     assert bool(torch.isfinite(out).all())
+    # Gamma sites (kind 7): per-word concentrations, Marsaglia-Tsang rejection on per-element streams
+    from scipy import stats
+    alphas = [0.3, 1.0, 2.5, 40.0]
+    sites = [("normal", 0, 1), ("gamma", 1, 4)]
+    conc = torch.tensor([1.0] + alphas, device=cuda_device)
+    gout = torch.zeros(T, 5 * B, device=cuda_device)
+    engine.draw_noise(T, B, sites, 99, draws, gout, conc)
+    again = torch.zeros_like(gout)
+    engine.draw_noise(T, B, sites, 99, draws, again, conc)
+    assert torch.equal(gout, again) and bool(torch.isfinite(gout).all())
+    gam = gout[:, B:5 * B].double().reshape(T, B, 4).cpu()
+    for k, a in enumerate(alphas):
+        x = gam[..., k].reshape(-1)
+        assert float(x.min()) > 0.0
+        assert abs(float(x.mean()) - a) < 6.0 * math.sqrt(a / n), (a, float(x.mean()))
+        assert abs(float(x.var()) / a - 1.0) < 0.06, (a, float(x.var()))
+        ks = stats.kstest(x.numpy()[::7], "gamma", args=(a,))
+        assert ks.statistic < 0.012, (a, ks)
+    assert abs(float((gam[..., 1] * gam[..., 2]).mean()) - 1.0 * 2.5) < 0.05     # independent words
 
 
 def test_drp_returns_loss_and_transpose_split(cuda_device):
