@@ -1232,8 +1232,12 @@ def nvcc_flags(relaxed: bool = False) -> List[str]:
     it, RK_FMAD=1 forces contraction everywhere."""
     fast = relaxed and os.environ.get("RK_FAST_RELAXED", "1") != "0"
     fmad = "true" if (fast or os.environ.get("RK_FMAD", "0") == "1") else "false"
-    return ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            f"-fmad={fmad}", "-cubin"]
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+             f"-fmad={fmad}", "-cubin"]
+    cap = os.environ.get("RK_MAXREG", "")
+    if cap:                                  # A/B switch: register cap of the generated kernels
+        flags.append(f"-maxrregcount={int(cap)}")
+    return flags
 
 
 def compile_cubin(prog: Program, verbose: bool = False) -> Tuple[str, str]:

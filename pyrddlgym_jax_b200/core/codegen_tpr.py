@@ -349,6 +349,9 @@ class _GenT:
         raise NotImplementedError(op)
 
     # ---- whole kernel ---------------------------------------------------------------------------
+    def _min_blocks(self) -> str:
+        return _min_blocks_env(self.p.kind)
+
     def source(self) -> str:
         p = self.p
         lists = [self.ins[:self.n_pro], self.ins[self.n_pro:self.n_pro + self.n_step],
@@ -381,7 +384,7 @@ class _GenT:
 #include "rk_launch.h"
 #include "rk_device.cuh"
 
-extern "C" __global__ void __launch_bounds__({THREADS}) {KERNEL_NAME}(const RkLaunch K) {{
+extern "C" __global__ void __launch_bounds__({THREADS}{self._min_blocks()}) {KERNEL_NAME}(const RkLaunch K) {{
   const uint32_t lane = threadIdx.x & 31u;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // this lane's rollout
   const long long gwarp = b >> 5;
@@ -410,3 +413,15 @@ extern "C" __global__ void __launch_bounds__({THREADS}) {KERNEL_NAME}(const RkLa
 
 def generate_source(prog: Program) -> str:
     return _GenT(prog).source()
+
+
+def _min_blocks_env(kind: str) -> str:
+    """A/B switch RK_TPR_MINBLOCKS (optionally 'forward=a,backward=b'): resident CTAs per SM the register
+    allocation of a thread-per-rollout kernel has to leave room for (second __launch_bounds__ argument)."""
+    raw = os.environ.get("RK_TPR_MINBLOCKS", "")
+    if not raw:
+        return ""
+    val = raw
+    if "=" in raw:
+        val = dict(kv.split("=") for kv in raw.split(",")).get(kind, "")
+    return f", {int(val)}" if val else ""
