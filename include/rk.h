@@ -307,7 +307,7 @@ int rk_transpose_split(void* stream, int r, int c, const float* W, float* WT, fl
 
 /* Supplied-noise tensor of a program from a counter-based generator (csrc/rk_optim.cu): one launch
  * fills out[T][N * B] (draw site s = block [B][n_s] at word offset offs[s] * B of every step's row;
- * offs[n_sites] = N) with Philox4x32-10 words (key = seed, counter = (element quad, draws[0])) through the
+ * offs[n_sites] = N) with Philox4x32-10 words (key = seed, counter = (quad of the row, step, draws[0])) through the
  * site's law -- kinds: 0 uniform, 1 normal, 2 exponential, 3 gumbel, 4 logistic, 5 laplace, 6 cauchy,
  * 7 standard Gamma (Marsaglia-Tsang rejection on the element's own Philox stream; conc [N] DEVICE floats =
  * the concentration of every noise word of a rollout, read at the gamma sites; NULL without such sites).

@@ -850,6 +850,13 @@ class JaxBackpropPlanner:
             return
         out.copy_(draw_noise(prog.noise_layout, T, B, self._gen, self.device).reshape(-1))
 
+    def _philox_all(self) -> bool:
+        """Every draw site of the train and test programs is served by the counter-based kernel."""
+        def ok(prog):
+            kinds = [k for k, *_ in prog.noise_layout]
+            return all(k in engine.NOISE_KINDS for k in kinds) and len(kinds) <= 64
+        return bool(self._philox and ok(self.train_fwd.program) and ok(self.test_fwd.program))
+
     def _gamma_conc(self, prog) -> Optional[torch.Tensor]:
         """[N] concentrations of the program's Gamma draw sites (build-time shapes), uploaded
         once; None when the program draws no Gamma noise."""
@@ -1133,6 +1140,14 @@ class JaxBackpropPlanner:
         (one warp per SM sub-partition), so they overlap almost perfectly.  Results per
         iteration are identical to update-then-test (planner.py:3245-3260)."""
         P = self.parallel_updates
+        # fresh noise of this replay, drawn where it is consumed: the train tensor on the main branch
+        # (next to the optimiser step, which it does not depend on), the test tensor at the head of the
+        # test branch -- the two counter-based launches overlap instead of preceding the iteration
+        draw = getattr(self, "_draw_in_body", False)
+        if draw:
+            self._draw(self.train_fwd.program, self.T, self.batch_size_train, self.train_noise, 0)
+            if side is None:
+                self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise, 1)
         # the two small copies that publish the previous stage's loss / gradient only READ what the
         # optimiser reads, so with a side stream they leave the critical chain (K = 1 only: with
         # more updates per iteration the intermediate stages overwrite what they read)
@@ -1151,6 +1166,8 @@ class JaxBackpropPlanner:
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                if draw:
+                    self._draw(self.test_fwd.program, self.T, self.batch_size_test, self.test_noise, 1)
                 if off_chain:
                     for p in range(P):
                         self._publish_kernels(p)
@@ -1170,6 +1187,8 @@ class JaxBackpropPlanner:
         self._loss_stream = None
         if side is not None:
             main.wait_stream(side)
+        if draw:
+            engine.noise_advance(self._draws)
         self._finish_iteration()
         self._defer_ar = False
 
@@ -1210,7 +1229,12 @@ class JaxBackpropPlanner:
         inner0 = (lambda: self._pipelined_kernels(side)) if self._pipeline else self._iteration_kernels
         if self._branches and self._pipeline:
             inner0 = self._branch_kernels
-        if self._noise_in_graph:
+        self._draw_in_body = False
+        if self._noise_in_graph and self._philox_all() and self._pipeline \
+                and not (self._branches and self._pipeline):
+            self._draw_in_body = True            # the pipelined body draws its own noise (see there)
+            inner = inner0
+        elif self._noise_in_graph:
             def inner():
                 self.redraw_noise(force=True)
                 inner0()

@@ -264,8 +264,27 @@ extern "C" int rk_optimizer_step(void* stream, int kind, const float* hyper, int
 __global__ void __launch_bounds__(1024)
 rk_mean_loss_kernel(const float* __restrict__ returns, int B, float* __restrict__ loss) {
   __shared__ float sh[32];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) s += returns[i];
+  // four independent float4 streams per thread: 16 loads in flight instead of one (a single CTA summing
+  // 262144 returns took 117 us with the scalar loop); the order is fixed, so the sum is reproducible
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int done = 0;
+  if ((((uintptr_t)returns) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(returns);
+    const int n4 = B >> 2;
+    for (int i = threadIdx.x; i < n4; i += 4 * blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = i + k * blockDim.x;
+        if (j < n4) {
+          const float4 v = r4[j];
+          acc[k] += (v.x + v.y) + (v.z + v.w);
+        }
+      }
+    }
+    done = n4 << 2;
+  }
+  float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  for (int i = done + threadIdx.x; i < B; i += blockDim.x) s += returns[i];
   s = block_sum_1024(s, sh);
   if (threadIdx.x == 0) loss[0] = -s / (float)B;
 }
@@ -596,60 +615,63 @@ __device__ float rk_gamma_draw(long long elem, unsigned long long d, uint32_t k0
   return g;
 }
 
+// grid = (quads of one step's row, T): no 64-bit division per element; a quad's word index and draw site
+// are found once and advanced element by element (block [B][n_s] of site s starts at column off_s * B)
 __global__ void __launch_bounds__(256)
-rk_draw_noise_kernel(long long total, long long row_words, int B, RkNoiseSites S, uint32_t seed_lo,
-                     uint32_t seed_hi, const unsigned long long* __restrict__ draws,
-                     float* __restrict__ out, const float* __restrict__ conc) {
-  const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long i0 = quad * 4;
-  if (i0 >= total) return;
+rk_draw_noise_kernel(uint32_t row_words, int B, RkNoiseSites S, uint32_t seed_lo, uint32_t seed_hi,
+                     const unsigned long long* __restrict__ draws, float* __restrict__ out,
+                     const float* __restrict__ conc) {
+  const uint32_t qx = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  const uint32_t c0 = qx * 4u;
+  if (c0 >= row_words) return;
   const unsigned long long d = draws != nullptr ? draws[0] : 0ull;
   uint32_t r[4];
-  rk_philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)d, (uint32_t)(d >> 32), seed_lo,
-                   seed_hi, r);
+  rk_philox4x32_10(qx, t, (uint32_t)d, (uint32_t)(d >> 32), seed_lo, seed_hi, r);
+  const long long i0 = (long long)t * row_words + c0;
+  uint32_t w = c0 / (uint32_t)B, rem = c0 - w * (uint32_t)B;        // word index, rollout
+  int s = 0;
+  while (s + 1 < S.n && (int)w >= S.off[s + 1]) ++s;
   // a normal site consumes its words in pairs (Box-Muller): (r0, r1) -> elements 0, 1; (r2, r3) -> 2, 3
   float z[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const long long i = i0 + j;
-    if (i >= total) break;
-    const long long c = i % row_words;             // column inside the step's [N * B] row
-    const int w = (int)(c / B);                    // word index 0 .. N - 1
-    int s = 0;
-    while (s + 1 < S.n && w >= S.off[s + 1]) ++s;
+    if (c0 + j >= row_words) break;
     const int kind = S.kind[s];
-    const float u = ((float)(r[j] >> 8) + 0.5f) * 5.9604644775390625e-8f;      // (0, 1)
     float v;
-    switch (kind) {
-      case 1: {                                    // normal: Box-Muller on the word pair (j & ~1, j | 1)
-        const float u1 = ((float)(r[j & ~1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
-        const float u2 = ((float)(r[j | 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
-        const float rad = sqrtf(-2.f * logf(u1));
-        float sn, cs;
-        sincospif(2.f * u2, &sn, &cs);
-        v = (j & 1) ? rad * sn : rad * cs;
-        break;
+    if (kind == 0) {                               // uniform [0, 1)
+      v = (float)(r[j] >> 8) * 5.9604644775390625e-8f;
+    } else if (kind == 1) {                        // normal: Box-Muller on the word pair (j & ~1, j | 1)
+      const float u1 = ((float)(r[j & ~1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+      const float u2 = ((float)(r[j | 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+      const float rad = sqrtf(-2.f * logf(u1));
+      float sn, cs;
+      sincospif(2.f * u2, &sn, &cs);
+      v = (j & 1) ? rad * sn : rad * cs;
+    } else if (kind == 7) {                        // gamma: word of the site -> its concentration
+      const uint32_t n_s = (uint32_t)(S.off[s + 1] - S.off[s]);
+      const uint32_t within = (c0 + j) - (uint32_t)S.off[s] * (uint32_t)B;
+      v = rk_gamma_draw(i0 + j, d, seed_lo, seed_hi, conc[S.off[s] + (int)(within % n_s)]);
+    } else {
+      const float u = ((float)(r[j] >> 8) + 0.5f) * 5.9604644775390625e-8f;      // (0, 1)
+      switch (kind) {
+        case 2: v = -log1pf(-u); break;              // exponential
+        case 3: v = -logf(-logf(u)); break;          // gumbel
+        case 4: v = logf(u) - log1pf(-u); break;     // logistic
+        case 5: v = (u < 0.5f) ? logf(2.f * u) : -logf(2.f * (1.f - u)); break;     // laplace
+        default: { float sn, cs; sincospif(u - 0.5f, &sn, &cs); v = sn / cs; break; }    // cauchy
       }
-      case 2: v = -log1pf(-u); break;              // exponential
-      case 3: v = -logf(-logf(u)); break;          // gumbel
-      case 4: v = logf(u) - log1pf(-u); break;     // logistic
-      case 5: v = (u < 0.5f) ? logf(2.f * u) : -logf(2.f * (1.f - u)); break;     // laplace
-      case 6: { float sn, cs; sincospif(u - 0.5f, &sn, &cs); v = sn / cs; break; }    // cauchy
-      case 7: {                                    // gamma: word w of a rollout has concentration conc[w]
-        // fluent-major block [B][n_s]: the element's word inside the site is (c - off * B) % n_s
-        const int n_s = S.off[s + 1] - S.off[s];
-        const int ws = S.off[s] + (int)((c - (long long)S.off[s] * B) % n_s);
-        v = rk_gamma_draw(i, d, seed_lo, seed_hi, conc[ws]);
-        break;
-      }
-      default: v = (float)(r[j] >> 8) * 5.9604644775390625e-8f; break;           // uniform [0, 1)
     }
     z[j] = v;
+    if (++rem == (uint32_t)B) {                    // next word of the row (maybe the next site)
+      rem = 0;
+      ++w;
+      if (s + 1 < S.n && (int)w >= S.off[s + 1]) ++s;
+    }
   }
-  if (i0 + 3 < total && (((uintptr_t)(out + i0)) & 15) == 0) {
+  if (c0 + 3 < row_words && (((uintptr_t)(out + i0)) & 15) == 0) {
     *reinterpret_cast<float4*>(out + i0) = make_float4(z[0], z[1], z[2], z[3]);
   } else {
-    for (int j = 0; j < 4 && i0 + j < total; ++j) out[i0 + j] = z[j];
+    for (int j = 0; j < 4 && c0 + j < row_words; ++j) out[i0 + j] = z[j];
   }
 }
 
@@ -672,10 +694,11 @@ extern "C" int rk_draw_noise(void* stream, int T, int B, int n_sites, const int3
   if (offs[0] != 0) return RK_E_BADARG;
   S.off[n_sites] = offs[n_sites];
   const long long row_words = (long long)offs[n_sites] * B;
-  const long long total = row_words * T;
-  const long long quads = (total + 3) / 4;
-  rk_draw_noise_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      total, row_words, B, S, (uint32_t)seed, (uint32_t)(seed >> 32), draws, out, conc);
+  if (row_words >= (1ll << 31) || T > 65535) return RK_E_BADARG;
+  const unsigned quads = (unsigned)((row_words + 3) / 4);
+  dim3 grid((quads + 255) / 256, (unsigned)T);
+  rk_draw_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (uint32_t)row_words, B, S, (uint32_t)seed, (uint32_t)(seed >> 32), draws, out, conc);
   return (int)cudaGetLastError();
 }
 
