@@ -187,7 +187,7 @@ int rk_sgemm(void* stream, int flags, int M, int N, int K, const float* A, int l
  * Replaces: DRPStateLayer + the first nn.Dense (planner.py:1287-1319, 1358-1361). */
 int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg, const int32_t* seg_off,
                   const int32_t* seg_len, const float* x, const float* W0, const float* b0,
-                  float* out, float* xp);
+                  float* out, float* xp, int act);
 /* Bias gradients: y[N] (+)= sum_b G[b][n], deterministic two-stage sum through
  * workspace[chunks][N]. */
 int rk_colsum(void* stream, int B, int N, const float* G, int ldg, float* y, int accumulate,
@@ -200,7 +200,7 @@ int rk_colsum(void* stream, int B, int N, const float* G, int ldg, float* y, int
  * Replaces: the VJP of the head nn.Dense + the last tanh (planner.py:1397-1421). */
 int rk_drp_head_backward_ctas(int B);
 int rk_drp_head_backward(void* stream, int B, int hl, int NH, const float* Hl, const float* G,
-                         const float* Wh, float* gz, float* grad_tail, float* workspace);
+                         const float* Wh, float* gz, float* grad_tail, float* workspace, int act);
 /* Backward of the first layer (D <= 16) in two passes over gz0 [B][H]:
  *   grad_W0b0 = [dW0 (D x H) | db0 (H)] += batch sums of x^T gz0 and gz0;
  *   gs (fluent-major state cotangent) += gz0 W0T, W0T = the transposed kernel [H][D].
@@ -233,13 +233,13 @@ int rk_state_scale_forward(void* stream, int B, int D, int n_seg, const int32_t*
 int rk_state_scale_backward(void* stream, int B, int D, int n_seg, const int32_t* seg_off,
                             const int32_t* seg_len, const float* lo, const float* hi,
                             const float* gy, float* gx);
-/* Hidden-layer activation of the DRP kernels (planner.py:1128, 1358-1361): 0 tanh (default), 1 relu,
- * 2 sigmoid, 3 softplus, 4 elu, 5 leaky_relu(0.01) -- the jax.nn functions whose derivative is a function
- * of the output, so the adjoints need only the stored activation.  Process-wide; every launcher of a
- * kernel with a fused activation (rk_sgemm / rk_tcgemm bias+activation and activation-adjoint epilogues,
- * rk_drp_layer0, rk_drp_head_backward, rk_film_backward) reads it at launch and passes it to the kernel,
- * so a captured CUDA graph keeps the value it was captured with. */
-int rk_drp_set_activation(int act);
+/* Hidden-layer activation ids of the DRP kernels (planner.py:1128, 1358-1361): 0 tanh, 1 relu, 2 sigmoid,
+ * 3 softplus, 4 elu, 5 leaky_relu(0.01) -- the jax.nn functions whose derivative is a function of the
+ * output, so the adjoints need only the stored activation.  The id is a LAUNCH ARGUMENT of every kernel
+ * with a fused activation: bits 8..15 of the `flags` word of rk_sgemm and of the `epi` word of rk_tcgemm
+ * (RK_ACT(id)), the `act` argument of rk_drp_layer0 / rk_drp_head_backward / rk_film_backward /
+ * rk_drp_mlp2_*.  The library keeps no process state: calls are re-entrant per stream. */
+#define RK_ACT(id) ((id) << 8)
 /* FiLM time conditioning of a hidden layer (planner.py:1083-1092, 1362-1363):
  * out[b][c] = gamma[c] z[b][c] + beta[c], gamma / beta [H] = the two Dense(time embedding) vectors of
  * the decision epoch.  backward: g = cotangent of out, z = the tanh output it was applied to;
@@ -249,7 +249,7 @@ int rk_film_chunks(int B);
 int rk_film_forward(void* stream, int B, int H, const float* z, const float* gamma,
                     const float* beta, float* out);
 int rk_film_backward(void* stream, int B, int H, const float* g, const float* z,
-                     const float* gamma, float* gz, float* grad_gamma_beta, float* workspace);
+                     const float* gamma, float* gz, float* grad_gamma_beta, float* workspace, int act);
 /* Skinny products with N <= 16 (action heads, state-cotangent blocks), A read exactly once:
  * out[b][n] = (accumulate ? out : 0) + sum_k A[b][k] W[k][n] (+ bias[n]). */
 int rk_rowdot(void* stream, int accumulate, int B, int N, int K, const float* A, int lda,

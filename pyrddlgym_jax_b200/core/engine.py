@@ -28,7 +28,7 @@ EXPORTS = [
     "rk_drp_head_backward_ctas", "rk_drp_layer0_backward", "rk_peer_allreduce",
     "rk_state_layernorm_ctas", "rk_state_layernorm_forward", "rk_state_layernorm_backward",
     "rk_drp_topk_limits", "rk_drp_topk_forward", "rk_drp_topk_backward",
-    "rk_film_chunks", "rk_film_forward", "rk_film_backward", "rk_drp_set_activation",
+    "rk_film_chunks", "rk_film_forward", "rk_film_backward",
     "rk_state_scale_forward", "rk_state_scale_backward", "rk_drp_mlp2_forward",
     "rk_drp_mlp2_backward", "rk_drp_mlp2_image_floats", "rk_drp_mlp2_prepare", "rk_drp_mlp2_set_timing",
     "rk_drp_wgrad_ctas", "rk_drp_wgrad_hidden", "rk_drp_wgrad_heads", "rk_drp_wgrad_input",
@@ -104,11 +104,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_drp_actions_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, cf, cf, fl, cf, cf, fl,
                                             fl, fl, cf, fl, ci, cf, cf]
     lib.rk_drp_actions_backward.restype = ci
-    lib.rk_drp_layer0.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf]
+    lib.rk_drp_layer0.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf, ci]
     lib.rk_drp_layer0.restype = ci
     lib.rk_drp_head_backward_ctas.argtypes = [ci]
     lib.rk_drp_head_backward_ctas.restype = ci
-    lib.rk_drp_head_backward.argtypes = [vp, ci, ci, ci, cf, cf, cf, cf, cf, cf]
+    lib.rk_drp_head_backward.argtypes = [vp, ci, ci, ci, cf, cf, cf, cf, cf, cf, ci]
     lib.rk_drp_head_backward.restype = ci
     lib.rk_drp_layer0_backward.argtypes = [vp, ci, ci, ci, ci, vp, vp, cf, cf, cf, cf, cf, cf]
     lib.rk_drp_layer0_backward.restype = ci
@@ -126,13 +126,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_state_scale_forward.restype = ci
     lib.rk_state_scale_backward.argtypes = [vp, ci, ci, ci, vp, vp, cf, cf, cf, cf]
     lib.rk_state_scale_backward.restype = ci
-    lib.rk_drp_set_activation.argtypes = [ci]
-    lib.rk_drp_set_activation.restype = ci
     lib.rk_film_chunks.argtypes = [ci]
     lib.rk_film_chunks.restype = ci
     lib.rk_film_forward.argtypes = [vp, ci, ci, cf, cf, cf, cf]
     lib.rk_film_forward.restype = ci
-    lib.rk_film_backward.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf]
+    lib.rk_film_backward.argtypes = [vp, ci, ci, cf, cf, cf, cf, cf, cf, ci]
     lib.rk_film_backward.restype = ci
     lib.rk_drp_topk_limits.argtypes = [vp, vp]
     lib.rk_drp_topk_limits.restype = ci
@@ -328,8 +326,8 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_DTANH = 0 << 4, 1 << 4, 2 << 4, 3 << 4
 
 
 def sgemm(flags: int, M: int, N: int, K: int, A, lda: int, Bm, ldb: int, C, ldc: int, bias=None,
-          aux=None, ldaux: int = 0, workspace=None, split_k: int = 1):
-    _check(load_library().rk_sgemm(_stream(), flags, M, N, K, _ptr(A), lda, _ptr(Bm), ldb,
+          aux=None, ldaux: int = 0, workspace=None, split_k: int = 1, act=None):
+    _check(load_library().rk_sgemm(_stream(), flags | (_act_id(act) << 8), M, N, K, _ptr(A), lda, _ptr(Bm), ldb,
                                    _ptr(C), ldc, _ptr(bias), _ptr(aux), ldaux, _ptr(workspace),
                                    split_k), "rk_sgemm")
 
@@ -390,9 +388,18 @@ def state_scale(B, D, segs, lo, hi, x, y, backward: bool = False):
 ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "elu": 4, "leaky_relu": 5}
 
 
+_ACT = 0
+
+
 def drp_set_activation(name: str) -> None:
-    """Hidden-layer activation read by the DRP kernels' launchers (see include/rk.h)."""
-    _check(load_library().rk_drp_set_activation(ACTIVATIONS[name]), "rk_drp_set_activation")
+    """Default hidden-layer activation of the wrappers below (a host-side convenience of this binding: the
+    library itself takes the activation id as an argument of every launch, include/rk.h)."""
+    global _ACT
+    _ACT = ACTIVATIONS[name]
+
+
+def _act_id(act) -> int:
+    return _ACT if act is None else (ACTIVATIONS[act] if isinstance(act, str) else int(act))
 
 
 def film_chunks(B: int) -> int:
@@ -404,9 +411,9 @@ def film_forward(B, H, z, gamma, beta, out):
                                           _ptr(out)), "rk_film_forward")
 
 
-def film_backward(B, H, g, z, gamma, gz, grad_gamma_beta, workspace):
+def film_backward(B, H, g, z, gamma, gz, grad_gamma_beta, workspace, act=None):
     _check(load_library().rk_film_backward(_stream(), B, H, _ptr(g), _ptr(z), _ptr(gamma), _ptr(gz),
-                                           _ptr(grad_gamma_beta), _ptr(workspace)),
+                                           _ptr(grad_gamma_beta), _ptr(workspace), _act_id(act)),
            "rk_film_backward")
 
 
@@ -448,9 +455,9 @@ def tf32_split(x: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, n: Optional[
 
 
 def tcgemm(epi: int, M: int, N: int, K: int, A, lda: int, Bt_hi, Bt_lo, ldb: int, C,
-           ldc: int, bias=None, aux=None, ldaux: int = 0):
+           ldc: int, bias=None, aux=None, ldaux: int = 0, act=None):
     """Tensor-core (tcgen05, 3xTF32) C = epi(A * Bt^T); epi as EPI_* >> 4."""
-    _check(load_library().rk_tcgemm(_stream(), epi, M, N, K, _ptr(A), lda,
+    _check(load_library().rk_tcgemm(_stream(), epi | (_act_id(act) << 8), M, N, K, _ptr(A), lda,
                                     _ptr(Bt_hi), _ptr(Bt_lo), ldb, _ptr(C), ldc, _ptr(bias),
                                     _ptr(aux), ldaux), "rk_tcgemm")
 
@@ -584,21 +591,21 @@ def drp_wgrad_input(accumulate, M, D, T, Bt, S_words, segs, gz0, x_tape, dW0, db
         _ptr(workspace)), "rk_drp_wgrad_input")
 
 
-def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None):
+def drp_layer0(B, D, H, segs, x, W0, b0, out, xp=None, act=None):
     n, off, ln = _segs(segs)
     _check(load_library().rk_drp_layer0(
         _stream(), B, D, H, n, ctypes.cast(off, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p),
-        _ptr(x), _ptr(W0), _ptr(b0), _ptr(out), _ptr(xp)), "rk_drp_layer0")
+        _ptr(x), _ptr(W0), _ptr(b0), _ptr(out), _ptr(xp), _act_id(act)), "rk_drp_layer0")
 
 
 def drp_head_backward_ctas(B: int) -> int:
     return int(load_library().rk_drp_head_backward_ctas(int(B)))
 
 
-def drp_head_backward(B, hl, NH, Hl, G, Wh, gz, grad_tail, workspace):
+def drp_head_backward(B, hl, NH, Hl, G, Wh, gz, grad_tail, workspace, act=None):
     _check(load_library().rk_drp_head_backward(
         _stream(), B, hl, NH, _ptr(Hl), _ptr(G), _ptr(Wh), _ptr(gz), _ptr(grad_tail),
-        _ptr(workspace)), "rk_drp_head_backward")
+        _ptr(workspace), _act_id(act)), "rk_drp_head_backward")
 
 
 def drp_layer0_backward(B, D, H, segs, x, gz0, W0, gs, grad_W0b0, workspace):

@@ -12,7 +12,6 @@
 #define RK_ACT_LEAKY_RELU 5
 #define RK_ACT_COUNT 6
 
-extern int g_rk_act;
 
 __device__ __forceinline__ float rk_act_fn(int act, float x) {
   switch (act) {

@@ -18,15 +18,10 @@
 #include "../../include/rk.h"
 #include "rk_act.cuh"
 
-// hidden-layer activation of the DRP kernels (rk_drp_set_activation); read by every launcher and
-// passed to its kernel as an argument, so a captured graph keeps the value it was captured with
-int g_rk_act = RK_ACT_TANH;
-
-extern "C" int rk_drp_set_activation(int act) {
-  if (act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
-  g_rk_act = act;
-  return 0;
-}
+// The hidden-layer activation (rk_act.cuh ids) is an argument of every launcher -- bits 8..15 of the
+// flags / epi word of the GEMMs, an explicit `act` elsewhere -- and of every kernel, so the library keeps
+// no process state: calls are re-entrant per stream and a captured graph keeps its own value.
+static inline bool rk_act_ok(int act) { return act >= 0 && act < RK_ACT_COUNT; }
 
 #define BM 128
 #define BN 128
@@ -253,6 +248,8 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
     return RK_E_BADARG;
   const int a_trans = flags & RK_GEMM_A_TRANS, accumulate = (flags & RK_GEMM_ACCUMULATE) ? 1 : 0;
   const int epi = (flags >> 4) & 0xf;
+  const int act_id = (flags >> 8) & 0xff;          // activation id of the tanh-family epilogues
+  if (!rk_act_ok(act_id)) return RK_E_BADARG;
   if (epi > 3 || ((epi == 1 || epi == 2) && bias == nullptr) || (epi == 3 && aux == nullptr))
     return RK_E_BADARG;
   // tile shape: skinny variants when one output dimension is <= 16
@@ -276,13 +273,13 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   // the tanh build of each kernel has the activation as a compile-time constant
 #define RK_LAUNCH(KERNEL, ...)                                                                \
   do {                                                                                        \
-    if (g_rk_act == RK_ACT_TANH)                                                              \
+    if (act_id == RK_ACT_TANH)                                                              \
       KERNEL<__VA_ARGS__, RK_ACT_TANH><<<grid, 256, 0, st>>>(                                 \
           M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi, accumulate, kchunk,         \
           workspace);                                                                         \
     else                                                                                      \
       KERNEL<__VA_ARGS__, -1><<<grid, 256, 0, st>>>(                                          \
-          M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi | (g_rk_act << 8),           \
+          M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, epi | (act_id << 8),           \
           accumulate, kchunk, workspace);                                                     \
   } while (0)
   if (bn == 16) {
@@ -299,7 +296,7 @@ extern "C" int rk_sgemm(void* stream, int flags, int M, int N, int K, const floa
   if (splits > 1) {
     const size_t total = (size_t)M * N;
     rk_sgemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        M, N, splits, workspace, C, ldc, bias, aux, ldaux, epi | (g_rk_act << 8), accumulate);
+        M, N, splits, workspace, C, ldc, bias, aux, ldaux, epi | (act_id << 8), accumulate);
   }
   return (int)cudaGetLastError();
 }
@@ -815,22 +812,23 @@ rk_drp_layer0_cols_kernel(int B, int D, int H, RkActSegs S, const float* __restr
 
 extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
                              const int32_t* seg_off, const int32_t* seg_len, const float* x,
-                             const float* W0, const float* b0, float* out, float* xp) {
+                             const float* W0, const float* b0, float* out, float* xp, int act) {
   if (B <= 0 || D <= 0 || H <= 0 || x == nullptr || W0 == nullptr || b0 == nullptr ||
-      out == nullptr)
+      out == nullptr || !rk_act_ok(act))
     return RK_E_BADARG;
+  const int act_id = act;
   RkActSegs S;
   int rc = make_segs(D, n_seg, seg_off, seg_len, &S);
   if (rc != 0) return rc;
   if (D < 16 && H <= 256) {       // (D < 16: slot D of a tile row carries the packed 1)
     int grid = (B + 63) / 64;
     if (grid > 148 * 4) grid = 148 * 4;
-    if (g_rk_act == RK_ACT_TANH)
+    if (act_id == RK_ACT_TANH)
       rk_drp_layer0_cols_kernel<RK_ACT_TANH><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+          B, D, H, S, x, W0, b0, out, xp, act_id);
     else
       rk_drp_layer0_cols_kernel<-1><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+          B, D, H, S, x, W0, b0, out, xp, act_id);
     return (int)cudaGetLastError();
   }
   const size_t smem = ((size_t)D * H + 64 * (size_t)D) * sizeof(float);
@@ -843,12 +841,12 @@ extern "C" int rk_drp_layer0(void* stream, int B, int D, int H, int n_seg,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
   }
-  if (g_rk_act == RK_ACT_TANH)
+  if (act_id == RK_ACT_TANH)
     rk_drp_layer0_kernel<RK_ACT_TANH><<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(
-        B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+        B, D, H, S, x, W0, b0, out, xp, act_id);
   else
     rk_drp_layer0_kernel<-1><<<(B + 63) / 64, 256, smem, (cudaStream_t)stream>>>(
-        B, D, H, S, x, W0, b0, out, xp, g_rk_act);
+        B, D, H, S, x, W0, b0, out, xp, act_id);
   return (int)cudaGetLastError();
 }
 
@@ -961,15 +959,16 @@ extern "C" int rk_film_forward(void* stream, int B, int H, const float* z, const
 
 extern "C" int rk_film_backward(void* stream, int B, int H, const float* g, const float* z,
                                 const float* gamma, float* gz, float* grad_gamma_beta,
-                                float* workspace) {
+                                float* workspace, int act) {
   if (B <= 0 || H <= 0 || g == nullptr || z == nullptr || gamma == nullptr || gz == nullptr ||
-      grad_gamma_beta == nullptr || workspace == nullptr)
+      grad_gamma_beta == nullptr || workspace == nullptr || !rk_act_ok(act))
     return RK_E_BADARG;
+  const int act_id = act;
   const int chunks = rk_film_chunks(B);
   const int rpc = (B + chunks - 1) / chunks;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((H + 31) / 32, chunks);
-  rk_film_bwd_kernel<<<grid, 256, 0, st>>>(B, H, rpc, g, z, gamma, gz, workspace, g_rk_act);
+  rk_film_bwd_kernel<<<grid, 256, 0, st>>>(B, H, rpc, g, z, gamma, gz, workspace, act_id);
   rk_add_rows_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(chunks, 2 * H, workspace,
                                                           grad_gamma_beta, 1);
   return (int)cudaGetLastError();
@@ -1097,22 +1096,23 @@ extern "C" int rk_drp_head_backward_ctas(int B) {     // row chunks of the fused
 
 extern "C" int rk_drp_head_backward(void* stream, int B, int hl, int NH, const float* Hl,
                                     const float* G, const float* Wh, float* gz, float* grad_tail,
-                                    float* workspace) {
+                                    float* workspace, int act) {
   if (B <= 0 || hl <= 0 || hl > 1024 || NH <= 0 || NH > 16 || Hl == nullptr || G == nullptr ||
-      Wh == nullptr || gz == nullptr || grad_tail == nullptr || workspace == nullptr)
+      Wh == nullptr || gz == nullptr || grad_tail == nullptr || workspace == nullptr || !rk_act_ok(act))
     return RK_E_BADARG;
+  const int act_id = act;
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks0 = rk_drp_head_backward_ctas(B);
   const int rpc = (B + chunks0 - 1) / chunks0;
   const int chunks = (B + rpc - 1) / rpc;
   dim3 grid((hl + 31) / 32, chunks);
   const size_t smem = (size_t)rpc * 16 * sizeof(float);     // <= 256 rows x 64 B
-  if (g_rk_act == RK_ACT_TANH)
+  if (act_id == RK_ACT_TANH)
     rk_drp_head_bwd_kernel<RK_ACT_TANH><<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace,
-                                                                 rpc, g_rk_act);
+                                                                 rpc, act_id);
   else
     rk_drp_head_bwd_kernel<-1><<<grid, 256, smem, st>>>(B, hl, NH, Hl, G, Wh, gz, workspace, rpc,
-                                                        g_rk_act);
+                                                        act_id);
   const int n = hl + hl * NH + NH;
   rk_add_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(chunks, n, workspace, grad_tail, 1);
   return (int)cudaGetLastError();

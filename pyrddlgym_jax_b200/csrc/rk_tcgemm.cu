@@ -409,6 +409,9 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
                          const float* bias, const float* aux, int ldaux) {
   if (M <= 0 || A == nullptr || Bt_hi == nullptr || Bt_lo == nullptr || C == nullptr)
     return RK_E_BADARG;
+  const int act_id = (epi >> 8) & 0xff;              // activation id of the epilogue (rk_act.cuh)
+  epi &= 0xff;
+  if (act_id < 0 || act_id >= RK_ACT_COUNT) return RK_E_BADARG;
   if (N < 32 || N > 256 || (N % 32) != 0 || K < TC_BK || (K % TC_BK) != 0) return RK_E_BADARG;
   if ((lda % 4) != 0 || (ldb % 4) != 0 || (ldc % 4) != 0) return RK_E_BADARG;
   if (epi < 0 || epi > 3 || ((epi == 1 || epi == 2) && bias == nullptr) ||
@@ -434,12 +437,12 @@ extern "C" int rk_tcgemm(void* stream, int epi, int M, int N, int K, const float
   }
   uint32_t cols = 32;
   while ((int)cols < N) cols <<= 1;
-  if (g_rk_act == RK_ACT_TANH)
+  if (act_id == RK_ACT_TANH)
     rk_tcgemm_kernel<RK_ACT_TANH><<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
-        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
+        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, act_id);
   else
     rk_tcgemm_kernel<-1><<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, (cudaStream_t)stream>>>(
-        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, g_rk_act);
+        mA, mBh, mBl, M, N, K, epi, C, ldc, bias, aux, ldaux, cols, act_id);
   return (int)cudaGetLastError();
 }
 

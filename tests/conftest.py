@@ -22,7 +22,7 @@ def cuda_device():
 
 @pytest.fixture(autouse=True)
 def _tanh_after_each_test():
-    """The DRP kernels' activation is process-wide (rk_drp_set_activation): tests that select
+    """The binding's default activation is a module variable (engine.drp_set_activation; the library itself takes the id per launch): tests that select
     another one must not leak it into kernel-level tests that expect tanh epilogues."""
     yield
     mod = sys.modules.get("pyrddlgym_jax_b200.core.engine")
