@@ -374,7 +374,8 @@ def drp_input_order(model) -> List[str]:
     """Order in which observed fluents enter the state vector (planner.py:1302-1313): the
     fluent dict crosses a jit boundary, so it iterates in sorted-key order; non-bool fluents
     first, then bool ones."""
-    names = sorted(model.state_fluents)
+    # partially observed models: the observ-fluents only (their carried copies in the observation view)
+    names = sorted(getattr(model, "observed_inputs", None) or model.state_fluents)
     return [v for v in names if model.variable_ranges[v] != "bool"] + \
            [v for v in names if model.variable_ranges[v] == "bool"]
 

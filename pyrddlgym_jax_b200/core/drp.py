@@ -157,8 +157,14 @@ class JaxDeepReactivePolicy(JaxPlan):
                 (4 if bool(np.ravel(np.asarray(rddl.action_fluents[v]))[0]) else 3)
                 if prange == "bool" else k
                 for k, (v, (_, _, prange)) in zip(self.action_kinds, self.layout.items())]
-        if rddl.observ_fluents:
-            raise NotImplementedError("DRP over observ-fluents (POMDP) is not built yet")
+        # partially observed models (planner.py:1300-1313: the policy reads the observ-fluents only): the
+        # planner hands over rddl.model.observation_view, where every observ-fluent has a carried copy in
+        # the state vector; the copies are the network's inputs, the hidden state words keep structurally
+        # zero first-layer rows (no initial weight, no gradient, absent from the parameter pytree)
+        if rddl.observ_fluents and not getattr(rddl, "observed_inputs", None):
+            raise ValueError("a partially observed model needs rddl.model.observation_view(model) "
+                             "(JaxBackpropPlanner applies it)")
+        inputs = list(getattr(rddl, "observed_inputs", None) or rddl.state_fluents)
         bounds = {}
         for name, (_, _, prange) in self.layout.items():
             shape = rddl.variable_shape(name)
@@ -186,10 +192,13 @@ class JaxDeepReactivePolicy(JaxPlan):
         # exact-model state words of bool / int fluents are int32: converted before the first layer
         self.state_is_int = [rddl.variable_ranges[v] != "real" for v in rddl.state_fluents]
         self.action_segs = [(o, n) for (o, n, _) in self.layout.values()]
-        names = sorted(rddl.state_fluents)
+        names = sorted(inputs)
         ref = [v for v in names if rddl.variable_ranges[v] != "bool"] + \
               [v for v in names if rddl.variable_ranges[v] == "bool"]
         self.input_perm = np.concatenate([np.arange(pos[v][0], pos[v][0] + pos[v][1]) for v in ref])
+        self.D_in = int(len(self.input_perm))
+        # word ranges of the state vector the network must not look at (hidden state of a POMDP)
+        self.frozen_segs = [pos[v] for v in rddl.state_fluents if v not in inputs]
         # optional state preprocessing before everything else (planner.py:1293-1296): per state word
         # (x - lo) / (hi - lo); words without stats keep lo = 0, hi = 1
         self.pre_lo = self.pre_hi = None
@@ -198,7 +207,7 @@ class JaxDeepReactivePolicy(JaxPlan):
             stats = preprocessor.initialize()
             lo_w, hi_w = np.zeros(self.D, np.float32), np.ones(self.D, np.float32)
             for v, (lower, upper) in stats.items():
-                o, n = pos[v]
+                o, n = pos[v] if v in pos else pos[v + "@seen"]
                 shape = rddl.variable_shape(v)
                 lo_w[o:o + n] = np.broadcast_to(lower, shape).reshape(-1)
                 hi_w[o:o + n] = np.broadcast_to(upper, shape).reshape(-1)
@@ -281,13 +290,18 @@ class JaxDeepReactivePolicy(JaxPlan):
         flat = torch.zeros(self.n_params)
         for name, off, r, c in self.segments:
             if name.startswith("W"):
+                rows = self.D_in if name == "W0" else r        # fan-in = the inputs the policy sees
                 if self._initializer_base is not None:
-                    w = self._initializer_base((r, c), generator)
+                    w = self._initializer_base((rows, c), generator)
                 else:
-                    std = math.sqrt(2.0 / r) / 0.87962566103423978
-                    w = torch.empty(r, c)
+                    std = math.sqrt(2.0 / rows) / 0.87962566103423978
+                    w = torch.empty(rows, c)
                     torch.nn.init.trunc_normal_(w, mean=0., std=1., a=-2., b=2., generator=generator)
                     w = w * std
+                if rows != r:                                   # hidden state words: zero rows
+                    full = torch.zeros(r, c)
+                    full[torch.as_tensor(np.sort(self.input_perm))] = w
+                    w = full
                 flat[off:off + r * c] = w.reshape(-1)
             elif name == "ln_scale":
                 flat[off:off + c] = 1.0
@@ -356,9 +370,9 @@ class JaxDeepReactivePolicy(JaxPlan):
             flat[sb + idx] = as_t(tree["inputs"][name]["bias"]).reshape(-1)
         for i in range(len(self._topology)):
             off, r, c = self.seg[f"W{i}"]
-            W = as_t(tree[f"dense_{i}"]["kernel"]).reshape(r, c)
+            W = as_t(tree[f"dense_{i}"]["kernel"]).reshape(-1, c)
             if i == 0:
-                Wi = torch.empty_like(W)
+                Wi = torch.zeros(r, c)
                 Wi[torch.as_tensor(self.input_perm)] = W
                 W = Wi
             flat[off:off + r * c] = W.reshape(-1)
@@ -925,6 +939,12 @@ class DrpPipeline:
             self.wgrad_all(grad, self.xn if self.Dn else (self.xa if self.pre else self.tape))
         if self.film:
             self.film_param_grads(params, grad, emb)
+        if plan.frozen_segs:
+            # hidden state words of a partially observed model: their first-layer rows are structural
+            # zeros, not parameters (planner.py:1300-1313 never feeds them to the network)
+            off, _, c = plan.seg["W0"]
+            for o, n in plan.frozen_segs:
+                grad[off + o * c:off + (o + n) * c].zero_()
 
     def test_kernels(self, p: int, params: Optional[torch.Tensor] = None, out=None):
         """Exact-model rollouts with the test policy (train = 0, planner.py:1482-1499).

@@ -628,6 +628,12 @@ class JaxBackpropPlanner:
 
     # ---------------------------------------------------------------------------------
     def _compile(self):
+        if getattr(self.plan, "kind", "slp") == "drp" and getattr(self.rddl, "observ_fluents", None):
+            # a closed-loop policy over a partially observed model reads the observ-fluents of the
+            # previous step (planner.py:1300-1313): they travel in the state vector as carried copies
+            from ..rddl.model import observation_view
+            self.rddl_observed = self.rddl
+            self.rddl = observation_view(self.rddl)
         rddl = self.rddl
         self.compiled = self.compiler_type(rddl, **self.compiler_kwargs)
         self.print_warnings = getattr(self.compiled, "print_warnings", True)
@@ -818,8 +824,9 @@ class JaxBackpropPlanner:
         vals = {}
         for name in layout:
             v = np.asarray(self.rddl.init_values[name])
-            if subs is not None and name in subs:
-                v = np.reshape(np.asarray(subs[name]), v.shape).astype(v.dtype)
+            key = name[:-len("@seen")] if name.endswith("@seen") else name     # carried observation
+            if subs is not None and key in subs:
+                v = np.reshape(np.asarray(subs[key]), v.shape).astype(v.dtype)
             t = torch.from_numpy(np.ascontiguousarray(v))
             vals[name] = t.unsqueeze(0)
         return pack_fluent_major(layout, vals, 1).pin_memory()
@@ -1732,8 +1739,12 @@ class JaxBackpropPlanner:
         """Action of the test policy at one decision epoch (planner.py:3527-3586)."""
         flat = self.plan.pytree_to_params(params)
         if self.is_drp:
-            vec = np.concatenate([np.asarray(state[name], np.float32).reshape(-1)
-                                  for name in self.rddl.state_fluents])
+            def words(name):        # a carried observation is looked up under the observ-fluent's name;
+                key = name[:-len("@seen")] if name.endswith("@seen") else name     # hidden words read 0
+                if key in state:
+                    return np.asarray(state[key], np.float32).reshape(-1)
+                return np.zeros(self.rddl.variable_size(name), np.float32)
+            vec = np.concatenate([words(name) for name in self.rddl.state_fluents])
             return self.plan.test_actions_host(flat, vec, step=int(step))
         step = min(int(step), flat.shape[0] - 1)
         return self.plan.test_actions(flat[step].numpy())

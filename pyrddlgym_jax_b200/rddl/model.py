@@ -307,3 +307,36 @@ def load_model(domain: str, instance: Optional[str] = None) -> RDDLLiftedModel:
         if inst["non-fluents"] is None or cand["name"] == inst["non-fluents"]:
             nf = cand
     return RDDLLiftedModel(blocks["domain"], nf, inst)
+
+
+SEEN = "@seen"
+
+
+def observation_view(model: "RDDLLiftedModel") -> "RDDLLiftedModel":
+    """POMDP view for closed-loop policies: every observ-fluent ``o`` gets a carried copy ``o@seen`` -- a
+    state fluent whose next value is the observation the step computes -- so that the value a policy may
+    look at in step t + 1 (the reference keeps it in ``sim_state.fls``, compiler.py:524-545; the policy
+    reads the observ-fluents only, planner.py:1300-1313) travels through the rollout kernels' state
+    vector and its cotangent through their adjoint.  Initial copies hold the observ-fluents' defaults.
+    Models without observ-fluents are returned unchanged."""
+    import copy
+    if not model.observ_fluents:
+        return model
+    m = copy.copy(model)
+    for attr in ("state_fluents", "next_state", "prev_state", "variable_types", "variable_ranges",
+                 "variable_params", "variable_defaults", "init_values", "state_bounds"):
+        setattr(m, attr, dict(getattr(model, attr)))
+    for o, default in model.observ_fluents.items():
+        s = o + SEEN
+        m.state_fluents[s] = default
+        m.next_state[s] = o
+        m.prev_state[o] = s
+        m.variable_types[s] = "state-fluent"
+        for table in (m.variable_ranges, m.variable_params, m.variable_defaults):
+            table[s] = table[o]
+        m.init_values[s] = np.array(model.init_values[o], copy=True)
+        shape = model.variable_shape(o)
+        m.state_bounds[s] = (np.full(shape, -np.inf, dtype=np.float32),
+                             np.full(shape, np.inf, dtype=np.float32))
+    m.observed_inputs = [o + SEEN for o in model.observ_fluents]
+    return m

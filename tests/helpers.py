@@ -31,6 +31,8 @@ FIXTURES = {
     "samplers": ("Samplers_Toy", "instance1"),
     # matrix algebra and random vectors
     "matrix": ("Matrix_Toy", "instance1"),
+    # partially observed: noisy sensors and a boolean alarm over hidden tank levels
+    "pomdp": ("Pomdp_Toy", "instance1"),
 }
 
 

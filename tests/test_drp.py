@@ -1,6 +1,8 @@
 """Deep reactive policy: host-side pytree / oracle checks on CPU, and GPU parity of the whole
 closed-loop update (dense layers, heads, T=1 rollout launches chained through GSIN/GS0, weight
 gradients) against the torch-CPU oracle restatement of planner.py:1122-1534."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -1585,3 +1587,123 @@ def test_drp_utility_update_matches_oracle(cuda_device, utility, kw):
     torch.cuda.synchronize()
     want_test = -fn(pl.test_returns[0].cpu(), **kw)
     assert abs(float(pl.test_loss_buf[0]) - float(want_test)) <= 2e-5 * abs(float(want_test))
+
+
+def test_observation_view_and_host_policy():
+    """Partially observed models (planner.py:1300-1313): the carried copies of the observ-fluents are the
+    only inputs of the policy -- parameter pytree, initialiser fan-in and host test policy ignore the
+    hidden state words."""
+    from pyrddlgym_jax_b200.rddl.model import observation_view
+    from pyrddlgym_jax_b200.core.compiler import JaxRDDLCompiler
+    base = fixture_model("pomdp")
+    m = observation_view(base)
+    assert list(m.state_fluents) == ["level", "sensor@seen", "alarm@seen"]
+    assert m.next_state["sensor@seen"] == "sensor" and m.observed_inputs == ["sensor@seen", "alarm@seen"]
+    assert observation_view(fixture_model("reservoir")).state_fluents.keys() == \
+        fixture_model("reservoir").state_fluents.keys()
+    plan = JaxDeepReactivePolicy(topology=[8, 8])
+    with pytest.raises(ValueError):
+        plan.compile(JaxRDDLCompiler(base), JaxRDDLCompiler(base), {}, 4)
+    plan.compile(JaxRDDLCompiler(m), JaxRDDLCompiler(m), {}, 4)
+    assert plan.D == 9 and plan.D_in == 6 and plan.frozen_segs == [(0, 3)]
+    g = torch.Generator().manual_seed(3)
+    flat = plan.initial_params(g)
+    off, r, c = plan.seg["W0"]
+    W0 = flat[off:off + r * c].reshape(r, c)
+    assert float(W0[:3].abs().max()) == 0.0 and float(W0[3:].abs().min()) > 0.0
+    assert abs(float(W0[3:].std()) - math.sqrt(2.0 / 6)) < 0.25          # fan-in 6, not 9
+    tree = plan.params_to_pytree(flat)["params"]
+    assert tuple(tree["dense_0"]["kernel"].shape) == (6, 8)             # non-bool (sensor) rows, then alarm
+    assert torch.equal(plan.pytree_to_params({"params": tree}), flat)
+    # the host policy does not react to the hidden level words
+    obs = np.array([0.4, 0.8, 0.1, 1.0, 0.0, 1.0], np.float32)
+    a = plan.test_actions_host(flat, np.concatenate([np.zeros(3, np.float32), obs]))
+    b = plan.test_actions_host(flat, np.concatenate([np.full(3, 7.0, np.float32), obs]))
+    np.testing.assert_array_equal(a["pump"], b["pump"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("topology,normalize", [((16, 16), False), ((8, 8), True)])
+def test_drp_pomdp_update_matches_oracle(cuda_device, topology, normalize):
+    """A deep reactive policy over observ-fluents: rewards, loss and parameter gradient of one update and
+    the exact test rollouts against the oracle, whose policy sees the sensors of the previous step (the
+    initial defaults at step 0) and never the hidden levels."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    base = fixture_model("pomdp")
+    T, B = 5, 21
+    plan = JaxDeepReactivePolicy(topology=list(topology), normalize=normalize)
+    pl = JaxBackpropPlanner(base, plan, batch_size_train=B, rollout_horizon=T, optimizer="sgd",
+                            optimizer_kwargs={"learning_rate": 0.0}, pgpe=None, use_cuda_graph=False)
+    m = pl.rddl                                        # the observation view
+    assert m is not base and plan.frozen_segs
+    pl.initialize(7)
+    g = torch.Generator().manual_seed(17)
+    flat = plan.initial_params(g)
+    pl.params[0].copy_(flat)
+    fw = pl.train_fwd.program
+    noise = torch.randn(T, fw.N * B, generator=g)
+    pol_noise = torch.randn(T, 3 * B, generator=g)
+    pl.train_noise.copy_(noise.reshape(-1))
+    pl.drp.pol_noise.copy_(pol_noise)
+    pl.drp.ent_coeff.fill_(0.05)
+    pl.update()
+    torch.cuda.synchronize()
+    tree = plan.params_to_pytree(flat)["params"]
+    P = _with_grad(tree)
+    om = OracleModel(m, pl.compiled.relax_config())
+    ents = []
+    seen = ("sensor@seen", "alarm@seen")
+
+    def pol(t, fls):
+        a, e = OP.drp_actions(m, P, {k: fls[k] for k in seen},
+                              {"pump": pol_noise[t].reshape(B, 3)}, 1.0, m.bounds, 2, True,
+                              normalize=normalize)
+        ents.append(e)
+        return a
+    out = OP.rollout(om, pol, B, T, [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)])
+    loss = OP.mean_loss(out["reward"], float(m.discount)) - 0.05 * torch.stack(ents, 1).sum(1).mean()
+    loss.backward()
+    want = plan.pytree_to_params(_grads(P)).numpy()
+    r_ref = out["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.train_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * abs(float(loss.detach()))
+    got = pl.grad[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    off, r, c = plan.seg["W0"]
+    assert float(np.abs(got[off:off + 3 * c]).max()) == 0.0          # hidden rows: no gradient
+    assert float(np.abs(want).max()) > 0
+    te = pl.test_fwd.program
+    tnoise = torch.randn(T, te.N * B, generator=g)
+    pl.test_noise.copy_(tnoise.reshape(-1))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    ref = OP.rollout(OracleModel(m, None), lambda t, fls: OP.drp_test_actions(
+        m, tree, {k: fls[k] for k in seen}, m.bounds, 2, normalize=normalize), B, T,
+        [noise_as_list(te.noise_layout, tnoise, t, B) for t in range(T)])
+    r_ref = ref["reward"].detach().numpy().T
+    np.testing.assert_allclose(pl.test_reward[0].view(T, B).cpu().numpy(), r_ref, rtol=1e-5,
+                               atol=1e-5 * np.abs(r_ref).max())
+
+
+@pytest.mark.gpu
+def test_drp_pomdp_optimize_and_act(cuda_device):
+    """End to end on the partially observed fixture: a few planner iterations (CUDA graph), returns
+    improve, and get_action takes the observation dict a POMDP environment hands out."""
+    from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
+    base = fixture_model("pomdp")
+    plan = JaxDeepReactivePolicy(topology=[16, 16])
+    pl = JaxBackpropPlanner(base, plan, batch_size_train=256, optimizer="rmsprop",
+                            optimizer_kwargs={"learning_rate": 0.01}, pgpe=None)
+    first = last = None
+    for cb in pl.optimize_generator(key=5, epochs=40, print_summary=False, print_progress=False):
+        first = cb if first is None else first
+        last = cb
+        assert np.isfinite(cb["train_return"]).all() and np.isfinite(cb["test_return"]).all()
+    assert last["best_return"] > first["best_return"]
+    obs = {"sensor": np.array([0.2, 0.7, 0.4], np.float32), "alarm": np.array([True, False, False])}
+    act = pl.get_action(None, last["best_params"], 0, obs)
+    assert set(act) == {"pump"} and act["pump"].shape == (3,)
+    assert (act["pump"] >= 0.0).all() and (act["pump"] <= 1.0).all()
+    tree = last["best_params"]["params"]
+    assert tuple(np.asarray(tree["dense_0"]["kernel"]).shape) == (6, 16)      # sensors + alarms only
