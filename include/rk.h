@@ -238,8 +238,13 @@ int rk_state_scale_backward(void* stream, int B, int D, int n_seg, const int32_t
  * output, so the adjoints need only the stored activation.  The id is a LAUNCH ARGUMENT of every kernel
  * with a fused activation: bits 8..15 of the `flags` word of rk_sgemm and of the `epi` word of rk_tcgemm
  * (RK_ACT(id)), the `act` argument of rk_drp_layer0 / rk_drp_head_backward / rk_film_backward /
- * rk_drp_mlp2_*.  The library keeps no process state: calls are re-entrant per stream. */
+ * rk_drp_mlp2_* / rk_act_apply.  The library keeps no process state: calls are re-entrant per stream. */
 #define RK_ACT(id) ((id) << 8)
+/* gelu (6, jax's default tanh approximation) and silu (7) are not monotone: their derivative needs the
+ * pre-activation.  A layer with one of them is  z = X W + b  (bias-only epilogue, or rk_drp_layer0 with the
+ * identity id 8)  followed by  y = act(z)  (rk_act_apply), both kept; an activation-adjoint epilogue with
+ * id 6 / 7 reads z as its aux operand.  The fused per-epoch kernels (rk_drp_mlp2_*) take ids 0-5 only. */
+int rk_act_apply(void* stream, int act, size_t n, const float* z, float* y);
 /* FiLM time conditioning of a hidden layer (planner.py:1083-1092, 1362-1363):
  * out[b][c] = gamma[c] z[b][c] + beta[c], gamma / beta [H] = the two Dense(time embedding) vectors of
  * the decision epoch.  backward: g = cotangent of out, z = the tanh output it was applied to;

@@ -553,7 +553,10 @@ def drp_actions(model, params, fls, noise: Optional[Dict[str, torch.Tensor]], tr
 DRP_ACTIVATIONS = {
     "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid,
     "softplus": torch.nn.functional.softplus, "elu": torch.nn.functional.elu,
-    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01)}
+    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01),
+    # jax.nn.gelu defaults to the tanh approximation; jax.nn.silu = jax.nn.swish
+    "gelu": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),
+    "silu": torch.nn.functional.silu, "swish": torch.nn.functional.silu}
 
 
 def drp_time_embedding(params, step: int, kind: str, dim: int = 8):

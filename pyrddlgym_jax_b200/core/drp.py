@@ -33,7 +33,9 @@ from .program import PlanSpec, action_layout
 HOST_ACTIVATIONS = {
     "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid,
     "softplus": torch.nn.functional.softplus, "elu": torch.nn.functional.elu,
-    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01)}
+    "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.01),
+    "gelu": lambda x: torch.nn.functional.gelu(x, approximate="tanh"),      # jax.nn.gelu's default form
+    "silu": torch.nn.functional.silu, "swish": torch.nn.functional.silu}
 
 
 class SinusoidalTimeEmbedding:
@@ -550,6 +552,15 @@ class DrpPipeline:
         # fused streaming backward kernels (one pass over [B][h] instead of four / three)
         import os as _os0
         fuse = _os0.environ.get("RK_DRP_FUSED", "1") != "0"
+        # gelu / silu: the derivative needs the pre-activation, so every layer is z = X W + b (kept) then
+        # y = act(z) (kept): the layer-wise path with a second tape; the fused kernels keep act(z) only
+        self.zact = plan._activation in engine.Z_ACTIVATIONS
+        if self.zact:
+            if plan.time_embed is not None:
+                raise NotImplementedError(f"activation <{plan._activation}> with time_dependent=True")
+            fuse = False
+            self.Z = [z(T, Bt, h) for h in self.hid]
+        self._Z = None                      # pre-activation buffers of the epoch being evaluated
         hl = self.hid[-1]
         self.fused_head = fuse and len(self.hid) >= 2 and self.NH <= 16 and hl <= 1024
         self.fused_l0 = fuse and self.D <= 16
@@ -591,6 +602,7 @@ class DrpPipeline:
         # exact test model: a single slot of activations is enough (forward only)
         self.t_state = [z(te.S * Be), z(te.S * Be)]
         self.t_H = [z(Be, h) for h in self.hid]
+        self.t_Z = [z(Be, h) for h in self.hid] if self.zact else None
         self.t_heads = z(Be, self.NH)
         self.t_act = z(self.A * Be)
         self.t_xf = z(te.S * Be) if any(plan.state_is_int) else None
@@ -703,6 +715,9 @@ class DrpPipeline:
                 self._W(self.wT_lo, "W1"), self._W(params, "b1"), self._W(params, "bh"),
                 H[0] if keep_hidden else None, H[1] if keep_hidden else None, heads)
             return
+        if self.zact:
+            self._mlp_forward_z(params, B, x_fm, H, heads, xp)
+            return
         engine.drp_layer0(B, self.D, h0, self.plan.state_segs, x_fm, self._W(params, "W0"),
                           self._W(params, "b0"), H[0], xp)
         fan, src = h0, H[0]
@@ -728,6 +743,31 @@ class DrpPipeline:
                           self.NH, bias=self._W(params, "bh"))
         else:
             engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, src, fan, self._W(params, "Wh"),
+                         self.NH, heads, self.NH, bias=self._W(params, "bh"))
+
+    def _mlp_forward_z(self, params, B, x_fm, H, heads, xp):
+        """Layers whose activation keeps its pre-activation (gelu, silu): z_i = X W_i + b_i into self._Z[i]
+        (bias-only epilogues), y_i = act(z_i) into H[i] (rk_act_apply)."""
+        act, Z = self.plan._activation, self._Z
+        engine.drp_layer0(B, self.D, self.hid[0], self.plan.state_segs, x_fm, self._W(params, "W0"),
+                          self._W(params, "b0"), Z[0], xp, act=engine.ACT_IDENTITY)
+        engine.act_apply(act, B * self.hid[0], Z[0], H[0])
+        fan = self.hid[0]
+        for i in range(1, len(self.hid)):
+            h = self.hid[i]
+            if i in self.tc_layers:
+                engine.tcgemm(1, B, h, fan, H[i - 1], fan, self._W(self.wT_hi, f"W{i}"),
+                              self._W(self.wT_lo, f"W{i}"), fan, Z[i], h, bias=self._W(params, f"b{i}"))
+            else:
+                engine.sgemm(engine.EPI_BIAS, B, h, fan, H[i - 1], fan, self._W(params, f"W{i}"),
+                             h, Z[i], h, bias=self._W(params, f"b{i}"))
+            engine.act_apply(act, B * h, Z[i], H[i])
+            fan = h
+        if self.NH <= 16:
+            engine.rowdot(False, B, self.NH, fan, H[-1], fan, self._W(params, "Wh"), self.NH, heads,
+                          self.NH, bias=self._W(params, "bh"))
+        else:
+            engine.sgemm(engine.EPI_BIAS, B, self.NH, fan, H[-1], fan, self._W(params, "Wh"),
                          self.NH, heads, self.NH, bias=self._W(params, "bh"))
 
     def wgrad_all(self, grad, x_tape):
@@ -778,7 +818,9 @@ class DrpPipeline:
             engine.colsum(B, self.NH, self.gheads, self.NH, self._W(grad, "bh"), True, self.cs_ws,
                           self.cs_chunks)
             engine.sgemm(engine.EPI_DTANH, B, hl, self.NH, self.gheads, self.NH,
-                         self._W(self.wT, "Wh"), hl, self.gz[last], hl, aux=H[last], ldaux=hl)
+                         self._W(self.wT, "Wh"), hl, self.gz[last], hl,
+                         aux=(self._Z if self.zact else H)[last], ldaux=hl)
+        AUX = self._Z if self.zact else H     # what the activation adjoint reads: z (gelu, silu) or act(z)
         for i in range(last, -1, -1):
             h = self.hid[i]
             fan = self.D if i == 0 else self.hid[i - 1]
@@ -813,10 +855,10 @@ class DrpPipeline:
             elif i > 0 and i in self.tc_layers:    # dX = (dZ W^T) * (1 - H^2): "Bt" is W itself
                 engine.tcgemm(3, B, fan, h, self.gz[i], h, self._W(self.w_hi, f"W{i}"),
                               self._W(self.w_lo, f"W{i}"), h, self.gz[i - 1], fan,
-                              aux=H[i - 1], ldaux=fan)
+                              aux=AUX[i - 1], ldaux=fan)
             elif i > 0:
                 engine.sgemm(engine.EPI_DTANH, B, fan, h, self.gz[i], h, self._W(self.wT, f"W{i}"),
-                             fan, self.gz[i - 1], fan, aux=H[i - 1], ldaux=fan)
+                             fan, self.gz[i - 1], fan, aux=AUX[i - 1], ldaux=fan)
             else:           # input cotangent, added block by block to the state cotangent
                 W0T = self._W(self.wT, "W0")
                 for off, n in self.plan.state_segs:
@@ -841,6 +883,8 @@ class DrpPipeline:
         for t in range(T):
             x = self.tape[t * S * B:(t + 1) * S * B]
             Ht = [Hl[t] for Hl in self.H]
+            if self.zact:
+                self._Z = [Zl[t] for Zl in self.Z]
             xin = x
             if self.pre:
                 engine.state_scale(B, self.D, plan.state_segs, self.pre_lo, self.pre_hi, x, self.xa[t])
@@ -891,6 +935,8 @@ class DrpPipeline:
         for t in range(T - 1, -1, -1):
             x = self.tape[t * S * B:(t + 1) * S * B]
             nxt, out = self.gs[cur], self.gs[cur ^ 1]
+            if self.zact:
+                self._Z = [Zl[t] for Zl in self.Z]
             gh = self.gheads_tape[t] if fused else self.gheads
             bwd.backward(B, 1, x, pl.gret, actions=self.act[t],
                          noise=None if pl.train_noise is None else pl.train_noise[t * N * B:],
@@ -979,6 +1025,7 @@ class DrpPipeline:
             if self.Dn:
                 self.layernorm_forward(params, B, xin, self.t_xn)
                 xin = self.t_xn
+            self._Z = self.t_Z
             self.mlp_forward(params, B, xin, self.t_H, self.t_heads,
                              film=(t, self.t_Hf) if self.film else None, keep_hidden=False)
             engine.drp_actions_forward(B, A, plan._stochastic, plan.action_segs, self.t_heads,

@@ -35,6 +35,7 @@ EXPORTS = [
     "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
     "rk_utility_loss", "rk_optimizer_chain_step", "rk_utility_loss_shard",
     "rk_utility_sorted_work_bytes", "rk_utility_sorted_loss", "rk_peer_allreduce_gather",
+    "rk_act_apply",
 ]
 
 
@@ -116,6 +117,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_peer_allreduce.restype = ci
     lib.rk_peer_allreduce_gather.argtypes = [vp, ci, ci, vp, vp, ci, ci, cf, cf, cf, ci, vp, vp, cf]
     lib.rk_peer_allreduce_gather.restype = ci
+    lib.rk_act_apply.argtypes = [vp, ci, ctypes.c_size_t, cf, cf]
+    lib.rk_act_apply.restype = ci
     lib.rk_state_layernorm_ctas.argtypes = [ci]
     lib.rk_state_layernorm_ctas.restype = ci
     lib.rk_state_layernorm_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf]
@@ -385,7 +388,17 @@ def state_scale(B, D, segs, lo, hi, x, y, backward: bool = False):
               _ptr(lo), _ptr(hi), _ptr(x), _ptr(y)), "rk_state_scale")
 
 
-ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "elu": 4, "leaky_relu": 5}
+ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "elu": 4, "leaky_relu": 5,
+               "gelu": 6, "silu": 7, "swish": 7}
+# activations whose derivative needs the pre-activation: the layer-wise path keeps z beside act(z)
+Z_ACTIVATIONS = ("gelu", "silu", "swish")
+ACT_IDENTITY = 8
+
+
+def act_apply(act, n: int, z, y):
+    """y = act(z) element-wise (the second half of a gelu / silu layer)."""
+    _check(load_library().rk_act_apply(_stream(), _act_id(act), ctypes.c_size_t(int(n)), _ptr(z), _ptr(y)),
+           "rk_act_apply")
 
 
 _ACT = 0

@@ -23,6 +23,19 @@
 // no process state: calls are re-entrant per stream and a captured graph keeps its own value.
 static inline bool rk_act_ok(int act) { return act >= 0 && act < RK_ACT_COUNT; }
 
+// y = act(z), element-wise: the second half of a layer whose pre-activation is kept (gelu / silu)
+__global__ void __launch_bounds__(256)
+rk_act_apply_kernel(int act, size_t n, const float* __restrict__ z, float* __restrict__ y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = rk_act_fn(act, z[i]);
+}
+
+extern "C" int rk_act_apply(void* stream, int act, size_t n, const float* z, float* y) {
+  if (!rk_act_ok(act) || n == 0 || z == nullptr || y == nullptr) return RK_E_BADARG;
+  rk_act_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(act, n, z, y);
+  return (int)cudaGetLastError();
+}
+
 #define BM 128
 #define BN 128
 #define BK 8

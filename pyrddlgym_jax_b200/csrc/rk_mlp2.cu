@@ -816,7 +816,7 @@ extern "C" int rk_drp_mlp2_forward(void* stream, int act, int B, int D, int H0n,
   if (B <= 0 || x_fm == nullptr || fwd_img == nullptr || b0 == nullptr || W1T_hi == nullptr ||
       W1T_lo == nullptr || b1 == nullptr || bh == nullptr || heads == nullptr)
     return RK_E_BADARG;
-  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
+  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act > RK_ACT_LEAKY_RELU) return RK_E_BADARG;
   if (((uintptr_t)fwd_img & 15) != 0 || ((uintptr_t)H0 & 31) != 0 || ((uintptr_t)H1 & 31) != 0)
     return RK_E_BADARG;
   M2Args P = {};
@@ -850,7 +850,7 @@ extern "C" int rk_drp_mlp2_backward(void* stream, int act, int B, int D, int H0n
   if (B <= 0 || gheads == nullptr || H0 == nullptr || H1 == nullptr || bwd_img == nullptr ||
       W1_hi == nullptr || W1_lo == nullptr || gz0 == nullptr || gz1 == nullptr || gs == nullptr)
     return RK_E_BADARG;
-  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act >= RK_ACT_COUNT) return RK_E_BADARG;
+  if (!m2_dims_ok(D, H0n, H1n, NH) || act < 0 || act > RK_ACT_LEAKY_RELU) return RK_E_BADARG;
   if (((uintptr_t)bwd_img & 15) != 0 || ((uintptr_t)H0 & 31) != 0 || ((uintptr_t)H1 & 31) != 0 ||
       ((uintptr_t)gz0 & 31) != 0 || ((uintptr_t)gz1 & 31) != 0)
     return RK_E_BADARG;

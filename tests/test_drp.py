@@ -1231,7 +1231,7 @@ def test_drp_film_update_matches_oracle(cuda_device, kind, topology, B, normaliz
 ACTS = ["relu", "sigmoid", "softplus", "elu", "leaky_relu"]
 
 
-@pytest.mark.parametrize("act", ACTS)
+@pytest.mark.parametrize("act", ACTS + ["gelu", "silu"])
 def test_activation_host_policy_matches_oracle(act):
     m = fixture_model("powergen")
     plan = JaxDeepReactivePolicy(topology=[8, 8], activation=act)
@@ -1244,7 +1244,7 @@ def test_activation_host_policy_matches_oracle(act):
     got = plan.test_actions_host(flat, vec)["curProd"].reshape(-1)
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
     with pytest.raises(NotImplementedError):
-        JaxDeepReactivePolicy(activation="gelu")
+        JaxDeepReactivePolicy(activation="hard_tanh")
 
 
 @pytest.mark.gpu
@@ -1344,7 +1344,12 @@ def test_activation_epilogues_against_torch(cuda_device, act):
 @pytest.mark.parametrize("act,topology,B,film", [("relu", (16, 16), 23, False),
                                                  ("softplus", (64, 64), 130, False),
                                                  ("elu", (32, 16), 19, True),
-                                                 ("sigmoid", (64, 64, 32), 129, False)])
+                                                 ("sigmoid", (64, 64, 32), 129, False),
+                                                 # gelu / silu: pre-activation tape, layer-wise path
+                                                 ("gelu", (16, 16), 23, False),
+                                                 ("gelu", (64, 64), 130, False),
+                                                 ("silu", (64, 32, 32), 129, False),
+                                                 ("silu", (256, 256), 256, False)])
 def test_drp_activation_update_matches_oracle(cuda_device, act, topology, B, film):
     from pyrddlgym_jax_b200.core.planner import JaxBackpropPlanner
     m = fixture_model("powergen")
