@@ -558,8 +558,16 @@ class JaxBackpropPlanner:
             else plateau_kwargs(reduce_on_plateau_kwargs)
         # optax.scale_by_zoom_linesearch (planner.py:2373-2374): host-driven trials, core/linesearch.py
         self.line_search_kwargs = None if line_search_kwargs is None else zoom_kwargs(line_search_kwargs)
-        for name, val in (("critic", critic),
-                          ("dashboard", dashboard)):
+        # terminal value function (planner.py:2721-2745).  The reference takes a JAX callable; this build has
+        # no JAX, so the critic is a TORCH callable with the same arguments, batched over the rollouts:
+        #   critic(critic_params, obs: {fluent: [B, *objects]}, action: {fluent: [*objects]}) -> [B]
+        # evaluated on the final state of every rollout and on the plan's step-0 action, differentiated by
+        # torch autograd; its state cotangent seeds the adjoint kernel (straight-line plans, one GPU, no graph)
+        if critic is not None and not callable(critic):
+            raise TypeError("critic must be a callable (critic_params, obs, action) -> [B] values")
+        self.critic_fn = critic
+        self.critic_params = None
+        for name, val in (("dashboard", dashboard),):
             if val is not None:
                 raise NotImplementedError(f"{name} is not supported by the B200 planner yet")
         self.use_symlog_reward = bool(use_symlog_reward)
@@ -645,12 +653,22 @@ class JaxBackpropPlanner:
         self.plan.compile(self.compiled, self.test_compiled, self._action_bounds, self.horizon,
                           preprocessor=preprocessor)
         spec = self.plan.spec
-        gamma = float(rddl.discount)
-        self.gamma = gamma
+        self.gamma = float(rddl.discount)
+        # the programs read the per-step weights of the rewards from a buffer only when asked to: an
+        # undiscounted model compiles without it unless a reward mask needs it (set_reward_mask)
+        gamma = self.gamma if (self.gamma != 1.0 or not getattr(self, "_weighted_rewards", False)) else 0.5
         train_log = tuple(rddl.state_fluents) if self.cache_full_train_rollouts else ()
         test_log = (tuple(rddl.next_state.values()) + tuple(rddl.action_fluents)) \
             if self.cache_full_test_rollouts else ()
         self.is_drp = getattr(self.plan, "kind", "slp") == "drp"
+        if self.critic_fn is not None:
+            plan = self.plan
+            if self.is_drp or self.world_size > 1 or self.parallel_updates > 1 or self.use_pgpe \
+                    or getattr(plan, "_stochastic", False) or getattr(plan, "_wrap_non_bool", False) \
+                    or getattr(plan, "_wrap_softmax", False):
+                raise NotImplementedError(
+                    "critic: built for deterministic straight-line plans (sigmoid-wrapped booleans, plain "
+                    "real / int parameters) on one GPU, parallel_updates = 1, pgpe = None")
         if self.is_drp and self._utility_eager:
             raise NotImplementedError(
                 "deep reactive policies take the built-in utilities by name (native cotangent kernels); a "
@@ -664,7 +682,7 @@ class JaxBackpropPlanner:
                 self.train_bwd = engine.DeviceProgram(
                     tb.backward(gamma=gamma, grad_s0=True, state_ct_in=True))
             else:   # adjoint first: it decides what the forward program tapes for it
-                bwd_prog = tb.backward(gamma=gamma)
+                bwd_prog = tb.backward(gamma=gamma, state_ct_in=self.critic_fn is not None)
                 self.train_fwd = engine.DeviceProgram(tb.forward(write_tape=True, gamma=gamma))
                 self.train_bwd = engine.DeviceProgram(bwd_prog)
             eb = self.test_compiled.builder(spec, False, test_log, self.batch_size_test)
@@ -700,6 +718,8 @@ class JaxBackpropPlanner:
         self._stats_host = torch.zeros(3 * P, dtype=torch.int32).pin_memory()
         self.train_loss = self._stats[0:P].view(torch.float32)
         self.gret = z(Bt)
+        if self.critic_fn is not None:
+            self.train_final, self.gs_in = z(fw.S * Bt), z(fw.S * Bt)
         if self._native_utility is not None:
             if self.world_size > 1:
                 self._ret_all, self._ret_all_test = z(self.world_size * Bt), z(self.world_size * Be)
@@ -715,8 +735,9 @@ class JaxBackpropPlanner:
         self.converged = torch.ones(P, dtype=torch.int32, device=dev)
         self.train_noise = z(T * fw.N * Bt) if fw.N else None
         self.test_noise = z(T * te.N * Be) if te.N else None
-        self.disc = None if self.gamma == 1.0 else torch.pow(
-            torch.tensor(self.gamma, device=dev), torch.arange(T, device=dev)).float().contiguous()
+        self.disc = None if (self.gamma == 1.0 and not getattr(self, "_weighted_rewards", False)) \
+            else torch.pow(torch.tensor(self.gamma, device=dev),
+                           torch.arange(T, device=dev)).float().contiguous()
         lo, hi = self.plan.box
         self.box_lo = None if lo is None else torch.from_numpy(lo.reshape(-1)).to(dev).contiguous()
         self.box_hi = None if hi is None else torch.from_numpy(hi.reshape(-1)).to(dev).contiguous()
@@ -805,6 +826,38 @@ class JaxBackpropPlanner:
         self._ctl_host = torch.zeros(2, dtype=torch.float32).pin_memory() \
             if torch.cuda.is_available() else torch.zeros(2, dtype=torch.float32)
 
+    # ---- reward mask (planner_state.reward_mask, planner.py:2802-2809) ------------------------------
+    def set_reward_mask(self, mask) -> None:
+        """Per-step weights of the rewards inside the loss (train and test): rewards[:, t] * mask[t] before
+        discounting.  None removes the mask.  The weights fold into the discount vector the rollout
+        kernels already take, so nothing else changes; plans with an entropy term (stochastic=True) would
+        need the same weights on their per-step entropies and are rejected."""
+        T = self.T
+        base = torch.pow(torch.tensor(float(self.gamma), dtype=torch.float64),
+                         torch.arange(T, dtype=torch.float64))
+        if mask is None:
+            self.disc = None if (self.gamma == 1.0 and not getattr(self, "_weighted_rewards", False)) \
+                else base.float().to(self.device).contiguous()
+        else:
+            m = torch.as_tensor(np.asarray(mask), dtype=torch.float64)
+            if m.dim() != 1:
+                raise ValueError("Reward mask must be 1-dimensional.")
+            if m.numel() != T:
+                raise ValueError("Reward mask size must match reward dimension.")
+            if getattr(self.plan, "_stochastic", False):
+                raise NotImplementedError("reward_mask with a stochastic plan (per-step entropy weights)")
+            if self.gamma == 1.0 and not getattr(self, "_weighted_rewards", False):
+                # an undiscounted model was compiled without the weight buffer: rebuild the programs with it
+                # (this re-creates the planner's device state, like a new planner: call before initialize)
+                self._weighted_rewards = True
+                if getattr(self, "rddl_observed", None) is not None:
+                    self.rddl = self.rddl_observed
+                self._compile()
+            self.disc = (base * m).float().to(self.device).contiguous()
+        self.reward_mask = mask
+        self._graph = self._graph_host = None        # the discount vector is baked into the captured launches
+        self._primed = False
+
     # ---- model parameters (relaxation weights), planner.py:3165-3168 ---------------------
     def model_parameter_info(self) -> Dict[Any, float]:
         fw = self.train_fwd.program
@@ -890,10 +943,15 @@ class JaxBackpropPlanner:
         if self.is_drp:
             self.drp.update_kernels(p, loss_out)
         else:
+            critic = self.critic_fn is not None
             self.train_fwd.forward(B, T, self.s0_train, policy=params, noise=self.train_noise,
                                    mparams=self.train_mparams, disc=self.disc,
                                    reward=self.train_reward[p], returns=self.train_returns[p],
-                                   err=self.train_err[p], tape=self.tape)
+                                   err=self.train_err[p], tape=self.tape,
+                                   final=self.train_final if critic else None)
+            if critic:      # returns += gamma^T critic(final state, step-0 action)   (planner.py:2758-2760)
+                crit = self._critic_values(params, self.train_final, self.train_fwd.program, B, train=True)
+                self.train_returns[p].add_(crit["values"].detach() * crit["scale"])
             main = torch.cuda.current_stream(self.device)
             if getattr(self, "_published", None) is not None:
                 main.wait_event(self._published)
@@ -928,10 +986,22 @@ class JaxBackpropPlanner:
                     (g,) = torch.autograd.grad(loss, r)
                 loss_out.copy_(loss.detach().reshape(1))
                 self.gret.copy_(g[self.rank * B:(self.rank + 1) * B])
+            gp0 = None
+            if critic:      # d loss / d critic_b = gret_b gamma^T: back through the critic by autograd
+                (self.gret * crit["values"] * crit["scale"]).sum().backward()
+                self.gs_in.zero_()
+                for name, (off, n, _) in self.train_fwd.program.state_layout.items():
+                    g = crit["obs"][name].grad
+                    if g is not None:
+                        self.gs_in[off * B:(off + n) * B].copy_(g.reshape(-1))
+                gp0 = crit["row"].grad
             self.train_bwd.backward(B, T, self.tape, self.gret, policy=params,
                                     noise=self.train_noise, mparams=self.train_mparams,
-                                    disc=self.disc, gradp=self.gradp)
+                                    disc=self.disc, gradp=self.gradp,
+                                    gs_in=self.gs_in if critic else None)
             engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
+            if gp0 is not None:       # the critic also sees the plan's step-0 action
+                self.grad[p][:A].add_(gp0)
         if self.world_size > 1 and not self._defer_ar:   # the exchange step of the path
             self._allreduce(self.grad[p])
         if not self.is_drp and getattr(self.plan, "_stochastic", False):
@@ -943,6 +1013,34 @@ class JaxBackpropPlanner:
             # regulariser (the same on every rank) goes in once, not world_size times
             scale = 1.0 / self.world_size if (self.world_size > 1 and self._defer_ar) else 1.0
             self.grad[p].view(T, A).sub_(self.ent_coeff * dH * scale)
+
+    def _critic_values(self, params: torch.Tensor, final: torch.Tensor, prog, B: int, train: bool):
+        """critic(critic_params, final observation, step-0 action) per rollout (planner.py:2721-2745).
+        train: float observations and the relaxed train action, both autograd leaves; test: the exact
+        model's typed state and the test policy's action."""
+        T, A = self.T, self.A
+        shapes = {name: tuple(self.rddl.variable_shape(name)) for name in prog.state_layout}
+        obs = unpack_fluent_major(prog.state_layout, final, B, shapes)
+        plan = self.plan
+        row = params.view(T, A)[0].detach().clone()
+        if train:
+            obs = {k: v.detach().clone().requires_grad_(True) for k, v in obs.items()}
+            row.requires_grad_(True)
+            action = {}
+            for name, (off, n, prange) in plan.layout.items():
+                a = row[off:off + n]
+                if prange == "bool" and plan._wrap_sigmoid:            # planner.py:741-745, 818
+                    a = torch.sigmoid(float(plan._sigmoid_weight) * a)
+                action[name] = a.reshape(self.rddl.variable_shape(name))
+        else:
+            acts = plan.test_actions(row.cpu().numpy())
+            action = {k: torch.as_tensor(np.asarray(v), device=self.device) for k, v in acts.items()}
+        with torch.enable_grad():
+            values = self.critic_fn(self.critic_params, obs, action)
+        values = torch.as_tensor(values, dtype=torch.float32, device=self.device).reshape(-1)
+        if values.numel() != B:
+            raise ValueError("Critic value must be a scalar per rollout.")
+        return {"values": values, "obs": obs, "row": row, "scale": float(self.gamma) ** T}
 
     def _native_utility_kernels(self, local_returns: torch.Tensor, loss_out: torch.Tensor,
                                 test: bool = False):
@@ -1076,6 +1174,10 @@ class JaxBackpropPlanner:
                               noise=self.test_noise, disc=self.disc,
                               reward=reward, returns=returns, err=err, final=final,
                               traj=None if (self.test_traj is None or scratch) else self.test_traj[p])
+        if self.critic_fn is not None:      # the test loss is the same loss function (planner.py:2695-2698)
+            crit = self._critic_values(self.params[p] if params is None else params, final,
+                                       self.test_fwd.program, B, train=False)
+            returns.add_(crit["values"].detach() * crit["scale"])
         self._test_loss_kernels(returns, loss_out)
 
     def _test_loss_kernels(self, returns: torch.Tensor, loss_out: torch.Tensor):
@@ -1295,7 +1397,8 @@ class JaxBackpropPlanner:
         JaxOnlineController): initial-state words of both models and the plan to start from go
         in, (train loss, test loss, zero-gradient flags, plan) come back -- one graph launch and
         one synchronisation.  Returns (train [P], test [P], zero [P], plan [P, NP] pinned view)."""
-        if self._utility_eager or self.line_search_kwargs is not None or not self.use_cuda_graph:
+        if self._utility_eager or self.line_search_kwargs is not None or self.critic_fn is not None \
+                or not self.use_cuda_graph:
             self.load_initial_state(init_train, init_test)
             self.params.copy_(params, non_blocking=True)
             self.iterate()
@@ -1328,7 +1431,8 @@ class JaxBackpropPlanner:
 
     def iterate(self):
         """One planner iteration on the device: update + test_loss (planner.py:3245-3260)."""
-        if self._utility_eager or self.line_search_kwargs is not None or not self.use_cuda_graph:
+        if self._utility_eager or self.line_search_kwargs is not None or self.critic_fn is not None \
+                or not self.use_cuda_graph:
             self._iteration_kernels()
             return
         if self._graph is None:
@@ -1466,7 +1570,7 @@ class JaxBackpropPlanner:
                f"    utility_fn         ={utility}\n"
                f"    utility args       ={self.utility_kwargs}\n"
                f"    use_symlog         ={self.use_symlog_reward}\n"
-               f"    use_critic         =False\n"
+               f"    use_critic         ={self.critic_fn is not None}\n"
                f"    lookahead          ={self.horizon}\n"
                f"    user_action_bounds ={self._action_bounds}\n"
                f"    start_entropy_coeff={self.start_entropy_coeff}\n"
@@ -1507,8 +1611,7 @@ class JaxBackpropPlanner:
                              "is not None.")
         if self.world_size > 1:
             raise NotImplementedError("as_optimization_problem runs on one GPU")
-        if critic_params is not None:
-            raise NotImplementedError("critic is not supported by the B200 planner yet")
+        self.critic_params = critic_params
         if key is None:
             key = round(time.time() * 1000) % (2 ** 31)
         self.initialize(int(key))
@@ -1606,6 +1709,7 @@ class JaxBackpropPlanner:
                   f"    provide_param_guess={guess is not None}\n"
                   f"    test_rolling_window={test_rolling_window}\n")
         self.initialize(key, subs, guess)
+        self.critic_params = critic_params
         P = self.parallel_updates
         if policy_hyperparams is not None:
             hyper = policy_hyperparams

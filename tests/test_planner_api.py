@@ -910,3 +910,119 @@ def test_zoom_line_search_link(cuda_device):
         plain.iterate()
     final_plain = float(plain.read_stats()[0][0])
     assert not np.isfinite(final_plain) or losses[-1] <= final_plain
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,utility,kw", [("quadcopter", "mean", {}), ("wildfire_free", "mean", {}),
+                                            ("quadcopter", "mean_var", {"beta": 0.3})])
+def test_critic_terminal_value_matches_oracle(cuda_device, key, utility, kw):
+    """critic (planner.py:2721-2745, 2758-2760): returns += gamma^T critic(final state, step-0 action).
+    Train loss and plan gradient (through the critic's state cotangent, which seeds the adjoint kernel,
+    and through the step-0 action) against the oracle's rollout + torch autograd; the test loss adds the
+    critic on the exact final state.  The critic is a torch callable here (no JAX in this build)."""
+    from oracle import planner as OP
+    from oracle.model_eval import OracleModel
+    from pyrddlgym_jax_b200.core import planner as PL
+    from tests.helpers import pack_params
+    m = fixture_model(key)
+    B, T = 24, 5
+    plan = JaxStraightLinePlan()
+    state_names = list(m.state_fluents)
+    wvec = {s: 0.3 + 0.1 * i for i, s in enumerate(state_names)}
+
+    def critic(cp, obs, action):
+        v = 0.0
+        for s in state_names:
+            x = obs[s].to(torch.float32)
+            v = v - cp["scale"] * wvec[s] * (x.reshape(x.shape[0], -1) - 0.25).square().sum(1)
+        for a in action.values():
+            v = v + 0.05 * a.to(torch.float32).sum()
+        return v
+    cp = {"scale": 0.7}
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, batch_size_test=B, rollout_horizon=T,
+                            optimizer="sgd", optimizer_kwargs={"learning_rate": 0.0}, pgpe=None,
+                            critic=critic, utility=utility, utility_kwargs=kw)
+    pl.initialize(4)
+    pl.critic_params = cp
+    gen = torch.Generator().manual_seed(9)
+    flat = torch.randn(T, plan.A, generator=gen) * 0.3
+    pl.params[0].copy_(flat.reshape(-1))
+    fw = pl.train_fwd.program
+    noise = None
+    if fw.N:
+        from pyrddlgym_jax_b200.core.layout import draw_noise, noise_as_list
+        noise = draw_noise(fw.noise_layout, T, B, gen)
+        pl.train_noise.copy_(noise.reshape(-1))
+    pl.iterate()
+    torch.cuda.synchronize()
+    assert pl._graph is None                      # host-driven mode
+    tree = plan.params_to_pytree(flat)
+    P = {}
+    for name in m.action_fluents:
+        kind = "bool" if m.variable_ranges[name] == "bool" else "real"
+        leaf = tree[kind][name]["logit" if kind == "bool" else "mu"]
+        P[name] = leaf.reshape(T, -1).clone().requires_grad_(True)
+    om = OracleModel(m, pl.compiled.relax_config())
+    nl = None if noise is None else [noise_as_list(fw.noise_layout, noise, t, B) for t in range(T)]
+    ref = OP.rollout(om, lambda t, fls: OP.slp_train_actions(m, P, t), B, T, nl)
+    a0 = {k: v.reshape(-1)[:m.variable_size(k)].reshape(m.variable_shape(k))
+          for k, v in OP.slp_train_actions(m, P, 0).items()}
+    gamma = float(m.discount)
+    R = OP.returns_from_rewards(ref["reward"], gamma) + gamma ** T * critic(cp, ref["final"], a0)
+    loss = -(R.mean() if utility == "mean" else PL.UTILITY_LOOKUP[utility](R, **kw))
+    loss.backward()
+    want = pack_params(m, {k: v.grad for k, v in P.items()}).numpy()
+    assert abs(float(pl.train_loss[0]) - float(loss.detach())) <= 2e-5 * max(1.0, abs(float(loss.detach())))
+    got = pl.grad_used[0].cpu().view(T, plan.A).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()))
+    assert float(np.abs(want[0]).max()) > 0
+    # test loss: exact rollouts + critic on the exact final state and the test policy's step-0 action
+    te = pl.test_fwd.program
+    finals = unpack_test_final(pl, te, B)
+    acts = plan.test_actions(flat[0].numpy())
+    acts = {k: torch.as_tensor(np.asarray(v)) for k, v in acts.items()}
+    Rt = pl.test_reward[0].view(T, B).cpu() * (gamma ** torch.arange(T, dtype=torch.float32)).view(T, 1)
+    Rt = Rt.sum(0) + gamma ** T * critic(cp, finals, acts)
+    want_t = -(Rt.mean() if utility == "mean" else PL.UTILITY_LOOKUP[utility](Rt, **kw))
+    assert abs(float(pl.test_loss_buf[0]) - float(want_t)) <= 2e-5 * max(1.0, abs(float(want_t)))
+
+
+def unpack_test_final(pl, te, B):
+    from pyrddlgym_jax_b200.core.layout import unpack_fluent_major
+    shapes = {name: tuple(pl.rddl.variable_shape(name)) for name in te.state_layout}
+    return {k: v.cpu() for k, v in unpack_fluent_major(te.state_layout, pl.test_final[0], B, shapes).items()}
+
+
+@pytest.mark.gpu
+def test_reward_mask(cuda_device):
+    """planner_state.reward_mask (planner.py:2802-2809): rewards[:, t] * mask[t] inside the loss.  The loss is
+    the masked sum of the logged rewards; with the tail masked out, the plan parameters of the masked steps
+    receive no gradient (their actions only reach rewards that no longer count)."""
+    m = fixture_model("quadcopter")
+    B, T = 32, 8
+    pl = JaxBackpropPlanner(m, JaxStraightLinePlan(), batch_size_train=B, rollout_horizon=T,
+                            optimizer="sgd", optimizer_kwargs={"learning_rate": 0.0}, pgpe=None)
+    mask = np.array([1, 1, 0.5, 1, 1, 0, 0, 0], np.float32)
+    pl.set_reward_mask(mask)
+    pl.initialize(3)
+    pl.params[0].copy_(torch.randn(pl.n_params, generator=torch.Generator().manual_seed(2)) * 0.1)
+    for _ in range(2):
+        pl.iterate()
+    torch.cuda.synchronize()
+    r = pl.train_reward[0].view(T, B).cpu().double()
+    want = -float((r * torch.from_numpy(mask).double().view(T, 1)).sum(0).mean())
+    assert abs(float(pl.train_loss[0]) - want) <= 1e-5 * abs(want)
+    rt = pl.test_reward[0].view(T, B).cpu().double()
+    want_t = -float((rt * torch.from_numpy(mask).double().view(T, 1)).sum(0).mean())
+    assert abs(float(pl.test_loss_buf[0]) - want_t) <= 1e-5 * abs(want_t)
+    g = pl.grad_used[0].cpu().view(T, -1)
+    assert float(g[:5].abs().max()) > 0 and float(g[5:].abs().max()) == 0.0
+    pl.set_reward_mask(None)
+    pl.iterate()
+    pl.iterate()
+    torch.cuda.synchronize()
+    assert float(pl.grad_used[0].cpu().view(T, -1)[5:].abs().max()) > 0
+    with pytest.raises(ValueError):
+        pl.set_reward_mask(np.ones(T + 1))
+    with pytest.raises(ValueError):
+        pl.set_reward_mask(np.ones((T, 1)))
