@@ -123,6 +123,16 @@ int rk_optimizer_step(void* stream, int kind, const float* hyper, int n,
                       float* params, float* state, const float* grad,
                       const float* lo, const float* hi, int32_t* zero_flag);
 
+/* Gradient reduction FUSED with the optimiser step: grad[i] = sum_w gradp[w][i] (the order of
+ * rk_reduce_partials) and, in the same launch, the update of parameter i from it (rk_optimizer_step without
+ * global-norm clipping, which needs the whole gradient first).  The tail of the adjoint and the optimiser
+ * are one kernel: planner.py:2873-2899 (value_and_grad's batch reduction, optax update, apply_updates, box).
+ *   counters [2] device int32, zeroed once by the caller: the CTAs agree on the all-zero flag through them
+ *   (integer atomics, order-independent) and leave them zero again. */
+int rk_reduce_optimizer_step(void* stream, const float* gradp, int num_rows, int n, float* grad, int kind,
+                             const float* hyper, float* params, float* state, const float* lo,
+                             const float* hi, int32_t* zero_flag, int32_t* counters);
+
 /* The optimiser step with the optional links of the optax chain (planner.py:2349-2387, 2885-2899):
  * clip_by_global_norm -> add_noise -> optimiser -> reduce_on_plateau -> ema -> apply_updates -> box.
  * Replaces: optax.chain(...).update + optax.apply_updates for planners built with noise_kwargs,

@@ -35,7 +35,7 @@ EXPORTS = [
     "rk_draw_noise", "rk_noise_advance", "rk_drp_returns_loss", "rk_transpose_split",
     "rk_utility_loss", "rk_optimizer_chain_step", "rk_utility_loss_shard",
     "rk_utility_sorted_work_bytes", "rk_utility_sorted_loss", "rk_peer_allreduce_gather",
-    "rk_act_apply",
+    "rk_act_apply", "rk_reduce_optimizer_step",
 ]
 
 
@@ -119,6 +119,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.rk_peer_allreduce_gather.restype = ci
     lib.rk_act_apply.argtypes = [vp, ci, ctypes.c_size_t, cf, cf]
     lib.rk_act_apply.restype = ci
+    lib.rk_reduce_optimizer_step.argtypes = [vp, cf, ci, ci, cf, ci, cf, cf, cf, cf, cf, cf, cf]
+    lib.rk_reduce_optimizer_step.restype = ci
     lib.rk_state_layernorm_ctas.argtypes = [ci]
     lib.rk_state_layernorm_ctas.restype = ci
     lib.rk_state_layernorm_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, fl, cf, cf, cf, cf]
@@ -284,6 +286,14 @@ def optimizer_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, 
     _check(load_library().rk_optimizer_step(
         _stream(), OPT_KIND[kind], _ptr(hyper), n, _ptr(params), _ptr(state), _ptr(grad),
         _ptr(lo), _ptr(hi), _ptr(zero_flag)), "rk_optimizer_step")
+
+
+def reduce_optimizer_step(gradp, rows: int, n: int, grad, kind: str, hyper, params, state, lo, hi,
+                          zero_flag, counters):
+    """rk_reduce_optimizer_step: partial-row reduction and optimiser step in one launch."""
+    _check(load_library().rk_reduce_optimizer_step(
+        _stream(), _ptr(gradp), rows, n, _ptr(grad), OPT_KIND[kind], _ptr(hyper), _ptr(params),
+        _ptr(state), _ptr(lo), _ptr(hi), _ptr(zero_flag), _ptr(counters)), "rk_reduce_optimizer_step")
 
 
 def optimizer_chain_step(kind: str, hyper: torch.Tensor, n: int, params, state, grad, lo, hi, zero_flag,

@@ -782,6 +782,19 @@ class JaxBackpropPlanner:
                 (z(T * fw.tape_words * Bt), z(self.nwarps * T * A), z(Bt)) for _ in range(P - 1)]
         self._use_chain = (self.noise_kwargs is not None or self.ema_decay is not None
                            or self.reduce_on_plateau_kwargs is not None)
+        # the tail of the adjoint fused with the optimiser (csrc/rk_optim.cu:rk_reduce_optimizer_step): in
+        # the pipelined order the partial rows of a replay's adjoint are reduced by the NEXT replay's
+        # optimiser kernel -- one launch less on the critical chain.  Needs the plain chain: one GPU (the
+        # exchange wants the reduced gradient), no global-norm clipping, no extra links, K = P = 1, no term
+        # added to the gradient after the reduction (stochastic plans, critic)
+        self._fuse_tail = (self._pipeline and not self.is_drp and self.world_size == 1 and P == 1
+                           and self.steps_per_update <= 1 and self.clip_grad is None
+                           and not self._use_chain and self.line_search_kwargs is None
+                           and self.critic_fn is None and not getattr(self.plan, "_stochastic", False)
+                           and not self._utility_eager
+                           and _os.environ.get("RK_FUSE_TAIL", "1") != "0")
+        self._tail_counters = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._defer_reduce = False
         if self.reduce_on_plateau_kwargs is not None and self.world_size > 1:
             raise NotImplementedError("reduce_on_plateau_kwargs with more than one GPU: the plateau "
                                       "test needs the all-reduced loss before the optimiser step")
@@ -999,7 +1012,8 @@ class JaxBackpropPlanner:
                                     noise=self.train_noise, mparams=self.train_mparams,
                                     disc=self.disc, gradp=self.gradp,
                                     gs_in=self.gs_in if critic else None)
-            engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
+            if not self._defer_reduce:      # (deferred: the next optimiser launch reduces the rows itself)
+                engine.reduce_partials(self.gradp, self.nwarps, T * A, self.grad[p])
             if gp0 is not None:       # the critic also sees the plan's step-0 action
                 self.grad[p][:A].add_(gp0)
         if self.world_size > 1 and not self._defer_ar:   # the exchange step of the path
@@ -1074,9 +1088,17 @@ class JaxBackpropPlanner:
         train stage left in self.grad; publishes that stage's loss."""
         T, A = self.T, self.A
         params = self.params[p]
-        if publish:
+        if self._defer_reduce:
+            engine.reduce_optimizer_step(self.gradp, self.nwarps, T * A, self.grad[p], self.optimizer_name,
+                                         self.hyper, params, self.opt_state[p], self.box_lo, self.box_hi,
+                                         self.zero_flag[p:p + 1], self._tail_counters)
+            if publish:
+                self._publish_kernels(p)
+        elif publish:
             self._publish_kernels(p)
-        if self.line_search_kwargs is not None:
+        if self._defer_reduce:
+            pass
+        elif self.line_search_kwargs is not None:
             self._line_search_update(p)
         elif not self._use_chain:
             engine.optimizer_step(self.optimizer_name, self.hyper, self.n_params, params,
@@ -1249,6 +1271,7 @@ class JaxBackpropPlanner:
         (one warp per SM sub-partition), so they overlap almost perfectly.  Results per
         iteration are identical to update-then-test (planner.py:3245-3260)."""
         P = self.parallel_updates
+        self._defer_reduce = self._fuse_tail
         # fresh noise of this replay, drawn where it is consumed: the train tensor on the main branch
         # (next to the optimiser step, which it does not depend on), the test tensor at the head of the
         # test branch -- the two counter-based launches overlap instead of preceding the iteration
@@ -1300,6 +1323,7 @@ class JaxBackpropPlanner:
             engine.noise_advance(self._draws)
         self._finish_iteration()
         self._defer_ar = False
+        self._defer_reduce = False
 
     def _use_scratch(self, p: int):
         if self._branches:
@@ -1412,10 +1436,12 @@ class JaxBackpropPlanner:
         if self._pipeline and not self._primed:
             self.load_initial_state(self._h_init_train, self._h_init_test)
             self.params.copy_(self._h_params_in, non_blocking=True)
+            self._defer_reduce = self._fuse_tail
             for p in range(self.parallel_updates):     # gradient for the first optimiser step
                 self._use_scratch(p)
                 self._train_grad_kernels(p)
             self._use_scratch(0)
+            self._defer_reduce = False
             self._primed = True
         self._graph_host.replay()
         torch.cuda.current_stream(self.device).synchronize()
@@ -1438,10 +1464,12 @@ class JaxBackpropPlanner:
         if self._graph is None:
             self._capture()
         if self._pipeline and not self._primed:
+            self._defer_reduce = self._fuse_tail
             for p in range(self.parallel_updates):     # gradient for the first optimiser step
                 self._use_scratch(p)
                 self._train_grad_kernels(p)
             self._use_scratch(0)
+            self._defer_reduce = False
             self._primed = True
         self._graph.replay()
 

@@ -133,21 +133,16 @@ rk_grad_stats_kernel(const float* __restrict__ g, int n, float* __restrict__ sta
   }
 }
 
+// One parameter's optimiser update + apply_updates + box projection (planner.py:2885-2899), shared by every
+// kernel that applies a step so that they agree to the bit.
 // hyper = {lr, decay|b1, eps, b2, clip_norm, momentum, step, 1 - decay|b1, 1 - b2}
-__global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, int n,
-                                    float* __restrict__ params, float* __restrict__ state,
-                                    const float* __restrict__ grad, const float* __restrict__ lo,
-                                    const float* __restrict__ hi, const float* __restrict__ stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ float rk_opt_update(int kind, const float* __restrict__ hyper, int n, int i,
+                                               float g, float p, float* __restrict__ state,
+                                               const float* __restrict__ lo,
+                                               const float* __restrict__ hi) {
   const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
-  const float clip = hyper[4], mom = hyper[5], step = hyper[6];
+  const float mom = hyper[5], step = hyper[6];
   const float om1 = hyper[7], om2 = hyper[8];      // 1 - decay|b1, 1 - b2 rounded from double (optax)
-  float g = grad[i];
-  if (clip > 0.f) {                      // optax.clip_by_global_norm (planner.py:2368-2369)
-    const float gn = sqrtf(stats[0]);
-    if (gn > clip) g = g * (clip / gn);
-  }
   float upd;
   if (kind == 1) {                       // optax.rmsprop: nu <- d nu + (1-d) g^2 ; g * rsqrt(nu + eps)
     float nu = d1 * state[i] + om1 * g * g;
@@ -170,10 +165,25 @@ __global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, i
       upd = g;
     }
   }
-  float p = params[i] - lr * upd;        // optax.apply_updates (planner.py:2898)
+  p = p - lr * upd;                      // optax.apply_updates (planner.py:2898)
   if (lo != nullptr) p = fmaxf(p, lo[i]);   // box projection (planner.py:896-904)
   if (hi != nullptr) p = fminf(p, hi[i]);
-  params[i] = p;
+  return p;
+}
+
+__global__ void rk_optimizer_kernel(int kind, const float* __restrict__ hyper, int n,
+                                    float* __restrict__ params, float* __restrict__ state,
+                                    const float* __restrict__ grad, const float* __restrict__ lo,
+                                    const float* __restrict__ hi, const float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float clip = hyper[4];
+  float g = grad[i];
+  if (clip > 0.f) {                      // optax.clip_by_global_norm (planner.py:2368-2369)
+    const float gn = sqrtf(stats[0]);
+    if (gn > clip) g = g * (clip / gn);
+  }
+  params[i] = rk_opt_update(kind, hyper, n, i, g, params[i], state, lo, hi);
 }
 
 // short parameter vectors: statistics and update in one single-CTA launch
@@ -192,9 +202,7 @@ rk_optimizer_small_kernel(int kind, const float* __restrict__ hyper, int n, floa
   ss = block_sum_1024(ss, sh);
   nz = block_sum_1024(nz, sh);
   if (threadIdx.x == 0 && zero_flag != nullptr) *zero_flag = (nz == 0.f) ? 1 : 0;
-  const float lr = hyper[0], d1 = hyper[1], eps = hyper[2], b2 = hyper[3];
-  const float clip = hyper[4], mom = hyper[5], step = hyper[6];
-  const float om1 = hyper[7], om2 = hyper[8];      // 1 - decay|b1, 1 - b2 rounded from double (optax)
+  const float clip = hyper[4];
   float scale = 1.f;
   bool clipped = false;
   if (clip > 0.f) {
@@ -204,32 +212,7 @@ rk_optimizer_small_kernel(int kind, const float* __restrict__ hyper, int n, floa
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float g = grad[i];
     if (clipped) g = g * scale;
-    float upd;
-    if (kind == 1) {
-      float nu = d1 * state[i] + om1 * g * g;
-      state[i] = nu;
-      upd = g / sqrtf(nu + eps);
-    } else if (kind == 2) {
-      float mu = d1 * state[i] + om1 * g;
-      float nu = b2 * state[n + i] + om2 * g * g;
-      state[i] = mu;
-      state[n + i] = nu;
-      float mh = mu / (1.f - powf(d1, step));
-      float nh = nu / (1.f - powf(b2, step));
-      upd = mh / (sqrtf(nh) + eps);
-    } else {
-      if (mom > 0.f) {
-        float m = g + mom * state[i];
-        state[i] = m;
-        upd = m;
-      } else {
-        upd = g;
-      }
-    }
-    float p = params[i] - lr * upd;
-    if (lo != nullptr) p = fmaxf(p, lo[i]);
-    if (hi != nullptr) p = fminf(p, hi[i]);
-    params[i] = p;
+    params[i] = rk_opt_update(kind, hyper, n, i, g, params[i], state, lo, hi);
   }
 }
 
@@ -257,6 +240,115 @@ extern "C" int rk_optimizer_step(void* stream, int kind, const float* hyper, int
   rk_grad_stats_kernel<<<1, 1024, 0, st>>>(grad, n, g_stats[dev], zero_flag);
   rk_optimizer_kernel<<<(n + 255) / 256, 256, 0, st>>>(kind, hyper, n, params, state, grad, lo, hi,
                                                         g_stats[dev]);
+  return (int)cudaGetLastError();
+}
+
+// ---- gradient reduction fused with the optimiser step ------------------------------------------------
+// The tail of the adjoint: the per-warp partial rows are summed (same order as rk_reduce_partials) and the
+// CTA that owns a column applies the optimiser step to it at once -- gradient, update, apply_updates, box
+// projection in ONE launch (no global-norm clipping: that needs the whole gradient first).  The all-zero
+// flag of planner.py:2861-2864 is agreed through two counters: every CTA adds its non-zero count, the last
+// one to arrive writes the flag and resets them (integer atomics: the result does not depend on the order).
+__device__ __forceinline__ void rk_zero_flag_vote(int nz_cta, int32_t* counters, int32_t* zero_flag) {
+  if (zero_flag == nullptr) return;
+  if (nz_cta) atomicAdd(&counters[0], nz_cta);
+  __threadfence();
+  const int ticket = atomicAdd(&counters[1], 1);
+  if (ticket == (int)gridDim.x - 1) {
+    *zero_flag = (atomicAdd(&counters[0], 0) == 0) ? 1 : 0;
+    counters[0] = 0;
+    counters[1] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+rk_reduce_opt_small_kernel(const float* __restrict__ gradp, int rows, int n, float* __restrict__ grad,
+                           int kind, const float* __restrict__ hyper, float* __restrict__ params,
+                           float* __restrict__ state, const float* __restrict__ lo,
+                           const float* __restrict__ hi, int32_t* zero_flag, int32_t* counters) {
+  __shared__ float part[32][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;
+  const int per = (rows + 31) / 32;
+  const int r0 = g * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  if (i < n) {
+    const float* p = gradp + (size_t)r0 * n + i;
+    for (int r = r0; r < r1; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (r + u < r1) ? p[(size_t)u * n] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+      p += 8 * (size_t)n;
+    }
+  }
+  part[g][c] = acc;
+  __syncthreads();
+  if (g == 0) {
+    int nz = 0;
+    if (i < n) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) s += part[q][c];
+      grad[i] = s;
+      nz = (fabsf(s) > 1e-8f || s != s) ? 1 : 0;
+      params[i] = rk_opt_update(kind, hyper, n, i, s, params[i], state, lo, hi);
+    }
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if (c == 0) rk_zero_flag_vote(nz, counters, zero_flag);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+rk_reduce_opt_heads_kernel(const float* __restrict__ gradp, int rows, int n, int chunks,
+                           float* __restrict__ grad, int kind, const float* __restrict__ hyper,
+                           float* __restrict__ params, float* __restrict__ state,
+                           const float* __restrict__ lo, const float* __restrict__ hi,
+                           int32_t* zero_flag, int32_t* counters) {
+  __shared__ int nz_s[4];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int nz = 0;
+  if (i < n) {
+    const int per = (rows + chunks - 1) / chunks;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      const int r0 = c * per;
+      if (r0 >= rows) break;
+      acc += gradp[(size_t)r0 * n + i];
+    }
+    grad[i] = acc;
+    nz = (fabsf(acc) > 1e-8f || acc != acc) ? 1 : 0;
+    params[i] = rk_opt_update(kind, hyper, n, i, acc, params[i], state, lo, hi);
+  }
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0) nz_s[threadIdx.x >> 5] = nz;
+  __syncthreads();
+  if (threadIdx.x == 0) rk_zero_flag_vote(nz_s[0] + nz_s[1] + nz_s[2] + nz_s[3], counters, zero_flag);
+}
+
+extern "C" int rk_reduce_optimizer_step(void* stream, const float* gradp, int num_rows, int n,
+                                        float* grad, int kind, const float* hyper, float* params,
+                                        float* state, const float* lo, const float* hi,
+                                        int32_t* zero_flag, int32_t* counters) {
+  if (gradp == nullptr || grad == nullptr || num_rows <= 0 || n <= 0 || hyper == nullptr ||
+      params == nullptr)
+    return RK_E_BADARG;
+  if (kind < 0 || kind > 2 || (kind != 0 && state == nullptr)) return RK_E_BADARG;
+  if (zero_flag != nullptr && counters == nullptr) return RK_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_rows <= 1024) {
+    rk_reduce_opt_small_kernel<<<(n + 31) / 32, 1024, 0, st>>>(gradp, num_rows, n, grad, kind, hyper,
+                                                               params, state, lo, hi, zero_flag, counters);
+    return (int)cudaGetLastError();
+  }
+  int chunks = 1;
+  const int col_blocks = (n + 127) / 128;
+  while (chunks < 64 && chunks * 2 * 32 <= num_rows && col_blocks * chunks < 148 * 8) chunks *= 2;
+  dim3 grid(col_blocks, chunks);
+  rk_reduce_rows_kernel<<<grid, 128, 0, st>>>((float*)gradp, num_rows, n, chunks);
+  rk_reduce_opt_heads_kernel<<<col_blocks, 128, 0, st>>>(gradp, num_rows, n, chunks, grad, kind, hyper,
+                                                         params, state, lo, hi, zero_flag, counters);
   return (int)cudaGetLastError();
 }
 

@@ -339,3 +339,37 @@ def test_native_utility_keeps_the_graph_and_matches_eager(cuda_device):
         assert (pl._graph is not None) == native
         plans.append((pl.params[0].cpu().clone(), pl.read_stats()[0].copy()))
     torch.testing.assert_close(plans[0][0], plans[1][0], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,n", [(7, 33), (512, 1600), (1024, 40), (1025, 40), (16384, 1000), (8192, 720)])
+@pytest.mark.parametrize("kind", ["sgd", "rmsprop", "adam"])
+def test_fused_reduce_optimizer_equals_separate_launches(cuda_device, rows, n, kind):
+    """rk_reduce_optimizer_step (partial-row reduction + optimiser step + box + all-zero flag in one launch)
+    against rk_reduce_partials followed by rk_optimizer_step: gradient, parameters, optimiser state and
+    flag agree to the bit, over several steps, and the counters are left at zero."""
+    import torch
+    from pyrddlgym_jax_b200.core import engine
+    g = torch.Generator().manual_seed(rows * 31 + n)
+    dev = cuda_device
+    hyper = torch.tensor([0.03, 0.9, 1e-8, 0.999, 0.0, 0.0 if kind != "sgd" else 0.5, 1.0,
+                          1.0 - 0.9, 1.0 - 0.999], dtype=torch.float32, device=dev)
+    n_state = {"sgd": 1, "rmsprop": 1, "adam": 2}[kind]
+    p0 = torch.randn(n, generator=g).to(dev)
+    lo, hi = (p0 - 0.05).contiguous(), (p0 + 0.04).contiguous()
+    pa, pb = p0.clone(), p0.clone()
+    sa, sb = torch.zeros(n_state * n, device=dev), torch.zeros(n_state * n, device=dev)
+    ga, gb = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    fa = torch.full((1,), -1, dtype=torch.int32, device=dev)
+    fb = torch.full((1,), -1, dtype=torch.int32, device=dev)
+    counters = torch.zeros(2, dtype=torch.int32, device=dev)
+    for step in range(4):
+        gp = (torch.randn(rows, n, generator=g) * (0.0 if step == 2 else 1e-2)).to(dev)
+        gp2 = gp.clone()                  # the large path reduces in place
+        engine.reduce_partials(gp.reshape(-1), rows, n, ga)
+        engine.optimizer_step(kind, hyper, n, pa, sa, ga, lo, hi, fa)
+        engine.reduce_optimizer_step(gp2.reshape(-1), rows, n, gb, kind, hyper, pb, sb, lo, hi, fb, counters)
+        torch.cuda.synchronize()
+        assert torch.equal(ga, gb) and torch.equal(pa, pb) and torch.equal(sa, sb), step
+        assert int(fa) == int(fb) == (1 if step == 2 else 0)
+        assert counters.tolist() == [0, 0]
+        hyper[6] += 1.0
