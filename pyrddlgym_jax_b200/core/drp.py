@@ -1134,7 +1134,12 @@ class DrpPipeline:
                     "kernel": "rk_mlp2_kernel<forward> (layer 0 + hidden layer tcgen05 3xTF32 + heads, one launch "
                               "per decision epoch; train sweep, H0 / H1 kept)",
                     "achieved": achieved_tf, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tf / tensor_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved_tf / tensor_peak,
+                    # dram__bytes of one launch from the committed ncu capture of this shape
+                    # (profiles/r02_ncu_mlp2.md: 1.39 MB read + 14.73 MB written by the end of the launch;
+                    # the rest of the 67 MB of H0 / H1 is still in the 126 MB L2 then)
+                    "traffic": 16116000 if (B, h0, h1) == (32768, 256, 256) else None,
+                    "peak_source": peak_src,
                     "algorithmic_flops": flops_fwd, "executed_tf32_tflops": 3 * achieved_tf,
                     "mlp_tflop_per_iteration": flops_iter / 1e12,
                     "hbm_bytes_per_launch": 4.0 * B * (h0 + h1 + self.NH + self.D),
