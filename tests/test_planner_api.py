@@ -808,7 +808,7 @@ def test_load_config_resolves_drp_options_and_preprocessor():
     assert planner_args["preprocessor"].fluent_bounds == {"temperature": (-30.0, 40.0)}
     assert "dashboard" not in planner_args and "preprocessor_kwargs" not in planner_args
     assert planner_args["reduce_on_plateau_kwargs"] == {"factor": 0.5, "patience": 5}
-    for bad in (DRP_FULL.replace("'relu'", "'gelu'"), DRP_FULL.replace("FixedTimeEmbedding", "Nope"),
+    for bad in (DRP_FULL.replace("'relu'", "'hard_tanh'"), DRP_FULL.replace("FixedTimeEmbedding", "Nope"),
                 DRP_FULL.replace("'StaticNormalizer'", "'JaxPlan'")):
         with pytest.raises(ValueError):
             load_config_from_string(bad)
