@@ -373,3 +373,69 @@ def test_fused_reduce_optimizer_equals_separate_launches(cuda_device, rows, n, k
         assert int(fa) == int(fb) == (1 if step == 2 else 0)
         assert counters.tolist() == [0, 0]
         hyper[6] += 1.0
+
+
+@pytest.mark.parametrize("n", [700, 40000])
+@pytest.mark.parametrize("kind", ["sgd", "rmsprop", "adam"])
+def test_chain_step_recurrences_both_paths(cuda_device, n, kind):
+    """rk_optimizer_chain_step on a short vector (single launch) and a long one (statistics launch + apply
+    launch): clip_by_global_norm -> optimiser -> reduce_on_plateau scale -> ema with debias -> box, against
+    the same recurrences written out in torch (fp64 where it matters), over several steps; with add_noise
+    on, the perturbation has the requested deviation."""
+    import torch
+    from oracle import planner as OP
+    from pyrddlgym_jax_b200.core import engine
+    from pyrddlgym_jax_b200.core.planner import plateau_init, plateau_kwargs
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n + len(kind))
+    lr, d1, eps, b2, clip, decay = 0.05, 0.9, 1e-8, 0.999, 0.5, 0.8
+    hyper = torch.tensor([lr, d1, eps, b2, clip, 0.0, 1.0, 1.0 - d1, 1.0 - b2], dtype=torch.float32, device=dev)
+    pk = plateau_kwargs({"factor": 0.5, "patience": 1, "rtol": 1e-3})
+    cfg = {"noise": None, "ema_decay": decay, "plateau": pk}
+    p0 = torch.randn(n, generator=g)
+    lo, hi = (p0 - 0.2), (p0 + 0.2)
+    params, state = p0.clone().to(dev), torch.zeros((2 if kind == "adam" else 1) * n, device=dev)
+    ema, count, scratch = torch.zeros(n, device=dev), torch.zeros(1, device=dev), torch.zeros(8, device=dev)
+    plat = plateau_init(1, dev)[0]
+    loss = torch.zeros(1, device=dev)
+    zero = torch.zeros(1, dtype=torch.int32, device=dev)
+    want, st_mu, st_nu, ema_w = p0.double().clone(), torch.zeros(n).double(), torch.zeros(n).double(), \
+        torch.zeros(n).double()
+    ref = OP.reduce_on_plateau_init()
+    for t in range(1, 5):
+        grad = torch.randn(n, generator=g) * 0.1
+        lval = 5.0 - 0.5 * t if t < 3 else 4.0            # improves twice, then stalls
+        loss.fill_(lval)
+        hyper[6] = float(t)
+        engine.optimizer_chain_step(kind, hyper, n, params, state, grad.to(dev), lo.to(dev), hi.to(dev), zero,
+                                    cfg, count, plat, ema, loss, 0, scratch)
+        torch.cuda.synchronize()
+        gd = grad.double()
+        gn = float(gd.norm())
+        gd = gd * min(1.0, clip / gn)
+        if kind == "rmsprop":
+            st_nu = d1 * st_nu + (1 - d1) * gd * gd
+            upd = gd / torch.sqrt(st_nu + eps)
+        elif kind == "adam":
+            st_mu = d1 * st_mu + (1 - d1) * gd
+            st_nu = b2 * st_nu + (1 - b2) * gd * gd
+            upd = (st_mu / (1 - d1 ** t)) / (torch.sqrt(st_nu / (1 - b2 ** t)) + eps)
+        else:
+            upd = gd
+        ref = OP.reduce_on_plateau_step(ref, lval, **pk)
+        delta = -lr * upd * ref["scale"]
+        ema_w = decay * ema_w + (1 - decay) * delta
+        want = torch.minimum(torch.maximum(want + ema_w / (1 - decay ** t), lo.double()), hi.double())
+        torch.testing.assert_close(params.cpu().double(), want, rtol=2e-5, atol=2e-6)
+        assert abs(float(plat[0]) - ref["scale"]) < 1e-7 and float(count) == t and int(zero) == 0
+    assert ref["scale"] < 1.0
+    # add_noise: N(0, eta / t^gamma) on every component, nothing else moving (sgd, lr 1, zero gradient)
+    hyper2 = torch.tensor([1.0, 0, 0, 0, 0, 0, 1, 1, 1], dtype=torch.float32, device=dev)
+    p2, cnt2 = torch.zeros(n, device=dev), torch.zeros(1, device=dev)
+    engine.optimizer_chain_step("sgd", hyper2, n, p2, None, torch.zeros(n, device=dev), None, None, zero,
+                                {"noise": (0.04, 0.55), "ema_decay": None, "plateau": None}, cnt2, None, None,
+                                loss, 17, scratch)
+    torch.cuda.synchronize()
+    assert int(zero) == 1                                   # the flag is about the RAW gradient
+    sd = float(p2.std())
+    assert abs(sd - 0.2) < 0.2 * (4.0 / (2 * n) ** 0.5 + 0.02) and abs(float(p2.mean())) < 4 * 0.2 / n ** 0.5
