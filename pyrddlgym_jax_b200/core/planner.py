@@ -692,6 +692,9 @@ class JaxBackpropPlanner:
         self.n_params = self.plan.n_params if self.is_drp else self.T * self.A
         self._alloc()
         self.drp = DrpPipeline(self) if self.is_drp else None
+        # JaxPlan.projection / initializer / test_policy (planner.py:386-420) resolve to the planner's seams
+        self.plan.projection, self.plan.initializer = self.projection, self.initializer
+        self.plan.test_policy = self.test_policy
         if self.use_pgpe:
             self.pgpe.compile(self)
 
@@ -1671,6 +1674,61 @@ class JaxBackpropPlanner:
     def test_loss(self):
         for p in range(self.parallel_updates):
             self._test_kernels(p)
+
+    # ---- the reference's closure seams as plain callables (planner.py:386-420, 2673-2698) ----------
+    # The reference hands out jitted closures over (sim_state, planner_state) pytrees; here the same work
+    # is done by kernels, and these thin callables take / return the parameter pytree directly.
+    def projection(self, params: Dict[str, Any]):
+        """plan.projection (planner.py:878-959): box clip and, when the instance limits concurrent actions,
+        the max-nondef-actions projection, on the device.  Returns (projected pytree, converged)."""
+        flat = self.plan.pytree_to_params(params).reshape(-1).to(self.device).contiguous()
+        self.project_params(flat, 0)
+        torch.cuda.synchronize(self.device)
+        return (self.plan.params_to_pytree(self._plan_view(flat.cpu())), bool(self.converged[0].item()))
+
+    def initializer(self, key: int):
+        """plan.initializer (planner.py:974-1009): (initial parameter pytree after the projection,
+        policy hyper-parameters)."""
+        flat = self.plan.initial_params(torch.Generator().manual_seed(int(key))).reshape(-1)
+        tree, _ = self.projection(self.plan.params_to_pytree(self._plan_view(flat)))
+        hyper = {var: self.plan._sigmoid_weight for var in self.rddl.action_fluents} \
+            if not self.is_drp else {"softmax_weight": self.plan._softmax_output_weight,
+                                     "sigmoid_weight": self.plan._sigmoid_weight}
+        return tree, hyper
+
+    def test_policy(self, key, params: Dict[str, Any], policy_hyperparams, step: int, fls: Dict[str, Any]):
+        """The test policy at one decision epoch (planner.py:842-868, 1482-1499): the same call as
+        get_action."""
+        return self.get_action(key, params, step, fls, policy_hyperparams)
+
+    def _rollouts(self, params: Optional[Dict[str, Any]], train: bool) -> Dict[str, Any]:
+        if self.is_drp:
+            raise NotImplementedError("train_rollouts / test_rollouts of a closed-loop policy: use update() "
+                                      "/ test_loss(), which walk the policy network between the steps")
+        if params is not None:
+            self.params[0].copy_(self.plan.pytree_to_params(params).reshape(-1).to(self.device))
+        if train:
+            T, B = self.T, self.batch_size_train
+            self.train_fwd.forward(B, T, self.s0_train, policy=self.params[0], noise=self.train_noise,
+                                   mparams=self.train_mparams, disc=self.disc,
+                                   reward=self.train_reward[0], returns=self.train_returns[0],
+                                   err=self.train_err[0], tape=self.tape)
+            log = self._train_log()
+            log.pop("grad", None)
+        else:
+            self._test_kernels(0)
+            log = self._test_log()
+        torch.cuda.synchronize(self.device)
+        return log
+
+    def train_rollouts(self, params: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Relaxed-model rollouts of the (given) plan on the current noise: the log of planner.py:2673-2680
+        (``reward`` / ``error`` as [P, B, T])."""
+        return self._rollouts(params, True)
+
+    def test_rollouts(self, params: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Exact-model rollouts of the (given) plan: the log of planner.py:2681-2687 (with ``fluents``)."""
+        return self._rollouts(params, False)
 
     # ---------------------------------------------------------------------------------
     def _train_log(self) -> Dict[str, Any]:

@@ -1026,3 +1026,40 @@ def test_reward_mask(cuda_device):
         pl.set_reward_mask(np.ones(T + 1))
     with pytest.raises(ValueError):
         pl.set_reward_mask(np.ones((T, 1)))
+
+
+@pytest.mark.gpu
+def test_closure_seams_as_callables(cuda_device):
+    """plan.projection / plan.initializer / test_policy and planner.train_rollouts / test_rollouts
+    (planner.py:386-420, 2673-2698): the reference's jitted closures as plain callables over the parameter
+    pytree."""
+    m = fixture_model("wildfire")                   # max-nondef-actions binds: concurrency projection
+    plan = JaxStraightLinePlan()
+    B, T = 16, 5
+    pl = JaxBackpropPlanner(m, plan, batch_size_train=B, rollout_horizon=T, pgpe=None)
+    pl.initialize(3)
+    tree, hyper = plan.initializer(7)
+    assert set(hyper) == set(m.action_fluents)
+    flat = plan.pytree_to_params(tree)
+    assert tuple(flat.shape) == (T, plan.A)
+    wild = plan.params_to_pytree(torch.randn(T, plan.A, generator=torch.Generator().manual_seed(1)) * 3)
+    proj, converged = plan.projection(wild)
+    assert converged
+    pflat = plan.pytree_to_params(proj)
+    for t in range(T):
+        acts = plan.test_actions(pflat[t].numpy())
+        on = sum(int(np.sum(a != plan.noop[name])) for name, a in acts.items())
+        assert on <= m.max_allowed_actions
+    a0 = plan.test_policy(None, proj, hyper, 0, {})
+    assert set(a0) == set(m.action_fluents)
+    log = pl.test_rollouts(proj)
+    assert tuple(log["reward"].shape) == (1, B, T) and tuple(log["error"].shape) == (1, B, T)
+    assert torch.isfinite(log["reward"]).all() and log["fluents"]
+    tlog = pl.train_rollouts(proj)
+    assert tuple(tlog["reward"].shape) == (1, B, T) and torch.isfinite(tlog["reward"]).all()
+    # the exact test rollouts of a projected plan and of the same plan set through update/test agree
+    pl.params[0].copy_(pflat.reshape(-1).to(pl.device))
+    pl.test_loss()
+    torch.cuda.synchronize()
+    again = pl._test_log()["reward"]
+    assert torch.equal(again, log["reward"])
