@@ -7,7 +7,7 @@ from pyrddlgym_jax_b200.core import logic
 from .parity import check_forward, check_gradient, forward_case, gradient_case
 
 KEYS = ["quadcopter", "reservoir", "wildfire", "marsrover", "powergen", "discrete",
-        "distributions", "ops", "samplers", "matrix"]
+        "distributions", "ops", "samplers", "matrix", "pomdp"]
 
 
 @pytest.mark.parametrize("key", KEYS)
