@@ -35,10 +35,11 @@ class GaussianPGPE(PGPE):
                  end_entropy_coeff: float = 1e-5, max_kl_update: Optional[float] = None,
                  eps: float = 1e-10) -> None:
         name = optimizer if isinstance(optimizer, str) else getattr(optimizer, "__name__", "")
-        if name != "adam":
-            raise NotImplementedError("GaussianPGPE: only the adam optimizer is built")
-        if project_samples or ema_decay is not None:
-            raise NotImplementedError("GaussianPGPE(project_samples / ema_decay) is not built yet")
+        if name not in ("adam", "rmsprop", "sgd"):
+            raise NotImplementedError(f"GaussianPGPE: optimizer <{name}> (adam, rmsprop, sgd)")
+        self.optimizer_name = name
+        self.project_samples = bool(project_samples)       # planner.py:1927-1940
+        self.ema_decay = None if ema_decay is None else float(ema_decay)   # optax.ema link, P:1790-1792
         self.batch_size = batch_size
         self.steps_per_update = steps_per_update
         self.init_sigma = init_sigma
@@ -73,6 +74,7 @@ class GaussianPGPE(PGPE):
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)   # noqa: E731
         self.mu, self.sigma = z(P, n), z(P, n)
         self.adam = {k: (z(P, n), z(P, n)) for k in ("mu", "sigma")}
+        self.ema = {k: z(P, n) for k in ("mu", "sigma")}
         self.r_max = torch.full((P,), -math.inf, device=dev)
         self.loss4 = z(4)
         self.step = 0
@@ -89,6 +91,8 @@ class GaussianPGPE(PGPE):
         for m, v in self.adam.values():
             m.zero_()
             v.zero_()
+        for e in self.ema.values():
+            e.zero_()
         self.r_max.fill_(-math.inf)
         self.step = 0
         self.gen = generator
@@ -138,16 +142,35 @@ class GaussianPGPE(PGPE):
         return g_mu, g_sigma
 
     def _adam(self, which: str, p: int, x: torch.Tensor, g: torch.Tensor, kw: Dict, clip) -> torch.Tensor:
-        """optax.adam (+ optional clip_by_global_norm), bias-corrected, step counted from 1."""
+        """One step of the meta-optimiser chain of planner.py:1786-1792 on the mean or the deviations:
+        [clip_by_global_norm] -> adam (bias-corrected, step counted from 1) / rmsprop / sgd -> [ema]."""
         if clip is not None:
             g = g * torch.clamp(clip / torch.linalg.vector_norm(g).clamp_min(1e-30), max=1.0)
         m, v = self.adam[which][0][p], self.adam[which][1][p]
-        b1, b2, eps = kw.get("b1", 0.9), kw.get("b2", 0.999), kw.get("eps", 1e-8)
-        m.mul_(b1).add_(g, alpha=1 - b1)
-        v.mul_(b2).addcmul_(g, g, value=1 - b2)
         t = self.step
-        mh, vh = m / (1 - b1 ** t), v / (1 - b2 ** t)
-        return x - kw.get("learning_rate", 0.1) * mh / (vh.sqrt() + eps)
+        if self.optimizer_name == "adam":
+            b1, b2, eps = kw.get("b1", 0.9), kw.get("b2", 0.999), kw.get("eps", 1e-8)
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            mh, vh = m / (1 - b1 ** t), v / (1 - b2 ** t)
+            upd = mh / (vh.sqrt() + eps)
+        elif self.optimizer_name == "rmsprop":
+            d, eps = kw.get("decay", 0.9), kw.get("eps", 1e-8)
+            v.mul_(d).addcmul_(g, g, value=1 - d)
+            upd = g / torch.sqrt(v + eps)
+        else:
+            mom = kw.get("momentum", None)
+            if mom:
+                m.mul_(mom).add_(g)
+                upd = m.clone()
+            else:
+                upd = g
+        delta = -kw.get("learning_rate", 0.1) * upd
+        if self.ema_decay is not None:             # optax.ema with debias
+            e = self.ema[which][p]
+            e.mul_(self.ema_decay).add_(delta, alpha=1 - self.ema_decay)
+            delta = e / (1 - self.ema_decay ** t)
+        return x + delta
 
     # ---- planner.py:2059-2128 -----------------------------------------------------------
     def update(self, progress: float) -> None:
@@ -170,6 +193,8 @@ class GaussianPGPE(PGPE):
                         ((mu + es, mu - es) if self.super_symmetric else ())
                     for i, c in enumerate(cands):
                         self.cand.copy_(c)
+                        if self.project_samples:      # planner.py:1927-1940
+                            pl.project_params(self.cand, p)
                         pl._test_kernels(p, params=self.cand, scratch=True,
                                          loss_out=self.loss4[i:i + 1])
                     if not self.super_symmetric:
@@ -183,6 +208,7 @@ class GaussianPGPE(PGPE):
                 self.r_max[p:p + 1].copy_(r_after.reshape(1))
                 old_mu, old_sigma = mu.clone(), sigma.clone()
                 state = {k: (m[p].clone(), v[p].clone()) for k, (m, v) in self.adam.items()}
+                ema_state = {k: e[p].clone() for k, e in self.ema.items()}
                 new_mu = self._adam("mu", p, mu, g_mu, self.optimizer_kwargs_mu, self.clip_grad_mu)
                 new_sigma = self._adam("sigma", p, sigma, g_sigma, self.optimizer_kwargs_sigma,
                                        self.clip_grad_sigma).clamp(lo, hi)
@@ -194,6 +220,7 @@ class GaussianPGPE(PGPE):
                     for k, (m, v) in self.adam.items():
                         m[p].copy_(state[k][0])
                         v[p].copy_(state[k][1])
+                        self.ema[k][p].copy_(ema_state[k])
                     new_mu = self._adam("mu", p, old_mu, g_mu * scale, self.optimizer_kwargs_mu,
                                         self.clip_grad_mu)
                     new_sigma = self._adam("sigma", p, old_sigma, g_sigma * scale,

@@ -247,6 +247,37 @@ def test_pgpe_formulas_known_answers():
     np.testing.assert_allclose(g_sigma.numpy(), want_sigma, rtol=2e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", ["adam", "rmsprop", "sgd"])
+def test_pgpe_meta_optimiser_chain(name):
+    """The meta-optimiser chain of GaussianPGPE (planner.py:1786-1792): optimiser -> ema with debias, against
+    the recurrences written out."""
+    from pyrddlgym_jax_b200.core.pgpe import GaussianPGPE
+    pg = GaussianPGPE(optimizer=name, ema_decay=0.8, optimizer_kwargs_mu={"learning_rate": 0.1})
+    n = 5
+    pg.adam = {k: (torch.zeros(1, n), torch.zeros(1, n)) for k in ("mu", "sigma")}
+    pg.ema = {k: torch.zeros(1, n) for k in ("mu", "sigma")}
+    x, ema, v, m = torch.zeros(n), torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    gen = torch.Generator().manual_seed(0)
+    for t in range(1, 5):
+        pg.step = t
+        g = torch.randn(n, generator=gen)
+        got = pg._adam("mu", 0, x, g, pg.optimizer_kwargs_mu, None)
+        if name == "adam":
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            upd = (m / (1 - 0.9 ** t)) / ((v / (1 - 0.999 ** t)).sqrt() + 1e-8)
+        elif name == "rmsprop":
+            v = 0.9 * v + 0.1 * g * g
+            upd = g / torch.sqrt(v + 1e-8)
+        else:
+            upd = g
+        ema = 0.8 * ema + 0.2 * (-0.1 * upd)
+        torch.testing.assert_close(got, x + ema / (1 - 0.8 ** t), rtol=1e-6, atol=1e-7)
+        x = got
+    with pytest.raises(NotImplementedError):
+        GaussianPGPE(optimizer="lion")
+
+
 def test_load_config_builds_pgpe():
     from pyrddlgym_jax_b200.core.pgpe import GaussianPGPE
     text = QUADCOPTER_SLP.replace("pgpe=None", "pgpe='GaussianPGPE'\npgpe_kwargs={'init_sigma': 0.5, 'batch_size': 2}")
@@ -286,6 +317,14 @@ def test_pgpe_runs_next_to_backprop_and_can_take_over(cuda_device, plan_kind):
             assert np.isfinite(cb["pgpe_return"]).all()
             seen.append(float(pg.r_max[0]))
         assert all(b >= a for a, b in zip(seen, seen[1:])) and np.isfinite(seen[-1])
+        # projected samples, rmsprop meta-optimiser with an EMA of its updates (planner.py:1786-1792, 1927-1940)
+        pg = GaussianPGPE(init_sigma=0.3, optimizer="rmsprop", ema_decay=0.9, project_samples=True,
+                          optimizer_kwargs_mu={"learning_rate": 0.05})
+        pl = JaxBackpropPlanner(m, plan, batch_size_train=64, rollout_horizon=8, optimizer="sgd",
+                                optimizer_kwargs={"learning_rate": 0.0}, pgpe=pg)
+        rets = [float(np.max(cb["pgpe_return"])) for cb in pl.optimize_generator(
+            key=4, epochs=25, print_summary=False, print_progress=False)]
+        assert np.isfinite(rets).all() and max(rets[-5:]) > rets[0]
 
 
 @pytest.mark.gpu
