@@ -684,7 +684,7 @@ class OracleModel:
         # switch
         pred_e, cases = e.args
         p, err = self.ev(pred_e, scope, fls, nfls, cur, B)
-        objs = self.model.type_to_objects[self._enum_type_of(pred_e)]
+        objs = self.model.type_to_objects[self._enum_type_of(pred_e, cases)]
         default = dict(cases).get(None)
         vals = []
         for o in objs:
@@ -711,12 +711,15 @@ class OracleModel:
         out = torch.gather(stack, 0, pb.to(torch.int64).unsqueeze(0))[0]   # compiler.py:1680-1683
         return out, err
 
-    def _enum_type_of(self, e: Expr) -> str:
+    def _enum_type_of(self, e: Expr, cases=()) -> str:
         if e.etype[0] == "pvar":
             name = e.args[0]
             if name in self.model.variable_ranges:
                 return self.model.variable_ranges[name]
-        raise NotImplementedError("switch predicate must be an enum-valued pvariable")
+        types = {self.model.object_to_type.get(lbl) for lbl, _ in cases if lbl is not None}
+        if len(types) == 1 and None not in types:          # a computed predicate: the labels' enum type
+            return types.pop()
+        raise NotImplementedError("switch predicate must be enum-valued")
 
     # -- random variables: compiler.py:1701-2241 ; logic.py:1010-1768 --------------------
     def _draw_shape(self, first_arg: Expr, scope):

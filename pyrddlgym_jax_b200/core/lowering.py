@@ -982,10 +982,18 @@ class Lowerer:
         pred_e, cases = e.args
         E = lambda name, *x: self.ew(name, list(x), sizes)     # noqa: E731
         C = lambda x: self.const_tv(np.float32(x))             # noqa: E731
-        if pred_e.etype[0] != "pvar" or pred_e.args[0] not in self.m.variable_ranges:
-            raise RDDLNotImplementedError("switch predicate must be an enum-valued pvariable")
-        objs = self.m.type_to_objects[self.m.variable_ranges[pred_e.args[0]]]
         table = dict(cases)
+        if pred_e.etype[0] == "pvar" and pred_e.args[0] in self.m.variable_ranges:
+            etype = self.m.variable_ranges[pred_e.args[0]]
+        else:
+            # a computed predicate (if / argmax / nested expression): the enum type is the one the case
+            # labels belong to (pyRDDLGym's tracer infers it from the predicate; the labels must agree)
+            types = {self.m.object_to_type.get(lbl) for lbl in table if lbl is not None}
+            if len(types) != 1 or None in types:
+                raise RDDLNotImplementedError(
+                    "switch over a computed predicate: the case labels must be objects of one enum type")
+            etype = types.pop()
+        objs = self.m.type_to_objects[etype]
         default = table.get(None)
         p = self.lower(pred_e, scope, env)
         vals = []

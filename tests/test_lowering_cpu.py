@@ -187,3 +187,44 @@ def test_matrix_and_random_vector_syntax():
     with pytest.raises(RDDLTraceError):
         lw.lower(multi, scope, env)
     assert RDDLNotImplementedError is not None
+
+
+SWITCH_RDDL = """
+domain switch_toy {
+    types { site : object; level : {@low, @mid, @high}; };
+    pvariables {
+        x(site)    : { state-fluent, real, default = 0.3 };
+        mode(site) : { state-fluent, level, default = @low };
+        push(site) : { action-fluent, real, default = 0.0 };
+    };
+    cpfs {
+        mode'(?s) = if (x(?s) > 0.6) then @high else (if (x(?s) > 0.35) then @mid else @low);
+        x'(?s) = x(?s) + switch (if (push(?s) > 0.5) then @high else mode(?s)) {
+                     case @low : 0.15, case @mid : 0.5 * push(?s), default : -0.2 * x(?s) };
+    };
+    reward = - (sum_{?s : site} [ pow[x'(?s) - 0.5, 2] ]);
+    action-preconditions { forall_{?s : site} [ push(?s) >= -1.0 ]; forall_{?s : site} [ push(?s) <= 1.0 ]; };
+}
+"""
+SWITCH_INST = """
+non-fluents nf { domain = switch_toy; objects { site : {s1, s2, s3}; }; }
+instance inst { domain = switch_toy; non-fluents = nf; init-state { x(s2) = 0.5; x(s3) = 0.8; mode(s3) = @high; };
+    max-nondef-actions = pos-inf; horizon = 5; discount = 1.0; }
+"""
+
+
+def test_switch_over_a_computed_predicate(tmp_path):
+    """switch whose predicate is an expression (compiler.py:1661-1684 compiles any predicate; the enum type
+    comes from the case labels here): exact and relaxed rollouts and the gradient, emulator vs oracle."""
+    from . import helpers
+    (tmp_path / "domain.rddl").write_text(SWITCH_RDDL)
+    (tmp_path / "instance1.rddl").write_text(SWITCH_INST)
+    helpers.FIXTURES["switch_toy"] = (str(tmp_path), "instance1")
+    try:
+        check_forward(forward_case("emu", "switch_toy", B=9, T=5, relaxed=False))
+        c = gradient_case("emu", "switch_toy", B=9, T=5)
+        check_forward(c)
+        check_gradient(c)
+        assert float(abs(c["grad"]).max()) > 0
+    finally:
+        helpers.FIXTURES.pop("switch_toy", None)
