@@ -1102,3 +1102,30 @@ def test_closure_seams_as_callables(cuda_device):
     torch.cuda.synchronize()
     again = pl._test_log()["reward"]
     assert torch.equal(again, log["reward"])
+
+
+def test_entry_point_resolution_and_defaults():
+    """Command line (entry_point.py:6-57, examples/run_plan.py): bundled fixtures resolve by name, the three
+    method names carry the reference's default settings, a .cfg path is loaded, bad input is rejected."""
+    import os
+    from pyrddlgym_jax_b200 import entry_point as EP
+    d, i = EP.resolve_model_files("Reservoir_Continuous", "1")
+    assert d.endswith("Reservoir_Continuous/domain.rddl") and i.endswith("instance1.rddl")
+    d2, i2 = EP.resolve_model_files(d, i)
+    assert (d2, i2) == (d, i)
+    with pytest.raises(FileNotFoundError):
+        EP.resolve_model_files("NoSuchDomain", "1")
+    with pytest.raises(FileNotFoundError):
+        EP.resolve_model_files("Reservoir_Continuous", "99")
+    pa, pk, ta, online = EP.load_method("slp")
+    assert pa["batch_size_train"] == 32 and pa["optimizer_kwargs"] == {"learning_rate": 0.01}
+    assert ta["epochs"] == 30000 and ta["train_seconds"] == 60 and not online
+    assert isinstance(pa["plan"], JaxStraightLinePlan)
+    pa, pk, ta, online = EP.load_method("replan", train_seconds=0.25)
+    assert online and pa["rollout_horizon"] == 5 and ta["train_seconds"] == 0.25 and ta["print_summary"] is False
+    pa, _, _, _ = EP.load_method("drp")
+    assert isinstance(pa["plan"], JaxDeepReactivePolicy) and pa["optimizer_kwargs"] == {"learning_rate": 0.0001}
+    with pytest.raises(ValueError):
+        EP.load_method("nope")
+    with pytest.raises(SystemExit):
+        EP.main(["tune", "a", "b", "c"])
