@@ -7,8 +7,11 @@ examples/run_plan.py:25-61):
 ``pyrddlgym_jax_b200/domains`` and of an instance file in it (rddlrepository is not part of this build).
 <method>: ``slp`` / ``drp`` (offline: optimise once, then act) or ``replan`` (online: re-optimise at every
 decision epoch), or the path of a ``.cfg`` file in the reference's format.  The environment is the
-``JaxRDDLSimulator`` of this package (one kernel launch per step).  ``tune`` (Bayesian hyper-parameter search,
-tuning.py) is outside the scope of this build.
+``JaxRDDLSimulator`` of this package (one kernel launch per step).
+
+    python -m pyrddlgym_jax_b200 tune <domain> <instance> <method> [-t TRIALS] [-i ITERS] [-w WORKERS] [-f FILE]
+
+runs the Bayesian hyper-parameter search of ``core/tuning.py`` on the reference's tuning templates.
 """
 from __future__ import annotations
 
@@ -118,6 +121,59 @@ def run_plan(domain: str, instance: str, method: str, episodes: int = 1,
     return totals
 
 
+# the tuning templates of the reference (examples/configs/tuning_{slp,drp,replan}.cfg): relaxation weight and
+# learning rate (and, for drp, the layer width; for replan, the lookahead) are the tuned tags
+_TUNE_CFG = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+sigmoid_weight=MODEL_WEIGHT_TUNE
+print_warnings=False
+
+[Planner]
+method='{plan}'
+method_kwargs={method_kwargs}
+optimizer='rmsprop'
+optimizer_kwargs={{'learning_rate': LEARNING_RATE_TUNE}}
+batch_size_train=32
+batch_size_test=32
+pgpe=None
+{extra}
+[Optimize]
+train_seconds={seconds}
+print_summary=False
+print_progress=False
+"""
+
+
+def run_tune(domain: str, instance: str, method: str, trials: int = 5, iters: int = 20, workers: int = 4,
+             filepath: str = "", train_seconds: float = 30.0):
+    """examples/run_tune.py of the reference: tune the relaxation weight and the learning rate (and the layer
+    width of a deep policy / the lookahead of online replanning)."""
+    from .core.tuning import Hyperparameter, JaxParameterTuning, power_10, power_2_int
+    from .rddl.model import load_model
+    if method not in ("slp", "drp", "replan"):
+        raise ValueError("method must be slp, drp or replan")
+    model = load_model(*resolve_model_files(domain, instance))
+    hyper = [Hyperparameter("MODEL_WEIGHT_TUNE", -1.0, 4.0, power_10),
+             Hyperparameter("LEARNING_RATE_TUNE", -5.0, 0.0, power_10)]
+    kw = dict(plan="JaxStraightLinePlan", method_kwargs="{}", extra="", seconds=train_seconds)
+    if method == "drp":
+        kw.update(plan="JaxDeepReactivePolicy", method_kwargs="{'topology': [LAYER1_TUNE, LAYER1_TUNE]}")
+        hyper.append(Hyperparameter("LAYER1_TUNE", 3.0, 8.0, power_2_int))
+    if method == "replan":
+        kw.update(extra="rollout_horizon=ROLLOUT_HORIZON_TUNE\n", seconds=min(train_seconds, 1.0))
+        hyper.append(Hyperparameter("ROLLOUT_HORIZON_TUNE", 1.0, min(40.0, float(model.horizon)),
+                                    lambda x: int(round(x))))
+    tuner = JaxParameterTuning(model, _TUNE_CFG.format(**kw), hyper, online=(method == "replan"),
+                               eval_trials=trials, gp_iters=iters, num_workers=workers)
+    tuner.tune(key=42, log_file=f"gp_{method}_{os.path.basename(domain)}_{instance}.csv")
+    if filepath:
+        with open(filepath, "w") as f:
+            f.write(tuner.best_config)
+    print(tuner.best_config)
+    return tuner
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser(prog="jaxplan", description="command line of the B200 JaxPlan planner")
     sub = parser.add_subparsers(dest="jaxplan", required=True)
@@ -127,13 +183,21 @@ def main(argv=None):
     plan.add_argument("method", type=str, help="slp, drp (offline), replan (online) or a .cfg file")
     plan.add_argument("-e", "--episodes", type=int, default=1, help="number of evaluation episodes")
     plan.add_argument("--train-seconds", type=float, default=None, help="override the training budget")
-    tune = sub.add_parser("tune", help="(hyper-parameter tuning is outside the scope of this build)")
-    tune.add_argument("rest", nargs="*")
+    tune = sub.add_parser("tune", help="tune the planner's hyper-parameters on a specified RDDL problem")
+    tune.add_argument("domain", type=str)
+    tune.add_argument("instance", type=str)
+    tune.add_argument("method", type=str, help="slp, drp (offline) or replan (online)")
+    tune.add_argument("-t", "--trials", type=int, default=5, help="evaluation trials per choice")
+    tune.add_argument("-i", "--iters", type=int, default=20, help="iterations of Bayesian optimisation")
+    tune.add_argument("-w", "--workers", type=int, default=4, help="suggestions evaluated per iteration")
+    tune.add_argument("-f", "--filepath", type=str, default="", help="where to save the best config")
+    tune.add_argument("--train-seconds", type=float, default=30.0, help="training budget of a trial")
     args = parser.parse_args(argv)
     if args.jaxplan == "plan":
         run_plan(args.domain, args.instance, args.method, args.episodes, args.train_seconds)
     else:
-        raise SystemExit("tune: Bayesian hyper-parameter search (tuning.py) is not part of this build")
+        run_tune(args.domain, args.instance, args.method, args.trials, args.iters, args.workers,
+                 args.filepath, args.train_seconds)
 
 
 if __name__ == "__main__":

@@ -1127,5 +1127,14 @@ def test_entry_point_resolution_and_defaults():
     assert isinstance(pa["plan"], JaxDeepReactivePolicy) and pa["optimizer_kwargs"] == {"learning_rate": 0.0001}
     with pytest.raises(ValueError):
         EP.load_method("nope")
-    with pytest.raises(SystemExit):
-        EP.main(["tune", "a", "b", "c"])
+    with pytest.raises(ValueError):
+        EP.run_tune("Reservoir_Continuous", "1", "nope")
+    # the tuning templates parse once their tags are replaced
+    from pyrddlgym_jax_b200.core.planner import load_config_from_string
+    cfg = EP._TUNE_CFG.format(plan="JaxDeepReactivePolicy", method_kwargs="{'topology': [LAYER1_TUNE, LAYER1_TUNE]}",
+                              extra="rollout_horizon=ROLLOUT_HORIZON_TUNE\n", seconds=3)
+    for tag, val in (("MODEL_WEIGHT_TUNE", "10.0"), ("LEARNING_RATE_TUNE", "0.01"), ("LAYER1_TUNE", "32"),
+                     ("ROLLOUT_HORIZON_TUNE", "5")):
+        cfg = cfg.replace(tag, val)
+    pa, pk, ta = load_config_from_string(cfg)
+    assert pa["rollout_horizon"] == 5 and pk["topology"] == [32, 32] and ta["train_seconds"] == 3

@@ -152,3 +152,44 @@ def test_controller_in_the_loop(cuda_device):
         state, reward, done = sim.step(action)
         total += reward
     assert np.isfinite(total)
+
+
+def test_tuning_on_a_small_budget(cuda_device, tmp_path):
+    """JaxParameterTuning with the real objective (train, then act in the simulator): a few iterations on
+    Reservoir with a tiny budget; the best configuration builds a controller that acts."""
+    from pyrddlgym_jax_b200.core.tuning import Hyperparameter, JaxParameterTuning, power_10
+    template = """
+[Compiler]
+method='DefaultJaxRDDLCompilerWithGrad'
+sigmoid_weight=MODEL_WEIGHT_TUNE
+
+[Planner]
+method='JaxStraightLinePlan'
+method_kwargs={}
+optimizer='rmsprop'
+optimizer_kwargs={'learning_rate': LEARNING_RATE_TUNE}
+batch_size_train=32
+batch_size_test=32
+rollout_horizon=8
+pgpe=None
+
+[Optimize]
+epochs=25
+train_seconds=5
+print_summary=False
+print_progress=False
+"""
+    m = fixture_model("reservoir")
+    tuner = JaxParameterTuning(m, template, [Hyperparameter("MODEL_WEIGHT_TUNE", 0.0, 3.0, power_10),
+                                             Hyperparameter("LEARNING_RATE_TUNE", -3.0, 0.0, power_10)],
+                               online=False, eval_trials=1, rollouts_per_trial=1, gp_iters=4, verbose=False)
+    best = tuner.tune(key=1, log_file=str(tmp_path / "log.csv"))
+    assert set(best) == {"MODEL_WEIGHT_TUNE", "LEARNING_RATE_TUNE"} and np.isfinite(tuner.best_target)
+    assert len(tuner.log) == 4
+    agent = tuner.build_best_controller()
+    from pyrddlgym_jax_b200.core.simulator import JaxRDDLSimulator
+    sim = JaxRDDLSimulator(m, key=2, keep_tensors=True)
+    state, _ = sim.reset()
+    agent.reset()
+    state, reward, _ = sim.step(agent.sample_action(state))
+    assert np.isfinite(reward)
